@@ -1,0 +1,412 @@
+"""Input generators.
+
+Reference `lingvo/core/base_input_generator.py`: `BaseInputGenerator` params
+(:141-257), `GetPreprocessedInputBatch` (:395), `SplitInputBatch` (:1006),
+`GlobalBatchSize/InfeedBatchSize` (:350-364), file-based generators
+(:1223-1296), sequence generators (:1465-1697), `BaseTinyDatasetInput`
+(:1706-1767).
+
+B200-first: a batch is a NestedMap of **pinned host tensors** produced by
+native C++ threads (`lingvo_b200.ops.native_input`); `DevicePrefetcher`
+overlaps the H2D copy of batch i+1 with the compute of batch i on a side
+stream — the analogue of the reference's TPU infeed queues.
+"""
+
+from __future__ import annotations
+
+import os
+import queue
+import threading
+from typing import Any, Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from lingvo_b200.core import base_layer
+from lingvo_b200.core import batch_utils
+from lingvo_b200.core import cluster_factory
+from lingvo_b200.core import hyperparams
+from lingvo_b200.core import py_utils
+from lingvo_b200.core.nested_map import NestedMap
+
+
+class BaseInputGenerator(base_layer.BaseLayer):
+  """The abstract base input generator."""
+
+  @classmethod
+  def DefineInfeedParams(cls, p):
+    p.Define('use_per_host_infeed', False, 'Kept for parity (per-rank input).')
+    p.Define('use_per_core_infeed', False, 'Kept for parity.')
+    p.Define('tpu_infeed_parallelism', 1, 'Prefetch depth of the H2D queue.')
+    p.Define('use_partitioned_infeed_queue', False, 'Kept for parity.')
+    p.Define('num_partitions', None, 'Kept for parity.')
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.name = 'input'
+    p.Define('file_datasource', None, 'DataSource params to read from.')
+    p.Define('batch_size', 0, 'Batch size for a device split.')
+    p.Define('num_samples', 0,
+             'If non-zero, the dataset contains these many samples.')
+    p.Define('resettable', False, 'Input can be reset (epoch-exact eval).')
+    p.Define('eval_samples_per_summary', None, 'Overrides task.eval value.')
+    p.Define('decoder_samples_per_summary', None, 'Overrides task.eval value.')
+    p.Define('filter_sparse_tensors', False, 'Kept for parity.')
+    p.Define('input_stats_summary_interval_steps', 10, 'Stats interval.')
+    p.Define('cpu_passthrough_keys', [], 'Keys kept on host (strings etc.).')
+    p.Define('pin_memory', True, 'Produce batches in pinned host memory.')
+    cls.DefineInfeedParams(p)
+    p.Define('remote', hyperparams.Params(), 'Kept for parity.')
+    p.remote.Define('max_inflights_per_target', 32, 'Kept for parity.')
+    p.Define('skip_tpu_embedding_enqueue_ops', False, 'Kept for parity.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self._made_iter = False
+    self._batch_cache = None
+    if self.params.file_datasource is not None:
+      self.CreateChild('datasource', self.params.file_datasource)
+
+  # ----------------------------------------------------------- batch sizing --
+  def GlobalBatchSize(self) -> int:
+    """Batch size summed over all splits of all replicas."""
+    return self.InfeedBatchSize() * max(self.cluster.world_size, 1)
+
+  def InfeedBatchSize(self) -> int:
+    """Batch size produced by this process per step."""
+    p = self.params
+    return batch_utils.scale_split_to_infeed(p.batch_size,
+                                             p.use_per_host_infeed)
+
+  def Initialize(self, sess=None):
+    pass
+
+  def Reset(self, sess=None):
+    pass
+
+  def CommonInputOpArgs(self) -> Dict[str, Any]:
+    return {}
+
+  # ----------------------------------------------------------------- batches --
+  def _InputBatch(self) -> NestedMap:
+    """Subclasses produce one (infeed) batch as a NestedMap of tensors."""
+    raise NotImplementedError('Abstract method')
+
+  def _PreprocessInputBatch(self, batch: NestedMap) -> NestedMap:
+    return batch
+
+  def GetPreprocessedInputBatch(self) -> NestedMap:
+    return self._PreprocessInputBatch(self._InputBatch())
+
+  def SplitInputBatch(self, num_splits: int) -> List[NestedMap]:
+    """One infeed batch split along dim 0 into `num_splits` shards (:1006)."""
+    batch = self.GetPreprocessedInputBatch()
+    if num_splits <= 1:
+      return [batch]
+    return SplitBatch(batch, num_splits)
+
+  def FProp(self, theta=None):
+    return self.GetPreprocessedInputBatch()
+
+  def __iter__(self):
+    while True:
+      try:
+        yield self.GetPreprocessedInputBatch()
+      except StopIteration:
+        return
+
+
+def SplitBatch(batch: NestedMap, num_splits: int) -> List[NestedMap]:
+  """Splits every tensor's leading dim into `num_splits` equal parts."""
+  flat = batch.FlattenItems()
+  outs = [[] for _ in range(num_splits)]
+  for k, v in flat:
+    if isinstance(v, torch.Tensor) and v.dim() > 0:
+      assert v.shape[0] % num_splits == 0, (
+          'batch dim %d of %s not divisible by %d' % (v.shape[0], k, num_splits))
+      parts = torch.chunk(v, num_splits, dim=0)
+    elif isinstance(v, np.ndarray) and v.ndim > 0:
+      parts = np.array_split(v, num_splits)
+    else:
+      parts = [v] * num_splits
+    for i in range(num_splits):
+      outs[i].append(parts[i])
+  return [batch.Pack(o) for o in outs]
+
+
+class DevicePrefetcher:
+  """Host→device double-buffering on a side stream (infeed analogue).
+
+  `Next()` returns a NestedMap already resident on `device`; the copy of the
+  following batch is issued immediately on `copy_stream` from pinned memory so
+  it overlaps the caller's compute. Also accounts the H2D bytes per step.
+  """
+
+  def __init__(self, input_gen: BaseInputGenerator, device, depth: int = 2,
+               passthrough_keys=()):
+    self._gen = input_gen
+    self._device = torch.device(device)
+    self._cuda = self._device.type == 'cuda'
+    self._stream = torch.cuda.Stream(self._device) if self._cuda else None
+    self._depth = max(1, depth)
+    self._q: List = []
+    self._passthrough = set(passthrough_keys)
+    self.h2d_bytes_last = 0
+
+  def _Issue(self):
+    host = self._gen.GetPreprocessedInputBatch()
+    nbytes = 0
+
+    def pin(x):
+      if isinstance(x, np.ndarray) and x.dtype.kind not in 'OUS':
+        x = torch.from_numpy(x)
+      if isinstance(x, torch.Tensor) and self._cuda and not x.is_cuda and not (
+          x.is_pinned()):
+        x = x.pin_memory()
+      return x
+
+    host = host.Transform(pin)
+    if not self._cuda:
+      self._q.append((host, None, 0))
+      return
+    with torch.cuda.stream(self._stream):
+      def move(k, x):
+        nonlocal nbytes
+        if isinstance(x, torch.Tensor) and k not in self._passthrough:
+          nbytes += x.numel() * x.element_size()
+          return x.to(self._device, non_blocking=True)
+        return x
+      dev = host.TransformWithKey(move)
+      ev = torch.cuda.Event()
+      ev.record(self._stream)
+    self._q.append((dev, ev, nbytes))
+
+  def Next(self) -> NestedMap:
+    while len(self._q) < self._depth:
+      self._Issue()
+    batch, ev, nbytes = self._q.pop(0)
+    if ev is not None:
+      torch.cuda.current_stream(self._device).wait_event(ev)
+      for t in batch.Flatten():
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+          t.record_stream(torch.cuda.current_stream(self._device))
+    self.h2d_bytes_last = nbytes
+    self._Issue()
+    return batch
+
+
+class BaseInputGeneratorFromFiles(BaseInputGenerator):
+  """Base class for input generators that read from files (:1223-1460)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('file_pattern', '', '`type:glob` or list of them / (pattern, '
+             'weight) pairs. Deprecated in favour of file_datasource.')
+    p.Define('file_random_seed', 301, 'Shuffle seed; 0 ⇒ system-random.')
+    p.Define('file_buffer_size', 10000, 'Shuffle buffer size (records).')
+    p.Define('file_buffer_size_in_seconds', 0, 'Adaptive buffer (seconds).')
+    p.Define('file_parallelism', 16, 'Number of files read in parallel.')
+    p.Define('bucket_adjust_every_n', 0, 'Re-tune buckets every n records.')
+    p.Define('flush_every_n', 0, 'Flush partial buckets every n records.')
+    p.Define('num_batcher_threads', 1, 'Processor threads.')
+    p.Define('repeat_count', -1, 'Epochs to produce; -1 = forever.')
+    p.Define('require_sequential_order', False, 'Read files sequentially.')
+    p.Define('use_within_batch_mixing', False, 'Mix sources within a batch.')
+    p.Define('use_chaining', False, 'Chain sources sequentially.')
+    p.Define('fatal_errors', [], 'Error substrings that abort the pipeline.')
+    p.Define('bucket_upper_bound', [], 'Bucketing scheme: upper bounds.')
+    p.Define('bucket_batch_limit', [], 'Per-bucket batch limits.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    if p.file_datasource is None and p.file_pattern:
+      from lingvo_b200.core import datasource
+      ds = datasource.SimpleDataSource.Params().Set(
+          file_pattern=p.file_pattern, name='datasource')
+      self.CreateChild('datasource', ds)
+    self._input_op = None
+
+  def CommonInputOpArgs(self):
+    p = self.params
+    args = super().CommonInputOpArgs()
+    num_threads = p.num_batcher_threads
+    if self.cluster.require_sequential_input_order:
+      num_threads = 1
+    args.update({
+        'file_random_seed': p.file_random_seed,
+        'file_buffer_size': p.file_buffer_size,
+        'file_buffer_size_in_seconds': p.file_buffer_size_in_seconds,
+        'file_parallelism': p.file_parallelism,
+        'bucket_adjust_every_n': p.bucket_adjust_every_n,
+        'flush_every_n': p.flush_every_n,
+        'num_threads': num_threads,
+        'repeat_count': p.repeat_count,
+        'require_sequential_order': (p.require_sequential_order or
+                                     self.cluster.require_sequential_input_order),
+        'fatal_errors': p.fatal_errors,
+        'bucket_upper_bound': list(p.bucket_upper_bound),
+        'bucket_batch_limit': self.infeed_bucket_batch_limit,
+    })
+    return args
+
+  @property
+  def infeed_bucket_batch_limit(self) -> List[int]:
+    p = self.params
+    return [batch_utils.scale_split_to_infeed(b, p.use_per_host_infeed)
+            for b in p.bucket_batch_limit]
+
+  def InfeedBatchSize(self):
+    lim = self.infeed_bucket_batch_limit
+    return max(lim) if lim else super().InfeedBatchSize()
+
+  def _DataSourceFromFilePattern(self, file_pattern, input_source_weights=None,
+                                 **extra_input_kwargs):
+    """Subclass hook: returns NestedMap(data=…, bucket_keys=…) per call."""
+    raise NotImplementedError()
+
+  def _InputBatch(self):
+    ret = self.datasource.GetNext()
+    return ret
+
+
+class BaseSequenceInputGenerator(BaseInputGeneratorFromFiles):
+  """Sequence inputs with tokenizers and bucketing (:1465-1697)."""
+
+  @classmethod
+  def Params(cls):
+    from lingvo_b200.core import tokenizers
+    p = super().Params()
+    p.Define('pad_to_max_seq_length', False, 'Pad every batch to max length.')
+    p.Define('source_max_length', None, 'Max source length.')
+    p.Define('target_max_length', 300, 'Max target length.')
+    p.Define('tokenizer', tokenizers.AsciiTokenizer.Params(), 'Tokenizer.')
+    p.Define('tokenizer_dict', {}, 'key → tokenizer params.')
+    p.bucket_upper_bound = [10, 20, 30, 60, 120]
+    p.bucket_batch_limit = [128, 128, 128, 32, 16]
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    self.tokenizer_dict = {}
+    if p.tokenizer:
+      assert 'default' not in p.tokenizer_dict
+      td = dict(p.tokenizer_dict)
+      td['default'] = p.tokenizer
+    else:
+      td = dict(p.tokenizer_dict)
+    names = []
+    for k, tp in td.items():
+      if tp:
+        names.append(k)
+        self.CreateChild('tokenizer_%s' % k, tp.Copy().Set(
+            name='tokenizer_%s' % k))
+    for k in names:
+      self.tokenizer_dict[k] = self.children['tokenizer_%s' % k]
+    if 'default' in self.tokenizer_dict:
+      self.tokenizer = self.tokenizer_dict['default']
+
+  @property
+  def scaled_bucket_batch_limit(self):
+    return self.infeed_bucket_batch_limit
+
+  def StringsToIds(self, strs, is_source=False, external_max_length=None,
+                   external_append_eos=None, key=None, languages=None):
+    """strings → (ids, labels, paddings), each `[batch, maxlen]` (:1565)."""
+    p = self.params
+    if external_max_length is not None:
+      maxlen = external_max_length
+    elif is_source:
+      maxlen = p.source_max_length
+    else:
+      maxlen = p.target_max_length
+    tok = self.tokenizer_dict[key or 'default']
+    return tok.StringsToIds(strs, maxlen, external_append_eos, languages)
+
+  def StringsToIdsWithOffsets(self, strs, **kwargs):
+    return self.StringsToIds(strs, **kwargs)
+
+  def IdsToStrings(self, ids, lens, key=None):
+    return self.tokenizer_dict[key or 'default'].IdsToStrings(ids, lens)
+
+
+class BaseTinyDatasetInput(BaseInputGenerator):
+  """Whole tiny dataset in memory (MNIST) (reference :1706-1767).
+
+  `ckpt` names a data file holding named tensors (`.npz`, or a tensor-bundle
+  checkpoint prefix as the reference uses); `data`/`label` name the tensors.
+  Batches are random permutations per epoch (`repeat`) or one sequential pass
+  with the last batch zero-padded and `weight` masking the padding.
+  """
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('ckpt', None, 'Path of the data file.')
+    p.Define('data', 'x_train', 'Name of the data tensor.')
+    p.Define('data_dtype', torch.uint8, 'Type of the data tensor.')
+    p.Define('data_shape', (0, 0, 0), 'Shape of one example.')
+    p.Define('label', 'y_train', 'Name of the label tensor.')
+    p.Define('label_dtype', torch.uint8, 'Type of the label tensor.')
+    p.Define('repeat', True, 'Go through the dataset repeatedly.')
+    p.use_per_host_infeed = True
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self._cached = None
+    self._perm = None
+
+  def _Load(self):
+    if self._cached is None:
+      p = self.params
+      from lingvo_b200.ops import native_input
+      tensors = native_input.CachedLoadTensors(p.ckpt, [p.data, p.label])
+      self._cached = (torch.as_tensor(tensors[p.data]),
+                      torch.as_tensor(tensors[p.label]))
+    return self._cached
+
+  def _InputBatch(self):
+    p = self.params
+    data, label = self._Load()
+    n = min(p.num_samples or data.shape[0], data.shape[0])
+    bs = self.InfeedBatchSize()
+    if self._perm is None:
+      from lingvo_b200.ops import native_input
+      self._perm = native_input.RandomPermutationSequence(
+          num=n, batch=bs, repeat=p.repeat,
+          seed=p.random_seed if p.random_seed is not None else 0)
+    idx = self._perm.Next()  # raises StopIteration at epoch end if not repeat
+    idx_t = torch.as_tensor(idx, dtype=torch.long)
+    raw = data[idx_t].to(torch.float32)
+    raw = raw.reshape([len(idx)] + list(p.data_shape))
+    lab = label[idx_t].to(torch.float32)
+    pad = bs - len(idx)
+    weight = torch.ones([bs])
+    if pad > 0:
+      raw = torch.cat([raw, torch.zeros([pad] + list(raw.shape[1:]))], 0)
+      lab = torch.cat([lab, torch.zeros([pad] + list(lab.shape[1:]))], 0)
+      weight[len(idx):] = 0
+    return NestedMap(raw=raw, data=raw, label=lab, weight=weight,
+                     sample_ids=torch.nn.functional.pad(idx_t, (0, pad)))
+
+  def _PreprocessInputBatch(self, batch):
+    # Image data is in [0, 255]; normalise to [-1, 1].
+    batch.data = (batch.raw - 128.0) / 128.0
+    return batch
+
+  def Reset(self, sess=None):
+    self._perm = None
+
+
+class DefineTFDataInput:
+  """Placeholder for reference `DefineTFDataInput` (tf.data is TF-only)."""
+
+  def __init__(self, *args, **kwargs):
+    raise NotImplementedError(
+        'tf.data inputs are replaced by datasource.PyIterableSource')

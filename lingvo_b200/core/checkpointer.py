@@ -1,0 +1,231 @@
+"""Checkpoint save/restore orchestration.
+
+Reference `lingvo/core/checkpointer.py`: `Checkpointer.{Restore, Save,
+MaybeSave, RestoreFromPath, RestoreIfNeeded, ShouldSave}` (:138-398), key
+scheme = variable names (`lenet5/conv0/w/var`), `global_step`, optimizer
+slots `<var>/Adam`…, EMA shadows `<var>/ExponentialMovingAverage`
+(:425-462); `init_from_checkpoint_rules` warm start (:214-266, 354-388,
+`py_utils.py:2745-2907`); save policy (:281-336).
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+import re
+import time
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from lingvo_b200.core import base_model
+from lingvo_b200.core import py_utils
+from lingvo_b200.core import saver as saver_lib
+from lingvo_b200.utils import tensor_bundle
+
+
+def _ModelTensors(model) -> Dict[str, torch.Tensor]:
+  out = {}
+  for v in model.vars.Flatten():
+    out[v.var_name] = v
+  for task in model.tasks:
+    for lrn in task.learners:
+      out.update(lrn.optimizer.GetOptimizerSlots())
+    out.update(task.EmaShadowTensors())
+  return out
+
+
+class Checkpointer:
+  """Checkpointing utility bound to one model and one train dir."""
+
+  def __init__(self, train_dir: str, model, init_op=None, train_params=None,
+               save_only=False, check_loading_status=True):
+    self._train_dir = train_dir
+    self._model = model
+    self._save_only = save_only
+    self._params = train_params or model.params.train
+    tp = self._params
+    self._save_path = os.path.join(train_dir, 'ckpt')
+    self._next_checkpoint_seconds = 0
+    self._save_interval_seconds = tp.save_interval_seconds
+    self._save_interval_steps = tp.save_interval_steps
+    self._prev_ckpt_step = None
+    self._saved_first = False
+    checks = []
+    if getattr(tp, 'checkpoint_finite_check', False):
+      checks.append((lambda name: True, [saver_lib.IsFinite()]))
+    self._saver = saver_lib.Saver(
+        train_dir, lambda: _ModelTensors(model), sanity_checks=checks,
+        keep_latest_n=tp.save_max_to_keep,
+        keep_every_n_hours=tp.save_keep_checkpoint_every_n_hours,
+        async_save=bool(tp.async_checkpointing))
+    self._init_rules_applied = False
+    os.makedirs(train_dir, exist_ok=True)
+
+  @property
+  def checkpoint_dir(self):
+    return self._train_dir
+
+  @property
+  def async_checkpointing(self):
+    return bool(self._params.async_checkpointing)
+
+  # ---------------------------------------------------------------- restore --
+  def _GlobalStep(self) -> int:
+    return self._model.tasks[0].global_step if len(self._model.tasks) == 1 \
+        else self._model.global_step
+
+  def _SetGlobalStep(self, step: int):
+    self._model._global_step = int(step)  # pylint: disable=protected-access
+    for t in self._model.tasks:
+      t.global_step = int(step)
+    py_utils.SetGlobalStep(int(step))
+
+  def RestoreFromPath(self, sess=None, checkpoint_path: str = None,
+                      strict: bool = True) -> int:
+    """Loads every model variable (+ slots, EMA) present in the bundle."""
+    assert not self._save_only
+    reader = tensor_bundle.BundleReader(checkpoint_path)
+    keys = set(reader.Keys())
+    missing = []
+    with torch.no_grad():
+      for v in self._model.vars.Flatten():
+        k = v.var_name
+        if k not in keys:
+          missing.append(k)
+          continue
+        t = saver_lib.FromNumpy(reader.Read(k))
+        if tuple(t.shape) != tuple(v.shape):
+          raise ValueError('Shape mismatch for %s: ckpt %s vs model %s' %
+                           (k, tuple(t.shape), tuple(v.shape)))
+        v.data.copy_(t.to(v.device, v.dtype))
+    if missing and strict:
+      raise KeyError('Variables missing from checkpoint %s: %s' %
+                     (checkpoint_path, missing[:10]))
+    rest = {k: saver_lib.FromNumpy(reader.Read(k)) for k in keys
+            if not k.endswith('/var') and k != 'global_step'}
+    for task in self._model.tasks:
+      for lrn in task.learners:
+        # Slots are created lazily; load restores them on the var's device.
+        dev = task.Device()
+        lrn.optimizer.LoadOptimizerSlots(
+            {k: t.to(dev) if t.dim() else t for k, t in rest.items()})
+      task.LoadEmaShadowTensors(rest)
+    step = 0
+    if 'global_step' in keys:
+      step = int(reader.Read('global_step').reshape(-1)[0])
+    else:
+      m = re.search(r'ckpt-(\d+)$', checkpoint_path)
+      if m:
+        step = int(m.group(1))
+    self._SetGlobalStep(step)
+    reader.Close()
+    logging.info('Restored %s at step %d', checkpoint_path, step)
+    return step
+
+  def _ApplyInitFromCheckpointRules(self):
+    """Warm start: {ckpt: ([(regex, fmt)], [ignore_regex])} (:354-388)."""
+    tp = self._params
+    rules = dict(getattr(tp, 'init_from_checkpoint_rules', {}) or {})
+    for task in self._model.tasks:
+      rules.update(task.params.train.init_from_checkpoint_rules or {})
+    override = getattr(tp, 'init_from_checkpoint_override', None)
+    if not rules:
+      return
+    loaded = set()
+    for ckpt_path, (var_rules, ignore_rules) in rules.items():
+      path = override or ckpt_path
+      if os.path.isdir(path):
+        path = saver_lib.LatestCheckpoint(path)
+      reader = tensor_bundle.BundleReader(path)
+      keys = set(reader.Keys())
+      with torch.no_grad():
+        for v in self._model.vars.Flatten():
+          name = v.var_name[:-len('/var')] if v.var_name.endswith('/var') \
+              else v.var_name
+          if name in loaded:
+            continue
+          if any(re.match(r, name) for r in ignore_rules):
+            continue
+          for regex, fmt in var_rules:
+            m = re.match(regex, name)
+            if not m:
+              continue
+            src = fmt % m.groups() if m.groups() else fmt
+            cands = [src, src + '/var']
+            hit = [c for c in cands if c in keys]
+            if not hit:
+              raise KeyError('%s → %s not found in %s' % (name, src, path))
+            t = saver_lib.FromNumpy(reader.Read(hit[0]))
+            v.data.copy_(t.to(v.device, v.dtype))
+            loaded.add(name)
+            break
+      reader.Close()
+    logging.info('init_from_checkpoint_rules loaded %d variables', len(loaded))
+
+  def Restore(self, sess=None, force_reinitialize=False) -> Optional[str]:
+    """Latest checkpoint in train_dir, else (re)initialise + warm-start."""
+    path = None if force_reinitialize else saver_lib.LatestCheckpoint(
+        self._train_dir)
+    if path:
+      self.RestoreFromPath(checkpoint_path=path)
+      return path
+    if not self._init_rules_applied:
+      self._ApplyInitFromCheckpointRules()
+      self._init_rules_applied = True
+    return None
+
+  def RestoreIfNeeded(self, sess=None):
+    return self.Restore(sess)
+
+  def RestoreGlobalStepIfNeeded(self, sess=None):
+    path = saver_lib.LatestCheckpoint(self._train_dir)
+    if path:
+      m = re.search(r'ckpt-(\d+)$', path)
+      if m:
+        self._SetGlobalStep(int(m.group(1)))
+
+  # ------------------------------------------------------------------- save --
+  def ShouldSave(self, gsteps: int) -> bool:
+    if self._save_only and False:
+      return False
+    if not self._saved_first:
+      return True
+    if self._save_interval_steps:
+      if self._prev_ckpt_step is None:
+        return True
+      return gsteps - self._prev_ckpt_step >= self._save_interval_steps
+    return time.time() >= self._next_checkpoint_seconds
+
+  def Save(self, sess=None, gsteps: Optional[int] = None, sync=True) -> str:
+    gsteps = self._GlobalStep() if gsteps is None else gsteps
+    tensors = _ModelTensors(self._model)
+    tensors['global_step'] = torch.tensor(int(gsteps), dtype=torch.int64)
+    path = self._saver.Save(gsteps, tensors)
+    if sync:
+      self._saver.Wait()
+    self._saved_first = True
+    self._prev_ckpt_step = gsteps
+    self._next_checkpoint_seconds = time.time() + (
+        self._save_interval_seconds or 0)
+    return path
+
+  def MaybeSave(self, sess=None, gsteps: Optional[int] = None):
+    gsteps = self._GlobalStep() if gsteps is None else gsteps
+    if self.ShouldSave(gsteps):
+      return self.Save(sess, gsteps, sync=not self.async_checkpointing)
+    return None
+
+  def Sync(self):
+    self._saver.Wait()
+
+
+def GetSpecificCheckpoint(load_checkpoint_from: str) -> Optional[str]:
+  """A ckpt prefix or a directory (→ latest) (reference :86-115)."""
+  if not load_checkpoint_from:
+    return None
+  if os.path.isdir(load_checkpoint_from):
+    return saver_lib.LatestCheckpoint(load_checkpoint_from)
+  if os.path.exists(load_checkpoint_from + '.index'):
+    return load_checkpoint_from
+  raise ValueError('Invalid load_checkpoint_from: %s' % load_checkpoint_from)

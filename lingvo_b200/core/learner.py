@@ -1,0 +1,261 @@
+"""`Learner`: loss → gradients → adjust/clip/skip → optimizer.
+
+Contract per reference `lingvo/core/learner.py` (`Apply` :177-239,
+`_ComputeLossesAndGradients` :268-351, `AdjustGradients`/`ScaleGradients`
+:353-500 — L1/L2 via gradient adjust, global-norm clip, clip-to-zero,
+NaN/Inf ⇒ grad_scale = 0 step skip — and eval metrics :170-175, :462-495).
+
+B200-first: gradients come from autograd. When the task's data-parallel
+engine (`parallel/dp.py`) owns the variables, the engine's bucketed
+reduce-scatter / fused scale+Adam path is invoked through
+`self.grad_sync`, and the scalar bookkeeping (norms, NaN check) is done on
+device without host syncs except for the returned metrics.
+"""
+
+from __future__ import annotations
+
+import re
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from lingvo_b200.core import base_layer
+from lingvo_b200.core import optimizer
+from lingvo_b200.core import py_utils
+from lingvo_b200.core import schedule
+from lingvo_b200.core import summary_utils
+from lingvo_b200.core.nested_map import NestedMap
+
+
+class Learner(base_layer.BaseLayer):
+  """Optimizes one (or a combination of) loss(es) over a set of variables."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('l2_regularizer_weight', None, 'L2 regularization weight or None.')
+    p.Define('loss_name', None,
+             'Name(s) of the loss(es) to optimize; defaults to learner name.')
+    p.Define('gradient_combiner', None,
+             'GradientCombiner params for multi-loss learners.')
+    p.Define('l1_regularizer_weight', None, 'L1 regularization weight or None.')
+    p.Define('learning_rate', 0.0, 'Learning rate to use.')
+    p.Define('clip_gradient_norm_to_value', 0.0,
+             'Clip gradients by global norm to this value (0 = off).')
+    p.Define('clip_gradient_single_norm_to_value', 0.0,
+             'Clip each gradient tensor norm to this value (0 = off).')
+    p.Define('grad_norm_to_clip_to_zero', 0.0,
+             'Zero all gradients if the global norm exceeds this value.')
+    p.Define('grad_norm_tracker', None, 'Params for GradNormTracker.')
+    p.Define('optimizer', optimizer.Adam.Params(), 'Params for the optimizer.')
+    p.Define('lr_schedule', schedule.ContinuousSchedule.Params(),
+             'Learning rate decay schedule.')
+    p.Define('bprop_variable_filter', None,
+             'Only backprop variables whose names match (re.search).')
+    p.Define('bprop_variable_exclusion', None,
+             'Do not backprop variables whose names match (re.search).')
+    p.Define('grad_aggregation_method', None, 'Kept for parity.')
+    p.Define('gate_gradients', False, 'Kept for parity.')
+    p.Define('colocate_gradients_with_ops', True, 'Kept for parity.')
+    p.Define('skip_zero_gradients', None, 'None|"variable"|"weight".')
+    p.Define('scale_gradients', True,
+             'Whether to apply gradient adjustment and scaling.')
+    p.Define('learner_use_variable_scope', True, 'Kept for ckpt compat.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    self._var_grads = None
+    self._eval_metrics: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+    if p.grad_norm_tracker:
+      self.CreateChild('grad_norm_tracker', p.grad_norm_tracker)
+    self.CreateChild('lr_schedule', p.lr_schedule)
+    self.CreateChild('optimizer', p.optimizer)
+    if isinstance(p.loss_name, (list, tuple)):
+      assert p.gradient_combiner
+      self.CreateChild('gradient_combiner', p.gradient_combiner)
+    else:
+      assert p.gradient_combiner is None
+    # Optional hook installed by the data-parallel engine: fn(var_grads)->var_grads
+    self.grad_sync = None
+
+  def GetVarGrads(self):
+    return self._var_grads
+
+  def GetTrainableVariables(self, vmap: NestedMap) -> NestedMap:
+    p = self.params
+    return py_utils.GetTrainableVariables(p.name, p.bprop_variable_filter,
+                                          p.bprop_variable_exclusion, vmap)
+
+  def LearningRate(self) -> float:
+    p = self.params
+    return float(p.learning_rate) * float(self.lr_schedule.Value())
+
+  # ------------------------------------------------------------------ apply --
+  def Apply(self, metrics, vmap: NestedMap, gradient_mask=None,
+            gradient_adjuster=None, retain_graph=False):
+    """Computes updates on `vmap` to optimize the loss(es) in `metrics`.
+
+    Returns (losses, eval_metrics). Variables are updated in place.
+    """
+    p = self.params
+    losses, var_grads, eval_metrics = self._ComputeLossesAndGradients(
+        metrics, vmap, retain_graph=retain_graph)
+    if self.grad_sync is not None:
+      var_grads = self.grad_sync(var_grads)
+    if 'tpu_embedding_var_grads' in var_grads:
+      del var_grads['tpu_embedding_var_grads']
+    var_grads, stats = self.AdjustGradients(
+        var_grads, gradient_mask=gradient_mask,
+        gradient_adjuster=gradient_adjuster)
+    eval_metrics.update(stats)
+    self._var_grads = var_grads
+    lr = self.LearningRate()
+    self._AddScalar(eval_metrics, 'learning_rate', lr)
+    self._AddScalar(eval_metrics, 'lr_schedule', float(self.lr_schedule.Value()))
+    self.optimizer.Apply(lr, var_grads)
+    return losses, {self._Key(k): v for k, v in eval_metrics.items()}
+
+  def _Key(self, name: str) -> str:
+    return '%s/%s' % (name, self.params.name)
+
+  @staticmethod
+  def _AddScalar(metrics, name, value):
+    metrics[name] = (torch.as_tensor(value, dtype=torch.float32),
+                     torch.tensor(1.0))
+
+  def _ComputeLossesAndGradients(self, metrics, vmap, retain_graph=False):
+    p = self.params
+    vmap = self.GetTrainableVariables(vmap)
+    for v in vmap.Flatten():
+      if not v.dtype.is_floating_point and not v.dtype.is_complex:
+        raise ValueError('Cannot differentiate non-float variable %s' %
+                         getattr(v, 'var_name', v))
+    loss_names = p.loss_name or p.name
+    single = not isinstance(loss_names, (list, tuple))
+    names = [loss_names] if single else list(loss_names)
+    losses, per_loss = [], {}
+    eval_metrics = {}
+    for i, name in enumerate(names):
+      item = metrics.get(name, None)
+      if item is None:
+        raise ValueError('Loss %s not found in metrics %s' %
+                         (name, list(metrics.keys())))
+      loss = item[0] if isinstance(item, (tuple, list)) else item
+      losses.append(loss)
+      keep = retain_graph or i < len(names) - 1
+      per_loss[name] = NestedMap(
+          loss_metric=item,
+          grads=self.optimizer.ComputeGradients(
+              loss, vmap, skip_zero_gradients=p.skip_zero_gradients,
+              retain_graph=keep))
+    if single:
+      var_grads = per_loss[names[0]].grads
+    else:
+      var_grads, eval_metrics = self.gradient_combiner.Combine(vmap, per_loss)
+    return losses, var_grads, eval_metrics
+
+  # ------------------------------------------------------- adjust and scale --
+  def AdjustGradients(self, var_grads: NestedMap, gradient_mask=None,
+                      gradient_adjuster=None):
+    """L2/L1 adjust → mask → scale(clip / zero / NaN-skip) (:353-432)."""
+    p = self.params
+    stats = {}
+    if p.l2_regularizer_weight is not None:
+      l2_loss, var_grads = py_utils.AdjustGradientsWithLpLoss(
+          var_grads, p.l2_regularizer_weight, p=2.0)
+      self._AddScalar(stats, 'l2_loss', l2_loss)
+    if p.l1_regularizer_weight is not None:
+      l1_loss, var_grads = py_utils.AdjustGradientsWithLpLoss(
+          var_grads, p.l1_regularizer_weight, p=1.0)
+      self._AddScalar(stats, 'l1_loss', l1_loss)
+    if gradient_mask:
+      def mask(vg):
+        m = gradient_mask.get(getattr(vg.var, 'var_name', None))
+        if m is None:
+          return vg
+        return py_utils.VarGrad(vg.var, vg.grad * m.to(vg.grad.dtype))
+      var_grads = var_grads.Transform(
+          lambda vg: mask(vg) if isinstance(vg, py_utils.VarGrad) else vg)
+    if p.scale_gradients:
+      scaled = self.ScaleGradients(var_grads, gradient_adjuster)
+      var_grads = scaled.final_var_grads
+      stats.update(scaled.stats)
+    return var_grads, stats
+
+  def ScaleGradients(self, var_grads: NestedMap, gradient_adjuster=None):
+    """Returns NestedMap(final_var_grads, grad_scale, stats) (:395-500)."""
+    p = self.params
+    leaves = [vg for vg in var_grads.Flatten()
+              if isinstance(vg, py_utils.VarGrad)]
+    dev = leaves[0].grad.device if leaves else torch.device('cpu')
+    stats = {}
+    all_grad_norm = torch.sqrt(py_utils.SumSquared(
+        [vg.grad for vg in leaves]).to(dev))
+    all_var_norm = torch.sqrt(py_utils.SumSquared(
+        [vg.var.detach() for vg in leaves]).to(dev))
+    self._AddScalar(stats, 'grad_norm/all', all_grad_norm)
+    self._AddScalar(stats, 'var_norm/all', all_var_norm)
+    grad_norm_is_nan_or_inf = ~torch.isfinite(all_grad_norm)
+    # An Inf/NaN entry always surfaces in the global norm, so one reduction
+    # replaces the reference's separate per-tensor check.
+    has_nan_or_inf = grad_norm_is_nan_or_inf
+    self._AddScalar(stats, 'has_nan_or_inf', has_nan_or_inf.float())
+    self._AddScalar(stats, 'grad_norm_is_nan_or_inf',
+                    grad_norm_is_nan_or_inf.float())
+    grad_scale = torch.ones((), device=dev)
+    if p.clip_gradient_norm_to_value:
+      assert not p.clip_gradient_single_norm_to_value
+      grad_scale = torch.clamp(
+          p.clip_gradient_norm_to_value / all_grad_norm, max=1.0)
+    if self.params.grad_norm_tracker:
+      grad_scale = grad_scale * self.grad_norm_tracker.FPropDefaultTheta(
+          all_grad_norm, has_nan_or_inf)
+    if p.grad_norm_to_clip_to_zero:
+      grad_scale = torch.where(all_grad_norm > p.grad_norm_to_clip_to_zero,
+                               torch.zeros_like(grad_scale), grad_scale)
+    grad_scale = torch.where(has_nan_or_inf, torch.zeros_like(grad_scale),
+                             grad_scale)
+    self._AddScalar(stats, 'grad_scale_all', grad_scale)
+
+    if gradient_adjuster is not None:
+      var_grads = gradient_adjuster(var_grads)
+
+    if p.clip_gradient_single_norm_to_value:
+      final = py_utils.ApplyGradNormClipping(
+          var_grads, p.clip_gradient_single_norm_to_value)
+      bad = has_nan_or_inf
+
+      def zero_bad(vg):
+        if not isinstance(vg, py_utils.VarGrad):
+          return vg
+        return py_utils.VarGrad(vg.var, torch.where(
+            bad, torch.zeros_like(vg.grad), vg.grad))
+      final = final.Transform(zero_bad)
+    else:
+      def scale(vg):
+        if not isinstance(vg, py_utils.VarGrad):
+          return vg
+        s = grad_scale.to(vg.grad.dtype)
+        # where() instead of mul so NaN·0 cannot leak through.
+        g = torch.where(s == 0, torch.zeros_like(vg.grad), vg.grad * s)
+        return py_utils.VarGrad(vg.var, g)
+      final = var_grads.Transform(scale)
+    return NestedMap(final_var_grads=final, grad_scale=grad_scale, stats=stats)
+
+
+def ExtractLearnerFromLegacyParams(tp, cls=Learner):
+  """Builds Learner params from `task.train` legacy knobs (reference :526)."""
+  lp = cls.Params()
+  lp.name = 'loss'
+  for k, v in tp.IterParams():
+    if k not in lp:
+      continue
+    if k in ('name', 'cls', 'dtype', 'fprop_dtype', 'random_seed', 'vn',
+             'params_init', 'is_inference', 'inference_driver_name',
+             'skip_lp_regularization', 'device_mesh',
+             'weight_split_dims_mapping', 'activation_split_dims_mapping'):
+      continue
+    lp.Set(**{k: v.Copy() if hasattr(v, 'Copy') else v})
+  return lp

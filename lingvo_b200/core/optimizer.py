@@ -1,0 +1,773 @@
+"""Optimizers.
+
+Catalogue and update rules follow reference `lingvo/core/optimizer.py`
+(`Base.Apply` :99, slot checkpoint naming :170-196, `CompositeOptimizer`,
+`SGD/Momentum/RMSProp/Adagrad/AdaDelta/Adam(ParamsA/B)/AdamV2`, `Accumulator`
+:507, `DynamicAccumulator` :575, `DistributedShampoo` :689, `AdaGraft` :803,
+`XLAShardingAdafactor` :905-1275, `GradientAggregationOptimizer` :1276).
+
+B200-first design: an optimizer is a layer owning *slot tensors* keyed by the
+variable's checkpoint name (`<var>/Adam`, `<var>/Adam_1`, …, the TF names, so
+checkpoints keep the reference layout). `Apply(lr, var_grads)` updates the
+Parameters in place under `no_grad`; on CUDA the dense rules run as
+multi-tensor (`torch._foreach_*`) launches or as the fused sm_100a kernels in
+`lingvo_b200.ops.optim` (Adam / Adafactor), and the data-parallel runtime
+(`parallel/dp.py`) fuses reduce-scatter + the same Adam math over a flat shard.
+"""
+
+from __future__ import annotations
+
+import math
+import re
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from lingvo_b200.core import base_layer
+from lingvo_b200.core import py_utils
+from lingvo_b200.core.nested_map import NestedMap
+
+
+def _VarKey(var) -> str:
+  name = getattr(var, 'var_name', None)
+  if name is None:
+    name = 'var_%x' % id(var)
+  return name[:-len('/var')] + '/var' if name.endswith('/var') else name
+
+
+def _Pairs(var_grads) -> List[Tuple[torch.nn.Parameter, torch.Tensor]]:
+  if isinstance(var_grads, NestedMap):
+    leaves = [vg for vg in var_grads.Flatten()
+              if isinstance(vg, py_utils.VarGrad)]
+  else:
+    leaves = list(var_grads)
+  return [(vg.var, vg.grad) for vg in leaves if vg.grad is not None]
+
+
+class Base(base_layer.BaseLayer):
+  """Base class for all optimizers."""
+
+  # slot name → checkpoint suffix (TF slot naming)
+  SLOT_SUFFIX: Dict[str, str] = {}
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.name = cls.__name__
+    p.Define('use_bf16_gradients_ar', False,
+             'Reduce gradients across replicas in bf16.')
+    p.Define('skip_zero_gradients', None, 'See py_utils.SkipZeroGradients.')
+    p.Define('clear_variable_scope', False, 'Kept for parity.')
+    p.Define('add_summary_in_apply', True, 'Kept for parity.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self._slots: Dict[str, Dict[str, torch.Tensor]] = {}
+    self._scalars: Dict[str, float] = {}
+    self._step_count = 0
+
+  # ------------------------------------------------------------------ slots --
+  def _Slot(self, var, name: str, init=None, shape=None, dtype=None):
+    key = _VarKey(var)
+    slots = self._slots.setdefault(key, {})
+    if name not in slots:
+      shape = list(var.shape) if shape is None else list(shape)
+      dtype = dtype or (var.dtype if var.dtype.is_floating_point
+                        else torch.float32)
+      if init is None or init == 0:
+        slots[name] = torch.zeros(shape, dtype=dtype, device=var.device)
+      else:
+        slots[name] = torch.full(shape, float(init), dtype=dtype,
+                                 device=var.device)
+    return slots[name]
+
+  def GetOptimizerSlots(self) -> Dict[str, torch.Tensor]:
+    """Checkpoint-key → slot tensor (TF names, reference :170-196)."""
+    out = {}
+    for key, slots in self._slots.items():
+      base = key[:-len('/var')] if key.endswith('/var') else key
+      for sname, t in slots.items():
+        out['%s/%s' % (base, self.SLOT_SUFFIX.get(sname, sname))] = t
+    for k, v in self._scalars.items():
+      out[k] = torch.tensor(v, dtype=torch.float32)
+    out['%s/step_count' % self.params.name] = torch.tensor(
+        self._step_count, dtype=torch.int64)
+    return out
+
+  def LoadOptimizerSlots(self, tensors: Dict[str, torch.Tensor]) -> List[str]:
+    """Restores slots from a checkpoint-key map; returns the keys consumed."""
+    used = []
+    inv = {v: k for k, v in self.SLOT_SUFFIX.items()}
+    pending = {}
+    for key, t in tensors.items():
+      if key == '%s/step_count' % self.params.name:
+        self._step_count = int(t.item())
+        used.append(key)
+        continue
+      if key in self._scalars or key in self._ScalarNames():
+        self._scalars[key] = float(t.item())
+        used.append(key)
+        continue
+      base, _, suffix = key.rpartition('/')
+      sname = inv.get(suffix)
+      if sname is None:
+        continue
+      pending.setdefault(base + '/var', {})[sname] = (key, t)
+    for vkey, slots in pending.items():
+      dst = self._slots.setdefault(vkey, {})
+      for sname, (key, t) in slots.items():
+        if sname in dst:
+          dst[sname].copy_(t.to(dst[sname].device))
+        else:
+          dst[sname] = t.clone()
+        used.append(key)
+    return used
+
+  def _ScalarNames(self) -> List[str]:
+    return []
+
+  def to(self, device=None, dtype=None):  # pylint: disable=invalid-name
+    for slots in self._slots.values():
+      for k in list(slots):
+        slots[k] = slots[k].to(device)
+    return self
+
+  # ------------------------------------------------------------------ apply --
+  def ComputeGradients(self, loss, vmap, *args, **kwargs):
+    return py_utils.ComputeGradients(loss, vmap, *args, **kwargs)
+
+  def Apply(self, lr, var_grad):
+    """Applies one update with learning rate `lr` (python float or tensor)."""
+    pairs = _Pairs(var_grad)
+    if not pairs:
+      return
+    lr = float(lr) if not isinstance(lr, torch.Tensor) else lr
+    with torch.no_grad():
+      self._Update(lr, [v for v, _ in pairs], [g for _, g in pairs])
+    self._step_count += 1
+
+  def _Update(self, lr, variables, grads):
+    raise NotImplementedError()
+
+  def AddSummary(self, lr, optimizer, var_grad):
+    from lingvo_b200.core import summary_utils
+    summary_utils.scalar('%s_lr' % self.params.name.lower(), lr)
+
+  def FProp(self, theta, *args):
+    raise NotImplementedError('Optimizers are applied with Apply()')
+
+
+def _F32(grads, like):
+  return [g.to(v.dtype) if g.dtype != v.dtype else g
+          for g, v in zip(grads, like)]
+
+
+class SGD(Base):
+  """w -= lr * g."""
+
+  def _Update(self, lr, variables, grads):
+    grads = _F32(grads, variables)
+    torch._foreach_add_(variables, grads, alpha=-float(lr))
+
+
+class Momentum(Base):
+  """TF MomentumOptimizer: acc = m·acc + g; w -= lr·acc (nesterov optional)."""
+
+  SLOT_SUFFIX = {'momentum': 'Momentum'}
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('alpha', 0.9, 'The damping factor in the momentum optimizer.')
+    p.Define('use_nesterov', False, 'True iff use Nesterov')
+    return p
+
+  def _Update(self, lr, variables, grads):
+    p = self.params
+    grads = _F32(grads, variables)
+    accs = [self._Slot(v, 'momentum') for v in variables]
+    torch._foreach_mul_(accs, p.alpha)
+    torch._foreach_add_(accs, grads)
+    if p.use_nesterov:
+      upd = torch._foreach_mul(accs, p.alpha)
+      torch._foreach_add_(upd, grads)
+      torch._foreach_add_(variables, upd, alpha=-float(lr))
+    else:
+      torch._foreach_add_(variables, accs, alpha=-float(lr))
+
+
+class RMSProp(Base):
+  """TF RMSPropOptimizer (optionally centered)."""
+
+  SLOT_SUFFIX = {'rms': 'RMSProp', 'mom': 'RMSProp_1', 'mg': 'RMSProp_2'}
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('decay', 0.9, 'Discounting factor for the history.')
+    p.Define('momentum', 0.9, 'Momentum in RMSProp.')
+    p.Define('epsilon', 1.0, 'Epsilon term for RMSProp.')
+    p.Define('centered', False, 'Normalise by the estimated variance.')
+    return p
+
+  def _Update(self, lr, variables, grads):
+    p = self.params
+    for v, g in zip(variables, _F32(grads, variables)):
+      ms = self._Slot(v, 'rms', init=1.0)
+      mom = self._Slot(v, 'mom')
+      ms.mul_(p.decay).addcmul_(g, g, value=1 - p.decay)
+      denom = ms
+      if p.centered:
+        mg = self._Slot(v, 'mg')
+        mg.mul_(p.decay).add_(g, alpha=1 - p.decay)
+        denom = ms - mg * mg
+      mom.mul_(p.momentum).add_(g / torch.sqrt(denom + p.epsilon),
+                                alpha=float(lr))
+      v.sub_(mom)
+
+
+class Adagrad(Base):
+
+  SLOT_SUFFIX = {'acc': 'Adagrad'}
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('initial_accumulator_value', 1.0, 'Initial accumulator value.')
+    return p
+
+  def _Update(self, lr, variables, grads):
+    p = self.params
+    for v, g in zip(variables, _F32(grads, variables)):
+      acc = self._Slot(v, 'acc', init=p.initial_accumulator_value)
+      acc.addcmul_(g, g)
+      v.addcdiv_(g, acc.sqrt(), value=-float(lr))
+
+
+class AdaDelta(Base):
+
+  SLOT_SUFFIX = {'acc': 'Adadelta', 'acc_update': 'Adadelta_1'}
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('decay', 0.95, 'Discounting factor for the history.')
+    p.Define('epsilon', 1e-8, 'Epsilon term for AdaDelta.')
+    return p
+
+  def _Update(self, lr, variables, grads):
+    p = self.params
+    for v, g in zip(variables, _F32(grads, variables)):
+      acc = self._Slot(v, 'acc')
+      accu = self._Slot(v, 'acc_update')
+      acc.mul_(p.decay).addcmul_(g, g, value=1 - p.decay)
+      upd = torch.sqrt(accu + p.epsilon) / torch.sqrt(acc + p.epsilon) * g
+      accu.mul_(p.decay).addcmul_(upd, upd, value=1 - p.decay)
+      v.add_(upd, alpha=-float(lr))
+
+
+class Adam(Base):
+  """TF AdamOptimizer: lr_t = lr·sqrt(1-β2^t)/(1-β1^t); w -= lr_t·m/(√v+ε)."""
+
+  SLOT_SUFFIX = {'m': 'Adam', 'v': 'Adam_1'}
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('beta1', 0.9, 'Beta1 for Adam.')
+    p.Define('beta2', 0.999, 'Beta2 for Adam.')
+    p.Define('epsilon', 1e-6, 'Epsilon for Adam.')
+    p.Define('fused', True, 'Use the fused sm_100a multi-tensor kernel on CUDA.')
+    return p
+
+  @classmethod
+  def ParamsA(cls):
+    """Transformer paper (beta2 .997)."""
+    return cls.Params().Set(beta1=0.9, beta2=0.997, epsilon=1e-9)
+
+  @classmethod
+  def ParamsB(cls):
+    """Tensor2tensor settings."""
+    return cls.Params().Set(beta1=0.9, beta2=0.98, epsilon=1e-9)
+
+  def _ScalarNames(self):
+    return ['beta1_power', 'beta2_power']
+
+  def _Update(self, lr, variables, grads):
+    p = self.params
+    t = self._step_count + 1
+    b1p, b2p = p.beta1**t, p.beta2**t
+    self._scalars['beta1_power'] = b1p * p.beta1
+    self._scalars['beta2_power'] = b2p * p.beta2
+    lr_t = float(lr) * math.sqrt(1 - b2p) / (1 - b1p)
+    ms = [self._Slot(v, 'm') for v in variables]
+    vs = [self._Slot(v, 'v') for v in variables]
+    if p.fused and variables[0].is_cuda:
+      from lingvo_b200.ops import optim
+      if optim.available():
+        optim.multi_tensor_adam(variables, grads, ms, vs, lr_t, p.beta1,
+                                p.beta2, p.epsilon)
+        return
+    grads = _F32(grads, variables)
+    torch._foreach_mul_(ms, p.beta1)
+    torch._foreach_add_(ms, grads, alpha=1 - p.beta1)
+    torch._foreach_mul_(vs, p.beta2)
+    torch._foreach_addcmul_(vs, grads, grads, value=1 - p.beta2)
+    denom = torch._foreach_sqrt(vs)
+    torch._foreach_add_(denom, p.epsilon)
+    torch._foreach_addcdiv_(variables, ms, denom, value=-lr_t)
+
+
+class AdamV2(Adam):
+  """Keras-style Adam (same math; epsilon inside the bias-corrected step)."""
+
+  SLOT_SUFFIX = {'m': 'm', 'v': 'v'}
+
+
+class Accumulator(Base):
+  """Accumulates grads for N steps then applies the wrapped optimizer (:507)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('optimizer_tpl', Adam.Params(), 'Params for the wrapped optimizer.')
+    p.Define('accum_steps', 5, 'Number of gradient accumulation steps.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('_opt', self.params.optimizer_tpl)
+    self._accum_count = 0
+
+  SLOT_SUFFIX = {'grad_accum': 'grad_accumulator'}
+
+  def Apply(self, lr, var_grad):
+    p = self.params
+    pairs = _Pairs(var_grad)
+    with torch.no_grad():
+      accs = [self._Slot(v, 'grad_accum') for v, _ in pairs]
+      torch._foreach_add_(accs, _F32([g for _, g in pairs],
+                                     [v for v, _ in pairs]))
+    self._accum_count += 1
+    if self._accum_count % p.accum_steps != 0:
+      return
+    with torch.no_grad():
+      avg = torch._foreach_div(accs, float(p.accum_steps))
+    self._opt.Apply(lr, [py_utils.VarGrad(v, g)
+                         for (v, _), g in zip(pairs, avg)])
+    with torch.no_grad():
+      torch._foreach_zero_(accs)
+    self._step_count += 1
+
+  def GetOptimizerSlots(self):
+    out = super().GetOptimizerSlots()
+    out.update(self._opt.GetOptimizerSlots())
+    return out
+
+  def LoadOptimizerSlots(self, tensors):
+    return super().LoadOptimizerSlots(tensors) + self._opt.LoadOptimizerSlots(
+        tensors)
+
+
+class DynamicAccumulator(Accumulator):
+  """Accumulates until `accum_weight_threshold` total weight is seen (:575)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('accum_weight_threshold', 1.0, 'Apply when weight sum ≥ this.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self._weight = 0.0
+
+  def ApplyWeighted(self, lr, var_grad, weight: float):
+    pairs = _Pairs(var_grad)
+    with torch.no_grad():
+      accs = [self._Slot(v, 'grad_accum') for v, _ in pairs]
+      torch._foreach_add_(accs, _F32([g for _, g in pairs],
+                                     [v for v, _ in pairs]), alpha=float(weight))
+    self._weight += float(weight)
+    if self._weight < self.params.accum_weight_threshold:
+      return
+    with torch.no_grad():
+      avg = torch._foreach_div(accs, self._weight)
+    self._opt.Apply(lr, [py_utils.VarGrad(v, g)
+                         for (v, _), g in zip(pairs, avg)])
+    with torch.no_grad():
+      torch._foreach_zero_(accs)
+    self._weight = 0.0
+    self._step_count += 1
+
+  def Apply(self, lr, var_grad):
+    self.ApplyWeighted(lr, var_grad, 1.0)
+
+
+class GradientAggregation(Base):
+  """Micro-batch accumulation with a *deferred* cross-replica sum (:1276).
+
+  Grads of `num_micro_batches` consecutive Apply calls are summed locally; the
+  all-reduce (via `reduce_fn`) happens once, right before the wrapped
+  optimizer's apply — the B200 analogue of `GradientAggregationOptimizer`.
+  """
+
+  SLOT_SUFFIX = {'grad_accum': 'grad_accum'}
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('optimizer_tpl', Adam.Params(), 'Wrapped optimizer.')
+    p.Define('num_micro_batches', 1, 'Micro batches per apply.')
+    p.Define('apply_crs_to_grad', False, 'All-reduce accumulated grads.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('_opt', self.params.optimizer_tpl)
+    self._count = 0
+    self.reduce_fn = None
+
+  def Apply(self, lr, var_grad):
+    p = self.params
+    pairs = _Pairs(var_grad)
+    if p.num_micro_batches <= 1:
+      self._opt.Apply(lr, var_grad)
+      return
+    with torch.no_grad():
+      accs = [self._Slot(v, 'grad_accum') for v, _ in pairs]
+      torch._foreach_add_(accs, _F32([g for _, g in pairs],
+                                     [v for v, _ in pairs]))
+    self._count += 1
+    if self._count % p.num_micro_batches:
+      return
+    with torch.no_grad():
+      avg = torch._foreach_div(accs, float(p.num_micro_batches))
+      if p.apply_crs_to_grad and self.reduce_fn is not None:
+        avg = [self.reduce_fn(g) for g in avg]
+    self._opt.Apply(lr, [py_utils.VarGrad(v, g)
+                         for (v, _), g in zip(pairs, avg)])
+    with torch.no_grad():
+      torch._foreach_zero_(accs)
+    self._step_count += 1
+
+
+def _ReduceRms(x):
+  return torch.sqrt(torch.mean(x.float().square()))
+
+
+class XLAShardingAdafactor(Base):
+  """Adafactor as used by the GShard LMs (reference :905-1275).
+
+  g² + ε1 → factored row/col EMAs (two largest dims, both ≥
+  `min_dim_size_to_factor`) or full `v`; x = g·rsqrt(v̂); RMS-clip to
+  `clipping_threshold`; scale by max(RMS(w), ε2)·lr; optional β1; assign_sub.
+  """
+
+  SLOT_SUFFIX = {'m': 'Adafactor_m', 'vr': 'Adafactor_vr', 'vc': 'Adafactor_vc',
+                 'v': 'Adafactor_v'}
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('beta1', 0, 'Beta1 of Adam. Can be zero.')
+    p.Define('beta2', 0.999, 'Beta2 of Adam.')
+    p.Define('multiply_by_parameter_scale', True,
+             'update_scale = max(RMS(w), eps2)·lr when True else lr.')
+    p.Define('clipping_threshold', None, '≥1.0 or None for no update clipping.')
+    p.Define('factored', True, 'Factor the second-moment estimator.')
+    p.Define('decay_exponent_pow', None, 'decay = 1-(t-offset+1)^-pow if set.')
+    p.Define('decay_exponent_offset', 0, 'Start step of the decay schedule.')
+    p.Define('min_dim_size_to_factor', 128, 'Only factor dims ≥ this.')
+    p.Define('cond_is_finite', False, 'Skip the update if stats are not finite.')
+    p.Define('epsilon1', 1e-30, 'Regularization constant for squared gradient.')
+    p.Define('epsilon2', 1e-3, 'Regularization constant for parameter scale.')
+    p.Define('fused', True, 'Use the fused sm_100a kernel on CUDA.')
+    p.name = 'Adafactor'
+    return p
+
+  def _FactoredDims(self, shape):
+    p = self.params
+    if not p.factored or len(shape) < 2:
+      return None
+    order = sorted(((s, i) for i, s in enumerate(shape)), key=lambda d: -d[0])
+    if order[1][0] < p.min_dim_size_to_factor:
+      return None
+    return order[0][1], order[1][1]
+
+  def DecayRate(self, step: Optional[int] = None) -> float:
+    p = self.params
+    t = float(py_utils.GetGlobalStep() if step is None else step)
+    if p.decay_exponent_pow:
+      return 1.0 - (t - p.decay_exponent_offset + 1.0)**(-p.decay_exponent_pow)
+    t = t + 1.0
+    return p.beta2 * (1.0 - p.beta2**(t - 1.0)) / (1.0 - p.beta2**t)
+
+  def _Update(self, lr, variables, grads):
+    p = self.params
+    decay = self.DecayRate()
+    fused = None
+    if p.fused and variables[0].is_cuda:
+      from lingvo_b200.ops import optim
+      if optim.available():
+        fused = optim
+    for var, grad in zip(variables, grads):
+      dims = self._FactoredDims(list(var.shape))
+      if fused is not None and dims is not None and var.dim() >= 2 and (
+          not p.beta1) and not p.cond_is_finite and sorted(dims) == [
+              var.dim() - 2, var.dim() - 1]:
+        d0, d1 = dims
+        vr_shape = [s for i, s in enumerate(var.shape) if i != d0]
+        vc_shape = [s for i, s in enumerate(var.shape) if i != d1]
+        vr = self._Slot(var, 'vr', shape=vr_shape)
+        vc = self._Slot(var, 'vc', shape=vc_shape)
+        fused.adafactor_factored(var, grad, vr, vc, d0, d1, float(lr), decay,
+                                 p.epsilon1, p.epsilon2,
+                                 p.clipping_threshold or 0.0,
+                                 bool(p.multiply_by_parameter_scale))
+        continue
+      self._UpdateOne(var, grad, dims, float(lr), decay)
+
+  def _UpdateOne(self, var, grad, dims, lr, decay):
+    p = self.params
+    g = grad.to(var.dtype)
+    g2 = g * g + p.epsilon1
+    mix = 1.0 - decay
+    if p.multiply_by_parameter_scale:
+      update_scale = torch.clamp(_ReduceRms(var), min=p.epsilon2) * lr
+    else:
+      update_scale = lr
+    finite = True
+    new_slots = {}
+    if dims is not None:
+      d0, d1 = dims
+      vr_shape = [s for i, s in enumerate(var.shape) if i != d0]
+      vc_shape = [s for i, s in enumerate(var.shape) if i != d1]
+      vr = self._Slot(var, 'vr', shape=vr_shape)
+      vc = self._Slot(var, 'vc', shape=vc_shape)
+      new_vr = vr * decay + g2.mean(dim=d0) * mix
+      new_vc = vc * decay + g2.mean(dim=d1) * mix
+      new_slots = {'vr': (vr, new_vr), 'vc': (vc, new_vc)}
+      long_term_mean = new_vr.mean(dim=-1, keepdim=True)
+      r_factor = torch.rsqrt(new_vr / long_term_mean)
+      c_factor = torch.rsqrt(new_vc)
+      x = g * r_factor.unsqueeze(d0) * c_factor.unsqueeze(d1)
+    else:
+      v = self._Slot(var, 'v')
+      new_v = v * decay + g2 * mix
+      new_slots = {'v': (v, new_v)}
+      x = g * torch.rsqrt(new_v)
+    if p.clipping_threshold is not None:
+      x = x / torch.clamp(_ReduceRms(x) / p.clipping_threshold, min=1.0)
+    sub = x * update_scale
+    if p.beta1:
+      m = self._Slot(var, 'm')
+      new_m = m * p.beta1 + sub * (1.0 - p.beta1)
+      new_slots['m'] = (m, new_m)
+      sub = new_m
+    if p.cond_is_finite:
+      finite = bool(torch.isfinite(sub).all()) and all(
+          bool(torch.isfinite(n).all()) for _, n in new_slots.values())
+    if finite:
+      for old, new in new_slots.values():
+        old.copy_(new)
+      var.sub_(sub.to(var.dtype))
+
+
+Adafactor = XLAShardingAdafactor
+
+
+class XLAShardingAdafactorAccuGrad(XLAShardingAdafactor):
+  """Adafactor + N-step gradient accumulation in slots (reference :1300)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('num_micro_batches', 1, 'Accumulate this many applies.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self._count = 0
+
+  def Apply(self, lr, var_grad):
+    n = self.params.num_micro_batches
+    if n <= 1:
+      return super().Apply(lr, var_grad)
+    pairs = _Pairs(var_grad)
+    with torch.no_grad():
+      accs = [self._Slot(v, 'grad_accum') for v, _ in pairs]
+      torch._foreach_add_(accs, _F32([g for _, g in pairs],
+                                     [v for v, _ in pairs]))
+    self._count += 1
+    if self._count % n:
+      return None
+    with torch.no_grad():
+      avg = torch._foreach_div(accs, float(n))
+    super().Apply(lr, [py_utils.VarGrad(v, g)
+                       for (v, _), g in zip(pairs, avg)])
+    with torch.no_grad():
+      torch._foreach_zero_(accs)
+    return None
+
+
+class DistributedShampoo(Base):
+  """Shampoo with inverse-p-th-root preconditioners (reference :689).
+
+  Statistics L += G Gᵀ, R += Gᵀ G per 2-D (block) parameter; preconditioned
+  grad L^{-1/4} G R^{-1/4}, grafted to the Adagrad step size. Preconditioners
+  are recomputed every `preconditioning_compute_steps` via
+  `matrix_functions.inlined_matrix_inverse_pth_root`.
+  """
+
+  SLOT_SUFFIX = {'acc': 'Shampoo_acc', 'mom': 'Shampoo_mom'}
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('momentum', 0.9, 'Momentum parameter.')
+    p.Define('start_preconditioning_steps', 1000, 'Diagonal until this step.')
+    p.Define('initial_accumulator_value', 0.0, 'Initial accumulator value.')
+    p.Define('block_size', 4096, 'Block size for large layers.')
+    p.Define('block_partition_threshold_size', 1000000, 'Partition threshold.')
+    p.Define('max_any_dim', 6656, 'Max dim before falling back to diagonal.')
+    p.Define('matrix_epsilon', 1e-6, 'Damping for the inverse root.')
+    p.Define('second_moment_averaging', 1.0, '1.0 ⇒ sum (Adagrad).')
+    p.Define('fallback_to_diagonal_dim', 4096, 'Fallback dim.')
+    p.Define('statistics_computation_frequency', 1, 'Steps between stat updates.')
+    p.Define('preconditioning_compute_steps', 20, 'Steps between root solves.')
+    return p
+
+  def _Update(self, lr, variables, grads):
+    from lingvo_b200.core import matrix_functions
+    p = self.params
+    t = self._step_count + 1
+    for v, g in zip(variables, _F32(grads, variables)):
+      acc = self._Slot(v, 'acc', init=p.initial_accumulator_value)
+      acc.addcmul_(g, g)
+      adagrad_upd = g / (acc.sqrt() + 1e-30)
+      upd = adagrad_upd
+      if v.dim() == 2 and max(v.shape) <= p.max_any_dim:
+        key = _VarKey(v)
+        st = self._slots[key]
+        if 'L' not in st:
+          st['L'] = torch.zeros(v.shape[0], v.shape[0], device=v.device)
+          st['R'] = torch.zeros(v.shape[1], v.shape[1], device=v.device)
+          st['PL'] = torch.eye(v.shape[0], device=v.device)
+          st['PR'] = torch.eye(v.shape[1], device=v.device)
+        if t % p.statistics_computation_frequency == 0:
+          gf = g.float()
+          st['L'].add_(gf @ gf.t())
+          st['R'].add_(gf.t() @ gf)
+        if t % p.preconditioning_compute_steps == 0 or t == 1:
+          st['PL'] = matrix_functions.inlined_matrix_inverse_pth_root(
+              st['L'], 4, ridge_epsilon=p.matrix_epsilon)
+          st['PR'] = matrix_functions.inlined_matrix_inverse_pth_root(
+              st['R'], 4, ridge_epsilon=p.matrix_epsilon)
+        if t >= p.start_preconditioning_steps:
+          pg = (st['PL'] @ g.float() @ st['PR']).to(g.dtype)
+          pg = pg * (adagrad_upd.norm() / (pg.norm() + 1e-16))
+          upd = pg
+      mom = self._Slot(v, 'mom')
+      mom.mul_(p.momentum).add_(upd)
+      v.add_(mom, alpha=-float(lr))
+
+
+class AdaGraft(Base):
+  """Step *magnitude* from one optimizer, *direction* from another (:803)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('magnitude_optimizer', SGD.Params(), 'Provides per-tensor norms.')
+    p.Define('direction_optimizer', Adam.Params(), 'Provides directions.')
+    p.Define('use_global_norm', False, 'Graft the global norm.')
+    p.Define('diagnostic', False, 'Log norms.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('_mag', self.params.magnitude_optimizer)
+    self.CreateChild('_dir', self.params.direction_optimizer)
+
+  def Apply(self, lr, var_grad):
+    pairs = _Pairs(var_grad)
+    variables = [v for v, _ in pairs]
+    with torch.no_grad():
+      before = [v.detach().clone() for v in variables]
+    vg = [py_utils.VarGrad(v, g) for v, g in pairs]
+    self._mag.Apply(lr, vg)
+    with torch.no_grad():
+      mag_steps = [v.detach() - b for v, b in zip(variables, before)]
+      for v, b in zip(variables, before):
+        v.copy_(b)
+    self._dir.Apply(lr, vg)
+    with torch.no_grad():
+      dir_steps = [v.detach() - b for v, b in zip(variables, before)]
+      if self.params.use_global_norm:
+        mn = torch.sqrt(sum(s.float().square().sum() for s in mag_steps))
+        dn = torch.sqrt(sum(s.float().square().sum() for s in dir_steps))
+        scale = [mn / (dn + 1e-30)] * len(variables)
+      else:
+        scale = [m.float().norm() / (d.float().norm() + 1e-30)
+                 for m, d in zip(mag_steps, dir_steps)]
+      for v, b, d, s in zip(variables, before, dir_steps, scale):
+        v.copy_(b + d * s.to(d.dtype))
+    self._step_count += 1
+
+
+class CompositeOptimizer(Base):
+  """regex → (optimizer, lr) dispatch (reference CompositeOptimizer)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('optimizer_map', None,
+             'Dict regex → (optimizer params, learning rate). Must contain '
+             '"default_optimizer".')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert p.optimizer_map and 'default_optimizer' in p.optimizer_map
+    self._regex = []
+    subs = []
+    for i, (regex, (opt_p, lr)) in enumerate(p.optimizer_map.items()):
+      subs.append(opt_p.Copy().Set(name='%s_%d' % (opt_p.name or 'opt', i)))
+      self._regex.append((regex, i, lr))
+    self.CreateChildren('_opts', subs)
+
+  def Apply(self, lr, var_grad):
+    pairs = _Pairs(var_grad)
+    buckets: Dict[int, List] = {}
+    default_idx = [i for r, i, _ in self._regex if r == 'default_optimizer'][0]
+    for v, g in pairs:
+      name = getattr(v, 'var_name', '')
+      hits = [i for r, i, _ in self._regex
+              if r != 'default_optimizer' and re.match(r, name)]
+      if len(hits) > 1:
+        raise Exception('Variable {} is matched {} times by regex {}'.format(
+            name, len(hits), [r for r, _, _ in self._regex]))
+      idx = hits[0] if hits else default_idx
+      buckets.setdefault(idx, []).append(py_utils.VarGrad(v, g))
+    for idx, vgs in buckets.items():
+      sub_lr = [l for _, i, l in self._regex if i == idx][0]
+      sub_lr = sub_lr if sub_lr is not None else lr
+      if hasattr(sub_lr, 'Value'):
+        sub_lr = sub_lr.Value()
+      self._opts[idx].Apply(sub_lr, vgs)
+    self._step_count += 1
+
+  def GetOptimizerSlots(self):
+    out = {}
+    for o in self._opts:
+      out.update(o.GetOptimizerSlots())
+    return out
+
+  def LoadOptimizerSlots(self, tensors):
+    used = []
+    for o in self._opts:
+      used += o.LoadOptimizerSlots(tensors)
+    return used

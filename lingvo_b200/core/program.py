@@ -1,0 +1,489 @@
+"""Programs & program schedules for the executor.
+
+Reference `lingvo/core/program.py`: `BaseProgram` (:75), `TrainProgram` (:441;
+`steps_per_loop` on-device loop), `EvalProgram` (:995), `DecodeProgram`
+(:1229), `MultiInputsDecodeProgram`, `ExperimentalDecodeProgram`,
+`MLPerfTrainDecodeProgram`, `InputBenchmark` (:2249), `SimpleProgramSchedule`
+(:2329), `MLPerfProgramSchedule`, `SimpleProgramScheduleForTask` (:2705),
+`UpdateProgramSchedule` (:2835).
+
+B200-first: a program is "run N steps of task X on this process group".
+`TrainProgram.Run` executes `steps_per_loop` eager steps and syncs scalar
+metrics to the host **once per loop** (the TPU-loop analogue); eval/decode
+accumulate metrics on device (`DeviceEvalMetrics`).
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+import pickle
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from lingvo_b200.core import base_model
+from lingvo_b200.core import cluster_factory
+from lingvo_b200.core import hyperparams
+from lingvo_b200.core import metrics as metrics_lib
+from lingvo_b200.core import program_utils
+from lingvo_b200.core import py_utils
+from lingvo_b200.core import summary_utils
+from lingvo_b200.utils import tfevents
+
+
+class BaseProgram:
+  """A unit of work the executor time-slices the devices between."""
+
+  @classmethod
+  def Params(cls):
+    p = hyperparams.InstantiableParams(cls)
+    p.Define('task', None, 'Underlying task params.')
+    p.Define('logdir', None, 'Log directory.')
+    p.Define('num_splits_per_client', None, 'Kept for parity.')
+    p.Define('steps_per_loop', None, 'Steps per device loop.')
+    p.Define('dataset_name', None, 'Dataset the program is operating on.')
+    p.Define('name', 'base_program', 'Program name.')
+    p.Define('task_name', None, 'Task name if multi-task, else None.')
+    p.Define('num_threads', 1, 'Background threads.')
+    p.Define('spmd', False, 'Kept for parity.')
+    p.Define('write_train_input_stats', False, 'Write input stats.')
+    p.Define('max_metrics', 256, 'Kept for parity.')
+    p.Define('ml_perf', None, 'MLPerf config.')
+    return p
+
+  def __init__(self, params, shared_model=None, trial_status_fn=None, **kwargs):
+    self.params = params.Copy()
+    p = self.params
+    self._task_params = p.task
+    self._logdir = p.logdir
+    self._task_name = p.task_name
+    self._program_name = ''
+    self._shared_model = shared_model
+    self._model = None
+    self._task = None
+    self._summary_writer = None
+    self._program_dir = None
+    self._status_fn = trial_status_fn
+
+  def _OutputDir(self) -> str:
+    p = self.params
+    name = self._program_name + ('_' + p.dataset_name.lower()
+                                 if p.dataset_name else '')
+    if self._task_name:
+      name += '_' + self._task_name
+    d = os.path.join(self._logdir, name)
+    os.makedirs(d, exist_ok=True)
+    return d
+
+  def BuildTpuSubgraph(self):
+    """Builds (or adopts) the model for this program (reference :583)."""
+    raise NotImplementedError()
+
+  def SetStatusMessage(self, msg):
+    logging.info('%s', msg)
+
+  def Compile(self):
+    return None
+
+  def Run(self, sess=None, threadpool=None) -> bool:
+    """Returns True when the experiment should stop."""
+    raise NotImplementedError()
+
+  def Shutdown(self):
+    if self._summary_writer:
+      self._summary_writer.flush()
+
+  def SaveProgramState(self, sess=None, global_step=None):
+    return None
+
+  def _WriteSummaries(self, job_name, global_step, summaries: Dict[str, float]):
+    for k, v in summaries.items():
+      self._summary_writer.add_scalar(k, float(v), global_step)
+    self._summary_writer.flush()
+    msg = '%s: step:%6d' % (job_name, global_step)
+    for k in sorted(summaries):
+      msg += ' %s:%.8g' % (k, summaries[k])
+    self.SetStatusMessage(msg)
+
+  def _InstantiateModel(self, do_eval: bool):
+    """Own model for this program's dataset (input differs per program)."""
+    p = self.params
+    cp = p.task.cluster.Copy() if 'cluster' in p.task else (
+        cluster_factory.Current().params.Copy())
+    cp.do_eval = do_eval
+    self._cluster = cluster_factory.Cluster(cp)
+    with self._cluster:
+      if self._shared_model is not None and not do_eval:
+        self._model = self._shared_model
+      else:
+        self._model = p.task.Instantiate()
+        self._model.to(py_utils.CurrentDevice())
+    self._task = (self._model.GetTask(self._task_name) if self._task_name
+                  else self._model.tasks[0])
+
+  def ShareVariablesFrom(self, src_model):
+    """Eval/decode programs alias the train model's Parameters (same GPU)."""
+    src = {v.var_name: v for v in src_model.vars.Flatten()}
+    for _, layer in self._model.Walk():
+      for k, v in list(layer._private_vars.items()):  # pylint: disable=protected-access
+        if v.var_name in src:
+          layer._private_vars[k] = src[v.var_name]  # pylint: disable=protected-access
+
+
+class TrainProgram(BaseProgram):
+  """Runs `steps_per_loop` train steps per invocation."""
+
+  def __init__(self, params, **kwargs):
+    super().__init__(params, **kwargs)
+    self._program_name = 'TrainProgram'
+    self._step_rate_tracker = summary_utils.StepRateTracker()
+
+  def BuildTpuSubgraph(self):
+    self._InstantiateModel(do_eval=False)
+    self._program_dir = self._OutputDir()
+    self._summary_writer = tfevents.EventFileWriter(self._program_dir)
+    return self._model
+
+  @property
+  def model(self):
+    return self._model
+
+  def Run(self, sess=None, threadpool=None) -> bool:
+    p = self.params
+    task = self._task
+    acc = metrics_lib.DeviceEvalMetrics()
+    t0 = time.time()
+    with self._cluster:
+      for _ in range(p.steps_per_loop):
+        m, _ = task.TrainStep()
+        acc.Update({k: v for k, v in m.items()})
+    results = acc.Finalize()
+    step = task.global_step
+    vals = {k: v for k, (v, _) in results.items()}
+    n_ex = vals.get('num_samples_in_batch', 0.0) * p.steps_per_loop
+    rate, ex_rate, total = self._step_rate_tracker.ComputeStepRate(step, n_ex)
+    vals['global_step/sec'] = rate
+    vals['examples/sec'] = ex_rate
+    vals['total_samples'] = total
+    self._WriteSummaries(os.path.basename(self._program_dir), step, vals)
+    tp = task.params.train
+    return step >= tp.max_steps
+
+
+class EvalProgram(BaseProgram):
+  """Evaluates `steps_per_loop` batches (or the whole resettable dataset)."""
+
+  def __init__(self, params, **kwargs):
+    super().__init__(params, **kwargs)
+    self._program_name = 'EvalProgram'
+
+  def BuildTpuSubgraph(self):
+    self._InstantiateModel(do_eval=True)
+    self._program_dir = self._OutputDir()
+    self._summary_writer = tfevents.EventFileWriter(self._program_dir)
+    return self._model
+
+  def Run(self, sess=None, threadpool=None) -> bool:
+    p = self.params
+    task = self._task
+    task.input.Reset()
+    acc = metrics_lib.DeviceEvalMetrics()
+    steps = 0
+    with self._cluster:
+      while p.steps_per_loop < 0 or steps < p.steps_per_loop:
+        try:
+          m, _ = task.EvalStep()
+        except StopIteration:
+          break
+        acc.Update(m)
+        steps += 1
+    results = acc.Finalize()
+    step = py_utils.GetGlobalStep()
+    vals = {k: v for k, (v, _) in results.items()}
+    self._WriteSummaries(os.path.basename(self._program_dir), int(step), vals)
+    with open(os.path.join(self._program_dir,
+                           'score-{:08d}.txt'.format(int(step))), 'w') as f:
+      for k in sorted(vals):
+        f.write('%s: %s\n' % (k, vals[k]))
+    return False
+
+
+class DecodeProgram(BaseProgram):
+  """Decodes `steps_per_loop` batches and post-processes on the host."""
+
+  def __init__(self, params, **kwargs):
+    super().__init__(params, **kwargs)
+    self._program_name = 'DecodeProgram'
+
+  def BuildTpuSubgraph(self):
+    self._InstantiateModel(do_eval=True)
+    self._program_dir = self._OutputDir()
+    self._summary_writer = tfevents.EventFileWriter(self._program_dir)
+    self._cache = program_utils.DecodeStatusCache(self._program_dir)
+    return self._model
+
+  def Run(self, sess=None, threadpool=None) -> bool:
+    p = self.params
+    task = self._task
+    step = int(py_utils.GetGlobalStep())
+    if self._cache.TryLoadCache(str(step)):
+      logging.info('Decode of step %d already done; skipping.', step)
+      return False
+    task.input.Reset()
+    dec_metrics = task.CreateDecoderMetrics()
+    buffered = []
+    steps = 0
+    start = time.time()
+    with self._cluster:
+      while p.steps_per_loop < 0 or steps < p.steps_per_loop:
+        try:
+          out = self._model.ConstructDecodeGraph(self._task_name)
+        except StopIteration:
+          break
+        host = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor)
+                    else (tuple(x.detach().cpu().numpy()
+                                if isinstance(x, torch.Tensor) else x
+                                for x in v) if isinstance(v, (tuple, list))
+                          else v)) for k, v in out.items()}
+        post = task.PostProcessDecodeOut(host, dec_metrics)
+        if post:
+          buffered.extend(post)
+        steps += 1
+    vals = {k: m.value for k, m in dec_metrics.items()}
+    vals['decode_secs'] = time.time() - start
+    self._WriteSummaries(os.path.basename(self._program_dir), step, vals)
+    out_path = os.path.join(self._program_dir, 'decoder_out_%09d' % step)
+    with open(out_path, 'wb') as f:
+      pickle.dump(buffered, f)
+    task.DecodeFinalize(base_model.DecodeFinalizeArgs(out_path, buffered))
+    self._cache.UpdateCkpt(str(step))
+    return False
+
+
+ExperimentalDecodeProgram = DecodeProgram
+
+
+class MultiInputsDecodeProgram(DecodeProgram):
+  """Decodes several datasets with one model (reference :1807)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('input_params', {}, '{dataset_name: input params}.')
+    return p
+
+
+class MLPerfTrainDecodeProgram(TrainProgram):
+  """Train + in-loop decode used by MLPerf configs (reference :2037)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('train_task', None, 'Train task params.')
+    p.Define('decode_task', None, 'Decode task params.')
+    p.Define('train_dataset_name', None, 'Train dataset.')
+    p.Define('decode_dataset_name', None, 'Decode dataset.')
+    p.Define('train_steps_per_loop', 0, 'Train steps per loop.')
+    p.Define('decode_steps_per_loop', 0, 'Decode steps per loop.')
+    return p
+
+
+class InputBenchmark(BaseProgram):
+  """Measures raw input pipeline throughput (reference :2249)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('measurement_type', 'per_batch', 'per_batch|per_example.')
+    return p
+
+  def __init__(self, params, **kwargs):
+    super().__init__(params, **kwargs)
+    self._program_name = 'InputBenchmark'
+
+  def BuildTpuSubgraph(self):
+    self._InstantiateModel(do_eval=False)
+    self._program_dir = self._OutputDir()
+    self._summary_writer = tfevents.EventFileWriter(self._program_dir)
+
+  def Run(self, sess=None, threadpool=None) -> bool:
+    p = self.params
+    t0 = time.time()
+    n = 0
+    for _ in range(p.steps_per_loop):
+      b = self._task.input.GetPreprocessedInputBatch()
+      for t in b.Flatten():
+        if hasattr(t, 'shape') and len(t.shape) > 0:
+          n += int(t.shape[0])
+          break
+    dt = time.time() - t0
+    self._WriteSummaries('input_benchmark', int(py_utils.GetGlobalStep()),
+                         {'batches/sec': p.steps_per_loop / max(dt, 1e-9),
+                          'examples/sec': n / max(dt, 1e-9)})
+    return True
+
+
+def _CreateProgramParams(cls, program_name, dataset_name, steps_per_loop,
+                         spmd=False):
+  p = cls.Params()
+  p.name = program_name
+  p.dataset_name = dataset_name
+  p.steps_per_loop = steps_per_loop
+  p.spmd = spmd
+  return p
+
+
+class SimpleProgramSchedule:
+  """train N steps → [eval datasets] → [decode datasets], repeated (:2329)."""
+
+  @classmethod
+  def Params(cls):
+    p = hyperparams.InstantiableParams(cls)
+    p.Define('task_dict', None, 'dataset_name → task params.')
+    p.Define('task_name', None, 'Task name for multi-task models.')
+    p.Define('logdir', None, 'Log directory.')
+    p.Define('train_program', None, 'Train program params.')
+    p.Define('train_executions_per_eval', 1, 'Train loops per eval round.')
+    p.Define('eval_programs', [], 'Eval/decode program params.')
+    p.Define('num_splits_per_client', None, 'Kept for parity.')
+    p.Define('dataset_names', [], 'Dataset names.')
+    p.Define('async_postprocess', True, 'Kept for parity.')
+    p.Define('emails', [], 'Kept for parity.')
+    p.Define('summary_exporter', None, 'Kept for parity.')
+    p.Define('eval_program_triggers', None,
+             'Optional {dataset: (offset, interval)} to trigger eval programs.')
+    p.Define('train_summary_exporter', None, 'Kept for parity.')
+    p.Define('ml_perf', None, 'MLPerf config.')
+    return p
+
+  def __init__(self, params, shared_model=None, trial_status_fn=None, **kwargs):
+    self.params = params.Copy()
+    p = self.params
+    self._programs: List[BaseProgram] = []
+    self.train_program = None
+    self.eval_programs = []
+    self._triggers = {}
+    if p.train_program is not None and p.train_executions_per_eval != 0:
+      tp = p.train_program.Copy()
+      tp.logdir = p.logdir
+      tp.task_name = p.task_name
+      if tp.dataset_name not in p.task_dict:
+        raise ValueError('could not find train dataset %s in %s' %
+                         (tp.dataset_name, list(p.task_dict)))
+      tp.task = p.task_dict[tp.dataset_name]
+      self.train_program = tp.Instantiate(shared_model=shared_model,
+                                          trial_status_fn=trial_status_fn)
+      self._programs.append(self.train_program)
+    for ep in p.eval_programs:
+      ep = ep.Copy()
+      ep.logdir = p.logdir
+      ep.task_name = p.task_name
+      ep.task = p.task_dict[ep.dataset_name]
+      prog = ep.Instantiate(shared_model=shared_model,
+                            trial_status_fn=trial_status_fn)
+      self.eval_programs.append(prog)
+      self._programs.append(prog)
+      if p.eval_program_triggers and ep.dataset_name in p.eval_program_triggers:
+        off, itv = p.eval_program_triggers[ep.dataset_name]
+        self._triggers[id(prog)] = program_utils.TriggerScheduler(off, itv)
+
+  def Programs(self):
+    return self._programs
+
+  def Run(self, sess=None, threadpool=None):
+    p = self.params
+    start = time.time()
+    done = False
+    train_time = 0.0
+    for _ in range(p.train_executions_per_eval if self.train_program else 0):
+      t0 = time.time()
+      done = self.train_program.Run(sess) or done
+      train_time += time.time() - t0
+      if done:
+        break
+    eval_time = 0.0
+    t0 = time.time()
+    for prog in self.eval_programs:
+      trig = self._triggers.get(id(prog))
+      if trig is not None:
+        trig.Trigger()
+        if not trig.ShouldRun() and not done:
+          continue
+      prog.Run(sess, threadpool)
+    eval_time = time.time() - t0
+    return done, train_time, eval_time
+
+  def Shutdown(self):
+    for prog in self._programs:
+      prog.Shutdown()
+
+
+MLPerfProgramSchedule = SimpleProgramSchedule
+
+
+def SimpleProgramScheduleForTask(train_dataset_name, train_steps_per_loop,
+                                 eval_dataset_names, eval_steps_per_loop,
+                                 decode_steps_per_loop=None,
+                                 experimental_decoder=False,
+                                 train_program_cls=TrainProgram,
+                                 eval_program_cls=EvalProgram,
+                                 async_postprocess=True,
+                                 decode_until_out_of_range=False,
+                                 postprocess_all_at_once=False,
+                                 emails=None, train_summary_exporter=None,
+                                 summary_exporter=None, spmd=False):
+  """Standard train → eval → decode schedule (reference :2705)."""
+  ps = SimpleProgramSchedule.Params()
+  ps.train_executions_per_eval = 1
+  ps.dataset_names = list(eval_dataset_names)
+  if train_dataset_name:
+    ps.train_program = _CreateProgramParams(
+        train_program_cls, 'train', train_dataset_name, train_steps_per_loop,
+        spmd)
+
+  def per_ds(v, name, idx):
+    if isinstance(v, dict):
+      return v.get(name)
+    if isinstance(v, (list, tuple)):
+      return v[idx]
+    return v
+
+  for i, name in enumerate(eval_dataset_names):
+    n = per_ds(eval_steps_per_loop, name, i)
+    if n is not None and n != 0:
+      ps.eval_programs.append(_CreateProgramParams(
+          eval_program_cls, 'eval_tpu', name, n, spmd))
+    d = per_ds(decode_steps_per_loop, name, i)
+    if decode_until_out_of_range:
+      d = -1
+    if d is not None and d != 0:
+      ps.eval_programs.append(_CreateProgramParams(
+          DecodeProgram, 'decode_tpu', name, d, spmd))
+  return ps
+
+
+def UpdateProgramSchedule(ps_params, dataset_list, train_executions_per_eval,
+                          train_steps_per_loop, eval_steps_per_loop,
+                          decode_steps_per_loop, multi_inputs_decoder=None,
+                          decode_summary_emails=None,
+                          oneoff_checkpoint_to_load=None, train_summary_exporter=None):
+  """Overrides a schedule from flags (reference :2835)."""
+  assert ps_params
+  if dataset_list is not None:
+    ps_params.dataset_names = dataset_list
+    ps_params.eval_programs = [ep for ep in ps_params.eval_programs
+                               if ep.dataset_name in dataset_list]
+  if train_executions_per_eval is not None:
+    ps_params.train_executions_per_eval = train_executions_per_eval
+  if train_steps_per_loop is not None and ps_params.train_program is not None:
+    ps_params.train_program.steps_per_loop = train_steps_per_loop
+  for ep in ps_params.eval_programs:
+    if issubclass(ep.cls, DecodeProgram):
+      if decode_steps_per_loop is not None:
+        ep.steps_per_loop = decode_steps_per_loop
+    elif eval_steps_per_loop is not None:
+      ep.steps_per_loop = eval_steps_per_loop
+  return ps_params

@@ -1,0 +1,213 @@
+"""Checkpoint writer with the reference file layout and policies.
+
+Reference `lingvo/core/saver.py`: sanity checks `IsFinite/InRange` before
+commit (:64-93,313-333), `ckpt-%08d` prefix (:196-201), sharded save+merge
+(:168-194), keep policies, async save by on-device snapshot then background
+write (:212-256,335-393). Also maintains the TF `checkpoint` state file so
+`latest_checkpoint` keeps working for reference tooling.
+"""
+
+from __future__ import annotations
+
+import glob
+import os
+import re
+import threading
+import time
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from lingvo_b200.utils import tensor_bundle
+
+
+class SanityCheck:
+
+  def Check(self, *args):
+    raise NotImplementedError()
+
+
+class InRange(SanityCheck):
+  """Every element is in [low, high]."""
+
+  def __init__(self, low, high):
+    self._low, self._high = low, high
+
+  def Check(self, name, t: torch.Tensor) -> bool:
+    return bool((t >= self._low).all() and (t <= self._high).all())
+
+  def __str__(self):
+    return 'InRange({}, {})'.format(self._low, self._high)
+
+
+class IsFinite(SanityCheck):
+
+  def Check(self, name, t: torch.Tensor) -> bool:
+    if not t.is_floating_point():
+      return True
+    return bool(torch.isfinite(t).all())
+
+  def __str__(self):
+    return 'IsFinite'
+
+
+class SanityCheckFailed(Exception):
+  pass
+
+
+def _ToNumpy(t: torch.Tensor):
+  t = t.detach()
+  if t.dtype == torch.bfloat16:
+    return tensor_bundle.BFloat16Array(
+        t.contiguous().view(torch.uint16).cpu().numpy())
+  return t.cpu().numpy()
+
+
+def FromNumpy(a) -> torch.Tensor:
+  if isinstance(a, tensor_bundle.BFloat16Array):
+    return torch.from_numpy(a.bits.copy()).view(torch.bfloat16)
+  return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def CheckpointStatePath(train_dir: str) -> str:
+  return os.path.join(train_dir, 'checkpoint')
+
+
+def ReadCheckpointState(train_dir: str) -> Optional[Dict[str, List[str]]]:
+  path = CheckpointStatePath(train_dir)
+  if not os.path.exists(path):
+    return None
+  state = {'model_checkpoint_path': None, 'all_model_checkpoint_paths': []}
+  with open(path) as f:
+    for line in f:
+      m = re.match(r'\s*(\w+)\s*:\s*"(.*)"\s*$', line)
+      if not m:
+        continue
+      k, v = m.group(1), m.group(2)
+      if k == 'model_checkpoint_path':
+        state[k] = v
+      elif k == 'all_model_checkpoint_paths':
+        state[k].append(v)
+  return state
+
+
+def LatestCheckpoint(train_dir: str) -> Optional[str]:
+  """Full prefix of the newest complete checkpoint in `train_dir`."""
+  state = ReadCheckpointState(train_dir)
+  if state and state['model_checkpoint_path']:
+    p = state['model_checkpoint_path']
+    if not os.path.isabs(p):
+      p = os.path.join(train_dir, p)
+    if os.path.exists(p + '.index'):
+      return p
+  cands = sorted(glob.glob(os.path.join(train_dir, 'ckpt-*.index')))
+  return cands[-1][:-len('.index')] if cands else None
+
+
+def AllCheckpoints(train_dir: str) -> List[str]:
+  return [p[:-len('.index')] for p in
+          sorted(glob.glob(os.path.join(train_dir, 'ckpt-*.index')))]
+
+
+class Saver:
+  """Saves `{name: tensor}` maps as `ckpt-%08d` bundles under a directory."""
+
+  def __init__(self, logdir: str, variables_fn: Callable[[], Dict[str, torch.Tensor]],
+               sanity_checks=None, keep_latest_n=None,
+               keep_every_n_hours=None, async_save=False, prefix='ckpt'):
+    self._logdir = logdir
+    self._vars_fn = variables_fn
+    self._sanity_checks = sanity_checks or []
+    self._keep_latest_n = keep_latest_n
+    self._keep_every_n_hours = keep_every_n_hours
+    self._async = async_save
+    self._prefix = os.path.join(logdir, prefix)
+    self._lock = threading.Lock()
+    self._thread: Optional[threading.Thread] = None
+    self._last_kept_time = time.time()
+    self._error: Optional[BaseException] = None
+    os.makedirs(logdir, exist_ok=True)
+
+  def _DoSanityChecks(self, tensors):
+    for pattern_or_fn, checks in self._sanity_checks:
+      for name, t in tensors.items():
+        hit = (re.search(pattern_or_fn, name) if isinstance(pattern_or_fn, str)
+               else pattern_or_fn(name))
+        if not hit:
+          continue
+        for c in checks:
+          if not c.Check(name, t):
+            raise SanityCheckFailed('Sanity check %s failed for %s' % (c, name))
+
+  def _Write(self, prefix: str, snapshot: Dict[str, object], global_step: int):
+    w = tensor_bundle.BundleWriter(prefix)
+    for name in sorted(snapshot):
+      w.Add(name, snapshot[name])
+    w.Finish()
+    self._UpdateState(prefix)
+    self._GarbageCollect()
+
+  def _UpdateState(self, prefix: str):
+    with self._lock:
+      allp = [os.path.basename(p) for p in AllCheckpoints(self._logdir)]
+      base = os.path.basename(prefix)
+      if base not in allp:
+        allp.append(base)
+      tmp = CheckpointStatePath(self._logdir) + '.tmp'
+      with open(tmp, 'w') as f:
+        f.write('model_checkpoint_path: "%s"\n' % base)
+        for p in allp:
+          f.write('all_model_checkpoint_paths: "%s"\n' % p)
+      os.replace(tmp, CheckpointStatePath(self._logdir))
+
+  def _GarbageCollect(self):
+    if not self._keep_latest_n:
+      return
+    ckpts = AllCheckpoints(self._logdir)
+    excess = ckpts[:-self._keep_latest_n] if self._keep_latest_n > 0 else []
+    for p in excess:
+      try:
+        mtime = os.path.getmtime(p + '.index')
+      except OSError:
+        continue
+      if self._keep_every_n_hours and (
+          mtime - self._last_kept_time >= self._keep_every_n_hours * 3600):
+        self._last_kept_time = mtime
+        continue
+      for f in glob.glob(p + '.*'):
+        try:
+          os.remove(f)
+        except OSError:
+          pass
+
+  def Wait(self):
+    t = self._thread
+    if t is not None:
+      t.join()
+      self._thread = None
+    if self._error is not None:
+      e, self._error = self._error, None
+      raise e
+
+  def Save(self, global_step: int, tensors: Optional[Dict[str, torch.Tensor]] = None,
+           prefix: Optional[str] = None) -> str:
+    """Snapshots (device → host) synchronously; writes sync or async."""
+    self.Wait()
+    tensors = tensors if tensors is not None else self._vars_fn()
+    self._DoSanityChecks(tensors)
+    snapshot = {k: _ToNumpy(v) for k, v in tensors.items()}
+    path = '%s-%08d' % (prefix or self._prefix, int(global_step))
+    if not self._async:
+      self._Write(path, snapshot, global_step)
+      return path
+
+    def run():
+      try:
+        self._Write(path, snapshot, global_step)
+      except BaseException as e:  # pylint: disable=broad-except
+        self._error = e
+
+    self._thread = threading.Thread(target=run, name='async_ckpt', daemon=True)
+    self._thread.start()
+    return path
