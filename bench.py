@@ -1,0 +1,247 @@
+#!/usr/bin/env python
+"""Headline benchmark: tokens/s of the GShard-MoE 8-expert LM training step.
+
+  python bench.py --gpus N --steps K --warmup W          (N = 1)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+      --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...   (N > 1)
+
+Metric (BASELINE.json): whole-job tokens/sec, device-timed (CUDA events on the
+launching stream, barrier + synchronize on both sides, max over ranks) for
+`lm.synthetic_packed_input.MoELm8E` (GShard MoE Transformer LM, 8 experts,
+expert-parallel over the ranks), bf16 compute / fp32 master weights,
+Adafactor step included, synthetic random-token data, random-init weights.
+Weak scaling: 8 sequences × 1024 tokens per GPU.
+
+`--impl reference` reports that the TF reference cannot run here.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+MODEL = 'lm.synthetic_packed_input.MoELm8E'
+
+
+def _ParseArgs():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=10)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--model', default=MODEL)
+  ap.add_argument('--comm', default=None, choices=[None, 'fused', 'nccl'],
+                  help='fused = hand-written peer-memory kernels (default); '
+                  'nccl = stock NCCL+cuBLAS baseline mode.')
+  ap.add_argument('--no-e2e', action='store_true')
+  return ap.parse_args()
+
+
+class ClockSampler:
+  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,'
+       'clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index=0):
+    self._idx = gpu_index
+    self._rows = []
+    self._stop = threading.Event()
+    self._t = None
+
+  def _Run(self):
+    while not self._stop.is_set():
+      try:
+        out = subprocess.run(
+            ['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+             '-i', str(self._idx)], capture_output=True, text=True, timeout=5)
+        for line in out.stdout.strip().splitlines():
+          self._rows.append([c.strip() for c in line.split(',')])
+      except Exception:  # pylint: disable=broad-except
+        pass
+      self._stop.wait(0.2)
+
+  def __enter__(self):
+    self._t = threading.Thread(target=self._Run, daemon=True)
+    self._t.start()
+    return self
+
+  def __exit__(self, *a):
+    self._stop.set()
+    self._t.join(timeout=6)
+
+  def Summary(self):
+    sm, smax, reasons = [], 0.0, set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    for r in self._rows:
+      try:
+        sm.append(float(r[1]))
+        smax = max(smax, float(r[2]))
+        for n, v in zip(names, r[4:8]):
+          if v.lower().startswith('active'):
+            reasons.add(n)
+      except (ValueError, IndexError):
+        continue
+    sm.sort()
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax or None,
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def _Reference(args):
+  print(json.dumps({
+      'impl': 'reference',
+      'unavailable': 'tensorflow/lingvo needs bazel + TensorFlow 2.13 (neither '
+                     'is installed; /root/reference has no setup.py/pyproject; '
+                     'pip install --no-index fails: "not installable") and TF '
+                     '2.13 has no sm_100 kernels',
+      'n_gpus': args.gpus}))
+  return 0
+
+
+def main():
+  args = _ParseArgs()
+  if args.impl == 'reference':
+    return _Reference(args)
+  if args.comm:
+    os.environ['LINGVO_B200_COMM'] = args.comm
+
+  import torch
+  import torch.distributed as dist
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  assert torch.cuda.is_available(), 'bench.py needs a GPU'
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  assert world == args.gpus, 'WORLD_SIZE %d != --gpus %d' % (world, args.gpus)
+  dev = torch.device('cuda', local_rank)
+
+  from lingvo_b200 import model_registry
+  from lingvo_b200 import ops
+  from lingvo_b200.core import base_input_generator
+  from lingvo_b200.core import cluster_factory
+  from lingvo_b200.parallel import mesh as mesh_lib
+  import lingvo_b200.models.lm.params.synthetic_packed_input  # noqa: F401
+  native = ops.native(required=True)
+  mesh_lib.Reset()
+
+  cfg = model_registry.GetParams(args.model, 'Train')
+  cfg.cluster.mode = 'sync'
+  cfg.cluster.job = 'trainer_client'
+  cfg.cluster.worker.replicas = world
+  cfg.cluster.worker.gpus_per_replica = 1
+  cluster = cluster_factory.Cluster(cfg.cluster)
+  with cluster:
+    model = cfg.Instantiate()
+    model.to(dev)
+    task = model.tasks[0]
+    from lingvo_b200.parallel import dp as dp_lib
+    dp_lib.Attach(task)
+
+    tp = task.params
+    per_gpu_batch = task.input.InfeedBatchSize()
+    seq_len = tp.sequence_length
+    tokens_per_step = per_gpu_batch * seq_len * world
+
+    def sync():
+      if world > 1:
+        dist.barrier()
+      torch.cuda.synchronize()
+
+    # ---- device-timed loop: inputs pre-staged on device --------------------
+    n_total = args.warmup + args.steps
+    batches = [task._MoveBatch(task.input.GetPreprocessedInputBatch(), dev)  # pylint: disable=protected-access
+               for _ in range(min(n_total, 8))]
+    for i in range(args.warmup):
+      task.TrainStep([batches[i % len(batches)]])
+    sync()
+    launches0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+      sync()
+      e0.record()
+      for i in range(args.steps):
+        metrics, _ = task.TrainStep([batches[(args.warmup + i) % len(batches)]])
+      e1.record()
+      sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    launches = native.launch_count() - launches0
+    loss = float(metrics['loss'][0])
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    value = tokens_per_step * args.steps / (ms_total / 1e3)
+
+    # ---- end-to-end loop through the public API ----------------------------
+    e2e = None
+    if not args.no_e2e:
+      prefetch = base_input_generator.DevicePrefetcher(task.input, dev, depth=2)
+      for _ in range(2):
+        task.TrainStep([prefetch.Next()])
+      sync()
+      h2d = 0
+      d2h = 0
+      t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      t0.record()
+      for _ in range(args.steps):
+        batch = prefetch.Next()          # pinned host → device on a side stream
+        h2d = prefetch.h2d_bytes_last
+        m, _ = task.TrainStep([batch])
+        host_loss = m['loss'][0].detach().float().cpu()   # D2H read of the loss
+        d2h = host_loss.numel() * host_loss.element_size()
+      t1.record()
+      sync()
+      ems = torch.tensor([t0.elapsed_time(t1)], device=dev)
+      if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+      e2e = {'value': tokens_per_step * args.steps / (float(ems.item()) / 1e3),
+             'unit': 'tokens/s', 'h2d_bytes_per_step': int(h2d),
+             'd2h_bytes_per_step': int(d2h)}
+
+  if rank == 0:
+    ctx = mesh_lib.Get()
+    out = {
+        'metric': 'tokens/sec (whole job, device-timed, max over ranks) '
+                  'GShard-MoE 8-expert LM training step',
+        'value': value, 'unit': 'tokens/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16', 'data': 'synthetic (uniform random token ids, packed '
+                                 'LM format; random-init weights)',
+        'impl': 'ours', 'comm_mode': ctx.mode,
+        'config': {
+            'model': args.model, 'global_batch': per_gpu_batch * world,
+            'seq_len': seq_len, 'parallelism': 'dp%d+ep%d' % (
+                world, min(world, tp.builder.e_dim or 1)),
+            'experts': tp.builder.e_dim, 'model_dim': tp.builder.model_dim,
+            'layers': tp.num_transformer_layers,
+            'optimizer': type(task.learners[0].optimizer).__name__,
+            'l2_flush': 'working set (1.4B fp32 params + bf16 activations) '
+                        'is >> 126 MB L2; no explicit flush',
+        },
+        'clocks': clocks.Summary(), 'gpu_launches': int(launches),
+        'final_loss': loss,
+    }
+    if e2e is not None:
+      out['e2e'] = e2e
+    print(json.dumps(out))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return 0
+
+
+if __name__ == '__main__':
+  sys.exit(main())

@@ -1,0 +1,1043 @@
+"""GShard builders (`MoEBuilder`, `DenseBuilder`) and the `UniTransformer` LM.
+
+Reference `lingvo/core/gshard_builder.py` (5375 LoC): builder params
+(:55-330, :2269-2330), `DecoderLayer` (:558-666), `DecoderLayerStack`
+(:675-906), attention (`_AttentionWeights :1973`, `Attention :2697`,
+`_ComputeQKVCombine :2819`, `_ComputeAttenOutputs :2908`, T5 relative bias
+:1431-1514, RoPE :409-426), norms (`_LN` RMS :1833, `_TrueLN :1856`, `_PN`),
+FFN (`DenseReluDense :2939`, gated :3054), MoE (`MoE :2465`,
+`_ShardedFeedForwardNetworksWeights :2484`, gating weights), embedding
+(:457-466, :2550), and `UniTransformer` (:3939-4483).
+
+Re-design: the reference composes every block from a string-signature graph
+DSL and relies on XLA to fuse/shard it. Here each block is an explicit layer
+class whose `FProp` calls the fused sm_100a kernels directly (RMS-norm,
+tcgen05 GEMM w/ fused epilogues, index-based MoE dispatch/combine, fused
+xent), and whose collectives are explicit (`lingvo_b200.parallel`). The
+builder API (method names, params, sub-layer type lists) is kept so
+experiment configs port 1:1.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from lingvo_b200 import ops
+from lingvo_b200.core import activations
+from lingvo_b200.core import base_layer
+from lingvo_b200.core import base_model
+from lingvo_b200.core import builder
+from lingvo_b200.core import gshard_layers
+from lingvo_b200.core import gshard_utils
+from lingvo_b200.core import layers
+from lingvo_b200.core import py_utils
+from lingvo_b200.core import summary_utils
+from lingvo_b200.core.nested_map import NestedMap
+
+WeightParams = py_utils.WeightParams
+WeightInit = py_utils.WeightInit
+
+
+def ShardedWeightParams(shape, init=None, dtype=None, collections=None,
+                        tensor_split_dims_mapping=None, device_mesh=None):
+  return WeightParams(shape, init, dtype, collections, device_mesh,
+                      tensor_split_dims_mapping)
+
+
+def _Act(name: str):
+  n = name.upper()
+  if n in ('GELU',):
+    return lambda x: F.gelu(x, approximate='tanh')
+  if n in ('SQR_RELU',):
+    return lambda x: torch.square(F.relu(x))
+  return activations.GetFn(n)
+
+
+# =========================================================================
+# Layer classes
+# =========================================================================
+class _BuilderLayer(base_layer.BaseLayer):
+  """Base of builder-produced layers; carries the builder params."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('b', None, 'Builder params (shared hyper-parameters).')
+    return p
+
+  @property
+  def bp(self):
+    return self.params.b
+
+
+class RmsNormLayer(_BuilderLayer):
+  """Bias-less RMS "layer norm" `x·rsqrt(mean(x²)+eps)·scale` (:1833-1854)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('dim', 0, 'Model dim.')
+    p.Define('epsilon', 1e-6, 'Epsilon.')
+    p.Define('no_scale', False, 'No learned scale (`_LNNoScale`).')
+    p.Define('kind', 'rms', 'rms|true_ln|pn|none.')
+    return p
+
+  def _CreateLayerVariables(self):
+    p = self.params
+    if p.kind == 'none' or (p.no_scale and p.kind == 'rms'):
+      return
+    self.CreateVariable('scale', WeightParams([p.dim], WeightInit.Constant(1.0),
+                                              p.dtype))
+    if p.kind == 'true_ln':
+      self.CreateVariable('shift', WeightParams(
+          [p.dim], WeightInit.Constant(0.0), p.dtype))
+
+  def FProp(self, theta, x):
+    p = self.params
+    if p.kind == 'none':
+      return x
+    if p.kind == 'rms':
+      scale = None if p.no_scale else theta.scale
+      if ops.use_cuda_kernels(x) and x.dtype == torch.bfloat16:
+        from lingvo_b200.ops import norm
+        if norm.available():
+          return norm.rms_norm(x, scale, p.epsilon)
+      xf = x.float()
+      y = xf * torch.rsqrt(xf.square().mean(-1, keepdim=True) + p.epsilon)
+      if scale is not None:
+        y = y * scale.float()
+      return y.to(x.dtype)
+    xf = x.float()
+    if p.kind == 'true_ln':
+      c = xf - xf.mean(-1, keepdim=True)
+      y = c * torch.rsqrt(c.square().mean(-1, keepdim=True) + p.epsilon)
+      return (y * theta.scale.float() + theta.shift.float()).to(x.dtype)
+    if p.kind == 'pn':   # power norm: mean |x| based
+      y = xf / (xf.abs().mean(-1, keepdim=True) + p.epsilon)
+      return (y * theta.scale.float()).to(x.dtype)
+    raise ValueError(p.kind)
+
+
+class EmbeddingLayer(_BuilderLayer):
+  """`w.embedding [V, M]`; gather lookup (reference one-hot einsum :457)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('vocab_dim', 0, 'Vocabulary size.')
+    p.Define('model_dim', 0, 'Model dim.')
+    p.Define('scale_by_dim', False, 'Multiply by sqrt(model_dim).')
+    return p
+
+  def _CreateLayerVariables(self):
+    p = self.params
+    self.CreateVariable('embedding', ShardedWeightParams(
+        [p.vocab_dim, p.model_dim], WeightInit.Gaussian(), p.dtype,
+        tensor_split_dims_mapping=p.b.emb_w_split if p.b else None))
+
+  def FProp(self, theta, ids):
+    p = self.params
+    out = F.embedding(ids.long(), theta.embedding)
+    if p.scale_by_dim:
+      out = out * (p.model_dim**0.5)
+    return out
+
+
+def RelativePositionBucket(relative_position, num_buckets, max_distance,
+                           bidirectional=False):
+  """T5 bucketing of `key_pos - query_pos` (reference :1431-1456)."""
+  ret = 0
+  n = -relative_position
+  if bidirectional:
+    num_buckets //= 2
+    ret = (n < 0).to(torch.int32) * num_buckets
+    n = n.abs()
+  else:
+    n = n.clamp(min=0)
+  max_exact = num_buckets // 2
+  is_small = n < max_exact
+  large = max_exact + (torch.log(n.float().clamp(min=1) / max_exact) /
+                       math.log(max_distance / max_exact) *
+                       (num_buckets - max_exact)).to(torch.int32)
+  large = large.clamp(max=num_buckets - 1)
+  return ret + torch.where(is_small, n.to(torch.int32), large)
+
+
+class SelfAttentionLayer(_BuilderLayer):
+  """Decoder/encoder self-attention in `BLHD` layout (:1249-1700, :2697).
+
+  Weights `w.{wq,wk,wv,wo}` are `[M, H·D]`/`[H·D, M]` (combine_dims) and
+  `wrb [H, buckets]` for the T5 relative bias. Logits are fp32; masking uses
+  packed `segment_id`/`segment_pos` (+ causal for decoders); MQA via
+  `attention_num_memory_heads == 1`.
+  """
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('decoder', True, 'Causal (decoder) masking.')
+    p.Define('relative_bias', False, 'Use T5 relative attention bias.')
+    return p
+
+  def _CreateLayerVariables(self):
+    b = self.bp
+    h, d, m = b.attention_num_heads, b.attention_key_value_dim, b.model_dim
+    hk = b.attention_num_memory_heads or h
+    q_std = (m * d)**-0.5
+    self.CreateVariable('wq', ShardedWeightParams(
+        [m, h * d], WeightInit.Gaussian(q_std), self.params.dtype))
+    self.CreateVariable('wk', ShardedWeightParams(
+        [m, hk * d], WeightInit.Gaussian(m**-0.5), self.params.dtype))
+    self.CreateVariable('wv', ShardedWeightParams(
+        [m, hk * d], WeightInit.Gaussian(m**-0.5), self.params.dtype))
+    self.CreateVariable('wo', ShardedWeightParams(
+        [h * d, m], WeightInit.Gaussian((h * d)**-0.5), self.params.dtype))
+    if self.params.relative_bias:
+      self.CreateVariable('wrb', WeightParams(
+          [h, b.relative_attention_num_buckets], WeightInit.Gaussian(1.0),
+          self.params.dtype))
+
+  def _Bias(self, theta, segment_id, segment_pos):
+    """Additive fp32 bias `[B or 1, H or 1, L, L]`."""
+    b = self.bp
+    a, c = segment_id.unsqueeze(-1), segment_id.unsqueeze(-2)
+    not_vis = ((a == 0) & (c == 0)) | (a != c)
+    if self.params.decoder and not b.decoder_skip_causal_mask:
+      not_vis = not_vis | (segment_pos.unsqueeze(-1) < segment_pos.unsqueeze(-2))
+    bias = not_vis.float().unsqueeze(1) * -1e9
+    if self.params.relative_bias:
+      if b.relative_attention_use_universal_1d_position:
+        l = segment_pos.shape[-1]
+        pos = torch.arange(l, device=segment_pos.device).unsqueeze(0)
+        qpos = kpos = pos
+      else:
+        qpos = kpos = segment_pos
+      rel = kpos.unsqueeze(-2) - qpos.unsqueeze(-1)
+      bucket = RelativePositionBucket(
+          rel, b.relative_attention_num_buckets,
+          b.relative_attention_max_distance,
+          bidirectional=(not self.params.decoder) or
+          b.decoder_bidirectional_relative_attention)
+      rb = theta.wrb.float()[:, bucket.long()]        # [H, (B|1), L, L]
+      rb = rb.permute(1, 0, 2, 3)
+      bias = bias + rb
+    return bias
+
+  def FProp(self, theta, x, segment_id, segment_pos):
+    b = self.bp
+    bsz, l, m = x.shape
+    h, d = b.attention_num_heads, b.attention_key_value_dim
+    hk = b.attention_num_memory_heads or h
+    from lingvo_b200.ops import gemm
+    wq, wk, wv, wo = theta.wq, theta.wk, theta.wv, theta.wo
+    if b.attention_combine_qkv and hk == h:
+      wqkv = torch.cat([wq, wk, wv], dim=1)
+      qkv = gemm.linear(x, wqkv.to(x.dtype))
+      q, k, v = qkv.split([h * d, hk * d, hk * d], dim=-1)
+    else:
+      q = gemm.linear(x, wq.to(x.dtype))
+      k = gemm.linear(x, wk.to(x.dtype))
+      v = gemm.linear(x, wv.to(x.dtype))
+    q = q.reshape(bsz, l, h, d)
+    k = k.reshape(bsz, l, hk, d)
+    v = v.reshape(bsz, l, hk, d)
+    if b.use_rotary_position_emb:
+      q = _Rope(q, segment_pos, b.rope_emb_max_timescale)
+      k = _Rope(k, segment_pos, b.rope_emb_max_timescale)
+    bias = self._Bias(theta, segment_id, segment_pos)
+    o = _AttentionCore(q, k, v, bias, b.atten_logit_cap,
+                       b.attention_extra_logit, b.attention_dropout_prob
+                       if not self.do_eval else 0.0)
+    out = gemm.linear(o.reshape(bsz, l, h * d), wo.to(x.dtype))
+    return out, torch.zeros((), device=x.device, dtype=torch.float32)
+
+
+def _Rope(x, pos, max_timescale):
+  """Half-split rotary embedding on `[B, L, H, D]` (reference :409-426)."""
+  d = x.shape[-1]
+  half = d // 2
+  frac = torch.arange(half, dtype=torch.float32, device=x.device) * 2.0 / d
+  ts = max_timescale**frac
+  ang = pos.float().unsqueeze(-1) / ts
+  sin, cos = torch.sin(ang).unsqueeze(-2), torch.cos(ang).unsqueeze(-2)
+  xf = x.float()
+  a, b = xf[..., :half], xf[..., half:]
+  return torch.cat([a * cos - b * sin, b * cos + a * sin], -1).to(x.dtype)
+
+
+def _AttentionCore(q, k, v, bias, logit_cap=0.0, extra_logit=None,
+                   dropout_prob=0.0):
+  """softmax(q·kᵀ + bias)·v with fp32 logits; `BLHD` in/out."""
+  bsz, l, h, d = q.shape
+  hk = k.shape[2]
+  if hk != h:
+    k = k.expand(bsz, k.shape[1], h, d) if hk == 1 else (
+        k.repeat_interleave(h // hk, dim=2))
+    v = v.expand(bsz, v.shape[1], h, d) if hk == 1 else (
+        v.repeat_interleave(h // hk, dim=2))
+  simple = (not logit_cap) and extra_logit is None
+  if simple and q.is_cuda:
+    # NOTE: no 1/sqrt(D) scaling in GShard attention (folded into wq init).
+    o = F.scaled_dot_product_attention(
+        q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+        attn_mask=bias.to(q.dtype).expand(bsz, h, l, k.shape[1]),
+        dropout_p=dropout_prob, scale=1.0)
+    return o.transpose(1, 2)
+  logits = torch.einsum('BLHD,BMHD->BHLM', q.float(), k.float())
+  if logit_cap and logit_cap > 0:
+    logits = logit_cap * torch.tanh(logits / logit_cap)
+  logits = logits + bias
+  if extra_logit is not None:
+    extra = torch.full_like(logits[..., :1], float(extra_logit))
+    probs = torch.softmax(torch.cat([logits, extra], -1), -1)[..., :-1]
+  else:
+    probs = torch.softmax(logits, -1)
+  probs = probs.to(q.dtype)
+  if dropout_prob:
+    probs = F.dropout(probs, dropout_prob, training=True)
+  return torch.einsum('BHLM,BMHD->BLHD', probs, v)
+
+
+class DenseReluDenseLayer(_BuilderLayer):
+  """`wi [M, H]` → act → dropout → `wo [H, M]` (:2939-2998); gated variant
+  with `wi_0, wi_1` (:3054-)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('activation', 'relu', 'relu|gelu|sqr_relu|silu.')
+    p.Define('gated', False, 'GLU variant: act(x·wi_0) ⊙ (x·wi_1).')
+    return p
+
+  def _CreateLayerVariables(self):
+    b = self.bp
+    m, h = b.model_dim, b.ff_dim
+    dt = self.params.dtype
+    wi_init = WeightInit.Uniform(((1. / m)**0.5) * 3.**0.5)
+    wo_init = WeightInit.Uniform(((1. / h)**0.5) * 3.**0.5)
+    if self.params.gated:
+      self.CreateVariable('wi_0', ShardedWeightParams(
+          [m, h], wi_init, dt, tensor_split_dims_mapping=b.mh_wi_split))
+      self.CreateVariable('wi_1', ShardedWeightParams(
+          [m, h], wi_init, dt, tensor_split_dims_mapping=b.mh_wi_split))
+    else:
+      self.CreateVariable('wi', ShardedWeightParams(
+          [m, h], wi_init, dt, tensor_split_dims_mapping=b.mh_wi_split))
+    self.CreateVariable('wo', ShardedWeightParams(
+        [h, m], wo_init, dt, tensor_split_dims_mapping=b.hm_wo_split))
+    if b.ff_use_bias:
+      self.CreateVariable('bi', WeightParams([h], WeightInit.Constant(0.), dt))
+      self.CreateVariable('bo', WeightParams([m], WeightInit.Constant(0.), dt))
+
+  def FProp(self, theta, x, segment_id=None, segment_pos=None):
+    from lingvo_b200.ops import gemm
+    b = self.bp
+    p = self.params
+    bi = theta.bi if b.ff_use_bias else None
+    bo = theta.bo if b.ff_use_bias else None
+    act = p.activation.upper()
+    if p.gated:
+      h = _Act(p.activation)(gemm.linear(x, theta.wi_0.to(x.dtype), bi)) * (
+          gemm.linear(x, theta.wi_1.to(x.dtype)))
+    elif act == 'RELU':
+      h = gemm.linear(x, theta.wi.to(x.dtype), bi, act='RELU')
+    else:
+      h = _Act(p.activation)(gemm.linear(x, theta.wi.to(x.dtype), bi))
+    if b.dropout_rate and not self.do_eval:
+      h = F.dropout(h, b.dropout_rate, training=True)
+    out = gemm.linear(h, theta.wo.to(x.dtype), bo)
+    return out, torch.zeros((), device=x.device, dtype=torch.float32)
+
+
+class MoELayer(_BuilderLayer):
+  """Sharded MoE position-wise FFN (reference :2465-2548).
+
+  Variables: `top_2_gating.w [M, E]`, `wi [E(_local), M, H]`,
+  `wo [E(_local), H, M]` (GLU: `wi_0/wi_1`). Tokens `[B, L, M]` are grouped
+  to `[G, S, M]`, gated (fp32 logits), dispatched to experts, and combined.
+  `mode`: 'indexed' (B200 path) or 'dense' (reference einsum oracle).
+  """
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('gated', False, 'GLU experts (`MoEGated`).')
+    p.Define('mode', 'indexed', 'indexed|dense.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    from lingvo_b200.parallel import mesh as mesh_lib
+    self._ep = mesh_lib.ExpertParallelFor(self.bp.e_dim)
+
+  @property
+  def ep_engine(self):
+    return self._ep
+
+  def _CreateLayerVariables(self):
+    b = self.bp
+    m, h, e = b.model_dim, b.moe_hidden_dim, b.e_dim
+    dt = self.params.dtype
+    e_local = e if self._ep is None else self._ep.num_local_experts
+    wi_init = WeightInit.Uniform(((1. / m)**0.5) * 3.**0.5)
+    wo_init = WeightInit.Uniform(((1. / h)**0.5) * 3.**0.5)
+    self.CreateVariable('gw', WeightParams(
+        [m, e], WeightInit.Gaussian(m**-0.5), dt))
+    names = ['wi_0', 'wi_1'] if self.params.gated else ['wi']
+    shard = None
+    if self._ep is not None:
+      shard = (0, self._ep.ep_rank, self._ep.ep_size)
+    for n in names:
+      wp = ShardedWeightParams(
+          [e_local, m, h], wi_init, dt, tensor_split_dims_mapping=b.emh_split)
+      wp.init_shard = shard
+      self.CreateVariable(n, wp)
+    wp = ShardedWeightParams(
+        [e_local, h, m], wo_init, dt, tensor_split_dims_mapping=b.ehm_split)
+    wp.init_shard = shard
+    self.CreateVariable('wo', wp)
+    # Expert weights are *not* replicated across the EP group: mark them so
+    # the data-parallel engine skips / narrows their gradient reduction.
+    self._expert_var_names = names + ['wo']
+
+  def _InstantiateSelfAndChildren(self):
+    super()._InstantiateSelfAndChildren()
+    for n in self._expert_var_names:
+      self._private_vars[n].expert_parallel = self._ep is not None
+
+  def FProp(self, theta, x, segment_id, segment_pos=None):
+    b = self.bp
+    p = self.params
+    bsz, l, m = x.shape
+    groups = b.num_groups or bsz
+    tokens = bsz * l
+    assert tokens % groups == 0
+    s = tokens // groups
+    xg = x.reshape(groups, s, m)
+    paddings = (segment_id == 0).float().reshape(groups, s)
+    ldt = b.gating_logits_dtype or torch.float32
+    act = b.moe_activation.upper()
+    if p.mode == 'dense':
+      gating = gshard_layers.ComputeGating(
+          theta.gw, xg, paddings, b.num_devices, b.e_dim, b.c_dim or 0, True,
+          x.dtype, b.gating_func, False, b.second_expert_policy,
+          b.second_expert_threshold, b.legacy_mtf_behavior, b.capacity_factor,
+          None, b.mask_dtype or torch.float32, ldt)
+      wi = torch.stack([theta.wi_0, theta.wi_1]) if p.gated else theta.wi
+      out, aux = gshard_layers.FeedForwardNetworksApplyGating(
+          gating, x, xg, wi, theta.wo, b.num_devices, groups,
+          dropout_rate=b.moe_dropout_rate if not self.do_eval else 0.0,
+          use_glu=p.gated, activation_name=act)
+      return out.reshape(bsz, l, m), aux.float()
+    # Gating logits in fp32: [G,S,M]·[M,E] is tiny (E = 8); keep it exact.
+    logits = torch.matmul(xg.to(ldt), theta.gw.to(ldt))
+    seeds = None
+    if b.second_expert_policy != 'all':
+      seeds = py_utils.GenerateStepSeedPair(p)
+    gating = gshard_layers.Top2GatingIndices(
+        logits, paddings, b.e_dim, b.c_dim or 0, torch.float32,
+        b.second_expert_policy, b.second_expert_threshold,
+        b.legacy_mtf_behavior, b.capacity_factor, seeds)
+    wi = torch.stack([theta.wi_0, theta.wi_1]) if p.gated else theta.wi
+    out = gshard_layers.MoEApplyIndexed(
+        xg, gating, wi, theta.wo, act, use_glu=p.gated, ep_engine=self._ep)
+    return out.reshape(bsz, l, m), gating.aux_loss.float()
+
+
+class DecoderBlock(_BuilderLayer):
+  """mask → norm → sub-layer → dropout → residual add (reference :558-666)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('layer', None, 'Sub-layer params.')
+    p.Define('norm', None, 'Norm layer params.')
+    p.Define('norm_policy', 'pre', 'pre|primer|primer_hybrid.')
+    p.Define('post_norm', None, 'Post-norm params for primer_hybrid.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    self.CreateChild('ln', p.norm)
+    self.CreateChild('layer', p.layer)
+    if p.post_norm is not None:
+      self.CreateChild('post_ln', p.post_norm)
+
+  def FProp(self, theta, i: NestedMap) -> NestedMap:
+    p = self.params
+    b = self.bp
+    mask = (i.segment_id != 0).unsqueeze(-1).to(i.vec.dtype)
+    x_in = i.vec * mask
+    x = self.ln.FProp(theta.ln, x_in) if p.norm_policy != 'primer_post' else x_in
+    y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos)
+    if p.post_norm is not None:
+      y = self.post_ln.FProp(theta.post_ln, y)
+    if b.dropout_rate and not self.do_eval:
+      y = F.dropout(y, b.dropout_rate, training=True)
+    o = i.copy()
+    o.vec = x_in + y
+    o.aux_loss = i.aux_loss + aux
+    return o
+
+
+class LayerStack(_BuilderLayer):
+  """`num` repetitions of the sub-layer list + final norm (:675-906)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('blocks', [], 'Flat list of DecoderBlock params.')
+    p.Define('final_norm', None, 'Final norm layer params (or None).')
+    p.Define('remat', False, 'Rematerialise each block in the backward pass.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    self.CreateChildren('layers', list(p.blocks))
+    if p.final_norm is not None:
+      self.CreateChild('final_layer_norm', p.final_norm)
+
+  def FProp(self, theta, i: NestedMap) -> NestedMap:
+    p = self.params
+    x = i
+    for idx, blk in enumerate(self.layers):
+      if p.remat and not self.do_eval:
+        keys = sorted(x.keys())
+
+        def run(*vals, blk=blk, th=theta.layers[idx], keys=keys):
+          o = blk.FProp(th, NestedMap(dict(zip(keys, vals))))
+          return tuple(o[k] for k in keys)
+        outs = py_utils.RematerializeFn(run, *[x[k] for k in keys])
+        x = NestedMap(dict(zip(keys, outs)))
+      else:
+        x = blk.FProp(theta.layers[idx], x)
+    if 'final_layer_norm' in self.children:
+      mask = (x.segment_id != 0).unsqueeze(-1).to(x.vec.dtype)
+      x.vec = self.final_layer_norm.FProp(theta.final_layer_norm, x.vec) * mask
+      if self.bp.dropout_rate and not self.do_eval and (
+          not self.bp.skip_output_dropout):
+        x.vec = F.dropout(x.vec, self.bp.dropout_rate, training=True)
+    return x
+
+
+class MeshSplitLayer(base_layer.BaseLayer):
+  """Sharding annotation layer (`MeshSplit`)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('tensor_split_dims_mapping', None, 'Mesh axis per tensor dim.')
+    return p
+
+  def FProp(self, theta, x):
+    p = self.params
+    return gshard_utils.MeshSplit(x, p.device_mesh, p.tensor_split_dims_mapping)
+
+
+# =========================================================================
+# Builders
+# =========================================================================
+class MoEBuilder(builder.Base):
+  """Mixture-of-Experts Transformer builder (reference :55-2268)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('num_devices', 1, 'Obsolete: number of devices for Split().')
+    p.Define('num_groups', None, 'MoE token groups G (default: batch dim).')
+    p.Define('layer_norm_epsilon', 1e-6, 'Epsilon for norms.')
+    p.Define('model_dim', 1024, 'Model dimension M.')
+    p.Define('dropout_rate', 0.0, 'Residual/FFN dropout.')
+    p.Define('noise_shape_broadcast_dims', None, 'Dropout broadcast dims.')
+    p.Define('attention_num_heads', 1, 'Attention heads H.')
+    p.Define('attention_num_memory_heads', None, '1 ⇒ multi-query attention.')
+    p.Define('attention_key_value_dim', None, 'Per-head dim D.')
+    p.Define('attention_dropout_prob', 0.0, 'Attention dropout.')
+    p.Define('moe_dropout_rate', 0.0, 'Dropout inside experts.')
+    p.Define('attention_combine_dims', False, 'Store weights as [M, H·D].')
+    p.Define('attention_combine_qkv', True, 'One GEMM for q, k, v.')
+    p.Define('mdha_rope', False, 'Primer multi-dconv-head attention w/ RoPE.')
+    p.Define('use_rotary_position_emb', False, 'Apply RoPE to q/k.')
+    p.Define('rope_emb_max_timescale', 10000.0, 'RoPE max timescale.')
+    p.Define('ff_dim', None, 'Dense FFN hidden dim.')
+    p.Define('e_dim', None, 'Number of experts E.')
+    p.Define('c_dim', None, 'Expert capacity C (0/None ⇒ from factor).')
+    p.Define('moe_hidden_dim', None, 'Expert hidden dim H.')
+    p.Define('moe_activation', 'RELU', 'Expert activation.')
+    p.Define('second_expert_policy', 'all', 'all|sampling|random.')
+    p.Define('second_expert_threshold', 0., 'Threshold for `random`.')
+    p.Define('legacy_mtf_behavior', True, 'Renormalise before capacity.')
+    p.Define('label_smoothing', 0.1, 'Label smoothing.')
+    p.Define('capacity_factor', None, 'C ≥ S·factor/E.')
+    p.Define('gating_func', 'top_2', 'top_2|token_shuffle|hashing.')
+    p.Define('relative_attention_type', None, 'None|bias|bias_shared.')
+    p.Define('relative_attention_num_buckets', 32, 'T5 buckets.')
+    p.Define('relative_attention_max_distance', 128, 'T5 max distance.')
+    p.Define('relative_attention_use_universal_1d_position', False,
+             'Positions 0..L-1 regardless of packing.')
+    p.Define('inflate_universal_relative_bias_to_match_batch_dimension', False,
+             'Kept for parity.')
+    p.Define('attention_extra_logit', None, 'Extra softmax logit.')
+    p.Define('attention_logits_dtype', None, 'Logits dtype (fp32 here).')
+    p.Define('mask_dtype', None, 'Mask dtype.')
+    p.Define('gating_logits_dtype', None, 'Gating logits dtype.')
+    p.Define('conv_vars_reshape', False, 'Kept for parity.')
+    p.Define('use_fused_depthwise_conv_autoregressive', False, 'Kept.')
+    p.Define('ln_no_scale', False, 'RMS norm without scale.')
+    p.Define('model_dim_reshape_segments', None, 'Reshape M → [segments, M/s].')
+    p.Define('use_xla_dynamic_update_slice', True, 'Kept for parity.')
+    p.Define('decoder_skip_causal_mask', False, 'Skip the causal mask.')
+    p.Define('decoder_bidirectional_relative_attention', False, 'Bidi buckets.')
+    p.Define('final_norm_type', 'ln', 'ln|true_ln|pn|none.')
+    p.Define('skip_output_dropout', False, 'No dropout after the final norm.')
+    p.Define('device_mesh_shape', None, 'Device mesh shape.')
+    p.Define('emb_w_split', None, 'Mesh split for embedding weight.')
+    p.Define('mhd_w_split', [0, 1, -1], 'Mesh split for attention MHD weight.')
+    p.Define('kv_mhd_w_split', None, 'Mesh split for K/V MHD weight.')
+    p.Define('mh_wi_split', [0, 1], 'Mesh split for dense MH weight.')
+    p.Define('hm_wo_split', [1, 0], 'Mesh split for dense HM weight.')
+    p.Define('one_hot_ids_split', None, 'Split for one-hot ids.')
+    p.Define('emb_out_split', [0, -1, -1], 'Split for embedding outputs.')
+    p.Define('qkv_split', [0, -1, 1, -1], 'Split for QKV BLHD activation.')
+    p.Define('blm_split', [0, -1, -1], 'Split for BLM activation.')
+    p.Define('blh_split', [0, -1, 1], 'Split for BLH activation.')
+    p.Define('egcm_split', [0, -1, -1, -1], 'Split for EGCM.')
+    p.Define('gecm_split', [0, -1, -1, -1], 'Split for GECM.')
+    p.Define('gsec_split', [0, -1, -1, -1], 'Split for GSEC.')
+    p.Define('gecs_split', [0, -1, -1, -1], 'Split for GECS.')
+    p.Define('gec_split', [0, -1, -1], 'Split for GEC.')
+    p.Define('eah_split', [0, -1, 1], 'Split for EAH.')
+    p.Define('eam_split', [0, -1, -1], 'Split for EAM.')
+    p.Define('emh_split', [0, -1, 1], 'Split for expert EMH weight.')
+    p.Define('ehm_split', [0, 1, -1], 'Split for expert EHM weight.')
+    p.Define('logits_split', [0, -1, -1], 'Split for logits.')
+    p.Define('experimental_fix_split_dims_mapping', False, 'Kept for parity.')
+    p.Define('atten_logit_cap', 0.0, 'tanh cap on attention logits.')
+    p.Define('scale_input_embedding_by_dim', False, 'Scale embeddings.')
+    p.Define('softplus_scale_q', False, 'Kept for parity.')
+    p.Define('ff_use_bias', False, 'Bias in dense FFN.')
+    p.Define('moe_mode', 'indexed', 'indexed (fused B200 path) | dense oracle.')
+    p.Define('remat', False, 'Rematerialise blocks in backward.')
+    return p
+
+  @property
+  def _device_mesh(self):
+    return self.params.device_mesh
+
+  def _Common(self, p, name):
+    p.name = name
+    p.b = self.params
+    p.dtype = self.params.dtype
+    p.fprop_dtype = self.params.fprop_dtype
+    return p
+
+  # ---- sharding -----------------------------------------------------------
+  def MeshSplit(self, name, tensor_split_dims_mapping):
+    return MeshSplitLayer.Params().Set(
+        name=name, device_mesh=self.params.device_mesh,
+        tensor_split_dims_mapping=tensor_split_dims_mapping)
+
+  def _AdjustMSplit(self, split, m_dim):
+    """Adjusts split dims for `model_dim_reshape_segments` (reference)."""
+    if split is None or self.params.model_dim_reshape_segments is None:
+      return split
+    seg = self.params.model_dim_reshape_segments
+    n = len(seg) if isinstance(seg, (list, tuple)) else 1
+    if m_dim < 0:
+      m_dim += len(split)
+    return list(split[:m_dim]) + [split[m_dim]] + [-1] * n + list(
+        split[m_dim + 1:])
+
+  # ---- norms --------------------------------------------------------------
+  def _Norm(self, name, kind):
+    p = self.params
+    return self._Common(RmsNormLayer.Params().Set(
+        dim=p.model_dim, epsilon=p.layer_norm_epsilon, kind=kind,
+        no_scale=p.ln_no_scale and kind == 'rms'), name)
+
+  def _LN(self, name):
+    return self._Norm(name, 'rms')
+
+  def _LNNoScale(self, name):
+    q = self._Norm(name, 'rms')
+    q.no_scale = True
+    return q
+
+  def _TrueLN(self, name):
+    return self._Norm(name, 'true_ln')
+
+  def _PN(self, name):
+    return self._Norm(name, 'pn')
+
+  def _NormByType(self, name, norm_type):
+    if norm_type == 'ln':
+      return self._LN(name)
+    if norm_type in ('true_ln', 'jax_replica_ln'):
+      return self._TrueLN(name)
+    if norm_type == 'pn':
+      return self._PN(name)
+    if norm_type in ('none', 'no_ln'):
+      return self._Norm(name, 'none')
+    raise ValueError('Norm type %s not supported.' % norm_type)
+
+  # ---- embedding ----------------------------------------------------------
+  def Embedding(self, name, vocab_dim):
+    p = self.params
+    return self._Common(EmbeddingLayer.Params().Set(
+        vocab_dim=vocab_dim, model_dim=p.model_dim,
+        scale_by_dim=p.scale_input_embedding_by_dim), name)
+
+  SharedEmbSoftmax = Embedding
+
+  # ---- attention ----------------------------------------------------------
+  def _Atten(self, name, decoder, relative_bias):
+    return self._Common(SelfAttentionLayer.Params().Set(
+        decoder=decoder, relative_bias=relative_bias), name)
+
+  def DecSelfAttention(self, name, *unused):
+    return self._Atten(name, True, False)
+
+  def DecSelfAttentionRelativeBias(self, name, *unused):
+    assert self.params.relative_attention_type in ('bias', 'bias_shared')
+    return self._Atten(name, True, True)
+
+  def SelfAttention(self, name, *unused):
+    return self._Atten(name, False, False)
+
+  def SelfAttentionRelativeBias(self, name, *unused):
+    return self._Atten(name, False, True)
+
+  EncSelfAttention = SelfAttention
+
+  # ---- FFN / MoE ----------------------------------------------------------
+  def DenseReluDense(self, name, decoder=False, activation='relu'):
+    return self._Common(DenseReluDenseLayer.Params().Set(
+        activation=activation, gated=False), name)
+
+  def DenseReluDenseGated(self, name, activation_fn, decoder=False):
+    act = activation_fn if isinstance(activation_fn, str) else getattr(
+        activation_fn, '_lingvo_name', 'gelu')
+    return self._Common(DenseReluDenseLayer.Params().Set(
+        activation=act, gated=True), name)
+
+  def MoE(self, name, decoder=False):
+    return self._Common(MoELayer.Params().Set(
+        gated=False, mode=self.params.moe_mode), name)
+
+  def MoEGated(self, name, decoder=False):
+    return self._Common(MoELayer.Params().Set(
+        gated=True, mode=self.params.moe_mode), name)
+
+  # ---- blocks & stacks ----------------------------------------------------
+  def DecoderLayer(self, name, layer, conv_kernel_size=None, norm_type='ln',
+                   norm_policy='pre'):
+    post = None
+    if norm_policy == 'primer_hybrid':
+      post = self._NormByType('post_' + norm_type, norm_type)
+    return self._Common(DecoderBlock.Params().Set(
+        layer=layer.Copy(), norm=self._NormByType(norm_type, norm_type),
+        norm_policy=norm_policy, post_norm=post), name)
+
+  EncoderLayer = DecoderLayer
+
+  def _LayerStack(self, name, sub_layers, num, conv_kernel_size=None,
+                  norm_type='ln', norm_policy='pre', start_layer_id=0,
+                  has_final_layer=True, decoder=True, **unused):
+    blocks = []
+    for i in range(num):
+      for j, sub in enumerate(sub_layers):
+        idx = start_layer_id + i * len(sub_layers) + j
+        blocks.append(self.DecoderLayer('layer_%03d' % idx, sub,
+                                        conv_kernel_size, norm_type,
+                                        norm_policy))
+    final = None
+    if has_final_layer:
+      final = self._NormByType('final_layer_norm', self.params.final_norm_type)
+    return self._Common(LayerStack.Params().Set(
+        blocks=blocks, final_norm=final, remat=self.params.remat), name)
+
+  def DecoderLayerStack(self, name, sub_layers, num=1, **kwargs):
+    return self._LayerStack(name, sub_layers, num, decoder=True, **kwargs)
+
+  def EncoderLayerStack(self, name, sub_layers, num=1, **kwargs):
+    return self._LayerStack(name, sub_layers, num, decoder=False, **kwargs)
+
+
+class DenseBuilder(MoEBuilder):
+  """Builder for dense / hybrid models with 2-D sharding (reference :2269)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.emb_w_split = None
+    return p
+
+
+RecurrentDenseBuilder = DenseBuilder
+
+
+# =========================================================================
+# UniTransformer LM task
+# =========================================================================
+class UniTransformer(base_model.BaseTask):
+  """Decoder-only LM with z-loss, label smoothing and MoE aux loss."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('debug', False, 'Emit per-example tensors.')
+    p.Define('builder', None, 'GShard builder params.')
+    p.Define('vocab_size', None, 'Vocabulary size.')
+    p.Define('sequence_length', None, 'Sequence length.')
+    p.Define('max_length', 512, 'Max sequence length (positional table).')
+    p.Define('batch_size', None, 'Batch size (unused).')
+    p.Define('num_transformer_layers', None, 'Number of blocks.')
+    p.Define('loss_denominator', 0, 'Fixed loss denominator if > 0.')
+    p.Define('use_tgt_labels_size_as_loss_denominator', True,
+             'Denominator = labels size instead of #non-pad tokens.')
+    p.Define('aux_loss_coef', 0.01, 'Multiplier for the MoE aux loss.')
+    p.Define('enable_tpu_summary', True, 'Kept for parity.')
+    p.Define('label_smoothing', 0.1, 'Label smoothing.')
+    p.Define('logits_abs_max', None, 'Logits clipping.')
+    p.Define('z_loss', 1e-4, 'z_loss · logsumexp(logits)² added to the loss.')
+    p.Define('positional_embedding', True, 'Learned positional embedding.')
+    p.Define('sub_layer_types', None, "e.g. ['attn','moe','attn','ffw'].")
+    p.Define('sinusoid_positional_embedding', False, 'Sinusoid positions.')
+    p.Define('gated_gelu', False, 'Deprecated: gated_ffn_activation=gelu.')
+    p.Define('moe_gated_gelu', False, 'GLU experts.')
+    p.Define('gated_ffn_activation', None, 'silu|gelu|None.')
+    p.Define('softmax_bias', False, 'Bias in the softmax.')
+    p.Define('parallel_ffn', False, 'Kept for parity.')
+    p.Define('hidden_dim_reshape_segments', 4, 'Kept for parity.')
+    p.Define('conv_kernel_size', None, 'Optional depthwise conv in the norm.')
+    p.Define('scale_decoder_outputs', True, 'Scale outputs by M^-0.5.')
+    p.Define('use_per_layer_vars_for_recurrent', False, 'Kept for parity.')
+    p.Define('use_repeat_layer', False, 'Kept for parity.')
+    p.Define('num_spmd_pipeline_stages', 1, 'SPMD pipeline stages.')
+    p.Define('num_spmd_pipeline_microbatches', None, 'SPMD micro-batches.')
+    p.Define('moe', False, 'Mixture-of-Experts model.')
+    p.Define('activation', 'relu', 'Non-gated FFN activation.')
+    p.Define('norm_type', 'ln', 'ln|pn|true_ln|jax_replica_ln|no_ln.')
+    p.Define('norm_policy', 'pre', 'pre|primer|primer_hybrid.')
+    p.Define('multi_dconv_head_att', False, 'Kept for parity.')
+    p.Define('decoder_max_steps', 64, 'Max decode steps.')
+    p.Define('decoder_beam_size', 4, 'Beam size.')
+    p.Define('decoder_eos_id', 1, '</s> id.')
+    p.Define('decoder_bos_id', 0, '<s> id.')
+    p.Define('start_layer_id', 0, 'Start layer id.')
+    p.Define('pos_emb_max_timescale', 10000.0, 'Sinusoid max timescale.')
+    p.Define('has_embedding_layer', True, 'Model has the embedding layer.')
+    p.Define('has_final_layer', True, 'Model has the final layer.')
+    p.Define('softmax_logit_cap', 0.0, 'Softmax logit cap.')
+    p.Define('is_quantize', False, 'Kept for parity.')
+    p.Define('use_log_softmax_normalization', True, 'Kept for parity.')
+    p.Define('fused_xent', True, 'Use the fused logits+xent kernel path.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    b = p.builder.Instantiate()
+    bp = b.params
+    gated = p.gated_ffn_activation or ('gelu' if p.gated_gelu else None)
+    if p.has_embedding_layer:
+      self.CreateChild('dec_emb', b.Embedding('dec_emb', p.vocab_size))
+      if p.positional_embedding:
+        if p.sinusoid_positional_embedding:
+          self.CreateChild('dec_pos_emb',
+                           layers.PositionalEmbeddingLayer.Params().Set(
+                               name='dec_pos_emb', embedding_dim=bp.model_dim,
+                               max_timescale=p.pos_emb_max_timescale))
+        else:
+          self.CreateChild('dec_pos_emb', b.Embedding('dec_pos_emb',
+                                                      p.max_length))
+    if p.positional_embedding:
+      atten = b.DecSelfAttention('dec_self_attention')
+    else:
+      atten = b.DecSelfAttentionRelativeBias('dec_self_attention')
+    if gated is None:
+      ffw = b.DenseReluDense('dense_relu_dense', decoder=True,
+                             activation=p.activation)
+    else:
+      ffw = b.DenseReluDenseGated('dense_relu_dense', gated, decoder=True)
+    if p.moe:
+      moe = (b.MoEGated('moe', decoder=True) if p.moe_gated_gelu
+             else b.MoE('moe', decoder=True))
+      table = {'attn': atten, 'moe': moe, 'ffw': ffw}
+      if p.sub_layer_types:
+        n_types = len(p.sub_layer_types)
+        if p.num_transformer_layers * 2 % n_types != 0:
+          raise ValueError('Unsupported Sub-layer types length!')
+        subs = [table[t] for t in p.sub_layer_types]
+        num = p.num_transformer_layers * 2 // n_types
+      else:
+        subs = [atten, moe, atten, ffw]
+        num = p.num_transformer_layers // 2
+    else:
+      subs = [atten, ffw]
+      num = p.num_transformer_layers
+    dec = b.DecoderLayerStack(
+        'decoder', subs, num, conv_kernel_size=p.conv_kernel_size,
+        norm_type=p.norm_type, norm_policy=p.norm_policy,
+        start_layer_id=p.start_layer_id, has_final_layer=p.has_final_layer)
+    dec.params_init = WeightInit.Xavier(scale=1.0, seed=0)
+    self.CreateChild('dec', dec)
+    self.CreateChild('emb_w_split', b.MeshSplit('w_split', bp.emb_w_split))
+    self.CreateChild('dec_out_split', b.MeshSplit('dec_out_split', bp.blm_split))
+    self.CreateChild('logits_split', b.MeshSplit('logits_split',
+                                                 bp.logits_split))
+    if p.has_final_layer and p.softmax_bias:
+      self.CreateVariable('softmax_bias', WeightParams(
+          [p.vocab_size], WeightInit.Constant(0.0), p.dtype))
+
+  # ---------------------------------------------------------------- input --
+  def _ComputeInputBatch(self, input_batch):
+    if 'tgt' not in input_batch:
+      input_batch.tgt = NestedMap(
+          ids=input_batch.ids, paddings=input_batch.paddings,
+          labels=input_batch.labels, segment_ids=input_batch.segment_ids,
+          segment_pos=input_batch.segment_pos)
+    return input_batch
+
+  def _ComputeDecoderInput(self, theta, input_batch):
+    p = self.params
+    input_batch = self._ComputeInputBatch(input_batch)
+    tgt = input_batch.tgt
+    fd = self.fprop_dtype
+    y = self.dec_emb.FProp(theta.dec_emb, tgt.ids).to(fd)
+    if p.positional_embedding:
+      if p.sinusoid_positional_embedding:
+        y = y + self.dec_pos_emb.FPropWithPosition(theta.dec_pos_emb,
+                                                   tgt.segment_pos).to(fd)
+      else:
+        y = y + self.dec_pos_emb.FProp(theta.dec_pos_emb,
+                                       tgt.segment_pos).to(fd)
+    return NestedMap(vec=y, segment_id=tgt.segment_ids,
+                     segment_pos=tgt.segment_pos,
+                     aux_loss=torch.zeros((), device=y.device))
+
+  # --------------------------------------------------------- predictions --
+  def ComputePredictions(self, theta, input_batch):
+    p = self.params
+    dec_in = self._ComputeDecoderInput(theta, input_batch)
+    out = self.dec.FProp(theta.dec, dec_in)
+    dec_outputs, aux_loss = out.vec, out.aux_loss
+    if not p.has_final_layer:
+      return dec_outputs, aux_loss
+    if p.scale_decoder_outputs:
+      dec_outputs = dec_outputs * (p.builder.model_dim**-0.5)
+    return NestedMap(dec_outputs=dec_outputs, aux_loss=aux_loss)
+
+  def _ComputeLogits(self, theta, dec_outputs):
+    p = self.params
+    w = theta.dec_emb.embedding.to(dec_outputs.dtype)    # [V, M]
+    from lingvo_b200.ops import gemm
+    logits = gemm.gemm(dec_outputs.reshape(-1, dec_outputs.shape[-1]), w,
+                       True, True) if (ops.use_cuda_kernels(dec_outputs) and
+                                       dec_outputs.dtype == torch.bfloat16 and
+                                       not torch.is_grad_enabled()) else (
+                                           torch.matmul(dec_outputs, w.t()))
+    logits = logits.reshape(list(dec_outputs.shape[:-1]) + [w.shape[0]])
+    if p.has_final_layer and p.softmax_bias:
+      logits = logits + theta.softmax_bias.to(logits.dtype)
+    if p.softmax_logit_cap and p.softmax_logit_cap > 0:
+      logits = p.softmax_logit_cap * torch.tanh(logits / p.softmax_logit_cap)
+    if p.logits_abs_max is not None:
+      logits = logits.clamp(-p.logits_abs_max, p.logits_abs_max)
+    return logits
+
+  def _ComputeNonPadding(self, input_batch):
+    tgt = input_batch.tgt
+    if 'paddings' in tgt:
+      return (1.0 - tgt.paddings.float())
+    non_padding = (tgt.segment_ids != 0).float()
+    return non_padding * (tgt.labels > 0).float()
+
+  # ----------------------------------------------------------------- loss --
+  def ComputeLoss(self, theta, predictions, input_batch):
+    p = self.params
+    input_batch = self._ComputeInputBatch(input_batch)
+    tgt = input_batch.tgt
+    v = p.vocab_size
+    aux_loss = predictions.aux_loss
+    x = predictions.dec_outputs
+    labels = tgt.labels.long().clamp(min=0)
+    non_padding = self._ComputeNonPadding(input_batch)
+    stats = None
+    if (p.fused_xent and ops.use_cuda_kernels(x) and x.dtype == torch.bfloat16
+        and p.logits_abs_max is None and not p.softmax_logit_cap and
+        not p.softmax_bias):
+      from lingvo_b200.ops import xent as xent_ops
+      if xent_ops.available():
+        stats = xent_ops.lm_head_xent(
+            x.reshape(-1, x.shape[-1]), theta.dec_emb.embedding.to(x.dtype),
+            labels.reshape(-1), p.label_smoothing, p.z_loss)
+    if stats is None:
+      logits = self._ComputeLogits(theta, x).float()
+      lse = torch.logsumexp(logits, -1)
+      true_logit = torch.gather(logits, -1, labels.unsqueeze(-1)).squeeze(-1)
+      entropy = lse - true_logit
+      off = p.label_smoothing / v
+      on = 1.0 - p.label_smoothing + off
+      # xent with soft labels: lse − Σ soft·logit
+      soft_dot = (on - off) * true_logit + off * logits.sum(-1)
+      loss = lse - soft_dot
+      zinc = p.z_loss * lse.square() if p.z_loss else torch.zeros_like(lse)
+      top1 = logits.argmax(-1)
+    else:
+      shape = labels.shape
+      entropy = stats.entropy.reshape(shape)
+      loss = stats.soft_xent.reshape(shape)
+      zinc = stats.z_inc.reshape(shape)
+      top1 = stats.argmax.reshape(shape)
+    soft_labels_entropy = loss
+    loss = loss + zinc
+    acc1 = (tgt.labels.long() == top1).float()
+    per_token_loss = loss * non_padding
+    if p.loss_denominator:
+      denom = float(p.loss_denominator)
+    elif p.use_tgt_labels_size_as_loss_denominator:
+      denom = float(non_padding.numel())
+    else:
+      denom = non_padding.sum()
+    avg_loss = per_token_loss.sum() / denom
+    avg_z = (zinc * non_padding).sum() / denom if p.z_loss else torch.zeros(
+        (), device=loss.device)
+    np_sum = non_padding.sum()
+    safe = torch.clamp(np_sum, min=1.0)
+    avg_loss = avg_loss + p.aux_loss_coef * aux_loss
+    num_items = tgt.segment_ids.amax(dim=1).sum().float()
+    num_nonpad = (tgt.segment_ids != 0).float().sum()
+    whole = ((acc1 * non_padding).sum(1) == non_padding.sum(1)).float()
+    one = torch.ones((), device=loss.device)
+    metrics = {
+        'num_packed_examples': (num_items, one),
+        'batch_utilized_ratio': (num_nonpad / float(tgt.labels.numel()), one),
+        'acc1': ((acc1 * non_padding).sum() / safe, np_sum),
+        'whole_tgt_accuracy': (whole.mean(), one),
+        'mean_xent': ((entropy * non_padding).sum() / safe, np_sum),
+        'soft_labels_xent': ((soft_labels_entropy * non_padding).sum() / safe,
+                             np_sum),
+        'weight': (np_sum, one),
+        'loss': (avg_loss, one),
+        'aux_loss': (p.aux_loss_coef * aux_loss, one),
+        'avg_z_loss_increment': (avg_z, one),
+    }
+    per_step = {'loss': avg_loss.reshape(1)}
+    return metrics, per_step
+
+  def FilterPerExampleTensors(self, per_step):
+    return per_step if self.params.debug else {}
+
+  # --------------------------------------------------------------- decode --
+  def Decode(self, input_batch):
+    """Greedy / beam decode of continuations (see gshard_decode)."""
+    from lingvo_b200.core import gshard_decode
+    return gshard_decode.DecodeIds(self, self.theta, input_batch)

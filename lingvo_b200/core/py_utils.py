@@ -275,6 +275,10 @@ def WeightParams(shape, init=None, dtype=None, collections=None,
            'np.ndarray of device ids describing the mesh topology.')
   p.Define('tensor_split_dims_mapping', tensor_split_dims_mapping,
            'Per-dim mesh axis (or -1) the weight is split on.')
+  p.Define('init_shard', None,
+           '(dim, index, count): `shape` is one of `count` equal shards along '
+           '`dim` of the logical variable; init draws the *logical* tensor '
+           '(so values match the unsharded model) and keeps shard `index`.')
   return p
 
 
@@ -490,6 +494,15 @@ def CreateVariable(name: str, params, trainable: bool = True,
     value = torch.empty(full_shape, dtype=dtype, device='meta')
   elif stub == 'zeros':
     value = torch.zeros((), dtype=dtype).expand(full_shape)
+  elif p.init_shard is not None:
+    sdim, sidx, scount = p.init_shard
+    sdim += len(prefixes)
+    logical = list(full_shape)
+    logical[sdim] *= scount
+    value = InitialValue(logical, p.init, dtype, seed,
+                         prefix_dims=len(prefixes)).narrow(
+                             sdim, sidx * full_shape[sdim],
+                             full_shape[sdim]).contiguous().to(device)
   else:
     value = InitialValue(full_shape, p.init, dtype, seed,
                          prefix_dims=len(prefixes)).to(device)

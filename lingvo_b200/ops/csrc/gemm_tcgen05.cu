@@ -28,6 +28,7 @@
 #include <unordered_map>
 
 #include "ptx.cuh"
+#include "registry.h"
 
 namespace lb {
 
@@ -389,6 +390,7 @@ static void Launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   const int tiles = p.G * ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, kNumThreads, smem, stream>>>(ta, tb, p);
+  CountLaunch();
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -1,0 +1,80 @@
+"""Data-parallel gradient synchronisation.
+
+Reference: TPU `cross_replica_sum` per variable (`py_utils.py:2942-3081`),
+PS AddN on GPU. Here `Attach(task)` installs `learner.grad_sync`:
+
+* `mode='nccl'`  — bucketed `all_reduce` (stock baseline);
+* `mode='fused'` — `parallel/zero.py`: hand-written bucketed reduce-scatter
+  over NVLink peer memory fused with cast/scale + the partitioned optimizer
+  update, followed by the parameter all-gather.
+
+Expert-parallel variables (`var.expert_parallel`) are owned by exactly one
+rank of the EP group and are therefore *not* reduced across it.
+"""
+
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from lingvo_b200.core import py_utils
+from lingvo_b200.parallel import mesh as mesh_lib
+
+_BUCKET_BYTES = 64 << 20
+
+
+def _AllReduceBuckets(grads: List[torch.Tensor], world: int, group=None):
+  """In-place mean all-reduce of `grads` in ~64 MiB flat buckets."""
+  bucket, size = [], 0
+
+  def flush():
+    if not bucket:
+      return
+    flat = torch.cat([g.reshape(-1) for g in bucket])
+    dist.all_reduce(flat, group=group)
+    flat.div_(world)
+    off = 0
+    for g in bucket:
+      n = g.numel()
+      g.copy_(flat[off:off + n].view_as(g))
+      off += n
+    bucket.clear()
+
+  for g in grads:
+    bucket.append(g)
+    size += g.numel() * g.element_size()
+    if size >= _BUCKET_BYTES:
+      flush()
+      size = 0
+  flush()
+
+
+def Attach(task):
+  """Installs gradient synchronisation on every learner of `task`."""
+  ctx = mesh_lib.Get()
+  if ctx.world <= 1:
+    return None
+
+  def sync(var_grads):
+    leaves = [vg for vg in var_grads.Flatten()
+              if isinstance(vg, py_utils.VarGrad) and vg.grad is not None]
+    by_dtype = {}
+    for vg in leaves:
+      if getattr(vg.var, 'expert_parallel', False):
+        continue
+      by_dtype.setdefault(vg.grad.dtype, []).append(vg.grad)
+    with torch.no_grad():
+      for grads in by_dtype.values():
+        _AllReduceBuckets(grads, ctx.world)
+    return var_grads
+
+  for lrn in task.learners:
+    lrn.grad_sync = sync
+  # Make replicated variables identical across ranks (rank 0 wins).
+  with torch.no_grad():
+    for v in task.vars.Flatten():
+      if not getattr(v, 'expert_parallel', False):
+        dist.broadcast(v.data, src=0)
+  return sync
