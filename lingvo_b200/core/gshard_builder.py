@@ -211,20 +211,28 @@ class SelfAttentionLayer(_BuilderLayer):
       not_vis = not_vis | (segment_pos.unsqueeze(-1) < segment_pos.unsqueeze(-2))
     bias = not_vis.float().unsqueeze(1) * -1e9
     if self.params.relative_bias:
-      if b.relative_attention_use_universal_1d_position:
-        l = segment_pos.shape[-1]
-        pos = torch.arange(l, device=segment_pos.device).unsqueeze(0)
-        qpos = kpos = pos
-      else:
-        qpos = kpos = segment_pos
-      rel = kpos.unsqueeze(-2) - qpos.unsqueeze(-1)
-      bucket = RelativePositionBucket(
-          rel, b.relative_attention_num_buckets,
-          b.relative_attention_max_distance,
-          bidirectional=(not self.params.decoder) or
+      bidi = (not self.params.decoder) or (
           b.decoder_bidirectional_relative_attention)
-      rb = theta.wrb.float()[:, bucket.long()]        # [H, (B|1), L, L]
-      rb = rb.permute(1, 0, 2, 3)
+      if b.relative_attention_use_universal_1d_position:
+        # Toeplitz structure: bias[h, i, j] = T[h, j - i + L - 1] with a
+        # (2L-1)-entry table per head. Building T costs a 2L-1 gather and the
+        # [H, L, L] expansion is a strided window view (no 16M-element
+        # scatter-add in the backward pass, unlike the one-hot einsum
+        # `HX,...LJX->...LHJ` of the reference :1487).
+        l = segment_pos.shape[-1]
+        rel = torch.arange(-(l - 1), l, device=segment_pos.device)
+        bucket = RelativePositionBucket(
+            rel, b.relative_attention_num_buckets,
+            b.relative_attention_max_distance, bidirectional=bidi)
+        table = theta.wrb.float()[:, bucket.long()]          # [H, 2L-1]
+        rb = table.unfold(-1, l, 1).flip(1).unsqueeze(0)      # [1, H, L, L]
+      else:
+        rel = segment_pos.unsqueeze(-2) - segment_pos.unsqueeze(-1)
+        bucket = RelativePositionBucket(
+            rel, b.relative_attention_num_buckets,
+            b.relative_attention_max_distance, bidirectional=bidi)
+        oh = F.one_hot(bucket.long(), b.relative_attention_num_buckets).float()
+        rb = torch.einsum('HX,BLJX->BHLJ', theta.wrb.float(), oh)
       bias = bias + rb
     return bias
 
@@ -344,6 +352,10 @@ class DenseReluDenseLayer(_BuilderLayer):
     if p.gated:
       h = _Act(p.activation)(gemm.linear(x, theta.wi_0.to(x.dtype), bi)) * (
           gemm.linear(x, theta.wi_1.to(x.dtype)))
+    elif act == 'RELU' and bi is None and bo is None and not (
+        b.dropout_rate and not self.do_eval):
+      out = gemm.ffn_relu(x, theta.wi.to(x.dtype), theta.wo.to(x.dtype))
+      return out, torch.zeros((), device=x.device, dtype=torch.float32)
     elif act == 'RELU':
       h = gemm.linear(x, theta.wi.to(x.dtype), bi, act='RELU')
     else:
@@ -410,6 +422,25 @@ class MoELayer(_BuilderLayer):
     for n in self._expert_var_names:
       self._private_vars[n].expert_parallel = self._ep is not None
 
+  def _FusedExchange(self, x, act):
+    """The fused gate+dispatch/expert-GEMM/combine engine when applicable."""
+    b = self.bp
+    p = self.params
+    if not (ops.use_cuda_kernels(x) and x.dtype == torch.bfloat16 and
+            act == 'RELU' and not p.gated and b.gating_func == 'top_2' and
+            b.second_expert_policy == 'all' and x.shape[-1] % 8 == 0 and
+            b.moe_hidden_dim % 8 == 0 and not (b.moe_dropout_rate and
+                                              not self.do_eval)):
+      return None
+    from lingvo_b200.ops import moe as moe_ops
+    from lingvo_b200.parallel import mesh as mesh_lib
+    if not moe_ops.available() or mesh_lib.Get().mode != 'fused':
+      return None
+    if self._ep is not None:
+      return self._ep.GetExchange(x.device)
+    from lingvo_b200.parallel import symm
+    return symm.LocalExchange(b.e_dim, x.device)
+
   def FProp(self, theta, x, segment_id, segment_pos=None):
     b = self.bp
     p = self.params
@@ -436,6 +467,14 @@ class MoELayer(_BuilderLayer):
       return out.reshape(bsz, l, m), aux.float()
     # Gating logits in fp32: [G,S,M]·[M,E] is tiny (E = 8); keep it exact.
     logits = torch.matmul(xg.to(ldt), theta.gw.to(ldt))
+    ex = self._FusedExchange(x, act)
+    if ex is not None:
+      cap = gshard_layers.ExpertCapacity(s, b.e_dim, b.c_dim or 0,
+                                         b.capacity_factor)
+      out, aux = ex.Apply(id(self), xg.reshape(groups * s, m).contiguous(),
+                          logits, paddings, cap, bool(b.legacy_mtf_behavior),
+                          theta.wi.to(x.dtype), theta.wo.to(x.dtype))
+      return out.reshape(bsz, l, m), aux.float()
     seeds = None
     if b.second_expert_policy != 'all':
       seeds = py_utils.GenerateStepSeedPair(p)

@@ -106,15 +106,21 @@ class Learner(base_layer.BaseLayer):
       var_grads = self.grad_sync(var_grads)
     if 'tpu_embedding_var_grads' in var_grads:
       del var_grads['tpu_embedding_var_grads']
+    defer = (self.optimizer.supports_grad_scale and
+             not p.clip_gradient_single_norm_to_value)
+    self._deferred_scale = None
     var_grads, stats = self.AdjustGradients(
         var_grads, gradient_mask=gradient_mask,
-        gradient_adjuster=gradient_adjuster)
+        gradient_adjuster=gradient_adjuster, defer_scale=defer)
     eval_metrics.update(stats)
     self._var_grads = var_grads
     lr = self.LearningRate()
     self._AddScalar(eval_metrics, 'learning_rate', lr)
     self._AddScalar(eval_metrics, 'lr_schedule', float(self.lr_schedule.Value()))
-    self.optimizer.Apply(lr, var_grads)
+    if self._deferred_scale is not None:
+      self.optimizer.Apply(lr, var_grads, grad_scale=self._deferred_scale)
+    else:
+      self.optimizer.Apply(lr, var_grads)
     return losses, {self._Key(k): v for k, v in eval_metrics.items()}
 
   def _Key(self, name: str) -> str:
@@ -158,7 +164,7 @@ class Learner(base_layer.BaseLayer):
 
   # ------------------------------------------------------- adjust and scale --
   def AdjustGradients(self, var_grads: NestedMap, gradient_mask=None,
-                      gradient_adjuster=None):
+                      gradient_adjuster=None, defer_scale=False):
     """L2/L1 adjust → mask → scale(clip / zero / NaN-skip) (:353-432)."""
     p = self.params
     stats = {}
@@ -179,12 +185,14 @@ class Learner(base_layer.BaseLayer):
       var_grads = var_grads.Transform(
           lambda vg: mask(vg) if isinstance(vg, py_utils.VarGrad) else vg)
     if p.scale_gradients:
-      scaled = self.ScaleGradients(var_grads, gradient_adjuster)
+      scaled = self.ScaleGradients(var_grads, gradient_adjuster,
+                                   defer_scale=defer_scale)
       var_grads = scaled.final_var_grads
       stats.update(scaled.stats)
     return var_grads, stats
 
-  def ScaleGradients(self, var_grads: NestedMap, gradient_adjuster=None):
+  def ScaleGradients(self, var_grads: NestedMap, gradient_adjuster=None,
+                     defer_scale=False):
     """Returns NestedMap(final_var_grads, grad_scale, stats) (:395-500)."""
     p = self.params
     leaves = [vg for vg in var_grads.Flatten()
@@ -233,6 +241,10 @@ class Learner(base_layer.BaseLayer):
         return py_utils.VarGrad(vg.var, torch.where(
             bad, torch.zeros_like(vg.grad), vg.grad))
       final = final.Transform(zero_bad)
+    elif defer_scale:
+      # The optimizer kernels fold grad_scale (0 ⇒ skip) into the update.
+      self._deferred_scale = grad_scale.float().reshape(1)
+      final = var_grads
     else:
       def scale(vg):
         if not isinstance(vg, py_utils.VarGrad):

@@ -137,14 +137,28 @@ class Base(base_layer.BaseLayer):
   def ComputeGradients(self, loss, vmap, *args, **kwargs):
     return py_utils.ComputeGradients(loss, vmap, *args, **kwargs)
 
-  def Apply(self, lr, var_grad):
+  # Optimizers whose kernels fold `grad_scale` (clip / NaN-skip factor, a
+  # device scalar) into the update avoid a full pass over the gradients.
+  supports_grad_scale = False
+
+  def Apply(self, lr, var_grad, grad_scale=None):
     """Applies one update with learning rate `lr` (python float or tensor)."""
     pairs = _Pairs(var_grad)
     if not pairs:
       return
     lr = float(lr) if not isinstance(lr, torch.Tensor) else lr
+    variables = [v for v, _ in pairs]
+    grads = [g for _, g in pairs]
+    self._refreshed = set()
     with torch.no_grad():
-      self._Update(lr, [v for v, _ in pairs], [g for _, g in pairs])
+      if grad_scale is not None and not self.supports_grad_scale:
+        grads = [torch.where(grad_scale == 0, torch.zeros_like(g),
+                             g * grad_scale.to(g.dtype)) for g in grads]
+        grad_scale = None
+      self._grad_scale = grad_scale
+      self._Update(lr, variables, grads)
+      py_utils.RefreshComputeCopies(
+          [v for v in variables if id(v) not in self._refreshed])
     self._step_count += 1
 
   def _Update(self, lr, variables, grads):
@@ -271,6 +285,7 @@ class Adam(Base):
   """TF AdamOptimizer: lr_t = lr·sqrt(1-β2^t)/(1-β1^t); w -= lr_t·m/(√v+ε)."""
 
   SLOT_SUFFIX = {'m': 'Adam', 'v': 'Adam_1'}
+  supports_grad_scale = True
 
   @classmethod
   def Params(cls):
@@ -307,8 +322,15 @@ class Adam(Base):
       from lingvo_b200.ops import optim
       if optim.available():
         optim.multi_tensor_adam(variables, grads, ms, vs, lr_t, p.beta1,
-                                p.beta2, p.epsilon)
+                                p.beta2, p.epsilon,
+                                grad_scale_t=self._grad_scale)
+        for v in variables:
+          self._refreshed.add(id(v))
         return
+    if getattr(self, '_grad_scale', None) is not None:
+      gs = self._grad_scale
+      grads = [torch.where(gs == 0, torch.zeros_like(g), g * gs.to(g.dtype))
+               for g in grads]
     grads = _F32(grads, variables)
     torch._foreach_mul_(ms, p.beta1)
     torch._foreach_add_(ms, grads, alpha=1 - p.beta1)
@@ -467,6 +489,7 @@ class XLAShardingAdafactor(Base):
 
   SLOT_SUFFIX = {'m': 'Adafactor_m', 'vr': 'Adafactor_vr', 'vc': 'Adafactor_vc',
                  'v': 'Adafactor_v'}
+  supports_grad_scale = True
 
   @classmethod
   def Params(cls):
@@ -516,7 +539,8 @@ class XLAShardingAdafactor(Base):
       dims = self._FactoredDims(list(var.shape))
       if fused is not None and dims is not None and var.dim() >= 2 and (
           not p.beta1) and not p.cond_is_finite and sorted(dims) == [
-              var.dim() - 2, var.dim() - 1]:
+              var.dim() - 2, var.dim() - 1] and var.shape[-1] % 8 == 0 and (
+                  var.is_contiguous()):
         d0, d1 = dims
         vr_shape = [s for i, s in enumerate(var.shape) if i != d0]
         vc_shape = [s for i, s in enumerate(var.shape) if i != d1]
@@ -525,8 +549,15 @@ class XLAShardingAdafactor(Base):
         fused.adafactor_factored(var, grad, vr, vc, d0, d1, float(lr), decay,
                                  p.epsilon1, p.epsilon2,
                                  p.clipping_threshold or 0.0,
-                                 bool(p.multiply_by_parameter_scale))
+                                 bool(p.multiply_by_parameter_scale),
+                                 self._grad_scale)
+        if getattr(var, 'compute', None) is not None:
+          self._refreshed.add(id(var))
         continue
+      if self._grad_scale is not None:
+        gs = self._grad_scale
+        grad = torch.where(gs == 0, torch.zeros_like(grad),
+                           grad * gs.to(grad.dtype))
       self._UpdateOne(var, grad, dims, float(lr), decay)
 
   def _UpdateOne(self, var, grad, dims, lr, decay):

@@ -516,6 +516,36 @@ def CreateVariable(name: str, params, trainable: bool = True,
   return var
 
 
+def AttachComputeCopies(root_layer, dtype=torch.bfloat16) -> int:
+  """Mixed precision: persistent low-precision *compute copies* of weights.
+
+  Every trainable fp32 variable of a layer whose `fprop_dtype` is `dtype`
+  gets `var.compute` (a leaf tensor in `dtype`) which `theta` returns instead
+  of casting the master weight every step. Gradients are taken w.r.t. the
+  copy (bf16), optimizers update the fp32 master and refresh the copy — the
+  fused kernels (`ops/optim`) write it in the same pass as the update.
+  """
+  n = 0
+  for _, layer in root_layer.Walk():
+    if layer.fprop_dtype != dtype:
+      continue
+    for name, var in layer._private_vars.items():  # pylint: disable=protected-access
+      if var.dtype == torch.float32 and var.requires_grad and (
+          getattr(var, 'compute', None) is None):
+        var.compute = var.data.to(dtype).requires_grad_(True)
+        layer.SetThetaOverride(name, var.compute)
+        n += 1
+  return n
+
+
+def RefreshComputeCopies(variables) -> None:
+  with torch.no_grad():
+    for v in variables:
+      c = getattr(v, 'compute', None)
+      if c is not None:
+        c.data.copy_(v.data)
+
+
 def SkipLpRegularization(var) -> bool:
   return _SKIP_LP_COLLECTION in getattr(var, 'collections', [])
 
@@ -737,8 +767,11 @@ def ComputeGradients(loss, vmap: NestedMap, skip_zero_gradients=None,
   assert isinstance(vmap, NestedMap)
   flat = [(k, v) for k, v in vmap.FlattenItems()
           if isinstance(v, torch.Tensor) and v.requires_grad]
-  grads = torch.autograd.grad(loss, [v for _, v in flat],
-                              retain_graph=retain_graph, allow_unused=True)
+  # Mixed precision: differentiate w.r.t. the bf16 compute copy when present.
+  grads = torch.autograd.grad(
+      loss, [getattr(v, 'compute', None) if getattr(v, 'compute', None)
+             is not None else v for _, v in flat],
+      retain_graph=retain_graph, allow_unused=True)
   out = NestedMap()
   for (k, v), g in zip(flat, grads):
     if g is None:
@@ -767,8 +800,7 @@ def SumSquared(tensors) -> torch.Tensor:
   if not tensors:
     return torch.zeros(())
   if tensors[0].is_cuda and len(tensors) > 1:
-    norms = torch._foreach_norm([t.float() if t.dtype != torch.float32 else t
-                                 for t in tensors])
+    norms = torch._foreach_norm(tensors, 2, dtype=torch.float32)
     return torch.stack(norms).square().sum()
   return sum((t.float().square().sum() for t in tensors))
 

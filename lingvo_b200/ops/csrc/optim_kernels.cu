@@ -1,0 +1,369 @@
+// Fused optimizer kernels (fp32 master weights, bf16/fp32 gradients, optional
+// bf16 compute-copy written in the same pass).
+//
+// Adafactor (factored second moment; reference optimizer.py:1129-1218) over a
+// variable viewed as [B, R, C] is four launches with no host sync:
+//   A  stats   : rowsum[B,R], colsum[B,C] of (g^2 + eps1); acc[0] += sum(w^2)
+//   B  factors : EMA-update vr / vc in place, long-term mean, write the two
+//                factor vectors fr[B,R], fc[B,C]
+//   C  rms     : acc[1] += sum((g * fr * fc)^2)
+//   D  apply   : w -= g*fr*fc * max(rms(w), eps2)*lr / max(1, rms(x)/clip);
+//                bf16 copy of w written alongside.
+// HBM traffic ~ 3 reads of g + read/write of w + write of the bf16 copy.
+//
+// adam_flat: elementwise Adam on a flat fp32 shard with grad scale and bf16
+// copy-out — the update half of the fused reduce-scatter + partitioned Adam.
+
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "ptx.cuh"
+#include "registry.h"
+
+namespace lb {
+namespace {
+
+constexpr int kRowsPerWarp = 64;
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename GT>
+__device__ __forceinline__ void load_g8(const GT* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load_g8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  int4 v = *reinterpret_cast<const int4*>(p);
+  const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 t = unpack_bf16x2(w[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_g8<float>(const float* p, float (&f)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+struct Tile {
+  int b, r0, r1, c0;
+  bool ok;
+};
+// Work item = (batch b, 64-row range, 256-column strip); one warp per item.
+__device__ __forceinline__ Tile get_tile(int item, int R, int C) {
+  const int strips = (C + 255) / 256;
+  const int ranges = (R + kRowsPerWarp - 1) / kRowsPerWarp;
+  Tile t;
+  t.b = item / (strips * ranges);
+  const int rem = item - t.b * strips * ranges;
+  const int range = rem / strips;
+  t.c0 = (rem - range * strips) * 256;
+  t.r0 = range * kRowsPerWarp;
+  t.r1 = min(t.r0 + kRowsPerWarp, R);
+  return t;
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(kWarps * 32)
+adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
+                       float* __restrict__ rowsum, float* __restrict__ colsum,
+                       float* __restrict__ acc, int B, int R, int C, float eps1, int items,
+                       const float* __restrict__ gscale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float gs = gscale ? *gscale : 1.f;
+  float wsq = 0.f;
+  for (int item = blockIdx.x * kWarps + warp; item < items; item += gridDim.x * kWarps) {
+    const Tile t = get_tile(item, R, C);
+    const int c = t.c0 + lane * 8;
+    const bool cok = c < C;
+    float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = t.r0; r < t.r1; ++r) {
+      const size_t off = (static_cast<size_t>(t.b) * R + r) * C + c;
+      float rs = 0.f;
+      if (cok) {
+        float gf[8], wf[8];
+        load_g8<GT>(g + off, gf);
+        load_g8<float>(w + off, wf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ge = gs == 0.f ? 0.f : gf[i] * gs;
+          const float q = ge * ge + eps1;
+          cs[i] += q;
+          rs += q;
+          wsq += wf[i] * wf[i];
+        }
+      }
+      rs = warp_sum(rs);
+      if (lane == 0) atomicAdd(&rowsum[static_cast<size_t>(t.b) * R + r], rs);
+    }
+    if (cok) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&colsum[static_cast<size_t>(t.b) * C + c + i], cs[i]);
+    }
+  }
+  wsq = warp_sum(wsq);
+  if (lane == 0) atomicAdd(&acc[0], wsq);
+}
+
+// vr_is_rows: vr has shape [B,R] (mean over C is "row mean" of the reference,
+// i.e. the largest dim d0 is the last dim); otherwise vr is [B,C].
+__global__ void adafactor_factors_kernel(float* __restrict__ vr, float* __restrict__ vc,
+                                         const float* __restrict__ rowsum,
+                                         const float* __restrict__ colsum, float* __restrict__ fr,
+                                         float* __restrict__ fc, int B, int R, int C, float decay,
+                                         int vr_is_rows) {
+  // One CTA per batch element b.
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float mix = 1.f - decay;
+  const int nvr = vr_is_rows ? R : C;
+  const int nvc = vr_is_rows ? C : R;
+  const float* sum_r = vr_is_rows ? rowsum + static_cast<size_t>(b) * R
+                                  : colsum + static_cast<size_t>(b) * C;
+  const float* sum_c = vr_is_rows ? colsum + static_cast<size_t>(b) * C
+                                  : rowsum + static_cast<size_t>(b) * R;
+  // mean over the reduced axis: rows were summed over C, cols over R.
+  const float inv_r = vr_is_rows ? 1.f / C : 1.f / R;
+  const float inv_c = vr_is_rows ? 1.f / R : 1.f / C;
+  float* vrb = vr + static_cast<size_t>(b) * nvr;
+  float* vcb = vc + static_cast<size_t>(b) * nvc;
+  float local = 0.f;
+  for (int i = threadIdx.x; i < nvr; i += blockDim.x) {
+    const float nv = vrb[i] * decay + sum_r[i] * inv_r * mix;
+    vrb[i] = nv;
+    local += nv;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v / nvr;
+  }
+  __syncthreads();
+  const float ltm = red[0];
+  float* f_r = vr_is_rows ? fr + static_cast<size_t>(b) * R : fc + static_cast<size_t>(b) * C;
+  float* f_c = vr_is_rows ? fc + static_cast<size_t>(b) * C : fr + static_cast<size_t>(b) * R;
+  for (int i = threadIdx.x; i < nvr; i += blockDim.x) f_r[i] = rsqrtf(vrb[i] / ltm);
+  for (int i = threadIdx.x; i < nvc; i += blockDim.x) {
+    const float nv = vcb[i] * decay + sum_c[i] * inv_c * mix;
+    vcb[i] = nv;
+    f_c[i] = rsqrtf(nv);
+  }
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(kWarps * 32)
+adafactor_rms_kernel(const GT* __restrict__ g, const float* __restrict__ fr,
+                     const float* __restrict__ fc, float* __restrict__ acc, int B, int R, int C,
+                     int items, const float* __restrict__ gscale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float gs = gscale ? *gscale : 1.f;
+  float s = 0.f;
+  for (int item = blockIdx.x * kWarps + warp; item < items; item += gridDim.x * kWarps) {
+    const Tile t = get_tile(item, R, C);
+    const int c = t.c0 + lane * 8;
+    if (c >= C) continue;
+    float cf[8];
+    load_g8<float>(fc + static_cast<size_t>(t.b) * C + c, cf);
+    for (int r = t.r0; r < t.r1; ++r) {
+      const float rf = fr[static_cast<size_t>(t.b) * R + r];
+      float gf[8];
+      load_g8<GT>(g + (static_cast<size_t>(t.b) * R + r) * C + c, gf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = (gs == 0.f ? 0.f : gf[i] * gs) * rf * cf[i];
+        s += x * x;
+      }
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) atomicAdd(&acc[1], s);
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(kWarps * 32)
+adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
+                       __nv_bfloat16* __restrict__ w_bf16, const float* __restrict__ fr,
+                       const float* __restrict__ fc, const float* __restrict__ acc, int B, int R,
+                       int C, float lr, float eps2, float clip, int mult_by_param_scale,
+                       float numel, int items, const float* __restrict__ gscale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float gs = gscale ? *gscale : 1.f;
+  float scale = lr;
+  if (mult_by_param_scale) scale *= fmaxf(sqrtf(acc[0] / numel), eps2);
+  if (clip > 0.f) scale /= fmaxf(1.f, sqrtf(acc[1] / numel) / clip);
+  for (int item = blockIdx.x * kWarps + warp; item < items; item += gridDim.x * kWarps) {
+    const Tile t = get_tile(item, R, C);
+    const int c = t.c0 + lane * 8;
+    if (c >= C) continue;
+    float cf[8];
+    load_g8<float>(fc + static_cast<size_t>(t.b) * C + c, cf);
+    for (int r = t.r0; r < t.r1; ++r) {
+      const float rf = fr[static_cast<size_t>(t.b) * R + r] * scale;
+      const size_t off = (static_cast<size_t>(t.b) * R + r) * C + c;
+      float gf[8], wf[8];
+      load_g8<GT>(g + off, gf);
+      load_g8<float>(w + off, wf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wf[i] -= (gs == 0.f ? 0.f : gf[i] * gs) * rf * cf[i];
+      *reinterpret_cast<float4*>(w + off) = make_float4(wf[0], wf[1], wf[2], wf[3]);
+      *reinterpret_cast<float4*>(w + off + 4) = make_float4(wf[4], wf[5], wf[6], wf[7]);
+      if (w_bf16 != nullptr) {
+        int4 o;
+        o.x = pack_bf16x2(wf[0], wf[1]);
+        o.y = pack_bf16x2(wf[2], wf[3]);
+        o.z = pack_bf16x2(wf[4], wf[5]);
+        o.w = pack_bf16x2(wf[6], wf[7]);
+        *reinterpret_cast<int4*>(w_bf16 + off) = o;
+      }
+    }
+  }
+}
+
+template <typename GT>
+__global__ void adam_flat_kernel(float* __restrict__ w, const GT* __restrict__ g,
+                                 float* __restrict__ m, float* __restrict__ v,
+                                 __nv_bfloat16* __restrict__ w_bf16,
+                                 const float* __restrict__ grad_scale_ptr, float lr_t, float b1,
+                                 float b2, float eps, float grad_scale, long long n) {
+  const float gs = grad_scale_ptr ? grad_scale * (*grad_scale_ptr) : grad_scale;
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    float gf[8], wf[8], mf[8], vf[8];
+    load_g8<GT>(g + i, gf);
+    load_g8<float>(w + i, wf);
+    load_g8<float>(m + i, mf);
+    load_g8<float>(v + i, vf);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float gg = gf[k] * gs;
+      mf[k] = b1 * mf[k] + (1.f - b1) * gg;
+      vf[k] = b2 * vf[k] + (1.f - b2) * gg * gg;
+      wf[k] -= lr_t * mf[k] / (sqrtf(vf[k]) + eps);
+    }
+    *reinterpret_cast<float4*>(w + i) = make_float4(wf[0], wf[1], wf[2], wf[3]);
+    *reinterpret_cast<float4*>(w + i + 4) = make_float4(wf[4], wf[5], wf[6], wf[7]);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mf[0], mf[1], mf[2], mf[3]);
+    *reinterpret_cast<float4*>(m + i + 4) = make_float4(mf[4], mf[5], mf[6], mf[7]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vf[0], vf[1], vf[2], vf[3]);
+    *reinterpret_cast<float4*>(v + i + 4) = make_float4(vf[4], vf[5], vf[6], vf[7]);
+    if (w_bf16) {
+      int4 o;
+      o.x = pack_bf16x2(wf[0], wf[1]);
+      o.y = pack_bf16x2(wf[2], wf[3]);
+      o.z = pack_bf16x2(wf[4], wf[5]);
+      o.w = pack_bf16x2(wf[6], wf[7]);
+      *reinterpret_cast<int4*>(w_bf16 + i) = o;
+    }
+  }
+}
+
+}  // namespace
+
+// In-place factored Adafactor step on `w` viewed as [B, R, C].
+// scratch: fp32 [2 + B*R*2 + B*C*2] = acc | rowsum | colsum | fr | fc  (zeroed here).
+void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor vr,
+                        torch::Tensor vc, torch::Tensor scratch,
+                        const c10::optional<torch::Tensor>& w_bf16, int64_t B, int64_t R,
+                        int64_t C, bool vr_is_rows, double lr, double decay, double eps1,
+                        double eps2, double clip, bool mult_by_param_scale,
+                        const c10::optional<torch::Tensor>& grad_scale) {
+  TORCH_CHECK(w.is_cuda() && w.scalar_type() == torch::kFloat32 && w.is_contiguous());
+  TORCH_CHECK(g.is_contiguous() && g.numel() == w.numel());
+  TORCH_CHECK(C % 8 == 0, "adafactor_factored: C must be a multiple of 8");
+  TORCH_CHECK(w.numel() == B * R * C);
+  TORCH_CHECK(scratch.numel() >= 2 + 2 * B * R + 2 * B * C);
+  const c10::cuda::CUDAGuard guard(w.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  float* sp = scratch.data_ptr<float>();
+  float* acc = sp;
+  float* rowsum = sp + 2;
+  float* colsum = rowsum + B * R;
+  float* fr = colsum + B * C;
+  float* fc = fr + B * R;
+  C10_CUDA_CHECK(cudaMemsetAsync(sp, 0, sizeof(float) * (2 + B * R + B * C), stream));
+  const int strips = static_cast<int>((C + 255) / 256);
+  const int ranges = static_cast<int>((R + kRowsPerWarp - 1) / kRowsPerWarp);
+  const int items = static_cast<int>(B) * strips * ranges;
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  int grid = (items + kWarps - 1) / kWarps;
+  if (grid > sms * 8) grid = sms * 8;
+  __nv_bfloat16* wb = nullptr;
+  if (w_bf16.has_value() && w_bf16->defined()) {
+    TORCH_CHECK(w_bf16->scalar_type() == torch::kBFloat16 && w_bf16->is_contiguous() &&
+                w_bf16->numel() == w.numel());
+    wb = reinterpret_cast<__nv_bfloat16*>(w_bf16->data_ptr());
+  }
+  const float numel = static_cast<float>(w.numel());
+  const float* gsp = (grad_scale.has_value() && grad_scale->defined())
+                         ? grad_scale->data_ptr<float>() : nullptr;
+  auto run = [&](auto tag) {
+    using GT = decltype(tag);
+    const GT* gp = reinterpret_cast<const GT*>(g.data_ptr());
+    adafactor_stats_kernel<GT><<<grid, kWarps * 32, 0, stream>>>(
+        gp, w.data_ptr<float>(), rowsum, colsum, acc, (int)B, (int)R, (int)C, (float)eps1, items, gsp);
+    adafactor_factors_kernel<<<static_cast<int>(B), 256, 0, stream>>>(
+        vr.data_ptr<float>(), vc.data_ptr<float>(), rowsum, colsum, fr, fc, (int)B, (int)R, (int)C,
+        (float)decay, vr_is_rows ? 1 : 0);
+    if (clip > 0)
+      adafactor_rms_kernel<GT><<<grid, kWarps * 32, 0, stream>>>(gp, fr, fc, acc, (int)B, (int)R,
+                                                                 (int)C, items, gsp);
+    adafactor_apply_kernel<GT><<<grid, kWarps * 32, 0, stream>>>(
+        gp, w.data_ptr<float>(), wb, fr, fc, acc, (int)B, (int)R, (int)C, (float)lr, (float)eps2,
+        (float)clip, mult_by_param_scale ? 1 : 0, numel, items, gsp);
+  };
+  if (g.scalar_type() == torch::kBFloat16) run(__nv_bfloat16());
+  else { TORCH_CHECK(g.scalar_type() == torch::kFloat32); run(float()); }
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  CountLaunch(clip > 0 ? 4 : 3);
+}
+
+void adam_flat(torch::Tensor w, const torch::Tensor& g, torch::Tensor m, torch::Tensor v,
+               const c10::optional<torch::Tensor>& w_bf16,
+               const c10::optional<torch::Tensor>& grad_scale_t, double lr_t, double b1, double b2,
+               double eps, double grad_scale) {
+  TORCH_CHECK(w.is_cuda() && w.scalar_type() == torch::kFloat32 && w.is_contiguous());
+  const long long n = w.numel();
+  TORCH_CHECK(n % 8 == 0, "adam_flat: numel must be a multiple of 8 (pad the flat buffer)");
+  const c10::cuda::CUDAGuard guard(w.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  long long blocks = (n / 8 + 255) / 256;
+  if (blocks > sms * 8) blocks = sms * 8;
+  if (blocks < 1) blocks = 1;
+  __nv_bfloat16* wb = (w_bf16.has_value() && w_bf16->defined())
+                          ? reinterpret_cast<__nv_bfloat16*>(w_bf16->data_ptr()) : nullptr;
+  const float* gsp = (grad_scale_t.has_value() && grad_scale_t->defined())
+                         ? grad_scale_t->data_ptr<float>() : nullptr;
+  if (g.scalar_type() == torch::kBFloat16)
+    adam_flat_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, stream>>>(
+        w.data_ptr<float>(), reinterpret_cast<const __nv_bfloat16*>(g.data_ptr()),
+        m.data_ptr<float>(), v.data_ptr<float>(), wb, gsp, (float)lr_t, (float)b1, (float)b2,
+        (float)eps, (float)grad_scale, n);
+  else
+    adam_flat_kernel<float><<<(int)blocks, 256, 0, stream>>>(
+        w.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), wb,
+        gsp, (float)lr_t, (float)b1, (float)b2, (float)eps, (float)grad_scale, n);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  CountLaunch();
+}
+
+}  // namespace lb
+
+LB_REGISTER(optim) {
+  m.attr("_has_optim") = true;
+  m.def("adafactor_factored", &lb::adafactor_factored);
+  m.def("adam_flat", &lb::adam_flat);
+}

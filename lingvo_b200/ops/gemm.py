@@ -139,3 +139,37 @@ def grouped_linear(x, w, bias=None, act=None):
       y = y + bias.to(y.dtype).unsqueeze(1)
     return _act_ref(y, act)
   return _LinearFn.apply(x, w, bias, act)
+
+
+class _FfnReluFn(torch.autograd.Function):
+  """y = relu(x·wi)·wo with the ReLU mask folded into the dgrad epilogue."""
+
+  @staticmethod
+  def forward(ctx, x, wi, wo):
+    h = gemm(x, wi, True, False, act=1)
+    y = gemm(h, wo, True, False)
+    ctx.save_for_backward(x, wi, wo, h)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    x, wi, wo, h = ctx.saved_tensors
+    dy = dy.contiguous()
+    dh = gemm(dy, wo, True, True, aux=h, aux_mode=AUX_RELU_MASK)
+    dwo = gemm(h, dy, False, False) if ctx.needs_input_grad[2] else None
+    dwi = gemm(x, dh, False, False) if ctx.needs_input_grad[1] else None
+    dx = gemm(dh, wi, True, True) if ctx.needs_input_grad[0] else None
+    return dx, dwi, dwo
+
+
+def ffn_relu(x, wi, wo):
+  """x[..., M] → relu(x·wi[M,H])·wo[H,M]; 4 tcgen05 GEMMs fwd+bwd, no
+  elementwise passes (bias-free FFN as in the GShard dense layers)."""
+  lead = x.shape[:-1]
+  x2 = x.reshape(-1, x.shape[-1])
+  ok = (x2.is_cuda and x2.dtype == torch.bfloat16 and wi.dtype == torch.bfloat16
+        and wo.dtype == torch.bfloat16 and ops.use_cuda_kernels(x2))
+  if not ok:
+    return torch.matmul(F.relu(torch.matmul(x2, wi.to(x2.dtype))),
+                        wo.to(x2.dtype)).reshape(*lead, wo.shape[-1])
+  return _FfnReluFn.apply(x2, wi, wo).reshape(*lead, wo.shape[-1])

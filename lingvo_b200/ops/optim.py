@@ -1,10 +1,68 @@
-"""Front-end of the fused sm_100a `optim` kernels (csrc/optim_kernels.cu)."""
+"""Front-end of the fused optimizer kernels (csrc/optim_kernels.cu)."""
 
 import torch
 
 from lingvo_b200 import ops
 
+_SCRATCH = {}
+
 
 def available() -> bool:
   mod = ops.native(required=False)
   return mod is not None and hasattr(mod, '_has_optim')
+
+
+def _Scratch(var, n):
+  key = id(var)
+  buf = _SCRATCH.get(key)
+  if buf is None or buf.numel() < n or buf.device != var.device:
+    buf = torch.empty(n, dtype=torch.float32, device=var.device)
+    _SCRATCH[key] = buf
+  return buf
+
+
+def adafactor_factored(var, grad, vr, vc, d0, d1, lr, decay, eps1, eps2, clip,
+                       mult_by_param_scale, grad_scale=None):
+  """In-place Adafactor step; factored dims (d0, d1) must be the last two.
+
+  d0 is the reference's `vr_axis` (largest dim): `vr` = mean over d0.
+  """
+  nd = var.dim()
+  assert sorted((d0, d1)) == [nd - 2, nd - 1]
+  r, c = var.shape[-2], var.shape[-1]
+  b = var.numel() // (r * c)
+  vr_is_rows = (d0 == nd - 1)   # vr = mean over C → per-row vector [B, R]
+  scratch = _Scratch(var, 2 + 2 * b * r + 2 * b * c)
+  g = grad if grad.is_contiguous() else grad.contiguous()
+  compute = getattr(var, 'compute', None)
+  ops.native().adafactor_factored(
+      var.data, g, vr, vc, scratch, compute.data if compute is not None else None,
+      b, r, c, vr_is_rows, float(lr), float(decay), float(eps1), float(eps2),
+      float(clip), bool(mult_by_param_scale), grad_scale)
+
+
+def adam_flat(w, g, m, v, w_bf16, lr_t, b1, b2, eps, grad_scale=1.0,
+              grad_scale_t=None):
+  ops.native().adam_flat(w, g, m, v, w_bf16, grad_scale_t, float(lr_t),
+                         float(b1), float(b2), float(eps), float(grad_scale))
+
+
+def multi_tensor_adam(variables, grads, ms, vs, lr_t, b1, b2, eps,
+                      grad_scale_t=None):
+  for w, g, m, v in zip(variables, grads, ms, vs):
+    n = w.numel()
+    if n % 8 == 0 and w.is_contiguous() and g.is_contiguous():
+      compute = getattr(w, 'compute', None)
+      adam_flat(w.data.view(-1), g.reshape(-1), m.view(-1), v.view(-1),
+                compute.data.view(-1) if compute is not None else None,
+                lr_t, b1, b2, eps, grad_scale_t=grad_scale_t)
+    else:
+      gg = g.to(w.dtype)
+      if grad_scale_t is not None:
+        gg = gg * grad_scale_t.to(gg.dtype)
+      m.mul_(b1).add_(gg, alpha=1 - b1)
+      v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
+      w.data.addcdiv_(m, v.sqrt().add_(eps), value=-lr_t)
+      compute = getattr(w, 'compute', None)
+      if compute is not None:
+        compute.data.copy_(w.data)

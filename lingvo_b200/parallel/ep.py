@@ -69,26 +69,19 @@ class ExpertParallel:
     self._fused = None
     self.last_a2a_ms = 0.0
 
-  def _Fused(self, device):
+  def GetExchange(self, device):
+    """The fused peer-memory exchange, or None (NCCL baseline / CPU)."""
     if self._fused is None:
       self._fused = False
       if self.ctx.mode == 'fused' and device.type == 'cuda':
-        try:
-          from lingvo_b200.parallel import symm
-          self._fused = symm.MoeExchange(self)
-        except Exception as e:  # pylint: disable=broad-except
-          import logging
-          logging.warning('fused EP unavailable, using NCCL: %r', e)
-          self._fused = False
-    return self._fused
+        from lingvo_b200.parallel import symm
+        self._fused = symm.MoeExchange(self, device=device)
+    return self._fused or None
 
   def Apply(self, x2d, gating: NestedMap, wi, wo, activation_name='RELU',
             bi=None, bo=None, use_glu=False):
     """tokens `[G_l·S, M]` → `[G_l·S, M]`; `wi/wo` hold the local experts."""
     from lingvo_b200.ops import gemm
-    fused = self._Fused(x2d.device)
-    if fused:
-      return fused.Apply(x2d, gating, wi, wo, activation_name, bi, bo, use_glu)
     g_l = gating.index.shape[1]
     s = gating.index.shape[2]
     e, ep, el = self.num_experts, self.ep_size, self.num_local_experts

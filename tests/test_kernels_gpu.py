@@ -1,0 +1,147 @@
+"""Fused sm_100a kernels vs plain PyTorch fp32 references."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+  a, b = a.float(), b.float()
+  return ((a - b).abs().max() / (b.abs().max() + 1e-6)).item()
+
+
+@pytest.mark.parametrize('dim', [256, 2048, 4096])
+def test_rms_norm(dim):
+  from lingvo_b200.ops import norm
+  x = torch.randn(300, dim, device='cuda').bfloat16().requires_grad_()
+  scale = (torch.rand(dim, device='cuda') + 0.5).requires_grad_()
+  y = norm.rms_norm(x, scale, 1e-6)
+  dy = torch.randn_like(y)
+  y.backward(dy)
+  xr = x.detach().float().requires_grad_()
+  sr = scale.detach().clone().requires_grad_()
+  yr = xr * torch.rsqrt(xr.square().mean(-1, keepdim=True) + 1e-6) * sr
+  yr.backward(dy.float())
+  assert _rel(y, yr) < 2e-2
+  assert _rel(x.grad, xr.grad) < 3e-2
+  assert _rel(scale.grad, sr.grad) < 3e-2
+
+
+def test_layer_norm():
+  from lingvo_b200.ops import norm
+  dim = 1024
+  x = torch.randn(200, dim, device='cuda').bfloat16().requires_grad_()
+  scale = (torch.rand(dim, device='cuda') + 0.5).requires_grad_()
+  bias = torch.randn(dim, device='cuda').requires_grad_()
+  y = norm.layer_norm(x, scale, bias, 1e-6)
+  dy = torch.randn_like(y)
+  y.backward(dy)
+  xr = x.detach().float().requires_grad_()
+  sr = scale.detach().clone().requires_grad_()
+  br = bias.detach().clone().requires_grad_()
+  yr = torch.nn.functional.layer_norm(xr, (dim,), sr, br, 1e-6)
+  yr.backward(dy.float())
+  assert _rel(y, yr) < 2e-2
+  assert _rel(x.grad, xr.grad) < 3e-2
+  assert _rel(scale.grad, sr.grad) < 3e-2
+  assert _rel(bias.grad, br.grad) < 3e-2
+
+
+@pytest.mark.parametrize('shape', [(512, 1024), (1024, 256), (4, 256, 512)])
+@pytest.mark.parametrize('gdtype', [torch.bfloat16, torch.float32])
+def test_adafactor_matches_reference(shape, gdtype):
+  from lingvo_b200.core import optimizer, py_utils
+  torch.manual_seed(0)
+  w0 = torch.randn(shape, device='cuda')
+  grads = [torch.randn(shape, device='cuda').to(gdtype) * 0.1 for _ in range(3)]
+
+  def run(fused):
+    p = optimizer.XLAShardingAdafactor.Params().Set(
+        name='adafactor', beta1=0.0, beta2=0.99, clipping_threshold=1.0,
+        factored=True, decay_exponent_pow=0.8, fused=fused)
+    opt = p.Instantiate()
+    w = torch.nn.Parameter(w0.clone())
+    w.var_name = 'w/var'
+    if gdtype == torch.bfloat16:
+      w.compute = w.data.bfloat16().requires_grad_()
+    for step, g in enumerate(grads):
+      with py_utils.GlobalStepContext(step):
+        opt.Apply(0.01, [py_utils.VarGrad(w, g)])
+    return w
+
+  a, b = run(True), run(False)
+  assert _rel(a, b) < 1e-4
+  if gdtype == torch.bfloat16:
+    assert torch.equal(a.compute.data, a.data.bfloat16())
+
+
+def test_lm_head_xent():
+  from lingvo_b200.ops import xent
+  t, m, v = 512, 256, 2048
+  x = (torch.randn(t, m, device='cuda') * 0.5).bfloat16().requires_grad_()
+  w = (torch.randn(v, m, device='cuda') * 0.1).bfloat16().requires_grad_()
+  labels = torch.randint(0, v, (t,), device='cuda')
+  st = xent.lm_head_xent(x, w, labels, 0.1, 1e-4)
+  wt = torch.rand(t, device='cuda')
+  ((st.soft_xent + st.z_inc) * wt).sum().backward()
+  xr = x.detach().float().requires_grad_()
+  wr = w.detach().float().requires_grad_()
+  ref = xent.lm_head_xent_ref(xr, wr, labels, 0.1, 1e-4)
+  ((ref.soft_xent + ref.z_inc) * wt).sum().backward()
+  assert _rel(st.entropy, ref.entropy) < 2e-2
+  assert _rel(st.soft_xent, ref.soft_xent) < 2e-2
+  assert (st.argmax == ref.argmax).float().mean() > 0.97
+  assert _rel(x.grad, xr.grad) < 5e-2
+  assert _rel(w.grad, wr.grad) < 5e-2
+
+
+def test_ffn_relu():
+  from lingvo_b200.ops import gemm
+  x = torch.randn(384, 256, device='cuda').bfloat16().requires_grad_()
+  wi = (torch.randn(256, 512, device='cuda') * 0.05).bfloat16().requires_grad_()
+  wo = (torch.randn(512, 256, device='cuda') * 0.05).bfloat16().requires_grad_()
+  y = gemm.ffn_relu(x, wi, wo)
+  dy = torch.randn_like(y)
+  y.backward(dy)
+  xr, wir, wor = [t.detach().float().requires_grad_() for t in (x, wi, wo)]
+  yr = torch.relu(xr @ wir) @ wor
+  yr.backward(dy.float())
+  for a, b in ((y, yr), (x.grad, xr.grad), (wi.grad, wir.grad), (wo.grad, wor.grad)):
+    assert _rel(a, b) < 3e-2
+
+
+@pytest.mark.parametrize('legacy', [True, False])
+def test_moe_exchange_matches_dense_oracle(legacy):
+  """Fused gate+dispatch / expert GEMMs / combine == dense GSEC einsums."""
+  from lingvo_b200.core import gshard_layers
+  from lingvo_b200.parallel import symm
+  torch.manual_seed(1)
+  g, s, m, h, e = 4, 128, 256, 512, 8
+  cap = gshard_layers.ExpertCapacity(s, e, 0, 2.0)
+  x = torch.randn(g, s, m, device='cuda').bfloat16().requires_grad_()
+  gw = (torch.randn(m, e, device='cuda') * 0.2).requires_grad_()
+  wi = (torch.randn(e, m, h, device='cuda') * 0.05).bfloat16().requires_grad_()
+  wo = (torch.randn(e, h, m, device='cuda') * 0.05).bfloat16().requires_grad_()
+  pad = torch.zeros(g, s, device='cuda')
+  pad[:, -7:] = 1.0
+  ex = symm.MoeExchange(None, e, torch.device('cuda', 0))
+  logits = torch.matmul(x.float(), gw)
+  y, aux = ex.Apply(('t', legacy), x.reshape(g * s, m), logits, pad, cap, legacy,
+                    wi, wo)
+  dy = torch.randn_like(y)
+  (y.float() * dy.float()).sum().add(aux * 3.0).backward()
+
+  xr, gwr, wir, wor = [t.detach().float().requires_grad_()
+                       for t in (x, gw, wi, wo)]
+  gating = gshard_layers.ComputeGating(
+      gwr, xr, pad, 1, e, 0, True, torch.float32, 'top_2', False, 'all', 0.0,
+      legacy, 2.0, None, torch.float32, torch.float32)
+  yr, auxr = gshard_layers.FeedForwardNetworksApplyGating(
+      gating, xr, xr, wir, wor, 1, g)
+  (yr.reshape(g * s, m) * dy.float()).sum().add(auxr * 3.0).backward()
+  assert _rel(y, yr.reshape(g * s, m)) < 3e-2
+  assert abs(float(aux) - float(auxr)) < 1e-4
+  assert _rel(x.grad, xr.grad) < 5e-2
+  assert _rel(gw.grad, gwr.grad) < 5e-2
+  assert _rel(wi.grad, wir.grad) < 5e-2
+  assert _rel(wo.grad, wor.grad) < 5e-2
