@@ -416,6 +416,14 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
   TORCH_CHECK(a_in.scalar_type() == torch::kBFloat16 && b_in.scalar_type() == torch::kBFloat16,
               "gemm_bf16: bf16 inputs required");
   const c10::cuda::CUDAGuard guard(a_in.device());
+  // cuTensorMapEncodeTiled is a *driver* call: make sure this thread (e.g. an
+  // autograd worker that has not issued a runtime call yet) has the primary
+  // context bound, otherwise it fails with CUDA_ERROR_INVALID_CONTEXT.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    C10_CUDA_CHECK(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   torch::Tensor a = a_in.dim() == 2 ? a_in.unsqueeze(0) : a_in;
   torch::Tensor b = b_in.dim() == 2 ? b_in.unsqueeze(0) : b_in;
   TORCH_CHECK(a.dim() == 3 && b.dim() == 3, "gemm_bf16: 2-D or 3-D operands");

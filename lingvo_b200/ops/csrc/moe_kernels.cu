@@ -458,7 +458,7 @@ std::vector<torch::Tensor> moe_gate_dispatch(const torch::Tensor& logits,
   a.pos = pos.data_ptr<int>();
   a.gate = gate.data_ptr<float>();
   a.slot_token = slot_token.data_ptr<int>();
-  a.peer_xe = peer_xe.data_ptr<long long>();
+  a.peer_xe = reinterpret_cast<long long*>(peer_xe.data_ptr<int64_t>());
   a.G_l = G; a.S = S; a.E = E; a.C = C; a.E_l = (int)e_local; a.G_t = (int)(ep * G);
   a.rank = (int)rank; a.legacy = legacy ? 1 : 0;
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
@@ -489,7 +489,7 @@ void moe_scatter_rows(const torch::Tensor& src, const torch::Tensor& slot_token,
   const int grid = GridWarps(E * G * C, 8);
   moe_scatter_rows_kernel<<<grid, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
       reinterpret_cast<const __nv_bfloat16*>(src.data_ptr()), slot_token.data_ptr<int>(),
-      index.data_ptr<int>(), gp, peer_dst.data_ptr<long long>(), E, G, C, M, (int)e_local,
+      index.data_ptr<int>(), gp, reinterpret_cast<long long*>(peer_dst.data_ptr<int64_t>()), E, G, C, M, (int)e_local,
       (int)(ep * G), (int)rank, T);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   CountLaunch();
@@ -546,7 +546,7 @@ void moe_signal(const torch::Tensor& peer_flags, int64_t world, int64_t rank, in
                 int64_t seq) {
   const c10::cuda::CUDAGuard guard(peer_flags.device());
   moe_signal_kernel<<<1, 32, 0, at::cuda::getCurrentCUDAStream()>>>(
-      peer_flags.data_ptr<long long>(), (int)world, (int)rank, (int)channel, (int)seq);
+      reinterpret_cast<long long*>(peer_flags.data_ptr<int64_t>()), (int)world, (int)rank, (int)channel, (int)seq);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   CountLaunch();
 }

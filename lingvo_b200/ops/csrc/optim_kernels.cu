@@ -284,16 +284,18 @@ void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor v
   TORCH_CHECK(g.is_contiguous() && g.numel() == w.numel());
   TORCH_CHECK(C % 8 == 0, "adafactor_factored: C must be a multiple of 8");
   TORCH_CHECK(w.numel() == B * R * C);
-  TORCH_CHECK(scratch.numel() >= 2 + 2 * B * R + 2 * B * C);
+  const int64_t br4 = (B * R + 3) / 4 * 4, bc4 = (B * C + 3) / 4 * 4;
+  TORCH_CHECK(scratch.numel() >= 4 + 2 * br4 + 2 * bc4);
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(scratch.data_ptr()) % 16 == 0);
   const c10::cuda::CUDAGuard guard(w.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   float* sp = scratch.data_ptr<float>();
   float* acc = sp;
-  float* rowsum = sp + 2;
-  float* colsum = rowsum + B * R;
-  float* fr = colsum + B * C;
-  float* fc = fr + B * R;
-  C10_CUDA_CHECK(cudaMemsetAsync(sp, 0, sizeof(float) * (2 + B * R + B * C), stream));
+  float* rowsum = sp + 4;
+  float* colsum = rowsum + br4;
+  float* fr = colsum + bc4;
+  float* fc = fr + br4;
+  C10_CUDA_CHECK(cudaMemsetAsync(sp, 0, sizeof(float) * (4 + br4 + bc4), stream));
   const int strips = static_cast<int>((C + 255) / 256);
   const int ranges = static_cast<int>((R + kRowsPerWarp - 1) / kRowsPerWarp);
   const int items = static_cast<int>(B) * strips * ranges;

@@ -146,9 +146,9 @@ std::vector<torch::Tensor> xent_stats(const torch::Tensor& logits, const torch::
   auto am = torch::empty({T}, logits.options().dtype(torch::kInt64));
   if (T > 0) {
     xent_stats_kernel<<<T, kThreads, 0, at::cuda::getCurrentCUDAStream()>>>(
-        reinterpret_cast<const __nv_bfloat16*>(logits.data_ptr()), labels.data_ptr<long long>(),
+        reinterpret_cast<const __nv_bfloat16*>(logits.data_ptr()), reinterpret_cast<const long long*>(labels.data_ptr<int64_t>()),
         lse.data_ptr<float>(), tl.data_ptr<float>(), sl.data_ptr<float>(),
-        am.data_ptr<long long>(), V, logits.stride(0));
+        reinterpret_cast<long long*>(am.data_ptr<int64_t>()), V, logits.stride(0));
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     CountLaunch();
   }
@@ -163,7 +163,7 @@ void xent_bwd(torch::Tensor logits, const torch::Tensor& labels, const torch::Te
   const int T = static_cast<int>(logits.size(0)), V = static_cast<int>(logits.size(1));
   if (T == 0) return;
   xent_bwd_kernel<<<T, kThreads, 0, at::cuda::getCurrentCUDAStream()>>>(
-      reinterpret_cast<__nv_bfloat16*>(logits.data_ptr()), labels.data_ptr<long long>(),
+      reinterpret_cast<__nv_bfloat16*>(logits.data_ptr()), reinterpret_cast<const long long*>(labels.data_ptr<int64_t>()),
       lse.data_ptr<float>(), a.data_ptr<float>(), b.data_ptr<float>(), c.data_ptr<float>(), V,
       logits.stride(0));
   C10_CUDA_KERNEL_LAUNCH_CHECK();

@@ -32,7 +32,7 @@ def adafactor_factored(var, grad, vr, vc, d0, d1, lr, decay, eps1, eps2, clip,
   r, c = var.shape[-2], var.shape[-1]
   b = var.numel() // (r * c)
   vr_is_rows = (d0 == nd - 1)   # vr = mean over C → per-row vector [B, R]
-  scratch = _Scratch(var, 2 + 2 * b * r + 2 * b * c)
+  scratch = _Scratch(var, 16 + 2 * (b * r + 4) + 2 * (b * c + 4))
   g = grad if grad.is_contiguous() else grad.contiguous()
   compute = getattr(var, 'compute', None)
   ops.native().adafactor_factored(

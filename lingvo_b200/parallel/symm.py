@@ -229,7 +229,12 @@ class MoeExchange:
       den = g1 + g2
       den = torch.where(den > 0, den, torch.ones_like(den))
       g1, g2 = g1 / den, g2 / den
-    aux_loss = (proxy.mean(1) * oh1.mean(1)).mean() * (e * e)
+    if legacy:
+      dden = 1.0
+    else:
+      imp = nonpad if nonpad is not None else torch.ones_like(g1)
+      dden = imp.mean(1)[:, None] + 1e-6
+    aux_loss = ((proxy.mean(1) / dden) * (oh1.mean(1) / dden)).mean() * (e * e)
     gate = torch.stack([g1, g2]).reshape(2, g_l * s)
     y = _MoeFn.apply(x2d, gate, wi, wo, self, bufs, g, g_l, s)
     return y, aux_loss
