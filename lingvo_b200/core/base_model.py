@@ -260,6 +260,22 @@ class BaseTask(base_layer.BaseLayer):
       return v.device
     return py_utils.CurrentDevice()
 
+  def EnableMixedPrecision(self) -> int:
+    """bf16 compute copies of fp32 master weights (see py_utils)."""
+    self._mixed_precision_attached = True
+    return py_utils.AttachComputeCopies(self)
+
+  def FPropDefaultTheta(self, input_batch=None):
+    if input_batch is None:
+      input_batch = self.GetInputBatch()
+    if not getattr(self, '_mixed_precision_attached', False):
+      # First step on a GPU: switch bf16-fprop layers to persistent compute
+      # copies (theta would otherwise re-cast 1.4 B weights every step).
+      self._mixed_precision_attached = True
+      if self.Device().type == 'cuda' and not self.do_eval:
+        py_utils.AttachComputeCopies(self)
+    return self.FProp(self.theta, input_batch)
+
   def FProp(self, theta, input_batch):
     """Forward over all towers of this process; returns (metrics, per_example)."""
     p = self.params
@@ -314,11 +330,6 @@ class BaseTask(base_layer.BaseLayer):
     self._eval_metrics = dict(metrics)
     self._per_example = self.FilterPerExampleTensors(per_example)
     return metrics, per_example
-
-  def FPropDefaultTheta(self, input_batch=None):
-    if input_batch is None:
-      input_batch = self.GetInputBatch()
-    return self.FProp(self.theta, input_batch)
 
   # ------------------------------------------------------------------ bprop --
   def AdjustGradients(self, vars_gradients):

@@ -99,6 +99,7 @@ class Checkpointer:
           raise ValueError('Shape mismatch for %s: ckpt %s vs model %s' %
                            (k, tuple(t.shape), tuple(v.shape)))
         v.data.copy_(t.to(v.device, v.dtype))
+    py_utils.RefreshComputeCopies(self._model.vars.Flatten())
     if missing and strict:
       raise KeyError('Variables missing from checkpoint %s: %s' %
                      (checkpoint_path, missing[:10]))

@@ -202,14 +202,28 @@ class SelfAttentionLayer(_BuilderLayer):
           [h, b.relative_attention_num_buckets], WeightInit.Gaussian(1.0),
           self.params.dtype))
 
-  def _Bias(self, theta, segment_id, segment_pos):
-    """Additive fp32 bias `[B or 1, H or 1, L, L]`."""
+  _MASK_CACHE = {}
+
+  def _Mask(self, segment_id, segment_pos, dtype):
+    """Additive visibility mask `[B, 1, L, L]`, shared by all layers of a step."""
     b = self.bp
+    key = (segment_id.data_ptr(), segment_pos.data_ptr(), tuple(segment_id.shape),
+           dtype, self.params.decoder, segment_id._version)
+    hit = SelfAttentionLayer._MASK_CACHE.get('k')
+    if hit is not None and hit[0] == key:
+      return hit[1]
     a, c = segment_id.unsqueeze(-1), segment_id.unsqueeze(-2)
     not_vis = ((a == 0) & (c == 0)) | (a != c)
     if self.params.decoder and not b.decoder_skip_causal_mask:
       not_vis = not_vis | (segment_pos.unsqueeze(-1) < segment_pos.unsqueeze(-2))
-    bias = not_vis.float().unsqueeze(1) * -1e9
+    mask = (not_vis.to(dtype) * -1e9).unsqueeze(1)
+    SelfAttentionLayer._MASK_CACHE['k'] = (key, mask)
+    return mask
+
+  def _Bias(self, theta, segment_id, segment_pos, dtype=torch.float32):
+    """Additive bias `[B or 1, H or 1, L, L]` in `dtype`."""
+    b = self.bp
+    bias = self._Mask(segment_id, segment_pos, dtype)
     if self.params.relative_bias:
       bidi = (not self.params.decoder) or (
           b.decoder_bidirectional_relative_attention)
@@ -224,15 +238,15 @@ class SelfAttentionLayer(_BuilderLayer):
         bucket = RelativePositionBucket(
             rel, b.relative_attention_num_buckets,
             b.relative_attention_max_distance, bidirectional=bidi)
-        table = theta.wrb.float()[:, bucket.long()]          # [H, 2L-1]
-        rb = table.unfold(-1, l, 1).flip(1).unsqueeze(0)      # [1, H, L, L]
+        table = theta.wrb.float()[:, bucket.long()].to(dtype)  # [H, 2L-1]
+        rb = table.unfold(-1, l, 1).flip(1).unsqueeze(0)       # [1, H, L, L]
       else:
         rel = segment_pos.unsqueeze(-2) - segment_pos.unsqueeze(-1)
         bucket = RelativePositionBucket(
             rel, b.relative_attention_num_buckets,
             b.relative_attention_max_distance, bidirectional=bidi)
         oh = F.one_hot(bucket.long(), b.relative_attention_num_buckets).float()
-        rb = torch.einsum('HX,BLJX->BHLJ', theta.wrb.float(), oh)
+        rb = torch.einsum('HX,BLJX->BHLJ', theta.wrb.float(), oh).to(dtype)
       bias = bias + rb
     return bias
 
@@ -257,7 +271,9 @@ class SelfAttentionLayer(_BuilderLayer):
     if b.use_rotary_position_emb:
       q = _Rope(q, segment_pos, b.rope_emb_max_timescale)
       k = _Rope(k, segment_pos, b.rope_emb_max_timescale)
-    bias = self._Bias(theta, segment_id, segment_pos)
+    simple = (not b.atten_logit_cap) and b.attention_extra_logit is None
+    bias = self._Bias(theta, segment_id, segment_pos,
+                      x.dtype if (simple and x.is_cuda) else torch.float32)
     o = _AttentionCore(q, k, v, bias, b.atten_logit_cap,
                        b.attention_extra_logit, b.attention_dropout_prob
                        if not self.do_eval else 0.0)
@@ -293,7 +309,7 @@ def _AttentionCore(q, k, v, bias, logit_cap=0.0, extra_logit=None,
     # NOTE: no 1/sqrt(D) scaling in GShard attention (folded into wq init).
     o = F.scaled_dot_product_attention(
         q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
-        attn_mask=bias.to(q.dtype).expand(bsz, h, l, k.shape[1]),
+        attn_mask=bias.expand(bsz, h, l, k.shape[1]),
         dropout_p=dropout_prob, scale=1.0)
     return o.transpose(1, 2)
   logits = torch.einsum('BLHD,BMHD->BHLM', q.float(), k.float())
