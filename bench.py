@@ -138,7 +138,7 @@ def main():
 
   cfg = model_registry.GetParams(args.model, 'Train')
   cfg.cluster.mode = 'sync'
-  cfg.cluster.job = 'trainer_client'
+  cfg.cluster.job = 'trainer'
   cfg.cluster.worker.replicas = world
   cfg.cluster.worker.gpus_per_replica = 1
   cluster = cluster_factory.Cluster(cfg.cluster)

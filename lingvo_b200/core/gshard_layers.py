@@ -208,11 +208,6 @@ def Top2GatingIndices(logits, paddings, experts_dim, expert_capacity_dim,
   g, s, e = logits.shape
   assert e == experts_dim
   cap = ExpertCapacity(s, experts_dim, expert_capacity_dim, capacity_factor)
-  if (use_kernel and ops.use_cuda_kernels(logits) and
-      second_expert_policy == 'all'):
-    from lingvo_b200.ops import moe as moe_ops
-    if moe_ops.available():
-      return moe_ops.top2_gate(logits, paddings, cap, legacy_mtf_behavior)
   raw = torch.softmax(logits.float(), dim=-1)
   nonpad = None if paddings is None else (1.0 - paddings.float())
   index_1 = raw.argmax(-1)

@@ -70,11 +70,17 @@ def Attach(task):
         _AllReduceBuckets(grads, ctx.world)
     return var_grads
 
-  for lrn in task.learners:
-    lrn.grad_sync = sync
   # Make replicated variables identical across ranks (rank 0 wins).
   with torch.no_grad():
     for v in task.vars.Flatten():
       if not getattr(v, 'expert_parallel', False):
         dist.broadcast(v.data, src=0)
-  return sync
+  fused = None
+  if ctx.mode == 'fused' and task.Device().type == 'cuda':
+    from lingvo_b200.parallel import zero
+    # Mixed-precision copies must exist before gradients are produced in bf16.
+    task.EnableMixedPrecision()
+    fused = zero.FusedAllReduce(task, ctx)
+  for lrn in task.learners:
+    lrn.grad_sync = fused if fused is not None else sync
+  return fused if fused is not None else sync

@@ -1,0 +1,38 @@
+"""Multi-GPU numerics checks (run under torchrun): fused EP/DP vs NCCL baseline."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+
+def run(mode, steps=3):
+  from lingvo_b200 import model_registry
+  from lingvo_b200.core import cluster_factory
+  from lingvo_b200.parallel import mesh as mesh_lib, dp as dp_lib
+  import lingvo_b200.models.lm.params.synthetic_packed_input  # noqa
+  mesh_lib.Reset(mode=mode)
+  cfg = model_registry.GetParams('lm.synthetic_packed_input.MoELm8ETiny', 'Train')
+  cfg.task.random_seed = 1
+  cfg.input.random_seed = 5
+  cfg.cluster.worker.gpus_per_replica = 1
+  losses = []
+  with cluster_factory.Cluster(cfg.cluster):
+    m = cfg.Instantiate(); m.to(torch.device('cuda', torch.cuda.current_device()))
+    task = m.tasks[0]
+    dp_lib.Attach(task)
+    for _ in range(steps):
+      metrics, _ = task.TrainStep()
+      losses.append(float(metrics['loss'][0].detach()))
+  return losses
+
+def main():
+  lr = int(os.environ.get('LOCAL_RANK', 0))
+  torch.cuda.set_device(lr)
+  dist.init_process_group('nccl', device_id=torch.device('cuda', lr))
+  a = run('nccl'); b = run('fused')
+  if dist.get_rank() == 0:
+    print(json.dumps({'nccl': a, 'fused': b}))
+    assert all(abs(x - y) < 5e-2 for x, y in zip(a, b)), (a, b)
+    print('MGPU_OK')
+  dist.barrier(); dist.destroy_process_group()
+
+if __name__ == '__main__':
+  main()
