@@ -455,12 +455,6 @@ class _DispatchFn(torch.autograd.Function):
 def MoEDispatchIndexed(x2d, gating: NestedMap, g: int, s: int, e: int):
   """tokens `[G*S, M]` → expert inputs `[E, G*C, M]`."""
   slot, valid = _Slots(gating, g, s)
-  if ops.use_cuda_kernels(x2d) and x2d.dtype == torch.bfloat16:
-    from lingvo_b200.ops import moe as moe_ops
-    if moe_ops.available():
-      return moe_ops.dispatch(x2d, slot.reshape(2, -1), valid.reshape(2, -1),
-                              e * g * gating.capacity).reshape(
-                                  e, g * gating.capacity, -1)
   buf = _DispatchFn.apply(x2d, slot.reshape(2, -1), valid.reshape(2, -1),
                           e * g * gating.capacity)
   return buf.reshape(e, g * gating.capacity, x2d.shape[-1])
@@ -470,10 +464,6 @@ def MoECombineIndexed(expert_out, gating: NestedMap, g: int, s: int):
   """expert outputs `[E, G*C, M]` → tokens `[G*S, M]` (gated 2-row gather)."""
   slot, valid = _Slots(gating, g, s)
   flat = expert_out.reshape(-1, expert_out.shape[-1])
-  if ops.use_cuda_kernels(flat) and flat.dtype == torch.bfloat16:
-    from lingvo_b200.ops import moe as moe_ops
-    if moe_ops.available():
-      return moe_ops.combine(flat, slot.reshape(2, -1), gating.gate.reshape(2, -1))
   out = 0
   for k in range(2):
     rows = flat.index_select(0, slot[k].reshape(-1).clamp(0, flat.shape[0] - 1))

@@ -8,7 +8,9 @@ torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, bool a_k
                         const c10::optional<torch::Tensor>& row_scale,
                         const c10::optional<torch::Tensor>& out, bool out_fp32, bool accumulate,
                         const c10::optional<torch::Tensor>& pre_act,
-                        const c10::optional<torch::Tensor>& row_ptrs);
+                        const c10::optional<torch::Tensor>& row_ptrs,
+                        const c10::optional<torch::Tensor>& nblk_ptrs,
+                        const c10::optional<torch::Tensor>& a_peer_ptrs);
 void RegisterAll(pybind11::module& m);
 }  // namespace lb
 
@@ -18,6 +20,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("b_kmajor") = true, py::arg("bias") = py::none(), py::arg("act") = 0,
         py::arg("aux") = py::none(), py::arg("aux_mode") = 0, py::arg("row_scale") = py::none(),
         py::arg("out") = py::none(), py::arg("out_fp32") = false, py::arg("accumulate") = false,
-        py::arg("pre_act") = py::none(), py::arg("row_ptrs") = py::none());
+        py::arg("pre_act") = py::none(), py::arg("row_ptrs") = py::none(),
+        py::arg("nblk_ptrs") = py::none(), py::arg("a_peer_ptrs") = py::none());
   lb::RegisterAll(m);
 }

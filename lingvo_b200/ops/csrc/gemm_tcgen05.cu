@@ -41,6 +41,14 @@ enum Act : int { kActNone = 0, kActRelu = 1, kActGelu = 2, kActSilu = 3, kActGel
                  kActSquaredRelu = 5 };
 enum AuxMode : int { kAuxNone = 0, kAuxReluMask = 1, kAuxAdd = 2 };
 
+// A operand may be split along K over several tensor maps (one per NVLink peer):
+// the TMA producer then *is* the all-gather (tiles are pulled straight from the
+// owning rank's memory), SURVEY K5/K6 "all-gather -> GEMM".
+constexpr int kMaxAMaps = 8;
+struct TmapArray {
+  CUtensorMap m[kMaxAMaps];
+};
+
 struct GemmParams {
   int G, M, N, K;
   void* c;                 // [G, M, N] out (bf16 or fp32)
@@ -51,6 +59,9 @@ struct GemmParams {
   void* pre_act;           // optional second output: pre-activation (bf16), same strides
   const float* row_scale;  // [G, M] or nullptr
   void* const* row_ptrs;   // [G * M] destination row pointers (peer memory) or nullptr
+  void* const* nblk_ptrs;  // [tiles_n] destination base per N-tile (peer slab) or nullptr;
+                           // element (row, col) goes to base[n_blk] + row*ldc + (col - n0)
+  int a_k_per_map;         // K elements covered by each A tensor map (all-gather prologue)
   int act;
   int aux_mode;
   int accumulate;          // C += result (fp32 out only)
@@ -72,7 +83,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 
 template <int BN, bool kAK, bool kBK, typename OutT>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+gemm_tcgen05_kernel(const __grid_constant__ TmapArray tmaps_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   constexpr int kStages = (BN == 256) ? 4 : 6;
   constexpr uint32_t kABytes = kBlockM * kBlockK * 2;   // 16 KiB
@@ -102,7 +113,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
 
   if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmaps_a.m[0]);
     tma_prefetch_desc(&tmap_b);
   }
   if (warp_idx == 1 && lane == 0) {
@@ -143,12 +154,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint32_t sb = sa + kABytes;
           const int k0 = kb * kBlockK;
+          const int amap = k0 / p.a_k_per_map;
+          const int ka = k0 - amap * p.a_k_per_map;
           if constexpr (kAK) {
-            tma_load_3d(sa, &tmap_a, fb, k0, m0, g);
+            tma_load_3d(sa, &tmaps_a.m[amap], fb, ka, m0, g);
           } else {
 #pragma unroll
             for (int i = 0; i < kBlockM / 64; ++i)
-              tma_load_3d(sa + i * (64 * kBlockK * 2), &tmap_a, fb, m0 + 64 * i, k0, g);
+              tma_load_3d(sa + i * (64 * kBlockK * 2), &tmaps_a.m[amap], fb, m0 + 64 * i, ka, g);
           }
           if constexpr (kBK) {
             tma_load_3d(sb, &tmap_b, fb, k0, n0, g);
@@ -222,6 +235,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       OutT* c_row;
       if (p.row_ptrs != nullptr && row_ok) {
         c_row = reinterpret_cast<OutT*>(p.row_ptrs[static_cast<long long>(g) * p.M + row]);
+      } else if (p.nblk_ptrs != nullptr) {
+        c_row = reinterpret_cast<OutT*>(p.nblk_ptrs[n_blk]) + static_cast<long long>(row) * p.ldc - n0;
       } else {
         c_row = reinterpret_cast<OutT*>(p.c) + row_off;
       }
@@ -376,7 +391,7 @@ static CUtensorMap MakeMap(const void* base, int64_t inner, int64_t rows, int64_
 }
 
 template <int BN, bool kAK, bool kBK, typename OutT>
-static void Launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+static void Launch(const TmapArray& ta, const CUtensorMap& tb, const GemmParams& p,
                    cudaStream_t stream, int num_sms) {
   constexpr int kStages = (BN == 256) ? 4 : 6;
   constexpr size_t smem = kStages * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + 1024 + 256;
@@ -395,7 +410,7 @@ static void Launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
 }
 
 template <int BN, typename OutT>
-static void Dispatch(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb,
+static void Dispatch(bool ak, bool bk, const TmapArray& ta, const CUtensorMap& tb,
                      const GemmParams& p, cudaStream_t s, int sms) {
   if (ak && bk) Launch<BN, true, true, OutT>(ta, tb, p, s, sms);
   else if (ak && !bk) Launch<BN, true, false, OutT>(ta, tb, p, s, sms);
@@ -411,7 +426,9 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
                         const c10::optional<torch::Tensor>& row_scale,
                         const c10::optional<torch::Tensor>& out_opt, bool out_fp32,
                         bool accumulate, const c10::optional<torch::Tensor>& pre_act,
-                        const c10::optional<torch::Tensor>& row_ptrs) {
+                        const c10::optional<torch::Tensor>& row_ptrs,
+                        const c10::optional<torch::Tensor>& nblk_ptrs,
+                        const c10::optional<torch::Tensor>& a_peer_ptrs) {
   TORCH_CHECK(a_in.is_cuda() && b_in.is_cuda(), "gemm_bf16: CUDA tensors required");
   TORCH_CHECK(a_in.scalar_type() == torch::kBFloat16 && b_in.scalar_type() == torch::kBFloat16,
               "gemm_bf16: bf16 inputs required");
@@ -435,7 +452,8 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
   const int64_t K = a_kmajor ? a.size(2) : a.size(1);
   const int64_t N = b_kmajor ? b.size(1) : b.size(2);
   const int64_t Kb = b_kmajor ? b.size(2) : b.size(1);
-  TORCH_CHECK(K == Kb, "gemm_bf16: K mismatch ", K, " vs ", Kb);
+  const bool ag_prologue = a_peer_ptrs.has_value() && a_peer_ptrs->defined();
+  TORCH_CHECK(ag_prologue || K == Kb, "gemm_bf16: K mismatch ", K, " vs ", Kb);
   TORCH_CHECK(N % 8 == 0, "gemm_bf16: N must be a multiple of 8");
   auto check_op = [](const torch::Tensor& t) {
     TORCH_CHECK(t.stride(1) % 8 == 0 && (t.size(0) == 1 || t.stride(0) % 8 == 0) &&
@@ -465,6 +483,8 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
   p.c_batch = G > 1 ? out3.stride(0) : 0;
   p.bias = nullptr; p.aux = nullptr; p.row_scale = nullptr; p.pre_act = nullptr;
   p.row_ptrs = nullptr;
+  p.nblk_ptrs = nullptr;
+  p.a_k_per_map = static_cast<int>(K);
   torch::Tensor bias_f;
   if (bias.has_value() && bias->defined()) {
     bias_f = bias->to(torch::kFloat32).contiguous();
@@ -497,6 +517,12 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
                     row_ptrs->is_contiguous(), "gemm_bf16: row_ptrs must be int64 [G, M]");
     p.row_ptrs = reinterpret_cast<void* const*>(row_ptrs->data_ptr());
   }
+  if (nblk_ptrs.has_value() && nblk_ptrs->defined()) {
+    TORCH_CHECK(nblk_ptrs->scalar_type() == torch::kInt64 && nblk_ptrs->is_cuda() &&
+                    nblk_ptrs->is_contiguous(), "gemm_bf16: nblk_ptrs must be CUDA int64");
+    TORCH_CHECK(G == 1, "gemm_bf16: nblk_ptrs needs G == 1");
+    p.nblk_ptrs = reinterpret_cast<void* const*>(nblk_ptrs->data_ptr());
+  }
   p.act = static_cast<int>(act);
   p.aux_mode = p.aux ? static_cast<int>(aux_mode) : 0;
   p.accumulate = accumulate ? 1 : 0;
@@ -507,9 +533,27 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
   // Tile-N: 256 unless N is small.
   const bool bn256 = N > 128;
   const int bn = bn256 ? 256 : 128;
-  CUtensorMap ta = a_kmajor
-      ? MakeMap(a.data_ptr(), K, M, G, a.stride(1), G > 1 ? a.stride(0) : a.stride(1) * a.size(1), kBlockM)
-      : MakeMap(a.data_ptr(), M, K, G, a.stride(1), G > 1 ? a.stride(0) : a.stride(1) * a.size(1), kBlockK);
+  TmapArray ta;
+  if (a_peer_ptrs.has_value() && a_peer_ptrs->defined()) {
+    // `a` is the local K-shard [M, K/W] (K-major); peers hold the other shards at
+    // the given base pointers with identical strides.
+    TORCH_CHECK(a_kmajor && G == 1, "all-gather prologue needs a K-major 2-D A");
+    TORCH_CHECK(a_peer_ptrs->device().is_cpu() && a_peer_ptrs->scalar_type() == torch::kInt64);
+    const int W = static_cast<int>(a_peer_ptrs->numel());
+    TORCH_CHECK(W <= kMaxAMaps);
+    const int64_t k_shard = a.size(2);
+    TORCH_CHECK(k_shard % kBlockK == 0, "K shard must be a multiple of 64");
+    TORCH_CHECK(Kb == k_shard * W, "B's K must equal W * shard K");
+    p.K = static_cast<int>(k_shard * W);
+    p.a_k_per_map = static_cast<int>(k_shard);
+    for (int r = 0; r < W; ++r)
+      ta.m[r] = MakeMap(reinterpret_cast<void*>(a_peer_ptrs->data_ptr<int64_t>()[r]), k_shard, M,
+                        1, a.stride(1), a.stride(1) * a.size(1), kBlockM);
+  } else {
+    ta.m[0] = a_kmajor
+        ? MakeMap(a.data_ptr(), K, M, G, a.stride(1), G > 1 ? a.stride(0) : a.stride(1) * a.size(1), kBlockM)
+        : MakeMap(a.data_ptr(), M, K, G, a.stride(1), G > 1 ? a.stride(0) : a.stride(1) * a.size(1), kBlockK);
+  }
   CUtensorMap tb = b_kmajor
       ? MakeMap(b.data_ptr(), K, N, G, b.stride(1), G > 1 ? b.stride(0) : b.stride(1) * b.size(1), bn)
       : MakeMap(b.data_ptr(), N, K, G, b.stride(1), G > 1 ? b.stride(0) : b.stride(1) * b.size(1), kBlockK);

@@ -64,7 +64,8 @@ def gemm_ref(a, b, a_kmajor=True, b_kmajor=True, bias=None, act=0, aux=None,
 
 def gemm(a, b, a_kmajor=True, b_kmajor=True, bias=None, act=0, aux=None,
          aux_mode=0, row_scale=None, out=None, out_fp32=False,
-         accumulate=False, pre_act=None, row_ptrs=None):
+         accumulate=False, pre_act=None, row_ptrs=None, nblk_ptrs=None,
+         a_peer_ptrs=None):
   """C[g] = epi(A[g] · B[g]^T); see csrc/gemm_tcgen05.cu for operand layouts."""
   act = ACT_IDS[act] if not isinstance(act, int) else act
   if not ops.use_cuda_kernels(a, b):
@@ -79,7 +80,7 @@ def gemm(a, b, a_kmajor=True, b_kmajor=True, bias=None, act=0, aux=None,
     return y
   res = ops.native().gemm_bf16(a, b, a_kmajor, b_kmajor, bias, act, aux,
                                aux_mode, row_scale, out, out_fp32, accumulate,
-                               pre_act, row_ptrs)
+                               pre_act, row_ptrs, nblk_ptrs, a_peer_ptrs)
   if out is None and a.dim() == 2:
     res = res[0]
   return res
