@@ -515,6 +515,13 @@ class BaseLayer(metaclass=BaseLayerMeta):
           acc._value = acc._value.to(device)  # pylint: disable=protected-access
     return self
 
+  def Device(self) -> torch.device:
+    """Device of this layer's (or its descendants') first variable."""
+    for _, layer in self.Walk():
+      for v in layer._private_vars.values():  # pylint: disable=protected-access
+        return v.device
+    return py_utils.CurrentDevice()
+
   def cuda(self, index=None):  # pylint: disable=invalid-name
     return self.to(torch.device('cuda', index if index is not None
                                 else torch.cuda.current_device()))

@@ -947,6 +947,22 @@ def CombineMetrics(loss_metric_weight_pairs):
 # ----------------------------------------------------------------------------
 # Padding / sequence helpers
 # ----------------------------------------------------------------------------
+def FPropDtype(params):
+  """`fprop_dtype` if set, else `dtype` (ref `py_utils.FPropDtype`)."""
+  return params.fprop_dtype if params.fprop_dtype is not None else params.dtype
+
+
+def Softmax(logits, axis=-1, extra_logit=None, name=None):
+  """Softmax with an optional constant extra logit in the denominator
+  (ref `py_utils.py` Softmax)."""
+  del name
+  if extra_logit is None:
+    return torch.softmax(logits, axis)
+  mx = torch.clamp(logits.max(axis, keepdim=True).values.detach(), min=float(extra_logit))
+  e = torch.exp(logits - mx)
+  return e / (e.sum(axis, keepdim=True) + torch.exp(extra_logit - mx))
+
+
 def ApplyPadding(padding, x, padded=None, use_select=True, ensure_shape=True):
   """Zeros (or substitutes `padded`) where padding==1; broadcasts trailing."""
   padding = padding.to(x.device)

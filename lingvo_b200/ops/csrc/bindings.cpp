@@ -10,7 +10,7 @@ torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, bool a_k
                         const c10::optional<torch::Tensor>& pre_act,
                         const c10::optional<torch::Tensor>& row_ptrs,
                         const c10::optional<torch::Tensor>& nblk_ptrs,
-                        const c10::optional<torch::Tensor>& a_peer_ptrs);
+                        const c10::optional<torch::Tensor>& a_peer_ptrs, int64_t nblk_ld);
 void RegisterAll(pybind11::module& m);
 }  // namespace lb
 
@@ -21,6 +21,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("aux") = py::none(), py::arg("aux_mode") = 0, py::arg("row_scale") = py::none(),
         py::arg("out") = py::none(), py::arg("out_fp32") = false, py::arg("accumulate") = false,
         py::arg("pre_act") = py::none(), py::arg("row_ptrs") = py::none(),
-        py::arg("nblk_ptrs") = py::none(), py::arg("a_peer_ptrs") = py::none());
+        py::arg("nblk_ptrs") = py::none(), py::arg("a_peer_ptrs") = py::none(), py::arg("nblk_ld") = 0);
   lb::RegisterAll(m);
 }

@@ -35,7 +35,7 @@ namespace lb {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 
 enum Act : int { kActNone = 0, kActRelu = 1, kActGelu = 2, kActSilu = 3, kActGeluTanh = 4,
                  kActSquaredRelu = 5 };
@@ -81,6 +81,116 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+struct EpiRow {
+  void* c_row;
+  long long row_off;
+  const float* bias;
+  float rscale;
+  bool store_ok;
+};
+
+template <int kAct>
+__device__ __forceinline__ void act32(float (&f)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], kAct);
+}
+
+// One 32-column chunk of one output row: bias / pre-act tap / activation /
+// aux (ReLU-mask or residual add) / row scale / convert / store.
+template <typename OutT>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const EpiRow& er,
+                                               const uint32_t (&v)[32], int col0) {
+  if (!er.store_ok || col0 >= p.N) return;
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (er.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (col0 + i < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(er.bias + col0 + i));
+        f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+      }
+    }
+  }
+  if (p.pre_act != nullptr) {
+    __nv_bfloat16* pr = reinterpret_cast<__nv_bfloat16*>(p.pre_act) + er.row_off + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      if (col0 + i < p.N) {
+        int4 o;
+        o.x = pack_bf16x2(f[i], f[i + 1]);
+        o.y = pack_bf16x2(f[i + 2], f[i + 3]);
+        o.z = pack_bf16x2(f[i + 4], f[i + 5]);
+        o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+        st_v4(pr + i, o);
+      }
+    }
+  }
+  switch (p.act) {   // hoisted: one uniform branch per chunk, not per element
+    case kActRelu: act32<kActRelu>(f); break;
+    case kActGelu: act32<kActGelu>(f); break;
+    case kActSilu: act32<kActSilu>(f); break;
+    case kActGeluTanh: act32<kActGeluTanh>(f); break;
+    case kActSquaredRelu: act32<kActSquaredRelu>(f); break;
+    default: break;
+  }
+  if (p.aux_mode != kAuxNone) {
+    const __nv_bfloat16* ax = p.aux + er.row_off + col0;
+    const bool mask = p.aux_mode == kAuxReluMask;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      if (col0 + i < p.N) {
+        const int4 a = *reinterpret_cast<const int4*>(ax + i);
+        const uint32_t w[4] = {static_cast<uint32_t>(a.x), static_cast<uint32_t>(a.y),
+                               static_cast<uint32_t>(a.z), static_cast<uint32_t>(a.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = unpack_bf16x2(w[j]);
+          if (mask) {
+            f[i + 2 * j] = t.x > 0.f ? f[i + 2 * j] : 0.f;
+            f[i + 2 * j + 1] = t.y > 0.f ? f[i + 2 * j + 1] : 0.f;
+          } else {
+            f[i + 2 * j] += t.x;
+            f[i + 2 * j + 1] += t.y;
+          }
+        }
+      }
+    }
+  }
+  if (p.row_scale != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] *= er.rscale;
+  }
+  if constexpr (sizeof(OutT) == 2) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(er.c_row) + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      if (col0 + i < p.N) {
+        int4 o;
+        o.x = pack_bf16x2(f[i], f[i + 1]);
+        o.y = pack_bf16x2(f[i + 2], f[i + 3]);
+        o.z = pack_bf16x2(f[i + 4], f[i + 5]);
+        o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+        st_v4(out + i, o);
+      }
+    }
+  } else {
+    float* out = reinterpret_cast<float*>(er.c_row) + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (col0 + i < p.N) {
+        float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        if (p.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(out + i);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(out + i) = o;
+      }
+    }
+  }
+}
+
 template <int BN, bool kAK, bool kBK, typename OutT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ TmapArray tmaps_a,
@@ -123,7 +233,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapArray tmaps_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 8);
     }
     fence_barrier_init();
   }
@@ -215,7 +325,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapArray tmaps_a,
     __syncwarp();
   } else if (warp_idx >= 4) {
     // ============================== epilogue ==============================
-    const int q = warp_idx - 4;                 // TMEM lane quarter
+    // 8 warps: warp w owns TMEM lanes 32*(w%4).. and one half of the tile's columns.
+    const int q = warp_idx & 3;                 // TMEM lane quarter
+    const int half = (warp_idx - 4) >> 2;       // column half
+    constexpr int kChunks = BN / 64;            // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -227,112 +340,38 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapArray tmaps_a,
       const int n0 = n_blk * BN;
       const bool row_ok = row < p.M;
 
+      EpiRow er;
+      er.row_off = static_cast<long long>(g) * p.c_batch + static_cast<long long>(row) * p.ldc;
+      if (p.row_ptrs != nullptr && row_ok) {
+        er.c_row = p.row_ptrs[static_cast<long long>(g) * p.M + row];
+      } else if (p.nblk_ptrs != nullptr) {
+        er.c_row = reinterpret_cast<OutT*>(p.nblk_ptrs[n_blk]) + static_cast<long long>(row) * p.ldc - n0;
+      } else {
+        er.c_row = reinterpret_cast<OutT*>(p.c) + er.row_off;
+      }
+      er.store_ok = row_ok && (er.c_row != nullptr);
+      er.rscale = (p.row_scale != nullptr && row_ok)
+                      ? p.row_scale[static_cast<long long>(g) * p.M + row] : 1.f;
+      er.bias = p.bias ? p.bias + static_cast<long long>(g) * p.N : nullptr;
+
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tc_fence_after();
 
-      const long long row_off = static_cast<long long>(g) * p.c_batch +
-                                static_cast<long long>(row) * p.ldc;
-      OutT* c_row;
-      if (p.row_ptrs != nullptr && row_ok) {
-        c_row = reinterpret_cast<OutT*>(p.row_ptrs[static_cast<long long>(g) * p.M + row]);
-      } else if (p.nblk_ptrs != nullptr) {
-        c_row = reinterpret_cast<OutT*>(p.nblk_ptrs[n_blk]) + static_cast<long long>(row) * p.ldc - n0;
-      } else {
-        c_row = reinterpret_cast<OutT*>(p.c) + row_off;
-      }
-      const bool store_ok = row_ok && (c_row != nullptr);
-      const float rscale = (p.row_scale != nullptr && row_ok)
-                               ? p.row_scale[static_cast<long long>(g) * p.M + row] : 1.f;
-      const float* bias = p.bias ? p.bias + static_cast<long long>(g) * p.N : nullptr;
-
+      // Software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is
+      // converted and stored.
+      const uint32_t tbase = tmem_base + acc * BN + half * (BN / 2) +
+                             (static_cast<uint32_t>(q * 32) << 16);
+      const int cbase = n0 + half * (BN / 2);
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(tbase, va);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16);
-        tmem_ld_32x32b_x32(taddr, v);
+      for (int c = 0; c < kChunks; c += 2) {
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (store_ok && col0 < p.N) {
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) f[i] += __ldg(bias + col0 + i);
-          }
-          if (p.pre_act != nullptr) {
-            __nv_bfloat16* pr = reinterpret_cast<__nv_bfloat16*>(p.pre_act) + row_off + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (col0 + i < p.N) {
-                int4 o;
-                o.x = pack_bf16x2(f[i], f[i + 1]);
-                o.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                o.z = pack_bf16x2(f[i + 4], f[i + 5]);
-                o.w = pack_bf16x2(f[i + 6], f[i + 7]);
-                st_v4(pr + i, o);
-              }
-            }
-          }
-          if (p.act != kActNone) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], p.act);
-          }
-          if (p.aux_mode != kAuxNone) {
-            const __nv_bfloat16* ax = p.aux + row_off + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (col0 + i < p.N) {
-                int4 a = *reinterpret_cast<const int4*>(ax + i);
-                const uint32_t w[4] = {static_cast<uint32_t>(a.x), static_cast<uint32_t>(a.y),
-                                       static_cast<uint32_t>(a.z), static_cast<uint32_t>(a.w)};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float2 t = unpack_bf16x2(w[j]);
-                  if (p.aux_mode == kAuxReluMask) {
-                    f[i + 2 * j] = t.x > 0.f ? f[i + 2 * j] : 0.f;
-                    f[i + 2 * j + 1] = t.y > 0.f ? f[i + 2 * j + 1] : 0.f;
-                  } else {
-                    f[i + 2 * j] += t.x;
-                    f[i + 2 * j + 1] += t.y;
-                  }
-                }
-              }
-            }
-          }
-          if (p.row_scale != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] *= rscale;
-          }
-          if constexpr (sizeof(OutT) == 2) {
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(c_row) + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (col0 + i < p.N) {
-                int4 o;
-                o.x = pack_bf16x2(f[i], f[i + 1]);
-                o.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                o.z = pack_bf16x2(f[i + 4], f[i + 5]);
-                o.w = pack_bf16x2(f[i + 6], f[i + 7]);
-                st_v4(out + i, o);
-              }
-            }
-          } else {
-            float* out = reinterpret_cast<float*>(c_row) + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (col0 + i < p.N) {
-                float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                if (p.accumulate) {
-                  float4 old = *reinterpret_cast<float4*>(out + i);
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                *reinterpret_cast<float4*>(out + i) = o;
-              }
-            }
-          }
-        }
+        tmem_ld_32x32b_x32(tbase + (c + 1) * 32, vb);
+        epilogue_chunk<OutT>(p, er, va, cbase + c * 32);
+        tmem_ld_wait();
+        if (c + 2 < kChunks) tmem_ld_32x32b_x32(tbase + (c + 2) * 32, va);
+        epilogue_chunk<OutT>(p, er, vb, cbase + (c + 1) * 32);
       }
       // Release this accumulator stage back to the MMA warp.
       tc_fence_before();
@@ -428,7 +467,7 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
                         bool accumulate, const c10::optional<torch::Tensor>& pre_act,
                         const c10::optional<torch::Tensor>& row_ptrs,
                         const c10::optional<torch::Tensor>& nblk_ptrs,
-                        const c10::optional<torch::Tensor>& a_peer_ptrs) {
+                        const c10::optional<torch::Tensor>& a_peer_ptrs, int64_t nblk_ld) {
   TORCH_CHECK(a_in.is_cuda() && b_in.is_cuda(), "gemm_bf16: CUDA tensors required");
   TORCH_CHECK(a_in.scalar_type() == torch::kBFloat16 && b_in.scalar_type() == torch::kBFloat16,
               "gemm_bf16: bf16 inputs required");
@@ -521,7 +560,12 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
     TORCH_CHECK(nblk_ptrs->scalar_type() == torch::kInt64 && nblk_ptrs->is_cuda() &&
                     nblk_ptrs->is_contiguous(), "gemm_bf16: nblk_ptrs must be CUDA int64");
     TORCH_CHECK(G == 1, "gemm_bf16: nblk_ptrs needs G == 1");
+    TORCH_CHECK(!fp32 && N > 128 && nblk_ld > 0 && nblk_ld % 8 == 0 &&
+                    nblk_ptrs->numel() == (N + 255) / 256,
+                "gemm_bf16: nblk_ptrs needs bf16 out, one pointer per 256-column tile and nblk_ld");
     p.nblk_ptrs = reinterpret_cast<void* const*>(nblk_ptrs->data_ptr());
+    p.ldc = nblk_ld;
+    TORCH_CHECK(p.aux == nullptr && p.pre_act == nullptr, "gemm_bf16: nblk_ptrs excludes aux/pre_act");
   }
   p.act = static_cast<int>(act);
   p.aux_mode = p.aux ? static_cast<int>(aux_mode) : 0;
@@ -555,8 +599,8 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
         : MakeMap(a.data_ptr(), M, K, G, a.stride(1), G > 1 ? a.stride(0) : a.stride(1) * a.size(1), kBlockK);
   }
   CUtensorMap tb = b_kmajor
-      ? MakeMap(b.data_ptr(), K, N, G, b.stride(1), G > 1 ? b.stride(0) : b.stride(1) * b.size(1), bn)
-      : MakeMap(b.data_ptr(), N, K, G, b.stride(1), G > 1 ? b.stride(0) : b.stride(1) * b.size(1), kBlockK);
+      ? MakeMap(b.data_ptr(), Kb, N, G, b.stride(1), G > 1 ? b.stride(0) : b.stride(1) * b.size(1), bn)
+      : MakeMap(b.data_ptr(), N, Kb, G, b.stride(1), G > 1 ? b.stride(0) : b.stride(1) * b.size(1), kBlockK);
 
   cudaStream_t stream = at::cuda::getCurrentCUDAStream();
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;

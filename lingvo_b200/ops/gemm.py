@@ -65,7 +65,7 @@ def gemm_ref(a, b, a_kmajor=True, b_kmajor=True, bias=None, act=0, aux=None,
 def gemm(a, b, a_kmajor=True, b_kmajor=True, bias=None, act=0, aux=None,
          aux_mode=0, row_scale=None, out=None, out_fp32=False,
          accumulate=False, pre_act=None, row_ptrs=None, nblk_ptrs=None,
-         a_peer_ptrs=None):
+         a_peer_ptrs=None, nblk_ld=0):
   """C[g] = epi(A[g] · B[g]^T); see csrc/gemm_tcgen05.cu for operand layouts."""
   act = ACT_IDS[act] if not isinstance(act, int) else act
   if not ops.use_cuda_kernels(a, b):
@@ -80,7 +80,7 @@ def gemm(a, b, a_kmajor=True, b_kmajor=True, bias=None, act=0, aux=None,
     return y
   res = ops.native().gemm_bf16(a, b, a_kmajor, b_kmajor, bias, act, aux,
                                aux_mode, row_scale, out, out_fp32, accumulate,
-                               pre_act, row_ptrs, nblk_ptrs, a_peer_ptrs)
+                               pre_act, row_ptrs, nblk_ptrs, a_peer_ptrs, nblk_ld)
   if out is None and a.dim() == 2:
     res = res[0]
   return res
@@ -130,6 +130,37 @@ def linear(x, w, bias=None, act=None):
     return _act_ref(y, act).reshape(*lead, w.shape[-1])
   y = _LinearFn.apply(x2, w, bias, act)
   return y.reshape(*lead, w.shape[-1])
+
+
+class _LinearTFn(torch.autograd.Function):
+  """y = x @ wᵀ + b for a weight stored `[N, K]` (K-major B operand)."""
+
+  @staticmethod
+  def forward(ctx, x, w, bias):
+    ctx.has_bias = bias is not None
+    ctx.save_for_backward(x, w)
+    return gemm(x, w, True, True, bias=bias)
+
+  @staticmethod
+  def backward(ctx, dy):
+    x, w = ctx.saved_tensors
+    dy = dy.contiguous()
+    dx = gemm(dy, w, True, False) if ctx.needs_input_grad[0] else None
+    dw = gemm(dy, x, False, False) if ctx.needs_input_grad[1] else None
+    db = dy.float().sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+    return dx, dw, db
+
+
+def linear_t(x, w, bias=None):
+  """x[..., K] @ w[N, K]ᵀ (+bias): output projections stored `[D, N·H]`."""
+  lead = x.shape[:-1]
+  x2 = x.reshape(-1, x.shape[-1])
+  if x2.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or not x2.is_cuda:
+    y = torch.matmul(x2, w.t())
+    if bias is not None:
+      y = y + bias.to(y.dtype)
+    return y.reshape(*lead, w.shape[0])
+  return _LinearTFn.apply(x2, w, bias).reshape(*lead, w.shape[0])
 
 
 def grouped_linear(x, w, bias=None, act=None):
