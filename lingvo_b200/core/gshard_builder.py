@@ -220,6 +220,16 @@ class SelfAttentionLayer(_BuilderLayer):
     SelfAttentionLayer._MASK_CACHE['k'] = (key, mask)
     return mask
 
+  def _RelTable(self, theta, l, device):
+    """fp32 `[H, 2L-1]` table indexed by (query_pos - key_pos + L - 1)."""
+    b = self.bp
+    bidi = (not self.params.decoder) or b.decoder_bidirectional_relative_attention
+    rel = torch.arange(l - 1, -l, -1, device=device)           # key - query
+    bucket = RelativePositionBucket(
+        rel, b.relative_attention_num_buckets,
+        b.relative_attention_max_distance, bidirectional=bidi)
+    return theta.wrb.float()[:, bucket.long()]
+
   def _Bias(self, theta, segment_id, segment_pos, dtype=torch.float32):
     """Additive bias `[B or 1, H or 1, L, L]` in `dtype`."""
     b = self.bp
@@ -272,6 +282,19 @@ class SelfAttentionLayer(_BuilderLayer):
       q = _Rope(q, segment_pos, b.rope_emb_max_timescale)
       k = _Rope(k, segment_pos, b.rope_emb_max_timescale)
     simple = (not b.atten_logit_cap) and b.attention_extra_logit is None
+    drop = b.attention_dropout_prob if not self.do_eval else 0.0
+    if (simple and self.params.relative_bias and
+        b.relative_attention_use_universal_1d_position):
+      from lingvo_b200.ops import attention as attention_ops
+      rel = self._RelTable(theta, l, x.device)
+      if attention_ops.rel_bias_attention_supported(q, k, rel, drop):
+        # cuDNN fused attention + our bias-build / tcgen05 bias-gradient kernels.
+        mask = self._Mask(segment_id, segment_pos, torch.float32)
+        o = attention_ops.rel_bias_attention(
+            q, k, v, rel, mask, 1.0,
+            causal=self.params.decoder and not b.decoder_skip_causal_mask)
+        out = gemm.linear(o.reshape(bsz, l, h * d), wo.to(x.dtype))
+        return out, torch.zeros((), device=x.device, dtype=torch.float32)
     bias = self._Bias(theta, segment_id, segment_pos,
                       x.dtype if (simple and x.is_cuda) else torch.float32)
     o = _AttentionCore(q, k, v, bias, b.atten_logit_cap,

@@ -76,3 +76,85 @@ def dot_product_attention(q, k, v, bias=None, scale=1.0, logit_cap=0.0,
       q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=mask,
       dropout_p=dropout_prob, scale=scale)
   return o.transpose(1, 2)
+
+
+# ------------------------------------------------- relative-bias attention ----
+def _RelToeplitz(rel, l):
+  """rel [H, 2L-1] indexed by (i - j + L - 1) → [H, L, L] (strided view)."""
+  return rel.flip(-1).unfold(-1, l, 1).flip(1)
+
+
+def rel_bias_attention_ref(q, k, v, rel, mask=None, scale=1.0):
+  """fp32 oracle: softmax(scale·q·kᵀ + rel[h, i-j+L-1] + mask[b,i,j])·v."""
+  l = q.shape[1]
+  bias = _RelToeplitz(rel.float(), l).unsqueeze(0)
+  if mask is not None:
+    bias = bias + mask.float().reshape(-1, 1, l, l)
+  return attention_ref(q, k, v, bias, scale)
+
+
+class _RelBiasAttnFn(torch.autograd.Function):
+  """Flash attention with a learned Toeplitz bias.
+
+  forward : `build_rel_bias` (ours) → cuDNN fused attention (library, like
+            cuBLAS for plain GEMMs) producing O and the log-sum-exp.
+  backward: cuDNN fused backward for dQ/dK/dV + `rel_bias_grad` (our tcgen05
+            kernel) for the bias-table gradient, which cuDNN cannot produce.
+  """
+
+  @staticmethod
+  def forward(ctx, q, k, v, rel, mask, scale, causal):
+    from lingvo_b200 import ops
+    nat = ops.native()
+    b, l, h, d = q.shape
+    bias = nat.build_rel_bias(rel.float().contiguous(), mask, b)
+    qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+    res = torch.ops.aten._scaled_dot_product_cudnn_attention(
+        qt, kt, vt, bias, True, 0.0, False, False, scale=scale)
+    out, lse = res[0], res[1]
+    ctx.save_for_backward(q, k, v, out, lse, bias, res[2], res[3], res[6], res[7])
+    ctx.meta = (res[4], res[5], scale, causal)
+    return out.transpose(1, 2)
+
+  @staticmethod
+  def backward(ctx, d_o):
+    from lingvo_b200 import ops
+    nat = ops.native()
+    q, k, v, out, lse, bias, cq, ck, seed, off = ctx.saved_tensors
+    max_q, max_k, scale, causal = ctx.meta
+    b, l, h, d = q.shape
+    d_o = d_o.contiguous()                                   # [B, L, H, D]
+    dq, dk, dv = torch.ops.aten._scaled_dot_product_cudnn_attention_backward(
+        d_o.transpose(1, 2), q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+        out, lse, seed, off, bias, cq, ck, max_q, max_k, 0.0, False, scale=scale)
+    drel = None
+    if ctx.needs_input_grad[3]:
+      o_blhd = out.transpose(1, 2)
+      delta = (d_o.float() * o_blhd.float()).sum(-1).permute(0, 2, 1).contiguous()
+      lse3 = lse.reshape(b, h, l).float().contiguous()
+      drel = nat.rel_bias_grad(q.contiguous(), k.contiguous(), v.contiguous(), d_o,
+                               lse3, delta, bias, scale, causal)
+    return (dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), drel,
+            None, None, None)
+
+
+def rel_bias_attention_supported(q, k, rel, dropout_prob=0.0):
+  from lingvo_b200 import ops
+  return (ops.use_cuda_kernels(q) and q.dtype == torch.bfloat16 and
+          q.shape[-1] == 128 and q.shape[1] % 128 == 0 and
+          q.shape[1] == k.shape[1] and q.shape[2] == k.shape[2] and
+          not dropout_prob and rel.shape[-1] == 2 * q.shape[1] - 1)
+
+
+def rel_bias_attention(q, k, v, rel, mask=None, scale=1.0, causal=False):
+  """`[B,L,H,D]` self-attention with bias `rel[h, i-j+L-1] + mask[b,i,j]`.
+
+  `causal=True` promises that `mask` hides every j > i, which lets the bias
+  gradient kernel skip the upper-triangular tiles.
+  """
+  if not rel_bias_attention_supported(q, k, rel):
+    return rel_bias_attention_ref(q, k, v, rel, mask, scale).to(q.dtype)
+  if mask is not None:
+    mask = mask.reshape(-1, q.shape[1], q.shape[1])
+  return _RelBiasAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(),
+                              rel, mask, float(scale), bool(causal))

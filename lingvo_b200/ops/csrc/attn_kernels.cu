@@ -1,0 +1,344 @@
+// Relative-position-bias attention support kernels.
+//
+//   build_rel_bias : bias[b,h,i,j] = rel[h, i-j+L-1] + mask[b,i,j]  (bf16)
+//       one pass, never materialises the fp32 Toeplitz or the broadcast sum.
+//   rel_bias_grad  : d rel[h, i-j+L-1] = sum_b sum_{(i,j) on that diagonal} dS[b,h,i,j],
+//       dS = P o (dP - delta),  P = exp(scale*QK^T + bias - lse),  dP = dO V^T.
+//       tcgen05 kernel: both 128x128x128 GEMMs of a (h, i-block, j-block) tile are
+//       issued by one thread into TMEM (S and dP, double buffered over the batch
+//       loop), operands arrive by TMA (SWIZZLE_128B), the four epilogue warps
+//       recompute the softmax from the saved log-sum-exp, accumulate dS over the
+//       batch in registers and reduce it along diagonals in shared memory, so
+//       neither P, dS nor the [H,L,L] bias gradient ever reaches HBM.
+//
+// Layouts: q,k,v,dO  [B, L, H, D] bf16 (BLHD, D = 128);  lse, delta [B, H, L] fp32;
+//          bias [B, H, L, L] bf16;  rel / drel [H, 2L-1] fp32.
+
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <torch/extension.h>
+
+#include "ptx.cuh"
+#include "registry.h"
+
+namespace lb {
+
+CUtensorMap MakeMap(const void* base, int64_t inner, int64_t rows, int64_t groups,
+                    int64_t row_stride, int64_t group_stride, int box_rows,
+                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, int elem_bytes = 2);
+
+namespace {
+
+// ------------------------------------------------------------ build_rel_bias --
+__global__ void __launch_bounds__(256)
+build_rel_bias_kernel(const float* __restrict__ rel, const float* __restrict__ mask,
+                      __nv_bfloat16* __restrict__ bias, int B, int H, int L, int mask_b) {
+  // one block per (b, i) row and a slab of heads; threads stride over j in 8-wide vectors
+  const int i = blockIdx.x;
+  const int b = blockIdx.y;
+  const float* mrow = mask ? mask + (static_cast<long long>(mask_b > 1 ? b : 0) * L + i) * L : nullptr;
+  const int vec_per_row = L / 8;
+  for (int t = threadIdx.x; t < H * vec_per_row; t += blockDim.x) {
+    const int h = t / vec_per_row;
+    const int j0 = (t - h * vec_per_row) * 8;
+    const float* r = rel + static_cast<long long>(h) * (2 * L - 1) + (i - j0 + L - 1);
+    float f[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float m = mrow ? mrow[j0 + u] : 0.f;
+      f[u] = fmaxf(r[-u] + m, -2.3e38f);
+    }
+    int4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    __nv_bfloat16* dst = bias + ((static_cast<long long>(b) * H + h) * L + i) * L + j0;
+    *reinterpret_cast<int4*>(dst) = o;
+  }
+}
+
+// -------------------------------------------------------------- rel_bias_grad --
+constexpr int kT = 128;                       // tile edge (queries / keys)
+constexpr int kD = 128;                       // head dim
+constexpr int kChunkBytes = kT * 64 * 2;      // one [128 x 64] SW128 sub-tile = 16 KiB
+constexpr int kTileBytes = 2 * kChunkBytes;   // [128 x 128] operand = 32 KiB
+constexpr int kSlotBytes = 2 * kTileBytes;    // A + B operand of one GEMM = 64 KiB
+constexpr int kSlots = 3;
+constexpr int kThreads = 256;
+constexpr uint32_t kTmemCols = 512;           // 2 stages x (S | dP) x 128 columns
+
+struct GradParams {
+  const float* lse;      // [B, H, L]
+  const float* delta;    // [B, H, L]
+  const __nv_bfloat16* bias;   // [B, H, L, L]
+  float* drel;           // [H, 2L-1]
+  int B, H, L;
+  float scale;
+  int causal;            // skip tiles strictly above the diagonal
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+rel_bias_grad_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_v,
+                     const GradParams p) {
+  const int nblk = p.L / kT;
+  const int i_blk = blockIdx.x / nblk;
+  const int j_blk = blockIdx.x - i_blk * nblk;
+  const int h = blockIdx.y;
+  if (p.causal && j_blk > i_blk) return;      // whole CTA exits together: no barriers touched yet
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSlots * kSlotBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kSlots;
+  uint64_t* tmem_full_bar = bars + 2 * kSlots;
+  uint64_t* tmem_empty_bar = bars + 2 * kSlots + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 4);
+  float* sdiag = reinterpret_cast<float*>(bars + 2 * kSlots + 6);   // [256]
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int i0 = i_blk * kT, j0 = j_blk * kT;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_do);
+    tma_prefetch_desc(&map_v);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tmem_full_bar[s]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc<kTmemCols>(smem_u32(tmem_ptr_smem));
+    tmem_relinquish();
+  }
+  if (threadIdx.x < 256) sdiag[threadIdx.x] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int b = 0; b < p.B; ++b) {
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[slot]);
+          mbar_arrive_expect_tx(fb, kSlotBytes);
+          const uint32_t sa = smem_u32(smem + slot * kSlotBytes);
+          const uint32_t sb = sa + kTileBytes;
+          const CUtensorMap* ma = g ? &map_do : &map_q;
+          const CUtensorMap* mb = g ? &map_v : &map_k;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tma_load_3d(sa + c * kChunkBytes, ma, fb, h * kD + c * 64, i0, b);
+            tma_load_3d(sb + c * kChunkBytes, mb, fb, h * kD + c * 64, j0, b);
+          }
+          if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ============================= MMA issuer =============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1, 1, false, false, kT, kT);
+      int slot = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int b = 0; b < p.B; ++b) {
+        mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(smem_u32(&full_bar[slot]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + slot * kSlotBytes);
+          const uint32_t sb = sa + kTileBytes;
+          const uint32_t tmem_d = tmem_base + acc * 256 + g * 128;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t adesc = make_smem_desc_sw128(sa + c * kChunkBytes + j * 32, 16, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(sb + c * kChunkBytes + j * 32, 16, 1024);
+              umma_f16(tmem_d, adesc, bdesc, idesc, (c | j) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[slot]));
+          if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tmem_full_bar[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx >= 4) {
+    // ======================= softmax-recompute epilogue ====================
+    const int q = warp_idx - 4;
+    const int row = q * 32 + lane;
+    const int i = i0 + row;
+    float ds[kT];
+#pragma unroll
+    for (int c = 0; c < kT; ++c) ds[c] = 0.f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int b = 0; b < p.B; ++b) {
+      const long long bh = static_cast<long long>(b) * p.H + h;
+      const float lse = p.lse[bh * p.L + i];
+      const float delta = p.delta[bh * p.L + i];
+      const __nv_bfloat16* brow = p.bias + (bh * p.L + i) * p.L + j0;
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t t_s = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t vs[32], vp[32];
+        tmem_ld_32x32b_x32(t_s + c * 32, vs);
+        tmem_ld_32x32b_x32(t_s + 128 + c * 32, vp);
+        int4 bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bv[u] = ld_nc_v4(brow + c * 32 + u * 8);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t w[4] = {static_cast<uint32_t>(bv[u].x), static_cast<uint32_t>(bv[u].y),
+                                 static_cast<uint32_t>(bv[u].z), static_cast<uint32_t>(bv[u].w)};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 bb = unpack_bf16x2(w[e]);
+            const int k0 = u * 8 + e * 2;
+            const float s0 = __uint_as_float(vs[k0]) * p.scale + bb.x - lse;
+            const float s1 = __uint_as_float(vs[k0 + 1]) * p.scale + bb.y - lse;
+            const float p0 = __expf(s0);
+            const float p1 = __expf(s1);
+            ds[c * 32 + k0] += p0 * (__uint_as_float(vp[k0]) - delta);
+            ds[c * 32 + k0 + 1] += p1 * (__uint_as_float(vp[k0 + 1]) - delta);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    // Diagonal (Toeplitz) reduction: element (row, col) lies on diagonal row - col.
+#pragma unroll
+    for (int c = 0; c < kT; ++c) atomicAdd(&sdiag[row - c + (kT - 1)], ds[c]);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float* out = p.drel + static_cast<long long>(h) * (2 * p.L - 1) + (i0 - j0) + (p.L - 1) - (kT - 1);
+    for (int t = row; t < 2 * kT - 1; t += 128) atomicAdd(out + t, sdiag[t]);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace
+
+torch::Tensor build_rel_bias(const torch::Tensor& rel, const c10::optional<torch::Tensor>& mask,
+                             int64_t batch) {
+  TORCH_CHECK(rel.is_cuda() && rel.scalar_type() == torch::kFloat32 && rel.dim() == 2 &&
+              rel.is_contiguous(), "build_rel_bias: rel must be fp32 [H, 2L-1]");
+  const int64_t H = rel.size(0);
+  const int64_t L = (rel.size(1) + 1) / 2;
+  TORCH_CHECK(L % 8 == 0, "build_rel_bias: L must be a multiple of 8");
+  const c10::cuda::CUDAGuard guard(rel.device());
+  const float* mptr = nullptr;
+  int mask_b = 1;
+  torch::Tensor m;
+  if (mask.has_value() && mask->defined()) {
+    m = mask->to(torch::kFloat32).contiguous();
+    TORCH_CHECK(m.numel() == L * L || m.numel() == batch * L * L, "build_rel_bias: mask shape");
+    mask_b = m.numel() == L * L ? 1 : static_cast<int>(batch);
+    mptr = m.data_ptr<float>();
+  }
+  auto bias = torch::empty({batch, H, L, L}, rel.options().dtype(torch::kBFloat16));
+  dim3 grid(static_cast<unsigned>(L), static_cast<unsigned>(batch));
+  build_rel_bias_kernel<<<grid, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      rel.data_ptr<float>(), mptr, reinterpret_cast<__nv_bfloat16*>(bias.data_ptr()),
+      static_cast<int>(batch), static_cast<int>(H), static_cast<int>(L), mask_b);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  CountLaunch();
+  return bias;
+}
+
+// Returns d rel [H, 2L-1] (fp32).
+torch::Tensor rel_bias_grad(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v,
+                            const torch::Tensor& d_out, const torch::Tensor& lse,
+                            const torch::Tensor& delta, const torch::Tensor& bias, double scale,
+                            bool causal) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == torch::kBFloat16 && q.dim() == 4 && q.is_contiguous(),
+              "rel_bias_grad: q must be contiguous bf16 [B, L, H, D]");
+  const int64_t B = q.size(0), L = q.size(1), H = q.size(2), D = q.size(3);
+  TORCH_CHECK(D == kD && L % kT == 0, "rel_bias_grad: needs D == 128 and L % 128 == 0");
+  for (const torch::Tensor* t : {&k, &v, &d_out})
+    TORCH_CHECK(t->sizes() == q.sizes() && t->is_contiguous() && t->scalar_type() == torch::kBFloat16,
+                "rel_bias_grad: k/v/dO must match q");
+  TORCH_CHECK(lse.scalar_type() == torch::kFloat32 && lse.is_contiguous() && lse.numel() == B * H * L);
+  TORCH_CHECK(delta.scalar_type() == torch::kFloat32 && delta.is_contiguous() && delta.numel() == B * H * L);
+  TORCH_CHECK(bias.scalar_type() == torch::kBFloat16 && bias.is_contiguous() &&
+              bias.numel() == B * H * L * L, "rel_bias_grad: bias must be bf16 [B, H, L, L]");
+  const c10::cuda::CUDAGuard guard(q.device());
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    C10_CUDA_CHECK(cudaFree(nullptr));
+    ctx_bound = true;
+  }
+  auto drel = torch::zeros({H, 2 * L - 1}, q.options().dtype(torch::kFloat32));
+  auto mk = [&](const torch::Tensor& t) {
+    return MakeMap(t.data_ptr(), H * D, L, B, H * D, L * H * D, kT);
+  };
+  const CUtensorMap mq = mk(q), mkk = mk(k), mdo = mk(d_out), mv = mk(v);
+  GradParams p;
+  p.lse = lse.data_ptr<float>();
+  p.delta = delta.data_ptr<float>();
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias.data_ptr());
+  p.drel = drel.data_ptr<float>();
+  p.B = static_cast<int>(B); p.H = static_cast<int>(H); p.L = static_cast<int>(L);
+  p.scale = static_cast<float>(scale);
+  p.causal = causal ? 1 : 0;
+  constexpr size_t smem = kSlots * kSlotBytes + 1024 + 128 + 1024 + 64;
+  static bool configured = false;
+  if (!configured) {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(rel_bias_grad_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    configured = true;
+  }
+  const int nblk = static_cast<int>(L / kT);
+  dim3 grid(nblk * nblk, static_cast<unsigned>(H));
+  rel_bias_grad_kernel<<<grid, kThreads, smem, at::cuda::getCurrentCUDAStream()>>>(mq, mkk, mdo, mv, p);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  CountLaunch();
+  return drel;
+}
+
+}  // namespace lb
+
+LB_REGISTER(attn) {
+  m.attr("_has_attn") = true;
+  m.def("build_rel_bias", &lb::build_rel_bias, py::arg("rel"), py::arg("mask"), py::arg("batch"));
+  m.def("rel_bias_grad", &lb::rel_bias_grad);
+}

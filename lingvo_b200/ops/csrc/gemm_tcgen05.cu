@@ -390,6 +390,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapArray tmaps_a,
 }
 
 // ------------------------------------------------------------------ host ----
+CUtensorMap MakeMap(const void* base, int64_t inner, int64_t rows, int64_t groups,
+                    int64_t row_stride, int64_t group_stride, int box_rows,
+                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, int elem_bytes = 2);
+
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                               const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -409,10 +413,9 @@ static EncodeFn GetEncodeFn() {
 }
 
 // 3-D bf16 map over a [G, rows, inner] view; box = [1, box_rows, 64], 128B swizzle.
-static CUtensorMap MakeMap(const void* base, int64_t inner, int64_t rows, int64_t groups,
-                           int64_t row_stride, int64_t group_stride, int box_rows,
-                           CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                           int elem_bytes = 2) {
+CUtensorMap MakeMap(const void* base, int64_t inner, int64_t rows, int64_t groups,
+                    int64_t row_stride, int64_t group_stride, int box_rows,
+                    CUtensorMapDataType dt, int elem_bytes) {
   CUtensorMap m;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows),
                         static_cast<cuuint64_t>(groups)};

@@ -330,3 +330,24 @@ def test_self_attentive_layer():
   x, pad = _Inputs()
   out, pen = l.FPropDefaultTheta(x, pad)
   assert out.shape == (2, 3, 8) and pen.dim() == 0
+
+
+def test_gshard_rel_table_matches_bias_path():
+  """`_RelTable` (fast path input) reproduces the Toeplitz bias of `_Bias`."""
+  from lingvo_b200.core import gshard_builder
+  from lingvo_b200.ops import attention as A
+  b = gshard_builder.DenseBuilder.Params().Set(
+      model_dim=16, attention_num_heads=2, attention_key_value_dim=8,
+      relative_attention_num_buckets=8, relative_attention_max_distance=16,
+      relative_attention_use_universal_1d_position=True)
+  lp = gshard_builder.SelfAttentionLayer.Params().Set(
+      name='sa', b=b, relative_bias=True, decoder=True)
+  layer = lp.Instantiate()
+  l = 12
+  seg = torch.ones(1, l, dtype=torch.int32)
+  pos = torch.arange(l).unsqueeze(0)
+  bias = layer._Bias(layer.theta, seg, pos)
+  mask = layer._Mask(seg, pos, torch.float32)
+  rel = layer._RelTable(layer.theta, l, torch.device('cpu'))
+  rebuilt = A._RelToeplitz(rel, l).unsqueeze(0) + mask
+  torch.testing.assert_close(bias, rebuilt)
