@@ -1,0 +1,174 @@
+"""RNN cell / layer tests (CPU): shapes, padding carry-over, hoisted FRNN ≡
+step-by-step FProp, packed-input reset, bidirectional symmetry, LSTM vs torch."""
+
+import pytest
+import torch
+
+from lingvo_b200.core import attention
+from lingvo_b200.core import py_utils
+from lingvo_b200.core import recurrent
+from lingvo_b200.core import rnn_cell
+from lingvo_b200.core import rnn_layers
+from lingvo_b200.core.nested_map import NestedMap
+
+CELLS = [
+    (rnn_cell.LSTMCellSimple, {}),
+    (rnn_cell.LSTMCellSimple, dict(num_hidden_nodes=10, couple_input_forget_gates=True)),
+    (rnn_cell.LayerNormalizedLSTMCellSimple, {}),
+    (rnn_cell.LayerNormalizedLSTMCellLean, {}),
+    (rnn_cell.DoubleProjectionLSTMCell, dict(num_input_hidden_nodes=4, num_hidden_nodes=8)),
+    (rnn_cell.WeightNormalizedLSTMCellSimple, {}),
+    (rnn_cell.SRUCell, {}),
+    (rnn_cell.SRUCell, dict(couple_input_forget_gates=False, pointwise_peephole=True,
+                            apply_layer_norm=True)),
+    (rnn_cell.GRUCell, {}),
+    (rnn_cell.LSTMCellGrouped, dict(num_groups=2, num_shuffle_shards=2)),
+]
+
+
+def _Cell(cls, kw, idim=6, odim=6):
+  p = cls.Params().Set(name='cell', num_input_nodes=idim, num_output_nodes=odim, **kw)
+  p.params_init = py_utils.WeightInit.Uniform(0.5)
+  return p
+
+
+@pytest.mark.parametrize('cls,kw', CELLS)
+def test_cell_step_and_padding(cls, kw):
+  cell = _Cell(cls, kw).Instantiate()
+  b = 3
+  s0 = cell.zero_state(cell.theta, b)
+  s0 = s0.Transform(lambda x: x + 0.1)
+  x = torch.randn(b, 6)
+  pad = torch.tensor([[0.], [1.], [0.]])
+  s1, _ = cell.FProp(cell.theta, s0, NestedMap(act=[x], padding=pad))
+  assert s1.m.shape == (b, 6)
+  # padded row keeps its state exactly
+  torch.testing.assert_close(s1.m[1], s0.m[1])
+  torch.testing.assert_close(s1.c[1], s0.c[1])
+  assert not torch.allclose(s1.m[0], s0.m[0])
+
+
+@pytest.mark.parametrize('cls,kw', CELLS[:9])
+def test_frnn_equals_stepwise(cls, kw):
+  p = rnn_layers.FRNN.Params().Set(name='frnn', cell=_Cell(cls, kw))
+  l = p.Instantiate()
+  t, b = 5, 2
+  x = torch.randn(t, b, 6)
+  pad = torch.zeros(t, b, 1)
+  pad[3:, 1] = 1.0
+  out, final = l.FPropDefaultTheta(x, pad)
+  state = l.zero_state(l.theta, b)
+  outs = []
+  for i in range(t):
+    state, _ = l.cell.FProp(l.theta.cell, state, NestedMap(act=[x[i]], padding=pad[i]))
+    outs.append(l.cell.GetOutput(state))
+  torch.testing.assert_close(out, torch.stack(outs), atol=1e-5, rtol=1e-5)
+  torch.testing.assert_close(final.m, state.m, atol=1e-5, rtol=1e-5)
+  out.sum().backward()
+  assert all(v.grad is not None for v in l.vars.Flatten())
+
+
+def test_lstm_matches_torch_lstm():
+  cell_p = _Cell(rnn_cell.LSTMCellSimple, dict(cell_value_cap=None), idim=4, odim=5)
+  l = rnn_layers.FRNN.Params().Set(name='f', cell=cell_p).Instantiate()
+  ref = torch.nn.LSTM(4, 5)
+  wm, b = l.theta.cell.wm.detach(), l.theta.cell.b.detach()
+  # ours: gate order (g, i, f, o) along columns; torch: (i, f, g, o) rows
+  def reorder(w):
+    g, i, f, o = w.chunk(4, -1)
+    return torch.cat([i, f, g, o], -1)
+  with torch.no_grad():
+    ref.weight_ih_l0.copy_(reorder(wm[:4]).t())
+    ref.weight_hh_l0.copy_(reorder(wm[4:]).t())
+    ref.bias_ih_l0.copy_(reorder(b))
+    ref.bias_hh_l0.zero_()
+  x = torch.randn(7, 3, 4)
+  out, _ = l.FPropDefaultTheta(x, torch.zeros(7, 3, 1))
+  want, _ = ref(x)
+  torch.testing.assert_close(out, want, atol=1e-5, rtol=1e-5)
+
+
+def test_reverse_and_bidirectional():
+  cell = _Cell(rnn_cell.LSTMCellSimple, {})
+  fwd = rnn_layers.FRNN.Params().Set(name='f', cell=cell).Instantiate()
+  bak = rnn_layers.FRNN.Params().Set(name='f', cell=cell, reverse=True).Instantiate()
+  x = torch.randn(4, 2, 6)
+  pad = torch.zeros(4, 2, 1)
+  o_f, _ = fwd.FPropDefaultTheta(x, pad)
+  o_b, _ = bak.FProp(fwd.theta, torch.flip(x, [0]), pad)
+  torch.testing.assert_close(o_f, torch.flip(o_b, [0]), atol=1e-6, rtol=1e-6)
+  bi = rnn_layers.BidirectionalFRNN.Params().Set(name='bi', fwd=cell, bak=cell).Instantiate()
+  assert bi.FPropDefaultTheta(x, pad).shape == (4, 2, 12)
+
+
+def test_packed_input_resets_state():
+  cell = _Cell(rnn_cell.LSTMCellSimple, {})
+  l = rnn_layers.FRNN.Params().Set(name='f', cell=cell, packed_input=True).Instantiate()
+  x = torch.randn(6, 1, 6)
+  pad = torch.zeros(6, 1, 1)
+  seg = torch.tensor([1, 1, 1, 2, 2, 2]).view(6, 1, 1)
+  out, _ = l.FPropDefaultTheta(x, pad, segment_id=seg)
+  plain = rnn_layers.FRNN.Params().Set(name='f', cell=cell).Instantiate()
+  second, _ = plain.FProp(l.theta, x[3:], pad[3:])
+  torch.testing.assert_close(out[3:], second, atol=1e-6, rtol=1e-6)
+
+
+def test_stacked_layers():
+  p = rnn_layers.StackedFRNNLayerByLayer.Params().Set(
+      name='s', num_layers=3, num_input_nodes=6, num_output_nodes=6,
+      cell_tpl=rnn_cell.LSTMCellSimple.Params())
+  l = p.Instantiate()
+  out, st = l.FPropDefaultTheta(torch.randn(4, 2, 6), torch.zeros(4, 2, 1))
+  assert out.shape == (4, 2, 6) and len(st.rnn) == 3
+  p = rnn_layers.StackedBiFRNNLayerByLayer.Params().Set(
+      name='sb', num_layers=2, num_input_nodes=6, num_output_nodes=8,
+      cell_tpl=rnn_cell.LSTMCellSimple.Params())
+  assert p.Instantiate().FPropDefaultTheta(
+      torch.randn(4, 2, 6), torch.zeros(4, 2, 1)).shape == (4, 2, 8)
+
+
+def test_frnn_with_attention():
+  cell = _Cell(rnn_cell.LSTMCellSimple, {}, idim=6 + 8, odim=6)
+  att = attention.AdditiveAttention.Params().Set(source_dim=8, query_dim=6, hidden_dim=5)
+  l = rnn_layers.FRNNWithAttention.Params().Set(
+      name='fa', cell=cell, attention=att).Instantiate()
+  src = torch.randn(7, 2, 8)
+  src_pad = torch.zeros(7, 2)
+  src_pad[5:, 0] = 1
+  x = torch.randn(4, 2, 6)
+  ctx, out, probs, final = l.FPropDefaultTheta(src, src_pad, x, torch.zeros(4, 2, 1))
+  assert ctx.shape == (4, 2, 8) and out.shape == (4, 2, 6) and probs.shape == (4, 2, 7)
+  assert float(probs[:, 0, 5:].abs().max()) == 0
+  torch.testing.assert_close(probs.sum(-1), torch.ones(4, 2), atol=1e-5, rtol=1e-5)
+
+
+def test_recurrent_remat_matches_plain():
+  cell = _Cell(rnn_cell.LSTMCellSimple, {}).Instantiate()
+  x = torch.randn(6, 2, 6)
+  pad = torch.zeros(6, 2, 1)
+  inputs = NestedMap(act=[x], padding=pad)
+  s0 = cell.zero_state(cell.theta, 2)
+
+  def cell_fn(theta, state, inp):
+    return cell.FProp(theta, state, NestedMap(act=inp.act, padding=inp.padding))
+
+  def run(remat):
+    for v in cell.vars.Flatten():
+      v.grad = None
+    acc, final = recurrent.Recurrent(cell.theta, s0, inputs, cell_fn, remat_steps=remat)
+    acc.m.sum().backward()
+    return acc.m.detach().clone(), [v.grad.clone() for v in cell.vars.Flatten()]
+  a0, g0 = run(0)
+  a1, g1 = run(2)
+  torch.testing.assert_close(a0, a1)
+  for x0, x1 in zip(g0, g1):
+    torch.testing.assert_close(x0, x1, atol=1e-6, rtol=1e-5)
+
+
+def test_qrnn_pooling():
+  cell = rnn_cell.QRNNPoolingCell.Params().Set(
+      name='q', num_input_nodes=12, num_output_nodes=4, pooling_formula='fo').Instantiate()
+  s0 = cell.zero_state(cell.theta, 2)
+  s1, _ = cell.FProp(cell.theta, s0, NestedMap(act=[torch.randn(2, 12)],
+                                               padding=torch.zeros(2, 1)))
+  assert s1.m.shape == (2, 4)
