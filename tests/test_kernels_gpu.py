@@ -191,3 +191,30 @@ def test_build_rel_bias():
   got = ops.native().build_rel_bias(rel, mask, b).float()
   want = A._RelToeplitz(rel, l).unsqueeze(0) + mask.unsqueeze(1)
   torch.testing.assert_close(got, want.bfloat16().float(), atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize('causal', [False, True])
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+def test_glu_dwconv1d_kernel(causal, dtype):
+  from lingvo_b200.ops import conv as C
+  torch.manual_seed(0)
+  dev = torch.device('cuda')
+  b, t, d, k = 3, 77, 200, 9
+  proj = torch.randn(b, t, 2 * d, device=dev).to(dtype).requires_grad_()
+  w = (torch.randn(k, d, device=dev) * 0.3).requires_grad_()
+  pad = torch.zeros(b, t, device=dev)
+  pad[1, 50:] = 1
+  pad[2, 10:] = 1
+  dy = torch.randn(b, t, d, device=dev).to(dtype)
+  y = C.glu_dwconv1d(proj, w, pad, causal)
+  y.backward(dy)
+  got = [y.detach().float(), proj.grad.float().clone(), w.grad.clone()]
+  proj.grad = None; w.grad = None
+  pr = proj.detach().float().requires_grad_()
+  wr = w.detach().clone().requires_grad_()
+  yr = C.glu_dwconv1d_ref(pr, wr, pad, causal)
+  yr.backward(dy.float())
+  tol = 3e-2 if dtype == torch.bfloat16 else 1e-4
+  for name, g, r in zip(['y', 'dproj', 'dw'], got, [yr.detach(), pr.grad, wr.grad]):
+    err = float((g - r).norm() / r.norm().clamp_min(1e-6))
+    assert err < tol, (name, err)
