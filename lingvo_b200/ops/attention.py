@@ -129,11 +129,8 @@ class _RelBiasAttnFn(torch.autograd.Function):
         out, lse, seed, off, bias, cq, ck, max_q, max_k, 0.0, False, scale=scale)
     drel = None
     if ctx.needs_input_grad[3]:
-      o_blhd = out.transpose(1, 2)
-      delta = (d_o.float() * o_blhd.float()).sum(-1).permute(0, 2, 1).contiguous()
       lse3 = lse.reshape(b, h, l).float().contiguous()
-      drel = nat.rel_bias_grad(q.contiguous(), k.contiguous(), v.contiguous(), d_o,
-                               lse3, delta, bias, scale, causal)
+      drel = nat.rel_bias_grad(q, k, v, d_o, out, lse3, bias, scale, causal)
     return (dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), drel,
             None, None, None)
 
@@ -156,5 +153,9 @@ def rel_bias_attention(q, k, v, rel, mask=None, scale=1.0, causal=False):
     return rel_bias_attention_ref(q, k, v, rel, mask, scale).to(q.dtype)
   if mask is not None:
     mask = mask.reshape(-1, q.shape[1], q.shape[1])
-  return _RelBiasAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(),
-                              rel, mask, float(scale), bool(causal))
+  def _View(t):   # [B,L,H,D] view with strides (*, *, D, 1), 16-byte aligned rows
+    ok = (t.stride(3) == 1 and t.stride(2) == t.shape[3] and t.stride(1) % 8 == 0 and
+          t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0)
+    return t if ok else t.contiguous()
+  return _RelBiasAttnFn.apply(_View(q), _View(k), _View(v), rel, mask,
+                              float(scale), bool(causal))

@@ -35,29 +35,53 @@ namespace {
 __global__ void __launch_bounds__(256)
 build_rel_bias_kernel(const float* __restrict__ rel, const float* __restrict__ mask,
                       __nv_bfloat16* __restrict__ bias, int B, int H, int L, int mask_b) {
-  // one block per (b, i) row and a slab of heads; threads stride over j in 8-wide vectors
+  // One block per (i, b) row. A thread owns a PAIR of adjacent columns so that a
+  // warp's loads (mask, reversed table) and its 4-byte stores are all contiguous;
+  // the mask value is loaded once and reused for every head.
   const int i = blockIdx.x;
   const int b = blockIdx.y;
   const float* mrow = mask ? mask + (static_cast<long long>(mask_b > 1 ? b : 0) * L + i) * L : nullptr;
-  const int vec_per_row = L / 8;
-  for (int t = threadIdx.x; t < H * vec_per_row; t += blockDim.x) {
-    const int h = t / vec_per_row;
-    const int j0 = (t - h * vec_per_row) * 8;
-    const float* r = rel + static_cast<long long>(h) * (2 * L - 1) + (i - j0 + L - 1);
-    float f[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      float m = mrow ? mrow[j0 + u] : 0.f;
-      f[u] = fmaxf(r[-u] + m, -2.3e38f);
+  for (int j = 2 * threadIdx.x; j < L; j += 2 * blockDim.x) {
+    float m0 = 0.f, m1 = 0.f;
+    if (mrow) {
+      const float2 mm = *reinterpret_cast<const float2*>(mrow + j);
+      m0 = mm.x; m1 = mm.y;
     }
-    int4 o;
-    o.x = pack_bf16x2(f[0], f[1]);
-    o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]);
-    o.w = pack_bf16x2(f[6], f[7]);
-    __nv_bfloat16* dst = bias + ((static_cast<long long>(b) * H + h) * L + i) * L + j0;
-    *reinterpret_cast<int4*>(dst) = o;
+    const float* r = rel + (i - j + L - 1);
+    __nv_bfloat16* dst = bias + ((static_cast<long long>(b) * H) * L + i) * L + j;
+#pragma unroll 4
+    for (int h = 0; h < H; ++h) {
+      const float f0 = fmaxf(r[0] + m0, -2.3e38f);
+      const float f1 = fmaxf(r[-1] + m1, -2.3e38f);
+      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(f0, f1);
+      r += 2 * L - 1;
+      dst += static_cast<long long>(L) * L;
+    }
   }
+}
+
+// ------------------------------------------------------------------ row_dot ----
+// delta[b,h,l] = sum_d dO[b,l,h,d] * O[b,l,h,d]  (O may be a strided [B,H,L,D] view).
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ d_o, const __nv_bfloat16* __restrict__ o,
+                  float* __restrict__ delta, int B, int L, int H, long long o_sb, long long o_sl,
+                  long long o_sh) {
+  // one warp per (b, l, h) row of D = 128: each lane 4 elements
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= static_cast<long long>(B) * L * H) return;
+  const int h = static_cast<int>(row % H);
+  const long long bl = row / H;
+  const int l = static_cast<int>(bl % L);
+  const int b = static_cast<int>(bl / L);
+  const uint2 a = *reinterpret_cast<const uint2*>(d_o + row * 128 + lane * 4);
+  const uint2 c = *reinterpret_cast<const uint2*>(o + b * o_sb + l * o_sl + h * o_sh + lane * 4);
+  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y);
+  const float2 c0 = unpack_bf16x2(c.x), c1 = unpack_bf16x2(c.y);
+  float s = a0.x * c0.x + a0.y * c0.y + a1.x * c1.x + a1.y * c1.y;
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (lane == 0) delta[(static_cast<long long>(b) * H + h) * L + l] = s;
 }
 
 // -------------------------------------------------------------- rel_bias_grad --
@@ -263,7 +287,7 @@ torch::Tensor build_rel_bias(const torch::Tensor& rel, const c10::optional<torch
               rel.is_contiguous(), "build_rel_bias: rel must be fp32 [H, 2L-1]");
   const int64_t H = rel.size(0);
   const int64_t L = (rel.size(1) + 1) / 2;
-  TORCH_CHECK(L % 8 == 0, "build_rel_bias: L must be a multiple of 8");
+  TORCH_CHECK(L % 2 == 0, "build_rel_bias: L must be even");
   const c10::cuda::CUDAGuard guard(rel.device());
   const float* mptr = nullptr;
   int mask_b = 1;
@@ -285,19 +309,26 @@ torch::Tensor build_rel_bias(const torch::Tensor& rel, const c10::optional<torch
 }
 
 // Returns d rel [H, 2L-1] (fp32).
+// q,k,v,dO: [B, L, H, D] views with unit D stride and head stride D (slices of a fused
+// qkv projection are fine); `out` is the attention output as a [B, H, L, D] view.
 torch::Tensor rel_bias_grad(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v,
-                            const torch::Tensor& d_out, const torch::Tensor& lse,
-                            const torch::Tensor& delta, const torch::Tensor& bias, double scale,
+                            const torch::Tensor& d_out, const torch::Tensor& out,
+                            const torch::Tensor& lse, const torch::Tensor& bias, double scale,
                             bool causal) {
-  TORCH_CHECK(q.is_cuda() && q.scalar_type() == torch::kBFloat16 && q.dim() == 4 && q.is_contiguous(),
-              "rel_bias_grad: q must be contiguous bf16 [B, L, H, D]");
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == torch::kBFloat16 && q.dim() == 4,
+              "rel_bias_grad: q must be bf16 [B, L, H, D]");
   const int64_t B = q.size(0), L = q.size(1), H = q.size(2), D = q.size(3);
   TORCH_CHECK(D == kD && L % kT == 0, "rel_bias_grad: needs D == 128 and L % 128 == 0");
-  for (const torch::Tensor* t : {&k, &v, &d_out})
-    TORCH_CHECK(t->sizes() == q.sizes() && t->is_contiguous() && t->scalar_type() == torch::kBFloat16,
-                "rel_bias_grad: k/v/dO must match q");
+  for (const torch::Tensor* t : {&q, &k, &v, &d_out})
+    TORCH_CHECK(t->sizes() == q.sizes() && t->scalar_type() == torch::kBFloat16 &&
+                    t->stride(3) == 1 && t->stride(2) == D && t->stride(1) % 8 == 0 &&
+                    t->stride(0) % 8 == 0 && reinterpret_cast<uintptr_t>(t->data_ptr()) % 16 == 0,
+                "rel_bias_grad: q/k/v/dO must be [B,L,H,D] views with strides (*, *, D, 1)");
+  TORCH_CHECK(d_out.is_contiguous(), "rel_bias_grad: dO must be contiguous");
+  TORCH_CHECK(out.scalar_type() == torch::kBFloat16 && out.dim() == 4 && out.size(0) == B &&
+                  out.size(1) == H && out.size(2) == L && out.size(3) == D && out.stride(3) == 1,
+              "rel_bias_grad: out must be a bf16 [B, H, L, D] view");
   TORCH_CHECK(lse.scalar_type() == torch::kFloat32 && lse.is_contiguous() && lse.numel() == B * H * L);
-  TORCH_CHECK(delta.scalar_type() == torch::kFloat32 && delta.is_contiguous() && delta.numel() == B * H * L);
   TORCH_CHECK(bias.scalar_type() == torch::kBFloat16 && bias.is_contiguous() &&
               bias.numel() == B * H * L * L, "rel_bias_grad: bias must be bf16 [B, H, L, L]");
   const c10::cuda::CUDAGuard guard(q.device());
@@ -307,8 +338,20 @@ torch::Tensor rel_bias_grad(const torch::Tensor& q, const torch::Tensor& k, cons
     ctx_bound = true;
   }
   auto drel = torch::zeros({H, 2 * L - 1}, q.options().dtype(torch::kFloat32));
+  auto delta = torch::empty({B, H, L}, q.options().dtype(torch::kFloat32));
+  {
+    const long long rows = B * L * H;
+    const int blocks = static_cast<int>((rows * 32 + 255) / 256);
+    attn_delta_kernel<<<blocks, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+        reinterpret_cast<const __nv_bfloat16*>(d_out.data_ptr()),
+        reinterpret_cast<const __nv_bfloat16*>(out.data_ptr()), delta.data_ptr<float>(),
+        static_cast<int>(B), static_cast<int>(L), static_cast<int>(H), out.stride(0),
+        out.stride(2), out.stride(1));
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    CountLaunch();
+  }
   auto mk = [&](const torch::Tensor& t) {
-    return MakeMap(t.data_ptr(), H * D, L, B, H * D, L * H * D, kT);
+    return MakeMap(t.data_ptr(), H * D, L, B, t.stride(1), t.stride(0), kT);
   };
   const CUtensorMap mq = mk(q), mkk = mk(k), mdo = mk(d_out), mv = mk(v);
   GradParams p;

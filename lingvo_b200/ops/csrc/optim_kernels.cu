@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(kWarps * 32)
 adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
                        float* __restrict__ rowsum, float* __restrict__ colsum,
                        float* __restrict__ acc, int B, int R, int C, float eps1, int items,
-                       const float* __restrict__ gscale) {
+                       const float* __restrict__ gscale, int with_w) {
+  // with_w: also accumulate sum(w^2) (only on the first step of a variable; later
+  // steps get it for free from the previous apply kernel, see acc[2]).
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float gs = gscale ? *gscale : 1.f;
   float wsq = 0.f;
@@ -86,32 +88,54 @@ adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
     const int c = t.c0 + lane * 8;
     const bool cok = c < C;
     float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int r = t.r0; r < t.r1; ++r) {
-      const size_t off = (static_cast<size_t>(t.b) * R + r) * C + c;
-      float rs = 0.f;
-      if (cok) {
-        float gf[8], wf[8];
-        load_g8<GT>(g + off, gf);
-        load_g8<float>(w + off, wf);
+    for (int r = t.r0; r < t.r1; r += 4) {
+      // 4 rows in flight: all loads issue before the first reduction.
+      float gf[4][8];
+      float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float ge = gs == 0.f ? 0.f : gf[i] * gs;
-          const float q = ge * ge + eps1;
-          cs[i] += q;
-          rs += q;
-          wsq += wf[i] * wf[i];
+      for (int u = 0; u < 4; ++u) {
+        if (cok && r + u < t.r1)
+          load_g8<GT>(g + (static_cast<size_t>(t.b) * R + r + u) * C + c, gf[u]);
+      }
+      if (with_w && cok) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (r + u < t.r1) {
+            float wf[8];
+            load_g8<float>(w + (static_cast<size_t>(t.b) * R + r + u) * C + c, wf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wsq += wf[i] * wf[i];
+          }
         }
       }
-      rs = warp_sum(rs);
-      if (lane == 0) atomicAdd(&rowsum[static_cast<size_t>(t.b) * R + r], rs);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (cok && r + u < t.r1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float ge = gs == 0.f ? 0.f : gf[u][i] * gs;
+            const float q = ge * ge + eps1;
+            cs[i] += q;
+            rs[u] += q;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rs[u] = warp_sum(rs[u]);
+      if (lane < 4 && r + lane < t.r1) {
+        const float v = lane == 0 ? rs[0] : lane == 1 ? rs[1] : lane == 2 ? rs[2] : rs[3];
+        atomicAdd(&rowsum[static_cast<size_t>(t.b) * R + r + lane], v);
+      }
     }
     if (cok) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) atomicAdd(&colsum[static_cast<size_t>(t.b) * C + c + i], cs[i]);
     }
   }
-  wsq = warp_sum(wsq);
-  if (lane == 0) atomicAdd(&acc[0], wsq);
+  if (with_w) {
+    wsq = warp_sum(wsq);
+    if (lane == 0) atomicAdd(&acc[0], wsq);
+  }
 }
 
 // vr_is_rows: vr has shape [B,R] (mean over C is "row mean" of the reference,
@@ -120,10 +144,16 @@ __global__ void adafactor_factors_kernel(float* __restrict__ vr, float* __restri
                                          const float* __restrict__ rowsum,
                                          const float* __restrict__ colsum, float* __restrict__ fr,
                                          float* __restrict__ fc, int B, int R, int C, float decay,
-                                         int vr_is_rows) {
+                                         int vr_is_rows, float* __restrict__ acc, int with_w) {
   // One CTA per batch element b.
   __shared__ float red[32];
   const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0) {
+    // acc[0] = sum(w^2) for this step: freshly computed (with_w) or carried over
+    // from the previous step's apply kernel (acc[2]); acc[2] restarts at 0.
+    if (!with_w) acc[0] = acc[2];
+    acc[2] = 0.f;
+  }
   const float mix = 1.f - decay;
   const int nvr = vr_is_rows ? R : C;
   const int nvc = vr_is_rows ? C : R;
@@ -176,6 +206,7 @@ adafactor_rms_kernel(const GT* __restrict__ g, const float* __restrict__ fr,
     if (c >= C) continue;
     float cf[8];
     load_g8<float>(fc + static_cast<size_t>(t.b) * C + c, cf);
+#pragma unroll 4
     for (int r = t.r0; r < t.r1; ++r) {
       const float rf = fr[static_cast<size_t>(t.b) * R + r];
       float gf[8];
@@ -203,12 +234,14 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
   float scale = lr;
   if (mult_by_param_scale) scale *= fmaxf(sqrtf(acc[0] / numel), eps2);
   if (clip > 0.f) scale /= fmaxf(1.f, sqrtf(acc[1] / numel) / clip);
+  float wsq = 0.f;
   for (int item = blockIdx.x * kWarps + warp; item < items; item += gridDim.x * kWarps) {
     const Tile t = get_tile(item, R, C);
     const int c = t.c0 + lane * 8;
     if (c >= C) continue;
     float cf[8];
     load_g8<float>(fc + static_cast<size_t>(t.b) * C + c, cf);
+#pragma unroll 2
     for (int r = t.r0; r < t.r1; ++r) {
       const float rf = fr[static_cast<size_t>(t.b) * R + r] * scale;
       const size_t off = (static_cast<size_t>(t.b) * R + r) * C + c;
@@ -216,7 +249,10 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
       load_g8<GT>(g + off, gf);
       load_g8<float>(w + off, wf);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) wf[i] -= (gs == 0.f ? 0.f : gf[i] * gs) * rf * cf[i];
+      for (int i = 0; i < 8; ++i) {
+        wf[i] -= (gs == 0.f ? 0.f : gf[i] * gs) * rf * cf[i];
+        wsq += wf[i] * wf[i];
+      }
       *reinterpret_cast<float4*>(w + off) = make_float4(wf[0], wf[1], wf[2], wf[3]);
       *reinterpret_cast<float4*>(w + off + 4) = make_float4(wf[4], wf[5], wf[6], wf[7]);
       if (w_bf16 != nullptr) {
@@ -229,6 +265,8 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
       }
     }
   }
+  wsq = warp_sum(wsq);                       // sum(w_new^2): next step's parameter scale
+  if (lane == 0) atomicAdd(const_cast<float*>(&acc[2]), wsq);
 }
 
 template <typename GT>
@@ -279,7 +317,7 @@ void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor v
                         const c10::optional<torch::Tensor>& w_bf16, int64_t B, int64_t R,
                         int64_t C, bool vr_is_rows, double lr, double decay, double eps1,
                         double eps2, double clip, bool mult_by_param_scale,
-                        const c10::optional<torch::Tensor>& grad_scale) {
+                        const c10::optional<torch::Tensor>& grad_scale, bool recompute_wsq) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == torch::kFloat32 && w.is_contiguous());
   TORCH_CHECK(g.is_contiguous() && g.numel() == w.numel());
   TORCH_CHECK(C % 8 == 0, "adafactor_factored: C must be a multiple of 8");
@@ -295,7 +333,12 @@ void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor v
   float* colsum = rowsum + br4;
   float* fr = colsum + bc4;
   float* fc = fr + br4;
-  C10_CUDA_CHECK(cudaMemsetAsync(sp, 0, sizeof(float) * (4 + br4 + bc4), stream));
+  // sp[0] = sum(w^2) used now, sp[1] = clipping RMS, sp[2] = sum(w^2) carried to the
+  // next step (persistent), sp[3] unused.
+  if (recompute_wsq) C10_CUDA_CHECK(cudaMemsetAsync(sp, 0, sizeof(float) * 4, stream));
+  else C10_CUDA_CHECK(cudaMemsetAsync(sp + 1, 0, sizeof(float), stream));
+  C10_CUDA_CHECK(cudaMemsetAsync(rowsum, 0, sizeof(float) * (br4 + bc4), stream));
+  const int with_w = (recompute_wsq && mult_by_param_scale) ? 1 : 0;
   const int strips = static_cast<int>((C + 255) / 256);
   const int ranges = static_cast<int>((R + kRowsPerWarp - 1) / kRowsPerWarp);
   const int items = static_cast<int>(B) * strips * ranges;
@@ -315,10 +358,10 @@ void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor v
     using GT = decltype(tag);
     const GT* gp = reinterpret_cast<const GT*>(g.data_ptr());
     adafactor_stats_kernel<GT><<<grid, kWarps * 32, 0, stream>>>(
-        gp, w.data_ptr<float>(), rowsum, colsum, acc, (int)B, (int)R, (int)C, (float)eps1, items, gsp);
+        gp, w.data_ptr<float>(), rowsum, colsum, acc, (int)B, (int)R, (int)C, (float)eps1, items, gsp, with_w);
     adafactor_factors_kernel<<<static_cast<int>(B), 256, 0, stream>>>(
         vr.data_ptr<float>(), vc.data_ptr<float>(), rowsum, colsum, fr, fc, (int)B, (int)R, (int)C,
-        (float)decay, vr_is_rows ? 1 : 0);
+        (float)decay, vr_is_rows ? 1 : 0, acc, (recompute_wsq || !mult_by_param_scale) ? 1 : 0);
     if (clip > 0)
       adafactor_rms_kernel<GT><<<grid, kWarps * 32, 0, stream>>>(gp, fr, fc, acc, (int)B, (int)R,
                                                                  (int)C, items, gsp);

@@ -13,12 +13,22 @@ def available() -> bool:
 
 
 def _Scratch(var, n):
+  """Per-variable fp32 scratch; returns (buffer, fresh). `fresh` means the
+  carried sum(w²) in it is not valid yet (first step, or after `Invalidate`)."""
   key = id(var)
-  buf = _SCRATCH.get(key)
-  if buf is None or buf.numel() < n or buf.device != var.device:
-    buf = torch.empty(n, dtype=torch.float32, device=var.device)
-    _SCRATCH[key] = buf
-  return buf
+  ent = _SCRATCH.get(key)
+  if (ent is None or ent[0].numel() < n or ent[0].device != var.device or
+      ent[1] != var.data_ptr()):
+    buf = torch.zeros(n, dtype=torch.float32, device=var.device)
+    _SCRATCH[key] = (buf, var.data_ptr())
+    return buf, True
+  return ent[0], False
+
+
+def Invalidate():
+  """Drops carried optimizer scratch (call after weights change outside the
+  optimizer, e.g. checkpoint restore)."""
+  _SCRATCH.clear()
 
 
 def adafactor_factored(var, grad, vr, vc, d0, d1, lr, decay, eps1, eps2, clip,
@@ -32,13 +42,13 @@ def adafactor_factored(var, grad, vr, vc, d0, d1, lr, decay, eps1, eps2, clip,
   r, c = var.shape[-2], var.shape[-1]
   b = var.numel() // (r * c)
   vr_is_rows = (d0 == nd - 1)   # vr = mean over C → per-row vector [B, R]
-  scratch = _Scratch(var, 16 + 2 * (b * r + 4) + 2 * (b * c + 4))
+  scratch, fresh = _Scratch(var, 16 + 2 * (b * r + 4) + 2 * (b * c + 4))
   g = grad if grad.is_contiguous() else grad.contiguous()
   compute = getattr(var, 'compute', None)
   ops.native().adafactor_factored(
       var.data, g, vr, vc, scratch, compute.data if compute is not None else None,
       b, r, c, vr_is_rows, float(lr), float(decay), float(eps1), float(eps2),
-      float(clip), bool(mult_by_param_scale), grad_scale)
+      float(clip), bool(mult_by_param_scale), grad_scale, fresh)
 
 
 def adam_flat(w, g, m, v, w_bf16, lr_t, b1, b2, eps, grad_scale=1.0,

@@ -1,0 +1,106 @@
+"""GPipe layers: partitioning, micro-batch equivalence, 2-rank pipeline engine."""
+
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lingvo_b200.core import gpipe
+from lingvo_b200.core import layers
+from lingvo_b200.core import py_utils
+from lingvo_b200.core import tshape
+
+
+def _Fc(name, i, o):
+  return layers.FCLayer.Params().Set(name=name, input_dim=i, output_dim=o,
+                                     activation='TANH')
+
+
+def _Pipe(num_micro, cells=2):
+  subs = [_Fc('fc%d' % i, 8, 8) for i in range(4)]
+  per = len(subs) // cells
+  cell_tpl = [gpipe.FeatureExtractionLayer.Params().Set(
+      name='cell_%d' % c, sub=subs[c * per:(c + 1) * per]) for c in range(cells)]
+  p = gpipe.PipeliningLayer.Params().Set(name='pipe', cell_tpl=cell_tpl,
+                                         num_micro_batches=num_micro)
+  p.params_init = py_utils.WeightInit.Uniform(0.5)
+  p.random_seed = 1234
+  return p
+
+
+def test_partition_sequential_layers_balances_flops():
+  subs = [_Fc('a', 8, 8), _Fc('b', 8, 32), _Fc('c', 32, 32), _Fc('d', 32, 8)]
+  parts = gpipe.PartitionSequentialLayers(subs, 2, tshape.Shape([4, 8]))
+  assert len(parts) == 2
+  assert sum(len(p.sub) for p in parts) == 4
+  assert len(parts[0].sub) >= 1 and len(parts[1].sub) >= 1
+
+
+def test_micro_batching_is_equivalent():
+  x = torch.randn(8, 8)
+  a = _Pipe(1).Instantiate()
+  b = _Pipe(4).Instantiate()
+  ya = a.FPropDefaultTheta(x)
+  yb = b.FProp(a.theta, x)
+  torch.testing.assert_close(ya, yb)
+  ya.sum().backward()
+  assert all(v.grad is not None for v in a.vars.Flatten())
+
+
+def test_feature_extraction_forwarding():
+  p = gpipe.FeatureExtractionLayer.Params().Set(
+      name='fe', sub=[_Fc('x', 8, 8)], num_act_inputs=1, num_act_outputs=1)
+  l = p.Instantiate()
+  x, extra = torch.randn(2, 8), torch.randn(2, 3)
+  out = l.FPropDefaultTheta(x, extra)
+  assert len(out) == 2 and out[1] is extra
+
+
+def _Worker(rank, world, port, q):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  from lingvo_b200.parallel import pp
+  torch.manual_seed(0)
+  x = torch.randn(8, 8)
+  layer = _Pipe(4).Instantiate()          # same seed → same weights on both ranks
+  eng = pp.PipelineEngine()
+  layer.AttachEngine(eng)
+  out = layer.FProp(layer.theta, x)
+  loss = out.pow(2).sum() if eng.is_last else None
+  eng.Backward(loss)
+  grads = {v.var_name: (v.grad.clone() if v.grad is not None else None)
+           for v in layer.vars.Flatten()}
+  q.put((rank, float(loss) if loss is not None else None, grads))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_pipeline_engine_two_ranks_matches_single_process():
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = 29600 + os.getpid() % 300
+  procs = [ctx.Process(target=_Worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=120) for _ in range(2)]
+  for p in procs:
+    p.join(timeout=60)
+  res = {r[0]: r for r in res}
+  # single-process oracle
+  torch.manual_seed(0)
+  x = torch.randn(8, 8)
+  ref = _Pipe(4).Instantiate()
+  loss = ref.FPropDefaultTheta(x).pow(2).sum()
+  loss.backward()
+  assert abs(res[1][1] - float(loss)) < 1e-4
+  for v in ref.vars.Flatten():
+    stage = 0 if 'cell_0' in v.var_name else 1
+    g = res[stage][2][v.var_name]
+    assert g is not None, v.var_name
+    torch.testing.assert_close(g, v.grad, atol=1e-5, rtol=1e-4)
+    other = res[1 - stage][2][v.var_name]
+    assert other is None        # a stage never touches the other stage's weights
