@@ -36,6 +36,27 @@ def native(required: bool = True):
   return _MOD
 
 
+_HOST = None
+
+
+def host():
+  """Loads (building on first use if needed) the torch-free host library `_H.so`:
+  record yielders / batcher, tokenizers, sequence packing, MASS, best_step."""
+  global _HOST
+  if _HOST is not None:
+    return _HOST
+  with _LOCK:
+    if _HOST is None:
+      try:
+        _HOST = importlib.import_module('lingvo_b200.ops._H')
+      except ImportError:
+        from lingvo_b200.ops import build as build_lib
+        build_lib.BuildHost(verbose=False)
+        importlib.invalidate_caches()
+        _HOST = importlib.import_module('lingvo_b200.ops._H')
+  return _HOST
+
+
 def has_native() -> bool:
   return native(required=False) is not None
 

@@ -104,5 +104,46 @@ def Build(force: bool = False, verbose: bool = True) -> str:
   return TARGET
 
 
+HOST_SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc_host')
+HOST_TARGET = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_H.so')
+
+
+def BuildHost(force: bool = False, verbose: bool = True) -> str:
+  """Builds the torch-free host library `_H.so` (records / batching / tokenizers /
+  packing) with g++ + pybind11."""
+  import pybind11  # pylint: disable=g-import-not-at-top
+  srcs = sorted(glob.glob(os.path.join(HOST_SRC, '*.cpp')))
+  deps = srcs + glob.glob(os.path.join(HOST_SRC, '*.h')) + [os.path.abspath(__file__)]
+  if (not force and os.path.exists(HOST_TARGET) and
+      os.path.getmtime(HOST_TARGET) >= _Newest(deps)):
+    return HOST_TARGET
+  os.makedirs(OBJ, exist_ok=True)
+  incs = ['-I' + pybind11.get_include(), '-I' + sysconfig.get_paths()['include'],
+          '-I' + HOST_SRC]
+
+  def _One(src):
+    obj = os.path.join(OBJ, 'host_' + os.path.basename(src) + '.o')
+    cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-fvisibility=hidden', '-pthread',
+           *incs, '-c', src, '-o', obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+      raise RuntimeError('compile failed: %s\n%s' % (src, (r.stdout + r.stderr)[-6000:]))
+    if verbose:
+      print('[build] compiled', os.path.basename(src))
+    return obj
+
+  with concurrent.futures.ThreadPoolExecutor(len(srcs)) as ex:
+    objs = list(ex.map(_One, srcs))
+  cmd = ['g++', '-shared', '-pthread', '-o', HOST_TARGET + '.tmp', *objs]
+  r = subprocess.run(cmd, capture_output=True, text=True)
+  if r.returncode != 0:
+    raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
+  os.replace(HOST_TARGET + '.tmp', HOST_TARGET)
+  if verbose:
+    print('[build] linked', HOST_TARGET)
+  return HOST_TARGET
+
+
 if __name__ == '__main__':
   Build(force='--force' in sys.argv)
+  BuildHost(force='--force' in sys.argv)

@@ -1,0 +1,372 @@
+// pybind11 module `_H`: host-side (CPU) natives of the input pipeline.
+// No torch / CUDA dependency, so it loads on any host.
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+#include "records.h"
+#include "text_ops.h"
+
+namespace py = pybind11;
+using namespace lbh;   // NOLINT
+
+namespace {
+
+// ------------------------------------------------------------- RecordBatcher ----
+// N worker threads pull records from a Yielder (no GIL), call the Python
+// `processor(record: bytes, source_id: int)` (GIL) which returns None (example
+// filtered out) or `(bucket_key: int, [np.ndarray, ...])`, and file the sample
+// under the first bucket whose upper bound >= key (over-range samples are skipped
+// and counted). When a bucket reaches its batch limit it is queued for the
+// consumer; `GetNext` pads every tensor slot to the per-batch max shape and stacks.
+// `flush_every_n > 0` flushes all partial buckets every n processed records (exact
+// evaluation); at end of data all partial buckets are flushed, then StopIteration.
+class RecordBatcher {
+ public:
+  RecordBatcher(std::shared_ptr<Yielder> yielder, py::function processor,
+                std::vector<int64_t> bucket_upper_bound, std::vector<int64_t> bucket_batch_limit,
+                int num_threads, int64_t flush_every_n)
+      : yielder_(std::move(yielder)), processor_(std::move(processor)),
+        bounds_(std::move(bucket_upper_bound)), limits_(std::move(bucket_batch_limit)),
+        flush_every_n_(flush_every_n), buckets_(bounds_.size()) {
+    if (bounds_.empty() || bounds_.size() != limits_.size())
+      throw std::runtime_error("RecordBatcher: bucket_upper_bound / bucket_batch_limit mismatch");
+    if (num_threads < 1) num_threads = 1;
+    live_workers_ = num_threads;
+    for (int i = 0; i < num_threads; ++i) workers_.emplace_back([this] { Work(); });
+  }
+
+  ~RecordBatcher() { Close(); }
+
+  void Close() {
+    if (closed_.exchange(true)) return;
+    stop_.store(true);
+    yielder_->Close();
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      cv_ready_.notify_all();
+      cv_space_.notify_all();
+    }
+    py::gil_scoped_release rel;
+    for (auto& t : workers_)
+      if (t.joinable()) t.join();
+    workers_.clear();
+  }
+
+  py::tuple GetNext() {
+    Batch batch;
+    {
+      py::gil_scoped_release rel;
+      std::unique_lock<std::mutex> l(mu_);
+      cv_ready_.wait(l, [&] { return stop_ || !ready_.empty() || live_workers_ == 0; });
+      if (!error_.empty()) {
+        std::string e = error_;
+        l.unlock();
+        py::gil_scoped_acquire acq;
+        throw std::runtime_error(e);
+      }
+      if (ready_.empty()) {
+        // end of data: flush whatever is left, one bucket per call
+        for (auto& b : buckets_) {
+          if (!b.empty()) {
+            batch = std::move(b);
+            b.clear();
+            break;
+          }
+        }
+      } else {
+        batch = std::move(ready_.front());
+        ready_.pop_front();
+        cv_space_.notify_all();
+      }
+    }
+    if (batch.empty()) throw py::stop_iteration();
+    return Merge(batch);
+  }
+
+  int64_t records_skipped() const { return skipped_.load(); }
+  int64_t records_processed() const { return processed_.load(); }
+
+ private:
+  struct Sample {
+    int64_t key;
+    std::vector<py::array> tensors;
+  };
+  using Batch = std::vector<Sample>;
+
+  void Work() {
+    Record rec;
+    while (!stop_) {
+      if (!yielder_->Yield(&rec)) break;
+      Sample s;
+      bool keep = false;
+      {
+        py::gil_scoped_acquire acq;
+        try {
+          py::object ret = processor_(py::bytes(rec.value), rec.source_id);
+          if (!ret.is_none()) {
+            auto tup = ret.cast<py::tuple>();
+            s.key = tup[0].cast<int64_t>();
+            for (auto item : tup[1]) s.tensors.push_back(py::array::ensure(item));
+            keep = true;
+          }
+        } catch (const std::exception& e) {
+          std::lock_guard<std::mutex> l(mu_);
+          error_ = std::string("RecordBatcher processor failed: ") + e.what();
+          stop_.store(true);
+          cv_ready_.notify_all();
+        }
+        if (!keep) s.tensors.clear();   // drop references while holding the GIL
+      }
+      if (!keep) continue;
+      const int64_t n = processed_.fetch_add(1) + 1;
+      const auto it = std::lower_bound(bounds_.begin(), bounds_.end(), s.key);
+      std::unique_lock<std::mutex> l(mu_);
+      if (it == bounds_.end()) {
+        skipped_.fetch_add(1);
+        l.unlock();
+        py::gil_scoped_acquire acq;
+        s.tensors.clear();
+        continue;
+      }
+      const size_t bi = static_cast<size_t>(it - bounds_.begin());
+      cv_space_.wait(l, [&] { return stop_ || ready_.size() < 4; });
+      if (stop_) break;
+      buckets_[bi].push_back(std::move(s));
+      if (static_cast<int64_t>(buckets_[bi].size()) >= limits_[bi]) {
+        ready_.push_back(std::move(buckets_[bi]));
+        buckets_[bi].clear();
+        cv_ready_.notify_one();
+      }
+      if (flush_every_n_ > 0 && n % flush_every_n_ == 0) {
+        for (auto& b : buckets_) {
+          if (!b.empty()) {
+            ready_.push_back(std::move(b));
+            b.clear();
+          }
+        }
+        cv_ready_.notify_all();
+      }
+    }
+    std::lock_guard<std::mutex> l(mu_);
+    --live_workers_;
+    cv_ready_.notify_all();
+  }
+
+  static void CopyInto(char* dst, const std::vector<py::ssize_t>& dst_strides, const char* src,
+                       const py::buffer_info& info, int dim) {
+    if (dim == info.ndim) {
+      memcpy(dst, src, info.itemsize);
+      return;
+    }
+    if (dim == info.ndim - 1 && info.strides[dim] == info.itemsize) {
+      memcpy(dst, src, info.itemsize * info.shape[dim]);
+      return;
+    }
+    for (py::ssize_t i = 0; i < info.shape[dim]; ++i)
+      CopyInto(dst + i * dst_strides[dim], dst_strides, src + i * info.strides[dim], info, dim + 1);
+  }
+
+  py::tuple Merge(Batch& batch) {
+    const size_t n = batch.size();
+    const size_t slots = batch[0].tensors.size();
+    py::array_t<int64_t> keys(static_cast<py::ssize_t>(n));
+    for (size_t i = 0; i < n; ++i) keys.mutable_at(i) = batch[i].key;
+    py::list outs;
+    for (size_t s = 0; s < slots; ++s) {
+      const py::array& first = batch[0].tensors[s];
+      const int nd = static_cast<int>(first.ndim());
+      std::vector<py::ssize_t> shape(nd + 1, 0);
+      shape[0] = static_cast<py::ssize_t>(n);
+      for (const auto& smp : batch) {
+        if (smp.tensors.size() != slots || smp.tensors[s].ndim() != nd ||
+            !smp.tensors[s].dtype().is(first.dtype()))
+          throw std::runtime_error("RecordBatcher: samples disagree on tensor rank/dtype");
+        for (int d = 0; d < nd; ++d) shape[d + 1] = std::max(shape[d + 1], smp.tensors[s].shape(d));
+      }
+      py::array out(first.dtype(), shape);
+      memset(out.mutable_data(), 0, static_cast<size_t>(out.nbytes()));
+      std::vector<py::ssize_t> inner_strides(out.strides() + 1, out.strides() + 1 + nd);
+      for (size_t i = 0; i < n; ++i) {
+        py::buffer_info info = batch[i].tensors[s].request();
+        if (info.size == 0) continue;
+        CopyInto(static_cast<char*>(out.mutable_data()) + i * out.strides(0), inner_strides,
+                 static_cast<const char*>(info.ptr), info, 0);
+      }
+      outs.append(out);
+    }
+    batch.clear();
+    return py::make_tuple(keys, outs);
+  }
+
+  std::shared_ptr<Yielder> yielder_;
+  py::function processor_;
+  std::vector<int64_t> bounds_, limits_;
+  int64_t flush_every_n_;
+  std::vector<Batch> buckets_;
+  std::deque<Batch> ready_;
+  std::mutex mu_;
+  std::condition_variable cv_ready_, cv_space_;
+  std::vector<std::thread> workers_;
+  int live_workers_ = 0;
+  std::atomic<bool> stop_{false}, closed_{false};
+  std::atomic<int64_t> skipped_{0}, processed_{0};
+  std::string error_;
+};
+
+py::array_t<int32_t> ToArray2D(const std::vector<int32_t>& v, int rows, int cols) {
+  py::array_t<int32_t> a({rows, cols});
+  memcpy(a.mutable_data(), v.data(), v.size() * sizeof(int32_t));
+  return a;
+}
+
+std::vector<int32_t> ToVec(const py::array_t<int32_t, py::array::c_style | py::array::forcecast>& a) {
+  return std::vector<int32_t>(a.data(), a.data() + a.size());
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_H, m) {
+  m.doc() = "lingvo_b200 host-side natives (records, batching, tokenizers, packing)";
+  m.def("crc32c", [](py::bytes b) { std::string s = b; return Crc32c(s.data(), s.size()); });
+  m.def("masked_crc32c", [](py::bytes b) { std::string s = b; return MaskCrc(Crc32c(s.data(), s.size())); });
+  m.def("glob_files", &GlobFiles);
+
+  py::class_<TFRecordWriter>(m, "TFRecordWriter")
+      .def(py::init<const std::string&>())
+      .def("write", [](TFRecordWriter& w, py::bytes b) { w.Write(b); })
+      .def("close", &TFRecordWriter::Close);
+
+  py::class_<Yielder, std::shared_ptr<Yielder>>(m, "Yielder")
+      .def("next", [](Yielder& y) -> py::object {
+        Record r;
+        bool ok;
+        {
+          py::gil_scoped_release rel;
+          ok = y.Yield(&r);
+        }
+        if (!ok) return py::none();
+        return py::make_tuple(py::bytes(r.value), r.source_id);
+      })
+      .def("close", [](Yielder& y) { py::gil_scoped_release rel; y.Close(); })
+      .def_property_readonly("current_epoch", &Yielder::current_epoch);
+
+  m.def("basic_record_yielder",
+        [](const std::string& file_pattern, uint64_t seed, int64_t bufsize, int parallelism,
+           int64_t num_epochs, int source_id) -> std::shared_ptr<Yielder> {
+          BasicYielderOptions o;
+          o.file_pattern = file_pattern; o.seed = seed; o.bufsize = bufsize;
+          o.parallelism = parallelism; o.num_epochs = num_epochs; o.source_id = source_id;
+          return std::make_shared<BasicRecordYielder>(o);
+        },
+        py::arg("file_pattern"), py::arg("seed") = 0, py::arg("bufsize") = 16384,
+        py::arg("parallelism") = 4, py::arg("num_epochs") = 0, py::arg("source_id") = 0);
+  m.def("sequential_record_yielder",
+        [](const std::string& fp, int64_t repeat, int source_id) -> std::shared_ptr<Yielder> {
+          return std::make_shared<SequentialRecordYielder>(fp, repeat, source_id);
+        },
+        py::arg("file_pattern"), py::arg("repeat_count") = 1, py::arg("source_id") = 0);
+  m.def("weighted_mix_record_yielder",
+        [](std::vector<std::shared_ptr<Yielder>> kids, std::vector<double> w,
+           uint64_t seed) -> std::shared_ptr<Yielder> {
+          return std::make_shared<WeightedMixRecordYielder>(std::move(kids), std::move(w), seed);
+        },
+        py::arg("children"), py::arg("weights"), py::arg("seed") = 0);
+
+  py::class_<RecordBatcher>(m, "RecordBatcher")
+      .def(py::init<std::shared_ptr<Yielder>, py::function, std::vector<int64_t>,
+                    std::vector<int64_t>, int, int64_t>(),
+           py::arg("yielder"), py::arg("processor"), py::arg("bucket_upper_bound"),
+           py::arg("bucket_batch_limit"), py::arg("num_threads") = 4,
+           py::arg("flush_every_n") = 0)
+      .def("get_next", &RecordBatcher::GetNext)
+      .def("close", &RecordBatcher::Close)
+      .def_property_readonly("records_skipped", &RecordBatcher::records_skipped)
+      .def_property_readonly("records_processed", &RecordBatcher::records_processed);
+
+  // ---- tokenizers ----
+  m.def("ascii_to_ids", [](const std::string& s) { return AsciiTokenizer::Get().StringToIds(s); });
+  m.def("ascii_to_string",
+        [](const std::vector<int32_t>& ids) { return AsciiTokenizer::Get().IdsToString(ids); });
+  m.def("ascii_num_tokens", []() { return AsciiTokenizer::Get().NumTokens(); });
+  py::class_<VocabTokenizer>(m, "VocabTokenizer")
+      .def(py::init<const std::string&, bool>(), py::arg("vocab_path"),
+           py::arg("load_token_ids_from_vocab") = false)
+      .def("to_ids", &VocabTokenizer::StringToIds)
+      .def("to_string", &VocabTokenizer::IdsToString)
+      .def("token_to_id", &VocabTokenizer::TokenToId)
+      .def("id_to_token", &VocabTokenizer::IdToToken)
+      .def_property_readonly("unk_id", &VocabTokenizer::unk_id)
+      .def_property_readonly("sos_id", &VocabTokenizer::sos_id)
+      .def_property_readonly("eos_id", &VocabTokenizer::eos_id)
+      .def("__len__", &VocabTokenizer::size);
+  py::class_<BpeTokenizer>(m, "BpeTokenizer")
+      .def(py::init<const std::string&, const std::string&>(), py::arg("codes_path"),
+           py::arg("vocab_path"))
+      .def("to_ids", &BpeTokenizer::StringToIds)
+      .def("to_string", &BpeTokenizer::IdsToString)
+      .def("encode_word", &BpeTokenizer::EncodeWord);
+
+  // ---- packing ----
+  m.def("pack_sequences",
+        [](py::array_t<int32_t, py::array::c_style | py::array::forcecast> src_lens,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> tgt_lens,
+           int packed_batch_size, int packed_src_seq_len, int packed_tgt_seq_len, uint64_t seed) {
+          PackResult r = PackSequences(ToVec(src_lens), ToVec(tgt_lens), packed_batch_size,
+                                       packed_src_seq_len, packed_tgt_seq_len, seed);
+          return py::make_tuple(ToArray2D(r.src_segment_ids, r.rows, r.src_len),
+                                ToArray2D(r.src_segment_pos, r.rows, r.src_len),
+                                ToArray2D(r.src_indices_in_input, r.rows, r.src_len),
+                                ToArray2D(r.tgt_segment_ids, r.rows, r.tgt_len),
+                                ToArray2D(r.tgt_segment_pos, r.rows, r.tgt_len),
+                                ToArray2D(r.tgt_indices_in_input, r.rows, r.tgt_len));
+        },
+        py::arg("src_actual_seq_len"), py::arg("tgt_actual_seq_len"), py::arg("packed_batch_size"),
+        py::arg("packed_src_seq_len"), py::arg("packed_tgt_seq_len"), py::arg("seed") = 0);
+  m.def("pack_single_sequence",
+        [](py::array_t<int32_t, py::array::c_style | py::array::forcecast> lens, int cap,
+           bool sequential) { return PackSingleSequence(ToVec(lens), cap, sequential); },
+        py::arg("input_lengths"), py::arg("max_packed_length"),
+        py::arg("require_sequential_order") = false);
+
+  m.def("mass",
+        [](py::array_t<int32_t, py::array::c_style | py::array::forcecast> ids,
+           py::array_t<float, py::array::c_style | py::array::forcecast> weights,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> lens, int32_t mask_id,
+           float mask_ratio, int mask_minlen, int span_len, float random_start_prob,
+           float keep_prob, float rand_prob, float mask_prob, bool mask_target, int vocab_size,
+           int first_unreserved_id, uint64_t seed) {
+          const int batch = static_cast<int>(ids.shape(0)), max_len = static_cast<int>(ids.shape(1));
+          MassOptions o;
+          o.mask_id = mask_id; o.mask_ratio = mask_ratio; o.mask_minlen = mask_minlen;
+          o.span_len = span_len; o.random_start_prob = random_start_prob; o.keep_prob = keep_prob;
+          o.rand_prob = rand_prob; o.mask_prob = mask_prob; o.mask_target = mask_target;
+          o.vocab_size = vocab_size; o.first_unreserved_id = first_unreserved_id;
+          MassResult r = Mass(ToVec(ids), std::vector<float>(weights.data(), weights.data() + weights.size()),
+                              ToVec(lens), batch, max_len, o, seed);
+          py::array_t<float> w({batch, max_len});
+          memcpy(w.mutable_data(), r.tgt_weights.data(), r.tgt_weights.size() * sizeof(float));
+          return py::make_tuple(ToArray2D(r.src_ids, batch, max_len), ToArray2D(r.tgt_ids, batch, max_len),
+                                ToArray2D(r.tgt_labels, batch, max_len), w);
+        },
+        py::arg("ids"), py::arg("weights"), py::arg("actual_seq_len"), py::arg("mask_id") = 3,
+        py::arg("mask_ratio") = 0.5f, py::arg("mask_minlen") = 0, py::arg("span_len") = 100000,
+        py::arg("random_start_prob") = 0.6f, py::arg("keep_prob") = 0.1f, py::arg("rand_prob") = 0.1f,
+        py::arg("mask_prob") = 0.8f, py::arg("mask_target") = true, py::arg("vocab_size") = 0,
+        py::arg("first_unreserved_id") = 4, py::arg("seed") = 0);
+
+  m.def("best_step", &BestStep, py::arg("hist_file"), py::arg("tol") = 0.0,
+        py::arg("minimize") = true);
+
+  py::class_<RandomPermutationSequence>(m, "RandomPermutationSequence")
+      .def(py::init<int64_t, int64_t, bool, uint64_t>(), py::arg("num"), py::arg("batch"),
+           py::arg("repeat"), py::arg("seed") = 0)
+      .def("next", &RandomPermutationSequence::Next);
+}

@@ -1,0 +1,334 @@
+#include "records.h"
+
+#include <glob.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace lbh {
+
+// ------------------------------------------------------------------ crc32c ----
+namespace {
+struct CrcTable {
+  uint32_t t[8][256];
+  CrcTable() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82f63b78u : c >> 1;
+      t[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int s = 1; s < 8; ++s) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xff];
+  }
+};
+const CrcTable& Table() {
+  static const CrcTable tab;
+  return tab;
+}
+}  // namespace
+
+uint32_t Crc32c(const char* data, size_t n, uint32_t crc) {
+  const CrcTable& tb = Table();
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(data);
+  uint32_t c = ~crc;
+  while (n >= 8) {   // slicing-by-8
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = tb.t[7][lo & 0xff] ^ tb.t[6][(lo >> 8) & 0xff] ^ tb.t[5][(lo >> 16) & 0xff] ^
+        tb.t[4][lo >> 24] ^ tb.t[3][hi & 0xff] ^ tb.t[2][(hi >> 8) & 0xff] ^
+        tb.t[1][(hi >> 16) & 0xff] ^ tb.t[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = tb.t[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+  return ~c;
+}
+
+std::vector<std::string> GlobFiles(const std::string& pattern) {
+  std::vector<std::string> out;
+  std::stringstream ss(pattern);
+  std::string item;
+  while (std::getline(ss, item, ',')) {
+    if (item.empty()) continue;
+    glob_t g;
+    if (glob(item.c_str(), 0, nullptr, &g) == 0) {
+      for (size_t i = 0; i < g.gl_pathc; ++i) out.emplace_back(g.gl_pathv[i]);
+    }
+    globfree(&g);
+  }
+  std::sort(out.begin(), out.end());
+  return out;
+}
+
+// --------------------------------------------------------------- iterators ----
+namespace {
+
+class TFRecordIterator : public RecordIterator {
+ public:
+  explicit TFRecordIterator(const std::string& file) : f_(fopen(file.c_str(), "rb")), name_(file) {
+    if (!f_) throw std::runtime_error("cannot open " + file);
+    setvbuf(f_, nullptr, _IOFBF, 1 << 20);
+  }
+  ~TFRecordIterator() override {
+    if (f_) fclose(f_);
+  }
+  bool Next(std::string* out) override {
+    char hdr[12];
+    const size_t got = fread(hdr, 1, 12, f_);
+    if (got == 0) return false;
+    if (got != 12) throw std::runtime_error("truncated tfrecord header in " + name_);
+    uint64_t len;
+    uint32_t len_crc;
+    memcpy(&len, hdr, 8);
+    memcpy(&len_crc, hdr + 8, 4);
+    if (MaskCrc(Crc32c(hdr, 8)) != len_crc) throw std::runtime_error("corrupt length crc in " + name_);
+    out->resize(len);
+    char foot[4];
+    if (fread(out->data(), 1, len, f_) != len || fread(foot, 1, 4, f_) != 4)
+      throw std::runtime_error("truncated tfrecord payload in " + name_);
+    uint32_t data_crc;
+    memcpy(&data_crc, foot, 4);
+    if (MaskCrc(Crc32c(out->data(), len)) != data_crc)
+      throw std::runtime_error("corrupt data crc in " + name_);
+    return true;
+  }
+
+ private:
+  FILE* f_;
+  std::string name_;
+};
+
+class TextLineIterator : public RecordIterator {
+ public:
+  explicit TextLineIterator(const std::string& file) : in_(file) {
+    if (!in_) throw std::runtime_error("cannot open " + file);
+  }
+  bool Next(std::string* out) override { return static_cast<bool>(std::getline(in_, *out)); }
+
+ private:
+  std::ifstream in_;
+};
+
+class IotaIterator : public RecordIterator {
+ public:
+  explicit IotaIterator(const std::string& n) : n_(std::stoll(n)) {}
+  bool Next(std::string* out) override {
+    if (i_ >= n_) return false;
+    *out = std::to_string(i_++);
+    return true;
+  }
+
+ private:
+  int64_t n_, i_ = 0;
+};
+
+void SplitPattern(const std::string& fp, std::string* type, std::string* glob) {
+  const size_t c = fp.find(':');
+  if (c == std::string::npos) {
+    *type = "tfrecord";
+    *glob = fp;
+  } else {
+    *type = fp.substr(0, c);
+    *glob = fp.substr(c + 1);
+  }
+}
+
+std::vector<std::string> ExpandFiles(const std::string& type, const std::string& glob) {
+  if (type == "iota") return {glob};
+  auto files = GlobFiles(glob);
+  if (files.empty()) throw std::runtime_error("no files match " + glob);
+  return files;
+}
+
+}  // namespace
+
+std::unique_ptr<RecordIterator> RecordIterator::Create(const std::string& type,
+                                                       const std::string& file) {
+  if (type == "tfrecord") return std::make_unique<TFRecordIterator>(file);
+  if (type == "text") return std::make_unique<TextLineIterator>(file);
+  if (type == "iota") return std::make_unique<IotaIterator>(file);
+  throw std::runtime_error("unknown record type '" + type + "'");
+}
+
+TFRecordWriter::TFRecordWriter(const std::string& path) : f_(fopen(path.c_str(), "wb")) {
+  if (!f_) throw std::runtime_error("cannot create " + path);
+}
+TFRecordWriter::~TFRecordWriter() { Close(); }
+void TFRecordWriter::Close() {
+  if (f_) fclose(f_);
+  f_ = nullptr;
+}
+void TFRecordWriter::Write(const std::string& rec) {
+  char hdr[12];
+  const uint64_t len = rec.size();
+  memcpy(hdr, &len, 8);
+  const uint32_t lc = MaskCrc(Crc32c(hdr, 8));
+  memcpy(hdr + 8, &lc, 4);
+  const uint32_t dc = MaskCrc(Crc32c(rec.data(), rec.size()));
+  fwrite(hdr, 1, 12, f_);
+  fwrite(rec.data(), 1, rec.size(), f_);
+  fwrite(&dc, 1, 4, f_);
+}
+
+// ----------------------------------------------------------- basic yielder ----
+BasicRecordYielder::BasicRecordYielder(const BasicYielderOptions& opts)
+    : opts_(opts), pop_rng_(opts.seed ? opts.seed * 7919 + 1 : std::random_device{}()) {
+  SplitPattern(opts_.file_pattern, &type_, &glob_);
+  if (opts_.parallelism < 1) opts_.parallelism = 1;
+  if (opts_.bufsize < 1) opts_.bufsize = 1;
+  ExpandFiles(type_, glob_);   // fail fast on a bad pattern
+  main_ = std::thread([this] { MainLoop(); });
+}
+
+BasicRecordYielder::~BasicRecordYielder() { Close(); }
+
+void BasicRecordYielder::Close() {
+  stop_.store(true);
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    cv_not_empty_.notify_all();
+    cv_not_full_.notify_all();
+  }
+  if (main_.joinable()) main_.join();
+}
+
+void BasicRecordYielder::Add(std::vector<std::string>* chunk, std::mt19937_64* rng) {
+  std::unique_lock<std::mutex> l(mu_);
+  for (auto& rec : *chunk) {
+    cv_not_full_.wait(l, [&] { return stop_ || static_cast<int64_t>(buf_.size()) < opts_.bufsize; });
+    if (stop_) return;
+    buf_.emplace_back(std::move(rec));
+    // random-swap insertion keeps the buffer uniformly shuffled
+    const size_t j = (*rng)() % buf_.size();
+    std::swap(buf_[j], buf_.back());
+    if (static_cast<int64_t>(buf_.size()) * 2 >= opts_.bufsize) cv_not_empty_.notify_one();
+  }
+  chunk->clear();
+}
+
+void BasicRecordYielder::ReadShard(const std::vector<std::string>& files, uint64_t seed) {
+  std::mt19937_64 rng(seed);
+  std::vector<std::string> chunk;
+  for (const auto& f : files) {
+    if (stop_) return;
+    auto it = RecordIterator::Create(type_, f);
+    std::string rec;
+    while (!stop_ && it->Next(&rec)) {
+      chunk.emplace_back(std::move(rec));
+      rec.clear();
+      if (chunk.size() >= 64) Add(&chunk, &rng);
+    }
+  }
+  Add(&chunk, &rng);
+}
+
+void BasicRecordYielder::MainLoop() {
+  for (int64_t epoch = 0; !stop_ && (opts_.num_epochs == 0 || epoch < opts_.num_epochs); ++epoch) {
+    epoch_.store(epoch);
+    auto files = ExpandFiles(type_, glob_);
+    const uint64_t eseed =
+        opts_.seed ? (opts_.seed * 0x9e3779b97f4a7c15ull) ^ static_cast<uint64_t>(epoch + 1)
+                   : std::random_device{}();
+    std::mt19937_64 rng(eseed);
+    std::shuffle(files.begin(), files.end(), rng);
+    const int shards = std::min<int>(opts_.parallelism, static_cast<int>(files.size()));
+    std::vector<std::vector<std::string>> per(shards);
+    for (size_t i = 0; i < files.size(); ++i) per[i % shards].push_back(files[i]);
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      epoch_draining_ = false;
+    }
+    std::vector<std::thread> readers;
+    for (int s = 0; s < shards; ++s)
+      readers.emplace_back([this, &per, s, eseed] { ReadShard(per[s], eseed + 1 + s); });
+    for (auto& t : readers) t.join();
+    // Everything of this epoch is in the buffer: let consumers drain it fully before
+    // the next epoch starts (so epochs never mix).
+    std::unique_lock<std::mutex> l(mu_);
+    epoch_draining_ = true;
+    cv_not_empty_.notify_all();
+    cv_not_full_.wait(l, [&] { return stop_ || buf_.empty(); });
+  }
+  std::lock_guard<std::mutex> l(mu_);
+  finished_ = true;
+  cv_not_empty_.notify_all();
+}
+
+bool BasicRecordYielder::Yield(Record* out) {
+  std::unique_lock<std::mutex> l(mu_);
+  cv_not_empty_.wait(l, [&] {
+    return stop_ || finished_ || (!buf_.empty() && (epoch_draining_ ||
+                                                    static_cast<int64_t>(buf_.size()) * 2 >= opts_.bufsize));
+  });
+  if (buf_.empty()) return false;
+  if (opts_.seed == 0) {   // extra extraction randomness for unseeded runs
+    const size_t j = pop_rng_() % buf_.size();
+    std::swap(buf_[j], buf_.back());
+  }
+  out->value = std::move(buf_.back());
+  out->source_id = opts_.source_id;
+  buf_.pop_back();
+  cv_not_full_.notify_all();
+  return true;
+}
+
+// ------------------------------------------------------ sequential yielder ----
+SequentialRecordYielder::SequentialRecordYielder(const std::string& file_pattern,
+                                                 int64_t repeat_count, int source_id)
+    : repeat_(repeat_count), source_id_(source_id) {
+  std::string glob;
+  SplitPattern(file_pattern, &type_, &glob);
+  files_ = ExpandFiles(type_, glob);
+}
+
+bool SequentialRecordYielder::Yield(Record* out) {
+  std::lock_guard<std::mutex> l(mu_);
+  while (true) {
+    if (!it_) {
+      if (file_idx_ >= files_.size()) {
+        ++epoch_;
+        if (repeat_ >= 0 && epoch_ >= std::max<int64_t>(repeat_, 1)) return false;
+        file_idx_ = 0;
+      }
+      it_ = RecordIterator::Create(type_, files_[file_idx_++]);
+    }
+    if (it_->Next(&out->value)) {
+      out->source_id = source_id_;
+      return true;
+    }
+    it_.reset();
+  }
+}
+
+// ---------------------------------------------------- weighted-mix yielder ----
+WeightedMixRecordYielder::WeightedMixRecordYielder(std::vector<std::shared_ptr<Yielder>> children,
+                                                   std::vector<double> weights, uint64_t seed)
+    : children_(std::move(children)), dist_(weights.begin(), weights.end()),
+      rng_(seed ? seed : std::random_device{}()) {
+  if (children_.size() != weights.size() || children_.empty())
+    throw std::runtime_error("WeightedMixRecordYielder: children/weights mismatch");
+}
+
+bool WeightedMixRecordYielder::Yield(Record* out) {
+  int pick;
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    pick = dist_(rng_);
+  }
+  if (!children_[pick]->Yield(out)) return false;
+  out->source_id = pick;
+  return true;
+}
+
+void WeightedMixRecordYielder::Close() {
+  for (auto& c : children_) c->Close();
+}
+
+}  // namespace lbh
