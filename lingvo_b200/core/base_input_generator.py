@@ -264,14 +264,47 @@ class BaseInputGeneratorFromFiles(BaseInputGenerator):
     lim = self.infeed_bucket_batch_limit
     return max(lim) if lim else super().InfeedBatchSize()
 
+  def ProcessRecord(self, record: bytes, source_id: int = 0):
+    """Subclass hook: one serialized record → `(NestedMap of np arrays, bucket_key)`
+    or None to drop it. Used by the default `_DataSourceFromFilePattern`."""
+    raise NotImplementedError(
+        '%s must implement ProcessRecord or _DataSourceFromFilePattern' %
+        type(self).__name__)
+
   def _DataSourceFromFilePattern(self, file_pattern, input_source_weights=None,
                                  **extra_input_kwargs):
-    """Subclass hook: returns NestedMap(data=…, bucket_keys=…) per call."""
-    raise NotImplementedError()
+    """Returns a callable producing one batch NestedMap per call. Default: the
+    native yielder + bucketing batcher (`core/generic_input.py`) over
+    `self.ProcessRecord` (the role of the per-task `generic_input_op` wrappers in
+    the reference, e.g. `tasks/mt/input_generator.py`)."""
+    from lingvo_b200.core import generic_input  # pylint: disable=g-import-not-at-top
+    args = self.CommonInputOpArgs()
+    gi = generic_input.GenericInput(
+        self.ProcessRecord, file_pattern=file_pattern,
+        bucket_upper_bound=args['bucket_upper_bound'] or [1 << 30],
+        bucket_batch_limit=args['bucket_batch_limit'] or [self.InfeedBatchSize()],
+        file_random_seed=args['file_random_seed'],
+        file_buffer_size=args['file_buffer_size'],
+        file_parallelism=args['file_parallelism'], num_threads=args['num_threads'],
+        flush_every_n=args['flush_every_n'], repeat_count=args['repeat_count'],
+        require_sequential_order=args['require_sequential_order'],
+        input_source_weights=input_source_weights, **extra_input_kwargs)
+    self._generic_input = gi
+
+    def _Next():
+      batch, keys = gi.GetNext()
+      batch = batch if isinstance(batch, NestedMap) else NestedMap(data=batch)
+      batch = batch.Transform(
+          lambda x: torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x)
+      batch.bucket_keys = torch.from_numpy(np.asarray(keys))
+      return batch
+    return _Next
 
   def _InputBatch(self):
-    ret = self.datasource.GetNext()
-    return ret
+    ds = self.datasource
+    if getattr(ds, '_input_generator', None) is None:
+      ds.SetInputGenerator(self)
+    return ds.GetNext()
 
 
 class BaseSequenceInputGenerator(BaseInputGeneratorFromFiles):
