@@ -185,11 +185,6 @@ class BaseTask(base_layer.BaseLayer):
     return self.input
 
   @property
-  def encoder(self):
-    return self.children.get('enc', self._encoder) if 'enc' in self.children \
-        else self._encoder
-
-  @property
   def global_step(self) -> int:
     return self._global_step
 
