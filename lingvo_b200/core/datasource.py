@@ -149,7 +149,6 @@ class CrossBatchMixingDataSource(DataSource):
     p = super().Params()
     p.Define('sub', None, 'List of DataSource params.')
     p.Define('weights', None, 'List of weights (or schedule layers).')
-    p.Define('random_seed', None, 'Seed of the source choice.')
     return p
 
   def __init__(self, params):
@@ -333,7 +332,6 @@ class MixerDataSource(DataSource):
     p = super().Params()
     p.Define('sub', None, 'List of DataSource params.')
     p.Define('weights', None, 'Sampling weights.')
-    p.Define('random_seed', None, 'Seed.')
     p.Define('broadcast_dataset_structures', False, 'Kept for parity.')
     return p
 

@@ -151,6 +151,8 @@ class Base(base_layer.BaseLayer):
     grads = [g for _, g in pairs]
     self._refreshed = set()
     with torch.no_grad():
+      if grad_scale is not None:
+        grad_scale = grad_scale.reshape(())     # 0-dim: never broadcasts scalar grads up
       if grad_scale is not None and not self.supports_grad_scale:
         grads = [torch.where(grad_scale == 0, torch.zeros_like(g),
                              g * grad_scale.to(g.dtype)) for g in grads]

@@ -1,0 +1,165 @@
+"""Dual-encoder (image↔text, …) retrieval model (ref `lingvo/tasks/milan/dual_encoder.py`).
+
+`DualEncoder` (ref :66): per-modality encoder → optional projection to a joint
+space → L2 normalise → all-pairs scores; symmetric multi-label contrastive loss
+with a learnable temperature. With data parallelism the result-side embeddings
+are concatenated across replicas (the reference's `tpu_utils.CrossReplicaConcat`
+with CollectivePermute) via an NCCL all-gather that keeps gradients for the
+local shard.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from lingvo_b200.core import base_layer
+from lingvo_b200.core import base_model
+from lingvo_b200.core import hyperparams
+from lingvo_b200.core import layers
+from lingvo_b200.core import py_utils
+from lingvo_b200.core.nested_map import NestedMap
+from lingvo_b200.models.milan import labels as label_lib
+from lingvo_b200.models.milan import score_functions
+
+
+def EncoderConfig() -> hyperparams.Params:
+  """One modality's config (ref :41)."""
+  p = hyperparams.Params()
+  p.Define('input_features', '', 'Key of the raw features in the input batch.')
+  p.Define('id_feature', '', 'Key of per-example ids (for label functions).')
+  p.Define('encoder', None, 'Encoder layer params: FProp(features) → [B, D].')
+  p.Define('output_dim', None, 'Encoder output dim.')
+  p.Define('encoder_output_dim', None, 'Alias of output_dim.')
+  return p
+
+
+class _AllGatherWithGrad(torch.autograd.Function):
+  """Concat over replicas; backward returns this replica's slice of the gradient."""
+
+  @staticmethod
+  def forward(ctx, x):
+    world = dist.get_world_size()
+    outs = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(outs, x.contiguous())
+    ctx.rank, ctx.n = dist.get_rank(), x.shape[0]
+    return torch.cat(outs, 0)
+
+  @staticmethod
+  def backward(ctx, g):
+    g = g.contiguous()
+    dist.all_reduce(g)
+    return g[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n]
+
+
+def CrossReplicaConcat(x):
+  """Concatenates `x` along dim 0 across data-parallel replicas (ref `tpu_utils.py:75`)."""
+  if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    return _AllGatherWithGrad.apply(x)
+  return x
+
+
+class DualEncoder(base_layer.BaseLayer):
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.name = 'dual_encoder'
+    p.Define('encoder_configs', {}, 'modality name → EncoderConfig().')
+    p.Define('score_function', score_functions.DotProductScoreFunction.Params(), 'Scores.')
+    p.Define('joint_embedding_dim', 0, 'Project every modality to this dim (0: none).')
+    p.Define('regularization_loss_weight', 1.0, 'Kept for parity.')
+    p.Define('loss_weights', {}, '(query, result) → weight.')
+    p.Define('label_fn', None, 'ExamplePairLabeler or callable.')
+    p.Define('learnable_temperature', True, 'Learn the softmax temperature.')
+    p.Define('initial_temperature', 0.07, 'Initial temperature.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert p.encoder_configs and p.loss_weights
+    self._modalities = sorted(p.encoder_configs)
+    for m in self._modalities:
+      cfg = p.encoder_configs[m]
+      self.CreateChild('encoder_%s' % m, cfg.encoder)
+      if p.joint_embedding_dim:
+        self.CreateChild('projection_%s' % m, layers.ProjectionLayer.Params().Set(
+            input_dim=cfg.output_dim or cfg.encoder_output_dim,
+            output_dim=p.joint_embedding_dim, activation='NONE', batch_norm=False,
+            has_bias=True))
+    self.CreateChild('score_function', p.score_function)
+
+  def _CreateLayerVariables(self):
+    p = self.params
+    import math
+    self.CreateVariable('log_temperature', py_utils.WeightParams(
+        [], py_utils.WeightInit.Constant(math.log(p.initial_temperature)), p.dtype),
+        trainable=p.learnable_temperature)
+
+  def EncodeModality(self, theta, modality, features):
+    p = self.params
+    emb = self.children['encoder_%s' % modality].FProp(theta['encoder_%s' % modality], features)
+    if p.joint_embedding_dim:
+      emb = self.children['projection_%s' % modality].FProp(
+          theta['projection_%s' % modality], emb)
+    return torch.nn.functional.normalize(emb.float(), dim=-1)
+
+  def EncodeBatch(self, theta, batch):
+    p = self.params
+    return NestedMap({m: self.EncodeModality(theta, m, batch[p.encoder_configs[m].input_features])
+                      for m in self._modalities})
+
+  def FProp(self, theta, batch):
+    """→ (loss, metrics NestedMap)."""
+    p = self.params
+    emb = self.EncodeBatch(theta, batch)
+    temp = torch.exp(theta.log_temperature.float())
+    total = 0.0
+    metrics = NestedMap()
+    for (q, r), w in sorted(p.loss_weights.items()):
+      if not w:
+        continue
+      results = CrossReplicaConcat(emb[r])
+      scores = self.score_function.FProp(theta.score_function, emb[q], results) / temp
+      n, m = scores.shape
+      offset = 0
+      if m != n and dist.is_available() and dist.is_initialized():
+        offset = dist.get_rank() * n
+      labels = torch.zeros(n, m, device=scores.device)
+      labels[torch.arange(n), torch.arange(n) + offset] = 1.0
+      if p.label_fn is not None and m == n:
+        labels = p.label_fn(n, scores.device, batch)
+      loss = label_lib.MultiLabelContrastiveLoss(labels, scores).mean()
+      total = total + w * loss
+      acc = (scores.argmax(-1) == torch.arange(n, device=scores.device) + offset).float().mean()
+      metrics['loss_%s_to_%s' % (q, r)] = loss
+      metrics['recall_at_1_%s_to_%s' % (q, r)] = acc
+    return total, metrics
+
+
+class MilanTask(base_model.BaseTask):
+  """Task wrapper (ref :299)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.name = 'milan'
+    p.Define('dual_encoder', DualEncoder.Params(), 'Dual encoder.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('dual_encoder', self.params.dual_encoder)
+
+  def FPropTower(self, theta, input_batch):
+    loss, m = self.dual_encoder.FProp(theta.dual_encoder, input_batch)
+    n = float(next(iter(input_batch.Flatten())).shape[0])
+    metrics = NestedMap(loss=(loss, n))
+    for k, v in m.items():
+      metrics[k] = (v, n)
+    return metrics, NestedMap()
+
+  def Inference(self):
+    return {m: (lambda feats, m=m: self.dual_encoder.EncodeModality(
+        self.theta.dual_encoder, m, feats)) for m in self.dual_encoder._modalities}  # pylint: disable=protected-access
