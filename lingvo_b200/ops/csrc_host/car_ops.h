@@ -1,0 +1,36 @@
+// 3-D detection geometry (SURVEY §2.7 "car ops"): rotated-box IoU, 3-D NMS,
+// point → pillar grid assignment, farthest-point sampling. Native re-designs of
+// `tasks/car/ops/{pairwise_iou_op,nms_3d_op,point_grid_op,sampling_ops}.cc`.
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+namespace lbh {
+
+// Boxes are 7-DOF: (x, y, z, dx, dy, dz, heading about +z).
+// iou[n, m] = volume(A_n ∩ B_m) / volume(A_n ∪ B_m): exact convex-polygon clipping
+// in the ground plane × overlap of the z extents.
+void PairwiseIou3D(const float* a, int n, const float* b, int m, float* iou);
+
+// Greedy per-class NMS. scores [n, num_classes]; a box is kept for class c if its
+// score > score_thresh[c] and its IoU with every already-kept box of that class is
+// <= nms_iou_thresh[c]. Returns for each class up to max_boxes_per_class indices
+// (padded with -1) in decreasing score order.
+std::vector<int32_t> NonMaxSuppression3D(const float* boxes, const float* scores, int n,
+                                         int num_classes, const std::vector<float>& nms_iou_thresh,
+                                         const std::vector<float>& score_thresh,
+                                         int max_boxes_per_class);
+
+// Assigns points to an (nx, ny) pillar grid over [x0,x1)×[y0,y1); keeps at most
+// `max_pillars` non-empty pillars and `points_per_pillar` points each (first come).
+// Outputs: pillar_points [P, K, dims] (zero padded), pillar_xy [P, 2] grid indices,
+// pillar_count [P]; returns number of occupied pillars.
+int PointsToPillars(const float* points, int n, int dims, float x0, float x1, float y0, float y1,
+                    int nx, int ny, int max_pillars, int points_per_pillar, float* pillar_points,
+                    int32_t* pillar_xy, int32_t* pillar_count);
+
+// Farthest-point sampling: indices of `k` points, starting from point 0.
+std::vector<int32_t> FarthestPointSample(const float* xyz, int n, int k);
+
+}  // namespace lbh

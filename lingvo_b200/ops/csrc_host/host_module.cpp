@@ -11,6 +11,7 @@
 #include <mutex>
 #include <thread>
 
+#include "car_ops.h"
 #include "records.h"
 #include "text_ops.h"
 
@@ -364,6 +365,48 @@ PYBIND11_MODULE(_H, m) {
 
   m.def("best_step", &BestStep, py::arg("hist_file"), py::arg("tol") = 0.0,
         py::arg("minimize") = true);
+
+  // ---- 3-D detection geometry ----
+  using FArr = py::array_t<float, py::array::c_style | py::array::forcecast>;
+  m.def("pairwise_iou_3d", [](FArr a, FArr b) {
+    const int n = static_cast<int>(a.shape(0)), k = static_cast<int>(b.shape(0));
+    py::array_t<float> out({n, k});
+    {
+      py::gil_scoped_release rel;
+      PairwiseIou3D(a.data(), n, b.data(), k, out.mutable_data());
+    }
+    return out;
+  });
+  m.def("nms_3d",
+        [](FArr boxes, FArr scores, std::vector<float> nms_iou, std::vector<float> score_thresh,
+           int max_boxes) {
+          const int n = static_cast<int>(boxes.shape(0));
+          const int c = scores.ndim() == 2 ? static_cast<int>(scores.shape(1)) : 1;
+          auto idx = NonMaxSuppression3D(boxes.data(), scores.data(), n, c, nms_iou, score_thresh,
+                                         max_boxes);
+          py::array_t<int32_t> out({c, max_boxes});
+          memcpy(out.mutable_data(), idx.data(), idx.size() * sizeof(int32_t));
+          return out;
+        },
+        py::arg("boxes"), py::arg("scores"), py::arg("nms_iou_threshold"),
+        py::arg("score_threshold"), py::arg("max_boxes_per_class"));
+  m.def("points_to_pillars",
+        [](FArr points, float x0, float x1, float y0, float y1, int nx, int ny, int max_pillars,
+           int points_per_pillar) {
+          const int n = static_cast<int>(points.shape(0)), d = static_cast<int>(points.shape(1));
+          py::array_t<float> pp({max_pillars, points_per_pillar, d});
+          py::array_t<int32_t> xy({max_pillars, 2}), cnt({max_pillars});
+          memset(pp.mutable_data(), 0, static_cast<size_t>(pp.nbytes()));
+          memset(xy.mutable_data(), 0, static_cast<size_t>(xy.nbytes()));
+          memset(cnt.mutable_data(), 0, static_cast<size_t>(cnt.nbytes()));
+          const int used = PointsToPillars(points.data(), n, d, x0, x1, y0, y1, nx, ny, max_pillars,
+                                           points_per_pillar, pp.mutable_data(), xy.mutable_data(),
+                                           cnt.mutable_data());
+          return py::make_tuple(pp, xy, cnt, used);
+        });
+  m.def("farthest_point_sample", [](FArr xyz, int k) {
+    return FarthestPointSample(xyz.data(), static_cast<int>(xyz.shape(0)), k);
+  });
 
   py::class_<RandomPermutationSequence>(m, "RandomPermutationSequence")
       .def(py::init<int64_t, int64_t, bool, uint64_t>(), py::arg("num"), py::arg("batch"),
