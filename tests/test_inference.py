@@ -1,0 +1,42 @@
+"""Inference export + Predictor round trip (CPU)."""
+
+import torch
+
+from lingvo_b200.core import base_model
+from lingvo_b200.core import inference_graph_exporter
+from lingvo_b200.core import predictor
+from lingvo_b200.core import tokenizers
+from lingvo_b200.models.lm import input_generator as lm_inp
+from lingvo_b200.models.lm import layers as lm_layers
+from lingvo_b200.models.lm import model as lm_model
+
+
+def _Cfg(tmp_path):
+  text = tmp_path / 't.txt'
+  text.write_text('the cat sat\n' * 50)
+  inp = lm_inp.LmInput.Params().Set(name='inp', file_pattern='text:' + str(text),
+                                    bucket_upper_bound=[40], bucket_batch_limit=[4],
+                                    file_buffer_size=8, file_parallelism=1)
+  inp.tokenizer = tokenizers.AsciiTokenizer.Params()
+  task = lm_model.LanguageModel.Params().Set(name='lm', input=inp)
+  task.lm = lm_layers.RnnLm.CommonParams(vocab_size=76, emb_dim=8, num_layers=1, rnn_dims=8)
+  cfg = base_model.SingleTaskModel.Params(task)
+  return cfg
+
+
+def test_export_and_predict(tmp_path):
+  cfg = _Cfg(tmp_path)
+  model = cfg.Instantiate()
+  out_dir = str(tmp_path / 'export')
+  graph = inference_graph_exporter.InferenceGraphExporter.Export(
+      cfg, export_path=out_dir, model=model)
+  assert 'default' in graph.subgraphs
+  assert graph.subgraphs['default']['feeds'] == ['ids', 'paddings']
+  loaded = inference_graph_exporter.LoadInferenceGraph(out_dir)
+  assert loaded.subgraphs == graph.subgraphs
+  pred = predictor.Predictor(out_dir, device='cpu', model_cfg=cfg.Copy())
+  ids = torch.randint(3, 30, (2, 7))
+  pads = torch.zeros(2, 7)
+  got = pred.Run(['log_pplx_per_token'], ids=ids, paddings=pads)[0]
+  want = model.tasks[0]._InferenceDefault(ids, pads).log_pplx_per_token
+  torch.testing.assert_close(got, want.detach(), atol=1e-5, rtol=1e-5)
