@@ -196,7 +196,7 @@ class BaseLayer(metaclass=BaseLayerMeta):
   def __init__(self, params):
     assert params.name, (
         'Layer params for %s must have a "name"' % self.__class__.__name__)
-    if not re.match(r'^[A-Za-z_][A-Za-z0-9_.\-]*$', params.name):
+    if not re.match(r'^[A-Za-z0-9_][A-Za-z0-9_.\-]*$', params.name):
       raise ValueError('Invalid layer name %r' % params.name)
     self._parent = _BUILD.stack[-2] if len(_BUILD.stack) > 1 else None
     self._params = params.Copy()

@@ -15,7 +15,6 @@ from lingvo_b200.models.mt import encoder
 def InitTrainDatasetParams(vocab_size=None, params=None):
   """Bucketing for RNMT-style training data (ref :31)."""
   p = params
-  p.is_nmt_example = True if 'is_nmt_example' in p else None
   p.file_random_seed = 0
   p.file_parallelism = 16
   p.file_buffer_size = 10000000
