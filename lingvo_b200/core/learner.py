@@ -102,6 +102,17 @@ class Learner(base_layer.BaseLayer):
     p = self.params
     losses, var_grads, eval_metrics = self._ComputeLossesAndGradients(
         metrics, vmap, retain_graph=retain_graph)
+    fused_update = getattr(self, 'fused_update', None)
+    if fused_update is not None:
+      # ZeRO path: reduce-scatter + clip + Adam on the master shard + all-gather of the
+      # new bf16 weights happen inside the engine (parallel/zero.py); nothing else to do.
+      lr = self.LearningRate()
+      gnorm = fused_update.Apply(lr, var_grads,
+                                 clip_norm=float(p.clip_gradient_norm_to_value or 0.0))
+      eval_metrics['grad_norm/all'] = (gnorm.reshape(()).float(), torch.tensor(1.0))
+      self._AddScalar(eval_metrics, 'learning_rate', lr)
+      self._var_grads = var_grads
+      return losses, {self._Key(k): v for k, v in eval_metrics.items()}
     if self.grad_sync is not None:
       var_grads = self.grad_sync(var_grads)
     if 'tpu_embedding_var_grads' in var_grads:

@@ -380,3 +380,20 @@ class MoELm8ETiny(MoELmTemplate):
   BATCH_SIZE_PER_GPU = 4
   VOCAB_SIZE = 256
   TRAIN_STEPS_PER_LOOP = 2
+
+
+@model_registry.RegisterSingleTaskModel
+class DenseLmTiny(DenseLmTemplate):
+  """Tiny dense LM for tests (data-parallel / ZeRO-Adam checks)."""
+  SEQUENCE_LENGTH = 64
+  MODEL_DIM = 64
+  HIDDEN_DIM = 128
+  NUM_HEADS = 4
+  ATTENTION_KEY_VALUE_DIM = 16
+  NUM_TRANSFORMER_LAYERS = 2
+  VOCAB_SIZE = 256
+  BATCH_DIM_PER_DEVICE = 4
+  NUM_DEVICES_PER_SPLIT = 1
+  DEVICE_MESH_SHAPE = [1, 1]
+  TRAIN_STEPS_PER_LOOP = 2
+  GATED_GELU = False

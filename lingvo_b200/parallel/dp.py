@@ -79,6 +79,14 @@ def Attach(task):
   if ctx.mode == 'fused' and task.Device().type == 'cuda':
     from lingvo_b200.parallel import zero
     # Mixed-precision copies must exist before gradients are produced in bf16.
+    has_ep = any(getattr(v, 'expert_parallel', False) for v in task.vars.Flatten())
+    adam_only = all(type(l.optimizer).__name__ in ('Adam', 'AdamV2') for l in task.learners)
+    if adam_only and not has_ep and len(task.learners) == 1:
+      # ZeRO-Adam: optimizer state + fp32 masters sharded 1/W, RS + Adam + AG in one kernel.
+      engine = zero.ZeroAdam(task, task.learners[0], ctx)
+      task.learners[0].fused_update = engine
+      task._mixed_precision_attached = True   # pylint: disable=protected-access
+      return engine
     task.EnableMixedPrecision()
     fused = zero.FusedAllReduce(task, ctx)
   for lrn in task.learners:
