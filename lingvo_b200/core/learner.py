@@ -212,8 +212,20 @@ class Learner(base_layer.BaseLayer):
     stats = {}
     all_grad_norm = torch.sqrt(py_utils.SumSquared(
         [vg.grad for vg in leaves]).to(dev))
-    all_var_norm = torch.sqrt(py_utils.SumSquared(
-        [vg.var.detach() for vg in leaves]).to(dev))
+    # Σw²: variables stepped by the fused Adafactor carry it from their last update
+    # (no extra pass over the fp32 masters); the rest are reduced directly.
+    carried, direct = [], []
+    if dev.type == 'cuda':
+      from lingvo_b200.ops import optim as fused_optim  # pylint: disable=g-import-not-at-top
+      for vg in leaves:
+        c = fused_optim.carried_sumsq(vg.var)
+        (carried if c is not None else direct).append(c if c is not None else vg.var.detach())
+    else:
+      direct = [vg.var.detach() for vg in leaves]
+    var_sumsq = py_utils.SumSquared(direct).to(dev) if direct else torch.zeros((), device=dev)
+    if carried:
+      var_sumsq = var_sumsq + torch.cat(carried).sum()
+    all_var_norm = torch.sqrt(var_sumsq)
     self._AddScalar(stats, 'grad_norm/all', all_grad_norm)
     self._AddScalar(stats, 'var_norm/all', all_var_norm)
     grad_norm_is_nan_or_inf = ~torch.isfinite(all_grad_norm)

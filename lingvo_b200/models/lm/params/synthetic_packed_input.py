@@ -69,6 +69,9 @@ class SyntheticTrain(base_input_generator.BaseInputGenerator):
         segment_pos=seg_pos.unsqueeze(0).expand(b, l).contiguous())
     if p.pin_memory and torch.cuda.is_available():
       batch = batch.Transform(lambda t: t.pin_memory())
+    # Host-side knowledge: every position belongs to a segment (ids ≥ 1), so the model
+    # may skip its padding masks. Computed from host data, no device sync involved.
+    batch.tgt.all_valid = True
     return batch
 
 

@@ -25,6 +25,15 @@ def _Scratch(var, n):
   return ent[0], False
 
 
+def carried_sumsq(var):
+  """Device scalar Σw² of `var` as left by its last fused Adafactor step (i.e. the norm²
+  of the *current* weights), or None if not available."""
+  ent = _SCRATCH.get(id(var))
+  if ent is None or ent[1] != var.data_ptr():
+    return None
+  return ent[0][2:3]
+
+
 def Invalidate():
   """Drops carried optimizer scratch (call after weights change outside the
   optimizer, e.g. checkpoint restore)."""
