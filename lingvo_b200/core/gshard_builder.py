@@ -263,7 +263,9 @@ class SelfAttentionLayer(_BuilderLayer):
       bias = bias + rb
     return bias
 
-  def FProp(self, theta, x, segment_id, segment_pos):
+  supports_fused_residual = True
+
+  def FProp(self, theta, x, segment_id, segment_pos, residual=None):
     b = self.bp
     bsz, l, m = x.shape
     h, d = b.attention_num_heads, b.attention_key_value_dim
@@ -296,14 +298,14 @@ class SelfAttentionLayer(_BuilderLayer):
         o = attention_ops.rel_bias_attention(
             q, k, v, rel, mask, 1.0,
             causal=self.params.decoder and not b.decoder_skip_causal_mask)
-        out = gemm.linear(o.reshape(bsz, l, h * d), wo.to(x.dtype))
+        out = gemm.linear(o.reshape(bsz, l, h * d), wo.to(x.dtype), residual=residual)
         return out, torch.zeros((), device=x.device, dtype=torch.float32)
     bias = self._Bias(theta, segment_id, segment_pos,
                       x.dtype if (simple and x.is_cuda) else torch.float32)
     o = _AttentionCore(q, k, v, bias, b.atten_logit_cap,
                        b.attention_extra_logit, b.attention_dropout_prob
                        if not self.do_eval else 0.0)
-    out = gemm.linear(o.reshape(bsz, l, h * d), wo.to(x.dtype))
+    out = gemm.linear(o.reshape(bsz, l, h * d), wo.to(x.dtype), residual=residual)
     return out, torch.zeros((), device=x.device, dtype=torch.float32)
 
 
@@ -384,7 +386,9 @@ class DenseReluDenseLayer(_BuilderLayer):
       self.CreateVariable('bi', WeightParams([h], WeightInit.Constant(0.), dt))
       self.CreateVariable('bo', WeightParams([m], WeightInit.Constant(0.), dt))
 
-  def FProp(self, theta, x, segment_id=None, segment_pos=None):
+  supports_fused_residual = True
+
+  def FProp(self, theta, x, segment_id=None, segment_pos=None, residual=None):
     from lingvo_b200.ops import gemm
     b = self.bp
     p = self.params
@@ -396,7 +400,7 @@ class DenseReluDenseLayer(_BuilderLayer):
           gemm.linear(x, theta.wi_1.to(x.dtype)))
     elif act == 'RELU' and bi is None and bo is None and not (
         b.dropout_rate and not self.do_eval):
-      out = gemm.ffn_relu(x, theta.wi.to(x.dtype), theta.wo.to(x.dtype))
+      out = gemm.ffn_relu(x, theta.wi.to(x.dtype), theta.wo.to(x.dtype), residual=residual)
       return out, torch.zeros((), device=x.device, dtype=torch.float32)
     elif act == 'RELU':
       h = gemm.linear(x, theta.wi.to(x.dtype), bi, act='RELU')
@@ -404,7 +408,7 @@ class DenseReluDenseLayer(_BuilderLayer):
       h = _Act(p.activation)(gemm.linear(x, theta.wi.to(x.dtype), bi))
     if b.dropout_rate and not self.do_eval:
       h = F.dropout(h, b.dropout_rate, training=True)
-    out = gemm.linear(h, theta.wo.to(x.dtype), bo)
+    out = gemm.linear(h, theta.wo.to(x.dtype), bo, residual=residual)
     return out, torch.zeros((), device=x.device, dtype=torch.float32)
 
 
@@ -561,6 +565,15 @@ class DecoderBlock(_BuilderLayer):
       mask = (i.segment_id != 0).unsqueeze(-1).to(i.vec.dtype)
       x_in = i.vec * mask
     x = self.ln.FProp(theta.ln, x_in) if p.norm_policy != 'primer_post' else x_in
+    fuse_res = (getattr(self.layer, 'supports_fused_residual', False) and
+                p.post_norm is None and not (b.dropout_rate and not self.do_eval))
+    if fuse_res:
+      # x_in + f(x) comes out of the sub-layer's last GEMM epilogue.
+      y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos, residual=x_in)
+      o = i.copy()
+      o.vec = y
+      o.aux_loss = i.aux_loss + aux
+      return o
     y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos)
     if p.post_norm is not None:
       y = self.post_ln.FProp(theta.post_ln, y)

@@ -1,0 +1,136 @@
+"""Matplotlib figure summaries (ref `lingvo/core/plot.py`): render numpy data into image
+summaries (`MatplotlibFigureSummary`, `Image`, `Scatter`, `Curve`). Matplotlib is optional;
+without it the helpers return None and summaries are skipped."""
+import io
+
+import numpy as np
+
+try:
+  import matplotlib  # pylint: disable=g-import-not-at-top
+  matplotlib.use('Agg')
+  from matplotlib import pyplot as plt  # pylint: disable=g-import-not-at-top
+  _HAS_MPL = True
+except Exception:  # pylint: disable=broad-except
+  plt = None
+  _HAS_MPL = False
+
+
+def ToUnicode(text):
+  return text.decode('utf-8') if isinstance(text, bytes) else text
+
+
+def AddPlot(unused_fig, axes, data, title=u'', xlabel=u'', ylabel=u'', fontsize='small',
+            xlim=None, ylim=None, suppress_xticks=False, suppress_yticks=False):
+  axes.plot(data)
+  axes.set_title(ToUnicode(title), size=fontsize)
+  axes.set_xlabel(ToUnicode(xlabel), size=fontsize)
+  axes.set_ylabel(ToUnicode(ylabel), size=fontsize)
+  if xlim:
+    axes.set_xlim(xlim)
+  if ylim:
+    axes.set_ylim(ylim)
+  if suppress_xticks:
+    axes.set_xticks([])
+  if suppress_yticks:
+    axes.set_yticks([])
+
+
+def AddImage(fig, axes, data, cmap='bone_r', clim=None, show_colorbar=True, title=u'',
+             xlabel=u'', ylabel=u'', fontsize='small', origin='lower', suppress_xticks=False,
+             suppress_yticks=False, aspect='auto', vmin=None, vmax=None):
+  image = axes.imshow(data, cmap=cmap, origin=origin, aspect=aspect, interpolation='nearest',
+                      vmin=vmin, vmax=vmax)
+  if show_colorbar:
+    fig.colorbar(image, ax=axes)
+  if clim is not None:
+    image.set_clim(clim)
+  axes.set_title(ToUnicode(title), size=fontsize)
+  axes.set_xlabel(ToUnicode(xlabel), size=fontsize)
+  axes.set_ylabel(ToUnicode(ylabel), size=fontsize)
+  if suppress_xticks:
+    axes.set_xticks([])
+  if suppress_yticks:
+    axes.set_yticks([])
+
+
+def AddScatterPlot(unused_fig, axes, xs, ys, title=u'', xlabel=u'', ylabel=u'',
+                   fontsize='small', xlim=None, ylim=None, **kwargs):
+  axes.scatter(xs, ys, **kwargs)
+  axes.set_title(ToUnicode(title), size=fontsize)
+  axes.set_xlabel(ToUnicode(xlabel), size=fontsize)
+  axes.set_ylabel(ToUnicode(ylabel), size=fontsize)
+  if xlim:
+    axes.set_xlim(xlim)
+  if ylim:
+    axes.set_ylim(ylim)
+
+
+def FigureToPng(fig):
+  buf = io.BytesIO()
+  fig.savefig(buf, format='png')
+  plt.close(fig)
+  return buf.getvalue()
+
+
+class MatplotlibFigureSummary:
+  """Collects subplots and renders one PNG per batch element."""
+
+  def __init__(self, name, figsize=(8, 10), max_outputs=3, subplot_grid_shape=None,
+               gridspec_kwargs=None, plot_func=AddImage, shared_subplot_kwargs=None):
+    self._name, self._figsize, self._max = name, figsize, max_outputs
+    self._grid, self._plot_func = subplot_grid_shape, plot_func
+    self._shared = shared_subplot_kwargs or {}
+    self._subplots = []
+
+  def AddSubplot(self, tensor_list, plot_func=None, **kwargs):
+    merged = dict(self._shared)
+    merged.update(kwargs)
+    self._subplots.append((tensor_list, plot_func or self._plot_func, merged))
+
+  def Finalize(self):
+    """→ list of PNG bytes (one per example) or None without matplotlib."""
+    if not _HAS_MPL or not self._subplots:
+      return None
+    n = min(self._max, min(len(np.asarray(t[0][0])) for t in self._subplots))
+    grid = self._grid or (len(self._subplots), 1)
+    out = []
+    for i in range(n):
+      fig = plt.figure(figsize=self._figsize)
+      for k, (tensors, fn, kw) in enumerate(self._subplots):
+        ax = fig.add_subplot(grid[0], grid[1], k + 1)
+        fn(fig, ax, *[np.asarray(t)[i] for t in tensors], **kw)
+      out.append(FigureToPng(fig))
+    return out
+
+
+def Image(name, figsize, image, setter=None, **kwargs):
+  if not _HAS_MPL:
+    return None
+  fig = plt.figure(figsize=figsize)
+  ax = fig.add_subplot(1, 1, 1)
+  AddImage(fig, ax, np.asarray(image), **kwargs)
+  if setter:
+    setter(fig, ax)
+  return FigureToPng(fig)
+
+
+def Scatter(name, figsize, xs, ys, setter=None, **kwargs):
+  if not _HAS_MPL:
+    return None
+  fig = plt.figure(figsize=figsize)
+  ax = fig.add_subplot(1, 1, 1)
+  AddScatterPlot(fig, ax, np.asarray(xs), np.asarray(ys), **kwargs)
+  if setter:
+    setter(fig, ax)
+  return FigureToPng(fig)
+
+
+def Curve(name, figsize, xs, ys, setter=None, **kwargs):
+  if not _HAS_MPL:
+    return None
+  fig = plt.figure(figsize=figsize)
+  ax = fig.add_subplot(1, 1, 1)
+  ax.plot(np.asarray(xs), np.asarray(ys), **kwargs)
+  if setter:
+    setter(fig, ax)
+  return FigureToPng(fig)

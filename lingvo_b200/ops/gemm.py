@@ -90,9 +90,14 @@ class _LinearFn(torch.autograd.Function):
   """y = act(x @ w + b) with grouped (leading-G) or plain 2-D operands."""
 
   @staticmethod
-  def forward(ctx, x, w, bias, act):
+  def forward(ctx, x, w, bias, act, residual=None):
     act_id = ACT_IDS[act] if not isinstance(act, int) else act
-    y = gemm(x, w, True, False, bias=bias, act=act_id)
+    if residual is not None:
+      assert act_id == 0, 'residual epilogue needs act=None'
+      y = gemm(x, w, True, False, bias=bias, aux=residual.contiguous(), aux_mode=AUX_ADD)
+    else:
+      y = gemm(x, w, True, False, bias=bias, act=act_id)
+    ctx.has_res = residual is not None
     ctx.act_id = act_id
     ctx.has_bias = bias is not None
     if act_id not in (0, 1):
@@ -116,19 +121,28 @@ class _LinearFn(torch.autograd.Function):
       dw = dw.to(w.dtype)
     if ctx.has_bias and ctx.needs_input_grad[2]:
       db = dy.float().sum(dim=-2)
-    return dx, dw, db, None
+    return dx, dw, db, None, (dy if ctx.has_res else None)
 
 
-def linear(x, w, bias=None, act=None):
-  """x[..., K] @ w[K, N] (+bias, act) on the tcgen05 path (bf16)."""
+def linear(x, w, bias=None, act=None, residual=None):
+  """x[..., K] @ w[K, N] (+bias, act | +residual) on the tcgen05 path (bf16).
+
+  `residual` (same shape as the output) is added in the GEMM epilogue — the
+  sub-layer's `x + f(x)` costs no extra pass."""
   lead = x.shape[:-1]
   x2 = x.reshape(-1, x.shape[-1])
   if x2.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or not x2.is_cuda:
     y = torch.matmul(x2, w)
     if bias is not None:
       y = y + bias.to(y.dtype)
-    return _act_ref(y, act).reshape(*lead, w.shape[-1])
-  y = _LinearFn.apply(x2, w, bias, act)
+    y = _act_ref(y, act)
+    if residual is not None:
+      y = y + residual.reshape(y.shape).to(y.dtype)
+    return y.reshape(*lead, w.shape[-1])
+  r2 = residual.reshape(-1, w.shape[-1]) if residual is not None else None
+  if r2 is not None and r2.dtype != torch.bfloat16:
+    r2 = r2.to(torch.bfloat16)
+  y = _LinearFn.apply(x2, w, bias, act, r2)
   return y.reshape(*lead, w.shape[-1])
 
 
@@ -177,9 +191,13 @@ class _FfnReluFn(torch.autograd.Function):
   """y = relu(x·wi)·wo with the ReLU mask folded into the dgrad epilogue."""
 
   @staticmethod
-  def forward(ctx, x, wi, wo):
+  def forward(ctx, x, wi, wo, residual=None):
     h = gemm(x, wi, True, False, act=1)
-    y = gemm(h, wo, True, False)
+    if residual is not None:
+      y = gemm(h, wo, True, False, aux=residual.contiguous(), aux_mode=AUX_ADD)
+    else:
+      y = gemm(h, wo, True, False)
+    ctx.has_res = residual is not None
     ctx.save_for_backward(x, wi, wo, h)
     return y
 
@@ -191,10 +209,10 @@ class _FfnReluFn(torch.autograd.Function):
     dwo = gemm(h, dy, False, False) if ctx.needs_input_grad[2] else None
     dwi = gemm(x, dh, False, False) if ctx.needs_input_grad[1] else None
     dx = gemm(dh, wi, True, True) if ctx.needs_input_grad[0] else None
-    return dx, dwi, dwo
+    return dx, dwi, dwo, (dy if ctx.has_res else None)
 
 
-def ffn_relu(x, wi, wo):
+def ffn_relu(x, wi, wo, residual=None):
   """x[..., M] → relu(x·wi[M,H])·wo[H,M]; 4 tcgen05 GEMMs fwd+bwd, no
   elementwise passes (bias-free FFN as in the GShard dense layers)."""
   lead = x.shape[:-1]
@@ -202,6 +220,11 @@ def ffn_relu(x, wi, wo):
   ok = (x2.is_cuda and x2.dtype == torch.bfloat16 and wi.dtype == torch.bfloat16
         and wo.dtype == torch.bfloat16 and ops.use_cuda_kernels(x2))
   if not ok:
-    return torch.matmul(F.relu(torch.matmul(x2, wi.to(x2.dtype))),
-                        wo.to(x2.dtype)).reshape(*lead, wo.shape[-1])
-  return _FfnReluFn.apply(x2, wi, wo).reshape(*lead, wo.shape[-1])
+    y = torch.matmul(F.relu(torch.matmul(x2, wi.to(x2.dtype))), wo.to(x2.dtype))
+    if residual is not None:
+      y = y + residual.reshape(y.shape).to(y.dtype)
+    return y.reshape(*lead, wo.shape[-1])
+  r2 = residual.reshape(-1, wo.shape[-1]) if residual is not None else None
+  if r2 is not None and r2.dtype != torch.bfloat16:
+    r2 = r2.to(torch.bfloat16)
+  return _FfnReluFn.apply(x2, wi, wo, r2).reshape(*lead, wo.shape[-1])

@@ -66,3 +66,31 @@ def test_linear_autograd():
   _check(x.grad, xr.grad, n)
   _check(w.grad, wr.grad, m)
   _check(b.grad, br.grad, m)
+
+
+def test_linear_and_ffn_residual_epilogue():
+  """x + f(x) fused into the last GEMM's epilogue matches the unfused computation."""
+  from lingvo_b200.ops import gemm as G
+  torch.manual_seed(0)
+  dev = torch.device('cuda')
+  bf = torch.bfloat16
+  x = torch.randn(512, 256, device=dev, dtype=bf, requires_grad=True)
+  r = torch.randn(512, 128, device=dev, dtype=bf, requires_grad=True)
+  w = (torch.randn(256, 128, device=dev) * 0.05).to(bf).requires_grad_()
+  y = G.linear(x, w, residual=r)
+  dy = torch.randn_like(y)
+  y.backward(dy)
+  ref = (x.float() @ w.float() + r.float())
+  assert float((y.float() - ref).norm() / ref.norm()) < 1e-2
+  assert float((r.grad.float() - dy.float()).abs().max()) == 0
+  wi = (torch.randn(256, 512, device=dev) * 0.05).to(bf).requires_grad_()
+  wo = (torch.randn(512, 256, device=dev) * 0.05).to(bf).requires_grad_()
+  x2 = x.detach().clone().requires_grad_()
+  y2 = G.ffn_relu(x2, wi, wo, residual=x2)
+  ref2 = torch.relu(x2.float() @ wi.float()) @ wo.float() + x2.float()
+  assert float((y2.float() - ref2.detach()).norm() / ref2.norm()) < 1e-2
+  dy2 = torch.randn_like(y2)
+  y2.backward(dy2)
+  xr = x2.detach().float().requires_grad_()
+  (torch.relu(xr @ wi.float()) @ wo.float() + xr).backward(dy2.float())
+  assert float((x2.grad.float() - xr.grad).norm() / xr.grad.norm()) < 2e-2
