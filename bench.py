@@ -39,6 +39,9 @@ def _ParseArgs():
                   help='fused = hand-written peer-memory kernels (default); '
                   'nccl = stock NCCL+cuBLAS baseline mode.')
   ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--cuda-graph', default='auto', choices=['auto', 'on', 'off'],
+                  help='Capture the whole train step into a CUDA graph (auto: fall back '
+                  'to eager launches if capture fails).')
   return ap.parse_args()
 
 
@@ -163,8 +166,24 @@ def main():
     n_total = args.warmup + args.steps
     batches = [task._MoveBatch(task.input.GetPreprocessedInputBatch(), dev)  # pylint: disable=protected-access
                for _ in range(min(n_total, 8))]
+    graphed = None
+    if args.cuda_graph != 'off':
+      from lingvo_b200.core import graph_step
+      try:
+        graphed = graph_step.GraphedTrainStep(task, batches[0], warmup=max(args.warmup, 3))
+      except Exception as e:  # pylint: disable=broad-except
+        if args.cuda_graph == 'on':
+          raise
+        sys.stderr.write('CUDA-graph capture failed (%r); eager launches.\n' % (e,))
+        graphed = None
+
+    def step(batch):
+      if graphed is not None:
+        return graphed(batch)
+      return task.TrainStep([batch])
+
     for i in range(args.warmup):
-      task.TrainStep([batches[i % len(batches)]])
+      step(batches[i % len(batches)])
     sync()
     launches0 = native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -172,11 +191,14 @@ def main():
       sync()
       e0.record()
       for i in range(args.steps):
-        metrics, _ = task.TrainStep([batches[(args.warmup + i) % len(batches)]])
+        metrics, _ = step(batches[(args.warmup + i) % len(batches)])
       e1.record()
       sync()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     launches = native.launch_count() - launches0
+    if graphed is not None:
+      # kernels of ours executed per replay (counted while capturing) × timed steps
+      launches = graphed.launches_per_step * args.steps
     loss = float(metrics['loss'][0])
     if world > 1:
       dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -189,7 +211,7 @@ def main():
     if not args.no_e2e:
       prefetch = base_input_generator.DevicePrefetcher(task.input, dev, depth=2)
       for _ in range(2):
-        task.TrainStep([prefetch.Next()])
+        step(prefetch.Next())
       sync()
       h2d = 0
       d2h = 0
@@ -198,7 +220,7 @@ def main():
       for _ in range(args.steps):
         batch = prefetch.Next()          # pinned host → device on a side stream
         h2d = prefetch.h2d_bytes_last
-        m, _ = task.TrainStep([batch])
+        m, _ = step(batch)
         host_loss = m['loss'][0].detach().float().cpu()   # D2H read of the loss
         d2h = host_loss.numel() * host_loss.element_size()
       t1.record()
@@ -221,6 +243,7 @@ def main():
         'dtype': 'bf16', 'data': 'synthetic (uniform random token ids, packed '
                                  'LM format; random-init weights)',
         'impl': 'ours', 'comm_mode': ctx.mode,
+        'cuda_graph': graphed is not None,
         'config': {
             'model': args.model, 'global_batch': per_gpu_batch * world,
             'seq_len': seq_len, 'parallelism': 'dp%d+ep%d' % (

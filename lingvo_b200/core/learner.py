@@ -210,8 +210,18 @@ class Learner(base_layer.BaseLayer):
               if isinstance(vg, py_utils.VarGrad)]
     dev = leaves[0].grad.device if leaves else torch.device('cpu')
     stats = {}
-    all_grad_norm = torch.sqrt(py_utils.SumSquared(
-        [vg.grad for vg in leaves]).to(dev))
+    # Optimizers with a fused two-phase step hand back Σg² of the variables they own as a
+    # by-product of their statistics pass; only the remaining gradients are reduced here.
+    pre_sumsq, handled = None, set()
+    pre_fn = getattr(self.optimizer, 'PreGradStats', None)
+    if (pre_fn is not None and defer_scale and gradient_adjuster is None and
+        dev.type == 'cuda'):
+      pre_sumsq, handled = pre_fn([(vg.var, vg.grad) for vg in leaves])
+    rest = [vg.grad for vg in leaves if id(vg.var) not in handled]
+    grad_sumsq = py_utils.SumSquared(rest).to(dev) if rest else torch.zeros((), device=dev)
+    if pre_sumsq is not None:
+      grad_sumsq = grad_sumsq + pre_sumsq.reshape(())
+    all_grad_norm = torch.sqrt(grad_sumsq)
     # Σw²: variables stepped by the fused Adafactor carry it from their last update
     # (no extra pass over the fp32 masters); the rest are reduced directly.
     carried, direct = [], []

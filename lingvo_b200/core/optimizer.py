@@ -529,30 +529,113 @@ class XLAShardingAdafactor(Base):
     t = t + 1.0
     return p.beta2 * (1.0 - p.beta2**(t - 1.0)) / (1.0 - p.beta2**t)
 
+  def _FusedModule(self, device_is_cuda):
+    p = self.params
+    if p.fused and device_is_cuda:
+      from lingvo_b200.ops import optim
+      if optim.available():
+        return optim
+    return None
+
+  def _FusedEligible(self, var, dims):
+    p = self.params
+    return (dims is not None and var.dim() >= 2 and not p.beta1 and not p.cond_is_finite and
+            sorted(dims) == [var.dim() - 2, var.dim() - 1] and var.shape[-1] % 8 == 0 and
+            var.is_contiguous())
+
+  def PreGradStats(self, var_grad_pairs):
+    """Phase A of the fused step for every eligible variable. The same pass that builds the
+    factored second-moment sums also yields Σg² — the learner gets the global gradient
+    norm without a separate sweep over the gradients.
+
+    Returns (device scalar Σg² over the handled variables, set of handled var ids)."""
+    p = self.params
+    self._pre = {}
+    if not var_grad_pairs or not var_grad_pairs[0][0].is_cuda:
+      return None, set()
+    fused = self._FusedModule(True)
+    if fused is None:
+      return None, set()
+    total = torch.zeros(1, dtype=torch.float32, device=var_grad_pairs[0][0].device)
+    handled = set()
+    for var, grad in var_grad_pairs:
+      dims = self._FactoredDims(list(var.shape))
+      if not self._FusedEligible(var, dims) or grad.device != var.device:
+        continue
+      fresh = fused.adafactor_stats(var, grad, dims[0], dims[1],
+                                    bool(p.multiply_by_parameter_scale), total)
+      self._pre[id(var)] = (grad.data_ptr(), fresh)
+      handled.add(id(var))
+    return total, handled
+
+  # -- device-resident hyper-parameters (CUDA-graph capture) ------------------------
+  graph_capturable = True
+
+  def EnableDeviceHyper(self, device):
+    """After this, the fused kernels read (lr, decay) from a device tensor that
+    `SetHyper` refreshes before every (graph) step; nothing step-dependent is baked
+    into a kernel argument."""
+    self._hyper = torch.zeros(2, dtype=torch.float32, device=device)
+    self._hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+  def SetHyper(self, lr, step=None):
+    self._hyper_host[0] = float(lr)
+    self._hyper_host[1] = self.DecayRate(step)
+    self._hyper.copy_(self._hyper_host, non_blocking=True)
+
+  def _UpdateSmallFused(self, fused, lr, decay, small):
+    """All non-factored variables in one multi-tensor launch."""
+    p = self.params
+    rows = []
+    for var, grad in small:
+      v = self._Slot(var, 'v')
+      g = grad if grad.is_contiguous() else grad.contiguous()
+      compute = getattr(var, 'compute', None)
+      rows.append((var.data.data_ptr(), g.data_ptr(), v.data_ptr(),
+                   compute.data.data_ptr() if compute is not None else 0, var.numel(),
+                   1 if g.dtype == torch.bfloat16 else 0))
+      self._small_keepalive = getattr(self, '_small_keepalive', [])
+      self._small_keepalive.append(g)
+      if compute is not None:
+        self._refreshed.add(id(var))
+    if getattr(self, '_small_table', None) is None:
+      self._small_table = fused.SmallVarTable(small[0][0].device)
+    table = self._small_table.Build(rows)
+    fused.adafactor_small(table, lr, decay, p.epsilon1, p.epsilon2,
+                          p.clipping_threshold or 0.0, bool(p.multiply_by_parameter_scale),
+                          self._grad_scale, getattr(self, '_hyper', None))
+    self._small_keepalive = self._small_keepalive[-2 * len(small):]
+
   def _Update(self, lr, variables, grads):
     p = self.params
     decay = self.DecayRate()
-    fused = None
-    if p.fused and variables[0].is_cuda:
-      from lingvo_b200.ops import optim
-      if optim.available():
-        fused = optim
+    fused = self._FusedModule(variables[0].is_cuda)
+    hyper = getattr(self, '_hyper', None)
+    pre = getattr(self, '_pre', {})
+    self._pre = {}
+    small = []
     for var, grad in zip(variables, grads):
       dims = self._FactoredDims(list(var.shape))
-      if fused is not None and dims is not None and var.dim() >= 2 and (
-          not p.beta1) and not p.cond_is_finite and sorted(dims) == [
-              var.dim() - 2, var.dim() - 1] and var.shape[-1] % 8 == 0 and (
-                  var.is_contiguous()):
+      if (fused is not None and dims is None and not p.beta1 and not p.cond_is_finite and
+          var.is_contiguous() and grad.dtype in (torch.float32, torch.bfloat16) and
+          var.dtype == torch.float32):
+        small.append((var, grad))
+        continue
+      if fused is not None and self._FusedEligible(var, dims):
         d0, d1 = dims
         vr_shape = [s for i, s in enumerate(var.shape) if i != d0]
         vc_shape = [s for i, s in enumerate(var.shape) if i != d1]
         vr = self._Slot(var, 'vr', shape=vr_shape)
         vc = self._Slot(var, 'vc', shape=vc_shape)
-        fused.adafactor_factored(var, grad, vr, vc, d0, d1, float(lr), decay,
-                                 p.epsilon1, p.epsilon2,
-                                 p.clipping_threshold or 0.0,
-                                 bool(p.multiply_by_parameter_scale),
-                                 self._grad_scale)
+        done = pre.get(id(var))
+        if done is not None and done[0] == grad.data_ptr():
+          fresh = done[1]                       # statistics already in the scratch
+        else:
+          fresh = fused.adafactor_stats(var, grad, d0, d1, bool(p.multiply_by_parameter_scale))
+        fused.adafactor_update(var, grad, vr, vc, d0, d1, float(lr), decay, p.epsilon1,
+                               p.epsilon2, p.clipping_threshold or 0.0,
+                               bool(p.multiply_by_parameter_scale), self._grad_scale, fresh,
+                               hyper)
         if getattr(var, 'compute', None) is not None:
           self._refreshed.add(id(var))
         continue
@@ -561,6 +644,8 @@ class XLAShardingAdafactor(Base):
         grad = torch.where(gs == 0, torch.zeros_like(grad),
                            grad * gs.to(grad.dtype))
       self._UpdateOne(var, grad, dims, float(lr), decay)
+    if small:
+      self._UpdateSmallFused(fused, float(lr), decay, small)
 
   def _UpdateOne(self, var, grad, dims, lr, decay):
     p = self.params

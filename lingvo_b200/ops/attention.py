@@ -93,6 +93,27 @@ def rel_bias_attention_ref(q, k, v, rel, mask=None, scale=1.0):
   return attention_ref(q, k, v, bias, scale)
 
 
+# Whether this cuDNN build accepts an additive bias together with its own causal mask
+# (it then skips the fully-masked upper-triangular tiles). Probed on first use.
+_CUDNN_BIAS_PLUS_CAUSAL = {'ok': None}
+
+
+def _CudnnFwd(qt, kt, vt, bias, scale, causal):
+  use = causal and _CUDNN_BIAS_PLUS_CAUSAL['ok'] is not False
+  if use:
+    try:
+      res = torch.ops.aten._scaled_dot_product_cudnn_attention(
+          qt, kt, vt, bias, True, 0.0, True, False, scale=scale)
+      _CUDNN_BIAS_PLUS_CAUSAL['ok'] = True
+      return res, True
+    except RuntimeError:
+      if _CUDNN_BIAS_PLUS_CAUSAL['ok'] is True:
+        raise
+      _CUDNN_BIAS_PLUS_CAUSAL['ok'] = False
+  return torch.ops.aten._scaled_dot_product_cudnn_attention(
+      qt, kt, vt, bias, True, 0.0, False, False, scale=scale), False
+
+
 class _RelBiasAttnFn(torch.autograd.Function):
   """Flash attention with a learned Toeplitz bias.
 
@@ -109,11 +130,10 @@ class _RelBiasAttnFn(torch.autograd.Function):
     b, l, h, d = q.shape
     bias = nat.build_rel_bias(rel.float().contiguous(), mask, b)
     qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
-    res = torch.ops.aten._scaled_dot_product_cudnn_attention(
-        qt, kt, vt, bias, True, 0.0, False, False, scale=scale)
+    res, cudnn_causal = _CudnnFwd(qt, kt, vt, bias, scale, causal)
     out, lse = res[0], res[1]
     ctx.save_for_backward(q, k, v, out, lse, bias, res[2], res[3], res[6], res[7])
-    ctx.meta = (res[4], res[5], scale, causal)
+    ctx.meta = (res[4], res[5], scale, causal, cudnn_causal)
     return out.transpose(1, 2)
 
   @staticmethod
@@ -121,12 +141,12 @@ class _RelBiasAttnFn(torch.autograd.Function):
     from lingvo_b200 import ops
     nat = ops.native()
     q, k, v, out, lse, bias, cq, ck, seed, off = ctx.saved_tensors
-    max_q, max_k, scale, causal = ctx.meta
+    max_q, max_k, scale, causal, cudnn_causal = ctx.meta
     b, l, h, d = q.shape
     d_o = d_o.contiguous()                                   # [B, L, H, D]
     dq, dk, dv = torch.ops.aten._scaled_dot_product_cudnn_attention_backward(
         d_o.transpose(1, 2), q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
-        out, lse, seed, off, bias, cq, ck, max_q, max_k, 0.0, False, scale=scale)
+        out, lse, seed, off, bias, cq, ck, max_q, max_k, 0.0, cudnn_causal, scale=scale)
     drel = None
     if ctx.needs_input_grad[3]:
       lse3 = lse.reshape(b, h, l).float().contiguous()

@@ -334,8 +334,14 @@ torch::Tensor rel_bias_grad(const torch::Tensor& q, const torch::Tensor& k, cons
   const c10::cuda::CUDAGuard guard(q.device());
   static thread_local bool ctx_bound = false;
   if (!ctx_bound) {
-    C10_CUDA_CHECK(cudaFree(nullptr));
-    ctx_bound = true;
+    // (skipped while a stream capture is in progress: cudaFree is not capturable, and a
+    // thread that reaches this point during capture already ran the warm-up steps)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(at::cuda::getCurrentCUDAStream(), &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      C10_CUDA_CHECK(cudaFree(nullptr));
+      ctx_bound = true;
+    }
   }
   auto drel = torch::zeros({H, 2 * L - 1}, q.options().dtype(torch::kFloat32));
   auto delta = torch::empty({B, H, L}, q.options().dtype(torch::kFloat32));

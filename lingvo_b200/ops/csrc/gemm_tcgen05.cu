@@ -480,8 +480,14 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
   // context bound, otherwise it fails with CUDA_ERROR_INVALID_CONTEXT.
   static thread_local bool ctx_bound = false;
   if (!ctx_bound) {
-    C10_CUDA_CHECK(cudaFree(nullptr));
-    ctx_bound = true;
+    // (skipped while a stream capture is in progress: cudaFree is not capturable, and a
+    // thread that reaches this point during capture already ran the warm-up steps)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(at::cuda::getCurrentCUDAStream(), &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      C10_CUDA_CHECK(cudaFree(nullptr));
+      ctx_bound = true;
+    }
   }
   torch::Tensor a = a_in.dim() == 2 ? a_in.unsqueeze(0) : a_in;
   torch::Tensor b = b_in.dim() == 2 ? b_in.unsqueeze(0) : b_in;

@@ -414,6 +414,29 @@ __global__ void moe_wait_kernel(const int* __restrict__ flags, int world, int ch
   __syncthreads();
 }
 
+// Device-counter flavour: one kernel = signal every peer, then wait for every peer. The
+// sequence number lives in device memory (`counter[channel]`, bumped by the kernel), so the
+// launch has no step-dependent argument and can be replayed from a CUDA graph.
+__global__ void moe_sync_kernel(const long long* __restrict__ peer_flags,
+                                const int* __restrict__ flags, int* __restrict__ counters,
+                                int world, int rank, int channel) {
+  __shared__ int seq_s;
+  if (threadIdx.x == 0) seq_s = ++counters[channel];
+  __syncthreads();
+  const int seq = seq_s;
+  const int r = threadIdx.x;
+  if (r < world) {
+    __threadfence_system();
+    int* f = reinterpret_cast<int*>(peer_flags[r]) + channel * world + rank;
+    st_release_sys(f, seq);
+    const int* mine = flags + channel * world + r;
+    while (ld_acquire_sys(mine) < seq) {
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+}
+
 int GridWarps(int items, int warps_per_cta) {
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   int g = (items + warps_per_cta - 1) / warps_per_cta;
@@ -550,6 +573,16 @@ void moe_signal(const torch::Tensor& peer_flags, int64_t world, int64_t rank, in
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   CountLaunch();
 }
+void moe_sync(const torch::Tensor& peer_flags, const torch::Tensor& flags, torch::Tensor counters,
+              int64_t world, int64_t rank, int64_t channel) {
+  TORCH_CHECK(counters.is_cuda() && counters.scalar_type() == torch::kInt32);
+  const c10::cuda::CUDAGuard guard(flags.device());
+  moe_sync_kernel<<<1, 32, 0, at::cuda::getCurrentCUDAStream()>>>(
+      reinterpret_cast<const long long*>(peer_flags.data_ptr<int64_t>()), flags.data_ptr<int>(), counters.data_ptr<int>(), (int)world, (int)rank, (int)channel);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  CountLaunch();
+}
+
 void moe_wait(const torch::Tensor& flags, int64_t world, int64_t channel, int64_t seq) {
   const c10::cuda::CUDAGuard guard(flags.device());
   moe_wait_kernel<<<1, 32, 0, at::cuda::getCurrentCUDAStream()>>>(flags.data_ptr<int>(),
@@ -598,6 +631,7 @@ LB_REGISTER(moe) {
   m.def("moe_gather_rows", &lb::moe_gather_rows);
   m.def("moe_signal", &lb::moe_signal);
   m.def("moe_wait", &lb::moe_wait);
+  m.def("moe_sync", &lb::moe_sync);
   m.def("symm_alloc", &lb::symm_alloc);
   m.def("symm_export", &lb::symm_export);
   m.def("symm_import", &lb::symm_import);

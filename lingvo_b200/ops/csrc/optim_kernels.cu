@@ -76,13 +76,15 @@ template <typename GT>
 __global__ void __launch_bounds__(kWarps * 32)
 adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
                        float* __restrict__ rowsum, float* __restrict__ colsum,
-                       float* __restrict__ acc, int B, int R, int C, float eps1, int items,
-                       const float* __restrict__ gscale, int with_w) {
+                       float* __restrict__ acc, int B, int R, int C, int items, int with_w,
+                       float* __restrict__ total_sumsq) {
   // with_w: also accumulate sum(w^2) (only on the first step of a variable; later
   // steps get it for free from the previous apply kernel, see acc[2]).
+  // Statistics are of the RAW gradient (no grad scale, no eps1): both are folded in by
+  // the factors kernel, which lets this pass also produce the global sum(g^2) that the
+  // clipping scale is computed from.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float gs = gscale ? *gscale : 1.f;
-  float wsq = 0.f;
+  float wsq = 0.f, gsq = 0.f;
   for (int item = blockIdx.x * kWarps + warp; item < items; item += gridDim.x * kWarps) {
     const Tile t = get_tile(item, R, C);
     const int c = t.c0 + lane * 8;
@@ -113,8 +115,7 @@ adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
         if (cok && r + u < t.r1) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float ge = gs == 0.f ? 0.f : gf[u][i] * gs;
-            const float q = ge * ge + eps1;
+            const float q = gf[u][i] * gf[u][i];
             cs[i] += q;
             rs[u] += q;
           }
@@ -122,6 +123,7 @@ adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) rs[u] = warp_sum(rs[u]);
+      gsq += rs[0] + rs[1] + rs[2] + rs[3];
       if (lane < 4 && r + lane < t.r1) {
         const float v = lane == 0 ? rs[0] : lane == 1 ? rs[1] : lane == 2 ? rs[2] : rs[3];
         atomicAdd(&rowsum[static_cast<size_t>(t.b) * R + r + lane], v);
@@ -136,6 +138,8 @@ adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
     wsq = warp_sum(wsq);
     if (lane == 0) atomicAdd(&acc[0], wsq);
   }
+  // rs[] were already warp-reduced (identical in all lanes): lane 0 owns the total.
+  if (total_sumsq != nullptr && lane == 0 && gsq != 0.f) atomicAdd(total_sumsq, gsq);
 }
 
 // vr_is_rows: vr has shape [B,R] (mean over C is "row mean" of the reference,
@@ -144,10 +148,15 @@ __global__ void adafactor_factors_kernel(float* __restrict__ vr, float* __restri
                                          const float* __restrict__ rowsum,
                                          const float* __restrict__ colsum, float* __restrict__ fr,
                                          float* __restrict__ fc, int B, int R, int C, float decay,
-                                         int vr_is_rows, float* __restrict__ acc, int with_w) {
+                                         int vr_is_rows, float* __restrict__ acc, int with_w,
+                                         const float* __restrict__ gscale, float eps1,
+                                         const float* __restrict__ hyper) {
+  if (hyper != nullptr) decay = hyper[1];   // device-resident hyper-parameters (CUDA graphs)
   // One CTA per batch element b.
   __shared__ float red[32];
   const int b = blockIdx.x;
+  const float gs = gscale ? *gscale : 1.f;
+  const float gs2 = gs * gs;   // mean((g*gs)^2 + eps1) = gs^2 * mean(g^2) + eps1
   if (b == 0 && threadIdx.x == 0) {
     // acc[0] = sum(w^2) for this step: freshly computed (with_w) or carried over
     // from the previous step's apply kernel (acc[2]); acc[2] restarts at 0.
@@ -168,7 +177,8 @@ __global__ void adafactor_factors_kernel(float* __restrict__ vr, float* __restri
   float* vcb = vc + static_cast<size_t>(b) * nvc;
   float local = 0.f;
   for (int i = threadIdx.x; i < nvr; i += blockDim.x) {
-    const float nv = vrb[i] * decay + sum_r[i] * inv_r * mix;
+    // gs == 0 marks a skipped (non-finite) step: ignore the sums, they may hold NaN/Inf.
+    const float nv = vrb[i] * decay + ((gs == 0.f ? 0.f : gs2 * sum_r[i] * inv_r) + eps1) * mix;
     vrb[i] = nv;
     local += nv;
   }
@@ -186,7 +196,7 @@ __global__ void adafactor_factors_kernel(float* __restrict__ vr, float* __restri
   float* f_c = vr_is_rows ? fc + static_cast<size_t>(b) * C : fr + static_cast<size_t>(b) * R;
   for (int i = threadIdx.x; i < nvr; i += blockDim.x) f_r[i] = rsqrtf(vrb[i] / ltm);
   for (int i = threadIdx.x; i < nvc; i += blockDim.x) {
-    const float nv = vcb[i] * decay + sum_c[i] * inv_c * mix;
+    const float nv = vcb[i] * decay + ((gs == 0.f ? 0.f : gs2 * sum_c[i] * inv_c) + eps1) * mix;
     vcb[i] = nv;
     f_c[i] = rsqrtf(nv);
   }
@@ -228,7 +238,9 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
                        __nv_bfloat16* __restrict__ w_bf16, const float* __restrict__ fr,
                        const float* __restrict__ fc, const float* __restrict__ acc, int B, int R,
                        int C, float lr, float eps2, float clip, int mult_by_param_scale,
-                       float numel, int items, const float* __restrict__ gscale) {
+                       float numel, int items, const float* __restrict__ gscale,
+                       const float* __restrict__ hyper) {
+  if (hyper != nullptr) lr = hyper[0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float gs = gscale ? *gscale : 1.f;
   float scale = lr;
@@ -310,41 +322,144 @@ __global__ void adam_flat_kernel(float* __restrict__ w, const GT* __restrict__ g
 
 }  // namespace
 
-// In-place factored Adafactor step on `w` viewed as [B, R, C].
-// scratch: fp32 [2 + B*R*2 + B*C*2] = acc | rowsum | colsum | fr | fc  (zeroed here).
-void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor vr,
-                        torch::Tensor vc, torch::Tensor scratch,
-                        const c10::optional<torch::Tensor>& w_bf16, int64_t B, int64_t R,
-                        int64_t C, bool vr_is_rows, double lr, double decay, double eps1,
-                        double eps2, double clip, bool mult_by_param_scale,
-                        const c10::optional<torch::Tensor>& grad_scale, bool recompute_wsq) {
+namespace {
+
+// ---- non-factored Adafactor for many small variables in ONE launch -------------------
+// table[i] = {w (fp32), g, v (fp32), w_bf16 or 0, numel, g_is_bf16}; one CTA per variable.
+//   v <- decay*v + (1-decay)*((g*gs)^2 + eps1);  x = g*gs*rsqrt(v)
+//   x /= max(1, RMS(x)/clip);  w -= lr * max(RMS(w), eps2)[if param scale] * x
+struct SmallVar {
+  long long w, g, v, wb, numel, g_bf16;
+};
+
+__global__ void __launch_bounds__(256)
+adafactor_small_kernel(const SmallVar* __restrict__ table, float lr, float decay, float eps1,
+                       float eps2, float clip, int mult_by_param_scale,
+                       const float* __restrict__ gscale, const float* __restrict__ hyper,
+                       float* __restrict__ total_sumsq_unused) {
+  __shared__ float red[2][8];
+  const SmallVar sv = table[blockIdx.x];
+  float* w = reinterpret_cast<float*>(sv.w);
+  float* v = reinterpret_cast<float*>(sv.v);
+  __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(sv.wb);
+  const float* gf = reinterpret_cast<const float*>(sv.g);
+  const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(sv.g);
+  const long long n = sv.numel;
+  if (hyper != nullptr) {
+    lr = hyper[0];
+    decay = hyper[1];
+  }
+  const float gs = gscale ? *gscale : 1.f;
+  const float mix = 1.f - decay;
+  float wsq = 0.f, xsq = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float g = gs == 0.f ? 0.f : (sv.g_bf16 ? __bfloat162float(gb[i]) : gf[i]) * gs;
+    const float nv = v[i] * decay + (g * g + eps1) * mix;
+    v[i] = nv;
+    const float x = g * rsqrtf(nv);
+    xsq += x * x;
+    const float wi = w[i];
+    wsq += wi * wi;
+  }
+  wsq = warp_sum(wsq);
+  xsq = warp_sum(xsq);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = wsq;
+    red[1][threadIdx.x >> 5] = xsq;
+  }
+  __syncthreads();
+  float tw = 0.f, tx = 0.f;
+  for (int k = 0; k < 8; ++k) {
+    tw += red[0][k];
+    tx += red[1][k];
+  }
+  float scale = lr;
+  if (mult_by_param_scale) scale *= fmaxf(sqrtf(tw / static_cast<float>(n)), eps2);
+  if (clip > 0.f) scale /= fmaxf(1.f, sqrtf(tx / static_cast<float>(n)) / clip);
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float g = gs == 0.f ? 0.f : (sv.g_bf16 ? __bfloat162float(gb[i]) : gf[i]) * gs;
+    const float nw = w[i] - scale * g * rsqrtf(v[i]);
+    w[i] = nw;
+    if (wb != nullptr) wb[i] = __float2bfloat16(nw);
+  }
+}
+
+struct AfLayout {
+  float *acc, *rowsum, *colsum, *fr, *fc;
+  int64_t br4, bc4;
+  int items, grid;
+};
+
+AfLayout Layout(const torch::Tensor& w, torch::Tensor& scratch, int64_t B, int64_t R, int64_t C) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == torch::kFloat32 && w.is_contiguous());
-  TORCH_CHECK(g.is_contiguous() && g.numel() == w.numel());
-  TORCH_CHECK(C % 8 == 0, "adafactor_factored: C must be a multiple of 8");
+  TORCH_CHECK(C % 8 == 0, "adafactor: C must be a multiple of 8");
   TORCH_CHECK(w.numel() == B * R * C);
-  const int64_t br4 = (B * R + 3) / 4 * 4, bc4 = (B * C + 3) / 4 * 4;
-  TORCH_CHECK(scratch.numel() >= 4 + 2 * br4 + 2 * bc4);
+  AfLayout l;
+  l.br4 = (B * R + 3) / 4 * 4;
+  l.bc4 = (B * C + 3) / 4 * 4;
+  TORCH_CHECK(scratch.numel() >= 4 + 2 * l.br4 + 2 * l.bc4);
   TORCH_CHECK(reinterpret_cast<uintptr_t>(scratch.data_ptr()) % 16 == 0);
-  const c10::cuda::CUDAGuard guard(w.device());
-  auto stream = at::cuda::getCurrentCUDAStream();
   float* sp = scratch.data_ptr<float>();
-  float* acc = sp;
-  float* rowsum = sp + 4;
-  float* colsum = rowsum + br4;
-  float* fr = colsum + bc4;
-  float* fc = fr + br4;
-  // sp[0] = sum(w^2) used now, sp[1] = clipping RMS, sp[2] = sum(w^2) carried to the
-  // next step (persistent), sp[3] unused.
-  if (recompute_wsq) C10_CUDA_CHECK(cudaMemsetAsync(sp, 0, sizeof(float) * 4, stream));
-  else C10_CUDA_CHECK(cudaMemsetAsync(sp + 1, 0, sizeof(float), stream));
-  C10_CUDA_CHECK(cudaMemsetAsync(rowsum, 0, sizeof(float) * (br4 + bc4), stream));
-  const int with_w = (recompute_wsq && mult_by_param_scale) ? 1 : 0;
+  l.acc = sp;
+  l.rowsum = sp + 4;
+  l.colsum = l.rowsum + l.br4;
+  l.fr = l.colsum + l.bc4;
+  l.fc = l.fr + l.br4;
   const int strips = static_cast<int>((C + 255) / 256);
   const int ranges = static_cast<int>((R + kRowsPerWarp - 1) / kRowsPerWarp);
-  const int items = static_cast<int>(B) * strips * ranges;
+  l.items = static_cast<int>(B) * strips * ranges;
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  int grid = (items + kWarps - 1) / kWarps;
-  if (grid > sms * 8) grid = sms * 8;
+  l.grid = (l.items + kWarps - 1) / kWarps;
+  if (l.grid > sms * 8) l.grid = sms * 8;
+  return l;
+}
+
+}  // namespace
+
+// Phase A of the factored Adafactor step on `w` viewed as [B, R, C]: row/column sums of
+// g^2 into `scratch`, optionally sum(w^2) (first step only) and the global sum(g^2).
+// scratch: fp32 [4 + B*R*2 + B*C*2] = acc | rowsum | colsum | fr | fc.
+//   acc[0] = sum(w^2) used now, acc[1] = clipping RMS, acc[2] = sum(w^2) carried to the
+//   next step (persistent), acc[3] unused.
+void adafactor_stats(const torch::Tensor& w, const torch::Tensor& g, torch::Tensor scratch,
+                     int64_t B, int64_t R, int64_t C, bool mult_by_param_scale,
+                     bool recompute_wsq, const c10::optional<torch::Tensor>& total_sumsq) {
+  TORCH_CHECK(g.is_contiguous() && g.numel() == w.numel());
+  const c10::cuda::CUDAGuard guard(w.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  AfLayout l = Layout(w, scratch, B, R, C);
+  if (recompute_wsq) C10_CUDA_CHECK(cudaMemsetAsync(l.acc, 0, sizeof(float) * 4, stream));
+  else C10_CUDA_CHECK(cudaMemsetAsync(l.acc + 1, 0, sizeof(float), stream));
+  C10_CUDA_CHECK(cudaMemsetAsync(l.rowsum, 0, sizeof(float) * (l.br4 + l.bc4), stream));
+  const int with_w = (recompute_wsq && mult_by_param_scale) ? 1 : 0;
+  float* tot = (total_sumsq.has_value() && total_sumsq->defined())
+                   ? total_sumsq->data_ptr<float>() : nullptr;
+  if (g.scalar_type() == torch::kBFloat16) {
+    adafactor_stats_kernel<__nv_bfloat16><<<l.grid, kWarps * 32, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(g.data_ptr()), w.data_ptr<float>(), l.rowsum,
+        l.colsum, l.acc, (int)B, (int)R, (int)C, l.items, with_w, tot);
+  } else {
+    TORCH_CHECK(g.scalar_type() == torch::kFloat32);
+    adafactor_stats_kernel<float><<<l.grid, kWarps * 32, 0, stream>>>(
+        g.data_ptr<float>(), w.data_ptr<float>(), l.rowsum, l.colsum, l.acc, (int)B, (int)R,
+        (int)C, l.items, with_w, tot);
+  }
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  CountLaunch();
+}
+
+// Phase B: factors (folding grad_scale^2 and eps1 into the raw sums) -> clip RMS -> apply.
+void adafactor_update(torch::Tensor w, const torch::Tensor& g, torch::Tensor vr, torch::Tensor vc,
+                      torch::Tensor scratch, const c10::optional<torch::Tensor>& w_bf16,
+                      int64_t B, int64_t R, int64_t C, bool vr_is_rows, double lr, double decay,
+                      double eps1, double eps2, double clip, bool mult_by_param_scale,
+                      const c10::optional<torch::Tensor>& grad_scale, bool recompute_wsq,
+                      const c10::optional<torch::Tensor>& hyper) {
+  TORCH_CHECK(g.is_contiguous() && g.numel() == w.numel());
+  const c10::cuda::CUDAGuard guard(w.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  AfLayout l = Layout(w, scratch, B, R, C);
+  const float* hp = (hyper.has_value() && hyper->defined()) ? hyper->data_ptr<float>() : nullptr;
   __nv_bfloat16* wb = nullptr;
   if (w_bf16.has_value() && w_bf16->defined()) {
     TORCH_CHECK(w_bf16->scalar_type() == torch::kBFloat16 && w_bf16->is_contiguous() &&
@@ -354,25 +469,56 @@ void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor v
   const float numel = static_cast<float>(w.numel());
   const float* gsp = (grad_scale.has_value() && grad_scale->defined())
                          ? grad_scale->data_ptr<float>() : nullptr;
+  adafactor_factors_kernel<<<static_cast<int>(B), 256, 0, stream>>>(
+      vr.data_ptr<float>(), vc.data_ptr<float>(), l.rowsum, l.colsum, l.fr, l.fc, (int)B, (int)R,
+      (int)C, (float)decay, vr_is_rows ? 1 : 0, l.acc,
+      (recompute_wsq || !mult_by_param_scale) ? 1 : 0, gsp, (float)eps1, hp);
   auto run = [&](auto tag) {
     using GT = decltype(tag);
     const GT* gp = reinterpret_cast<const GT*>(g.data_ptr());
-    adafactor_stats_kernel<GT><<<grid, kWarps * 32, 0, stream>>>(
-        gp, w.data_ptr<float>(), rowsum, colsum, acc, (int)B, (int)R, (int)C, (float)eps1, items, gsp, with_w);
-    adafactor_factors_kernel<<<static_cast<int>(B), 256, 0, stream>>>(
-        vr.data_ptr<float>(), vc.data_ptr<float>(), rowsum, colsum, fr, fc, (int)B, (int)R, (int)C,
-        (float)decay, vr_is_rows ? 1 : 0, acc, (recompute_wsq || !mult_by_param_scale) ? 1 : 0);
     if (clip > 0)
-      adafactor_rms_kernel<GT><<<grid, kWarps * 32, 0, stream>>>(gp, fr, fc, acc, (int)B, (int)R,
-                                                                 (int)C, items, gsp);
-    adafactor_apply_kernel<GT><<<grid, kWarps * 32, 0, stream>>>(
-        gp, w.data_ptr<float>(), wb, fr, fc, acc, (int)B, (int)R, (int)C, (float)lr, (float)eps2,
-        (float)clip, mult_by_param_scale ? 1 : 0, numel, items, gsp);
+      adafactor_rms_kernel<GT><<<l.grid, kWarps * 32, 0, stream>>>(
+          gp, l.fr, l.fc, l.acc, (int)B, (int)R, (int)C, l.items, gsp);
+    adafactor_apply_kernel<GT><<<l.grid, kWarps * 32, 0, stream>>>(
+        gp, w.data_ptr<float>(), wb, l.fr, l.fc, l.acc, (int)B, (int)R, (int)C, (float)lr,
+        (float)eps2, (float)clip, mult_by_param_scale ? 1 : 0, numel, l.items, gsp, hp);
   };
   if (g.scalar_type() == torch::kBFloat16) run(__nv_bfloat16());
   else { TORCH_CHECK(g.scalar_type() == torch::kFloat32); run(float()); }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
-  CountLaunch(clip > 0 ? 4 : 3);
+  CountLaunch(clip > 0 ? 3 : 2);
+}
+
+// table: int64 [n_vars, 6] device tensor of SmallVar records.
+void adafactor_small(const torch::Tensor& table, double lr, double decay, double eps1, double eps2,
+                     double clip, bool mult_by_param_scale,
+                     const c10::optional<torch::Tensor>& grad_scale,
+                     const c10::optional<torch::Tensor>& hyper) {
+  TORCH_CHECK(table.is_cuda() && table.scalar_type() == torch::kInt64 && table.is_contiguous() &&
+              table.dim() == 2 && table.size(1) == 6);
+  const int n = static_cast<int>(table.size(0));
+  if (n == 0) return;
+  const c10::cuda::CUDAGuard guard(table.device());
+  const float* gsp = (grad_scale.has_value() && grad_scale->defined())
+                         ? grad_scale->data_ptr<float>() : nullptr;
+  const float* hp = (hyper.has_value() && hyper->defined()) ? hyper->data_ptr<float>() : nullptr;
+  adafactor_small_kernel<<<n, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      reinterpret_cast<const SmallVar*>(table.data_ptr<int64_t>()), (float)lr, (float)decay,
+      (float)eps1, (float)eps2, (float)clip, mult_by_param_scale ? 1 : 0, gsp, hp, nullptr);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  CountLaunch();
+}
+
+// One-call form (stats + update) kept for callers that do not need the global norm.
+void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor vr,
+                        torch::Tensor vc, torch::Tensor scratch,
+                        const c10::optional<torch::Tensor>& w_bf16, int64_t B, int64_t R,
+                        int64_t C, bool vr_is_rows, double lr, double decay, double eps1,
+                        double eps2, double clip, bool mult_by_param_scale,
+                        const c10::optional<torch::Tensor>& grad_scale, bool recompute_wsq) {
+  adafactor_stats(w, g, scratch, B, R, C, mult_by_param_scale, recompute_wsq, c10::nullopt);
+  adafactor_update(w, g, vr, vc, scratch, w_bf16, B, R, C, vr_is_rows, lr, decay, eps1, eps2, clip,
+                   mult_by_param_scale, grad_scale, recompute_wsq, c10::nullopt);
 }
 
 void adam_flat(torch::Tensor w, const torch::Tensor& g, torch::Tensor m, torch::Tensor v,
@@ -410,5 +556,8 @@ void adam_flat(torch::Tensor w, const torch::Tensor& g, torch::Tensor m, torch::
 LB_REGISTER(optim) {
   m.attr("_has_optim") = true;
   m.def("adafactor_factored", &lb::adafactor_factored);
+  m.def("adafactor_stats", &lb::adafactor_stats);
+  m.def("adafactor_update", &lb::adafactor_update);
+  m.def("adafactor_small", &lb::adafactor_small);
   m.def("adam_flat", &lb::adam_flat);
 }

@@ -60,6 +60,85 @@ def adafactor_factored(var, grad, vr, vc, d0, d1, lr, decay, eps1, eps2, clip,
       float(clip), bool(mult_by_param_scale), grad_scale, fresh)
 
 
+def _Geometry(var, d0, d1):
+  nd = var.dim()
+  assert sorted((d0, d1)) == [nd - 2, nd - 1]
+  r, c = var.shape[-2], var.shape[-1]
+  b = var.numel() // (r * c)
+  return b, r, c, (d0 == nd - 1)
+
+
+def adafactor_stats(var, grad, d0, d1, mult_by_param_scale, total_sumsq=None):
+  """Phase A (see csrc): row/col sums of g² (+ global Σg² into `total_sumsq`)."""
+  b, r, c, _ = _Geometry(var, d0, d1)
+  scratch, fresh = _Scratch(var, 16 + 2 * (b * r + 4) + 2 * (b * c + 4))
+  g = grad if grad.is_contiguous() else grad.contiguous()
+  ops.native().adafactor_stats(var.data, g, scratch, b, r, c, bool(mult_by_param_scale),
+                               fresh, total_sumsq)
+  return fresh
+
+
+def adafactor_update(var, grad, vr, vc, d0, d1, lr, decay, eps1, eps2, clip,
+                     mult_by_param_scale, grad_scale=None, fresh=False, hyper=None):
+  """Phase B: factors → clip RMS → apply, using the sums left by `adafactor_stats`."""
+  b, r, c, vr_is_rows = _Geometry(var, d0, d1)
+  scratch, _ = _Scratch(var, 16 + 2 * (b * r + 4) + 2 * (b * c + 4))
+  g = grad if grad.is_contiguous() else grad.contiguous()
+  compute = getattr(var, 'compute', None)
+  ops.native().adafactor_update(
+      var.data, g, vr, vc, scratch, compute.data if compute is not None else None,
+      b, r, c, vr_is_rows, float(lr), float(decay), float(eps1), float(eps2),
+      float(clip), bool(mult_by_param_scale), grad_scale, bool(fresh), hyper)
+
+
+class SmallVarTable:
+  """Pointer table for `adafactor_small`: rows (w, g, v, w_bf16|0, numel, g_is_bf16).
+
+  Built on the host into a ring of pinned buffers and copied asynchronously, so neither the
+  eager loop nor CUDA-graph capture ever touches pageable memory."""
+
+  _RING = 8
+
+  def __init__(self, device):
+    self._dev = device
+    self._host = []
+    self._events = []
+    self._i = 0
+    self._last_key = None
+    self._table = None
+
+  def Build(self, rows):
+    key = tuple(tuple(r) for r in rows)
+    if key == self._last_key and self._table is not None:
+      return self._table                       # static addresses (graph replay / fused DP)
+    n = len(rows)
+    if len(self._host) < self._RING:
+      self._host.append(torch.empty((max(n, 1), 6), dtype=torch.int64).pin_memory())
+      self._events.append(None)
+    slot = self._i % len(self._host)
+    self._i += 1
+    if self._host[slot].shape[0] < n:
+      self._host[slot] = torch.empty((n, 6), dtype=torch.int64).pin_memory()
+    if self._events[slot] is not None:
+      self._events[slot].synchronize()
+    host = self._host[slot][:n]
+    host.copy_(torch.tensor(rows, dtype=torch.int64))
+    table = torch.empty((n, 6), dtype=torch.int64, device=self._dev)
+    table.copy_(host, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    self._events[slot] = ev
+    self._last_key, self._table = key, table
+    return table
+
+
+def adafactor_small(table, lr, decay, eps1, eps2, clip, mult_by_param_scale,
+                    grad_scale=None, hyper=None):
+  """Non-factored Adafactor for every variable in `table` with ONE kernel launch."""
+  ops.native().adafactor_small(table, float(lr), float(decay), float(eps1), float(eps2),
+                               float(clip), bool(mult_by_param_scale), grad_scale, hyper)
+
+
 def adam_flat(w, g, m, v, w_bf16, lr_t, b1, b2, eps, grad_scale=1.0,
               grad_scale_t=None):
   ops.native().adam_flat(w, g, m, v, w_bf16, grad_scale_t, float(lr_t),

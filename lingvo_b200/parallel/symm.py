@@ -122,6 +122,7 @@ class MoeExchange:
     self._layers: Dict[int, _LayerBufs] = {}
     self._next_chan = 0
     self._geom = None
+    self._counters = None
 
   # -------------------------------------------------------------- plumbing --
   def _EnsureArena(self, g_l, s, c, m, n_layers_hint=8):
@@ -184,13 +185,11 @@ class MoeExchange:
 
   def _Sync(self, bufs: _LayerBufs, phase: int):
     """Release-signal all peers on this channel, then acquire-wait on all."""
-    nat = ops.native()
-    bufs.seq[phase] += 1
-    seq = bufs.seq[phase]
     ch = bufs.chan[phase]
     if self.ep > 1:
-      nat.moe_signal(self.peer_flags, self.ep, self.rank, ch, seq)
-      nat.moe_wait(self.flags, self.ep, ch, seq)
+      if self._counters is None:
+        self._counters = torch.zeros(4096, dtype=torch.int32, device=self.flags.device)
+      ops.native().moe_sync(self.peer_flags, self.flags, self._counters, self.ep, self.rank, ch)
 
   # ------------------------------------------------------------------ apply --
   def GateAndDispatch(self, key, x2d, logits, paddings, capacity, legacy):

@@ -58,13 +58,13 @@ class _Channels:
     self.off = arena.Alloc(n * world * 4)
     self.flags = arena.Local(self.off, (n * world,), torch.int32)
     self.peer_flags = arena.PeerPtrs(self.off)
-    self.seq = [0] * n
+    # Sequence numbers live on the device (bumped by the sync kernel itself), so a Sync
+    # has no step-dependent launch argument and replays correctly from a CUDA graph.
+    self.counters = torch.zeros(n, dtype=torch.int32, device=self.flags.device)
 
   def Sync(self, ch):
-    nat = ops.native()
-    self.seq[ch] += 1
-    nat.moe_signal(self.peer_flags, self.world, self.rank, ch, self.seq[ch])
-    nat.moe_wait(self.flags, self.world, ch, self.seq[ch])
+    ops.native().moe_sync(self.peer_flags, self.flags, self.counters, self.world,
+                          self.rank, ch)
 
 
 class FusedAllReduce:

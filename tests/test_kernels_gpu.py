@@ -218,3 +218,76 @@ def test_glu_dwconv1d_kernel(causal, dtype):
   for name, g, r in zip(['y', 'dproj', 'dw'], got, [yr.detach(), pr.grad, wr.grad]):
     err = float((g - r).norm() / r.norm().clamp_min(1e-6))
     assert err < tol, (name, err)
+
+
+def test_adafactor_small_multi_tensor_matches_python_path():
+  """One-launch non-factored Adafactor == the per-variable PyTorch implementation."""
+  from lingvo_b200.core import optimizer as opt_lib
+  from lingvo_b200.core import py_utils
+  from lingvo_b200.core.nested_map import NestedMap
+  dev = torch.device('cuda')
+  torch.manual_seed(0)
+  shapes = [(2048,), (16, 32), (2048, 8), (77,)]
+
+  def make():
+    vs = [torch.nn.Parameter(torch.randn(s, device=dev) * 0.5) for s in shapes]
+    for i, v in enumerate(vs):
+      v.var_name = 'v%d/var' % i
+    return vs
+  a, b = make(), make()
+  for x, y in zip(a, b):
+    y.data.copy_(x.data)
+  pa = opt_lib.XLAShardingAdafactor.Params().Set(
+      name='a', beta1=0.0, beta2=0.99, multiply_by_parameter_scale=True,
+      clipping_threshold=1.0, factored=True, decay_exponent_pow=0.8)
+  fa = pa.Instantiate()
+  fb = pa.Copy().Set(fused=False).Instantiate()
+  for step in range(3):
+    py_utils.SetGlobalStep(step)
+    grads = [torch.randn_like(v) * (0.1 + step) for v in a]
+    fa.Apply(0.01, NestedMap({'v%d' % i: py_utils.VarGrad(v, g.to(torch.bfloat16) if i % 2 else g)
+                              for i, (v, g) in enumerate(zip(a, grads))}))
+    fb.Apply(0.01, NestedMap({'v%d' % i: py_utils.VarGrad(v, (g.to(torch.bfloat16).float() if i % 2 else g))
+                              for i, (v, g) in enumerate(zip(b, grads))}))
+  for x, y in zip(a, b):
+    torch.testing.assert_close(x.data, y.data, atol=2e-5, rtol=2e-4)
+
+
+def test_graphed_train_step_matches_eager():
+  """CUDA-graph replay of the whole train step reproduces the eager losses."""
+  from lingvo_b200 import model_registry
+  from lingvo_b200.core import cluster_factory
+  from lingvo_b200.core import graph_step
+  import lingvo_b200.models.lm.params.synthetic_packed_input  # noqa: F401
+  dev = torch.device('cuda', 0)
+
+  def build():
+    cfg = model_registry.GetParams('lm.synthetic_packed_input.MoELm8ETiny', 'Train')
+    cfg.task.random_seed = 3
+    cfg.input.random_seed = 9
+    cfg.cluster.worker.gpus_per_replica = 1
+    return cfg
+  losses = {}
+  for mode in ('eager', 'graph'):
+    cfg = build()
+    with cluster_factory.Cluster(cfg.cluster):
+      m = cfg.Instantiate()
+      m.to(dev)
+      task = m.tasks[0]
+      batch = task._MoveBatch(task.input.GetPreprocessedInputBatch(), dev)
+      out = []
+      if mode == 'eager':
+        for _ in range(6):
+          mt, _ = task.TrainStep([batch])
+          out.append(float(mt['loss'][0]))
+        out = out[3:]
+      else:
+        g = graph_step.GraphedTrainStep(task, batch, warmup=3)
+        assert g.launches_per_step > 10
+        for _ in range(3):
+          mt, _ = g(batch)
+          out.append(float(mt['loss'][0]))
+      losses[mode] = out
+  for x, y in zip(losses['eager'], losses['graph']):
+    assert abs(x - y) < 2e-3 * max(1.0, abs(x)), losses
+  assert losses['graph'][-1] < losses['graph'][0]
