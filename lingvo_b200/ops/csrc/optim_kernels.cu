@@ -72,74 +72,114 @@ __device__ __forceinline__ Tile get_tile(int item, int R, int C) {
   return t;
 }
 
+constexpr int kStatRowsPerWarp = 4;
+constexpr int kStatRows = kStatRowsPerWarp * kWarps;   // rows per CTA
+
+// One CTA per (batch b, 32-row block), sweeping the full width strip by strip. Row sums
+// are complete inside a warp (plain stores); column sums accumulate in shared memory and
+// leave as one partial row per CTA (colpart[b][blk][C], plain stores) that
+// adafactor_colreduce_kernel folds. No global atomics on the statistics, so the pass is
+// bandwidth-bound and bitwise reproducible.
 template <typename GT>
 __global__ void __launch_bounds__(kWarps * 32)
 adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
-                       float* __restrict__ rowsum, float* __restrict__ colsum,
-                       float* __restrict__ acc, int B, int R, int C, int items, int with_w,
+                       float* __restrict__ rowsum, float* __restrict__ colpart,
+                       float* __restrict__ acc, int B, int R, int C, int nblk, int with_w,
                        float* __restrict__ total_sumsq) {
   // with_w: also accumulate sum(w^2) (only on the first step of a variable; later
   // steps get it for free from the previous apply kernel, see acc[2]).
   // Statistics are of the RAW gradient (no grad scale, no eps1): both are folded in by
   // the factors kernel, which lets this pass also produce the global sum(g^2) that the
   // clipping scale is computed from.
+  extern __shared__ float scol[];           // [C] column sums of this CTA's rows
+  __shared__ float red[2][kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float wsq = 0.f, gsq = 0.f;
-  for (int item = blockIdx.x * kWarps + warp; item < items; item += gridDim.x * kWarps) {
-    const Tile t = get_tile(item, R, C);
-    const int c = t.c0 + lane * 8;
-    const bool cok = c < C;
+  const int b = blockIdx.x / nblk, blk = blockIdx.x - b * nblk;
+  const int r0 = blk * kStatRows + warp * kStatRowsPerWarp;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) scol[i] = 0.f;
+  __syncthreads();
+  float wsq = 0.f;
+  float rs[kStatRowsPerWarp];
+#pragma unroll
+  for (int u = 0; u < kStatRowsPerWarp; ++u) rs[u] = 0.f;
+  const size_t base = static_cast<size_t>(b) * R;
+  for (int c = lane * 8; c < C; c += 256) {
+    float gf[kStatRowsPerWarp][8];
+#pragma unroll
+    for (int u = 0; u < kStatRowsPerWarp; ++u) {
+      if (r0 + u < R) load_g8<GT>(g + (base + r0 + u) * C + c, gf[u]);
+    }
+    if (with_w) {
+#pragma unroll
+      for (int u = 0; u < kStatRowsPerWarp; ++u) {
+        if (r0 + u < R) {
+          float wf[8];
+          load_g8<float>(w + (base + r0 + u) * C + c, wf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wsq += wf[i] * wf[i];
+        }
+      }
+    }
     float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int r = t.r0; r < t.r1; r += 4) {
-      // 4 rows in flight: all loads issue before the first reduction.
-      float gf[4][8];
-      float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (cok && r + u < t.r1)
-          load_g8<GT>(g + (static_cast<size_t>(t.b) * R + r + u) * C + c, gf[u]);
-      }
-      if (with_w && cok) {
+    for (int u = 0; u < kStatRowsPerWarp; ++u) {
+      if (r0 + u < R) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (r + u < t.r1) {
-            float wf[8];
-            load_g8<float>(w + (static_cast<size_t>(t.b) * R + r + u) * C + c, wf);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) wsq += wf[i] * wf[i];
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float q = gf[u][i] * gf[u][i];
+          cs[i] += q;
+          rs[u] += q;
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (cok && r + u < t.r1) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float q = gf[u][i] * gf[u][i];
-            cs[i] += q;
-            rs[u] += q;
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rs[u] = warp_sum(rs[u]);
-      gsq += rs[0] + rs[1] + rs[2] + rs[3];
-      if (lane < 4 && r + lane < t.r1) {
-        const float v = lane == 0 ? rs[0] : lane == 1 ? rs[1] : lane == 2 ? rs[2] : rs[3];
-        atomicAdd(&rowsum[static_cast<size_t>(t.b) * R + r + lane], v);
-      }
     }
-    if (cok) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&colsum[static_cast<size_t>(t.b) * C + c + i], cs[i]);
+    for (int i = 0; i < 8; ++i) atomicAdd(&scol[c + i], cs[i]);   // shared-memory atomics
+  }
+  float gsq = 0.f;
+#pragma unroll
+  for (int u = 0; u < kStatRowsPerWarp; ++u) {
+    rs[u] = warp_sum(rs[u]);
+    gsq += rs[u];
+    if (lane == 0 && r0 + u < R) rowsum[base + r0 + u] = rs[u];
+  }
+  wsq = warp_sum(wsq);
+  if (lane == 0) {
+    red[0][warp] = gsq;
+    red[1][warp] = wsq;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x)
+    colpart[(static_cast<size_t>(b) * nblk + blk) * C + i] = scol[i];
+  if (threadIdx.x == 0) {
+    float tg = 0.f, tw = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWarps; ++k) {
+      tg += red[0][k];
+      tw += red[1][k];
     }
+    if (with_w) atomicAdd(&acc[0], tw);
+    if (total_sumsq != nullptr && tg != 0.f) atomicAdd(total_sumsq, tg);
   }
-  if (with_w) {
-    wsq = warp_sum(wsq);
-    if (lane == 0) atomicAdd(&acc[0], wsq);
+}
+
+// colsum[b][c] = sum over row blocks of colpart[b][blk][c].
+__global__ void __launch_bounds__(256)
+adafactor_colreduce_kernel(const float* __restrict__ colpart, float* __restrict__ colsum, int C,
+                           int nblk) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= C) return;
+  const float* p = colpart + static_cast<size_t>(b) * nblk * C + c;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= nblk; k += 4) {
+    s0 += p[static_cast<size_t>(k) * C];
+    s1 += p[static_cast<size_t>(k + 1) * C];
+    s2 += p[static_cast<size_t>(k + 2) * C];
+    s3 += p[static_cast<size_t>(k + 3) * C];
   }
-  // rs[] were already warp-reduced (identical in all lanes): lane 0 owns the total.
-  if (total_sumsq != nullptr && lane == 0 && gsq != 0.f) atomicAdd(total_sumsq, gsq);
+  for (; k < nblk; ++k) s0 += p[static_cast<size_t>(k) * C];
+  colsum[static_cast<size_t>(b) * C + c] = (s0 + s1) + (s2 + s3);
 }
 
 // vr_is_rows: vr has shape [B,R] (mean over C is "row mean" of the reference,
@@ -216,15 +256,24 @@ adafactor_rms_kernel(const GT* __restrict__ g, const float* __restrict__ fr,
     if (c >= C) continue;
     float cf[8];
     load_g8<float>(fc + static_cast<size_t>(t.b) * C + c, cf);
-#pragma unroll 4
-    for (int r = t.r0; r < t.r1; ++r) {
-      const float rf = fr[static_cast<size_t>(t.b) * R + r];
-      float gf[8];
-      load_g8<GT>(g + (static_cast<size_t>(t.b) * R + r) * C + c, gf);
+    for (int r = t.r0; r < t.r1; r += 4) {
+      float gf[4][8], rf[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float x = (gs == 0.f ? 0.f : gf[i] * gs) * rf * cf[i];
-        s += x * x;
+      for (int u = 0; u < 4; ++u) {
+        if (r + u < t.r1) {
+          load_g8<GT>(g + (static_cast<size_t>(t.b) * R + r + u) * C + c, gf[u]);
+          rf[u] = fr[static_cast<size_t>(t.b) * R + r + u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u < t.r1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x = (gs == 0.f ? 0.f : gf[u][i] * gs) * rf[u] * cf[i];
+            s += x * x;
+          }
+        }
       }
     }
   }
@@ -253,27 +302,41 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
     if (c >= C) continue;
     float cf[8];
     load_g8<float>(fc + static_cast<size_t>(t.b) * C + c, cf);
-#pragma unroll 2
-    for (int r = t.r0; r < t.r1; ++r) {
-      const float rf = fr[static_cast<size_t>(t.b) * R + r] * scale;
-      const size_t off = (static_cast<size_t>(t.b) * R + r) * C + c;
-      float gf[8], wf[8];
-      load_g8<GT>(g + off, gf);
-      load_g8<float>(w + off, wf);
+    for (int r = t.r0; r < t.r1; r += 4) {
+      // 4 rows in flight: every load issues before the first store (w aliases itself, so
+      // the compiler cannot hoist the next row's loads above this row's stores).
+      float gf[4][8], wf[4][8], rf[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        wf[i] -= (gs == 0.f ? 0.f : gf[i] * gs) * rf * cf[i];
-        wsq += wf[i] * wf[i];
+      for (int u = 0; u < 4; ++u) {
+        if (r + u < t.r1) {
+          const size_t off = (static_cast<size_t>(t.b) * R + r + u) * C + c;
+          load_g8<GT>(g + off, gf[u]);
+          load_g8<float>(w + off, wf[u]);
+          rf[u] = fr[static_cast<size_t>(t.b) * R + r + u] * scale;
+        }
       }
-      *reinterpret_cast<float4*>(w + off) = make_float4(wf[0], wf[1], wf[2], wf[3]);
-      *reinterpret_cast<float4*>(w + off + 4) = make_float4(wf[4], wf[5], wf[6], wf[7]);
-      if (w_bf16 != nullptr) {
-        int4 o;
-        o.x = pack_bf16x2(wf[0], wf[1]);
-        o.y = pack_bf16x2(wf[2], wf[3]);
-        o.z = pack_bf16x2(wf[4], wf[5]);
-        o.w = pack_bf16x2(wf[6], wf[7]);
-        *reinterpret_cast<int4*>(w_bf16 + off) = o;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u < t.r1) {
+          const size_t off = (static_cast<size_t>(t.b) * R + r + u) * C + c;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            wf[u][i] -= (gs == 0.f ? 0.f : gf[u][i] * gs) * rf[u] * cf[i];
+            wsq += wf[u][i] * wf[u][i];
+          }
+          *reinterpret_cast<float4*>(w + off) =
+              make_float4(wf[u][0], wf[u][1], wf[u][2], wf[u][3]);
+          *reinterpret_cast<float4*>(w + off + 4) =
+              make_float4(wf[u][4], wf[u][5], wf[u][6], wf[u][7]);
+          if (w_bf16 != nullptr) {
+            int4 o;
+            o.x = pack_bf16x2(wf[u][0], wf[u][1]);
+            o.y = pack_bf16x2(wf[u][2], wf[u][3]);
+            o.z = pack_bf16x2(wf[u][4], wf[u][5]);
+            o.w = pack_bf16x2(wf[u][6], wf[u][7]);
+            *reinterpret_cast<int4*>(w_bf16 + off) = o;
+          }
+        }
       }
     }
   }
@@ -414,6 +477,23 @@ AfLayout Layout(const torch::Tensor& w, torch::Tensor& scratch, int64_t B, int64
   return l;
 }
 
+// Shared staging buffer for the per-row-block column partials (stream-ordered reuse: the
+// stats kernel of a variable and its fold run back to back on one stream). Grows on demand;
+// warm-up steps size it before any CUDA-graph capture.
+float* ColPartials(const c10::Device& dev, int64_t floats) {
+  static auto* bufs = new std::vector<torch::Tensor>(64);   // leaked: outlives the CUDA context
+  auto& t = (*bufs)[dev.index() < 0 ? 0 : dev.index()];
+  if (!t.defined() || t.numel() < floats) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(at::cuda::getCurrentCUDAStream(), &st);
+    TORCH_CHECK(st == cudaStreamCaptureStatusNone,
+                "adafactor_stats: staging buffer would grow during graph capture; run one "
+                "eager step first");
+    t = torch::empty({floats}, torch::TensorOptions().dtype(torch::kFloat32).device(dev));
+  }
+  return t.data_ptr<float>();
+}
+
 }  // namespace
 
 // Phase A of the factored Adafactor step on `w` viewed as [B, R, C]: row/column sums of
@@ -430,22 +510,31 @@ void adafactor_stats(const torch::Tensor& w, const torch::Tensor& g, torch::Tens
   AfLayout l = Layout(w, scratch, B, R, C);
   if (recompute_wsq) C10_CUDA_CHECK(cudaMemsetAsync(l.acc, 0, sizeof(float) * 4, stream));
   else C10_CUDA_CHECK(cudaMemsetAsync(l.acc + 1, 0, sizeof(float), stream));
-  C10_CUDA_CHECK(cudaMemsetAsync(l.rowsum, 0, sizeof(float) * (l.br4 + l.bc4), stream));
   const int with_w = (recompute_wsq && mult_by_param_scale) ? 1 : 0;
   float* tot = (total_sumsq.has_value() && total_sumsq->defined())
                    ? total_sumsq->data_ptr<float>() : nullptr;
-  if (g.scalar_type() == torch::kBFloat16) {
-    adafactor_stats_kernel<__nv_bfloat16><<<l.grid, kWarps * 32, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(g.data_ptr()), w.data_ptr<float>(), l.rowsum,
-        l.colsum, l.acc, (int)B, (int)R, (int)C, l.items, with_w, tot);
-  } else {
-    TORCH_CHECK(g.scalar_type() == torch::kFloat32);
-    adafactor_stats_kernel<float><<<l.grid, kWarps * 32, 0, stream>>>(
-        g.data_ptr<float>(), w.data_ptr<float>(), l.rowsum, l.colsum, l.acc, (int)B, (int)R,
-        (int)C, l.items, with_w, tot);
-  }
+  const int nblk = static_cast<int>((R + kStatRows - 1) / kStatRows);
+  float* colpart = ColPartials(w.device(), B * nblk * C);
+  const size_t smem = sizeof(float) * static_cast<size_t>(C);
+  TORCH_CHECK(smem <= 200 * 1024, "adafactor_stats: C too large for the column accumulator");
+  auto run = [&](auto tag) {
+    using GT = decltype(tag);
+    auto kern = adafactor_stats_kernel<GT>;
+    if (smem > 48 * 1024) {
+      C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+    }
+    kern<<<static_cast<int>(B) * nblk, kWarps * 32, smem, stream>>>(
+        reinterpret_cast<const GT*>(g.data_ptr()), w.data_ptr<float>(), l.rowsum, colpart, l.acc,
+        (int)B, (int)R, (int)C, nblk, with_w, tot);
+  };
+  if (g.scalar_type() == torch::kBFloat16) run(__nv_bfloat16());
+  else { TORCH_CHECK(g.scalar_type() == torch::kFloat32); run(float()); }
+  adafactor_colreduce_kernel<<<dim3(static_cast<unsigned>((C + 255) / 256),
+                                    static_cast<unsigned>(B)), 256, 0, stream>>>(
+      colpart, l.colsum, (int)C, nblk);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
-  CountLaunch();
+  CountLaunch(2);
 }
 
 // Phase B: factors (folding grad_scale^2 and eps1 into the raw sums) -> clip RMS -> apply.
