@@ -129,6 +129,31 @@ class Librispeech960Grapheme(Librispeech960Base):
     return self.InitializeTokenizer(super()._CommonInputParams(is_eval))
 
 
+class _StaticShapeMixin:
+  """Fixed-shape batches (ref `…TpuV2` variants, :217/:310): every training batch is
+  padded to the longest bucket with a constant batch size, so the whole step has one
+  shape signature and can be replayed from a CUDA graph."""
+
+  def _CommonInputParams(self, is_eval):
+    p = super()._CommonInputParams(is_eval)
+    if not is_eval:
+      p.pad_to_max_seq_length = True
+      p.bucket_batch_limit = [48] * len(p.bucket_upper_bound)
+      p.source_max_length = p.bucket_upper_bound[-1]
+    return p
+
+  def Task(self):
+    p = super().Task()
+    p.encoder.pad_steps = 0
+    p.decoder.emb.max_num_shards = 1
+    return p
+
+
+@model_registry.RegisterSingleTaskModel
+class Librispeech960GraphemeTpuV2(_StaticShapeMixin, Librispeech960Grapheme):
+  """Static-shape grapheme model (ref :217)."""
+
+
 @model_registry.RegisterSingleTaskModel
 class Librispeech960Wpm(Librispeech960Base):
   """16k word-piece targets (ref :239)."""
@@ -156,3 +181,8 @@ class Librispeech960Wpm(Librispeech960Base):
     dp.target_seq_len = self.WPM_TARGET_SEQUENCE_LENGTH
     dp.label_smoothing.num_classes = self.WPM_VOCAB_SIZE
     return p
+
+
+@model_registry.RegisterSingleTaskModel
+class Librispeech960WpmTpuV2(_StaticShapeMixin, Librispeech960Wpm):
+  """Static-shape word-piece model (ref :310)."""
