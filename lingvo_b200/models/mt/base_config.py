@@ -169,3 +169,41 @@ def SetupRNMTParams(p, name, vocab_size, embedding_dim, hidden_dim, num_heads,
                     decay_end=lr_decay_end, min=lr_min))
   p.eval.samples_per_summary = 12000
   return p
+
+
+def SetupXEnDecTransformerParams(p, name, vocab_size, model_dim, hidden_dim, num_heads,
+                                 num_layers, learning_rate, warmup_steps,
+                                 residual_dropout_prob=0.1, input_dropout_prob=0.0,
+                                 atten_dropout_prob=0.0, relu_dropout_prob=0.0,
+                                 label_smoothing_uncertainty=0.1):
+  """Fills a `TransformerXEnDecModel.Params()` (ref :593): X-encoder / X-decoder with the
+  Transformer-base training recipe."""
+  del atten_dropout_prob, relu_dropout_prob
+  p.name = name
+  enc = p.encoder
+  enc.name = 'enc'
+  enc.model_dim = model_dim
+  enc.token_emb.Set(vocab_size=vocab_size, embedding_dim=model_dim,
+                    params_init=py_utils.WeightInit.Gaussian(1.0 / model_dim ** 0.5))
+  enc.position_emb.Set(embedding_dim=model_dim)
+  enc.input_dropout_prob = input_dropout_prob
+  enc.transformer_stack.Set(num_layers=num_layers, mdl_dim=model_dim, hidden_dim=hidden_dim,
+                            num_atten_heads=num_heads, dropout_prob=residual_dropout_prob)
+  dec = p.decoder
+  dec.name = 'dec'
+  dec.Set(source_dim=model_dim, model_dim=model_dim, num_trans_layers=num_layers,
+          num_atten_heads=num_heads, hidden_dim=hidden_dim,
+          input_dropout_prob=input_dropout_prob, per_word_avg_loss=True, target_seq_len=300)
+  dec.token_emb.Set(vocab_size=vocab_size, embedding_dim=model_dim,
+                    params_init=py_utils.WeightInit.Gaussian(1.0 / model_dim ** 0.5))
+  dec.position_emb.Set(embedding_dim=model_dim)
+  dec.softmax.Set(num_classes=vocab_size, input_dim=model_dim)
+  if label_smoothing_uncertainty:
+    dec.label_smoothing = layers.UniformLabelSmoother.Params().Set(
+        num_classes=vocab_size, uncertainty=label_smoothing_uncertainty)
+  p.train.Set(learning_rate=learning_rate, optimizer=optimizer.Adam.ParamsB(),
+              clip_gradient_norm_to_value=0.0, grad_norm_to_clip_to_zero=0.0,
+              lr_schedule=schedule.TransformerSchedule.Params().Set(
+                  warmup_steps=warmup_steps, worker_replicas=1, model_dim=model_dim))
+  p.eval.samples_per_summary = 12000
+  return p

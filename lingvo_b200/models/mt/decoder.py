@@ -276,4 +276,228 @@ class TransformerDecoder(MTBaseDecoder):
             NestedMap(cache=new_cache, time_step=states.time_step + 1))
 
 
-TransformerBatchMajorDecoder = TransformerDecoder   # ref :2361
+class TransformerBatchMajorDecoder(TransformerDecoder):
+  """Batch-major Transformer decoder (ref :2361). `TransformerDecoder` here already runs
+  batch-major over the fused attention kernels with a pre-allocated KV cache; this class
+  carries the reference's extra knobs."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('input_data_format', 'TBC', "Encoder output layout: 'TBC' or 'BTC'.")
+    p.Define('prediction_data_format', 'TBC', "Layout of softmax_input: 'TBC' or 'BTC'.")
+    p.Define('use_fused_layernorm', False, 'Kept for parity (LN is always fused).')
+    p.Define('use_fast_softmax', False, 'Kept for parity.')
+    return p
+
+  def ComputePredictions(self, theta, encoder_outputs, targets):
+    p = self.params
+    if p.input_data_format == 'BTC':
+      encoder_outputs = NestedMap(encoded=encoder_outputs.encoded.transpose(0, 1),
+                                  padding=encoder_outputs.padding.t())
+    out = super().ComputePredictions(theta, encoder_outputs, targets)
+    if p.prediction_data_format == 'BTC':
+      out.softmax_input = out.softmax_input.transpose(0, 1)
+    return out
+
+  def ComputeLoss(self, theta, predictions, targets):
+    if self.params.prediction_data_format == 'BTC':
+      predictions = NestedMap(softmax_input=predictions.softmax_input.transpose(0, 1))
+    return super().ComputeLoss(theta, predictions, targets)
+
+
+class TransformerXDecoder(MTBaseDecoder):
+  """Decoder for XEnDec (ref :2935): target embeddings of two sentences can be
+  interpolated (`other_targets`, `lambdas`), the cross-attention distribution is returned
+  (it drives the label mixing ratios), and the loss accepts soft target distributions."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('token_emb', layers.SimpleEmbeddingLayer.Params(), 'Token embedding.')
+    p.Define('position_emb', layers.PositionalEmbeddingLayer.Params(), 'Positions.')
+    p.Define('source_dim', 512, 'Encoder dim.')
+    p.Define('model_dim', 512, 'Model dim.')
+    p.Define('num_trans_layers', 6, 'Layers.')
+    p.Define('trans_tpl', None, 'Time-major TransformerLayer template.')
+    p.Define('input_dropout_prob', 0.0, 'Input dropout.')
+    p.Define('hidden_dim', 2048, 'FFN hidden dim.')
+    p.Define('num_atten_heads', 8, 'Heads.')
+    p.softmax.num_classes = 32000
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    from lingvo_b200.core import layers_with_attention as lwa
+    from lingvo_b200.models.mt import layers as mt_layers
+    p = self.params
+    self.CreateChild('token_emb', p.token_emb.Copy().Set(embedding_dim=p.model_dim))
+    self.CreateChild('position_emb', p.position_emb.Copy().Set(embedding_dim=p.model_dim))
+    self.CreateChild('input_dropout', layers.DropoutLayer.Params().Set(
+        keep_prob=1.0 - p.input_dropout_prob))
+    tpl = (p.trans_tpl or lwa.TransformerLayer.Params()).Copy()
+    tpl.tr_atten_tpl.num_attention_heads = p.num_atten_heads
+    tpl.tr_fflayer_tpl.hidden_dim = p.hidden_dim
+    self.CreateChild('stack', mt_layers.TransformerStack.Params().Set(
+        model_dim=p.model_dim, num_transformer_layers=p.num_trans_layers,
+        transformer_tpl=tpl, ln_output=True, has_aux_attention=True, mask_self_atten=True))
+    self.CreateChild('softmax', p.softmax.Copy().Set(input_dim=p.model_dim))
+
+  def ComputePredictions(self, theta, encoder_outputs, targets, other_targets=None,
+                         lambdas=None):
+    p = self.params
+    ids = targets.ids.long()
+    emb = targets.get('embs')
+    if emb is None or other_targets is None:
+      emb = self.token_emb.EmbLookup(theta.token_emb, ids)
+    pad = targets.paddings.float()
+    if other_targets is not None:
+      other = other_targets.get('embs')
+      if other is None:
+        other = self.token_emb.EmbLookup(theta.token_emb, other_targets.ids.long())
+      emb = lambdas[0].unsqueeze(-1).to(emb.dtype) * emb + \
+          lambdas[1].unsqueeze(-1).to(emb.dtype) * other
+      pad = (pad + other_targets.paddings.float() - 1.0).clamp(0.0, 1.0)
+    orig = emb
+    x = emb * (p.model_dim ** 0.5)
+    pos = self.position_emb.FProp(theta.position_emb, ids.shape[1]).unsqueeze(0)
+    x = self.input_dropout.FProp(theta.input_dropout, x + pos.to(x.dtype)).transpose(0, 1)
+    out, _, _, probs = self.stack.FProp(
+        theta.stack, x, pad.t(), aux_vecs=encoder_outputs.encoded,
+        aux_paddings=encoder_outputs.padding, return_atten_probs=True)
+    # probs: [T, B, S] cross-attention of the last layer → [B, T, S]
+    return NestedMap(softmax_input=out, attention=NestedMap(probs=probs.transpose(0, 1)),
+                     source_embs=encoder_outputs.get('embedded_inputs'), target_embs=orig)
+
+  def ComputeLoss(self, theta, predictions, targets, target_probs=None):
+    """Hard-label loss, or cross entropy against `target_probs [B,T,V]` (mixed labels)."""
+    p = self.params
+    x = predictions.softmax_input                      # [T,B,D]
+    t, b, d = x.shape
+    w = targets.weights.t().float()
+    lab = targets.labels.t().long()
+    logits = self.softmax.Logits(theta.softmax, x.reshape(t * b, d)).float()
+    logp = torch.log_softmax(logits, -1)
+    hard = torch.nn.functional.one_hot(lab.reshape(-1), logits.shape[-1]).float()
+    if target_probs is None:
+      tp = hard
+      if p.label_smoothing is not None:
+        tp = self.smoother.FProp(theta.smoother, targets.paddings.t(), lab,
+                                 target_ids=None).reshape(t * b, -1)
+    else:
+      tp = target_probs.transpose(0, 1).reshape(t * b, -1)
+    per_tok = -(tp * logp).sum(-1).reshape(t, b)
+    total = (per_tok * w).sum()
+    num_words = w.sum().clamp_min(1e-8)
+    if p.per_word_avg_loss:
+      loss, loss_w = total / num_words, num_words
+    else:
+      loss, loss_w = total / float(b), torch.tensor(float(b), device=w.device)
+    correct = ((logits.argmax(-1).reshape(t, b) == lab).float() * w).sum()
+    metrics = NestedMap(
+        loss=(loss, loss_w), log_pplx=(total / num_words, num_words),
+        fraction_of_correct_next_step_preds=(correct / num_words, num_words),
+        num_predictions=(num_words, 1.0))
+    per_seq = NestedMap(
+        per_sequence_xent=(per_tok * w).sum(0),
+        reshape_probs=torch.softmax(logits, -1).reshape(t, b, -1).transpose(0, 1).detach(),
+        target_hard_probs=hard.reshape(t, b, -1).transpose(0, 1))
+    return metrics, per_seq
+
+  # decode: greedy/beam through full re-computation of the prefix (XEnDec is a training
+  # recipe; serving uses TransformerDecoder with the same weights layout).
+  def _InitBeamSearchStateCallback(self, theta, encoder_outputs, num_hyps_per_beam):
+    p = self.params
+    src_b = encoder_outputs.encoded.shape[1]
+    n = src_b * num_hyps_per_beam
+    dev = encoder_outputs.encoded.device
+    encoder_outputs.enc_tiled = encoder_outputs.encoded.repeat(1, num_hyps_per_beam, 1)
+    encoder_outputs.pad_tiled = encoder_outputs.padding.repeat(1, num_hyps_per_beam)
+    init = NestedMap(log_probs=torch.zeros(n, p.softmax.num_classes, device=dev),
+                     atten_probs=torch.zeros(n, encoder_outputs.encoded.shape[0], device=dev))
+    prefix = torch.zeros(n, p.target_seq_len, dtype=torch.int64, device=dev)
+    return init, NestedMap(prefix=prefix)
+
+  def _PreBeamSearchStepCallback(self, theta, encoder_outputs, step_ids, states,
+                                 num_hyps_per_beam, cur_step):
+    prefix = states.prefix.clone()
+    prefix[:, cur_step] = step_ids.squeeze(1)
+    ids = prefix[:, :cur_step + 1]
+    enc = NestedMap(encoded=encoder_outputs.enc_tiled, padding=encoder_outputs.pad_tiled)
+    pred = self.ComputePredictions(
+        theta, enc, NestedMap(ids=ids, paddings=torch.zeros_like(ids, dtype=torch.float32)))
+    logits = self.softmax.Logits(theta.softmax, pred.softmax_input[-1])
+    return (NestedMap(log_probs=torch.log_softmax(logits.float(), -1),
+                      atten_probs=pred.attention.probs[:, -1]),
+            NestedMap(prefix=prefix))
+
+
+class InsertionDecoder(base_decoder.BaseBeamSearchDecoder):
+  """Insertion Transformer / KERMIT decoder (ref :2179): a bidirectional Transformer over
+  the current canvas whose softmax at slot *i* scores the token to insert after canvas
+  position *i*. The token embedding holds 2× the vocabulary so that source-side canvas
+  tokens (offset by `softmax.num_classes`) are distinguishable from target-side ones."""
+
+  @classmethod
+  def Params(cls):
+    from lingvo_b200.core import layers_with_attention as lwa
+    p = super().Params()
+    p.Define('token_emb', layers.SimpleEmbeddingLayer.Params(), 'Token embedding (2·V rows).')
+    p.Define('position_emb', layers.PositionalEmbeddingLayer.Params(), 'Positions.')
+    p.Define('model_dim', 1024, 'Model dim.')
+    p.Define('num_trans_layers', 6, 'Layers.')
+    p.Define('trans_tpl', lwa.TransformerLayer.Params(), 'Layer template.')
+    p.Define('softmax', layers.SimpleFullSoftmax.Params(), 'Softmax.')
+    p.Define('input_dropout_prob', 0.0, 'Input dropout.')
+    p.token_emb.vocab_size = 32000 * 2
+    p.trans_tpl.tr_atten_tpl.num_attention_heads = 8
+    p.trans_tpl.tr_fflayer_tpl.hidden_dim = 4096
+    p.softmax.num_classes = 32000
+    p.target_seq_len = 300
+    return p
+
+  @classmethod
+  def UpdateTargetVocabSize(cls, p, vocab_size, wpm_model=None):
+    p.softmax.num_classes = vocab_size
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert p.token_emb.vocab_size % p.softmax.num_classes == 0
+    self.CreateChild('token_emb', p.token_emb.Copy().Set(embedding_dim=p.model_dim))
+    self.CreateChild('position_emb', p.position_emb.Copy().Set(embedding_dim=p.model_dim))
+    self.CreateChild('input_dropout', layers.DropoutLayer.Params().Set(
+        keep_prob=1.0 - p.input_dropout_prob))
+    self.CreateChildren('trans', [
+        p.trans_tpl.Copy().Set(name='trans_layer_%d' % i, source_dim=p.model_dim,
+                               packed_input=p.packed_input, has_aux_atten=False,
+                               mask_self_atten=False)
+        for i in range(p.num_trans_layers)])
+    self.CreateChild('softmax', p.softmax.Copy().Set(input_dim=p.model_dim))
+
+  def ComputePredictions(self, theta, encoder_outputs, targets):
+    """targets.ids/paddings `[B, C]` = the canvas → outputs `[B, C, D]`."""
+    assert encoder_outputs is None
+    p = self.params
+    ids = targets.ids.long()
+    x = self.token_emb.EmbLookup(theta.token_emb, ids) * (p.model_dim ** 0.5)
+    x = x + self.position_emb.FProp(theta.position_emb, ids.shape[1]).unsqueeze(0).to(x.dtype)
+    x = self.input_dropout.FProp(theta.input_dropout, x).transpose(0, 1)
+    pad = targets.paddings.float().t()
+    for i, layer in enumerate(self.trans):
+      x, _ = layer.FProp(theta.trans[i], x, pad)
+    return NestedMap(outputs=x.transpose(0, 1))
+
+  def ComputeLoss(self, theta, predictions, targets=None):
+    """−Σ w · log p(token | slot) over `predictions.tgt.target_indices [N,3]` =
+    (batch, slot, token) with weights `target_weights [N]`."""
+    out = predictions.outputs
+    b, c, d = out.shape
+    logits = self.softmax.Logits(theta.softmax, out.reshape(b * c, d)).reshape(b, c, -1)
+    logp = torch.log_softmax(logits.float(), -1)
+    idx = predictions.tgt.target_indices.long()
+    picked = logp[idx[:, 0], idx[:, 1], idx[:, 2]]
+    loss = -(picked * predictions.tgt.target_weights.float()).sum() / float(b)
+    return ({'loss': (loss, torch.tensor(float(b), device=out.device))},
+            {'log_probs': logp, 'logits': logits})

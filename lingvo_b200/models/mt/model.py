@@ -70,7 +70,8 @@ class MTBaseModel(base_model.BaseTask):
   def __init__(self, params):
     super().__init__(params)
     p = self.params
-    self.CreateChild('enc', p.encoder)
+    if p.encoder is not None:
+      self.CreateChild('enc', p.encoder)
     self.CreateChild('dec', p.decoder)
 
   def ComputePredictions(self, theta, batch):
@@ -141,3 +142,181 @@ class HybridModel(MTBaseModel):
     p.encoder = mt_encoder.TransformerEncoder.Params()
     p.decoder = mt_decoder.MTDecoderV1.Params()
     return p
+
+
+class InsertionModel(MTBaseModel):
+  """Insertion-based translation (KERMIT-style, ref :391): source and target are
+  concatenated into one canvas; training samples a partial canvas of each side and
+  learns to insert the missing tokens."""
+
+  @classmethod
+  def Params(cls):
+    from lingvo_b200.core import insertion
+    from lingvo_b200.models.mt import decoder as mt_decoder
+    p = super().Params()
+    p.encoder = None
+    p.decoder = mt_decoder.InsertionDecoder.Params()
+    p.Define('insertion', insertion.SymbolInsertionLayer.Params(), 'Roll-in / oracle policy.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('insertion', self.params.insertion)
+
+  def _SampleCanvasAndTargets(self, x, x_paddings):
+    return self.insertion.FProp(None, x, x_paddings, self.params.decoder.target_eos_id, True)
+
+  def _CreateCanvasAndTargets(self, batch):
+    """→ NestedMap(canvas, canvas_paddings[, target_indices, target_weights])."""
+    from lingvo_b200.core import insertion
+    p = self.params
+    vocab = p.decoder.softmax.num_classes
+    if self.do_eval:
+      # eval: the canvas is the full source followed by an empty target side
+      canvas = torch.where(batch.src.paddings < 0.5, batch.src.ids + vocab, batch.src.ids)
+      return NestedMap(canvas=canvas, canvas_paddings=batch.src.paddings.float())
+    src = self._SampleCanvasAndTargets(batch.src.ids, batch.src.paddings.float())
+    tgt = self._SampleCanvasAndTargets(batch.tgt.ids, batch.tgt.paddings.float())
+    src.canvas = torch.where(src.canvas_paddings < 0.5, src.canvas + vocab, src.canvas)
+    src_lens = (1.0 - src.canvas_paddings).sum(1).long()
+    # target-side slots sit after the kept source tokens of the same row
+    tgt_idx = tgt.target_indices.clone()
+    tgt_idx[:, 1] += src_lens[tgt_idx[:, 0]]
+    canvas, canvas_pad = insertion.SequenceConcat(
+        src.canvas, src.canvas_paddings, tgt.canvas, tgt.canvas_paddings)
+    return NestedMap(
+        canvas=canvas, canvas_paddings=canvas_pad,
+        target_indices=torch.cat([src.target_indices, tgt_idx], 0),
+        target_weights=torch.cat([src.target_weights, tgt.target_weights], 0))
+
+  def ComputePredictions(self, theta, batch):
+    desc = self._CreateCanvasAndTargets(batch)
+    pred = self.dec.ComputePredictions(
+        theta.dec, None, NestedMap(ids=desc.canvas, paddings=desc.canvas_paddings))
+    pred.tgt = desc
+    return pred
+
+  def ComputeLoss(self, theta, predictions, batch):
+    return self.dec.ComputeLoss(theta.dec, predictions)
+
+  def Decode(self, batch):
+    raise NotImplementedError('InsertionModel: parallel insertion decoding is not exposed '
+                              '(the reference has none either).')
+
+
+class TransformerXEnDecModel(TransformerModel):
+  """XEnDec (crossover encoder-decoder, arXiv 2106.04060; ref :459).
+
+  Three losses per step: the *clean* loss on the batch, the *mono* loss on a partner batch
+  (the batch rolled by one unless `other_src/other_tgt` are given), and the *mix* loss on
+  the crossover of the two — source embeddings mixed by `src.source_mask`, target input
+  embeddings and soft labels mixed by ratios derived from the (stop-gradient)
+  cross-attention of both parents."""
+
+  @classmethod
+  def Params(cls):
+    from lingvo_b200.models.mt import decoder as mt_decoder
+    from lingvo_b200.models.mt import encoder as mt_encoder
+    p = super().Params()
+    p.encoder = mt_encoder.TransformerXEncoder.Params()
+    p.decoder = mt_decoder.TransformerXDecoder.Params()
+    p.Define('loss_mix_weight', 1.0, 'Weight of the crossover loss.')
+    p.Define('loss_clean_weight', 1.0, 'Weight of the clean loss.')
+    p.Define('loss_mono_weight', 1.0, 'Weight of the partner-batch loss.')
+    p.Define('use_prob_cl', False, 'Curriculum from hard labels to model probabilities.')
+    p.Define('use_prob_drop', False, 'Kept for parity.')
+    p.Define('atten_drop', 0.0, 'Dropout on the attention used for mixing ratios.')
+    return p
+
+  @staticmethod
+  def _CreateTargetLambdas(atten_probs, source_lambdas_pair, source_paddings_pair,
+                           target_paddings_pair, smooth=0.0):
+    """Target mixing ratios from attention mass on each parent's kept source tokens."""
+    mass = []
+    for k in range(2):
+      src_w = source_lambdas_pair[k] * (1.0 - source_paddings_pair[k])          # [B,S]
+      m = (atten_probs[k].detach() * src_w.unsqueeze(1)).sum(-1)                # [B,T]
+      mass.append((m + smooth) * (1.0 - target_paddings_pair[k]))
+    lab0 = mass[0] / (mass[0] + mass[1] + 1e-9)
+    label_lambdas = [lab0, 1.0 - lab0]
+    inp0 = torch.nn.functional.pad(lab0, (1, 0), value=1.0)[:, :-1]
+    input_lambdas = [inp0 * (1.0 - target_paddings_pair[0]),
+                     (1.0 - inp0) * (1.0 - target_paddings_pair[1])]
+    return source_lambdas_pair, input_lambdas, label_lambdas
+
+  def ComputePredictions(self, theta, batch, other_batch=None, source_lambdas=None,
+                         target_lambdas=None):
+    enc = self.enc.FProp(theta.enc, batch.src,
+                             other_batch.src if other_batch is not None else None,
+                             source_lambdas)
+    pred = self.dec.ComputePredictions(
+        theta.dec, enc, batch.tgt,
+        other_batch.tgt if other_batch is not None else None, target_lambdas)
+    pred.encoder_outputs = enc
+    return pred
+
+  def ComputeLoss(self, theta, predictions, batch):
+    p = self.params
+    clean = self.dec.ComputeLoss(theta.dec, predictions, batch.tgt)
+    if self.do_eval:
+      return clean
+    roll = lambda x: torch.roll(x, 1, 0)
+    if 'other_src' in batch and 'other_tgt' in batch:
+      other = NestedMap(src=batch.other_src.DeepCopy(), tgt=batch.other_tgt.DeepCopy())
+    else:
+      other = NestedMap(src=batch.src.DeepCopy(), tgt=batch.tgt.DeepCopy()).Transform(roll)
+    if p.loss_mono_weight > 0 or 'other_src' in batch:
+      other_pred = self.ComputePredictions(theta, other)
+      mono = self.dec.ComputeLoss(theta.dec, other_pred, other.tgt)
+      other_att, other_aux = other_pred.attention.probs, mono[1]
+      other_src_embs, other_tgt_embs = other_pred.source_embs, other_pred.target_embs
+    else:
+      mono = None
+      other_att = roll(predictions.attention.probs)
+      other_aux = NestedMap(reshape_probs=roll(clean[1].reshape_probs),
+                            target_hard_probs=roll(clean[1].target_hard_probs))
+      other_src_embs, other_tgt_embs = roll(predictions.source_embs), roll(predictions.target_embs)
+    terms = []
+    if p.loss_clean_weight > 0:
+      terms.append(('clean_loss', clean, p.loss_clean_weight))
+    if p.loss_mono_weight > 0:
+      terms.append(('other_loss', mono, p.loss_mono_weight))
+    if p.loss_mix_weight > 0:
+      att, oatt = predictions.attention.probs, other_att
+      if p.atten_drop > 0:
+        att = torch.nn.functional.dropout(att, p.atten_drop)
+        oatt = torch.nn.functional.dropout(oatt, p.atten_drop)
+      if p.use_prob_cl:
+        ratio = min(float(self.global_step) / 20000.0, 1.0)
+        mixp = lambda aux, w: aux.target_hard_probs * (1 - w.unsqueeze(-1) * ratio) + \
+            aux.reshape_probs * (w.unsqueeze(-1) * ratio)
+        probs, oprobs = mixp(clean[1], batch.tgt.weights), mixp(other_aux, other.tgt.weights)
+      else:
+        probs, oprobs = clean[1].target_hard_probs, other_aux.target_hard_probs
+      src_pads = [batch.src.paddings.float(), other.src.paddings.float()]
+      tgt_pads = [batch.tgt.paddings.float(), other.tgt.paddings.float()]
+      mask = batch.src.source_mask.float()
+      other_lam = mask * (1.0 - src_pads[1])
+      src_lam = [(1.0 - other_lam) * (1.0 - src_pads[0]), other_lam]
+      src_lam, inp_lam, lab_lam = self._CreateTargetLambdas(
+          [att, oatt], src_lam, src_pads, tgt_pads)
+      mix_batch = NestedMap(src=batch.src.DeepCopy(), tgt=batch.tgt.DeepCopy())
+      mix_batch.tgt.weights = (batch.tgt.weights + other.tgt.weights).clamp(0.0, 1.0)
+      mix_batch.src.embs, mix_batch.tgt.embs = predictions.source_embs, predictions.target_embs
+      other.src.embs, other.tgt.embs = other_src_embs, other_tgt_embs
+      mix_pred = self.ComputePredictions(theta, mix_batch, other, src_lam, inp_lam)
+      tp = probs * lab_lam[0].unsqueeze(-1) + oprobs * lab_lam[1].unsqueeze(-1) + 1e-9
+      tp = tp / tp.sum(-1, keepdim=True)
+      mix = self.dec.ComputeLoss(theta.dec, mix_pred, mix_batch.tgt, tp)
+      terms.append(('mix_loss', mix, p.loss_mix_weight))
+    metrics = NestedMap()
+    total, npred = 0.0, torch.tensor(1.0)
+    for name, (m, _), w in terms:
+      total = total + m.loss[0] * w
+      metrics[name] = (m.loss[0] * w, m.loss[1])
+      if name == 'clean_loss':
+        npred = m.loss[1]
+    metrics.loss = (total, npred)
+    for k in ('log_pplx', 'fraction_of_correct_next_step_preds', 'num_predictions'):
+      metrics[k] = clean[0][k]
+    return metrics, clean[1]
