@@ -4,7 +4,10 @@
   python tools/adafactor_probe.py ncu        # one pass of each kernel for an ncu capture
 """
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 

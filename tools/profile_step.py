@@ -23,7 +23,7 @@ def main():
         task.TrainStep([batches[i % 2]])
       torch.cuda.synchronize()
   os.makedirs('gpurun_out', exist_ok=True)
-  tbl = prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=70)
+  tbl = prof.key_averages().table(sort_by='cuda_time_total', row_limit=70, max_name_column_width=70)
   open('gpurun_out/profile_step.txt', 'w').write(tbl)
   print(tbl[-9000:])
 
