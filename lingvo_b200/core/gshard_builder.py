@@ -309,6 +309,53 @@ class SelfAttentionLayer(_BuilderLayer):
     return out, torch.zeros((), device=x.device, dtype=torch.float32)
 
 
+def _SelfAttentionInitCache(layer, batch, max_len, device, dtype):
+  b = layer.bp
+  hk = b.attention_num_memory_heads or b.attention_num_heads
+  d = b.attention_key_value_dim
+  return NestedMap(k=torch.zeros(batch, max_len, hk, d, device=device, dtype=dtype),
+                   v=torch.zeros(batch, max_len, hk, d, device=device, dtype=dtype))
+
+
+def _SelfAttentionExtendStep(layer, theta, x, cache, t):
+  """One decode step: x `[B,1,M]` at position `t` (python int or 0-dim tensor) attends to
+  the cached keys/values of positions ≤ t. The cache is updated in place (static
+  buffers → the whole step is CUDA-graph capturable with `t` as a device scalar)."""
+  b = layer.bp
+  bsz, _, m = x.shape
+  h, d = b.attention_num_heads, b.attention_key_value_dim
+  hk = b.attention_num_memory_heads or h
+  xd = x.dtype
+  q = torch.matmul(x, theta.wq.to(xd)).reshape(bsz, 1, h, d)
+  k = torch.matmul(x, theta.wk.to(xd)).reshape(bsz, 1, hk, d)
+  v = torch.matmul(x, theta.wv.to(xd)).reshape(bsz, 1, hk, d)
+  tmax = cache.k.shape[1]
+  dev = x.device
+  tt = torch.as_tensor(t, device=dev).reshape(())
+  if b.use_rotary_position_emb:
+    pos = tt.reshape(1, 1).expand(bsz, 1)
+    q, k = _Rope(q, pos, b.rope_emb_max_timescale), _Rope(k, pos, b.rope_emb_max_timescale)
+  onehot = (torch.arange(tmax, device=dev) == tt).to(xd).reshape(1, tmax, 1, 1)
+  cache.k.mul_(1 - onehot).add_(k * onehot)
+  cache.v.mul_(1 - onehot).add_(v * onehot)
+  kk, vv = cache.k, cache.v
+  if hk != h:
+    kk, vv = kk.expand(bsz, tmax, h, d), vv.expand(bsz, tmax, h, d)
+  logits = torch.einsum('bqhd,bkhd->bhqk', q.float(), kk.float())      # [B,H,1,T]
+  key_pos = torch.arange(tmax, device=dev)
+  if layer.params.relative_bias:
+    bucket = RelativePositionBucket(
+        key_pos - tt, b.relative_attention_num_buckets, b.relative_attention_max_distance,
+        bidirectional=b.decoder_bidirectional_relative_attention)
+    logits = logits + theta.wrb.float()[:, bucket.long()].reshape(1, h, 1, tmax)
+  logits = logits + ((key_pos > tt).float() * -1e9).reshape(1, 1, 1, tmax)
+  if b.atten_logit_cap:
+    logits = b.atten_logit_cap * torch.tanh(logits / b.atten_logit_cap)
+  probs = torch.softmax(logits, -1)
+  o = torch.einsum('bhqk,bkhd->bqhd', probs, vv.float()).to(xd).reshape(bsz, 1, h * d)
+  return torch.matmul(o, theta.wo.to(xd))
+
+
 def _Rope(x, pos, max_timescale):
   """Half-split rotary embedding on `[B, L, H, D]` (reference :409-426)."""
   d = x.shape[-1]
@@ -487,7 +534,7 @@ class MoELayer(_BuilderLayer):
     from lingvo_b200.parallel import symm
     return symm.LocalExchange(b.e_dim, x.device)
 
-  def FProp(self, theta, x, segment_id, segment_pos=None):
+  def FProp(self, theta, x, segment_id, segment_pos=None, expert_id=None):
     b = self.bp
     p = self.params
     bsz, l, m = x.shape
@@ -499,12 +546,15 @@ class MoELayer(_BuilderLayer):
     paddings = (segment_id == 0).float().reshape(groups, s)
     ldt = b.gating_logits_dtype or torch.float32
     act = b.moe_activation.upper()
-    if p.mode == 'dense':
+    pad_idx = b.Get('expert_padding_idx') if 'expert_padding_idx' in b else None
+    if p.mode == 'dense' or b.gating_func == 'hashing' or pad_idx is not None:
+      eid = expert_id.reshape(groups, s) if expert_id is not None else None
       gating = gshard_layers.ComputeGating(
           theta.gw, xg, paddings, b.num_devices, b.e_dim, b.c_dim or 0, True,
           x.dtype, b.gating_func, False, b.second_expert_policy,
           b.second_expert_threshold, b.legacy_mtf_behavior, b.capacity_factor,
-          None, b.mask_dtype or torch.float32, ldt)
+          None, b.mask_dtype or torch.float32, ldt, expert_id=eid,
+          expert_padding_idx=pad_idx)
       wi = torch.stack([theta.wi_0, theta.wi_1]) if p.gated else theta.wi
       out, aux = gshard_layers.FeedForwardNetworksApplyGating(
           gating, x, xg, wi, theta.wo, b.num_devices, groups,
@@ -566,7 +616,7 @@ class DecoderBlock(_BuilderLayer):
       x_in = i.vec * mask
     x = self.ln.FProp(theta.ln, x_in) if p.norm_policy != 'primer_post' else x_in
     fuse_res = (getattr(self.layer, 'supports_fused_residual', False) and
-                p.post_norm is None and not (b.dropout_rate and not self.do_eval))
+                i.get('expert_id') is None and p.post_norm is None and not (b.dropout_rate and not self.do_eval))
     if fuse_res:
       # x_in + f(x) comes out of the sub-layer's last GEMM epilogue.
       y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos, residual=x_in)
@@ -574,7 +624,11 @@ class DecoderBlock(_BuilderLayer):
       o.vec = y
       o.aux_loss = i.aux_loss + aux
       return o
-    y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos)
+    if i.get('expert_id') is not None and isinstance(self.layer, MoELayer):
+      y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos,
+                                expert_id=i.expert_id)
+    else:
+      y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos)
     if p.post_norm is not None:
       y = self.post_ln.FProp(theta.post_ln, y)
     if b.dropout_rate and not self.do_eval:
@@ -587,6 +641,32 @@ class DecoderBlock(_BuilderLayer):
 
 class LayerStack(_BuilderLayer):
   """`num` repetitions of the sub-layer list + final norm (:675-906)."""
+
+  # -- incremental decoding ----------------------------------------------------------
+  def InitDecodeState(self, batch, max_len, device, dtype):
+    """KV caches for every self-attention block (None for the other blocks)."""
+    return [(_SelfAttentionInitCache(blk.layer, batch, max_len, device, dtype)
+             if isinstance(blk.layer, SelfAttentionLayer) else None) for blk in self.layers]
+
+  def ExtendStep(self, theta, vec, state, t):
+    """vec `[B,1,M]` at position t → `[B,1,M]`; `state` from `InitDecodeState`."""
+    bsz = vec.shape[0]
+    seg = torch.ones(bsz, 1, dtype=torch.long, device=vec.device)
+    pos = torch.as_tensor(t, device=vec.device).reshape(1, 1).expand(bsz, 1)
+    x = vec
+    for idx, blk in enumerate(self.layers):
+      th = theta.layers[idx]
+      y = blk.ln.FProp(th.ln, x)
+      if state[idx] is not None:
+        y = _SelfAttentionExtendStep(blk.layer, th.layer, y, state[idx], t)
+      else:
+        y, _ = blk.layer.FProp(th.layer, y, seg, pos)
+      if blk.params.post_norm is not None:
+        y = blk.post_ln.FProp(th.post_ln, y)
+      x = x + y
+    if 'final_layer_norm' in self.children:
+      x = self.final_layer_norm.FProp(theta.final_layer_norm, x)
+    return x
 
   @classmethod
   def Params(cls):
@@ -884,6 +964,76 @@ class DenseBuilder(MoEBuilder):
 RecurrentDenseBuilder = DenseBuilder
 
 
+class RecurrentDenseBuilderParallelDecode(DenseBuilder):
+  """`DenseBuilder` whose projection weights are split into *micro variables* of shape
+  `[model_dim, proj_weight_hdim, d_kv]` (reference :3478) so that no single variable of a
+  very deep repeated stack exceeds one host's memory. On B200 the 180 GB of HBM hold the
+  fused `[M, H·D]` weights directly and the kernels want them contiguous, so the weights
+  stay fused; the class keeps the knob (checkpoint converters use it to split / merge the
+  micro variables) and forces deterministic dropout like the reference."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('proj_weight_hdim', 64,
+             'Micro-variable width (None disables); used by checkpoint conversion.')
+    p.deterministic_dropout = True
+    return p
+
+  def MicroVariableShapes(self, out_dim):
+    """Shapes the reference would create for a `[model_dim, out_dim]` projection."""
+    p = self.params
+    d_kv = p.attention_key_value_dim
+    if not p.proj_weight_hdim or not d_kv:
+      return [[p.model_dim, out_dim]]
+    per = p.proj_weight_hdim * d_kv
+    assert out_dim % per == 0, (out_dim, per)
+    return [[p.model_dim, p.proj_weight_hdim, d_kv]] * (out_dim // per)
+
+
+class MoEHashBuilder(DenseBuilder):
+  """MoE with hash routing (reference :3829): a token goes to expert `id mod E`; there is
+  no learned gate and no auxiliary loss. The task passes `expert_id` alongside the
+  activations (see `BertTransformer._ComputeEncInput`)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.gating_func = 'hashing'
+    return p
+
+
+class DenseLifelongBuilder(DenseBuilder):
+  """Builder for lifelong learning with growing expert sets (reference :3198): the gate
+  can be widened from `e_dim_old` to `e_dim` experts, ranges of experts can be masked out
+  of the routing (`expert_padding_idx = [lo, hi)`), and a learning-without-forgetting
+  penalty (`lwf_scale`) ties the new model's outputs to the frozen old model's."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('e_dim_old', None, 'Number of experts of the previous stage.')
+    p.Define('expert_padding_idx', None, '[lo, hi): experts excluded from routing.')
+    p.Define('expert_padding_idx_old', None, 'Same, for the old model in LwF.')
+    p.Define('lwf_scale', 0, 'Weight of the LwF distillation loss.')
+    return p
+
+  @staticmethod
+  def ExpandGate(old_gw, e_dim, init_scale=None):
+    """Widens a trained gate `[M, E_old]` to `[M, E]`, new columns ~ U(±init_scale)."""
+    m, e_old = old_gw.shape
+    scale = init_scale if init_scale is not None else (1.0 / m) ** 0.5 * 3.0 ** 0.5
+    extra = (torch.rand(m, e_dim - e_old, dtype=old_gw.dtype, device=old_gw.device) * 2 - 1)
+    return torch.cat([old_gw, extra * scale], 1)
+
+  @staticmethod
+  def ExpandExperts(old_w, e_dim):
+    """Grows expert weights `[E_old, …]` to `[E, …]` by cloning experts round-robin."""
+    e_old = old_w.shape[0]
+    idx = torch.arange(e_dim, device=old_w.device) % e_old
+    return old_w.index_select(0, idx).clone()
+
+
 # =========================================================================
 # UniTransformer LM task
 # =========================================================================
@@ -1139,7 +1289,291 @@ class UniTransformer(base_model.BaseTask):
     return per_step if self.params.debug else {}
 
   # --------------------------------------------------------------- decode --
+  def InitDecodeState(self, batch, max_len, device):
+    return self.dec.InitDecodeState(batch, max_len, device, self.fprop_dtype)
+
+  def DecodeStep(self, theta, ids, state, t):
+    """ids `[B]` at position t → logits `[B, V]` (fp32); updates `state` in place."""
+    p = self.params
+    fd = self.fprop_dtype
+    y = self.dec_emb.FProp(theta.dec_emb, ids.reshape(-1, 1)).to(fd)
+    if p.positional_embedding:
+      pos = torch.as_tensor(t, device=y.device).reshape(1, 1).expand(y.shape[0], 1)
+      if p.sinusoid_positional_embedding:
+        y = y + self.dec_pos_emb.FPropWithPosition(theta.dec_pos_emb, pos).to(fd)
+      else:
+        y = y + self.dec_pos_emb.FProp(theta.dec_pos_emb, pos).to(fd)
+    out = self.dec.ExtendStep(theta.dec, y, state, t)
+    if p.scale_decoder_outputs:
+      out = out * (p.builder.model_dim ** -0.5)
+    return self._ComputeLogits(theta, out).float().squeeze(1)
+
   def Decode(self, input_batch):
     """Greedy / beam decode of continuations (see gshard_decode)."""
     from lingvo_b200.core import gshard_decode
     return gshard_decode.DecodeIds(self, self.theta, input_batch)
+
+
+class TunableUniTransformer(UniTransformer):
+  """UniTransformer whose stack is `top_layer_types` + repeated `sub_layer_types` +
+  `bottom_layer_types` (reference :5001), e.g. dense layers at both ends and MoE in the
+  middle."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('top_layer_types', None, 'Layer types of the first layers.')
+    p.Define('bottom_layer_types', None, 'Layer types of the last layers.')
+    return p
+
+  def __init__(self, params):
+    p = params
+    if p.top_layer_types and p.bottom_layer_types:
+      n_mid = (p.num_transformer_layers * 2 - len(p.top_layer_types) -
+               len(p.bottom_layer_types))
+      if not p.sub_layer_types or n_mid % len(p.sub_layer_types) != 0:
+        raise ValueError('Undivided Sub-layer types length!')
+      params = p.Copy()
+      params.sub_layer_types = (list(p.top_layer_types) +
+                                list(p.sub_layer_types) * (n_mid // len(p.sub_layer_types)) +
+                                list(p.bottom_layer_types))
+      params.moe = True
+    super().__init__(params)
+
+
+class LifelongUniTransformer(UniTransformer):
+  """UniTransformer for continual training with `DenseLifelongBuilder` (reference :4643).
+
+  With `builder.lwf_scale > 0` and `builder.e_dim_old` set, a frozen copy of the previous
+  stage's model (`old`, `e_dim_old` experts, restored from its checkpoint by the caller
+  via `LoadOldModel`) is run on the same batch and the KL between the two output
+  distributions is added to the loss (learning without forgetting)."""
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    bp = p.builder
+    self._has_old = bool('lwf_scale' in bp and bp.lwf_scale and bp.e_dim_old)
+    if self._has_old:
+      old = p.Copy()
+      old.name = 'old'
+      old.cls = UniTransformer
+      old_dict = {k: v for k, v in old.IterParams()}
+      op = UniTransformer.Params()
+      for k, v in old_dict.items():
+        if k in op and k != 'cls':
+          op.Set(**{k: v})
+      ob = DenseBuilder.Params()
+      for k, v in bp.IterParams():
+        if k in ob and k != 'cls':
+          ob.Set(**{k: v})
+      ob.e_dim = bp.e_dim_old
+      op.builder = ob
+      op.name = 'old'
+      self.CreateChild('old', op)
+
+  def _InstantiateSelfAndChildren(self):
+    super()._InstantiateSelfAndChildren()
+    if self._has_old:
+      for v in self.old.vars.Flatten():
+        v.requires_grad_(False)
+
+  def LoadOldModel(self, state):
+    """Copies a NestedMap of tensors (same structure as `self.old.vars`) into the frozen
+    old model."""
+    with torch.no_grad():
+      for dst, src in zip(self.old.vars.Flatten(), state.Flatten()):
+        dst.copy_(src)
+
+  def ComputeLoss(self, theta, predictions, input_batch):
+    metrics, per_step = super().ComputeLoss(theta, predictions, input_batch)
+    if not self._has_old or self.do_eval:
+      return metrics, per_step
+    p = self.params
+    with torch.no_grad():
+      old_pred = self.old.ComputePredictions(self.old.theta, input_batch)
+      old_logits = self.old._ComputeLogits(self.old.theta, old_pred.dec_outputs).float()
+    new_logits = self._ComputeLogits(theta, predictions.dec_outputs).float()
+    non_padding = self._ComputeNonPadding(self._ComputeInputBatch(input_batch))
+    kl = (torch.softmax(old_logits, -1) *
+          (torch.log_softmax(old_logits, -1) - torch.log_softmax(new_logits, -1))).sum(-1)
+    lwf = (kl * non_padding).sum() / non_padding.sum().clamp_min(1.0)
+    one = torch.ones((), device=lwf.device)
+    total = metrics['loss'][0] + p.builder.lwf_scale * lwf
+    metrics['lwf_loss'] = (lwf, one)
+    metrics['loss'] = (total, one)
+    per_step['loss'] = total.reshape(1)
+    return metrics, per_step
+
+
+class BertTransformer(base_model.BaseTask):
+  """Encoder-only masked-LM Transformer on the GShard builder (reference :5054).
+
+  Input batch: `ids, segment_ids, segment_pos` (+ `paddings`); either pre-masked
+  (`masked_ids`, `masked_pos`) or masked on the fly by `masked_lm`. The loss is the
+  (label-smoothed, z-regularised) cross entropy at the masked positions; the softmax
+  shares the embedding matrix."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('builder', None, 'GShard builder params.')
+    p.Define('vocab_size', None, 'Vocabulary size.')
+    p.Define('sequence_length', None, 'Sequence length.')
+    p.Define('max_length', 512, 'Positional table size.')
+    p.Define('batch_size', None, 'Unused.')
+    p.Define('num_transformer_layers', None, 'Number of blocks.')
+    p.Define('loss_denominator', 0, 'Fixed loss denominator if > 0.')
+    p.Define('aux_loss_coef', 0.01, 'Multiplier of the MoE aux loss.')
+    p.Define('label_smoothing', 0.1, 'Label smoothing.')
+    p.Define('logits_abs_max', None, 'Logits clipping.')
+    p.Define('z_loss', 1e-4, 'z_loss · logsumexp(logits)².')
+    p.Define('positional_embedding', True, 'Learned positions (else relative bias).')
+    p.Define('gated_ffn_activation', None, 'silu|gelu|None.')
+    p.Define('use_repeat_layer', False, 'Kept for parity.')
+    p.Define('num_spmd_pipeline_stages', 1, 'SPMD pipeline stages.')
+    p.Define('num_spmd_pipeline_microbatches', None, 'SPMD micro-batches.')
+    p.Define('moe', False, 'Mixture-of-Experts model.')
+    p.Define('moe_gated_gelu', False, 'GLU experts.')
+    p.Define('activation', 'relu', 'Non-gated FFN activation.')
+    p.Define('mlm_loss_weight', 1.0, 'Weight of the masked-LM loss.')
+    p.Define('masked_lm', layers.MaskedLmDataAugmenter.Params(), 'On-the-fly masking.')
+    p.Define('mask_token_id', 0, 'Id of the [MASK] token.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    if p.mlm_loss_weight > 0:
+      self.CreateChild('masked_lm', p.masked_lm.Copy().Set(
+          vocab_size=p.vocab_size, mask_token_id=p.mask_token_id))
+    assert p.num_transformer_layers % p.num_spmd_pipeline_stages == 0
+    b = p.builder.Instantiate()
+    self.CreateChild('enc_emb', b.Embedding('enc_emb', p.vocab_size))
+    if p.positional_embedding:
+      self.CreateChild('enc_pos_emb', b.Embedding('enc_pos_emb', p.max_length))
+      atten = b.SelfAttention('self_attention')
+    else:
+      atten = b.SelfAttentionRelativeBias('dec_self_attention')
+    if p.gated_ffn_activation:
+      ffw = b.DenseReluDenseGated('dense_relu_dense', p.gated_ffn_activation)
+    else:
+      ffw = b.DenseReluDense('dense_relu_dense', activation=p.activation)
+    if p.moe:
+      moe = b.MoEGated('moe') if p.moe_gated_gelu else b.MoE('moe')
+      subs, num = [atten, moe, atten, ffw], p.num_transformer_layers // 2
+    else:
+      subs, num = [atten, ffw], p.num_transformer_layers
+    enc = b.EncoderLayerStack('encoder', subs, num)
+    enc.params_init = WeightInit.Xavier(scale=1.0, seed=0)
+    self.CreateChild('enc', enc)
+    bp = b.params
+    self.CreateChild('emb_w_split', b.MeshSplit('w_split', bp.emb_w_split))
+    self.CreateChild('enc_out_split', b.MeshSplit('enc_out_split', bp.blm_split))
+    self.CreateChild('logits_split', b.MeshSplit('logits_split', bp.logits_split))
+
+  def _ComputeNonPadding(self, input_batch):
+    if 'paddings' in input_batch:
+      return 1.0 - input_batch.paddings.float()
+    return (input_batch.segment_ids != 0).float() * (input_batch.ids > 0).float()
+
+  def _ComputeEncInput(self, theta, input_batch):
+    p = self.params
+    maskables = self._ComputeNonPadding(input_batch)
+    if 'masked_pos' in input_batch:
+      emb_ids, masked_pos = input_batch.masked_ids, input_batch.masked_pos.float()
+    elif p.mlm_loss_weight > 0:
+      emb_ids, masked_pos = self.masked_lm.FProp(theta.masked_lm, input_batch.ids,
+                                                 1.0 - maskables)
+    else:
+      emb_ids, masked_pos = input_batch.ids, 1.0 - maskables
+    fd = self.fprop_dtype
+    y = self.enc_emb.FProp(theta.enc_emb, emb_ids.long()).to(fd)
+    if p.positional_embedding:
+      y = y + self.enc_pos_emb.FProp(theta.enc_pos_emb, input_batch.segment_pos.long()).to(fd)
+    out = NestedMap(vec=y, segment_id=input_batch.segment_ids.long(),
+                    segment_pos=input_batch.segment_pos.long(), masked_pos=masked_pos,
+                    aux_loss=torch.zeros((), device=y.device))
+    if p.moe and p.builder.gating_func == 'hashing':
+      out.expert_id = emb_ids.long() % p.builder.e_dim
+    return out
+
+  def ComputePredictions(self, theta, input_batch):
+    p = self.params
+    enc_in = self._ComputeEncInput(theta, input_batch)
+    out = self.enc.FProp(theta.enc, enc_in)
+    x = out.vec * (p.builder.model_dim ** -0.5)
+    w = theta.enc_emb.embedding.to(x.dtype)
+    logits = torch.matmul(x, w.t())
+    if p.logits_abs_max is not None:
+      logits = logits.clamp(-p.logits_abs_max, p.logits_abs_max)
+    return NestedMap(mlm_logits=logits, mlm_masked_pos=enc_in.masked_pos,
+                     aux_loss=out.aux_loss)
+
+  def ComputePerTokenLoss(self, logits, input_batch):
+    """Smoothed xent (+ z-loss) at every non-padded position."""
+    p = self.params
+    logits = logits.float()
+    lse = torch.logsumexp(logits, -1)
+    labels = input_batch.ids.long().clamp_min(0)
+    true_logit = logits.gather(-1, labels.unsqueeze(-1)).squeeze(-1)
+    off = p.label_smoothing / p.vocab_size
+    on = 1.0 - p.label_smoothing + off
+    loss = lse - ((on - off) * true_logit + off * logits.sum(-1))
+    if p.z_loss > 0:
+      loss = loss + p.z_loss * lse.square()
+    return loss * self._ComputeNonPadding(input_batch)
+
+  def ComputeLoss(self, theta, predictions, input_batch):
+    p = self.params
+    logits = predictions.mlm_logits.float()
+    ids = input_batch.ids.long()
+    lse = torch.logsumexp(logits, -1)
+    true_logit = logits.gather(-1, ids.clamp_min(0).unsqueeze(-1)).squeeze(-1)
+    entropy = lse - true_logit
+    off = p.label_smoothing / p.vocab_size
+    on = 1.0 - p.label_smoothing + off
+    soft_xent = lse - ((on - off) * true_logit + off * logits.sum(-1))
+    zinc = p.z_loss * lse.square() if p.z_loss > 0 else torch.zeros_like(lse)
+    loss = soft_xent + zinc
+    acc1 = (logits.argmax(-1) == ids).float()
+    non_padding = self._ComputeNonPadding(input_batch)
+    masked = non_padding * predictions.mlm_masked_pos.to(non_padding.dtype)
+    n_masked = masked.sum()
+    safe = n_masked.clamp_min(1.0)
+    denom = float(p.loss_denominator) if p.loss_denominator else safe
+    avg = (loss * masked).sum() / denom
+    total = p.mlm_loss_weight * avg + p.aux_loss_coef * predictions.aux_loss
+    one = torch.ones((), device=logits.device)
+    n_items = input_batch.segment_ids.amax(dim=1).sum().float()
+    metrics = {
+        'num_packed_examples': (n_items, one),
+        'batch_utilized_ratio': ((input_batch.segment_ids != 0).float().mean(), one),
+        'acc1': ((acc1 * masked).sum() / safe, n_masked),
+        'mean_xent': ((entropy * masked).sum() / safe, n_masked),
+        'soft_labels_xent': ((soft_xent * masked).sum() / safe, n_masked),
+        'num_masked': (n_masked, one),
+        'loss': (total, one),
+        'mlm_loss': (avg, one),
+        'aux_loss': (p.aux_loss_coef * predictions.aux_loss, one),
+        'avg_z_loss_increment': ((zinc * masked).sum() / safe, one),
+    }
+    return metrics, {'loss': total.reshape(1)}
+
+  def Decode(self, input_batch):
+    """Eval-as-decode: returns per-example masked accuracy."""
+    with torch.no_grad():
+      pred = self.ComputePredictions(self.theta, input_batch)
+      masked = self._ComputeNonPadding(input_batch) * pred.mlm_masked_pos
+      hit = (pred.mlm_logits.argmax(-1) == input_batch.ids.long()).float() * masked
+    return NestedMap(acc1=hit.sum(1) / masked.sum(1).clamp_min(1.0), num_masked=masked.sum(1))
+
+  def CreateDecoderMetrics(self):
+    from lingvo_b200.core import metrics as metrics_lib
+    return {'acc1': metrics_lib.AverageMetric()}
+
+  def PostProcessDecodeOut(self, dec_out, dec_metrics):
+    for a, n in zip(dec_out.acc1.tolist(), dec_out.num_masked.tolist()):
+      if n > 0:
+        dec_metrics['acc1'].Update(a, n)
+    return []

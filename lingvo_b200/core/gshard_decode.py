@@ -154,3 +154,59 @@ class GShardDecode:
 
   def stop(self):  # pylint: disable=invalid-name
     self._stop.set()
+
+
+def DecodeIds(task, theta, input_batch, max_steps=None, temperature=0.0, top_k=0, seed=0):
+  """Continues every row of a prefix batch with the task's incremental decoder (greedy,
+  or temperature / top-k sampling) (ref :186 `_DecodeStep` + `gshard_builder` decode).
+
+  `input_batch.tgt.ids [B, T]` with `paddings` (or `segment_ids`) marking each prefix.
+  Returns NestedMap(ids [B, T+steps], prefix_lens [B], lens [B], scores [B] = Σ log p of the
+  generated tokens). All control flow is on the device; the host checks `all done` every
+  8 steps only."""
+  from lingvo_b200.core.nested_map import NestedMap
+  p = task.params
+  tgt = input_batch.tgt if 'tgt' in input_batch else input_batch
+  ids = tgt.ids.long()
+  b, t0 = ids.shape
+  dev = ids.device
+  if 'paddings' in tgt:
+    plen = (1.0 - tgt.paddings.float()).sum(1).long()
+  else:
+    plen = (tgt.segment_ids != 0).sum(1).long()
+  plen = plen.clamp_min(1)
+  steps = int(max_steps or p.decoder_max_steps)
+  total = t0 + steps
+  out = torch.full((b, total), int(p.decoder_eos_id), dtype=torch.long, device=dev)
+  out[:, :t0] = ids
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(int(seed))
+  with torch.no_grad():
+    state = task.InitDecodeState(b, total, dev)
+    done = torch.zeros(b, dtype=torch.bool, device=dev)
+    scores = torch.zeros(b, device=dev)
+    lens = plen.clone()
+    cur = out[:, 0]
+    for t in range(total - 1):
+      logits = task.DecodeStep(theta, cur, state, t)
+      logp = torch.log_softmax(logits, -1)
+      if temperature and temperature > 0:
+        z = logits / temperature
+        if top_k:
+          kth = z.topk(top_k, -1).values[:, -1:]
+          z = torch.where(z < kth, torch.full_like(z, -1e9), z)
+        nxt = torch.multinomial(torch.softmax(z, -1), 1, generator=gen).squeeze(1)
+      else:
+        nxt = logits.argmax(-1)
+      in_prefix = (t + 1) < plen                      # still teacher-forcing the prefix
+      active = ~in_prefix & ~done
+      nxt = torch.where(in_prefix, out[:, t + 1], nxt)
+      out[:, t + 1] = torch.where(active | in_prefix, nxt, out[:, t + 1])
+      scores = scores + torch.where(active, logp.gather(1, nxt.unsqueeze(1)).squeeze(1),
+                                    torch.zeros_like(scores))
+      lens = lens + active.long()
+      done = done | (active & (nxt == int(p.decoder_eos_id)))
+      cur = out[:, t + 1]
+      if (t + 1) % 8 == 0 and t + 1 >= int(t0) and bool(done.all()):
+        break
+  return NestedMap(ids=out, prefix_lens=plen, lens=lens, scores=scores)

@@ -162,6 +162,7 @@ class TrainProgram(BaseProgram):
         acc.Update({k: v for k, v in m.items()})
     results = acc.Finalize()
     step = task.global_step
+    self.global_step = int(step)
     vals = {k: v for k, (v, _) in results.items()}
     n_ex = vals.get('num_samples_in_batch', 0.0) * p.steps_per_loop
     rate, ex_rate, total = self._step_rate_tracker.ComputeStepRate(step, n_ex)
@@ -203,6 +204,7 @@ class EvalProgram(BaseProgram):
     results = acc.Finalize()
     step = py_utils.GetGlobalStep()
     vals = {k: v for k, (v, _) in results.items()}
+    self.last_metrics = vals
     self._WriteSummaries(os.path.basename(self._program_dir), int(step), vals)
     with open(os.path.join(self._program_dir,
                            'score-{:08d}.txt'.format(int(step))), 'w') as f:
@@ -253,6 +255,7 @@ class DecodeProgram(BaseProgram):
           buffered.extend(post)
         steps += 1
     vals = {k: m.value for k, m in dec_metrics.items()}
+    self.last_metrics = dict(vals)
     vals['decode_secs'] = time.time() - start
     self._WriteSummaries(os.path.basename(self._program_dir), step, vals)
     out_path = os.path.join(self._program_dir, 'decoder_out_%09d' % step)
@@ -414,7 +417,43 @@ class SimpleProgramSchedule:
           continue
       prog.Run(sess, threadpool)
     eval_time = time.time() - t0
+    done = self._MlPerfCheck() or done
     return done, train_time, eval_time
+
+  def _MlPerfCheck(self):
+    """MLPerf epoch / stop logging; True once the run should stop."""
+    mp = self.params.ml_perf
+    if mp is None or mp.benchmark_name is None or mp.steps_per_epoch is None:
+      return False
+    from lingvo_b200.core import ml_perf_log as mlp_log
+    step = 0
+    if self.train_program is not None:
+      step = int(getattr(self.train_program, 'global_step', 0) or 0)
+    epoch = int(step / mp.steps_per_epoch) if mp.steps_per_epoch else 0
+    if not getattr(self, '_mlperf_started', False):
+      self._mlperf_started = True
+      for k, v in (mp.submission_metadata or {}).items():
+        mlp_log.mlperf_print(k, v)
+      mlp_log.mlperf_print('init_stop', None)
+      mlp_log.mlperf_print('run_start', None)
+    mlp_log.mlperf_print('eval_stop', None, metadata={'epoch_num': epoch})
+    value = None
+    for prog in self.eval_programs:
+      res = getattr(prog, 'last_metrics', None) or {}
+      if mp.decoder_metric_name in res:
+        value = res[mp.decoder_metric_name]
+        if isinstance(value, (tuple, list)):
+          value = value[0]
+    if value is not None:
+      mlp_log.mlperf_print('eval_accuracy', float(value), metadata={'epoch_num': epoch})
+      if (mp.decoder_metric_success_threshold is not None and
+          float(value) > mp.decoder_metric_success_threshold):
+        mlp_log.mlperf_print('run_stop', None, metadata={'status': 'success'})
+        return True
+    if mp.max_steps_to_train is not None and step >= mp.max_steps_to_train:
+      mlp_log.mlperf_print('run_stop', None, metadata={'status': 'abort'})
+      return True
+    return False
 
   def Shutdown(self):
     for prog in self._programs:
@@ -422,6 +461,25 @@ class SimpleProgramSchedule:
 
 
 MLPerfProgramSchedule = SimpleProgramSchedule
+
+
+def MlPerfParams():
+  """MLPerf run description attached to a schedule (reference :2669-2700): when
+  `benchmark_name` and `steps_per_epoch` are set the schedule emits MLPerf log lines and
+  stops as soon as `decoder_metric_name` reaches the success threshold."""
+  mp = hyperparams.Params()
+  mp.Define('submission_metadata', None, 'Dict of static submission fields.')
+  mp.Define('benchmark_name', None, 'MLPerf benchmark name, e.g. "bert".')
+  mp.Define('steps_per_epoch', None, 'Training steps per (possibly fractional) epoch.')
+  mp.Define('decoder_metric_name', None, 'Eval/decode metric compared to the threshold.')
+  mp.Define('decoder_metric_success_threshold', None, 'Target quality.')
+  mp.Define('max_steps_to_train', None, 'Give up after this many steps.')
+  mp.Define('global_batch_size', None, 'Logged.')
+  mp.Define('max_sequence_length', None, 'Logged.')
+  mp.Define('optimizer_name', None, 'Logged.')
+  mp.Define('base_learning_rate', None, 'Logged.')
+  mp.Define('warmup_steps', None, 'Logged.')
+  return mp
 
 
 def SimpleProgramScheduleForTask(train_dataset_name, train_steps_per_loop,
@@ -439,6 +497,7 @@ def SimpleProgramScheduleForTask(train_dataset_name, train_steps_per_loop,
   ps = SimpleProgramSchedule.Params()
   ps.train_executions_per_eval = 1
   ps.dataset_names = list(eval_dataset_names)
+  ps.ml_perf = MlPerfParams()
   if train_dataset_name:
     ps.train_program = _CreateProgramParams(
         train_program_cls, 'train', train_dataset_name, train_steps_per_loop,

@@ -85,3 +85,143 @@ class PackedTextInputGenerator(LmInput):
     out.weights = (out.segment_ids > 0).float()
     out.paddings = 1.0 - out.weights
     return out
+
+
+class TFRecordBertInput(base_input_generator.BaseInputGenerator):
+  """MLPerf-BERT TFRecords (ref :267): fixed-length `input_ids / input_mask /
+  masked_lm_positions / masked_lm_ids / masked_lm_weights`. Restores the un-masked ids,
+  drops the first `[SEP]` (documents are `A [SEP] B [SEP]`), and optionally packs several
+  documents per row with the native packer. Output `[batch_size, max_sequence_length]`:
+  `ids, masked_ids, masked_pos, segment_ids, segment_pos, paddings`."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('input_file', None, 'File pattern(s) of TFRecord files.')
+    p.Define('max_sequence_length', 512, 'Tokens per example.')
+    p.Define('max_predictions_per_seq', 76, 'Masked positions per example.')
+    p.Define('eos_token_id', 102, '[SEP] id.')
+    p.Define('shuffle', False, 'Shuffle records.')
+    p.Define('file_buffer_size', 10000000, 'Shuffle buffer (records).')
+    p.Define('enable_packing', False, 'Pack several documents per row.')
+    p.Define('prepacking_batch_size', 1 << 14, 'Documents gathered before packing.')
+    p.Define('remove_mask', False, 'Drop the stored masking (mask on the fly instead).')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    if self.do_eval:
+      p.shuffle = False
+      p.enable_packing = False
+    self._files = [p.input_file] if isinstance(p.input_file, str) else list(p.input_file)
+    self._yielder = None
+    self._pending = []
+
+  def _Yielder(self):
+    if self._yielder is None:
+      import glob
+      from lingvo_b200 import ops
+      p = self.params
+      files = sorted(f for pat in self._files for f in glob.glob(pat))
+      if not files:
+        raise FileNotFoundError('TFRecordBertInput: no files match %s' % self._files)
+      pattern = 'tfrecord:' + ','.join(files)
+      h = ops.host()
+      if p.shuffle:
+        self._yielder = h.basic_record_yielder(
+            pattern, seed=int(p.random_seed or 0) + 1,
+            bufsize=int(min(p.file_buffer_size, 1 << 16)), parallelism=4, num_epochs=0)
+      else:
+        self._yielder = h.sequential_record_yielder(pattern, 1 if self.do_eval else -1)
+    return self._yielder
+
+  def _ParseRecord(self, record):
+    from lingvo_b200.utils import tf_example
+    p = self.params
+    f = tf_example.ParseExample(record)
+    masked_ids = np.asarray(f['input_ids'], np.int64)[:p.max_sequence_length]
+    valid = np.asarray(f['input_mask'], np.float32)[:p.max_sequence_length]
+    w = np.asarray(f['masked_lm_weights'], np.float32)
+    n = int(w.sum())
+    pos = np.asarray(f['masked_lm_positions'], np.int64)[:n]
+    ids = masked_ids.copy()
+    ids[pos] = np.asarray(f['masked_lm_ids'], np.int64)[:n]
+    masked_pos = np.zeros_like(valid)
+    masked_pos[pos] = 1.0
+    sep = np.nonzero(ids == p.eos_token_id)[0]
+    def _Drop(x):
+      if sep.size == 0:
+        return x
+      k = int(sep[0])
+      return np.concatenate([x[:k], x[k + 1:], np.zeros(1, x.dtype)])
+    out = NestedMap(ids=_Drop(ids), masked_ids=_Drop(masked_ids), masked_pos=_Drop(masked_pos),
+                    segment_ids=_Drop(valid))
+    out.paddings = 1.0 - out.segment_ids
+    out.segment_pos = (out.segment_ids * np.arange(len(valid))).astype(np.int64)
+    if p.remove_mask:
+      del out['masked_pos']
+      del out['masked_ids']
+    return out
+
+  def _Next(self):
+    rec = self._Yielder().next()
+    if rec is None:
+      return None
+    return self._ParseRecord(rec[0] if isinstance(rec, tuple) else rec)
+
+  def _Pack(self, docs):
+    """List of parsed documents → list of packed rows."""
+    p = self.params
+    lens = np.asarray([int(d.segment_ids.sum()) for d in docs], np.int32)
+    seg, pos, idx, _, _, _ = host_ops.PackSequences(
+        lens, lens, 0, p.max_sequence_length, p.max_sequence_length,
+        seed=int(p.random_seed or 0))
+    rows = NestedMap()
+    for k in docs[0].keys():
+      if k in ('segment_ids', 'segment_pos', 'paddings'):
+        continue
+      rows[k] = host_ops.ApplyPacking(np.stack([d[k] for d in docs]), 0, seg, idx)
+    rows.segment_ids = seg.astype(np.float32)
+    rows.segment_pos = pos.astype(np.int64)
+    rows.paddings = (seg == 0).astype(np.float32)
+    n = seg.shape[0]
+    return [rows.Transform(lambda x, i=i: x[i]) for i in range(n) if seg[i].any()]
+
+  def _InputBatch(self):
+    p = self.params
+    rows = []
+    while len(rows) < p.batch_size:
+      if self._pending:
+        rows.append(self._pending.pop())
+        continue
+      if p.enable_packing:
+        docs = []
+        while len(docs) < p.prepacking_batch_size:
+          d = self._Next()
+          if d is None:
+            break
+          docs.append(d)
+        if not docs:
+          break
+        self._pending = self._Pack(docs)
+        continue
+      d = self._Next()
+      if d is None:
+        break
+      rows.append(d)
+    if not rows:
+      raise StopIteration('TFRecordBertInput: end of data')
+    batch = NestedMap()
+    for k in rows[0].keys():
+      x = np.stack([r[k] for r in rows])
+      need = p.batch_size - x.shape[0]
+      if need > 0:                     # pad the final eval batch
+        fill = 1.0 if k == 'paddings' else 0
+        x = np.concatenate([x, np.full((need,) + x.shape[1:], fill, x.dtype)])
+      batch[k] = torch.from_numpy(np.ascontiguousarray(x))
+    return batch
+
+  def Reset(self, sess=None):
+    self._yielder = None
+    self._pending = []

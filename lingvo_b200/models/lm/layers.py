@@ -182,6 +182,112 @@ class RnnLm(RnnLmNoEmbedding):
     return super().FProp(theta, acts, paddings, state0, labels, direct_features)
 
 
+class ConditionalRnnLm(RnnLmNoEmbedding):
+  """RNN LM whose every input step is the token embedding concatenated with a
+  per-sequence condition vector (ref :679)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('condition_dim', 128, 'Size of the condition vector.')
+    p.Define('emb', layers.SimpleEmbeddingLayer.Params(), 'Embedding.')
+    p.Define('embedding_dropout_keep_prob', 1.0, 'Embedding dropout keep prob.')
+    p.Define('embedding_dropout_seed', None, 'Kept for parity.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert p.emb.vocab_size == p.vocab_size
+    assert p.emb.embedding_dim + p.condition_dim == p.rnns.num_input_nodes, (
+        'rnn input = embedding ⊕ condition')
+    self.CreateChild('emb', p.emb)
+    self.CreateChild('emb_dropout', layers.DropoutLayer.Params().Set(
+        keep_prob=p.embedding_dropout_keep_prob))
+
+  def FProp(self, theta, inputs, paddings, state0, condition, labels=None,
+            direct_features=None):
+    """inputs/paddings [T,B]; condition [B, condition_dim]."""
+    p = self.params
+    assert condition.shape == (paddings.shape[1], p.condition_dim)
+    acts = self.emb.EmbLookup(theta.emb, inputs.long())
+    cond = condition.to(acts.dtype).unsqueeze(0).expand(acts.shape[0], -1, -1)
+    acts = self.emb_dropout.FProp(theta.emb_dropout, torch.cat([acts, cond], -1))
+    return super().FProp(theta, acts, paddings, state0, labels, direct_features)
+
+
+class MoeLm(BaseLanguageModel):
+  """Mixture of RNN-LM experts (ref :763): one RNN stack predicts a soft domain
+  assignment per step; `number_of_experts` further stacks run in parallel and their
+  outputs are mixed by that assignment, then fed to a merging LM (or a plain softmax)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('emb', layers.SimpleEmbeddingLayer.Params(), 'Embedding.')
+    p.Define('shared_emb', True, 'One embedding for the gate and all experts.')
+    p.Define('add_postgating_rnn', True, 'Merge with an RNN LM (else a softmax only).')
+    p.Define('rnns', rnn_layers.StackedFRNNLayerByLayer.Params(), 'RNN stack template.')
+    p.Define('number_of_experts', 7, 'Number of experts.')
+    p.Define('merge', RnnLmNoEmbedding.Params(), 'The LM applied to the mixed features.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    n = 1 + p.number_of_experts
+    assert p.emb.vocab_size == p.vocab_size
+    assert p.emb.embedding_dim == p.rnns.num_input_nodes
+    if p.shared_emb:
+      self.CreateChild('emb', p.emb)
+    else:
+      self.CreateChildren('emb', [p.emb.Copy().Set(name='emb_%d' % i) for i in range(n)])
+    self.CreateChildren('rnns', [p.rnns.Copy().Set(name='rnns_%d' % i) for i in range(n)])
+    dim = p.rnns.num_output_nodes
+    self.CreateChild('domain_predictor_softmax', layers.SimpleFullSoftmax.Params().Set(
+        input_dim=dim, num_classes=p.number_of_experts))
+    if p.add_postgating_rnn:
+      assert p.merge.vocab_size == p.vocab_size
+      self.CreateChild('merge', p.merge)
+    else:
+      self.CreateChild('output_softmax', layers.SimpleFullSoftmax.Params().Set(
+          input_dim=dim, num_classes=p.vocab_size))
+
+  def zero_state(self, theta, batch_size):
+    st = NestedMap(rnns=[r.zero_state(theta.rnns[i], batch_size)
+                         for i, r in enumerate(self.rnns)])
+    if self.params.add_postgating_rnn:
+      st.merge = self.merge.zero_state(theta.merge, batch_size)
+    return st
+
+  def FProp(self, theta, inputs, paddings, state0, labels=None, direct_features=None):
+    p = self.params
+    ids = inputs.long()
+    t, b = ids.shape
+    pad3 = paddings.unsqueeze(-1)
+    n = 1 + p.number_of_experts
+    if p.shared_emb:
+      embs = [self.emb.EmbLookup(theta.emb, ids)] * n
+    else:
+      embs = [self.emb[i].EmbLookup(theta.emb[i], ids) for i in range(n)]
+    acts, state1 = [], NestedMap(rnns=[])
+    for i in range(n):
+      a, st = self.rnns[i].FProp(theta.rnns[i], embs[i], pad3, state0.rnns[i])
+      acts.append(a)
+      state1.rnns.append(st)
+    gate_logits = self.domain_predictor_softmax.Logits(
+        theta.domain_predictor_softmax, acts[0].reshape(t * b, -1))
+    gating = torch.softmax(gate_logits.float(), -1).reshape(t, b, -1).to(acts[0].dtype)
+    experts = torch.stack(acts[1:], 2)                      # [T,B,E,D]
+    mixed = (gating.unsqueeze(-1) * experts).sum(2)
+    if p.add_postgating_rnn:
+      out, state1.merge = self.merge.FProp(theta.merge, mixed, paddings, state0.merge, labels)
+    else:
+      out = self._Xent(self.output_softmax, theta.output_softmax, mixed, labels)
+    out.gating = gating
+    return out, state1
+
+
 class TransformerLmNoEmbedding(BaseLanguageModel):
   """Causal Transformer stack over pre-embedded `[T,B,D]` inputs (ref :560)."""
 

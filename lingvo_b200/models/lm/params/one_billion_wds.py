@@ -132,3 +132,60 @@ class OneBwdsTransformerLm(WordLevelOneBwdsBase):
         warmup_steps=4000, model_dim=self.MODEL_DIM) if hasattr(
             schedule, 'TransformerSchedule') else schedule.Constant.Params()
     return p
+
+
+@model_registry.RegisterSingleTaskModel
+class OneBWdsGPipeTransformerWPM(WordLevelOneBwdsBase):
+  """32-layer, d=2048 Transformer LM trained with GPipe (ref :181). The reference reports
+  relative throughput 1.0 / 0.93 / 0.85 / 0.775 on 1 / 2 / 4 / 8 V100s; here the stack is
+  cut into `GPUS` cells run by `parallel.pp.PipelineEngine` (one rank per cell, P2P
+  activations over NVLink)."""
+
+  VOCAB_SIZE = 32000
+  EMBEDDING_DIM = 2048
+  BATCH_SIZE = 32
+  MAX_TOKENS = 1024
+  GPUS = 4
+  SPLITS = [8 * (i + 1) for i in range(GPUS)]     # cumulative layer index per cell
+  LAYERS = SPLITS[-1]
+  NUM_MICRO_BATCHES = 32
+
+  def Train(self):
+    p = super().Train()
+    p.tokenizer = tokenizers.AsciiTokenizer.Params().Set(
+        target_sos_id=1, target_eos_id=2, target_unk_id=0, vocab_size=self.VOCAB_SIZE)
+    p.target_max_length = self.MAX_TOKENS
+    p.bucket_upper_bound = [self.MAX_TOKENS]
+    p.bucket_batch_limit = [self.BATCH_SIZE]
+    p.fixed_input_shape = True
+    return p
+
+  def _Heldout(self, shard, name, n):
+    p = self.Train()
+    p.file_pattern = 'text:' + os.path.join(
+        self.CORPUS_DIR, 'heldout-monolingual.tokenized.shuffled', shard)
+    p.Set(name=name, num_batcher_threads=1, num_samples=n)
+    return p
+
+  def Dev(self):
+    return self._Heldout('news.en.heldout-00001*', '1bwds_dev_set', 6206)
+
+  def Test(self):
+    return self._Heldout('news.en.heldout-00000*', '1bwds_test_set', 6075)
+
+  def Task(self):
+    p = model.BatchMajorLanguageModel.Params()
+    p.eval.samples_per_summary = 0
+    p.name = '1bwds_wpm_level_lm'
+    p.lm = lm_layers.GPipeTransformerLm.CommonParams(
+        model_dim=self.EMBEDDING_DIM, vocab_size=self.VOCAB_SIZE,
+        hidden_dim=self.EMBEDDING_DIM * 4, num_layers=self.LAYERS, num_heads=16,
+        softmax_max_alloc=128 * (2 ** 20), atten_dropout_prob=0.1,
+        residual_dropout_prob=0.1)
+    p.lm.Set(num_splits=len(self.SPLITS), num_micro_batches=self.NUM_MICRO_BATCHES)
+    p.train.Set(
+        learning_rate=0.5, optimizer=optimizer.Adam.ParamsA(),
+        clip_gradient_norm_to_value=0.0, grad_norm_to_clip_to_zero=0.0,
+        lr_schedule=schedule.TransformerSchedule.Params().Set(
+            warmup_steps=40000, worker_replicas=1, model_dim=self.EMBEDDING_DIM))
+    return p

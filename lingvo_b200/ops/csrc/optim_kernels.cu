@@ -72,58 +72,57 @@ __device__ __forceinline__ Tile get_tile(int item, int R, int C) {
   return t;
 }
 
-constexpr int kStatRowsPerWarp = 4;
-constexpr int kStatRows = kStatRowsPerWarp * kWarps;   // rows per CTA
+constexpr int kStatRows = 32;            // rows per CTA tile
+constexpr int kStatCols = kWarps * 256;  // columns per CTA tile (one 256-wide strip per warp)
 
-// One CTA per (batch b, 32-row block), sweeping the full width strip by strip. Row sums
-// are complete inside a warp (plain stores); column sums accumulate in shared memory and
-// leave as one partial row per CTA (colpart[b][blk][C], plain stores) that
-// adafactor_colreduce_kernel folds. No global atomics on the statistics, so the pass is
-// bandwidth-bound and bitwise reproducible.
+// One CTA per (batch b, 32-row block, 2048-column chunk); warp w sweeps the 32 rows of its
+// own 256-column strip. Column sums stay in registers and leave as one partial row per
+// row block (colpart[b][blk][C], plain stores, folded by adafactor_colreduce_kernel); row
+// sums are warp-reduced, combined across the 8 strips in shared memory and reach global
+// memory as one add per (row, chunk). No shared-memory atomics (fp32 ATOMS is a CAS spin
+// loop) and no contended global atomics.
 template <typename GT>
 __global__ void __launch_bounds__(kWarps * 32)
 adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
                        float* __restrict__ rowsum, float* __restrict__ colpart,
-                       float* __restrict__ acc, int B, int R, int C, int nblk, int with_w,
-                       float* __restrict__ total_sumsq) {
+                       float* __restrict__ acc, int B, int R, int C, int nblk, int nchunk,
+                       int with_w, float* __restrict__ total_sumsq) {
   // with_w: also accumulate sum(w^2) (only on the first step of a variable; later
   // steps get it for free from the previous apply kernel, see acc[2]).
   // Statistics are of the RAW gradient (no grad scale, no eps1): both are folded in by
   // the factors kernel, which lets this pass also produce the global sum(g^2) that the
   // clipping scale is computed from.
-  extern __shared__ float scol[];           // [C] column sums of this CTA's rows
-  __shared__ float red[2][kWarps];
+  __shared__ float rpart[kWarps][kStatRows];
+  __shared__ float wpart[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / nblk, blk = blockIdx.x - b * nblk;
-  const int r0 = blk * kStatRows + warp * kStatRowsPerWarp;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) scol[i] = 0.f;
-  __syncthreads();
+  const int chunk = blockIdx.x % nchunk;
+  const int blk = (blockIdx.x / nchunk) % nblk;
+  const int b = blockIdx.x / (nchunk * nblk);
+  const int c = chunk * kStatCols + warp * 256 + lane * 8;
+  const bool cok = c < C;
+  const int r0 = blk * kStatRows;
+  const int nrows = min(kStatRows, R - r0);
+  const size_t base = (static_cast<size_t>(b) * R + r0) * C + c;
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float wsq = 0.f;
-  float rs[kStatRowsPerWarp];
+#pragma unroll 2
+  for (int r = 0; r < kStatRows; r += 4) {
+    float gf[4][8];
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cok && r + 4 <= nrows) {           // common case: no per-row predicates
 #pragma unroll
-  for (int u = 0; u < kStatRowsPerWarp; ++u) rs[u] = 0.f;
-  const size_t base = static_cast<size_t>(b) * R;
-  for (int c = lane * 8; c < C; c += 256) {
-    float gf[kStatRowsPerWarp][8];
+      for (int u = 0; u < 4; ++u) load_g8<GT>(g + base + static_cast<size_t>(r + u) * C, gf[u]);
+      if (with_w) {
 #pragma unroll
-    for (int u = 0; u < kStatRowsPerWarp; ++u) {
-      if (r0 + u < R) load_g8<GT>(g + (base + r0 + u) * C + c, gf[u]);
-    }
-    if (with_w) {
-#pragma unroll
-      for (int u = 0; u < kStatRowsPerWarp; ++u) {
-        if (r0 + u < R) {
+        for (int u = 0; u < 4; ++u) {
           float wf[8];
-          load_g8<float>(w + (base + r0 + u) * C + c, wf);
+          load_g8<float>(w + base + static_cast<size_t>(r + u) * C, wf);
 #pragma unroll
           for (int i = 0; i < 8; ++i) wsq += wf[i] * wf[i];
         }
       }
-    }
-    float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int u = 0; u < kStatRowsPerWarp; ++u) {
-      if (r0 + u < R) {
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float q = gf[u][i] * gf[u][i];
@@ -131,34 +130,60 @@ adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
           rs[u] += q;
         }
       }
+    } else if (cok) {
+      for (int u = 0; u < 4 && r + u < nrows; ++u) {
+        float t[8];
+        load_g8<GT>(g + base + static_cast<size_t>(r + u) * C, t);
+        if (with_w) {
+          float wf[8];
+          load_g8<float>(w + base + static_cast<size_t>(r + u) * C, wf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wsq += wf[i] * wf[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float q = t[i] * t[i];
+          cs[i] += q;
+          rs[u] += q;
+        }
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&scol[c + i], cs[i]);   // shared-memory atomics
+    for (int u = 0; u < 4; ++u) rs[u] = warp_sum(rs[u]);
+    if (lane < 4)
+      rpart[warp][r + lane] = lane == 0 ? rs[0] : lane == 1 ? rs[1] : lane == 2 ? rs[2] : rs[3];
   }
-  float gsq = 0.f;
-#pragma unroll
-  for (int u = 0; u < kStatRowsPerWarp; ++u) {
-    rs[u] = warp_sum(rs[u]);
-    gsq += rs[u];
-    if (lane == 0 && r0 + u < R) rowsum[base + r0 + u] = rs[u];
+  if (cok) {
+    float* cp = colpart + (static_cast<size_t>(b) * nblk + blk) * C + c;
+    *reinterpret_cast<float4*>(cp) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+    *reinterpret_cast<float4*>(cp + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
   }
-  wsq = warp_sum(wsq);
-  if (lane == 0) {
-    red[0][warp] = gsq;
-    red[1][warp] = wsq;
+  if (with_w) {
+    wsq = warp_sum(wsq);
+    if (lane == 0) wpart[warp] = wsq;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x)
-    colpart[(static_cast<size_t>(b) * nblk + blk) * C + i] = scol[i];
-  if (threadIdx.x == 0) {
-    float tg = 0.f, tw = 0.f;
+  if (warp == 0) {
+    float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kWarps; ++k) {
-      tg += red[0][k];
-      tw += red[1][k];
+    for (int k = 0; k < kWarps; ++k) s += rpart[k][lane];
+    if (lane < nrows) {
+      float* dst = rowsum + static_cast<size_t>(b) * R + r0 + lane;
+      if (nchunk == 1) *dst = s;
+      else atomicAdd(dst, s);
+    } else {
+      s = 0.f;
     }
-    if (with_w) atomicAdd(&acc[0], tw);
-    if (total_sumsq != nullptr && tg != 0.f) atomicAdd(total_sumsq, tg);
+    const float tg = warp_sum(s);
+    if (lane == 0) {
+      if (total_sumsq != nullptr && tg != 0.f) atomicAdd(total_sumsq, tg);
+      if (with_w) {
+        float tw = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWarps; ++k) tw += wpart[k];
+        atomicAdd(&acc[0], tw);
+      }
+    }
   }
 }
 
@@ -256,24 +281,33 @@ adafactor_rms_kernel(const GT* __restrict__ g, const float* __restrict__ fr,
     if (c >= C) continue;
     float cf[8];
     load_g8<float>(fc + static_cast<size_t>(t.b) * C + c, cf);
-    for (int r = t.r0; r < t.r1; r += 4) {
+    const GT* gp = g + (static_cast<size_t>(t.b) * R) * C + c;
+    const float* frp = fr + static_cast<size_t>(t.b) * R;
+    int r = t.r0;
+    for (; r + 4 <= t.r1; r += 4) {        // 4 rows in flight, no per-row predicates
       float gf[4][8], rf[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (r + u < t.r1) {
-          load_g8<GT>(g + (static_cast<size_t>(t.b) * R + r + u) * C + c, gf[u]);
-          rf[u] = fr[static_cast<size_t>(t.b) * R + r + u];
-        }
+        load_g8<GT>(gp + static_cast<size_t>(r + u) * C, gf[u]);
+        rf[u] = frp[r + u];
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (r + u < t.r1) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x = (gs == 0.f ? 0.f : gf[u][i] * gs) * rf[u] * cf[i];
-            s += x * x;
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float x = (gs == 0.f ? 0.f : gf[u][i] * gs) * rf[u] * cf[i];
+          s += x * x;
         }
+      }
+    }
+    for (; r < t.r1; ++r) {
+      float t8[8];
+      load_g8<GT>(gp + static_cast<size_t>(r) * C, t8);
+      const float rf = frp[r];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = (gs == 0.f ? 0.f : t8[i] * gs) * rf * cf[i];
+        s += x * x;
       }
     }
   }
@@ -302,42 +336,46 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
     if (c >= C) continue;
     float cf[8];
     load_g8<float>(fc + static_cast<size_t>(t.b) * C + c, cf);
-    for (int r = t.r0; r < t.r1; r += 4) {
-      // 4 rows in flight: every load issues before the first store (w aliases itself, so
-      // the compiler cannot hoist the next row's loads above this row's stores).
+    // 4 rows in flight: every load issues before the first store (w aliases itself, so
+    // the compiler cannot hoist the next row's loads above this row's stores).
+    const size_t tb = (static_cast<size_t>(t.b) * R) * C + c;
+    const float* frp = fr + static_cast<size_t>(t.b) * R;
+    auto update_row = [&](size_t off, float (&gf)[8], float (&wf)[8], float rf) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        wf[i] -= (gs == 0.f ? 0.f : gf[i] * gs) * rf * cf[i];
+        wsq += wf[i] * wf[i];
+      }
+      *reinterpret_cast<float4*>(w + off) = make_float4(wf[0], wf[1], wf[2], wf[3]);
+      *reinterpret_cast<float4*>(w + off + 4) = make_float4(wf[4], wf[5], wf[6], wf[7]);
+      if (w_bf16 != nullptr) {
+        int4 o;
+        o.x = pack_bf16x2(wf[0], wf[1]);
+        o.y = pack_bf16x2(wf[2], wf[3]);
+        o.z = pack_bf16x2(wf[4], wf[5]);
+        o.w = pack_bf16x2(wf[6], wf[7]);
+        *reinterpret_cast<int4*>(w_bf16 + off) = o;
+      }
+    };
+    int r = t.r0;
+    for (; r + 4 <= t.r1; r += 4) {
       float gf[4][8], wf[4][8], rf[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (r + u < t.r1) {
-          const size_t off = (static_cast<size_t>(t.b) * R + r + u) * C + c;
-          load_g8<GT>(g + off, gf[u]);
-          load_g8<float>(w + off, wf[u]);
-          rf[u] = fr[static_cast<size_t>(t.b) * R + r + u] * scale;
-        }
+        const size_t off = tb + static_cast<size_t>(r + u) * C;
+        load_g8<GT>(g + off, gf[u]);
+        load_g8<float>(w + off, wf[u]);
+        rf[u] = frp[r + u] * scale;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (r + u < t.r1) {
-          const size_t off = (static_cast<size_t>(t.b) * R + r + u) * C + c;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            wf[u][i] -= (gs == 0.f ? 0.f : gf[u][i] * gs) * rf[u] * cf[i];
-            wsq += wf[u][i] * wf[u][i];
-          }
-          *reinterpret_cast<float4*>(w + off) =
-              make_float4(wf[u][0], wf[u][1], wf[u][2], wf[u][3]);
-          *reinterpret_cast<float4*>(w + off + 4) =
-              make_float4(wf[u][4], wf[u][5], wf[u][6], wf[u][7]);
-          if (w_bf16 != nullptr) {
-            int4 o;
-            o.x = pack_bf16x2(wf[u][0], wf[u][1]);
-            o.y = pack_bf16x2(wf[u][2], wf[u][3]);
-            o.z = pack_bf16x2(wf[u][4], wf[u][5]);
-            o.w = pack_bf16x2(wf[u][6], wf[u][7]);
-            *reinterpret_cast<int4*>(w_bf16 + off) = o;
-          }
-        }
-      }
+      for (int u = 0; u < 4; ++u) update_row(tb + static_cast<size_t>(r + u) * C, gf[u], wf[u], rf[u]);
+    }
+    for (; r < t.r1; ++r) {
+      const size_t off = tb + static_cast<size_t>(r) * C;
+      float gf[8], wf[8];
+      load_g8<GT>(g + off, gf);
+      load_g8<float>(w + off, wf);
+      update_row(off, gf, wf, frp[r] * scale);
     }
   }
   wsq = warp_sum(wsq);                       // sum(w_new^2): next step's parameter scale
@@ -514,19 +552,15 @@ void adafactor_stats(const torch::Tensor& w, const torch::Tensor& g, torch::Tens
   float* tot = (total_sumsq.has_value() && total_sumsq->defined())
                    ? total_sumsq->data_ptr<float>() : nullptr;
   const int nblk = static_cast<int>((R + kStatRows - 1) / kStatRows);
+  const int nchunk = static_cast<int>((C + kStatCols - 1) / kStatCols);
   float* colpart = ColPartials(w.device(), B * nblk * C);
-  const size_t smem = sizeof(float) * static_cast<size_t>(C);
-  TORCH_CHECK(smem <= 200 * 1024, "adafactor_stats: C too large for the column accumulator");
+  if (nchunk > 1)
+    C10_CUDA_CHECK(cudaMemsetAsync(l.rowsum, 0, sizeof(float) * l.br4, stream));
   auto run = [&](auto tag) {
     using GT = decltype(tag);
-    auto kern = adafactor_stats_kernel<GT>;
-    if (smem > 48 * 1024) {
-      C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          200 * 1024));
-    }
-    kern<<<static_cast<int>(B) * nblk, kWarps * 32, smem, stream>>>(
+    adafactor_stats_kernel<GT><<<static_cast<int>(B) * nblk * nchunk, kWarps * 32, 0, stream>>>(
         reinterpret_cast<const GT*>(g.data_ptr()), w.data_ptr<float>(), l.rowsum, colpart, l.acc,
-        (int)B, (int)R, (int)C, nblk, with_w, tot);
+        (int)B, (int)R, (int)C, nblk, nchunk, with_w, tot);
   };
   if (g.scalar_type() == torch::kBFloat16) run(__nv_bfloat16());
   else { TORCH_CHECK(g.scalar_type() == torch::kFloat32); run(float()); }

@@ -228,6 +228,8 @@ PackResult PackSequences(const std::vector<int32_t>& src_lens, const std::vector
     dst->tgt_used += t;
     dst->items.push_back(static_cast<int>(i));
   }
+  // packed_batch_size == 0: output as many rows as the packing needs (no dropping).
+  if (packed_batch_size <= 0) packed_batch_size = static_cast<int>(rows.size());
   // reservoir sample rows down to packed_batch_size
   std::vector<int> keep;
   std::mt19937_64 rng(seed ? seed : std::random_device{}());

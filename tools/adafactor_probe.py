@@ -18,7 +18,7 @@ from lingvo_b200.ops import optim
 def main():
   ncu = len(sys.argv) > 1 and sys.argv[1] == 'ncu'
   dev = torch.device('cuda:0')
-  C = ops.load()
+  C = ops.native()
   shapes = [(8, 2048, 8192), (8, 8192, 2048), (1, 2048, 2048), (1, 32000, 2048), (1, 2048, 8192)]
   if ncu:
     shapes = shapes[:1]
