@@ -227,7 +227,12 @@ class Learner(base_layer.BaseLayer):
     carried, direct = [], []
     if dev.type == 'cuda':
       from lingvo_b200.ops import optim as fused_optim  # pylint: disable=g-import-not-at-top
+      pre_w = getattr(self.optimizer, '_pre_var_sumsq', None) if pre_sumsq is not None else None
+      if pre_w is not None:
+        carried.append(pre_w[0])
       for vg in leaves:
+        if pre_w is not None and id(vg.var) in pre_w[1]:
+          continue
         c = fused_optim.carried_sumsq(vg.var)
         (carried if c is not None else direct).append(c if c is not None else vg.var.detach())
     else:

@@ -11,7 +11,7 @@ from __future__ import annotations
 import re
 from typing import Any, Callable, Iterator, List, Optional, Sequence, Tuple
 
-_KEY_RE = re.compile(r'[A-Za-z_][A-Za-z0-9_]*')
+_KEY_RE = re.compile(r'[A-Za-z_][A-Za-z0-9_/]*')
 _PATH_TOKEN = re.compile(r'([A-Za-z_][A-Za-z0-9_]*)((?:\[\d+\])*)$')
 
 

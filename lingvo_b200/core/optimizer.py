@@ -558,14 +558,27 @@ class XLAShardingAdafactor(Base):
       return None, set()
     total = torch.zeros(1, dtype=torch.float32, device=var_grad_pairs[0][0].device)
     handled = set()
+    small = []
+    self._pre_var_sumsq = None
     for var, grad in var_grad_pairs:
       dims = self._FactoredDims(list(var.shape))
+      if grad.device == var.device and self._SmallEligible(var, grad, dims):
+        small.append((var, grad))
+        continue
       if not self._FusedEligible(var, dims) or grad.device != var.device:
         continue
       fresh = fused.adafactor_stats(var, grad, dims[0], dims[1],
                                     bool(p.multiply_by_parameter_scale), total)
       self._pre[id(var)] = (grad.data_ptr(), fresh)
       handled.add(id(var))
+    if small:
+      # all small variables: Σg² and Σw² with one launch (instead of one reduction each)
+      acc = torch.zeros(2, dtype=torch.float32, device=total.device)
+      self._UpdateSmallFused(fused, 0.0, 0.0, small, sumsq_out=acc)
+      total = total + acc[0:1]
+      ids = {id(v) for v, _ in small}
+      handled |= ids
+      self._pre_var_sumsq = (acc[1:2], ids)
     return total, handled
 
   # -- device-resident hyper-parameters (CUDA-graph capture) ------------------------
@@ -583,8 +596,14 @@ class XLAShardingAdafactor(Base):
     self._hyper_host[1] = self.DecayRate(step)
     self._hyper.copy_(self._hyper_host, non_blocking=True)
 
-  def _UpdateSmallFused(self, fused, lr, decay, small):
-    """All non-factored variables in one multi-tensor launch."""
+  def _SmallEligible(self, var, grad, dims):
+    p = self.params
+    return (dims is None and not p.beta1 and not p.cond_is_finite and var.is_contiguous() and
+            grad.dtype in (torch.float32, torch.bfloat16) and var.dtype == torch.float32)
+
+  def _UpdateSmallFused(self, fused, lr, decay, small, sumsq_out=None):
+    """All non-factored variables in one multi-tensor launch (`sumsq_out`: only reduce
+    Σg² / Σw² into it — the pre-pass that feeds global gradient clipping)."""
     p = self.params
     rows = []
     for var, grad in small:
@@ -596,11 +615,14 @@ class XLAShardingAdafactor(Base):
                    1 if g.dtype == torch.bfloat16 else 0))
       self._small_keepalive = getattr(self, '_small_keepalive', [])
       self._small_keepalive.append(g)
-      if compute is not None:
+      if compute is not None and sumsq_out is None:
         self._refreshed.add(id(var))
     if getattr(self, '_small_table', None) is None:
       self._small_table = fused.SmallVarTable(small[0][0].device)
     table = self._small_table.Build(rows)
+    if sumsq_out is not None:
+      fused.small_sumsq(table, sumsq_out)
+      return
     fused.adafactor_small(table, lr, decay, p.epsilon1, p.epsilon2,
                           p.clipping_threshold or 0.0, bool(p.multiply_by_parameter_scale),
                           self._grad_scale, getattr(self, '_hyper', None))
@@ -616,9 +638,7 @@ class XLAShardingAdafactor(Base):
     small = []
     for var, grad in zip(variables, grads):
       dims = self._FactoredDims(list(var.shape))
-      if (fused is not None and dims is None and not p.beta1 and not p.cond_is_finite and
-          var.is_contiguous() and grad.dtype in (torch.float32, torch.bfloat16) and
-          var.dtype == torch.float32):
+      if fused is not None and self._SmallEligible(var, grad, dims):
         small.append((var, grad))
         continue
       if fused is not None and self._FusedEligible(var, dims):

@@ -34,29 +34,7 @@ def EncoderConfig() -> hyperparams.Params:
   return p
 
 
-class _AllGatherWithGrad(torch.autograd.Function):
-  """Concat over replicas; backward returns this replica's slice of the gradient."""
-
-  @staticmethod
-  def forward(ctx, x):
-    world = dist.get_world_size()
-    outs = [torch.empty_like(x) for _ in range(world)]
-    dist.all_gather(outs, x.contiguous())
-    ctx.rank, ctx.n = dist.get_rank(), x.shape[0]
-    return torch.cat(outs, 0)
-
-  @staticmethod
-  def backward(ctx, g):
-    g = g.contiguous()
-    dist.all_reduce(g)
-    return g[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n]
-
-
-def CrossReplicaConcat(x):
-  """Concatenates `x` along dim 0 across data-parallel replicas (ref `tpu_utils.py:75`)."""
-  if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-    return _AllGatherWithGrad.apply(x)
-  return x
+from lingvo_b200.models.milan.tpu_utils import CrossReplicaConcat  # noqa: E402,F401
 
 
 class DualEncoder(base_layer.BaseLayer):
@@ -98,16 +76,24 @@ class DualEncoder(base_layer.BaseLayer):
         trainable=p.learnable_temperature)
 
   def EncodeModality(self, theta, modality, features):
+    """`features`: one tensor, or a tuple of tensors passed to the encoder positionally
+    (e.g. (token_features, lengths))."""
     p = self.params
-    emb = self.children['encoder_%s' % modality].FProp(theta['encoder_%s' % modality], features)
+    enc, th = self.children['encoder_%s' % modality], theta['encoder_%s' % modality]
+    emb = enc.FProp(th, *features) if isinstance(features, (tuple, list)) else enc.FProp(th, features)
     if p.joint_embedding_dim:
       emb = self.children['projection_%s' % modality].FProp(
           theta['projection_%s' % modality], emb)
     return torch.nn.functional.normalize(emb.float(), dim=-1)
 
+  def _Features(self, batch, modality):
+    key = self.params.encoder_configs[modality].input_features
+    if isinstance(key, (tuple, list)):
+      return tuple(batch[k] for k in key)
+    return batch[key]
+
   def EncodeBatch(self, theta, batch):
-    p = self.params
-    return NestedMap({m: self.EncodeModality(theta, m, batch[p.encoder_configs[m].input_features])
+    return NestedMap({m: self.EncodeModality(theta, m, self._Features(batch, m))
                       for m in self._modalities})
 
   def FProp(self, theta, batch):
@@ -128,8 +114,12 @@ class DualEncoder(base_layer.BaseLayer):
         offset = dist.get_rank() * n
       labels = torch.zeros(n, m, device=scores.device)
       labels[torch.arange(n), torch.arange(n) + offset] = 1.0
-      if p.label_fn is not None and m == n:
-        labels = p.label_fn(n, scores.device, batch)
+      if p.label_fn is not None:
+        ids = NestedMap({k: v for k, v in batch.items()
+                         if isinstance(v, torch.Tensor) and v.dim() == 1 and v.shape[0] == n})
+        make = (label_lib.ExamplePairs.WithinBatch if m == n
+                else label_lib.ExamplePairs.BetweenLocalAndGlobalBatches)
+        labels = p.label_fn(make(ids, query_modality=q, result_modality=r))
       loss = label_lib.MultiLabelContrastiveLoss(labels, scores).mean()
       total = total + w * loss
       acc = (scores.argmax(-1) == torch.arange(n, device=scores.device) + offset).float().mean()

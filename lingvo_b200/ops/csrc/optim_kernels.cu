@@ -485,6 +485,40 @@ adafactor_small_kernel(const SmallVar* __restrict__ table, float lr, float decay
   }
 }
 
+// Σg² and Σw² over every variable of a SmallVar table: one CTA per variable, two adds.
+__global__ void __launch_bounds__(256)
+small_sumsq_kernel(const SmallVar* __restrict__ table, float* __restrict__ out) {
+  __shared__ float red[2][8];
+  const SmallVar sv = table[blockIdx.x];
+  const float* w = reinterpret_cast<const float*>(sv.w);
+  const float* gf = reinterpret_cast<const float*>(sv.g);
+  const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(sv.g);
+  float gs = 0.f, ws = 0.f;
+  for (long long i = threadIdx.x; i < sv.numel; i += blockDim.x) {
+    const float g = sv.g_bf16 ? __bfloat162float(gb[i]) : gf[i];
+    const float wi = w[i];
+    gs += g * g;
+    ws += wi * wi;
+  }
+  gs = warp_sum(gs);
+  ws = warp_sum(ws);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = gs;
+    red[1][threadIdx.x >> 5] = ws;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tg = 0.f, tw = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      tg += red[0][k];
+      tw += red[1][k];
+    }
+    atomicAdd(&out[0], tg);
+    atomicAdd(&out[1], tw);
+  }
+}
+
 struct AfLayout {
   float *acc, *rowsum, *colsum, *fr, *fc;
   int64_t br4, bc4;
@@ -632,6 +666,20 @@ void adafactor_small(const torch::Tensor& table, double lr, double decay, double
   CountLaunch();
 }
 
+// out[0] += Σg², out[1] += Σw² over the table's variables.
+void small_sumsq(const torch::Tensor& table, torch::Tensor out) {
+  TORCH_CHECK(table.is_cuda() && table.scalar_type() == torch::kInt64 && table.is_contiguous() &&
+              table.dim() == 2 && table.size(1) == 6);
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == torch::kFloat32 && out.numel() >= 2);
+  const int n = static_cast<int>(table.size(0));
+  if (n == 0) return;
+  const c10::cuda::CUDAGuard guard(table.device());
+  small_sumsq_kernel<<<n, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
+      reinterpret_cast<const SmallVar*>(table.data_ptr<int64_t>()), out.data_ptr<float>());
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  CountLaunch();
+}
+
 // One-call form (stats + update) kept for callers that do not need the global norm.
 void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor vr,
                         torch::Tensor vc, torch::Tensor scratch,
@@ -682,5 +730,6 @@ LB_REGISTER(optim) {
   m.def("adafactor_stats", &lb::adafactor_stats);
   m.def("adafactor_update", &lb::adafactor_update);
   m.def("adafactor_small", &lb::adafactor_small);
+  m.def("small_sumsq", &lb::small_sumsq);
   m.def("adam_flat", &lb::adam_flat);
 }

@@ -139,6 +139,11 @@ def adafactor_small(table, lr, decay, eps1, eps2, clip, mult_by_param_scale,
                                float(clip), bool(mult_by_param_scale), grad_scale, hyper)
 
 
+def small_sumsq(table, out):
+  """out[0] += Σg², out[1] += Σw² over every variable of a `SmallVarTable` (one launch)."""
+  ops.native().small_sumsq(table, out)
+
+
 def adam_flat(w, g, m, v, w_bf16, lr_t, b1, b2, eps, grad_scale=1.0,
               grad_scale_t=None):
   ops.native().adam_flat(w, g, m, v, w_bf16, grad_scale_t, float(lr_t),
