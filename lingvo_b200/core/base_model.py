@@ -336,9 +336,15 @@ class BaseTask(base_layer.BaseLayer):
     with py_utils.GlobalStepContext(self._global_step):
       vmap = self.vars
       n = len(self.learners)
+      # Only hand the learner an adjuster when a subclass really overrides it: the fused
+      # optimizers fold the global-norm reduction into their statistics pass, which they
+      # can only do when nothing rewrites the gradients in between.
+      adjuster = self.AdjustGradients
+      if getattr(type(self).AdjustGradients, '__func__', type(self).AdjustGradients) is \
+          BaseTask.AdjustGradients:
+        adjuster = None
       for i, lrn in enumerate(self.learners):
-        losses, lm = lrn.Apply(self._metrics, vmap,
-                               gradient_adjuster=self.AdjustGradients,
+        losses, lm = lrn.Apply(self._metrics, vmap, gradient_adjuster=adjuster,
                                retain_graph=i < n - 1)
         self._last_var_grads = lrn.GetVarGrads()
         self._eval_metrics.update(lm)
