@@ -171,4 +171,101 @@ std::vector<int32_t> FarthestPointSample(const float* xyz, int n, int k) {
   return out;
 }
 
+ApResult AveragePrecision3D(float iou_threshold, const float* gt_bbox, const int32_t* gt_imageid,
+                            const int32_t* gt_ignore, int n, const float* pd_bbox,
+                            const int32_t* pd_imageid, const int32_t* pd_ignore,
+                            const float* pd_score, int m, int num_recall_points, bool kitti) {
+  ApResult res;
+  res.score_and_hit.assign(static_cast<size_t>(m) * 2, 0.f);
+  res.precision_recall.assign(static_cast<size_t>(num_recall_points) * 2, 0.f);
+  // ground truth grouped by image
+  std::unordered_map<int32_t, std::vector<int>> by_image;
+  int num_valid_gt = 0;
+  for (int i = 0; i < n; ++i) {
+    by_image[gt_imageid[i]].push_back(i);
+    if (gt_ignore[i] == 0) ++num_valid_gt;
+  }
+  std::vector<int> order(m);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int a, int b) { return pd_score[a] > pd_score[b]; });
+  std::vector<char> used(n, 0);
+  // running (tp, fp) after each counted prediction
+  std::vector<float> tps, fps;
+  int tp = 0, fp = 0;
+  for (int rank = 0; rank < m; ++rank) {
+    const int j = order[rank];
+    res.score_and_hit[2 * j] = pd_score[j];
+    int best = -1;
+    float best_iou = iou_threshold;
+    bool touches_ignore_all = false;
+    auto it = by_image.find(pd_imageid[j]);
+    if (it != by_image.end()) {
+      for (int g : it->second) {
+        const float iou = Iou3D(pd_bbox + 7 * j, gt_bbox + 7 * g);
+        if (iou < iou_threshold) continue;
+        if (gt_ignore[g] == 2) {
+          touches_ignore_all = true;
+          continue;
+        }
+        if (used[g]) continue;
+        // prefer real boxes over "ignore first match" boxes at equal footing, then IoU
+        const bool better = best < 0 || (gt_ignore[best] != 0 && gt_ignore[g] == 0) ||
+                            ((gt_ignore[best] != 0) == (gt_ignore[g] != 0) && iou > best_iou);
+        if (better) {
+          best = g;
+          best_iou = iou;
+        }
+      }
+    }
+    if (best >= 0) {
+      used[best] = 1;
+      if (gt_ignore[best] == 0) {
+        ++tp;
+        res.score_and_hit[2 * j + 1] = 1.f;
+        tps.push_back(static_cast<float>(tp));
+        fps.push_back(static_cast<float>(fp));
+      }
+      continue;   // matched an "ignore first" box: neither TP nor FP
+    }
+    if (touches_ignore_all || pd_ignore[j] == 1) continue;
+    ++fp;
+    tps.push_back(static_cast<float>(tp));
+    fps.push_back(static_cast<float>(fp));
+  }
+  if (num_valid_gt == 0 || tps.empty()) return res;
+  const size_t k = tps.size();
+  std::vector<float> prec(k), rec(k);
+  for (size_t i = 0; i < k; ++i) {
+    prec[i] = tps[i] / (tps[i] + fps[i]);
+    rec[i] = tps[i] / static_cast<float>(num_valid_gt);
+  }
+  // interpolated precision: max precision at recall >= r
+  for (size_t i = k - 1; i-- > 0;) prec[i] = std::max(prec[i], prec[i + 1]);
+  auto prec_at = [&](float r) {
+    auto lo = std::lower_bound(rec.begin(), rec.end(), r - 1e-7f);
+    return lo == rec.end() ? 0.f : prec[lo - rec.begin()];
+  };
+  if (kitti) {
+    double sum = 0;
+    for (int i = 0; i <= num_recall_points; ++i)
+      sum += prec_at(static_cast<float>(i) / num_recall_points);
+    res.average_precision = static_cast<float>(sum / (num_recall_points + 1));
+  } else {
+    double area = 0, prev_r = 0;
+    for (size_t i = 0; i < k; ++i) {
+      if (i + 1 < k && rec[i + 1] == rec[i]) continue;
+      area += (rec[i] - prev_r) * prec[i];
+      prev_r = rec[i];
+    }
+    res.average_precision = static_cast<float>(area);
+  }
+  for (int i = 0; i < num_recall_points; ++i) {       // recall descending
+    const float r = static_cast<float>(num_recall_points - i) / num_recall_points;
+    res.precision_recall[2 * i] = prec_at(r);
+    res.precision_recall[2 * i + 1] = prec_at(r) > 0.f ? r : 0.f;
+  }
+  return res;
+}
+
 }  // namespace lbh

@@ -33,4 +33,22 @@ int PointsToPillars(const float* points, int n, int dims, float x0, float x1, fl
 // Farthest-point sampling: indices of `k` points, starting from point 0.
 std::vector<int32_t> FarthestPointSample(const float* xyz, int n, int k);
 
+// Average precision of 3-D detections of ONE class (re-design of
+// `average_precision_3d_op.cc`). Predictions are visited by decreasing score; each is
+// matched to the unmatched ground-truth box of the same image with the highest
+// IoU >= iou_threshold. Ground-truth `ignore`: 0 = normal, 1 = ignore the first match
+// (matched prediction is neither TP nor FP, box then counts as consumed), 2 = ignore every
+// match. Prediction `ignore` 1 = the prediction never counts as FP (KITTI "too small").
+// algorithm "KITTI": mean of the interpolated precision at num_recall_points+1 equally
+// spaced recalls; "VOC": area under the interpolated PR curve.
+struct ApResult {
+  float average_precision = 0.f;
+  std::vector<float> precision_recall;   // [num_recall_points, 2] (precision, recall), recall descending
+  std::vector<float> score_and_hit;      // [M, 2]
+};
+ApResult AveragePrecision3D(float iou_threshold, const float* gt_bbox, const int32_t* gt_imageid,
+                            const int32_t* gt_ignore, int n, const float* pd_bbox,
+                            const int32_t* pd_imageid, const int32_t* pd_ignore,
+                            const float* pd_score, int m, int num_recall_points, bool kitti);
+
 }  // namespace lbh

@@ -390,6 +390,30 @@ PYBIND11_MODULE(_H, m) {
         },
         py::arg("boxes"), py::arg("scores"), py::arg("nms_iou_threshold"),
         py::arg("score_threshold"), py::arg("max_boxes_per_class"));
+  m.def("average_precision_3d",
+        [](float iou_threshold, FArr gt_bbox, py::array_t<int32_t, py::array::c_style | py::array::forcecast> gt_imageid,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> gt_ignore, FArr pd_bbox,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> pd_imageid,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> pd_ignore, FArr pd_score,
+           int num_recall_points, const std::string& algorithm) {
+          const int n = static_cast<int>(gt_bbox.shape(0)), k = static_cast<int>(pd_bbox.shape(0));
+          ApResult r;
+          {
+            py::gil_scoped_release rel;
+            r = AveragePrecision3D(iou_threshold, gt_bbox.data(), gt_imageid.data(), gt_ignore.data(),
+                                   n, pd_bbox.data(), pd_imageid.data(), pd_ignore.data(),
+                                   pd_score.data(), k, num_recall_points, algorithm == "KITTI");
+          }
+          py::array_t<float> pr({num_recall_points, 2});
+          memcpy(pr.mutable_data(), r.precision_recall.data(), r.precision_recall.size() * 4);
+          py::array_t<float> sh({k, 2});
+          if (k) memcpy(sh.mutable_data(), r.score_and_hit.data(), r.score_and_hit.size() * 4);
+          return py::make_tuple(r.average_precision, pr, sh);
+        },
+        py::arg("iou_threshold"), py::arg("groundtruth_bbox"), py::arg("groundtruth_imageid"),
+        py::arg("groundtruth_ignore"), py::arg("prediction_bbox"), py::arg("prediction_imageid"),
+        py::arg("prediction_ignore"), py::arg("prediction_score"),
+        py::arg("num_recall_points") = 1, py::arg("algorithm") = "KITTI");
   m.def("points_to_pillars",
         [](FArr points, float x0, float x1, float y0, float y1, int nx, int ny, int max_pillars,
            int points_per_pillar) {

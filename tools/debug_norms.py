@@ -1,4 +1,5 @@
-"""Prints which tensors still go through the generic SumSquared reduction in a train step."""
+"""Checks the fused global-norm path (Σg² from the Adafactor stats pass + multi-tensor small
+vars, carried Σw²) against plain torch reductions over the same gradients / variables."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,18 +13,19 @@ dev = torch.device('cuda', 0)
 with cluster_factory.Cluster(cfg.cluster):
   model = cfg.Instantiate(); model.to(dev); task = model.tasks[0]
   batch = task._MoveBatch(task.input.GetPreprocessedInputBatch(), dev)
-  task.TrainStep([batch])
-  names = {v.data_ptr(): v.var_name for v in task.vars.Flatten()}
+  calls = []
   orig = py_utils.SumSquared
   def spy(ts):
-    ts = list(ts)
-    print('SumSquared over', len(ts), 'tensors:',
-          [(names.get(t.data_ptr(), '?'), tuple(t.shape), str(t.dtype)) for t in ts][:60])
-    return orig(ts)
+    ts = list(ts); calls.append(len(ts)); return orig(ts)
   py_utils.SumSquared = spy
-  task.TrainStep([batch])
-  opt = task.learners[0].optimizer
-  for v in task.vars.Flatten():
-    dims = opt._FactoredDims(list(v.shape))
-    if dims is not None and not opt._FusedEligible(v, dims):
-      print('factored but not fused:', v.var_name, tuple(v.shape), dims)
+  for step in range(3):
+    calls.clear()
+    w_before = (sum(float(v.detach().double().square().sum()) for v in task.vars.Flatten())) ** 0.5
+    m, _ = task.TrainStep([batch])
+    vg = task._last_var_grads
+    leaves = [x for x in vg.Flatten() if isinstance(x, py_utils.VarGrad)]
+    ref_g = (sum(float(x.grad.double().square().sum()) for x in leaves)) ** 0.5
+    em = task._eval_metrics
+    get = lambda k: float(em[k][0]) if k in em else float('nan')
+    print('step %d: SumSquared calls %s | grad_norm fused %.6f ref %.6f | var_norm fused %.6f ref(before step) %.6f | loss %.5f' % (
+        step, calls, get('grad_norm/all'), ref_g, get('var_norm/all'), w_before, float(m['loss'][0])))
