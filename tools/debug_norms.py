@@ -26,6 +26,10 @@ with cluster_factory.Cluster(cfg.cluster):
     leaves = [x for x in vg.Flatten() if isinstance(x, py_utils.VarGrad)]
     ref_g = (sum(float(x.grad.double().square().sum()) for x in leaves)) ** 0.5
     em = task._eval_metrics
-    get = lambda k: float(em[k][0]) if k in em else float('nan')
+    def get(k):
+      for kk, v in em.items():
+        if kk.startswith(k):
+          return float(v[0])
+      return float('nan')
     print('step %d: SumSquared calls %s | grad_norm fused %.6f ref %.6f | var_norm fused %.6f ref(before step) %.6f | loss %.5f' % (
         step, calls, get('grad_norm/all'), ref_g, get('var_norm/all'), w_before, float(m['loss'][0])))
