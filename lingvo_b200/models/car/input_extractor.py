@@ -44,7 +44,8 @@ class FieldsExtractor(base_layer.BaseLayer):
         sorted(out.keys()), sorted(shapes.keys()))
     for (k, v), (_, s) in zip(sorted(out.FlattenItems()), sorted(shapes.FlattenItems())):
       if isinstance(v, np.ndarray) and s is not None:
-        assert tuple(v.shape) == tuple(s), '%s: %s vs. %s' % (k, v.shape, s)
+        ok = len(v.shape) == len(s) and all(b is None or a == b for a, b in zip(v.shape, s))
+        assert ok, '%s: %s vs. %s' % (k, v.shape, s)
     return out
 
   def _ExtractBatch(self, features):
@@ -145,9 +146,8 @@ class LaserExtractor(FieldsExtractor):
   def Shape(self):
     p = self.params
     m = p.max_num_points
-    return NestedMap(points_xyz=(m, 3) if m else None,
-                     points_feature=(m, p.num_features) if m else None,
-                     points_padding=(m,) if m else None)
+    return NestedMap(points_xyz=(m, 3), points_feature=(m, p.num_features),
+                     points_padding=(m,))
 
   def DType(self):
     return NestedMap(points_xyz=np.float32, points_feature=np.float32,
