@@ -97,12 +97,14 @@ class _Conv2D(base_layer.BaseLayer):
     x = x.permute(0, 3, 1, 2)
     if p.transpose:
       w = theta.w.permute(2, 3, 0, 1)                      # [in, out, kh, kw]
-      out_pad = (p.stride[0] - 1 if kh > p.stride[0] else 0,
-                 p.stride[1] - 1 if kw > p.stride[1] else 0)
-      y = F.conv_transpose2d(x, w, stride=tuple(p.stride),
-                             padding=((kh - p.stride[0] + out_pad[0]) // 2,
-                                      (kw - p.stride[1] + out_pad[1]) // 2),
-                             output_padding=out_pad)
+      def _SamePad(k, st):        # output = input · stride
+        if k >= st:
+          pad = (k - st + 1) // 2
+          return pad, 2 * pad - (k - st)
+        return 0, st - k
+      (ph, oph), (pw, opw) = _SamePad(kh, p.stride[0]), _SamePad(kw, p.stride[1])
+      y = F.conv_transpose2d(x, w, stride=tuple(p.stride), padding=(ph, pw),
+                             output_padding=(oph, opw))
     else:
       w = theta.w.permute(3, 2, 0, 1)                      # [out, in, kh, kw]
       y = F.conv2d(x, w, stride=tuple(p.stride), padding=((kh - 1) // 2, (kw - 1) // 2))

@@ -250,3 +250,199 @@ class ModelV1(base_model.BaseTask):
           boxes, scores, p.nms_iou_threshold, p.nms_score_threshold, p.max_nms_boxes)
     return NestedMap(per_class_predicted_bboxes=boxes, per_class_scores=scores,
                      per_class_indices=idx, per_class_valid_mask=mask)
+
+
+# --------------------------------------------------------------------------------------
+# Reference-named building blocks (ref `pillars.py`: PointsToGridFeaturizer :33, Builder
+# :92, LossNormType :325, DynamicVoxelizationFeaturizer :647). They compose the same model
+# from `builder_lib` recipes and consume the `KITTIGrid` / dynamic-voxel input formats.
+# --------------------------------------------------------------------------------------
+import enum  # pylint: disable=g-import-not-at-top,wrong-import-position
+
+from lingvo_b200.models.car import builder_lib  # pylint: disable=wrong-import-position
+from lingvo_b200.models.car import car_layers  # pylint: disable=wrong-import-position
+from lingvo_b200.models.car import point_detector  # pylint: disable=wrong-import-position
+
+
+class LossNormType(enum.Enum):
+  NO_NORM = 0
+  NORM_BY_NUM_POSITIVES = 1
+
+
+class PointsToGridFeaturizer(base_layer.BaseLayer):
+  """Pillars from the `GridToPillars` preprocessor → BEV feature image (ref :33): augment
+  every point with its offset to the pillar's point mean and to the pillar centre, run the
+  per-point `featurizer`, max over the pillar's points, scatter the pillar vectors to
+  `[B, gx, gy, C]`."""
+
+  @classmethod
+  def Params(cls, num_laser_features=1, num_output_features=64):
+    p = super().Params()
+    b = builder_lib.ModelBuilderBase(builder_lib.ModelBuilderBase.Params())
+    idims = 3 + num_laser_features + 3 + 3
+    p.Define('num_laser_features', num_laser_features, 'Laser features per point.')
+    p.Define('featurizer', b._FC('pillar_fc', idims, num_output_features),   # pylint: disable=protected-access
+             'Per-point featurizer.')
+    p.Define('num_output_features', num_output_features, 'Pillar feature dim.')
+    p.Define('grid_size', (432, 496, 1), '(gx, gy, gz).')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('featurizer', self.params.featurizer)
+
+  def FProp(self, theta, input_batch):
+    p = self.params
+    pts = input_batch.pillar_points                         # [B, N, K, 3+F]
+    cnt = input_batch.point_count.to(pts.dtype)             # [B, N]
+    loc = input_batch.point_locations.long()                # [B, N, 3]
+    b, n, k, _ = pts.shape
+    valid = (torch.arange(k, device=pts.device).view(1, 1, k) < cnt.unsqueeze(-1)).to(pts.dtype)
+    mean = (pts[..., :3] * valid.unsqueeze(-1)).sum(2, keepdim=True) / cnt.clamp_min(1.0).view(
+        b, n, 1, 1)
+    centers = input_batch.get('pillar_centers')
+    if centers is None:
+      centers = mean.squeeze(2)
+    feats = torch.cat([pts, pts[..., :3] - mean, pts[..., :3] - centers.unsqueeze(2)], -1)
+    feats = self.featurizer.FProp(theta.featurizer, feats * valid.unsqueeze(-1))
+    neg = torch.finfo(feats.dtype).min
+    pooled = feats.masked_fill(valid.unsqueeze(-1) < 0.5, neg).max(2).values
+    pooled = torch.where(cnt.unsqueeze(-1) > 0, pooled, torch.zeros_like(pooled))
+    gx, gy, _ = p.grid_size
+    flat = loc[..., 0] * gy + loc[..., 1]
+    image = torch.zeros(b, gx * gy, pooled.shape[-1], device=pts.device, dtype=pooled.dtype)
+    image.scatter_(1, flat.unsqueeze(-1).expand(-1, -1, pooled.shape[-1]),
+                   pooled * (cnt.unsqueeze(-1) > 0))
+    return image.reshape(b, gx, gy, -1)
+
+
+class DynamicVoxelizationFeaturizer(base_layer.BaseLayer):
+  """Raw padded points → BEV feature image through dynamic voxelisation (no per-pillar
+  point budget) (ref :647)."""
+
+  @classmethod
+  def Params(cls, num_laser_features=1, num_output_features=64):
+    p = super().Params()
+    b = builder_lib.ModelBuilderBase(builder_lib.ModelBuilderBase.Params())
+    dv = car_layers.DynamicVoxelization.Params().Set(num_laser_features=num_laser_features)
+    enc = car_layers.PointEncoder.Params().Instantiate().NumEncodingFeatures(num_laser_features)
+    dv.featurizer = b._FC('point_fc', enc, num_output_features)   # pylint: disable=protected-access
+    p.Define('dynamic_voxelization', dv, 'Voxelisation + encoding + pooling.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('dynamic_voxelization', self.params.dynamic_voxelization)
+
+  def FProp(self, theta, input_batch):
+    las = input_batch.lasers
+    return self.dynamic_voxelization.FProp(theta.dynamic_voxelization, las.points_xyz,
+                                           las.points_feature, las.points_padding)
+
+
+class Builder(builder_lib.ModelBuilderBase):
+  """PointPillars layer recipes (ref :92)."""
+
+  def Featurizer(self, name, idims, odims):
+    return self._FC(name, idims, odims)
+
+  def _Block(self, name, stride, repeats, idims, odims):
+    layers_ = [self._Conv('c0', (3, 3, idims, odims), (stride, stride))]
+    layers_ += [self._Conv('c%d' % (i + 1), (3, 3, odims, odims)) for i in range(repeats)]
+    return self._Seq(name, *layers_)
+
+  def Backbone(self, idims, dims=(64, 128, 256), repeats=(3, 5, 5), up_dims=128,
+               first_stride=2):
+    """Three strided conv blocks; each block's output is upsampled back to the first
+    block's resolution and the three are concatenated → `3·up_dims` channels at 1/`first_
+    stride` of the input resolution."""
+    b0 = self._Block('b0', first_stride, repeats[0], idims, dims[0])
+    b1 = self._Block('b1', 2, repeats[1], dims[0], dims[1])
+    b2 = self._Block('b2', 2, repeats[2], dims[1], dims[2])
+    u0 = self._Deconv('u0', (3, 3, dims[0], up_dims), (1, 1))
+    u1 = self._Deconv('u1', (3, 3, dims[1], up_dims), (2, 2))
+    u2 = self._Deconv('u2', (3, 3, dims[2], up_dims), (4, 4))
+    s0 = self._Seq('s0', b0)
+    s1 = self._Seq('s1', b0.Copy(), b1)
+    s2 = self._Seq('s2', b0.Copy(), b1.Copy(), b2)
+    # the three stages share nothing in this formulation (clear dataflow, 3 small convs
+    # recomputed); the hand-fused `PillarsBackbone` above is the production path
+    return self._Concat('backbone', self._Seq('p0', s0, u0), self._Seq('p1', s1, u1),
+                        self._Seq('p2', s2, u2))
+
+  def Detector(self, name, idims, odims, conv_init_method=None, bias_params_init=None):
+    del conv_init_method
+    del bias_params_init
+    return self._ConvPlain(name, (3, 3, idims, odims))
+
+
+class ModelV2(point_detector.PointDetectorBase):
+  """PointPillars on the extractor-based input (`KITTIGrid`): `PointsToGridFeaturizer` →
+  `Builder.Backbone` → conv heads; anchors / assignments come from the preprocessors, NMS
+  and metrics from `PointDetectorBase` and the output decoder (ref :330 `ModelV1`)."""
+
+  NUM_OUTPUT_CHANNELS = 128
+
+  @classmethod
+  def Params(cls, grid_size_z=1, num_anchors=2, num_classes=2, num_laser_features=1):
+    p = super().Params(num_classes)
+    b = Builder(Builder.Params())
+    c = cls.NUM_OUTPUT_CHANNELS
+    p.Define('grid_size_z', grid_size_z, 'Grid size along z.')
+    p.Define('num_anchors', num_anchors, 'Anchors per cell.')
+    p.Define('num_laser_features', num_laser_features, 'Laser features per point.')
+    p.Define('input_featurizer', PointsToGridFeaturizer.Params(num_laser_features, 64),
+             'Points → BEV image.')
+    p.Define('backbone', b.Backbone(64 * grid_size_z, up_dims=c), 'BEV backbone.')
+    p.Define('class_detector', b.Detector('class', 3 * c, num_anchors * num_classes),
+             'Classification head.')
+    p.Define('regression_detector', b.Detector('reg', 3 * c, num_anchors * 7), 'Box head.')
+    p.Define('focal_loss_alpha', 0.25, 'Focal α.')
+    p.Define('focal_loss_gamma', 2.0, 'Focal γ.')
+    p.Define('localization_loss_weight', 2.0, 'Localisation weight.')
+    p.Define('classification_loss_weight', 1.0, 'Classification weight.')
+    p.Define('loss_norm_type', LossNormType.NORM_BY_NUM_POSITIVES, 'Normalisation.')
+    p.Define('huber_loss_delta', 1.0 / 9.0, 'Huber δ.')
+    p.name = 'pillars_v2'
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    for n in ('input_featurizer', 'backbone', 'class_detector', 'regression_detector'):
+      self.CreateChild(n, p.Get(n))
+
+  def ComputePredictions(self, theta, input_batch):
+    p = self.params
+    img = self.input_featurizer.FProp(theta.input_featurizer, input_batch)
+    feat = self.backbone.FProp(theta.backbone, img)
+    cls = self.class_detector.FProp(theta.class_detector, feat)
+    reg = self.regression_detector.FProp(theta.regression_detector, feat)
+    b = cls.shape[0]
+    return NestedMap(classification_logits=cls.reshape(b, -1, p.num_anchors, p.num_classes),
+                     residuals=reg.reshape(b, -1, p.num_anchors, 7))
+
+  def ComputeLoss(self, theta, predictions, input_batch):
+    p = self.params
+    u = self._utils_3d
+    res, logits = predictions.residuals, predictions.classification_logits
+    b = res.shape[0]
+    gt = input_batch.anchor_localization_residuals.reshape(res.shape).to(res.dtype)
+    labels = input_batch.assigned_gt_labels.reshape(res.shape[:-1]).long().clamp(
+        max=p.num_classes - 1)
+    cls_w = input_batch.assigned_cls_mask.reshape(res.shape[:-1]).to(res.dtype)
+    reg_w = input_batch.assigned_reg_mask.reshape(res.shape[:-1]).to(res.dtype)
+    focal = u.SigmoidFocalLoss(logits.float(), F.one_hot(labels, p.num_classes).float(),
+                               p.focal_loss_alpha, p.focal_loss_gamma)
+    cls_loss = focal[..., 1:].sum(-1) * cls_w
+    d_rot = torch.sin(res[..., 6:] - gt[..., 6:])
+    reg = torch.cat([u.ScaledHuberLoss(gt[..., :6], res[..., :6], p.huber_loss_delta),
+                     u.ScaledHuberLoss(torch.zeros_like(d_rot), d_rot, p.huber_loss_delta)],
+                    -1).sum(-1) * reg_w
+    norm = reg_w.sum().clamp_min(1.0) if p.loss_norm_type == LossNormType.NORM_BY_NUM_POSITIVES \
+        else torch.tensor(float(b), device=res.device)
+    cls_total, reg_total = cls_loss.sum() / norm, reg.sum() / norm
+    loss = p.classification_loss_weight * cls_total + p.localization_loss_weight * reg_total
+    bs = float(b)
+    return NestedMap(loss=(loss, bs), **{'loss/classification': (cls_total, bs),
+                                         'loss/localization': (reg_total, bs)}), NestedMap()
