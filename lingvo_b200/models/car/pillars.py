@@ -325,7 +325,8 @@ class DynamicVoxelizationFeaturizer(base_layer.BaseLayer):
     p = super().Params()
     b = builder_lib.ModelBuilderBase(builder_lib.ModelBuilderBase.Params())
     dv = car_layers.DynamicVoxelization.Params().Set(num_laser_features=num_laser_features)
-    enc = car_layers.PointEncoder.Params().Instantiate().NumEncodingFeatures(num_laser_features)
+    enc = car_layers.PointEncoder.Params().Set(name='enc').Instantiate().NumEncodingFeatures(
+        num_laser_features)
     dv.featurizer = b._FC('point_fc', enc, num_output_features)   # pylint: disable=protected-access
     p.Define('dynamic_voxelization', dv, 'Voxelisation + encoding + pooling.')
     return p
