@@ -116,3 +116,29 @@ def parse_dict(buf: bytes) -> Dict[int, List]:
 
 def to_signed64(v: int) -> int:
   return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def as_double(v) -> float:
+  """Value of a fixed64 field (8 raw bytes from `parse`) as a double; numbers pass through."""
+  if isinstance(v, (bytes, bytearray)):
+    return struct.unpack('<d', v)[0] if len(v) == 8 else struct.unpack('<f', v)[0]
+  return float(v)
+
+
+def as_float(v) -> float:
+  if isinstance(v, (bytes, bytearray)):
+    return struct.unpack('<f', v)[0] if len(v) == 4 else struct.unpack('<d', v)[0]
+  return float(v)
+
+
+def parse_packed_varints(buf: bytes) -> List[int]:
+  out, pos = [], 0
+  while pos < len(buf):
+    v, pos = read_varint(buf, pos)
+    out.append(v)
+  return out
+
+
+def f_packed_double(field: int, vals) -> bytes:
+  payload = b''.join(struct.pack('<d', float(v)) for v in vals)
+  return f_bytes(field, payload)
