@@ -23,30 +23,40 @@ flags.DEFINE_integer('num_mel_bins', 80, 'Mel bins.')
 FLAGS = flags.FLAGS
 
 
-def main(argv):
-  del argv
-  n_shards = FLAGS.num_output_shards
-  writers = [ops.host().TFRecordWriter(FLAGS.output_template % (i, n_shards))
+def WriteFeatures(utterances, output_template, n_shards=1, num_mel_bins=80):
+  """`utterances`: iterable of (utt id, transcript, wav bytes) → sharded TFRecords of
+  {uttid, transcript, frames}; returns the number written."""
+  writers = [ops.host().TFRecordWriter(output_template % (i, n_shards))
              for i in range(n_shards)]
   n = 0
-  with open(FLAGS.transcripts, encoding='utf-8') as f:
+  for uttid, text, wav in utterances:
+    feats = audio_lib.ExtractLogMelFeatures(wav, num_mel_bins)
+    writers[n % n_shards].write(tf_example.MakeExample({
+        'uttid': [uttid.encode()], 'transcript': [text.lower().encode()],
+        'frames': feats.reshape(-1)}))
+    n += 1
+  for w in writers:
+    w.close()
+  return n
+
+
+def _FromDir(input_dir, transcripts):
+  with open(transcripts, encoding='utf-8') as f:
     for line in f:
       parts = line.strip().split(' ', 1)
       if len(parts) != 2:
         continue
-      uttid, text = parts
-      path = os.path.join(FLAGS.input_dir, uttid + '.wav')
-      if not os.path.exists(path):
-        continue
-      with open(path, 'rb') as wf:
-        feats = audio_lib.ExtractLogMelFeatures(wf.read(), FLAGS.num_mel_bins)
-      writers[n % n_shards].write(tf_example.MakeExample({
-          'uttid': [uttid.encode()], 'transcript': [text.lower().encode()],
-          'frames': feats.reshape(-1)}))
-      n += 1
-  for w in writers:
-    w.close()
-  print('wrote %d utterances to %d shards' % (n, n_shards))
+      path = os.path.join(input_dir, parts[0] + '.wav')
+      if os.path.exists(path):
+        with open(path, 'rb') as wf:
+          yield parts[0], parts[1], wf.read()
+
+
+def main(argv):
+  del argv
+  n = WriteFeatures(_FromDir(FLAGS.input_dir, FLAGS.transcripts), FLAGS.output_template,
+                    FLAGS.num_output_shards, FLAGS.num_mel_bins)
+  print('wrote %d utterances to %d shards' % (n, FLAGS.num_output_shards))
 
 
 if __name__ == '__main__':
