@@ -27,6 +27,21 @@ from lingvo_b200.core import summary_utils
 from lingvo_b200.core.nested_map import NestedMap
 
 
+def _EpAllReduce(t):
+  """Sums a small device tensor over the expert-parallel group (no-op without EP)."""
+  import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+  if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+    return t
+  from lingvo_b200.parallel import mesh as mesh_lib  # pylint: disable=g-import-not-at-top
+  ctx = mesh_lib.Get()
+  engines = list(getattr(ctx, '_ep_engines', {}).values())
+  if not engines:
+    return t
+  t = t.clone()
+  dist.all_reduce(t, group=engines[0].group)
+  return t
+
+
 class Learner(base_layer.BaseLayer):
   """Optimizes one (or a combination of) loss(es) over a set of variables."""
 
@@ -217,10 +232,21 @@ class Learner(base_layer.BaseLayer):
     if (pre_fn is not None and defer_scale and gradient_adjuster is None and
         dev.type == 'cuda'):
       pre_sumsq, handled = pre_fn([(vg.var, vg.grad) for vg in leaves])
-    rest = [vg.grad for vg in leaves if id(vg.var) not in handled]
+    is_ep = lambda v: bool(getattr(v, 'expert_parallel', False))
+    rest = [vg.grad for vg in leaves if id(vg.var) not in handled and not is_ep(vg.var)]
+    rest_ep = [vg.grad for vg in leaves if id(vg.var) not in handled and is_ep(vg.var)]
     grad_sumsq = py_utils.SumSquared(rest).to(dev) if rest else torch.zeros((), device=dev)
     if pre_sumsq is not None:
       grad_sumsq = grad_sumsq + pre_sumsq.reshape(())
+    # Σg² of expert-parallel variables: every rank holds different experts, so the global
+    # norm needs the sum over the EP group (one 4-byte all-reduce).
+    ep_sumsq = getattr(self.optimizer, '_pre_ep_sumsq', None) if pre_sumsq is not None else None
+    if rest_ep:
+      extra = py_utils.SumSquared(rest_ep).to(dev).reshape(1)
+      ep_sumsq = extra if ep_sumsq is None else ep_sumsq + extra
+    if ep_sumsq is not None:
+      ep_sumsq = _EpAllReduce(ep_sumsq)
+      grad_sumsq = grad_sumsq + ep_sumsq.reshape(())
     all_grad_norm = torch.sqrt(grad_sumsq)
     # Σw²: variables stepped by the fused Adafactor carry it from their last update
     # (no extra pass over the fp32 masters); the rest are reduced directly.

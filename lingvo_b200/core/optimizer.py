@@ -557,9 +557,14 @@ class XLAShardingAdafactor(Base):
     if fused is None:
       return None, set()
     total = torch.zeros(1, dtype=torch.float32, device=var_grad_pairs[0][0].device)
+    # Expert-parallel variables differ across ranks: their Σg² is accumulated separately so
+    # that the learner can all-reduce just that scalar for the true global norm.
+    total_ep = torch.zeros(1, dtype=torch.float32, device=total.device)
+    any_ep = False
     handled = set()
     small = []
     self._pre_var_sumsq = None
+    self._pre_ep_sumsq = None
     for var, grad in var_grad_pairs:
       dims = self._FactoredDims(list(var.shape))
       if grad.device == var.device and self._SmallEligible(var, grad, dims):
@@ -567,10 +572,15 @@ class XLAShardingAdafactor(Base):
         continue
       if not self._FusedEligible(var, dims) or grad.device != var.device:
         continue
+      is_ep = bool(getattr(var, 'expert_parallel', False))
+      any_ep = any_ep or is_ep
       fresh = fused.adafactor_stats(var, grad, dims[0], dims[1],
-                                    bool(p.multiply_by_parameter_scale), total)
+                                    bool(p.multiply_by_parameter_scale),
+                                    total_ep if is_ep else total)
       self._pre[id(var)] = (grad.data_ptr(), fresh)
       handled.add(id(var))
+    if any_ep:
+      self._pre_ep_sumsq = total_ep
     if small:
       # all small variables: Σg² and Σw² with one launch (instead of one reduction each)
       acc = torch.zeros(2, dtype=torch.float32, device=total.device)

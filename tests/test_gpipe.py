@@ -104,3 +104,40 @@ def test_pipeline_engine_two_ranks_matches_single_process():
     torch.testing.assert_close(g, v.grad, atol=1e-5, rtol=1e-4)
     other = res[1 - stage][2][v.var_name]
     assert other is None        # a stage never touches the other stage's weights
+
+
+def _EpNormWorker(rank, world, port, q):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  from lingvo_b200.core import learner as learner_lib
+  from lingvo_b200.core import py_utils
+  from lingvo_b200.core.nested_map import NestedMap
+  from lingvo_b200.parallel import mesh
+  mesh.Reset()
+  assert mesh.ExpertParallelFor(2) is not None
+  lrn = learner_lib.Learner.Params().Set(name='l', learning_rate=0.1).Instantiate()
+  shared = torch.nn.Parameter(torch.ones(4))
+  expert = torch.nn.Parameter(torch.ones(3))
+  expert.expert_parallel = True
+  vgs = NestedMap(
+      a=py_utils.VarGrad(shared, torch.full((4,), 2.0)),
+      e=py_utils.VarGrad(expert, torch.full((3,), float(rank + 1))))
+  out = lrn.ScaleGradients(vgs)
+  q.put((rank, float(out.stats['grad_norm/all'][0])))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_global_grad_norm_sums_expert_parallel_grads_over_ranks():
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = 29900 + os.getpid() % 90
+  procs = [ctx.Process(target=_EpNormWorker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = dict(q.get(timeout=60) for _ in range(2))
+  for p in procs:
+    p.join(timeout=60)
+  want = (4 * 4.0 + 3 * 1.0 + 3 * 4.0) ** 0.5
+  assert abs(res[0] - want) < 1e-5 and abs(res[1] - want) < 1e-5, res

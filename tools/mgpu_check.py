@@ -27,6 +27,15 @@ def run(mode, steps=3, dense_adam=False):
     for _ in range(steps):
       metrics, _ = task.TrainStep()
       losses.append(float(metrics['loss'][0].detach()))
+    # The global gradient norm must agree on every rank (expert grads are rank-local and
+    # are summed over the EP group inside the learner).
+    gn = metrics.get('grad_norm/all')
+    if gn is not None:
+      g = gn[0].detach().float().reshape(1).cuda()
+      gs = [torch.zeros_like(g) for _ in range(dist.get_world_size())]
+      dist.all_gather(gs, g)
+      vals = [float(x) for x in gs]
+      assert max(vals) - min(vals) <= 1e-4 * max(vals), ('grad norm differs across ranks', vals)
   return losses
 
 def main():
