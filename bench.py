@@ -259,10 +259,25 @@ def main():
     }
     if e2e is not None:
       out['e2e'] = e2e
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
   if world > 1:
+    # Tear-down: a CUDA graph that holds captured NCCL kernels must be gone before the
+    # communicator is destroyed, and a stuck destroy must never hold the job open — the
+    # measurement is already printed, so a watchdog ends the process if it takes too long.
+    import gc
+    import threading
+    graphed = None
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    watchdog = threading.Timer(20.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
     dist.destroy_process_group()
+    watchdog.cancel()
   return 0
 
 

@@ -63,3 +63,34 @@ def inlined_matrix_inverse_pth_root(mat_g, p, mat_g_size=None, iter_count=100,
       break
     mat_m, mat_h, err = new_m, new_h, new_err
   return mat_h
+
+
+def inverse_pth_root_no_sync(mat_g, p, iter_count=40, epsilon=1e-6, ridge_epsilon=1e-6):
+  """Same coupled iteration with a fixed trip count and device-side convergence masking, so
+  no iteration reads a value back to the host — safe to enqueue on a side stream (used by
+  `preconditioner_captain`). Once converged (or diverging) the iterate is frozen by `where`."""
+  mat_g = mat_g.float()
+  n = mat_g.shape[0]
+  ident = torch.eye(n, dtype=mat_g.dtype, device=mat_g.device)
+  v = torch.ones(n, dtype=mat_g.dtype, device=mat_g.device) / (n ** 0.5)
+  for _ in range(30):                                   # power iteration, no early exit
+    w = mat_g @ v
+    v = w / torch.clamp(w.norm(), min=1e-30)
+  max_ev = v @ (mat_g @ v)
+  damped = mat_g + ridge_epsilon * torch.clamp(max_ev, min=1e-16) * ident
+  alpha = -1.0 / p
+  z = (1 + p) / (2 * damped.norm())
+  mat_m = damped * z
+  mat_h = ident * (z ** (1.0 / p))
+  err = (mat_m - ident).abs().max()
+  live = torch.ones((), dtype=torch.bool, device=mat_g.device)
+  for _ in range(iter_count):
+    m_i = (1 - alpha) * ident + alpha * mat_m
+    new_m = torch.linalg.matrix_power(m_i, p) @ mat_m
+    new_h = mat_h @ m_i
+    new_err = (new_m - ident).abs().max()
+    live = live & (err > epsilon) & (new_err <= err * 1.2)
+    mat_m = torch.where(live, new_m, mat_m)
+    mat_h = torch.where(live, new_h, mat_h)
+    err = torch.where(live, new_err, err)
+  return mat_h

@@ -785,6 +785,9 @@ class DistributedShampoo(Base):
     p.Define('fallback_to_diagonal_dim', 4096, 'Fallback dim.')
     p.Define('statistics_computation_frequency', 1, 'Steps between stat updates.')
     p.Define('preconditioning_compute_steps', 20, 'Steps between root solves.')
+    p.Define('async_preconditioning', False,
+             'Solve the inverse roots on a low-priority side stream '
+             '(`preconditioner_captain`) and step with the last finished ones.')
     return p
 
   def _Update(self, lr, variables, grads):
@@ -808,7 +811,17 @@ class DistributedShampoo(Base):
           gf = g.float()
           st['L'].add_(gf @ gf.t())
           st['R'].add_(gf.t() @ gf)
-        if t % p.preconditioning_compute_steps == 0 or t == 1:
+        if p.async_preconditioning:
+          from lingvo_b200.core import preconditioner_captain
+          cap = preconditioner_captain.GetCaptain()
+          if t % p.preconditioning_compute_steps == 0 or t == 1:
+            cap.InsertGradientStatistics(key + '/L', st['L'], 4, t)
+            cap.InsertGradientStatistics(key + '/R', st['R'], 4, t)
+          for side in ('L', 'R'):
+            done, ok = cap.GetPreconditioner(key + '/' + side)
+            if ok:
+              st['P' + side] = done
+        elif t % p.preconditioning_compute_steps == 0 or t == 1:
           st['PL'] = matrix_functions.inlined_matrix_inverse_pth_root(
               st['L'], 4, ridge_epsilon=p.matrix_epsilon)
           st['PR'] = matrix_functions.inlined_matrix_inverse_pth_root(

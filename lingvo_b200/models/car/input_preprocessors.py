@@ -1422,16 +1422,13 @@ class SparseSampler(Preprocessor):
     las = prepared.lasers
     pad = las.get('points_padding')
     pad = pad if pad is not None else torch.zeros(las.points_xyz.shape[0])
-    z = las.points_xyz[:, 2]
-    center_pad = torch.maximum(pad, ((z < p.keep_z_range[0]) | (z > p.keep_z_range[1])).float())
     seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self._Gen()))
-    c, cpad, _, _ = car_ops.sample_points(las.points_xyz.unsqueeze(0), center_pad.unsqueeze(0),
-                                          p.num_centers, 1, None, p.center_selector, seed)
+    # One native call: centre selection restricted to keep_z_range + ball query.
+    c, cpad, idx, ipad = car_ops.sample_points(
+        las.points_xyz.unsqueeze(0), pad.unsqueeze(0), p.num_centers, p.num_neighbors,
+        p.max_distance, p.center_selector, seed, neighbor_sampler=p.neighbor_sampler,
+        center_z_min=p.keep_z_range[0], center_z_max=p.keep_z_range[1])
     centers = las.points_xyz[c[0]]
-    idx, ipad = car_lib.NeighborhoodIndices(
-        las.points_xyz.unsqueeze(0), centers.unsqueeze(0), p.num_neighbors,
-        (pad > 0.5).unsqueeze(0), p.max_distance,
-        sample_neighbors_uniformly=p.neighbor_sampler == 'uniform')
     features.cell_center_xyz = centers
     features.anchor_centers = centers.clone()
     features.cell_center_padding = cpad[0]

@@ -69,34 +69,40 @@ def point_to_grid(points, x_range, y_range, grid_size, max_pillars, points_per_p
 
 
 def sample_points(points, points_padding, num_centers, num_neighbors, max_distance=None,  # pylint: disable=invalid-name
-                  center_selector='farthest', random_seed=-1):
-  """Centre selection (farthest-point or uniform) + neighbour gathering for one batch of
-  scenes `[B, P, 3]` → (center `[B, C]`, center_padding, indices `[B, C, K]`,
-  indices_padding)."""
-  from lingvo_b200.models.car import car_lib  # pylint: disable=g-import-not-at-top
-  pts = torch.as_tensor(_F(points))
-  pad = torch.as_tensor(_F(points_padding))
-  b, p, _ = pts.shape
-  if center_selector == 'farthest':
-    centers = []
-    for i in range(b):
-      real = np.nonzero(pad[i].numpy() < 0.5)[0]
-      k = min(num_centers, len(real))
-      if k == 0:
-        centers.append(np.zeros(num_centers, np.int64))
-        continue
-      loc = np.asarray(_ops.host().farthest_point_sample(pts[i, real].numpy(), k))
-      idx = real[loc]
-      centers.append(np.concatenate([idx, np.repeat(idx[:1], num_centers - k)]))
-    center = torch.from_numpy(np.stack(centers)).long()
-  else:
-    g = torch.Generator()
-    if random_seed >= 0:
-      g.manual_seed(int(random_seed))
-    noise = torch.rand(b, p, generator=g).masked_fill(pad > 0.5, -1.0)
-    center = noise.topk(num_centers, -1).indices
-  n_real = (pad < 0.5).sum(1, keepdim=True)
-  center_padding = (torch.arange(num_centers).unsqueeze(0) >= n_real).float()
-  q = pts.gather(1, center.unsqueeze(-1).expand(-1, -1, 3))
-  idx, idx_pad = car_lib.NeighborhoodIndices(pts, q, num_neighbors, pad > 0.5, max_distance)
-  return center, center_padding, idx, idx_pad
+                  center_selector='farthest', random_seed=-1, num_seeded_points=0,
+                  neighbor_sampler='closest', neighbor_algorithm='auto',
+                  center_z_min=None, center_z_max=None):
+  """Centre selection (farthest-point or uniform) + neighbourhood gathering for a batch of
+  scenes `[B, P, ≥3]` → (center `[B, M]`, center_padding, indices `[B, M, K]`,
+  indices_padding); ref `car_ops.cc:189-255` / `ps_utils.cc`. Runs in the native host
+  library, scenes in parallel.
+
+  The first `num_seeded_points` points seed the farthest-point criterion but are never
+  returned; only points with z in [center_z_min, center_z_max] can be centres;
+  `neighbor_sampler` 'closest' keeps the K nearest points within `max_distance`, 'uniform'
+  a uniform sample of them; `neighbor_algorithm='hash'` forces the grid-hash ball query.
+  """
+  big = 3.4e38
+  pts = np.ascontiguousarray(_F(points), np.float32)
+  pad = np.ascontiguousarray(_F(points_padding), np.float32)
+  c, cp, idx, ip = _ops.host().sample_points(
+      pts, pad, int(num_seeded_points), center_selector, neighbor_sampler, neighbor_algorithm,
+      int(num_centers), -big if center_z_min is None else float(center_z_min),
+      big if center_z_max is None else float(center_z_max), int(num_neighbors),
+      big if max_distance is None else float(max_distance), int(random_seed))
+  return (torch.from_numpy(np.asarray(c)).long(), torch.from_numpy(np.asarray(cp)),
+          torch.from_numpy(np.asarray(idx)).long(), torch.from_numpy(np.asarray(ip)))
+
+
+
+def average_precision2d(iou_threshold, groundtruth_bbox, groundtruth_imageid,  # pylint: disable=invalid-name
+                        groundtruth_ignore, prediction_bbox, prediction_imageid,
+                        prediction_ignore, prediction_score, num_recall_points=1,
+                        algorithm='VOC'):
+  """Image-plane AP over `(ymin, xmin, ymax, xmax)` boxes with the same matching protocol as
+  `average_precision3d` (ref `image_metrics.cc` `AveragePrecision<Box2D>`)."""
+  ap, pr, sh = _ops.host().average_precision_2d(
+      float(iou_threshold), _F(groundtruth_bbox).reshape(-1, 4), _I(groundtruth_imageid),
+      _I(groundtruth_ignore), _F(prediction_bbox).reshape(-1, 4), _I(prediction_imageid),
+      _I(prediction_ignore), _F(prediction_score), int(num_recall_points), algorithm)
+  return float(ap), torch.from_numpy(np.asarray(pr)), torch.from_numpy(np.asarray(sh))

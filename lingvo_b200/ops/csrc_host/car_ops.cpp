@@ -4,7 +4,9 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <numeric>
+#include <random>
 #include <unordered_map>
 
 namespace lbh {
@@ -171,10 +173,14 @@ std::vector<int32_t> FarthestPointSample(const float* xyz, int n, int k) {
   return out;
 }
 
-ApResult AveragePrecision3D(float iou_threshold, const float* gt_bbox, const int32_t* gt_imageid,
-                            const int32_t* gt_ignore, int n, const float* pd_bbox,
-                            const int32_t* pd_imageid, const int32_t* pd_ignore,
-                            const float* pd_score, int m, int num_recall_points, bool kitti) {
+namespace {
+
+// Shared matcher / PR-curve integration; `iou(j, g)` scores prediction j against box g.
+template <class IouFn>
+ApResult AveragePrecisionImpl(float iou_threshold, IouFn iou_of, const int32_t* gt_imageid,
+                              const int32_t* gt_ignore, int n, const int32_t* pd_imageid,
+                              const int32_t* pd_ignore, const float* pd_score, int m,
+                              int num_recall_points, bool kitti) {
   ApResult res;
   res.score_and_hit.assign(static_cast<size_t>(m) * 2, 0.f);
   res.precision_recall.assign(static_cast<size_t>(num_recall_points) * 2, 0.f);
@@ -202,7 +208,7 @@ ApResult AveragePrecision3D(float iou_threshold, const float* gt_bbox, const int
     auto it = by_image.find(pd_imageid[j]);
     if (it != by_image.end()) {
       for (int g : it->second) {
-        const float iou = Iou3D(pd_bbox + 7 * j, gt_bbox + 7 * g);
+        const float iou = iou_of(j, g);
         if (iou < iou_threshold) continue;
         if (gt_ignore[g] == 2) {
           touches_ignore_all = true;
@@ -254,7 +260,7 @@ ApResult AveragePrecision3D(float iou_threshold, const float* gt_bbox, const int
   } else {
     double area = 0, prev_r = 0;
     for (size_t i = 0; i < k; ++i) {
-      if (i + 1 < k && rec[i + 1] == rec[i]) continue;
+      if (i > 0 && rec[i] == rec[i - 1]) continue;   // first entry at a recall has the max precision
       area += (rec[i] - prev_r) * prec[i];
       prev_r = rec[i];
     }
@@ -266,6 +272,180 @@ ApResult AveragePrecision3D(float iou_threshold, const float* gt_bbox, const int
     res.precision_recall[2 * i + 1] = prec_at(r) > 0.f ? r : 0.f;
   }
   return res;
+}
+
+}  // namespace
+
+ApResult AveragePrecision3D(float iou_threshold, const float* gt_bbox, const int32_t* gt_imageid,
+                            const int32_t* gt_ignore, int n, const float* pd_bbox,
+                            const int32_t* pd_imageid, const int32_t* pd_ignore,
+                            const float* pd_score, int m, int num_recall_points, bool kitti) {
+  return AveragePrecisionImpl(
+      iou_threshold, [&](int j, int g) { return Iou3D(pd_bbox + 7 * j, gt_bbox + 7 * g); },
+      gt_imageid, gt_ignore, n, pd_imageid, pd_ignore, pd_score, m, num_recall_points, kitti);
+}
+
+float Iou2D(const float* a, const float* b) {
+  const float ih = std::min(a[2], b[2]) - std::max(a[0], b[0]);
+  const float iw = std::min(a[3], b[3]) - std::max(a[1], b[1]);
+  if (ih <= 0.f || iw <= 0.f) return 0.f;
+  const float inter = ih * iw;
+  const float ua = std::max(a[2] - a[0], 0.f) * std::max(a[3] - a[1], 0.f) +
+                   std::max(b[2] - b[0], 0.f) * std::max(b[3] - b[1], 0.f) - inter;
+  return ua > 0.f ? inter / ua : 0.f;
+}
+
+ApResult AveragePrecision2D(float iou_threshold, const float* gt_bbox, const int32_t* gt_imageid,
+                            const int32_t* gt_ignore, int n, const float* pd_bbox,
+                            const int32_t* pd_imageid, const int32_t* pd_ignore,
+                            const float* pd_score, int m, int num_recall_points, bool kitti) {
+  return AveragePrecisionImpl(
+      iou_threshold, [&](int j, int g) { return Iou2D(pd_bbox + 4 * j, gt_bbox + 4 * g); },
+      gt_imageid, gt_ignore, n, pd_imageid, pd_ignore, pd_score, m, num_recall_points, kitti);
+}
+
+// ------------------------------------------------------------- point sampling ----
+namespace {
+
+inline float Dist2(const float* a, const float* b) {
+  const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  return dx * dx + dy * dy + dz * dz;
+}
+
+// Uniform spatial hash over the valid points: cell edge = max_dist, so a ball query only
+// has to visit the 27 cells around the centre.
+class CellGrid {
+ public:
+  CellGrid(const float* pts, int dims, const std::vector<int>& ids, float cell)
+      : pts_(pts), dims_(dims), inv_(1.f / cell) {
+    cells_.reserve(ids.size());
+    for (int i : ids) cells_[Key(pts_ + static_cast<size_t>(i) * dims_, 0, 0, 0)].push_back(i);
+  }
+  template <class F>
+  void ForEachNear(const float* c, F&& f) const {
+    for (int dx = -1; dx <= 1; ++dx)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dz = -1; dz <= 1; ++dz) {
+          auto it = cells_.find(Key(c, dx, dy, dz));
+          if (it == cells_.end()) continue;
+          for (int i : it->second) f(i);
+        }
+  }
+
+ private:
+  uint64_t Key(const float* p, int dx, int dy, int dz) const {
+    const int64_t x = static_cast<int64_t>(std::floor(p[0] * inv_)) + dx;
+    const int64_t y = static_cast<int64_t>(std::floor(p[1] * inv_)) + dy;
+    const int64_t z = static_cast<int64_t>(std::floor(p[2] * inv_)) + dz;
+    return (static_cast<uint64_t>(x & 0x1FFFFF) << 42) | (static_cast<uint64_t>(y & 0x1FFFFF) << 21) |
+           static_cast<uint64_t>(z & 0x1FFFFF);
+  }
+  const float* pts_;
+  int dims_;
+  float inv_;
+  std::unordered_map<uint64_t, std::vector<int>> cells_;
+};
+
+}  // namespace
+
+SampleResult SamplePoints(const float* pts, const float* padding, int n, int dims, int num_seeded,
+                          const SampleOptions& o) {
+  SampleResult r;
+  const int m = o.num_centers, k = o.num_neighbors;
+  r.center.assign(m, 0);
+  r.center_padding.assign(m, 1.f);
+  r.indices.assign(static_cast<size_t>(m) * k, 0);
+  r.indices_padding.assign(static_cast<size_t>(m) * k, 1.f);
+  if (n <= 0 || m <= 0) return r;
+  num_seeded = std::max(0, std::min(num_seeded, n));
+  std::mt19937_64 rng(o.seed >= 0 ? static_cast<uint64_t>(o.seed) : std::random_device{}());
+  auto P = [&](int i) { return pts + static_cast<size_t>(i) * dims; };
+
+  // --- centre selection -------------------------------------------------------
+  std::vector<int> cand;                  // may become a centre
+  std::vector<int> members;               // may become a neighbour
+  for (int i = num_seeded; i < n; ++i) {
+    if (padding[i] > 0.5f) continue;
+    members.push_back(i);
+    const float z = P(i)[2];
+    if (z >= o.center_z_min && z <= o.center_z_max) cand.push_back(i);
+  }
+  std::vector<int> centers;
+  if (!o.farthest) {
+    std::shuffle(cand.begin(), cand.end(), rng);
+    centers.assign(cand.begin(), cand.begin() + std::min<size_t>(m, cand.size()));
+  } else if (!cand.empty()) {
+    // min squared distance to everything chosen so far; unseeded runs start at a random point
+    std::vector<float> far(cand.size(), std::numeric_limits<float>::max());
+    int next = static_cast<int>(rng() % cand.size());
+    if (num_seeded > 0) {
+      float best = -1.f;
+      for (size_t c = 0; c < cand.size(); ++c) {
+        for (int s = 0; s < num_seeded; ++s) far[c] = std::min(far[c], Dist2(P(cand[c]), P(s)));
+        if (far[c] > best) {
+          best = far[c];
+          next = static_cast<int>(c);
+        }
+      }
+    }
+    const int want = std::min<int>(m, static_cast<int>(cand.size()));
+    for (int s = 0; s < want; ++s) {
+      const int cur = cand[next];
+      centers.push_back(cur);
+      far[next] = -1.f;                    // never picked twice
+      float best = -1.f;
+      for (size_t c = 0; c < cand.size(); ++c) {
+        if (far[c] < 0.f) continue;
+        far[c] = std::min(far[c], Dist2(P(cand[c]), P(cur)));
+        if (far[c] > best) {
+          best = far[c];
+          next = static_cast<int>(c);
+        }
+      }
+      if (best < 0.f) break;
+    }
+  }
+
+  // --- neighbourhoods -----------------------------------------------------------
+  const bool bounded = o.max_dist > 0.f && o.max_dist < 1e18f;
+  const float max_d2 = bounded ? o.max_dist * o.max_dist : std::numeric_limits<float>::max();
+  const bool hash = bounded && (o.use_hash || members.size() > 2048);
+  std::unique_ptr<CellGrid> grid;
+  if (hash) grid.reset(new CellGrid(pts, dims, members, o.max_dist));
+  std::vector<std::pair<float, int>> near;
+  for (size_t ci = 0; ci < centers.size(); ++ci) {
+    const int c = centers[ci];
+    r.center[ci] = c;
+    r.center_padding[ci] = 0.f;
+    near.clear();
+    auto visit = [&](int i) {
+      const float d = Dist2(P(i), P(c));
+      if (d <= max_d2) near.emplace_back(d, i);
+    };
+    if (hash) {
+      grid->ForEachNear(P(c), visit);
+    } else {
+      for (int i : members) visit(i);
+    }
+    const int take = std::min<int>(k, static_cast<int>(near.size()));
+    if (o.closest) {
+      std::partial_sort(near.begin(), near.begin() + take, near.end());
+    } else {
+      // uniform without replacement: partial Fisher–Yates (order made canonical first so the
+      // hash and brute-force paths draw the same sample for a given seed)
+      std::sort(near.begin(), near.end(),
+                [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.second < b.second; });
+      for (int j = 0; j < take; ++j) {
+        const size_t pick = j + rng() % (near.size() - j);
+        std::swap(near[j], near[pick]);
+      }
+    }
+    for (int j = 0; j < take; ++j) {
+      r.indices[ci * k + j] = near[j].second;
+      r.indices_padding[ci * k + j] = 0.f;
+    }
+  }
+  return r;
 }
 
 }  // namespace lbh

@@ -51,4 +51,39 @@ ApResult AveragePrecision3D(float iou_threshold, const float* gt_bbox, const int
                             const int32_t* pd_imageid, const int32_t* pd_ignore,
                             const float* pd_score, int m, int num_recall_points, bool kitti);
 
+// Same protocol for axis-aligned image boxes (ymin, xmin, ymax, xmax) — re-design of
+// `image_metrics.cc`.
+float Iou2D(const float* a, const float* b);
+ApResult AveragePrecision2D(float iou_threshold, const float* gt_bbox, const int32_t* gt_imageid,
+                            const int32_t* gt_ignore, int n, const float* pd_bbox,
+                            const int32_t* pd_imageid, const int32_t* pd_ignore,
+                            const float* pd_score, int m, int num_recall_points, bool kitti);
+
+// Point-cloud sampling for one scene (re-design of `ps_utils.cc` / `sampling_ops.cc`):
+// picks `num_centers` centres (uniform without replacement, or farthest-point; only
+// un-padded points with z in [center_z_min, center_z_max] qualify) and for each centre up
+// to `num_neighbors` un-padded points within `max_dist` (the `closest` ones, or a uniform
+// sample). The first `num_seeded` points count as already-chosen centres for the
+// farthest-point criterion but are never emitted as centres or neighbours.
+// use_hash: answer ball queries from a uniform grid of edge max_dist instead of a scan
+// (picked automatically for large scenes).
+struct SampleOptions {
+  bool farthest = true;
+  bool closest = true;
+  bool use_hash = false;
+  int num_centers = 0;
+  int num_neighbors = 0;
+  float center_z_min = -3.4e38f, center_z_max = 3.4e38f;
+  float max_dist = 3.4e38f;
+  int64_t seed = -1;
+};
+struct SampleResult {
+  std::vector<int32_t> center;           // [M]
+  std::vector<float> center_padding;     // [M]
+  std::vector<int32_t> indices;          // [M, K]
+  std::vector<float> indices_padding;    // [M, K]
+};
+SampleResult SamplePoints(const float* points, const float* padding, int n, int dims,
+                          int num_seeded, const SampleOptions& o);
+
 }  // namespace lbh

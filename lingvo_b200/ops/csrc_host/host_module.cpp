@@ -307,7 +307,29 @@ PYBIND11_MODULE(_H, m) {
       .def_property_readonly("unk_id", &VocabTokenizer::unk_id)
       .def_property_readonly("sos_id", &VocabTokenizer::sos_id)
       .def_property_readonly("eos_id", &VocabTokenizer::eos_id)
+      .def("join_ids", &VocabTokenizer::JoinIds, py::arg("ids"), py::arg("separator") = "")
+      .def("__contains__", &VocabTokenizer::Contains)
       .def("__len__", &VocabTokenizer::size);
+  py::class_<MlPerfSubword>(m, "MlPerfSubword")
+      .def(py::init<const std::string&>(), py::arg("vocab_path"))
+      .def(py::init<const std::vector<std::string>&>(), py::arg("lines"))
+      .def("decode", &MlPerfSubword::Decode)
+      .def("__len__", &MlPerfSubword::size);
+  py::class_<StaticMap<int64_t, int64_t>>(m, "StaticMapIntInt")
+      .def(py::init<const std::vector<int64_t>&, const std::vector<int64_t>&, int64_t>(),
+           py::arg("keys"), py::arg("vals") = std::vector<int64_t>(), py::arg("unk") = -1)
+      .def("lookup", &StaticMap<int64_t, int64_t>::Lookup)
+      .def("__len__", &StaticMap<int64_t, int64_t>::size);
+  py::class_<StaticMap<int64_t, std::string>>(m, "StaticMapIntString")
+      .def(py::init<const std::vector<int64_t>&, const std::vector<std::string>&, std::string>(),
+           py::arg("keys"), py::arg("vals"), py::arg("unk") = "")
+      .def("lookup", &StaticMap<int64_t, std::string>::Lookup)
+      .def("__len__", &StaticMap<int64_t, std::string>::size);
+  py::class_<StaticMap<std::string, int64_t>>(m, "StaticMapStringInt")
+      .def(py::init<const std::vector<std::string>&, const std::vector<int64_t>&, int64_t>(),
+           py::arg("keys"), py::arg("vals") = std::vector<int64_t>(), py::arg("unk") = -1)
+      .def("lookup", &StaticMap<std::string, int64_t>::Lookup)
+      .def("__len__", &StaticMap<std::string, int64_t>::size);
   py::class_<BpeTokenizer>(m, "BpeTokenizer")
       .def(py::init<const std::string&, const std::string&>(), py::arg("codes_path"),
            py::arg("vocab_path"))
@@ -331,6 +353,60 @@ PYBIND11_MODULE(_H, m) {
         },
         py::arg("src_actual_seq_len"), py::arg("tgt_actual_seq_len"), py::arg("packed_batch_size"),
         py::arg("packed_src_seq_len"), py::arg("packed_tgt_seq_len"), py::arg("seed") = 0);
+  // Gathers [N, T, …] rows into the packed [B, L, …] layout (any dtype: rows move as bytes).
+  m.def("apply_packing",
+        [](py::array inputs, py::array padding,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> seg,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> idx) {
+          if (inputs.ndim() < 2) throw std::invalid_argument("apply_packing: inputs must be [N, T, ...]");
+          if (!(inputs.flags() & py::array::c_style)) throw std::invalid_argument("apply_packing: inputs must be C-contiguous");
+          if (seg.ndim() != 2 || idx.ndim() != 2 || seg.shape(0) != idx.shape(0) || seg.shape(1) != idx.shape(1))
+            throw std::invalid_argument("apply_packing: segment_ids / indices_in_input must both be [B, L]");
+          const int64_t n = inputs.shape(0), t = inputs.shape(1), b = seg.shape(0), l = seg.shape(1);
+          size_t inner = static_cast<size_t>(inputs.itemsize());
+          std::vector<py::ssize_t> shape{b, l};
+          for (int d = 2; d < inputs.ndim(); ++d) {
+            inner *= static_cast<size_t>(inputs.shape(d));
+            shape.push_back(inputs.shape(d));
+          }
+          if (static_cast<size_t>(padding.nbytes()) != static_cast<size_t>(inputs.itemsize()))
+            throw std::invalid_argument("apply_packing: padding must be one element of the input dtype");
+          py::array out(inputs.dtype(), shape);
+          char* o = static_cast<char*>(out.mutable_data());
+          const char* in = static_cast<const char*>(inputs.data());
+          const char* pad = static_cast<const char*>(padding.data());
+          const size_t isz = static_cast<size_t>(inputs.itemsize());
+          const int32_t* sp = seg.data();
+          const int32_t* ip = idx.data();
+          std::string err;
+          {
+            py::gil_scoped_release rel;
+            for (int64_t r = 0; r < b && err.empty(); ++r) {
+              int32_t prev_seg = 0, prev_idx = -1;
+              int64_t run = 0;
+              for (int64_t c = 0; c < l; ++c) {
+                char* dst = o + (r * l + c) * inner;
+                const int32_t sg = sp[r * l + c], ix = ip[r * l + c];
+                if (sg <= 0) {
+                  for (size_t k = 0; k < inner; k += isz) memcpy(dst + k, pad, isz);
+                  prev_seg = 0;
+                  continue;
+                }
+                run = (sg == prev_seg && ix == prev_idx) ? run + 1 : 0;
+                prev_seg = sg;
+                prev_idx = ix;
+                if (ix < 0 || ix >= n || run >= t) {
+                  err = "apply_packing: index out of range at row " + std::to_string(r);
+                  break;
+                }
+                memcpy(dst, in + (static_cast<size_t>(ix) * t + run) * inner, inner);
+              }
+            }
+          }
+          if (!err.empty()) throw std::out_of_range(err);
+          return out;
+        },
+        py::arg("inputs"), py::arg("padding"), py::arg("segment_ids"), py::arg("indices_in_input"));
   m.def("pack_single_sequence",
         [](py::array_t<int32_t, py::array::c_style | py::array::forcecast> lens, int cap,
            bool sequential) { return PackSingleSequence(ToVec(lens), cap, sequential); },
@@ -414,6 +490,94 @@ PYBIND11_MODULE(_H, m) {
         py::arg("groundtruth_ignore"), py::arg("prediction_bbox"), py::arg("prediction_imageid"),
         py::arg("prediction_ignore"), py::arg("prediction_score"),
         py::arg("num_recall_points") = 1, py::arg("algorithm") = "KITTI");
+  m.def("average_precision_2d",
+        [](float iou_threshold, FArr gt_bbox, py::array_t<int32_t, py::array::c_style | py::array::forcecast> gt_imageid,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> gt_ignore, FArr pd_bbox,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> pd_imageid,
+           py::array_t<int32_t, py::array::c_style | py::array::forcecast> pd_ignore, FArr pd_score,
+           int num_recall_points, const std::string& algorithm) {
+          const int n = static_cast<int>(gt_bbox.shape(0)), k = static_cast<int>(pd_bbox.shape(0));
+          ApResult r;
+          {
+            py::gil_scoped_release rel;
+            r = AveragePrecision2D(iou_threshold, gt_bbox.data(), gt_imageid.data(), gt_ignore.data(),
+                                   n, pd_bbox.data(), pd_imageid.data(), pd_ignore.data(),
+                                   pd_score.data(), k, num_recall_points, algorithm == "KITTI");
+          }
+          py::array_t<float> pr({num_recall_points, 2});
+          memcpy(pr.mutable_data(), r.precision_recall.data(), r.precision_recall.size() * 4);
+          py::array_t<float> sh({k, 2});
+          if (k) memcpy(sh.mutable_data(), r.score_and_hit.data(), r.score_and_hit.size() * 4);
+          return py::make_tuple(r.average_precision, pr, sh);
+        },
+        py::arg("iou_threshold"), py::arg("groundtruth_bbox"), py::arg("groundtruth_imageid"),
+        py::arg("groundtruth_ignore"), py::arg("prediction_bbox"), py::arg("prediction_imageid"),
+        py::arg("prediction_ignore"), py::arg("prediction_score"),
+        py::arg("num_recall_points") = 1, py::arg("algorithm") = "VOC");
+  // Batched point sampling: scenes are independent, so they are spread over threads.
+  m.def("sample_points",
+        [](FArr points, FArr padding, int num_seeded, const std::string& center_selector,
+           const std::string& neighbor_sampler, const std::string& neighbor_algorithm,
+           int num_centers, float center_z_min, float center_z_max, int num_neighbors,
+           float max_distance, int64_t random_seed) {
+          if (points.ndim() != 3 || padding.ndim() != 2)
+            throw std::invalid_argument("sample_points: points [B,N,D>=3], padding [B,N]");
+          const int b = static_cast<int>(points.shape(0)), n = static_cast<int>(points.shape(1)),
+                    d = static_cast<int>(points.shape(2));
+          if (d < 3) throw std::invalid_argument("sample_points: need xyz");
+          if (center_selector != "farthest" && center_selector != "uniform")
+            throw std::invalid_argument("center_selector must be farthest|uniform");
+          if (neighbor_sampler != "closest" && neighbor_sampler != "uniform")
+            throw std::invalid_argument("neighbor_sampler must be closest|uniform");
+          if (neighbor_algorithm != "auto" && neighbor_algorithm != "hash")
+            throw std::invalid_argument("neighbor_algorithm must be auto|hash");
+          SampleOptions o;
+          o.farthest = center_selector == "farthest";
+          o.closest = neighbor_sampler == "closest";
+          o.use_hash = neighbor_algorithm == "hash";
+          o.num_centers = num_centers;
+          o.num_neighbors = num_neighbors;
+          o.center_z_min = center_z_min;
+          o.center_z_max = center_z_max;
+          o.max_dist = max_distance;
+          py::array_t<int32_t> center({b, num_centers}), idx({b, num_centers, num_neighbors});
+          py::array_t<float> cpad({b, num_centers}), ipad({b, num_centers, num_neighbors});
+          const float* pp = points.data();
+          const float* pd = padding.data();
+          int32_t* c_out = center.mutable_data();
+          int32_t* i_out = idx.mutable_data();
+          float* cp_out = cpad.mutable_data();
+          float* ip_out = ipad.mutable_data();
+          {
+            py::gil_scoped_release rel;
+            std::atomic<int> next{0};
+            auto work = [&] {
+              for (int i = next.fetch_add(1); i < b; i = next.fetch_add(1)) {
+                SampleOptions oi = o;
+                oi.seed = random_seed >= 0 ? random_seed + i : -1;
+                SampleResult r = SamplePoints(pp + static_cast<size_t>(i) * n * d,
+                                              pd + static_cast<size_t>(i) * n, n, d, num_seeded, oi);
+                const size_t mk = static_cast<size_t>(num_centers) * num_neighbors;
+                memcpy(c_out + static_cast<size_t>(i) * num_centers, r.center.data(), num_centers * 4);
+                memcpy(cp_out + static_cast<size_t>(i) * num_centers, r.center_padding.data(), num_centers * 4);
+                memcpy(i_out + i * mk, r.indices.data(), mk * 4);
+                memcpy(ip_out + i * mk, r.indices_padding.data(), mk * 4);
+              }
+            };
+            const int nt = std::max(1, std::min<int>(b, static_cast<int>(std::thread::hardware_concurrency())));
+            std::vector<std::thread> ts;
+            for (int t = 1; t < nt; ++t) ts.emplace_back(work);
+            work();
+            for (auto& t : ts) t.join();
+          }
+          return py::make_tuple(center, cpad, idx, ipad);
+        },
+        py::arg("points"), py::arg("points_padding"), py::arg("num_seeded_points") = 0,
+        py::arg("center_selector") = "farthest", py::arg("neighbor_sampler") = "closest",
+        py::arg("neighbor_algorithm") = "auto", py::arg("num_centers") = 1,
+        py::arg("center_z_min") = -3.4e38f, py::arg("center_z_max") = 3.4e38f,
+        py::arg("num_neighbors") = 1, py::arg("max_distance") = 3.4e38f,
+        py::arg("random_seed") = -1);
   m.def("points_to_pillars",
         [](FArr points, float x0, float x1, float y0, float y1, int nx, int ny, int max_pillars,
            int points_per_pillar) {

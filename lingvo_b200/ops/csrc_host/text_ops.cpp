@@ -420,4 +420,97 @@ std::vector<int64_t> RandomPermutationSequence::Next() {
   return out;
 }
 
+// ------------------------------------------------------------ n-gram / MLPerf ----
+std::string VocabTokenizer::JoinIds(const std::vector<int32_t>& ids,
+                                    const std::string& separator) const {
+  std::string out;
+  for (size_t i = 0; i < ids.size(); ++i) {
+    if (i) out += separator;
+    out += IdToToken(ids[i]);
+  }
+  return out;
+}
+
+namespace {
+
+// Decodes the UTF-8 code point at the start of `s` (U+FFFD on malformed input).
+uint32_t FirstCodePoint(const std::string& s) {
+  if (s.empty()) return 0;
+  const auto b = [&](size_t i) { return static_cast<uint32_t>(static_cast<unsigned char>(s[i])); };
+  const uint32_t c = b(0);
+  int extra = c < 0x80 ? 0 : (c >> 5) == 0x6 ? 1 : (c >> 4) == 0xE ? 2 : (c >> 3) == 0x1E ? 3 : -1;
+  if (extra < 0 || s.size() < static_cast<size_t>(extra) + 1) return 0xFFFD;
+  uint32_t cp = extra == 0 ? c : c & (0x3F >> extra);
+  for (int i = 1; i <= extra; ++i) {
+    if ((b(i) & 0xC0) != 0x80) return 0xFFFD;
+    cp = (cp << 6) | (b(i) & 0x3F);
+  }
+  return cp;
+}
+
+// Letter-or-digit test without ICU: ASCII exactly, the rest by Unicode block (letters of
+// the living scripts, CJK, Hangul, full-width forms); punctuation / symbol blocks excluded.
+bool IsAlnumCodePoint(uint32_t cp) {
+  if (cp < 0x80) return std::isalnum(static_cast<int>(cp)) != 0;
+  if (cp == 0xAA || cp == 0xB5 || cp == 0xBA) return true;
+  if (cp >= 0xC0 && cp <= 0x24F) return cp != 0xD7 && cp != 0xF7;
+  struct Range { uint32_t lo, hi; };
+  static const Range kRanges[] = {
+      {0x250, 0x2AF},   {0x370, 0x373},   {0x376, 0x377},   {0x37B, 0x37D},   {0x386, 0x386},
+      {0x388, 0x3FF},   {0x400, 0x481},   {0x48A, 0x52F},   {0x531, 0x556},   {0x561, 0x587},
+      {0x5D0, 0x5EA},   {0x620, 0x64A},   {0x660, 0x669},   {0x671, 0x6D3},   {0x6F0, 0x6FC},
+      {0x904, 0x939},   {0x958, 0x961},   {0x966, 0x96F},   {0x985, 0x9B9},   {0x9E6, 0x9F1},
+      {0xA05, 0xA39},   {0xA85, 0xAB9},   {0xB05, 0xB39},   {0xB85, 0xBB9},   {0xC05, 0xC39},
+      {0xC85, 0xCB9},   {0xD05, 0xD3A},   {0xE01, 0xE30},   {0xE40, 0xE46},   {0xE50, 0xE59},
+      {0x10A0, 0x10FF}, {0x1100, 0x11FF}, {0x1E00, 0x1FFF}, {0x3041, 0x3096}, {0x30A1, 0x30FA},
+      {0x3105, 0x312F}, {0x3400, 0x4DBF}, {0x4E00, 0x9FFF}, {0xAC00, 0xD7A3}, {0xF900, 0xFAFF},
+      {0xFF10, 0xFF19}, {0xFF21, 0xFF3A}, {0xFF41, 0xFF5A}, {0xFF66, 0xFFDC}, {0x20000, 0x2FA1F}};
+  for (const Range& r : kRanges)
+    if (cp >= r.lo && cp <= r.hi) return true;
+  return false;
+}
+
+}  // namespace
+
+MlPerfSubword::MlPerfSubword(const std::string& vocab_path) {
+  std::ifstream f(vocab_path);
+  if (!f) throw std::runtime_error("MlPerfSubword: cannot open " + vocab_path);
+  std::vector<std::string> lines;
+  for (std::string line; std::getline(f, line);) lines.push_back(line);
+  LoadLines(lines);
+}
+
+void MlPerfSubword::LoadLines(const std::vector<std::string>& lines) {
+  for (std::string line : lines) {
+    while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
+    if (line.empty()) continue;
+    if (line.size() < 2) throw std::runtime_error("MlPerfSubword: bad vocab line: " + line);
+    id_to_tok_.push_back(line.substr(1, line.size() - 2));      // drop the quotes
+  }
+}
+
+std::string MlPerfSubword::Decode(const std::vector<int32_t>& ids) const {
+  std::string joined;
+  for (int32_t id : ids) {
+    if (id < 0 || static_cast<size_t>(id) >= id_to_tok_.size())
+      throw std::out_of_range("MlPerfSubword: id out of range: " + std::to_string(id));
+    joined += id_to_tok_[id];
+  }
+  std::string out;
+  bool prev_alnum = false, first = true;
+  size_t start = 0;
+  while (true) {
+    const size_t end = joined.find('_', start);
+    const std::string tok = joined.substr(start, end == std::string::npos ? end : end - start);
+    const bool alnum = IsAlnumCodePoint(FirstCodePoint(tok));
+    if (!first && prev_alnum && alnum) out += ' ';
+    out += tok;
+    prev_alnum = alnum;
+    first = false;
+    if (end == std::string::npos) break;
+    start = end + 1;
+  }
+  return out;
+}
+
 }  // namespace lbh

@@ -8,7 +8,9 @@
 #include <cstdint>
 #include <map>
 #include <random>
+#include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -38,6 +40,9 @@ class VocabTokenizer {
   const std::string& IdToToken(int32_t id) const;
   std::vector<int32_t> StringToIds(const std::string& text) const;
   std::string IdsToString(const std::vector<int32_t>& ids) const;
+  // N-gram vocabularies: concatenates the tokens with `separator` (ref `NgramIdToToken`).
+  std::string JoinIds(const std::vector<int32_t>& ids, const std::string& separator) const;
+  bool Contains(const std::string& tok) const { return tok_to_id_.count(tok) > 0; }
   int32_t unk_id() const { return unk_id_; }
   int32_t sos_id() const { return sos_id_; }
   int32_t eos_id() const { return eos_id_; }
@@ -64,6 +69,53 @@ class BpeTokenizer {
   std::unordered_map<std::string, int32_t> tok_to_id_;
   std::vector<std::string> id_to_tok_;
   int32_t unk_id_ = 0;
+};
+
+// ---- MLPerf transformer sub-word vocabulary: one quoted sub-token per line; '_' ends a
+// token. Decoding joins the sub-tokens, splits on '_' and re-inserts a blank between two
+// neighbouring tokens that both start with a letter or digit (ref `ml_perf_subword_op.cc`).
+class MlPerfSubword {
+ public:
+  explicit MlPerfSubword(const std::string& vocab_path);
+  explicit MlPerfSubword(const std::vector<std::string>& lines) { LoadLines(lines); }
+  std::string Decode(const std::vector<int32_t>& ids) const;
+  size_t size() const { return id_to_tok_.size(); }
+
+ private:
+  void LoadLines(const std::vector<std::string>& lines);
+  std::vector<std::string> id_to_tok_;
+};
+
+// ---- immutable lookup tables with a default (ref `static_map_op.cc`) ----
+template <class K, class V>
+class StaticMap {
+ public:
+  StaticMap(const std::vector<K>& keys, const std::vector<V>& vals, V unk) : unk_(std::move(unk)) {
+    if (!vals.empty() && vals.size() != keys.size())
+      throw std::invalid_argument("StaticMap: keys / vals size mismatch");
+    map_.reserve(keys.size());
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (!map_.emplace(keys[i], vals.empty() ? Default(i) : vals[i]).second)
+        throw std::invalid_argument("StaticMap: duplicate key");
+  }
+  std::vector<V> Lookup(const std::vector<K>& xs) const {
+    std::vector<V> out;
+    out.reserve(xs.size());
+    for (const K& x : xs) {
+      auto it = map_.find(x);
+      out.push_back(it == map_.end() ? unk_ : it->second);
+    }
+    return out;
+  }
+  size_t size() const { return map_.size(); }
+
+ private:
+  static V Default(size_t i) {
+    if constexpr (std::is_integral<V>::value) return static_cast<V>(i);
+    else throw std::invalid_argument("StaticMap: vals required for non-integer values");
+  }
+  std::unordered_map<K, V> map_;
+  V unk_;
 };
 
 // ---- packing ----
