@@ -134,7 +134,7 @@ def BuildHost(force: bool = False, verbose: bool = True) -> str:
 
   with concurrent.futures.ThreadPoolExecutor(len(srcs)) as ex:
     objs = list(ex.map(_One, srcs))
-  cmd = ['g++', '-shared', '-pthread', '-o', HOST_TARGET + '.tmp', *objs]
+  cmd = ['g++', '-shared', '-pthread', '-o', HOST_TARGET + '.tmp', *objs, '-lz']
   r = subprocess.run(cmd, capture_output=True, text=True)
   if r.returncode != 0:
     raise RuntimeError('link failed:\n' + r.stdout + r.stderr)

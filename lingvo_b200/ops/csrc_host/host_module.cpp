@@ -6,6 +6,7 @@
 #include <pybind11/stl.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -66,7 +67,13 @@ class RecordBatcher {
     {
       py::gil_scoped_release rel;
       std::unique_lock<std::mutex> l(mu_);
-      cv_ready_.wait(l, [&] { return stop_ || !ready_.empty() || live_workers_ == 0; });
+      {
+        // time the consumer spends starved: the input pipeline is the bottleneck
+        const auto t0 = std::chrono::steady_clock::now();
+        cv_ready_.wait(l, [&] { return stop_ || !ready_.empty() || live_workers_ == 0; });
+        consumer_wait_us_ += std::chrono::duration_cast<std::chrono::microseconds>(
+                                 std::chrono::steady_clock::now() - t0).count();
+      }
       if (!error_.empty()) {
         std::string e = error_;
         l.unlock();
@@ -94,6 +101,20 @@ class RecordBatcher {
 
   int64_t records_skipped() const { return skipped_.load(); }
   int64_t records_processed() const { return processed_.load(); }
+  // Wait-time diagnostics (the reference logs these from `record_debug.cc`).
+  py::dict Stats() {
+    std::lock_guard<std::mutex> l(mu_);
+    py::dict d;
+    d["records_processed"] = processed_.load();
+    d["records_skipped"] = skipped_.load();
+    d["batches_ready"] = static_cast<int64_t>(ready_.size());
+    d["consumer_wait_s"] = consumer_wait_us_ * 1e-6;
+    d["producer_wait_s"] = producer_wait_us_ * 1e-6;
+    d["hint"] = consumer_wait_us_ > 2 * producer_wait_us_
+                    ? "consumer starved: raise num_threads / file parallelism or speed up the processor"
+                    : "producers blocked: batches are consumed slower than they are made";
+    return d;
+  }
 
  private:
   struct Sample {
@@ -138,7 +159,13 @@ class RecordBatcher {
         continue;
       }
       const size_t bi = static_cast<size_t>(it - bounds_.begin());
-      cv_space_.wait(l, [&] { return stop_ || ready_.size() < 4; });
+      {
+        // time producers spend blocked on a full queue: the trainer is the bottleneck
+        const auto t0 = std::chrono::steady_clock::now();
+        cv_space_.wait(l, [&] { return stop_ || ready_.size() < 4; });
+        producer_wait_us_ += std::chrono::duration_cast<std::chrono::microseconds>(
+                                 std::chrono::steady_clock::now() - t0).count();
+      }
       if (stop_) break;
       buckets_[bi].push_back(std::move(s));
       if (static_cast<int64_t>(buckets_[bi].size()) >= limits_[bi]) {
@@ -219,6 +246,7 @@ class RecordBatcher {
   int live_workers_ = 0;
   std::atomic<bool> stop_{false}, closed_{false};
   std::atomic<int64_t> skipped_{0}, processed_{0};
+  int64_t consumer_wait_us_ = 0, producer_wait_us_ = 0;   // guarded by mu_
   std::string error_;
 };
 
@@ -290,7 +318,8 @@ PYBIND11_MODULE(_H, m) {
       .def("get_next", &RecordBatcher::GetNext)
       .def("close", &RecordBatcher::Close)
       .def_property_readonly("records_skipped", &RecordBatcher::records_skipped)
-      .def_property_readonly("records_processed", &RecordBatcher::records_processed);
+      .def_property_readonly("records_processed", &RecordBatcher::records_processed)
+      .def("stats", &RecordBatcher::Stats);
 
   // ---- tokenizers ----
   m.def("ascii_to_ids", [](const std::string& s) { return AsciiTokenizer::Get().StringToIds(s); });

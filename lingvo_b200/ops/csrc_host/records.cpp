@@ -1,5 +1,7 @@
 #include "records.h"
 
+#include <zlib.h>
+
 #include <glob.h>
 
 #include <algorithm>
@@ -51,12 +53,25 @@ uint32_t Crc32c(const char* data, size_t n, uint32_t crc) {
   return ~c;
 }
 
+// "base@N" names N shards "base-?????-of-0000N"; "base@*" any shard count.
+std::string ExpandShardSpec(const std::string& item) {
+  const size_t at = item.rfind('@');
+  if (at == std::string::npos || at + 1 >= item.size()) return item;
+  const std::string n = item.substr(at + 1);
+  if (n == "*") return item.substr(0, at) + "-?????-of-?????";
+  if (n.find_first_not_of("0123456789") != std::string::npos) return item;
+  char buf[16];
+  snprintf(buf, sizeof(buf), "%05d", std::stoi(n));
+  return item.substr(0, at) + "-?????-of-" + buf;
+}
+
 std::vector<std::string> GlobFiles(const std::string& pattern) {
   std::vector<std::string> out;
   std::stringstream ss(pattern);
   std::string item;
   while (std::getline(ss, item, ',')) {
     if (item.empty()) continue;
+    item = ExpandShardSpec(item);
     glob_t g;
     if (glob(item.c_str(), 0, nullptr, &g) == 0) {
       for (size_t i = 0; i < g.gl_pathc; ++i) out.emplace_back(g.gl_pathv[i]);
@@ -105,6 +120,48 @@ class TFRecordIterator : public RecordIterator {
   std::string name_;
 };
 
+// TFRecord framing inside a gzip stream ("tfrecord_gzip:").
+class GzTFRecordIterator : public RecordIterator {
+ public:
+  explicit GzTFRecordIterator(const std::string& file) : f_(gzopen(file.c_str(), "rb")), name_(file) {
+    if (!f_) throw std::runtime_error("cannot open " + file);
+    gzbuffer(f_, 1 << 20);
+  }
+  ~GzTFRecordIterator() override {
+    if (f_) gzclose(f_);
+  }
+  bool Next(std::string* out) override {
+    char hdr[12];
+    const int got = gzread(f_, hdr, 12);
+    if (got == 0) return false;
+    if (got != 12) throw std::runtime_error("truncated tfrecord header in " + name_);
+    uint64_t len;
+    uint32_t len_crc;
+    memcpy(&len, hdr, 8);
+    memcpy(&len_crc, hdr + 8, 4);
+    if (MaskCrc(Crc32c(hdr, 8)) != len_crc) throw std::runtime_error("corrupt length crc in " + name_);
+    out->resize(len);
+    size_t done = 0;
+    while (done < len) {                               // gzread takes an unsigned int
+      const unsigned want = static_cast<unsigned>(std::min<uint64_t>(len - done, 1u << 30));
+      const int r = gzread(f_, out->data() + done, want);
+      if (r <= 0) throw std::runtime_error("truncated tfrecord payload in " + name_);
+      done += static_cast<size_t>(r);
+    }
+    char foot[4];
+    if (gzread(f_, foot, 4) != 4) throw std::runtime_error("truncated tfrecord payload in " + name_);
+    uint32_t data_crc;
+    memcpy(&data_crc, foot, 4);
+    if (MaskCrc(Crc32c(out->data(), len)) != data_crc)
+      throw std::runtime_error("corrupt data crc in " + name_);
+    return true;
+  }
+
+ private:
+  gzFile f_;
+  std::string name_;
+};
+
 class TextLineIterator : public RecordIterator {
  public:
   explicit TextLineIterator(const std::string& file) : in_(file) {
@@ -140,8 +197,54 @@ void SplitPattern(const std::string& fp, std::string* type, std::string* glob) {
   }
 }
 
+// "text_indirect:<dir>/ckpt": the file is a text-format VersionedFileSet
+//   current { file_pattern: "rel/a@8" file_pattern: "rel/b*" create_timestamp: … } history { … }
+// and the data are the `current` patterns, relative to the directory of the ckpt file.
+std::vector<std::string> IndirectPatterns(const std::string& ckpt) {
+  std::ifstream in(ckpt);
+  if (!in) throw std::runtime_error("cannot open fileset " + ckpt);
+  std::stringstream buf;
+  buf << in.rdbuf();
+  const std::string text = buf.str();
+  const size_t cur = text.find("current");
+  if (cur == std::string::npos) throw std::runtime_error("no `current` fileset in " + ckpt);
+  const size_t open = text.find('{', cur);
+  if (open == std::string::npos) throw std::runtime_error("malformed fileset " + ckpt);
+  int depth = 0;
+  size_t close = open;
+  for (; close < text.size(); ++close) {
+    if (text[close] == '{') ++depth;
+    if (text[close] == '}' && --depth == 0) break;
+  }
+  const std::string body = text.substr(open + 1, close - open - 1);
+  const size_t slash = ckpt.rfind('/');
+  const std::string dir = slash == std::string::npos ? std::string() : ckpt.substr(0, slash + 1);
+  std::vector<std::string> out;
+  size_t pos = 0;
+  while ((pos = body.find("file_pattern", pos)) != std::string::npos) {
+    const size_t q0 = body.find_first_of("\"'", pos);
+    if (q0 == std::string::npos) break;
+    const size_t q1 = body.find(body[q0], q0 + 1);
+    if (q1 == std::string::npos) break;
+    const std::string rel = body.substr(q0 + 1, q1 - q0 - 1);
+    out.push_back(!rel.empty() && rel[0] == '/' ? rel : dir + rel);
+    pos = q1 + 1;
+  }
+  if (out.empty()) throw std::runtime_error("fileset " + ckpt + " lists no file_pattern");
+  return out;
+}
+
 std::vector<std::string> ExpandFiles(const std::string& type, const std::string& glob) {
   if (type == "iota") return {glob};
+  if (type == "text_indirect") {
+    std::vector<std::string> files;
+    for (const std::string& pat : IndirectPatterns(glob)) {
+      auto more = GlobFiles(pat);
+      if (more.empty()) throw std::runtime_error("no files match " + pat);
+      files.insert(files.end(), more.begin(), more.end());
+    }
+    return files;
+  }
   auto files = GlobFiles(glob);
   if (files.empty()) throw std::runtime_error("no files match " + glob);
   return files;
@@ -152,7 +255,8 @@ std::vector<std::string> ExpandFiles(const std::string& type, const std::string&
 std::unique_ptr<RecordIterator> RecordIterator::Create(const std::string& type,
                                                        const std::string& file) {
   if (type == "tfrecord") return std::make_unique<TFRecordIterator>(file);
-  if (type == "text") return std::make_unique<TextLineIterator>(file);
+  if (type == "tfrecord_gzip") return std::make_unique<GzTFRecordIterator>(file);
+  if (type == "text" || type == "text_indirect") return std::make_unique<TextLineIterator>(file);
   if (type == "iota") return std::make_unique<IotaIterator>(file);
   throw std::runtime_error("unknown record type '" + type + "'");
 }

@@ -193,3 +193,101 @@ def test_shampoo_async_preconditioning_trains():
     opt.Apply(0.1, [py_utils.VarGrad(w, g)])
     losses.append(float(loss))
   assert losses[-1] < 0.2 * losses[0]
+
+
+def _WriteGz(path, recs):
+  import gzip, struct
+  h = ops.host()
+  with gzip.open(path, 'wb') as f:
+    for r in recs:
+      hdr = struct.pack('<Q', len(r))
+      f.write(hdr + struct.pack('<I', h.masked_crc32c(hdr)) + r + struct.pack('<I', h.masked_crc32c(r)))
+
+
+def _Drain(y):
+  out = []
+  while True:
+    r = y.next()
+    if r is None:
+      return out
+    out.append(r[0])
+
+
+def test_gzip_tfrecords_shard_specs_and_indirect_filesets(tmp_path):
+  h = ops.host()
+  _WriteGz(str(tmp_path / 'z.gz'), [b'alpha', b'beta' * 1000, b''])
+  y = h.sequential_record_yielder('tfrecord_gzip:' + str(tmp_path / 'z.gz'), 1)
+  assert _Drain(y) == [b'alpha', b'beta' * 1000, b'']
+  # sharded spec: data@2 → data-?????-of-00002
+  for i in range(2):
+    w = h.TFRecordWriter(str(tmp_path / ('data-%05d-of-00002' % i)))
+    w.write(b'r%d' % i); w.close()
+  y = h.sequential_record_yielder('tfrecord:' + str(tmp_path / 'data@2'), 1)
+  assert sorted(_Drain(y)) == [b'r0', b'r1']
+  y = h.sequential_record_yielder('tfrecord:' + str(tmp_path / 'data@*'), 1)
+  assert len(_Drain(y)) == 2
+  # text_indirect: a VersionedFileSet text proto next to the data
+  (tmp_path / 'v1.txt').write_text('one\ntwo\n')
+  (tmp_path / 'v0.txt').write_text('old\n')
+  (tmp_path / 'ckpt').write_text(
+      'current {\n  file_pattern: "v1.txt"\n  create_timestamp: 12.5\n}\n'
+      'history { file_pattern: "v0.txt" }\n')
+  y = h.sequential_record_yielder('text_indirect:' + str(tmp_path / 'ckpt'), 1)
+  assert _Drain(y) == [b'one', b'two']
+
+
+def test_record_batcher_wait_stats(tmp_path):
+  h = ops.host()
+  y = h.sequential_record_yielder('iota:50', 1)
+  def Proc(rec, source_id):
+    v = int(rec)
+    return v % 7, [np.array([v], np.int64)]
+  b = h.RecordBatcher(y, Proc, [10], [8], num_threads=2)
+  n = 0
+  while True:
+    try:
+      out = b.get_next()
+    except StopIteration:
+      break
+    n += out[1][0].shape[0] if isinstance(out[1], (list, tuple)) else 1
+  st = b.stats()
+  assert st['records_processed'] == 50 and st['records_skipped'] == 0
+  assert st['consumer_wait_s'] >= 0 and st['producer_wait_s'] >= 0 and isinstance(st['hint'], str)
+  b.close()
+
+
+def test_hypothesis_proto_and_hyp_ops():
+  from lingvo_b200.core import hyps as hyps_lib
+  h = hyps_lib.Hypothesis(beam_id=3, ids=[5, 9, 2], scores=[-0.5, -1.25, -0.125],
+                          atten_vecs=[[0.5, 0.5], [1.0, 0.0], [0.25, 0.75]], normalized_score=-0.75)
+  back = hyps_lib.Hypothesis.FromString(h.SerializeToString())
+  assert back == h
+  # hand-encoded bytes: field 1 varint 3; field 2 packed [5, 9, 2]
+  assert h.SerializeToString().startswith(b'\x08\x03\x12\x03\x05\x09\x02')
+  # two beams × two hyps, three steps; slot 1 terminates at step 2 with path 0 ← 1 ← 1
+  hyps = np.array([[11, 12, 13, 14], [21, 22, 23, 24], [31, 32, 33, 34]], np.int32)
+  prev = np.array([[0, 1, 2, 3], [1, 0, 2, 3], [0, 1, 2, 3]], np.int32)
+  done = np.zeros((3, 4), bool); done[2, 1] = True
+  scores = -np.arange(12, dtype=np.float32).reshape(3, 4)
+  att = np.random.RandomState(0).rand(3, 4, 2).astype(np.float32)
+  eos_scores = np.full((3, 4), -9.0, np.float32)
+  eos_att = np.random.RandomState(1).rand(3, 4, 2).astype(np.float32)
+  out = hyps_lib.HypsFromBeamSearchOuts(hyps, prev, done, scores, att, eos_scores, eos_att,
+                                        eos_id=2, num_hyps_per_beam=2)
+  assert out.shape == (3, 4) and out[0, 0] == b''
+  got = hyps_lib.Hypothesis.FromString(out[2, 1])
+  # step 1 read slot 1 (token 22, parent 0) → step 0 read slot 0 (token 11)
+  assert got.ids == [11, 22, 2] and got.beam_id == 1
+  np.testing.assert_allclose(got.scores, [scores[0, 0], scores[1, 1], -9.0])
+  np.testing.assert_allclose(got.atten_vecs[0], att[0, 0]); np.testing.assert_allclose(got.atten_vecs[2], eos_att[2, 1])
+  ids, lens, sc = hyps_lib.UnpackHyp([out[2, 1], h.SerializeToString(), b''], max_seq_length=4)
+  np.testing.assert_array_equal(ids, [[11, 22, 2, 0], [5, 9, 2, 0], [0, 0, 0, 0]])
+  np.testing.assert_array_equal(lens, [3, 3, 0]); assert sc[1] == -0.75
+
+
+def test_generate_proto_def(tmp_path):
+  from lingvo_b200.tools import generate_proto_def
+  paths = generate_proto_def.Generate(str(tmp_path))
+  assert any(p.endswith('hyps.proto') for p in paths)
+  text = open([p for p in paths if p.endswith('hyps.proto')][0]).read()
+  assert 'repeated int32 ids = 2 [packed = true];' in text
