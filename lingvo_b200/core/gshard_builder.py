@@ -580,8 +580,13 @@ class MoELayer(_BuilderLayer):
           dropout_rate=b.moe_dropout_rate if not self.do_eval else 0.0,
           use_glu=p.gated, activation_name=act)
       return out.reshape(bsz, l, m), aux.float()
-    # Gating logits in fp32: [G,S,M]·[M,E] is tiny (E = 8); keep it exact.
-    logits = torch.matmul(xg.to(ldt), theta.gw.to(ldt))
+    # Gating logits in fp32: [G,S,M]·[M,E] is tiny (E = 8); keep it exact. On the GPU one
+    # streaming kernel reads the bf16 activations directly (no fp32 upcast, no N=8 SGEMM).
+    from lingvo_b200.ops import gate as gate_ops
+    if ldt == torch.float32 and gate_ops.supported(xg, theta.gw):
+      logits = gate_ops.gate_logits(xg, theta.gw)
+    else:
+      logits = torch.matmul(xg.to(ldt), theta.gw.to(ldt))
     ex = self._FusedExchange(x, act)
     if ex is not None:
       cap = gshard_layers.ExpertCapacity(s, b.e_dim, b.c_dim or 0,

@@ -17,6 +17,9 @@ multi-tensor (`torch._foreach_*`) launches or as the fused sm_100a kernels in
 
 from __future__ import annotations
 
+import contextlib
+import os
+
 import math
 import re
 from typing import Dict, List, Optional, Tuple
@@ -509,8 +512,50 @@ class XLAShardingAdafactor(Base):
     p.Define('epsilon1', 1e-30, 'Regularization constant for squared gradient.')
     p.Define('epsilon2', 1e-3, 'Regularization constant for parameter scale.')
     p.Define('fused', True, 'Use the fused sm_100a kernel on CUDA.')
+    p.Define('num_update_streams', 8,
+             'Factored variables are spread round-robin over this many CUDA streams, so that '
+             'the latency-bound kernels of small tensors overlap (also inside a captured '
+             'graph, where the streams become parallel branches). ≤1: single stream.')
     p.name = 'Adafactor'
     return p
+
+  class _Fan:
+    """Fork/join helper: `with fan.On(i):` runs on side stream i % n (after everything already
+    queued on the caller's stream); `Join()` makes the caller's stream wait for all of them."""
+
+    def __init__(self, streams):
+      self._streams = streams
+      self._used = set()
+      if streams:
+        self._main = torch.cuda.current_stream(streams[0].device)
+        self._fork = torch.cuda.Event()
+        self._fork.record(self._main)
+
+    def On(self, i):
+      if not self._streams:
+        return contextlib.nullcontext()
+      k = i % len(self._streams)
+      s = self._streams[k]
+      if k not in self._used:
+        s.wait_event(self._fork)
+        self._used.add(k)
+      return torch.cuda.stream(s)
+
+    def Slot(self, i):
+      return 1 + i % len(self._streams) if self._streams else 0
+
+    def Join(self):
+      for k in sorted(self._used):
+        self._main.wait_stream(self._streams[k])
+      self._used.clear()
+
+  def _UpdateFan(self, device):
+    n = int(os.environ.get('LINGVO_B200_ADAFACTOR_STREAMS', self.params.num_update_streams or 0))
+    if n <= 1 or device.type != 'cuda':
+      return self._Fan([])
+    if getattr(self, '_side_streams', None) is None:
+      self._side_streams = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return self._Fan(self._side_streams)
 
   def _FactoredDims(self, shape):
     p = self.params
@@ -565,6 +610,7 @@ class XLAShardingAdafactor(Base):
     small = []
     self._pre_var_sumsq = None
     self._pre_ep_sumsq = None
+    fan = self._UpdateFan(total.device)
     for var, grad in var_grad_pairs:
       dims = self._FactoredDims(list(var.shape))
       if grad.device == var.device and self._SmallEligible(var, grad, dims):
@@ -574,11 +620,13 @@ class XLAShardingAdafactor(Base):
         continue
       is_ep = bool(getattr(var, 'expert_parallel', False))
       any_ep = any_ep or is_ep
-      fresh = fused.adafactor_stats(var, grad, dims[0], dims[1],
-                                    bool(p.multiply_by_parameter_scale),
-                                    total_ep if is_ep else total)
+      with fan.On(len(handled)):
+        fresh = fused.adafactor_stats(var, grad, dims[0], dims[1],
+                                      bool(p.multiply_by_parameter_scale),
+                                      total_ep if is_ep else total, fan.Slot(len(handled)))
       self._pre[id(var)] = (grad.data_ptr(), fresh)
       handled.add(id(var))
+    fan.Join()
     if any_ep:
       self._pre_ep_sumsq = total_ep
     if small:
@@ -646,6 +694,7 @@ class XLAShardingAdafactor(Base):
     pre = getattr(self, '_pre', {})
     self._pre = {}
     small = []
+    factored = []
     for var, grad in zip(variables, grads):
       dims = self._FactoredDims(list(var.shape))
       if fused is not None and self._SmallEligible(var, grad, dims):
@@ -655,25 +704,33 @@ class XLAShardingAdafactor(Base):
         d0, d1 = dims
         vr_shape = [s for i, s in enumerate(var.shape) if i != d0]
         vc_shape = [s for i, s in enumerate(var.shape) if i != d1]
-        vr = self._Slot(var, 'vr', shape=vr_shape)
-        vc = self._Slot(var, 'vc', shape=vc_shape)
-        done = pre.get(id(var))
-        if done is not None and done[0] == grad.data_ptr():
-          fresh = done[1]                       # statistics already in the scratch
-        else:
-          fresh = fused.adafactor_stats(var, grad, d0, d1, bool(p.multiply_by_parameter_scale))
-        fused.adafactor_update(var, grad, vr, vc, d0, d1, float(lr), decay, p.epsilon1,
-                               p.epsilon2, p.clipping_threshold or 0.0,
-                               bool(p.multiply_by_parameter_scale), self._grad_scale, fresh,
-                               hyper)
-        if getattr(var, 'compute', None) is not None:
-          self._refreshed.add(id(var))
+        # Slots are created (zero-filled) here, on the caller's stream, *before* the side
+        # streams fork: anything enqueued after the fork would race with them.
+        factored.append((var, grad, d0, d1, self._Slot(var, 'vr', shape=vr_shape),
+                         self._Slot(var, 'vc', shape=vc_shape)))
         continue
       if self._grad_scale is not None:
         gs = self._grad_scale
         grad = torch.where(gs == 0, torch.zeros_like(grad),
                            grad * gs.to(grad.dtype))
       self._UpdateOne(var, grad, dims, float(lr), decay)
+    fan = self._UpdateFan(variables[0].device) if factored else None
+    for i, (var, grad, d0, d1, vr, vc) in enumerate(factored):
+      done = pre.get(id(var))
+      with fan.On(i):
+        if done is not None and done[0] == grad.data_ptr():
+          fresh = done[1]                       # statistics already in the scratch
+        else:
+          fresh = fused.adafactor_stats(var, grad, d0, d1, bool(p.multiply_by_parameter_scale),
+                                        None, fan.Slot(i))
+        fused.adafactor_update(var, grad, vr, vc, d0, d1, float(lr), decay, p.epsilon1,
+                               p.epsilon2, p.clipping_threshold or 0.0,
+                               bool(p.multiply_by_parameter_scale), self._grad_scale, fresh,
+                               hyper)
+      if getattr(var, 'compute', None) is not None:
+        self._refreshed.add(id(var))
+    if fan is not None:
+      fan.Join()
     if small:
       self._UpdateSmallFused(fused, float(lr), decay, small)
 

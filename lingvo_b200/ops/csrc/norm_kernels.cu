@@ -116,8 +116,9 @@ norm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   }
 }
 
-// Backward. dscale/dbias partials are kept per-lane for this CTA's rows and
-// flushed once with atomicAdd (fp32).
+// Backward. dscale/dbias partials are kept per-lane for this CTA's rows, folded across the
+// CTA's warps in shared memory and written as one partial row per CTA (`dscale`/`dbias` here
+// are the [grid, dim] partial buffers).
 template <bool kCenter, bool kRegAcc>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 norm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
@@ -125,7 +126,7 @@ norm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
                 const float* __restrict__ scale, const float* __restrict__ stats,
                 __nv_bfloat16* __restrict__ dx, float* __restrict__ dscale,
                 float* __restrict__ dbias, int rows, int dim) {
-  extern __shared__ float smem[];   // [2][dim] accumulators for the CTA
+  extern __shared__ __align__(16) float smem[];   // [2][dim] accumulators for the CTA
   float* acc_s = smem;
   float* acc_b = smem + dim;
   for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) smem[i] = 0.f;
@@ -203,23 +204,65 @@ norm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
     }
   }
   if constexpr (kRegAcc) {
+    // Fold the 8 warps' register tiles into the CTA accumulators one warp at a time: every
+    // lane owns distinct columns, so plain 128-bit read-modify-writes suffice (shared-memory
+    // fp32 atomics are CAS spin loops and all 8 warps would hit the same addresses).
+    for (int w = 0; w < kWarpsPerCta; ++w) {
+      if (warp == w) {
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      const int c = lane * 8 + 256 * a;
-      if (c < dim) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (dscale) atomicAdd(&acc_s[c + i], racc_s[a][i]);
-          if (kCenter && dbias) atomicAdd(&acc_b[c + i], racc_b[a][i]);
+        for (int a = 0; a < 8; ++a) {
+          const int c = lane * 8 + 256 * a;
+          if (c < dim) {
+            if (dscale) {
+              float4* q = reinterpret_cast<float4*>(acc_s + c);
+              float4 lo = q[0], hi = q[1];
+              lo.x += racc_s[a][0]; lo.y += racc_s[a][1]; lo.z += racc_s[a][2]; lo.w += racc_s[a][3];
+              hi.x += racc_s[a][4]; hi.y += racc_s[a][5]; hi.z += racc_s[a][6]; hi.w += racc_s[a][7];
+              q[0] = lo; q[1] = hi;
+            }
+            if (kCenter && dbias) {
+              float4* q = reinterpret_cast<float4*>(acc_b + c);
+              float4 lo = q[0], hi = q[1];
+              lo.x += racc_b[kCenter ? a : 0][0]; lo.y += racc_b[kCenter ? a : 0][1];
+              lo.z += racc_b[kCenter ? a : 0][2]; lo.w += racc_b[kCenter ? a : 0][3];
+              hi.x += racc_b[kCenter ? a : 0][4]; hi.y += racc_b[kCenter ? a : 0][5];
+              hi.z += racc_b[kCenter ? a : 0][6]; hi.w += racc_b[kCenter ? a : 0][7];
+              q[0] = lo; q[1] = hi;
+            }
+          }
         }
       }
+      __syncthreads();
     }
+  } else {
+    __syncthreads();
   }
-  __syncthreads();
+  // One partial row per CTA (plain coalesced stores); norm_bwd_fold_kernel sums them.
   for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-    if (dscale) atomicAdd(&dscale[i], acc_s[i]);
-    if (kCenter && dbias) atomicAdd(&dbias[i], acc_b[i]);
+    if (dscale) dscale[static_cast<size_t>(blockIdx.x) * dim + i] = acc_s[i];
+    if (kCenter && dbias) dbias[static_cast<size_t>(blockIdx.x) * dim + i] = acc_b[i];
   }
+}
+
+// out[i] = Σ_k part[k][i]
+__global__ void norm_bwd_fold_kernel(const float* __restrict__ part_s, const float* __restrict__ part_b,
+                                     float* __restrict__ out_s, float* __restrict__ out_b, int dim,
+                                     int nblk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dim) return;
+  const float* part = blockIdx.y == 0 ? part_s : part_b;
+  float* out = blockIdx.y == 0 ? out_s : out_b;
+  if (part == nullptr) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= nblk; k += 4) {
+    s0 += part[static_cast<size_t>(k) * dim + i];
+    s1 += part[static_cast<size_t>(k + 1) * dim + i];
+    s2 += part[static_cast<size_t>(k + 2) * dim + i];
+    s3 += part[static_cast<size_t>(k + 3) * dim + i];
+  }
+  for (; k < nblk; ++k) s0 += part[static_cast<size_t>(k) * dim + i];
+  out[i] = (s0 + s1) + (s2 + s3);
 }
 
 int GridFor(int rows) {
@@ -286,19 +329,26 @@ std::vector<torch::Tensor> norm_bwd(const torch::Tensor& x, const torch::Tensor&
   auto dx = torch::empty_like(x);
   torch::Tensor sc, ds, db;
   if (scale.has_value() && scale->defined()) sc = scale->to(torch::kFloat32).contiguous();
-  if (need_dscale) ds = torch::zeros({dim}, x.options().dtype(torch::kFloat32));
-  if (need_dbias) db = torch::zeros({dim}, x.options().dtype(torch::kFloat32));
-  if (rows == 0) return {dx, ds, db};
+  if (need_dscale) ds = torch::empty({dim}, x.options().dtype(torch::kFloat32));
+  if (need_dbias) db = torch::empty({dim}, x.options().dtype(torch::kFloat32));
+  if (rows == 0) {
+    if (ds.defined()) ds.zero_();
+    if (db.defined()) db.zero_();
+    return {dx, ds, db};
+  }
   const __nv_bfloat16* drp = nullptr;
   if (dres.has_value() && dres->defined()) {
     TORCH_CHECK(dres->is_contiguous() && dres->scalar_type() == torch::kBFloat16);
     drp = reinterpret_cast<const __nv_bfloat16*>(dres->data_ptr());
   }
   auto stream = at::cuda::getCurrentCUDAStream();
-  // Fewer CTAs than forward: each CTA flushes `dim` atomics at the end.
+  // Persistent grid: each CTA leaves one partial row of dscale / dbias.
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   int grid = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (grid > sms * 2) grid = sms * 2;
+  if (grid > sms * 4) grid = sms * 4;
+  torch::Tensor part_s, part_b;
+  if (need_dscale) part_s = torch::empty({grid, dim}, x.options().dtype(torch::kFloat32));
+  if (need_dbias) part_b = torch::empty({grid, dim}, x.options().dtype(torch::kFloat32));
   const size_t smem = 2 * dim * sizeof(float);
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x.data_ptr());
   auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr());
@@ -310,14 +360,23 @@ std::vector<torch::Tensor> norm_bwd(const torch::Tensor& x, const torch::Tensor&
                                           (int)smem));
     kern<<<grid, kWarpsPerCta * 32, smem, stream>>>(
         xp, dyp, drp, sc.defined() ? sc.data_ptr<float>() : nullptr, stats.data_ptr<float>(), dxp,
-        ds.defined() ? ds.data_ptr<float>() : nullptr, db.defined() ? db.data_ptr<float>() : nullptr,
-        rows, dim);
+        part_s.defined() ? part_s.data_ptr<float>() : nullptr,
+        part_b.defined() ? part_b.data_ptr<float>() : nullptr, rows, dim);
   };
   if (center) {
     if (reg) launch(norm_bwd_kernel<true, true>); else launch(norm_bwd_kernel<true, false>);
   } else {
     if (reg) launch(norm_bwd_kernel<false, true>); else launch(norm_bwd_kernel<false, false>);
   }
+  if (need_dscale || (need_dbias && center)) {
+    norm_bwd_fold_kernel<<<dim3((dim + 255) / 256, 2), 256, 0, stream>>>(
+        part_s.defined() ? part_s.data_ptr<float>() : nullptr,
+        (part_b.defined() && center) ? part_b.data_ptr<float>() : nullptr,
+        ds.defined() ? ds.data_ptr<float>() : nullptr, db.defined() ? db.data_ptr<float>() : nullptr,
+        dim, grid);
+    CountLaunch();
+  }
+  if (need_dbias && !center) db.zero_();
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   CountLaunch();
   return {dx, ds.defined() ? ds : torch::Tensor(), db.defined() ? db : torch::Tensor()};

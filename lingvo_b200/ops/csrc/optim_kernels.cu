@@ -18,6 +18,10 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "ptx.cuh"
 #include "registry.h"
 
@@ -549,15 +553,21 @@ AfLayout Layout(const torch::Tensor& w, torch::Tensor& scratch, int64_t B, int64
   return l;
 }
 
-// Shared staging buffer for the per-row-block column partials (stream-ordered reuse: the
-// stats kernel of a variable and its fold run back to back on one stream). Grows on demand;
-// warm-up steps size it before any CUDA-graph capture.
-float* ColPartials(const c10::Device& dev, int64_t floats) {
-  static auto* bufs = new std::vector<torch::Tensor>(64);   // leaked: outlives the CUDA context
-  auto& t = (*bufs)[dev.index() < 0 ? 0 : dev.index()];
+// Staging buffer for the per-row-block column partials, one per (device, stream): the stats
+// kernel of a variable and its fold run back to back on one stream, and the optimizer spreads
+// variables over a few streams so that small tensors overlap. Grows on demand; warm-up steps
+// size it before any CUDA-graph capture.
+float* ColPartials(const c10::Device& dev, cudaStream_t stream, int64_t slot, int64_t floats) {
+  // slot 0: the caller's own stream (whatever it is — warm-up and capture streams differ);
+  // slot k > 0: the optimizer's k-th side stream.
+  using Key = std::pair<int, int64_t>;
+  static auto* bufs = new std::map<Key, torch::Tensor>();   // leaked: outlives the CUDA context
+  static auto* mu = new std::mutex();
+  std::lock_guard<std::mutex> lock(*mu);
+  auto& t = (*bufs)[Key(dev.index() < 0 ? 0 : dev.index(), slot)];
   if (!t.defined() || t.numel() < floats) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(at::cuda::getCurrentCUDAStream(), &st);
+    cudaStreamIsCapturing(stream, &st);
     TORCH_CHECK(st == cudaStreamCaptureStatusNone,
                 "adafactor_stats: staging buffer would grow during graph capture; run one "
                 "eager step first");
@@ -575,7 +585,8 @@ float* ColPartials(const c10::Device& dev, int64_t floats) {
 //   next step (persistent), acc[3] unused.
 void adafactor_stats(const torch::Tensor& w, const torch::Tensor& g, torch::Tensor scratch,
                      int64_t B, int64_t R, int64_t C, bool mult_by_param_scale,
-                     bool recompute_wsq, const c10::optional<torch::Tensor>& total_sumsq) {
+                     bool recompute_wsq, const c10::optional<torch::Tensor>& total_sumsq,
+                     int64_t slot) {
   TORCH_CHECK(g.is_contiguous() && g.numel() == w.numel());
   const c10::cuda::CUDAGuard guard(w.device());
   auto stream = at::cuda::getCurrentCUDAStream();
@@ -587,7 +598,7 @@ void adafactor_stats(const torch::Tensor& w, const torch::Tensor& g, torch::Tens
                    ? total_sumsq->data_ptr<float>() : nullptr;
   const int nblk = static_cast<int>((R + kStatRows - 1) / kStatRows);
   const int nchunk = static_cast<int>((C + kStatCols - 1) / kStatCols);
-  float* colpart = ColPartials(w.device(), B * nblk * C);
+  float* colpart = ColPartials(w.device(), stream.stream(), slot, B * nblk * C);
   if (nchunk > 1)
     C10_CUDA_CHECK(cudaMemsetAsync(l.rowsum, 0, sizeof(float) * l.br4, stream));
   auto run = [&](auto tag) {
@@ -687,7 +698,7 @@ void adafactor_factored(torch::Tensor w, const torch::Tensor& g, torch::Tensor v
                         int64_t C, bool vr_is_rows, double lr, double decay, double eps1,
                         double eps2, double clip, bool mult_by_param_scale,
                         const c10::optional<torch::Tensor>& grad_scale, bool recompute_wsq) {
-  adafactor_stats(w, g, scratch, B, R, C, mult_by_param_scale, recompute_wsq, c10::nullopt);
+  adafactor_stats(w, g, scratch, B, R, C, mult_by_param_scale, recompute_wsq, c10::nullopt, 0);
   adafactor_update(w, g, vr, vc, scratch, w_bf16, B, R, C, vr_is_rows, lr, decay, eps1, eps2, clip,
                    mult_by_param_scale, grad_scale, recompute_wsq, c10::nullopt);
 }

@@ -68,13 +68,14 @@ def _Geometry(var, d0, d1):
   return b, r, c, (d0 == nd - 1)
 
 
-def adafactor_stats(var, grad, d0, d1, mult_by_param_scale, total_sumsq=None):
-  """Phase A (see csrc): row/col sums of g² (+ global Σg² into `total_sumsq`)."""
+def adafactor_stats(var, grad, d0, d1, mult_by_param_scale, total_sumsq=None, slot=0):
+  """Phase A (see csrc): row/col sums of g² (+ global Σg² into `total_sumsq`). `slot`
+  names the staging buffer: 0 for the caller's stream, k for the k-th optimizer side stream."""
   b, r, c, _ = _Geometry(var, d0, d1)
   scratch, fresh = _Scratch(var, 16 + 2 * (b * r + 4) + 2 * (b * c + 4))
   g = grad if grad.is_contiguous() else grad.contiguous()
   ops.native().adafactor_stats(var.data, g, scratch, b, r, c, bool(mult_by_param_scale),
-                               fresh, total_sumsq)
+                               fresh, total_sumsq, int(slot))
   return fresh
 
 

@@ -291,3 +291,28 @@ def test_graphed_train_step_matches_eager():
   for x, y in zip(losses['eager'], losses['graph']):
     assert abs(x - y) < 2e-3 * max(1.0, abs(x)), losses
   assert losses['graph'][-1] < losses['graph'][0]
+
+
+@pytest.mark.parametrize('t,m,e,wdtype', [(8192, 2048, 8, torch.bfloat16), (1000, 1024, 4, torch.float32),
+                                          (37, 2056, 16, torch.bfloat16), (3, 64, 2, torch.float32)])
+def test_gate_logits_matches_fp32_oracle(t, m, e, wdtype):
+  from lingvo_b200.ops import gate
+  torch.manual_seed(0)
+  x = torch.randn(t, m, device='cuda').to(torch.bfloat16).requires_grad_(True)
+  gw = (torch.randn(m, e, device='cuda') * 0.05).to(wdtype).requires_grad_(True)
+  assert gate.supported(x, gw)
+  y = gate.gate_logits(x, gw)
+  assert y.dtype == torch.float32 and y.shape == (t, e)
+  dl = torch.randn(t, e, device='cuda')
+  dx, dgw = torch.autograd.grad(y, [x, gw], dl)
+  xr = x.detach().float().requires_grad_(True)
+  gr = gw.detach().float().requires_grad_(True)
+  yr = gate.gate_logits_ref(xr, gr)
+  dxr, dgr = torch.autograd.grad(yr, [xr, gr], dl)
+  torch.testing.assert_close(y, yr, atol=2e-3, rtol=1e-3)
+  torch.testing.assert_close(dx.float(), dxr, atol=2e-2, rtol=2e-2)       # bf16 output
+  tol = 3e-2 if wdtype == torch.bfloat16 else 2e-3
+  torch.testing.assert_close(dgw.float(), dgr, atol=tol * dgr.abs().max().item(), rtol=tol)
+  # 3-D input keeps its leading dims
+  y3 = gate.gate_logits(x.detach().reshape(1, t, m), gw.detach())
+  assert y3.shape == (1, t, e)
