@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(kWarps * 32)
 adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
                        float* __restrict__ rowsum, float* __restrict__ colpart,
                        float* __restrict__ acc, int B, int R, int C, int nblk, int nchunk,
-                       int with_w, float* __restrict__ total_sumsq) {
+                       int with_w, float* __restrict__ total_sumsq, long long ldg) {
+  // ldg: row stride of g in elements (== C unless g is a column slice of a wider matrix;
+  // strided gradients are only accepted for B == 1).
   // with_w: also accumulate sum(w^2) (only on the first step of a variable; later
   // steps get it for free from the previous apply kernel, see acc[2]).
   // Statistics are of the RAW gradient (no grad scale, no eps1): both are folded in by
@@ -107,6 +109,7 @@ adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
   const int r0 = blk * kStatRows;
   const int nrows = min(kStatRows, R - r0);
   const size_t base = (static_cast<size_t>(b) * R + r0) * C + c;
+  const size_t gbase = (static_cast<size_t>(b) * R + r0) * ldg + c;
   float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float wsq = 0.f;
 #pragma unroll 2
@@ -115,7 +118,7 @@ adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     if (cok && r + 4 <= nrows) {           // common case: no per-row predicates
 #pragma unroll
-      for (int u = 0; u < 4; ++u) load_g8<GT>(g + base + static_cast<size_t>(r + u) * C, gf[u]);
+      for (int u = 0; u < 4; ++u) load_g8<GT>(g + gbase + static_cast<size_t>(r + u) * ldg, gf[u]);
       if (with_w) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -137,7 +140,7 @@ adafactor_stats_kernel(const GT* __restrict__ g, const float* __restrict__ w,
     } else if (cok) {
       for (int u = 0; u < 4 && r + u < nrows; ++u) {
         float t[8];
-        load_g8<GT>(g + base + static_cast<size_t>(r + u) * C, t);
+        load_g8<GT>(g + gbase + static_cast<size_t>(r + u) * ldg, t);
         if (with_w) {
           float wf[8];
           load_g8<float>(w + base + static_cast<size_t>(r + u) * C, wf);
@@ -275,7 +278,7 @@ template <typename GT>
 __global__ void __launch_bounds__(kWarps * 32)
 adafactor_rms_kernel(const GT* __restrict__ g, const float* __restrict__ fr,
                      const float* __restrict__ fc, float* __restrict__ acc, int B, int R, int C,
-                     int items, const float* __restrict__ gscale) {
+                     int items, const float* __restrict__ gscale, long long ldg) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float gs = gscale ? *gscale : 1.f;
   float s = 0.f;
@@ -285,14 +288,14 @@ adafactor_rms_kernel(const GT* __restrict__ g, const float* __restrict__ fr,
     if (c >= C) continue;
     float cf[8];
     load_g8<float>(fc + static_cast<size_t>(t.b) * C + c, cf);
-    const GT* gp = g + (static_cast<size_t>(t.b) * R) * C + c;
+    const GT* gp = g + (static_cast<size_t>(t.b) * R) * ldg + c;
     const float* frp = fr + static_cast<size_t>(t.b) * R;
     int r = t.r0;
     for (; r + 4 <= t.r1; r += 4) {        // 4 rows in flight, no per-row predicates
       float gf[4][8], rf[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        load_g8<GT>(gp + static_cast<size_t>(r + u) * C, gf[u]);
+        load_g8<GT>(gp + static_cast<size_t>(r + u) * ldg, gf[u]);
         rf[u] = frp[r + u];
       }
 #pragma unroll
@@ -306,7 +309,7 @@ adafactor_rms_kernel(const GT* __restrict__ g, const float* __restrict__ fr,
     }
     for (; r < t.r1; ++r) {
       float t8[8];
-      load_g8<GT>(gp + static_cast<size_t>(r) * C, t8);
+      load_g8<GT>(gp + static_cast<size_t>(r) * ldg, t8);
       const float rf = frp[r];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -326,7 +329,7 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
                        const float* __restrict__ fc, const float* __restrict__ acc, int B, int R,
                        int C, float lr, float eps2, float clip, int mult_by_param_scale,
                        float numel, int items, const float* __restrict__ gscale,
-                       const float* __restrict__ hyper) {
+                       const float* __restrict__ hyper, long long ldg) {
   if (hyper != nullptr) lr = hyper[0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float gs = gscale ? *gscale : 1.f;
@@ -343,6 +346,7 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
     // 4 rows in flight: every load issues before the first store (w aliases itself, so
     // the compiler cannot hoist the next row's loads above this row's stores).
     const size_t tb = (static_cast<size_t>(t.b) * R) * C + c;
+    const size_t gtb = (static_cast<size_t>(t.b) * R) * ldg + c;
     const float* frp = fr + static_cast<size_t>(t.b) * R;
     auto update_row = [&](size_t off, float (&gf)[8], float (&wf)[8], float rf) {
 #pragma unroll
@@ -367,7 +371,7 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const size_t off = tb + static_cast<size_t>(r + u) * C;
-        load_g8<GT>(g + off, gf[u]);
+        load_g8<GT>(g + gtb + static_cast<size_t>(r + u) * ldg, gf[u]);
         load_g8<float>(w + off, wf[u]);
         rf[u] = frp[r + u] * scale;
       }
@@ -377,7 +381,7 @@ adafactor_apply_kernel(const GT* __restrict__ g, float* __restrict__ w,
     for (; r < t.r1; ++r) {
       const size_t off = tb + static_cast<size_t>(r) * C;
       float gf[8], wf[8];
-      load_g8<GT>(g + off, gf);
+      load_g8<GT>(g + gtb + static_cast<size_t>(r) * ldg, gf);
       load_g8<float>(w + off, wf);
       update_row(off, gf, wf, frp[r] * scale);
     }
@@ -529,6 +533,23 @@ struct AfLayout {
   int items, grid;
 };
 
+// Row stride (elements) of a gradient viewed as [B, R, C]: contiguous, or — for B == 1 — a
+// column slice of a wider row-major matrix (e.g. one third of a fused qkv weight gradient)
+// whose rows stay 16-byte aligned.
+int64_t GradRowStride(const torch::Tensor& g, const torch::Tensor& w, int64_t B, int64_t R,
+                      int64_t C) {
+  TORCH_CHECK(g.numel() == w.numel(), "adafactor: gradient / variable size mismatch");
+  if (g.is_contiguous()) return C;
+  TORCH_CHECK(B == 1 && g.dim() >= 2 && g.size(-1) == C && g.size(-2) == R && g.stride(-1) == 1,
+              "adafactor: gradient must be contiguous or a column slice of a 2-D matrix");
+  const int64_t ld = g.stride(-2);
+  const int64_t es = g.element_size();
+  TORCH_CHECK(ld >= C && (ld * es) % 16 == 0 &&
+              reinterpret_cast<uintptr_t>(g.data_ptr()) % 16 == 0,
+              "adafactor: strided gradient rows must be 16-byte aligned");
+  return ld;
+}
+
 AfLayout Layout(const torch::Tensor& w, torch::Tensor& scratch, int64_t B, int64_t R, int64_t C) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == torch::kFloat32 && w.is_contiguous());
   TORCH_CHECK(C % 8 == 0, "adafactor: C must be a multiple of 8");
@@ -587,7 +608,7 @@ void adafactor_stats(const torch::Tensor& w, const torch::Tensor& g, torch::Tens
                      int64_t B, int64_t R, int64_t C, bool mult_by_param_scale,
                      bool recompute_wsq, const c10::optional<torch::Tensor>& total_sumsq,
                      int64_t slot) {
-  TORCH_CHECK(g.is_contiguous() && g.numel() == w.numel());
+  const int64_t ldg = GradRowStride(g, w, B, R, C);
   const c10::cuda::CUDAGuard guard(w.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   AfLayout l = Layout(w, scratch, B, R, C);
@@ -605,7 +626,7 @@ void adafactor_stats(const torch::Tensor& w, const torch::Tensor& g, torch::Tens
     using GT = decltype(tag);
     adafactor_stats_kernel<GT><<<static_cast<int>(B) * nblk * nchunk, kWarps * 32, 0, stream>>>(
         reinterpret_cast<const GT*>(g.data_ptr()), w.data_ptr<float>(), l.rowsum, colpart, l.acc,
-        (int)B, (int)R, (int)C, nblk, nchunk, with_w, tot);
+        (int)B, (int)R, (int)C, nblk, nchunk, with_w, tot, (long long)ldg);
   };
   if (g.scalar_type() == torch::kBFloat16) run(__nv_bfloat16());
   else { TORCH_CHECK(g.scalar_type() == torch::kFloat32); run(float()); }
@@ -623,7 +644,7 @@ void adafactor_update(torch::Tensor w, const torch::Tensor& g, torch::Tensor vr,
                       double eps1, double eps2, double clip, bool mult_by_param_scale,
                       const c10::optional<torch::Tensor>& grad_scale, bool recompute_wsq,
                       const c10::optional<torch::Tensor>& hyper) {
-  TORCH_CHECK(g.is_contiguous() && g.numel() == w.numel());
+  const int64_t ldg = GradRowStride(g, w, B, R, C);
   const c10::cuda::CUDAGuard guard(w.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   AfLayout l = Layout(w, scratch, B, R, C);
@@ -646,10 +667,11 @@ void adafactor_update(torch::Tensor w, const torch::Tensor& g, torch::Tensor vr,
     const GT* gp = reinterpret_cast<const GT*>(g.data_ptr());
     if (clip > 0)
       adafactor_rms_kernel<GT><<<l.grid, kWarps * 32, 0, stream>>>(
-          gp, l.fr, l.fc, l.acc, (int)B, (int)R, (int)C, l.items, gsp);
+          gp, l.fr, l.fc, l.acc, (int)B, (int)R, (int)C, l.items, gsp, (long long)ldg);
     adafactor_apply_kernel<GT><<<l.grid, kWarps * 32, 0, stream>>>(
         gp, w.data_ptr<float>(), wb, l.fr, l.fc, l.acc, (int)B, (int)R, (int)C, (float)lr,
-        (float)eps2, (float)clip, mult_by_param_scale ? 1 : 0, numel, l.items, gsp, hp);
+        (float)eps2, (float)clip, mult_by_param_scale ? 1 : 0, numel, l.items, gsp, hp,
+        (long long)ldg);
   };
   if (g.scalar_type() == torch::kBFloat16) run(__nv_bfloat16());
   else { TORCH_CHECK(g.scalar_type() == torch::kFloat32); run(float()); }

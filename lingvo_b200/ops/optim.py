@@ -60,6 +60,19 @@ def adafactor_factored(var, grad, vr, vc, d0, d1, lr, decay, eps1, eps2, clip,
       float(clip), bool(mult_by_param_scale), grad_scale, fresh)
 
 
+def _KernelGrad(grad, b):
+  """The fused kernels take a contiguous gradient or (for a single matrix) a column slice of
+  a wider row-major matrix — e.g. dwq/dwk/dwv as views of the fused qkv weight gradient —
+  so those never need a `.contiguous()` copy."""
+  if grad.is_contiguous():
+    return grad
+  if (b == 1 and grad.dim() >= 2 and grad.stride(-1) == 1 and grad.stride(-2) >= grad.shape[-1]
+      and (grad.stride(-2) * grad.element_size()) % 16 == 0 and grad.data_ptr() % 16 == 0 and
+      all(s == 1 for s in grad.shape[:-2])):
+    return grad
+  return grad.contiguous()
+
+
 def _Geometry(var, d0, d1):
   nd = var.dim()
   assert sorted((d0, d1)) == [nd - 2, nd - 1]
@@ -73,7 +86,7 @@ def adafactor_stats(var, grad, d0, d1, mult_by_param_scale, total_sumsq=None, sl
   names the staging buffer: 0 for the caller's stream, k for the k-th optimizer side stream."""
   b, r, c, _ = _Geometry(var, d0, d1)
   scratch, fresh = _Scratch(var, 16 + 2 * (b * r + 4) + 2 * (b * c + 4))
-  g = grad if grad.is_contiguous() else grad.contiguous()
+  g = _KernelGrad(grad, b)
   ops.native().adafactor_stats(var.data, g, scratch, b, r, c, bool(mult_by_param_scale),
                                fresh, total_sumsq, int(slot))
   return fresh
@@ -84,7 +97,7 @@ def adafactor_update(var, grad, vr, vc, d0, d1, lr, decay, eps1, eps2, clip,
   """Phase B: factors → clip RMS → apply, using the sums left by `adafactor_stats`."""
   b, r, c, vr_is_rows = _Geometry(var, d0, d1)
   scratch, _ = _Scratch(var, 16 + 2 * (b * r + 4) + 2 * (b * c + 4))
-  g = grad if grad.is_contiguous() else grad.contiguous()
+  g = _KernelGrad(grad, b)
   compute = getattr(var, 'compute', None)
   ops.native().adafactor_update(
       var.data, g, vr, vc, scratch, compute.data if compute is not None else None,

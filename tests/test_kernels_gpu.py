@@ -316,3 +316,36 @@ def test_gate_logits_matches_fp32_oracle(t, m, e, wdtype):
   # 3-D input keeps its leading dims
   y3 = gate.gate_logits(x.detach().reshape(1, t, m), gw.detach())
   assert y3.shape == (1, t, e)
+
+
+def test_adafactor_accepts_column_slice_gradients():
+  """dwq/dwk/dwv arrive as column slices of the fused qkv gradient: the fused kernels read
+  them in place and must match the step taken on contiguous copies."""
+  from lingvo_b200.core import optimizer, py_utils
+  torch.manual_seed(1)
+  k, n = 512, 256
+  fused_grads = [torch.randn(k, 3 * n, device='cuda').to(torch.bfloat16) * 0.1 for _ in range(3)]
+  w0 = [torch.randn(k, n, device='cuda') for _ in range(3)]
+
+  def run(slice_views):
+    opt = optimizer.XLAShardingAdafactor.Params().Set(
+        name='adafactor', beta1=0.0, beta2=0.99, clipping_threshold=1.0, factored=True,
+        decay_exponent_pow=0.8, fused=True).Instantiate()
+    ws = []
+    for i, w in enumerate(w0):
+      p = torch.nn.Parameter(w.clone())
+      p.var_name = 'w%d/var' % i
+      p.compute = p.data.bfloat16().requires_grad_()
+      ws.append(p)
+    for step, fg in enumerate(fused_grads):
+      views = [fg[:, i * n:(i + 1) * n] for i in range(3)]
+      assert not views[1].is_contiguous()
+      gs = views if slice_views else [v.contiguous() for v in views]
+      with py_utils.GlobalStepContext(step):
+        opt.Apply(0.01, [py_utils.VarGrad(w, g) for w, g in zip(ws, gs)])
+    return ws
+
+  a, b = run(True), run(False)
+  for x, y in zip(a, b):
+    assert _rel(x, y) < 1e-6
+    assert torch.equal(x.compute.data, y.compute.data)
