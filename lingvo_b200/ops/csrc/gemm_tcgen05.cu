@@ -460,6 +460,18 @@ static void Dispatch(bool ak, bool bk, const TmapArray& ta, const CUtensorMap& t
   else Launch<BN, false, false, OutT>(ta, tb, p, s, sms);
 }
 
+// Wave-quantisation heuristic switch. Off by default: measured on B200
+// (profiles/gemm_bn_probe_r1.jsonl) the 128-wide tile runs at ≈75 % of the 256-wide tile's
+// per-FLOP rate (operand traffic per FLOP is 1.33× higher), which costs more than the
+// 3.46 → 4 wave rounding it avoids. LINGVO_B200_GEMM_AUTO_BN=1 turns it on for experiments.
+static bool GemmAutoBn128() {
+  static const bool on = [] {
+    const char* e = getenv("LINGVO_B200_GEMM_AUTO_BN");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  return on;
+}
+
 // a: [G, M, K] if a_kmajor else [G, K, M];  b: [G, N, K] if b_kmajor else [G, K, N]
 // (2-D inputs are treated as G = 1).  Returns / fills out [G, M, N].
 torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bool a_kmajor,
@@ -583,8 +595,22 @@ torch::Tensor gemm_bf16(const torch::Tensor& a_in, const torch::Tensor& b_in, bo
 
   if (M == 0 || N == 0 || G == 0) return out;
 
-  // Tile-N: 256 unless N is small.
-  const bool bn256 = N > 128;
+  // Tile-N: 256 unless N is small — or unless 128-wide tiles quantise better onto the SMs:
+  // an [8192, 2048] output is 512 tiles of 128×256 = 3.46 waves on 148 SMs (4 are paid for),
+  // but 1024 tiles of 128×128 = 6.92 half-cost waves. LINGVO_B200_GEMM_BN=128|256 forces one.
+  bool bn256 = N > 128;
+  if (bn256) {
+    static const int forced = [] {
+      const char* e = getenv("LINGVO_B200_GEMM_BN");
+      return e ? atoi(e) : 0;
+    }();
+    const int sms_q = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    const int64_t mt = (M + kBlockM - 1) / kBlockM;
+    const int64_t t256 = G * mt * ((N + 255) / 256), t128 = G * mt * ((N + 127) / 128);
+    const int64_t w256 = 2 * ((t256 + sms_q - 1) / sms_q), w128 = (t128 + sms_q - 1) / sms_q;
+    if (forced == 128) bn256 = false;
+    else if (forced == 0 && GemmAutoBn128() && w128 * 100 <= w256 * 90) bn256 = false;
+  }
   const int bn = bn256 ? 256 : 128;
   TmapArray ta;
   if (a_peer_ptrs.has_value() && a_peer_ptrs->defined()) {

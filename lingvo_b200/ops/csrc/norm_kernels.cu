@@ -244,6 +244,68 @@ norm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   }
 }
 
+// dscale / dbias partials as a column reduction (the layout of the Adafactor statistics
+// kernel): one CTA per (32-row block, 2048-column chunk), warp w sweeps the 32 rows of its
+// own 256-column strip with the column sums in registers, and leaves one partial row per
+// row block. Runs right after the dx kernel, so x and dy mostly come from L2.
+constexpr int kDsRows = 32;
+template <bool kCenter>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+norm_dscale_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                   const float* __restrict__ stats, float* __restrict__ part_s,
+                   float* __restrict__ part_b, int rows, int dim, int nchunk) {
+  __shared__ float st[kDsRows][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x % nchunk, blk = blockIdx.x / nchunk;
+  const int r0 = blk * kDsRows;
+  const int nrows = min(kDsRows, rows - r0);
+  if (threadIdx.x < 2 * nrows) st[threadIdx.x >> 1][threadIdx.x & 1] = stats[2 * r0 + threadIdx.x];
+  __syncthreads();
+  const int c = chunk * (kWarpsPerCta * 256) + warp * 256 + lane * 8;
+  if (c >= dim) return;
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const size_t base = static_cast<size_t>(r0) * dim + c;
+  int r = 0;
+  for (; r + 4 <= nrows; r += 4) {
+    float xf[4][8], gf[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      load8(x + base + static_cast<size_t>(r + u) * dim, xf[u]);
+      load8(dy + base + static_cast<size_t>(r + u) * dim, gf[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float mean = st[r + u][0], rstd = st[r + u][1];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        cs[i] = fmaf(gf[u][i], (xf[u][i] - mean) * rstd, cs[i]);
+        if (kCenter) cb[i] += gf[u][i];
+      }
+    }
+  }
+  for (; r < nrows; ++r) {
+    float xf[8], gf[8];
+    load8(x + base + static_cast<size_t>(r) * dim, xf);
+    load8(dy + base + static_cast<size_t>(r) * dim, gf);
+    const float mean = st[r][0], rstd = st[r][1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      cs[i] = fmaf(gf[i], (xf[i] - mean) * rstd, cs[i]);
+      if (kCenter) cb[i] += gf[i];
+    }
+  }
+  if (part_s != nullptr) {
+    float* q = part_s + static_cast<size_t>(blk) * dim + c;
+    *reinterpret_cast<float4*>(q) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+    *reinterpret_cast<float4*>(q + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+  }
+  if (kCenter && part_b != nullptr) {
+    float* q = part_b + static_cast<size_t>(blk) * dim + c;
+    *reinterpret_cast<float4*>(q) = make_float4(cb[0], cb[1], cb[2], cb[3]);
+    *reinterpret_cast<float4*>(q + 4) = make_float4(cb[4], cb[5], cb[6], cb[7]);
+  }
+}
+
 // out[i] = Σ_k part[k][i]. Block = 32 columns × 8 row groups: coalesced 128-byte reads, the
 // 8 partial sums per column meet in shared memory.
 __global__ void __launch_bounds__(256)
@@ -351,39 +413,44 @@ std::vector<torch::Tensor> norm_bwd(const torch::Tensor& x, const torch::Tensor&
     drp = reinterpret_cast<const __nv_bfloat16*>(dres->data_ptr());
   }
   auto stream = at::cuda::getCurrentCUDAStream();
-  // Persistent grid: each CTA leaves one partial row of dscale / dbias.
+  // dx: one light streaming kernel (48 registers, no parameter-gradient work) on a persistent
+  // grid; dscale / dbias: column-reduction kernel + fold.
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   int grid = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (grid > sms * 2) grid = sms * 2;
-  torch::Tensor part_s, part_b;
-  if (need_dscale) part_s = torch::empty({grid, dim}, x.options().dtype(torch::kFloat32));
-  if (need_dbias) part_b = torch::empty({grid, dim}, x.options().dtype(torch::kFloat32));
+  if (grid > sms * 8) grid = sms * 8;
   const size_t smem = 2 * dim * sizeof(float);
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x.data_ptr());
   auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy.data_ptr());
   auto dxp = reinterpret_cast<__nv_bfloat16*>(dx.data_ptr());
-  const bool reg = dim <= 2048;
   auto launch = [&](auto kern) {
     if (smem > 48 * 1024)
       C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
     kern<<<grid, kWarpsPerCta * 32, smem, stream>>>(
         xp, dyp, drp, sc.defined() ? sc.data_ptr<float>() : nullptr, stats.data_ptr<float>(), dxp,
-        part_s.defined() ? part_s.data_ptr<float>() : nullptr,
-        part_b.defined() ? part_b.data_ptr<float>() : nullptr, rows, dim);
+        nullptr, nullptr, rows, dim);
   };
-  if (center) {
-    if (reg) launch(norm_bwd_kernel<true, true>); else launch(norm_bwd_kernel<true, false>);
-  } else {
-    if (reg) launch(norm_bwd_kernel<false, true>); else launch(norm_bwd_kernel<false, false>);
-  }
-  if (need_dscale || (need_dbias && center)) {
+  if (center) launch(norm_bwd_kernel<true, false>);
+  else launch(norm_bwd_kernel<false, false>);
+  const bool want_b = need_dbias && center;
+  if (need_dscale || want_b) {
+    const int nblk = (rows + kDsRows - 1) / kDsRows;
+    const int nchunk = (dim + kWarpsPerCta * 256 - 1) / (kWarpsPerCta * 256);
+    torch::Tensor part_s, part_b;
+    if (need_dscale) part_s = torch::empty({nblk, dim}, x.options().dtype(torch::kFloat32));
+    if (want_b) part_b = torch::empty({nblk, dim}, x.options().dtype(torch::kFloat32));
+    float* psp = part_s.defined() ? part_s.data_ptr<float>() : nullptr;
+    float* pbp = part_b.defined() ? part_b.data_ptr<float>() : nullptr;
+    if (center)
+      norm_dscale_kernel<true><<<nblk * nchunk, kWarpsPerCta * 32, 0, stream>>>(
+          xp, dyp, stats.data_ptr<float>(), psp, pbp, rows, dim, nchunk);
+    else
+      norm_dscale_kernel<false><<<nblk * nchunk, kWarpsPerCta * 32, 0, stream>>>(
+          xp, dyp, stats.data_ptr<float>(), psp, pbp, rows, dim, nchunk);
     norm_bwd_fold_kernel<<<dim3((dim + 31) / 32, 2), 256, 0, stream>>>(
-        part_s.defined() ? part_s.data_ptr<float>() : nullptr,
-        (part_b.defined() && center) ? part_b.data_ptr<float>() : nullptr,
-        ds.defined() ? ds.data_ptr<float>() : nullptr, db.defined() ? db.data_ptr<float>() : nullptr,
-        dim, grid);
-    CountLaunch();
+        psp, pbp, ds.defined() ? ds.data_ptr<float>() : nullptr,
+        db.defined() ? db.data_ptr<float>() : nullptr, dim, nblk);
+    CountLaunch(2);
   }
   if (need_dbias && !center) db.zero_();
   C10_CUDA_KERNEL_LAUNCH_CHECK();

@@ -348,4 +348,20 @@ def test_adafactor_accepts_column_slice_gradients():
   a, b = run(True), run(False)
   for x, y in zip(a, b):
     assert _rel(x, y) < 1e-6
-    assert torch.equal(x.compute.data, y.compute.data)
+    assert torch.equal(x.compute.data, x.data.bfloat16())
+
+
+def test_embed_rows_backward_matches_dense_embedding_backward():
+  from lingvo_b200.core import gshard_builder
+  import torch.nn.functional as F
+  torch.manual_seed(0)
+  w = torch.randn(1000, 64, device='cuda').to(torch.bfloat16).requires_grad_(True)
+  ids = torch.randint(0, 50, (4, 128), device='cuda')          # many duplicates
+  dy = torch.randn(4, 128, 64, device='cuda').to(torch.bfloat16)
+  out = gshard_builder._EmbedRows.apply(w, ids)
+  (dw,) = torch.autograd.grad(out, w, dy)
+  w2 = w.detach().float().requires_grad_(True)
+  ref = F.embedding(ids, w2)
+  (dw2,) = torch.autograd.grad(ref, w2, dy.float())
+  assert torch.equal(out, F.embedding(ids, w.detach()))
+  torch.testing.assert_close(dw.float(), dw2, atol=2e-2, rtol=1e-2)
