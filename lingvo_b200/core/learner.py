@@ -21,6 +21,7 @@ import torch
 
 from lingvo_b200.core import base_layer
 from lingvo_b200.core import optimizer
+from lingvo_b200.core import fault_injection
 from lingvo_b200.core import py_utils
 from lingvo_b200.core import schedule
 from lingvo_b200.core import summary_utils
@@ -175,6 +176,9 @@ class Learner(base_layer.BaseLayer):
         raise ValueError('Loss %s not found in metrics %s' %
                          (name, list(metrics.keys())))
       loss = item[0] if isinstance(item, (tuple, list)) else item
+      injector = fault_injection.Get()
+      if injector is not None:
+        loss = injector.OnLoss(py_utils.GetGlobalStep(), loss)
       losses.append(loss)
       keep = retain_graph or i < len(names) - 1
       per_loss[name] = NestedMap(
@@ -186,6 +190,9 @@ class Learner(base_layer.BaseLayer):
       var_grads = per_loss[names[0]].grads
     else:
       var_grads, eval_metrics = self.gradient_combiner.Combine(vmap, per_loss)
+    injector = fault_injection.Get()
+    if injector is not None:
+      var_grads = injector.OnGradients(py_utils.GetGlobalStep(), var_grads)
     return losses, var_grads, eval_metrics
 
   # ------------------------------------------------------- adjust and scale --

@@ -30,6 +30,7 @@ from lingvo_b200.core import cluster_factory
 from lingvo_b200.core import metrics as metrics_lib
 from lingvo_b200.core import py_utils
 from lingvo_b200.core import saver as saver_lib
+from lingvo_b200.core import fault_injection
 from lingvo_b200.core import summary_utils
 from lingvo_b200.utils import tfevents
 
@@ -134,6 +135,9 @@ class Trainer(base_runner.BaseRunner):
       while True:
         if self._ShouldStop(step=global_step):
           break
+        injector = fault_injection.Get()
+        if injector is not None:
+          injector.BeforeStep(global_step, self._train_dir)
         want_summary = (tp.summary_interval_steps and
                         global_step % tp.summary_interval_steps == 0)
         collector = summary_utils.SummaryCollector() if want_summary else None

@@ -1,6 +1,8 @@
 """Native host ops added for inventory parity: MLPerf sub-words, n-gram vocab, static maps,
 apply_packing, 2-D AP, point sampling, preconditioner captain."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -291,3 +293,17 @@ def test_generate_proto_def(tmp_path):
   assert any(p.endswith('hyps.proto') for p in paths)
   text = open([p for p in paths if p.endswith('hyps.proto')][0]).read()
   assert 'repeated int32 ids = 2 [packed = true];' in text
+
+
+def test_record_pipeline_is_tsan_clean():
+  """Builds the yielders with -fsanitize=thread and runs the concurrency stress (≈10 s)."""
+  import importlib.util
+  import shutil
+  if shutil.which('g++') is None:
+    pytest.skip('no g++')
+  path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools', 'tsan_host.py')
+  spec = importlib.util.spec_from_file_location('tsan_host', path)
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  ok, out = mod.Run('thread')
+  assert ok, out[-3000:]
