@@ -91,8 +91,14 @@ constexpr int kChunkBytes = kT * 64 * 2;      // one [128 x 64] SW128 sub-tile =
 constexpr int kTileBytes = 2 * kChunkBytes;   // [128 x 128] operand = 32 KiB
 constexpr int kSlotBytes = 2 * kTileBytes;    // A + B operand of one GEMM = 64 KiB
 constexpr int kSlots = 3;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;                 // 4 control warps + 8 epilogue warps
 constexpr uint32_t kTmemCols = 512;           // 2 stages x (S | dP) x 128 columns
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct GradParams {
   const float* lse;      // [B, H, L]
@@ -142,7 +148,7 @@ rel_bias_grad_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[s]), 4);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), 8);
     }
     fence_barrier_init();
   }
@@ -216,24 +222,32 @@ rel_bias_grad_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     __syncwarp();
   } else if (warp_idx >= 4) {
     // ======================= softmax-recompute epilogue ====================
-    const int q = warp_idx - 4;
+    // 8 warps: warp w reads TMEM lanes 32·(w % 4).. (one query row per lane) and owns one
+    // half of the tile's 128 key columns, so every SM sub-partition has two epilogue warps
+    // to switch between (with four warps each scheduler had a single warp and every
+    // FFMA / MUFU latency was exposed) and the per-thread tile is 64 registers, not 128.
+    const int q = warp_idx & 3;
+    const int half = (warp_idx - 4) >> 2;
     const int row = q * 32 + lane;
     const int i = i0 + row;
-    float ds[kT];
+    constexpr int kCols = kT / 2;
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float sl2 = p.scale * kLog2e;
+    float ds[kCols];
 #pragma unroll
-    for (int c = 0; c < kT; ++c) ds[c] = 0.f;
+    for (int c = 0; c < kCols; ++c) ds[c] = 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int b = 0; b < p.B; ++b) {
       const long long bh = static_cast<long long>(b) * p.H + h;
-      const float lse = p.lse[bh * p.L + i];
+      const float lse2 = p.lse[bh * p.L + i] * kLog2e;
       const float delta = p.delta[bh * p.L + i];
-      const __nv_bfloat16* brow = p.bias + (bh * p.L + i) * p.L + j0;
+      const __nv_bfloat16* brow = p.bias + (bh * p.L + i) * p.L + j0 + half * kCols;
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tc_fence_after();
-      const uint32_t t_s = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t t_s = tmem_base + acc * 256 + half * kCols + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t vs[32], vp[32];
         tmem_ld_32x32b_x32(t_s + c * 32, vs);
         tmem_ld_32x32b_x32(t_s + 128 + c * 32, vp);
@@ -249,12 +263,11 @@ rel_bias_grad_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           for (int e = 0; e < 4; ++e) {
             const float2 bb = unpack_bf16x2(w[e]);
             const int k0 = u * 8 + e * 2;
-            const float s0 = __uint_as_float(vs[k0]) * p.scale + bb.x - lse;
-            const float s1 = __uint_as_float(vs[k0 + 1]) * p.scale + bb.y - lse;
-            const float p0 = __expf(s0);
-            const float p1 = __expf(s1);
-            ds[c * 32 + k0] += p0 * (__uint_as_float(vp[k0]) - delta);
-            ds[c * 32 + k0 + 1] += p1 * (__uint_as_float(vp[k0 + 1]) - delta);
+            // p = exp(s·scale + bias − lse) = 2^(s·scale·log2e + (bias·log2e − lse·log2e))
+            const float p0 = fast_exp2(fmaf(__uint_as_float(vs[k0]), sl2, fmaf(bb.x, kLog2e, -lse2)));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(vs[k0 + 1]), sl2, fmaf(bb.y, kLog2e, -lse2)));
+            ds[c * 32 + k0] = fmaf(p0, __uint_as_float(vp[k0]) - delta, ds[c * 32 + k0]);
+            ds[c * 32 + k0 + 1] = fmaf(p1, __uint_as_float(vp[k0 + 1]) - delta, ds[c * 32 + k0 + 1]);
           }
         }
       }
@@ -265,10 +278,10 @@ rel_bias_grad_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
     // Diagonal (Toeplitz) reduction: element (row, col) lies on diagonal row - col.
 #pragma unroll
-    for (int c = 0; c < kT; ++c) atomicAdd(&sdiag[row - c + (kT - 1)], ds[c]);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int c = 0; c < kCols; ++c) atomicAdd(&sdiag[row - (half * kCols + c) + (kT - 1)], ds[c]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     float* out = p.drel + static_cast<long long>(h) * (2 * p.L - 1) + (i0 - j0) + (p.L - 1) - (kT - 1);
-    for (int t = row; t < 2 * kT - 1; t += 128) atomicAdd(out + t, sdiag[t]);
+    for (int t = half * kT + row; t < 2 * kT - 1; t += 2 * kT) atomicAdd(out + t, sdiag[t]);
   }
 
   tc_fence_before();

@@ -194,21 +194,31 @@ gate_logits_dgw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
     for (int e = 0; e < E; ++e) out[i * E + e] = acc[i][e];
 }
 
+// dgw[i] = Σ_k part[k][i]: block = 32 elements × 8 partial groups (coalesced 128-byte reads).
 template <typename WT>
-__global__ void gate_logits_dgw_fold_kernel(const float* __restrict__ part, WT* __restrict__ dgw,
-                                            int ME, int nblk) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ME) return;
+__global__ void __launch_bounds__(256)
+gate_logits_dgw_fold_kernel(const float* __restrict__ part, WT* __restrict__ dgw, int ME, int nblk) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cx;
   float s0 = 0.f, s1 = 0.f;
-  int k = 0;
-  for (; k + 2 <= nblk; k += 2) {
-    s0 += part[static_cast<size_t>(k) * ME + i];
-    s1 += part[static_cast<size_t>(k + 1) * ME + i];
+  if (i < ME) {
+    int k = ky;
+    for (; k + 8 < nblk; k += 16) {
+      s0 += part[static_cast<size_t>(k) * ME + i];
+      s1 += part[static_cast<size_t>(k + 8) * ME + i];
+    }
+    if (k < nblk) s0 += part[static_cast<size_t>(k) * ME + i];
   }
-  if (k < nblk) s0 += part[static_cast<size_t>(k) * ME + i];
-  const float s = s0 + s1;
-  if constexpr (std::is_same<WT, float>::value) dgw[i] = s;
-  else dgw[i] = __float2bfloat16(s);
+  red[ky][cx] = s0 + s1;
+  __syncthreads();
+  if (ky == 0 && i < ME) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][cx];
+    if constexpr (std::is_same<WT, float>::value) dgw[i] = s;
+    else dgw[i] = __float2bfloat16(s);
+  }
 }
 
 int Sms() { return at::cuda::getCurrentDeviceProperties()->multiProcessorCount; }
@@ -317,7 +327,7 @@ std::vector<torch::Tensor> gate_logits_bwd(const torch::Tensor& x, const torch::
     if (T == 0) {
       dgw.zero_();
     } else {
-      const int nblk = std::min(Sms(), (T + kDgwTile - 1) / kDgwTile);
+      const int nblk = std::min(Sms() * 3, (T + kDgwTile - 1) / kDgwTile);
       const int tok_per_blk = (T + nblk - 1) / nblk;
       const int used = (T + tok_per_blk - 1) / tok_per_blk;
       auto part = torch::empty({used, x.size(1), E}, x.options().dtype(torch::kFloat32));
@@ -329,10 +339,10 @@ std::vector<torch::Tensor> gate_logits_bwd(const torch::Tensor& x, const torch::
       });
       const int me = static_cast<int>(M * E);
       if (gw.scalar_type() == torch::kFloat32)
-        gate_logits_dgw_fold_kernel<float><<<(me + 255) / 256, 256, 0, stream>>>(
+        gate_logits_dgw_fold_kernel<float><<<(me + 31) / 32, 256, 0, stream>>>(
             part.data_ptr<float>(), dgw.data_ptr<float>(), me, used);
       else
-        gate_logits_dgw_fold_kernel<__nv_bfloat16><<<(me + 255) / 256, 256, 0, stream>>>(
+        gate_logits_dgw_fold_kernel<__nv_bfloat16><<<(me + 31) / 32, 256, 0, stream>>>(
             part.data_ptr<float>(), reinterpret_cast<__nv_bfloat16*>(dgw.data_ptr()), me, used);
       C10_CUDA_KERNEL_LAUNCH_CHECK();
       CountLaunch(2);

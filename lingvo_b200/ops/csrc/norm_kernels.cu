@@ -248,7 +248,7 @@ norm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 // kernel): one CTA per (32-row block, 2048-column chunk), warp w sweeps the 32 rows of its
 // own 256-column strip with the column sums in registers, and leaves one partial row per
 // row block. Runs right after the dx kernel, so x and dy mostly come from L2.
-constexpr int kDsRows = 32;
+constexpr int kDsRows = 16;
 template <bool kCenter>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 norm_dscale_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
