@@ -97,6 +97,18 @@ class RmsNormLayer(_BuilderLayer):
       self.CreateVariable('shift', WeightParams(
           [p.dim], WeightInit.Constant(0.0), p.dtype))
 
+  def FPropPass(self, theta, x):
+    """→ (norm(x), x_pass). `x_pass` is x routed through the same autograd node as the norm,
+    so `x_pass + f(norm(x))` back-propagates with the residual-gradient add fused into the
+    norm backward kernel (ops/norm.py `_NormPassFn`). Falls back to (FProp(x), x)."""
+    p = self.params
+    if (p.kind == 'rms' and ops.use_cuda_kernels(x) and x.dtype == torch.bfloat16 and
+        x.requires_grad):
+      from lingvo_b200.ops import norm
+      if norm.available():
+        return norm.rms_norm_pass(x, None if p.no_scale else theta.scale, p.epsilon)
+    return self.FProp(theta, x), x
+
   def FProp(self, theta, x):
     p = self.params
     if p.kind == 'none':
@@ -663,12 +675,16 @@ class DecoderBlock(_BuilderLayer):
     else:
       mask = (i.segment_id != 0).unsqueeze(-1).to(i.vec.dtype)
       x_in = i.vec * mask
-    x = self.ln.FProp(theta.ln, x_in) if p.norm_policy != 'primer_post' else x_in
+    x_res = x_in
+    if p.norm_policy != 'primer_post':
+      x, x_res = self.ln.FPropPass(theta.ln, x_in)
+    else:
+      x = x_in
     fuse_res = (getattr(self.layer, 'supports_fused_residual', False) and
                 i.get('expert_id') is None and p.post_norm is None and not (b.dropout_rate and not self.do_eval))
     if fuse_res:
       # x_in + f(x) comes out of the sub-layer's last GEMM epilogue.
-      y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos, residual=x_in)
+      y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos, residual=x_res)
       o = i.copy()
       o.vec = y
       o.aux_loss = i.aux_loss + aux
@@ -683,7 +699,7 @@ class DecoderBlock(_BuilderLayer):
     if b.dropout_rate and not self.do_eval:
       y = F.dropout(y, b.dropout_rate, training=True)
     o = i.copy()
-    o.vec = x_in + y
+    o.vec = x_res + y
     o.aux_loss = i.aux_loss + aux
     return o
 

@@ -365,3 +365,27 @@ def test_embed_rows_backward_matches_dense_embedding_backward():
   (dw2,) = torch.autograd.grad(ref, w2, dy.float())
   assert torch.equal(out, F.embedding(ids, w.detach()))
   torch.testing.assert_close(dw.float(), dw2, atol=2e-2, rtol=1e-2)
+
+
+def test_rms_norm_pass_fuses_residual_gradient():
+  """x_pass + f(norm(x)) through `_NormPassFn` == the plain two-branch graph."""
+  from lingvo_b200.ops import norm
+  torch.manual_seed(0)
+  x = (torch.randn(512, 1024, device='cuda')).to(torch.bfloat16).requires_grad_(True)
+  scale = torch.rand(1024, device='cuda').add(0.5).requires_grad_(True)
+  w = (torch.randn(1024, 1024, device='cuda') * 0.03).to(torch.bfloat16)
+  dy = torch.randn(512, 1024, device='cuda').to(torch.bfloat16)
+  xn, xp = norm.rms_norm_pass(x, scale, 1e-6)
+  y = xp + xn @ w
+  gx, gs = torch.autograd.grad(y, [x, scale], dy)
+  xr = x.detach().float().requires_grad_(True)
+  sr = scale.detach().clone().requires_grad_(True)
+  yr = xr + (norm.rms_norm_ref(xr, sr, 1e-6) @ w.float())
+  gxr, gsr = torch.autograd.grad(yr, [xr, sr], dy.float())
+  torch.testing.assert_close(y.float(), yr, atol=5e-2, rtol=2e-2)
+  torch.testing.assert_close(gx.float(), gxr, atol=6e-2, rtol=3e-2)
+  torch.testing.assert_close(gs, gsr, atol=0.5, rtol=3e-2)
+  # only the residual branch used → gradient passes straight through
+  xn2, xp2 = norm.rms_norm_pass(x, scale, 1e-6)
+  (g_only,) = torch.autograd.grad(xp2, x, dy)
+  assert torch.equal(g_only, dy)
