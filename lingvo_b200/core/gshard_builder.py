@@ -21,6 +21,7 @@ experiment configs port 1:1.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -47,6 +48,10 @@ def ShardedWeightParams(shape, init=None, dtype=None, collections=None,
                         tensor_split_dims_mapping=None, device_mesh=None):
   return WeightParams(shape, init, dtype, collections, device_mesh,
                       tensor_split_dims_mapping)
+
+
+# Pass-through autograd nodes that fuse gradient adds into backward kernels (A/B switch).
+_FUSE_PASS = os.environ.get('LINGVO_B200_FUSE_PASS', '1') != '0'
 
 
 def _Act(name: str):
@@ -102,8 +107,8 @@ class RmsNormLayer(_BuilderLayer):
     so `x_pass + f(norm(x))` back-propagates with the residual-gradient add fused into the
     norm backward kernel (ops/norm.py `_NormPassFn`). Falls back to (FProp(x), x)."""
     p = self.params
-    if (p.kind == 'rms' and ops.use_cuda_kernels(x) and x.dtype == torch.bfloat16 and
-        x.requires_grad):
+    if (p.kind == 'rms' and _FUSE_PASS and ops.use_cuda_kernels(x) and
+        x.dtype == torch.bfloat16 and x.requires_grad):
       from lingvo_b200.ops import norm
       if norm.available():
         return norm.rms_norm_pass(x, None if p.no_scale else theta.scale, p.epsilon)
@@ -621,7 +626,12 @@ class MoELayer(_BuilderLayer):
     # streaming kernel reads the bf16 activations directly (no fp32 upcast, no N=8 SGEMM).
     from lingvo_b200.ops import gate as gate_ops
     if ldt == torch.float32 and gate_ops.supported(xg, theta.gw):
-      logits = gate_ops.gate_logits(xg, theta.gw)
+      if xg.requires_grad and _FUSE_PASS:
+        # x also feeds the expert exchange: take it from the router's autograd node so the
+        # two input gradients are summed inside the router's dx kernel.
+        logits, xg = gate_ops.gate_logits_pass(xg, theta.gw)
+      else:
+        logits = gate_ops.gate_logits(xg, theta.gw)
     else:
       logits = torch.matmul(xg.to(ldt), theta.gw.to(ldt))
     ex = self._FusedExchange(x, act)

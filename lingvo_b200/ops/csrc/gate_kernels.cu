@@ -110,7 +110,10 @@ gate_logits_fwd_kernel(const __nv_bfloat16* __restrict__ x, const WT* __restrict
 template <int E, typename WT>
 __global__ void __launch_bounds__(kGateThreads)
 gate_logits_dx_kernel(const float* __restrict__ dl, const WT* __restrict__ gw,
-                      __nv_bfloat16* __restrict__ dx, int T, int M) {
+                      const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, int T,
+                      int M) {
+  // dres (optional): gradient arriving at x along another branch; added here so that
+  // autograd does not launch a separate [T, M] add.
   extern __shared__ __align__(16) float gws[];
   stage_weights<E, WT>(gw, gws, M);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,9 +128,14 @@ gate_logits_dx_kernel(const float* __restrict__ dl, const WT* __restrict__ gw,
     for (int m = lane * 8; m < M; m += 256) {
       float o[kTok][8];
 #pragma unroll
-      for (int u = 0; u < kTok; ++u)
+      for (int u = 0; u < kTok; ++u) {
+        if (dres != nullptr && t0 + u < T) {
+          gate_load8(dres + static_cast<size_t>(t0 + u) * M + m, o[u]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[u][i] = 0.f;
+          for (int i = 0; i < 8; ++i) o[u][i] = 0.f;
+        }
+      }
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const float4 a = *reinterpret_cast<const float4*>(gws + e * M + m);
@@ -286,7 +294,8 @@ torch::Tensor gate_logits_fwd(const torch::Tensor& x, const torch::Tensor& gw) {
 // → (dx bf16 [T, M] or undefined, dgw [M, E] in gw's dtype or undefined)
 std::vector<torch::Tensor> gate_logits_bwd(const torch::Tensor& x, const torch::Tensor& gw,
                                            const torch::Tensor& dlogits, bool need_dx,
-                                           bool need_dgw) {
+                                           bool need_dgw,
+                                           const c10::optional<torch::Tensor>& dres) {
   CheckArgs(x, gw);
   TORCH_CHECK(dlogits.is_cuda() && dlogits.scalar_type() == torch::kFloat32 &&
               dlogits.is_contiguous() && dlogits.dim() == 2 && dlogits.size(0) == x.size(0) &&
@@ -297,6 +306,12 @@ std::vector<torch::Tensor> gate_logits_bwd(const torch::Tensor& x, const torch::
   auto stream = at::cuda::getCurrentCUDAStream();
   torch::Tensor dx, dgw;
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x.data_ptr());
+  const __nv_bfloat16* drp = nullptr;
+  if (dres.has_value() && dres->defined()) {
+    TORCH_CHECK(dres->is_cuda() && dres->scalar_type() == torch::kBFloat16 && dres->is_contiguous() &&
+                dres->numel() == x.numel(), "gate_logits_bwd: dres must be contiguous bf16 like x");
+    drp = reinterpret_cast<const __nv_bfloat16*>(dres->data_ptr());
+  }
   if (need_dx) {
     dx = torch::empty_like(x);
     if (T > 0) {
@@ -309,13 +324,13 @@ std::vector<torch::Tensor> gate_logits_bwd(const torch::Tensor& x, const torch::
           auto k = gate_logits_dx_kernel<kE, float>;
           AllowSmem(k, smem);
           k<<<grid, kGateThreads, smem, stream>>>(dlogits.data_ptr<float>(), gw.data_ptr<float>(),
-                                                  dxp, T, M);
+                                                  drp, dxp, T, M);
         } else {
           auto k = gate_logits_dx_kernel<kE, __nv_bfloat16>;
           AllowSmem(k, smem);
           k<<<grid, kGateThreads, smem, stream>>>(
-              dlogits.data_ptr<float>(), reinterpret_cast<const __nv_bfloat16*>(gw.data_ptr()), dxp,
-              T, M);
+              dlogits.data_ptr<float>(), reinterpret_cast<const __nv_bfloat16*>(gw.data_ptr()), drp,
+              dxp, T, M);
         }
       });
       C10_CUDA_KERNEL_LAUNCH_CHECK();

@@ -389,3 +389,22 @@ def test_rms_norm_pass_fuses_residual_gradient():
   xn2, xp2 = norm.rms_norm_pass(x, scale, 1e-6)
   (g_only,) = torch.autograd.grad(xp2, x, dy)
   assert torch.equal(g_only, dy)
+
+
+def test_gate_logits_pass_adds_the_other_branch_gradient():
+  from lingvo_b200.ops import gate
+  torch.manual_seed(0)
+  t, m, e = 777, 512, 8
+  x = torch.randn(t, m, device='cuda').to(torch.bfloat16).requires_grad_(True)
+  gw = (torch.randn(m, e, device='cuda') * 0.05).to(torch.bfloat16).requires_grad_(True)
+  w2 = (torch.randn(m, m, device='cuda') * 0.03).to(torch.bfloat16)
+  dl = torch.randn(t, e, device='cuda')
+  dy = torch.randn(t, m, device='cuda').to(torch.bfloat16)
+  logits, xp = gate.gate_logits_pass(x, gw)
+  other = xp @ w2                                   # second consumer of x
+  gx, ggw = torch.autograd.grad([logits, other], [x, gw], [dl, dy])
+  xr = x.detach().float().requires_grad_(True)
+  gr = gw.detach().float().requires_grad_(True)
+  gxr, ggr = torch.autograd.grad([gate.gate_logits_ref(xr, gr), xr @ w2.float()], [xr, gr], [dl, dy.float()])
+  torch.testing.assert_close(gx.float(), gxr, atol=6e-2, rtol=3e-2)
+  torch.testing.assert_close(ggw.float(), ggr, atol=3e-2 * ggr.abs().max().item(), rtol=3e-2)
