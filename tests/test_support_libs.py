@@ -83,3 +83,29 @@ def test_model_validator_and_models_helper():
   res = unittest.TextTestRunner(verbosity=0).run(
       unittest.defaultTestLoader.loadTestsFromTestCase(_Models))
   assert res.wasSuccessful(), res.failures + res.errors
+
+
+def test_profiling_roofline_and_nvtx_wrappers():
+  import torch
+  from lingvo_b200.utils import profiling
+  r = profiling.Roofline({'hbm_gbs': 6000.0, 'bf16_tflops': 1400.0})
+  g = r.Gemm(8192, 2048, 2048)
+  assert abs(g['flops'] - 2 * 8192 * 2048 * 2048) < 1
+  rep = r.Report('gemm', 60.0, **g)
+  assert rep['limiter'] == 'compute' and 0.7 < rep['fraction_of_roofline'] < 0.9
+  rep = r.Report('adafactor', 400.0, **r.AdafactorFactored(8 * 2048 * 8192))
+  assert rep['limiter'] == 'memory' and rep['achieved_gbs'] > 5000
+  assert r.BoundUs(**r.NormBwd(8192, 2048)) > r.BoundUs(**r.NormFwd(8192, 2048))
+  peaks = profiling.MeasuredPeaks('/nonexistent.json')
+  assert 'fallback' in peaks['source']
+  # NVTX instrumentation is a transparent wrapper (no CUDA needed when disabled)
+  from lingvo_b200.core import layers
+  p = layers.ProjectionLayer.Params().Set(name='proj', input_dim=4, output_dim=3)
+  layer = p.Instantiate()
+  x = torch.randn(2, 4)
+  want = layer.FPropDefaultTheta(x)
+  assert profiling.InstrumentLayers(layer) >= 1
+  assert profiling.InstrumentLayers(layer) == 0          # idempotent
+  torch.testing.assert_close(layer.FPropDefaultTheta(x), want)
+  with profiling.Range('noop'):
+    pass
