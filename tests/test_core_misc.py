@@ -1,0 +1,179 @@
+"""Behavioural tests of core modules that have no dedicated suite elsewhere."""
+
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lingvo_b200.core import layers, py_utils
+from lingvo_b200.core.nested_map import NestedMap
+
+
+def test_entmax_and_sparsemax():
+  from lingvo_b200.core import entmax
+  x = torch.tensor([[2.0, 1.0, 0.1, -3.0], [0.0, 0.0, 0.0, 0.0]], requires_grad=True)
+  for fn in (entmax.entmax15, entmax.sparsemax):
+    p = fn(x)
+    torch.testing.assert_close(p.sum(-1), torch.ones(2))
+    assert (p >= 0).all()
+    assert p[0, 3] == 0                                   # sparse: far-away logit gets exactly 0
+    torch.testing.assert_close(p[1], torch.full((4,), 0.25))
+  g, = torch.autograd.grad(entmax.entmax15(x)[0, 0], x)
+  assert abs(float(g[0].sum())) < 1e-5                    # gradients live on the simplex tangent
+  assert entmax.entmax_support(x)[0].tolist()[-1] in (0, False)
+
+
+def test_favor_attention_approximates_softmax_attention():
+  from lingvo_b200.core import favor_attention as fa
+  torch.manual_seed(0)
+  b, l, h, d = 2, 12, 2, 16
+  q, k, v = (torch.randn(b, l, h, d) * 0.3 for _ in range(3))
+  proj = fa.create_projection_matrix(512, d, seed=1)
+  out = fa.favor_attention(q, k, v, None, fa.softmax_kernel_transformation, causal=False,
+                           projection_matrix=proj)
+  ref = torch.einsum('blhm,bmhd->blhd', torch.softmax(
+      torch.einsum('blhd,bmhd->blhm', q, k) / math.sqrt(d), -1), v)
+  assert (out - ref).abs().mean() < 0.1 * ref.abs().mean() + 0.05
+  # causal variant: position t must not depend on the future
+  v2 = v.clone(); v2[:, -1] += 10.0
+  o1 = fa.favor_attention(q, k, v, None, fa.relu_kernel_transformation, causal=True, projection_matrix=proj)
+  o2 = fa.favor_attention(q, k, v2, None, fa.relu_kernel_transformation, causal=True, projection_matrix=proj)
+  torch.testing.assert_close(o1[:, :-1], o2[:, :-1])
+
+
+def _Fc(name, i, o):
+  return layers.FCLayer.Params().Set(name=name, input_dim=i, output_dim=o, activation='TANH')
+
+
+def test_revnet_matches_plain_autograd():
+  from lingvo_b200.core import reversible_layers as rev
+  torch.manual_seed(0)
+  p = rev.StackedRevNetLayer.Params().Set(name='rev', sub_layer_params=[
+      rev.RevNetLayer.Params().Set(name='r%d' % i, f_params=_Fc('f', 6, 6), g_params=_Fc('g', 6, 6))
+      for i in range(3)])
+  layer = p.Instantiate()
+  x1, x2 = torch.randn(4, 6, requires_grad=True), torch.randn(4, 6, requires_grad=True)
+  out = layer.FPropDefaultTheta(NestedMap(split1=x1, split2=x2))
+  loss = (out.split1 * out.split2).sum()
+  grads = torch.autograd.grad(loss, [x1, x2] + list(layer.vars.Flatten()))
+  # oracle: the same computation written out without the memory-saving Function
+  def Plain(a, b):
+    for blk in layer.sub_layers:
+      a2 = a + blk.f_block.FPropDefaultTheta(b)
+      b2 = b + blk.g_block.FPropDefaultTheta(a2)
+      a, b = a2, b2
+    return a, b
+  a, b = Plain(x1, x2)
+  ref = torch.autograd.grad((a * b).sum(), [x1, x2] + list(layer.vars.Flatten()))
+  for g, r in zip(grads, ref):
+    torch.testing.assert_close(g, r, atol=1e-5, rtol=1e-4)
+
+
+def test_generic_repeat_layer_shares_or_separates_variables():
+  from lingvo_b200.core import repeat_layer
+  p = repeat_layer.GenericRepeatLayer.Params().Set(name='rep', body=_Fc('b', 5, 5), repeat=3)
+  layer = p.Instantiate()
+  x = torch.randn(2, 5)
+  y = layer.FPropDefaultTheta(x)
+  z = x
+  for i in range(3):
+    z = layer.body_iter[i].FPropDefaultTheta(z)
+  torch.testing.assert_close(y, z)
+  assert len(layer.vars.Flatten()) == 6                     # w, b per iteration
+
+
+def test_graddrop_masks_conflicting_gradient_signs():
+  from lingvo_b200.core import graddrop
+  layer = graddrop.GradDrop.Params().Set(name='gd', keep_gradnorm_constant=False,
+                                         marginalize_batch_dim=False, use_input_sign_only=False,
+                                         random_seed=1).Instantiate()
+  x = torch.ones(3, 4)
+  layer.FPropDefaultTheta(x)
+  agree = layer.CombineLossGrads([torch.ones(3, 4), 2 * torch.ones(3, 4)])
+  torch.testing.assert_close(agree, 3 * torch.ones(3, 4))   # same sign: nothing dropped
+  conflict = layer.CombineLossGrads([torch.ones(3, 4), -torch.ones(3, 4)])
+  assert set(conflict.unique().tolist()) <= {-1.0, 1.0}     # exactly one side survives per element
+
+
+def test_pcgrad_projects_conflicting_task_gradients():
+  from lingvo_b200.core import gradient_combiner as gc
+  w = torch.nn.Parameter(torch.zeros(2)); w.var_name = 'w/var'
+  vmap = NestedMap(w=w)
+  def Entry(g):
+    return NestedMap(loss_metric=(torch.tensor(1.0), torch.tensor(1.0)),
+                     grads=NestedMap(w=py_utils.VarGrad(w, torch.tensor(g))))
+  comb = gc.PCGradCombiner.Params().Set(name='pc').Instantiate()
+  out, _ = comb.Combine(vmap, {'a': Entry([1.0, 0.0]), 'b': Entry([-1.0, 1.0])})
+  g = out.w.grad
+  # each task gradient is projected onto the normal plane of the other: no component of the sum
+  # points against either original gradient
+  assert float(g @ torch.tensor([1.0, 0.0])) >= -1e-6 and float(g @ torch.tensor([-1.0, 1.0])) >= -1e-6
+  summed, _ = gc.SumCombiner.Params().Set(name='s').Instantiate().Combine(
+      vmap, {'a': Entry([1.0, 0.0]), 'b': Entry([-1.0, 1.0])})
+  torch.testing.assert_close(summed.w.grad, torch.tensor([0.0, 1.0]))
+
+
+def test_bleu_scorers_agree_on_perfect_and_imperfect_hyps():
+  from lingvo_b200.core import ml_perf_bleu_metric as mlb, scorers
+  refs = ['the quick brown fox jumps over the lazy dog', 'hello there general kenobi you are bold']
+  s = scorers.BleuScorer()
+  for r in refs:
+    s.AddSentence(r, r)
+  assert abs(s.ComputeOverallScore() - 1.0) < 1e-6
+  assert abs(mlb.bleu_wrapper(refs, refs) - 1.0) < 1e-6       # fraction, like the reference
+  hyps = ['the quick brown cat jumps over the lazy dog', 'hello there general kenobi you are old']
+  m = mlb.MlPerfBleuMetric()
+  for r, h in zip(refs, hyps):
+    m.Update(r, h)
+  assert 0.40 < m.value < 0.95
+  assert mlb.bleu_tokenize('Hello, world!') == ['Hello', ',', 'world', '!']
+
+
+def test_early_stop_and_metric_history(tmp_path):
+  from lingvo_b200.core import early_stop
+  mh = early_stop.MetricHistory.Params().Set(logdir=str(tmp_path), jobname='eval',
+                                             metric='loss').Instantiate()
+  for step, v in [(10, 3.0), (20, 2.0), (30, 2.5), (40, 2.4), (50, 2.3)]:
+    mh.ConditionalAppend('eval', 'loss', step, v)
+  best, last = early_stop.BestStep(mh.hist_file, 0.0, True)
+  assert (best, last) == (20, 50)
+  es = early_stop.EarlyStop.Params().Set(name='es', window=20, tolerance=0.0,
+                                         metric_history=mh.params).Instantiate()
+  assert es.Stop()                                          # 30 steps since the best > window
+  es2 = early_stop.EarlyStop.Params().Set(name='es', window=100, metric_history=mh.params).Instantiate()
+  assert not es2.Stop()
+
+
+def test_differentiable_assignment_respects_marginals():
+  from lingvo_b200.core import differentiable_assignment as da
+  torch.manual_seed(0)
+  score = torch.randn(2, 4, 6, requires_grad=True)
+  rows, cols = torch.full((2, 4), 1.5), torch.full((2, 6), 1.0)
+  a, iters, eps, delta = da.max_assignment(
+      score, elementwise_upper_bound=torch.ones(2, 4, 6), row_sums=rows, col_sums=cols,
+      epsilon=0.05, num_iterations=200)
+  assert a.shape == score.shape and (a >= -1e-6).all() and (a <= 1 + 1e-4).all()
+  torch.testing.assert_close(a.sum(-1), rows, atol=2e-2, rtol=2e-2)
+  torch.testing.assert_close(a.sum(-2), cols, atol=2e-2, rtol=2e-2)
+  assert iters == 200 and abs(eps - 0.05) < 1e-9 and float(delta) < 0.05
+  # low temperature → near-integral, and it prefers high scores
+  assert float(((a > 0.9) | (a < 0.1)).float().mean()) > 0.7
+  assert float((a * score).sum()) > float((score.detach().mean() * a.sum()))
+  g, = torch.autograd.grad((a * torch.randn_like(a)).sum(), score)
+  assert torch.isfinite(g).all() and g.abs().sum() > 0
+
+
+def test_egdd_optimizer_descends():
+  from lingvo_b200.core import egdd
+  torch.manual_seed(0)
+  w = torch.nn.Parameter(torch.randn(6)); w.var_name = 'w/var'
+  opt = egdd.EGDD.Params().Set(name='egdd').Instantiate()
+  first = None
+  for _ in range(60):
+    loss = (w ** 2).sum()
+    g, = torch.autograd.grad(loss, w)
+    opt.Apply(0.05, [py_utils.VarGrad(w, g)])
+    first = first or float(loss)
+  assert float((w ** 2).sum()) < 0.5 * first
