@@ -177,3 +177,88 @@ def test_egdd_optimizer_descends():
     opt.Apply(0.05, [py_utils.VarGrad(w, g)])
     first = first or float(loss)
   assert float((w ** 2).sum()) < 0.5 * first
+
+
+def test_task_schedulers():
+  from lingvo_b200.core import task_scheduler as ts
+  c = ts.ConstantScheduler.Params().Set(name='c', task_probs=[('a', 0.8), ('b', 0.2)], random_seed=3).Instantiate()
+  picks = [c.Sample(s) for s in range(2000)]
+  assert 0.74 < picks.count('a') / 2000 < 0.86
+  assert [c.Sample(7) for _ in range(3)] == [c.Sample(7)] * 3          # seeded: a function of the step
+  e = ts.ExponentialScheduler.Params().Set(name='e', alpha=0.01, random_seed=1,
+                                           task_probs=[('a', (1.0, 0.0)), ('b', (0.0, 1.0))]).Instantiate()
+  e.Sample(0); p0 = e.cur_probs
+  e.Sample(2000); p1 = e.cur_probs
+  assert p0[0] > 0.99 and p1[1] > 0.99                                   # drifts from a to b
+  rr = ts.RoundRobinScheduler.Params().Set(name='r', tasks=['x', 'y', 'z']).Instantiate()
+  assert [rr.Sample(i) for i in range(5)] == ['x', 'y', 'z', 'x', 'y']
+  sq = ts.SequentialScheduler.Params().Set(name='s', task_steps=[('p', 2), ('q', 3)]).Instantiate()
+  assert [sq.Sample(i) for i in range(6)] == ['p', 'p', 'q', 'q', 'q', 'q']
+
+
+def test_wpm_encoder_roundtrip(tmp_path):
+  from lingvo_b200.core import wpm_encoder
+  bow = wpm_encoder.BOW_STR
+  vocab = ['<unk>', '<s>', '</s>', bow + 'hel', 'lo', bow + 'wor', 'ld', bow, 'h', 'e', 'l', 'o']
+  f = tmp_path / 'wpm.txt'
+  f.write_text('\n'.join(vocab) + '\n', encoding='utf-8')
+  enc = wpm_encoder.WpmEncoder(str(f))
+  ids, pieces = enc.Encode('hello world')
+  assert pieces == [bow + 'hel', 'lo', bow + 'wor', 'ld']
+  assert enc.Decode(ids) == 'hello world'
+  assert enc.EncodeWord('zzz')[0] == bow and '<unk>' in enc.EncodeWord('zzz')
+  assert (enc.sentence_start_id, enc.sentence_end_id, enc.unk_id) == (1, 2, 0)
+
+
+def test_flat_beam_search_finds_the_most_likely_sequence():
+  from lingvo_b200.core import flat_beam_search_helper as fbs
+  # A fixed first-order model: after token t the next-token log-probs are row t of `table`.
+  v, eos = 5, 2
+  table = torch.full((v, v), -4.0)
+  table[1, 3] = 0.0      # <s> → 3
+  table[3, 4] = 0.0      # 3 → 4
+  table[4, eos] = 0.0    # 4 → </s>
+  table[1, 4] = -0.5     # a tempting but worse branch: <s> → 4 → </s>
+
+  def Callback(ids, pos, seg, mask, state, t):
+    del pos, seg, mask, t
+    return table[ids], state
+
+  (out_ids, lens, scores), _ = fbs.flat_beam_search(2, 3, 6, Callback, None, bos_id=1, eos_id=eos,
+                                                    beam_gap=None)
+  assert out_ids.shape[:2] == (2, 3)
+  best = out_ids[0, 0, :int(lens[0, 0])].tolist()
+  assert best == [3, 4, eos], (best, scores[0])
+  assert scores[0, 0] >= scores[0, 1] >= scores[0, 2]
+  second = out_ids[0, 1, :int(lens[0, 1])].tolist()
+  assert second == [4, eos]
+  m, s = fbs.update_nbest((torch.zeros(1, 2, 4, dtype=torch.bool), torch.tensor([[0.5, 0.1]])),
+                          (torch.ones(1, 2, 4, dtype=torch.bool), torch.tensor([[0.3, 0.9]])))
+  torch.testing.assert_close(s, torch.tensor([[0.9, 0.5]]))
+  assert m[0, 0].all() and not m[0, 1].any()
+
+
+def test_activations_table_and_inspect_utils():
+  from lingvo_b200.core import activations, hyperparams, inspect_utils
+  x = torch.linspace(-2, 2, 9)
+  torch.testing.assert_close(activations.GetFn('RELU')(x), torch.relu(x))
+  torch.testing.assert_close(activations.GetFn('SWISH')(x), x * torch.sigmoid(x))
+  assert activations.IsSupported('GELU') and not activations.IsSupported('NOPE')
+  assert activations.DimMultiplier('GATED_GELU') == 2 and activations.DimMultiplier('RELU') == 1
+  assert activations.GetFlops('NONE') == 0 and activations.GetFlops('TANH') > 0
+
+  def Fn(a, b=2, *, c='x'):
+    return (a, b, c)
+  p = hyperparams.Params()
+  inspect_utils.DefineParams(Fn, p)
+  assert (p.a, p.b, p.c) == (None, 2, 'x')
+  p.a = 5
+  assert inspect_utils.CallWithParams(Fn, p, c='y') == (5, 2, 'y')
+
+  class Thing:
+    def __init__(self, size, name='t'):
+      self.size, self.name = size, name
+  q = inspect_utils.ParamsFromCallable(Thing.__init__, ignore=['self'])
+  q.size = 3
+  t = inspect_utils.ConstructWithParams(Thing, q)
+  assert (t.size, t.name) == (3, 't')
