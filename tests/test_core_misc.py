@@ -262,3 +262,90 @@ def test_activations_table_and_inspect_utils():
   q.size = 3
   t = inspect_utils.ConstructWithParams(Thing, q)
   assert (t.size, t.name) == (3, 't')
+
+
+def _Lin(name, i, o):
+  from lingvo_b200.core import builder_layers as bl
+  return bl.LinearLayer.Params().Set(name=name, input_dims=i, output_dims=o)
+
+
+def test_builder_layers_combinators():
+  from lingvo_b200.core import builder_layers as bl
+  torch.manual_seed(0)
+  x = torch.randn(3, 4)
+  seq = bl.SequentialLayer.Params().Set(name='seq', sub=[
+      _Lin('a', 4, 6), bl.MapLayer.Params().Set(name='act', fn=torch.tanh), _Lin('b', 6, 2)]).Instantiate()
+  y = seq.FPropDefaultTheta(x)
+  want = torch.tanh(x @ seq.a.vars.w) @ seq.b.vars.w
+  torch.testing.assert_close(y, want)
+  # stacked-variable repeat: one [repeat, …] variable, applied slice by slice
+  rep = bl.RepeatLayer.Params().Set(name='rep', body=_Lin('l', 4, 4), repeat=3).Instantiate()
+  w = rep.body.vars.w
+  assert tuple(w.shape) == (3, 4, 4)
+  z = x
+  for i in range(3):
+    z = z @ w[i]
+  torch.testing.assert_close(rep.FPropDefaultTheta(x), z, atol=1e-5, rtol=1e-5)
+  par = bl.ParallelLayer.Params().Set(
+      name='par', sub=[_Lin('left', 4, 2), _Lin('right', 4, 2)],
+      merge=lambda outs: tuple(sum(o[0] for o in outs) for _ in range(1))).Instantiate()
+  torch.testing.assert_close(par.FPropDefaultTheta(x), x @ par.left.vars.w + x @ par.right.vars.w)
+  g = bl.GraphLayer.Params().Set(name='g', input_endpoints=['x'], output_endpoints=['y', 'h'], sub=[
+      ('x->h', _Lin('first', 4, 5)),
+      ('h->t', bl.MapLayer.Params().Set(name='sq', fn=torch.square)),
+      ('t->y', _Lin('second', 5, 1))]).Instantiate()
+  gy, gh = g.FPropDefaultTheta(x)
+  torch.testing.assert_close(gh, x @ g.first.vars.w)
+  torch.testing.assert_close(gy, torch.square(gh) @ g.second.vars.w)
+  first = bl.FirstNLayer.Params().Set(name='f', n=2).Instantiate()
+  assert first.FPropDefaultTheta(1, 2, 3) == (1, 2)
+  remat = bl.RematerializationLayer.Params().Set(name='rm', body=_Lin('inner', 4, 4)).Instantiate()
+  xr = x.clone().requires_grad_(True)
+  out = remat.FPropDefaultTheta(xr)
+  gx, = torch.autograd.grad(out.sum(), xr)
+  torch.testing.assert_close(gx, (torch.ones(3, 4) @ remat.body.vars.w.t()))
+  sig = bl.GraphSignature('a,b.c,[d,e],(k=f)->g,h.i')
+  assert sig.outputs == ['g', 'h.i'] and len(sig.inputs) == 4
+  with pytest.raises(ValueError):
+    bl.GraphSignature('a->1bad')
+
+
+def test_pruning_schedule_and_masks():
+  from lingvo_b200.core import pruning_utils as pu
+  pu.PruningOp.Reset()
+  hp = dict(begin_pruning_step=10, end_pruning_step=110, initial_sparsity=0.0, target_sparsity=0.75,
+            sparsity_function_exponent=3.0)
+
+  class Obj:
+    pass
+  torch.manual_seed(0)
+  w = torch.nn.Parameter(torch.randn(16, 8)); w.var_name = 'lstm/wm/var'
+  obj = Obj(); obj.vars = NestedMap(wm=w)
+  mask = pu.PruningOp.ApplyPruning(hp, obj, 'wm', None, torch.float32)
+  assert mask.all()
+  assert pu.PruningOp.Sparsity(0) == 0.0 and abs(pu.PruningOp.Sparsity(110) - 0.75) < 1e-9
+  assert 0.0 < pu.PruningOp.Sparsity(40) < pu.PruningOp.Sparsity(80) < 0.75      # cubic ramp
+  s = pu.PruningOp.UpdateMasks(110)
+  kept = float(mask.mean())
+  assert abs(s - 0.75) < 1e-9 and abs(kept - 0.25) < 0.02
+  # the smallest-magnitude weights are the ones removed
+  assert float(w.detach().abs()[mask == 0].max()) <= float(w.detach().abs()[mask == 1].min())
+  mw = pu.PruningOp.MaskedWeight(w)
+  assert float((mw == 0).float().mean()) >= 0.74
+  pu.PruningOp.Reset()
+
+
+def test_saver_sanity_checks_block_bad_checkpoints(tmp_path):
+  from lingvo_b200.core import saver as saver_lib
+  state = {'w/var': torch.ones(3), 'global_step': torch.tensor(5)}
+  sv = saver_lib.Saver(str(tmp_path), lambda: state,
+                       sanity_checks=[(r'w/', [saver_lib.IsFinite()])])
+  path = sv.Save(5)
+  assert saver_lib.LatestCheckpoint(str(tmp_path)) == path
+  assert saver_lib.ReadCheckpointState(str(tmp_path))['model_checkpoint_path']
+  state['w/var'] = torch.tensor([1.0, float('nan'), 0.0])
+  with pytest.raises(saver_lib.SanityCheckFailed):
+    sv.Save(6)
+  assert saver_lib.LatestCheckpoint(str(tmp_path)) == path                       # nothing committed
+  rng = saver_lib.InRange(-1.0, 1.0)
+  assert rng.Check('v', torch.tensor([0.5])) and not rng.Check('v', torch.tensor([2.0]))
