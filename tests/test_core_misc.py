@@ -349,3 +349,55 @@ def test_saver_sanity_checks_block_bad_checkpoints(tmp_path):
   assert saver_lib.LatestCheckpoint(str(tmp_path)) == path                       # nothing committed
   rng = saver_lib.InRange(-1.0, 1.0)
   assert rng.Check('v', torch.tensor([0.5])) and not rng.Check('v', torch.tensor([2.0]))
+
+
+def test_tpu_embedding_layer_sparse_updates_touch_only_looked_up_rows():
+  from lingvo_b200.core import tpu_embedding_layers as tel
+  torch.manual_seed(0)
+  table = tel.TPUEmbeddingTable.Params().Set(
+      name='t', vocab_size=20, embedding_dim=4, input_keys=['a', 'b'], combiner='mean')
+  layer = tel.TPUEmbeddingLayer.Params().Set(
+      name='emb', tables=[table], learning_rate=0.5,
+      optimizer=tel.TPUEmbeddingSGDOptimizer.Params()).Instantiate()
+  before = layer.tables[0].table.detach().clone()
+  ids = NestedMap(a=torch.tensor([[1, 3, -1], [3, 3, 5]]), b=torch.tensor([[7, -1, -1], [-1, -1, -1]]))
+  out = layer.EmbLookup(layer.theta, ids)
+  assert out.a.shape == (2, 4) and out.b.shape == (2, 4)
+  torch.testing.assert_close(out.a[0], (before[1] + before[3]) / 2)            # mean over valid ids
+  torch.testing.assert_close(out.b[1], torch.zeros(4))                          # all-missing row
+  (out.a.sum() + out.b.sum()).backward()
+  layer.ApplyGradients(global_step=0)
+  after = layer.tables[0].table.detach()
+  changed = (after != before).any(-1).nonzero().flatten().tolist()
+  assert changed == [1, 3, 5, 7]
+  # row 3 was hit with weights 1/2 (example 0) and 2·1/3 (example 1): SGD step = lr · Σ
+  torch.testing.assert_close(before[3] - after[3], torch.full((4,), 0.5 * (0.5 + 2.0 / 3.0)))
+
+
+def test_attention_util_blocks_masks_and_sparse_attention():
+  from lingvo_b200.core import attention_util as au
+  x = torch.arange(2 * 7 * 3, dtype=torch.float32).reshape(2, 7, 3)
+  blocks = au.ConvertToBlocks(x, 3)
+  assert blocks.shape == (2, 3, 3, 3) and (blocks[:, 2, 1:] == 0).all()
+  ctx = au.ExtractBlockContext(x, block_size=3, left_context=2, right_context=1)
+  assert ctx.shape == (2, 3, 5, 3)
+  torch.testing.assert_close(ctx[:, 1, 1:4], x[:, 3:6])                        # the block itself
+  torch.testing.assert_close(ctx[:, 1, 0], x[:, 2])                            # one step of left context
+  mask = au.MakeLocalMask(7, 3, 2, 1)
+  assert mask.shape == (3, 3, 5)
+  # query t=4 (block 1, w=1) sees keys 3..5: context positions k = block*3 - 1 + c
+  assert mask[1, 1].tolist() == [0.0, 1.0, 1.0, 1.0, 0.0]
+  t = 4
+  rel = torch.randn(1, 1, t, 2 * t - 1)
+  shifted = au.RelShift(rel)
+  for i in range(t):
+    for j in range(t):
+      assert shifted[0, 0, i, j] == rel[0, 0, i, j - i + t - 1]
+  torch.manual_seed(0)
+  q, k, v = torch.randn(1, 2, 5, 8), torch.randn(1, 2, 6, 8), torch.randn(1, 2, 6, 8)
+  idx = torch.tensor([0, 2, -1]).expand(1, 2, 5, 3)
+  out, probs = au.ComputeSparseAttention(q, k, v, idx)
+  logits = torch.einsum('bnth,bnsh->bnts', q, k)[..., [0, 2]] / math.sqrt(8)
+  want = torch.einsum('bntw,bnwh->bnth', torch.softmax(logits, -1), v[:, :, [0, 2]])
+  torch.testing.assert_close(out, want, atol=1e-5, rtol=1e-5)
+  assert (probs[..., 2] == 0).all()
