@@ -18,8 +18,7 @@ class DistillationTask(base_model.BaseTask):
     p = super().Params()
     p.Define('teacher', None, 'Teacher task params.')
     p.Define('student', None, 'Student task params.')
-    p.Define('distillation_loss_weight', schedule.Constant.Params().Set(value=1.0)
-             if hasattr(schedule.Constant.Params(), 'value') else schedule.Constant.Params(),
+    p.Define('distillation_loss_weight', schedule.Constant.Params().Set(value=1.0),
              'Schedule of the distillation-loss weight.')
     p.Define('teacher_target_type', 'truth', 'truth | beam (kept for parity).')
     p.Define('beam_search_temperature', 1.0, 'Softmax temperature T.')
@@ -35,7 +34,11 @@ class DistillationTask(base_model.BaseTask):
     self.CreateChild('teacher', p.teacher)
     self.CreateChild('student', p.student)
     self.CreateChild('distillation_loss_weight', p.distillation_loss_weight)
-    if not p.train_teacher:
+
+  def _CreateChildrenVariables(self):
+    # Variables are materialised after __init__; the teacher is frozen once they exist.
+    super()._CreateChildrenVariables()
+    if not self.params.train_teacher:
       for v in self.teacher.vars.Flatten():
         v.requires_grad_(False)
 

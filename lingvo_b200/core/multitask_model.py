@@ -52,8 +52,10 @@ class RegExSharedVariableModel(base_model.MultiTaskModel):
     p.Define('variable_renaming_rules', None, 'List of (regex, format string).')
     return p
 
-  def __init__(self, params):
-    super().__init__(params)
+  def _CreateChildrenVariables(self):
+    # Variables are created lazily (after __init__), so sharing is applied right after the
+    # children's variables exist.
+    super()._CreateChildrenVariables()
     rules = [(re.compile(r), fmt) for r, fmt in (self.params.variable_renaming_rules or [])]
     canon = {}
     for task in self.tasks:

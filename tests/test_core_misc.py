@@ -401,3 +401,30 @@ def test_attention_util_blocks_masks_and_sparse_attention():
   want = torch.einsum('bntw,bnwh->bnth', torch.softmax(logits, -1), v[:, :, [0, 2]])
   torch.testing.assert_close(out, want, atol=1e-5, rtol=1e-5)
   assert (probs[..., 2] == 0).all()
+
+
+def test_lstm_frnn_matches_generic_frnn():
+  from lingvo_b200.core import lstm_frnn_layer, rnn_cell, rnn_layers
+  torch.manual_seed(0)
+  cell = lstm_frnn_layer.LSTMCellSimpleExt.Params().Set(name='cell', num_input_nodes=5, num_output_nodes=7)
+  fast = lstm_frnn_layer.LstmFRNN.Params().Set(name='fast', cell=cell, remat_steps=3).Instantiate()
+  slow = rnn_layers.FRNN.Params().Set(
+      name='slow', cell=rnn_cell.LSTMCellSimple.Params().Set(name='cell', num_input_nodes=5,
+                                                             num_output_nodes=7)).Instantiate()
+  for a, b in zip(slow.vars.Flatten(), fast.vars.Flatten()):
+    a.data.copy_(b.data)
+  x = torch.randn(9, 2, 5, requires_grad=True)
+  pad = torch.zeros(9, 2, 1); pad[6:, 1] = 1.0
+  y1, s1 = fast.FPropDefaultTheta(x, pad)
+  y2, s2 = slow.FPropDefaultTheta(x, pad)
+  torch.testing.assert_close(y1, y2, atol=1e-5, rtol=1e-5)
+  torch.testing.assert_close(s1.c, s2.c, atol=1e-5, rtol=1e-5)
+  g1, = torch.autograd.grad(y1.sum(), x, retain_graph=True)
+  g2, = torch.autograd.grad(y2.sum(), x)
+  torch.testing.assert_close(g1, g2, atol=1e-5, rtol=1e-4)
+  rev = lstm_frnn_layer.LstmFRNN.Params().Set(name='rev', cell=cell, reverse=True).Instantiate()
+  for a, b in zip(rev.vars.Flatten(), fast.vars.Flatten()):
+    a.data.copy_(b.data)
+  yr, _ = rev.FPropDefaultTheta(x, torch.zeros(9, 2, 1))
+  yf, _ = fast.FPropDefaultTheta(torch.flip(x, [0]), torch.zeros(9, 2, 1))
+  torch.testing.assert_close(yr, torch.flip(yf, [0]), atol=1e-5, rtol=1e-5)
