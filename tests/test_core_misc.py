@@ -428,3 +428,56 @@ def test_lstm_frnn_matches_generic_frnn():
   yr, _ = rev.FPropDefaultTheta(x, torch.zeros(9, 2, 1))
   yf, _ = fast.FPropDefaultTheta(torch.flip(x, [0]), torch.zeros(9, 2, 1))
   torch.testing.assert_close(yr, torch.flip(yf, [0]), atol=1e-5, rtol=1e-5)
+
+
+def test_gshard_utils_sharding_specs():
+  from lingvo_b200.core import gshard_utils as gu
+  mesh = np.arange(8).reshape(2, 4)
+  spec = gu.TensorShardingSpec.FromFullShape([10, 16, 3], [1, 0, -1], mesh)
+  assert not spec.is_replicated and spec.uneven_padding == [2, 0, 0]
+  assert spec.ShardShape([10, 16, 3]) == [3, 8, 3] and spec.NumShards(0) == 4
+  # shards tile the tensor exactly once (last shard of an uneven dim is shorter)
+  cover = np.zeros((10, 16, 3), int)
+  for a in range(2):
+    for b in range(4):
+      cover[spec.ShardSlices([10, 16, 3], (a, b))] += 1
+  assert (cover == 1).all()
+  assert spec.AddLeadingDims(2).split_dims_mapping == [-1, -1, 1, 0, -1]
+  assert spec.RemoveDim(1).split_dims_mapping == [1, -1]
+  assert gu.TensorShardingSpec.ReplicatedSpec().is_replicated
+  x = torch.zeros(4, 6)
+  y = gu.Split(x, 1, 2)
+  assert gu.GetSharding(y).split_dims_mapping == [-1, 0]
+  with gu.MeshSplitDimPrefixContext(1):
+    z = gu.MeshSplit(torch.zeros(3, 4, 6), mesh, [0, -1])
+    assert gu.GetMeshSplitDimPrefixContext() == [1]
+  assert gu.GetSharding(z).split_dims_mapping == [1, 0, -1]
+  assert gu.GetMeshSplitDimPrefixContext() == []
+  zz = gu.ZigzagOrderOnDeviceMesh(np.arange(8), 0)
+  assert zz.tolist() == [0, 2, 4, 6, 7, 5, 3, 1]
+  v = torch.nn.Parameter(torch.zeros(10, 16)); v.device_mesh = mesh; v.tensor_split_dims_mapping = [0, 1]
+  assert gu.GetVarSharding(v).ShardShape([10, 16]) == [5, 4]
+  assert gu.GetVarSharding(torch.nn.Parameter(torch.zeros(2))).is_replicated
+
+
+def test_datasources_mixing_curriculum_and_iterators():
+  from lingvo_b200.core import datasource as ds
+  mk = lambda tag: ds.IteratorDataSource.Params().Set(
+      name='it_' + tag, iter_fn=lambda: iter([NestedMap(src=tag, i=k) for k in range(3)]))
+  it = mk('a').Instantiate()
+  assert [it.GetNext().i for _ in range(5)] == [0, 1, 2, 0, 1]           # repeats
+  once = ds.IteratorDataSource.Params().Set(name='once', repeat=False,
+                                            iter_fn=lambda: iter([NestedMap(i=0)])).Instantiate()
+  once.GetNext()
+  with pytest.raises(StopIteration):
+    once.GetNext()
+  mix = ds.CrossBatchMixingDataSource.Params().Set(
+      name='mix', sub=[mk('a'), mk('b')], weights=[0.9, 0.1], random_seed=1).Instantiate()
+  picks = [mix.GetNext() for _ in range(400)]
+  frac_a = sum(b.src == 'a' for b in picks) / 400
+  assert 0.84 < frac_a < 0.96 and int(picks[0].source_selected[0]) in (0, 1)
+  cur = ds.CurriculumDataSource.Params().Set(name='cur', sub=[mk('a'), mk('b')], boundaries=[10]).Instantiate()
+  with py_utils.GlobalStepContext(3):
+    assert cur.GetNext().src == 'a'
+  with py_utils.GlobalStepContext(10):
+    assert cur.GetNext().src == 'b'
