@@ -176,3 +176,24 @@ def test_trainer_mnist_logdir_artifacts(tmp_path, monkeypatch):
   score = open(os.path.join(logdir, 'eval_test', 'score-00000002.txt')).read()
   assert 'accuracy:' in score and 'log_pplx:' in score
   flags.FLAGS.reset()
+
+
+def test_executor_job_runs_program_schedule(tmp_path, monkeypatch):
+  """`--job=executor_tpu` (reference call stack §3.4): train program → eval program per loop,
+  checkpoints and per-program event files / scores in the logdir."""
+  from lingvo_b200 import flags, trainer
+  from lingvo_b200.models.image import input_generator
+  data = input_generator.FakeMnistData(str(tmp_path), train_size=64, test_size=32)
+  monkeypatch.setenv('LINGVO_B200_MNIST', data)
+  logdir = str(tmp_path / 'log')
+  flags.FLAGS.reset()
+  trainer.main(['trainer', '--run_locally=cpu', '--mode=sync', '--model=image.mnist.LeNet5',
+                '--job=executor_tpu', '--logdir=' + logdir,
+                '--model_params_override=task.train.max_steps:6;input.batch_size:8'])
+  flags.FLAGS.reset()
+  for f in ['control/params.txt', 'train/checkpoint', 'train/ckpt-00000100.index',
+            'EvalProgram_test/score-00000100.txt']:
+    assert os.path.exists(os.path.join(logdir, f)), f
+  assert glob.glob(os.path.join(logdir, 'TrainProgram_train', 'events.out.tfevents.*'))
+  score = open(os.path.join(logdir, 'EvalProgram_test', 'score-00000100.txt')).read()
+  assert 'accuracy' in score
