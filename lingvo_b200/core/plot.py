@@ -114,6 +114,18 @@ def Image(name, figsize, image, setter=None, **kwargs):
   return FigureToPng(fig)
 
 
+def Custom(name, figsize, setter):
+  """One-axes figure drawn entirely by `setter(fig, axes)` → PNG bytes (None without
+  matplotlib)."""
+  del name
+  if not _HAS_MPL:
+    return None
+  fig = plt.figure(figsize=figsize)
+  ax = fig.add_subplot(1, 1, 1)
+  setter(fig, ax)
+  return FigureToPng(fig)
+
+
 def Scatter(name, figsize, xs, ys, setter=None, **kwargs):
   if not _HAS_MPL:
     return None

@@ -118,11 +118,10 @@ class BreakdownMetric:
         axes.set_xticklabels(self.BinLabels(), rotation=45, fontsize=6)
         axes.set_ylim(0, 1)
         axes.set_title('%s AP by %s' % (names[c], type(self).__name__))
-      try:
-        images.append(('%s/%s/%s' % (name, type(self).__name__, names[c]),
-                       plot.Image(_Setter, figsize=(5, 3))))
-      except Exception:  # pylint: disable=broad-except   (no matplotlib backend)
-        pass
+      tag = '%s/%s/%s' % (name, type(self).__name__, names[c])
+      png = plot.Custom(tag, (5, 3), _Setter)       # None when matplotlib is not installed
+      if png is not None:
+        images.append((tag, png))
     return self.Scalars(name), images
 
 

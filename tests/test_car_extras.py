@@ -432,3 +432,49 @@ def test_registered_car_params():
   assert 'images' in mp.input.extractors and mp.task.location_loss.cls is paf.LaplaceKL
   assert os.environ.get('LINGVO_B200_KITTI', '/tmp/kitti/') in model_registry.GetParams(
       'car.kitti.StarNetCarModel0701', 'Train').input.file_pattern
+
+
+def test_breakdown_metrics_bins_and_tables():
+  from lingvo_b200.core.nested_map import NestedMap
+  from lingvo_b200.models.car import breakdown_metric as bm
+  from lingvo_b200.models.car import kitti_metadata
+  meta = kitti_metadata.KITTIMetadata()
+  dist = bm.ByName('distance').Params().Set(metadata=meta).Instantiate()
+  w = meta.DistanceBinWidth()
+  boxes = np.array([[w * 0.5, 0, 0, 1, 1, 1, 0.0], [w * 2.2, 0, 0, 1, 1, 1, 2.0],
+                    [1e6, 0, 0, 1, 1, 1, 0.0]], np.float32)
+  bins = dist.Discretize(boxes)
+  assert bins.tolist() == [0, 2, dist.NumBinsOfHistogram() - 1]              # far boxes clip
+  dist.AccumulateHistogram(NestedMap(bboxes=boxes, labels=np.array([1, 1, 4])))
+  assert dist._histogram[0, 1] == 1 and dist._histogram[2, 1] == 1 and dist._histogram[-1, 4] == 1
+  assert len(dist.BinLabels()) == dist.NumBinsOfHistogram()
+  rot = bm.ByRotation.Params().Set(metadata=meta).Instantiate()
+  rb = rot.Discretize(np.array([[0, 0, 0, 1, 1, 1, 0.01], [0, 0, 0, 1, 1, 1, meta.MaximumRotation() - 0.01]]))
+  assert rb[0] == 0 and rb[1] == rot.NumBinsOfHistogram() - 1
+  pts = bm.ByNumPoints.Params().Set(metadata=meta).Instantiate()
+  pb = pts.Discretize([1, 10, 10 ** 9])
+  assert pb[0] == 0 and pb[0] <= pb[1] <= pb[2] == pts.NumBinsOfHistogram() - 1
+  pts.AccumulateCumulative(NestedMap(num_points=np.array([1, 10])))
+  assert pts._values.sum() == 11
+  diff = bm.ByDifficulty.Params().Set(metadata=meta).Instantiate()
+  assert diff.BinLabels()[-1] == 'default' and diff.NumBinsOfHistogram() == 4
+  # ComputeMetrics fills AP / recall tables from whatever the AP metric returns per bin
+  n_eval, pr_pts = len(meta.EvalClassIndices()), meta.NumberOfPrecisionRecallPoints()
+  calls = []
+  def Fn(difficulty=None):
+    calls.append(difficulty)
+    if difficulty == 'hard':
+      return None                                                     # no ground truth in this bin
+    pr = np.zeros((n_eval, pr_pts, 2), np.float32)
+    pr[..., 0] = 0.9
+    pr[..., 1] = np.linspace(1.0, 0.0, pr_pts)[None, :]
+    return np.full(n_eval, 0.5, np.float32), pr
+  diff.ComputeMetrics(Fn)
+  assert calls == ['hard', 'moderate', 'easy', None]
+  scalars, images = diff.GenerateSummaries('kitti')
+  assert any(k.endswith('_default') and v == 0.5 for k, v in scalars.items())
+  assert not any('_hard' in k for k in scalars)
+  assert isinstance(images, list)
+  assert np.allclose(diff._max_recall[1:], 1.0)
+  with pytest.raises(Exception):
+    bm.ByName('nope')

@@ -481,3 +481,36 @@ def test_datasources_mixing_curriculum_and_iterators():
     assert cur.GetNext().src == 'a'
   with py_utils.GlobalStepContext(10):
     assert cur.GetNext().src == 'b'
+
+
+def test_summary_collector_step_rate_and_model_analysis(tmp_path):
+  from lingvo_b200.core import plot, summary_utils
+  from lingvo_b200.utils import tfevents
+  with summary_utils.SummaryCollector() as col:
+    summary_utils.scalar('a/loss', torch.tensor(1.5))
+    summary_utils.scalar('b/const', 2)
+    summary_utils.histogram('h', torch.arange(10.0))
+    summary_utils.text('t', 'hello')
+  summary_utils.scalar('ignored', 3.0)                       # no active collector: dropped
+  vals = col.Resolve()
+  assert vals == {'a/loss': 1.5, 'b/const': 2.0}
+  w = tfevents.EventFileWriter(str(tmp_path))
+  col.WriteTo(w, step=7)
+  w.close()
+  scalars = list(tfevents.ReadScalars(w.path))
+  assert (7, 'a/loss', 1.5) in scalars and (7, 'b/const', 2.0) in scalars
+  tr = summary_utils.StepRateTracker()
+  import time
+  r0 = tr.ComputeStepRate(0, 0)
+  time.sleep(0.05)
+  rate, ex_rate, total = tr.ComputeStepRate(10, 320)
+  assert r0[0] == 0.0 and 50 < rate < 400 and abs(ex_rate / rate - 32.0) < 1e-6 and total == 320
+  layer = layers.FCLayer.Params().Set(name='fc', input_dim=4, output_dim=3).Instantiate()
+  table, n = summary_utils.ModelAnalysis(layer)
+  assert n == 4 * 3 + 3 and 'fc/w/var' in table and '(4, 3)' in table
+  # plotting degrades to None without matplotlib instead of failing
+  fig = plot.MatplotlibFigureSummary('fig')
+  fig.AddSubplot([np.zeros((2, 3, 3))])
+  out = fig.Finalize()
+  assert out is None or isinstance(out, list)
+  assert plot.ToUnicode(b'abc') == 'abc'
