@@ -514,3 +514,35 @@ def test_summary_collector_step_rate_and_model_analysis(tmp_path):
   out = fig.Finalize()
   assert out is None or isinstance(out, list)
   assert plot.ToUnicode(b'abc') == 'abc'
+
+
+def test_target_sequence_sampler_filters_and_stops():
+  from lingvo_b200.core import target_sequence_sampler as tss
+  v, eos = 6, 2
+  table = torch.full((v, v), -8.0)
+  table[1, 3] = 0.0; table[1, 4] = -0.1        # after <s>: 3 or 4 about equally likely
+  table[3, eos] = 0.0; table[4, eos] = 0.0      # then always </s>
+  table[eos, eos] = 0.0
+
+  def Init(theta, enc, k):
+    return NestedMap(log_probs=torch.zeros(4 * k, v)), NestedMap(step=torch.zeros(1))
+
+  def Pre(theta, enc, ids, state, k, t):
+    return NestedMap(log_probs=table[ids.squeeze(1)]), state
+
+  s = tss.TargetSequenceSampler.Params().Set(target_seq_len=5, top_k=2, temperature=1.0).Instantiate()
+  out = s.Sample(None, None, 7, Init, Pre, None)
+  assert out.ids.shape == (4, 5) and out.logits.shape == (4, 5, v)
+  assert set(out.ids[:, 0].tolist()) <= {3, 4}                       # top-2 filter
+  assert (out.ids[:, 1:] == eos).all()
+  torch.testing.assert_close(out.paddings[:, 2:], torch.ones(4, 3))  # padded after </s>
+  assert out.paddings[:, :2].sum() == 0
+  again = s.Sample(None, None, 7, Init, Pre, None)
+  assert torch.equal(out.ids, again.ids)                             # seeded
+  greedy = tss.TargetSequenceSampler.Params().Set(target_seq_len=3, top_k=1).Instantiate()
+  assert (greedy.Sample(None, None, 0, Init, Pre, None).ids[:, 0] == 3).all()
+  nucleus = tss.TargetSequenceSampler.Params().Set(target_seq_len=1, nucleus_p=0.3).Instantiate()
+  f = nucleus._Filter(table[1:2])
+  assert int((f > -1e29).sum()) == 1                                 # only the head of the nucleus survives
+  eps = tss.TargetSequenceSampler.Params().Set(target_seq_len=1, epsilon=0.9).Instantiate()
+  assert int((eps._Filter(table[1:2]) > -1e29).sum()) == 1           # fail-safe keeps the arg-max
