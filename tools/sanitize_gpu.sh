@@ -10,7 +10,7 @@ SAN=${COMPUTE_SANITIZER:-/usr/local/cuda/bin/compute-sanitizer}
 TESTS=${SANITIZE_TESTS:-"tests/test_kernels_gpu.py tests/test_gemm_gpu.py"}
 SELECT=${SANITIZE_K:-"rms_norm or layer_norm or gate_logits or adafactor or lm_head or ffn_relu or layouts or build_rel_bias"}
 rc=0
-for tool in memcheck racecheck synccheck initcheck; do
+for tool in ${SANITIZE_TOOLS:-memcheck racecheck synccheck initcheck}; do
   log=gpurun_out/sanitizer_${tool}.log
   timeout ${SANITIZE_TIMEOUT:-1200} "$SAN" --tool "$tool" --error-exitcode 77 --print-limit 20 \
       --launch-timeout 0 python -m pytest $TESTS -x -q -k "$SELECT" -p no:cacheprovider \
