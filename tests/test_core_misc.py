@@ -546,3 +546,47 @@ def test_target_sequence_sampler_filters_and_stops():
   assert int((f > -1e29).sum()) == 1                                 # only the head of the nucleus survives
   eps = tss.TargetSequenceSampler.Params().Set(target_seq_len=1, epsilon=0.9).Instantiate()
   assert int((eps._Filter(table[1:2]) > -1e29).sum()) == 1           # fail-safe keeps the arg-max
+
+
+def test_conv_layers_builder_blocks_respect_paddings():
+  from lingvo_b200.core import conv_layers_builder as clb
+  torch.manual_seed(0)
+  b = clb.Builder.Params().Set(norm_layer_tpl=None).Instantiate()
+  x = torch.randn(2, 10, 8, 3)                       # [batch, time, freq, channels]
+  pad = torch.zeros(2, 10); pad[1, 6:] = 1.0
+  conv = b.Conv2D('c', (3, 3, 3, 5), stride=(2, 2)).Instantiate()
+  y, yp = conv.FPropDefaultTheta(x, pad)
+  assert y.shape == (2, 5, 4, 5) and yp.shape == (2, 5)
+  # reference (non-v2) rule: an output frame is padding if ANY input frame of its window is
+  assert yp[1].tolist() == [0, 0, 1, 1, 1]
+  assert (y[1, 2:] == 0).all()                       # padded frames stay zero
+  sep = b.SeparableConv2D('s', (3, 3, 3, 7), depth_multiplier=2).Instantiate()
+  y2, _ = sep.FPropDefaultTheta(x, pad)
+  assert y2.shape == (2, 10, 8, 7)
+  causal = b.Conv2D('cc', (3, 1, 3, 4), is_causal=True, activation='NONE').Instantiate()
+  xa = x.clone(); xa[:, 7:] += 5.0                   # change the future …
+  za, _ = causal.FPropDefaultTheta(x, torch.zeros(2, 10))
+  zb, _ = causal.FPropDefaultTheta(xa, torch.zeros(2, 10))
+  torch.testing.assert_close(za[:, :7], zb[:, :7])   # … the past does not move
+  pool = b.CausalPooling('p', 'AVG', left_context=2).Instantiate()
+  ones = torch.ones(1, 4, 1, 1)
+  out, _ = pool.FPropDefaultTheta(ones * torch.arange(4.0).reshape(1, 4, 1, 1), torch.zeros(1, 4))
+  assert out.flatten().tolist() == [0.0, 0.5, 1.5, 2.5]
+
+
+def test_stacked_transformer_encoder_layers_wrapper():
+  from lingvo_b200.core import self_attention_layer as sal
+  torch.manual_seed(0)
+  p = sal.StackedTransformerEncoderLayers.Params().Set(
+      name='enc', num_layers=2, mdl_dim=16, hidden_dim=32, num_atten_heads=4)
+  layer = p.Instantiate()
+  x = torch.randn(2, 7, 16)
+  pad = torch.zeros(2, 7); pad[0, 5:] = 1.0
+  y, yp = layer.FPropDefaultTheta(x, pad)
+  assert y.shape == x.shape and torch.equal(yp, pad)
+  x2 = x.clone(); x2[0, 5:] += 3.0                    # padded positions must not influence the rest
+  y2, _ = layer.FPropDefaultTheta(x2, pad)
+  torch.testing.assert_close(y[0, :5], y2[0, :5], atol=1e-5, rtol=1e-5)
+  cast = sal.StackedTransformerEncoderLayers.Cast(
+      p.Copy().Set(name='again'))
+  assert cast.num_layers == 2 and cast.mdl_dim == 16
