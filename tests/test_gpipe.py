@@ -192,3 +192,55 @@ def test_context_parallel_attention_matches_single_device():
   for i in range(3):
     got = torch.cat([res[0][2][i], res[1][2][i]], 1)
     torch.testing.assert_close(got, full[i].grad, atol=1e-4, rtol=1e-3)
+
+
+def test_gpipe_transformer_stacks_split_invariance():
+  """The GPipe transformer stacks give the same output for 1 and 2 pipeline cells and for
+  1 and 2 micro-batches (same seeds → same weights)."""
+  from lingvo_b200.core import layers_with_gpipe as lg
+
+  def Build(splits, micro):
+    torch.manual_seed(0)
+    p = lg.GPipeTransformerStack.Params().Set(
+        name='stack', model_dim=16, num_encoder_layers=2, num_decoder_layers=0, num_splits=splits,
+        splits=splits, num_micro_batches=micro, random_seed=123)
+    p.encoder_tpl.tr_atten_tpl.num_attention_heads = 2
+    p.encoder_tpl.tr_fflayer_tpl.hidden_dim = 32
+    return p.Instantiate()
+  x = torch.randn(5, 4, 16)                      # [time, batch, dim]
+  pad = torch.zeros(5, 4); pad[3:, 1] = 1.0
+  import re
+
+  def Key(v):                                   # variable identity independent of the cell split
+    return re.sub(r'cell_\d+/', '', v.var_name)
+
+  def CopyWeights(dst, src):
+    table = {Key(v): v for v in src.vars.Flatten()}
+    for v in dst.vars.Flatten():
+      v.data.copy_(table[Key(v)].data)
+  outs = []
+  ref_layer = None
+  for splits, micro in [(1, 1), (2, 1), (2, 2)]:
+    layer = Build(splits, micro)
+    if ref_layer is None:
+      ref_layer = layer
+    else:
+      CopyWeights(layer, ref_layer)
+    outs.append(layer.FPropDefaultTheta(x, pad))
+    assert outs[-1].shape == x.shape
+  torch.testing.assert_close(outs[0], outs[1], atol=1e-5, rtol=1e-5)
+  torch.testing.assert_close(outs[0], outs[2], atol=1e-5, rtol=1e-5)
+
+  def BuildBm(splits):
+    torch.manual_seed(0)
+    p = lg.GPipeBatchMajorTransformerStack.Params().Set(
+        name='bm', model_dim=16, num_encoder_layers=2, num_splits=splits, random_seed=7)
+    p.encoder_tpl.tr_atten_tpl.num_heads = 2
+    p.encoder_tpl.tr_fflayer_tpl.hidden_dim = 32
+    return p.Instantiate()
+  xb = torch.randn(4, 5, 16)                     # [batch, time, dim]
+  pb = torch.zeros(4, 5)
+  one, two = BuildBm(1), BuildBm(2)
+  CopyWeights(two, one)
+  torch.testing.assert_close(one.FPropDefaultTheta(xb, pb), two.FPropDefaultTheta(xb, pb),
+                             atol=1e-5, rtol=1e-5)
