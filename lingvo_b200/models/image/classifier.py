@@ -146,14 +146,18 @@ class ModelV2(BaseClassifier):
     self.CreateChild('extract', p.extract)
     self.CreateChild('softmax', p.softmax)
 
-  def _Logits(self, theta, data):
+  def _Features(self, theta, data):
     act = self.extract.FProp(theta.extract, data)
     if isinstance(act, tuple):
       act = act[0]
     return act.reshape(act.shape[0], -1)
 
+  def _Logits(self, theta, data):
+    """Class logits (what the serving subgraph of `BaseClassifier.Inference` exposes)."""
+    return self.softmax.Logits(theta.softmax, self._Features(theta, data))
+
   def ComputePredictions(self, theta, input_batch):
-    act = self._Logits(theta, input_batch.data)
+    act = self._Features(theta, input_batch.data)
     logits = self.softmax.Logits(theta.softmax, act)
     return NestedMap(logits=logits, act=act)
 

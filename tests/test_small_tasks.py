@@ -90,3 +90,34 @@ def test_milan_dual_encoder_learns_alignment():
       first = float(m['loss'][0])
   assert float(m['loss'][0]) < 0.6 * first
   assert float(m['recall_at_1_image_to_text'][0]) > 0.5
+
+
+class _BlobInput(base_input_generator.BaseInputGenerator):
+  """Two Gaussian blobs rendered as tiny 4×4 single-channel images."""
+
+  def _InputBatch(self):
+    y = torch.randint(0, 2, (32,))
+    x = torch.randn(32, 4, 4, 1) * 0.5 + (y.float() * 2 - 1).reshape(32, 1, 1, 1)
+    return NestedMap(data=x, label=y, weight=torch.ones(32))
+
+
+def test_image_classifier_v2_trains_and_serves():
+  from lingvo_b200.models.image import classifier
+  torch.manual_seed(0)
+  assert float(classifier.TopKAccuracy(
+      2, torch.tensor([[0.1, 0.9, 0.5], [0.8, 0.1, 0.3]]), torch.tensor([2, 1]), torch.ones(2))) == 0.5
+  p = classifier.ModelV2.Params().Set(name='v2', label_smoothing=0.1)
+  p.extract = layers.FCLayer.Params().Set(name='fc', input_dim=1, output_dim=3, activation='TANH')
+  p.softmax = layers.SimpleFullSoftmax.Params().Set(name='softmax', input_dim=4 * 4 * 3, num_classes=2)
+  p.input = _BlobInput.Params().Set(name='blobs', batch_size=32)
+  p.train.optimizer = optimizer.Adam.Params()
+  p.train.learning_rate = 1e-2
+  p.train.lr_schedule = schedule.Constant.Params()
+  task = p.Instantiate()
+  for _ in range(60):
+    m, _ = task.TrainStep()
+  assert float(m['accuracy'][0]) > 0.95 and float(m['error'][0]) < 0.05
+  sub = task.Inference()['default']
+  out = sub(torch.ones(3, 4, 4, 1))
+  assert out.prediction.tolist() == [1, 1, 1] and out.probs.shape == (3, 2)
+  torch.testing.assert_close(out.probs.sum(-1), torch.ones(3))
