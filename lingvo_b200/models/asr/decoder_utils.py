@@ -12,7 +12,11 @@ def SetRnnCellNodes(decoder_params, rnn_cell_params):
 
 
 def Tokenize(string):
-  return string.lower().split()
+  """Whitespace tokens, case preserved (ref `decoder_utils.py:37`; callers lower-case
+  explicitly for the case-insensitive rates)."""
+  if isinstance(string, bytes):
+    string = string.decode('utf-8')
+  return string.split()
 
 
 def EditDistance(ref_str, hyp_str):

@@ -131,3 +131,34 @@ def test_simple_wer_tools():
   assert (j, f1, p_, r_) == (1.0, 1.0, 1.0, 1.0)
   assert w.GetMostFrequentErrPatterns()['sub'][0][0] == ('was', 'is')
   assert '<br>' in w.aligned_htmls[1] or 'eol' in w.aligned_htmls[1]
+
+
+def test_metrics_calculator_aggregates_error_rates():
+  import collections
+  import numpy as np
+  from lingvo_b200.core import metrics
+  from lingvo_b200.models.asr import metrics_calculator as mc
+  d = collections.defaultdict(metrics.AverageMetric)
+  pi = mc.PostProcessInputs(
+      transcripts=['the cat sat', 'Hello World'],
+      topk_decoded=[['the cat sat', 'the cat'], ['hello word', 'Hello World']],
+      filtered_transcripts=['the cat sat', 'Hello World'],
+      filtered_top_hyps=['the cat sat', 'hello word'],
+      topk_scores=[[-0.1, -0.5], [-0.2, -0.3]], utt_id=['u0', 'u1'],
+      norm_wer_errors=[[0, 1], [2, 0]],                       # per-hyp word errors
+      target_labels=np.array([[5, 6, 7, 2], [8, 9, 2, 0]]),
+      target_paddings=np.array([[0, 0, 0, 0], [0, 0, 0, 1]]),
+      topk_ids=np.array([[5, 6, 7, 2], [5, 6, 2, 0], [8, 4, 2, 0], [8, 9, 2, 0]]),
+      topk_lens=np.array([4, 3, 3, 3]))
+  mc.CalculateMetrics(pi, d)
+  # cased: utt0 exact, utt1 "hello word" vs "Hello World" = 2 substitutions over 5 ref words
+  assert abs(d['wer'].value - 2 / 5) < 1e-9
+  assert abs(d['error_rates/sub'].value - 2 / 5) < 1e-9 and d['error_rates/ins'].value == 0
+  # case-insensitive: only "word" vs "world" is wrong
+  assert abs(d['case_insensitive_error_rates/wer'].value - 1 / 5) < 1e-9
+  # oracle picks the best hypothesis of each list: 0 + 0 errors
+  assert d['oracle_norm_wer'].value == 0.0
+  assert abs(d['sacc'].value - 0.5) < 1e-9                     # top hyp exact for 1 of 2 utterances
+  # token error rate: utt0 exact (4 tokens), utt1 one substitution over 3 tokens
+  assert abs(d['ter'].value - 1 / 7) < 1e-9
+  assert mc.GetRefIds([1, 2, 3], [0, 1, 0]) == [1, 3]
