@@ -9,7 +9,7 @@ import time
 
 from absl import logging
 
-from lingvo_b200.core import checkpointer as checkpointer_lib
+from lingvo_b200.core import saver as saver_lib
 
 
 class PredictorRunnerBase:
@@ -59,8 +59,7 @@ class PredictorRunnerBase:
   def Run(self):
     seen = set()
     while True:
-      latest = checkpointer_lib.LatestCheckpoint(self._ckpt_dir) if hasattr(
-          checkpointer_lib, 'LatestCheckpoint') else None
+      latest = saver_lib.LatestCheckpoint(self._ckpt_dir)
       if latest and latest not in seen:
         step = int(latest.rsplit('-', 1)[-1]) if '-' in os.path.basename(latest) else 0
         if not self._Done(step):

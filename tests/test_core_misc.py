@@ -590,3 +590,49 @@ def test_stacked_transformer_encoder_layers_wrapper():
   cast = sal.StackedTransformerEncoderLayers.Cast(
       p.Copy().Set(name='again'))
   assert cast.num_layers == 2 and cast.mdl_dim == 16
+
+
+def test_tpu_summary_context_and_predictor_runner(tmp_path):
+  from lingvo_b200.core import predictor_runner_base as prb, saver as saver_lib, tpu_summary
+  tpu_summary.scalar('outside', torch.tensor(1.0))               # no context: ignored
+  with tpu_summary.context() as ctx:
+    tpu_summary.scalar('loss', torch.tensor(2.5))
+    tpu_summary.tensor('vec', torch.arange(3.0))
+    tpu_summary.pw_tensor('pw', torch.ones(2))
+    merged = tpu_summary.merge_all()
+    assert merged['loss'] == 2.5 and merged['vec'].tolist() == [0.0, 1.0, 2.0]
+    assert list(tpu_summary.merge_all_pw_tensor()) == ['pw']
+    assert len(ctx.summary_tensors) == 2
+  assert tpu_summary.merge_all() == {}
+
+  # predictor runner: picks the newest checkpoint, runs every batch once, marks the step DONE
+  ckpt_dir, out_dir = tmp_path / 'train', tmp_path / 'out'
+  state = {'w/var': torch.ones(2), 'global_step': torch.tensor(12)}
+  saver_lib.Saver(str(ckpt_dir), lambda: state).Save(12)
+
+  class FakePredictor:
+    def __init__(self):
+      self.loaded, self.calls = [], 0
+    def Load(self, path):
+      self.loaded.append(path)
+    def Run(self, fetch, subgraph_name='default', **feeds):
+      self.calls += 1
+      return {'y': feeds['x'] * 2}
+
+  class Runner(prb.PredictorRunnerBase):
+    def InputGenerator(self):
+      for i in range(3):
+        yield {'x': np.full(2, i)}
+    def OutputWriter(self, output_dir, outputs):
+      with open(os.path.join(output_dir, 'out.txt'), 'a') as f:
+        f.write('%s\n' % outputs['y'].tolist())
+
+  pred = FakePredictor()
+  r = Runner(str(ckpt_dir), str(out_dir), 'inference_graph.pbtxt', pred, batch_size=2)
+  r.Run()
+  assert len(pred.loaded) == 1 and pred.loaded[0].endswith('ckpt-00000012') and pred.calls == 3
+  step_dir = out_dir / 'step_00000012'
+  assert (step_dir / 'DONE').read_text().startswith('3 batches')
+  assert (step_dir / 'out.txt').read_text().splitlines() == ['[0, 0]', '[2, 2]', '[4, 4]']
+  r.Run()                                                         # already DONE: nothing re-runs
+  assert pred.calls == 3
