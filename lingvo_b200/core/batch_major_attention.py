@@ -338,8 +338,7 @@ class MultiHeadedAttention(quant_utils.QuantizableLayer):
       probs = F.relu(logits)
       probs = probs / probs.sum(-1, keepdim=True).clamp_min(1e-30)
     else:
-      probs = py_utils.Softmax(logits, extra_logit=p.atten_extra_logit) if hasattr(
-          py_utils, 'Softmax') else torch.softmax(logits, -1)
+      probs = py_utils.Softmax(logits, extra_logit=p.atten_extra_logit)
     if p.enable_shaped_attention:
       t, s = probs.shape[-2:]
       eye = torch.eye(t, s, device=probs.device)
@@ -1364,8 +1363,7 @@ class StackedTransformerLayers(base_layer.BaseLayer):
     return x, new_states
 
 
-class RepeatedTransformerLayer(builder_layers.RepeatLayer if hasattr(
-    builder_layers, 'RepeatLayer') else base_layer.BaseLayer):
+class RepeatedTransformerLayer(builder_layers.RepeatLayer):
   """`repeat` copies of one TransformerLayer body with stacked weights (:6976)."""
 
   @classmethod

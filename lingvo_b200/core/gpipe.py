@@ -261,7 +261,7 @@ class PipeliningLayer(SeqLayer):
       outs = self._engine.Forward(self, theta, micro_in)
     else:
       outs = []
-      step0 = py_utils.GetGlobalStep() if hasattr(py_utils, 'GetGlobalStep') else 0
+      step0 = py_utils.GetGlobalStep()
       for i, mi in enumerate(micro_in):
         SetOverWriteGlobalStep(step0 * n + i if isinstance(step0, int) else None)
         outs.append(self._RunCells(theta, mi))

@@ -79,9 +79,7 @@ class WordLevelOneBwdsBase(base_model_params.SingleTaskModelParams):
     tp.max_lstm_gradient_norm = 16
     tp.clip_gradient_norm_to_value = 0.0
     tp.optimizer = optimizer.Adagrad.Params()
-    tp.lr_schedule = schedule.PiecewiseConstantSchedule.Params().Set(
-        boundaries=[], values=[1.0]) if hasattr(
-            schedule, 'PiecewiseConstantSchedule') else schedule.Constant.Params()
+    tp.lr_schedule = schedule.PiecewiseConstantSchedule.Params().Set(boundaries=[], values=[1.0])
     return p
 
 
@@ -129,8 +127,7 @@ class OneBwdsTransformerLm(WordLevelOneBwdsBase):
     tp.learning_rate = 1e-3
     tp.optimizer = optimizer.Adam.Params().Set(beta1=0.9, beta2=0.98, epsilon=1e-9)
     tp.lr_schedule = schedule.TransformerSchedule.Params().Set(
-        warmup_steps=4000, model_dim=self.MODEL_DIM) if hasattr(
-            schedule, 'TransformerSchedule') else schedule.Constant.Params()
+        warmup_steps=4000, model_dim=self.MODEL_DIM)
     return p
 
 

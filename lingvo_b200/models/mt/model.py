@@ -24,7 +24,7 @@ def _NGrams(tokens, n):
   return collections.Counter(tuple(tokens[i:i + n]) for i in range(len(tokens) - n + 1))
 
 
-class CorpusBleuMetric(metrics_lib.BaseMetric if hasattr(metrics_lib, 'BaseMetric') else object):
+class CorpusBleuMetric(metrics_lib.BaseMetric):
   """Corpus-level BLEU-4 with brevity penalty (ref `core/metrics.py` CorpusBleuMetric)."""
 
   def __init__(self, separator_type='wpm'):
