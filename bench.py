@@ -12,7 +12,11 @@ expert-parallel over the ranks), bf16 compute / fp32 master weights,
 Adafactor step included, synthetic random-token data, random-init weights.
 Weak scaling: 8 sequences × 1024 tokens per GPU.
 
-`--impl reference` reports that the TF reference cannot run here.
+`--impl reference` runs the stock-PyTorch comparator (`baseline/stock_moe_lm.py`: cuBLAS
+matmul/einsum + SDPA + NCCL all_to_all/all_reduce + unfused Adafactor; the reference's dense
+GSEC dispatch math) — TF lingvo itself cannot be installed here.
+The measured arm is driven through the product entry point (`trainer.RunnerManager` →
+`runners.Trainer` → `TrainEngine`), not a private loop.
 """
 
 import argparse
@@ -39,6 +43,8 @@ def _ParseArgs():
                   help='fused = hand-written peer-memory kernels (default); '
                   'nccl = stock NCCL+cuBLAS baseline mode.')
   ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--no-a2a', action='store_true',
+                  help='skip the exposed all-to-all measurement (N > 1)')
   ap.add_argument('--cuda-graph', default='auto', choices=['auto', 'on', 'off'],
                   help='Capture the whole train step into a CUDA graph (auto: fall back '
                   'to eager launches if capture fails).')
@@ -100,14 +106,36 @@ class ClockSampler:
 
 
 def _Reference(args):
-  print(json.dumps({
-      'impl': 'reference',
-      'unavailable': 'tensorflow/lingvo needs bazel + TensorFlow 2.13 (neither '
-                     'is installed; /root/reference has no setup.py/pyproject; '
-                     'pip install --no-index fails: "not installable") and TF '
-                     '2.13 has no sm_100 kernels',
-      'n_gpus': args.gpus}))
+  """Stock-PyTorch comparator (`baseline/stock_moe_lm.py`): nothing of lingvo_b200 —
+  no kernels, no engine, no model — is imported on this path."""
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'baseline'))
+  import torch
+  if not torch.cuda.is_available():
+    print(json.dumps({'impl': 'reference', 'unavailable': 'no GPU visible',
+                      'n_gpus': args.gpus}))
+    return 0
+  import stock_moe_lm
+  out = stock_moe_lm.RunBenchmark(args, ClockSampler)
+  if out is not None:
+    print(json.dumps(out), flush=True)
   return 0
+
+
+def _CreateTrainer(args, logdir):
+  """The product entry point: `lingvo_b200.trainer.RunnerManager` builds the same
+  `runners.Trainer` that `python -m lingvo_b200.trainer --job=trainer_client` runs."""
+  from lingvo_b200 import flags
+  from lingvo_b200 import model_imports
+  from lingvo_b200 import trainer as trainer_lib
+  argv = ['bench', '--model=' + args.model, '--logdir=' + logdir, '--mode=sync',
+          '--job=trainer_client', '--worker_gpus=1',
+          '--use_cuda_graph=' + args.cuda_graph]
+  flags.FLAGS(argv)
+  model_imports.ImportParams(args.model)
+  mgr = trainer_lib.RunnerManager(args.model)
+  mgr.MaybeConfigRunDistributed()
+  runner = mgr.CreateRunners(['trainer_client'], logdir)[0]
+  return runner
 
 
 def main():
@@ -117,6 +145,7 @@ def main():
   if args.comm:
     os.environ['LINGVO_B200_COMM'] = args.comm
 
+  import tempfile
   import torch
   import torch.distributed as dist
   world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -130,28 +159,16 @@ def main():
   assert world == args.gpus, 'WORLD_SIZE %d != --gpus %d' % (world, args.gpus)
   dev = torch.device('cuda', local_rank)
 
-  from lingvo_b200 import model_registry
   from lingvo_b200 import ops
-  from lingvo_b200.core import base_input_generator
-  from lingvo_b200.core import cluster_factory
   from lingvo_b200.parallel import mesh as mesh_lib
-  import lingvo_b200.models.lm.params.synthetic_packed_input  # noqa: F401
   native = ops.native(required=True)
   mesh_lib.Reset()
 
-  cfg = model_registry.GetParams(args.model, 'Train')
-  cfg.cluster.mode = 'sync'
-  cfg.cluster.job = 'trainer'
-  cfg.cluster.worker.replicas = world
-  cfg.cluster.worker.gpus_per_replica = 1
-  cluster = cluster_factory.Cluster(cfg.cluster)
-  with cluster:
-    model = cfg.Instantiate()
-    model.to(dev)
-    task = model.tasks[0]
-    from lingvo_b200.parallel import dp as dp_lib
-    dp_lib.Attach(task)
-
+  logdir = tempfile.mkdtemp(prefix='lingvo_b200_bench_')
+  runner = _CreateTrainer(args, logdir)
+  task = runner.task
+  with runner._cluster:   # pylint: disable=protected-access
+    engine = runner.engine                      # DP attach + prefetcher + graph capture
     tp = task.params
     per_gpu_batch = task.input.InfeedBatchSize()
     seq_len = tp.sequence_length
@@ -166,61 +183,49 @@ def main():
     n_total = args.warmup + args.steps
     batches = [task._MoveBatch(task.input.GetPreprocessedInputBatch(), dev)  # pylint: disable=protected-access
                for _ in range(min(n_total, 8))]
-    graphed = None
-    if args.cuda_graph != 'off':
-      from lingvo_b200.core import graph_step
-      try:
-        graphed = graph_step.GraphedTrainStep(task, batches[0], warmup=max(args.warmup, 3))
-      except Exception as e:  # pylint: disable=broad-except
-        if args.cuda_graph == 'on':
-          raise
-        sys.stderr.write('CUDA-graph capture failed (%r); eager launches.\n' % (e,))
-        graphed = None
 
-    def step(batch):
-      if graphed is not None:
-        return graphed(batch)
-      return task.TrainStep([batch])
+    def timed(n_warm, n_steps, sampler=None):
+      for i in range(n_warm):
+        engine.Step(batches[i % len(batches)])
+      sync()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      ctx = sampler if sampler is not None else _Null()
+      with ctx:
+        sync()
+        e0.record()
+        for i in range(n_steps):
+          m, _ = engine.Step(batches[(n_warm + i) % len(batches)])
+        e1.record()
+        sync()
+      ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+      if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+      return float(ms.item()), m
 
-    for i in range(args.warmup):
-      step(batches[i % len(batches)])
-    sync()
     launches0 = native.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-      sync()
-      e0.record()
-      for i in range(args.steps):
-        metrics, _ = step(batches[(args.warmup + i) % len(batches)])
-      e1.record()
-      sync()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    clocks = ClockSampler(local_rank)
+    ms_total, metrics = timed(args.warmup, args.steps, clocks)
     launches = native.launch_count() - launches0
-    if graphed is not None:
+    if engine.cuda_graph:
       # kernels of ours executed per replay (counted while capturing) × timed steps
-      launches = graphed.launches_per_step * args.steps
+      launches = engine.launches_per_step * args.steps
     loss = float(metrics['loss'][0])
-    if world > 1:
-      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
     ms_per_step = ms_total / args.steps
     value = tokens_per_step * args.steps / (ms_total / 1e3)
 
     # ---- end-to-end loop through the public API ----------------------------
     e2e = None
     if not args.no_e2e:
-      prefetch = base_input_generator.DevicePrefetcher(task.input, dev, depth=2)
       for _ in range(2):
-        step(prefetch.Next())
+        engine.Step()
       sync()
       h2d = 0
       d2h = 0
       t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       t0.record()
       for _ in range(args.steps):
-        batch = prefetch.Next()          # pinned host → device on a side stream
-        h2d = prefetch.h2d_bytes_last
-        m, _ = step(batch)
+        m, _ = engine.Step()               # pinned host → device on a side stream + step
+        h2d = engine.h2d_bytes_last
         host_loss = m['loss'][0].detach().float().cpu()   # D2H read of the loss
         d2h = host_loss.numel() * host_loss.element_size()
       t1.record()
@@ -231,6 +236,11 @@ def main():
       e2e = {'value': tokens_per_step * args.steps / (float(ems.item()) / 1e3),
              'unit': 'tokens/s', 'h2d_bytes_per_step': int(h2d),
              'd2h_bytes_per_step': int(d2h)}
+
+    # ---- exposed all-to-all: same step with the EP exchange looped back locally ---------
+    exposed_a2a = None
+    if world > 1 and not args.no_a2a:
+      exposed_a2a = _ExposedA2A(task, engine, batches, ms_per_step, timed, args)
 
   if rank == 0:
     ctx = mesh_lib.Get()
@@ -243,7 +253,9 @@ def main():
         'dtype': 'bf16', 'data': 'synthetic (uniform random token ids, packed '
                                  'LM format; random-init weights)',
         'impl': 'ours', 'comm_mode': ctx.mode,
-        'cuda_graph': graphed is not None,
+        'entry_point': 'lingvo_b200.trainer.RunnerManager → runners.Trainer.engine '
+                       '(core/train_engine.py)',
+        'cuda_graph': engine.cuda_graph,
         'config': {
             'model': args.model, 'global_batch': per_gpu_batch * world,
             'seq_len': seq_len, 'parallelism': 'dp%d+ep%d' % (
@@ -259,14 +271,15 @@ def main():
     }
     if e2e is not None:
       out['e2e'] = e2e
+    if exposed_a2a is not None:
+      out['exposed_a2a_ms_per_step'] = exposed_a2a
     print(json.dumps(out), flush=True)
   if world > 1:
     # Tear-down: a CUDA graph that holds captured NCCL kernels must be gone before the
     # communicator is destroyed, and a stuck destroy must never hold the job open — the
     # measurement is already printed, so a watchdog ends the process if it takes too long.
     import gc
-    import threading
-    graphed = None
+    engine._graphed = None   # pylint: disable=protected-access
     gc.collect()
     torch.cuda.synchronize()
     dist.barrier()
@@ -278,7 +291,46 @@ def main():
     watchdog.start()
     dist.destroy_process_group()
     watchdog.cancel()
+  import shutil
+  shutil.rmtree(logdir, ignore_errors=True)
   return 0
+
+
+class _Null:
+
+  def __enter__(self):
+    return self
+
+  def __exit__(self, *a):
+    return False
+
+
+def _ExposedA2A(task, engine, batches, ms_normal, timed, args):
+  """ms/step the expert exchange costs on the critical path: step time minus the time of
+  the *same* step with every peer store/load redirected to local memory and the peer
+  flag waits removed (`MoeExchange.loopback`). NCCL mode: not measured this way."""
+  import torch
+  from lingvo_b200.core import graph_step
+  from lingvo_b200.parallel import mesh as mesh_lib
+  ctx = mesh_lib.Get()
+  exchanges = [e._fused for e in ctx._ep_engines.values() if getattr(e, '_fused', None)]  # pylint: disable=protected-access
+  if not exchanges:
+    return None
+  saved = engine._graphed   # pylint: disable=protected-access
+  try:
+    for ex in exchanges:
+      ex.loopback = True
+    if saved is not None:
+      engine._graphed = graph_step.GraphedTrainStep(task, batches[0], warmup=2)  # pylint: disable=protected-access
+    ms_lb, _ = timed(2, args.steps)
+    return max(0.0, ms_normal - ms_lb / args.steps)
+  except Exception as e:  # pylint: disable=broad-except
+    sys.stderr.write('exposed-a2a measurement failed: %r\n' % (e,))
+    return None
+  finally:
+    for ex in exchanges:
+      ex.loopback = False
+    engine._graphed = saved   # pylint: disable=protected-access
 
 
 if __name__ == '__main__':

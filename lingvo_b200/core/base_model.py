@@ -72,6 +72,12 @@ class BaseTask(base_layer.BaseLayer):
     tp.Define('max_steps', 4 * 10**6, 'Maximum number of training steps.')
     tp.Define('tpu_steps_per_loop', 1000,
               'Steps per device loop (CUDA-graph replay length).')
+    tp.Define('use_cuda_graph', 'auto',
+              "Capture FProp+BProp+sync+optimizer into one CUDA graph and replay it: 'auto' "
+              "(when on a GPU and the optimizer is capturable), 'on' (required) or 'off'.")
+    tp.Define('device_prefetch_depth', 2,
+              'Input batches staged on the device ahead of the step (pinned H2D copies on '
+              'a side stream).')
     tp.Define('tpu_device_order_mode', None, 'Kept for parity.')
     tp.Define('tpu_computation_shape', None, 'Kept for parity.')
     tp.Define('vn_start_step', 200000000, 'Step at which VN starts.')

@@ -21,17 +21,67 @@ import torch
 from lingvo_b200.core import base_model
 from lingvo_b200.core import py_utils
 from lingvo_b200.core import saver as saver_lib
+from lingvo_b200.core import train_engine
 from lingvo_b200.utils import tensor_bundle
 
 
-def _ModelTensors(model) -> Dict[str, torch.Tensor]:
+def _RankWorld() -> Tuple[int, int]:
+  import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_rank(), dist.get_world_size()
+  return 0, 1
+
+
+def _EpSlices(model) -> Dict[str, Tuple[int, int, int, int]]:
+  """`<var base name>` → (lo, hi, num_experts, ep_size) for expert-parallel variables:
+  this rank holds rows [lo, hi) of dim 0 of the logical `[E, …]` tensor."""
   out = {}
   for v in model.vars.Flatten():
-    out[v.var_name] = v
+    shard = getattr(v, 'ep_shard', None)
+    if shard is None or not getattr(v, 'expert_parallel', False):
+      continue
+    ep_rank, ep_size, e = shard
+    el = e // ep_size
+    base = v.var_name[:-len('/var')] if v.var_name.endswith('/var') else v.var_name
+    out[base] = (ep_rank * el, (ep_rank + 1) * el, e, ep_size)
+  return out
+
+
+def _EpBaseOf(key: str, ep: Dict[str, Tuple[int, int, int, int]]) -> Optional[str]:
+  """The expert-parallel variable a checkpoint key (var, slot or EMA shadow) belongs to."""
+  probe = key
+  while probe:
+    if probe in ep:
+      return probe
+    probe, _, _ = probe.rpartition('/')
+  return None
+
+
+def _ModelTensors(model, rank: int = 0, world: int = 1) -> Dict[str, torch.Tensor]:
+  """The tensors *this rank* writes. Rank 0 owns everything replicated; every rank of the
+  first EP group additionally owns its dim-0 slice of the expert-parallel variables and of
+  their optimizer slots / EMA shadows (saved under `tensor_bundle.SliceKey` names)."""
+  ep = _EpSlices(model) if world > 1 else {}
+  named = {}
+  for v in model.vars.Flatten():
+    named[v.var_name] = v
   for task in model.tasks:
     for lrn in task.learners:
-      out.update(lrn.optimizer.GetOptimizerSlots())
-    out.update(task.EmaShadowTensors())
+      named.update(lrn.optimizer.GetOptimizerSlots())
+    named.update(task.EmaShadowTensors())
+  if world <= 1:
+    return named
+  out = {}
+  for key, t in named.items():
+    base = _EpBaseOf(key, ep)
+    if base is not None:
+      lo, hi, e, ep_size = ep[base]
+      if isinstance(t, torch.Tensor) and t.dim() >= 1 and t.shape[0] == hi - lo:
+        if rank < ep_size:
+          out[tensor_bundle.SliceKey(key, lo, hi, e)] = t
+        continue
+    if rank == 0:
+      out[key] = t
   return out
 
 
@@ -54,13 +104,25 @@ class Checkpointer:
     checks = []
     if getattr(tp, 'checkpoint_finite_check', False):
       checks.append((lambda name: True, [saver_lib.IsFinite()]))
+    self._rank, self._world = _RankWorld()
+    # Sharded bundle only when some variable differs per rank (expert parallelism);
+    # otherwise rank 0 alone writes a single-shard bundle.
+    self._sharded = self._world > 1 and bool(_EpSlices(model))
     self._saver = saver_lib.Saver(
-        train_dir, lambda: _ModelTensors(model), sanity_checks=checks,
+        train_dir, lambda: _ModelTensors(model, self._rank, self._world),
+        sanity_checks=checks,
         keep_latest_n=tp.save_max_to_keep,
         keep_every_n_hours=tp.save_keep_checkpoint_every_n_hours,
-        async_save=bool(tp.async_checkpointing))
+        async_save=bool(tp.async_checkpointing),
+        shard_id=self._rank if self._sharded else 0,
+        num_shards=self._world if self._sharded else 1)
+    self._engines = []
     self._init_rules_applied = False
     os.makedirs(train_dir, exist_ok=True)
+
+  def AttachEngine(self, engine):
+    """`TrainEngine`s whose `PreSave()` must run before tensors are snapshotted."""
+    self._engines.append(engine)
 
   @property
   def checkpoint_dir(self):
@@ -86,24 +148,34 @@ class Checkpointer:
     """Loads every model variable (+ slots, EMA) present in the bundle."""
     assert not self._save_only
     reader = tensor_bundle.BundleReader(checkpoint_path)
-    keys = set(reader.Keys())
+    keys = set(reader.LogicalKeys())
+    ep = _EpSlices(self._model) if self._world > 1 else {}
     missing = []
+
+    def read(key):
+      base = _EpBaseOf(key, ep)
+      if base is not None:
+        lo, hi, e, _ = ep[base]
+        shape = reader.LogicalShape(key)
+        if shape and shape[0] == e:
+          return saver_lib.FromNumpy(reader.ReadRange(key, lo, hi))
+      return saver_lib.FromNumpy(reader.ReadRange(key))
+
     with torch.no_grad():
       for v in self._model.vars.Flatten():
         k = v.var_name
         if k not in keys:
           missing.append(k)
           continue
-        t = saver_lib.FromNumpy(reader.Read(k))
+        t = read(k)
         if tuple(t.shape) != tuple(v.shape):
           raise ValueError('Shape mismatch for %s: ckpt %s vs model %s' %
                            (k, tuple(t.shape), tuple(v.shape)))
         v.data.copy_(t.to(v.device, v.dtype))
-    py_utils.RefreshComputeCopies(self._model.vars.Flatten())
     if missing and strict:
       raise KeyError('Variables missing from checkpoint %s: %s' %
                      (checkpoint_path, missing[:10]))
-    rest = {k: saver_lib.FromNumpy(reader.Read(k)) for k in keys
+    rest = {k: read(k) for k in keys
             if not k.endswith('/var') and k != 'global_step'}
     for task in self._model.tasks:
       for lrn in task.learners:
@@ -112,6 +184,8 @@ class Checkpointer:
         lrn.optimizer.LoadOptimizerSlots(
             {k: t.to(dev) if t.dim() else t for k, t in rest.items()})
       task.LoadEmaShadowTensors(rest)
+      # compute copies, carried optimizer scratch, sharded-optimizer engines
+      train_engine.PostRestore(task)
     step = 0
     if 'global_step' in keys:
       step = int(reader.Read('global_step').reshape(-1)[0])
@@ -162,6 +236,8 @@ class Checkpointer:
             loaded.add(name)
             break
       reader.Close()
+    for task in self._model.tasks:
+      train_engine.PostRestore(task)
     logging.info('init_from_checkpoint_rules loaded %d variables', len(loaded))
 
   def Restore(self, sess=None, force_reinitialize=False) -> Optional[str]:
@@ -200,20 +276,44 @@ class Checkpointer:
 
   def Save(self, sess=None, gsteps: Optional[int] = None, sync=True) -> str:
     gsteps = self._GlobalStep() if gsteps is None else gsteps
-    tensors = _ModelTensors(self._model)
-    tensors['global_step'] = torch.tensor(int(gsteps), dtype=torch.int64)
-    path = self._saver.Save(gsteps, tensors)
-    if sync:
-      self._saver.Wait()
+    if self._saved_first and self._prev_ckpt_step == gsteps:
+      if sync:
+        self._saver.Wait()
+      return '%s-%08d' % (self._save_path, int(gsteps))      # this step is already saved
+    for eng in self._engines:
+      eng.PreSave()                # collective: every rank calls Save at the same step
+    path = '%s-%08d' % (self._save_path, int(gsteps))
+    if self._rank == 0 or self._sharded:
+      tensors = _ModelTensors(self._model, self._rank, self._world)
+      if self._rank == 0:
+        tensors['global_step'] = torch.tensor(int(gsteps), dtype=torch.int64)
+      path = self._saver.Save(gsteps, tensors)   # device → host snapshot happens here
+      if sync:
+        self._saver.Wait()
+    for eng in self._engines:
+      eng.PostSave()
     self._saved_first = True
     self._prev_ckpt_step = gsteps
     self._next_checkpoint_seconds = time.time() + (
         self._save_interval_seconds or 0)
     return path
 
+  def _AgreedShouldSave(self, gsteps: int) -> bool:
+    """Same decision on every rank. Step-based policies are deterministic; the wall-clock
+    policy is decided by rank 0 and broadcast, at most once every 20 steps."""
+    if self._world <= 1 or self._save_interval_steps or not self._saved_first:
+      return self.ShouldSave(gsteps)
+    if gsteps % 20:
+      return False
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+    flag = torch.tensor([int(self.ShouldSave(gsteps))], device=dev)
+    dist.broadcast(flag, src=0)
+    return bool(flag.item())
+
   def MaybeSave(self, sess=None, gsteps: Optional[int] = None):
     gsteps = self._GlobalStep() if gsteps is None else gsteps
-    if self.ShouldSave(gsteps):
+    if self._AgreedShouldSave(gsteps):
       return self.Save(sess, gsteps, sync=not self.async_checkpointing)
     return None
 

@@ -575,6 +575,9 @@ class MoELayer(_BuilderLayer):
     super()._InstantiateSelfAndChildren()
     for n in self._expert_var_names:
       self._private_vars[n].expert_parallel = self._ep is not None
+      if self._ep is not None:
+        # (ep_rank, ep_size, num_experts): dim-0 slice of the logical `[E, …]` tensor.
+        self._private_vars[n].ep_shard = (self._ep.ep_rank, self._ep.ep_size, self.bp.e_dim)
 
   def _FusedExchange(self, x, act):
     """The fused gate+dispatch/expert-GEMM/combine engine when applicable."""

@@ -52,6 +52,10 @@ class Base(base_layer.BaseLayer):
 
   # slot name → checkpoint suffix (TF slot naming)
   SLOT_SUFFIX: Dict[str, str] = {}
+  # Slot names saved under their own name (no TF alias) that must also be restored.
+  EXTRA_SLOT_NAMES: tuple = ()
+  # Host-side integer/float counters that are part of the optimizer state.
+  COUNTER_ATTRS: tuple = ()
 
   @classmethod
   def Params(cls):
@@ -96,6 +100,9 @@ class Base(base_layer.BaseLayer):
       out[k] = torch.tensor(v, dtype=torch.float32)
     out['%s/step_count' % self.params.name] = torch.tensor(
         self._step_count, dtype=torch.int64)
+    for attr in self.COUNTER_ATTRS:
+      out['%s/%s' % (self.params.name, attr.strip('_'))] = torch.tensor(
+          float(getattr(self, attr)), dtype=torch.float64)
     return out
 
   def LoadOptimizerSlots(self, tensors: Dict[str, torch.Tensor]) -> List[str]:
@@ -112,8 +119,19 @@ class Base(base_layer.BaseLayer):
         self._scalars[key] = float(t.item())
         used.append(key)
         continue
+      hit = False
+      for attr in self.COUNTER_ATTRS:
+        if key == '%s/%s' % (self.params.name, attr.strip('_')):
+          cur = getattr(self, attr)
+          setattr(self, attr, type(cur)(t.item()))
+          used.append(key)
+          hit = True
+      if hit:
+        continue
       base, _, suffix = key.rpartition('/')
       sname = inv.get(suffix)
+      if sname is None and suffix in self.EXTRA_SLOT_NAMES:
+        sname = suffix
       if sname is None:
         continue
       pending.setdefault(base + '/var', {})[sname] = (key, t)
@@ -175,6 +193,15 @@ class Base(base_layer.BaseLayer):
 
   def FProp(self, theta, *args):
     raise NotImplementedError('Optimizers are applied with Apply()')
+
+
+def _ScaledF32(pairs, grad_scale):
+  """fp32 (variable-dtype) gradients of `pairs`, times the optional device scalar."""
+  grads = _F32([g for _, g in pairs], [v for v, _ in pairs])
+  if grad_scale is None:
+    return grads
+  gs = grad_scale.reshape(())
+  return [torch.where(gs == 0, torch.zeros_like(g), g * gs.to(g.dtype)) for g in grads]
 
 
 def _F32(grads, like):
@@ -368,14 +395,14 @@ class Accumulator(Base):
     self._accum_count = 0
 
   SLOT_SUFFIX = {'grad_accum': 'grad_accumulator'}
+  COUNTER_ATTRS = ('_accum_count',)
 
-  def Apply(self, lr, var_grad):
+  def Apply(self, lr, var_grad, grad_scale=None):
     p = self.params
     pairs = _Pairs(var_grad)
     with torch.no_grad():
       accs = [self._Slot(v, 'grad_accum') for v, _ in pairs]
-      torch._foreach_add_(accs, _F32([g for _, g in pairs],
-                                     [v for v, _ in pairs]))
+      torch._foreach_add_(accs, _ScaledF32(pairs, grad_scale))
     self._accum_count += 1
     if self._accum_count % p.accum_steps != 0:
       return
@@ -406,16 +433,17 @@ class DynamicAccumulator(Accumulator):
     p.Define('accum_weight_threshold', 1.0, 'Apply when weight sum ≥ this.')
     return p
 
+  COUNTER_ATTRS = ('_accum_count', '_weight')
+
   def __init__(self, params):
     super().__init__(params)
     self._weight = 0.0
 
-  def ApplyWeighted(self, lr, var_grad, weight: float):
+  def ApplyWeighted(self, lr, var_grad, weight: float, grad_scale=None):
     pairs = _Pairs(var_grad)
     with torch.no_grad():
       accs = [self._Slot(v, 'grad_accum') for v, _ in pairs]
-      torch._foreach_add_(accs, _F32([g for _, g in pairs],
-                                     [v for v, _ in pairs]), alpha=float(weight))
+      torch._foreach_add_(accs, _ScaledF32(pairs, grad_scale), alpha=float(weight))
     self._weight += float(weight)
     if self._weight < self.params.accum_weight_threshold:
       return
@@ -428,8 +456,8 @@ class DynamicAccumulator(Accumulator):
     self._weight = 0.0
     self._step_count += 1
 
-  def Apply(self, lr, var_grad):
-    self.ApplyWeighted(lr, var_grad, 1.0)
+  def Apply(self, lr, var_grad, grad_scale=None):
+    self.ApplyWeighted(lr, var_grad, 1.0, grad_scale=grad_scale)
 
 
 class GradientAggregation(Base):
@@ -441,6 +469,7 @@ class GradientAggregation(Base):
   """
 
   SLOT_SUFFIX = {'grad_accum': 'grad_accum'}
+  COUNTER_ATTRS = ('_count',)
 
   @classmethod
   def Params(cls):
@@ -456,16 +485,26 @@ class GradientAggregation(Base):
     self._count = 0
     self.reduce_fn = None
 
-  def Apply(self, lr, var_grad):
+  def GetOptimizerSlots(self):
+    out = super().GetOptimizerSlots()
+    out.update(self._opt.GetOptimizerSlots())
+    return out
+
+  def LoadOptimizerSlots(self, tensors):
+    return super().LoadOptimizerSlots(tensors) + self._opt.LoadOptimizerSlots(tensors)
+
+  def Apply(self, lr, var_grad, grad_scale=None):
     p = self.params
     pairs = _Pairs(var_grad)
     if p.num_micro_batches <= 1:
+      if grad_scale is not None:
+        var_grad = [py_utils.VarGrad(v, g) for (v, _), g in zip(
+            pairs, _ScaledF32(pairs, grad_scale))]
       self._opt.Apply(lr, var_grad)
       return
     with torch.no_grad():
       accs = [self._Slot(v, 'grad_accum') for v, _ in pairs]
-      torch._foreach_add_(accs, _F32([g for _, g in pairs],
-                                     [v for v, _ in pairs]))
+      torch._foreach_add_(accs, _ScaledF32(pairs, grad_scale))
     self._count += 1
     if self._count % p.num_micro_batches:
       return
@@ -792,19 +831,28 @@ class XLAShardingAdafactorAccuGrad(XLAShardingAdafactor):
     p.Define('num_micro_batches', 1, 'Accumulate this many applies.')
     return p
 
+  SLOT_SUFFIX = dict(XLAShardingAdafactor.SLOT_SUFFIX, grad_accum='grad_accum')
+  COUNTER_ATTRS = ('_count',)
+
   def __init__(self, params):
     super().__init__(params)
     self._count = 0
 
-  def Apply(self, lr, var_grad):
+  def PreGradStats(self, *args, **kwargs):
+    """Micro-batch gradients are not the gradients the update sees: no fused pre-pass."""
+    if self.params.num_micro_batches <= 1:
+      return super().PreGradStats(*args, **kwargs)
+    return None, set()
+
+  def Apply(self, lr, var_grad, grad_scale=None):
     n = self.params.num_micro_batches
     if n <= 1:
-      return super().Apply(lr, var_grad)
+      return super().Apply(lr, var_grad, grad_scale=grad_scale)
     pairs = _Pairs(var_grad)
     with torch.no_grad():
       accs = [self._Slot(v, 'grad_accum') for v, _ in pairs]
-      torch._foreach_add_(accs, _F32([g for _, g in pairs],
-                                     [v for v, _ in pairs]))
+      # The clip / NaN-skip factor applies to *this* micro-batch's gradients.
+      torch._foreach_add_(accs, _ScaledF32(pairs, grad_scale))
     self._count += 1
     if self._count % n:
       return None
@@ -827,6 +875,7 @@ class DistributedShampoo(Base):
   """
 
   SLOT_SUFFIX = {'acc': 'Shampoo_acc', 'mom': 'Shampoo_mom'}
+  EXTRA_SLOT_NAMES = ('L', 'R', 'PL', 'PR')
 
   @classmethod
   def Params(cls):

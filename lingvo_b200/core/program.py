@@ -151,14 +151,24 @@ class TrainProgram(BaseProgram):
   def model(self):
     return self._model
 
+  @property
+  def engine(self):
+    """DP sync + device prefetch + CUDA-graph replay (`core/train_engine.py`)."""
+    if getattr(self, '_engine', None) is None:
+      from lingvo_b200.core import train_engine  # pylint: disable=g-import-not-at-top
+      with self._cluster:
+        self._engine = train_engine.TrainEngine(self._task)
+    return self._engine
+
   def Run(self, sess=None, threadpool=None) -> bool:
     p = self.params
     task = self._task
     acc = metrics_lib.DeviceEvalMetrics()
     t0 = time.time()
     with self._cluster:
+      engine = self.engine
       for _ in range(p.steps_per_loop):
-        m, _ = task.TrainStep()
+        m, _ = engine.Step()
         acc.Update({k: v for k, v in m.items()})
     results = acc.Finalize()
     step = task.global_step

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import glob
 import os
+import pickle
 import re
 import threading
 import time
@@ -115,7 +116,15 @@ class Saver:
 
   def __init__(self, logdir: str, variables_fn: Callable[[], Dict[str, torch.Tensor]],
                sanity_checks=None, keep_latest_n=None,
-               keep_every_n_hours=None, async_save=False, prefix='ckpt'):
+               keep_every_n_hours=None, async_save=False, prefix='ckpt',
+               shard_id: int = 0, num_shards: int = 1, shard_timeout_s: float = 600.0):
+    """`num_shards > 1`: one Saver per rank. Each rank writes the tensors it owns into
+    `…data-0000r-of-0000N` plus a small entries side-car; shard 0 merges them into the
+    index (reference `saver.py:168-194` sharded save + merge), keeps the `checkpoint`
+    state file and runs the keep policy. No collective is involved, so async saves are
+    safe on any thread."""
+    self._shard, self._num_shards = int(shard_id), int(num_shards)
+    self._shard_timeout_s = shard_timeout_s
     self._logdir = logdir
     self._vars_fn = variables_fn
     self._sanity_checks = sanity_checks or []
@@ -140,11 +149,48 @@ class Saver:
           if not c.Check(name, t):
             raise SanityCheckFailed('Sanity check %s failed for %s' % (c, name))
 
-  def _Write(self, prefix: str, snapshot: Dict[str, object], global_step: int):
-    w = tensor_bundle.BundleWriter(prefix)
+  def _SidecarPath(self, prefix: str, shard: int, seq: int) -> str:
+    # `seq` counts this Saver's saves (all ranks save in lockstep), so a fast rank that is
+    # already writing the *next* save of the same prefix cannot be mistaken for this one.
+    return '%s.entries-%05d-%d' % (prefix, shard, seq)
+
+  def _Write(self, prefix: str, snapshot: Dict[str, object], global_step: int,
+             seq: int = 0):
+    if self._num_shards == 1:
+      w = tensor_bundle.BundleWriter(prefix)
+      for name in sorted(snapshot):
+        w.Add(name, snapshot[name])
+      w.Finish()
+      self._UpdateState(prefix)
+      self._GarbageCollect()
+      return
+    w = tensor_bundle.BundleWriter(prefix, self._shard, self._num_shards)
     for name in sorted(snapshot):
       w.Add(name, snapshot[name])
-    w.Finish()
+    entries = w.FinishShard()
+    side = self._SidecarPath(prefix, self._shard, seq)
+    with open(side + '.tmp', 'wb') as f:
+      pickle.dump(entries, f, protocol=pickle.HIGHEST_PROTOCOL)
+    os.replace(side + '.tmp', side)
+    if self._shard != 0:
+      return
+    # Shard 0 commits the checkpoint once every shard's side-car has appeared.
+    deadline = time.time() + self._shard_timeout_s
+    all_entries = []
+    for r in range(self._num_shards):
+      path = self._SidecarPath(prefix, r, seq)
+      while not os.path.exists(path):
+        if time.time() > deadline:
+          raise TimeoutError('checkpoint shard %d of %s never arrived' % (r, prefix))
+        time.sleep(0.01)
+      with open(path, 'rb') as f:
+        all_entries.append(pickle.load(f))
+    tensor_bundle.MergeShardIndex(prefix, all_entries, self._num_shards)
+    for r in range(self._num_shards):
+      try:
+        os.remove(self._SidecarPath(prefix, r, seq))
+      except OSError:
+        pass
     self._UpdateState(prefix)
     self._GarbageCollect()
 
@@ -198,13 +244,15 @@ class Saver:
     self._DoSanityChecks(tensors)
     snapshot = {k: _ToNumpy(v) for k, v in tensors.items()}
     path = '%s-%08d' % (prefix or self._prefix, int(global_step))
+    self._seq = getattr(self, '_seq', 0) + 1
+    seq = self._seq
     if not self._async:
-      self._Write(path, snapshot, global_step)
+      self._Write(path, snapshot, global_step, seq)
       return path
 
     def run():
       try:
-        self._Write(path, snapshot, global_step)
+        self._Write(path, snapshot, global_step, seq)
       except BaseException as e:  # pylint: disable=broad-except
         self._error = e
 

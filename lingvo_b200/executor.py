@@ -108,13 +108,16 @@ class ExecutorTpu(base_runner.BaseRunner):
         self._train_dir, self._model, train_params=tp)
     if self._is_multi_task:
       self._task_scheduler = self._model.task_schedule
-    os.makedirs(os.path.join(logdir, 'control'), exist_ok=True)
-    with open(os.path.join(logdir, 'control', 'params.txt'), 'w') as f:
-      f.write(train_cfg.ToText())
-    from lingvo_b200.core import summary_utils
-    text, _ = summary_utils.ModelAnalysis(self._model)
-    with open(os.path.join(logdir, 'control', 'model_analysis.txt'), 'w') as f:
-      f.write(text)
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    if rank == 0:
+      os.makedirs(os.path.join(logdir, 'control'), exist_ok=True)
+      with open(os.path.join(logdir, 'control', 'params.txt'), 'w') as f:
+        f.write(train_cfg.ToText())
+      from lingvo_b200.core import summary_utils
+      text, _ = summary_utils.ModelAnalysis(self._model)
+      with open(os.path.join(logdir, 'control', 'model_analysis.txt'), 'w') as f:
+        f.write(text)
 
   def Start(self):
     self._RunLoop('executor_tpu', self._Loop)
@@ -125,6 +128,11 @@ class ExecutorTpu(base_runner.BaseRunner):
   def _Loop(self):
     with self._cluster:
       self._checkpointer.Restore()
+      # Engines attach data parallelism (rank 0's variables win) after the restore.
+      for sched in self._program_schedule_dict.values():
+        if sched.train_program is not None:
+          self._checkpointer.AttachEngine(sched.train_program.engine)
+          sched.train_program.engine.PostRestore()
       while True:
         global_step = self._GlobalStep()
         py_utils.SetGlobalStep(global_step)

@@ -20,7 +20,8 @@ def _Scratch(var, n):
   if (ent is None or ent[0].numel() < n or ent[0].device != var.device or
       ent[1] != var.data_ptr()):
     buf = torch.zeros(n, dtype=torch.float32, device=var.device)
-    _SCRATCH[key] = (buf, var.data_ptr())
+    # The entry holds `var` itself: id() keys are only unique while the object is alive.
+    _SCRATCH[key] = (buf, var.data_ptr(), var)
     return buf, True
   return ent[0], False
 
@@ -35,9 +36,16 @@ def carried_sumsq(var):
 
 
 def Invalidate():
-  """Drops carried optimizer scratch (call after weights change outside the
-  optimizer, e.g. checkpoint restore)."""
-  _SCRATCH.clear()
+  """Re-derives the carried Σw² of every variable from its current weights (call after
+  weights change outside the optimizer, e.g. checkpoint restore). The scratch buffers keep
+  their addresses, so a captured CUDA graph of the step stays valid."""
+  with torch.no_grad():
+    for key, ent in list(_SCRATCH.items()):
+      buf, ptr, var = ent
+      if var.data_ptr() != ptr or buf.device != var.device:
+        del _SCRATCH[key]
+        continue
+      buf[2:3] = var.data.float().square().sum().reshape(1)
 
 
 def adafactor_factored(var, grad, vr, vc, d0, d1, lr, decay, eps1, eps2, clip,

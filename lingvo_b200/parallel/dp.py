@@ -51,6 +51,41 @@ def _AllReduceBuckets(grads: List[torch.Tensor], world: int, group=None):
   flush()
 
 
+def _ReduceExpertReplicas(leaves, ctx):
+  """`ep_size < world`: consecutive EP groups hold replicas of the same experts; their
+  gradients are averaged over the ranks with equal `ep_rank`."""
+  eps = [vg for vg in leaves if getattr(vg.var, 'expert_parallel', False)]
+  if not eps:
+    return
+  shard = getattr(eps[0].var, 'ep_shard', None)
+  if shard is None or shard[1] >= ctx.world:
+    return
+  ep_size = shard[1]
+  group = _ReplicaGroup(ctx, ep_size)
+  n_rep = ctx.world // ep_size
+  with torch.no_grad():
+    by_dtype = {}
+    for vg in eps:
+      by_dtype.setdefault(vg.grad.dtype, []).append(vg.grad)
+    for grads in by_dtype.values():
+      _AllReduceBuckets(grads, n_rep, group)
+
+
+_REPLICA_GROUPS = {}
+
+
+def _ReplicaGroup(ctx, ep_size):
+  key = (ctx.world, ep_size)
+  if key not in _REPLICA_GROUPS:
+    mine = None
+    for r in range(ep_size):
+      g = dist.new_group(list(range(r, ctx.world, ep_size)))
+      if ctx.rank % ep_size == r:
+        mine = g
+    _REPLICA_GROUPS[key] = mine
+  return _REPLICA_GROUPS[key]
+
+
 def Attach(task):
   """Installs gradient synchronisation on every learner of `task`."""
   ctx = mesh_lib.Get()
@@ -68,6 +103,7 @@ def Attach(task):
     with torch.no_grad():
       for grads in by_dtype.values():
         _AllReduceBuckets(grads, ctx.world)
+    _ReduceExpertReplicas(leaves, ctx)
     return var_grads
 
   # Make replicated variables identical across ranks (rank 0 wins).

@@ -45,6 +45,20 @@ class _AllToAll(torch.autograd.Function):
     return out, None
 
 
+class _ScaleGrad(torch.autograd.Function):
+  """Identity forward; multiplies the gradient by a constant (expert weights under EP get
+  the sum over all ranks' tokens — 1/ep makes it the mean, like the replicated variables)."""
+
+  @staticmethod
+  def forward(ctx, w, scale):
+    ctx.scale = scale
+    return w.view_as(w)
+
+  @staticmethod
+  def backward(ctx, dw):
+    return dw * ctx.scale, None
+
+
 class ExpertParallel:
   """EP engine shared by all MoE layers with the same (E, ep) geometry."""
 
@@ -87,6 +101,9 @@ class ExpertParallel:
     e, ep, el = self.num_experts, self.ep_size, self.num_local_experts
     c = gating.capacity
     m = x2d.shape[-1]
+    if ep > 1 and torch.is_grad_enabled():
+      wi = _ScaleGrad.apply(wi, 1.0 / ep)
+      wo = _ScaleGrad.apply(wo, 1.0 / ep)
     xin = gshard_layers.MoEDispatchIndexed(x2d, gating, g_l, s, e)  # [E,Gl*C,M]
     send = xin.reshape(ep, el * g_l * c, m)
     recv = _AllToAll.apply(send, self.group)          # [src, El*Gl*C, M]

@@ -81,8 +81,11 @@ class SymmArena:
     nb = n * torch.empty((), dtype=dtype).element_size()
     return self._slab[off:off + nb].view(dtype).view(*shape)
 
-  def PeerPtrs(self, off: int) -> torch.Tensor:
-    return torch.tensor([b + off for b in self.peer_base], dtype=torch.int64,
+  def PeerPtrs(self, off: int, loopback: bool = False) -> torch.Tensor:
+    """Device table of every peer's address of offset `off`; `loopback` points all
+    entries at this rank's own slab (timing-only mode: same stores, no NVLink)."""
+    bases = [self.peer_base[self.rank]] * self.world if loopback else self.peer_base
+    return torch.tensor([b + off for b in bases], dtype=torch.int64,
                         device=self.device)
 
 
@@ -98,10 +101,25 @@ class _LayerBufs:
     self.yc_off = a.Alloc(e * g_l * c * m * 2)
     self.xe = a.Local(self.xe_off, (el, g_t * c, m), bf)
     self.yc = a.Local(self.yc_off, (e, g_l * c, m), bf)
-    self.peer_xe = a.PeerPtrs(self.xe_off)
-    self.row_ptrs_yc = ex.RowPtrTable(self.yc_off, g_l, c, m)
+    self._peer_xe = {False: a.PeerPtrs(self.xe_off)}
+    self._row_ptrs_yc = {False: ex.RowPtrTable(self.yc_off, g_l, c, m)}
+    self._ex, self._geom = ex, (g_l, c, m)
     self.chan = ex.NewChannels(4)
     self.seq = [0, 0, 0, 0]
+
+  @property
+  def peer_xe(self):
+    lb = self._ex.loopback
+    if lb not in self._peer_xe:
+      self._peer_xe[lb] = self._ex.arena.PeerPtrs(self.xe_off, loopback=True)
+    return self._peer_xe[lb]
+
+  @property
+  def row_ptrs_yc(self):
+    lb = self._ex.loopback
+    if lb not in self._row_ptrs_yc:
+      self._row_ptrs_yc[lb] = self._ex.RowPtrTable(self.yc_off, *self._geom, loopback=True)
+    return self._row_ptrs_yc[lb]
 
 
 class MoeExchange:
@@ -123,6 +141,11 @@ class MoeExchange:
     self._next_chan = 0
     self._geom = None
     self._counters = None
+    # Timing-only mode used to measure the *exposed* cost of the exchange: every peer
+    # pointer is redirected to this rank's own buffers and the flag waits are skipped, so
+    # a step does exactly the same work with zero NVLink traffic and zero peer waiting.
+    # (Numerically meaningless; `bench.py` reports step(normal) − step(loopback).)
+    self.loopback = False
 
   # -------------------------------------------------------------- plumbing --
   def _EnsureArena(self, g_l, s, c, m, n_layers_hint=8):
@@ -143,11 +166,31 @@ class MoeExchange:
     self.dxc_off = a.Alloc(e * g_l * c * m * 2)
     self.dye = a.Local(self.dye_off, (el, g_t * c, m), torch.bfloat16)
     self.dxc = a.Local(self.dxc_off, (e, g_l * c, m), torch.bfloat16)
-    self.peer_dye = a.PeerPtrs(self.dye_off)
-    self.row_ptrs_dxc = self.RowPtrTable(self.dxc_off, g_l, c, m)
+    self._peer_dye = {False: a.PeerPtrs(self.dye_off), True: a.PeerPtrs(self.dye_off, True)}
+    self._row_ptrs_dxc = {False: self.RowPtrTable(self.dxc_off, g_l, c, m),
+                          True: self.RowPtrTable(self.dxc_off, g_l, c, m, loopback=True)}
     self._geom = (g_l, s, c, m)
     if self.ep > 1:
       dist.barrier(group=self.group)
+
+  @property
+  def peer_dye(self):
+    return self._peer_dye[self.loopback]
+
+  @property
+  def row_ptrs_dxc(self):
+    return self._row_ptrs_dxc[self.loopback]
+
+  def WgradScale(self, groups, rows):
+    """fp32 `[groups, rows]` filled with 1/ep (None when ep == 1)."""
+    if self.ep <= 1:
+      return None
+    key = (groups, rows)
+    cache = self.__dict__.setdefault('_wscale', {})
+    if key not in cache:
+      cache[key] = torch.full((groups, rows), 1.0 / self.ep, dtype=torch.float32,
+                              device=self.device)
+    return cache[key]
 
   def NewChannels(self, n):
     base = self._next_chan
@@ -155,7 +198,7 @@ class MoeExchange:
     assert self._next_chan <= 256, 'out of flag channels'
     return list(range(base, base + n))
 
-  def RowPtrTable(self, dst_off, g_l, c, m):
+  def RowPtrTable(self, dst_off, g_l, c, m, loopback=False):
     """Pointer of the destination row for every local expert-buffer row.
 
     Expert-buffer row (e_l, g_glob, c) → rank g_glob // G_l, combine-layout
@@ -163,8 +206,10 @@ class MoeExchange:
     """
     el, ep = self.e_local, self.ep
     dev = self.device
-    base = torch.tensor([b + dst_off for b in self.arena.peer_base],
-                        dtype=torch.int64, device=dev)
+    bases = self.arena.peer_base
+    if loopback:
+      bases = [bases[self.arena.rank]] * len(bases)
+    base = torch.tensor([b + dst_off for b in bases], dtype=torch.int64, device=dev)
     e_l = torch.arange(el, device=dev).view(el, 1, 1)
     g_glob = torch.arange(ep * g_l, device=dev).view(1, ep * g_l, 1)
     cc = torch.arange(c, device=dev).view(1, 1, c)
@@ -186,7 +231,7 @@ class MoeExchange:
   def _Sync(self, bufs: _LayerBufs, phase: int):
     """Release-signal all peers on this channel, then acquire-wait on all."""
     ch = bufs.chan[phase]
-    if self.ep > 1:
+    if self.ep > 1 and not self.loopback:
       if self._counters is None:
         self._counters = torch.zeros(4096, dtype=torch.int32, device=self.flags.device)
       ops.native().moe_sync(self.peer_flags, self.flags, self._counters, self.ep, self.rank, ch)
@@ -275,8 +320,12 @@ class _MoeFn(torch.autograd.Function):
     ex._Sync(bufs, 2)
     dye = ex.dye
     dh = gemm.gemm(dye, wo, True, True, aux=h, aux_mode=gemm.AUX_RELU_MASK)
-    dwo = gemm.gemm(h, dye, False, False)                   # [El, H, M]
-    dwi = gemm.gemm(bufs.xe, dh, False, False)              # [El, M, H]
+    # Every rank's tokens reach these experts while the replicated variables get the
+    # *mean* gradient over ranks: the same 1/ep goes on the expert weight gradients, for
+    # free in the wgrad epilogue (`row_scale`), so the global norm is consistent.
+    dwo = gemm.gemm(h, dye, False, False, row_scale=ex.WgradScale(h.shape[0], h.shape[-1]))
+    dwi = gemm.gemm(bufs.xe, dh, False, False,
+                    row_scale=ex.WgradScale(dh.shape[0], bufs.xe.shape[-1]))
     # Peer-store GEMM last: once peers see the flag, every read of this
     # layer's xe/h/dye on this rank has been issued before it in stream order.
     gemm.gemm(dh, wi, True, True, row_ptrs=ex.row_ptrs_dxc)

@@ -99,6 +99,10 @@ class FusedAllReduce:
       self.chan.Sync(1)                                       # all shards written
     for vg, view in zip(leaves, dst):
       vg.grad = view
+    from lingvo_b200.parallel import dp as dp_lib  # pylint: disable=g-import-not-at-top
+    dp_lib._ReduceExpertReplicas(   # pylint: disable=protected-access
+        [vg for vg in var_grads.Flatten() if isinstance(vg, py_utils.VarGrad) and
+         vg.grad is not None], self.ctx)
     return var_grads
 
 
@@ -178,6 +182,60 @@ class ZeroAdam:
                     p.beta2, p.epsilon)
       self.chan.Sync(1)
     return gnorm
+
+  # -- checkpoint hooks (called through core/train_engine.py) -------------------------------
+  def _Full(self, shard):
+    full = torch.empty(self.flat.total, dtype=torch.float32, device=shard.device)
+    dist.all_gather_into_tensor(full, shard)
+    return full
+
+  def PreSave(self):
+    """Makes `var.data` (fp32 masters) and the optimizer's `<var>/Adam`, `<var>/Adam_1`
+    slots authoritative on every rank, so the checkpoint has the reference layout."""
+    from lingvo_b200.core import optimizer as optimizer_lib  # pylint: disable=g-import-not-at-top
+    self.GatherMasters()
+    opt = self.learner.optimizer
+    fm, fv = self._Full(self.m), self._Full(self.v)
+    with torch.no_grad():
+      for var, o in zip(self.flat.vars, self.flat.offsets):
+        n = var.numel()
+        slots = opt._slots.setdefault(optimizer_lib._VarKey(var), {})  # pylint: disable=protected-access
+        slots['m'] = fm[o:o + n].view(var.shape).clone()
+        slots['v'] = fv[o:o + n].view(var.shape).clone()
+    opt._step_count = self.step   # pylint: disable=protected-access
+
+  def PostSave(self):
+    """Drops the gathered full-size moments again (they only exist for the snapshot)."""
+    from lingvo_b200.core import optimizer as optimizer_lib  # pylint: disable=g-import-not-at-top
+    opt = self.learner.optimizer
+    for var in self.flat.vars:
+      slots = opt._slots.get(optimizer_lib._VarKey(var), {})  # pylint: disable=protected-access
+      slots.pop('m', None)
+      slots.pop('v', None)
+
+  def PostRestore(self):
+    """Re-shards masters / moments / step from the restored variables and slots."""
+    from lingvo_b200.core import optimizer as optimizer_lib  # pylint: disable=g-import-not-at-top
+    opt = self.learner.optimizer
+    n, shard = self.flat.total, self.flat.shard
+    dev = self.master.device
+    lo, hi = self.rank * shard, (self.rank + 1) * shard
+    full = torch.zeros(n, dtype=torch.float32, device=dev)
+    fm, fv = torch.zeros_like(full), torch.zeros_like(full)
+    with torch.no_grad():
+      for var, o in zip(self.flat.vars, self.flat.offsets):
+        k = var.numel()
+        full[o:o + k] = var.data.reshape(-1).float()
+        slots = opt._slots.get(optimizer_lib._VarKey(var), {})  # pylint: disable=protected-access
+        if 'm' in slots:
+          fm[o:o + k] = slots['m'].reshape(-1).float().to(dev)
+        if 'v' in slots:
+          fv[o:o + k] = slots['v'].reshape(-1).float().to(dev)
+      self.master.copy_(full[lo:hi])
+      self.m.copy_(fm[lo:hi])
+      self.v.copy_(fv[lo:hi])
+      self.pbuf.copy_(full)
+    self.step = int(opt._step_count)   # pylint: disable=protected-access
 
   def GatherMasters(self):
     """fp32 masters of all shards → `var.data` (for checkpointing)."""

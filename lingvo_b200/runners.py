@@ -32,7 +32,13 @@ from lingvo_b200.core import py_utils
 from lingvo_b200.core import saver as saver_lib
 from lingvo_b200.core import fault_injection
 from lingvo_b200.core import summary_utils
+from lingvo_b200.core import train_engine
 from lingvo_b200.utils import tfevents
+
+
+def _Rank() -> int:
+  import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+  return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
 def _WriteParamsFiles(params, out_dir: str, prefix: str = 'params'):
@@ -99,11 +105,19 @@ class Controller(base_runner.BaseRunner):
 
 
 class Trainer(base_runner.BaseRunner):
-  """Trains a model: the hot loop (reference runners.py:266-360)."""
+  """Trains a model: the hot loop (reference runners.py:266-360).
+
+  One process per GPU. With `WORLD_SIZE > 1` (torchrun) every rank runs this runner: the
+  `TrainEngine` attaches data-parallel gradient sync (and the expert-parallel exchange
+  the model asks for), replays the step from a CUDA graph when `train.use_cuda_graph`
+  allows it, and feeds it from the device prefetcher. Rank 0 writes summaries and the
+  replicated part of the checkpoint; every rank writes its expert / optimizer shards.
+  """
 
   def __init__(self, *args, **kwargs):
     super().__init__(*args, **kwargs)
     self._job_name = 'trainer'
+    self._rank = _Rank()
     with self._cluster:
       self._model = self._params.Instantiate()
       device = py_utils.CurrentDevice()
@@ -115,9 +129,25 @@ class Trainer(base_runner.BaseRunner):
     self._step_rate_tracker = summary_utils.StepRateTracker()
     self._checkpointer = checkpointer.Checkpointer(
         self._train_dir, self._model, train_params=tp)
-    _WriteParamsFiles(self._params, self._train_dir, 'trainer_params')
-    self._summary_writer = tfevents.EventFileWriter(self._train_dir)
+    self._engine = None
+    self._summary_writer = None
+    if self._rank == 0:
+      _WriteParamsFiles(self._params, self._train_dir, 'trainer_params')
+      self._summary_writer = tfevents.EventFileWriter(self._train_dir)
     self._done = False
+
+  @property
+  def engine(self) -> train_engine.TrainEngine:
+    """The fast-path stepper (created after the first Restore)."""
+    if self._engine is None:
+      with self._cluster:
+        self._engine = train_engine.TrainEngine(self._task)
+      self._checkpointer.AttachEngine(self._engine)
+    return self._engine
+
+  @property
+  def task(self):
+    return self._task
 
   def Start(self):
     self._RunLoop('trainer', self._Loop)
@@ -128,8 +158,12 @@ class Trainer(base_runner.BaseRunner):
   def _Loop(self):
     tp = self._params.train
     with self._cluster:
+      # Variables are made identical across ranks when the engine attaches DP (rank 0
+      # wins), so restore first and attach afterwards.
       self._checkpointer.Restore()
       task = self._task
+      engine = self.engine
+      engine.PostRestore()
       global_step = task.global_step
       self._checkpointer.MaybeSave(gsteps=global_step)
       while True:
@@ -138,14 +172,16 @@ class Trainer(base_runner.BaseRunner):
         injector = fault_injection.Get()
         if injector is not None:
           injector.BeforeStep(global_step, self._train_dir)
-        want_summary = (tp.summary_interval_steps and
+        want_summary = (self._rank == 0 and tp.summary_interval_steps and
                         global_step % tp.summary_interval_steps == 0)
-        collector = summary_utils.SummaryCollector() if want_summary else None
+        # Layer-level summaries need the eager Python step; all other steps replay the graph.
+        collector = summary_utils.SummaryCollector() if (
+            want_summary and not engine.cuda_graph) else None
         if collector:
           with collector:
-            eval_metrics, per_example = task.TrainStep()
+            eval_metrics, per_example = engine.Step()
         else:
-          eval_metrics, per_example = task.TrainStep()
+          eval_metrics, per_example = engine.Step()
         global_step = task.global_step
         vals = _MetricsToFloats(eval_metrics)
         task.ProcessFPropResults(None, global_step, eval_metrics, per_example)
@@ -163,7 +199,8 @@ class Trainer(base_runner.BaseRunner):
           scalars['examples/sec'] = example_rate
           scalars['total_samples'] = total_examples
           self._summary_writer.add_scalars(scalars, global_step)
-          collector.WriteTo(self._summary_writer, global_step)
+          if collector:
+            collector.WriteTo(self._summary_writer, global_step)
           self._summary_writer.flush()
         if self._trial.ShouldStopAndMaybeReport(global_step, vals):
           break
@@ -171,7 +208,8 @@ class Trainer(base_runner.BaseRunner):
       # Always save the final state.
       self._checkpointer.Save(gsteps=global_step, sync=True)
       self._checkpointer.Sync()
-      self._summary_writer.flush()
+      if self._summary_writer is not None:
+        self._summary_writer.flush()
       self._done = True
 
 

@@ -69,6 +69,8 @@ flags.DEFINE_bool('add_summary', None, 'Overrides cluster.add_summary.')
 flags.DEFINE_bool('use_eager', True, 'Always eager here; kept for parity.')
 flags.DEFINE_bool('checkpoint_in_trainer_tpu', False, 'Kept for parity.')
 flags.DEFINE_bool('pdb_on_exception', False, 'Post-mortem debugger.')
+flags.DEFINE_string('use_cuda_graph', None, "auto|on|off: overrides train.use_cuda_graph "
+                    '(whole-step CUDA-graph replay in the trainer / executor).')
 
 FLAGS = flags.FLAGS
 
@@ -184,6 +186,10 @@ class RunnerManager:
         raise
       cfg = model_registry.GetParams(self._model_name, match[0])
     self.UpdateClusterParamsFromFlags(cfg.cluster, self._ClusterJobName(job_name))
+    if FLAGS.use_cuda_graph:
+      for tp in ([cfg.task.train] if 'task' in cfg else
+                 [t.train for _, t in cfg.task_params.IterParams()]):
+        tp.use_cuda_graph = FLAGS.use_cuda_graph
     if FLAGS.saver_max_to_keep is not None:
       cfg.train.save_max_to_keep = FLAGS.saver_max_to_keep
     if FLAGS.saver_keep_checkpoint_every_n_hours is not None:

@@ -18,6 +18,7 @@ The hot paths (crc32c, block encode) use the native extension when present.
 from __future__ import annotations
 
 import os
+import re
 import struct
 from typing import Dict, Iterable, List, Optional, Tuple
 
@@ -210,12 +211,21 @@ def DataPath(prefix: str, shard: int, num_shards: int) -> str:
 
 
 class BundleWriter:
-  """Writes `{name: ndarray}` as `<prefix>.index` + one data shard."""
+  """Writes `{name: ndarray}` as `<prefix>.index` + data shard(s).
 
-  def __init__(self, prefix: str):
+  Single-process use: `BundleWriter(prefix)` → `Add…` → `Finish()`.
+  Sharded use (one writer per rank, reference `saver.py:168-194` save-then-merge): rank r
+  constructs `BundleWriter(prefix, shard_id=r, num_shards=W)`, adds the tensors it owns and
+  calls `FinishShard()`, which returns the index entries of its shard; one process then
+  calls `MergeShardIndex(prefix, [entries…], W)`.
+  """
+
+  def __init__(self, prefix: str, shard_id: int = 0, num_shards: int = 1):
     self._prefix = prefix
+    self._shard, self._num_shards = int(shard_id), int(num_shards)
     os.makedirs(os.path.dirname(prefix) or '.', exist_ok=True)
-    self._tmp_data = DataPath(prefix, 0, 1) + '.tempstate'
+    self._data_path = DataPath(prefix, self._shard, self._num_shards)
+    self._tmp_data = self._data_path + '.tempstate'
     self._f = open(self._tmp_data, 'wb')
     self._entries: Dict[str, bytes] = {}
     self._offset = 0
@@ -237,20 +247,51 @@ class BundleWriter:
       raw, shape = arr.tobytes(), arr.shape
     crc = tfrecord.masked_crc32c(raw)
     self._f.write(raw)
-    self._entries[name] = _EntryProto(dt, shape, 0, self._offset, len(raw), crc)
+    self._entries[name] = _EntryProto(dt, shape, self._shard, self._offset, len(raw), crc)
     self._offset += len(raw)
 
-  def Finish(self):
+  def FinishShard(self) -> Dict[str, bytes]:
+    """Commits this shard's data file; returns its `{name: BundleEntryProto bytes}`."""
     self._f.flush()
     os.fsync(self._f.fileno())
     self._f.close()
-    os.replace(self._tmp_data, DataPath(self._prefix, 0, 1))
-    items = [(b'', _HeaderProto(1))]
-    for name in sorted(self._entries, key=lambda s: s.encode('utf-8')):
-      items.append((name.encode('utf-8'), self._entries[name]))
-    tmp_index = self._prefix + '.index.tempstate'
-    WriteTable(tmp_index, items)
-    os.replace(tmp_index, self._prefix + '.index')
+    os.replace(self._tmp_data, self._data_path)
+    return dict(self._entries)
+
+  def Finish(self):
+    assert self._num_shards == 1, 'sharded writers use FinishShard + MergeShardIndex'
+    MergeShardIndex(self._prefix, [self.FinishShard()], 1)
+
+
+def MergeShardIndex(prefix: str, shard_entries, num_shards: int):
+  """Writes `<prefix>.index` over the entries of all shards (atomic rename)."""
+  merged: Dict[str, bytes] = {}
+  for entries in shard_entries:
+    for name, proto in entries.items():
+      if name in merged:
+        raise ValueError('tensor %s written by more than one shard' % name)
+      merged[name] = proto
+  items = [(b'', _HeaderProto(num_shards))]
+  for name in sorted(merged, key=lambda s: s.encode('utf-8')):
+    items.append((name.encode('utf-8'), merged[name]))
+  tmp_index = prefix + '.index.tempstate'
+  WriteTable(tmp_index, items)
+  os.replace(tmp_index, prefix + '.index')
+
+
+# -- dim-0 slices of one logical tensor spread over shards (expert-parallel variables) -----
+_SLICE_RE = re.compile(r'^(.*)/__slice_(\d+)_(\d+)_of_(\d+)$')
+
+
+def SliceKey(name: str, lo: int, hi: int, total: int) -> str:
+  return '%s/__slice_%d_%d_of_%d' % (name, lo, hi, total)
+
+
+def ParseSliceKey(key: str):
+  m = _SLICE_RE.match(key)
+  if not m:
+    return None
+  return m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4))
 
 
 class BundleReader:
@@ -310,6 +351,65 @@ class BundleReader:
     if dt == _DT_STRING:
       raise TypeError('string tensor %s is not supported' % name)
     return np.frombuffer(raw, dtype=_DT_INV[dt]).reshape(shape).copy()
+
+  def LogicalKeys(self) -> List[str]:
+    """Keys with dim-0 slice entries folded back into their logical tensor names."""
+    out = set()
+    for k in self._entries:
+      sl = ParseSliceKey(k)
+      out.add(sl[0] if sl else k)
+    return sorted(out)
+
+  def _Slices(self, name: str):
+    out = []
+    for k in self._entries:
+      sl = ParseSliceKey(k)
+      if sl and sl[0] == name:
+        out.append((sl[1], sl[2], sl[3], k))
+    return sorted(out)
+
+  def HasLogical(self, name: str) -> bool:
+    return name in self._entries or bool(self._Slices(name))
+
+  def LogicalShape(self, name: str):
+    if name in self._entries:
+      return self.ShapeAndDtype(name)[0]
+    sl = self._Slices(name)
+    shape = self.ShapeAndDtype(sl[0][3])[0]
+    return (sl[0][2],) + tuple(shape[1:])
+
+  def ReadRange(self, name: str, lo: Optional[int] = None, hi: Optional[int] = None):
+    """Rows [lo, hi) of dim 0 of logical tensor `name` (whole tensor by default), whether
+    it was saved whole or as per-rank dim-0 slices."""
+    if name in self._entries:
+      full = self.Read(name)
+      if lo is None:
+        return full
+      if isinstance(full, BFloat16Array):
+        return BFloat16Array(full.bits[lo:hi])
+      return full[lo:hi]
+    slices = self._Slices(name)
+    if not slices:
+      raise KeyError(name)
+    total = slices[0][2]
+    lo = 0 if lo is None else lo
+    hi = total if hi is None else hi
+    parts, cursor = [], lo
+    for s_lo, s_hi, _, key in slices:
+      if s_hi <= cursor or s_lo >= hi:
+        continue
+      if s_lo > cursor:
+        raise IOError('slices of %s do not cover row %d' % (name, cursor))
+      part = self.Read(key)
+      bits = part.bits if isinstance(part, BFloat16Array) else part
+      parts.append(bits[cursor - s_lo:min(hi, s_hi) - s_lo])
+      cursor = min(hi, s_hi)
+    if cursor < hi:
+      raise IOError('slices of %s do not cover rows up to %d' % (name, hi))
+    cat = np.concatenate(parts, axis=0) if len(parts) > 1 else parts[0]
+    if isinstance(part, BFloat16Array):
+      return BFloat16Array(np.ascontiguousarray(cat))
+    return np.ascontiguousarray(cat)
 
   def ReadAll(self) -> Dict[str, np.ndarray]:
     return {k: self.Read(k) for k in self.Keys()}
