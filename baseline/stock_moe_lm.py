@@ -80,20 +80,22 @@ class _AllToAll(torch.autograd.Function):
   @staticmethod
   def forward(ctx, x, group, timer):
     ctx.group, ctx.timer = group, timer
+    x = x.contiguous()
     out = torch.empty_like(x)
     if timer is not None:
       timer.Begin()
-    dist.all_to_all_single(out, x.contiguous(), group=group)
+    dist.all_to_all_single(out, x, group=group)
     if timer is not None:
       timer.End()
     return out
 
   @staticmethod
   def backward(ctx, dy):
+    dy = dy.contiguous()
     out = torch.empty_like(dy)
     if ctx.timer is not None:
       ctx.timer.Begin()
-    dist.all_to_all_single(out, dy.contiguous(), group=ctx.group)
+    dist.all_to_all_single(out, dy, group=ctx.group)
     if ctx.timer is not None:
       ctx.timer.End()
     return out, None, None

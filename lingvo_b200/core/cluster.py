@@ -230,7 +230,12 @@ class _Cluster:
 
   @property
   def num_splits_per_client(self):
-    """Splits handled by this process: in-graph replication under sync."""
+    """Splits handled by this process. Under torchrun every replica is its own process
+    (one per GPU), so a process only ever owns its replica's splits; the reference's
+    in-graph replication (one `trainer_client` driving all replicas) applies only to a
+    single-process launch."""
+    if self._world > 1:
+      return self.num_splits_per_replica
     if self.synchronous and self.job in ('trainer_client', 'executor_tpu'):
       return self.num_splits_per_replica * self.num_replicas
     return self.num_splits_per_replica

@@ -265,6 +265,19 @@ std::vector<int32_t> ToVec(const py::array_t<int32_t, py::array::c_style | py::a
 PYBIND11_MODULE(_H, m) {
   m.doc() = "lingvo_b200 host-side natives (records, batching, tokenizers, packing)";
   m.def("crc32c", [](py::bytes b) { std::string s = b; return Crc32c(s.data(), s.size()); });
+  // Zero-copy CRC over any contiguous buffer (numpy arrays of checkpoint tensors); the
+  // GIL is released so an async checkpoint thread does not stall the training loop.
+  m.def("crc32c_buffer", [](py::buffer b, uint32_t crc) {
+    py::buffer_info info = b.request();
+    const char* ptr = static_cast<const char*>(info.ptr);
+    const size_t n = static_cast<size_t>(info.size) * static_cast<size_t>(info.itemsize);
+    uint32_t out;
+    {
+      py::gil_scoped_release release;
+      out = Crc32c(ptr, n, crc);
+    }
+    return out;
+  }, py::arg("buffer"), py::arg("crc") = 0);
   m.def("masked_crc32c", [](py::bytes b) { std::string s = b; return MaskCrc(Crc32c(s.data(), s.size())); });
   m.def("glob_files", &GlobFiles);
 

@@ -34,9 +34,106 @@ const CrcTable& Table() {
 }
 }  // namespace
 
+#if defined(__x86_64__)
+// Hardware CRC32C (SSE4.2 `crc32` instruction): three independent streams hide the
+// 3-cycle latency, their CRCs are merged with precomputed "shift by N zero bytes"
+// operators. ~15-20 GB/s per core vs ~1.5 GB/s for slicing-by-8 — checkpoint bundles
+// checksum tens of GB.
+__attribute__((target("sse4.2"))) static uint32_t HwCrcBlock(const uint8_t* p, size_t n,
+                                                               uint32_t c) {
+  while (n >= 8) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    c = static_cast<uint32_t>(__builtin_ia32_crc32di(c, v));
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = __builtin_ia32_crc32qi(c, *p++);
+  return c;
+}
+
+// GF(2) 32x32 matrix helpers (zlib's crc32_combine construction, CRC32C polynomial).
+static uint32_t GfTimes(const uint32_t* mat, uint32_t vec) {
+  uint32_t sum = 0;
+  while (vec) {
+    if (vec & 1) sum ^= *mat;
+    vec >>= 1;
+    ++mat;
+  }
+  return sum;
+}
+static void GfSquare(uint32_t* sq, const uint32_t* mat) {
+  for (int i = 0; i < 32; ++i) sq[i] = GfTimes(mat, mat[i]);
+}
+// Operator that advances a (raw, un-inverted) CRC register over `len` zero bytes.
+struct ZeroShift {
+  uint32_t m[32];
+  explicit ZeroShift(size_t len) {
+    uint32_t even[32], odd[32];
+    odd[0] = 0x82f63b78u;
+    uint32_t row = 1;
+    for (int i = 1; i < 32; ++i) {
+      odd[i] = row;
+      row <<= 1;
+    }
+    GfSquare(even, odd);
+    GfSquare(odd, even);
+    // identity
+    for (int i = 0; i < 32; ++i) m[i] = 1u << i;
+    uint32_t tmp[32];
+    do {
+      GfSquare(even, odd);
+      if (len & 1) {
+        for (int i = 0; i < 32; ++i) tmp[i] = GfTimes(even, m[i]);
+        memcpy(m, tmp, sizeof(m));
+      }
+      len >>= 1;
+      if (!len) break;
+      GfSquare(odd, even);
+      if (len & 1) {
+        for (int i = 0; i < 32; ++i) tmp[i] = GfTimes(odd, m[i]);
+        memcpy(m, tmp, sizeof(m));
+      }
+      len >>= 1;
+    } while (len);
+  }
+  uint32_t Apply(uint32_t c) const { return GfTimes(m, c); }
+};
+
+__attribute__((target("sse4.2"))) static uint32_t HwCrc32c(const uint8_t* p, size_t n,
+                                                             uint32_t crc) {
+  constexpr size_t kLane = 8192;                 // bytes per stream per round
+  static const ZeroShift shift(kLane);
+  uint32_t c = ~crc;
+  while (n >= 3 * kLane) {
+    uint32_t c0 = c, c1 = 0, c2 = 0;
+    const uint8_t* a = p;
+    const uint8_t* b = p + kLane;
+    const uint8_t* d = p + 2 * kLane;
+    for (size_t i = 0; i < kLane; i += 8) {
+      uint64_t v0, v1, v2;
+      memcpy(&v0, a + i, 8);
+      memcpy(&v1, b + i, 8);
+      memcpy(&v2, d + i, 8);
+      c0 = static_cast<uint32_t>(__builtin_ia32_crc32di(c0, v0));
+      c1 = static_cast<uint32_t>(__builtin_ia32_crc32di(c1, v1));
+      c2 = static_cast<uint32_t>(__builtin_ia32_crc32di(c2, v2));
+    }
+    c = shift.Apply(shift.Apply(c0) ^ c1) ^ c2;
+    p += 3 * kLane;
+    n -= 3 * kLane;
+  }
+  return ~HwCrcBlock(p, n, c);
+}
+#endif
+
 uint32_t Crc32c(const char* data, size_t n, uint32_t crc) {
-  const CrcTable& tb = Table();
   const uint8_t* p = reinterpret_cast<const uint8_t*>(data);
+#if defined(__x86_64__)
+  static const bool hw = __builtin_cpu_supports("sse4.2");
+  if (hw) return HwCrc32c(p, n, crc);
+#endif
+  const CrcTable& tb = Table();
   uint32_t c = ~crc;
   while (n >= 8) {   // slicing-by-8
     uint32_t lo, hi;

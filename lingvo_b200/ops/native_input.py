@@ -38,7 +38,10 @@ class RandomPermutationSequence:
   """Epoch-wise random permutation batches of [0, num)."""
 
   def __init__(self, num: int, batch: int, repeat: bool, seed: int = 0):
-    mod = ops.native(required=False)
+    try:
+      mod = ops.host()           # the C++ class lives in the torch-free host library `_H`
+    except Exception:  # pylint: disable=broad-except
+      mod = None
     self._impl = None
     if mod is not None and hasattr(mod, 'RandomPermutationSequence'):
       self._impl = mod.RandomPermutationSequence(num, batch, repeat, seed)

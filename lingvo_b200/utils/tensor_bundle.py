@@ -232,7 +232,8 @@ class BundleWriter:
 
   def Add(self, name: str, value):
     if isinstance(value, BFloat16Array):
-      raw = value.bits.tobytes()
+      bits = np.ascontiguousarray(value.bits)
+      raw = memoryview(bits).cast('B') if bits.size else b''
       dt, shape = _DT_BFLOAT16, value.bits.shape
     else:
       arr = np.asarray(value, order="C")
@@ -244,11 +245,14 @@ class BundleWriter:
         if arr.dtype not in _DT:
           raise TypeError('unsupported dtype %s for %s' % (arr.dtype, name))
         dt = _DT[arr.dtype]
-      raw, shape = arr.tobytes(), arr.shape
+      # zero-copy view of the tensor bytes (no `tobytes()` duplicate of multi-GB tensors)
+      raw = memoryview(arr).cast('B') if arr.size and arr.dtype != bool else arr.tobytes()
+      shape = arr.shape
     crc = tfrecord.masked_crc32c(raw)
     self._f.write(raw)
-    self._entries[name] = _EntryProto(dt, shape, self._shard, self._offset, len(raw), crc)
-    self._offset += len(raw)
+    nbytes = raw.nbytes if isinstance(raw, memoryview) else len(raw)
+    self._entries[name] = _EntryProto(dt, shape, self._shard, self._offset, nbytes, crc)
+    self._offset += nbytes
 
   def FinishShard(self) -> Dict[str, bytes]:
     """Commits this shard's data file; returns its `{name: BundleEntryProto bytes}`."""

@@ -25,14 +25,28 @@ def _MakeTable():
 _MakeTable()
 
 
-def crc32c(data: bytes, crc: int = 0) -> int:
-  try:
-    from lingvo_b200 import ops
-    mod = ops.native(required=False)
-    if mod is not None and hasattr(mod, 'crc32c'):
-      return mod.crc32c(data, crc)
-  except Exception:  # pylint: disable=broad-except
-    pass
+_NATIVE_CRC = None
+
+
+def _NativeCrc():
+  """`_H.crc32c_buffer` (hardware CRC32C, zero-copy, GIL released) or False."""
+  global _NATIVE_CRC
+  if _NATIVE_CRC is None:
+    try:
+      from lingvo_b200 import ops  # pylint: disable=g-import-not-at-top
+      _NATIVE_CRC = getattr(ops.host(), 'crc32c_buffer', False)
+    except Exception:  # pylint: disable=broad-except
+      _NATIVE_CRC = False
+  return _NATIVE_CRC
+
+
+def crc32c(data, crc: int = 0) -> int:
+  """CRC32C of a bytes-like / buffer object (numpy arrays included)."""
+  fn = _NativeCrc()
+  if fn:
+    return fn(data, crc)
+  if not isinstance(data, (bytes, bytearray)):
+    data = bytes(memoryview(data).cast('B'))
   c = crc ^ 0xFFFFFFFF
   tbl = _TABLE
   for b in data:

@@ -37,3 +37,11 @@ def test_tensor_parallel_ffn_matches_oracle():
   _NeedGpus(2)
   rc, out = _Run('tools/tp_check.py', 2, 29622, '2048', '1024', '2048')
   assert rc == 0 and 'TP_OK' in out, out[-3000:]
+
+
+def test_product_trainer_two_gpus_identical_replicas_resume_and_gradients():
+  """`runners.Trainer` under torchrun: replicated weights identical across ranks after 10
+  steps, sharded checkpoint + resume, and per-variable gradients fused ≈ NCCL baseline."""
+  _NeedGpus(2)
+  rc, out = _Run('tools/trainer_mgpu_check.py', 2, 29623)
+  assert rc == 0 and 'TRAINER_MGPU_OK' in out, out[-4000:]
