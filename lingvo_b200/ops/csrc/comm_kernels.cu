@@ -184,13 +184,18 @@ int Blocks(long long n8) {
 
 }  // namespace
 
+// `max_blocks` > 0 caps the grid: a bucket reduced on the communication stream *during*
+// backward only needs enough CTAs to keep NVLink busy (≈2 µs × 900 GB/s of 16-byte loads in
+// flight ≈ 32–64 CTAs) and must leave the SMs to the GEMMs it overlaps with.
 void allreduce_mean_bf16(const torch::Tensor& peer_ptrs_cpu, int64_t shard_elems, int64_t rank,
                          int64_t world, double scale, int64_t device, bool store_all,
-                         const c10::optional<torch::Tensor>& sumsq) {
+                         const c10::optional<torch::Tensor>& sumsq, int64_t max_blocks) {
   TORCH_CHECK(shard_elems % 8 == 0);
   const c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
   const long long n8 = shard_elems / 8;
-  allreduce_mean_bf16_kernel<<<Blocks(n8), 512, 0, at::cuda::getCurrentCUDAStream()>>>(
+  int blocks = Blocks(n8);
+  if (max_blocks > 0 && blocks > max_blocks) blocks = static_cast<int>(max_blocks);
+  allreduce_mean_bf16_kernel<<<blocks, 512, 0, at::cuda::getCurrentCUDAStream()>>>(
       ToPeers(peer_ptrs_cpu), n8, (int)rank, (int)world, (float)scale, store_all ? 1 : 0,
       (sumsq.has_value() && sumsq->defined()) ? sumsq->data_ptr<float>() : nullptr);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
@@ -253,7 +258,10 @@ void tp_reduce_bcast(const torch::Tensor& slabs, int64_t world, const torch::Ten
 LB_REGISTER(comm) {
   m.def("tp_reduce_bcast", &lb::tp_reduce_bcast);
   m.attr("_has_comm") = true;
-  m.def("allreduce_mean_bf16", &lb::allreduce_mean_bf16);
+  m.def("allreduce_mean_bf16", &lb::allreduce_mean_bf16, pybind11::arg("peer_ptrs_cpu"),
+        pybind11::arg("shard_elems"), pybind11::arg("rank"), pybind11::arg("world"),
+        pybind11::arg("scale"), pybind11::arg("device"), pybind11::arg("store_all"),
+        pybind11::arg("sumsq"), pybind11::arg("max_blocks") = 0);
   m.def("zero_adam", &lb::zero_adam);
   m.def("tp_reduce_slabs", &lb::tp_reduce_slabs);
 }

@@ -15,6 +15,7 @@ Two engines, both built on `comm_kernels.cu` + the flag protocol:
 from __future__ import annotations
 
 import math
+import os
 from typing import List
 
 import torch
@@ -68,35 +69,179 @@ class _Channels:
 
 
 class FusedAllReduce:
-  """`learner.grad_sync` implementation: mean all-reduce of replicated grads."""
+  """`learner.grad_sync` implementation: mean all-reduce of replicated grads, bucketed
+  and **overlapped with backward**.
 
-  def __init__(self, task, ctx):
+  Gradients are produced by autograd in a fixed order. Tensor hooks on the differentiated
+  leaves (the bf16 compute copies) store each gradient straight into its slot of the
+  symmetric bf16 buffer the moment it exists; slots are laid out in arrival order, so a
+  bucket is a contiguous range and is complete as soon as its last gradient arrived. The
+  hook that completes a bucket launches, on the communication stream (a parallel branch
+  of the step's CUDA graph), `flag sync → two-shot all-reduce kernel over NVLink peer
+  memory → flag sync` for just that range, capped at `_COMM_BLOCKS` CTAs so the GEMMs of
+  the remaining backward keep the SMs. After backward only the last bucket is exposed.
+
+  The arrival order is learned during the first step (which runs the monolithic path).
+  """
+
+  _COMM_BLOCKS = 48
+  _MAX_BUCKETS = 60
+
+  def __init__(self, task, ctx, overlap: bool = True, bucket_bytes: int = 48 << 20):
     self.ctx = ctx
     self.world, self.rank = ctx.world, ctx.rank
     dev = task.Device()
     self.flat = _Flat(_ReplicatedVars(task), self.world)
-    self.arena = symm_lib.SymmArena(self.flat.total * 2 + 65536, dev)
+    self.arena = symm_lib.SymmArena(
+        self.flat.total * 2 + (2 * self._MAX_BUCKETS + 16) * self.world * 4 + 65536, dev)
     self.goff = self.arena.Alloc(self.flat.total * 2)
     self.gbuf = self.arena.Local(self.goff, (self.flat.total,), torch.bfloat16)
     self.gviews = self.flat.Views(self.gbuf)
     self.peers = torch.tensor([b + self.goff for b in self.arena.peer_base],
                               dtype=torch.int64)
-    self.chan = _Channels(self.arena, self.world, self.rank)
+    self.chan = _Channels(self.arena, self.world, self.rank, n=2 * self._MAX_BUCKETS + 8)
     self._index = {id(v): i for i, v in enumerate(self.flat.vars)}
+    self._overlap = (bool(overlap) and dev.type == 'cuda' and
+                     os.environ.get('LINGVO_B200_DP_OVERLAP', '1') != '0')
+    self._bucket_bytes = int(bucket_bytes)
+    self._arrival: List[int] = []
+    self._phase = 0                      # 0: learning the order, 1: overlapped
+    self._buckets = []                   # (start_elem, n_elems, [var indices])
+    self._bucket_of = {}
+    self._pending = []
+    self._launched = []
+    self._seen = set()
+    self.comm = torch.cuda.Stream(dev) if self._overlap else None
+    self._hooks = []
+    if self._overlap:
+      for i, v in enumerate(self.flat.vars):
+        leaf = getattr(v, 'compute', None)
+        leaf = leaf if leaf is not None else v
+        self._hooks.append(leaf.register_hook(self._MakeHook(i)))
     dist.barrier()
+
+  # ---------------------------------------------------------------- hooks --
+  def _MakeHook(self, i):
+    def hook(g):
+      if self._phase == 0:
+        self._arrival.append(i)
+        return None
+      if i in self._seen:                # a second backward through the same leaf
+        return None
+      self._seen.add(i)
+      with torch.no_grad():
+        self.gviews[i].copy_(g)          # cast → bf16 slot, on the backward's stream
+      b = self._bucket_of[i]
+      self._pending[b] -= 1
+      if self._pending[b] == 0:
+        self._LaunchBucket(b)
+      return None
+    return hook
+
+  def _LaunchBucket(self, b):
+    start, n, _ = self._buckets[b]
+    cur = torch.cuda.current_stream(self.gbuf.device)
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    self.comm.wait_event(ev)
+    with torch.cuda.stream(self.comm), torch.no_grad():
+      self.chan.Sync(2 * b)                                   # every rank staged bucket b
+      ops.native().allreduce_mean_bf16(
+          self._bucket_peers[b], n // self.world, self.rank, self.world, 1.0 / self.world,
+          self.gbuf.device.index, True, None, self._COMM_BLOCKS)
+      self.chan.Sync(2 * b + 1)                               # every shard written everywhere
+    self._launched[b] = True
+
+  def _PlanBuckets(self):
+    """Re-lays the flat buffer out in gradient-arrival order and cuts it into buckets."""
+    order, seen = [], set()
+    for i in self._arrival:
+      if i not in seen:
+        seen.add(i)
+        order.append(i)
+    order += [i for i in range(len(self.flat.vars)) if i not in seen]   # never arrived: last
+    variables = [self.flat.vars[i] for i in order]
+    unit = self.world * 8
+    offsets, buckets = [], []
+    off = start = 0
+    members = []
+    target = max(self._bucket_bytes // 2, (self.flat.total * 2) // self._MAX_BUCKETS + 1)
+    for k, v in enumerate(variables):
+      offsets.append(off)
+      members.append(k)
+      off += (v.numel() + 7) // 8 * 8
+      if (off - start) * 2 >= target or k == len(variables) - 1:
+        off = (off + unit - 1) // unit * unit                 # bucket = multiple of W·8
+        buckets.append((start, off - start, members))
+        start, members = off, []
+    if off > self.flat.total:
+      return False                                            # padding does not fit: keep monolithic
+    self.flat.vars = variables
+    self.flat.offsets = offsets
+    self.gviews = self.flat.Views(self.gbuf)
+    self._index = {id(v): i for i, v in enumerate(self.flat.vars)}
+    self._buckets = buckets
+    self._bucket_of = {k: b for b, (_, _, ms) in enumerate(buckets) for k in ms}
+    self._bucket_peers = [
+        torch.tensor([base + self.goff + s * 2 for base in self.arena.peer_base],
+                     dtype=torch.int64) for s, _, _ in buckets]
+    # hooks were registered with the old indices: re-register in the new order
+    for h in self._hooks:
+      h.remove()
+    self._hooks = []
+    for i, v in enumerate(self.flat.vars):
+      leaf = getattr(v, 'compute', None)
+      leaf = leaf if leaf is not None else v
+      self._hooks.append(leaf.register_hook(self._MakeHook(i)))
+    self._ResetStep()
+    return True
+
+  def _ResetStep(self):
+    self._pending = [len(ms) for _, _, ms in self._buckets]
+    self._launched = [False] * len(self._buckets)
+    self._seen = set()
+
+  # ------------------------------------------------------------------ call --
+  def _Monolithic(self, leaves):
+    dst = [self.gviews[self._index[id(vg.var)]] for vg in leaves]
+    with torch.no_grad():
+      torch._foreach_copy_(dst, [vg.grad for vg in leaves])   # cast → bf16 slots
+      self.chan.Sync(2 * self._MAX_BUCKETS)                   # all copies staged
+      ops.native().allreduce_mean_bf16(
+          self.peers, self.flat.shard, self.rank, self.world, 1.0 / self.world,
+          self.gbuf.device.index, True, None)
+      self.chan.Sync(2 * self._MAX_BUCKETS + 1)               # all shards written
+    return dst
 
   def __call__(self, var_grads):
     leaves = [vg for vg in var_grads.Flatten()
               if isinstance(vg, py_utils.VarGrad) and vg.grad is not None and
               id(vg.var) in self._index]
-    dst = [self.gviews[self._index[id(vg.var)]] for vg in leaves]
-    with torch.no_grad():
-      torch._foreach_copy_(dst, [vg.grad for vg in leaves])   # cast → bf16 slots
-      self.chan.Sync(0)                                       # all copies staged
-      ops.native().allreduce_mean_bf16(
-          self.peers, self.flat.shard, self.rank, self.world, 1.0 / self.world,
-          self.gbuf.device.index, True, None)
-      self.chan.Sync(1)                                       # all shards written
+    if self._phase == 0 or not self._overlap:
+      dst = self._Monolithic(leaves)
+      if self._overlap and self._arrival:
+        # Every rank saw the same autograd order; switch to the overlapped schedule.
+        torch.cuda.synchronize()
+        dist.barrier()
+        if self._PlanBuckets():
+          self._phase = 1
+          dst = [self.gviews[self._index[id(vg.var)]] for vg in leaves]
+          # this step's reduced values live at the old offsets: re-reduce in the new layout
+          dst = self._Monolithic(leaves)
+        else:
+          self._overlap = False
+    else:
+      with torch.no_grad():
+        for b, (start, n, ms) in enumerate(self._buckets):
+          if self._launched[b]:
+            continue
+          for k in ms:                                       # gradients that never arrived
+            if k not in self._seen:
+              self.gviews[k].zero_()
+          self._LaunchBucket(b)
+      torch.cuda.current_stream(self.gbuf.device).wait_stream(self.comm)
+      dst = [self.gviews[self._index[id(vg.var)]] for vg in leaves]
+      self._ResetStep()
     for vg, view in zip(leaves, dst):
       vg.grad = view
     from lingvo_b200.parallel import dp as dp_lib  # pylint: disable=g-import-not-at-top
