@@ -14,6 +14,7 @@ Dispatch:
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -179,3 +180,80 @@ def rel_bias_attention(q, k, v, rel, mask=None, scale=1.0, causal=False):
     return t if ok else t.contiguous()
   return _RelBiasAttnFn.apply(_View(q), _View(k), _View(v), rel, mask,
                               float(scale), bool(causal))
+
+
+# ------------------------------------------------------------ tcgen05 flash attention ----
+def flash_attention_ref(q, k, v, rel=None, seg=None, pos=None, scale=1.0, causal=False):
+  """fp32 oracle of `flash_attention`: packed-input mask built from segment ids / positions
+  (visible ⇔ same non-zero segment and, if causal, pos_k <= pos_q) + Toeplitz bias."""
+  b, l = q.shape[0], q.shape[1]
+  dev = q.device
+  if seg is None:
+    seg = torch.ones(b, l, dtype=torch.int32, device=dev)
+  if pos is None:
+    pos = torch.arange(l, dtype=torch.int32, device=dev).unsqueeze(0).expand(b, l)
+  a, c = seg.unsqueeze(-1), seg.unsqueeze(-2)
+  vis = (a == c) & (a != 0)
+  if causal:
+    vis = vis & (pos.unsqueeze(-1) >= pos.unsqueeze(-2))
+  bias = (~vis).float().unsqueeze(1) * -1e9
+  if rel is not None:
+    bias = bias + _RelToeplitz(rel.float(), l).unsqueeze(0)
+  return attention_ref(q, k, v, bias, scale)
+
+
+class _FlashAttnFn(torch.autograd.Function):
+  """Our tcgen05 flash attention (csrc/flash_attn.cu): forward, dQ/dK/dV and the gradient
+  of the relative-bias table in two kernels; no `[B,H,L,L]` tensor, no library call."""
+
+  @staticmethod
+  def forward(ctx, q, k, v, rel, seg, pos, scale, causal):
+    from lingvo_b200 import ops
+    out, lse = ops.native().flash_attn_fwd(q, k, v, rel, seg, pos, scale, causal)
+    ctx.save_for_backward(q, k, v, out, lse, rel, seg, pos)
+    ctx.meta = (scale, causal)
+    return out
+
+  @staticmethod
+  def backward(ctx, d_o):
+    from lingvo_b200 import ops
+    q, k, v, out, lse, rel, seg, pos = ctx.saved_tensors
+    scale, causal = ctx.meta
+    need_drel = rel is not None and ctx.needs_input_grad[3]
+    dq, dk, dv, drel = ops.native().flash_attn_bwd(
+        q, k, v, out, d_o, lse, rel, seg, pos, scale, causal, need_drel)
+    return dq, dk, dv, (drel if need_drel else None), None, None, None, None
+
+
+def flash_attention_supported(q, k, dropout_prob=0.0):
+  from lingvo_b200 import ops
+  mod = ops.native(required=False) if q.is_cuda else None
+  return (mod is not None and hasattr(mod, '_has_flash_attn') and
+          os.environ.get('LINGVO_B200_ATTN', 'flash') == 'flash' and
+          ops.use_cuda_kernels(q) and q.dtype == torch.bfloat16 and q.dim() == 4 and
+          q.shape[-1] == 128 and q.shape[1] % 128 == 0 and q.shape == k.shape and
+          not dropout_prob)
+
+
+def flash_attention(q, k, v, rel=None, seg=None, pos=None, scale=1.0, causal=False):
+  """`[B,L,H,128]` self-attention, bias `rel[h, i-j+L-1]` (fp32 `[H, 2L-1]`, optional) and
+  the packed-input mask from int32 `seg` / `pos` `[B, L]` (optional). Returns `[B,L,H,128]`.
+
+  `causal=True` additionally assumes positions grow with the index inside a segment (packed
+  LM inputs), which lets both kernels skip the key blocks above the diagonal.
+  """
+  if not flash_attention_supported(q, k):
+    return flash_attention_ref(q, k, v, rel, seg, pos, scale, causal).to(q.dtype)
+
+  def _View(t):   # [B,L,H,D] view with strides (*, *, D, 1), 16-byte aligned rows
+    ok = (t.stride(3) == 1 and t.stride(2) == t.shape[3] and t.stride(1) % 8 == 0 and
+          t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0)
+    return t if ok else t.contiguous()
+  if rel is not None:
+    rel = rel.float().contiguous()
+  if seg is not None:
+    seg = seg.to(torch.int32).contiguous()
+  if pos is not None:
+    pos = pos.to(torch.int32).contiguous()
+  return _FlashAttnFn.apply(_View(q), _View(k), _View(v), rel, seg, pos, float(scale),
+                            bool(causal))
