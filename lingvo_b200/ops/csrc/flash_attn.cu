@@ -76,6 +76,32 @@ __device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float
                "f"(d)
                : "memory");
 }
+// Explicit shared-space accesses: the tile base is re-aligned through integer arithmetic,
+// after which the compiler can only emit *generic* LD/ST for C++ pointers into it.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s16(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_s16(uint32_t a, int v) {
+  asm volatile("st.shared.s16 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // smem byte offset of the 16-byte unit holding columns [8u, 8u+8) of row r in a
@@ -146,9 +172,16 @@ struct FwdParams {
   float scale;
 };
 
-constexpr int kFwdStages = 2;
-constexpr size_t kFwdSmem = kTile * (1 + 2 * kFwdStages + 1) + 4096 + 1024;
+// smem: Q | K x2 | V | P x2 (each 32 KiB) + 8 KiB of barriers / per-block tables.
+constexpr size_t kFwdSmem = kTile * 6 + 8192 + 1024;
 
+// Software pipeline (steady state, block j):
+//   tensor pipe : ... PV(j-1) | S(j+1) ...          (issued while the warps work on block j)
+//   warps       : softmax(j) -> P(j) to smem -> signal -> O = alpha·O + PV(j-1)
+// S and PV are double-buffered in TMEM (4 x 128 columns), P in smem, K has two stages and
+// V one (V(j+1) is only needed after softmax(j+1)); the per-block bias/mask tables for
+// block j+1 are fetched while block j is processed. The warps never wait for a GEMM that
+// was not issued a whole softmax earlier.
 __global__ void __launch_bounds__(kThreads, 1)
 flash_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const FwdParams p) {
@@ -162,21 +195,23 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t s_q = smem_u32(smem);
-  const uint32_t s_kv = s_q + kTile;                         // stage s: K at +2s·kTile, V behind it
-  const uint32_t s_p = s_kv + 2 * kFwdStages * kTile;
-  uint8_t* meta = smem + kTile * (2 + 2 * kFwdStages);
+  const uint32_t s_k = s_q + kTile;                          // 2 stages
+  const uint32_t s_v = s_k + 2 * kTile;                      // 1 stage
+  const uint32_t s_p = s_v + kTile;                          // 2 buffers
+  uint8_t* meta = smem + kTile * 6;
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta);
   uint64_t* q_bar = bars;                 // 1
-  uint64_t* full_bar = bars + 1;          // kFwdStages
-  uint64_t* empty_bar = bars + 3;         // kFwdStages
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_ready = bars + 6;
-  uint64_t* pv_full = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
-  float* rel_s = reinterpret_cast<float*>(meta + 128);      // [256]
-  int* segk_s = reinterpret_cast<int*>(meta + 128 + 1024);  // [128]
-  int* posk_s = segk_s + 128;                               // [128]
-  float* xch = reinterpret_cast<float*>(posk_s + 128);      // [2][128]
+  uint64_t* k_full = bars + 1;            // 2
+  uint64_t* k_empty = bars + 3;           // 2
+  uint64_t* v_full = bars + 5;            // 1
+  uint64_t* v_empty = bars + 6;           // 1
+  uint64_t* s_full = bars + 7;            // 2
+  uint64_t* p_ready = bars + 9;           // 2
+  uint64_t* pv_full = bars + 11;          // 2
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  const uint32_t s_xch = smem_u32(meta + 128);              // float [2][128]
+  const uint32_t s_tab = s_xch + 1024;                      // 2 x {rel[256] f32, seg[128], pos[128]}
+  constexpr int kTableBytes = 1024 + 512 + 512;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -186,40 +221,60 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
     mbar_init(smem_u32(q_bar), 1);
-    for (int s = 0; s < kFwdStages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&k_full[s]), 1);
+      mbar_init(smem_u32(&k_empty[s]), 1);
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&p_ready[s]), 8);
+      mbar_init(smem_u32(&pv_full[s]), 1);
     }
-    mbar_init(smem_u32(s_full), 1);
-    mbar_init(smem_u32(p_ready), 8);
-    mbar_init(smem_u32(pv_full), 1);
+    mbar_init(smem_u32(v_full), 1);
+    mbar_init(smem_u32(v_empty), 1);
     fence_barrier_init();
   }
   if (warp_idx == 1) {
-    tmem_alloc<256>(smem_u32(tmem_ptr_smem));
+    tmem_alloc<512>(smem_u32(tmem_ptr_smem));
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t t_s = tmem_base;            // S   : columns [0, 128)
-  const uint32_t t_o = tmem_base + 128;      // P·V : columns [128, 256)
+  // S buffers: columns [0,128), [128,256);  PV buffers: [256,384), [384,512)
+
+  // ordered list of visible key blocks is implicit: every role walks jb = 0..nblk-1 and
+  // skips with the same predicate.
+  int n_vis = 0;
+  for (int jb = 0; jb < nblk; ++jb)
+    n_vis += pair_visible(p.mask, qmeta, block_meta(p.mask, b, nblk, jb)) ? 1 : 0;
 
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       mbar_arrive_expect_tx(smem_u32(q_bar), kTile);
       load_tile(s_q, &map_q, smem_u32(q_bar), h, i0, b);
+      // K runs one block ahead of V: K(0), then for each visible block it: K(it+1), V(it).
+      int jk = 0;                                  // scan position of the K stream
+      int itk = 0;
+      auto next_k = [&]() {
+        while (jk < nblk && !pair_visible(p.mask, qmeta, block_meta(p.mask, b, nblk, jk))) ++jk;
+        if (jk >= nblk) return;
+        const int s = itk & 1;
+        mbar_wait(smem_u32(&k_empty[s]), ((itk >> 1) & 1) ^ 1);
+        const uint32_t fb = smem_u32(&k_full[s]);
+        mbar_arrive_expect_tx(fb, kTile);
+        load_tile(s_k + s * kTile, &map_k, fb, h, jk * kT, b);
+        ++itk;
+        ++jk;
+      };
+      next_k();
       int it = 0;
       for (int jb = 0; jb < nblk; ++jb) {
         if (!pair_visible(p.mask, qmeta, block_meta(p.mask, b, nblk, jb))) continue;
-        const int s = it % kFwdStages;
-        mbar_wait(smem_u32(&empty_bar[s]), ((it / kFwdStages) & 1) ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_arrive_expect_tx(fb, 2 * kTile);
-        load_tile(s_kv + (2 * s) * kTile, &map_k, fb, h, jb * kT, b);
-        load_tile(s_kv + (2 * s + 1) * kTile, &map_v, fb, h, jb * kT, b);
+        next_k();
+        mbar_wait(smem_u32(v_empty), (it & 1) ^ 1);
+        mbar_arrive_expect_tx(smem_u32(v_full), kTile);
+        load_tile(s_v, &map_v, smem_u32(v_full), h, jb * kT, b);
         ++it;
       }
     }
@@ -227,30 +282,26 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   } else if (warp_idx == 1) {
     // ============================= MMA issuer =============================
     if (lane == 0) {
-      int n_vis = 0;
-      for (int jb = 0; jb < nblk; ++jb)
-        n_vis += pair_visible(p.mask, qmeta, block_meta(p.mask, b, nblk, jb)) ? 1 : 0;
       mbar_wait(smem_u32(q_bar), 0);        // always: the Q load must land before the CTA exits
-      if (n_vis > 0) {
-        mbar_wait(smem_u32(&full_bar[0]), 0);
+      auto issue_s = [&](int it) {          // S(it) into S buffer it & 1 from K stage it & 1
+        const int s = it & 1;
+        mbar_wait(smem_u32(&k_full[s]), (it >> 1) & 1);
         tc_fence_after();
-        issue_gemm<false, false>(t_s, s_q, s_kv, false);             // S_0 = Q·K_0^T
-        umma_commit(smem_u32(s_full));
-      }
+        issue_gemm<false, false>(tmem_base + s * 128, s_q, s_k + s * kTile, false);
+        umma_commit(smem_u32(&s_full[s]));
+        umma_commit(smem_u32(&k_empty[s]));
+      };
+      if (n_vis > 0) issue_s(0);
+      if (n_vis > 1) issue_s(1);
       for (int it = 0; it < n_vis; ++it) {
-        const int s = it % kFwdStages;
-        mbar_wait(smem_u32(p_ready), it & 1);
+        const int s = it & 1;
+        mbar_wait(smem_u32(&p_ready[s]), (it >> 1) & 1);
+        mbar_wait(smem_u32(v_full), it & 1);
         tc_fence_after();
-        issue_gemm<false, true>(t_o, s_p, s_kv + (2 * s + 1) * kTile, false);   // P·V_j
-        umma_commit(smem_u32(pv_full));
-        umma_commit(smem_u32(&empty_bar[s]));
-        if (it + 1 < n_vis) {
-          const int s2 = (it + 1) % kFwdStages;
-          mbar_wait(smem_u32(&full_bar[s2]), ((it + 1) / kFwdStages) & 1);
-          tc_fence_after();
-          issue_gemm<false, false>(t_s, s_q, s_kv + (2 * s2) * kTile, false);   // S_{j+1}
-          umma_commit(smem_u32(s_full));
-        }
+        issue_gemm<false, true>(tmem_base + 256 + s * 128, s_p + s * kTile, s_v, false);   // P·V
+        umma_commit(smem_u32(&pv_full[s]));
+        umma_commit(smem_u32(v_empty));
+        if (it + 2 < n_vis) issue_s(it + 2);      // S buffer `s` was drained before p_ready(it)
       }
     }
     __syncwarp();
@@ -271,34 +322,66 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     for (int c = 0; c < 64; ++c) o[c] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
 
-    int it = 0;
-    for (int jb = 0; jb < nblk; ++jb) {
-      if (!pair_visible(p.mask, qmeta, block_meta(p.mask, b, nblk, jb))) continue;
+    // per-block tables → smem buffer `buf` (published by the next epi_bar_sync)
+    auto fetch_tables = [&](int jb, int buf) {
+      const uint32_t tb = s_tab + buf * kTableBytes;
       const int j0 = jb * kT;
-      // per-block metadata → smem (previous readers are past the exchange barrier)
       if (et < 255)
-        rel_s[et] = p.rel ? p.rel[static_cast<long long>(h) * (2 * p.L - 1) + (i0 - j0 + p.L - 1) - 127 + et] * kLog2e
-                          : 0.f;
+        sts_f32(tb + et * 4,
+                p.rel ? p.rel[static_cast<long long>(h) * (2 * p.L - 1) + (i0 - j0 + p.L - 1) - 127 + et] * kLog2e
+                      : 0.f);
       if (et < 128) {
-        segk_s[et] = p.mask.seg ? p.mask.seg[bl + j0 + et] : 1;
-        posk_s[et] = p.mask.pos ? p.mask.pos[bl + j0 + et] : j0 + et;
+        sts_s32(tb + 1024 + et * 4, p.mask.seg ? p.mask.seg[bl + j0 + et] : 1);
+        sts_s32(tb + 1536 + et * 4, p.mask.pos ? p.mask.pos[bl + j0 + et] : j0 + et);
       }
-      epi_bar_sync();
-      mbar_wait(smem_u32(s_full), it & 1);
+    };
+    auto next_vis = [&](int jb) {
+      while (jb < nblk && !pair_visible(p.mask, qmeta, block_meta(p.mask, b, nblk, jb))) ++jb;
+      return jb;
+    };
+    // O = alpha·O + PV(buffer)
+    auto o_update = [&](int it, float alpha) {
+      const int s = it & 1;
+      mbar_wait(smem_u32(&pv_full[s]), (it >> 1) & 1);
       tc_fence_after();
-      float sv[64];
-      float mloc = -INFINITY;
-      const bool full = pair_full(p.mask, qmeta, block_meta(p.mask, b, nblk, jb));
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(t_s + lane_off + hf * 64 + cc * 32, v);
+        tmem_ld_32x32b_x32(tmem_base + 256 + s * 128 + lane_off + hf * 64 + cc * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          o[cc * 32 + k] = fmaf(o[cc * 32 + k], alpha, __uint_as_float(v[k]));
+      }
+      tc_fence_before();
+    };
+
+    int jb = next_vis(0);
+    if (jb < nblk) fetch_tables(jb, 0);
+    float alpha_prev = 0.f;
+    for (int it = 0; it < n_vis; ++it) {
+      const int s = it & 1;
+      const uint32_t rel_a = s_tab + s * kTableBytes + (r + 127) * 4;   // rel_s[r - c + 127]
+      const uint32_t seg_a = s_tab + s * kTableBytes + 1024;
+      const uint32_t pos_a = seg_a + 512;
+      const bool full = pair_full(p.mask, qmeta, block_meta(p.mask, b, nblk, jb));
+      const int jb_next = next_vis(jb + 1);
+      epi_bar_sync();                                  // tables of block `it` are in place
+      if (jb_next < nblk) fetch_tables(jb_next, s ^ 1);    // buffer s^1: readers left it at the barrier
+      mbar_wait(smem_u32(&s_full[s]), (it >> 1) & 1);
+      tc_fence_after();
+      float sv[64];
+      float mloc = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + s * 128 + lane_off + hf * 64 + cc * 32, v);
         tmem_ld_wait();
         if (full) {                    // interior block: bias only, no mask arithmetic
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const int c = hf * 64 + cc * 32 + k;
-            const float x = fmaf(__uint_as_float(v[k]), sl2, rel_s[r - c + 127]);
+            const float x = fmaf(__uint_as_float(v[k]), sl2, lds_f32(rel_a - c * 4));
             sv[cc * 32 + k] = x;
             mloc = fmaxf(mloc, x);
           }
@@ -306,20 +389,21 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const int c = hf * 64 + cc * 32 + k;
-            float x = fmaf(__uint_as_float(v[k]), sl2, rel_s[r - c + 127]);
-            const bool vis = (segq == segk_s[c]) && (segq != 0) &&
-                             (!p.mask.causal || posq >= posk_s[c]);
+            float x = fmaf(__uint_as_float(v[k]), sl2, lds_f32(rel_a - c * 4));
+            const bool vis = (segq == lds_s32(seg_a + c * 4)) && (segq != 0) &&
+                             (!p.mask.causal || posq >= lds_s32(pos_a + c * 4));
             x = vis ? x : kMasked;
             sv[cc * 32 + k] = x;
             mloc = fmaxf(mloc, x);
           }
         }
       }
-      xch[hf * 128 + r] = mloc;
+      sts_f32(s_xch + (hf * 128 + r) * 4, mloc);
       epi_bar_sync();
-      const float m_new = fmaxf(m_run, fmaxf(mloc, xch[(1 - hf) * 128 + r]));
+      const float m_new = fmaxf(m_run, fmaxf(mloc, lds_f32(s_xch + ((1 - hf) * 128 + r) * 4)));
       const float alpha = ex2(m_run - m_new);
       float lsum = 0.f;
+      const uint32_t s_pb = s_p + s * kTile;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         uint32_t w[4];
@@ -330,33 +414,25 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           lsum += p0 + p1;
           w[e] = pack_bf16x2(p0, p1);
         }
-        st_shared_v4(s_p + tile_unit_off(r, hf * 8 + u), w[0], w[1], w[2], w[3]);
+        st_shared_v4(s_pb + tile_unit_off(r, hf * 8 + u), w[0], w[1], w[2], w[3]);
       }
       l_run = l_run * alpha + lsum;
       m_run = m_new;
       fence_proxy_async();          // P (generic-proxy stores) → visible to the MMA's async proxy
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(p_ready));
-      mbar_wait(smem_u32(pv_full), it & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_o + lane_off + hf * 64 + cc * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 32; ++k)
-          o[cc * 32 + k] = fmaf(o[cc * 32 + k], alpha, __uint_as_float(v[k]));
-      }
-      tc_fence_before();
-      ++it;
+      if (lane == 0) mbar_arrive(smem_u32(&p_ready[s]));
+      // the previous block's P·V has been running during this softmax: fold it in now
+      if (it > 0) o_update(it - 1, alpha_prev);
+      alpha_prev = alpha;
+      jb = jb_next;
     }
+    if (n_vis > 0) o_update(n_vis - 1, alpha_prev);
     // ---- finalize: O / l, log-sum-exp ----
     epi_bar_sync();
-    xch[hf * 128 + r] = l_run;
+    sts_f32(s_xch + (hf * 128 + r) * 4, l_run);
     epi_bar_sync();
-    const float l_tot = l_run + xch[(1 - hf) * 128 + r];
+    const float l_tot = l_run + lds_f32(s_xch + ((1 - hf) * 128 + r) * 4);
     const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;      // query block that sees nothing: 0
     __nv_bfloat16* dst = p.out + ((bl + i) * p.H + h) * kD + hf * 64;
 #pragma unroll
@@ -377,7 +453,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -428,9 +504,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint64_t* dq_full = bars + 9;
   uint64_t* dq_read = bars + 10;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
-  float* rel_s = reinterpret_cast<float*>(meta + 128);        // [256]
-  short* segk_s = reinterpret_cast<short*>(meta + 128 + 1024);   // [128]
-  short* posk_s = segk_s + 128;                                  // [128]
+  const uint32_t s_rel = smem_u32(meta + 128);                // float [256]
+  const uint32_t s_seg = s_rel + 1024;                        // short [128]
+  const uint32_t s_pos = s_seg + 256;                         // short [128]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -525,8 +601,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const float sl2 = p.scale * kLog2e;
     const uint32_t lane_off = static_cast<uint32_t>(q4 * 32) << 16;
     if (et < 128) {
-      segk_s[et] = static_cast<short>(p.mask.seg ? p.mask.seg[bl + j0 + et] : 1);
-      posk_s[et] = static_cast<short>(p.mask.pos ? p.mask.pos[bl + j0 + et] : j0 + et);
+      sts_s16(s_seg + et * 2, p.mask.seg ? p.mask.seg[bl + j0 + et] : 1);
+      sts_s16(s_pos + et * 2, p.mask.pos ? p.mask.pos[bl + j0 + et] : j0 + et);
     }
 
     int it = 0;
@@ -535,8 +611,10 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const int i0 = ib * kT;
       const int i = i0 + r;
       if (et < 255)
-        rel_s[et] = p.rel ? p.rel[static_cast<long long>(h) * (2 * p.L - 1) + (i0 - j0 + p.L - 1) - 127 + et] * kLog2e
-                          : 0.f;
+        sts_f32(s_rel + et * 4,
+                p.rel ? p.rel[static_cast<long long>(h) * (2 * p.L - 1) + (i0 - j0 + p.L - 1) - 127 + et] * kLog2e
+                      : 0.f);
+      const uint32_t rel_a = s_rel + (r + 127) * 4;
       const int segq = p.mask.seg ? p.mask.seg[bl + i] : 1;
       const int posq = p.mask.pos ? p.mask.pos[bl + i] : i;
       const float lse2 = p.lse[bh * p.L + i] * kLog2e;
@@ -564,9 +642,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             for (int t = 0; t < 2; ++t) {
               const int k = u * 8 + 2 * e + t;
               const int c = hf * 64 + cc * 32 + k;
-              const float x = fmaf(__uint_as_float(vs[k]), sl2, rel_s[r - c + 127]);
-              const bool vis = full || ((segq == segk_s[c]) && (segq != 0) &&
-                                        (!p.mask.causal || posq >= posk_s[c]));
+              const float x = fmaf(__uint_as_float(vs[k]), sl2, lds_f32(rel_a - c * 4));
+              const bool vis = full || ((segq == lds_s16(s_seg + c * 2)) && (segq != 0) &&
+                                        (!p.mask.causal || posq >= lds_s16(s_pos + c * 2)));
               pr[t] = vis ? ex2(x - lse2) : 0.f;
               ds[k] = pr[t] * (__uint_as_float(vp[k]) - delta);
             }
