@@ -1598,3 +1598,381 @@ def TransformerFlops(inputs_shape, num_heads, ff_dim, atten_dim, model_dim):
   attn = 2 * 2 * b * t * t * atten_dim
   ff = 2 * 2 * b * t * model_dim * ff_dim
   return proj + attn + ff
+
+
+# ==================================================================================
+# Sub-quadratic / structured attention variants (long-context toolbox)
+# ==================================================================================
+class ChunkwiseSelfAttentionXL(ChunkwiseSelfAttention):
+  """Chunk-wise attention + Transformer-XL relative term (reference :4318)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('rel_pos_emb_dim', None, 'Sinusoid embedding dim.')
+    p.Define('skip_term_b', False, 'Drop the position term.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert p.rel_pos_emb_dim and p.rel_pos_emb_dim > 0
+    self.CreateChild('pos_proj', p.proj_tpl.Copy().Set(
+        input_dim=p.rel_pos_emb_dim, num_heads=p.num_heads,
+        dim_per_head=self.dim_per_head, use_bias=False))
+
+  def _CreateLayerVariables(self):
+    super()._CreateLayerVariables()
+    p = self.params
+    shape = [p.num_heads, self.dim_per_head]
+    coll = [self.__class__.__name__ + '_vars']
+    self.CreateVariable('u', WeightParams(shape, WeightInit.Constant(0.0), p.dtype, coll))
+    self.CreateVariable('v', WeightParams(shape, WeightInit.Constant(0.0), p.dtype, coll))
+
+  _RelativeBias = MultiHeadedAttentionXL._RelativeBias
+
+
+class MultiHeadedFavorAttention(MultiHeadedAttention):
+  """Performer (FAVOR+) attention: O(L) softmax-kernel approximation (reference :2125).
+
+  `attention_type`: 'softmax' (positive random features), 'relu' (deterministic) or
+  'cossim'. Probabilities are never formed, so `probs` is None. `causal` selects the
+  prefix-sum form (the reference only exposes the bidirectional one).
+  """
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('num_random_features', 384, 'Random projection features.')
+    p.Define('attention_type', 'softmax', 'relu|softmax|cossim.')
+    p.Define('redraw', False, 'Redraw the random features at every call.')
+    p.Define('causal', False, 'Causal (prefix-sum) FAVOR.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    assert not self.params.packed_input, 'Packed input not supported.'
+    self._proj = None
+    self._draws = 0
+
+  def _Projection(self, dim, device):
+    from lingvo_b200.core import favor_attention as favor  # pylint: disable=g-import-not-at-top
+    p = self.params
+    if p.redraw or self._proj is None or self._proj.device != device:
+      seed = self._draws if p.redraw else 0
+      self._draws += 1
+      self._proj = favor.create_projection_matrix(p.num_random_features, dim, seed=seed).to(device)
+    return self._proj
+
+  def FProp(self, theta, query_vec, key_vec, value_vec, paddings,
+            segment_mask=None, per_step_padding=None):
+    from lingvo_b200.core import favor_attention as favor  # pylint: disable=g-import-not-at-top
+    p = self.params
+    q, k, v = self._HeadsProj(theta, query_vec, key_vec, value_vec)
+    q = self._RoPE(theta, q)
+    k = self._RoPE(theta, k)
+    if p.enable_query_scale and p.enable_per_dim_scale:
+      q = self.per_dim_scale.FProp(theta.per_dim_scale, q)
+    n = q.shape[2]
+    k, v = attention_ops._ExpandKv(k, n), attention_ops._ExpandKv(v, n)  # pylint: disable=protected-access
+    qf, kf, vf = q.float(), k.float(), v.float()
+    if p.attention_type == 'relu':
+      ctx = favor.favor_attention(qf, kf, vf, paddings, favor.relu_kernel_transformation,
+                                  p.causal)
+    elif p.attention_type == 'softmax':
+      ctx = favor.favor_attention(qf, kf, vf, paddings, favor.softmax_kernel_transformation,
+                                  p.causal, self._Projection(q.shape[-1], q.device))
+    elif p.attention_type == 'cossim':
+      proj = self._Projection(q.shape[-1], q.device)
+      kp = favor.cossim_kernel_transformation(kf, False, proj)
+      qp = favor.cossim_kernel_transformation(qf, True, proj)
+      scores = torch.einsum('BXHD,BYHD->BXYH', qp, kp)
+      if paddings is not None:
+        scores = scores + (paddings.float() * GetDtypeMin()).view(
+            paddings.shape[0], 1, -1, 1)
+      ctx = torch.einsum('BXYH,BYHD->BXHD', torch.softmax(scores, dim=2), vf)
+    else:
+      raise ValueError('FAVOR attention type %s is not supported' % p.attention_type)
+    return self._PostProj(theta, ctx.to(v.dtype)), None
+
+
+class RoutingAttention(MultiHeadedAttention):
+  """Sparse attention by online k-means routing (Routing Transformer; reference :4458).
+
+  Queries and keys are layer-normalised and assigned to `num_clusters` centroids per head
+  (`attention_util.KMeansClusteringForAtten`, EMA-updated while training). A query only
+  attends to the `attention_window` keys closest to *its* centroid: O(T·W) instead of
+  O(T·S). `causal_masking` additionally hides keys at later positions.
+  """
+
+  @classmethod
+  def Params(cls):
+    from lingvo_b200.core import attention_util  # pylint: disable=g-import-not-at-top
+    p = super().Params()
+    p.Define('num_clusters', 0, 'Clusters per head (≈ sqrt(sequence length)).')
+    p.Define('attention_window', 0, 'Keys each query attends to.')
+    p.Define('clustering', attention_util.KMeansClusteringForAtten.Params(), 'k-means tpl.')
+    p.Define('causal_masking', False, 'Position idx only sees positions <= idx.')
+    p.Define('fast_path', True, 'Kept for parity (one gather-based implementation).')
+    p.Define('query_group_size_factor', 1.2, 'Kept for parity.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert p.num_clusters and p.attention_window
+    assert not p.packed_input
+    self.CreateChild('clustering', p.clustering.Copy().Set(
+        num_clusters=p.num_clusters, num_heads=p.num_heads,
+        dim_per_head=self.dim_per_head, apply_layer_norm=False))
+    self._clustering_loss = None
+
+  @property
+  def clustering_loss(self):
+    return self._clustering_loss
+
+  def FProp(self, theta, query_vec, key_vec, value_vec, paddings,
+            segment_mask=None, per_step_padding=None, query_paddings=None):
+    from lingvo_b200.core import attention_util  # pylint: disable=g-import-not-at-top
+    p = self.params
+    q, k, v = self._HeadsProj(theta, query_vec, key_vec, value_vec)
+    n = q.shape[2]
+    k, v = attention_ops._ExpandKv(k, n), attention_ops._ExpandKv(v, n)  # pylint: disable=protected-access
+    h = q.shape[-1]
+    # Euclidean closeness must imply a large dot product: normalise both sides.
+    qn = F.layer_norm(q.float(), (h,))
+    kn = F.layer_norm(k.float(), (h,))
+    b, t = q.shape[0], q.shape[1]
+    s = k.shape[1]
+    q_dists, q_loss = self.clustering.FProp(theta.clustering, qn, query_paddings,
+                                            update=not self.do_eval)
+    k_dists, k_loss = self.clustering.FProp(theta.clustering, kn, paddings,
+                                            update=not self.do_eval)
+    self._clustering_loss = q_loss + k_loss
+    # keys never selectable when padded
+    if paddings is not None:
+      k_dists = k_dists + paddings.float().view(b, s, 1, 1) * 1e6
+    w = min(p.attention_window, s)
+    # closest W keys of every (head, cluster): [B, N, K, W]
+    top = torch.topk(-k_dists.permute(0, 2, 3, 1), w, dim=-1).indices
+    q_cluster = q_dists.argmin(-1)                               # [B, T, N]
+    idx = torch.gather(top, 2, q_cluster.permute(0, 2, 1).unsqueeze(-1).expand(b, n, t, w))
+    if p.causal_masking:
+      pos = torch.arange(t, device=q.device).view(1, 1, t, 1)
+      idx = torch.where(idx <= pos, idx, torch.full_like(idx, -1))
+    qs = qn.permute(0, 2, 1, 3)
+    ctx, probs = attention_util.ComputeSparseAttention(
+        qs, kn.permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3), idx, paddings)
+    ctx = ctx.permute(0, 2, 1, 3).to(v.dtype)
+    return self._PostProj(theta, ctx), probs
+
+
+class FunnelTransformerAttentionLayer(TransformerAttentionLayer):
+  """Self-attention whose *queries* are pooled first (Funnel-Transformer; reference :5943):
+  `[B, T, D]` in, `[B, T/stride, D]` out, keys/values at full resolution."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('query_pooling_tpl', FunnelPoolingLayer.Params(), 'Pooling of the queries.')
+    p.Define('begin_intact', 0, 'Leading positions (e.g. [CLS]) kept un-pooled.')
+    p.Define('trunc_seq', True, 'Truncate so that the length divides the stride.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    self.CreateChild('query_pooling', p.query_pooling_tpl.Copy().Set(
+        begin_intact=p.begin_intact, trunc_seq=p.trunc_seq))
+
+  def FProp(self, theta, query_vec, source_vecs, paddings,
+            per_step_padding_override=None, segment_mask=None):
+    p = self.params
+    assert source_vecs is None, 'funnel attention is self-attention'
+    normed = self._Norm(theta, query_vec) if p.pre_layer_norm else query_vec
+    pooled, pooled_paddings = self.query_pooling.FProp(theta.query_pooling, normed, paddings)
+    res_in, _ = self.query_pooling.FProp(theta.query_pooling, query_vec, paddings)
+    ctx, probs = self.atten.FProp(theta.atten, pooled, normed, normed, paddings,
+                                  segment_mask=segment_mask,
+                                  per_step_padding=per_step_padding_override)
+    return self._Finish(theta, res_in, pooled, ctx), probs, pooled_paddings
+
+
+class MemoryAddLayer(base_layer.BaseLayer):
+  """Adds a learned (or supplied) memory bank in front of a sequence (reference
+  `MemoryAddLayer`, used by the sketch-memory builder): `[B, T, D]` → `[B, M + T, D]`."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('input_dim', 0, 'Model dim.')
+    p.Define('num_memory_slots', 0, 'M.')
+    return p
+
+  def _CreateLayerVariables(self):
+    p = self.params
+    self.CreateVariable('memory', WeightParams(
+        [p.num_memory_slots, p.input_dim], WeightInit.Gaussian(p.input_dim**-0.5), p.dtype))
+
+  def FProp(self, theta, inputs, paddings=None):
+    b = inputs.shape[0]
+    mem = theta.memory.to(inputs.dtype).unsqueeze(0).expand(b, -1, -1)
+    out = torch.cat([mem, inputs], 1)
+    if paddings is None:
+      return out
+    pad = torch.cat([torch.zeros(b, mem.shape[1], dtype=paddings.dtype,
+                                 device=paddings.device), paddings], 1)
+    return out, pad
+
+
+class PerformerBuilder(Builder):
+  """`Builder` whose self-attention is FAVOR+ (reference `PerformerBuilder`)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('num_random_features', 384, 'Random features.')
+    p.Define('attention_type', 'softmax', 'relu|softmax|cossim.')
+    return p
+
+  def _MultiHeadedAtten(self, name, num_heads=None):
+    p = self.params
+    return MultiHeadedFavorAttention.Params().Set(
+        name=name, input_dim=p.model_dim, hidden_dim=p.attention_hidden_dim or p.model_dim,
+        num_heads=num_heads or p.num_heads, num_random_features=p.num_random_features,
+        attention_type=p.attention_type, use_bias=p.use_bias,
+        enable_per_dim_scale=p.enable_per_dim_scale, return_atten_probs=False)
+
+  def SelfAttention(self, name, is_causal=False, num_heads=None):
+    """FAVOR has no [T, S] mask: causality is the prefix-sum form of the kernel."""
+    adapter = super().SelfAttention(name, False, num_heads)
+    adapter.body.atten_tpl.causal = is_causal
+    return adapter
+
+
+class SketchMemTransformerBuilder(Builder):
+  """Transformer whose layers read a small learned sketch memory in addition to the
+  sequence (reference `SketchMemTransformerBuilder`): memory slots are prepended once and
+  every layer attends over [memory; tokens]."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('num_memory_slots', 16, 'Sketch memory size M.')
+    return p
+
+  def MemoryAdd(self, name):
+    return MemoryAddLayer.Params().Set(name=name, input_dim=self.params.model_dim,
+                                       num_memory_slots=self.params.num_memory_slots)
+
+  def TransformerEncoderStack(self, name, num_layers, is_causal=False):
+    """[memory; tokens] → layers → tokens (memory slots are dropped at the end)."""
+    body = super().TransformerEncoderStack('body', num_layers, is_causal)
+    return _SketchMemStack.Params().Set(name=name, memory=self.MemoryAdd('memory'), body=body,
+                                        num_memory_slots=self.params.num_memory_slots)
+
+  Stack = TransformerEncoderStack
+
+
+class _SketchMemStack(base_layer.BaseLayer):
+  """NestedMap(vec, paddings) → same, running `body` over [memory; tokens]."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('memory', None, 'MemoryAddLayer params.')
+    p.Define('body', None, 'Stack params.')
+    p.Define('num_memory_slots', 0, 'M.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('memory', self.params.memory)
+    self.CreateChild('body', self.params.body)
+
+  def FProp(self, theta, i):
+    vec, pad = self.memory.FProp(theta.memory, i.vec, i.paddings)
+    o = self.body.FProp(theta.body, NestedMap(vec=vec, paddings=pad))
+    m = self.params.num_memory_slots
+    return NestedMap(vec=o.vec[:, m:], paddings=o.paddings[:, m:])
+
+
+class _PipelineStageAdapter(base_layer.BaseLayer):
+  """NestedMap(vec, paddings[, segment_mask]) in/out around a `StackedTransformerLayers`
+  stage, so the shifting-buffer pipeline can carry the side inputs with the activations."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('stage', None, 'StackedTransformerLayers params.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('stage', self.params.stage)
+
+  def FProp(self, theta, i):
+    vec, pad = self.stage.FProp(theta.stage, i.vec, i.paddings,
+                                segment_mask=i.get('segment_mask'))
+    o = NestedMap(vec=vec, paddings=pad)
+    if 'segment_mask' in i:
+      o.segment_mask = i.segment_mask
+    return o
+
+
+class PipelinedTransformerLayers(base_layer.BaseLayer):
+  """`num_pipeline_stages` (× `circular_repeat`) `StackedTransformerLayers` stages run
+  through `gshard_layers.LayerwiseShardablePipelinedLayer` (reference :7512): micro-batches
+  flow through a shifting buffer; with `AttachStageGroup` each rank holds one stage."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('pipeline_stage', StackedTransformerLayers.Params(), 'Params of each stage.')
+    p.Define('num_pipeline_stages', None, 'Number of pipeline stages.')
+    p.Define('num_pipeline_microbatches', None, 'Number of micro-batches.')
+    p.Define('pipeline_microbatch_size', None, 'Size of each micro-batch.')
+    p.Define('shard_stages_1d', False, 'One stage per rank (see `stage_group`).')
+    p.Define('final_layer_norm', False, 'LN after all stages.')
+    p.Define('final_ln_at_each_stage', False, 'LN at the end of each stage instead.')
+    p.Define('circular_repeat', 1, 'Circular pipeline repeats.')
+    p.Define('pipeline_stage_mesh_dim', None, 'Kept for parity.')
+    p.Define('unroll', 'never', 'Kept for parity.')
+    return p
+
+  def __init__(self, params, stage_group=None):
+    super().__init__(params)
+    from lingvo_b200.core import gshard_layers  # pylint: disable=g-import-not-at-top
+    p = self.params
+    assert p.num_pipeline_stages and p.num_pipeline_stages > 0
+    stage = p.pipeline_stage.Copy().Set(name='stage')
+    stage.final_layer_norm = bool(p.final_ln_at_each_stage)
+    pp = gshard_layers.LayerwiseShardablePipelinedLayer.Params().Set(
+        name='pipeline', num_stages=p.num_pipeline_stages,
+        single_stage_body=_PipelineStageAdapter.Params().Set(name='body', stage=stage),
+        num_microbatches=p.num_pipeline_microbatches,
+        microbatch_size=p.pipeline_microbatch_size, circular_repeat=p.circular_repeat)
+    if p.shard_stages_1d and stage_group is not False:
+      import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+      if dist.is_available() and dist.is_initialized() and (
+          dist.get_world_size(stage_group) == p.num_pipeline_stages):
+        self.AddChild('pipeline', gshard_layers.LayerwiseShardablePipelinedLayer.ForStageGroup(
+            pp, stage_group))
+    if 'pipeline' not in self.children:
+      self.CreateChild('pipeline', pp)
+    if p.final_layer_norm:
+      self.CreateChild('final_ln', p.pipeline_stage.layernorm_tpl.Copy().Set(
+          input_dim=p.pipeline_stage.mdl_dim))
+
+  def FProp(self, theta, query_vec, paddings, aux_vec=None, aux_paddings=None,
+            segment_mask=None, aux_segment_mask=None):
+    p = self.params
+    assert aux_vec is None, 'pipelined cross attention is not supported'
+    inp = NestedMap(vec=query_vec, paddings=paddings)
+    if segment_mask is not None:
+      inp.segment_mask = segment_mask
+    out = self.pipeline.FProp(theta.pipeline, inp)
+    x = out.vec
+    if p.final_layer_norm:
+      x = self.final_ln.FProp(theta.final_ln, x)
+    return x, out.paddings

@@ -652,3 +652,410 @@ class OverrideLayer(base_layer.BaseLayer):
 
   def FProp(self, theta, x):
     return self._OVERRIDE.get(self.params.key, x)
+
+
+# ==================================================================================
+# SPMD shifting-buffer / circular pipeline (reference :180-1185)
+# ==================================================================================
+class _RingShift(torch.autograd.Function):
+  """Stage r hands its tensor to stage r+1 (and receives stage r-1's): the collective-
+  permute of the shifting-buffer pipeline, as one batched NCCL/gloo P2P exchange. The
+  backward pass is the reverse rotation."""
+
+  @staticmethod
+  def forward(ctx, x, group, direction):
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    ctx.group, ctx.direction = group, direction
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dst = dist.get_global_rank(group, (rank + direction) % world) if group is not None else (
+        (rank + direction) % world)
+    src = dist.get_global_rank(group, (rank - direction) % world) if group is not None else (
+        (rank - direction) % world)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    ops = [dist.P2POp(dist.isend, x, dst, group), dist.P2POp(dist.irecv, out, src, group)]
+    for req in dist.batch_isend_irecv(ops):
+      req.wait()
+    return out
+
+  @staticmethod
+  def backward(ctx, dy):
+    return _RingShift.apply(dy, ctx.group, -ctx.direction), None, None
+
+
+class LayerwiseShardablePipelinedLayer(base_layer.BaseLayer):
+  """Pipelines `num_stages × circular_repeat` copies of `single_stage_body` over
+  micro-batches with a *shifting buffer*: iteration t lets every stage work on the
+  micro-batch that reached it, then the buffer moves one stage forward
+  (`num_microbatches + num_stages·circular_repeat − 1` iterations in total).
+
+  Two execution modes with identical math:
+
+  * **local** (default): all stages live in this process; the shift is a roll of the
+    stage buffer. Useful to test a pipelined model definition and as the oracle.
+  * **rank-sharded** (`stage_group` passed to `AttachStageGroup`, world = `num_stages`):
+    rank r builds only the bodies of stage r (layer r, r+S, r+2S, … under a circular
+    schedule), so weights and optimizer state are partitioned 1/S; the shift is one
+    batched P2P ring exchange per iteration (`_RingShift`, NVLink via NCCL), overlapping
+    the next iteration's compute of the other stages. Autograd runs the reverse ring.
+
+  `FProp(theta, inputs, *shared)`: `inputs` is `[batch, …]` (micro-batched here with
+  `num_microbatches` / `microbatch_size`) or already `[num_microbatches, mb, …]`;
+  `shared` tensors are passed unchanged to every stage (e.g. a causal mask). Per-batch
+  side inputs with a leading batch dim (paddings, segment ids) travel through the buffer
+  with the activations when given as a NestedMap of tensors.
+  """
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('num_stages', 1, 'Number of pipeline stages.')
+    p.Define('stage_parallel_body', None, 'Kept for parity (bodies are built per stage).')
+    p.Define('single_stage_body', None, 'Layer params of one stage.')
+    p.Define('num_microbatches', None, 'Split the batch into this many micro-batches.')
+    p.Define('microbatch_size', None, 'Or: micro-batch size.')
+    p.Define('shard_stages_1d', False, 'Kept for parity (see AttachStageGroup).')
+    p.Define('pipeline_stage_mesh_dim', None, 'Kept for parity.')
+    p.Define('per_stage_vars', True, 'Separate variables per stage (always true here).')
+    p.Define('circular_repeat', 1, 'Circular pipeline: repeats of each stage.')
+    p.Define('unroll', 'eval_only', 'Kept for parity (the loop is always explicit).')
+    p.Define('aux_loss_microbatch_accumulation', 'mean', 'mean | sum.')
+    return p
+
+  def __init__(self, params, stage_group=None, stage_rank=None):
+    super().__init__(params)
+    p = self.params
+    assert p.single_stage_body is not None or p.stage_parallel_body is not None
+    body = p.single_stage_body or p.stage_parallel_body
+    self._group = stage_group
+    self._stage_rank = stage_rank
+    self._num_layers = p.num_stages * p.circular_repeat
+    owned = range(self._num_layers)
+    if stage_rank is not None:
+      owned = [k for k in owned if k % p.num_stages == stage_rank]
+    self._owned = list(owned)
+    for k in self._owned:
+      self.CreateChild('body_%03d' % k, body.Copy().Set(name='body_%03d' % k))
+
+  @classmethod
+  def ForStageGroup(cls, params, group=None):
+    """Rank-sharded instance: this process is stage `rank(group)` of `num_stages`."""
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    assert dist.is_initialized()
+    world = dist.get_world_size(group)
+    assert world == params.num_stages, (world, params.num_stages)
+    return cls(params, stage_group=group, stage_rank=dist.get_rank(group))
+
+  # ---------------------------------------------------------------- helpers --
+  def _Microbatch(self, x):
+    p = self.params
+    if p.num_microbatches is None and p.microbatch_size is None:
+      return x, False
+    def split(t):
+      if not isinstance(t, torch.Tensor) or t.dim() == 0:
+        return t
+      b = t.shape[0]
+      nmb = p.num_microbatches or b // p.microbatch_size
+      assert b % nmb == 0, (b, nmb)
+      return t.reshape(nmb, b // nmb, *t.shape[1:])
+    if isinstance(x, NestedMap):
+      return x.Transform(split), True
+    return split(x), True
+
+  @staticmethod
+  def _Lead(x):
+    for t in (x.Flatten() if isinstance(x, NestedMap) else [x]):
+      if isinstance(t, torch.Tensor):
+        return t.shape[0]
+    raise ValueError('no tensor input')
+
+  @staticmethod
+  def _Index(x, i):
+    f = lambda t: t[i] if isinstance(t, torch.Tensor) and t.dim() > 0 else t
+    return x.Transform(f) if isinstance(x, NestedMap) else f(x)
+
+  def _RunBody(self, theta, k, x, shared):
+    name = 'body_%03d' % k
+    out = getattr(self, name).FProp(theta[name], x, *shared)
+    return out
+
+  # ------------------------------------------------------------------ FProp --
+  def FProp(self, theta, inputs, *shared):
+    p = self.params
+    x, did_split = self._Microbatch(inputs)
+    nmb = self._Lead(x)
+    outs = (self._FPropLocal(theta, x, nmb, shared) if self._stage_rank is None
+            else self._FPropSharded(theta, x, nmb, shared))
+    def stack(items):
+      if isinstance(items[0], NestedMap):
+        flat = [it.Flatten() for it in items]
+        return items[0].Pack([torch.stack([f[j] for f in flat])
+                              if isinstance(flat[0][j], torch.Tensor) else flat[0][j]
+                              for j in range(len(flat[0]))])
+      return torch.stack(items)
+    y = stack(outs)
+    if did_split:
+      merge = lambda t: t.reshape(-1, *t.shape[2:]) if isinstance(t, torch.Tensor) and t.dim() > 1 else t
+      y = y.Transform(merge) if isinstance(y, NestedMap) else merge(y)
+    return y
+
+  def _FPropLocal(self, theta, x, nmb, shared):
+    """All stages in-process. The buffer slot of stage s at iteration t holds micro-batch
+    (t − s) mod …; with a circular schedule a micro-batch re-enters stage 0 after stage
+    S−1 until it has visited all `num_layers` bodies."""
+    p = self.params
+    s_n, rep = p.num_stages, p.circular_repeat
+    n_iter = nmb * rep + s_n - 1 if rep > 1 else nmb + s_n - 1
+    if rep > 1:
+      assert nmb >= s_n, 'circular pipeline needs num_microbatches >= num_stages'
+    buf = [None] * s_n                 # (microbatch id, pass index, activation)
+    outs = [None] * nmb
+    feed = 0
+    pending = []                       # micro-batches that wrapped around, FIFO
+    for t in range(n_iter):
+      # stage 0 intake: a wrapped micro-batch has priority once the first wave has entered
+      new_buf = [None] * s_n
+      if pending and (feed >= nmb or pending[0][3] <= t):
+        mb, pas, act, _ = pending.pop(0)
+        new_buf[0] = (mb, pas, act)
+      elif feed < nmb:
+        new_buf[0] = (feed, 0, self._Index(x, feed))
+        feed += 1
+      for s in range(1, s_n):
+        new_buf[s] = buf[s - 1]
+      results = [None] * s_n
+      for s in range(s_n):
+        if new_buf[s] is None:
+          continue
+        mb, pas, act = new_buf[s]
+        results[s] = (mb, pas, self._RunBody(theta, pas * s_n + s, act, shared))
+      # last stage output: finished, or wraps to stage 0 for the next pass
+      last = results[s_n - 1]
+      if last is not None:
+        mb, pas, act = last
+        if pas + 1 < rep:
+          pending.append((mb, pas + 1, act, t + 1))
+        else:
+          outs[mb] = act
+      buf = results
+    assert all(o is not None for o in outs), 'pipeline schedule did not drain'
+    return outs
+
+  def _FPropSharded(self, theta, x, nmb, shared):
+    """This rank is one stage. Iteration t: run my body on what sits in my slot, then the
+    ring shift moves every slot one stage forward. Stage 0 injects fresh micro-batches,
+    the last stage's results come back around to stage 0, which either re-injects them
+    (circular) or records them; the final outputs are broadcast from stage 0."""
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    p = self.params
+    s_n, rep, r = p.num_stages, p.circular_repeat, self._stage_rank
+    if rep > 1:
+      assert nmb >= s_n
+    n_iter = (nmb * rep if rep > 1 else nmb) + s_n - 1
+    template = self._Index(x, 0)
+    is_map = isinstance(template, NestedMap)
+    def zeros_like(v):
+      f = lambda t: torch.zeros_like(t) if isinstance(t, torch.Tensor) else t
+      return v.Transform(f) if is_map else f(v)
+    def shift(v):
+      f = lambda t: _RingShift.apply(t, self._group, 1) if isinstance(t, torch.Tensor) and (
+          t.is_floating_point()) else t
+      if not is_map:
+        return f(v)
+      # integer side inputs (segment ids …) ride along un-differentiated
+      def g(t):
+        if isinstance(t, torch.Tensor) and not t.is_floating_point():
+          return _RingShift.apply(t.float(), self._group, 1).to(t.dtype)
+        return f(t)
+      return v.Transform(g)
+    slot = zeros_like(template)        # what currently sits in my stage
+    if torch.is_grad_enabled():
+      # Every rank must record (and later replay, reversed) every ring exchange, also the
+      # ones that only carry bubbles: make the bubble a leaf that requires grad.
+      mk = lambda t: t.requires_grad_(True) if isinstance(t, torch.Tensor) and (
+          t.is_floating_point()) else t
+      slot = slot.Transform(mk) if is_map else mk(slot)
+    outs = [None] * nmb
+    # Deterministic schedule (identical on all ranks): which (mb, pass) is at stage s at t.
+    sched = self._Schedule(nmb)
+    # Every rank must replay *every* ring exchange in its backward pass, in the same
+    # (reverse) order — also those whose payload this rank later overwrote or that only
+    # carried a bubble. `alive` (always exactly 0) hangs every exchange onto the outputs.
+    alive = None
+    def touch(v):
+      nonlocal alive
+      for t_ in (v.Flatten() if is_map else [v]):
+        if isinstance(t_, torch.Tensor) and t_.is_floating_point() and t_.requires_grad:
+          z = t_.reshape(-1)[:1].sum() * 0
+          alive = z if alive is None else alive + z
+    for t in range(n_iter):
+      cur = sched[t][r]
+      if r == 0 and cur is not None and cur[1] == 0:
+        slot = self._Index(x, cur[0])                     # fresh micro-batch enters
+      if cur is not None:
+        slot = self._RunBody(theta, cur[1] * s_n + r, slot, shared)
+      arrived = shift(slot)                               # collective: every rank, every t
+      touch(arrived)
+      done = sched[t][s_n - 1]
+      if r == 0 and done is not None and done[1] + 1 == rep:
+        outs[done[0]] = arrived                           # finished micro-batch came round
+      slot = arrived
+    # everyone returns the outputs (stage 0 has them): broadcast, differentiable via shift
+    root = dist.get_global_rank(self._group, 0) if self._group is not None else 0
+    res = []
+    def with_alive(v):
+      if alive is None:
+        return v
+      f = lambda t: t + alive.to(t.dtype) if isinstance(t, torch.Tensor) and (
+          t.is_floating_point()) else t
+      return v.Transform(f) if is_map else f(v)
+    for mb in range(nmb):
+      o = with_alive(outs[mb] if r == 0 else zeros_like(template))
+      f = lambda t: _Broadcast.apply(t, self._group, root) if isinstance(t, torch.Tensor) and (
+          t.is_floating_point()) else t
+      res.append(o.Transform(f) if is_map else f(o))
+    return res
+
+  def _Schedule(self, nmb):
+    """sched[t][s] = (micro-batch, pass) processed by stage s at iteration t, or None —
+    the same wave pattern as `_FPropLocal`, computed without touching data."""
+    p = self.params
+    s_n, rep = p.num_stages, p.circular_repeat
+    n_iter = (nmb * rep if rep > 1 else nmb) + s_n - 1
+    sched = [[None] * s_n for _ in range(n_iter)]
+    buf = [None] * s_n
+    feed = 0
+    pending = []
+    for t in range(n_iter):
+      new_buf = [None] * s_n
+      if pending and (feed >= nmb or pending[0][2] <= t):
+        mb, pas, _ = pending.pop(0)
+        new_buf[0] = (mb, pas)
+      elif feed < nmb:
+        new_buf[0] = (feed, 0)
+        feed += 1
+      for s in range(1, s_n):
+        new_buf[s] = buf[s - 1]
+      last = new_buf[s_n - 1]
+      if last is not None and last[1] + 1 < rep:
+        pending.append((last[0], last[1] + 1, t + 1))
+      sched[t] = list(new_buf)
+      buf = new_buf
+    return sched
+
+
+class _Broadcast(torch.autograd.Function):
+  """Differentiable broadcast from `root`. Every rank then computes the same (replicated)
+  loss from the same outputs, so the backward pass averages the identical incoming
+  gradients back onto the root."""
+
+  @staticmethod
+  def forward(ctx, x, group, root):
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    ctx.group, ctx.root = group, root
+    out = x.contiguous().clone()
+    dist.broadcast(out, src=root, group=group)
+    return out
+
+  @staticmethod
+  def backward(ctx, dy):
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    g = dy.contiguous().clone()
+    dist.reduce(g, dst=ctx.root, group=ctx.group)
+    if dist.get_rank() != ctx.root:
+      g = torch.zeros_like(g)
+    else:
+      g = g / dist.get_world_size(ctx.group)
+    return g, None, None
+
+
+class MultiHeadAttentionStateLayer(base_layer.BaseLayer):
+  """Key/value decode cache of one attention layer `[B, T, N, H]` written one time step at
+  a time (reference `MultiHeadAttentionStateLayer`); thin typed wrapper over `StateLayer`
+  that also supports beam re-ordering."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('shape', [None, None, None, None], 'batch, time, heads, dim_per_head.')
+    p.Define('use_xla_dynamic_update_slice', True, 'Kept for parity.')
+    return p
+
+  def InitState(self, batch, max_len, device=None, dtype=None):
+    p = self.params
+    shape = [batch, max_len] + list(p.shape[2:])
+    return torch.zeros(shape, dtype=dtype or self.fprop_dtype,
+                       device=device or py_utils.CurrentDevice())
+
+  def FProp(self, theta, state):
+    return state
+
+  def UpdateState(self, state, value, t):
+    """value `[B, N, H]` (or `[B, 1, N, H]`) written at time `t`; returns the new state."""
+    if value.dim() == state.dim():
+      value = value[:, 0]
+    out = state.clone()
+    out[:, int(t)] = value.to(out.dtype)
+    return out
+
+  @staticmethod
+  def Reorder(state, beam_parent):
+    """Beam search: row b continues hypothesis `beam_parent[b]`."""
+    return state.index_select(0, beam_parent.long())
+
+
+class SharedEmbeddingSoftmaxLayer(base_layer.BaseLayer):
+  """One `[V, M]` table used both as the input embedding (with optional positional
+  embeddings added) and as the output softmax weights (reference
+  `SharedEmbeddingSoftmaxLayer`)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('vocab_size', 0, 'Vocabulary size.')
+    p.Define('max_len', 0, 'Max positions (0 ⇒ no learned positional embedding).')
+    p.Define('embedding_dim', 0, 'Model dim M.')
+    p.Define('z_loss_coef', 1e-4, 'z-loss coefficient.')
+    p.Define('num_devices', 1, 'Kept for parity.')
+    p.Define('logits_abs_max', None, 'Clip logits to ± this value.')
+    p.Define('label_smoothing', 0.1, 'Label smoothing.')
+    p.Define('use_tgt_labels_size_as_loss_denominator', True, 'Loss denominator.')
+    return p
+
+  def _CreateLayerVariables(self):
+    p = self.params
+    self.CreateVariable('embedding', WeightParams(
+        [p.vocab_size, p.embedding_dim], WeightInit.Gaussian(1.0), p.dtype))
+    if p.max_len:
+      self.CreateVariable('pos_embedding', WeightParams(
+          [p.max_len, p.embedding_dim], WeightInit.Gaussian(1.0), p.dtype))
+
+  def FProp(self, theta, ids, segment_pos=None):
+    """ids `[B, L]` → `[B, L, M]`."""
+    p = self.params
+    y = F.embedding(ids.long(), theta.embedding)
+    if p.max_len and segment_pos is not None:
+      y = y + F.embedding(segment_pos.long(), theta.pos_embedding)
+    return y.to(self.fprop_dtype)
+
+  def ComputeLoss(self, theta, activation, labels, segment_ids):
+    """activation `[B, L, M]`, labels/segment_ids `[B, L]` → (loss, per-token stats)."""
+    p = self.params
+    non_padding = ((segment_ids > 0) & (labels > 0)).float()
+    logits = torch.matmul(activation.float() * (p.embedding_dim**-0.5),
+                          theta.embedding.float().t())
+    if p.logits_abs_max is not None:
+      logits = logits.clamp(-p.logits_abs_max, p.logits_abs_max)
+    lse = torch.logsumexp(logits, -1)
+    true_logit = logits.gather(-1, labels.long().unsqueeze(-1)).squeeze(-1)
+    off = p.label_smoothing / p.vocab_size
+    on = 1.0 - p.label_smoothing + off
+    soft = (on - off) * true_logit + off * logits.sum(-1)
+    per_tok = (lse - soft) + p.z_loss_coef * lse.square()
+    denom = float(non_padding.numel()) if p.use_tgt_labels_size_as_loss_denominator else (
+        non_padding.sum().clamp_min(1.0))
+    loss = (per_tok * non_padding).sum() / denom
+    return loss, NestedMap(per_token_loss=per_tok * non_padding, non_padding=non_padding,
+                           mean_xent=((lse - true_logit) * non_padding).sum() /
+                           non_padding.sum().clamp_min(1.0))
