@@ -288,7 +288,11 @@ class BaseInputGeneratorFromFiles(BaseInputGenerator):
         file_parallelism=args['file_parallelism'], num_threads=args['num_threads'],
         flush_every_n=args['flush_every_n'], repeat_count=args['repeat_count'],
         require_sequential_order=args['require_sequential_order'],
-        input_source_weights=input_source_weights, **extra_input_kwargs)
+        input_source_weights=input_source_weights,
+        bucket_adjust_every_n=args['bucket_adjust_every_n'],
+        fatal_errors=(list(args['fatal_errors']) if args['fatal_errors'] else None),
+        file_buffer_size_in_seconds=args['file_buffer_size_in_seconds'],
+        **extra_input_kwargs)
     self._generic_input = gi
 
     def _Next():

@@ -25,11 +25,31 @@ from lingvo_b200 import ops
 from lingvo_b200.core.nested_map import NestedMap
 
 
+def ReplicaInfo():
+  """(num_input_replicas, input_replica_id) of this process: one data-parallel rank per
+  GPU under torchrun, so every rank reads a disjoint shard of the records (reference
+  `record_yielder.h:84-85`; there the trainer passes its replica index explicitly)."""
+  try:
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    if dist.is_available() and dist.is_initialized():
+      return dist.get_world_size(), dist.get_rank()
+  except Exception:  # pylint: disable=broad-except
+    pass
+  return 1, 0
+
+
 def MakeYielder(file_pattern, file_random_seed=0, file_buffer_size=10000,
                 file_parallelism=4, repeat_count=-1, require_sequential_order=False,
-                input_source_weights: Optional[Sequence[float]] = None):
-  """Yielder for a `type:glob` pattern or a list of patterns (weighted mix)."""
+                input_source_weights: Optional[Sequence[float]] = None,
+                num_input_replicas: Optional[int] = None,
+                input_replica_id: Optional[int] = None,
+                file_buffer_size_in_seconds: float = 0.0):
+  """Yielder for a `type:glob` pattern or a list of patterns (weighted mix).
+  `num_input_replicas` / `input_replica_id` default to this process's data-parallel
+  coordinates (`ReplicaInfo`)."""
   h = ops.host()
+  if num_input_replicas is None or input_replica_id is None:
+    num_input_replicas, input_replica_id = ReplicaInfo()
   if isinstance(file_pattern, (list, tuple)):
     pats = list(file_pattern)
     weights = list(input_source_weights) if input_source_weights else [1.0] * len(pats)
@@ -38,15 +58,22 @@ def MakeYielder(file_pattern, file_random_seed=0, file_buffer_size=10000,
       pats = [p for p, _ in pats]
     kids = [MakeYielder(p, file_random_seed + i if file_random_seed else 0,
                         file_buffer_size, file_parallelism, repeat_count,
-                        require_sequential_order) for i, p in enumerate(pats)]
-    return h.weighted_mix_record_yielder(kids, weights, file_random_seed)
+                        require_sequential_order, None, num_input_replicas,
+                        input_replica_id, file_buffer_size_in_seconds)
+            for i, p in enumerate(pats)]
+    # every replica must draw its own mixing sequence, or all would pick the same source
+    mix_seed = file_random_seed * 1000003 + input_replica_id + 1 if file_random_seed else 0
+    return h.weighted_mix_record_yielder(kids, weights, mix_seed)
   if require_sequential_order:
-    return h.sequential_record_yielder(file_pattern,
-                                       repeat_count if repeat_count > 0 else -1)
+    return h.sequential_record_yielder(
+        file_pattern, repeat_count if repeat_count > 0 else -1, 0,
+        num_input_replicas, input_replica_id)
   return h.basic_record_yielder(
       file_pattern, seed=file_random_seed, bufsize=file_buffer_size,
       parallelism=file_parallelism,
-      num_epochs=repeat_count if repeat_count > 0 else 0)
+      num_epochs=repeat_count if repeat_count > 0 else 0,
+      num_input_replicas=num_input_replicas, input_replica_id=input_replica_id,
+      bufsize_in_seconds=float(file_buffer_size_in_seconds or 0.0))
 
 
 class GenericInput:
@@ -56,11 +83,30 @@ class GenericInput:
                bucket_upper_bound=(1 << 30,), bucket_batch_limit=(1,),
                file_random_seed=0, file_buffer_size=10000, file_parallelism=4,
                num_threads=4, flush_every_n=0, repeat_count=-1,
-               require_sequential_order=False, input_source_weights=None):
+               require_sequential_order=False, input_source_weights=None,
+               bucket_adjust_every_n=0, fatal_errors=None,
+               dynamic_padding_dimensions=None, dynamic_padding_constants=None,
+               num_input_replicas=None, input_replica_id=None,
+               file_buffer_size_in_seconds=0.0):
+    """`bucket_adjust_every_n`: native `BucketAdjuster` re-optimises the bucket bounds.
+    `fatal_errors`: None ⇒ any processor exception aborts; a list ⇒ only matching ones do,
+    the rest skip the record. `dynamic_padding_constants`: per flattened tensor slot pad
+    value (list, or a NestedMap / dict matching the sample); `dynamic_padding_dimensions`
+    is accepted for parity (every dimension is padded to the batch maximum)."""
     self._h = ops.host()
+    del dynamic_padding_dimensions
     self._yielder = yielder or MakeYielder(
         file_pattern, file_random_seed, file_buffer_size, file_parallelism,
-        repeat_count, require_sequential_order, input_source_weights)
+        repeat_count, require_sequential_order, input_source_weights,
+        num_input_replicas, input_replica_id, file_buffer_size_in_seconds)
+    pad_values = []
+    if dynamic_padding_constants is not None:
+      if isinstance(dynamic_padding_constants, NestedMap):
+        pad_values = [float(v) for v in dynamic_padding_constants.Flatten()]
+      elif isinstance(dynamic_padding_constants, dict):
+        pad_values = [float(v) for v in NestedMap(dynamic_padding_constants).Flatten()]
+      else:
+        pad_values = [float(v) for v in dynamic_padding_constants]
     self._template = None
     takes_source = len(inspect.signature(processor).parameters) >= 2
 
@@ -80,7 +126,9 @@ class GenericInput:
     self._batcher = self._h.RecordBatcher(
         self._yielder, _Proc, [int(b) for b in bucket_upper_bound],
         [int(b) for b in bucket_batch_limit],
-        1 if require_sequential_order else num_threads, flush_every_n)
+        1 if require_sequential_order else num_threads, flush_every_n,
+        int(bucket_adjust_every_n or 0),
+        None if fatal_errors is None else [str(e) for e in fatal_errors], pad_values)
 
   def GetNext(self):
     """→ (NestedMap or list of batched np arrays, bucket_keys [n])."""
@@ -100,6 +148,15 @@ class GenericInput:
   @property
   def records_skipped(self):
     return self._batcher.records_skipped
+
+  @property
+  def records_failed(self):
+    return self._batcher.records_failed
+
+  @property
+  def bucket_upper_bound(self):
+    """Current bounds (they move when `bucket_adjust_every_n` is set)."""
+    return list(self._batcher.bucket_upper_bound)
 
   def Close(self):
     self._batcher.close()

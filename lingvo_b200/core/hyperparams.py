@@ -449,6 +449,24 @@ class Params:
       text += '%s : %s\n' % (k, types[k])
     return text
 
+  # ------------------------------------------------------------------ proto --
+  # Wire-compatible with `lingvo/core/hyperparams.proto` (Hyperparam / HyperparamValue;
+  # reference `ToProto` :529, `FromProto` :611) without generated code: a serialized
+  # `Hyperparam` message as bytes, plus the protobuf text format for `params.pbtxt`.
+  def ToProto(self) -> bytes:
+    """Serialized `tensorflow.lingvo.Hyperparam` message."""
+    return _HyperparamMsg(self)
+
+  def ToProtoText(self) -> str:
+    """`params.pbtxt`: the protobuf text format of `ToProto()`."""
+    return _HyperparamText(self, 0)
+
+  @classmethod
+  def FromProto(cls, data: bytes) -> 'Params':
+    """Rebuilds a Params tree from `ToProto()` bytes (classes are resolved by import
+    path; an `InstantiableParams` comes back bound to its class)."""
+    return _ParamsFromMsg(data)
+
   def FromTextWithTypes(self, text: str) -> None:
     body, type_block = text.split('\n\n\n')
     types = {}
@@ -619,3 +637,202 @@ def CopyFieldsTo(from_p: Params, to_p: Params,
     else:
       to_p.Set(**{n: p})
   return to_p
+
+
+# -------------------------------------------------------------- hyperparams.proto ----
+# HyperparamValue oneof field numbers
+_PV_PARAM, _PV_LIST, _PV_TUPLE, _PV_DICT, _PV_TYPE, _PV_DTYPE, _PV_STR, _PV_BOOL, _PV_INT, \
+    _PV_FLOAT, _PV_PROTO, _PV_ENUM, _PV_NTUPLE, _PV_REPR, _PV_SYMBOLIC = range(1, 16)
+
+
+def _TypeName(val) -> str:
+  mod = inspect.getmodule(val)
+  return '%s/%s' % (mod.__name__ if mod else '?', getattr(val, '__qualname__', val.__name__))
+
+
+def _ValueMsg(val) -> bytes:
+  """One `HyperparamValue` (empty ⇒ None)."""
+  from lingvo_b200.utils import protowire as pw  # pylint: disable=g-import-not-at-top
+  if val is None:
+    return b''
+  if isinstance(val, Params):
+    return pw.f_msg(_PV_PARAM, _HyperparamMsg(val))
+  if _IsNamedTuple(val):
+    body = pw.f_string(1, _TypeName(type(val)))
+    for v in val:
+      body += pw.f_msg(2, _ValueMsg(v))
+    return pw.f_msg(_PV_NTUPLE, body)
+  if isinstance(val, (list, tuple)):
+    body = b''.join(pw.f_msg(1, _ValueMsg(v)) for v in val)
+    return pw.f_msg(_PV_LIST if isinstance(val, list) else _PV_TUPLE, body)
+  if isinstance(val, dict):
+    body = b''
+    for k in val:
+      entry = pw.f_string(1, str(k)) + pw.f_msg(2, _ValueMsg(val[k]))
+      body += pw.f_msg(1, entry)
+    return pw.f_msg(_PV_DICT, body)
+  if isinstance(val, bool):
+    return pw.f_bool(_PV_BOOL, val)
+  if isinstance(val, enum.Enum):
+    return pw.f_msg(_PV_ENUM, pw.f_string(1, _TypeName(type(val))) + pw.f_string(2, val.name))
+  if isinstance(val, (int, np.integer)):
+    return pw.f_varint(_PV_INT, int(val))
+  if isinstance(val, (float, np.floating)):
+    # float_val is a 32-bit float in the schema; keep full precision when it matters
+    if float(np.float32(val)) == float(val):
+      return pw.f_float(_PV_FLOAT, float(val))
+    return pw.f_string(_PV_REPR, repr(float(val)))
+  if isinstance(val, str):
+    return pw.f_string(_PV_STR, val)
+  if _IsDtype(val):
+    return pw.f_string(_PV_DTYPE, DtypeName(val))
+  if isinstance(val, np.dtype) or (isinstance(val, type) and issubclass(val, np.generic)):
+    return pw.f_string(_PV_DTYPE, 'np.' + np.dtype(val).name)
+  if inspect.isclass(val) or inspect.isroutine(val):
+    return pw.f_string(_PV_TYPE, _TypeName(val))
+  if dataclasses.is_dataclass(val):
+    body = pw.f_string(1, _TypeName(type(val)))
+    for f in dataclasses.fields(val):
+      body += pw.f_msg(2, _ValueMsg(getattr(val, f.name)))
+    return pw.f_msg(_PV_NTUPLE, body)
+  return pw.f_string(_PV_REPR, repr(val))
+
+
+def _HyperparamMsg(params: 'Params') -> bytes:
+  from lingvo_b200.utils import protowire as pw  # pylint: disable=g-import-not-at-top
+  out = b''
+  for name, val in sorted(params.IterParams()):
+    out += pw.f_msg(1, pw.f_string(1, name) + pw.f_msg(2, _ValueMsg(val)))
+  return out
+
+
+def _ResolveType(path: str):
+  mod_name, _, qual = path.partition('/')
+  obj = importlib.import_module(mod_name)
+  for part in qual.split('.'):
+    obj = getattr(obj, part)
+  return obj
+
+
+def _ValueFromMsg(data: bytes):
+  from lingvo_b200.utils import protowire as pw  # pylint: disable=g-import-not-at-top
+  import struct  # pylint: disable=g-import-not-at-top
+  fields = list(pw.parse(data))
+  if not fields:
+    return None
+  field, _, v = fields[0]
+  if field == _PV_PARAM:
+    return _ParamsFromMsg(v)
+  if field in (_PV_LIST, _PV_TUPLE):
+    items = [_ValueFromMsg(x) for f, _, x in pw.parse(v) if f == 1]
+    return items if field == _PV_LIST else tuple(items)
+  if field == _PV_DICT:
+    out = {}
+    for f, _, entry in pw.parse(v):
+      d = pw.parse_dict(entry)
+      out[d[1][0].decode('utf-8')] = _ValueFromMsg(d.get(2, [b''])[0])
+    return out
+  if field == _PV_TYPE:
+    return _ResolveType(v.decode('utf-8'))
+  if field == _PV_DTYPE:
+    name = v.decode('utf-8')
+    if name.startswith('np.'):
+      return np.dtype(name[3:])
+    try:
+      return DtypeFromName(name)
+    except ValueError:
+      return np.dtype(name)
+  if field == _PV_STR:
+    return v.decode('utf-8')
+  if field == _PV_BOOL:
+    return bool(v)
+  if field == _PV_INT:
+    return pw.to_signed64(v)
+  if field == _PV_FLOAT:
+    return float(struct.unpack('<f', v)[0])
+  if field == _PV_ENUM:
+    d = pw.parse_dict(v)
+    return _ResolveType(d[1][0].decode('utf-8'))[d[2][0].decode('utf-8')]
+  if field == _PV_NTUPLE:
+    d = pw.parse_dict(v)
+    cls = _ResolveType(d[1][0].decode('utf-8'))
+    return cls(*[_ValueFromMsg(x) for x in d.get(2, [])])
+  if field == _PV_REPR:
+    text = v.decode('utf-8')
+    try:
+      return ast.literal_eval(text)
+    except (ValueError, SyntaxError):
+      return text
+  raise ValueError('unsupported HyperparamValue field %d' % field)
+
+
+def _ParamsFromMsg(data: bytes) -> 'Params':
+  from lingvo_b200.utils import protowire as pw  # pylint: disable=g-import-not-at-top
+  items = {}
+  for f, _, entry in pw.parse(data):
+    if f != 1:
+      continue
+    d = pw.parse_dict(entry)
+    items[d[1][0].decode('utf-8')] = _ValueFromMsg(d.get(2, [b''])[0])
+  if 'cls' in items and items['cls'] is not None:
+    out = InstantiableParams(items.pop('cls'))
+  else:
+    items.pop('cls', None)
+    out = Params()
+  for k, v in items.items():
+    out.Define(k, v, '')
+  return out
+
+
+def _TextValue(val, indent: int) -> str:
+  pad = '  ' * indent
+  if val is None:
+    return ''
+  esc = lambda t: t.replace('\\', '\\\\').replace('"', '\\"').replace('\n', '\\n')
+  if isinstance(val, Params):
+    return '%sparam_val {\n%s%s}\n' % (pad, _HyperparamText(val, indent + 1), pad)
+  if _IsNamedTuple(val) or (dataclasses.is_dataclass(val) and not isinstance(val, type)):
+    vals = list(val) if _IsNamedTuple(val) else [
+        getattr(val, f.name) for f in dataclasses.fields(val)]
+    body = '%s  type: "%s"\n' % (pad, _TypeName(type(val)))
+    for v in vals:
+      body += '%s  items {\n%s%s  }\n' % (pad, _TextValue(v, indent + 2), pad)
+    return '%snamed_tuple_val {\n%s%s}\n' % (pad, body, pad)
+  if isinstance(val, (list, tuple)):
+    kind = 'list_val' if isinstance(val, list) else 'tuple_val'
+    body = ''.join('%s  items {\n%s%s  }\n' % (pad, _TextValue(v, indent + 2), pad)
+                   for v in val)
+    return '%s%s {\n%s%s}\n' % (pad, kind, body, pad)
+  if isinstance(val, dict):
+    body = ''
+    for k in val:
+      body += '%s  items {\n%s    key: "%s"\n%s    value {\n%s%s    }\n%s  }\n' % (
+          pad, pad, esc(str(k)), pad, _TextValue(val[k], indent + 3), pad, pad)
+    return '%sdict_val {\n%s%s}\n' % (pad, body, pad)
+  if isinstance(val, bool):
+    return '%sbool_val: %s\n' % (pad, 'true' if val else 'false')
+  if isinstance(val, enum.Enum):
+    return '%senum_val {\n%s  type: "%s"\n%s  name: "%s"\n%s}\n' % (
+        pad, pad, _TypeName(type(val)), pad, val.name, pad)
+  if isinstance(val, (int, np.integer)):
+    return '%sint_val: %d\n' % (pad, int(val))
+  if isinstance(val, (float, np.floating)):
+    return '%sfloat_val: %r\n' % (pad, float(val))
+  if isinstance(val, str):
+    return '%sstring_val: "%s"\n' % (pad, esc(val))
+  if _IsDtype(val):
+    return '%sdtype_val: "%s"\n' % (pad, DtypeName(val))
+  if isinstance(val, np.dtype) or (isinstance(val, type) and issubclass(val, np.generic)):
+    return '%sdtype_val: "np.%s"\n' % (pad, np.dtype(val).name)
+  if inspect.isclass(val) or inspect.isroutine(val):
+    return '%stype_val: "%s"\n' % (pad, _TypeName(val))
+  return '%sstring_repr_val: "%s"\n' % (pad, esc(repr(val)))
+
+
+def _HyperparamText(params: 'Params', indent: int) -> str:
+  pad = '  ' * indent
+  out = ''
+  for name, val in sorted(params.IterParams()):
+    out += '%sitems {\n%s  key: "%s"\n%s  value {\n%s%s  }\n%s}\n' % (
+        pad, pad, name, pad, _TextValue(val, indent + 2), pad, pad)
+  return out

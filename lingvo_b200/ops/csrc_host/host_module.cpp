@@ -21,6 +21,95 @@ using namespace lbh;   // NOLINT
 
 namespace {
 
+// ------------------------------------------------------------ BucketAdjuster ----
+// Re-derives the bucket upper bounds (all but the last) from a histogram of the observed
+// bucket keys so that the total padding cost  Σ_buckets count(bucket) · bound(bucket)  is
+// minimal (reference `BucketAdjuster`, record_batcher.h:72 / record_batcher.cc:387-390).
+// Exact dynamic programme over the distinct observed keys (thinned to ≤ 2048 candidates).
+class BucketAdjuster {
+ public:
+  BucketAdjuster(int64_t max_bucket_key, int64_t num_buckets)
+      : max_key_(max_bucket_key), num_buckets_(num_buckets),
+        hist_(static_cast<size_t>(max_bucket_key) + 1, 0) {}
+
+  void IncrementHistogram(int64_t key) {
+    if (key < 0 || key > max_key_) return;
+    std::lock_guard<std::mutex> l(mu_);
+    ++hist_[static_cast<size_t>(key)];
+  }
+
+  // Rewrites bounds[0 .. n-2]; bounds[n-1] (the hard cap) is kept.
+  void AdjustBuckets(std::vector<int64_t>* bounds) {
+    std::vector<std::pair<int64_t, int64_t>> pts;          // (key, count), ascending
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      for (int64_t k = 0; k <= max_key_; ++k)
+        if (hist_[static_cast<size_t>(k)] > 0) pts.emplace_back(k, hist_[static_cast<size_t>(k)]);
+    }
+    const int64_t nb = static_cast<int64_t>(bounds->size());
+    if (nb < 2 || pts.size() < 2) return;
+    // thin very long supports: merge neighbours (counts move up to the larger key)
+    const size_t kMax = 2048;
+    if (pts.size() > kMax) {
+      std::vector<std::pair<int64_t, int64_t>> thin;
+      const size_t step = (pts.size() + kMax - 1) / kMax;
+      for (size_t i = 0; i < pts.size(); i += step) {
+        int64_t c = 0;
+        const size_t hi = std::min(pts.size(), i + step);
+        for (size_t j = i; j < hi; ++j) c += pts[j].second;
+        thin.emplace_back(pts[hi - 1].first, c);
+      }
+      pts.swap(thin);
+    }
+    const int64_t m = static_cast<int64_t>(pts.size());
+    std::vector<double> pre(m + 1, 0.0);
+    for (int64_t i = 0; i < m; ++i) pre[i + 1] = pre[i] + static_cast<double>(pts[i].second);
+    // cost[b][i]: min cost of covering points [0, i) with b buckets, the b-th ending at
+    // point i-1 (bound = pts[i-1].first). The final bucket always ends at the hard cap.
+    const int64_t free = std::min<int64_t>(nb - 1, m);      // adjustable buckets in use
+    const double kInf = 1e300;
+    std::vector<std::vector<double>> cost(free + 1, std::vector<double>(m + 1, kInf));
+    std::vector<std::vector<int64_t>> arg(free + 1, std::vector<int64_t>(m + 1, 0));
+    cost[0][0] = 0.0;
+    for (int64_t b = 1; b <= free; ++b)
+      for (int64_t i = b; i <= m; ++i)
+        for (int64_t j = b - 1; j < i; ++j) {
+          if (cost[b - 1][j] >= kInf) continue;
+          const double c = cost[b - 1][j] + (pre[i] - pre[j]) * static_cast<double>(pts[i - 1].first);
+          if (c < cost[b][i]) { cost[b][i] = c; arg[b][i] = j; }
+        }
+    // choose how many points the adjustable buckets cover; the rest pays the hard cap
+    const double cap = static_cast<double>(bounds->back());
+    double best = kInf;
+    int64_t best_i = 0, best_b = 0;
+    for (int64_t b = 0; b <= free; ++b)
+      for (int64_t i = b; i <= m; ++i) {
+        if (cost[b][i] >= kInf) continue;
+        const double c = cost[b][i] + (pre[m] - pre[i]) * cap;
+        if (c < best) { best = c; best_i = i; best_b = b; }
+      }
+    std::vector<int64_t> chosen;
+    for (int64_t b = best_b, i = best_i; b > 0; --b) {
+      chosen.push_back(pts[i - 1].first);
+      i = arg[b][i];
+    }
+    std::sort(chosen.begin(), chosen.end());
+    // keep exactly nb-1 adjustable bounds: unused ones collapse onto their neighbour
+    std::vector<int64_t> out;
+    for (int64_t v : chosen)
+      if (v < bounds->back()) out.push_back(v);
+    while (static_cast<int64_t>(out.size()) < nb - 1)
+      out.push_back(out.empty() ? bounds->back() : out.back());
+    std::sort(out.begin(), out.end());
+    for (int64_t i = 0; i < nb - 1; ++i) (*bounds)[static_cast<size_t>(i)] = out[static_cast<size_t>(i)];
+  }
+
+ private:
+  const int64_t max_key_, num_buckets_;
+  std::mutex mu_;
+  std::vector<int64_t> hist_;
+};
+
 // ------------------------------------------------------------- RecordBatcher ----
 // N worker threads pull records from a Yielder (no GIL), call the Python
 // `processor(record: bytes, source_id: int)` (GIL) which returns None (example
@@ -32,14 +121,27 @@ namespace {
 // evaluation); at end of data all partial buckets are flushed, then StopIteration.
 class RecordBatcher {
  public:
+  // `bucket_adjust_every_n > 0`: re-optimise the bounds (all but the last) every n records.
+  // `fatal_errors`: None ⇒ every processor exception aborts the pipeline; a list ⇒ only
+  // exceptions whose message contains one of the strings abort, all others skip the
+  // record and are counted (`records_failed`) — the reference's `fatal_errors` option.
+  // `pad_values`: per tensor slot padding constant (reference `dynamic_padding_constants`).
   RecordBatcher(std::shared_ptr<Yielder> yielder, py::function processor,
                 std::vector<int64_t> bucket_upper_bound, std::vector<int64_t> bucket_batch_limit,
-                int num_threads, int64_t flush_every_n)
+                int num_threads, int64_t flush_every_n, int64_t bucket_adjust_every_n,
+                py::object fatal_errors, std::vector<double> pad_values)
       : yielder_(std::move(yielder)), processor_(std::move(processor)),
         bounds_(std::move(bucket_upper_bound)), limits_(std::move(bucket_batch_limit)),
-        flush_every_n_(flush_every_n), buckets_(bounds_.size()) {
+        flush_every_n_(flush_every_n), adjust_every_n_(bucket_adjust_every_n),
+        pad_values_(std::move(pad_values)), buckets_(bounds_.size()) {
     if (bounds_.empty() || bounds_.size() != limits_.size())
       throw std::runtime_error("RecordBatcher: bucket_upper_bound / bucket_batch_limit mismatch");
+    if (!fatal_errors.is_none()) {
+      lenient_ = true;
+      for (auto item : fatal_errors) fatal_errors_.push_back(item.cast<std::string>());
+    }
+    if (adjust_every_n_ > 0)
+      adjuster_ = std::make_unique<BucketAdjuster>(bounds_.back(), static_cast<int64_t>(bounds_.size()));
     if (num_threads < 1) num_threads = 1;
     live_workers_ = num_threads;
     for (int i = 0; i < num_threads; ++i) workers_.emplace_back([this] { Work(); });
@@ -100,6 +202,11 @@ class RecordBatcher {
   }
 
   int64_t records_skipped() const { return skipped_.load(); }
+  int64_t records_failed() const { return failed_.load(); }
+  std::vector<int64_t> bucket_upper_bound() {
+    std::lock_guard<std::mutex> l(mu_);
+    return bounds_;
+  }
   int64_t records_processed() const { return processed_.load(); }
   // Wait-time diagnostics (the reference logs these from `record_debug.cc`).
   py::dict Stats() {
@@ -107,6 +214,7 @@ class RecordBatcher {
     py::dict d;
     d["records_processed"] = processed_.load();
     d["records_skipped"] = skipped_.load();
+    d["records_failed"] = failed_.load();
     d["batches_ready"] = static_cast<int64_t>(ready_.size());
     d["consumer_wait_s"] = consumer_wait_us_ * 1e-6;
     d["producer_wait_s"] = producer_wait_us_ * 1e-6;
@@ -140,17 +248,38 @@ class RecordBatcher {
             keep = true;
           }
         } catch (const std::exception& e) {
-          std::lock_guard<std::mutex> l(mu_);
-          error_ = std::string("RecordBatcher processor failed: ") + e.what();
-          stop_.store(true);
-          cv_ready_.notify_all();
+          const std::string what = e.what();
+          bool fatal = !lenient_;
+          for (const auto& f : fatal_errors_)
+            if (what.find(f) != std::string::npos) fatal = true;
+          if (fatal) {
+            std::lock_guard<std::mutex> l(mu_);
+            error_ = std::string("RecordBatcher processor failed: ") + what;
+            stop_.store(true);
+            cv_ready_.notify_all();
+          } else {
+            failed_.fetch_add(1);
+          }
         }
         if (!keep) s.tensors.clear();   // drop references while holding the GIL
       }
       if (!keep) continue;
       const int64_t n = processed_.fetch_add(1) + 1;
-      const auto it = std::lower_bound(bounds_.begin(), bounds_.end(), s.key);
+      if (adjuster_) adjuster_->IncrementHistogram(s.key);
       std::unique_lock<std::mutex> l(mu_);
+      if (adjuster_ && n % adjust_every_n_ == 0) {
+        // Samples already filed keep their bucket; a bucket is only ever *larger* than the
+        // keys it holds if its bound shrank, so flush everything before re-bucketing.
+        for (auto& b : buckets_) {
+          if (!b.empty()) {
+            ready_.push_back(std::move(b));
+            b.clear();
+          }
+        }
+        cv_ready_.notify_all();
+        adjuster_->AdjustBuckets(&bounds_);
+      }
+      const auto it = std::lower_bound(bounds_.begin(), bounds_.end(), s.key);
       if (it == bounds_.end()) {
         skipped_.fetch_add(1);
         l.unlock();
@@ -221,6 +350,10 @@ class RecordBatcher {
       }
       py::array out(first.dtype(), shape);
       memset(out.mutable_data(), 0, static_cast<size_t>(out.nbytes()));
+      if (s < pad_values_.size() && pad_values_[s] != 0.0) {
+        // dynamic padding constant of this slot (numpy fills with the proper dtype)
+        out.attr("fill")(pad_values_[s]);
+      }
       std::vector<py::ssize_t> inner_strides(out.strides() + 1, out.strides() + 1 + nd);
       for (size_t i = 0; i < n; ++i) {
         py::buffer_info info = batch[i].tensors[s].request();
@@ -238,6 +371,12 @@ class RecordBatcher {
   py::function processor_;
   std::vector<int64_t> bounds_, limits_;
   int64_t flush_every_n_;
+  int64_t adjust_every_n_ = 0;
+  std::unique_ptr<BucketAdjuster> adjuster_;
+  bool lenient_ = false;
+  std::vector<std::string> fatal_errors_;
+  std::vector<double> pad_values_;
+  std::atomic<int64_t> failed_{0};
   std::vector<Batch> buckets_;
   std::deque<Batch> ready_;
   std::mutex mu_;
@@ -302,19 +441,34 @@ PYBIND11_MODULE(_H, m) {
 
   m.def("basic_record_yielder",
         [](const std::string& file_pattern, uint64_t seed, int64_t bufsize, int parallelism,
-           int64_t num_epochs, int source_id) -> std::shared_ptr<Yielder> {
+           int64_t num_epochs, int source_id, int num_input_replicas, int input_replica_id,
+           double bufsize_in_seconds) -> std::shared_ptr<Yielder> {
           BasicYielderOptions o;
           o.file_pattern = file_pattern; o.seed = seed; o.bufsize = bufsize;
           o.parallelism = parallelism; o.num_epochs = num_epochs; o.source_id = source_id;
+          o.num_input_replicas = num_input_replicas; o.input_replica_id = input_replica_id;
+          o.bufsize_in_seconds = bufsize_in_seconds;
           return std::make_shared<BasicRecordYielder>(o);
         },
         py::arg("file_pattern"), py::arg("seed") = 0, py::arg("bufsize") = 16384,
-        py::arg("parallelism") = 4, py::arg("num_epochs") = 0, py::arg("source_id") = 0);
+        py::arg("parallelism") = 4, py::arg("num_epochs") = 0, py::arg("source_id") = 0,
+        py::arg("num_input_replicas") = 1, py::arg("input_replica_id") = 0,
+        py::arg("bufsize_in_seconds") = 0.0);
   m.def("sequential_record_yielder",
-        [](const std::string& fp, int64_t repeat, int source_id) -> std::shared_ptr<Yielder> {
-          return std::make_shared<SequentialRecordYielder>(fp, repeat, source_id);
+        [](const std::string& fp, int64_t repeat, int source_id, int num_input_replicas,
+           int input_replica_id) -> std::shared_ptr<Yielder> {
+          return std::make_shared<SequentialRecordYielder>(fp, repeat, source_id,
+                                                           num_input_replicas, input_replica_id);
         },
-        py::arg("file_pattern"), py::arg("repeat_count") = 1, py::arg("source_id") = 0);
+        py::arg("file_pattern"), py::arg("repeat_count") = 1, py::arg("source_id") = 0,
+        py::arg("num_input_replicas") = 1, py::arg("input_replica_id") = 0);
+  py::class_<BucketAdjuster>(m, "BucketAdjuster")
+      .def(py::init<int64_t, int64_t>(), py::arg("max_bucket_key"), py::arg("num_buckets"))
+      .def("increment_histogram", &BucketAdjuster::IncrementHistogram)
+      .def("adjust_buckets", [](BucketAdjuster& a, std::vector<int64_t> bounds) {
+        a.AdjustBuckets(&bounds);
+        return bounds;
+      });
   m.def("weighted_mix_record_yielder",
         [](std::vector<std::shared_ptr<Yielder>> kids, std::vector<double> w,
            uint64_t seed) -> std::shared_ptr<Yielder> {
@@ -324,13 +478,17 @@ PYBIND11_MODULE(_H, m) {
 
   py::class_<RecordBatcher>(m, "RecordBatcher")
       .def(py::init<std::shared_ptr<Yielder>, py::function, std::vector<int64_t>,
-                    std::vector<int64_t>, int, int64_t>(),
+                    std::vector<int64_t>, int, int64_t, int64_t, py::object,
+                    std::vector<double>>(),
            py::arg("yielder"), py::arg("processor"), py::arg("bucket_upper_bound"),
            py::arg("bucket_batch_limit"), py::arg("num_threads") = 4,
-           py::arg("flush_every_n") = 0)
+           py::arg("flush_every_n") = 0, py::arg("bucket_adjust_every_n") = 0,
+           py::arg("fatal_errors") = py::none(), py::arg("pad_values") = std::vector<double>())
       .def("get_next", &RecordBatcher::GetNext)
       .def("close", &RecordBatcher::Close)
       .def_property_readonly("records_skipped", &RecordBatcher::records_skipped)
+      .def_property_readonly("records_failed", &RecordBatcher::records_failed)
+      .def_property_readonly("bucket_upper_bound", &RecordBatcher::bucket_upper_bound)
       .def_property_readonly("records_processed", &RecordBatcher::records_processed)
       .def("stats", &RecordBatcher::Stats);
 

@@ -384,6 +384,10 @@ BasicRecordYielder::BasicRecordYielder(const BasicYielderOptions& opts)
   SplitPattern(opts_.file_pattern, &type_, &glob_);
   if (opts_.parallelism < 1) opts_.parallelism = 1;
   if (opts_.bufsize < 1) opts_.bufsize = 1;
+  if (opts_.num_input_replicas < 1) opts_.num_input_replicas = 1;
+  if (opts_.input_replica_id < 0 || opts_.input_replica_id >= opts_.num_input_replicas)
+    throw std::runtime_error("BasicRecordYielder: input_replica_id out of range");
+  limit_.store(opts_.bufsize);
   ExpandFiles(type_, glob_);   // fail fast on a bad pattern
   main_ = std::thread([this] { MainLoop(); });
 }
@@ -403,25 +407,32 @@ void BasicRecordYielder::Close() {
 void BasicRecordYielder::Add(std::vector<std::string>* chunk, std::mt19937_64* rng) {
   std::unique_lock<std::mutex> l(mu_);
   for (auto& rec : *chunk) {
-    cv_not_full_.wait(l, [&] { return stop_ || static_cast<int64_t>(buf_.size()) < opts_.bufsize; });
+    cv_not_full_.wait(l, [&] { return stop_ || static_cast<int64_t>(buf_.size()) < limit_.load(); });
     if (stop_) return;
     buf_.emplace_back(std::move(rec));
     // random-swap insertion keeps the buffer uniformly shuffled
     const size_t j = (*rng)() % buf_.size();
     std::swap(buf_[j], buf_.back());
-    if (static_cast<int64_t>(buf_.size()) * 2 >= opts_.bufsize) cv_not_empty_.notify_one();
+    if (static_cast<int64_t>(buf_.size()) * 2 >= limit_.load()) cv_not_empty_.notify_one();
   }
   chunk->clear();
 }
 
-void BasicRecordYielder::ReadShard(const std::vector<std::string>& files, uint64_t seed) {
+void BasicRecordYielder::ReadShard(const std::vector<std::string>& files, uint64_t seed,
+                                   bool shard_records) {
   std::mt19937_64 rng(seed);
   std::vector<std::string> chunk;
   for (const auto& f : files) {
     if (stop_) return;
     auto it = RecordIterator::Create(type_, f);
     std::string rec;
+    int64_t idx = 0;
     while (!stop_ && it->Next(&rec)) {
+      // fewer files than replicas: shard by record position inside each file
+      if (shard_records && (idx++ % opts_.num_input_replicas) != opts_.input_replica_id) {
+        rec.clear();
+        continue;
+      }
       chunk.emplace_back(std::move(rec));
       rec.clear();
       if (chunk.size() >= 64) Add(&chunk, &rng);
@@ -433,7 +444,19 @@ void BasicRecordYielder::ReadShard(const std::vector<std::string>& files, uint64
 void BasicRecordYielder::MainLoop() {
   for (int64_t epoch = 0; !stop_ && (opts_.num_epochs == 0 || epoch < opts_.num_epochs); ++epoch) {
     epoch_.store(epoch);
-    auto files = ExpandFiles(type_, glob_);
+    auto files = ExpandFiles(type_, glob_);     // sorted ⇒ identical on every replica
+    bool shard_records = false;
+    if (opts_.num_input_replicas > 1) {
+      if (static_cast<int>(files.size()) >= opts_.num_input_replicas) {
+        std::vector<std::string> mine;
+        for (size_t i = 0; i < files.size(); ++i)
+          if (static_cast<int>(i % opts_.num_input_replicas) == opts_.input_replica_id)
+            mine.push_back(files[i]);
+        files.swap(mine);
+      } else {
+        shard_records = true;
+      }
+    }
     const uint64_t eseed =
         opts_.seed ? (opts_.seed * 0x9e3779b97f4a7c15ull) ^ static_cast<uint64_t>(epoch + 1)
                    : std::random_device{}();
@@ -448,7 +471,9 @@ void BasicRecordYielder::MainLoop() {
     }
     std::vector<std::thread> readers;
     for (int s = 0; s < shards; ++s)
-      readers.emplace_back([this, &per, s, eseed] { ReadShard(per[s], eseed + 1 + s); });
+      readers.emplace_back([this, &per, s, eseed, shard_records] {
+        ReadShard(per[s], eseed + 1 + s, shard_records);
+      });
     for (auto& t : readers) t.join();
     // Everything of this epoch is in the buffer: let consumers drain it fully before
     // the next epoch starts (so epochs never mix).
@@ -466,9 +491,23 @@ bool BasicRecordYielder::Yield(Record* out) {
   std::unique_lock<std::mutex> l(mu_);
   cv_not_empty_.wait(l, [&] {
     return stop_ || finished_ || (!buf_.empty() && (epoch_draining_ ||
-                                                    static_cast<int64_t>(buf_.size()) * 2 >= opts_.bufsize));
+                                                    static_cast<int64_t>(buf_.size()) * 2 >= limit_.load()));
   });
   if (buf_.empty()) return false;
+  if (opts_.bufsize_in_seconds > 0) {
+    // adapt the buffer to `bufsize_in_seconds` of the measured consumption rate
+    const int64_t n = yielded_.fetch_add(1) + 1;
+    if (n == 1) t_first_yield_ = std::chrono::steady_clock::now();
+    if (n % 1024 == 0) {
+      const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() -
+                                                        t_first_yield_).count();
+      if (secs > 0) {
+        int64_t want = static_cast<int64_t>(n / secs * opts_.bufsize_in_seconds);
+        want = std::max<int64_t>(1024, std::min<int64_t>(want, opts_.bufsize));
+        limit_.store(want);
+      }
+    }
+  }
   if (opts_.seed == 0) {   // extra extraction randomness for unseeded runs
     const size_t j = pop_rng_() % buf_.size();
     std::swap(buf_[j], buf_.back());
@@ -482,8 +521,10 @@ bool BasicRecordYielder::Yield(Record* out) {
 
 // ------------------------------------------------------ sequential yielder ----
 SequentialRecordYielder::SequentialRecordYielder(const std::string& file_pattern,
-                                                 int64_t repeat_count, int source_id)
-    : repeat_(repeat_count), source_id_(source_id) {
+                                                 int64_t repeat_count, int source_id,
+                                                 int num_input_replicas, int input_replica_id)
+    : repeat_(repeat_count), source_id_(source_id),
+      replicas_(num_input_replicas < 1 ? 1 : num_input_replicas), replica_id_(input_replica_id) {
   std::string glob;
   SplitPattern(file_pattern, &type_, &glob);
   files_ = ExpandFiles(type_, glob);
@@ -501,6 +542,8 @@ bool SequentialRecordYielder::Yield(Record* out) {
       it_ = RecordIterator::Create(type_, files_[file_idx_++]);
     }
     if (it_->Next(&out->value)) {
+      // in-order evaluation data: round-robin records over the replicas
+      if (replicas_ > 1 && (rec_idx_++ % replicas_) != replica_id_) continue;
       out->source_id = source_id_;
       return true;
     }

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <functional>
@@ -62,6 +63,15 @@ struct BasicYielderOptions {
   int parallelism = 4;        // reader threads
   int64_t num_epochs = 0;     // 0: forever
   int source_id = 0;
+  // Data-parallel input sharding (reference record_yielder.h:84-85): replica
+  // `input_replica_id` of `num_input_replicas` reads every num_input_replicas-th file of
+  // the sorted file list; with fewer files than replicas every replica reads all files
+  // and keeps every num_input_replicas-th record instead.
+  int num_input_replicas = 1;
+  int input_replica_id = 0;
+  // > 0: size the shuffle buffer to this many seconds of consumption (measured yield
+  // rate), within [1024, bufsize] (reference `bufsize_in_seconds`).
+  double bufsize_in_seconds = 0.0;
 };
 
 // Shuffling yielder: per epoch the file list is shuffled and dealt round-robin to
@@ -78,7 +88,7 @@ class BasicRecordYielder : public Yielder {
 
  private:
   void MainLoop();
-  void ReadShard(const std::vector<std::string>& files, uint64_t seed);
+  void ReadShard(const std::vector<std::string>& files, uint64_t seed, bool shard_records);
   void Add(std::vector<std::string>* chunk, std::mt19937_64* rng);
 
   BasicYielderOptions opts_;
@@ -91,13 +101,17 @@ class BasicRecordYielder : public Yielder {
   bool finished_ = false;
   std::atomic<bool> stop_{false};
   std::atomic<int64_t> epoch_{0};
+  std::atomic<int64_t> limit_;            // current shuffle-buffer capacity
+  std::atomic<int64_t> yielded_{0};
+  std::chrono::steady_clock::time_point t_first_yield_;
   std::thread main_;
 };
 
 // In-order yielder (evaluation): files sorted, records in file order.
 class SequentialRecordYielder : public Yielder {
  public:
-  SequentialRecordYielder(const std::string& file_pattern, int64_t repeat_count, int source_id);
+  SequentialRecordYielder(const std::string& file_pattern, int64_t repeat_count, int source_id,
+                          int num_input_replicas = 1, int input_replica_id = 0);
   bool Yield(Record* out) override;
   int64_t current_epoch() const override { return epoch_; }
 
@@ -107,6 +121,8 @@ class SequentialRecordYielder : public Yielder {
   int64_t repeat_, epoch_ = 0;
   size_t file_idx_ = 0;
   int source_id_;
+  int replicas_ = 1, replica_id_ = 0;
+  int64_t rec_idx_ = 0;
   std::unique_ptr<RecordIterator> it_;
   std::mutex mu_;
 };

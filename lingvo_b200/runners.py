@@ -45,10 +45,12 @@ def _WriteParamsFiles(params, out_dir: str, prefix: str = 'params'):
   os.makedirs(out_dir, exist_ok=True)
   with open(os.path.join(out_dir, prefix + '.txt'), 'w') as f:
     f.write(params.ToText())
-  # params.pbtxt of the reference is the Hyperparams proto; we emit the typed
-  # text form (key : value + key : type) which round-trips through FromText.
+  # params.pbtxt: the Hyperparam proto of the reference in protobuf text format;
+  # params.pb: the same message serialized (round-trips through Params.FromProto).
   with open(os.path.join(out_dir, prefix + '.pbtxt'), 'w') as f:
-    f.write(params.ToTextWithTypes())
+    f.write(params.ToProtoText())
+  with open(os.path.join(out_dir, prefix + '.pb'), 'wb') as f:
+    f.write(params.ToProto())
 
 
 def _MetricsToFloats(metrics: Dict) -> Dict[str, float]:
