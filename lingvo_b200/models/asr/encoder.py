@@ -113,3 +113,99 @@ class AsrEncoder(base_layer.BaseLayer):
       xs = self.final_proj.FProp(theta.final_proj, xs, pad_t)
     xs = xs * (1.0 - pad_t)
     return NestedMap(encoded=xs, padding=pad.t(), state=None)
+
+
+class ConformerEncoder(base_layer.BaseLayer):
+  """Conformer ASR encoder (Gulati et al. 2020), assembled from the reference building
+  block `core/conformer_layer.py:471 ConformerLayer` (no registered reference model uses
+  it — SURVEY §0.4): SpecAugment → 2× strided conv subsampling (time/4) → linear →
+  dropout → N × ConformerLayer (½FFN, MHSA with relative positions, LConv, ½FFN, LN) →
+  `[T', B, D]`, the interface of `AsrEncoder`.
+
+  On a GPU the LConv module runs the fused GLU+mask+depthwise-conv kernel
+  (`ops/csrc/conv_kernels.cu`), the norms the fused LN kernels, attention the fused
+  attention path; `remat` recomputes each block in the backward pass.
+  """
+
+  @classmethod
+  def Params(cls):
+    from lingvo_b200.core import conformer_layer  # pylint: disable=g-import-not-at-top
+    p = super().Params()
+    p.Define('specaugment_network', spectrum_augmenter.SpectrumAugmenter.Params(),
+             'SpecAugment params.')
+    p.Define('use_specaugment', False, 'Apply SpecAugment in training.')
+    p.Define('input_shape', [None, None, 80, 1], '[B, T, F, C].')
+    p.Define('conv_filter_shapes', [(3, 3, 1, 32), (3, 3, 32, 32)], 'Subsampling convs.')
+    p.Define('conv_filter_strides', [(2, 2), (2, 2)], 'Subsampling strides.')
+    p.Define('cnn_tpl', conv_lib.Conv2DLayerWithPadding.Params(), 'Conv template.')
+    p.Define('model_dim', 512, 'Encoder dim D.')
+    p.Define('num_layers', 17, 'Conformer blocks.')
+    p.Define('num_heads', 8, 'Attention heads.')
+    p.Define('kernel_size', 32, 'Depthwise conv kernel.')
+    p.Define('ff_hidden_dim', None, 'FFN hidden dim (default 4·D).')
+    p.Define('atten_left_context', None, 'Attention left context (None: full).')
+    p.Define('atten_right_context', None, 'Attention right context (None: full).')
+    p.Define('use_relative_atten', True, 'Transformer-XL relative attention.')
+    p.Define('dropout_prob', 0.1, 'Dropout.')
+    p.Define('is_causal', False, 'Streaming (causal conv, limited right context).')
+    p.Define('remat', False, 'Rematerialise every block in backward.')
+    p.Define('conformer_tpl', conformer_layer.ConformerLayer.Params(), 'Block template.')
+    p.Define('pad_steps', 0, 'Extra padded frames appended to the input.')
+    return p
+
+  def __init__(self, params):
+    from lingvo_b200.core import conformer_layer  # pylint: disable=g-import-not-at-top
+    super().__init__(params)
+    p = self.params
+    if p.use_specaugment:
+      self.CreateChild('specaugment', p.specaugment_network)
+    convs = []
+    f, c = p.input_shape[2], p.input_shape[3]
+    for i, (shape, stride) in enumerate(zip(p.conv_filter_shapes, p.conv_filter_strides)):
+      convs.append(p.cnn_tpl.Copy().Set(name='conv_L%d' % i, filter_shape=tuple(shape),
+                                        filter_stride=tuple(stride)))
+      f = -(-f // stride[1])
+      c = shape[3]
+    self.CreateChildren('conv', convs)
+    self.CreateChild('input_proj', layers.FCLayer.Params().Set(
+        input_dim=f * c, output_dim=p.model_dim, activation='NONE'))
+    self.CreateChild('input_dropout', layers.DropoutLayer.Params().Set(
+        keep_prob=1.0 - p.dropout_prob))
+    blocks = []
+    for i in range(p.num_layers):
+      bp = conformer_layer.ConformerLayer.CommonParams(
+          input_dim=p.model_dim, atten_num_heads=p.num_heads,
+          atten_left_context=p.atten_left_context, atten_right_context=p.atten_right_context,
+          use_relative_atten=p.use_relative_atten, kernel_size=p.kernel_size,
+          fflayer_hidden_dim=p.ff_hidden_dim or 4 * p.model_dim,
+          dropout_prob=p.dropout_prob, is_causal=p.is_causal)
+      bp.name = 'conformer_%d' % i
+      bp.remat = p.remat
+      blocks.append(bp)
+    self.CreateChildren('blocks', blocks)
+
+  @property
+  def output_dim(self):
+    return self.params.model_dim
+
+  def FProp(self, theta, batch, state0=None):
+    """batch.src_inputs [B,T,F,C], batch.paddings [B,T] → encoded [T',B,D]."""
+    p = self.params
+    x, pad = batch.src_inputs.float(), batch.paddings.float()
+    if p.use_specaugment and not self.do_eval:
+      x, pad = self.specaugment.FProp(theta.specaugment, x, pad)
+    if p.pad_steps > 0:
+      x = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, p.pad_steps))
+      pad = torch.nn.functional.pad(pad, (0, p.pad_steps), value=1.0)
+    for i, conv in enumerate(self.conv):
+      x, pad = conv.FProp(theta.conv[i], x, pad)
+      x = torch.relu(x)
+    b, t = x.shape[:2]
+    h = self.input_proj.FProp(theta.input_proj, x.reshape(b, t, -1))
+    h = self.input_dropout.FProp(theta.input_dropout, h)
+    h = self._CastToFPropDtype(h)
+    nm = NestedMap(features=h, paddings=pad)
+    for i, blk in enumerate(self.blocks):
+      nm = blk.FProp(theta.blocks[i], nm)
+    out = nm.features * (1.0 - pad).unsqueeze(-1).to(nm.features.dtype)
+    return NestedMap(encoded=out.transpose(0, 1), padding=pad.t(), state=None)

@@ -2,9 +2,12 @@
 
 import os
 
+import torch
+
 from lingvo_b200 import model_registry
 from lingvo_b200.core import base_model_params
 from lingvo_b200.core import layers
+from lingvo_b200.core import optimizer
 from lingvo_b200.core import py_utils
 from lingvo_b200.core import schedule
 from lingvo_b200.core import tokenizers
@@ -185,3 +188,57 @@ class Librispeech960Wpm(Librispeech960Base):
 @model_registry.RegisterSingleTaskModel
 class Librispeech960WpmTpuV2(_StaticShapeMixin, Librispeech960Wpm):
   """Static-shape word-piece model (ref :310)."""
+
+
+@model_registry.RegisterSingleTaskModel
+class Librispeech960ConformerWpm(Librispeech960Wpm):
+  """Conformer encoder (17 × D=512, 8 heads, kernel 32, relative attention) + the LAS
+  word-piece decoder: BASELINE.json config #4 ("asr.librispeech Conformer encoder bf16").
+  The reference ships the block (`core/conformer_layer.py:471`) but registers no model
+  with it; hyper-parameters follow Conformer-L of the paper."""
+
+  CONFORMER_DIM = 512
+  CONFORMER_LAYERS = 17
+  CONFORMER_HEADS = 8
+  CONFORMER_KERNEL = 32
+
+  def Task(self):
+    from lingvo_b200.models.asr import encoder as asr_encoder
+    p = super().Task()
+    old = p.encoder
+    p.encoder = asr_encoder.ConformerEncoder.Params().Set(
+        name='enc', model_dim=self.CONFORMER_DIM, num_layers=self.CONFORMER_LAYERS,
+        num_heads=self.CONFORMER_HEADS, kernel_size=self.CONFORMER_KERNEL,
+        use_specaugment=True, dropout_prob=0.1, input_shape=list(old.input_shape))
+    p.encoder.fprop_dtype = torch.bfloat16
+    p.decoder.source_dim = self.CONFORMER_DIM
+    tp = p.train
+    tp.learning_rate = 1e-3
+    tp.lr_schedule = schedule.TransformerSchedule.Params().Set(
+        warmup_steps=10000, model_dim=self.CONFORMER_DIM)
+    tp.optimizer = optimizer.Adam.Params().Set(beta1=0.9, beta2=0.98, epsilon=1e-9)
+    tp.vn_std = 0.0
+    return p
+
+
+@model_registry.RegisterSingleTaskModel
+class Librispeech960ConformerWpmTpuV2(_StaticShapeMixin, Librispeech960ConformerWpm):
+  """Static-shape variant: one shape signature ⇒ whole-step CUDA-graph replay."""
+
+
+@model_registry.RegisterSingleTaskModel
+class Librispeech960ConformerTiny(Librispeech960Grapheme):
+  """2-block Conformer for tests / smoke runs."""
+
+  def Task(self):
+    from lingvo_b200.models.asr import encoder as asr_encoder
+    p = super().Task()
+    old = p.encoder
+    p.encoder = asr_encoder.ConformerEncoder.Params().Set(
+        name='enc', model_dim=32, num_layers=2, num_heads=2, kernel_size=8,
+        dropout_prob=0.0, input_shape=list(old.input_shape))
+    p.decoder.source_dim = 32
+    p.decoder.rnn_cell_dim = 32
+    p.decoder.attention.hidden_dim = 16
+    p.decoder.emb_dim = 16
+    return p

@@ -320,3 +320,121 @@ class TransformerXEnDecModel(TransformerModel):
     for k in ('log_pplx', 'fraction_of_correct_next_step_preds', 'num_predictions'):
       metrics[k] = clean[0][k]
     return metrics, clean[1]
+
+
+class GPipeTransformerModel(base_model.BaseTask):
+  """Transformer NMT whose embeddings, encoder, decoder and softmax form one
+  `layers_with_gpipe.GPipeTransformerStack` pipeline (reference building block
+  `core/layers_with_gpipe.py:576`; BASELINE.json config #5 "TransformerBig GPipe").
+
+  Single process: the micro-batched stack runs in place. Under torchrun with
+  `pipeline_parallel=True` and world == `num_splits`, rank r executes cell r only:
+  `parallel.pp.PipelineEngine` moves micro-batch activations / gradients between ranks
+  (NCCL p2p over NVLink, overlapped with compute, optional rematerialisation) and every
+  rank updates the variables of its own cell.
+  """
+
+  @classmethod
+  def Params(cls):
+    from lingvo_b200.core import layers_with_gpipe  # pylint: disable=g-import-not-at-top
+    p = super().Params()
+    p.Define('stack', layers_with_gpipe.GPipeTransformerStack.Params(), 'Pipeline stack.')
+    p.Define('label_smoothing', 0.1, 'Label smoothing uncertainty.')
+    p.Define('pipeline_parallel', True, 'One rank per cell when launched distributed.')
+    p.Define('remat', True, 'Re-run stage forwards in backward (O(1) activations).')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    self.CreateChild('stack', p.stack)
+    self._engine = None
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    if (p.pipeline_parallel and dist.is_available() and dist.is_initialized() and
+        dist.get_world_size() > 1):
+      from lingvo_b200.parallel import pp  # pylint: disable=g-import-not-at-top
+      assert dist.get_world_size() == self.stack.num_stages, (
+          'GPipeTransformerModel: %d ranks but %d pipeline cells' %
+          (dist.get_world_size(), self.stack.num_stages))
+      self._engine = pp.PipelineEngine(remat=p.remat)
+      self.stack.AttachEngine(self._engine)
+
+  @property
+  def engine(self):
+    return self._engine
+
+  def ComputePredictions(self, theta, batch):
+    src, tgt = batch.src, batch.tgt
+    # GPipe stacks are time-major: ids [T, B]
+    logits = self.stack.FProp(
+        theta.stack, src.ids.t(), src.paddings.t().float(), tgt.ids.t(),
+        tgt.paddings.t().float())
+    return NestedMap(logits=logits)
+
+  def ComputeLoss(self, theta, predictions, batch):
+    p = self.params
+    tgt = batch.tgt
+    if self._engine is not None and not self._engine.is_last:
+      # placeholder: only the last stage sees logits; metrics are broadcast after BProp
+      z = torch.zeros((), device=tgt.ids.device)
+      one = torch.ones((), device=tgt.ids.device)
+      return {'loss': (z, one), 'log_pplx': (z, one)}, {}
+    logits = predictions.logits.float().transpose(0, 1)        # [B, T, V]
+    v = logits.shape[-1]
+    w = (1.0 - tgt.paddings.float()) * tgt.get('weights', torch.ones_like(tgt.paddings)).float()
+    logp = torch.log_softmax(logits, -1)
+    nll = -logp.gather(-1, tgt.labels.long().unsqueeze(-1)).squeeze(-1)
+    if p.label_smoothing:
+      smooth = -logp.mean(-1)
+      xent = (1.0 - p.label_smoothing) * nll + p.label_smoothing * smooth
+    else:
+      xent = nll
+    tot = w.sum().clamp_min(1.0)
+    loss = (xent * w).sum() / tot
+    del v
+    return {'loss': (loss, tot), 'log_pplx': ((nll * w).sum() / tot, tot)}, {}
+
+  def BProp(self):
+    """With a pipeline engine every rank runs the backward phase of the GPipe schedule and
+    applies the optimizer to its own cell; otherwise the standard learner path."""
+    if self._engine is None:
+      return super().BProp()
+    from lingvo_b200.core import py_utils  # pylint: disable=g-import-not-at-top
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    eng = self._engine
+    for v in self.vars.Flatten():
+      v.grad = None
+    loss = self._metrics['loss'][0] if eng.is_last else None
+    eng.Backward(loss)
+    lrn = self.learners[0]
+    with py_utils.GlobalStepContext(self._global_step):
+      pairs = [py_utils.VarGrad(v, v.grad) for v in self.vars.Flatten()
+               if v.requires_grad and v.grad is not None]
+      # global gradient norm over all stages (each variable lives on exactly one rank)
+      sq = torch.stack([g.grad.float().square().sum() for g in pairs]).sum() if pairs else (
+          torch.zeros((), device=self.Device()))
+      dist.all_reduce(sq)
+      gnorm = sq.sqrt()
+      tp = lrn.params
+      scale = torch.ones_like(gnorm)
+      if tp.clip_gradient_norm_to_value:
+        scale = torch.clamp(tp.clip_gradient_norm_to_value / gnorm, max=1.0)
+      scale = torch.where(torch.isfinite(gnorm), scale, torch.zeros_like(scale))
+      if pairs:
+        with torch.no_grad():
+          for vg in pairs:
+            vg.grad.mul_(scale.to(vg.grad.dtype))
+        lrn.optimizer.Apply(lrn.LearningRate(), pairs)
+      # share the last stage's metrics so every rank logs / stops identically
+      vals = torch.stack([self._metrics['loss'][0].detach().float(),
+                          self._metrics['log_pplx'][0].detach().float(),
+                          self._metrics['loss'][1].detach().float()])
+      dist.broadcast(vals, src=eng.world - 1)
+      one = torch.ones((), device=vals.device)
+      self._eval_metrics = {'loss': (vals[0], vals[2]), 'log_pplx': (vals[1], vals[2]),
+                            'grad_norm/all': (gnorm, one)}
+      self.ApplyExponentialMovingAverage()
+    self._global_step += 1
+    py_utils.SetGlobalStep(self._global_step)
+    self._metrics = None
+    return None

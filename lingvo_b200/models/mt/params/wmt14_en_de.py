@@ -97,3 +97,65 @@ class WmtEnDeRNMT(WmtEnDeTransformerBase):
         residual_dropout_prob=0.3, adam_beta2=0.98, adam_epsilon=1e-6)
     p.eval.samples_per_summary = 7500
     return p
+
+
+@model_registry.RegisterSingleTaskModel
+class WmtEnDeTransformerBigGPipe(WmtEnDeTransformerBase):
+  """Transformer-big (d = 1024, ff = 4096, 16 heads, 6 + 6 layers, shared 32k word pieces)
+  as one GPipe pipeline of `GPUS` cells — BASELINE.json config #5. The reference registers
+  no MT GPipe model; this assembles `layers_with_gpipe.GPipeTransformerStack` (:576) the
+  way `lm.one_billion_wds.OneBWdsGPipeTransformerWPM` does for the LM."""
+
+  MODEL_DIM = 1024
+  HIDDEN_DIM = 4096
+  NUM_HEADS = 16
+  NUM_LAYERS = 6
+  GPUS = 4
+  NUM_MICRO_BATCHES = 8
+
+  def _CommonInputParams(self, is_eval):
+    p = super()._CommonInputParams(is_eval)
+    if not is_eval:
+      # one bucket, fixed batch: every micro-batch has the same shape (static pipeline links)
+      p.bucket_upper_bound = [96]
+      p.bucket_batch_limit = [128]
+      p.pad_to_max_seq_length = True
+      p.source_max_length = 96
+      p.target_max_length = 96
+    return p
+
+  def Task(self):
+    from lingvo_b200.core import layers_with_gpipe
+    from lingvo_b200.core import optimizer
+    from lingvo_b200.core import schedule
+    p = model.GPipeTransformerModel.Params().Set(name='wmt14_en_de_transformer_big_gpipe')
+    st = p.stack
+    st.Set(name='stack', model_dim=self.MODEL_DIM, num_encoder_layers=self.NUM_LAYERS,
+           num_decoder_layers=self.NUM_LAYERS, use_pipelined_embeddings=True,
+           num_splits=self.GPUS, splits=self.GPUS, num_micro_batches=self.NUM_MICRO_BATCHES)
+    st.emb_tpl.Set(vocab_size=self.VOCAB_SIZE, model_dim=self.MODEL_DIM,
+                   input_dropout_prob=0.1, max_seq_len=1024)
+    st.softmax_tpl.Set(num_classes=self.VOCAB_SIZE, input_dim=self.MODEL_DIM)
+    for tpl in (st.encoder_tpl, st.decoder_tpl):
+      tpl.tr_atten_tpl.num_attention_heads = self.NUM_HEADS
+      tpl.tr_atten_tpl.residual_dropout_prob = 0.1
+      tpl.tr_fflayer_tpl.hidden_dim = self.HIDDEN_DIM
+      tpl.tr_fflayer_tpl.residual_dropout_prob = 0.1
+    p.train.Set(learning_rate=3.0, optimizer=optimizer.Adam.ParamsB(),
+                clip_gradient_norm_to_value=0.0, grad_norm_to_clip_to_zero=0.0,
+                lr_schedule=schedule.TransformerSchedule.Params().Set(
+                    warmup_steps=40000, worker_replicas=1, model_dim=self.MODEL_DIM))
+    p.eval.samples_per_summary = 7500
+    return p
+
+
+@model_registry.RegisterSingleTaskModel
+class WmtEnDeTransformerGPipeTiny(WmtEnDeTransformerBigGPipe):
+  """2-cell toy variant for tests."""
+  MODEL_DIM = 32
+  HIDDEN_DIM = 64
+  NUM_HEADS = 2
+  NUM_LAYERS = 1
+  GPUS = 2
+  NUM_MICRO_BATCHES = 2
+  VOCAB_SIZE = 64

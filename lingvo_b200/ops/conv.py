@@ -38,6 +38,9 @@ class _GluDwConvFn(torch.autograd.Function):
 
 def glu_dwconv1d_supported(x, conv_layer):
   p = conv_layer.params
+  import os  # pylint: disable=g-import-not-at-top
+  if os.environ.get('LINGVO_B200_DISABLE_FUSED_CONV') == '1':   # A/B switch for benchmarks
+    return False
   return (ops.use_cuda_kernels(x) and x.dtype in (torch.bfloat16, torch.float32) and
           type(conv_layer).__name__ in ('DepthwiseConv2DLayer',
                                         'CausalDepthwiseConv2DLayer') and

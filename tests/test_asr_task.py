@@ -122,3 +122,57 @@ def test_asr_trains_and_decodes(asr_records):
   kv = task.PostProcessDecodeOut(out, dm)
   assert len(kv) == batch.src.src_inputs.shape[0]
   assert 0.0 <= dm['wer'].value <= 3.0
+
+
+def test_conformer_asr_model_trains(asr_records):
+  """BASELINE config #4: Conformer encoder (core/conformer_layer.ConformerLayer) + LAS
+  decoder through the regular AsrModel task."""
+  from lingvo_b200.models.asr import encoder as asr_encoder
+  inp = input_generator.AsrInput.Params().Set(
+      name='inp', file_pattern=asr_records, frame_size=8, bucket_upper_bound=[40],
+      bucket_batch_limit=[16], file_buffer_size=32, file_parallelism=1,
+      num_batcher_threads=2, target_max_length=16)
+  inp.tokenizer = tokenizers.AsciiTokenizer.Params()
+  p = asr_model.AsrModel.Params().Set(name='asr', input=inp)
+  p.encoder = asr_encoder.ConformerEncoder.Params().Set(
+      name='enc', input_shape=[None, None, 8, 1], conv_filter_shapes=[(3, 3, 1, 4)],
+      conv_filter_strides=[(2, 2)], model_dim=32, num_layers=2, num_heads=2, kernel_size=4,
+      dropout_prob=0.0)
+  dp = p.decoder
+  dp.source_dim = 32
+  dp.emb_dim = 8
+  dp.emb.vocab_size = 76
+  dp.emb.max_num_shards = 1
+  dp.rnn_cell_dim = 24
+  dp.rnn_layers = 2
+  dp.attention.hidden_dim = 16
+  dp.softmax.num_classes = 76
+  dp.target_seq_len = 14
+  dp.beam_search.num_hyps_per_beam = 2
+  p.train.optimizer = optimizer.Adam.Params()
+  p.train.learning_rate = 5e-3
+  p.train.lr_schedule = schedule.Constant.Params()
+  p.train.vn_std = 0.0
+  p.train.l2_regularizer_weight = None
+  task = p.Instantiate()
+  assert len(task.encoder.blocks) == 2
+  losses = []
+  for _ in range(50):
+    m, _ = task.TrainStep()
+    losses.append(float(m['log_pplx'][0].detach()))
+  assert min(losses[-5:]) < 0.75 * losses[0], (losses[0], losses[-5:])
+  out = task.Decode(task.input.GetPreprocessedInputBatch())
+  assert out.topk_ids.shape[0] > 0
+
+
+def test_registered_conformer_configs_instantiate():
+  from lingvo_b200 import model_registry
+  import lingvo_b200.models.asr.params.librispeech  # noqa: F401
+  from lingvo_b200.core import py_utils
+  cfg = model_registry.GetParams('asr.librispeech.Librispeech960ConformerWpm', 'Train')
+  enc = cfg.task.encoder
+  assert enc.num_layers == 17 and enc.model_dim == 512 and enc.num_heads == 8
+  with py_utils.StubVariablesScope('meta'):
+    task = cfg.task.Instantiate()
+  n = sum(v.numel() for v in task.encoder.vars.Flatten())
+  assert 1.0e8 < n < 1.4e8, n           # Conformer-L encoder ≈ 118 M parameters

@@ -59,7 +59,7 @@ def test_feature_extraction_forwarding():
   assert len(out) == 2 and out[1] is extra
 
 
-def _Worker(rank, world, port, q):
+def _Worker(rank, world, port, q, remat=False):
   os.environ['MASTER_ADDR'] = '127.0.0.1'
   os.environ['MASTER_PORT'] = str(port)
   dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -67,7 +67,7 @@ def _Worker(rank, world, port, q):
   torch.manual_seed(0)
   x = torch.randn(8, 8)
   layer = _Pipe(4).Instantiate()          # same seed → same weights on both ranks
-  eng = pp.PipelineEngine()
+  eng = pp.PipelineEngine(remat=remat)
   layer.AttachEngine(eng)
   out = layer.FProp(layer.theta, x)
   loss = out.pow(2).sum() if eng.is_last else None
@@ -79,11 +79,17 @@ def _Worker(rank, world, port, q):
   dist.destroy_process_group()
 
 
-def test_pipeline_engine_two_ranks_matches_single_process():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize('remat', [False, True])
+def test_pipeline_engine_two_ranks_matches_single_process(remat):
+  """GPipe over 2 ranks (overlapped isend/irecv links, tensor-header handshake) — with and
+  without rematerialisation — reproduces the single-process loss and gradients."""
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
-  port = 29600 + os.getpid() % 300
-  procs = [ctx.Process(target=_Worker, args=(r, 2, port, q)) for r in range(2)]
+  port = 29600 + (os.getpid() + 7 * int(remat)) % 300
+  procs = [ctx.Process(target=_Worker, args=(r, 2, port, q, remat)) for r in range(2)]
   for p in procs:
     p.start()
   res = [q.get(timeout=120) for _ in range(2)]
