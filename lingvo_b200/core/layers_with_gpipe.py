@@ -119,7 +119,8 @@ class GPipeTransformerEmbeddingLayer(base_layer.BaseLayer):
     t = ids.shape[0]
     x = self.children[side + '_token_emb'].EmbLookup(theta[side + '_token_emb'], ids.long())
     pos = self.children[side + '_pos_emb'].FProp(theta[side + '_pos_emb'], t).unsqueeze(1)
-    return self.src_dropout.FProp(theta.src_dropout, x * (p.model_dim ** 0.5) + pos.to(x.dtype))
+    return self.src_dropout.FProp(theta.src_dropout,
+                                  x * (p.model_dim ** 0.5) + pos.to(device=x.device, dtype=x.dtype))
 
   def FProp(self, theta, source_id, source_paddings, target_id=None, target_paddings=None,
             source_segment_id=None, target_segment_id=None, *args):
