@@ -52,13 +52,15 @@ class BeamSearchSharedParams(base_layer.BaseLayer):
     p.Define('target_eos_id', 2, 'EOS id.')
     p.Define('target_eoc_id', -1, 'End-of-chunk id (NT only).')
     p.Define('target_seq_len', 0, 'Max decode steps.')
-    p.Define('merge_paths', False, 'Kept for parity (RNN-T).')
-    p.Define('force_eos_in_top_k', False, 'Kept for parity.')
+    p.Define('merge_paths', False, 'Merge hyps equal up to epsilons (RNN-T / NT; needs '
+             'target_eoc_id).')
+    p.Define('force_eos_in_top_k', False, 'EOS is always a candidate of its hyp.')
     p.Define('force_last_chunk_eoc_in_top_k', False, 'Kept for parity.')
     p.Define('batch_major_state', True, 'States are [hyp, …].')
     p.Define('batch_major_compute', False, 'Kept for parity.')
     p.Define('short_seq_limit', 0, 'Kept for parity.')
-    p.Define('terminate_beams_independently', False, 'Kept for parity.')
+    p.Define('terminate_beams_independently', False,
+             'Finished beams become no-ops (always the case here).')
     return p
 
 
@@ -103,10 +105,11 @@ class BeamSearchHelper(BeamSearchSharedParams):
     state = bs_ops.init_state(b, k, max_steps, src_len, dev)
     step_ids = torch.full((n, 1), p.target_sos_id, dtype=torch.int64, device=dev)
     steps_run = 0
+    path_ids = torch.zeros(n, dtype=torch.int64, device=dev) if p.merge_paths else None
     for t in range(max_steps):
       results, other_states = pre_beam_search_step_callback(
           theta, encoder_outputs, step_ids, other_states, k, t)
-      state, all_done = bs_ops.beam_search_step(
+      step_out = bs_ops.beam_search_step(
           results.log_probs, results.get('atten_probs'), state, t,
           eos_id=p.target_eos_id, beam_size=p.beam_size, num_hyps_per_beam=k,
           valid_eos_max_logit_delta=p.valid_eos_max_logit_delta,
@@ -114,7 +117,14 @@ class BeamSearchHelper(BeamSearchSharedParams):
           ensure_full_beam=p.ensure_full_beam,
           force_eos_in_last_step=p.force_eos_in_last_step,
           is_last_step=(t == max_steps - 1),
-          allow_empty_terminated_hyp=p.allow_empty_terminated_hyp)
+          allow_empty_terminated_hyp=p.allow_empty_terminated_hyp,
+          force_eos_in_top_k=p.force_eos_in_top_k,
+          beam_independence=True, merge_paths=p.merge_paths, eoc_id=p.target_eoc_id,
+          path_ids=path_ids)
+      if p.merge_paths:
+        state, all_done, path_ids = step_out
+      else:
+        state, all_done = step_out
       steps_run = t + 1
       parent = state.prev_hyps[t]
       step_ids = state.hyps[t].reshape(n, 1)

@@ -16,7 +16,8 @@ Index convention (same as the reference, `…kernels.cc:336`): flat hyp index =
 Semantics kept from the reference:
   * candidate order: global score desc, then word id asc, then hyp id asc;
   * step 0 expands only hyp 0 of each beam;
-  * EOS terminates a hyp iff `global > best_in_hyp − valid_eos_max_logit_delta`
+  * EOS terminates a hyp iff it is among the hyp's own K best tokens (or
+    `force_eos_in_top_k`), `global > best_in_hyp − valid_eos_max_logit_delta`
     and `local > local_eos_threshold`;
   * a beam is done when no active hyp scores above
     `best_terminated − beam_size` (and, with `ensure_full_beam`, K hyps have
@@ -59,6 +60,32 @@ def init_state(num_beams, num_hyps_per_beam, max_steps, src_len, device,
       num_done=torch.zeros(num_beams, device=device, dtype=torch.int64))
 
 
+def _TopKRef(log_probs, cum, active, k, eos_id):
+  """Plain-PyTorch form of `beam_topk` (CPU path and numerics oracle of the kernel)."""
+  lp = log_probs.float()
+  glob = cum.unsqueeze(1) + lp
+  best_in_hyp = glob.max(1).values
+  eos_glob = glob[:, eos_id]
+  glob_no_eos = glob.clone()
+  glob_no_eos[:, eos_id] = NEG
+  glob_no_eos = torch.where(active.unsqueeze(1), glob_no_eos, torch.full_like(glob_no_eos, NEG))
+  # score desc, word id asc on ties: stable sort of the (ascending-id) row
+  order = torch.argsort(glob_no_eos, dim=1, descending=True, stable=True)[:, :k]
+  top_s = glob_no_eos.gather(1, order)
+  top_w = torch.where(top_s > NEG / 2, order, torch.zeros_like(order))
+  return top_s, top_w, best_in_hyp, eos_glob, lp[:, eos_id]
+
+
+def _TopK(log_probs, cum, active, k, eos_id):
+  """Fused score-add + EOS mask + per-hyp top-K (`csrc/beam_kernels.cu` on the GPU)."""
+  if log_probs.is_cuda and k <= 16 and log_probs.dtype in (torch.float32, torch.bfloat16):
+    from lingvo_b200 import ops  # pylint: disable=g-import-not-at-top
+    nat = ops.native(required=False)
+    if nat is not None and hasattr(nat, '_has_beam'):
+      return tuple(nat.beam_topk(log_probs.contiguous(), cum, active, int(k), int(eos_id)))
+  return _TopKRef(log_probs, cum, active, k, eos_id)
+
+
 def beam_search_step(log_probs, atten_probs, state: BeamState, cur_step: int,
                      eos_id: int, beam_size: float, num_hyps_per_beam: int,
                      valid_eos_max_logit_delta: float = 5.0,
@@ -66,18 +93,34 @@ def beam_search_step(log_probs, atten_probs, state: BeamState, cur_step: int,
                      ensure_full_beam: bool = False,
                      force_eos_in_last_step: bool = False,
                      is_last_step: bool = False,
-                     allow_empty_terminated_hyp: bool = True):
+                     allow_empty_terminated_hyp: bool = True,
+                     force_eos_in_top_k: bool = False,
+                     beam_independence: bool = True,
+                     merge_paths: bool = False,
+                     eoc_id: int = -1,
+                     path_ids: Optional[torch.Tensor] = None):
   """One step. log_probs `[num_hyps, V]`, atten_probs `[num_hyps, S]`.
 
-  Returns (new_state, all_done [scalar bool tensor]).
+  Options beyond the basics (reference `beam_search_step_op_kernels.cc:47-76,115,154`):
+    * `force_eos_in_top_k`: EOS is always a candidate of its hyp; otherwise (default) a hyp
+      can only terminate when EOS is among *its own* K best tokens. The
+      `valid_eos_max_logit_delta` / `local_eos_threshold` tests always apply.
+    * `beam_independence` (always honoured here): a finished beam's rows are frozen, the
+      step is a no-op for it, other beams continue.
+    * `merge_paths` (+ `eoc_id`, `path_ids`): for epsilon-emitting models (RNN-T / NT).
+      Surviving candidates of a beam whose label sequences are identical once epsilons
+      (`eoc_id`) are removed are merged: one survivor keeps the log-sum-exp of their
+      scores. `path_ids [num_hyps]` is an int64 hash of each row's epsilon-free prefix
+      (maintained by this function; pass the previous step's `state_path_ids`).
+
+  Returns (new_state, all_done [scalar bool tensor]) — and, with `merge_paths`,
+  (new_state, all_done, new_path_ids).
   """
   n, v = log_probs.shape
   k = num_hyps_per_beam
   b = n // k
   dev = log_probs.device
-  lp = log_probs.float()
   cum = state.cumulative_scores.float()
-  glob = cum.unsqueeze(1) + lp                                   # [n, V]
 
   # hyp (row) is active unless its beam is done; on step 0 only hyp_id 0 is live.
   beam_of = torch.arange(n, device=dev) % b
@@ -86,24 +129,21 @@ def beam_search_step(log_probs, atten_probs, state: BeamState, cur_step: int,
   if cur_step == 0:
     active = active & (hyp_id == 0)
 
+  # ---- fused: global scores, EOS column, per-hyp top-K --------------------------
+  kk = min(k, v - 1) if v > 1 else 1
+  top_s, top_w, best_in_hyp, eos_glob, eos_local = _TopK(log_probs, cum, active, kk, eos_id)
+  lp = log_probs
+
   # ---- EOS handling ----------------------------------------------------------
-  best_in_hyp = glob.max(1).values
-  eos_glob = glob[:, eos_id]
   eos_ok = (eos_glob > best_in_hyp - valid_eos_max_logit_delta) & (
-      lp[:, eos_id] > local_eos_threshold) & active
+      eos_local > local_eos_threshold) & active
+  if not force_eos_in_top_k:
+    # EOS must be one of the hyp's own K best tokens: at most K−1 others beat it
+    eos_ok = eos_ok & (eos_glob >= top_s[:, kk - 1])
   if not allow_empty_terminated_hyp and cur_step == 0:
     eos_ok = torch.zeros_like(eos_ok)
   if force_eos_in_last_step and is_last_step:
     eos_ok = active
-  # A terminated candidate still has to be among the beam's K best candidates.
-  glob_no_eos = glob.clone()
-  glob_no_eos[:, eos_id] = NEG
-  glob_no_eos = torch.where(active.unsqueeze(1), glob_no_eos,
-                            torch.full_like(glob_no_eos, NEG))
-
-  # ---- per-hyp top-(K) then per-beam top-K -------------------------------------
-  kk = min(k, v)
-  top_s, top_w = torch.topk(glob_no_eos, kk, dim=1)               # [n, kk]
   # regroup rows by beam: [b, k(hyp), kk]
   s_b = top_s.view(k, b, kk).permute(1, 0, 2).reshape(b, k * kk)
   w_b = top_w.view(k, b, kk).permute(1, 0, 2).reshape(b, k * kk)
@@ -116,9 +156,30 @@ def beam_search_step(log_probs, atten_probs, state: BeamState, cur_step: int,
   order = torch.argsort(s_b, dim=1, descending=True, stable=True)[:, :k]
   sel_s, sel_w, sel_h = s_b.gather(1, order), w_b.gather(1, order), h_b.gather(1, order)
 
-  # EOS candidates must beat the K-th surviving continuation to be recorded.
-  kth = sel_s[:, -1]                                              # [b]
-  eos_keep = eos_ok & ((eos_glob >= kth[beam_of]) | (kth[beam_of] <= NEG / 2))
+  new_path_ids = None
+  if merge_paths:
+    # Epsilon-free label hash of every surviving candidate: emitting `eoc_id` keeps the
+    # parent's hash, any other token extends it. Equal hashes inside a beam ⇒ same path:
+    # the best one absorbs the probability mass (log-sum-exp), duplicates are dropped.
+    assert path_ids is not None, 'merge_paths needs the previous path_ids'
+    par = (sel_h * b + torch.arange(b, device=dev).unsqueeze(1))
+    ph = path_ids[par]
+    ext = (ph * 1000003 + sel_w + 1) & 0x7FFFFFFFFFFFFFF
+    cand_hash = torch.where(sel_w == eoc_id, ph, ext)
+    same = (cand_hash.unsqueeze(2) == cand_hash.unsqueeze(1)) & (
+        sel_s.unsqueeze(2) > NEG / 2) & (sel_s.unsqueeze(1) > NEG / 2)
+    earlier = torch.tril(torch.ones(k, k, dtype=torch.bool, device=dev), -1)
+    dup = (same & earlier.unsqueeze(0)).any(2)                      # a better twin exists
+    merged = torch.logsumexp(
+        torch.where(same, sel_s.unsqueeze(1).expand(b, k, k), torch.full_like(same, NEG, dtype=sel_s.dtype)),
+        dim=2)
+    sel_s = torch.where(dup, torch.full_like(sel_s, NEG), torch.where(
+        sel_s > NEG / 2, merged, sel_s))
+    new_path_ids = cand_hash.t().reshape(-1)
+
+  # A hyp whose EOS candidate passed the tests above is moved off the beam and recorded
+  # as terminated (reference :281-293, :795-812) — it does not compete with continuations.
+  eos_keep = eos_ok
   done_row = torch.where(eos_keep, eos_glob, torch.full_like(eos_glob, NEG))
   done_scores = state.done_scores.clone()
   done_scores[cur_step] = done_row.to(done_scores.dtype)
@@ -137,7 +198,7 @@ def beam_search_step(log_probs, atten_probs, state: BeamState, cur_step: int,
   frozen = state.beam_done[beam_of]                                # done beams keep state
   keep_old = frozen | ~valid
   new_cum = torch.where(keep_old, torch.where(frozen, cum, torch.full_like(cum, NEG)), new_cum)
-  local = torch.where(valid, lp[parent, new_w], torch.zeros_like(new_cum))
+  local = torch.where(valid, lp[parent, new_w].float(), torch.zeros_like(new_cum))
   scores = state.scores.clone()
   hyps = state.hyps.clone()
   prev = state.prev_hyps.clone()
@@ -158,6 +219,10 @@ def beam_search_step(log_probs, atten_probs, state: BeamState, cur_step: int,
   new_state = BeamState(best_scores.to(state.best_scores.dtype),
                         new_cum.to(state.cumulative_scores.dtype), scores, hyps, prev,
                         done_scores, attn, beam_done, num_done)
+  del beam_independence
+  if merge_paths:
+    keep_ids = torch.where(valid & ~frozen, new_path_ids, path_ids)
+    return new_state, beam_done.all(), keep_ids
   return new_state, beam_done.all()
 
 

@@ -124,3 +124,50 @@ def test_merge_outputs():
                                        post_beam_search_step_callback=post)
   m = beam_search_helper.MergeBeamSearchOutputs(3, [o, o])
   assert m.topk_hyps.ids.shape[:2] == (1, 3)
+
+
+# ---- round 2: option surface of the reference op (force_eos_in_top_k, merge_paths) ----
+def _OneStep(log_probs, k, **kw):
+  from lingvo_b200.ops import beam_search as bs
+  n = log_probs.shape[0]
+  st = bs.init_state(n // k, k, 4, 1, log_probs.device)
+  return bs.beam_search_step(log_probs, None, st, 0, eos_id=2, beam_size=3.0,
+                             num_hyps_per_beam=k, **kw)
+
+
+def test_force_eos_in_top_k_controls_whether_low_ranked_eos_may_terminate():
+  import torch
+  from lingvo_b200.ops import beam_search as bs
+  k, v = 2, 8
+  lp = torch.full((k, v), -9.0)
+  lp[:, 5], lp[:, 6], lp[:, 2] = -0.5, -1.0, -2.0          # EOS (id 2) is only third best
+  lp = torch.log_softmax(lp, -1)
+  st, _ = _OneStep(lp, k, valid_eos_max_logit_delta=10.0)
+  assert float(st.done_scores[0].max()) < bs.NEG / 2        # not in the hyp's top-2 ⇒ no EOS
+  st2, _ = _OneStep(lp, k, valid_eos_max_logit_delta=10.0, force_eos_in_top_k=True)
+  assert float(st2.done_scores[0].max()) > bs.NEG / 2       # forced into the candidate set
+  assert st2.hyps[0].tolist() == st.hyps[0].tolist() == [5, 6]
+
+
+def test_merge_paths_combines_candidates_that_differ_only_by_epsilons():
+  import torch
+  from lingvo_b200.ops import beam_search as bs
+  k, v, eoc = 3, 6, 1
+  n = k                                     # one beam
+  st = bs.init_state(1, k, 4, 1, 'cpu')
+  # after step 0 force three live hyps with distinct histories: h0 = [4], h1 = [eps], h2 = [5]
+  st = st._replace(cumulative_scores=torch.tensor([-1.0, -1.2, -3.0]))
+  path_ids = torch.tensor([(0 * 1000003 + 4 + 1), 0, (0 * 1000003 + 5 + 1)], dtype=torch.int64)
+  lp = torch.full((n, v), -20.0)
+  lp[0, eoc] = -0.1          # h0 emits epsilon   → path [4]
+  lp[1, 4] = -0.2            # h1 emits 4         → path [4]  (same label sequence)
+  lp[2, 3] = -0.3            # h2 emits 3         → path [5, 3]
+  new, _, new_ids = bs.beam_search_step(lp, None, st, 1, eos_id=2, beam_size=100.0,
+                                        num_hyps_per_beam=k, merge_paths=True, eoc_id=eoc,
+                                        path_ids=path_ids)
+  cum = new.cumulative_scores
+  live = cum > bs.NEG / 2
+  assert int(live.sum()) == 2                                  # the duplicate path is gone
+  want = torch.logsumexp(torch.tensor([-1.0 - 0.1, -1.2 - 0.2]), 0)
+  assert abs(float(cum[live].max()) - float(want)) < 1e-5     # mass of both alignments
+  assert len(set(new_ids[live].tolist())) == 2

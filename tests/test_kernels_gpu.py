@@ -478,3 +478,24 @@ def test_flash_attention_reference_quirk_positions_are_not_assumed_causal():
   out = A.flash_attention(q, k, v, None, seg, pos, 1.0, True)
   ref = A.flash_attention_ref(q, k, v, None, seg, pos, 1.0, True)
   assert _rel(out, ref) < 2e-2
+
+
+@pytest.mark.parametrize('k,v,dtype', [(4, 1000, torch.float32), (8, 32000, torch.float32),
+                                       (3, 4099, torch.bfloat16), (16, 515, torch.float32)])
+def test_beam_topk_kernel_matches_torch_oracle(k, v, dtype):
+  """K13: fused score-add + EOS mask + per-hyp top-K vs the plain PyTorch formulation,
+  including the (score desc, word id asc) tie order."""
+  from lingvo_b200.ops import beam_search as bs
+  torch.manual_seed(k + v)
+  n = 24
+  lp = torch.log_softmax(torch.randn(n, v, device='cuda') * 3, -1)
+  lp[:, 7] = lp[:, 11]                                   # exact ties
+  lp = lp.to(dtype)
+  cum = torch.randn(n, device='cuda')
+  active = torch.rand(n, device='cuda') > 0.2
+  got = bs._TopK(lp, cum, active, k, 2)
+  want = bs._TopKRef(lp, cum, active, k, 2)
+  torch.testing.assert_close(got[0], want[0])
+  assert torch.equal(got[1], want[1])
+  for a, b in zip(got[2:], want[2:]):
+    torch.testing.assert_close(a, b)
