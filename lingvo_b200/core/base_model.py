@@ -51,6 +51,24 @@ def _VarByName(layer) -> Dict[str, Tuple[base_layer.BaseLayer, str, torch.nn.Par
   return out
 
 
+def DecodeOutAsTensors(dec_out):
+  """Decode outputs reach `PostProcessDecodeOut` either as device/CPU tensors (direct
+  calls) or as the host numpy dict the runners / programs hand over: normalise to a
+  NestedMap of CPU tensors so task code can use tensor ops in both cases."""
+  def conv(x):
+    if isinstance(x, np.ndarray) and x.dtype.kind not in 'OUS':
+      return torch.from_numpy(np.ascontiguousarray(x))
+    if isinstance(x, torch.Tensor):
+      return x.detach().cpu()
+    if isinstance(x, (tuple, list)):
+      return type(x)(conv(v) for v in x)
+    return x
+  out = NestedMap()
+  for k, v in dict(dec_out).items():
+    out[k] = conv(v)
+  return out
+
+
 class BaseTask(base_layer.BaseLayer):
   """A single task: one input generator, learners, metrics."""
 

@@ -276,9 +276,6 @@ class DecodeProgram(BaseProgram):
     return False
 
 
-ExperimentalDecodeProgram = DecodeProgram
-
-
 class MultiInputsDecodeProgram(DecodeProgram):
   """Decodes several datasets with one model (reference :1807)."""
 
@@ -289,8 +286,131 @@ class MultiInputsDecodeProgram(DecodeProgram):
     return p
 
 
-class MLPerfTrainDecodeProgram(TrainProgram):
-  """Train + in-loop decode used by MLPerf configs (reference :2037)."""
+class HostDrivenTrainProgram(TrainProgram):
+  """Train program whose loop is driven step by step from the host (reference :771
+  `HostDrivenTrainProgram`): no on-device loop / CUDA-graph replay — every step is an
+  eager `TrainStep`, metrics reach the host every `metrics_every_n` steps and per-step
+  callbacks may inspect or alter the model in between (debugging, curriculum, custom
+  hooks)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('metrics_every_n', 1, 'Fetch metrics to the host every n steps.')
+    return p
+
+  def __init__(self, params, **kwargs):
+    super().__init__(params, **kwargs)
+    self._program_name = 'HostDrivenTrainProgram'
+    self._step_callbacks = []
+
+  def AddStepCallback(self, fn):
+    """fn(global_step, metrics_dict_or_None) called after every step."""
+    self._step_callbacks.append(fn)
+
+  @property
+  def engine(self):
+    if getattr(self, '_engine', None) is None:
+      from lingvo_b200.core import train_engine  # pylint: disable=g-import-not-at-top
+      with self._cluster:
+        self._engine = train_engine.TrainEngine(self._task, use_cuda_graph='off')
+    return self._engine
+
+  def Run(self, sess=None, threadpool=None) -> bool:
+    p = self.params
+    task = self._task
+    acc = metrics_lib.DeviceEvalMetrics()
+    with self._cluster:
+      engine = self.engine
+      for i in range(p.steps_per_loop):
+        m, _ = engine.Step()
+        acc.Update(dict(m))
+        host = None
+        if (i + 1) % max(p.metrics_every_n, 1) == 0:
+          host = {k: float(v[0]) for k, v in m.items()}
+        for fn in self._step_callbacks:
+          fn(task.global_step, host)
+    results = acc.Finalize()
+    step = task.global_step
+    self.global_step = int(step)
+    vals = {k: v for k, (v, _) in results.items()}
+    self._WriteSummaries(os.path.basename(self._program_dir), step, vals)
+    return step >= task.params.train.max_steps
+
+
+class ExperimentalDecodeProgram(DecodeProgram):
+  """Decode program that overlaps device decoding with host post-processing (reference
+  :1807): batch i+1 is decoded on the device while a worker thread runs
+  `PostProcessDecodeOut` (detokenisation, BLEU/WER bookkeeping) on batch i."""
+
+  def __init__(self, params, **kwargs):
+    super().__init__(params, **kwargs)
+    self._program_name = 'ExperimentalDecodeProgram'
+
+  def Run(self, sess=None, threadpool=None) -> bool:
+    import queue  # pylint: disable=g-import-not-at-top
+    import threading  # pylint: disable=g-import-not-at-top
+    p = self.params
+    task = self._task
+    step = int(py_utils.GetGlobalStep())
+    if self._cache.TryLoadCache(str(step)):
+      logging.info('Decode of step %d already done; skipping.', step)
+      return False
+    task.input.Reset()
+    dec_metrics = task.CreateDecoderMetrics()
+    buffered = []
+    q = queue.Queue(maxsize=4)
+    err = []
+
+    def worker():
+      while True:
+        host = q.get()
+        if host is None:
+          return
+        try:
+          post = task.PostProcessDecodeOut(host, dec_metrics)
+          if post:
+            buffered.extend(post)
+        except BaseException as e:  # pylint: disable=broad-except
+          err.append(e)
+
+    th = threading.Thread(target=worker, name='decode_postprocess', daemon=True)
+    th.start()
+    steps = 0
+    start = time.time()
+    with self._cluster:
+      while (p.steps_per_loop < 0 or steps < p.steps_per_loop) and not err:
+        try:
+          out = self._model.ConstructDecodeGraph(self._task_name)
+        except StopIteration:
+          break
+        # async D2H: the copy of batch i overlaps the device decode of batch i+1
+        host = {k: (v.detach().to('cpu', non_blocking=True) if isinstance(v, torch.Tensor)
+                    else v) for k, v in out.items()}
+        if torch.cuda.is_available():
+          torch.cuda.current_stream().synchronize()
+        q.put({k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in host.items()})
+        steps += 1
+    q.put(None)
+    th.join()
+    if err:
+      raise err[0]
+    vals = {k: m.value for k, m in dec_metrics.items()}
+    self.last_metrics = dict(vals)
+    vals['decode_secs'] = time.time() - start
+    self._WriteSummaries(os.path.basename(self._program_dir), step, vals)
+    out_path = os.path.join(self._program_dir, 'decoder_out_%09d' % step)
+    with open(out_path, 'wb') as f:
+      pickle.dump(buffered, f, protocol=pickle.HIGHEST_PROTOCOL)
+    task.DecodeFinalize(base_model.DecodeFinalizeArgs(out_path, buffered))
+    self._cache.UpdateCkpt(str(step))
+    return False
+
+
+class MLPerfTrainDecodeProgram(BaseProgram):
+  """One program that alternates `train_steps_per_loop` train steps with
+  `decode_steps_per_loop` decode batches on the *same* variables (reference :2037), so an
+  MLPerf run needs no checkpoint round-trip between training and scoring."""
 
   @classmethod
   def Params(cls):
@@ -302,6 +422,40 @@ class MLPerfTrainDecodeProgram(TrainProgram):
     p.Define('train_steps_per_loop', 0, 'Train steps per loop.')
     p.Define('decode_steps_per_loop', 0, 'Decode steps per loop.')
     return p
+
+  def __init__(self, params, **kwargs):
+    super().__init__(params, **kwargs)
+    self._program_name = 'MLPerfTrainDecodeProgram'
+    p = self.params
+    tp = TrainProgram.Params().Set(
+        name='train', task=p.train_task, logdir=p.logdir, task_name=p.task_name,
+        dataset_name=p.train_dataset_name, steps_per_loop=p.train_steps_per_loop)
+    dp = DecodeProgram.Params().Set(
+        name='decode', task=p.decode_task, logdir=p.logdir, task_name=p.task_name,
+        dataset_name=p.decode_dataset_name, steps_per_loop=p.decode_steps_per_loop)
+    self._train = tp.Instantiate(shared_model=kwargs.get('shared_model'))
+    self._decode = dp.Instantiate()
+
+  def BuildTpuSubgraph(self):
+    model = self._train.BuildTpuSubgraph()
+    self._decode.BuildTpuSubgraph()
+    self._decode.ShareVariablesFrom(model)
+    self._model = model
+    return model
+
+  @property
+  def last_metrics(self):
+    return getattr(self._decode, 'last_metrics', None)
+
+  def Run(self, sess=None, threadpool=None) -> bool:
+    done = self._train.Run(sess)
+    self.global_step = self._train.global_step
+    self._decode.Run(sess, threadpool)
+    return done
+
+  def Shutdown(self):
+    self._train.Shutdown()
+    self._decode.Shutdown()
 
 
 class InputBenchmark(BaseProgram):
@@ -469,8 +623,85 @@ class SimpleProgramSchedule:
     for prog in self._programs:
       prog.Shutdown()
 
+  # -- program state (reference `SaveProgramState` :545): what a resumed executor needs
+  #    besides the model checkpoint — trigger counters and decode bookkeeping.
+  def SaveProgramState(self, path: str):
+    import json  # pylint: disable=g-import-not-at-top
+    state = {'triggers': {}, 'programs': [type(pr).__name__ for pr in self._programs]}
+    for prog in self.eval_programs:
+      trig = self._triggers.get(id(prog))
+      if trig is not None:
+        state['triggers'][prog.params.dataset_name] = trig.State()
+    tmp = path + '.tmp'
+    with open(tmp, 'w') as f:
+      json.dump(state, f)
+    os.replace(tmp, path)
+
+  def LoadProgramState(self, path: str) -> bool:
+    import json  # pylint: disable=g-import-not-at-top
+    if not os.path.exists(path):
+      return False
+    with open(path) as f:
+      state = json.load(f)
+    for prog in self.eval_programs:
+      trig = self._triggers.get(id(prog))
+      st = state.get('triggers', {}).get(prog.params.dataset_name)
+      if trig is not None and st is not None:
+        trig.SetState(st)
+    return True
+
 
 MLPerfProgramSchedule = SimpleProgramSchedule
+
+
+class MultiTaskProgramSchedule:
+  """One `SimpleProgramSchedule` per task of a multi-task model (reference :2319): the
+  executor samples a task per loop (`task_scheduler`), runs that task's schedule, and all
+  tasks train the shared variables of one `MultiTaskModel`."""
+
+  @classmethod
+  def Params(cls):
+    p = hyperparams.InstantiableParams(cls)
+    p.Define('program_schedule_dict', None, 'task name → SimpleProgramSchedule params.')
+    p.Define('logdir', None, 'Log directory.')
+    return p
+
+  def __init__(self, params, shared_model=None, **kwargs):
+    self.params = params.Copy()
+    p = self.params
+    assert p.program_schedule_dict
+    self.schedules = {}
+    self._programs = []
+    self.train_program = None
+    self.eval_programs = []
+    for name in sorted(p.program_schedule_dict):
+      sp = p.program_schedule_dict[name].Copy()
+      sp.logdir = p.logdir
+      sp.task_name = sp.task_name or name
+      sched = sp.Instantiate(shared_model=shared_model, **kwargs)
+      self.schedules[name] = sched
+      self._programs.extend(sched.Programs())
+      self.eval_programs.extend(sched.eval_programs)
+      if self.train_program is None:
+        self.train_program = sched.train_program
+    self.steps_run = {name: 0 for name in self.schedules}
+
+  def Programs(self):
+    return self._programs
+
+  def Run(self, task_name=None, sess=None, threadpool=None):
+    """Runs the schedule of `task_name` (all tasks round-robin when None)."""
+    names = [task_name] if task_name is not None else sorted(self.schedules)
+    done, train_s, eval_s = False, 0.0, 0.0
+    for name in names:
+      d, t, e = self.schedules[name].Run(sess, threadpool)
+      self.steps_run[name] += 1
+      done, train_s, eval_s = done or d, train_s + t, eval_s + e
+    return done, train_s, eval_s
+
+  def Shutdown(self):
+    for s in self.schedules.values():
+      s.Shutdown()
 
 
 def MlPerfParams():

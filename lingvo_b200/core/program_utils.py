@@ -44,6 +44,12 @@ class TriggerScheduler:
       return False
     return (self.count - self.offset) % self.interval == 0
 
+  def State(self) -> Dict[str, int]:
+    return {'offset': self.offset, 'interval': self.interval, 'count': self.count}
+
+  def SetState(self, state: Dict[str, int]):
+    self.count = int(state.get('count', 0))
+
 
 def SummaryToCsv(summaries: Dict[str, float]) -> str:
   return '\n'.join('%s,%s' % (k, v) for k, v in sorted(summaries.items()))

@@ -128,6 +128,7 @@ class ExecutorTpu(base_runner.BaseRunner):
   def _Loop(self):
     with self._cluster:
       self._checkpointer.Restore()
+      self._LoadProgramState()
       # Engines attach data parallelism (rank 0's variables win) after the restore.
       for sched in self._program_schedule_dict.values():
         if sched.train_program is not None:
@@ -148,11 +149,28 @@ class ExecutorTpu(base_runner.BaseRunner):
         logging.info('executor: train %.2fs eval %.2fs', train_s, eval_s)
         self._ExportMetrics(train_time=train_s, eval_time=eval_s,
                             global_step=self._GlobalStep())
+        self._SaveProgramState()
         if done:
           break
       self._checkpointer.Save(gsteps=self._GlobalStep(), sync=True)
       for sched in self._program_schedule_dict.values():
         sched.Shutdown()
+
+  def _SaveProgramState(self):
+    """Trigger counters etc. next to the checkpoints (reference `RunSave` :473)."""
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
+      return
+    for name, sched in self._program_schedule_dict.items():
+      if hasattr(sched, 'SaveProgramState'):
+        sched.SaveProgramState(os.path.join(
+            self._train_dir, 'program_state%s.json' % (('_' + name) if name else '')))
+
+  def _LoadProgramState(self):
+    for name, sched in self._program_schedule_dict.items():
+      if hasattr(sched, 'LoadProgramState'):
+        sched.LoadProgramState(os.path.join(
+            self._train_dir, 'program_state%s.json' % (('_' + name) if name else '')))
 
   def _ExportMetrics(self, **kwargs):
     self._cluster.ExportMetrics(**kwargs)

@@ -79,6 +79,7 @@ class AsrModel(base_model.BaseTask):
             'oracle_norm_wer': metrics_lib.AverageMetric()}
 
   def PostProcessDecodeOut(self, dec_out, dec_metrics):
+    dec_out = base_model.DecodeOutAsTensors(dec_out)
     gen = self.input_generator
     tgt_lens = (1.0 - dec_out.target_paddings.float()).sum(1).long()
     refs = gen.IdsToStrings(dec_out.target_labels, (tgt_lens - 1).clamp_min(0))

@@ -102,6 +102,7 @@ class MTBaseModel(base_model.BaseTask):
             'corpus_bleu': CorpusBleuMetric()}
 
   def PostProcessDecodeOut(self, dec_out, dec_metrics):
+    dec_out = base_model.DecodeOutAsTensors(dec_out)
     gen = self.input_generator
     tgt_lens = (1.0 - dec_out.target_paddings.float()).sum(1).long()
     refs = gen.IdsToStrings(dec_out.target_labels, (tgt_lens - 1).clamp_min(0))

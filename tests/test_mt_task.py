@@ -101,3 +101,37 @@ def test_rnmt_trains(records):
   assert min(losses[-5:]) < losses[0] - 0.2, (losses[0], losses[-5:])
   out = task.Decode(task.input.GetPreprocessedInputBatch())
   assert out.topk_scores.shape[1] == 2
+
+
+def test_experimental_decode_program_overlaps_postprocessing(records, tmp_path):
+  """`ExperimentalDecodeProgram` (reference program.py:1807): device decode of batch i+1
+  overlaps host post-processing of batch i; same artefacts as `DecodeProgram`."""
+  import os
+  import pickle
+  from lingvo_b200.core import base_model
+  from lingvo_b200.core import program
+  task_p = base_config.SetupTransformerParams(
+      mt_model.TransformerModel.Params(), name='mt', vocab_size=VOCAB, model_dim=16,
+      hidden_dim=32, num_heads=2, num_layers=1, learning_rate=1e-3, warmup_steps=1,
+      residual_dropout_prob=0.0, label_smoothing_uncertainty=0.0)
+  task_p.input = _Input(records)
+  task_p.decoder.target_seq_len = 6
+  task_p.decoder.beam_search.num_hyps_per_beam = 2
+  task_p.decoder.beam_search.sync_every = 1
+  cfg = base_model.SingleTaskModel.Params(task_p)
+  outs = {}
+  for cls in (program.DecodeProgram, program.ExperimentalDecodeProgram):
+    logdir = str(tmp_path / cls.__name__)
+    pp = cls.Params().Set(name='decode', task=cfg, logdir=logdir, dataset_name='Test',
+                          steps_per_loop=3)
+    prog = pp.Instantiate()
+    prog.BuildTpuSubgraph()
+    assert prog.Run() is False
+    files = [f for f in os.listdir(prog._program_dir) if f.startswith('decoder_out_')]
+    assert len(files) == 1
+    with open(os.path.join(prog._program_dir, files[0]), 'rb') as f:
+      outs[cls.__name__] = pickle.load(f)
+    assert 'corpus_bleu' in prog.last_metrics
+    # second run on the same step is skipped through the decode-status cache
+    assert prog.Run() is False
+  assert len(outs['DecodeProgram']) == len(outs['ExperimentalDecodeProgram']) > 0
