@@ -436,6 +436,7 @@ class ProjectionLayer(quant_utils.QuantizableLayer):
     assert p.name
     assert p.input_dim > 0 and p.output_dim > 0
     assert activations.IsSupported(p.activation)
+    self.TrackQActs(self.output_qt_name)
     if p.batch_norm:
       bn = p.bn_params.Copy()
       bn.name = p.name + '_bn'

@@ -28,7 +28,7 @@ class SampleQuantizedProjectionLayer(quant_utils.QuantizableLayer):
 
   def __init__(self, params):
     super().__init__(params)
-    self.TrackQTensor('inputs', 'transformed')
+    self.TrackQActs('inputs', 'transformed')
 
   def _CreateLayerVariables(self):
     super()._CreateLayerVariables()
@@ -39,7 +39,7 @@ class SampleQuantizedProjectionLayer(quant_utils.QuantizableLayer):
   def FProp(self, theta, inputs, paddings):
     p = self.params
     w = self.QWeight(theta.w)
-    inputs = self.QTensorMulti('inputs', inputs)[0] if False else self.QAct('inputs', inputs)
+    inputs = self.QAct('inputs', inputs)
     out = self.QMatmul(inputs.reshape(-1, p.input_dim), w)
     out = self.QAct('transformed', out)
     if p.activation == 'TANH':

@@ -69,3 +69,12 @@ def ReplaceGoldenSingleFloat(old, float_value):
 
 def main(*args, **kwargs):  # pylint: disable=invalid-name
   unittest.main(*args, **kwargs)
+
+
+def FreePort() -> int:
+  """A TCP port that is free right now on 127.0.0.1 (for multi-process rendezvous in tests;
+  asking the kernel avoids collisions between parallel pytest-xdist workers)."""
+  import socket
+  with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+    s.bind(('127.0.0.1', 0))
+    return int(s.getsockname()[1])

@@ -11,6 +11,8 @@ import tempfile
 
 import numpy as np
 import torch
+
+from lingvo_b200.core import test_utils
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -60,7 +62,7 @@ def _Worker(rank, world, port, logdir, phase, q):
 def _RunPhase(world, logdir, phase):
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
-  port = 29300 + (os.getpid() + 17 * phase) % 500
+  port = test_utils.FreePort()
   procs = [ctx.Process(target=_Worker, args=(r, world, port, logdir, phase, q))
            for r in range(world)]
   for p in procs:

@@ -5,6 +5,8 @@ import sys
 
 import pytest
 import torch
+
+from lingvo_b200.core import test_utils
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -88,7 +90,7 @@ def test_pipeline_engine_two_ranks_matches_single_process(remat):
   without rematerialisation — reproduces the single-process loss and gradients."""
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
-  port = 29600 + (os.getpid() + 7 * int(remat)) % 300
+  port = test_utils.FreePort()
   procs = [ctx.Process(target=_Worker, args=(r, 2, port, q, remat)) for r in range(2)]
   for p in procs:
     p.start()
@@ -138,7 +140,7 @@ def _EpNormWorker(rank, world, port, q):
 def test_global_grad_norm_sums_expert_parallel_grads_over_ranks():
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
-  port = 29900 + os.getpid() % 90
+  port = test_utils.FreePort()
   procs = [ctx.Process(target=_EpNormWorker, args=(r, 2, port, q)) for r in range(2)]
   for p in procs:
     p.start()
@@ -175,7 +177,7 @@ def test_context_parallel_attention_matches_single_device():
   from lingvo_b200.parallel import cp
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
-  port = 29750 + os.getpid() % 100
+  port = test_utils.FreePort()
   procs = [ctx.Process(target=_CpWorker, args=(r, 2, port, q)) for r in range(2)]
   for p in procs:
     p.start()

@@ -6,6 +6,8 @@ import os
 
 import pytest
 import torch
+
+from lingvo_b200.core import test_utils
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -78,7 +80,7 @@ def _Worker(rank, world, port, q):
 def test_gpipe_mt_task_two_ranks_match_single_process():
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
-  port = 29450 + os.getpid() % 400
+  port = test_utils.FreePort()
   procs = [ctx.Process(target=_Worker, args=(r, 2, port, q)) for r in range(2)]
   for p in procs:
     p.start()

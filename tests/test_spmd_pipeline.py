@@ -5,6 +5,8 @@ import os
 
 import pytest
 import torch
+
+from lingvo_b200.core import test_utils
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -79,7 +81,7 @@ def test_rank_sharded_pipeline_matches_local(rep, nmb):
   world = 2
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
-  port = 29100 + (os.getpid() * 3 + rep) % 700
+  port = test_utils.FreePort()
   procs = [ctx.Process(target=_Worker, args=(r, world, port, rep, nmb, q))
            for r in range(world)]
   for pr in procs:

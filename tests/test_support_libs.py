@@ -23,7 +23,7 @@ class QuantLibTest(quant_test_lib.QuantUtilsBaseTest):
     q = p.Copy()
     q.qdomain.default = quant_utils.SymmetricScheduledClipQDomain.Params().Set(
         cc_schedule=quant_utils.FakeQuantizationSchedule.Params().Set(
-            clip_start_step=0, clip_end_step=1, quant_start_step=0, start_cap=1.0, end_cap=1.0))
+            clip_start_step=0, clip_end_step=1, quant_start_step=1, start_cap=1.0, end_cap=1.0))
     with cluster_factory.SetEval(True):
       self._testLayerHelper('quant', q, not_expected=plain, global_step=10)
 
