@@ -78,3 +78,30 @@ def FreePort() -> int:
   with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
     s.bind(('127.0.0.1', 0))
     return int(s.getsockname()[1])
+
+
+def ToNumpyTree(x):
+  """Tensors → numpy arrays, recursively through tuples/lists/dicts. Multi-process tests
+  send results through `mp.Queue` as numpy: a torch tensor travels as a shared-memory
+  handle that dies with the producer process, numpy arrays are pickled by value."""
+  import torch
+  if isinstance(x, torch.Tensor):
+    return x.detach().cpu().numpy()
+  if isinstance(x, dict):
+    return {k: ToNumpyTree(v) for k, v in x.items()}
+  if isinstance(x, (list, tuple)):
+    return type(x)(ToNumpyTree(v) for v in x)
+  return x
+
+
+def ToTorchTree(x):
+  """Inverse of `ToNumpyTree`."""
+  import numpy as np
+  import torch
+  if isinstance(x, np.ndarray):
+    return torch.from_numpy(x)
+  if isinstance(x, dict):
+    return {k: ToTorchTree(v) for k, v in x.items()}
+  if isinstance(x, (list, tuple)):
+    return type(x)(ToTorchTree(v) for v in x)
+  return x

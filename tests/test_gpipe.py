@@ -76,7 +76,7 @@ def _Worker(rank, world, port, q, remat=False):
   eng.Backward(loss)
   grads = {v.var_name: (v.grad.clone() if v.grad is not None else None)
            for v in layer.vars.Flatten()}
-  q.put((rank, float(loss) if loss is not None else None, grads))
+  q.put(test_utils.ToNumpyTree((rank, float(loss) if loss is not None else None, grads)))
   dist.barrier()
   dist.destroy_process_group()
 
@@ -94,7 +94,7 @@ def test_pipeline_engine_two_ranks_matches_single_process(remat):
   procs = [ctx.Process(target=_Worker, args=(r, 2, port, q, remat)) for r in range(2)]
   for p in procs:
     p.start()
-  res = [q.get(timeout=120) for _ in range(2)]
+  res = [test_utils.ToTorchTree(q.get(timeout=120)) for _ in range(2)]
   for p in procs:
     p.join(timeout=60)
   res = {r[0]: r for r in res}
@@ -168,7 +168,7 @@ def _CpWorker(rank, world, port, q):
   dy = torch.randn(b, l, h, d)
   valid = cp.ShardSequence((seg != 0).reshape(b, l, 1, 1).float(), 1)
   (out * valid).backward(cp.ShardSequence(dy, 1))
-  q.put((rank, out.detach(), [t.grad.clone() for t in loc]))
+  q.put(test_utils.ToNumpyTree((rank, out.detach(), [t.grad.clone() for t in loc])))
   dist.barrier()
   dist.destroy_process_group()
 
@@ -181,7 +181,7 @@ def test_context_parallel_attention_matches_single_device():
   procs = [ctx.Process(target=_CpWorker, args=(r, 2, port, q)) for r in range(2)]
   for p in procs:
     p.start()
-  res = {r[0]: r for r in (q.get(timeout=120) for _ in range(2))}
+  res = {r[0]: r for r in (test_utils.ToTorchTree(q.get(timeout=120)) for _ in range(2))}
   for p in procs:
     p.join(timeout=60)
   torch.manual_seed(0)

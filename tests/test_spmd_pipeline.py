@@ -70,8 +70,8 @@ def _Worker(rank, world, port, rep, nmb, q):
   y = layer.FPropDefaultTheta(x)
   (y * torch.arange(8.0)).sum().backward()
   grads = {v.var_name: v.grad.clone() for v in layer.vars.Flatten()}
-  q.put((rank, y.detach(), x.grad.clone() if rank == 0 else None, grads,
-         sorted(layer._owned)))
+  q.put(test_utils.ToNumpyTree((rank, y.detach(), x.grad.clone() if rank == 0 else None, grads,
+                                sorted(layer._owned))))
   dist.barrier()
   dist.destroy_process_group()
 
@@ -86,7 +86,7 @@ def test_rank_sharded_pipeline_matches_local(rep, nmb):
            for r in range(world)]
   for pr in procs:
     pr.start()
-  res = {r[0]: r for r in [q.get(timeout=180) for _ in range(world)]}
+  res = {r[0]: r for r in [test_utils.ToTorchTree(q.get(timeout=180)) for _ in range(world)]}
   for pr in procs:
     pr.join(timeout=60)
   # oracle: everything in one process (same name-seeded weights)
