@@ -5,13 +5,16 @@
   state = step.ZeroState(theta, prepared, batch_size)
   for t: out, state = step.FProp(theta, prepared, step_inputs_t, padding_t, state)
 
-`StatelessLayerStep` (ref :240) adapts any layer, `StackStep` (ref :300) chains
-steps with optional residuals, `ParallelStep` (ref :420) runs steps side by side,
-`IteratorStep` (ref :560) feeds a pre-computed sequence one frame per call,
-`RecurrentStepWrapper` (ref :620) runs a step over a whole sequence.
+`StatelessLayerStep` (ref :168) adapts any layer, `StackStep` (ref :212) chains
+steps with optional residuals, `ParallelStep` (ref :341) runs steps side by side,
+`GraphStep` (ref :404) wires sub-steps into a data-flow graph with string signatures,
+`IteratorStep` (ref :572) feeds a pre-computed sequence one frame per call,
+`RecurrentStepWrapper` (ref :660) runs a step over a whole sequence.
 """
 
 from __future__ import annotations
+
+import collections
 
 import torch
 
@@ -64,6 +67,11 @@ class Step(base_layer.BaseLayer):
     """→ (output NestedMap(output=…), state1)."""
     raise NotImplementedError(type(self))
 
+  def StatelessInference(self, theta, prepared_inputs, step_inputs, padding):
+    """Like FProp, but `step_inputs` carries everything the step needs (no recurrent
+    state); returns only the outputs (ref :143)."""
+    raise NotImplementedError(type(self))
+
 
 class StatelessLayerStep(Step):
   """Wraps a stateless layer: output = layer.FProp(*step_inputs.inputs) (ref :240)."""
@@ -79,21 +87,36 @@ class StatelessLayerStep(Step):
     self.CreateChild('layer', self.params.layer)
 
   def FProp(self, theta, prepared_inputs, step_inputs, padding, state0):
+    del prepared_inputs, state0
     args = {k: v for k, v in step_inputs.items() if k != 'inputs'}
-    out = self.layer.FProp(theta.layer, *step_inputs.inputs, **args)
-    return NestedMap(output=out), state0
+    ins = step_inputs.inputs
+    ins = list(ins) if isinstance(ins, (list, tuple)) else [ins]
+    out = self.layer.FProp(theta.layer, *ins, **args)
+    return (out if isinstance(out, NestedMap) and 'output' in out else NestedMap(output=out),
+            NestedMap())
+
+  def StatelessInference(self, theta, prepared_inputs, step_inputs, padding):
+    return self.FProp(theta, prepared_inputs, step_inputs, padding, NestedMap())[0]
 
 
 class StackStep(Step):
-  """Feeds each sub-step's output to the next; optional residual connections
-  starting at `residual_start` every `residual_stride` layers (ref :300)."""
+  """A stack of steps (ref :212). Each sub-step takes `NestedMap(inputs=[…])` and returns
+  `NestedMap(output=tensor)`; the output of layer n-1 is the input of layer n.
+
+  Three ways to feed the stack: `step_inputs.inputs` reach only the lowest layer,
+  `step_inputs.context` (optional) is appended to every layer's inputs, and the prepared
+  external inputs are visible to every layer and constant over time.
+
+  Residuals: for i >= residual_start >= 0,
+    output[i] = output[i - residual_stride] + sub[i](output[i - 1]),   output[-1] = input.
+  """
 
   @classmethod
   def Params(cls):
     p = super().Params()
     p.Define('sub', [], 'List of step params.')
     p.Define('residual_start', -1, 'First layer with a residual (-1: none).')
-    p.Define('residual_stride', 1, 'Residual every n layers.')
+    p.Define('residual_stride', 1, 'Number of layers each residual connection skips.')
     return p
 
   def __init__(self, params):
@@ -107,9 +130,9 @@ class StackStep(Step):
     self.CreateChildren('sub', subs)
 
   def PrepareExternalInputs(self, theta, external_inputs):
-    external_inputs = external_inputs or NestedMap()
-    return NestedMap(sub=[s.PrepareExternalInputs(theta.sub[i], external_inputs.get(
-        s.params.name, NestedMap())) for i, s in enumerate(self.sub)])
+    external_inputs = external_inputs if external_inputs is not None else NestedMap()
+    return NestedMap(sub=[s.PrepareExternalInputs(theta.sub[i], external_inputs)
+                          for i, s in enumerate(self.sub)])
 
   def ZeroState(self, theta, prepared_inputs, batch_size):
     return NestedMap(sub=[s.ZeroState(theta.sub[i], prepared_inputs.sub[i], batch_size)
@@ -119,23 +142,21 @@ class StackStep(Step):
     p = self.params
     state1 = NestedMap(sub=[])
     inputs = list(step_inputs.inputs)
-    extra = {k: v for k, v in step_inputs.items() if k != 'inputs'}
-    res_in = None
+    residual_inputs = [inputs[0] if len(inputs) == 1 else torch.cat(inputs, 1)]
+    additional = [step_inputs.context] if 'context' in step_inputs else []
+    output = None
     for i, s in enumerate(self.sub):
-      if p.residual_start >= 0 and i >= p.residual_start and \
-          (i - p.residual_start) % p.residual_stride == 0:
-        res_in = inputs[0]
-      else:
-        res_in = None if (p.residual_start < 0 or i < p.residual_start) else res_in
-      out, st = s.FProp(theta.sub[i], prepared_inputs.sub[i],
-                        NestedMap(inputs=inputs, **extra), padding, state0.sub[i])
-      y = out.output
-      if res_in is not None and isinstance(y, torch.Tensor) and y.shape == res_in.shape \
-          and (i - p.residual_start + 1) % p.residual_stride == 0:
-        y = y + res_in
-      inputs = [y]
+      sub_out, st = s.FProp(theta.sub[i], prepared_inputs.sub[i],
+                            NestedMap(inputs=inputs + additional), padding, state0.sub[i])
       state1.sub.append(st)
-    return NestedMap(output=inputs[0]), state1
+      output = sub_out.output
+      if i >= p.residual_start >= 0:
+        src = i + 1 - p.residual_stride
+        assert 0 <= src < len(residual_inputs), (i, p.residual_start, p.residual_stride)
+        output = output + residual_inputs[src]
+      residual_inputs.append(output)
+      inputs = [output]
+    return NestedMap(output=output), state1
 
 
 class ParallelStep(Step):
@@ -153,9 +174,9 @@ class ParallelStep(Step):
                                 for i, sp in enumerate(self.params.sub)])
 
   def PrepareExternalInputs(self, theta, external_inputs):
-    external_inputs = external_inputs or NestedMap()
-    return NestedMap(sub=[s.PrepareExternalInputs(theta.sub[i], external_inputs.get(
-        s.params.name, NestedMap())) for i, s in enumerate(self.sub)])
+    external_inputs = external_inputs if external_inputs is not None else NestedMap()
+    return NestedMap(sub=[s.PrepareExternalInputs(theta.sub[i], external_inputs)
+                          for i, s in enumerate(self.sub)])
 
   def ZeroState(self, theta, prepared_inputs, batch_size):
     return NestedMap(sub=[s.ZeroState(theta.sub[i], prepared_inputs.sub[i], batch_size)
@@ -167,11 +188,111 @@ class ParallelStep(Step):
       o, st = s.FProp(theta.sub[i], prepared_inputs.sub[i], step_inputs, padding, state0.sub[i])
       outs.append(o.output)
       states.append(st)
-    return NestedMap(output=torch.cat(outs, -1)), NestedMap(sub=states)
+    return NestedMap(output=torch.cat(outs, 1)), NestedMap(sub=states)
+
+
+SubStep = collections.namedtuple('SubStep', ['signature', 'external_signature', 'params'])
+
+
+class GraphStep(Step):
+  """Sub-steps connected by a data-flow graph (ref :404) — `builder_layers.GraphLayer` for
+  steps. `p.sub` is a list of `SubStep(signature, external_signature, params)`:
+
+    * signature: `'<one input expression>-><output name>'` in `GraphSignature` syntax. The
+      input expression is evaluated over the names `step_inputs`, `prepared_inputs` and the
+      outputs of earlier sub-steps and becomes that sub-step's `step_inputs`; state0/state1
+      are threaded automatically.
+    * external_signature: `'external_inputs.<path>'` (or None): which part of this step's
+      external inputs the sub-step's `PrepareExternalInputs` receives.
+    * params: the sub-step params.
+
+  e.g. `SubStep('(inputs=[rnn.output,step_inputs.context])->atten', 'external_inputs.src', ap)`.
+  No cycles; every output name is unique. `p.output_signature` selects the step's output.
+  """
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('output_signature', '', 'Signature of the step output.')
+    p.Define('sub', [], 'A list of SubSteps.')
+    p.Define('dict_type', NestedMap, 'Type of nested dicts.')
+    return p
+
+  _Seq = collections.namedtuple('_Seq', ['name', 'signature', 'external_signature', 'step'])
+
+  def __init__(self, params):
+    from lingvo_b200.core import builder_layers   # pylint: disable=g-import-not-at-top
+    super().__init__(params)
+    p = self.params
+    assert p.name
+    self._seq = []
+    produced = set()
+    for i, (signature, external_signature, sub_params) in enumerate(p.sub):
+      assert signature, 'sub-step %d has no signature' % i
+      sig = builder_layers.GraphSignature(signature)
+      assert len(sig.inputs) == 1, signature
+      assert sig.outputs, signature
+      assert sig.outputs[0] not in produced, 'output %r is produced twice' % sig.outputs[0]
+      produced.add(sig.outputs[0])
+      external_sig = None
+      if external_signature:
+        external_sig = builder_layers.GraphSignature(
+            external_signature if '->' in external_signature else external_signature + '->')
+        assert len(external_sig.inputs) == 1 and not external_sig.outputs, external_signature
+      sub_params = sub_params.Copy()
+      if not sub_params.name:
+        sub_params.name = '%s_%02d' % (sig.outputs[0], i)
+      self.CreateChild(sub_params.name, sub_params)
+      self._seq.append(GraphStep._Seq(sub_params.name, sig, external_sig,
+                                      self.children[sub_params.name]))
+    osig = p.output_signature
+    self.output_signature = builder_layers.GraphSignature(osig if '->' in osig else osig + '->')
+    self._graph_tensors_cls = builder_layers.GraphTensors
+
+  @staticmethod
+  def _Gather(graph_tensors, sig_inputs):
+    return NestedMap(inputs=sig_inputs).Transform(graph_tensors.GetTensor).inputs[0]
+
+  def PrepareExternalInputs(self, theta, external_inputs):
+    """→ NestedMap keyed by sub-step name (empty map for steps without externals)."""
+    gt = self._graph_tensors_cls()
+    gt.StoreTensor('external_inputs', external_inputs)
+    prepared = NestedMap()
+    for seq in self._seq:
+      if seq.external_signature is not None:
+        sub_ext = self._Gather(gt, seq.external_signature.inputs)
+        prepared[seq.name] = seq.step.PrepareExternalInputs(theta[seq.name], sub_ext)
+      else:
+        prepared[seq.name] = NestedMap()
+    return prepared
+
+  def ZeroState(self, theta, prepared_inputs, batch_size):
+    return NestedMap({seq.name: seq.step.ZeroState(theta[seq.name], prepared_inputs[seq.name],
+                                                   batch_size) for seq in self._seq})
+
+  def FProp(self, theta, prepared_inputs, step_inputs, padding, state0):
+    gt = self._graph_tensors_cls()
+    gt.StoreTensor('prepared_inputs', prepared_inputs)
+    gt.StoreTensor('step_inputs', step_inputs)
+    state1 = NestedMap()
+    for seq in self._seq:
+      external = prepared_inputs[seq.name] if seq.external_signature is not None else None
+      sub_in = self._Gather(gt, seq.signature.inputs)
+      out, st = seq.step.FProp(theta[seq.name], external, sub_in, padding, state0[seq.name])
+      gt.StoreTensor(seq.signature.outputs[0], out)
+      state1[seq.name] = st
+    return self._Gather(gt, self.output_signature.inputs), state1
 
 
 class IteratorStep(Step):
-  """Each call emits the next frame of a `[B, T, …]` external sequence (ref :560)."""
+  """Steps through the time axis `p.axis` of the external tensors: each call emits the
+  `[batch, …]` slice at the current time (ref :572). `step_inputs` is unused."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('axis', 1, 'The time dimension of the tensors.')
+    return p
 
   def PrepareExternalInputs(self, theta, external_inputs):
     return external_inputs
@@ -180,9 +301,14 @@ class IteratorStep(Step):
     return NestedMap(t=0)
 
   def FProp(self, theta, prepared_inputs, step_inputs, padding, state0):
-    t = state0.t
-    out = prepared_inputs.Transform(lambda x: x[:, t])
-    return NestedMap(output=out), NestedMap(t=t + 1)
+    del theta, step_inputs, padding
+    t, axis = state0.t, self.params.axis
+    if isinstance(t, torch.Tensor):
+      out = prepared_inputs.Transform(
+          lambda x: x.index_select(axis, t.reshape(1).to(x.device)).squeeze(axis))
+    else:
+      out = prepared_inputs.Transform(lambda x: x.select(axis, t))
+    return out, NestedMap(t=t + 1)
 
 
 class RecurrentStepWrapper(base_layer.BaseLayer):
@@ -205,13 +331,29 @@ class RecurrentStepWrapper(base_layer.BaseLayer):
     return self.step.ZeroState(theta.step, prepared_inputs, batch_size)
 
   def FProp(self, theta, prepared_inputs, inputs, padding, state0):
-    """inputs: NestedMap of `[T, B, …]`; padding `[T, B, 1]` → (outputs [T,…], final state)."""
+    """Runs the step over every time step (ref :690).
+
+    inputs: NestedMap of `[T, B, …]`; padding `[T, B(, 1)]`.
+    Returns (outputs, states): the per-step outputs and recurrent states stacked on a new
+    leading time axis (non-tensor state leaves, e.g. python counters, keep their last value).
+    The loop is a plain host loop: every step launches the same kernels, so under
+    `GraphedTrainStep` the whole unrolled sequence is one CUDA graph.
+    """
     t = padding.shape[0]
     state = state0
-    outs = []
+    outs, states = [], []
     for i in range(t):
-      step_in = inputs.Transform(lambda x: x[i])
+      step_in = inputs.Transform(lambda x, i=i: x[i])
       o, state = self.step.FProp(theta.step, prepared_inputs, step_in, padding[i], state)
       outs.append(o)
-    flat = [torch.stack([o.Flatten()[k] for o in outs]) for k in range(len(outs[0].Flatten()))]
-    return outs[0].Pack(flat), state
+      states.append(state)
+
+    def _Stack(maps):
+      flats = [m.Flatten() for m in maps]
+      merged = []
+      for k in range(len(flats[0])):
+        vals = [f[k] for f in flats]
+        merged.append(torch.stack(vals) if isinstance(vals[0], torch.Tensor) else vals[-1])
+      return maps[0].Pack(merged)
+
+    return _Stack(outs), _Stack(states)
