@@ -316,7 +316,139 @@ class WeightNormalizedLSTMCellSimple(LSTMCellSimple):
     return super()._Step(th, state0, xw, padding, inputs)
 
 
-NormalizedLSTMCellSimple = LayerNormalizedLSTMCellSimple   # ref :1438 (same math path)
+class NormalizedLSTMCellSimple(LSTMCellSimple):
+  """LSTM whose gate pre-activations each go through a configurable normalisation layer
+  (`norm_layer_tpl`, children `norm_i_i / norm_i_g / norm_f_g / norm_o_g`) (ref :1438).
+  Requires `enable_lstm_bias=False` and `forget_gate_bias=0` (the norm layers own the
+  affine terms)."""
+
+  _GATES = ('i_i', 'i_g', 'f_g', 'o_g')
+
+  @classmethod
+  def Params(cls):
+    from lingvo_b200.core import layers   # pylint: disable=g-import-not-at-top
+    p = super().Params()
+    p.Define('norm_layer_tpl', layers.LayerNorm.Params().Set(epsilon=1e-8),
+             'The normalization layer params.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert p.forget_gate_bias == 0.0
+    assert not p.enable_lstm_bias
+    for gate in self._GATES:
+      self.CreateChild('norm_' + gate, p.norm_layer_tpl.Copy().Set(
+          name='norm_' + gate, input_dim=self.hidden_size))
+
+  def _Normalize(self, theta, gates):
+    p = self.params
+    parts = list(gates.chunk(self.num_gates, -1))
+    names = ('i_i', 'f_g', 'o_g') if p.couple_input_forget_gates else self._GATES
+    out = [self.children['norm_' + n].FProp(theta['norm_' + n], x)
+           for n, x in zip(names, parts)]
+    return torch.cat(out, -1)
+
+
+class LayerNormalizedLSTMCell(RNNCell):
+  """The original (deprecated in the reference) layer-normalised LSTM (ref :1010): LN on each
+  of the four gate pre-activations with scale `1 + ln_scale` and bias, both packed in one
+  vector `b` of size 8·H = [4 gate biases | 4 LN scales]; optional clipping-cap schedule for
+  the cell value."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('cell_value_cap', 10.0, 'Cell values are capped to ±cap (python number).')
+    p.Define('forget_gate_bias', 0.0, 'Bias to apply to the forget gate.')
+    p.Define('output_nonlinearity', True, 'm = o·tanh(c) (else o·c).')
+    p.Define('layer_norm_epsilon', 1e-8, 'Tiny value to guard rsqrt.')
+    p.Define('cc_schedule', None, 'Clipping cap schedule (overrides cell_value_cap).')
+    p.Define('use_fused_layernorm', False, 'Kept for parity: one fused LN expression is used '
+             'either way.')
+    p.Define('pruning_hparams_dict', None, 'Kept for parity.')
+    p.Define('apply_pruning', False, 'Multiply wm by a (non-trainable) `mask` variable.')
+    p.Define('no_wm_if_compress', False, 'Kept for parity.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    if not isinstance(p.cell_value_cap, (int, float)):
+      raise ValueError('Cell value cap must be of type int or float!')
+    assert p.num_input_nodes > 0 and p.num_output_nodes > 0
+    if p.cc_schedule is not None:
+      self.CreateChild('cc_schedule', p.cc_schedule)
+    self.TrackQWeight('wm', shape=[p.num_input_nodes + p.num_output_nodes,
+                                   4 * p.num_output_nodes], feature_axis=-1)
+
+  @property
+  def output_size(self):
+    return self.params.num_output_nodes
+
+  hidden_size = output_size
+
+  def _CreateLayerVariables(self):
+    p = self.params
+    shape = [p.num_input_nodes + p.num_output_nodes, 4 * p.num_output_nodes]
+    self.CreateVariable('wm', WeightParams(shape, p.params_init, p.dtype))
+    if p.apply_pruning:
+      self.CreateVariable('mask', WeightParams(shape, WeightInit.Constant(1.0), p.dtype),
+                          trainable=False)
+      self.CreateVariable('threshold', WeightParams([], WeightInit.Constant(0.0), p.dtype),
+                          trainable=False)
+    self.CreateVariable('b', WeightParams([8 * p.num_output_nodes], WeightInit.Constant(0.0),
+                                          p.dtype))
+
+  def zero_state(self, theta, batch_size):
+    p = self.params
+    dev, dt = self.Device(), py_utils.FPropDtype(p)
+    return NestedMap(m=torch.zeros(batch_size, p.num_output_nodes, device=dev, dtype=dt),
+                     c=torch.zeros(batch_size, p.num_output_nodes, device=dev, dtype=dt))
+
+  def GetOutput(self, state):
+    return state.m
+
+  def _ResetState(self, state, inputs):
+    if inputs.get('reset_mask') is not None:
+      return state.Transform(lambda x: x * inputs.reset_mask.to(x.dtype))
+    return state
+
+  def _Wm(self, theta):
+    w = theta.wm
+    if self.params.apply_pruning:
+      w = self.QWeight(w * theta.mask)
+    return w
+
+  def ProjectInput(self, theta, acts):
+    p = self.params
+    return torch.matmul(acts, self._Wm(theta)[:p.num_input_nodes].to(acts.dtype))
+
+  def _Step(self, theta, state0, xw, padding, inputs=None):
+    p = self.params
+    h = p.num_output_nodes
+    gates = xw + torch.matmul(state0.m.to(xw.dtype), self._Wm(theta)[p.num_input_nodes:].to(
+        xw.dtype))
+    g = gates.float().reshape(-1, 4, h)
+    mean = g.mean(-1, keepdim=True)
+    var = (g - mean).square().mean(-1, keepdim=True)
+    bias = theta.b[:4 * h].float().reshape(4, h)
+    scale = theta.b[4 * h:].float().reshape(4, h) + 1.0
+    g = ((g - mean) * torch.rsqrt(var + p.layer_norm_epsilon) * scale + bias).to(xw.dtype)
+    i_i, i_g, f_g, o_g = g.unbind(1)
+    if p.forget_gate_bias != 0.0:
+      f_g = f_g + p.forget_gate_bias
+    new_c = torch.sigmoid(f_g) * state0.c + torch.sigmoid(i_g) * torch.tanh(i_i)
+    if p.cc_schedule is not None:
+      cap = self.cc_schedule.GetState(theta.cc_schedule).to(device=new_c.device,
+                                                            dtype=new_c.dtype)
+      new_c = torch.maximum(torch.minimum(new_c, cap), -cap)
+    else:
+      new_c = new_c.clamp(-p.cell_value_cap, p.cell_value_cap)
+    new_m = torch.sigmoid(o_g) * (torch.tanh(new_c) if p.output_nonlinearity else new_c)
+    new_c = _ZoneOut(state0.c, new_c, padding, p.zo_prob, self.do_eval)
+    new_m = _ZoneOut(state0.m, new_m, padding, p.zo_prob, self.do_eval)
+    return NestedMap(m=new_m, c=new_c)
 
 
 class LayerNormalizedLSTMCellLean(RNNCell):
@@ -748,3 +880,52 @@ class GRUCell(RNNCell):
     new_c = _ZoneOut(state0.c, new_c, pad, p.zo_prob, self.do_eval)
     new_m = _ZoneOut(state0.m, new_m, pad, p.zo_prob, self.do_eval)
     return NestedMap(m=new_m, c=new_c), NestedMap()
+
+
+class EmbeddingAugmentedLayerNormalizedLSTMCellSimple(LayerNormalizedLSTMCellSimple):
+  """LN-LSTM whose input is augmented with an embedding of the current (and previous) token
+  ids (ref :1715): `inputs.ids [B]` go through a `StatefulEmbeddingStep` and the result is
+  added to the activations (`inject_emb_method='add'`), or — for 'concat' — added into the
+  last `emb_dim` columns of the activations, which the caller must have left as zeros.
+  State gains `emb` (the embedding step's state: position + previous ids)."""
+
+  @classmethod
+  def Params(cls):
+    from lingvo_b200.core.steps import embedding_steps   # pylint: disable=g-import-not-at-top
+    p = super().Params()
+    p.Define('emb', embedding_steps.StatefulEmbeddingStep.Params(),
+             'Inject this embedding into the input to the cell.')
+    p.Define('inject_emb_method', 'add', "How to inject the embedding: 'add' or 'concat'.")
+    p.name = 'embedding_augmented_lstm'
+    return p
+
+  def __init__(self, params):
+    from lingvo_b200.core.steps import embedding_steps   # pylint: disable=g-import-not-at-top
+    super().__init__(params)
+    p = self.params
+    assert issubclass(p.emb.cls, embedding_steps.StatefulEmbeddingStep), (
+        'Only StatefulEmbeddingStep is supported for p.emb')
+    assert p.inject_emb_method in ('add', 'concat'), p.inject_emb_method
+    self.CreateChild('emb', p.emb)
+
+  def zero_state(self, theta, batch_size):
+    state0 = super().zero_state(theta, batch_size)
+    state0.emb = self.emb.ZeroState(theta.emb, None, batch_size)
+    return state0
+
+  def FProp(self, theta, state0, inputs):
+    p = self.params
+    emb_out, emb_state1 = self.emb.FProp(theta.emb, None, NestedMap(inputs=[inputs.ids]), None,
+                                         state0.emb)
+    embedding = emb_out.output
+    act = self._Act(inputs)
+    if p.inject_emb_method == 'concat':
+      emb_dim = embedding.shape[-1]
+      # "concatenation" by addition into the zero-padded tail of the activations
+      embedding = F.pad(embedding, (p.num_input_nodes - emb_dim, 0))
+    inner = NestedMap(inputs)
+    inner.act = [act + embedding.to(act.dtype)]
+    lstm_state0 = NestedMap(m=state0.m, c=state0.c)
+    state1, extras = super().FProp(theta, lstm_state0, inner)
+    state1.emb = emb_state1
+    return state1, extras

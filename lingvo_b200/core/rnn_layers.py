@@ -193,7 +193,45 @@ class BidirectionalRNN(base_layer.BaseLayer):
     return torch.cat([f, b], -1)
 
 
-BidirectionalRNNV2 = BidirectionalRNN   # ref :659 (differs only in graph construction)
+class BidirectionalRNNV2(base_layer.BaseLayer):
+  """Bidirectional RNN unrolled over a fixed `sequence_length` (ref :659): shorter inputs are
+  padded (activations with 0, paddings with 1) up to `sequence_length`, the wrapped
+  `BidirectionalRNN` runs on the fixed-length sequence — one static unroll that captures
+  into a single CUDA graph whatever the batch's true length — and the output is cut back."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('fwd', rnn_cell.LSTMCellSimple.Params(), 'Forward cell.')
+    p.Define('bak', rnn_cell.LSTMCellSimple.Params(), 'Backward cell.')
+    p.Define('sequence_length', 0, 'Sequence length.')
+    p.Define('packed_input', False, 'Not supported (as in the reference).')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert not p.packed_input, 'Packed input is not supported by BidirectionalRNNV2'
+    self.CreateChild('brnn', BidirectionalRNN.Params().Set(
+        name='%s_brnn' % p.name, fwd=p.fwd.Copy(), bak=p.bak.Copy(),
+        sequence_length=p.sequence_length))
+
+  @staticmethod
+  def _PadSequenceToLength(x, length, pad_value):
+    t = x.shape[0]
+    assert t <= length, 'sequence of %d steps exceeds sequence_length=%d' % (t, length)
+    if t == length:
+      return x
+    return torch.cat([x, x.new_full((length - t,) + tuple(x.shape[1:]), pad_value)], 0)
+
+  def FProp(self, theta, inputs, paddings):
+    """inputs `[T, B, D]`, paddings `[T, B, 1]` → `[T, B, fwd+bak dims]`."""
+    p = self.params
+    seq_len = paddings.shape[0]
+    length = p.sequence_length or seq_len
+    x = self._PadSequenceToLength(inputs, length, 0.0)
+    pad = self._PadSequenceToLength(_Pad3(paddings), length, 1.0)
+    return self.brnn.FProp(theta.brnn, x, pad)[:seq_len]
 
 
 class StackedRNNBase(base_layer.BaseLayer):

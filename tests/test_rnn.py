@@ -22,6 +22,8 @@ CELLS = [
     (rnn_cell.SRUCell, dict(couple_input_forget_gates=False, pointwise_peephole=True,
                             apply_layer_norm=True)),
     (rnn_cell.GRUCell, {}),
+    (rnn_cell.LayerNormalizedLSTMCell, {}),
+    (rnn_cell.NormalizedLSTMCellSimple, dict(enable_lstm_bias=False)),
     (rnn_cell.LSTMCellGrouped, dict(num_groups=2, num_shuffle_shards=2)),
 ]
 
@@ -48,7 +50,7 @@ def test_cell_step_and_padding(cls, kw):
   assert not torch.allclose(s1.m[0], s0.m[0])
 
 
-@pytest.mark.parametrize('cls,kw', CELLS[:9])
+@pytest.mark.parametrize('cls,kw', CELLS[:11])
 def test_frnn_equals_stepwise(cls, kw):
   p = rnn_layers.FRNN.Params().Set(name='frnn', cell=_Cell(cls, kw))
   l = p.Instantiate()
@@ -172,3 +174,109 @@ def test_qrnn_pooling():
   s1, _ = cell.FProp(cell.theta, s0, NestedMap(act=[torch.randn(2, 12)],
                                                padding=torch.zeros(2, 1)))
   assert s1.m.shape == (2, 4)
+
+
+def test_layer_normalized_lstm_cell_packs_bias_and_scale_in_b():
+  """`b` = [4 gate biases | 4 LN scales (offset 1)]; matches a hand-written LN-LSTM."""
+  cell = _Cell(rnn_cell.LayerNormalizedLSTMCell, dict(forget_gate_bias=0.5)).Instantiate()
+  assert cell.vars.b.shape == (8 * 6,)
+  with torch.no_grad():
+    cell.vars.b.copy_(torch.randn(48) * 0.1)
+  b = 3
+  s0 = cell.zero_state(cell.theta, b).Transform(lambda x: x + 0.2)
+  x = torch.randn(b, 6)
+  s1, _ = cell.FProp(cell.theta, s0, NestedMap(act=[x], padding=torch.zeros(b, 1)))
+  z = (torch.cat([x, s0.m], 1) @ cell.vars.wm).reshape(b, 4, 6)
+  z = (z - z.mean(-1, keepdim=True)) * torch.rsqrt(z.var(-1, unbiased=False, keepdim=True) + 1e-8)
+  z = z * (cell.vars.b[24:].reshape(4, 6) + 1.0) + cell.vars.b[:24].reshape(4, 6)
+  i_i, i_g, f_g, o_g = z.unbind(1)
+  c = torch.sigmoid(f_g + 0.5) * s0.c + torch.sigmoid(i_g) * torch.tanh(i_i)
+  torch.testing.assert_close(s1.c, c.clamp(-10, 10), atol=1e-5, rtol=1e-5)
+  torch.testing.assert_close(s1.m, torch.sigmoid(o_g) * torch.tanh(c), atol=1e-5, rtol=1e-5)
+
+
+def test_layer_normalized_lstm_cell_cc_schedule_caps_the_cell():
+  from lingvo_b200.core import quant_utils
+  p = _Cell(rnn_cell.LayerNormalizedLSTMCell, dict(
+      cc_schedule=quant_utils.LinearClippingCapSchedule.Params().Set(
+          start_step=0, end_step=10, start_cap=5.0, end_cap=0.05)))
+  cell = p.Instantiate()
+  py_utils.SetGlobalStep(10)
+  try:
+    s0 = cell.zero_state(cell.theta, 2).Transform(lambda x: x + 3.0)
+    s1, _ = cell.FProp(cell.theta, s0, NestedMap(act=[torch.randn(2, 6)],
+                                                 padding=torch.zeros(2, 1)))
+    assert float(s1.c.abs().max()) <= 0.05 + 1e-6
+  finally:
+    py_utils.SetGlobalStep(0)
+
+
+def test_normalized_lstm_cell_uses_per_gate_norm_layers():
+  from lingvo_b200.core import layers
+  cell = _Cell(rnn_cell.NormalizedLSTMCellSimple, dict(enable_lstm_bias=False)).Instantiate()
+  assert sorted(k for k in cell.children.keys() if k.startswith('norm_')) == [
+      'norm_f_g', 'norm_i_g', 'norm_i_i', 'norm_o_g']
+  assert isinstance(cell.norm_i_i, layers.LayerNorm)
+  with pytest.raises(AssertionError):
+    _Cell(rnn_cell.NormalizedLSTMCellSimple, {}).Instantiate()       # bias must be off
+  b = 2
+  s0 = cell.zero_state(cell.theta, b).Transform(lambda x: x + 0.1)
+  x = torch.randn(b, 6)
+  s1, _ = cell.FProp(cell.theta, s0, NestedMap(act=[x], padding=torch.zeros(b, 1)))
+  z = (torch.cat([x, s0.m], 1) @ cell.vars.wm).chunk(4, -1)
+  n = [getattr(cell, 'norm_' + g).FPropDefaultTheta(v) for g, v in
+       zip(('i_i', 'i_g', 'f_g', 'o_g'), z)]
+  c = torch.sigmoid(n[2]) * s0.c + torch.sigmoid(n[1]) * torch.tanh(n[0])
+  torch.testing.assert_close(s1.c, c, atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize('method', ['add', 'concat'])
+def test_embedding_augmented_cell(method):
+  from lingvo_b200.core.steps import embedding_steps
+  emb_dim = 6 if method == 'add' else 2
+  p = _Cell(rnn_cell.EmbeddingAugmentedLayerNormalizedLSTMCellSimple, dict(
+      inject_emb_method=method,
+      emb=embedding_steps.StatefulEmbeddingStep.Params().Set(
+          name='emb', target_vocab_size=11, embedding_dim=emb_dim, num_prev_tokens=1)))
+  cell = p.Instantiate()
+  b = 3
+  state = cell.zero_state(cell.theta, b)
+  assert 'emb' in state and state.emb.prev.shape == (b, 1)
+  x = torch.randn(b, 6)
+  if method == 'concat':
+    x[:, -emb_dim:] = 0.0
+  ids = torch.tensor([1, 2, 3])
+  s1, _ = cell.FProp(cell.theta, state, NestedMap(act=[x], padding=torch.zeros(b, 1), ids=ids))
+  s1b, _ = cell.FProp(cell.theta, state, NestedMap(act=[x], padding=torch.zeros(b, 1),
+                                                   ids=torch.tensor([4, 5, 6])))
+  assert s1.m.shape == (b, 6) and not torch.allclose(s1.m, s1b.m)   # ids matter
+  assert s1.emb.t == 1 and torch.equal(s1.emb.prev[:, -1], ids)
+  # equals the plain LN cell fed with act + (padded) embedding
+  e, _ = cell.emb.FProp(cell.theta.emb, None, NestedMap(inputs=[ids]), None, state.emb)
+  e = e.output
+  if method == 'concat':
+    e = torch.nn.functional.pad(e, (6 - emb_dim, 0))
+  ref, _ = rnn_cell.LayerNormalizedLSTMCellSimple.FProp(
+      cell, cell.theta, NestedMap(m=state.m, c=state.c),
+      NestedMap(act=[x + e], padding=torch.zeros(b, 1)))
+  torch.testing.assert_close(s1.m, ref.m)
+  # a second step sees the first step's id as "previous token"
+  s2, _ = cell.FProp(cell.theta, s1, NestedMap(act=[x], padding=torch.zeros(b, 1), ids=ids))
+  assert s2.emb.t == 2
+
+
+def test_bidirectional_rnn_v2_pads_to_sequence_length():
+  fwd = _Cell(rnn_cell.LSTMCellSimple, {})
+  p = rnn_layers.BidirectionalRNNV2.Params().Set(name='bi', fwd=fwd, bak=fwd.Copy(),
+                                                 sequence_length=8)
+  l = p.Instantiate()
+  t, b = 5, 2
+  x = torch.randn(t, b, 6)
+  pad = torch.zeros(t, b, 1)
+  pad[4:, 1] = 1.0
+  out = l.FPropDefaultTheta(x, pad)
+  assert out.shape == (t, b, 12)
+  ref = l.brnn.FProp(l.theta.brnn, x, pad)          # unpadded run of the same weights
+  torch.testing.assert_close(out, ref, atol=1e-6, rtol=1e-5)
+  with pytest.raises(AssertionError):
+    l.FPropDefaultTheta(torch.randn(9, b, 6), torch.zeros(9, b, 1))
