@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from lingvo_b200.core import base_input_generator
+from lingvo_b200.core import input_policy
 from lingvo_b200.core import base_layer
 from lingvo_b200.core import cluster_factory
 from lingvo_b200.core import early_stop
@@ -185,7 +186,7 @@ class BaseTask(base_layer.BaseLayer):
         p2.name = 'input'
       else:
         p2 = p.input
-      self.CreateChild('input', p2)
+      self.CreateChild('input', input_policy.Apply(p2))
 
     tp = p.train
     if tp:

@@ -71,39 +71,138 @@ def _MetricsToFloats(metrics: Dict) -> Dict[str, float]:
   return dict(zip(names, stacked.cpu().tolist()))
 
 
-class Controller(base_runner.BaseRunner):
-  """Writes experiment artefacts; (re)initialises the model if needed."""
+class _CheckpointFollower(base_runner.BaseRunner):
+  """A job that follows the trainer through its checkpoints and writes *training* summaries
+  (the trainer-side counterpart of the Evaler, which follows them in eval mode).
+
+  Every time a new checkpoint appears it is restored into this job's own copy of the model,
+  one training batch goes through FProp + backward **without** an optimizer step, and the
+  job writes: the task's training metrics, per-layer summaries collected during that eager
+  step, global gradient / variable norms, `total_num_params`, and the trainer's progress
+  (`global_step`, checkpoints seen). Runs on any device (a spare GPU or the host), never
+  touches the trainer's step time.
+  """
+
+  _OUT_DIR = 'train_summaries'
+
+  def __init__(self, *args, **kwargs):
+    super().__init__(*args, **kwargs)
+    self._out_dir = os.path.join(self._logdir, self._OUT_DIR)
+    if self._model_task_name and self._OUT_DIR != 'control':
+      self._out_dir += '_' + str(self._model_task_name)
+    os.makedirs(self._out_dir, exist_ok=True)
+    with self._cluster:
+      self._model = self._params.Instantiate()
+      self._model.to(py_utils.CurrentDevice())
+    self._max_steps = min([self._params.train.max_steps] + [
+        t.params.train.max_steps for t in self._model.tasks])
+    self._checkpointer = checkpointer.Checkpointer(
+        self._train_dir, self._model, train_params=self._params.train)
+    self._summary_writer = tfevents.EventFileWriter(self._out_dir)
+    self._model_analysis, self._total_num_params = summary_utils.ModelAnalysis(self._model)
+    self._num_summaries = 0
+    self._last_step = 0
+
+  def Start(self):
+    self._RunLoop(self._job_name, self._Loop)
+
+  @property
+  def num_summaries_written(self):
+    return self._num_summaries
+
+  def _TasksToSummarize(self):
+    if self._model_task_name:
+      return [self._model.GetTask(self._model_task_name)]
+    return list(self._model.tasks)
+
+  def SummarizeCheckpoint(self, path: str) -> int:
+    """Restores `path` and writes one round of training summaries. Returns its step."""
+    with self._cluster:
+      self._checkpointer.RestoreFromPath(checkpoint_path=path)
+      scalars = {}
+      step = 0
+      collector = summary_utils.SummaryCollector()
+      for task in self._TasksToSummarize():
+        prefix = '' if len(self._model.tasks) == 1 else task.params.name + '/'
+        step = max(step, int(task.global_step))
+        with collector, py_utils.GlobalStepContext(int(task.global_step)):
+          metrics, _ = task.FPropDefaultTheta()
+          loss = task.loss
+          trainable = [v for v in task.vars.Flatten() if v.requires_grad]
+          for v in trainable:
+            v.grad = None
+          if isinstance(loss, torch.Tensor) and loss.requires_grad:
+            loss.backward()
+        for k, v in _MetricsToFloats(metrics).items():
+          scalars[prefix + k] = v
+        gsq = sum(float(v.grad.detach().float().pow(2).sum()) for v in trainable
+                  if v.grad is not None)
+        vsq = sum(float(v.detach().float().pow(2).sum()) for v in trainable)
+        scalars[prefix + 'grad_norm/all'] = gsq ** 0.5
+        scalars[prefix + 'var_norm/all'] = vsq ** 0.5
+        for v in trainable:
+          v.grad = None
+        task._metrics = None   # pylint: disable=protected-access  (no BProp follows)
+      scalars['total_num_params'] = float(self._total_num_params)
+      scalars['global_step'] = float(step)
+      self._summary_writer.add_scalars(scalars, step)
+      collector.WriteTo(self._summary_writer, step)
+      self._summary_writer.flush()
+      self._num_summaries += 1
+      self._last_step = step
+      self._SetStatusMessage('Write summary @%d' % step)
+      return step
+
+  def _Loop(self):
+    tp = self._params.train
+    next_summary_step = 1
+    last_path = None
+    while not self._should_stop.is_set():
+      path = saver_lib.LatestCheckpoint(self._train_dir)
+      if path and path != last_path:
+        step = base_runner._StepOf(path)   # pylint: disable=protected-access
+        if step >= next_summary_step or (self._max_steps is not None and
+                                         step >= self._max_steps):
+          self.SummarizeCheckpoint(path)
+          next_summary_step = step + (tp.summary_interval_steps or 1)
+        last_path = path
+      step = base_runner._StepOf(last_path) if last_path else 0   # pylint: disable=protected-access
+      if self._max_steps is not None and step >= self._max_steps:
+        return
+      if getattr(self, '_peer_done', None) is not None and self._peer_done():
+        # the trainer finished: pick up its final checkpoint before leaving
+        path = saver_lib.LatestCheckpoint(self._train_dir)
+        if path and path != last_path:
+          self.SummarizeCheckpoint(path)
+        return
+      time.sleep(self._poll_seconds)
+
+  _poll_seconds = 0.2
+
+
+class Controller(_CheckpointFollower):
+  """The bookkeeping job of a training cluster (ref runners.py:70-189).
+
+  The reference controller shares the trainer's variables through the parameter server and
+  so can initialise / checkpoint them and evaluate the summary op against live weights. With
+  one process per GPU the trainer owns its variables — and therefore checkpointing — and
+  the controller keeps the other responsibilities: it writes the experiment artefacts
+  (`control/params.txt`, `params.pbtxt`, `params.pb`, `model_analysis.txt`) and then follows
+  the trainer through its checkpoints, writing training summaries and `total_num_params`
+  to `control/` every `summary_interval_steps` (see `_CheckpointFollower`).
+  """
+
+  _OUT_DIR = 'control'
 
   def __init__(self, *args, **kwargs):
     super().__init__(*args, **kwargs)
     self._job_name = 'controller'
-    self._control_dir = os.path.join(self._logdir, 'control')
-    os.makedirs(self._control_dir, exist_ok=True)
-    with self._cluster:
-      self._model = self._params.Instantiate()
-    self._max_steps = min([self._params.train.max_steps] + [
-        t.params.train.max_steps for t in self._model.tasks])
+    self._control_dir = self._out_dir
     _WriteParamsFiles(self._params, self._control_dir)
-    text, _ = summary_utils.ModelAnalysis(self._model)
     with open(os.path.join(self._control_dir, 'model_analysis.txt'), 'w') as f:
-      f.write(text)
-    self._summary_writer = tfevents.EventFileWriter(self._control_dir)
-    self._summary_writer.add_text('model_analysis', text, 0)
+      f.write(self._model_analysis)
+    self._summary_writer.add_text('model_analysis', self._model_analysis, 0)
     self._summary_writer.flush()
-
-  def Start(self):
-    self._RunLoop('controller', self._Loop)
-
-  def _Loop(self):
-    """Waits for training to finish, mirroring trainer progress."""
-    while not self._should_stop.is_set():
-      path = saver_lib.LatestCheckpoint(self._train_dir)
-      step = base_runner._StepOf(path) if path else 0  # pylint: disable=protected-access
-      if self._max_steps is not None and step >= self._max_steps:
-        return
-      if getattr(self, '_peer_done', None) is not None and self._peer_done():
-        return
-      time.sleep(0.2)
 
 
 class Trainer(base_runner.BaseRunner):
@@ -218,15 +317,14 @@ class Trainer(base_runner.BaseRunner):
 TrainerTpu = Trainer
 
 
-class TrainSummaries(base_runner.BaseRunner):
-  """Writes training summaries from checkpoints (reference eager :118)."""
+class TrainSummaries(_CheckpointFollower):
+  """Writes training summaries from checkpoints into `train_summaries/` (reference
+  eager_runners.py:118): restore the newest checkpoint, run the training graph once without
+  applying gradients, write the summaries, wait for the next checkpoint."""
 
   def __init__(self, *args, **kwargs):
     super().__init__(*args, **kwargs)
     self._job_name = 'train_summaries'
-
-  def Start(self):
-    return None
 
 
 class Evaler(base_runner.BaseRunner):

@@ -51,6 +51,16 @@ def test_punctuator_pipeline_and_training(tmp_path):
   for _ in range(25):
     m, _ = task.TrainStep()
   assert float(m['log_pplx'][0]) < l0
+  # string-in / string-out inference subgraph (ref punctuator/model.py:37)
+  sub = task.Inference()
+  assert list(sub) == ['default']
+  out = sub['default'](['hello world', 'yes no'])
+  k = out.topk_scores.shape[1]
+  assert len(out.topk_decoded) == 2 and all(len(h) == k for h in out.topk_decoded)
+  assert all(isinstance(s, str) for h in out.topk_decoded for s in h)
+  assert out.src_ids.shape[0] == 2 and out.topk_ids.shape[:2] == (2, k)
+  assert (out.topk_scores[:, :-1] >= out.topk_scores[:, 1:] - 1e-5).all()   # best first
+  assert isinstance(task.Punctuate('hello world'), str)
 
 
 class _PairInput(base_input_generator.BaseInputGenerator):

@@ -165,6 +165,18 @@ def test_trainer_mnist_logdir_artifacts(tmp_path, monkeypatch):
             'train/ckpt-00000002.index', 'train/trainer_params.txt']:
     assert os.path.exists(os.path.join(logdir, f)), f
   assert glob.glob(os.path.join(logdir, 'train', 'events.out.tfevents.*'))
+  # the controller followed the trainer: it wrote training summaries (metrics, grad/var
+  # norms, total_num_params) for the final checkpoint into control/
+  from lingvo_b200.utils import tfevents
+  events = glob.glob(os.path.join(logdir, 'control', 'events.out.tfevents.*'))
+  assert events
+  tags = {}
+  for path in events:
+    for step, tag, val in tfevents.ReadScalars(path):
+      tags.setdefault(tag, []).append((step, val))
+  assert 'total_num_params' in tags and tags['total_num_params'][-1][1] > 1000
+  assert tags['global_step'][-1] == (2, 2.0)
+  assert 'log_pplx' in tags and 'grad_norm/all' in tags and tags['grad_norm/all'][-1][1] > 0
   flags.FLAGS.reset()
   trainer.main(['trainer', '--run_locally=cpu', '--mode=sync',
                 '--model=image.mnist.LeNet5', '--logdir=' + logdir,
