@@ -865,125 +865,6 @@ class XLAShardingAdafactorAccuGrad(XLAShardingAdafactor):
     return None
 
 
-class DistributedShampoo(Base):
-  """Shampoo with inverse-p-th-root preconditioners (reference :689).
-
-  Statistics L += G Gᵀ, R += Gᵀ G per 2-D (block) parameter; preconditioned
-  grad L^{-1/4} G R^{-1/4}, grafted to the Adagrad step size. Preconditioners
-  are recomputed every `preconditioning_compute_steps` via
-  `matrix_functions.inlined_matrix_inverse_pth_root`.
-  """
-
-  SLOT_SUFFIX = {'acc': 'Shampoo_acc', 'mom': 'Shampoo_mom'}
-  EXTRA_SLOT_NAMES = ('L', 'R', 'PL', 'PR')
-
-  @classmethod
-  def Params(cls):
-    p = super().Params()
-    p.Define('momentum', 0.9, 'Momentum parameter.')
-    p.Define('start_preconditioning_steps', 1000, 'Diagonal until this step.')
-    p.Define('initial_accumulator_value', 0.0, 'Initial accumulator value.')
-    p.Define('block_size', 4096, 'Block size for large layers.')
-    p.Define('block_partition_threshold_size', 1000000, 'Partition threshold.')
-    p.Define('max_any_dim', 6656, 'Max dim before falling back to diagonal.')
-    p.Define('matrix_epsilon', 1e-6, 'Damping for the inverse root.')
-    p.Define('second_moment_averaging', 1.0, '1.0 ⇒ sum (Adagrad).')
-    p.Define('fallback_to_diagonal_dim', 4096, 'Fallback dim.')
-    p.Define('statistics_computation_frequency', 1, 'Steps between stat updates.')
-    p.Define('preconditioning_compute_steps', 20, 'Steps between root solves.')
-    p.Define('async_preconditioning', False,
-             'Solve the inverse roots on a low-priority side stream '
-             '(`preconditioner_captain`) and step with the last finished ones.')
-    return p
-
-  def _Update(self, lr, variables, grads):
-    from lingvo_b200.core import matrix_functions
-    p = self.params
-    t = self._step_count + 1
-    for v, g in zip(variables, _F32(grads, variables)):
-      acc = self._Slot(v, 'acc', init=p.initial_accumulator_value)
-      acc.addcmul_(g, g)
-      adagrad_upd = g / (acc.sqrt() + 1e-30)
-      upd = adagrad_upd
-      if v.dim() == 2 and max(v.shape) <= p.max_any_dim:
-        key = _VarKey(v)
-        st = self._slots[key]
-        if 'L' not in st:
-          st['L'] = torch.zeros(v.shape[0], v.shape[0], device=v.device)
-          st['R'] = torch.zeros(v.shape[1], v.shape[1], device=v.device)
-          st['PL'] = torch.eye(v.shape[0], device=v.device)
-          st['PR'] = torch.eye(v.shape[1], device=v.device)
-        if t % p.statistics_computation_frequency == 0:
-          gf = g.float()
-          st['L'].add_(gf @ gf.t())
-          st['R'].add_(gf.t() @ gf)
-        if p.async_preconditioning:
-          from lingvo_b200.core import preconditioner_captain
-          cap = preconditioner_captain.GetCaptain()
-          if t % p.preconditioning_compute_steps == 0 or t == 1:
-            cap.InsertGradientStatistics(key + '/L', st['L'], 4, t)
-            cap.InsertGradientStatistics(key + '/R', st['R'], 4, t)
-          for side in ('L', 'R'):
-            done, ok = cap.GetPreconditioner(key + '/' + side)
-            if ok:
-              st['P' + side] = done
-        elif t % p.preconditioning_compute_steps == 0 or t == 1:
-          st['PL'] = matrix_functions.inlined_matrix_inverse_pth_root(
-              st['L'], 4, ridge_epsilon=p.matrix_epsilon)
-          st['PR'] = matrix_functions.inlined_matrix_inverse_pth_root(
-              st['R'], 4, ridge_epsilon=p.matrix_epsilon)
-        if t >= p.start_preconditioning_steps:
-          pg = (st['PL'] @ g.float() @ st['PR']).to(g.dtype)
-          pg = pg * (adagrad_upd.norm() / (pg.norm() + 1e-16))
-          upd = pg
-      mom = self._Slot(v, 'mom')
-      mom.mul_(p.momentum).add_(upd)
-      v.add_(mom, alpha=-float(lr))
-
-
-class AdaGraft(Base):
-  """Step *magnitude* from one optimizer, *direction* from another (:803)."""
-
-  @classmethod
-  def Params(cls):
-    p = super().Params()
-    p.Define('magnitude_optimizer', SGD.Params(), 'Provides per-tensor norms.')
-    p.Define('direction_optimizer', Adam.Params(), 'Provides directions.')
-    p.Define('use_global_norm', False, 'Graft the global norm.')
-    p.Define('diagnostic', False, 'Log norms.')
-    return p
-
-  def __init__(self, params):
-    super().__init__(params)
-    self.CreateChild('_mag', self.params.magnitude_optimizer)
-    self.CreateChild('_dir', self.params.direction_optimizer)
-
-  def Apply(self, lr, var_grad):
-    pairs = _Pairs(var_grad)
-    variables = [v for v, _ in pairs]
-    with torch.no_grad():
-      before = [v.detach().clone() for v in variables]
-    vg = [py_utils.VarGrad(v, g) for v, g in pairs]
-    self._mag.Apply(lr, vg)
-    with torch.no_grad():
-      mag_steps = [v.detach() - b for v, b in zip(variables, before)]
-      for v, b in zip(variables, before):
-        v.copy_(b)
-    self._dir.Apply(lr, vg)
-    with torch.no_grad():
-      dir_steps = [v.detach() - b for v, b in zip(variables, before)]
-      if self.params.use_global_norm:
-        mn = torch.sqrt(sum(s.float().square().sum() for s in mag_steps))
-        dn = torch.sqrt(sum(s.float().square().sum() for s in dir_steps))
-        scale = [mn / (dn + 1e-30)] * len(variables)
-      else:
-        scale = [m.float().norm() / (d.float().norm() + 1e-30)
-                 for m, d in zip(mag_steps, dir_steps)]
-      for v, b, d, s in zip(variables, before, dir_steps, scale):
-        v.copy_(b + d * s.to(d.dtype))
-    self._step_count += 1
-
-
 class CompositeOptimizer(Base):
   """regex → (optimizer, lr) dispatch (reference CompositeOptimizer)."""
 
@@ -1038,3 +919,16 @@ class CompositeOptimizer(Base):
     for o in self._opts:
       used += o.LoadOptimizerSlots(tensors)
     return used
+
+
+# Shampoo and AdaGraft live in their own modules (as in the reference) and import this one;
+# `optimizer.DistributedShampoo` / `optimizer.AdaGraft` resolve lazily (PEP 562) so either
+# import order works.
+def __getattr__(name):
+  if name in ('AdaGraft', 'AdaGraftOptimizer'):
+    from lingvo_b200.core import adagraft  # pylint: disable=g-import-not-at-top
+    return getattr(adagraft, name)
+  if name == 'DistributedShampoo':
+    from lingvo_b200.core import distributed_shampoo  # pylint: disable=g-import-not-at-top
+    return distributed_shampoo.DistributedShampoo
+  raise AttributeError('module %r has no attribute %r' % (__name__, name))

@@ -186,13 +186,13 @@ def test_shampoo_async_preconditioning_trains():
   w.var_name = 'layer/w/var'
   target = torch.randn(8, 6)
   opt = optimizer.DistributedShampoo.Params().Set(
-      name='sh', start_preconditioning_steps=2, preconditioning_compute_steps=2,
+      name='sh', momentum=0.0, start_preconditioning_steps=2, preconditioning_compute_steps=2,
       async_preconditioning=True).Instantiate()
   losses = []
-  for _ in range(30):
+  for _ in range(60):
     loss = (w - target).square().sum()
     g, = torch.autograd.grad(loss, w)
-    opt.Apply(0.1, [py_utils.VarGrad(w, g)])
+    opt.Apply(0.3, [py_utils.VarGrad(w, g)])
     losses.append(float(loss))
   assert losses[-1] < 0.2 * losses[0]
 
