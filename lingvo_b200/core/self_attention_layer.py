@@ -1,25 +1,167 @@
-"""Self-attention stacks built with the Builder DSL (ref `lingvo/core/self_attention_layer.py`):
-`Builder` (:294) / `SimplifiedTransformerBuilder` (:428) and
-`StackedTransformerEncoderLayers` (:696)."""
+"""Self-attention layers and stacks (ref `lingvo/core/self_attention_layer.py`):
+`BlockSparseAttention` (:30), the `Builder` (:294) / `SimplifiedTransformerBuilder` (:428)
+DSL for encoder stacks, and `StackedTransformerEncoderLayers` (:696)."""
 
 from __future__ import annotations
 
+import torch
+
 from lingvo_b200.core import base_layer
 from lingvo_b200.core import batch_major_attention as bma
+from lingvo_b200.core import py_utils
 from lingvo_b200.core.nested_map import NestedMap
+
+MultiHeadedSelfAttention = bma.MultiHeadedAttention
+
+
+class BlockSparseAttention(MultiHeadedSelfAttention):
+  """Block-sparse attention with the diagonal band only (ref :30; BigBird, arXiv 2007.14062,
+  without global / random blocks): query block l attends to key block l and nothing else.
+
+  B200 mapping: a block-diagonal attention *is* a batched dense attention — the `L = T / w`
+  blocks are folded into the batch dimension (`[B, T, N, H] → [B·L, w, N, H]`, a free view),
+  and the regular attention core (flash kernel on the device) runs on B·L short sequences.
+  Cost O(T·w) instead of O(T²), and no `[B, N, L, w, w]` mask tensor is materialised: key
+  padding enters as the usual additive bias of the folded batch.
+  """
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('src_block_size', None, 'Query block size.')
+    p.Define('tgt_block_size', None, 'Key/value block size (defaults to src_block_size).')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert p.src_block_size is not None, 'src_block_size is not set'
+    assert p.src_block_size > 0, 'src_block_size should be greater than 0'
+    assert not p.packed_input, 'packed_input is not supported'
+    assert not p.use_scale_invariant_atten, 'use_scale_invariant_atten is not supported.'
+    assert not p.enable_scaling_code_motion, 'enable_scaling_code_motion is not supported.'
+
+  def FProp(self, theta, query_vec, key_vec, value_vec, paddings, segment_mask=None,
+            per_step_padding=None):
+    """query_vec `[B, T, D]`, key/value_vec `[B, S, D]`, paddings `[B, S]` →
+    (encoded `[B, T, D]`, None)."""
+    p = self.params
+    assert per_step_padding is None, 'per_step_padding is not supported.'
+    assert segment_mask is None, 'segment_mask is not supported.'
+    wt = p.src_block_size
+    ws = p.tgt_block_size or p.src_block_size
+    b, t = query_vec.shape[:2]
+    s = key_vec.shape[1]
+    assert tuple(paddings.shape) == (b, s), (paddings.shape, b, s)
+    assert t % wt == 0, 'seq_length % src_block_size != 0'
+    assert s % ws == 0, 'seq_length % tgt_block_size != 0'
+    nblk = t // wt
+    assert s // ws == nblk, 'tgt_num_blocks != src_num_blocks'
+    q, k, v = self._HeadsProj(theta, query_vec, key_vec, value_vec)
+    q = self._RoPE(theta, q)
+    k = self._RoPE(theta, k)
+    q = self._MaybeScaleQuery(theta, q)
+    fold = lambda x, w: x.reshape(b * nblk, w, *x.shape[2:])
+    bias = self._Bias(paddings.reshape(b * nblk, ws), None, None)
+    ctx, _ = self._Core(theta, fold(q, wt), fold(k, ws), fold(v, ws), bias, False)
+    ctx = ctx.reshape(b, t, *ctx.shape[2:])
+    return self._PostProj(theta, ctx), None
 
 
 class Builder(bma.Builder):
-  """Encoder-stack builder: pre-LN self-attention + FFN blocks."""
+  """Encoder-stack builder: pre-LN self-attention + FFN blocks (ref :294).
+
+  `p.atten_tpl` may be a list with one attention template per layer (e.g. dense attention in
+  the lower layers, `BlockSparseAttention` above). `TransformerStackV2` lets the final layer
+  compute strided queries or only the first n positions (`final_layer_stride`,
+  `final_layer_first_n`): the output sequence — vec and paddings — shrinks accordingly, which
+  is how sequence-summary encoders avoid computing positions nobody reads.
+  """
+
+  def _AttenTplFor(self, layer_idx):
+    tpl = self.params.atten_tpl
+    if isinstance(tpl, (list, tuple)):
+      assert layer_idx is not None, 'layer_idx must be specified.'
+      return tpl[layer_idx]
+    return tpl
+
+  def _LayerBuilder(self, layer_idx):
+    """A builder identical to this one but with the layer's own attention template."""
+    tpl = self._AttenTplFor(layer_idx)
+    if tpl is self.params.atten_tpl:
+      return self
+    return self.params.Copy().Set(atten_tpl=tpl.Copy()).Instantiate()
+
+  def SelfAttention(self, name, is_causal=False, num_heads=None, layer_idx=None):
+    return bma.Builder.SelfAttention(self._LayerBuilder(layer_idx), name, is_causal, num_heads)
+
+  def _StridedAttention(self, name, stride=1, first_n=None, num_heads=None, layer_idx=None):
+    """Self-attention whose queries are strided / truncated; paddings follow (ref
+    batch_major_attention.Builder._StridedAttention)."""
+    inner = bma.Builder.SelfAttention(self._LayerBuilder(layer_idx), name, False, num_heads)
+    if stride == 1 and first_n is None:
+      return inner
+    return _StridedSelfAtten.Params().Set(name=name, body=inner, stride=stride, first_n=first_n)
+
+  def _TransformerLayerBlock(self, name, feed_forward_qdomain=None, layer_idx=None):
+    del feed_forward_qdomain
+    return self._Seq(name, self.SelfAttention('self_atten', layer_idx=layer_idx),
+                     self.Feedforward('ff'))
+
+  def _CheckTplList(self, num_layers):
+    tpl = self.params.atten_tpl
+    if isinstance(tpl, (list, tuple)):
+      assert len(tpl) == num_layers, 'atten_tpl list must have the same length as num_layers.'
 
   def TransformerStack(self, name, num_layers=1, feed_forward_qdomain=None):
-    del feed_forward_qdomain
-    return self.TransformerEncoderStack(name, num_layers)
+    self._CheckTplList(num_layers)
+    return self._Seq(name, *[
+        self._Seq('iter_%03d' % i, self._TransformerLayerBlock(
+            'block', feed_forward_qdomain=feed_forward_qdomain, layer_idx=i))
+        for i in range(num_layers)])
 
   def TransformerStackV2(self, name, num_layers=1, *, final_layer_first_n=None,
                          final_layer_stride=1, feed_forward_qdomain=None):
-    del final_layer_first_n, final_layer_stride, feed_forward_qdomain
-    return self.TransformerEncoderStack(name, num_layers)
+    del feed_forward_qdomain
+    self._CheckTplList(num_layers)
+    blocks = []
+    for i in range(num_layers):
+      last = i == num_layers - 1
+      stride, first_n = (final_layer_stride, final_layer_first_n) if last else (1, None)
+      blocks.append(self._Seq('iter_%03d' % i, self._Seq(
+          'block', self._StridedAttention('self_atten', stride=stride, first_n=first_n,
+                                          layer_idx=i),
+          self.Feedforward('ff'))))
+    return self._Seq(name, *blocks)
+
+
+class _StridedSelfAtten(base_layer.BaseLayer):
+  """Runs a `Builder.SelfAttention` block and keeps every `stride`-th (or the first n)
+  position of its output: residual, vec, paddings and segment mask shrink together."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('body', None, 'Self-attention block params (NestedMap in/out).')
+    p.Define('stride', 1, 'Keep every stride-th position.')
+    p.Define('first_n', None, 'Keep only the first n positions.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('body', self.params.body)
+
+  def FProp(self, theta, i):
+    p = self.params
+    o = self.body.FProp(theta.body, i)
+    sel = (lambda x: x[:, :p.first_n]) if p.first_n is not None else (
+        lambda x: x[:, ::p.stride])
+    out = NestedMap(vec=sel(o.vec), paddings=sel(o.paddings))
+    if 'segment_mask' in o and o.segment_mask is not None:
+      m = o.segment_mask
+      out.segment_mask = (m[:, :, :p.first_n, :p.first_n] if p.first_n is not None
+                          else m[:, :, ::p.stride, ::p.stride])
+    return out
 
 
 class SimplifiedTransformerBuilder(Builder):
@@ -28,7 +170,8 @@ class SimplifiedTransformerBuilder(Builder):
   @classmethod
   def Params(cls):
     p = super().Params()
-    p.Define('parallel_attention_mlp', True, 'Attention and MLP share one residual.')
+    p.Define('parallel_attention_mlp', False,
+             'Attention and MLP are computed in parallel (Fig. 10 of the paper).')
     p.atten_tpl = bma.MultiHeadedAttention.Params().Set(enable_shaped_attention=True)
     return p
 

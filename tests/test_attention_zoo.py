@@ -139,3 +139,69 @@ def test_performer_and_sketchmem_builders():
   mem = bma.MemoryAddLayer.Params().Set(name='m', input_dim=8, num_memory_slots=3).Instantiate()
   y, p2 = mem.FProp(mem.theta, x, pad)
   assert y.shape == (2, 19, 8) and float(p2[:, :3].sum()) == 0
+
+
+# ------------------------------------------------------------- self_attention_layer.py --
+def test_block_sparse_attention_equals_dense_with_block_diagonal_mask():
+  from lingvo_b200.core import self_attention_layer as sal
+  p = sal.BlockSparseAttention.Params().Set(
+      name='bs', input_dim=16, hidden_dim=16, num_heads=4, src_block_size=4, tgt_block_size=4)
+  layer = p.Instantiate()
+  x = torch.randn(2, 12, 16, requires_grad=True)
+  pad = torch.zeros(2, 12)
+  pad[1, 10:] = 1
+  y, probs = layer.FPropDefaultTheta(x, x, x, pad)
+  assert y.shape == (2, 12, 16) and probs is None
+  dense = bma.MultiHeadedAttention.Params().Set(name='bs', input_dim=16, hidden_dim=16,
+                                                num_heads=4).Instantiate()
+  blk = torch.arange(12) // 4
+  psp = (blk[:, None] != blk[None, :]).float().unsqueeze(0).expand(2, 12, 12)
+  want, _ = dense.FProp(layer.theta, x, x, x, pad, per_step_padding=psp)
+  valid = (1 - pad).unsqueeze(-1)
+  torch.testing.assert_close(y * valid, want * valid, atol=1e-5, rtol=1e-5)
+  # block l never sees other blocks: perturbing block 2 leaves blocks 0-1 untouched
+  x2 = x.detach().clone()
+  x2[:, 8:] += 1.0
+  y2, _ = layer.FPropDefaultTheta(x2, x2, x2, pad)
+  torch.testing.assert_close(y2[:, :8], y.detach()[:, :8])
+  y.sum().backward()
+  assert x.grad is not None
+  for bad in (dict(src_block_size=None), dict(src_block_size=4, packed_input=True)):
+    with pytest.raises(AssertionError):
+      sal.BlockSparseAttention.Params().Set(name='b', input_dim=8, hidden_dim=8,
+                                            **bad).Instantiate()
+  with pytest.raises(AssertionError):
+    layer.FPropDefaultTheta(x[:, :10], x[:, :10], x[:, :10], pad[:, :10])   # 10 % 4 != 0
+
+
+def test_self_attention_builder_per_layer_templates_and_strided_final_layer():
+  from lingvo_b200.core import self_attention_layer as sal
+  dense = bma.MultiHeadedAttention.Params()
+  sparse = sal.BlockSparseAttention.Params().Set(src_block_size=4, tgt_block_size=4)
+  b = sal.Builder.Params().Set(model_dim=16, num_heads=2, ff_hidden_dim=32,
+                               atten_tpl=[dense, sparse]).Instantiate()
+  stack = b.TransformerStack('stack', 2).Instantiate()
+  x = NestedMap(vec=torch.randn(2, 8, 16), paddings=torch.zeros(2, 8))
+  out = stack.FPropDefaultTheta(x)
+  assert out.vec.shape == (2, 8, 16)
+  def Walk(layer):
+    yield layer
+    for c in layer.children.Flatten():
+      yield from Walk(c)
+  kinds = [type(l).__name__ for l in Walk(stack) if isinstance(l, bma.MultiHeadedAttention)]
+  assert kinds == ['MultiHeadedAttention', 'BlockSparseAttention']
+  with pytest.raises(AssertionError):
+    b.TransformerStack('bad', 3)                                  # list length ≠ layers
+
+  b1 = sal.Builder.Params().Set(model_dim=16, num_heads=2, ff_hidden_dim=32).Instantiate()
+  strided = b1.TransformerStackV2('s', 2, final_layer_stride=2).Instantiate()
+  pad = torch.zeros(2, 8)
+  pad[1, 6:] = 1
+  o = strided.FPropDefaultTheta(NestedMap(vec=torch.randn(2, 8, 16), paddings=pad))
+  assert o.vec.shape == (2, 4, 16) and torch.equal(o.paddings, pad[:, ::2])
+  firstn = b1.TransformerStackV2('f', 2, final_layer_first_n=3).Instantiate()
+  o = firstn.FPropDefaultTheta(NestedMap(vec=torch.randn(2, 8, 16), paddings=pad))
+  assert o.vec.shape == (2, 3, 16) and o.paddings.shape == (2, 3)
+  plain = b1.TransformerStackV2('p', 2).Instantiate()
+  assert plain.FPropDefaultTheta(NestedMap(vec=torch.randn(2, 8, 16),
+                                           paddings=pad)).vec.shape == (2, 8, 16)
