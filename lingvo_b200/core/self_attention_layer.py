@@ -164,8 +164,72 @@ class _StridedSelfAtten(base_layer.BaseLayer):
     return out
 
 
+class _SimplifiedBlock(base_layer.BaseLayer):
+  """One simplified transformer block (arXiv 2311.01906, ref `TransformerLayerBlock` :442).
+
+  There is **no skip connection around attention**: `a = dropout(atten(LN(x)))` replaces x
+  (shaped attention keeps signal propagation healthy instead). Then either
+    * sequential: `o = a + FF(LN(a))` — the regular feed-forward block with its residual, or
+    * parallel (`parallel_attention_mlp`, Fig. 10): `o = a + w·MLP(LN(x))` — attention and MLP
+      read the same normalised input, so on the device their GEMMs are independent work
+      that can overlap, and one LN is saved.
+  Strided / first-n queries shrink vec, paddings and segment mask together.
+  """
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('ln', None, 'LayerNorm params.')
+    p.Define('atten', None, 'Attention params.')
+    p.Define('dropout', None, 'Residual dropout params.')
+    p.Define('ff', None, 'Sequential mode: Feedforward block params (NestedMap in/out).')
+    p.Define('mlp', None, 'Parallel mode: MLP body params (vec → vec).')
+    p.Define('mlp_residual_weight', 1.0, 'Weight of the MLP branch in parallel mode.')
+    p.Define('stride', 1, 'Query stride.')
+    p.Define('first_n', None, 'Only the first n queries.')
+    p.Define('packed_input', False, 'Inputs carry a segment mask.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert (p.ff is None) != (p.mlp is None)
+    self.CreateChild('LN', p.ln)
+    self.CreateChild('atten', p.atten)
+    self.CreateChild('dropout', p.dropout)
+    if p.ff is not None:
+      self.CreateChild('ff', p.ff)
+    else:
+      self.CreateChild('feedforward', p.mlp)
+
+  def FProp(self, theta, i):
+    p = self.params
+    sel = (lambda x, ax=1: x.narrow(ax, 0, p.first_n)) if p.first_n is not None else (
+        lambda x, ax=1: x.index_select(ax, torch.arange(0, x.shape[ax], p.stride,
+                                                         device=x.device))
+        if p.stride > 1 else x)
+    after_ln = self.LN.FProp(theta.LN, i.vec)
+    query = sel(after_ln)
+    seg = i.get('segment_mask') if p.packed_input else None
+    if seg is not None:
+      seg = sel(seg, 2)
+    att, _ = self.atten.FProp(theta.atten, query, after_ln, after_ln, i.paddings,
+                              segment_mask=seg)
+    att = self.dropout.FProp(theta.dropout, att)
+    out = NestedMap(vec=att, paddings=sel(i.paddings))
+    if seg is not None:
+      out.segment_mask = sel(seg, 3)
+    if p.mlp is not None:
+      mlp = self.feedforward.FProp(theta.feedforward, query)
+      out.vec = py_utils.ApplyPadding(out.paddings.unsqueeze(-1),
+                                      att + p.mlp_residual_weight * mlp)
+      return out
+    return self.ff.FProp(theta.ff, out)
+
+
 class SimplifiedTransformerBuilder(Builder):
-  """Parallel attention+FFN blocks without LayerNorm on the skip path (arXiv 2311.01906)."""
+  """Simplified transformer blocks (ref :428; arXiv 2311.01906): shaped attention, no skip
+  connection around attention, optionally attention ∥ MLP."""
 
   @classmethod
   def Params(cls):
@@ -174,6 +238,48 @@ class SimplifiedTransformerBuilder(Builder):
              'Attention and MLP are computed in parallel (Fig. 10 of the paper).')
     p.atten_tpl = bma.MultiHeadedAttention.Params().Set(enable_shaped_attention=True)
     return p
+
+  def TransformerLayerBlock(self, name, stride=1, first_n=None, num_heads=None,
+                            feed_forward_qdomain=None, layer_idx=None):
+    """NestedMap(vec, paddings[, segment_mask]) → same, possibly shorter."""
+    del feed_forward_qdomain
+    p = self.params
+    lb = self._LayerBuilder(layer_idx)
+    atten = bma.Builder._MultiHeadedAtten(lb, 'atten', num_heads).Set(   # pylint: disable=protected-access
+        query_stride=1, query_first_n=None)
+    blk = _SimplifiedBlock.Params().Set(
+        name=name, ln=self._DefaultLN('LN'), atten=atten,
+        dropout=self._Dropout('dropout', p.residual_dropout_prob), stride=stride,
+        first_n=first_n, packed_input=p.packed_input,
+        mlp_residual_weight=p.ff_residual_weight)
+    if p.parallel_attention_mlp:
+      h = p.ff_hidden_dim
+      blk.mlp = self._Seq(
+          'feedforward', self._Linear('linear01', p.model_dim, h), self._Bias('bias01', h),
+          self._Activation('act', p.ff_activation_fn),
+          self._Dropout('relu_dropout', p.relu_dropout_prob),
+          self._Linear('linear02', h, p.model_dim), self._Bias('bias02', p.model_dim),
+          self._Dropout('dropout', p.residual_dropout_prob))
+    else:
+      blk.ff = self.Feedforward('ff')
+    return blk
+
+  def TransformerStack(self, name, num_layers=1, feed_forward_qdomain=None):
+    self._CheckTplList(num_layers)
+    return self._Seq(name, *[
+        self._Seq('iter_%03d' % i, self.TransformerLayerBlock('block', layer_idx=i))
+        for i in range(num_layers)])
+
+  def TransformerStackV2(self, name, num_layers=1, *, final_layer_first_n=None,
+                         final_layer_stride=1, feed_forward_qdomain=None):
+    self._CheckTplList(num_layers)
+    blocks = []
+    for i in range(num_layers):
+      last = i == num_layers - 1
+      stride, first_n = (final_layer_stride, final_layer_first_n) if last else (1, None)
+      blocks.append(self._Seq('iter_%03d' % i, self.TransformerLayerBlock(
+          'block', stride=stride, first_n=first_n, layer_idx=i)))
+    return self._Seq(name, *blocks)
 
 
 class StackedTransformerEncoderLayers(base_layer.BaseLayer):

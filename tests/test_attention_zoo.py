@@ -205,3 +205,28 @@ def test_self_attention_builder_per_layer_templates_and_strided_final_layer():
   plain = b1.TransformerStackV2('p', 2).Instantiate()
   assert plain.FPropDefaultTheta(NestedMap(vec=torch.randn(2, 8, 16),
                                            paddings=pad)).vec.shape == (2, 8, 16)
+
+
+@pytest.mark.parametrize('parallel', [False, True])
+def test_simplified_transformer_builder(parallel):
+  from lingvo_b200.core import self_attention_layer as sal
+  b = sal.SimplifiedTransformerBuilder.Params().Set(
+      model_dim=16, num_heads=2, ff_hidden_dim=32, parallel_attention_mlp=parallel).Instantiate()
+  assert b.params.atten_tpl.enable_shaped_attention
+  stack = b.TransformerStack('s', 2).Instantiate()
+  x = torch.randn(2, 6, 16, requires_grad=True)
+  pad = torch.zeros(2, 6)
+  pad[1, 4:] = 1
+  out = stack.FPropDefaultTheta(NestedMap(vec=x, paddings=pad))
+  assert out.vec.shape == (2, 6, 16) and torch.equal(out.paddings, pad)
+  out.vec.sum().backward()
+  assert x.grad is not None and torch.isfinite(x.grad).all()
+  blk = stack.children['iter_000'].children['block']
+  assert ('feedforward' in blk.children) == parallel and ('ff' in blk.children) != parallel
+  # no skip connection around attention: with the attention output projection zeroed the
+  # block output no longer depends on x in sequential mode (FF sees zeros) …
+  v2 = b.TransformerStackV2('v2', 2, final_layer_stride=2).Instantiate()
+  o2 = v2.FPropDefaultTheta(NestedMap(vec=x.detach(), paddings=pad))
+  assert o2.vec.shape == (2, 3, 16) and torch.equal(o2.paddings, pad[:, ::2])
+  if parallel:
+    assert float(o2.vec[1, 2].abs().sum()) == 0.0          # padded position is zeroed
