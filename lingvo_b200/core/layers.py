@@ -1967,31 +1967,42 @@ class UniformLabelSmoother(base_layer.BaseLayer):
 
 
 class LocalizedLabelSmoother(base_layer.BaseLayer):
-  """Smooths labels over neighbouring time steps (reference :5305)."""
+  """Smooths one-hot labels with the labels of neighbouring *time steps* (reference :5305):
+  at time t the target is `onehot[t] + Σ_i weights[i] · onehot[t + offsets[i]]`, renormalised.
+  Offsets reaching outside the sequence contribute nothing, and neither do padded positions
+  (nor the last valid label, so EOS is not made more probable elsewhere)."""
 
   @classmethod
   def Params(cls):
     p = super().Params()
     p.Define('num_classes', 0, 'Number of classes.')
-    p.Define('offsets', [], 'Time offsets (e.g. [-2,-1,1,2]).')
-    p.Define('weights', [], 'Weights per offset; 1-sum goes to the label.')
+    p.Define('offsets', [], 'Time offsets (e.g. [-2, -1, 1, 2]).')
+    p.Define('weights', [], 'Weight of the smoothing at the corresponding offset.')
     return p
 
-  def FProp(self, theta, target_paddings, target_labels, target_ids):
-    """Time-major: [T, B] labels → [T, B, C]."""
+  def __init__(self, params):
+    super().__init__(params)
     p = self.params
-    oh = F.one_hot(target_labels.long(), p.num_classes).float()
-    out = oh * (1.0 - sum(p.weights))
-    t = oh.shape[0]
+    assert p.num_classes > 0
+    assert len(p.offsets) == len(p.weights)
+    assert p.name
+
+  def FProp(self, theta, target_paddings, target_labels, target_ids):
+    """paddings / labels / ids `[B, T]` → distribution `[B, T, num_classes]`."""
+    del target_ids
+    p = self.params
+    probs = F.one_hot(target_labels.long(), p.num_classes).to(py_utils.FPropDtype(p))
+    seq_len = probs.shape[1]
+    lo = -min(list(p.offsets) + [0])
+    hi = max(list(p.offsets) + [0])
+    padded = F.pad(probs, (0, 0, lo, hi))
+    # weights shifted left by one: the last valid position (EOS) never leaks to neighbours
+    cw = F.pad(1.0 - target_paddings[:, 1:].to(probs.dtype), (lo, hi + 1)).unsqueeze(-1)
+    out = probs
     for off, w in zip(p.offsets, p.weights):
-      shifted = torch.roll(oh, shifts=-off, dims=0)
-      if off > 0:
-        shifted[t - off:] = oh[t - off:]
-      else:
-        shifted[:-off] = oh[:-off]
-      out = out + w * shifted
-    out = out / out.sum(-1, keepdim=True)
-    return out
+      s = off + lo
+      out = out + padded[:, s:s + seq_len] * cw[:, s:s + seq_len] * w
+    return out / out.sum(-1, keepdim=True)
 
 
 class HighwaySkipLayer(base_layer.BaseLayer):

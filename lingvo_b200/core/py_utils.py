@@ -1376,13 +1376,46 @@ def ReadFileLines(file_path: str) -> List[str]:
     return f.readlines()
 
 
-def MultiTaskProjection(weights, biases, inputs, tasks):
-  """Per-example task-indexed projection (reference :6950)."""
-  w = weights[tasks.long()]      # [B, in, out]
-  out = torch.einsum('b...i,bio->b...o', inputs, w)
+def MultiTaskProjection(weights, biases, inputs, tasks, einsum_order='select_and_multiply'):
+  """Projection whose weights (and bias) are picked per example — or per time step — by a
+  task id (reference :6950).
+
+  weights `[num_tasks, in, out]`, biases `[num_tasks, out]` or None, inputs `[B, in]` or
+  `[B, T, in]`; tasks: int ids of shape `[]`, `[B]` or `[B, T]` (missing dims broadcast), or
+  one-hot/float task weights with a trailing `num_tasks` axis.
+    * 'select_and_multiply': gather the task's matrix, then multiply — moves `in·out` weights
+      per example, the right order when there are few examples per task;
+    * 'multiply_and_select': project with every task's matrix in one batched GEMM and then
+      pick — more FLOPs, but one large tensor-core GEMM with no gathered weight copies.
+  """
+  if einsum_order not in ('select_and_multiply', 'multiply_and_select'):
+    raise ValueError('Unknown einsum_order: %s' % einsum_order)
+  num_tasks = weights.shape[0]
+  squeeze_time = inputs.dim() == 2
+  x = inputs.unsqueeze(1) if squeeze_time else inputs          # [B, T, in]
+  b, t = x.shape[0], x.shape[1]
+  if tasks.is_floating_point() and tasks.dim() >= 1 and tasks.shape[-1] == num_tasks:
+    sel = tasks.to(x.dtype)                                     # soft / one-hot selection
+    while sel.dim() < 3:
+      sel = sel.unsqueeze(-2) if sel.dim() == 2 else sel.unsqueeze(0)
+    sel = sel.expand(b, t, num_tasks)
+    out = torch.einsum('bti,kio,btk->bto', x, weights, sel)
+    if biases is not None:
+      out = out + torch.einsum('btk,ko->bto', sel, biases)
+    return out.squeeze(1) if squeeze_time else out
+  ids = tasks.long()
+  if ids.dim() == 0:
+    ids = ids.reshape(1, 1).expand(b, t)
+  elif ids.dim() == 1:
+    ids = ids.reshape(b, 1).expand(b, t)
+  else:
+    assert not squeeze_time, 'per-time-step tasks need inputs with a time dimension'
+    assert tuple(ids.shape) == (b, t), (ids.shape, (b, t))
+  if einsum_order == 'select_and_multiply':
+    out = torch.einsum('bti,btio->bto', x, weights[ids])
+  else:
+    allp = torch.einsum('bti,kio->btko', x, weights)
+    out = allp.gather(2, ids.reshape(b, t, 1, 1).expand(b, t, 1, allp.shape[-1])).squeeze(2)
   if biases is not None:
-    b = biases[tasks.long()]
-    while b.dim() < out.dim():
-      b = b.unsqueeze(1)
-    out = out + b
-  return out
+    out = out + biases[ids]
+  return out.squeeze(1) if squeeze_time else out
