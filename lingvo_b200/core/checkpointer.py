@@ -57,6 +57,53 @@ def _EpBaseOf(key: str, ep: Dict[str, Tuple[int, int, int, int]]) -> Optional[st
   return None
 
 
+def _TpShards(model) -> Dict[str, Tuple[int, int, int, int]]:
+  """`<var base name>` → (tp_rank, tp_size, dim, logical_size) of tensor-parallel shards."""
+  out = {}
+  for v in model.vars.Flatten():
+    shard = getattr(v, 'tp_shard', None)
+    if shard is None:
+      continue
+    base = v.var_name[:-len('/var')] if v.var_name.endswith('/var') else v.var_name
+    out[base] = tuple(shard)
+  return out
+
+
+def _TpKey(key: str, tp_rank: int, tp_size: int) -> str:
+  """Name of a per-TP-rank tensor (optimizer slots / EMA of a sharded variable)."""
+  return '%s/__tp%d_of_%d' % (key, tp_rank, tp_size)
+
+
+def _TpTensors(named, model, rank) -> Dict[str, torch.Tensor]:
+  """Tensor-parallel jobs. Variables are written once, *gathered to their logical shape*
+  (so evalers, decoders and jobs with another TP degree read an ordinary checkpoint);
+  optimizer slots and EMA shadows of sharded variables stay per-rank (`__tp<r>_of_<n>`
+  keys: factored second-moment statistics of a shard are not a slice of the unsharded
+  statistics). Written by the dp_rank-0 replica: rank 0 the replicated tensors and the
+  gathered variables, every rank of TP group 0 its own slot shards."""
+  from lingvo_b200.parallel import mesh as mesh_lib   # pylint: disable=g-import-not-at-top
+  from lingvo_b200.parallel import tp_layers   # pylint: disable=g-import-not-at-top
+  ctx = mesh_lib.TensorParallel()
+  tp = _TpShards(model)
+  out = {}
+  var_keys = {v.var_name for v in model.vars.Flatten()}
+  for key in sorted(named):                       # same order on all ranks: collectives inside
+    t = named[key]
+    base = _EpBaseOf(key, tp)
+    if base is None:
+      if rank == 0:
+        out[key] = t
+      continue
+    _, tp_size, dim, _ = tp[base]
+    if key in var_keys:
+      full = tp_layers.GatherShards(t.detach(), ctx, dim)
+      if rank == 0:
+        out[key] = full
+    elif ctx.dp_rank == 0:
+      out[_TpKey(key, ctx.tp_rank, tp_size)] = t
+  return out
+
+
 def _ModelTensors(model, rank: int = 0, world: int = 1) -> Dict[str, torch.Tensor]:
   """The tensors *this rank* writes. Rank 0 owns everything replicated; every rank of the
   first EP group additionally owns its dim-0 slice of the expert-parallel variables and of
@@ -71,6 +118,8 @@ def _ModelTensors(model, rank: int = 0, world: int = 1) -> Dict[str, torch.Tenso
     named.update(task.EmaShadowTensors())
   if world <= 1:
     return named
+  if _TpShards(model):
+    return _TpTensors(named, model, rank)
   out = {}
   for key, t in named.items():
     base = _EpBaseOf(key, ep)
@@ -107,7 +156,7 @@ class Checkpointer:
     self._rank, self._world = _RankWorld()
     # Sharded bundle only when some variable differs per rank (expert parallelism);
     # otherwise rank 0 alone writes a single-shard bundle.
-    self._sharded = self._world > 1 and bool(_EpSlices(model))
+    self._sharded = self._world > 1 and bool(_EpSlices(model) or _TpShards(model))
     self._saver = saver_lib.Saver(
         train_dir, lambda: _ModelTensors(model, self._rank, self._world),
         sanity_checks=checks,
@@ -150,6 +199,7 @@ class Checkpointer:
     reader = tensor_bundle.BundleReader(checkpoint_path)
     keys = set(reader.LogicalKeys())
     ep = _EpSlices(self._model) if self._world > 1 else {}
+    tp = _TpShards(self._model)
     missing = []
 
     def read(key):
@@ -159,6 +209,17 @@ class Checkpointer:
         shape = reader.LogicalShape(key)
         if shape and shape[0] == e:
           return saver_lib.FromNumpy(reader.ReadRange(key, lo, hi))
+      tbase = _EpBaseOf(key, tp)
+      if tbase is not None:
+        tp_rank, tp_size, dim, logical = tp[tbase]
+        shape = reader.LogicalShape(key)
+        if shape and len(shape) > dim and shape[dim] == logical:
+          # a variable stored with its logical shape: keep this rank's slice
+          n = logical // tp_size
+          if dim == 0:
+            return saver_lib.FromNumpy(reader.ReadRange(key, tp_rank * n, (tp_rank + 1) * n))
+          full = saver_lib.FromNumpy(reader.ReadRange(key))
+          return full.narrow(dim, tp_rank * n, n).contiguous()
       return saver_lib.FromNumpy(reader.ReadRange(key))
 
     with torch.no_grad():
@@ -176,7 +237,15 @@ class Checkpointer:
       raise KeyError('Variables missing from checkpoint %s: %s' %
                      (checkpoint_path, missing[:10]))
     rest = {k: read(k) for k in keys
-            if not k.endswith('/var') and k != 'global_step'}
+            if not k.endswith('/var') and k != 'global_step' and '/__tp' not in k}
+    if tp:
+      # per-TP-rank slot / EMA tensors of this rank (absent when the checkpoint was written
+      # with another TP degree: those slots then start from their initial values)
+      tp_rank, tp_size = next(iter(tp.values()))[:2]
+      suffix = '/__tp%d_of_%d' % (tp_rank, tp_size)
+      for k in keys:
+        if k.endswith(suffix):
+          rest[k[:-len(suffix)]] = saver_lib.FromNumpy(reader.ReadRange(k))
     for task in self._model.tasks:
       for lrn in task.learners:
         # Slots are created lazily; load restores them on the var's device.

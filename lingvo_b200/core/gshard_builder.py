@@ -79,6 +79,25 @@ class _BuilderLayer(base_layer.BaseLayer):
   def bp(self):
     return self.params.b
 
+  def _TensorParallel(self, split, dim):
+    """The tensor-parallel context if `split[dim]` puts that weight dim on the model axis
+    (mesh axis 1) of a [dp, tp] device mesh and the job runs with tp_size > 1; else None."""
+    from lingvo_b200.parallel import mesh as mesh_lib   # pylint: disable=g-import-not-at-top
+    b = self.bp
+    if 'device_mesh_shape' in b:
+      mesh_lib.ConfigureFromMeshShape(b.device_mesh_shape)
+    ctx = mesh_lib.TensorParallel()
+    if ctx is None or split is None or len(split) <= dim or split[dim] != 1:
+      return None
+    return ctx
+
+  def _TagTpVars(self, names_dims):
+    """Tags `{var name: (sharded dim, logical size)}` after instantiation."""
+    from lingvo_b200.parallel import tp_layers   # pylint: disable=g-import-not-at-top
+    for n, (dim, logical) in names_dims.items():
+      if n in self._private_vars:
+        tp_layers.MarkSharded(self._private_vars[n], self._tp, dim, logical)
+
 
 class RmsNormLayer(_BuilderLayer):
   """Bias-less RMS "layer norm" `x·rsqrt(mean(x²)+eps)·scale` (:1833-1854)."""
@@ -243,23 +262,61 @@ class SelfAttentionLayer(_BuilderLayer):
     p.Define('relative_bias', False, 'Use T5 relative attention bias.')
     return p
 
+  def __init__(self, params):
+    super().__init__(params)
+    b = self.bp
+    # Heads on the model axis (`mhd_w_split = [0, 1, -1]`, ref :2806-2851): every TP rank owns
+    # H/tp heads — wq/wk/wv column-parallel, wo row-parallel, one all-reduce per direction.
+    self._tp = self._TensorParallel(b.mhd_w_split if 'mhd_w_split' in b else None, 1)
+    if self._tp is not None:
+      h = b.attention_num_heads
+      hk = b.attention_num_memory_heads or h
+      assert h % self._tp.tp_size == 0 and hk % self._tp.tp_size == 0, (
+          'tensor parallelism needs heads (%d, kv %d) divisible by tp_size %d' %
+          (h, hk, self._tp.tp_size))
+
+  def _LocalHeads(self):
+    b = self.bp
+    h = b.attention_num_heads
+    hk = b.attention_num_memory_heads or h
+    if self._tp is None:
+      return h, hk
+    return h // self._tp.tp_size, hk // self._tp.tp_size
+
   def _CreateLayerVariables(self):
     b = self.bp
     h, d, m = b.attention_num_heads, b.attention_key_value_dim, b.model_dim
     hk = b.attention_num_memory_heads or h
+    hl, hkl = self._LocalHeads()
     q_std = (m * d)**-0.5
-    self.CreateVariable('wq', ShardedWeightParams(
-        [m, h * d], WeightInit.Gaussian(q_std), self.params.dtype))
-    self.CreateVariable('wk', ShardedWeightParams(
-        [m, hk * d], WeightInit.Gaussian(m**-0.5), self.params.dtype))
-    self.CreateVariable('wv', ShardedWeightParams(
-        [m, hk * d], WeightInit.Gaussian(m**-0.5), self.params.dtype))
-    self.CreateVariable('wo', ShardedWeightParams(
-        [h * d, m], WeightInit.Gaussian((h * d)**-0.5), self.params.dtype))
+    tp = self._tp
+
+    def Shard(wp, dim):
+      if tp is not None:
+        wp.init_shard = (dim, tp.tp_rank, tp.tp_size)
+      return wp
+
+    self.CreateVariable('wq', Shard(ShardedWeightParams(
+        [m, hl * d], WeightInit.Gaussian(q_std), self.params.dtype), 1))
+    self.CreateVariable('wk', Shard(ShardedWeightParams(
+        [m, hkl * d], WeightInit.Gaussian(m**-0.5), self.params.dtype), 1))
+    self.CreateVariable('wv', Shard(ShardedWeightParams(
+        [m, hkl * d], WeightInit.Gaussian(m**-0.5), self.params.dtype), 1))
+    self.CreateVariable('wo', Shard(ShardedWeightParams(
+        [hl * d, m], WeightInit.Gaussian((h * d)**-0.5), self.params.dtype), 0))
     if self.params.relative_bias:
-      self.CreateVariable('wrb', WeightParams(
-          [h, b.relative_attention_num_buckets], WeightInit.Gaussian(1.0),
-          self.params.dtype))
+      self.CreateVariable('wrb', Shard(WeightParams(
+          [hl, b.relative_attention_num_buckets], WeightInit.Gaussian(1.0),
+          self.params.dtype), 0))
+
+  def _InstantiateSelfAndChildren(self):
+    super()._InstantiateSelfAndChildren()
+    if self._tp is not None:
+      b = self.bp
+      h, d = b.attention_num_heads, b.attention_key_value_dim
+      hk = b.attention_num_memory_heads or h
+      self._TagTpVars({'wq': (1, h * d), 'wk': (1, hk * d), 'wv': (1, hk * d),
+                       'wo': (0, h * d), 'wrb': (0, h)})
 
   _MASK_CACHE = {}
 
@@ -327,10 +384,21 @@ class SelfAttentionLayer(_BuilderLayer):
   supports_fused_residual = True
 
   def FProp(self, theta, x, segment_id, segment_pos, residual=None):
+    if self._tp is not None:
+      # f: identity / all-reduce(dx); the partial outputs of the head shards are summed by
+      # g before the residual is added (once, on the replicated result).
+      from lingvo_b200.parallel import tp_layers   # pylint: disable=g-import-not-at-top
+      out, aux = self._FPropLocal(theta, tp_layers.CopyToTensorParallel(x, self._tp),
+                                  segment_id, segment_pos, None)
+      out = tp_layers.ReduceFromTensorParallel(out, self._tp)
+      return (out + residual if residual is not None else out), aux
+    return self._FPropLocal(theta, x, segment_id, segment_pos, residual)
+
+  def _FPropLocal(self, theta, x, segment_id, segment_pos, residual=None):
     b = self.bp
     bsz, l, m = x.shape
-    h, d = b.attention_num_heads, b.attention_key_value_dim
-    hk = b.attention_num_memory_heads or h
+    d = b.attention_key_value_dim
+    h, hk = self._LocalHeads()
     from lingvo_b200.ops import gemm
     wq, wk, wv, wo = theta.wq, theta.wk, theta.wv, theta.wo
     if b.attention_combine_qkv and hk == h:
@@ -383,7 +451,7 @@ class SelfAttentionLayer(_BuilderLayer):
 
 def _SelfAttentionInitCache(layer, batch, max_len, device, dtype):
   b = layer.bp
-  hk = b.attention_num_memory_heads or b.attention_num_heads
+  _, hk = layer._LocalHeads()   # pylint: disable=protected-access
   d = b.attention_key_value_dim
   return NestedMap(k=torch.zeros(batch, max_len, hk, d, device=device, dtype=dtype),
                    v=torch.zeros(batch, max_len, hk, d, device=device, dtype=dtype))
@@ -395,8 +463,8 @@ def _SelfAttentionExtendStep(layer, theta, x, cache, t):
   buffers → the whole step is CUDA-graph capturable with `t` as a device scalar)."""
   b = layer.bp
   bsz, _, m = x.shape
-  h, d = b.attention_num_heads, b.attention_key_value_dim
-  hk = b.attention_num_memory_heads or h
+  d = b.attention_key_value_dim
+  h, hk = layer._LocalHeads()   # pylint: disable=protected-access  (this rank's heads under TP)
   xd = x.dtype
   q = torch.matmul(x, theta.wq.to(xd)).reshape(bsz, 1, h, d)
   k = torch.matmul(x, theta.wk.to(xd)).reshape(bsz, 1, hk, d)
@@ -425,7 +493,11 @@ def _SelfAttentionExtendStep(layer, theta, x, cache, t):
     logits = b.atten_logit_cap * torch.tanh(logits / b.atten_logit_cap)
   probs = torch.softmax(logits, -1)
   o = torch.einsum('bhqk,bkhd->bqhd', probs, vv.float()).to(xd).reshape(bsz, 1, h * d)
-  return torch.matmul(o, theta.wo.to(xd))
+  out = torch.matmul(o, theta.wo.to(xd))
+  if layer._tp is not None:   # pylint: disable=protected-access
+    from lingvo_b200.parallel import tp_layers   # pylint: disable=g-import-not-at-top
+    out = tp_layers.ReduceFromTensorParallel(out, layer._tp)   # pylint: disable=protected-access
+  return out
 
 
 def _Rope(x, pos, max_timescale):
@@ -485,29 +557,69 @@ class DenseReluDenseLayer(_BuilderLayer):
     p.Define('gated', False, 'GLU variant: act(x·wi_0) ⊙ (x·wi_1).')
     return p
 
+  def __init__(self, params):
+    super().__init__(params)
+    b = self.bp
+    # Hidden dim on the model axis (`mh_wi_split = [0, 1]`, `hm_wo_split = [1, 0]`, ref
+    # :2939-2998): wi column-parallel, wo row-parallel — Megatron's MLP.
+    self._tp = self._TensorParallel(b.mh_wi_split if 'mh_wi_split' in b else None, 1)
+    if self._tp is not None:
+      assert b.ff_dim % self._tp.tp_size == 0, (b.ff_dim, self._tp.tp_size)
+
   def _CreateLayerVariables(self):
     b = self.bp
     m, h = b.model_dim, b.ff_dim
+    tp = self._tp
+    hl = h // tp.tp_size if tp is not None else h
     dt = self.params.dtype
     wi_init = WeightInit.Uniform(((1. / m)**0.5) * 3.**0.5)
     wo_init = WeightInit.Uniform(((1. / h)**0.5) * 3.**0.5)
+
+    def Shard(wp, dim):
+      if tp is not None:
+        wp.init_shard = (dim, tp.tp_rank, tp.tp_size)
+      return wp
+
     if self.params.gated:
-      self.CreateVariable('wi_0', ShardedWeightParams(
-          [m, h], wi_init, dt, tensor_split_dims_mapping=b.mh_wi_split))
-      self.CreateVariable('wi_1', ShardedWeightParams(
-          [m, h], wi_init, dt, tensor_split_dims_mapping=b.mh_wi_split))
+      self.CreateVariable('wi_0', Shard(ShardedWeightParams(
+          [m, hl], wi_init, dt, tensor_split_dims_mapping=b.mh_wi_split), 1))
+      self.CreateVariable('wi_1', Shard(ShardedWeightParams(
+          [m, hl], wi_init, dt, tensor_split_dims_mapping=b.mh_wi_split), 1))
     else:
-      self.CreateVariable('wi', ShardedWeightParams(
-          [m, h], wi_init, dt, tensor_split_dims_mapping=b.mh_wi_split))
-    self.CreateVariable('wo', ShardedWeightParams(
-        [h, m], wo_init, dt, tensor_split_dims_mapping=b.hm_wo_split))
+      self.CreateVariable('wi', Shard(ShardedWeightParams(
+          [m, hl], wi_init, dt, tensor_split_dims_mapping=b.mh_wi_split), 1))
+    self.CreateVariable('wo', Shard(ShardedWeightParams(
+        [hl, m], wo_init, dt, tensor_split_dims_mapping=b.hm_wo_split), 0))
     if b.ff_use_bias:
-      self.CreateVariable('bi', WeightParams([h], WeightInit.Constant(0.), dt))
+      self.CreateVariable('bi', Shard(WeightParams([hl], WeightInit.Constant(0.), dt), 0))
       self.CreateVariable('bo', WeightParams([m], WeightInit.Constant(0.), dt))
+
+  def _InstantiateSelfAndChildren(self):
+    super()._InstantiateSelfAndChildren()
+    if self._tp is not None:
+      h = self.bp.ff_dim
+      self._TagTpVars({'wi': (1, h), 'wi_0': (1, h), 'wi_1': (1, h), 'wo': (0, h),
+                       'bi': (0, h)})
 
   supports_fused_residual = True
 
   def FProp(self, theta, x, segment_id=None, segment_pos=None, residual=None):
+    if self._tp is not None:
+      from lingvo_b200.parallel import tp_layers   # pylint: disable=g-import-not-at-top
+      th = theta
+      bo = None
+      if self.bp.ff_use_bias:          # the output bias is added once, after the reduction
+        th = NestedMap(theta)
+        bo = theta.bo
+        th.bo = torch.zeros_like(theta.bo)
+      out, aux = self._FPropLocal(th, tp_layers.CopyToTensorParallel(x, self._tp), None)
+      out = tp_layers.ReduceFromTensorParallel(out, self._tp)
+      if bo is not None:
+        out = out + bo.to(out.dtype)
+      return (out + residual if residual is not None else out), aux
+    return self._FPropLocal(theta, x, residual)
+
+  def _FPropLocal(self, theta, x, residual=None):
     from lingvo_b200.ops import gemm
     b = self.bp
     p = self.params

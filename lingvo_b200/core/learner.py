@@ -236,15 +236,30 @@ class Learner(base_layer.BaseLayer):
     # by-product of their statistics pass; only the remaining gradients are reduced here.
     pre_sumsq, handled = None, set()
     pre_fn = getattr(self.optimizer, 'PreGradStats', None)
-    if (pre_fn is not None and defer_scale and gradient_adjuster is None and
-        dev.type == 'cuda'):
-      pre_sumsq, handled = pre_fn([(vg.var, vg.grad) for vg in leaves])
     is_ep = lambda v: bool(getattr(v, 'expert_parallel', False))
+    is_tp = lambda v: getattr(v, 'tp_shard', None) is not None
+    has_tp = any(is_tp(vg.var) for vg in leaves)
+    if (pre_fn is not None and defer_scale and gradient_adjuster is None and
+        dev.type == 'cuda' and not has_tp):
+      pre_sumsq, handled = pre_fn([(vg.var, vg.grad) for vg in leaves])
+    # Tensor-parallel shards: every TP rank holds a different slice, so their Σg² is summed
+    # over the TP group (replicated variables carry identical gradients on all TP ranks).
+    tp_leaves = [vg for vg in leaves if is_tp(vg.var)]
+    tp_sumsq = None
+    if tp_leaves:
+      from lingvo_b200.parallel import mesh as mesh_lib   # pylint: disable=g-import-not-at-top
+      from lingvo_b200.parallel import tp_layers   # pylint: disable=g-import-not-at-top
+      handled = set(handled) | {id(vg.var) for vg in tp_leaves}
+      tp_sumsq = tp_layers.AllReduceScalar(
+          py_utils.SumSquared([vg.grad for vg in tp_leaves]).to(dev).reshape(1),
+          mesh_lib.TensorParallel())
     rest = [vg.grad for vg in leaves if id(vg.var) not in handled and not is_ep(vg.var)]
     rest_ep = [vg.grad for vg in leaves if id(vg.var) not in handled and is_ep(vg.var)]
     grad_sumsq = py_utils.SumSquared(rest).to(dev) if rest else torch.zeros((), device=dev)
     if pre_sumsq is not None:
       grad_sumsq = grad_sumsq + pre_sumsq.reshape(())
+    if tp_sumsq is not None:
+      grad_sumsq = grad_sumsq + tp_sumsq.reshape(())
     # Σg² of expert-parallel variables: every rank holds different experts, so the global
     # norm needs the sum over the EP group (one 4-byte all-reduce).
     ep_sumsq = getattr(self.optimizer, '_pre_ep_sumsq', None) if pre_sumsq is not None else None

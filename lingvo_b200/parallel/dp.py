@@ -101,16 +101,36 @@ def Attach(task):
         continue
       by_dtype.setdefault(vg.grad.dtype, []).append(vg.grad)
     with torch.no_grad():
-      for grads in by_dtype.values():
-        _AllReduceBuckets(grads, ctx.world)
+      if ctx.tp_size > 1:
+        # [dp, tp] mesh: parameters (sharded or replicated) are replicated only along the dp
+        # axis; within a TP group the replicated parameters already carry identical
+        # gradients (their inputs are replicated, f/g make the activations' grads whole).
+        if ctx.dp_size > 1:
+          for grads in by_dtype.values():
+            _AllReduceBuckets(grads, ctx.dp_size, ctx.dp_group)
+      else:
+        for grads in by_dtype.values():
+          _AllReduceBuckets(grads, ctx.world)
     _ReduceExpertReplicas(leaves, ctx)
     return var_grads
 
-  # Make replicated variables identical across ranks (rank 0 wins).
+  # Make replicated variables identical across ranks (rank 0 wins); a tensor-parallel shard
+  # is replicated only across the ranks with the same tp_rank (source: dp_rank 0).
   with torch.no_grad():
     for v in task.vars.Flatten():
-      if not getattr(v, 'expert_parallel', False):
+      if getattr(v, 'expert_parallel', False):
+        continue
+      if getattr(v, 'tp_shard', None) is not None:
+        if ctx.dp_size > 1:
+          dist.broadcast(v.data, src=ctx.tp_rank, group=ctx.dp_group)
+      else:
         dist.broadcast(v.data, src=0)
+  if ctx.tp_size > 1:
+    assert not any(getattr(v, 'expert_parallel', False) for v in task.vars.Flatten()), (
+        'tensor parallelism and expert parallelism are not combined in one job yet')
+    for lrn in task.learners:
+      lrn.grad_sync = sync
+    return sync
   fused = None
   if ctx.mode == 'fused' and task.Device().type == 'cuda':
     from lingvo_b200.parallel import zero

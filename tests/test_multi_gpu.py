@@ -45,3 +45,11 @@ def test_product_trainer_two_gpus_identical_replicas_resume_and_gradients():
   _NeedGpus(2)
   rc, out = _Run('tools/trainer_mgpu_check.py', 2, 29623)
   assert rc == 0 and 'TRAINER_MGPU_OK' in out, out[-4000:]
+
+
+def test_tensor_parallel_model_matches_single_gpu():
+  """DenseBuilder UniTransformer with heads / FFN hidden sharded over 2 GPUs (NCCL f/g +
+  local tcgen05 GEMMs): loss, gathered gradients and 8 Adam steps ≈ the unsharded model."""
+  _NeedGpus(2)
+  rc, out = _Run('tools/tp_model_check.py', 2, 29624)
+  assert rc == 0 and 'TP_MODEL_OK' in out, out[-4000:]
