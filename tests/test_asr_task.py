@@ -176,3 +176,162 @@ def test_registered_conformer_configs_instantiate():
     task = cfg.task.Instantiate()
   n = sum(v.numel() for v in task.encoder.vars.Flatten())
   assert 1.0e8 < n < 1.4e8, n           # Conformer-L encoder ≈ 118 M parameters
+
+
+# --------------------------------------------------------------- decoder features (r2) --
+def _Decoder(**kw):
+  from lingvo_b200.models.asr import decoder as asr_decoder
+  p = asr_decoder.AsrDecoder.Params().Set(
+      name='dec', source_dim=6, emb_dim=4, rnn_cell_dim=8, rnn_layers=2, residual_start=2,
+      target_seq_len=6, **kw)
+  p.emb.vocab_size = 12
+  p.emb.max_num_shards = 1
+  p.attention.hidden_dim = 5
+  p.softmax.num_classes = 12
+  p.random_seed = 99
+  dec = p.Instantiate()
+  dec.InstantiateVariables()
+  return dec
+
+
+def _DecInputs(b=3, t=5, s=7):
+  g = torch.Generator().manual_seed(1)
+  enc = NestedMap(encoded=torch.randn(s, b, 6, generator=g), padding=torch.zeros(s, b))
+  ids = torch.randint(1, 12, (b, t), generator=g)
+  pad = torch.zeros(b, t)
+  pad[0, 3:] = 1
+  tgt = NestedMap(ids=ids, labels=torch.roll(ids, -1, 1), paddings=pad, weights=1 - pad)
+  return enc, tgt
+
+
+def test_asr_decoder_step_plan_equals_sequence_plan():
+  """Teacher forcing: unrolling with SingleDecodeStep gives the same logits / loss as the
+  hoisted whole-sequence plan (same cells, same weights)."""
+  dec = _Decoder()
+  enc, tgt = _DecInputs()
+  seq = dec.ComputePredictions(dec.theta, enc, tgt)
+  assert 'logits' not in seq
+  dyn = dec.ComputePredictionsDynamic(dec.theta, enc, tgt)
+  torch.testing.assert_close(dyn.softmax_input, seq.softmax_input, atol=1e-5, rtol=1e-5)
+  torch.testing.assert_close(dyn.attention.probs, seq.attention.probs, atol=1e-5, rtol=1e-5)
+  m_seq, ps_seq = dec.ComputeLoss(dec.theta, seq, tgt)
+  m_dyn, ps_dyn = dec.ComputeLoss(dec.theta, dyn, tgt)
+  assert float(m_seq['loss'][0]) == pytest.approx(float(m_dyn['loss'][0]), rel=1e-5)
+  torch.testing.assert_close(ps_seq.loss, ps_dyn.loss, atol=1e-5, rtol=1e-5)
+  assert ps_seq.loss.shape == (3,)
+  assert set(m_seq) >= {'loss', 'log_pplx', 'token_normed_prob',
+                        'fraction_of_correct_next_step_preds', 'loss/logits'}
+  assert float(m_seq['token_normed_prob'][0]) == pytest.approx(
+      float(torch.exp(-m_seq['log_pplx'][0])), rel=1e-6)
+
+
+def test_asr_decoder_loss_variants():
+  import torch.nn.functional as F
+  from lingvo_b200.core import layers
+  from lingvo_b200.models.asr import decoder as asr_decoder
+  enc, tgt = _DecInputs()
+  base = _Decoder()
+  pred = base.ComputePredictions(base.theta, enc, tgt)
+  logits = base._ComputeLogits(base.theta, pred.softmax_input).transpose(0, 1)
+  nll = F.cross_entropy(logits.reshape(-1, 12), tgt.labels.reshape(-1),
+                        reduction='none').reshape(3, 5)
+  w = tgt.weights
+  m, ps = base.ComputeLoss(base.theta, pred, tgt)
+  assert float(m['loss'][0]) == pytest.approx(float((nll * w).sum() / w.sum()), rel=1e-4)
+  torch.testing.assert_close(ps.loss, (nll * w).sum(1), atol=1e-4, rtol=1e-4)
+  # per-sequence averaging + length normalisation
+  seq = _Decoder(per_token_avg_loss=False, token_normalized_per_seq_loss=True)
+  m2, ps2 = seq.ComputeLoss(seq.theta, NestedMap(logits=logits), tgt)
+  want = (nll * w).sum(1) / (w.sum(1) + 0.001)
+  torch.testing.assert_close(ps2.loss, want, atol=1e-4, rtol=1e-4)
+  assert float(m2['loss'][0]) == pytest.approx(float(want.mean()), rel=1e-4)
+  assert float(m2['loss'][1]) == 3.0
+  # focal loss down-weights confident tokens
+  foc = _Decoder(focal_loss_gamma=2.0)
+  _, ps3 = foc.ComputeLoss(foc.theta, NestedMap(logits=logits), tgt)
+  p_t = torch.exp(-nll)
+  torch.testing.assert_close(ps3.loss, (((1 - p_t) ** 2) * nll * w).sum(1), atol=1e-4,
+                             rtol=1e-4)
+  # label smoothing and explicit target distributions go through the soft-label path
+  ls = _Decoder(label_smoothing=layers.UniformLabelSmoother.Params().Set(uncertainty=0.1))
+  m4, _ = ls.ComputeLoss(ls.theta, NestedMap(logits=logits), tgt)
+  lp = F.log_softmax(logits, -1)
+  probs = torch.full((3, 5, 12), 0.1 / 11)
+  probs.scatter_(-1, tgt.labels.unsqueeze(-1), 0.9)
+  want4 = (-(probs * lp).sum(-1) * w).sum() / w.sum()
+  assert float(m4['loss'][0]) == pytest.approx(float(want4), rel=1e-3)
+  t2 = NestedMap(tgt)
+  t2.probs = probs
+  m5, _ = base.ComputeLoss(base.theta, NestedMap(logits=logits), t2)
+  assert float(m5['loss'][0]) == pytest.approx(float(want4), rel=1e-3)
+  # several heads with weights
+  two = _Decoder(logit_types={'logits': 1.0, 'aux_logits': 0.5})
+  m6, ps6 = two.ComputeLoss(two.theta, NestedMap(logits=logits, aux_logits=logits * 0.0), tgt)
+  uniform = float(np.log(12.0))
+  assert float(m6['loss/aux_logits'][0]) == pytest.approx(uniform, rel=1e-5)
+  assert float(m6['loss'][0]) == pytest.approx(float(m['loss'][0]) + 0.5 * uniform, rel=1e-4)
+  del asr_decoder
+
+
+def test_asr_decoder_scheduled_sampling_feeds_its_own_samples():
+  from lingvo_b200.core import py_utils
+  dec = _Decoder(min_ground_truth_prob=0.0, prob_decay_start_step=0, min_prob_step=10)
+  enc, tgt = _DecInputs()
+  py_utils.SetGlobalStep(0)
+  try:
+    assert float(dec.GroundTruthProbability()) == 1.0
+    torch.manual_seed(0)
+    gt = dec.ComputePredictions(dec.theta, enc, tgt)        # step plan, always ground truth
+    ref = dec.ComputePredictionsDynamic(dec.theta, enc, tgt)
+    torch.testing.assert_close(gt.logits, ref.logits)
+    py_utils.SetGlobalStep(5)
+    assert float(dec.GroundTruthProbability()) == pytest.approx(0.5)
+    py_utils.SetGlobalStep(10)
+    assert float(dec.GroundTruthProbability()) == 0.0
+    torch.manual_seed(0)
+    ss = dec.ComputePredictions(dec.theta, enc, tgt)        # always its own samples
+    # step 0 sees <s> either way; later steps are conditioned on sampled tokens
+    torch.testing.assert_close(ss.logits[:, 0], gt.logits[:, 0])
+    assert not torch.allclose(ss.logits[:, 1:], gt.logits[:, 1:])
+    m, _ = dec.ComputeLoss(dec.theta, ss, tgt)
+    m['loss'][0].backward()
+    assert dec.vars.Flatten()[0].grad is not None
+  finally:
+    py_utils.SetGlobalStep(0)
+  with pytest.raises(AssertionError):
+    _Decoder(min_ground_truth_prob=0.5, use_while_loop_based_unrolling=False)
+
+
+def test_asr_decoder_shallow_fusion_and_adapters():
+  from lingvo_b200.models.asr import fusion
+  from lingvo_b200.models.lm import layers as lm_layers
+  enc, tgt = _DecInputs()
+  plain = _Decoder()
+  fused = _Decoder(fusion=fusion.ShallowFusion.Params().Set(
+      lm=lm_layers.NullLm.Params().Set(vocab_size=12), lm_weight=0.5))
+  a = plain.ComputePredictionsDynamic(plain.theta, enc, tgt)
+  b = fused.ComputePredictions(fused.theta, enc, tgt)       # fusion forces the step plan
+  # a uniform LM shifts every log-prob by the same constant: log_softmax(am) + λ·log(1/V)
+  want = torch.log_softmax(a.logits, -1) + 0.5 * float(np.log(1 / 12.0))
+  torch.testing.assert_close(b.logits, want, atol=1e-5, rtol=1e-5)
+  # beam search runs through the same step function and the fusion state
+  enc2, _ = _DecInputs()
+  out = fused.BeamSearchDecodeWithTheta(fused.theta, enc2)
+  assert out.topk_ids.shape[0] == 3 * fused.params.beam_search.num_hyps_per_beam
+  # adapters: per-utterance task ids select per-task residual adapters after every layer
+  from lingvo_b200.core import layers
+  ad = _Decoder(adapter_task_id_field='domain_ids',
+                adapter_layer_tpl=layers.MultitaskAdapterLayer.Params().Set(
+                    num_tasks=2, bottleneck_dim=3))
+  enc3, _ = _DecInputs()
+  enc3.domain_ids = torch.tensor([0, 1, 0])
+  assert len(ad.adapters) == 2
+  with torch.no_grad():
+    for v in ad.vars.Flatten():
+      if 'adapter' in v.var_name and 'up' in v.var_name:
+        v.copy_(torch.randn_like(v) * 0.5)
+  pa = ad.ComputePredictions(ad.theta, enc3, tgt)
+  enc3.domain_ids = torch.tensor([1, 1, 0])
+  pb = ad.ComputePredictions(ad.theta, enc3, tgt)
+  assert not torch.allclose(pa.logits[0], pb.logits[0])      # utterance 0 changed task
+  torch.testing.assert_close(pa.logits[1:], pb.logits[1:])   # the others did not
