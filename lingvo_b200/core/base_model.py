@@ -97,6 +97,13 @@ class BaseTask(base_layer.BaseLayer):
     tp.Define('device_prefetch_depth', 2,
               'Input batches staged on the device ahead of the step (pinned H2D copies on '
               'a side stream).')
+    tp.Define('async_data_parallel', False,
+              'With cluster mode `async` and several replicas: every replica applies its own '
+              'gradients and parameters are reconciled by delayed non-blocking averaging '
+              '(parallel/async_dp.py) — the parameter-server-free form of asynchronous training. '
+              '`trainer --mode=async` turns it on.')
+    tp.Define('async_sync_every_n_steps', 1,
+              'Asynchronous mode: steps between parameter reconciliations (staleness bound).')
     tp.Define('tpu_device_order_mode', None, 'Kept for parity.')
     tp.Define('tpu_computation_shape', None, 'Kept for parity.')
     tp.Define('vn_start_step', 200000000, 'Step at which VN starts.')

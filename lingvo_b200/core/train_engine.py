@@ -39,6 +39,18 @@ def _GraphMode(task) -> str:
   return str(mode)
 
 
+def _AsyncMode(task) -> bool:
+  """Cluster `mode == 'async'` requested explicitly (`--mode=async`); the default cluster
+  params of a bare task count as sync."""
+  try:
+    return bool(task.cluster.params.mode == 'async' and
+                getattr(task.cluster.params, 'job', '') in ('trainer', 'trainer_client',
+                                                             'worker') and
+                task.params.train.Get('async_data_parallel'))
+  except Exception:  # pylint: disable=broad-except
+    return False
+
+
 class TrainEngine:
   """Steps `task` with DP sync, prefetch and (optionally) CUDA-graph replay."""
 
@@ -52,11 +64,20 @@ class TrainEngine:
     if depth is None:
       depth = tp.Get('device_prefetch_depth') if 'device_prefetch_depth' in tp else 2
     self.dp = None
+    self.async_dp = None
     if attach_dp:
       from lingvo_b200.parallel import dp as dp_lib  # pylint: disable=g-import-not-at-top
       from lingvo_b200.parallel import mesh as mesh_lib  # pylint: disable=g-import-not-at-top
       if mesh_lib.Get().world > 1 and not getattr(task, '_dp_attached', False):
-        self.dp = dp_lib.Attach(task)
+        if _AsyncMode(task):
+          # `--mode=async`: replicas step independently and exchange parameters with
+          # bounded staleness (parallel/async_dp.py) instead of synchronising gradients.
+          from lingvo_b200.parallel import async_dp  # pylint: disable=g-import-not-at-top
+          every = tp.Get('async_sync_every_n_steps') if 'async_sync_every_n_steps' in tp else 1
+          self.async_dp = async_dp.Attach(task, sync_every=every)
+          self._graph_mode = 'off' if self._graph_mode == 'auto' else self._graph_mode
+        else:
+          self.dp = dp_lib.Attach(task)
         task._dp_attached = True   # pylint: disable=protected-access
     self._prefetch = None
     self._prefetch_depth = depth
@@ -116,12 +137,18 @@ class TrainEngine:
       batch = self.NextBatch()
     self._MaybeCapture(batch)
     if self._graphed is not None:
-      return self._graphed(batch)
-    return self.task.TrainStep([batch] if not isinstance(batch, list) else batch)
+      out = self._graphed(batch)
+    else:
+      out = self.task.TrainStep([batch] if not isinstance(batch, list) else batch)
+    if self.async_dp is not None:
+      self.async_dp.PostStep()
+    return out
 
   # ------------------------------------------------------------ checkpoints --
   def PreSave(self):
     """Makes `var.data` / optimizer slots authoritative before a checkpoint is cut."""
+    if self.async_dp is not None:
+      self.async_dp.Finalize()       # replicas agree on what is written
     for lrn in self.task.learners:
       eng = getattr(lrn, 'fused_update', None)
       if eng is not None and hasattr(eng, 'PreSave'):

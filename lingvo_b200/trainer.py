@@ -186,10 +186,16 @@ class RunnerManager:
         raise
       cfg = model_registry.GetParams(self._model_name, match[0])
     self.UpdateClusterParamsFromFlags(cfg.cluster, self._ClusterJobName(job_name))
+    task_trains = ([cfg.task.train] if 'task' in cfg else
+                   [t.train for _, t in cfg.task_params.IterParams()])
     if FLAGS.use_cuda_graph:
-      for tp in ([cfg.task.train] if 'task' in cfg else
-                 [t.train for _, t in cfg.task_params.IterParams()]):
+      for tp in task_trains:
         tp.use_cuda_graph = FLAGS.use_cuda_graph
+    if FLAGS['mode'].present and FLAGS.mode == 'async' and int(
+        os.environ.get('WORLD_SIZE', '1')) > 1:
+      # explicit `--mode=async` under torchrun: asynchronous data parallelism
+      for tp in task_trains:
+        tp.async_data_parallel = True
     if FLAGS.saver_max_to_keep is not None:
       cfg.train.save_max_to_keep = FLAGS.saver_max_to_keep
     if FLAGS.saver_keep_checkpoint_every_n_hours is not None:
