@@ -68,6 +68,9 @@ class BaseInputGenerator(base_layer.BaseLayer):
     self._batch_cache = None
     if self.params.file_datasource is not None:
       self.CreateChild('datasource', self.params.file_datasource)
+      # the reference does this in `CreateDatasource` (:296): sources call back into the
+      # generator (`LoadDataset`, `GetSequenceLength`, custom transforms …)
+      self.datasource.SetInputGenerator(self)
 
   # ----------------------------------------------------------- batch sizing --
   def GlobalBatchSize(self) -> int:
@@ -441,9 +444,69 @@ class BaseTinyDatasetInput(BaseInputGenerator):
     self._perm = None
 
 
-class DefineTFDataInput:
-  """Placeholder for reference `DefineTFDataInput` (tf.data is TF-only)."""
+def DefineTFDataInput(name, func, ignore_args=None, map_args=None,
+                      base_class=BaseInputGenerator):
+  """Defines an InputGenerator class from a dataset-pipeline function (reference :2022).
 
-  def __init__(self, *args, **kwargs):
-    raise NotImplementedError(
-        'tf.data inputs are replaced by datasource.PyIterableSource')
+  `func(**args)` returns a `datasource.Dataset` (or any re-iterable) of dict-like elements;
+  its signature is analysed to generate `Params().args` so the pipeline's configuration
+  lives in Params like everything else. `map_args = {func_param: layer_param}` feeds existing
+  params (e.g. `batch_size`) into the function instead. The generated generator behaves like
+  a one-shot iterator of the pipeline (`GetPreprocessedInputBatch()` yields its elements in
+  order, as `NestedMap`s); with `cluster.tf_data_service_address` set, training inputs are
+  produced by the background worker pool (`TFDataServiceSource`) behind a prefetch.
+
+    def my_dataset(begin=0, end=10):
+      return datasource.Dataset.FromElements({'value': i} for i in range(begin, end))
+    MyInput = DefineTFDataInput('MyInput', my_dataset)
+    p = MyInput.Params(); p.args.end = 3
+    MyInput(p).GetPreprocessedInputBatch()      # NestedMap(value=0), then 1, 2
+  """
+  import inspect  # pylint: disable=g-import-not-at-top
+  from lingvo_b200.core import cluster_factory  # pylint: disable=g-import-not-at-top
+  from lingvo_b200.core import datasource  # pylint: disable=g-import-not-at-top
+  from lingvo_b200.core import hyperparams  # pylint: disable=g-import-not-at-top
+  from lingvo_b200.core import inspect_utils  # pylint: disable=g-import-not-at-top
+  ignore_args = set(ignore_args or ())
+  map_args = dict(map_args or {})
+  generated_cls = type(name, (base_class,), {})
+
+  @classmethod
+  def _Params(cls):
+    p = super(generated_cls, cls).Params()
+    p.Define('args', hyperparams.Params(), 'Parameter list of the pipeline.')
+    inspect_utils.DefineParams(func, p.args, ignore_args | set(map_args.keys()))
+    ds = datasource.TFDatasetFnInput.Params().Set(load_fn='GetDataset', shuffle_buffer_size=1)
+    cur = cluster_factory.Current()
+    if getattr(cur.params, 'tf_data_service_address', None) and not cur.do_eval:
+      ds = datasource.TFDataServiceSource.Params().Set(sub=ds)
+      ds = datasource.TFDatasetPrefetch.Params().Set(sub=ds)
+    p.file_datasource = ds
+    return p
+
+  def _GetDataset(self):
+    p = self.params
+    overrides = {k: p.Get(v) for k, v in map_args.items()}
+    dataset = inspect_utils.CallWithParams(func, p.args, **overrides)
+    if not isinstance(dataset, datasource.Dataset):
+      src = dataset
+      assert hasattr(src, '__iter__') or callable(src), (
+          'DefineTFDataInput must take a callable which returns a Dataset / iterable. '
+          'The given callable `%s` returned `%s`' % (func, dataset))
+      dataset = datasource.Dataset(lambda: iter(src() if callable(src) else src))
+    return dataset
+
+  def _GetPreprocessedInputBatch(self):
+    data = self.datasource.GetNext()
+    assert isinstance(data, dict), (
+        'DefineTFDataInput accepts only datasets that return a dict or its subclasses.')
+    if not isinstance(data, NestedMap):
+      data = NestedMap.FromNestedDict(data) if hasattr(NestedMap, 'FromNestedDict') else (
+          NestedMap(data))
+    return data
+
+  generated_cls.Params = _Params
+  generated_cls.GetDataset = _GetDataset
+  generated_cls.GetPreprocessedInputBatch = _GetPreprocessedInputBatch
+  generated_cls.__module__ = inspect.stack()[1].frame.f_globals.get('__name__', '__main__')
+  return generated_cls

@@ -37,7 +37,18 @@ class DataSource(base_layer.BaseLayer):
 
   def __init__(self, params):
     super().__init__(params)
-    self._input_generator = None
+    self._ig_ref = [None]
+
+  # The owning input generator is a back-reference, not a child layer: it is kept in a
+  # one-element holder so that the layer tree's "every BaseLayer attribute is a registered
+  # child" check (and theta / vars traversals) do not see it.
+  @property
+  def _input_generator(self):
+    return self._ig_ref[0]
+
+  @_input_generator.setter
+  def _input_generator(self, value):
+    self._ig_ref[0] = value
 
   def SetInputGenerator(self, input_generator):
     self._input_generator = input_generator

@@ -182,3 +182,39 @@ def test_prefetch_and_data_service_cover_each_element_once():
     svc = _Wire(svc_p, n=41)
     got = sorted(int(e.id) for e in _Drain(svc))
   assert got == list(range(41))                                           # exactly once each
+
+
+def _my_dataset(begin=0, end=10, scale=1.0, batch=1):
+  return ds.Dataset.FromElements({'value': np.float32(i * scale), 'b': np.int32(batch)}
+                                 for i in range(begin, end))
+
+
+MyInput = base_input_generator.DefineTFDataInput('MyInput', _my_dataset,
+                                                 map_args={'batch': 'batch_size'})
+
+
+def test_define_tfdata_input_generates_params_from_the_signature():
+  p = MyInput.Params()
+  assert p.args.begin == 0 and p.args.end == 10 and p.args.scale == 1.0
+  assert 'batch' not in p.args                       # mapped from p.batch_size instead
+  assert MyInput.__module__ == __name__
+  p.name = 'my'
+  p.batch_size = 7
+  p.args.begin, p.args.end, p.args.scale = 2, 5, 0.5
+  with cluster_factory.Cluster(cluster_factory.Current().params.Copy().Set(
+      do_eval=True, require_sequential_input_order=True)):
+    ig = p.Instantiate()
+    assert isinstance(ig, MyInput)
+    vals = []
+    with pytest.raises(StopIteration):
+      while True:
+        b = ig.GetPreprocessedInputBatch()
+        assert isinstance(b, NestedMap) and int(b.b) == 7
+        vals.append(float(b.value))
+  assert vals == [1.0, 1.5, 2.0]
+  # text round trip keeps the pipeline arguments
+  from lingvo_b200.core import hyperparams
+  q = MyInput.Params()
+  q.FromText(p.ToText())
+  assert q.args.end == 5 and q.args.scale == 0.5
+  del hyperparams
