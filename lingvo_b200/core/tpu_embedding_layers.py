@@ -171,6 +171,8 @@ class TPUEmbeddingTable(base_layer.BaseLayer):
       self.CreateChild('schedule', p.lr_schedule)
     self._slots = None
     self._pending = []
+    self._pending_grads = []         # (local rows, gradient rows) received from other ranks
+    self.gradient_multiplier = 1.0   # set by the layer's gradient-multiplier schedule
 
   def _CreateLayerVariables(self):
     p = self.params
@@ -184,18 +186,56 @@ class TPUEmbeddingTable(base_layer.BaseLayer):
 
   def Lookup(self, ids):
     """ids (any shape, global row ids; −1 = missing) → embeddings `[..., D]` with grad
-    hooks that feed the sparse optimizer."""
+    hooks that feed the sparse optimizer. With several ranks the table is row-sharded
+    (`row % world` owns row, stored at `row // world`): ids travel to their owners and rows
+    come back in two all-to-alls; the backward sends the row gradients to the owners, which
+    queue them for their sparse optimizer."""
     p = self.params
     flat = ids.reshape(-1)
     valid = flat >= 0
-    if self._world > 1:
-      raise NotImplementedError('cross-rank lookup uses parallel.sparse_embedding (EP all-to-all)')
     rows = flat.clamp_min(0)
+    if self._world > 1:
+      # a differentiable anchor makes autograd call the backward (ids are integers)
+      anchor = torch.zeros((), device=self.table.device, requires_grad=torch.is_grad_enabled())
+      emb = _ShardedLookup.apply(self, rows, anchor)
+      out = emb * valid.unsqueeze(-1).to(emb.dtype)
+      return out.reshape(*ids.shape, p.embedding_dim)
     emb = self.table[rows].detach().clone().requires_grad_(True)
     out = emb * valid.unsqueeze(-1).to(emb.dtype)
     if torch.is_grad_enabled():
       self._pending.append((rows, emb))
     return out.reshape(*ids.shape, p.embedding_dim)
+
+  # -- cross-rank exchange ------------------------------------------------------------
+  def _ExchangePlan(self, rows):
+    """Sorts the requested global rows by owner and exchanges the per-owner counts."""
+    w = self._world
+    owner = rows % w
+    order = torch.argsort(owner, stable=True)
+    send_ids = rows[order]
+    send_counts = torch.bincount(owner, minlength=w)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts)
+    return order, send_ids, send_counts.tolist(), recv_counts.tolist()
+
+  def _FetchRows(self, rows):
+    order, send_ids, sc, rc = self._ExchangePlan(rows)
+    req = torch.empty(sum(rc), dtype=send_ids.dtype, device=send_ids.device)
+    dist.all_to_all_single(req, send_ids.contiguous(), rc, sc)
+    local = req // self._world
+    reply = self.table[local].contiguous()
+    got = torch.empty(len(send_ids), reply.shape[1], dtype=reply.dtype, device=reply.device)
+    dist.all_to_all_single(got, reply, sc, rc)
+    out = torch.empty_like(got)
+    out[order] = got
+    return out, (order, sc, rc, local)
+
+  def _ReturnGrads(self, grad, plan):
+    order, sc, rc, local = plan
+    send = grad[order].contiguous()
+    recv = torch.empty(sum(rc), grad.shape[1], dtype=grad.dtype, device=grad.device)
+    dist.all_to_all_single(recv, send, rc, sc)
+    self._pending_grads.append((local, recv))
 
   def ApplyGradients(self, global_step=0):
     """Applies the sparse optimizer to every row looked up since the last call."""
@@ -206,14 +246,33 @@ class TPUEmbeddingTable(base_layer.BaseLayer):
     if p.lr_schedule is not None:
       lr = lr * float(self.schedule.Value(global_step))
     with torch.no_grad():
-      for rows, emb in self._pending:
-        if emb.grad is None:
-          continue
+      todo = [(rows, emb.grad) for rows, emb in self._pending if emb.grad is not None]
+      todo += self._pending_grads
+      for rows, grad in todo:
         uniq, inv = torch.unique(rows, return_inverse=True)
-        g = torch.zeros(uniq.shape[0], emb.shape[1], device=emb.device, dtype=emb.dtype)
-        g.index_add_(0, inv, emb.grad)
+        g = torch.zeros(uniq.shape[0], grad.shape[1], device=grad.device, dtype=grad.dtype)
+        g.index_add_(0, inv, grad)
+        if self.gradient_multiplier != 1.0:
+          g = g * self.gradient_multiplier
         self.optimizer.Apply(lr, self.table, self._slots, uniq, g)
     self._pending = []
+    self._pending_grads = []
+
+
+class _ShardedLookup(torch.autograd.Function):
+  """Row fetch from a row-sharded table; the backward routes row gradients to the owners."""
+
+  @staticmethod
+  def forward(ctx, table_layer, rows, anchor):
+    del anchor
+    emb, plan = table_layer._FetchRows(rows)   # pylint: disable=protected-access
+    ctx.layer, ctx.plan = table_layer, plan
+    return emb
+
+  @staticmethod
+  def backward(ctx, grad):
+    ctx.layer._ReturnGrads(grad.contiguous(), ctx.plan)   # pylint: disable=protected-access
+    return None, None, None
 
 
 class TPUEmbeddingLayer(base_layer.BaseLayer):
@@ -230,7 +289,8 @@ class TPUEmbeddingLayer(base_layer.BaseLayer):
     p.Define('learning_rate', 0.0, 'Default learning rate.')
     p.Define('lr_schedule', None, 'Default LR schedule.')
     p.Define('partition_strategy', 'div', 'Kept for parity.')
-    p.Define('gradient_multiplier_schedule', None, 'Kept for parity.')
+    p.Define('gradient_multiplier_schedule', None,
+             'Schedule params: table gradients are multiplied by its value at the step.')
     return p
 
   def __init__(self, params):
@@ -244,6 +304,8 @@ class TPUEmbeddingLayer(base_layer.BaseLayer):
       tp.lr_schedule = tp.lr_schedule or p.lr_schedule
       tables.append(tp)
     self.CreateChildren('tables', tables)
+    if p.gradient_multiplier_schedule is not None:
+      self.CreateChild('gradient_multiplier_schedule', p.gradient_multiplier_schedule)
     self._route = {}
     for t in self.tables:
       for k in t.params.input_keys:
@@ -266,5 +328,9 @@ class TPUEmbeddingLayer(base_layer.BaseLayer):
     return out
 
   def ApplyGradients(self, global_step=0):
+    mult = 1.0
+    if self.params.gradient_multiplier_schedule is not None:
+      mult = float(self.gradient_multiplier_schedule.Value(global_step))
     for t in self.tables:
+      t.gradient_multiplier = mult
       t.ApplyGradients(global_step)

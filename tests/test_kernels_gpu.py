@@ -499,3 +499,25 @@ def test_beam_topk_kernel_matches_torch_oracle(k, v, dtype):
   assert torch.equal(got[1], want[1])
   for a, b in zip(got[2:], want[2:]):
     torch.testing.assert_close(a, b)
+
+
+def test_moe_row_movers_match_oracles():
+  """ops/moe.py: token-major combine / gather / gate-gradient kernels vs fp32 oracles."""
+  from lingvo_b200.ops import moe
+  torch.manual_seed(0)
+  e, g, c, m, s = 8, 4, 64, 512, 96
+  t = g * s
+  dev = 'cuda'
+  yc = torch.randn(e, g, c, m, device=dev).bfloat16()
+  index = torch.randint(0, e, (2, t), device=dev, dtype=torch.int32)
+  pos = torch.randint(0, c, (2, t), device=dev, dtype=torch.int32)
+  gate = torch.rand(2, t, device=dev)
+  gate[torch.rand(2, t, device=dev) < 0.2] = 0.0                 # dropped choices
+  y = moe.combine(yc, index, pos, gate, s, g, c)
+  assert _rel(y, moe.combine_ref(yc, index, pos, gate, s, g, c)) < 1e-2
+  ga = moe.gather_rows(yc, index, pos, gate, s, g, c)
+  assert _rel(ga, moe.gather_rows_ref(yc, index, pos, gate, s, g, c)) < 1e-2
+  dy = torch.randn(t, m, device=dev).bfloat16()
+  dg = moe.combine_bwd_gate(yc, dy, index, pos, gate, s, g, c)
+  ref = moe.combine_bwd_gate_ref(yc, dy, index, pos, gate, s, g, c)
+  assert _rel(dg, ref) < 1e-2 and bool((dg[gate == 0] == 0).all())

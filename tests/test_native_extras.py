@@ -22,6 +22,12 @@ def test_mlperf_subword_decode(tmp_path):
   assert out[1] == 'überall 日本 語'
   with pytest.raises(IndexError):
     host_ops.MlPerfSubwordIdToString(np.array([[99]], np.int32), [1], str(f))
+  # the tokenizer layer on top of the native decoder (ref core/ml_perf_tokenizer.py)
+  from lingvo_b200.core import ml_perf_tokenizer
+  tok = ml_perf_tokenizer.MlPerfTokenizer.Params().Set(vocab_filepath=str(f)).Instantiate()
+  assert tok.IdsToStrings(torch.as_tensor(ids), torch.tensor([6, 4])) == out
+  with pytest.raises(NotImplementedError):
+    tok.StringsToIds(['x'], 4)
 
 
 def test_ngram_id_to_token_and_token_in_vocab(tmp_path):
