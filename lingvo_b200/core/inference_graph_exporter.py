@@ -25,6 +25,7 @@ import torch
 
 from lingvo_b200.core import hyperparams
 from lingvo_b200.core import py_utils
+from lingvo_b200.utils import protowire as pw
 
 BUNDLE_VERSION = 1
 InferenceDeviceOptions = collections.namedtuple(
@@ -51,6 +52,99 @@ class InferenceGraph:
     d = json.loads(text)
     return cls(d.get('model_name', ''), d.get('task_name', ''), d.get('subgraphs', {}),
                asset_dir)
+
+  # -- `tensorflow.lingvo.InferenceGraph` wire format (ref core/inference_graph.proto) ----
+  # Serving tools of the reference read subgraph signatures (feeds / fetches and their
+  # dtype / shape metadata), the hyper-parameters and the asset list from this message. The
+  # `graph_def` field cannot carry a TF graph here; it holds a one-node GraphDef naming the
+  # bundle, so that the message stays well-formed for any protobuf reader.
+  _DTYPES = {'float32': 1, 'float64': 2, 'int32': 3, 'uint8': 4, 'int16': 5, 'int8': 6,
+             'string': 7, 'int64': 9, 'bool': 10, 'bfloat16': 14, 'float16': 19}
+
+  @staticmethod
+  def _MapEntry(field, key, value_bytes):
+    return pw.f_bytes(field, pw.f_bytes(1, key) + pw.f_bytes(2, value_bytes))
+
+  def _MetaBytes(self, meta):
+    out = b''
+    dt = self._DTYPES.get(str(meta.get('dtype', '')).replace('torch.', ''))
+    if dt is not None:
+      out += pw.f_varint(2, dt)
+    if meta.get('shape') is not None:
+      out += pw.f_packed_varint(3, [int(d) if d is not None and d >= 0 else (1 << 64) - 1
+                                    for d in meta['shape']])
+    if meta.get('layout'):
+      out += pw.f_bytes(4, meta['layout'])
+    return out
+
+  def ToProto(self, hyperparameters: str = '', assets=()) -> bytes:
+    node = pw.f_bytes(1, 'lingvo_b200/bundle') + pw.f_bytes(2, 'NoOp')
+    msg = pw.f_bytes(1, pw.f_bytes(1, node))                     # graph_def { node {…} }
+    for name in sorted(self.subgraphs):
+      spec = self.subgraphs[name]
+      sub = b''
+      for fname in spec.get('feeds', []):
+        sub += self._MapEntry(2, fname, '%s/%s:0' % (name, fname))
+      for fname in spec.get('fetches', []):
+        sub += self._MapEntry(3, fname, '%s/%s:0' % (name, fname))
+      for fname, meta in sorted((spec.get('feeds_meta') or {}).items()):
+        sub += self._MapEntry(4, fname, self._MetaBytes(meta))
+      for fname, meta in sorted((spec.get('fetches_meta') or {}).items()):
+        sub += self._MapEntry(5, fname, self._MetaBytes(meta))
+      msg += self._MapEntry(5, name, sub)
+    if hyperparameters:
+      msg += pw.f_bytes(7, hyperparameters)
+    for fn in assets:
+      info = pw.f_bytes(1, 'asset/%s:0' % fn)                    # TensorInfo.name
+      msg += pw.f_bytes(10, pw.f_bytes(1, info) + pw.f_bytes(2, fn))
+    return msg
+
+  @classmethod
+  def FromProto(cls, buf: bytes, asset_dir=''):
+    """Parses `ToProto` output (or any InferenceGraph message) → (graph, hyperparameters,
+    asset file names)."""
+    inv = {v: k for k, v in cls._DTYPES.items()}
+    subgraphs, hyper, assets = {}, '', []
+
+    def Str(b):
+      return b.decode('utf-8') if isinstance(b, (bytes, bytearray)) else str(b)
+
+    def Meta(mb):
+      m = {}
+      for f, _, v in pw.parse(mb):
+        if f == 2:
+          m['dtype'] = inv.get(int(v), int(v))
+        elif f == 3:
+          vals = pw.parse_packed_varints(v) if isinstance(v, (bytes, bytearray)) else [v]
+          m['shape'] = [None if d == (1 << 64) - 1 else int(d) for d in vals]
+        elif f == 4:
+          m['layout'] = Str(v)
+      return m
+
+    for f, _, v in pw.parse(buf):
+      if f == 5:
+        entry = pw.parse_dict(v)
+        name = Str(entry[1][0])
+        spec = {'feeds': [], 'fetches': [], 'feeds_meta': {}, 'fetches_meta': {}}
+        for sf, _, sv in pw.parse(entry.get(2, [b''])[0]):
+          kv = pw.parse_dict(sv)
+          k = Str(kv[1][0])
+          if sf == 2:
+            spec['feeds'].append(k)
+          elif sf == 3:
+            spec['fetches'].append(k)
+          elif sf == 4:
+            spec['feeds_meta'][k] = Meta(kv.get(2, [b''])[0])
+          elif sf == 5:
+            spec['fetches_meta'][k] = Meta(kv.get(2, [b''])[0])
+        subgraphs[name] = spec
+      elif f == 7:
+        hyper = Str(v)
+      elif f == 10:
+        d = pw.parse_dict(v)
+        if 2 in d:
+          assets.append(Str(d[2][0]))
+    return cls(subgraphs=subgraphs, asset_dir=asset_dir), hyper, assets
 
 
 def _SubgraphSpec(fn):
@@ -112,11 +206,25 @@ class InferenceGraphExporter:
         f.write(model_cfg.ToText())
       with open(os.path.join(export_path, 'inference_graph.json'), 'w') as f:
         f.write(graph.ToJson())
+      # the reference's `InferenceGraph` proto next to the bundle manifest
+      with open(os.path.join(export_path, 'inference_graph.pb'), 'wb') as f:
+        f.write(graph.ToProto(hyperparameters=model_cfg.ToText(),
+                              assets=('weights.pt', 'params.txt', 'inference_graph.json')))
       graph.asset_dir = export_path
     return graph
 
 
 def LoadInferenceGraph(path) -> InferenceGraph:
+  """Loads a bundle directory, its `inference_graph.json`, or its `inference_graph.pb`."""
   d = path if os.path.isdir(path) else os.path.dirname(path)
+  if not os.path.isdir(path) and path.endswith('.pb'):
+    with open(path, 'rb') as f:
+      graph, _, _ = InferenceGraph.FromProto(f.read(), d)
+    js = os.path.join(d, 'inference_graph.json')
+    if os.path.exists(js):                     # names of model / task live in the manifest
+      with open(js) as f:
+        full = InferenceGraph.FromJson(f.read(), d)
+      graph.model_name, graph.task_name = full.model_name, full.task_name
+    return graph
   with open(os.path.join(d, 'inference_graph.json')) as f:
     return InferenceGraph.FromJson(f.read(), d)

@@ -40,3 +40,34 @@ def test_export_and_predict(tmp_path):
   got = pred.Run(['log_pplx_per_token'], ids=ids, paddings=pads)[0]
   want = model.tasks[0]._InferenceDefault(ids, pads).log_pplx_per_token
   torch.testing.assert_close(got, want.detach(), atol=1e-5, rtol=1e-5)
+
+
+def test_inference_graph_proto_round_trip(tmp_path):
+  """`inference_graph.pb` is a well-formed `tensorflow.lingvo.InferenceGraph` message:
+  subgraph feeds / fetches (+ dtype / shape metadata), hyper-parameters, asset list."""
+  import os
+  from lingvo_b200.utils import protowire as pw
+  cfg = _Cfg(tmp_path)
+  out_dir = str(tmp_path / 'export')
+  inference_graph_exporter.InferenceGraphExporter.Export(cfg, export_path=out_dir,
+                                                         model=cfg.Instantiate())
+  pb = os.path.join(out_dir, 'inference_graph.pb')
+  assert os.path.exists(pb)
+  buf = open(pb, 'rb').read()
+  fields = pw.parse_dict(buf)
+  assert set(fields) >= {1, 5, 7, 10}                              # graph_def, subgraphs, …
+  graph, hyper, assets = inference_graph_exporter.InferenceGraph.FromProto(buf)
+  assert graph.subgraphs['default']['feeds'] == ['ids', 'paddings']
+  assert hyper == cfg.ToText() and 'weights.pt' in assets
+  via_pb = inference_graph_exporter.LoadInferenceGraph(pb)
+  assert via_pb.subgraphs['default']['feeds'] == ['ids', 'paddings']
+  # metadata round trip
+  g = inference_graph_exporter.InferenceGraph(subgraphs={
+      'enc': {'feeds': ['x'], 'fetches': ['y', 'z'],
+              'feeds_meta': {'x': {'dtype': 'bfloat16', 'shape': [None, 128], 'layout': 'BD'}},
+              'fetches_meta': {'y': {'dtype': 'int64', 'shape': [4]}}}})
+  g2, _, _ = inference_graph_exporter.InferenceGraph.FromProto(g.ToProto())
+  assert g2.subgraphs['enc']['fetches'] == ['y', 'z']
+  assert g2.subgraphs['enc']['feeds_meta']['x'] == {'dtype': 'bfloat16',
+                                                   'shape': [None, 128], 'layout': 'BD'}
+  assert g2.subgraphs['enc']['fetches_meta']['y'] == {'dtype': 'int64', 'shape': [4]}
