@@ -386,5 +386,10 @@ def main(argv=None):
   RunnerManager(FLAGS.model).Start()
 
 
+def main_cli():
+  """Console-script entry point (`lingvo_b200_trainer`, see setup.py / pip_package)."""
+  main(sys.argv)
+
+
 if __name__ == '__main__':
   main()

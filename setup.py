@@ -21,11 +21,12 @@ class BuildWithExtensions(build_py):
 
 setup(
     name='lingvo_b200',
-    version='0.1.0',
+    version='0.2.0',
     description='B200-native (sm_100a) sequence-modelling framework with the capabilities of Lingvo',
     packages=find_packages(include=['lingvo_b200', 'lingvo_b200.*']),
     package_data={'lingvo_b200.ops': ['*.so', 'csrc/*', 'csrc_host/*']},
     python_requires='>=3.10',
-    install_requires=['torch>=2.4', 'numpy', 'absl-py'],
+    install_requires=['torch>=2.4', 'numpy', 'pyyaml'],
+    entry_points={'console_scripts': ['lingvo_b200_trainer = lingvo_b200.trainer:main_cli']},
     cmdclass={'build_py': BuildWithExtensions},
 )
