@@ -36,12 +36,20 @@ def _Slots(index, pos, s, g_l, c):
 
 
 # ---------------------------------------------------------------------------- combine --
+def _K(t, g_l, s):
+  """The kernels take the per-choice tables as `[2, G_l, S]` (T = G_l·S is derived from the
+  last two dims); callers may hold them flat as `[2, T]`."""
+  t = t.contiguous()
+  assert t.shape[0] == 2 and t.numel() == 2 * g_l * s, (tuple(t.shape), g_l, s)
+  return t.view(2, g_l, s)
+
+
 def combine(yc, index, pos, gate, s, g_l, c):
   """yc `[E, G_l, C, M]` bf16 (any leading layout with E·G_l·C rows), index/pos `[2, T]`
   int32, gate `[2, T]` fp32 → y `[T, M]` bf16. One warp per token, 16-byte loads, fp32
   accumulate; dropped choices (gate 0) are never read."""
-  return ops.native().moe_combine(yc.contiguous(), index.contiguous(), pos.contiguous(),
-                                  gate.contiguous(), int(s), int(g_l), int(c))
+  return ops.native().moe_combine(yc.contiguous(), _K(index, g_l, s), _K(pos, g_l, s),
+                                  _K(gate.float(), g_l, s), int(s), int(g_l), int(c))
 
 
 def combine_ref(yc, index, pos, gate, s, g_l, c):
@@ -56,8 +64,8 @@ def combine_ref(yc, index, pos, gate, s, g_l, c):
 def gather_rows(src, index, pos, gate, s, g_l, c):
   """The transpose of the dispatch scatter: every token sums the rows of its (kept) slots —
   the input gradient of the dispatch."""
-  return ops.native().moe_gather_rows(src.contiguous(), index.contiguous(), pos.contiguous(),
-                                      gate.contiguous(), int(s), int(g_l), int(c))
+  return ops.native().moe_gather_rows(src.contiguous(), _K(index, g_l, s), _K(pos, g_l, s),
+                                      _K(gate.float(), g_l, s), int(s), int(g_l), int(c))
 
 
 def gather_rows_ref(src, index, pos, gate, s, g_l, c):
@@ -67,9 +75,10 @@ def gather_rows_ref(src, index, pos, gate, s, g_l, c):
 
 def combine_bwd_gate(yc, dy, index, pos, gate, s, g_l, c):
   """dgate `[2, T]` = ⟨yc[slot], dy[t]⟩ for kept choices (0 for dropped ones)."""
-  return ops.native().moe_combine_bwd_gate(yc.contiguous(), dy.contiguous(), index.contiguous(),
-                                           pos.contiguous(), gate.contiguous(), int(s),
-                                           int(g_l), int(c))
+  return ops.native().moe_combine_bwd_gate(yc.contiguous(), dy.contiguous(),
+                                           _K(index, g_l, s), _K(pos, g_l, s),
+                                           _K(gate.float(), g_l, s), int(s), int(g_l),
+                                           int(c)).view(2, -1)
 
 
 def combine_bwd_gate_ref(yc, dy, index, pos, gate, s, g_l, c):
