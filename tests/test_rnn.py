@@ -280,3 +280,131 @@ def test_bidirectional_rnn_v2_pads_to_sequence_length():
   torch.testing.assert_close(out, ref, atol=1e-6, rtol=1e-5)
   with pytest.raises(AssertionError):
     l.FPropDefaultTheta(torch.randn(9, b, 6), torch.zeros(9, b, 1))
+
+
+# ----------------------------------------------------------------------- recurrent.py --
+def _GruLikeCell(theta, state0, inputs):
+  h = torch.tanh(inputs.x @ theta.w + state0.h @ theta.u)
+  pad = inputs.padding
+  h = torch.where(pad > 0, state0.h, h)
+  return NestedMap(h=h), NestedMap(pre=h * 2.0)
+
+
+def _RecInputs(t=6, b=3, d=4):
+  g = torch.Generator().manual_seed(0)
+  theta = NestedMap(w=torch.randn(d, d, generator=g).requires_grad_(True),
+                    u=(torch.randn(d, d, generator=g) * 0.3).requires_grad_(True))
+  x = torch.randn(t, b, d, generator=g).requires_grad_(True)
+  pad = torch.zeros(t, b, 1)
+  pad[4:, 0] = 1.0
+  return theta, NestedMap(h=torch.zeros(b, d)), NestedMap(x=x, padding=pad)
+
+
+def test_recurrent_acc_extras_stop_fn_and_single_step():
+  theta, s0, inp = _RecInputs()
+  acc, final, ex = recurrent.Recurrent(theta, s0, inp, _GruLikeCell, return_acc_extras=True)
+  assert acc.h.shape == (6, 3, 4) and ex.pre.shape == (6, 3, 4)
+  torch.testing.assert_close(acc.h[-1], final.h)
+  torch.testing.assert_close(ex.pre, acc.h * 2.0)
+  torch.testing.assert_close(acc.h[5, 0], acc.h[3, 0])            # padded rows carry state
+  # stop after 3 steps: the tail repeats the last computed state
+  acc2, final2 = recurrent.Recurrent(theta, s0, inp, _GruLikeCell,
+                                     stop_fn=lambda t, th, st: t >= 3)
+  torch.testing.assert_close(acc2.h[:3], acc.h[:3])
+  torch.testing.assert_close(acc2.h[5], acc.h[2])
+  torch.testing.assert_close(final2.h, acc.h[2])
+  one = NestedMap(x=inp.x[:1], padding=inp.padding[:1])
+  a1, f1 = recurrent.Recurrent(theta, s0, one, _GruLikeCell, remat_steps=2)
+  torch.testing.assert_close(a1.h[0], acc.h[0])
+
+
+def test_recurrent_custom_cell_grad_matches_autograd():
+  theta, s0, inp = _RecInputs()
+  acc, _ = recurrent.Recurrent(theta, s0, inp, _GruLikeCell)
+  acc.h.pow(2).sum().backward()
+  want = (theta.w.grad.clone(), theta.u.grad.clone(), inp.x.grad.clone())
+  theta.w.grad = theta.u.grad = inp.x.grad = None
+  calls = []
+
+  def CellGrad(th, state0, inputs, extras, dstate1):
+    calls.append(1)
+    pre = inputs.x @ th.w + state0.h @ th.u
+    h = torch.tanh(pre)
+    live = (inputs.padding <= 0).float()
+    dpre = dstate1.h * live * (1 - h * h)
+    dth = NestedMap(w=inputs.x.t() @ dpre, u=state0.h.t() @ dpre)
+    dst = NestedMap(h=dpre @ th.u.t() + dstate1.h * (1 - live))
+    din = NestedMap(x=dpre @ th.w.t(), padding=None)
+    return dth, dst, din, None
+
+  acc2, _ = recurrent.Recurrent(theta, s0, inp, _GruLikeCell, cell_grad=CellGrad)
+  torch.testing.assert_close(acc2.h, acc.h.detach())
+  acc2.h.pow(2).sum().backward()
+  assert len(calls) == 6
+  torch.testing.assert_close(theta.w.grad, want[0], atol=1e-5, rtol=1e-4)
+  torch.testing.assert_close(theta.u.grad, want[1], atol=1e-5, rtol=1e-4)
+  torch.testing.assert_close(inp.x.grad, want[2], atol=1e-5, rtol=1e-4)
+
+
+def test_recurrent_accumulators_and_step_seeds():
+  from lingvo_b200.core import base_layer
+  from lingvo_b200.core import py_utils
+
+  class Counter(base_layer.Accumulator):
+
+    def DefaultValue(self):
+      return torch.zeros(())
+
+  class Holder(base_layer.BaseLayer):
+
+    def __init__(self, params):
+      super().__init__(params)
+      self.RegisterAccumulator('count', Counter())
+
+  layer = Holder.Params().Set(name='holder').Instantiate()
+  seeds = []
+
+  def Cell(theta, state0, inputs):
+    acc = layer.accumulators.count
+    acc.Update(acc.GetValue() + inputs.x.sum() * 0 + 1.0)
+    seeds.append(py_utils.GetStepSeed())
+    return _GruLikeCell(theta, state0, inputs)
+
+  theta, s0, inp = _RecInputs()
+  py_utils.ResetStepSeed(100)
+  acc, final = recurrent.Recurrent(theta, s0, inp, Cell, accumulator_layer=layer)
+  assert 'accumulators' not in final and 'accumulators' not in acc
+  assert float(layer.accumulators.count.GetValue()) == 6.0        # carried to the layer
+  assert seeds == list(range(100, 106)) and py_utils.GetStepSeed() == 106
+  # rematerialised: the re-run in backward sees the same per-step seeds
+  seeds.clear()
+  py_utils.ResetStepSeed(100)
+  acc2, _ = recurrent.Recurrent(theta, s0, inp, Cell, remat_steps=2)
+  acc2.h.sum().backward()
+  assert seeds[:6] == list(range(100, 106)) and sorted(set(seeds)) == list(range(100, 106))
+  assert len(seeds) == 12
+  torch.testing.assert_close(acc2.h, acc.h)
+  with pytest.raises(ValueError):
+    bad = NestedMap(s0)
+    bad.accumulators = NestedMap()
+    recurrent.Recurrent(theta, bad, inp, Cell, accumulator_layer=layer)
+  py_utils.ResetStepSeed(0)
+
+
+def test_stacked_recurrent_matches_layer_by_layer():
+  theta, s0, inp = _RecInputs()
+  g = torch.Generator().manual_seed(9)
+  theta2 = NestedMap(w=torch.randn(4, 4, generator=g), u=torch.randn(4, 4, generator=g) * 0.3)
+  out_fn = lambda st: NestedMap(x=st.h)
+  acc, finals = recurrent.StackedRecurrent(
+      [None, None], [_GruLikeCell, _GruLikeCell], [None, None], [out_fn, out_fn], [None, None],
+      [theta, theta2], [s0, s0], inp)
+  a1, f1 = recurrent.Recurrent(theta, s0, inp, _GruLikeCell)
+  a2, f2 = recurrent.Recurrent(theta2, s0, NestedMap(x=a1.h, padding=inp.padding), _GruLikeCell)
+  torch.testing.assert_close(acc.x, a2.h)
+  torch.testing.assert_close(finals[0].h, f1.h)
+  torch.testing.assert_close(finals[1].h, f2.h)
+  none_acc, _ = recurrent.StackedRecurrent(
+      [None, None], [_GruLikeCell, _GruLikeCell], [None, None], [out_fn, out_fn], [None, None],
+      [theta, theta2], [s0, s0], inp, unused_acc_state=True)
+  assert none_acc is None
