@@ -63,6 +63,14 @@ def _Act(name: str):
   return activations.GetFn(n)
 
 
+def _ContextParallel(b) -> bool:
+  """Context parallelism requested by the builder and a process group to run it on."""
+  if not ('context_parallel' in b and b.context_parallel):
+    return False
+  import torch.distributed as dist   # pylint: disable=g-import-not-at-top
+  return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 # =========================================================================
 # Layer classes
 # =========================================================================
@@ -381,6 +389,27 @@ class SelfAttentionLayer(_BuilderLayer):
       bias = bias + rb
     return bias
 
+  def _ContextParallelCore(self, theta, q, k, v, segment_id):
+    """Sequence-sharded attention: local queries against the all-gathered keys / values.
+    Causality and the relative bias use *global* token indices (inside a packed segment the
+    index difference equals the position difference; across segments the mask removes the
+    pair), so the result equals the unsharded layer's rows of this rank."""
+    from lingvo_b200.parallel import cp   # pylint: disable=g-import-not-at-top
+    import torch.distributed as dist   # pylint: disable=g-import-not-at-top
+    b = self.bp
+    w, r = dist.get_world_size(), dist.get_rank()
+    lq = q.shape[1]
+    lg = lq * w
+    bias = None
+    if self.params.relative_bias:
+      table = self._RelTable(theta, lg, q.device)                 # [H, 2L−1], idx q−k+L−1
+      qpos = torch.arange(lq, device=q.device) + r * lq
+      kpos = torch.arange(lg, device=q.device)
+      idx = qpos.unsqueeze(1) - kpos.unsqueeze(0) + lg - 1
+      bias = table[:, idx]                                        # [H, L/W, L]
+    causal = self.params.decoder and not b.decoder_skip_causal_mask
+    return cp.Attention(q, k, v, causal=causal, segment_ids=segment_id, bias=bias, scale=1.0)
+
   supports_fused_residual = True
 
   def FProp(self, theta, x, segment_id, segment_pos, residual=None):
@@ -415,6 +444,10 @@ class SelfAttentionLayer(_BuilderLayer):
     if b.use_rotary_position_emb:
       q = _Rope(q, segment_pos, b.rope_emb_max_timescale)
       k = _Rope(k, segment_pos, b.rope_emb_max_timescale)
+    if _ContextParallel(b):
+      o = self._ContextParallelCore(theta, q, k, v, segment_id)
+      out = gemm.linear(o.reshape(bsz, l, h * d), wo.to(x.dtype), residual=residual)
+      return out, torch.zeros((), device=x.device, dtype=torch.float32)
     simple = (not b.atten_logit_cap) and b.attention_extra_logit is None
     drop = b.attention_dropout_prob if not self.do_eval else 0.0
     toeplitz = (not self.params.relative_bias) or b.relative_attention_use_universal_1d_position
@@ -1007,6 +1040,11 @@ class MoEBuilder(builder.Base):
     p.Define('ff_use_bias', False, 'Bias in dense FFN.')
     p.Define('moe_mode', 'indexed', 'indexed (fused B200 path) | dense oracle.')
     p.Define('remat', False, 'Rematerialise blocks in backward.')
+    p.Define('context_parallel', False,
+             'Shard the *sequence* dimension over the ranks (context parallelism, '
+             '`parallel/cp.py`): every rank holds L/W tokens of each sequence, attention '
+             'all-gathers K/V (dK/dV are reduce-scattered in backward), everything else is '
+             'token-local. For sequences too long for one GPU.')
     return p
 
   @property
@@ -1356,6 +1394,15 @@ class UniTransformer(base_model.BaseTask):
           ids=input_batch.ids, paddings=input_batch.paddings,
           labels=input_batch.labels, segment_ids=input_batch.segment_ids,
           segment_pos=input_batch.segment_pos)
+    if _ContextParallel(self.params.builder) and not input_batch.tgt.get('_cp_sharded', False):
+      # context parallelism: this rank keeps its L/W slice of every [B, L, …] input
+      from lingvo_b200.parallel import cp   # pylint: disable=g-import-not-at-top
+      tgt = input_batch.tgt
+      full_len = tgt.ids.shape[1]
+      for k, v in list(tgt.items()):
+        if isinstance(v, torch.Tensor) and v.dim() >= 2 and v.shape[1] == full_len:
+          tgt[k] = cp.ShardSequence(v, 1)
+      tgt._cp_sharded = True   # pylint: disable=protected-access
     return input_batch
 
   def _ComputeDecoderInput(self, theta, input_batch):
