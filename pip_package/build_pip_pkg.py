@@ -58,7 +58,7 @@ def BuildWheel(out_dir, skip_native=False, plat=None):
     meta = ('Metadata-Version: 2.1\nName: %s\nVersion: %s\nSummary: B200-native (sm_100a) '
             'sequence-modelling framework with the capabilities of Lingvo\n'
             'Requires-Python: >=3.10\nRequires-Dist: torch>=2.4\nRequires-Dist: numpy\n'
-            'Requires-Dist: pyyaml\n' % (NAME, VERSION))
+            'Requires-Dist: pyyaml\nRequires-Dist: absl-py\n' % (NAME, VERSION))
     Add('%s/METADATA' % dist_info, meta.encode())
     Add('%s/WHEEL' % dist_info, ('Wheel-Version: 1.0\nGenerator: lingvo_b200-build_pip_pkg\n'
                                  'Root-Is-Purelib: %s\nTag: %s\n' %

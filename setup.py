@@ -26,7 +26,7 @@ setup(
     packages=find_packages(include=['lingvo_b200', 'lingvo_b200.*']),
     package_data={'lingvo_b200.ops': ['*.so', 'csrc/*', 'csrc_host/*']},
     python_requires='>=3.10',
-    install_requires=['torch>=2.4', 'numpy', 'pyyaml'],
+    install_requires=['torch>=2.4', 'numpy', 'pyyaml', 'absl-py'],
     entry_points={'console_scripts': ['lingvo_b200_trainer = lingvo_b200.trainer:main_cli']},
     cmdclass={'build_py': BuildWithExtensions},
 )
