@@ -217,7 +217,7 @@ class PipeliningLayer(SeqLayer):
   def _CalculateOutputShapes(self, input_shapes):
     """Output shapes of every cell from `FPropMeta` (ref :339)."""
     p = self.params
-    shapes = tuple(tshape.Shape(list(s)) if not isinstance(s, tshape.Shape) else s
+    shapes = tuple(s if s is None or isinstance(s, tshape.Shape) else tshape.Shape(list(s))
                    for s in input_shapes)
     outs = []
     for tpl in p.cell_tpl:

@@ -1059,3 +1059,268 @@ class SharedEmbeddingSoftmaxLayer(base_layer.BaseLayer):
     return loss, NestedMap(per_token_loss=per_tok * non_padding, non_padding=non_padding,
                            mean_xent=((lse - true_logit) * non_padding).sum() /
                            non_padding.sum().clamp_min(1.0))
+
+
+# ------------------------------------------------------------------------------------------
+# More gating policies (ref gshard_layers.py:2564-2990, 3166-3527). All return the packed
+# `GSEC` combine / dispatch pair `FeedForwardNetworksApplyGating` and the indexed movers use.
+# ------------------------------------------------------------------------------------------
+def ShardedWeightParams(shape, init=None, dtype=None, collections=None,
+                        tensor_split_dims_mapping=None):
+  """WeightParams that also records how the variable is split over the device mesh (:104)."""
+  p = py_utils.WeightParams(shape, init, dtype, collections)
+  if tensor_split_dims_mapping is not None:
+    assert len(tensor_split_dims_mapping) == len(shape)
+    p.tensor_split_dims_mapping = list(tensor_split_dims_mapping)
+  return p
+
+
+def TokenShufflingOnlogitsV2(logits, paddings, num_devices, experts_dim, expert_capacity_dim,
+                             fprop_dtype, use_xla_sharding=True, capacity_factor=None,
+                             mask_dtype=None):
+  """Expert-choice routing on raw gate scores with padded tokens excluded (:2564): each
+  expert picks its `C` best non-padded tokens; a token keeps, for every expert that picked
+  it, that expert's softmax weight; its slot is its rank among the expert's picks in
+  sequence order. Returns (0, combine `GSEC`, dispatch `GSEC`)."""
+  del num_devices, use_xla_sharding, mask_dtype
+  g, s, e = logits.shape
+  gates = torch.softmax(logits.float(), -1)
+  nonpad = torch.ones(g, s, device=logits.device) if paddings is None else 1.0 - paddings.float()
+  scores = (gates * nonpad.unsqueeze(-1)).transpose(1, 2)                    # GES
+  cap = min(ExpertCapacity(s, e, expert_capacity_dim, capacity_factor), s)
+  picked = scores.topk(cap, dim=-1).indices                                  # GEC
+  mask = torch.zeros(g, e, s, device=logits.device)
+  mask.scatter_(2, picked, 1.0)
+  mask = mask.transpose(1, 2) * nonpad.unsqueeze(-1)                         # GSE
+  pos = (torch.cumsum(mask, dim=1) - mask).long()                            # exclusive, GSE
+  keep = mask * (pos < cap)
+  combine = (gates * keep).unsqueeze(-1) * F.one_hot(pos.clamp(max=cap - 1), cap)
+  combine = combine.to(fprop_dtype)
+  return (torch.zeros((), device=logits.device, dtype=fprop_dtype), combine,
+          (keep.unsqueeze(-1) * F.one_hot(pos.clamp(max=cap - 1), cap)).to(fprop_dtype))
+
+
+def OptimalTransportOnlogits(logits, experts_dim, use_xla_sharding=False, epsilon=0.1,
+                             num_iterations=50, fprop_dtype=None):
+  """Balanced expert-choice routing (:2736): an entropic optimal-transport plan between
+  experts (each takes `C = 2S/E` tokens) and tokens (each goes to ≤ 2 experts, the slack
+  absorbed by a dummy expert) re-weights the softmax scores before every expert's top-C pick.
+  The plan itself is treated as a constant (stop-gradient), as in the reference."""
+  del use_xla_sharding
+  from lingvo_b200.core import differentiable_assignment
+  g, s, e = logits.shape
+  assert e == experts_dim
+  fprop_dtype = fprop_dtype or logits.dtype
+  max_token_capacity = 2
+  cap = s * 2 // e
+  scores = torch.softmax(logits.float().transpose(1, 2), -1)                 # GES, over tokens
+  scores_plus = torch.cat([scores, scores.new_zeros(g, 1, s)], 1)
+  upper = torch.cat([torch.ones_like(scores),
+                     scores.new_full((g, 1, s), float(max_token_capacity))], 1)
+  rows = torch.cat([scores.new_full((g, e), float(cap)),
+                    scores.new_full((g, 1), float(max_token_capacity * s - cap * e))], 1)
+  cols = scores.new_full((g, s), float(max_token_capacity))
+  with torch.no_grad():
+    plan = differentiable_assignment.max_assignment(
+        scores_plus, elementwise_upper_bound=upper, row_sums=rows, col_sums=cols,
+        epsilon=epsilon, num_iterations=num_iterations, use_epsilon_scaling=True)[0][:, :e]
+  gate, idx = (plan * scores).topk(cap, dim=-1)                              # GEC
+  combine = torch.zeros(g, s, e, cap, device=logits.device, dtype=fprop_dtype)
+  gi = torch.arange(g, device=logits.device)[:, None, None].expand(g, e, cap)
+  ei = torch.arange(e, device=logits.device)[None, :, None].expand(g, e, cap)
+  ci = torch.arange(cap, device=logits.device)[None, None, :].expand(g, e, cap)
+  combine = combine.index_put((gi, idx, ei, ci), gate.to(fprop_dtype))
+  return (torch.zeros((), device=logits.device, dtype=fprop_dtype), combine,
+          (combine != 0).to(fprop_dtype))
+
+
+def GetSentenceEmbeddings(inputs, segment_id):
+  """Mean input embedding of each token's segment (:3293); segment 0 (padding) maps to 0.
+  Segments are identified over the WHOLE `[G, S]` block, as in the reference."""
+  m = inputs.shape[-1]
+  flat = inputs.reshape(-1, m).float()
+  seg = segment_id.reshape(-1).long()
+  n = flat.shape[0]
+  sums = torch.zeros(n + 1, m, device=inputs.device).index_add_(0, seg.clamp(max=n), flat)
+  counts = torch.zeros(n + 1, device=inputs.device).index_add_(
+      0, seg.clamp(max=n), torch.ones_like(seg, dtype=torch.float32))
+  means = sums / counts.clamp(min=1.0).unsqueeze(-1)
+  means[0] = 0.0
+  return means[seg.clamp(max=n)].reshape(inputs.shape).to(inputs.dtype)
+
+
+def _GateOnEmbeddings(w, embeddings, orig_inputs, paddings, num_devices, experts_dim,
+                      expert_capacity_dim, local_dispatch, fprop_dtype, use_xla_sharding,
+                      second_expert_policy, second_expert_threshold, legacy_mtf_behavior,
+                      capacity_factor=None, seeds=None):
+  logits = torch.einsum('GSM,ME->GSE', embeddings.to(w.dtype), w)
+  aux, comb, disp = Top2GatingOnLogits(
+      embeddings, paddings, logits, num_devices, experts_dim, expert_capacity_dim,
+      fprop_dtype, use_xla_sharding, second_expert_policy, second_expert_threshold,
+      legacy_mtf_behavior, capacity_factor, seeds=seeds)
+  if not local_dispatch:
+    disp = disp.reshape(list(orig_inputs.shape[:2]) + list(disp.shape[2:]))
+    comb = comb.reshape(list(orig_inputs.shape[:2]) + list(comb.shape[2:]))
+  return NestedMap(combine_tensor=comb, dispatch_tensor=disp, aux_loss=aux)
+
+
+def SentenceTop2Gating(w, inputs, paddings, segment_id, num_devices, experts_dim,   # pylint: disable=function-redefined
+                       expert_capacity_dim, local_dispatch, fprop_dtype,
+                       use_xla_sharding=True, second_expert_policy='all',
+                       second_expert_threshold=0.0, legacy_mtf_behavior=True,
+                       embedding_type='sentence', capacity_factor=None, seeds=None):
+  """Top-2 gating on per-sentence mean embeddings: every token of a segment is routed by the
+  same logits (:3359)."""
+  assert embedding_type == 'sentence'
+  orig = inputs
+  if not local_dispatch:
+    inputs = inputs.reshape(1, inputs.shape[0] * inputs.shape[1], -1)
+    segment_id = segment_id.reshape(1, -1)
+    paddings = None if paddings is None else paddings.reshape(1, -1)
+  emb = GetSentenceEmbeddings(inputs, segment_id)
+  return _GateOnEmbeddings(w, emb, orig, paddings, num_devices, experts_dim,
+                           expert_capacity_dim, local_dispatch, fprop_dtype, use_xla_sharding,
+                           second_expert_policy, second_expert_threshold, legacy_mtf_behavior,
+                           capacity_factor, seeds)
+
+
+def TaskTop2Gating(w, inputs, paddings, task_embeddings, num_devices, experts_dim,
+                   expert_capacity_dim, local_dispatch, fprop_dtype, use_xla_sharding=True,
+                   second_expert_policy='all', second_expert_threshold=0.0,
+                   legacy_mtf_behavior=True, seeds=None):
+  """Top-2 gating on task embeddings instead of token activations (:3450)."""
+  orig = inputs
+  if not local_dispatch:
+    task_embeddings = task_embeddings.reshape(
+        1, task_embeddings.shape[0] * task_embeddings.shape[1], -1)
+    paddings = None if paddings is None else paddings.reshape(1, -1)
+  return _GateOnEmbeddings(w, task_embeddings, orig, paddings, num_devices, experts_dim,
+                           expert_capacity_dim, local_dispatch, fprop_dtype, use_xla_sharding,
+                           second_expert_policy, second_expert_threshold, legacy_mtf_behavior,
+                           None, seeds)
+
+
+_BaseComputeGating = ComputeGating
+
+
+def ComputeGating(w, inputs, paddings, num_devices, experts_dim, expert_capacity_dim,   # pylint: disable=function-redefined
+                  local_dispatch, fprop_dtype, gating_func='top_2', **kwargs):
+  """`ComputeGating` including the `token_shuffle_v2` and `optimal_transport` policies."""
+  if gating_func not in ('token_shuffle_v2', 'optimal_transport'):
+    return _BaseComputeGating(w, inputs, paddings, num_devices, experts_dim,
+                              expert_capacity_dim, local_dispatch, fprop_dtype,
+                              gating_func=gating_func, **kwargs)
+  orig = inputs
+  if not local_dispatch:
+    inputs = inputs.reshape(1, inputs.shape[0] * inputs.shape[1], -1)
+    paddings = None if paddings is None else paddings.reshape(1, -1)
+  ldt = kwargs.get('gating_logits_dtype') or fprop_dtype
+  logits = EinsumWithModelDim('GSM,ME->GSE', inputs.to(ldt), w.to(ldt),
+                              kwargs.get('model_dim_reshape_segments'))
+  if gating_func == 'token_shuffle_v2':
+    aux, comb, disp = TokenShufflingOnlogitsV2(
+        logits, paddings, num_devices, experts_dim, expert_capacity_dim, fprop_dtype,
+        capacity_factor=kwargs.get('capacity_factor'))
+  else:
+    aux, comb, disp = OptimalTransportOnlogits(logits, experts_dim, fprop_dtype=fprop_dtype)
+  if not local_dispatch:
+    disp = disp.reshape(list(orig.shape[:2]) + list(disp.shape[2:]))
+    comb = comb.reshape(list(orig.shape[:2]) + list(comb.shape[2:]))
+  return NestedMap(combine_tensor=comb, dispatch_tensor=disp, aux_loss=aux)
+
+
+def HashGating(*args, **kwargs):
+  return ComputeGating(*args, gating_func='hashing', **kwargs)
+
+
+def Top2Gating(*args, **kwargs):
+  return ComputeGating(*args, gating_func='top_2', **kwargs)
+
+
+def TokenShuffleGating(*args, **kwargs):
+  return ComputeGating(*args, gating_func='token_shuffle', **kwargs)
+
+
+def TokenShuffleGatingV2(*args, **kwargs):
+  return ComputeGating(*args, gating_func='token_shuffle_v2', **kwargs)
+
+
+def OptimalTransportGating(*args, **kwargs):
+  return ComputeGating(*args, gating_func='optimal_transport', **kwargs)
+
+
+def GatherK(selected_pos, values, k, num_devices=1):
+  """Packs, per row, the LAST `k` selected positions of every `[B, T, …]` tensor in `values`
+  to the right of a `[B, k, …]` output, in sequence order (:3166). Returns (outputs,
+  padding `[B, k]` with 1 at unfilled slots; those read position 0, as in the reference)."""
+  del num_devices
+  b, t = selected_pos.shape
+  for v in values:
+    assert tuple(v.shape[:2]) == (b, t), (v.shape, selected_pos.shape)
+  one_based = torch.arange(1, t + 1, device=selected_pos.device).unsqueeze(0)
+  top = (one_based * selected_pos.to(one_based.dtype)).topk(k, dim=-1).values
+  idx = top.flip(-1)                                                     # ascending, 0 = empty
+  padding = (idx == 0).to(values[0].dtype if values[0].is_floating_point() else torch.float32)
+  src = (idx - 1).clamp(min=0)
+  outs = []
+  for v in values:
+    gi = src.reshape(b, k, *([1] * (v.dim() - 2))).expand(b, k, *v.shape[2:])
+    outs.append(v.gather(1, gi))
+  return outs, padding
+
+
+ZERO_STATE_MAX_ABS_TOLERANCE = 1e-6
+
+
+class Conv1DStateLayer(base_layer.BaseLayer):
+  """Sliding window of the last `kernel_size` inputs of a causal conv1d during incremental
+  (flat-beam) decoding (:1432). Explicit-state API like `MultiHeadAttentionStateLayer`:
+  `InitState` → `LoadPrefix` (optional) → `Step` per decoded position."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('shape', [None, None, None], 'batch, time, trailing dims….')
+    p.Define('kernel_size', 0, 'Width of the convolution window.')
+    p.Define('skip_store_zero_state', False,
+             'All-zero inputs (zeroed padding positions) do not enter the window.')
+    return p
+
+  def InitState(self, batch, beam, device=None, dtype=None):
+    p = self.params
+    assert p.kernel_size > 0
+    return torch.zeros([batch, beam, p.kernel_size] + list(p.shape[2:]),
+                       dtype=dtype or self.fprop_dtype,
+                       device=device or py_utils.CurrentDevice())
+
+  def LoadPrefix(self, state, x):
+    """x `[B, prefix_len, …]`: the window becomes the prefix's last `kernel_size` inputs
+    (left-padded with zeros), shared by all beams."""
+    k = self.params.kernel_size
+    tail = x[:, -k:]
+    if tail.shape[1] < k:
+      tail = torch.cat([tail.new_zeros(tail.shape[0], k - tail.shape[1], *tail.shape[2:]),
+                        tail], 1)
+    return tail.unsqueeze(1).expand_as(state).to(state.dtype).contiguous()
+
+  def Step(self, state, x):
+    """x `[B, beam, …]` → (window `[B*beam, kernel_size, …]`, new state)."""
+    p = self.params
+    new_state = torch.cat([state[:, :, 1:], x.unsqueeze(2).to(state.dtype)], 2)
+    if p.skip_store_zero_state:
+      is_zero = x.reshape(x.shape[0], x.shape[1], -1).abs().amax(-1) < ZERO_STATE_MAX_ABS_TOLERANCE
+      mask = is_zero.reshape(list(is_zero.shape) + [1] * (state.dim() - 2)).to(state.dtype)
+      new_state = state * mask + new_state * (1 - mask)
+    b, beam = new_state.shape[:2]
+    return new_state.reshape(b * beam, *new_state.shape[2:]), new_state
+
+  def FProp(self, theta, x):
+    """Training: the convolution sees the whole sequence; nothing to do."""
+    return x
+
+  @staticmethod
+  def Reorder(state, batch_index, beam_parent):
+    """Flat beam search: hypothesis (b, k) continues (b, beam_parent[b, k])."""
+    del batch_index
+    idx = beam_parent.long().reshape(list(beam_parent.shape) + [1] * (state.dim() - 2))
+    return state.gather(1, idx.expand_as(state))

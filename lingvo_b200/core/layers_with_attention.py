@@ -243,10 +243,14 @@ class TransformerFeedForwardLayer(base_layer.BaseLayer):
     self._odim = odim
     act = p.activation
     self._gated = isinstance(act, str) and act.startswith('GATED_')
+    # `fflayer_tpl.dropout` (a single Params) chooses the dropout flavour of the hidden
+    # layer — GPipe swaps in DeterministicDropoutLayer there (ref layers_with_gpipe.py:207)
+    drop_tpl = p.fflayer_tpl.dropout if hasattr(p.fflayer_tpl.dropout, 'Copy') \
+        else layers.DropoutLayer.Params()
     ff = p.fflayer_tpl.Copy().Set(
         input_dim=p.input_dim, hidden_layer_dims=[p.hidden_dim, odim],
-        dropout=[layers.DropoutLayer.Params().Set(keep_prob=1.0 - p.relu_dropout_prob),
-                 layers.DropoutLayer.Params().Set(keep_prob=1.0)])
+        dropout=[drop_tpl.Copy().Set(keep_prob=1.0 - p.relu_dropout_prob),
+                 drop_tpl.Copy().Set(keep_prob=1.0)])
     if self._gated:
       ff.activation = [act[len('GATED_'):], 'NONE']
       self.CreateChild('gate', layers.ProjectionLayer.Params().Set(

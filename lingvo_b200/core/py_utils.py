@@ -1419,3 +1419,831 @@ def MultiTaskProjection(weights, biases, inputs, tasks, einsum_order='select_and
   if biases is not None:
     out = out + biases[ids]
   return out.squeeze(1) if squeeze_time else out
+
+
+# =========================================================================================
+# Tensor / structure helpers of the reference's py_utils used across tasks (the
+# framework-agnostic ones; TF-session / TPU-rewrite helpers have no counterpart here).
+# =========================================================================================
+def IsEagerMode() -> bool:
+  """This runtime always executes eagerly (CUDA graphs replay eager captures)."""
+  return True
+
+
+def IsTpuTraining(p=None) -> bool:
+  del p
+  return False
+
+
+def Log(value, prefix, **kwargs):
+  """Logs the given tensors (host sync: debugging only) and returns `value`."""
+  parts = ['%s=%s' % (k, v.tolist() if isinstance(v, torch.Tensor) and v.numel() <= 16 else v)
+           for k, v in kwargs.items()]
+  logging.info('%s: %s', prefix, ', '.join(parts))
+  return value
+
+
+def LogMultiLines(label, lines):
+  if isinstance(lines, str):
+    lines = lines.split('\n')
+  for line in lines:
+    logging.info('%s: %s', label, line)
+
+
+def Assert(condition, data, *args, **kwargs):
+  del args, kwargs
+  ok = bool(condition.all()) if isinstance(condition, torch.Tensor) else bool(condition)
+  if not ok:
+    raise AssertionError('Assertion failed: %s' % (data,))
+  return True
+
+
+def with_dependencies(dependencies, output_tensor):   # pylint: disable=invalid-name
+  """Eager execution already ran `dependencies`; kept so ported code reads the same."""
+  del dependencies
+  return output_tensor
+
+
+def _AssertCmp(op, name, x, y, summarize=None, message=None):
+  del summarize
+  xt, yt = torch.as_tensor(x), torch.as_tensor(y)
+  if not bool(op(xt, yt).all()):
+    raise AssertionError(message or 'assert_%s failed: %s vs %s' % (name, xt, yt))
+  return True
+
+
+def assert_greater(x, y, *args, **kwargs):   # pylint: disable=invalid-name
+  return _AssertCmp(torch.gt, 'greater', x, y, *args, **kwargs)
+
+
+def assert_greater_equal(x, y, *args, **kwargs):   # pylint: disable=invalid-name
+  return _AssertCmp(torch.ge, 'greater_equal', x, y, *args, **kwargs)
+
+
+def assert_less(x, y, *args, **kwargs):   # pylint: disable=invalid-name
+  return _AssertCmp(torch.lt, 'less', x, y, *args, **kwargs)
+
+
+def assert_less_equal(x, y, *args, **kwargs):   # pylint: disable=invalid-name
+  return _AssertCmp(torch.le, 'less_equal', x, y, *args, **kwargs)
+
+
+def clip_by_value(t, clip_value_min, clip_value_max, name=None):   # pylint: disable=invalid-name
+  del name
+  lo = clip_value_min if isinstance(clip_value_min, torch.Tensor) else torch.as_tensor(
+      clip_value_min, dtype=t.dtype, device=t.device)
+  hi = clip_value_max if isinstance(clip_value_max, torch.Tensor) else torch.as_tensor(
+      clip_value_max, dtype=t.dtype, device=t.device)
+  return torch.maximum(torch.minimum(t, hi.to(t.dtype)), lo.to(t.dtype))
+
+
+def HasSameShape(x, ref):
+  return HasShape(x, GetShape(ref))
+
+
+def IsCompatible(lhs, rhs) -> bool:
+  """True if the two (nested) structures have the same nesting and keys."""
+  def Sig(x):
+    if isinstance(x, dict):
+      return ('d', tuple((k, Sig(v)) for k, v in sorted(x.items())))
+    if isinstance(x, (list, tuple)):
+      return ('l', tuple(Sig(v) for v in x))
+    return 'x'
+  return Sig(lhs) == Sig(rhs)
+
+
+def AssertIsCompatible(lhs, rhs):
+  if not IsCompatible(lhs, rhs):
+    raise ValueError('Structures are not compatible:\n%s\nvs\n%s' % (lhs, rhs))
+
+
+def AssertIdShape(expected_ids_shape_pattern, ids_shape, *args):
+  """Checks `ids_shape` against a pattern (None entries are wildcards) and that every
+  further shape in `args` equals `ids_shape`."""
+  ids_shape = list(ids_shape)
+  assert len(expected_ids_shape_pattern) == len(ids_shape), (expected_ids_shape_pattern,
+                                                             ids_shape)
+  for want, got in zip(expected_ids_shape_pattern, ids_shape):
+    if want is not None and int(want) != int(got):
+      raise AssertionError('ids shape %s does not match %s' % (ids_shape,
+                                                              expected_ids_shape_pattern))
+  for other in args:
+    if list(other) != ids_shape:
+      raise AssertionError('shape %s != ids shape %s' % (list(other), ids_shape))
+  return True
+
+
+def CheckShapes(shapes):
+  """Asserts that `shapes` is a tuple of fully defined shapes (gpipe FPropMeta contract)."""
+  assert isinstance(shapes, tuple), str(shapes)
+  for s in shapes:
+    if s is None:
+      continue
+    dims = list(getattr(s, 'ToTensorShape', lambda: s)()) if not isinstance(
+        s, (list, tuple)) else list(s)
+    assert all(d is not None for d in dims), '%s is not fully defined' % (s,)
+
+
+def Chunked(values):
+  """[a, b, c, d] → [(a, b), (c, d)]."""
+  return list(zip(values[::2], values[1::2]))
+
+
+def ToUniqueList(nmap):
+  """Flattened `nmap` without duplicate objects (first occurrence wins)."""
+  seen, out = set(), []
+  for v in nmap.Flatten():
+    if id(v) not in seen:
+      seen.add(id(v))
+      out.append(v)
+  return out
+
+
+def MergeDictsWithValueCheck(dict1, dict2):
+  """Merges two dicts; a key present in both must map to the *same object*."""
+  for key in set(dict1) & set(dict2):
+    if dict1[key] is not dict2[key]:
+      raise RuntimeError('The same key %s corresponds to different values in the '
+                         'dictionaries: %s vs %s.' % (key, dict1[key], dict2[key]))
+  return {**dict1, **dict2}
+
+
+class ReadOnlyAttrDictView:
+  """Read-only attribute / item view of a dict; used to hand layers' children out."""
+
+  def __init__(self, backing):
+    object.__setattr__(self, '_backing', backing)
+
+  def __getattr__(self, name):
+    try:
+      return self._backing[name]
+    except KeyError:
+      raise AttributeError(name) from None
+
+  def __getitem__(self, name):
+    return self._backing[name]
+
+  def __len__(self):
+    return len(self._backing)
+
+  def __iter__(self):
+    return iter(self._backing)
+
+  def __contains__(self, name):
+    return name in self._backing
+
+  def __setattr__(self, name, value):
+    raise AttributeError('Dictionary is read-only.')
+
+  def __setitem__(self, name, value):
+    raise AttributeError('Dictionary is read-only.')
+
+  def keys(self):   # pylint: disable=invalid-name
+    return self._backing.keys()
+
+  def items(self):   # pylint: disable=invalid-name
+    return self._backing.items()
+
+
+def SanitizeScopeKey(key: str) -> str:
+  if key.startswith('_'):
+    key = key[1:]
+  return key.replace('[', '_').replace(']', '')
+
+
+def ShardedFilePatternToGlob(file_pattern: str) -> str:
+  """`path@shards` → `path-?????-of-000NN` (`@*` → `-of-*`)."""
+  if ',' in file_pattern:
+    raise ValueError('ShardedFilePatternToGlob does not support multiple file patterns.')
+  if '@' not in file_pattern:
+    return file_pattern
+  path, shards = file_pattern.split('@')
+  if shards == '*':
+    return '%s-?????-of-*' % path
+  return '%s-?????-of-%05d' % (path, int(shards))
+
+
+_RECORD_FORMAT_RE = re.compile(r'(^[A-Za-z_]+):(.*)')
+
+
+def RecordFormatFromFilePattern(file_pattern: str):
+  """`tfrecord:/path/x*` → ('tfrecord', '/path/x*'); no prefix → ('sstable', pattern)."""
+  m = _RECORD_FORMAT_RE.match(file_pattern)
+  if m is None:
+    return 'sstable', file_pattern
+  return m.groups()
+
+
+def GenerateSeedFromId(obj_id) -> int:
+  md5 = hashlib.md5()
+  md5.update(np.int64(obj_id).tobytes())
+  return int(int(md5.hexdigest(), 16) % (2**31 - 1))
+
+
+def AppendDims(x, ndims: int):
+  return x.reshape(list(x.shape) + [1] * int(ndims))
+
+
+def ExpandTo(x, target_rank: int):
+  """Appends unit dims until `x` has rank `target_rank`."""
+  if x is None:
+    return None
+  return x.reshape(list(x.shape) + [1] * (int(target_rank) - x.dim()))
+
+
+def ExpandAndPadOrTrimTo(x, target_shape, pad_val=0):
+  """Makes `x` broadcast-compatible with `target_shape`: expand to its rank, then pad / trim
+  every non-unit dim to the target size."""
+  if x is None:
+    return None
+  target_shape = [int(d) for d in target_shape]
+  x = ExpandTo(x, len(target_shape))
+  masked = [1 if x.shape[i] == 1 else target_shape[i] for i in range(x.dim())]
+  return PadOrTrimTo(x, masked, pad_val).reshape(masked)
+
+
+def PadSequenceTo(xs, padding, length: int, pad_val):
+  """Pads `[B, T, …]` tensor(s) with `pad_val` and `padding [B, T]` with 1 to `length`."""
+  many = isinstance(xs, (list, tuple))
+  res = []
+  for x in (xs if many else [xs]):
+    assert tuple(x.shape[:2]) == tuple(padding.shape), (x.shape, padding.shape)
+    res.append(PadSequenceDimension(x, length, pad_val))
+  padding = PadSequenceDimension(padding, length, 1)
+  return (tuple(res), padding) if many else (res[0], padding)
+
+
+def CausalSelfAttenPadding(seqlen: int, dtype=torch.float32, device=None):
+  """`[T, T]` padding with 1 where key index > query index (the future)."""
+  r = torch.arange(seqlen, device=device)
+  return (r.unsqueeze(-1) < r.unsqueeze(0)).to(dtype)
+
+
+def ArgMax(inputs):
+  return inputs.argmax(-1)
+
+
+def TopK(x_in, k: int):
+  """(values, indices) of the top-k entries of the last dim."""
+  return torch.topk(x_in, k, dim=-1)
+
+
+def DivideNoNan(x, y):
+  """x / y with 0 where y == 0 (any float dtype, bf16 included)."""
+  zero = y == 0
+  safe = torch.where(zero, torch.ones_like(y), y)
+  return torch.where(zero, torch.zeros((), dtype=x.dtype, device=x.device), x / safe)
+
+
+def ReduceRms(x):
+  """Root mean square (fp32 accumulation)."""
+  if x.dim() == 0:
+    return x
+  return torch.sqrt(x.float().square().mean()).to(x.dtype if x.is_floating_point()
+                                                   else torch.float32)
+
+
+def SumAbs(tensor_list):
+  ts = [t for t in tensor_list if t is not None]
+  if not ts:
+    return torch.zeros(())
+  return torch.stack([t.float().abs().sum() for t in ts]).sum()
+
+
+def HasNanOrInf(x):
+  """0-d bool tensor: any element of `x` (tensor or list / NestedMap of tensors) is not finite."""
+  ts = x.Flatten() if isinstance(x, NestedMap) else (list(x) if isinstance(x, (list, tuple))
+                                                     else [x])
+  ts = [t for t in ts if isinstance(t, torch.Tensor) and t.is_floating_point()]
+  if not ts:
+    return torch.zeros((), dtype=torch.bool)
+  return torch.stack([~torch.isfinite(t).all() for t in ts]).any()
+
+
+def MaybeSoftCapLogits(x, cap: float = 0.0):
+  return x if cap <= 0.0 else cap * torch.tanh(x / cap)
+
+
+def PiecewiseConstant(x_in, boundaries, values, vdtype=torch.float32):
+  """values[k] where k = number of boundaries ≤ x_in (device-side, no sync)."""
+  assert len(values) == len(boundaries) + 1 and sorted(boundaries) == list(boundaries)
+  x = torch.as_tensor(x_in, dtype=torch.float32)
+  bs = torch.tensor(list(boundaries), dtype=torch.float32, device=x.device)
+  vs = torch.tensor(list(values), dtype=vdtype, device=x.device)
+  return vs[(x >= bs).sum()] if bs.numel() else vs[0]
+
+
+def GatherTensorValuesBySeqIndices(tensor, class_indices, keepdims=False):
+  """ret[b, t] = tensor[b, t, class_indices[b, t]]."""
+  assert tensor.dim() == 3 and class_indices.dim() == 2
+  assert tuple(tensor.shape[:2]) == tuple(class_indices.shape)
+  ret = tensor.gather(-1, class_indices.long().unsqueeze(-1))
+  return ret if keepdims else ret.squeeze(-1)
+
+
+def GetSoftmaxProbsBySeqIndices(logits, indices, keepdims=False):
+  return GatherTensorValuesBySeqIndices(torch.softmax(logits.float(), -1), indices, keepdims)
+
+
+def CreateIdsAndLabels(ids, paddings, sos_id=1, eos_id=2, trim=False):
+  """Decoder targets from raw ids `[B, T]`: `ids` with sos prepended, `labels` with eos
+  appended, `paddings`, `weights` — one longer than the input unless `trim`."""
+  ids = torch.where(paddings == 0, ids, torch.full_like(ids, eos_id))
+  targets = NestedMap()
+  targets.ids = F.pad(ids, (1, 0), value=sos_id)
+  targets.labels = F.pad(ids, (0, 1), value=eos_id)
+  targets.paddings = F.pad(paddings, (1, 0))
+  targets.weights = 1.0 - targets.paddings
+  if trim:
+    targets = targets.Transform(lambda v: v[:, :-1])
+  return targets
+
+
+def MergeDuplicateIds(ids, paddings, extra_tensors=None):
+  """Collapses runs of equal consecutive ids (CTC-style): `[4,4,5,6,6,5,0,0]` with paddings
+  `[0,0,0,0,0,0,1,1]` → ids `[4,5,6,5,0,0,0,0]`, paddings `[0,0,0,0,1,1,1,1]`. Tensors in
+  `extra_tensors` (`[B, T, …]`) are compacted with the same selection."""
+  assert bool((ids >= 0).all())
+  b, t = ids.shape
+  prev = F.pad(ids, (1, 0), value=-1)[:, :-1]
+  keep = ((ids != prev) & (paddings == 0)).to(torch.int64)
+  descend = keep * torch.arange(t, 0, -1, device=ids.device)
+  order = torch.argsort(descend, dim=1, descending=True, stable=True)
+  n = keep.sum(-1, keepdim=True)
+  seq_mask = (torch.arange(t, device=ids.device).unsqueeze(0) < n)
+  ret_paddings = 1.0 - seq_mask.to(paddings.dtype)
+  ret_ids = ids.gather(1, order) * seq_mask.to(ids.dtype)
+  ret_tensors = NestedMap()
+  for key, tensor in (extra_tensors or {}).items():
+    idx = order.reshape(b, t, *([1] * (tensor.dim() - 2))).expand_as(tensor)
+    ret_tensors[key] = tensor.gather(1, idx) * ExpandTo(seq_mask, tensor.dim()).to(tensor.dtype)
+  return ret_ids, ret_paddings, ret_tensors
+
+
+def MixByWeight(inputs, weights, seed=None):
+  """Calls ONE of the callables `inputs`, chosen with probability ∝ `weights`; returns
+  (its result, one-hot of the chosen source). Unchosen streams are not advanced."""
+  w = torch.as_tensor(weights, dtype=torch.float32)
+  assert w.shape == (len(inputs),) and float(w.min()) >= 0.0
+  gen = None
+  if seed is not None:
+    gen = torch.Generator().manual_seed(int(seed))
+  r = torch.rand((), generator=gen) * w.sum()
+  idx = int(torch.searchsorted(torch.cumsum(w, 0), r, right=True).clamp(max=len(inputs) - 1))
+  return inputs[idx](), F.one_hot(torch.tensor(idx), len(inputs)).float()
+
+
+def MaskGradients(var_grad, grad_mask):
+  """`grad_mask`: variable name → mask; returns var_grads with `mask * gradient`."""
+  def ApplyMask(entry):
+    var, grad = entry
+    name = getattr(var, 'var_name', getattr(var, 'name', None))
+    return VarGrad(var, grad * grad_mask[name])
+  return var_grad.Transform(ApplyMask)
+
+
+def SkipNoneGradients(var_grads):
+  """Drops (var, None) pairs."""
+  return var_grads.Filter(lambda vg: vg.grad is not None) if isinstance(
+      var_grads, NestedMap) else [vg for vg in var_grads if vg.grad is not None]
+
+
+def ConvertNoneGradientToZeros(xs, dxs):
+  """None gradients become zeros shaped like their `xs` entry."""
+  return xs.Pack([torch.zeros_like(x) if dx is None else dx
+                  for x, dx in zip(xs.Flatten(), dxs.Flatten() if isinstance(
+                      dxs, NestedMap) else dxs)])
+
+
+def ComputeNceAndAuc(probs, targets, mask):
+  """Normalised cross entropy and PR-curve AUC of per-token confidence scores
+  (`probs`, `targets ∈ {0,1}`, `mask`, all `[B, T]`)."""
+  probs, targets, mask = probs.float(), targets.float(), mask.float()
+
+  def LogClip(t):
+    return torch.log(t.clamp(1e-8, 1.0))
+
+  bce = -targets * LogClip(probs) - (1 - targets) * LogClip(1 - probs)
+  num_tokens = mask.sum()
+  wcr = (targets * mask).sum() / num_tokens
+  entropy = -wcr * LogClip(wcr) - (1 - wcr) * LogClip(1 - wcr)
+  nce = (entropy - (bce * mask).sum() / num_tokens) / entropy
+  # PR AUC by the trapezoid rule over 200 thresholds (what tf.metrics.auc does)
+  sel = mask > 0
+  p, y = probs[sel], targets[sel]
+  th = torch.linspace(0.0, 1.0, 200, device=p.device).unsqueeze(1)
+  pred = (p.unsqueeze(0) > th).float()
+  tp = (pred * y).sum(1)
+  fp = (pred * (1 - y)).sum(1)
+  fn = ((1 - pred) * y).sum(1)
+  precision = (tp + 1e-7) / (tp + fp + 1e-7)
+  recall = (tp + 1e-7) / (tp + fn + 1e-7)
+  auc = torch.trapz(precision.flip(0), recall.flip(0)).abs()
+  return nce, auc
+
+
+class UniformSampler:
+  """Reservoir sampler keeping a uniform sample of `num_samples` items of a stream."""
+
+  def __init__(self, num_samples, seed=None):
+    assert num_samples > 0
+    self._num_samples = num_samples
+    self._num_seen_items = 0
+    self._samples = []
+    self._rng = np.random.RandomState(seed)
+
+  def Add(self, item):
+    self._num_seen_items += 1
+    if len(self._samples) < self._num_samples:
+      self._samples.append(item)
+      return
+    index = self._rng.randint(0, self._num_seen_items)
+    if index < self._num_samples:
+      self._samples[index] = item
+
+  @property
+  def samples(self):
+    return self._samples
+
+
+_SAMPLE_STEP_STACK = []
+
+
+@contextlib.contextmanager
+def SampleStep(step):
+  """Context naming the current decode step (`with py_utils.SampleStep(t): …`)."""
+  _SAMPLE_STEP_STACK.append(step)
+  try:
+    yield step
+  finally:
+    _SAMPLE_STEP_STACK.pop()
+
+
+# -- task call scopes (which task is calling into shared layers) ---------------------
+_TASK_CALL_SCOPE = []
+
+
+@contextlib.contextmanager
+def TaskCallScope(task):
+  _TASK_CALL_SCOPE.append(task)
+  try:
+    yield
+  finally:
+    _TASK_CALL_SCOPE.pop()
+
+
+def GetTaskCallScope():
+  return _TASK_CALL_SCOPE[-1] if _TASK_CALL_SCOPE else None
+
+
+def TaskCallScopeName(task):
+  return getattr(getattr(task, 'params', None), 'name', None) or str(task)
+
+
+# -- params helpers -----------------------------------------------------------------------
+def UpdateDtype(params, dtype):
+  """Sets `dtype` on `params` and every nested layer params that has the field."""
+  def Visit(p):
+    if isinstance(p, hyperparams.Params):
+      if 'dtype' in p and 'cls' in p:
+        p.dtype = dtype
+      for _, v in p.IterParams():
+        Visit(v)
+    elif isinstance(p, (list, tuple)):
+      for v in p:
+        Visit(v)
+    elif isinstance(p, dict):
+      for v in p.values():
+        Visit(v)
+  Visit(params)
+  return params
+
+
+def UpdateFpropDtype(params, fprop_dtype):
+  """Sets `fprop_dtype` on `params` and every nested layer params."""
+  def Visit(p):
+    if isinstance(p, hyperparams.Params):
+      if 'fprop_dtype' in p:
+        p.fprop_dtype = fprop_dtype
+      for _, v in p.IterParams():
+        Visit(v)
+    elif isinstance(p, (list, tuple)):
+      for v in p:
+        Visit(v)
+    elif isinstance(p, dict):
+      for v in p.values():
+        Visit(v)
+  Visit(params)
+  return params
+
+
+def GetVariableName(name: str) -> str:
+  """Full variable name under the current variable scope (as CreateVariable would use)."""
+  scope = CurrentVariableScope()
+  return (scope + '/' if scope else '') + name
+
+
+# -- functional control flow (host loops: every iteration launches device work) -------------
+def ForLoop(body, start, limit, delta, loop_state):
+  """state = body(i, state) for i in range(start, limit, delta)."""
+  state = loop_state
+  for i in range(int(start), int(limit), int(delta)):
+    state = body(i, state)
+  return state
+
+
+def WhileLoop(cond, body, loop_state):
+  """while cond(state): state = body(state) — `cond` may return a 0-d tensor (host sync)."""
+  state = loop_state
+  while bool(cond(state)):
+    state = body(state)
+  return state
+
+
+def If(cond, inputs, then_branch, else_branch):
+  return then_branch(inputs) if bool(cond) else else_branch(inputs)
+
+
+def Pack(tmpl, values):
+  """Packs the flat list `values` into the structure of `tmpl`."""
+  return tmpl.Pack(list(values))
+
+
+# -- RNN initial-state policy (ref py_utils.py:1014-1080) --------------------------------------
+class RNNCellStateInit:
+  """Params describing how a cell's initial state is drawn."""
+
+  @staticmethod
+  def _Params(method, seed):
+    p = hyperparams.Params()
+    p.Define('method', method, 'One of zeros, random_normal.')
+    p.Define('seed', seed, 'Random seed of random_normal.')
+    p.Freeze()
+    return p
+
+  @staticmethod
+  def Zeros():
+    return RNNCellStateInit._Params('zeros', None)
+
+  @staticmethod
+  def RandomNormal(seed=None):
+    return RNNCellStateInit._Params('random_normal', seed)
+
+
+def DefaultRNNCellStateInit():
+  return RNNCellStateInit.Zeros()
+
+
+def InitRNNCellState(shape, init=None, dtype=None, name=None, is_eval=False, device=None):
+  """Initial state tensor of `shape`: zeros, or N(0,1) in training for `random_normal`
+  (seeded from (name, init.seed) when either is given so replicas agree)."""
+  init = init or DefaultRNNCellStateInit()
+  dtype = dtype or torch.float32
+  shape = [int(d) for d in shape]
+  if init.method == 'zeros' or (init.method == 'random_normal' and is_eval):
+    return torch.zeros(shape, dtype=dtype, device=device)
+  if init.method != 'random_normal':
+    raise ValueError('Initialization method (%s) not supported.' % init.method)
+  gen = None
+  if init.seed is not None or name is not None:
+    seed = GenerateSeedFromName(name or 'rnn_state') ^ int(init.seed or 0)
+    gen = torch.Generator().manual_seed(seed % (2**31 - 1))
+  return torch.randn(shape, generator=gen, dtype=torch.float32).to(device=device, dtype=dtype)
+
+
+# -- functions with hand-written gradients (ref py_utils.py:5560-6110: Function / CallDefun) ------
+def _PackLike(tmpl, flat):
+  """Inverse of Flatten for NestedMap / dict / list / tuple / leaf templates."""
+  it = iter(flat)
+
+  def Build(t):
+    if isinstance(t, NestedMap):
+      return t.Pack([next(it) for _ in t.Flatten()])
+    if isinstance(t, dict):
+      return {k: Build(t[k]) for k in sorted(t)}
+    if isinstance(t, (list, tuple)):
+      return type(t)(Build(e) for e in t)
+    return next(it)
+
+  return Build(tmpl)
+
+
+def CallDefun(fwd, args=None, bak=None, bak_as_function=False, device=None):
+  """ys = fwd(args); with `bak`, the backward pass calls `bak(xs, ys, dys) -> dxs` instead of
+  differentiating `fwd` (which then runs without building an autograd graph).
+
+  `args` / results are arbitrary nested structures of tensors. The forward activations are
+  not kept: `bak` sees the saved inputs and outputs only — the memory contract the reference's
+  Defun gives (it is what `recurrent` and reversible layers are built on).
+  """
+  del bak_as_function, device
+  if bak is None:
+    return fwd(args) if args is not None else fwd()
+  flat_in = Flatten(args)
+  is_t = [isinstance(x, torch.Tensor) for x in flat_in]
+  holder = {}
+
+  class _Fn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, *tensors):
+      it = iter(tensors)
+      xs = _PackLike(args, [next(it) if t else x for t, x in zip(is_t, flat_in)])
+      with torch.no_grad():
+        ys = fwd(xs)
+      flat_out = Flatten(ys)
+      holder['tmpl'] = ys
+      ctx.n_in = len(tensors)
+      ctx.save_for_backward(*tensors, *[y for y in flat_out if isinstance(y, torch.Tensor)])
+      ctx.out_is_t = [isinstance(y, torch.Tensor) for y in flat_out]
+      ctx.out_consts = [None if isinstance(y, torch.Tensor) else y for y in flat_out]
+      nondiff = [y for y in flat_out if isinstance(y, torch.Tensor)
+                 and not y.is_floating_point()]
+      ctx.mark_non_differentiable(*nondiff)
+      return tuple(y for y in flat_out if isinstance(y, torch.Tensor))
+
+    @staticmethod
+    def backward(ctx, *grads):
+      saved = ctx.saved_tensors
+      ins, outs = saved[:ctx.n_in], saved[ctx.n_in:]
+      it = iter(ins)
+      xs = _PackLike(args, [next(it) if t else x for t, x in zip(is_t, flat_in)])
+      oi, gi = iter(outs), iter(grads)
+      flat_y, flat_dy = [], []
+      for t, c in zip(ctx.out_is_t, ctx.out_consts):
+        if t:
+          y, g = next(oi), next(gi)
+          flat_y.append(y)
+          flat_dy.append(torch.zeros_like(y) if g is None else g)
+        else:
+          flat_y.append(c)
+          flat_dy.append(None)
+      ys = _PackLike(holder['tmpl'], flat_y)
+      dys = _PackLike(holder['tmpl'], flat_dy)
+      with torch.no_grad():
+        dxs = bak(xs, ys, dys)
+      flat_dx = Flatten(dxs)
+      assert len(flat_dx) == len(flat_in), 'bak must return one gradient per input leaf'
+      res = []
+      for t, x, dx in zip(is_t, flat_in, flat_dx):
+        if t:
+          res.append(dx if (isinstance(dx, torch.Tensor) and x.is_floating_point()) else None)
+      return tuple(res)
+
+  outs = _Fn.apply(*[x for x, t in zip(flat_in, is_t) if t])
+  oi = iter(outs)
+  flat_out = [next(oi) if isinstance(y, torch.Tensor) else y
+              for y in Flatten(holder['tmpl'])]
+  return _PackLike(holder['tmpl'], flat_out)
+
+
+def Function(fwd_sig=None, bak=None, bak_as_function=False, device=None):
+  """Decorator form: `@Function(bak=Grad) def Fwd(xs): …` → a callable using `Grad` backward."""
+  del fwd_sig
+
+  def Decorate(fwd):
+    @functools.wraps(fwd)
+    def Call(args=None):
+      return CallDefun(fwd, args, bak=bak, bak_as_function=bak_as_function, device=device)
+    Call.func = fwd
+    return Call
+
+  return Decorate
+
+
+DefinedFunction = Function
+
+
+def ComputeGradientsSimple(loss_or_activations, all_vars, grad_aggregation_method=None,
+                           colocate_gradients_with_ops=None, gate_gradients=None,
+                           activations_grad=None):
+  """Plain autograd of a loss (or of activations seeded with `activations_grad`) w.r.t. a
+  flat list of variables; unused variables get None."""
+  del grad_aggregation_method, colocate_gradients_with_ops, gate_gradients
+  return list(torch.autograd.grad(loss_or_activations, list(all_vars),
+                                  grad_outputs=activations_grad, allow_unused=True,
+                                  retain_graph=True))
+
+
+@contextlib.contextmanager
+def GradientTape(*args, **kwargs):
+  """Autograd records eagerly; the context exists so reference-shaped code runs unchanged."""
+  del args, kwargs
+  with torch.enable_grad():
+    yield None
+
+
+def CurrentGradientTape():
+  return None
+
+
+def DisableVN():
+  return VariationalNoiseParams(1.0, False, False)
+
+
+def FindDataType(var_name):
+  """dtype of the first VariableListDtypeRegexScope rule matching `var_name`, else None."""
+  for rules in _VAR_DTYPE_OVERRIDES.items:
+    for regex, dtype in rules:
+      if re.match(regex, var_name):
+        return dtype
+  return None
+
+
+def Save(value, filename_prefix, **kwargs):
+  """Debug helper: writes every tensor in kwargs to `<prefix>.<step>.<name>.npy`."""
+  step = int(GetGlobalStep())
+  for name, t in sorted(kwargs.items()):
+    arr = t.detach().float().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    np.save('%s.%08d.%s.npy' % (filename_prefix, step, name), arr)
+  return value
+
+
+def ReadVariable(var):
+  return var.detach() if isinstance(var, torch.Tensor) else var
+
+
+def SetShapes(dst_nmap, src_nmap):
+  """Checks that both structures carry tensors of the same shapes (shapes are always static
+  here, so there is nothing to set)."""
+  AssertIsCompatible(src_nmap, dst_nmap)
+  for d, s in zip(dst_nmap.Flatten(), src_nmap.Flatten()):
+    assert tuple(d.shape) == tuple(s.shape), (d.shape, s.shape)
+
+
+@contextlib.contextmanager
+def RemoveAssertContext(remove=True):
+  """Disables the py_utils shape / value asserts inside the context."""
+  if not remove:
+    yield
+    return
+  prev = flags.enable_asserts
+  flags.enable_asserts = lambda: False
+  try:
+    yield
+  finally:
+    flags.enable_asserts = prev
+
+
+@contextlib.contextmanager
+def outside_all_rewrites():   # pylint: disable=invalid-name
+  yield
+
+
+@contextlib.contextmanager
+def tpu_host(func=None):   # pylint: disable=invalid-name
+  yield func
+
+
+def RunOnTpuHost(func, *args, **kwargs):
+  return func(*args, **kwargs)
+
+
+def RetryOnTransientTfError(*args, **kwargs):
+  """Retry decorator for transient IO / collective errors."""
+  kwargs.setdefault('retry_value', (OSError, RuntimeError))
+  return Retry(*args, **kwargs)
+
+
+def OverrideVarsFromCheckpoint(all_vars, checkpoint_path, variable_loading_rules,
+                               var_ignore_rules, **unused):
+  """Loads the variables of `all_vars` matched by `variable_loading_rules` ([(regex, fmt)])
+  and not by `var_ignore_rules` from the bundle at `checkpoint_path` (ref :5200-5330)."""
+  from lingvo_b200.core import saver as saver_lib
+  from lingvo_b200.utils import tensor_bundle
+  if os.path.isdir(checkpoint_path):
+    checkpoint_path = saver_lib.LatestCheckpoint(checkpoint_path)
+  reader = tensor_bundle.BundleReader(checkpoint_path)
+  keys = set(reader.Keys())
+  loaded = []
+  with torch.no_grad():
+    for v in all_vars:
+      name = v.var_name[:-len('/var')] if v.var_name.endswith('/var') else v.var_name
+      if any(re.match(r, name) for r in var_ignore_rules):
+        continue
+      for regex, fmt in variable_loading_rules:
+        m = re.match(regex, name)
+        if not m:
+          continue
+        src = fmt % m.groups() if m.groups() else fmt
+        hit = [c for c in (src, src + '/var') if c in keys]
+        if not hit:
+          raise KeyError('%s → %s not found in %s' % (name, src, checkpoint_path))
+        v.data.copy_(saver_lib.FromNumpy(reader.Read(hit[0])).to(v.device, v.dtype))
+        loaded.append(name)
+        break
+  reader.Close()
+  return loaded
+
+
+def OverrideVarsFromCheckpoints(all_vars, ckpts_loading_rules, **unused):
+  """`ckpts_loading_rules`: {ckpt_path: ([(regex, fmt)], [ignore_regex])}; a variable may be
+  claimed by one checkpoint only."""
+  claimed = {}
+  for ckpt, (rules, ignore) in ckpts_loading_rules.items():
+    for name in OverrideVarsFromCheckpoint(all_vars, ckpt, rules, ignore):
+      if name in claimed:
+        raise ValueError('Variable %s is overridden by both %s and %s' % (name, claimed[name],
+                                                                         ckpt))
+      claimed[name] = ckpt
+  return claimed

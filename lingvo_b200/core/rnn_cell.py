@@ -55,7 +55,15 @@ class RNNCell(quant_utils.QuantizableLayer):
     p.Define('num_output_nodes', 0, 'Output (m) width.')
     p.Define('reset_cell_state', False, 'Reset state where inputs.reset_mask == 0.')
     p.Define('zo_prob', 0.0, 'Zoneout probability.')
+    p.Define('zero_state_init_params', py_utils.DefaultRNNCellStateInit(),
+             'How zero_state draws the initial state (py_utils.RNNCellStateInit).')
     return p
+
+  def _InitState(self, shape, name):
+    p = self.params
+    return py_utils.InitRNNCellState(
+        shape, init=p.zero_state_init_params, dtype=py_utils.FPropDtype(p),
+        name='%s/%s' % (self.path, name), is_eval=self.do_eval, device=self.Device())
 
   def _Act(self, inputs):
     act = inputs.act
@@ -142,10 +150,8 @@ class LSTMCellSimple(RNNCell):
 
   def zero_state(self, theta, batch_size):
     p = self.params
-    dev, dt = self.Device(), py_utils.FPropDtype(p)
-    return NestedMap(
-        m=torch.zeros(batch_size, p.num_output_nodes, device=dev, dtype=dt),
-        c=torch.zeros(batch_size, self.hidden_size, device=dev, dtype=dt))
+    return NestedMap(m=self._InitState([batch_size, p.num_output_nodes], 'zero_m'),
+                     c=self._InitState([batch_size, self.hidden_size], 'zero_c'))
 
   def GetOutput(self, state):
     return state.m

