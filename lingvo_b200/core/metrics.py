@@ -17,6 +17,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from lingvo_b200.core import hyperparams
+
 
 def CreateScalarSummary(name: str, simple_value: float):
   from lingvo_b200.utils import tfevents
@@ -208,26 +210,88 @@ class AUCMetric(BaseMetric):
       self._prob = self._prob[-self._samples:]
       self._weight = self._weight[-self._samples:]
 
-  @property
-  def value(self):
+  def _Sorted(self):
     y = np.asarray(self._label, dtype=np.float64)
     s = np.asarray(self._prob, dtype=np.float64)
     w = np.asarray(self._weight, dtype=np.float64)
     if y.size == 0 or (y * w).sum() == 0 or ((1 - y) * w).sum() == 0:
-      return 0.0
+      return None
     order = np.argsort(-s, kind='mergesort')
     y, s, w = y[order], s[order], w[order]
     tp = np.cumsum(y * w)
     fp = np.cumsum((1 - y) * w)
     last = np.r_[np.where(np.diff(s))[0], y.size - 1]
-    tp, fp = tp[last], fp[last]
+    return tp[last], fp[last], s[last]
+
+  def _PrCurve(self):
+    """(precision, recall, thresholds) in sklearn's order: thresholds ascending, recall
+    descending, with the final (precision=1, recall=0) point appended."""
+    st = self._Sorted()
+    if st is None:
+      return np.array([1.0]), np.array([0.0]), np.array([])
+    tp, fp, th = st
+    precision = tp / np.maximum(tp + fp, 1e-12)
+    recall = tp / tp[-1]
+    stop = int(np.searchsorted(tp, tp[-1]))      # first threshold reaching full recall
+    sl = slice(stop, None, -1)
+    return np.r_[precision[sl], 1.0], np.r_[recall[sl], 0.0], th[sl]
+
+  @property
+  def value(self):
+    st = self._Sorted()
+    if st is None:
+      return 0.0
+    tp, fp, _ = st
     if self._mode == 'roc':
       tpr = np.r_[0.0, tp / tp[-1]]
       fpr = np.r_[0.0, fp / fp[-1]]
-      return float(np.trapz(tpr, fpr))
+      return float(np.trapezoid(tpr, fpr))
     precision = tp / np.maximum(tp + fp, 1e-12)
     recall = tp / tp[-1]
     return float(np.sum(np.diff(np.r_[0.0, recall]) * precision))
+
+  def _PrecisionAtRecall(self, recall):
+    """Precision at the highest threshold whose recall is still ≥ `recall` (ref :552)."""
+    assert self._mode == 'pr'
+    p, r, t = self._PrCurve()
+    last_p = 0.0
+    for pp, rr, _ in zip(p, r, t):
+      if rr >= recall:
+        last_p = pp
+    return float(last_p)
+
+  def _RecallAtPrecision(self, precision):
+    """Recall at the lowest threshold whose precision reaches `precision` (ref :564)."""
+    assert self._mode == 'pr'
+    p, r, t = self._PrCurve()
+    for pp, rr, _ in zip(p, r, t):
+      if pp >= precision:
+        return float(rr)
+    return 0.0
+
+
+class PrecisionAtRecall(AUCMetric):
+  """Precision of the PR curve at a recall threshold (ref :576)."""
+
+  def __init__(self, recall_threshold, samples=-1):
+    super().__init__(mode='pr', samples=samples)
+    self._recall_threshold = recall_threshold
+
+  @property
+  def value(self):
+    return self._PrecisionAtRecall(self._recall_threshold)
+
+
+class RecallAtPrecision(AUCMetric):
+  """Recall of the PR curve at a precision threshold (ref :587)."""
+
+  def __init__(self, precision_threshold, samples=-1):
+    super().__init__(mode='pr', samples=samples)
+    self._precision_threshold = precision_threshold
+
+  @property
+  def value(self):
+    return self._RecallAtPrecision(self._precision_threshold)
 
 
 class MultiClassAUCMetric(BaseMetric):
@@ -246,10 +310,46 @@ class MultiClassAUCMetric(BaseMetric):
     return float(np.mean([m.value for m in self._metrics]))
 
 
+def _Ranks(x):
+  """Average ranks (ties share the mean rank), as scipy.stats.rankdata."""
+  x = np.asarray(x, np.float64)
+  order = np.argsort(x, kind='mergesort')
+  ranks = np.empty(x.size, np.float64)
+  sx = x[order]
+  i = 0
+  while i < x.size:
+    j = i
+    while j + 1 < x.size and sx[j + 1] == sx[i]:
+      j += 1
+    ranks[order[i:j + 1]] = 0.5 * (i + j) + 1.0
+    i = j + 1
+  return ranks
+
+
+def _Correlation(mode, target, pred):
+  """pearson | spearman | kendalltau (tau-b) of two sequences; NaN when undefined."""
+  t, p = np.asarray(target, np.float64), np.asarray(pred, np.float64)
+  if t.size < 2:
+    return float('nan')
+  if mode == 'kendalltau':
+    dt = np.sign(t[:, None] - t[None, :])
+    dp = np.sign(p[:, None] - p[None, :])
+    iu = np.triu_indices(t.size, 1)
+    dt, dp = dt[iu], dp[iu]
+    denom = np.sqrt(float((dt != 0).sum()) * float((dp != 0).sum()))
+    return float((dt * dp).sum() / denom) if denom > 0 else float('nan')
+  if mode == 'spearman':
+    t, p = _Ranks(t), _Ranks(p)
+  if t.std() == 0 or p.std() == 0:
+    return float('nan')
+  return float(np.corrcoef(t, p)[0, 1])
+
+
 class CorrelationMetric(BaseMetric):
+  """Pearson / Spearman / Kendall-tau correlation of accumulated (target, pred) (ref :652)."""
 
   def __init__(self, mode='pearson'):
-    assert mode in ('pearson', 'spearman')
+    assert mode in ('pearson', 'spearman', 'kendalltau')
     self._mode = mode
     self._t, self._p = [], []
 
@@ -259,46 +359,90 @@ class CorrelationMetric(BaseMetric):
 
   @property
   def value(self):
-    t, p = np.asarray(self._t, np.float64), np.asarray(self._p, np.float64)
-    if t.size < 2:
-      return 0.0
-    if self._mode == 'spearman':
-      t = np.argsort(np.argsort(t)).astype(np.float64)
-      p = np.argsort(np.argsort(p)).astype(np.float64)
-    c = np.corrcoef(t, p)[0, 1]
+    c = _Correlation(self._mode, self._t, self._p)
     return float(0.0 if np.isnan(c) else c)
 
 
-class SamplingMetric(BaseMetric):
-  """Keeps a uniform sample of `num_samples` updates (reservoir)."""
+class AverageKeyedCorrelationMetric(BaseMetric):
+  """Correlation computed per key, averaged over keys (ref :700); keys whose correlation is
+  undefined (a single example, constant values) are skipped when `bypass_nan`."""
 
-  def __init__(self, num_samples):
-    self._num_samples = num_samples
-    self._samples = []
-    self._num_seen = 0
-    self._rng = np.random.RandomState(0)
+  def __init__(self, mode='pearson', bypass_nan=True):
+    assert mode in ('pearson', 'spearman', 'kendalltau')
+    self._mode = mode
+    self._bypass_nan = bypass_nan
+    self._target = collections.defaultdict(list)
+    self._pred = collections.defaultdict(list)
 
-  def Update(self, *args, **kwargs):
-    sample = (args, kwargs)
-    self._num_seen += 1
-    if len(self._samples) < self._num_samples:
-      self._samples.append(sample)
-    else:
-      i = self._rng.randint(0, self._num_seen)
-      if i < self._num_samples:
-        self._samples[i] = sample
+  def Update(self, key, target, pred):
+    self._target[key] += list(target)
+    self._pred[key] += list(pred)
 
-  samples = property(lambda self: self._samples)
+  @property
+  def value(self):
+    results = []
+    for k in self._target:
+      c = _Correlation(self._mode, self._target[k], self._pred[k])
+      if not self._bypass_nan or not np.isnan(c):
+        results.append(c)
+    if results:
+      return float(np.mean(results))
+    return 0.0 if self._bypass_nan else float('nan')
+
+
+class ConfigurableMetric(BaseMetric):
+  """A metric constructed from Params (ref :67)."""
+
+  @classmethod
+  def Params(cls):
+    return hyperparams.InstantiableParams(cls)
+
+  def __init__(self, params):
+    self.params = params
+
+
+class SamplingMetric(ConfigurableMetric):
+  """Keeps a uniform sample of `num_samples` decoded outputs; subclasses turn them into a
+  summary in `_CreateSummary` (ref :764). Accepts Params or (legacy) a plain sample count."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('num_samples', 8, 'The number of samples to store uniformly.')
+    return p
+
+  def __init__(self, params=8):
+    if not isinstance(params, hyperparams.Params):
+      params = self.Params().Set(num_samples=int(params))
+    super().__init__(params)
+    self._NewSampler()
+    self._summary = None
+
+  def _NewSampler(self):
+    from lingvo_b200.core import py_utils  # pylint: disable=g-import-not-at-top
+    self._sampler = py_utils.UniformSampler(num_samples=self.params.num_samples, seed=0)
+
+  @property
+  def samples(self):
+    return self._sampler.samples
+
+  def Update(self, decoded_outputs, *args, **kwargs):
+    self._sampler.Add(decoded_outputs if not (args or kwargs)
+                      else ((decoded_outputs,) + args, kwargs))
+    self._summary = None
 
   @property
   def value(self):
     return 0
 
   def Summary(self, name):
-    return self._CreateSummary(name)
+    if self._summary is None:
+      self._summary = self._CreateSummary(name)
+      self._NewSampler()
+    return self._summary
 
   def _CreateSummary(self, name):
-    return CreateScalarSummary(name, float(len(self._samples)))
+    return CreateScalarSummary(name, float(len(self.samples)))
 
 
 class AverageKeyedCustomMetric(BaseMetric):
@@ -318,27 +462,34 @@ class AverageKeyedCustomMetric(BaseMetric):
     return float(np.mean([self._fn(v) for v in self._vals.values()]))
 
 
-class GroupPairAUCMetric(BaseMetric):
-  """Pairwise AUC within groups."""
+class GroupPairAUCMetric(AUCMetric):
+  """AUC over all pairs of items with different targets inside each group (ref :810): pair
+  (i, j) is a binary example with label `target[i] > target[j]` and probability
+  `sigmoid(logits[i] - logits[j])`. Groups are the *contiguous* runs of equal `group_ids`."""
 
-  def __init__(self):
-    self._groups = collections.defaultdict(list)
-
-  def UpdateRaw(self, group_ids, target, logits, weight=None):
-    for g, t, l in zip(group_ids, target, logits):
-      self._groups[g].append((t, l))
-
-  @property
-  def value(self):
-    good = total = 0.0
-    for items in self._groups.values():
-      for i in range(len(items)):
-        for j in range(len(items)):
-          if items[i][0] > items[j][0]:
-            total += 1
-            good += 1.0 if items[i][1] > items[j][1] else (
-                0.5 if items[i][1] == items[j][1] else 0.0)
-    return good / total if total else 0.0
+  def UpdateRaw(self, group_ids, target, logits, weight=None, ignore_ids=None):
+    if ignore_ids is not None:
+      keep = np.asarray(ignore_ids) == 0
+      group_ids = np.asarray(group_ids)[keep].tolist()
+      target = np.asarray(target)[keep].tolist()
+      logits = np.asarray(logits)[keep].tolist()
+      if weight is not None:
+        weight = np.asarray(weight)[keep].tolist()
+    assert self._samples <= 0
+    n = len(target)
+    s = 0
+    for e in range(1, n + 1):
+      if e < n and group_ids[e] == group_ids[s]:
+        continue
+      for i in range(s, e):
+        for j in range(i + 1, e):
+          if target[i] == target[j]:
+            continue
+          self._label.append(1 if target[i] > target[j] else 0)
+          self._prob.append(1.0 / (1.0 + math.exp(-(logits[i] - logits[j]))))
+          self._weight.append(min(1.0, weight[i] + weight[j]) if weight is not None
+                              and len(weight) else 1.0)
+      s = e
 
 
 class DeviceEvalMetrics:
@@ -393,3 +544,51 @@ class DeviceEvalMetrics:
 
 
 TpuEvalMetrics = DeviceEvalMetrics
+
+
+class DeviceVariableMetrics:
+  """Fixed-capacity twin of `DeviceEvalMetrics` (ref `TpuVariableMetrics` :386): `2 *
+  max_metrics` persistent device scalars (Σ value·weight, Σ weight per metric, metrics in
+  sorted-name order) that a CUDA-graph-captured eval step can add into without reallocating;
+  `FinalizeMetricsWithStructure` all-reduces them over the ranks and packs the averages back
+  into the caller's dict structure."""
+
+  def __init__(self, max_metrics: int, strategy=None, device=None):
+    del strategy
+    self._max_metrics = int(max_metrics)
+    self._vars = torch.zeros(2 * self._max_metrics, dtype=torch.float32, device=device)
+
+  @property
+  def variables(self):
+    return [self._vars[i] for i in range(self._vars.numel())]
+
+  def ResetState(self):
+    self._vars.zero_()
+
+  def AccumulateStepMetrics(self, metric_dict):
+    n = len(metric_dict)
+    assert n <= self._max_metrics, 'Increase max_metrics to >= %d' % n
+    dev = self._vars.device
+    vw, w = [], []
+    for _, (value, weight) in sorted(metric_dict.items()):
+      value = torch.as_tensor(value, dtype=torch.float32, device=dev).reshape(())
+      weight = torch.as_tensor(weight, dtype=torch.float32, device=dev).reshape(())
+      vw.append(value.detach() * weight.detach())
+      w.append(weight.detach())
+    upd = torch.stack([torch.stack(vw), torch.stack(w)], 1).reshape(-1)
+    self._vars[:2 * n] += upd
+
+  def FinalizeMetricsWithStructure(self, structure, group=None):
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    acc = self._vars.clone()
+    if dist.is_available() and dist.is_initialized():
+      dist.all_reduce(acc, group=group)
+    pairs = acc.reshape(-1, 2)
+    out = {}
+    for i, k in enumerate(sorted(structure)):
+      vw, w = pairs[i, 0], pairs[i, 1]
+      out[k] = (torch.where(w > 0, vw / w.clamp(min=1e-30), torch.zeros_like(vw)), w)
+    return out if type(structure) is dict else type(structure)(out)   # pylint: disable=unidiomatic-typecheck
+
+
+TpuVariableMetrics = DeviceVariableMetrics
