@@ -146,3 +146,55 @@ def Curve(name, figsize, xs, ys, setter=None, **kwargs):
   if setter:
     setter(fig, ax)
   return FigureToPng(fig)
+
+
+def _AddMultiCurveRowPlots(fig, axes, data, length, x_label_override=None, row_labels=None,
+                           title=u'', xlabel=u'', ylabel=u'', fontsize='small'):
+  """One line per row of `data [rows, time]`, cut at `length` (ref :497)."""
+  del fig
+  colors = ['b-', 'r-', 'g-', 'm-', 'y-']
+  for row in range(data.shape[0]):
+    label = row_labels[row] if row_labels else '{}'.format(row)
+    axes.plot(data[row, :int(length)], colors[row % len(colors)], label=label)
+  axes.set_xlim([0, int(length)])
+  axes.legend()
+  axes.set_title(ToUnicode(title), size=fontsize)
+  if x_label_override is not None:
+    axes.set_xlabel(ToUnicode(x_label_override), size='x-small', wrap=True)
+  else:
+    axes.set_xlabel(ToUnicode(xlabel), size=fontsize)
+  axes.set_ylabel(ToUnicode(ylabel), size=fontsize)
+
+
+def MultiCurveData(tensors, paddings, labels):
+  """Stacks the non-None `[batch, length]` tensors (zeroed under their paddings) into
+  `[batch, rows, length]` and returns (data, per-example max length, row labels)."""
+  tensors = [None if t is None else np.asarray(t, np.float64) for t in tensors]
+  if not isinstance(paddings, (list, tuple)):
+    paddings = [paddings] * len(tensors)
+  paddings = [np.asarray(p, np.float64) for p in paddings]
+  max_lengths = np.zeros(paddings[0].shape[0], np.int32)
+  data, row_labels = [], []
+  for t, l, p in zip(tensors, labels, paddings):
+    max_lengths = np.maximum(max_lengths, np.round((1.0 - p).sum(1)).astype(np.int32))
+    if t is not None:
+      data.append(t * (1.0 - p))
+      row_labels.append(l)
+  return np.stack(data, 1), max_lengths, row_labels
+
+
+def AddMultiCurveSubplot(fig, tensors, paddings, labels, xlabels=None, **kwargs):
+  """Adds to the `MatplotlibFigureSummary` `fig` a subplot with one labelled curve per tensor
+  (`[batch, length]` each; `paddings` one `[batch, length]` array or one per tensor),
+  optionally with a per-example x label (ref :456)."""
+  data, max_lengths, row_labels = MultiCurveData(tensors, paddings, labels)
+  args = [data, max_lengths]
+  if xlabels is not None:
+    args.append(np.asarray(xlabels))
+  fig.AddSubplot(args, plot_func=_AddMultiCurveRowPlots, row_labels=row_labels, **kwargs)
+
+
+def FigureToSummary(name, fig):
+  """A matplotlib figure → serialized Summary with one `<name>/image` PNG value (ref :341)."""
+  from lingvo_b200.utils import tfevents  # pylint: disable=g-import-not-at-top
+  return tfevents.ImageValue('%s/image' % name, FigureToPng(fig))
