@@ -200,6 +200,86 @@ class DevicePrefetcher:
     return batch
 
 
+def MaybeOffsetDataSourceId(ds, p, offset):
+  """Gives datasource params `ds` the source-id offset unless the legacy all-zero behaviour
+  is requested (ref :1055)."""
+  if not p.all_zero_source_id_without_within_batch_mixing:
+    ds.Set(source_id_offset=offset)
+
+
+def PartitionFilePatternsIntoDataSources(p):
+  """`batch_mixing_partition_boundaries` → (list of SimpleDataSource params, one per
+  partition, each mixing its patterns within a batch; the partitions' summed weights)
+  (ref :1065)."""
+  from lingvo_b200.core import datasource  # pylint: disable=g-import-not-at-top
+  if max(len(e) for e in p.file_pattern) >= 3:
+    raise ValueError('Cannot use batch_mixing_partition_boundaries with backprop filters, '
+                     'i.e. file_pattern cannot have triplets: %s' % (p.file_pattern,))
+  bounds = list(p.batch_mixing_partition_boundaries)
+  if any(b <= a for a, b in zip([0] + bounds, bounds)):
+    raise ValueError('batch_mixing_partition_boundaries must be an increasing series '
+                     'greater than 0. Values were: %s' % bounds)
+  if bounds[-1] >= len(p.file_pattern):
+    raise ValueError('batch_mixing_partition_boundaries cannot have a boundary >= the number '
+                     'of file patterns: %s vs %d' % (bounds, len(p.file_pattern)))
+  datasources, weights = [], []
+  for start, end in zip([0] + bounds, bounds + [len(p.file_pattern)]):
+    pats = [e[0] for e in p.file_pattern[start:end]]
+    ws = [float(e[1]) for e in p.file_pattern[start:end]]
+    ds = datasource.SimpleDataSource.Params().Set(file_pattern=pats, weights=ws)
+    MaybeOffsetDataSourceId(ds, p, start)
+    datasources.append(ds)
+    weights.append(float(np.sum(ws)))
+  return datasources, weights
+
+
+def FilePatternToDataSource(p):
+  """The (deprecated) `file_pattern` forms → datasource params (ref :1144):
+
+  * `'type:glob'` or a list of them → one `SimpleDataSource`;
+  * `[(pattern, weight), …]` with `use_within_batch_mixing` → one weighted source;
+  * `[(pattern, weight[, bprop_filter]), …]` otherwise → `CrossBatchMixingDataSource`
+    (optionally partitioned by `batch_mixing_partition_boundaries`).
+  """
+  from lingvo_b200.core import datasource  # pylint: disable=g-import-not-at-top
+  fp = p.file_pattern
+  if isinstance(fp, str):
+    ds = datasource.SimpleDataSource.Params().Set(file_pattern=fp)
+  elif isinstance(fp, (list, tuple)):
+    if all(isinstance(x, str) for x in fp):
+      ds = datasource.SimpleDataSource.Params().Set(file_pattern=list(fp))
+    elif p.use_within_batch_mixing:
+      if max(len(e) for e in fp) >= 3:
+        raise ValueError('Expected a list of pairs, got %s' % (fp,))
+      pats, weights = (list(x) for x in zip(*fp))
+      ds = datasource.SimpleDataSource.Params().Set(file_pattern=pats, weights=weights)
+    else:
+      for e in fp:
+        if isinstance(e, str):
+          raise ValueError('Should explicitly specify weights, got string: %s' % e)
+      if p.Get('batch_mixing_partition_boundaries') is not None:
+        subs, weights = PartitionFilePatternsIntoDataSources(p)
+        ds = datasource.CrossBatchMixingDataSource.Params().Set(sub=subs, weights=weights)
+      else:
+        subs, weights, filters = [], [], []
+        for source_id, e in enumerate(fp):
+          subs.append(datasource.SimpleDataSource.Params().Set(file_pattern=e[0]))
+          MaybeOffsetDataSourceId(subs[-1], p, source_id)
+          weights.append(e[1])
+          filters.append(e[2] if len(e) > 2 else '')
+        ds = datasource.CrossBatchMixingDataSource.Params().Set(
+            sub=subs, weights=weights, bprop_variable_filters=filters)
+  else:
+    raise ValueError('Cannot parse p.file_pattern into a datasource.')
+  cluster = cluster_factory.Current()
+  if (getattr(cluster, 'tf_data_service_address', '') and not cluster.do_eval and
+      p.Get('use_tf_data_service')):
+    ds = datasource.TFDataServiceSource.Params().Set(
+        sub=ds, bucket_upper_bound=p.Get('bucket_upper_bound'))
+    ds = datasource.TFDatasetPrefetch.Params().Set(sub=ds)
+  return ds
+
+
 class BaseInputGeneratorFromFiles(BaseInputGenerator):
   """Base class for input generators that read from files (:1223-1460)."""
 
@@ -218,6 +298,14 @@ class BaseInputGeneratorFromFiles(BaseInputGenerator):
     p.Define('repeat_count', -1, 'Epochs to produce; -1 = forever.')
     p.Define('require_sequential_order', False, 'Read files sequentially.')
     p.Define('use_within_batch_mixing', False, 'Mix sources within a batch.')
+    p.Define('batch_mixing_partition_boundaries', None,
+             'With cross-batch mixing: ascending indices into file_pattern that start a new '
+             'partition; patterns inside a partition are mixed WITHIN a batch, partitions '
+             'are mixed across batches with the summed weights (ref :1268).')
+    p.Define('all_zero_source_id_without_within_batch_mixing', True,
+             'Legacy behaviour: every cross-batch source reports source_id 0. False gives '
+             'source k the id k.')
+    p.Define('use_tf_data_service', True, 'Allow the host-parallel data service wrapper.')
     p.Define('use_chaining', False, 'Chain sources sequentially.')
     p.Define('fatal_errors', [], 'Error substrings that abort the pipeline.')
     p.Define('bucket_upper_bound', [], 'Bucketing scheme: upper bounds.')
@@ -228,10 +316,8 @@ class BaseInputGeneratorFromFiles(BaseInputGenerator):
     super().__init__(params)
     p = self.params
     if p.file_datasource is None and p.file_pattern:
-      from lingvo_b200.core import datasource
-      ds = datasource.SimpleDataSource.Params().Set(
-          file_pattern=p.file_pattern, name='datasource')
-      self.CreateChild('datasource', ds)
+      self.CreateChild('datasource', FilePatternToDataSource(p).Set(name='datasource'))
+      self.datasource.SetInputGenerator(self)
     self._input_op = None
 
   def CommonInputOpArgs(self):
@@ -373,6 +459,209 @@ class BaseSequenceInputGenerator(BaseInputGeneratorFromFiles):
 
   def IdsToStrings(self, ids, lens, key=None):
     return self.tokenizer_dict[key or 'default'].IdsToStrings(ids, lens)
+
+
+class TFDataSequenceInputGenerator(BaseSequenceInputGenerator):
+  """Sequence inputs assembled from `datasource.Dataset` pipelines (ref :1770): subclasses
+  provide `LoadDataset(file_pattern)` (examples without a batch dim), `ProcessDataset`,
+  `GetSequenceLength`, `_InputShape`; this class adds eval truncation, length bucketing +
+  padding, optional host-parallel service and prefetch. A drop-in for generators derived
+  from `BaseSequenceInputGenerator` (file_pattern / bucket params keep their meaning)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('prefetch_buffer_size', 1, 'Local prefetch buffer size (batches).')
+    p.resettable = True
+    return p
+
+  def __init__(self, params):
+    from lingvo_b200.core import datasource  # pylint: disable=g-import-not-at-top
+    p = params.Copy()
+    ds = p.file_datasource
+    if not ds:
+      ds = self.ConvertFilePatternToDataSource(p, p.file_pattern)
+      p.file_pattern = ''
+    ds = datasource.CustomTFDatasetTransform.Params().Set(sub=ds, fn='TakeEvalSamples')
+    ds = datasource.TFDatasetBatchBySequenceLength.Params().Set(
+        sub=ds, seqlen_fn='GetSequenceLength', input_shape_fn='_InputShape',
+        input_padding_fn='_InputPaddingValue', bucket_upper_bound=p.bucket_upper_bound,
+        bucket_batch_limit=p.bucket_batch_limit)
+    cluster = cluster_factory.Current()
+    if getattr(cluster, 'tf_data_service_address', '') and not cluster.do_eval:
+      ds = datasource.TFDataServiceSource.Params().Set(
+          sub=ds, bucket_upper_bound=p.bucket_upper_bound)
+    p.file_datasource = datasource.TFDatasetPrefetch.Params().Set(
+        sub=ds, buffer_size=p.prefetch_buffer_size)
+    super().__init__(p)
+
+  @classmethod
+  def ConvertFilePatternToDataSource(cls, p, file_pattern):
+    from lingvo_b200.core import datasource  # pylint: disable=g-import-not-at-top
+    weights = None
+    if isinstance(file_pattern, str):
+      patterns = file_pattern.split(',')
+    elif all(isinstance(x, str) for x in file_pattern):
+      patterns = list(file_pattern)
+    elif all(isinstance(x, tuple) for x in file_pattern):
+      patterns, weights = (list(x) for x in zip(*file_pattern))
+    else:
+      raise ValueError('file_pattern must be all strings or all tuples, but got: %s.' %
+                       (file_pattern,))
+    for fp in patterns:
+      if ',' in fp:
+        raise ValueError('file_pattern should not contain comma: %s' % fp)
+    subs = [datasource.TFDatasetFnInput.Params().Set(
+        load_fn='LoadDataset', kwargs=dict(file_pattern=fp),
+        shuffle_buffer_size=p.file_buffer_size) for fp in patterns]
+    if len(subs) > 1:
+      if not p.use_within_batch_mixing:
+        raise ValueError('Only p.use_within_batch_mixing is supported with multiple '
+                         'file_patterns.')
+      subs = [datasource.TFDatasetMixer.Params().Set(sub=subs, weights=weights)]
+    return datasource.CustomTFDatasetTransform.Params().Set(sub=subs[0], fn='ProcessDataset')
+
+  def Reset(self, sess=None):
+    self.datasource.Reset(sess)
+
+  def _InputBatch(self):
+    return self.datasource.GetNext()
+
+  def LoadDataset(self, file_pattern):
+    """→ `datasource.Dataset` of single examples (no batch dim) read from `file_pattern`."""
+    raise NotImplementedError()
+
+  def TakeEvalSamples(self, dataset):
+    p = self.params
+    if self.do_eval and p.num_samples > 0:
+      dataset = dataset.take(p.num_samples)
+    return dataset
+
+  def ProcessDataset(self, dataset):
+    """→ Dataset of processed example NestedMaps (still no batch dim)."""
+    raise NotImplementedError()
+
+  def GetSequenceLength(self, example):
+    raise NotImplementedError()
+
+  def _InputShape(self, key):
+    """Final per-example shape of tensor `key` (None entries = pad to the bucket bound)."""
+    if key in ('source_id', 'bucket_keys'):
+      return ()
+    raise ValueError('Unexpected key %s' % key)
+
+  def _InputPaddingValue(self, key, tensorspec):
+    dtype = getattr(tensorspec, 'dtype', None) or np.float32
+    return np.ones([], dtype) if key.endswith('_paddings') else np.zeros([], dtype)
+
+
+class BaseDataExampleInputGenerator(BaseInputGenerator):
+  """Batches of parsed `tf.Example` features read from record files (ref :1916):
+  list files → interleaved readers → shuffle → take → repeat → batch → parse with
+  `GetFeatureSpec()` → `_PreprocessInputBatch`."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('input_files', None, 'Comma-delimited glob(s) of input files.')
+    p.Define('dataset_type', None, 'Callable filename → iterable of serialized records '
+             '(e.g. `lingvo_b200.utils.tfrecord.ReadRecords`).')
+    p.Define('randomize_order', True, 'Shuffle files and records.')
+    p.Define('parallel_readers', 1, 'Files read concurrently (round-robin interleave).')
+    p.Define('num_examples', -1, 'Number of examples (-1 for unlimited).')
+    p.Define('num_epochs', -1, 'Passes over the data (-1 for unlimited); the input raises '
+             'StopIteration afterwards.')
+    p.Define('randomize_shuffle_size', 500, 'Size of the random shuffle buffer.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    assert p.input_files, 'input_files is required for an example input generator'
+    assert p.dataset_type, 'dataset_type is required for an example input generator'
+    self._iterator = iter(self._InitDataset())
+
+  def GetFeatureSpec(self):
+    """→ {feature name: (dtype, shape) | FixedLenFeature-like with .dtype/.shape}; an empty
+    spec keeps every feature of the record as a 1-D array."""
+    return {}
+
+  def _AdditionalPreprocessInputBatch(self, batch):
+    return batch
+
+  def _ParseBatch(self, records):
+    from lingvo_b200.utils import tf_example  # pylint: disable=g-import-not-at-top
+    spec = self.GetFeatureSpec()
+    parsed = [tf_example.ParseExample(r) for r in records]
+    names = list(spec) if spec else sorted(parsed[0])
+    out = NestedMap()
+    for name in names:
+      cols = []
+      for ex in parsed:
+        if name not in ex:
+          raise KeyError('Feature %r missing from a record' % name)
+        v = ex[name]
+        if spec:
+          sp = spec[name]
+          dtype, shape = (sp.dtype, sp.shape) if hasattr(sp, 'dtype') else sp
+          if v.dtype.kind not in 'OSU':
+            v = v.astype(dtype)
+          v = v.reshape(list(shape))
+        cols.append(v)
+      arr = np.stack(cols)
+      out[name] = arr if arr.dtype.kind in 'OSU' else torch.from_numpy(
+          np.ascontiguousarray(arr))
+    return out
+
+  def _InitDataset(self):
+    import glob  # pylint: disable=g-import-not-at-top
+    from lingvo_b200.core import datasource  # pylint: disable=g-import-not-at-top
+    p = self.params
+    files = sorted(f for pat in p.input_files.split(',') for f in glob.glob(pat))
+    assert files, 'No files match %s' % p.input_files
+    rng = np.random.RandomState(p.random_seed)
+
+    def Records():
+      order = list(files)
+      if p.randomize_order:
+        rng.shuffle(order)
+      pending = list(order)
+      readers = []
+      while pending or readers:
+        while pending and len(readers) < max(p.parallel_readers, 1):
+          readers.append(iter(p.dataset_type(pending.pop(0))))
+        for r in list(readers):
+          try:
+            yield next(r)
+          except StopIteration:
+            readers.remove(r)
+
+    ds = datasource.Dataset.FromGenerator(Records)
+    if p.randomize_order:
+      ds = ds.shuffle(p.randomize_shuffle_size, seed=p.random_seed)
+    if p.num_examples >= 0:
+      ds = ds.take(p.num_examples)
+    ds = ds.repeat(None if p.num_epochs < 0 else p.num_epochs)
+    bs = self.InfeedBatchSize()
+
+    def Batches():
+      buf = []
+      for rec in ds:
+        buf.append(rec)
+        if len(buf) == bs:
+          yield self._ParseBatch(buf)
+          buf = []          # remainder dropped, as drop_remainder=True
+
+    return datasource.Dataset.FromGenerator(Batches).prefetch(2)
+
+  def _InputBatch(self):
+    return next(self._iterator)
+
+  def GetPreprocessedInputBatch(self):
+    return self._AdditionalPreprocessInputBatch(super().GetPreprocessedInputBatch())
+
+  def Reset(self, sess=None):
+    self._iterator = iter(self._InitDataset())
 
 
 class BaseTinyDatasetInput(BaseInputGenerator):

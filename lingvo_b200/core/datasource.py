@@ -80,6 +80,8 @@ class SimpleDataSource(DataSource):
     p.Define('bprop_variable_filters', None, 'Per-source variable filters (kept for parity).')
     p.Define('file_type', '', 'Prepended as `type:` when the pattern has no type.')
     p.Define('pass_weights_by_param', False, 'Kept for parity.')
+    p.Define('source_id_offset', 0, 'Added to the `source_id` of every batch: gives the '
+             'sub-sources of a cross-batch mixer distinct ids (ref :104).')
     return p
 
   def __init__(self, params):
@@ -114,7 +116,11 @@ class SimpleDataSource(DataSource):
       self._stream = self._input_generator._DataSourceFromFilePattern(  # pylint: disable=protected-access
           pats, **kwargs)
     nxt = self._stream
-    return nxt() if callable(nxt) else next(nxt)
+    batch = nxt() if callable(nxt) else next(nxt)
+    off = self.params.source_id_offset
+    if off and isinstance(batch, NestedMap) and 'source_id' in batch:
+      batch.source_id = batch.source_id + off
+    return batch
 
   def Reset(self, sess=None):
     self._stream = None
@@ -160,12 +166,22 @@ class CrossBatchMixingDataSource(DataSource):
     p = super().Params()
     p.Define('sub', None, 'List of DataSource params.')
     p.Define('weights', None, 'List of weights (or schedule layers).')
+    p.Define('bprop_variable_filters', None,
+             'One variable-name regex per sub-source: a batch drawn from source i only '
+             'updates the variables matching filter i (read by the learner via GetMeta).')
     return p
+
+  def GetMeta(self):
+    ret = NestedMap()
+    if self.params.bprop_variable_filters:
+      ret.bprop_variable_filters = list(self.params.bprop_variable_filters)
+    return ret
 
   def __init__(self, params):
     super().__init__(params)
     p = self.params
     assert p.sub and len(p.sub) == len(p.weights)
+    assert not p.bprop_variable_filters or len(p.bprop_variable_filters) == len(p.sub)
     self.CreateChildren('sub', list(p.sub))
     self._rng = np.random.RandomState(p.random_seed)
 
