@@ -399,3 +399,66 @@ def GetSpecificCheckpoint(load_checkpoint_from: str) -> Optional[str]:
   if os.path.exists(load_checkpoint_from + '.index'):
     return load_checkpoint_from
   raise ValueError('Invalid load_checkpoint_from: %s' % load_checkpoint_from)
+
+
+def SortCheckpointPaths(ckpts):
+  """Checkpoint prefixes ordered by the step number at the end of the path (ref :31)."""
+  return sorted(ckpts, key=lambda x: int(x.split('-')[-1]))
+
+
+class SaverWrapper:
+  """The save / restore / sync trio over a flat `{name: tensor}` view (ref :36): the piece
+  runners use when they checkpoint something that is not a `BaseModel` (EMA-substituted
+  eval variables, auxiliary state). `variables_to_restore_dict` restricts / renames what is
+  restored: {checkpoint name: tensor}."""
+
+  def __init__(self, logdir, train_params, variables_to_restore_dict=None, async_save=False,
+               variables_fn=None):
+    assert variables_to_restore_dict is not None or variables_fn is not None
+    self._logdir = logdir
+    self._save_path = os.path.join(logdir, 'ckpt')
+    self._restore_dict = variables_to_restore_dict
+    vars_fn = variables_fn or (lambda: dict(variables_to_restore_dict))
+    checks = []
+    max_steps = getattr(train_params, 'max_steps', 0)
+    per_loop = getattr(train_params, 'tpu_steps_per_loop', 0)
+    if max_steps and per_loop:
+      checks.append((r'^global_step$', [saver_lib.InRange(0, max_steps + per_loop)]))
+    if getattr(train_params, 'checkpoint_finite_check', False):
+      checks.append((lambda name: True, [saver_lib.IsFinite()]))
+    self._saver = saver_lib.Saver(
+        logdir, vars_fn, sanity_checks=checks,
+        keep_latest_n=getattr(train_params, 'save_max_to_keep', None),
+        keep_every_n_hours=getattr(train_params, 'save_keep_checkpoint_every_n_hours', None),
+        async_save=async_save)
+
+  def Save(self, sess, gsteps):
+    del sess
+    tensors = dict(self._saver._vars_fn())   # pylint: disable=protected-access
+    tensors.setdefault('global_step', torch.tensor(int(gsteps), dtype=torch.int64))
+    return self._saver.Save(int(gsteps), tensors)
+
+  def Restore(self, sess, path):
+    del sess
+    return self._saver.Restore(path=path, strict=self._restore_dict is not None)[1]
+
+  def Sync(self):
+    self._saver.Sync()
+
+
+# Execution is always eager here: the V1 flavour of the reference's eager checkpointer
+# (`ckpt-%08d` bundles in the train dir) IS `Checkpointer`.
+EagerCheckpointerV1 = Checkpointer
+
+
+class EagerCheckpointerV2(Checkpointer):
+  """Object-graph flavour (ref :638): checkpoints live in `<train_dir>/ckpt_V2/` so both
+  generations can coexist in one log dir; optional asynchronous writes."""
+
+  def __init__(self, train_dir, model, train_params=None, save_only=False,
+               check_loading_status=True, experimental_enable_async_checkpoint=False):
+    tp = (train_params or model.params.train)
+    if experimental_enable_async_checkpoint and not tp.async_checkpointing:
+      tp = tp.Copy().Set(async_checkpointing=True)
+    super().__init__(os.path.join(train_dir, 'ckpt_V2'), model, train_params=tp,
+                     save_only=save_only, check_loading_status=check_loading_status)

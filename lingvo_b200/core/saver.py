@@ -259,3 +259,56 @@ class Saver:
     self._thread = threading.Thread(target=run, name='async_ckpt', daemon=True)
     self._thread.start()
     return path
+
+
+def _SaverRestore(self, sess=None, path: Optional[str] = None,
+                  checkpoint_basename: Optional[str] = None, strict: bool = True):
+  """Loads the bundle at `path` (default: the latest in the log dir) into the tensors
+  `variables_fn()` returns, in place. Returns (global_step or None, path) (ref :420)."""
+  del sess, checkpoint_basename
+  from lingvo_b200.utils import tensor_bundle as tb  # pylint: disable=g-import-not-at-top
+  self.Wait()
+  path = path or LatestCheckpoint(self._logdir)
+  if path is None:
+    raise FileNotFoundError('No checkpoint under %s' % self._logdir)
+  reader = tb.BundleReader(path)
+  keys = set(reader.Keys())
+  with torch.no_grad():
+    for name, t in self._vars_fn().items():
+      if name not in keys:
+        if strict:
+          raise KeyError('%s not found in %s' % (name, path))
+        continue
+      t.copy_(FromNumpy(reader.Read(name)).to(device=t.device, dtype=t.dtype))
+  step = int(reader.Read('global_step')) if 'global_step' in keys else None
+  reader.Close()
+  return step, path
+
+
+Saver.Restore = _SaverRestore
+Saver.Sync = Saver.Wait
+
+
+def WriteNpArrays(file_prefix: str, nmap) -> None:
+  """Writes a NestedMap of numpy arrays as a TF tensor bundle keyed by the flattened
+  NestedMap paths (ref :574)."""
+  from lingvo_b200.utils import tensor_bundle as tb  # pylint: disable=g-import-not-at-top
+  w = tb.BundleWriter(file_prefix)
+  for k, v in sorted(nmap.FlattenItems()):
+    assert isinstance(v, np.ndarray), (k, type(v))
+    w.Add(k, v)
+  w.Finish()
+
+
+def ReadNpArrays(file_prefix: str, nmap):
+  """Reads the bundle back into the structure of `nmap` (a NestedMap of numpy dtypes or
+  arrays, whose dtypes the result is cast to) (ref :605)."""
+  from lingvo_b200.utils import tensor_bundle as tb  # pylint: disable=g-import-not-at-top
+  reader = tb.BundleReader(file_prefix)
+  vals = []
+  for k, spec in nmap.FlattenItems():
+    arr = reader.Read(k)
+    dtype = spec.dtype if isinstance(spec, np.ndarray) else np.dtype(spec)
+    vals.append(np.asarray(arr).astype(dtype, copy=False))
+  reader.Close()
+  return nmap.Pack(vals)
