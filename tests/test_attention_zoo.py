@@ -231,3 +231,28 @@ def test_simplified_transformer_builder(parallel):
   assert o2.vec.shape == (2, 3, 16) and torch.equal(o2.paddings, pad[:, ::2])
   if parallel:
     assert float(o2.vec[1, 2].abs().sum()) == 0.0          # padded position is zeroed
+
+
+def test_favor_chunked_causal_custom_gradients_match_autograd():
+  from lingvo_b200.core import favor_attention as fa
+  torch.manual_seed(0)
+  l, b, h, m, d = 150, 2, 2, 5, 3                   # not a multiple of the 64-step chunk
+  qs = torch.rand(l, b, h, m, dtype=torch.float64, requires_grad=True)
+  ks = torch.rand(l, b, h, m, dtype=torch.float64, requires_grad=True)
+  vs = torch.randn(l, b, h, d, dtype=torch.float64, requires_grad=True)
+  num = fa.chunked_causal_numerator(qs, ks, vs)
+  den = fa.chunked_causal_denominator(qs, ks)
+  ref_num = fa.causal_numerator(qs, ks, vs)         # plain autograd formulation
+  ref_den = fa.causal_denominator(qs, ks)
+  torch.testing.assert_close(num, ref_num)
+  torch.testing.assert_close(den, ref_den)
+  wn, wd = torch.randn_like(num), torch.randn_like(den)
+  got = torch.autograd.grad((num * wn).sum() + (den * wd).sum(), [qs, ks, vs])
+  want = torch.autograd.grad((ref_num * wn).sum() + (ref_den * wd).sum(), [qs, ks, vs])
+  for g, w in zip(got, want):
+    torch.testing.assert_close(g, w, rtol=1e-9, atol=1e-9)
+  # the func / grad pairs are usable on their own (reference API)
+  out, sums = fa.chunked_causal_numerator_func(qs.detach(), ks.detach(), vs.detach())
+  dq, dk, dv = fa.chunked_causal_numerator_grad(qs.detach(), ks.detach(), vs.detach(), sums, wn)
+  torch.testing.assert_close(out, ref_num.detach())
+  assert dq.shape == qs.shape and dk.shape == ks.shape and dv.shape == vs.shape
