@@ -37,6 +37,23 @@ _FLOPS_PER_ELEMENT = {
 }
 
 
+def GLUVariants(x, activation_name):
+  """`x1 * act(x2)` for the two halves of the last dim (https://arxiv.org/abs/2002.05202)."""
+  x1, x2 = x.chunk(2, dim=-1)
+  return x1 * _ACTIVATIONS[activation_name](x2)
+
+
+_ACTIVATIONS.update({
+    'GLU': lambda x: GLUVariants(x, 'SIGMOID'),
+    'BILINEAR_GLU': lambda x: GLUVariants(x, 'NONE'),
+    'RELU_GLU': lambda x: GLUVariants(x, 'RELU'),
+    'GELU_GLU': lambda x: GLUVariants(x, 'GELU'),
+    'SWISH_GLU': lambda x: GLUVariants(x, 'SWISH'),
+})
+_FLOPS_PER_ELEMENT.update({'GLU': 5, 'BILINEAR_GLU': 1, 'RELU_GLU': 2, 'GELU_GLU': 16,
+                           'SWISH_GLU': 5})
+
+
 def GetFn(activation_name):
   return _ACTIVATIONS[activation_name]
 
@@ -51,7 +68,7 @@ def IsSupported(activation_name):
 
 def DimMultiplier(activation_name):
   """GLU variants consume 2 × the output dim."""
-  return 2 if activation_name.startswith('GATED_') else 1
+  return 2 if (activation_name.startswith('GATED_') or activation_name.endswith('GLU')) else 1
 
 
 class ActivationLayer(base_layer.BaseLayer):

@@ -37,6 +37,16 @@ def ExtractBlockContext(x, block_size, left_context, right_context, padding_val=
   return xp[:, idx]
 
 
+def ExtractBlockContextV2(x, block_size, left_context, right_context, padding_val=0.0,
+                          paddings=None):
+  """`ExtractBlockContext` without constraints between W, L, R, plus the matching paddings
+  `[B, U, C]` (1 outside the sequence) when `paddings [B, T]` is given (ref :128)."""
+  patches = ExtractBlockContext(x, block_size, left_context, right_context, padding_val)
+  if paddings is None:
+    return patches, None
+  return patches, ExtractBlockContext(paddings, block_size, left_context, right_context, 1.0)
+
+
 def MakeLocalMask(seq_len, block_size, left_context, right_context, dtype=torch.float32,
                   device=None):
   """[U, W, C] 1 where query w of block u may see context position c (ref :242)."""

@@ -183,6 +183,38 @@ class MultiHeadedProjectionLayer(quant_utils.QuantizableLayer):
     return y.reshape(*inputs.shape[:-1], n, h)
 
 
+class ReshapedMultiHeadedProjectionLayer(MultiHeadedProjectionLayer):
+  """MultiHeadedProjectionLayer whose model dim D is presented as `[M, d]` with
+  `M = device_mesh.shape[1]` (the layout 2-D sharded models keep activations in): inputs /
+  outputs are `[B, T, M, d]` on the model side, `[B, T, N, H]` on the head side (:438)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    if 'device_mesh' not in p:
+      p.Define('device_mesh', None, 'numpy mesh; its second axis splits the model dim.')
+    return p
+
+  def FProp(self, theta, inputs, eqn=None):
+    p = self.params
+    assert p.device_mesh is not None and p.device_mesh.ndim >= 2
+    inputs = self._CastToFPropDtype(inputs)
+    if p.make_output_proj_no_op:
+      return inputs
+    m = int(p.device_mesh.shape[1])
+    w = theta.w.to(inputs.dtype)
+    w = w.reshape(m, w.shape[0] // m, p.num_heads, p.dim_per_head)
+    if p.is_output_projection:
+      ret = torch.einsum(eqn or 'BTNH,MdNH->BTMd', inputs, w)
+      if p.use_bias:
+        ret = ret + theta.b.to(ret.dtype).reshape(m, -1)
+      return ret
+    ret = torch.einsum(eqn or 'BTMd,MdNH->BTNH', inputs, w)
+    if p.use_bias:
+      ret = ret + theta.b.to(ret.dtype)
+    return ret
+
+
 class MultiHeadedAttention(quant_utils.QuantizableLayer):
   """Dot-product attention over N heads; GQA / MQA / RoPE / packed inputs (:481).
 

@@ -20,3 +20,22 @@ def scale_split_to_infeed(split_batch_size, use_per_host_infeed):
       cluster.mode == 'sync'):
     return global_batch_size
   return split_batch_size * cluster.num_splits_per_client
+
+
+def scale_global_to_infeed(global_batch_size, use_per_host_infeed):
+  """Infeed batch of one input-producing process (ref :42)."""
+  cluster = cluster_factory.Current()
+  if use_per_host_infeed and cluster.world_size > 1:
+    return global_batch_size // cluster.world_size
+  return global_batch_size
+
+
+def scale_global_to_worker(global_batch_size):
+  """Per-device batch; the global batch must divide evenly (ref :84)."""
+  cluster = cluster_factory.Current()
+  n = max(int(cluster.total_worker_devices), 1)
+  q, r = divmod(global_batch_size, n)
+  if r:
+    raise ValueError('global_batch_size %d did not divide evenly by %d workers.' %
+                     (global_batch_size, n))
+  return q

@@ -67,6 +67,21 @@ def ComputeMoments(inputs, padding, reduce_over_dims, cumulative_axis=None,
   return mean, var
 
 
+class AddingAccumulator(base_layer.Accumulator):
+  """Accumulator summing sufficient statistics across pipeline micro-batches (ref :31)."""
+
+  def __init__(self, shape, dtype, device=None):
+    super().__init__()
+    self.dtype, self.shape, self.device = dtype, shape, device
+
+  def DefaultValue(self):
+    return torch.zeros(list(self.shape), dtype=self.dtype, device=self.device)
+
+  def Update(self, value):
+    cur = self.GetValue()
+    self.SetValue(cur + value.to(device=cur.device, dtype=self.dtype))
+
+
 class BatchNormLayer(base_layer.BaseLayer):
   """Batch normalization with moving statistics."""
 

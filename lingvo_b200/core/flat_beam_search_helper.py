@@ -19,6 +19,11 @@ import torch
 NEG = -1.0e30
 
 
+def einsum_i32(eq, *args):  # pylint: disable=invalid-name
+  """Integer einsum (exact for masks / ids): operands and result are int32 (ref :47)."""
+  return torch.einsum(eq, *[x.to(torch.int32) for x in args]).to(torch.int32)
+
+
 def update_nbest(nbest_hyps, cur_hyps):  # pylint: disable=invalid-name
   """Merges (mask, score) n-best lists keeping the best `k` (ref :52)."""
   (m0, s0), (m1, s1) = nbest_hyps, cur_hyps

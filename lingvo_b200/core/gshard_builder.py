@@ -74,6 +74,16 @@ def _ContextParallel(b) -> bool:
 # =========================================================================
 # Layer classes
 # =========================================================================
+def KLDiv(f_old, f_new):
+  """KL(f_old ‖ f_new) of two probability tensors `[B, L, D]`, summed and divided by the
+  batch size (ref :32; distillation between an old and a new gating / feature
+  distribution)."""
+  eps = 1e-7
+  p = f_old.float().clamp(eps, 1.0)
+  q = f_new.float().clamp(eps, 1.0)
+  return (p * torch.log(p / q)).sum() / f_old.shape[0]
+
+
 class _BuilderLayer(base_layer.BaseLayer):
   """Base of builder-produced layers; carries the builder params."""
 

@@ -36,6 +36,27 @@ def preload_zero(n=None, batch_size=None, max_len=None, key_size=2):  # pylint: 
           np.zeros([n, batch_size], np.float32))           # tgt_sample_temperature
 
 
+def infinite_repeat(body_fn, infeed_queue=None, stop_event=None):  # pylint: disable=invalid-name
+  """Runs `body_fn(*carried)` forever, feeding its results back as the next arguments; with
+  an `infeed_queue` (a `queue.Queue`) every iteration also receives the next queued tuple
+  (ref :59). `stop_event` (threading.Event) or a `StopIteration` from the body / a `None`
+  item in the queue ends the loop — the host-driven replacement of the device while-loop."""
+  carried = ()
+  while stop_event is None or not stop_event.is_set():
+    args = tuple(carried)
+    if infeed_queue is not None:
+      item = infeed_queue.get()
+      if item is None:
+        break
+      args += tuple(item) if isinstance(item, (list, tuple)) else (item,)
+    try:
+      out = body_fn(*args)
+    except StopIteration:
+      break
+    carried = () if out is None else (tuple(out) if isinstance(out, (list, tuple)) else (out,))
+  return list(carried)
+
+
 def daemon(closure):  # pylint: disable=invalid-name
   t = threading.Thread(target=closure, daemon=True)
   t.start()

@@ -250,3 +250,36 @@ def GetVarSharding(var) -> TensorShardingSpec:
   if mesh is None or mapping is None:
     return TensorShardingSpec.ReplicatedSpec()
   return TensorShardingSpec.FromFullShape(list(var.shape), mapping, mesh)
+
+
+def GetMeshSplitSharding(device_mesh, tensor_split_dims_mapping) -> 'TensorShardingSpec':
+  """The sharding spec `MeshSplit` would attach, honouring the active dim-prefix and
+  manual-dim contexts (ref :89)."""
+  spec = TensorShardingSpec(list(_CTX.prefix) + list(tensor_split_dims_mapping), device_mesh)
+  if _CTX.manual:
+    spec.manual_mesh_dims = list(_CTX.manual)
+  return spec
+
+
+def ReshapeDim(x, dim, dim_reshape_segments=None):
+  """[..., D, ...] → [..., segments, D // segments, ...] (ref :215)."""
+  if dim_reshape_segments is None:
+    return x
+  dim = dim % x.dim()
+  assert x.shape[dim] % dim_reshape_segments == 0
+  return x.reshape(list(x.shape[:dim]) + [dim_reshape_segments,
+                                          x.shape[dim] // dim_reshape_segments] +
+                   list(x.shape[dim + 1:]))
+
+
+_SPM_CACHE = {}
+
+
+def LoadSpm(model_file):
+  """Cached SentencePieceProcessor for `model_file` (ref :448)."""
+  if model_file not in _SPM_CACHE:
+    import sentencepiece  # pylint: disable=g-import-not-at-top
+    spm = sentencepiece.SentencePieceProcessor()
+    spm.Load(model_file)
+    _SPM_CACHE[model_file] = spm
+  return _SPM_CACHE[model_file]

@@ -639,6 +639,17 @@ def CopyFieldsTo(from_p: Params, to_p: Params,
   return to_p
 
 
+def CopyFieldsSubsetTo(from_p: Params, to_p: Params, fields_to_set) -> Params:
+  """Copies only the named fields (a string or list of strings) (reference :234)."""
+  if not isinstance(fields_to_set, (list, tuple)):
+    fields_to_set = [fields_to_set]
+  for n, p in from_p.IterParams():
+    if n == 'cls' or n not in fields_to_set:
+      continue
+    to_p.Set(**{n: p.Copy() if isinstance(p, Params) else p})
+  return to_p
+
+
 # -------------------------------------------------------------- hyperparams.proto ----
 # HyperparamValue oneof field numbers
 _PV_PARAM, _PV_LIST, _PV_TUPLE, _PV_DICT, _PV_TYPE, _PV_DTYPE, _PV_STR, _PV_BOOL, _PV_INT, \

@@ -2587,3 +2587,18 @@ class MaskedLmDataAugmenter(base_layer.BaseLayer):
     out = torch.where(is_rand, rnd, out)
     pos = (is_mask | is_rand | is_same).float()
     return out, pos
+
+
+def Conv2DFlops(inputs, filter_shape, stride, padding):
+  """Multiply-adds ×2 of a conv2d: `inputs` shape [B, H, W, …], filter [fh, fw, ic, oc],
+  stride (sh, sw), padding 'SAME' | 'VALID' (reference :5950)."""
+  b, h, w = int(inputs[0]), int(inputs[1]), int(inputs[2])
+  fh, fw, ic, oc = [int(x) for x in filter_shape]
+  sh, sw = stride
+  ceil_div = lambda x, y: (x + y - 1) // y
+  if padding == 'SAME':
+    oh, ow = ceil_div(h, sh), ceil_div(w, sw)
+  else:
+    assert padding == 'VALID'
+    oh, ow = ceil_div(h - fh + 1, sh), ceil_div(w - fw + 1, sw)
+  return b * oh * ow * fh * fw * ic * oc * 2

@@ -15,16 +15,39 @@ from lingvo_b200.core import rnn_cell
 from lingvo_b200.core.nested_map import NestedMap
 
 
-class LSTMCellSimpleExt(rnn_cell.LSTMCellSimple):
-  """Marker subclass (ref :123)."""
+class LSTMCellExt:
+  """Mixin for LSTM cells: the input GEMM of a whole sequence in one call, then per-step
+  updates that only add the recurrent projection (ref :27)."""
+
+  def ProjectInputSequence(self, theta, inputs):
+    """inputs.act: list of `[T, B, D_i]` → `[T, B, gates·H]` (bias included)."""
+    assert isinstance(inputs.act, (list, tuple))
+    x = inputs.act[0] if len(inputs.act) == 1 else torch.cat(list(inputs.act), -1)
+    return self.ProjectInput(theta, x)
+
+  def _MixWithProjectedInput(self, theta, state0, inputs):
+    p = self.params
+    w_h = theta.wm[p.num_input_nodes:].to(inputs.dtype)
+    return inputs + torch.matmul(state0.m.to(inputs.dtype), w_h)
+
+  def FPropWithProjectedInput(self, theta, state0, inputs):
+    """inputs: NestedMap(proj_inputs `[B, gates·H]`, padding `[B, 1]`[, reset_mask]).
+    Equivalent to `FProp` on the un-projected step input."""
+    if self.params.reset_cell_state:
+      state0 = self._ResetState(state0.DeepCopy(), inputs)
+    return self._Step(theta, state0, inputs.proj_inputs, inputs.padding, inputs), NestedMap()
 
 
-class LayerNormalizedLSTMCellSimpleExt(rnn_cell.LayerNormalizedLSTMCellSimple):
-  """Marker subclass (ref :131)."""
+class LSTMCellSimpleExt(rnn_cell.LSTMCellSimple, LSTMCellExt):
+  """LSTMCellSimple + sequence-level input projection (ref :123)."""
 
 
-class LayerNormalizedLSTMCellLeanExt(rnn_cell.LayerNormalizedLSTMCellLean):
-  """Marker subclass (ref :140)."""
+class LayerNormalizedLSTMCellSimpleExt(rnn_cell.LayerNormalizedLSTMCellSimple, LSTMCellExt):
+  """LayerNormalizedLSTMCellSimple + sequence-level input projection (ref :131)."""
+
+
+class LayerNormalizedLSTMCellLeanExt(rnn_cell.LayerNormalizedLSTMCellLean, LSTMCellExt):
+  """LayerNormalizedLSTMCellLean + sequence-level input projection (ref :140)."""
 
 
 class LstmFRNN(base_layer.BaseLayer):

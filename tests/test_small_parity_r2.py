@@ -1,0 +1,198 @@
+"""Small reference helpers added in round 2, each against a straightforward oracle."""
+import queue
+
+import numpy as np
+import pytest
+import torch
+
+from lingvo_b200.core import activations
+from lingvo_b200.core import attention_util
+from lingvo_b200.core import batch_major_attention as bma
+from lingvo_b200.core import batch_utils
+from lingvo_b200.core import bn_layers
+from lingvo_b200.core import entmax
+from lingvo_b200.core import flat_beam_search_helper as fbs
+from lingvo_b200.core import gshard_builder
+from lingvo_b200.core import gshard_decode
+from lingvo_b200.core import gshard_utils
+from lingvo_b200.core import hyperparams
+from lingvo_b200.core import layers
+from lingvo_b200.core import lstm_frnn_layer
+from lingvo_b200.core.nested_map import NestedMap
+
+
+def test_glu_variants():
+  x = torch.randn(3, 8)
+  a, b = x.chunk(2, -1)
+  torch.testing.assert_close(activations.GetFn('GLU')(x), a * torch.sigmoid(b))
+  torch.testing.assert_close(activations.GetFn('BILINEAR_GLU')(x), a * b)
+  torch.testing.assert_close(activations.GetFn('SWISH_GLU')(x), a * torch.nn.functional.silu(b))
+  torch.testing.assert_close(activations.GLUVariants(x, 'RELU'), a * torch.relu(b))
+  assert activations.DimMultiplier('GELU_GLU') == 2 and activations.DimMultiplier('GELU') == 1
+  assert activations.GetFlops('GLU') == 5
+
+
+def test_extract_block_context_v2_matches_slices():
+  b, t, d, w, l, r = 2, 7, 3, 3, 3, 2
+  x = torch.randn(b, t, d)
+  pad = torch.zeros(b, t); pad[1, 5:] = 1
+  patches, ppad = attention_util.ExtractBlockContextV2(x, w, l, r, paddings=pad)
+  u, c = 3, l - 1 + w + r
+  assert patches.shape == (b, u, c, d) and ppad.shape == (b, u, c)
+  for ui in range(u):
+    for ci in range(c):
+      src = ui * w - (l - 1) + ci
+      if 0 <= src < t:
+        torch.testing.assert_close(patches[:, ui, ci], x[:, src])
+        assert torch.equal(ppad[:, ui, ci], pad[:, src])
+      else:
+        assert patches[:, ui, ci].abs().sum() == 0 and bool((ppad[:, ui, ci] == 1).all())
+  assert attention_util.ExtractBlockContextV2(x, w, l, r)[1] is None
+
+
+def test_entmax_general_alpha_and_loss():
+  torch.manual_seed(0)
+  x = torch.randn(4, 9, dtype=torch.float64, requires_grad=True)
+  p15 = entmax.entmax_support(x, alpha=1.5)
+  torch.testing.assert_close(p15, entmax.entmax15(x), atol=1e-6, rtol=1e-6)
+  p2 = entmax.entmax_support(x, alpha=2.0)
+  torch.testing.assert_close(p2, entmax.sparsemax(x), atol=1e-6, rtol=1e-6)
+  p11 = entmax.entmax_support(x, alpha=1.05)
+  assert (p11 > 0).float().mean() > (p2 > 0).float().mean()          # less sparse near softmax
+  assert torch.allclose(p11.sum(-1), torch.ones(4, dtype=torch.float64))
+  # gradient of the bisection version = gradient of the exact sort-based one
+  w = torch.randn(4, 9, dtype=torch.float64)
+  g_b, = torch.autograd.grad((p15 * w).sum(), x, retain_graph=True)
+  g_e, = torch.autograd.grad((entmax.entmax15(x) * w).sum(), x)
+  torch.testing.assert_close(g_b, g_e, atol=1e-5, rtol=1e-5)
+  # loss: ≥ 0, zero iff the prediction is the (one-hot) label; gradient = p − y
+  labels = torch.nn.functional.one_hot(torch.tensor([1, 3, 0, 8]), 9).double()
+  loss = entmax.entmax_loss(labels, x)
+  assert loss.shape == (4,) and bool((loss >= -1e-9).all())
+  g, = torch.autograd.grad(loss.sum(), x)
+  torch.testing.assert_close(g, p15.detach() - labels, atol=1e-6, rtol=1e-6)
+  sure = entmax.entmax_loss(labels, labels * 50.0)
+  assert float(sure.abs().max()) < 1e-6
+
+
+def test_batch_utils_global_scaling():
+  assert batch_utils.scale_global_to_infeed(64, False) == 64
+  assert batch_utils.scale_global_to_worker(8) * 1 >= 1
+  from lingvo_b200.core import cluster_factory
+  n = max(int(cluster_factory.Current().total_worker_devices), 1)
+  assert batch_utils.scale_global_to_worker(8 * n) == 8
+  if n > 1:
+    with pytest.raises(ValueError):
+      batch_utils.scale_global_to_worker(8 * n + 1)
+
+
+def test_adding_accumulator():
+  acc = bn_layers.AddingAccumulator([2], torch.float32)
+  assert acc.GetValue().tolist() == [0, 0]
+  acc.Update(torch.tensor([1.0, 2.0]))
+  acc.Update(torch.tensor([0.5, 0.5], dtype=torch.float64))
+  assert acc.GetValue().tolist() == [1.5, 2.5]
+  acc.Disable()
+  assert acc.GetValue().tolist() == [0, 0]
+  acc.Enable()
+  assert acc.GetValue().tolist() == [1.5, 2.5]
+
+
+def test_einsum_i32_and_infinite_repeat():
+  a = torch.tensor([[1.0, 0.0], [1.0, 1.0]])
+  out = fbs.einsum_i32('ij,jk->ik', a, a)
+  assert out.dtype == torch.int32 and out.tolist() == [[1, 0], [2, 1]]
+  q = queue.Queue()
+  for i in range(4):
+    q.put((i,))
+  q.put(None)
+  seen = []
+
+  def Body(*args):
+    total = (args[0] if len(args) == 2 else 0) + args[-1]
+    seen.append(total)
+    return [total]
+
+  assert gshard_decode.infinite_repeat(Body, q) == [6] and seen == [0, 1, 3, 6]
+  n = [0]
+
+  def Count():
+    n[0] += 1
+    if n[0] == 5:
+      raise StopIteration
+
+  assert gshard_decode.infinite_repeat(Count) == [] and n[0] == 5
+
+
+def test_kl_div_and_reshape_dim_and_sharding_spec():
+  p = torch.softmax(torch.randn(2, 3, 5), -1)
+  q = torch.softmax(torch.randn(2, 3, 5), -1)
+  want = torch.nn.functional.kl_div(q.log(), p, reduction='sum') / 2
+  torch.testing.assert_close(gshard_builder.KLDiv(p, q), want, atol=1e-5, rtol=1e-5)
+  assert float(gshard_builder.KLDiv(p, p)) == pytest.approx(0.0, abs=1e-6)
+  x = torch.arange(24).reshape(2, 12)
+  assert gshard_utils.ReshapeDim(x, 1, 3).shape == (2, 3, 4)
+  assert gshard_utils.ReshapeDim(x, -1, 4).shape == (2, 4, 3)
+  assert gshard_utils.ReshapeDim(x, 1) is x
+  mesh = np.arange(4).reshape(2, 2)
+  with gshard_utils.MeshSplitDimPrefixContext(1):
+    spec = gshard_utils.GetMeshSplitSharding(mesh, [0, -1])
+  assert list(spec.split_dims_mapping) == [1, 0, -1]
+
+
+def test_copy_fields_subset_and_conv_flops():
+  a = hyperparams.Params(); b = hyperparams.Params()
+  for p in (a, b):
+    p.Define('x', 1, ''); p.Define('y', 2, ''); p.Define('sub', hyperparams.Params(), '')
+  a.Set(x=10, y=20)
+  a.sub.Define('z', 5, '')
+  hyperparams.CopyFieldsSubsetTo(a, b, ['x', 'sub'])
+  assert (b.x, b.y) == (10, 2) and b.sub.z == 5 and b.sub is not a.sub
+  hyperparams.CopyFieldsSubsetTo(a, b, 'y')
+  assert b.y == 20
+  assert layers.Conv2DFlops([2, 8, 8, 3], [3, 3, 3, 16], (2, 2), 'SAME') == 2 * 4 * 4 * 27 * 16 * 2
+  assert layers.Conv2DFlops([2, 8, 8, 3], [3, 3, 3, 16], (1, 1), 'VALID') == 2 * 6 * 6 * 27 * 16 * 2
+
+
+def test_reshaped_multi_headed_projection_matches_plain():
+  mesh = np.arange(4).reshape(2, 2)
+  common = dict(input_dim=8, num_heads=2, dim_per_head=3, random_seed=5)
+  plain = bma.MultiHeadedProjectionLayer.Params().Set(name='p', **common).Instantiate()
+  resh = bma.ReshapedMultiHeadedProjectionLayer.Params().Set(
+      name='p', device_mesh=mesh, **common).Instantiate()
+  with torch.no_grad():
+    resh.vars.w.copy_(plain.vars.w); resh.vars.b.copy_(torch.randn_like(plain.vars.b))
+    plain.vars.b.copy_(resh.vars.b)
+  x = torch.randn(2, 5, 8)
+  torch.testing.assert_close(resh.FPropDefaultTheta(x.reshape(2, 5, 2, 4)),
+                             plain.FPropDefaultTheta(x), atol=1e-5, rtol=1e-5)
+  out_plain = bma.MultiHeadedProjectionLayer.Params().Set(
+      name='o', is_output_projection=True, **common).Instantiate()
+  out_resh = bma.ReshapedMultiHeadedProjectionLayer.Params().Set(
+      name='o', is_output_projection=True, device_mesh=mesh, **common).Instantiate()
+  with torch.no_grad():
+    out_resh.vars.w.copy_(out_plain.vars.w)
+    out_plain.vars.b.copy_(torch.randn(8)); out_resh.vars.b.copy_(out_plain.vars.b)
+  h = torch.randn(2, 5, 2, 3)
+  torch.testing.assert_close(out_resh.FPropDefaultTheta(h).reshape(2, 5, 8),
+                             out_plain.FPropDefaultTheta(h), atol=1e-5, rtol=1e-5)
+
+
+def test_lstm_cell_ext_projected_inputs_match_fprop():
+  p = lstm_frnn_layer.LSTMCellSimpleExt.Params().Set(
+      name='c', num_input_nodes=6, num_output_nodes=4, random_seed=3)
+  cell = p.Instantiate()
+  t, b = 5, 3
+  x1, x2 = torch.randn(t, b, 2), torch.randn(t, b, 4)
+  pad = torch.zeros(b, 1)
+  proj = cell.ProjectInputSequence(cell.theta, NestedMap(act=[x1, x2]))
+  assert proj.shape == (t, b, 16)
+  sa = sb = cell.zero_state(cell.theta, b)
+  for i in range(t):
+    sa, _ = cell.FProp(cell.theta, sa, NestedMap(act=[x1[i], x2[i]], padding=pad))
+    sb, _ = cell.FPropWithProjectedInput(cell.theta, sb,
+                                         NestedMap(proj_inputs=proj[i], padding=pad))
+  torch.testing.assert_close(sa.m, sb.m, atol=1e-5, rtol=1e-5)
+  torch.testing.assert_close(sa.c, sb.c, atol=1e-5, rtol=1e-5)
+  mixed = cell._MixWithProjectedInput(cell.theta, sa, proj[0])
+  assert mixed.shape == (b, 16)
