@@ -290,6 +290,50 @@ class _Cluster:
     return None
 
 
+# -- infeed context / device strings (ref cluster.py:33-63, 657) ------------------------------
+InfeedContext = collections.namedtuple('InfeedContext', ['infeed_host_index',
+                                                         'num_infeed_hosts'])
+_INFEED_CONTEXT_STACK = _LocalStack()
+
+
+@contextlib.contextmanager
+def InfeedContextScope(infeed_host_index, num_infeed_hosts):
+  """Names which input shard the enclosed input-generator construction serves."""
+  _INFEED_CONTEXT_STACK.stack.append(InfeedContext(infeed_host_index, num_infeed_hosts))
+  try:
+    yield
+  finally:
+    _INFEED_CONTEXT_STACK.stack.pop()
+
+
+def GetInfeedContext():
+  """Innermost `InfeedContextScope`, else this process' rank / world size."""
+  if _INFEED_CONTEXT_STACK.stack:
+    return _INFEED_CONTEXT_STACK.stack[-1]
+  return InfeedContext(infeed_host_index=int(os.environ.get('RANK', 0)),
+                       num_infeed_hosts=int(os.environ.get('WORLD_SIZE', 1)))
+
+
+def MakeDeviceString(job_name, replica_id, task_id, device_name, device_id):
+  return '%s/replica:%d/task:%d/device:%s:%d' % (job_name, replica_id, task_id, device_name,
+                                                 device_id)
+
+
+def ParseDeviceString(device_str):
+  """`/job:x/replica:r/task:t/device:GPU:i` → NestedMap(job, replica, task, device)."""
+  parsed = NestedMap()
+  for part in device_str.split('/'):
+    if part.startswith('job:'):
+      parsed.job = part[4:]
+    elif part.startswith('replica:'):
+      parsed.replica = int(part[8:])
+    elif part.startswith('task:'):
+      parsed.task = int(part[5:])
+    elif part.startswith('device:'):
+      parsed.device = part[7:].split(':')[0]
+  return parsed
+
+
 class VarPlacer:
   """Assigns each variable to an owner rank; default: everything on rank 0."""
 

@@ -6,6 +6,14 @@ Cluster = cluster_lib._Cluster  # pylint: disable=protected-access
 _DEFAULT = [None]
 
 
+def SetCluster(cls):
+  """Swaps the cluster implementation (`cls.Params().Instantiate()` builds clusters from
+  now on) (ref :23)."""
+  global Cluster  # pylint: disable=invalid-name,global-statement
+  Cluster = cls
+  _DEFAULT[0] = None
+
+
 def Current():
   """The innermost active cluster, or a default single-process one."""
   top = cluster_lib._Cluster._TopOrNone()  # pylint: disable=protected-access

@@ -160,3 +160,88 @@ class GenericInput:
 
   def Close(self):
     self._batcher.close()
+
+
+# -- keyed pipelines + replicated input (ref generic_input.py:28-47, 211-400) -----------------
+_GENERIC_CACHE_V2 = {}
+_ALLOW_V2_IN_EAGER = [True]
+
+
+def SetAllowGenericInputV2InEager(allowed=True):
+  _ALLOW_V2_IN_EAGER[0] = bool(allowed)
+
+
+def IsGenericInputV2AllwedInEager():   # (sic) the reference's spelling
+  return _ALLOW_V2_IN_EAGER[0]
+
+
+def GenericInputV2Create(processor, **kwargs):
+  """Creates — or returns the cached — pipeline for `generic_input_v2_key`. The key makes the
+  pipeline a process-level resource: re-building the input generator (e.g. eval after train,
+  program re-instantiation) keeps reading where the previous owner stopped (ref :211).
+  Returns (resource, out_types, output_tmpl); `GenericInputV2GetNext` reads from it."""
+  key = kwargs.pop('generic_input_v2_key', None)
+  if key is None:
+    raise RuntimeError('GenericInputV2Create needs a `generic_input_v2_key` identifying the '
+                       'pipeline (any hashable, e.g. the input generator\'s path).')
+  if key not in _GENERIC_CACHE_V2:
+    _GENERIC_CACHE_V2[key] = GenericInput(processor, **kwargs)
+  resource = _GENERIC_CACHE_V2[key]
+  return resource, None, None
+
+
+def GenericInputV2GetNext(resource, out_types=None, output_tmpl=None):
+  del out_types, output_tmpl
+  return resource.GetNext()
+
+
+def ResetGenericInputV2Cache(key=None):
+  """Closes and forgets one keyed pipeline (or all)."""
+  for k in ([key] if key is not None else list(_GENERIC_CACHE_V2)):
+    gi = _GENERIC_CACHE_V2.pop(k, None)
+    if gi is not None:
+      gi.Close()
+
+
+class ReplicatedGenericInput:
+  """`num_replicas` independent pipelines — replica i reads input shard i of `num_replicas`
+  — whose batches are concatenated along the batch dim: one process feeding several
+  model replicas (ref :319). All bucket batch limits must be equal so every replica
+  contributes the same batch size."""
+
+  def __init__(self, processor, num_replicas, replica_device_fn=None, **kwargs):
+    del replica_device_fn                      # host pipelines: no device placement needed
+    limits = kwargs.get('bucket_batch_limit')
+    if num_replicas > 1 and limits:
+      assert all(b == max(limits) for b in limits), limits
+    key = kwargs.pop('generic_input_v2_key', None)
+    self._replicas = []
+    for i in range(num_replicas):
+      kw = dict(kwargs, num_input_replicas=num_replicas, input_replica_id=i)
+      if key is not None:
+        self._replicas.append(GenericInputV2Create(processor, generic_input_v2_key=(key, i),
+                                                   **kw)[0])
+      else:
+        self._replicas.append(GenericInput(processor, **kw))
+
+  def GetNext(self):
+    """All replicas are read for the same step; a batch is only as long as the bucket the
+    replicas agree on (shorter ones are padded up to the longest)."""
+    outs = [r.GetNext() for r in self._replicas]
+    batches, keys = zip(*outs)
+    is_map = isinstance(batches[0], NestedMap)
+    flats = [b.Flatten() if is_map else list(b) for b in batches]
+    merged = []
+    for parts in zip(*flats):
+      parts = [np.asarray(x) for x in parts]
+      if parts[0].ndim > 1:
+        width = [max(x.shape[d] for x in parts) for d in range(1, parts[0].ndim)]
+        parts = [np.pad(x, [(0, 0)] + [(0, w - s) for w, s in zip(width, x.shape[1:])])
+                 for x in parts]
+      merged.append(np.concatenate(parts, 0))
+    out = batches[0].Pack(merged) if is_map else merged
+    return out, np.concatenate([np.asarray(k) for k in keys], 0)
+
+  def Close(self):
+    for r in self._replicas:
+      r.Close()

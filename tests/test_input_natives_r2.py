@@ -126,3 +126,47 @@ def test_crc32c_hardware_path_matches_table_implementation():
     if n > 20:
       assert h.crc32c_buffer(d[n // 3:], h.crc32c_buffer(d[:n // 3], 0)) == want
   assert tfrecord.crc32c(b'123456789') == 0xE3069283
+
+
+def test_keyed_and_replicated_generic_input():
+  pattern, total = _WriteShards(4, 40)
+
+  def proc(rec):
+    k = int(rec)
+    n = 2 + k % 3
+    return generic_input.NestedMap(ids=np.full([n], k, np.int32)), n
+
+  kw = dict(file_pattern=pattern, bucket_upper_bound=[8], bucket_batch_limit=[4],
+            repeat_count=1, file_buffer_size=1, file_parallelism=1, num_threads=1,
+            require_sequential_order=True)
+  with pytest.raises(RuntimeError):
+    generic_input.GenericInputV2Create(proc, **kw)
+  res, _, _ = generic_input.GenericInputV2Create(proc, generic_input_v2_key='eval', **kw)
+  first, _ = generic_input.GenericInputV2GetNext(res)
+  res2, _, _ = generic_input.GenericInputV2Create(proc, generic_input_v2_key='eval', **kw)
+  assert res2 is res                                   # same key → same live pipeline
+  second, _ = generic_input.GenericInputV2GetNext(res2)
+  assert set(first.ids[:, 0].tolist()).isdisjoint(second.ids[:, 0].tolist())
+  generic_input.ResetGenericInputV2Cache('eval')
+  res3, _, _ = generic_input.GenericInputV2Create(proc, generic_input_v2_key='eval', **kw)
+  again, _ = generic_input.GenericInputV2GetNext(res3)
+  assert again.ids[:, 0].tolist() == first.ids[:, 0].tolist()   # a fresh pipeline restarts
+  generic_input.ResetGenericInputV2Cache()
+  assert generic_input.IsGenericInputV2AllwedInEager()
+
+  rep = generic_input.ReplicatedGenericInput(proc, 2, lambda i: 'cpu:%d' % i, **kw)
+  seen = []
+  try:
+    while True:
+      batch, keys = rep.GetNext()
+      assert batch.ids.shape[0] == 8 and keys.shape == (8,)
+      seen += batch.ids[:, 0].tolist()
+      # rows 0-3 come from replica 0, rows 4-7 from replica 1: disjoint input shards
+      assert set(batch.ids[:4, 0].tolist()).isdisjoint(batch.ids[4:, 0].tolist())
+  except StopIteration:
+    pass
+  rep.Close()
+  assert len(seen) == len(set(seen)) and len(seen) >= total - 8
+  with pytest.raises(AssertionError):
+    generic_input.ReplicatedGenericInput(proc, 2, None, **dict(
+        kw, bucket_upper_bound=[4, 8], bucket_batch_limit=[8, 4]))

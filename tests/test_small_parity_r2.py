@@ -196,3 +196,57 @@ def test_lstm_cell_ext_projected_inputs_match_fprop():
   torch.testing.assert_close(sa.c, sb.c, atol=1e-5, rtol=1e-5)
   mixed = cell._MixWithProjectedInput(cell.theta, sa, proj[0])
   assert mixed.shape == (b, 16)
+
+
+def test_cluster_device_strings_and_infeed_context():
+  from lingvo_b200.core import cluster
+  s = cluster.MakeDeviceString('/job:trainer', 1, 2, 'GPU', 3)
+  assert s == '/job:trainer/replica:1/task:2/device:GPU:3'
+  d = cluster.ParseDeviceString(s)
+  assert (d.job, d.replica, d.task, d.device) == ('trainer', 1, 2, 'GPU')
+  assert 'task' not in cluster.ParseDeviceString('/job:a/replica:0')
+  base = cluster.GetInfeedContext()
+  assert base.num_infeed_hosts >= 1
+  with cluster.InfeedContextScope(3, 8):
+    assert cluster.GetInfeedContext() == (3, 8)
+    with cluster.InfeedContextScope(1, 2):
+      assert cluster.GetInfeedContext().infeed_host_index == 1
+    assert cluster.GetInfeedContext().num_infeed_hosts == 8
+  assert cluster.GetInfeedContext() == base
+
+
+def test_set_cluster_swaps_implementation():
+  from lingvo_b200.core import cluster_factory
+  orig = cluster_factory.Cluster
+
+  class MyCluster(orig):
+    marker = True
+
+  try:
+    cluster_factory.SetCluster(MyCluster)
+    assert getattr(cluster_factory.Current(), 'marker', False) or \
+        cluster_factory.Cluster is MyCluster
+  finally:
+    cluster_factory.SetCluster(orig)
+  assert cluster_factory.Cluster is orig
+
+
+def test_nested_map_assertions():
+  import unittest
+  from lingvo_b200.core import compare
+
+  class T(compare.NestedMapAssertions):
+    def runTest(self):
+      pass
+
+  t = T()
+  a = NestedMap(x=torch.zeros(2, 3), y=NestedMap(z=torch.ones(4)))
+  t.assertNestedMapEqual(a, a.DeepCopy())
+  t.assertNestedMapEqual({'x': torch.zeros(2, 3), 'y': NestedMap(z=torch.ones(4))}, a)
+  b = a.DeepCopy(); b.y.z = torch.ones(5)
+  with pytest.raises(AssertionError) as e:
+    t.assertNestedMapEqual(a, b)
+  assert 'y.z' in str(e.value)
+  with pytest.raises(AssertionError):
+    compare.assertNestedMapEqual(None, a, b)
+  del unittest
