@@ -47,6 +47,11 @@ def _Pairs(var_grads) -> List[Tuple[torch.nn.Parameter, torch.Tensor]]:
   return [(vg.var, vg.grad) for vg in leaves if vg.grad is not None]
 
 
+def GetLrValue(lr_or_callable):
+  """A learning rate given as a number or as a zero-arg callable (ref :29)."""
+  return lr_or_callable() if callable(lr_or_callable) else lr_or_callable
+
+
 class Base(base_layer.BaseLayer):
   """Base class for all optimizers."""
 
@@ -820,6 +825,47 @@ class XLAShardingAdafactor(Base):
 
 
 Adafactor = XLAShardingAdafactor
+
+
+class XLAShardingAdafactorOptimizer(torch.optim.Optimizer):
+  """The same Adafactor as a plain `torch.optim.Optimizer` (ref :905, the raw optimizer the
+  `XLAShardingAdafactor` layer wraps): for code that drives its own training loop.
+  `learning_rate` / `decay_rate` may be numbers or zero-arg callables evaluated every step.
+  Runs the fused sm_100a kernels on CUDA parameters, the eager formulation elsewhere."""
+
+  def __init__(self, params, multiply_by_parameter_scale=True, learning_rate=None,
+               decay_rate=None, beta1=0.0, clipping_threshold=1.0, factored=True,
+               epsilon1=1e-30, epsilon2=1e-3, min_dim_size_to_factor=128, use_locking=False,
+               cond_is_finite=False, name='Adafactor'):
+    del use_locking
+    assert learning_rate is not None and decay_rate is not None
+    super().__init__(list(params), dict(name=name))
+    self._learning_rate, self._decay_rate = learning_rate, decay_rate
+    decay_of = self
+
+    class _Impl(XLAShardingAdafactor):
+      def DecayRate(self, step=None):   # pylint: disable=invalid-name
+        return float(GetLrValue(decay_of._decay_rate))   # pylint: disable=protected-access
+
+    self._impl = _Impl.Params().Set(
+        name=name, beta1=beta1, multiply_by_parameter_scale=multiply_by_parameter_scale,
+        clipping_threshold=clipping_threshold, factored=factored, epsilon1=epsilon1,
+        epsilon2=epsilon2, min_dim_size_to_factor=min_dim_size_to_factor,
+        cond_is_finite=cond_is_finite).Instantiate()
+
+  def slots(self):   # pylint: disable=invalid-name
+    return self._impl._slots   # pylint: disable=protected-access
+
+  @torch.no_grad()
+  def step(self, closure=None):   # pylint: disable=invalid-name
+    loss = None
+    if closure is not None:
+      with torch.enable_grad():
+        loss = closure()
+    pairs = [py_utils.VarGrad(p, p.grad) for g in self.param_groups for p in g['params']
+             if p.grad is not None]
+    self._impl.Apply(float(GetLrValue(self._learning_rate)), pairs)
+    return loss
 
 
 class XLAShardingAdafactorAccuGrad(XLAShardingAdafactor):

@@ -250,3 +250,32 @@ def test_nested_map_assertions():
   with pytest.raises(AssertionError):
     compare.assertNestedMapEqual(None, a, b)
   del unittest
+
+
+def test_standalone_adafactor_optimizer_matches_layer():
+  from lingvo_b200.core import optimizer
+  from lingvo_b200.core import py_utils
+  assert optimizer.GetLrValue(0.5) == 0.5 and optimizer.GetLrValue(lambda: 0.25) == 0.25
+  torch.manual_seed(0)
+  w_a = torch.nn.Parameter(torch.randn(160, 130))
+  b_a = torch.nn.Parameter(torch.randn(130))
+  w_b, b_b = [torch.nn.Parameter(t.detach().clone()) for t in (w_a, b_a)]
+  lr = [0.1]
+  opt = optimizer.XLAShardingAdafactorOptimizer(
+      [w_a, b_a], learning_rate=lambda: lr[0], decay_rate=lambda: 0.8, clipping_threshold=1.0)
+  layer = optimizer.XLAShardingAdafactor.Params().Set(
+      name='af', clipping_threshold=1.0, decay_exponent_pow=None).Instantiate()
+  layer.DecayRate = lambda step=None: 0.8
+  x = torch.randn(16, 160)
+  for step in range(3):
+    lr[0] = 0.1 / (step + 1)
+    for w, b in ((w_a, b_a), (w_b, b_b)):
+      w.grad = b.grad = None
+      ((x @ w + b) ** 2).mean().backward()
+    opt.step()
+    layer.Apply(lr[0], [py_utils.VarGrad(w_b, w_b.grad), py_utils.VarGrad(b_b, b_b.grad)])
+  torch.testing.assert_close(w_a, w_b)
+  torch.testing.assert_close(b_a, b_b)
+  # the 2-D variable is factored: row / column accumulators, no full second moment
+  kinds = {k for slots in opt.slots().values() for k in slots}
+  assert {'vr', 'vc', 'v'} <= kinds
