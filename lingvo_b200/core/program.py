@@ -15,6 +15,7 @@ accumulate metrics on device (`DeviceEvalMetrics`).
 
 from __future__ import annotations
 
+import abc
 import logging
 import os
 import pickle
@@ -503,7 +504,28 @@ def _CreateProgramParams(cls, program_name, dataset_name, steps_per_loop,
   return p
 
 
-class SimpleProgramSchedule:
+class BaseProgramSchedule(abc.ABC):
+  """What the executor drives (:2287): `Run()` advances every program of the schedule by
+  its share of steps and returns (done, train seconds, eval seconds)."""
+
+  @classmethod
+  def Params(cls):
+    return hyperparams.InstantiableParams(cls)
+
+  @abc.abstractmethod
+  def Run(self, sess=None, threadpool=None):
+    """Runs the programs for some number of steps according to the schedule."""
+
+  @abc.abstractmethod
+  def Shutdown(self):
+    """Cleans up every program."""
+
+  @abc.abstractmethod
+  def Programs(self) -> List['BaseProgram']:
+    """The programs managed by the schedule."""
+
+
+class SimpleProgramSchedule(BaseProgramSchedule):
   """train N steps → [eval datasets] → [decode datasets], repeated (:2329)."""
 
   @classmethod
@@ -651,7 +673,50 @@ class SimpleProgramSchedule:
     return True
 
 
-MLPerfProgramSchedule = SimpleProgramSchedule
+class MLPerfProgramSchedule(SimpleProgramSchedule):
+  """MLPerf schedule (:2835): ONE `MLPerfTrainDecodeProgram` that trains and scores on the
+  same live variables; the compliance log / early stop come from the `ml_perf` params."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.ml_perf = MlPerfParams()
+    return p
+
+  def __init__(self, params, shared_model=None, trial_status_fn=None, **kwargs):   # pylint: disable=super-init-not-called
+    self.params = params.Copy()
+    p = self.params
+    tp = p.train_program.Copy()
+    for name in (tp.train_dataset_name, tp.decode_dataset_name):
+      if name not in p.task_dict:
+        raise ValueError('could not find %s in %s' % (name, list(p.task_dict)))
+    tp.logdir = p.logdir
+    tp.task_name = p.task_name
+    tp.train_task = p.task_dict[tp.train_dataset_name]
+    tp.decode_task = p.task_dict[tp.decode_dataset_name]
+    tp.ml_perf = p.ml_perf.Copy() if p.ml_perf is not None else None
+    self.train_program = tp.Instantiate(shared_model=shared_model,
+                                        trial_status_fn=trial_status_fn)
+    self._programs = [self.train_program]
+    # `_MlPerfCheck` reads the decode metrics from the "eval programs"
+    self.eval_programs = []
+    self._mlperf_metric_sources = [self.train_program]
+    self._triggers = {}
+
+  def Run(self, sess=None, threadpool=None):
+    start = time.time()
+    done = False
+    for _ in range(self.params.train_executions_per_eval):
+      done = self.train_program.Run(sess, threadpool) or done
+      if done:
+        break
+    train_time = time.time() - start
+    self.eval_programs = self._mlperf_metric_sources
+    try:
+      done = self._MlPerfCheck() or done
+    finally:
+      self.eval_programs = []
+    return done, train_time, 0.0
 
 
 class MultiTaskProgramSchedule:
@@ -721,6 +786,18 @@ def MlPerfParams():
   mp.Define('base_learning_rate', None, 'Logged.')
   mp.Define('warmup_steps', None, 'Logged.')
   return mp
+
+
+def MLPerfProgramScheduleForTask(train_dataset_name, train_steps_per_loop, decode_dataset_name,
+                                 decode_steps_per_loop):
+  """`MLPerfProgramSchedule` params for one train and one decode dataset (:2913)."""
+  ps = MLPerfProgramSchedule.Params()
+  ps.train_program = MLPerfTrainDecodeProgram.Params().Set(
+      name='train_and_decode', train_steps_per_loop=train_steps_per_loop,
+      decode_steps_per_loop=decode_steps_per_loop, dataset_name=train_dataset_name,
+      train_dataset_name=train_dataset_name, decode_dataset_name=decode_dataset_name)
+  ps.dataset_names = [train_dataset_name, decode_dataset_name]
+  return ps
 
 
 def SimpleProgramScheduleForTask(train_dataset_name, train_steps_per_loop,

@@ -53,11 +53,14 @@ class _ModelRegistryHelper:
 
   @classmethod
   def _GetSourceInfo(cls, src_cls):
-    info = '%s@%s' % (cls._ModelParamsClassKey(src_cls),
-                      inspect.getsourcefile(src_cls))
+    try:
+      src_file = inspect.getsourcefile(src_cls)
+    except (TypeError, OSError):        # classes built at run time have no source file
+      src_file = '<dynamic>'
+    info = '%s@%s' % (cls._ModelParamsClassKey(src_cls), src_file)
     try:
       return '%s:%d' % (info, inspect.getsourcelines(src_cls)[-1])
-    except OSError:
+    except (TypeError, OSError):
       return info
 
   @classmethod

@@ -80,3 +80,34 @@ def test_multi_task_program_schedule_runs_the_sampled_task(tmp_path):
   done, _, _ = sched.Run()                     # round-robin over both
   assert done is True or done is False
   assert sched.schedules['a'].train_program.global_step == 4
+
+
+def test_mlperf_program_schedule_trains_and_decodes_in_one_program(tmp_path):
+  from lingvo_b200.core import trainer_test_utils
+  cls = trainer_test_utils.RegisterIdentityRegressionModel('MlperfIdentity', max_train_steps=4)
+  cfg = model_registry.GetParams('test.test.MlperfIdentity', 'Train')
+  assert cfg.input is not None and cls is not None
+  ps = program.MLPerfProgramScheduleForTask('Train', 2, 'Train', 1)
+  assert isinstance(ps.cls, type) and issubclass(ps.cls, program.BaseProgramSchedule)
+  assert ps.dataset_names == ['Train', 'Train']
+  ps.task_dict = {'Train': cfg}
+  ps.logdir = str(tmp_path)
+  ps.ml_perf.Set(benchmark_name='lm', steps_per_epoch=2, decoder_metric_name='diff',
+                 decoder_metric_success_threshold=1e9, max_steps_to_train=4)
+  sched = ps.Instantiate()
+  progs = sched.Programs()
+  assert len(progs) == 1 and isinstance(progs[0], program.MLPerfTrainDecodeProgram)
+  progs[0].BuildTpuSubgraph()
+  done, train_s, eval_s = sched.Run()
+  assert not done and train_s > 0 and eval_s == 0.0
+  assert sched.train_program.global_step == 2
+  done, _, _ = sched.Run()
+  assert done                                           # max_steps_to_train reached
+  sched.Shutdown()
+  import pytest
+  with pytest.raises(ValueError):
+    bad = ps.Copy()
+    bad.task_dict = {'Dev': cfg}
+    bad.Instantiate()
+  with pytest.raises(TypeError):
+    program.BaseProgramSchedule()                       # abstract
