@@ -224,8 +224,8 @@ class ModelV1(base_model.BaseTask):
       pred = res[i].reshape(-1, 7)
       # heading: penalise sin(Δφ) so a flipped box costs nothing
       d_rot = torch.sin(pred[:, 6:] - tgt[:, 6:])
-      rl = torch.cat([u.ScaledHuberLoss(tgt[:, :6], pred[:, :6]),
-                      u.ScaledHuberLoss(torch.zeros_like(d_rot), d_rot)], -1).sum(-1)
+      rl = torch.cat([u.ScaledHuberLoss(tgt[:, :6], pred[:, :6], delta=1.0 / 9.0),
+                      u.ScaledHuberLoss(torch.zeros_like(d_rot), d_rot, delta=1.0 / 9.0)], -1).sum(-1)
       fg = asg['assigned_reg_mask'].to(dev)
       cls_losses.append(cl.sum())
       reg_losses.append((rl * fg).sum())
@@ -437,8 +437,8 @@ class ModelV2(point_detector.PointDetectorBase):
                                p.focal_loss_alpha, p.focal_loss_gamma)
     cls_loss = focal[..., 1:].sum(-1) * cls_w
     d_rot = torch.sin(res[..., 6:] - gt[..., 6:])
-    reg = torch.cat([u.ScaledHuberLoss(gt[..., :6], res[..., :6], p.huber_loss_delta),
-                     u.ScaledHuberLoss(torch.zeros_like(d_rot), d_rot, p.huber_loss_delta)],
+    reg = torch.cat([u.ScaledHuberLoss(gt[..., :6], res[..., :6], delta=p.huber_loss_delta),
+                     u.ScaledHuberLoss(torch.zeros_like(d_rot), d_rot, delta=p.huber_loss_delta)],
                     -1).sum(-1) * reg_w
     norm = reg_w.sum().clamp_min(1.0) if p.loss_norm_type == LossNormType.NORM_BY_NUM_POSITIVES \
         else torch.tensor(float(b), device=res.device)

@@ -257,7 +257,7 @@ class AnchorFreePillarsBase(point_detector.PointDetectorBase):
     rot_cls = F.cross_entropy(bin_logits.reshape(-1, p.angle_bin_num).float(), idx.reshape(-1),
                               reduction='none').reshape(idx.shape) * w
     pred_res = bin_res.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
-    rot_reg = self._utils_3d.ScaledHuberLoss(res, pred_res) * w
+    rot_reg = self._utils_3d.ScaledHuberLoss(res, pred_res, delta=1.0 / 9.0) * w
     return dict(location=loc, dimension=dim, rot_cls=rot_cls, rot_reg=rot_reg)
 
   def ComputeLoss(self, theta, predictions, input_batch):

@@ -171,9 +171,9 @@ class ModelBase(point_detector.PointDetectorBase):
     cls_loss = (focal[..., 1:].sum(-1) * cls_w)
     # heading: sin(Δφ) so that a box flipped by π costs nothing
     d_rot = torch.sin(res[..., 6:] - gt_res[..., 6:])
-    loc = u.ScaledHuberLoss(gt_res[..., :3], res[..., :3], p.huber_loss_delta).sum(-1)
-    dim = u.ScaledHuberLoss(gt_res[..., 3:6], res[..., 3:6], p.huber_loss_delta).sum(-1)
-    rot = u.ScaledHuberLoss(torch.zeros_like(d_rot), d_rot, p.huber_loss_delta).sum(-1)
+    loc = u.ScaledHuberLoss(gt_res[..., :3], res[..., :3], delta=p.huber_loss_delta).sum(-1)
+    dim = u.ScaledHuberLoss(gt_res[..., 3:6], res[..., 3:6], delta=p.huber_loss_delta).sum(-1)
+    rot = u.ScaledHuberLoss(torch.zeros_like(d_rot), d_rot, delta=p.huber_loss_delta).sum(-1)
     reg_loss = (p.location_loss_weight * loc + p.dimension_loss_weight * dim +
                 p.rotation_loss_weight * rot) * reg_w
     if p.loss_norm_type == LossNormType.NORM_BY_NUM_POSITIVES:
