@@ -390,3 +390,179 @@ class ModelBuilderBase(builder.Base):
       return NestedMap(points=center.unsqueeze(-2), features=f.unsqueeze(-2),
                        padding=(~any_real).to(inp.padding.dtype))
     return self._Fn(name, Fn)
+
+
+# ------------------------------------------------------------------------------------------
+# Point-set recipes of the reference builder (ref builder_lib.py:75, 690-1167), added as a
+# mixin so the class above stays readable.
+# ------------------------------------------------------------------------------------------
+def _PaddedMask(inp):
+  return (1.0 - inp.padding).unsqueeze(-1).to(inp.features.dtype)
+
+
+class _PointSetRecipes:
+
+  def _Branch(self, name, body, fetches):
+    """Runs `body`; its output is followed by the activations saved at `fetches` (dotted
+    paths of `_Fetch` layers inside `body`)."""
+    from lingvo_b200.core import builder_layers  # pylint: disable=g-import-not-at-top
+    return builder_layers.BranchLayer.Params().Set(name=name, body=body, fetches=list(fetches))
+
+  def _MakeNestedMap(self, name, keys):
+    return self._Fn(name, lambda *vals: NestedMap(dict(zip(keys, vals))))
+
+  def _SqueezeFn(self, axis=None):
+    return (lambda x: x.squeeze(axis)) if axis is not None else (lambda x: x.squeeze())
+
+  # -- padding-aware pooling over the points dim ----------------------------------------------
+  def _PaddedMean(self, name):
+    """Mean of `features` over the real points → `[..., F]` (0 when all are padded)."""
+    def Fn(inp):
+      mask = _PaddedMask(inp)
+      return (inp.features * mask).sum(-2) / mask.sum(-2).clamp_min(1.0)
+    return self._Fn(name, Fn)
+
+  def _PaddedSum(self, name):
+    return self._Fn(name, lambda inp: (inp.features * _PaddedMask(inp)).sum(-2))
+
+  # -- per-point MLPs on a points NestedMap ------------------------------------------------------
+  def _FeaturesFC(self, name, idims, odims, use_bn=True, activation_fn=None):
+    """FC on `.features`, rest of the NestedMap passed through (ref :752)."""
+    mid = self._BN('bn', odims) if use_bn else self._Bias('bias', odims)
+    return self._SeqOnFeatures(name, self._Linear('linear', idims, odims), mid,
+                               self._Activation('activation', activation_fn))
+
+  def _FeaturesMLP(self, name, dims, use_bn=True, activation_fn=None):
+    return self._Seq(name, *[
+        self._FeaturesFC('l%03d' % n, i, o, use_bn=use_bn, activation_fn=activation_fn)
+        for n, (i, o) in enumerate(zip(dims[:-1], dims[1:]))])
+
+  def _ConcatPointsToFeatures(self, name):
+    return self._SeqToKey(name, 'features', self._Concat(
+        'concat', self._GetValue('get_points', 'points'),
+        self._GetValue('get_features', 'features')))
+
+  # -- GIN ------------------------------------------------------------------------------------------
+  def _CondFC(self, name, idims, adims, odims, use_bn=True, activation_fn=None):
+    """(features `[..., P, idims]`, aggregate `[..., 1, adims]`) → `[..., P, odims]`: the
+    aggregate predicts a per-example `[idims, odims]` matrix applied to every point — a
+    T-Net-like conditional linear layer (ref :798)."""
+    def ReshapeTransform(t):
+      return t.reshape(list(t.shape[:-1]) + [idims, odims])
+    transform = self._Matmul(
+        'cond_transform',
+        self._Seq('prep_features', self._ArgIdx('arg0', [0]),
+                  self._BN('bn', idims) if use_bn else self._Identity('id')),
+        self._Seq('compute_linear_transform', self._ArgIdx('arg1', [1]),
+                  self._Squeeze('squeeze', axis=-2),
+                  self._FC('fc0', adims, adims * 2, use_bn=use_bn, activation_fn=activation_fn),
+                  self._FC('fc1', adims * 2, idims * odims, use_bn=use_bn,
+                           activation_fn='NONE'),
+                  self._Fn('reshape', ReshapeTransform)))
+    return self._Seq(name, transform,
+                     self._Identity('id') if use_bn else self._Bias('bias', odims),
+                     self._Activation('activation', activation_fn))
+
+  def _GINCondFC(self, name, lhs, rhs, idims, adims, odims, use_bn=True, activation_fn=None):
+    return self._Seq(name, self._Join('join', lhs, rhs),
+                     self._CondFC('cond_fc', idims, adims, odims, use_bn=use_bn,
+                                  activation_fn=activation_fn))
+
+  def _GINIntermediateLayer(self, name, dims, aggregate_sub, combine_method='add', eps=0.,
+                            use_bn=True):
+    """f'_i = MLP(combine((1 + eps)·f_i, aggregate_j f_j)) over a points NestedMap
+    (ref :960; eq. 4.1 of "How Powerful are Graph Neural Networks?")."""
+    combine = {
+        'add': self._Add,
+        'concat': self._BroadcastConcat,
+        'cond_fc': functools.partial(self._GINCondFC, idims=dims[0], odims=dims[0],
+                                     adims=dims[0], use_bn=use_bn),
+    }
+    if combine_method not in combine:
+      raise ValueError('Unexpected combine method: {}'.format(combine_method))
+    return self._Seq(
+        name,
+        self._SeqToKey(
+            'map_features', 'features',
+            combine[combine_method](
+                'combine',
+                self._Seq('left', self._GetValue('get_features', 'features'),
+                          self._Fn('eps_scale', lambda t: (1.0 + eps) * t)),
+                self._Seq('right', aggregate_sub,
+                          self._Fn('expand_dims', lambda t: t.unsqueeze(-2))))),
+        self._FeaturesMLP('mlp', dims, use_bn=use_bn))
+
+  def _GIN(self, name, mlp_dims, aggregate_sub, readout_sub, combine_method='add', eps=0.,
+           use_bn=True):
+    """Graph Isomorphism Network over a point set (ref :860): a chain of intermediate
+    layers; the output concatenates the read-out of the input and of every layer's output
+    (eq. 4.2) — `readout(f0) ‖ readout(f1) ‖ … ‖ readout(fN)`."""
+    if combine_method not in ('add', 'concat', 'cond_fc'):
+      raise ValueError('Unexpected combine method: {}'.format(combine_method))
+    for idx, (a, b) in enumerate(zip(mlp_dims[:-1], mlp_dims[1:])):
+      prev = a[-1] * (2 if combine_method == 'concat' else 1)
+      if prev != b[0]:
+        raise ValueError('mlp_dims do not match ({} != {}) at layer {} with dims: {} and {}'
+                         .format(prev, b[0], idx, a, b))
+
+    def Build(depth):
+      if depth == len(mlp_dims):
+        return readout_sub.Copy()
+      return self._Concat(
+          'gin_concat', readout_sub.Copy(),
+          self._Seq('seq', self._GINIntermediateLayer(
+              'gin_intermediate', mlp_dims[depth], aggregate_sub.Copy(), combine_method, eps,
+              use_bn), Build(depth + 1)))
+
+    return self._Seq(name, Build(0))
+
+  # -- PointNet++ / PointConv -------------------------------------------------------------------------
+  def _SetAbstraction(self, name, feature_extraction_sub, num_samples, group_size, ball_radius,
+                      sample_neighbors_uniformly=True):
+    """Farthest-point sample `num_samples` centres, group `group_size` neighbours within
+    `ball_radius` of each, featurize every group with `feature_extraction_sub` (points
+    NestedMap with leading dims `[B, num_samples, group_size]` → `[B, num_samples, F]`)
+    (ref :1040). Points NestedMap in, points NestedMap (the centres) out."""
+    from lingvo_b200.models.car import car_layers  # pylint: disable=g-import-not-at-top
+    return self._Seq(
+        name,
+        car_layers.SamplingAndGroupingLayer.Params().Set(
+            name='sample_group', num_samples=num_samples, ball_radius=ball_radius,
+            group_size=group_size, sample_neighbors_uniformly=sample_neighbors_uniformly),
+        self._Fn('pack', lambda grouped, query: NestedMap(grouped_points=grouped,
+                                                          query_points=query)),
+        self._ParMap('pmap', dict(
+            points=self._Seq('seq_points', self._GetValue('get_query', 'query_points'),
+                             self._GetValue('get_points', 'points')),
+            features=self._Seq('seq_features', self._GetValue('get_grouped', 'grouped_points'),
+                               feature_extraction_sub),
+            padding=self._Seq('seq_padding', self._GetValue('get_query', 'query_points'),
+                              self._GetValue('get_padding', 'padding')))))
+
+  def _PointConvParametricConv(self, name, mlp_dims, num_in_channels, num_out_channels):
+    """PointConv's parametric convolution (ref :1110, Fig. 5 of the paper without the
+    inverse-density scaling): `featuresᵀ [C_in, P] · MLP(points) [P, C_mid]`, flattened,
+    followed by an FC to `num_out_channels`."""
+    if mlp_dims[0] != 3:
+      raise ValueError('First dimension of mlp_dims must be 3. mlp_dims={}'.format(mlp_dims))
+
+    def CombineLastTwoDims(x):
+      return x.reshape(list(x.shape[:-2]) + [x.shape[-2] * x.shape[-1]])
+
+    return self._Seq(
+        name,
+        self._ApplyFnMulti(
+            'transpose_matmul', lambda x, y: torch.matmul(x.transpose(-1, -2), y),
+            self._GetValue('get_features', 'features'),
+            self._Seq('transform_points',
+                      self._SeqToKey('points_as_features', 'features',
+                                     self._GetValue('get_points', 'points')),
+                      self._FeaturesMLP('points_mlp', mlp_dims),
+                      self._GetValue('get_transformed_points', 'features'))),
+        self._Fn('reshape', CombineLastTwoDims),
+        self._FC('fc', num_in_channels * mlp_dims[-1], num_out_channels))
+
+
+for _name, _fn in list(vars(_PointSetRecipes).items()):
+  if callable(_fn) and not _name.startswith('__') and not hasattr(ModelBuilderBase, _name):
+    setattr(ModelBuilderBase, _name, _fn)

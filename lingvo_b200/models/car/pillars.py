@@ -341,8 +341,23 @@ class DynamicVoxelizationFeaturizer(base_layer.BaseLayer):
                                            las.points_feature, las.points_padding)
 
 
+def SparseToDense(grid_shape, locations, feats):
+  """Scatters pillar features back onto the dense grid (ref :36): `locations [B, P, 3]`
+  integer (x, y, z) cells, `feats [B, P, F]` → `[B, nx, ny, nz·F]`. Pillars sharing a cell
+  are summed (as `tf.scatter_nd` does); padded pillars should carry zero features."""
+  nx, ny, nz = grid_shape
+  b, p, f = feats.shape
+  assert tuple(locations.shape) == (b, p, 3)
+  loc = locations.long()
+  flat = ((torch.arange(b, device=feats.device).view(b, 1) * nx + loc[..., 0]) * ny +
+          loc[..., 1]) * nz + loc[..., 2]
+  grid = feats.new_zeros(b * nx * ny * nz, f)
+  grid.index_add_(0, flat.reshape(-1), feats.reshape(-1, f))
+  return grid.reshape(b, nx, ny, nz * f)
+
+
 class Builder(builder_lib.ModelBuilderBase):
-  """PointPillars layer recipes (ref :92)."""
+  """PointPillars layer recipes (ref :148)."""
 
   def Featurizer(self, name, idims, odims):
     return self._FC(name, idims, odims)
@@ -352,24 +367,83 @@ class Builder(builder_lib.ModelBuilderBase):
     layers_ += [self._Conv('c%d' % (i + 1), (3, 3, odims, odims)) for i in range(repeats)]
     return self._Seq(name, *layers_)
 
+  def _FetchBlock(self, name, stride, repeats, idims, odims, activation=None):
+    """Strided 3×3 conv + `repeats` 3×3 convs whose output is a fetch point `<name>.final`
+    (ref :169)."""
+    act = activation or 'RELU'
+    return self._Seq(
+        name,
+        self._Conv('c3x3', (3, 3, idims, odims), (stride, stride), activation_fn=act),
+        self._Rep('rep', repeats, self._Conv('c3x3', (3, 3, odims, odims), activation_fn=act)),
+        self._Fetch('final'))
+
+  def _TopDown(self, name, strides=(2, 2, 2), channel_multiplier=1, activation=None,
+               idims=None, repeats=(3, 5, 5)):
+    """The three strided blocks of [PointPillars §2.2] (ref :180)."""
+    if len(strides) != 3:
+      raise ValueError('`strides` expected to be list/tuple of len 3.')
+    m = channel_multiplier
+    return self._Seq(
+        name,
+        self._FetchBlock('b0', strides[0], repeats[0], idims or m * 64, m * 64, activation),
+        self._FetchBlock('b1', strides[1], repeats[1], m * 64, m * 128, activation),
+        self._FetchBlock('b2', strides[2], repeats[2], m * 128, m * 256, activation))
+
+  def _Upsample(self, name, stride, idims, odims, activation=None):
+    """Transposed conv (kernel = stride) + BN + activation (ref :195)."""
+    act = activation or 'RELU'
+    return builder_lib._Conv2D.Params().Set(   # pylint: disable=protected-access
+        name=name, filter_shape=(stride, stride, idims, odims), stride=(stride, stride),
+        transpose=True, use_bn=True, activation=act)
+
+  def Contract(self, down_strides=(2, 2, 2), channel_multiplier=1, activation=None,
+               idims=None, repeats=(3, 5, 5)):
+    """Contracting half (ref :208): runs the blocks once and returns
+    (b2 output, b1 output, b0 output) — the finer maps are *fetched*, not recomputed."""
+    return self._Branch(
+        'branch',
+        self._TopDown('topdown', strides=down_strides, channel_multiplier=channel_multiplier,
+                      activation=activation, idims=idims, repeats=repeats),
+        ['b1.final', 'b0.final'])
+
+  def Expand(self, odims, channel_multiplier=1, activation=None):
+    """Expanding half (ref :218): every scale is upsampled to the b0 resolution (×4, ×2, ×1)
+    and the three maps are concatenated → `3·odims` channels."""
+    m = channel_multiplier
+    return self._Concat(
+        'concat',
+        self._Seq('b2', self._ArgIdx('idx', [0]), self._Upsample('ups', 4, m * 256, odims,
+                                                                  activation)),
+        self._Seq('b1', self._ArgIdx('idx', [1]), self._Upsample('ups', 2, m * 128, odims,
+                                                                  activation)),
+        self._Seq('b0', self._ArgIdx('idx', [2]), self._Upsample('ups', 1, m * 64, odims,
+                                                                  activation)))
+
   def Backbone(self, idims, dims=(64, 128, 256), repeats=(3, 5, 5), up_dims=128,
-               first_stride=2):
-    """Three strided conv blocks; each block's output is upsampled back to the first
-    block's resolution and the three are concatenated → `3·up_dims` channels at 1/`first_
-    stride` of the input resolution."""
-    b0 = self._Block('b0', first_stride, repeats[0], idims, dims[0])
-    b1 = self._Block('b1', 2, repeats[1], dims[0], dims[1])
-    b2 = self._Block('b2', 2, repeats[2], dims[1], dims[2])
-    u0 = self._Deconv('u0', (3, 3, dims[0], up_dims), (1, 1))
-    u1 = self._Deconv('u1', (3, 3, dims[1], up_dims), (2, 2))
-    u2 = self._Deconv('u2', (3, 3, dims[2], up_dims), (4, 4))
-    s0 = self._Seq('s0', b0)
-    s1 = self._Seq('s1', b0.Copy(), b1)
-    s2 = self._Seq('s2', b0.Copy(), b1.Copy(), b2)
-    # the three stages share nothing in this formulation (clear dataflow, 3 small convs
-    # recomputed); the hand-fused `PillarsBackbone` above is the production path
-    return self._Concat('backbone', self._Seq('p0', s0, u0), self._Seq('p1', s1, u1),
-                        self._Seq('p2', s2, u2))
+               first_stride=2, channel_multiplier=None, activation=None):
+    """Contract → Expand (ref :238): `idims` input channels → `3·up_dims` channels at
+    1/`first_stride` of the input resolution. Every block runs exactly once."""
+    if channel_multiplier is None:
+      assert tuple(dims) == (dims[0], 2 * dims[0], 4 * dims[0]) and dims[0] % 64 == 0, dims
+      channel_multiplier = dims[0] // 64
+    return self._Seq(
+        'backbone',
+        self.Contract((first_stride, 2, 2), channel_multiplier, activation, idims=idims,
+                      repeats=tuple(repeats)),
+        self.Expand(up_dims, channel_multiplier, activation))
+
+  def MLPFeaturizer(self, name, dims, use_bn=True, activation_fn='RELU'):
+    """Per-point MLP over `.features` of a points NestedMap → the feature tensor (ref :261)."""
+    return self._Seq(
+        name,
+        self._FeaturesMLP('feat', dims, use_bn=use_bn, activation_fn=activation_fn),
+        self._GetValue('get_features', 'features'))
+
+  def ScalePillarsFeaturizer(self, name, input_dims, output_dims):
+    """The wider swish featurizer of the scaled-up pillars models (ref :268)."""
+    del name
+    return self.MLPFeaturizer('feat', [input_dims, 256, 256, 256, output_dims],
+                              activation_fn='SWISH')
 
   def Detector(self, name, idims, odims, conv_init_method=None, bias_params_init=None):
     del conv_init_method
