@@ -16,7 +16,9 @@ batcher's worker threads.
 
 from __future__ import annotations
 
+import atexit
 import inspect
+import weakref
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -76,6 +78,24 @@ def MakeYielder(file_pattern, file_random_seed=0, file_buffer_size=10000,
       bufsize_in_seconds=float(file_buffer_size_in_seconds or 0.0))
 
 
+# Worker threads of the native batcher call back into Python (the record processor). A worker
+# that is still alive when the interpreter finalises gets killed while it waits for the GIL,
+# which aborts the process ("terminate called without an active exception"). Every live
+# pipeline is therefore closed from an atexit hook, i.e. *before* finalisation starts.
+_LIVE_PIPELINES = weakref.WeakSet()
+
+
+def _CloseLivePipelines():
+  for gi in list(_LIVE_PIPELINES):
+    try:
+      gi.Close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+
+atexit.register(_CloseLivePipelines)
+
+
 class GenericInput:
   """Bucketing batcher over a record yielder."""
 
@@ -129,6 +149,7 @@ class GenericInput:
         1 if require_sequential_order else num_threads, flush_every_n,
         int(bucket_adjust_every_n or 0),
         None if fatal_errors is None else [str(e) for e in fatal_errors], pad_values)
+    _LIVE_PIPELINES.add(self)
 
   def GetNext(self):
     """→ (NestedMap or list of batched np arrays, bucket_keys [n])."""

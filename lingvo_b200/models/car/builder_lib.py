@@ -27,6 +27,15 @@ _ACTS = {'RELU': F.relu, 'SWISH': F.silu, 'SILU': F.silu, 'SIGMOID': torch.sigmo
          'TANH': torch.tanh, 'GELU': F.gelu, 'NONE': lambda x: x, None: lambda x: x}
 
 
+def _MovingStats(layer, theta):
+  """The running statistics F.batch_norm updates in place. Inside a `RepeatLayer` the layer's
+  variables are stacked `[repeat, C]` and `theta` holds this iteration's slice (a view)."""
+  mean, var = layer.vars.moving_mean.data, layer.vars.moving_variance.data
+  if mean.shape != theta.gamma.shape:
+    mean, var = theta.moving_mean.detach(), theta.moving_variance.detach()
+  return mean, var
+
+
 class _PointBN(base_layer.BaseLayer):
   """Batch norm over all leading dims of `[..., D]` (per-point features); padded points
   do not matter for the statistics in practice and are re-masked by the pooling."""
@@ -52,8 +61,8 @@ class _PointBN(base_layer.BaseLayer):
     p = self.params
     shape = x.shape
     flat = x.reshape(-1, shape[-1])
-    out = F.batch_norm(flat, self.vars.moving_mean.data, self.vars.moving_variance.data,
-                       theta.gamma, theta.beta, training=not self.do_eval,
+    mean, var = _MovingStats(self, theta)
+    out = F.batch_norm(flat, mean, var, theta.gamma, theta.beta, training=not self.do_eval,
                        momentum=1.0 - p.decay, eps=p.epsilon)
     return out.reshape(shape)
 
@@ -109,9 +118,9 @@ class _Conv2D(base_layer.BaseLayer):
       w = theta.w.permute(3, 2, 0, 1)                      # [out, in, kh, kw]
       y = F.conv2d(x, w, stride=tuple(p.stride), padding=((kh - 1) // 2, (kw - 1) // 2))
     if p.use_bn:
-      y = F.batch_norm(y, self.vars.moving_mean.data, self.vars.moving_variance.data,
-                       theta.gamma, theta.beta, training=not self.do_eval, momentum=0.01,
-                       eps=1e-3)
+      mean, var = _MovingStats(self, theta)
+      y = F.batch_norm(y, mean, var, theta.gamma, theta.beta, training=not self.do_eval,
+                       momentum=0.01, eps=1e-3)
     elif p.bias:
       y = y + theta.b.view(1, -1, 1, 1)
     return _ACTS[p.activation](y).permute(0, 2, 3, 1)

@@ -295,7 +295,14 @@ class RecordBatcher {
         producer_wait_us_ += std::chrono::duration_cast<std::chrono::microseconds>(
                                  std::chrono::steady_clock::now() - t0).count();
       }
-      if (stop_) break;
+      if (stop_) {
+        // `s` owns numpy arrays: they must be released under the GIL, not by this thread's
+        // stack unwinding.
+        l.unlock();
+        py::gil_scoped_acquire acq;
+        s.tensors.clear();
+        break;
+      }
       buckets_[bi].push_back(std::move(s));
       if (static_cast<int64_t>(buckets_[bi].size()) >= limits_[bi]) {
         ready_.push_back(std::move(buckets_[bi]));

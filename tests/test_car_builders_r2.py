@@ -107,7 +107,7 @@ def test_set_abstraction_and_pointconv():
 def test_pillars_backbone_runs_each_block_once_and_sparse_to_dense():
   pb = pillars.Builder.Params().Instantiate() if hasattr(
       pillars.Builder.Params(), 'Instantiate') else pillars.Builder()
-  bb = _Make(pb.Backbone(idims=8, dims=(64, 128, 256), repeats=(1, 1, 1), up_dims=16))
+  bb = _Make(pb.Backbone(idims=8, dims=(64, 128, 256), repeats=(2, 1, 1), up_dims=16))
   x = torch.randn(2, 16, 16, 8)
   y = bb.FPropDefaultTheta(x)
   assert y.shape == (2, 8, 8, 48)                        # 1/2 resolution, 3 · up_dims
