@@ -306,6 +306,88 @@ class AsrDecoder(AsrDecoderBase):
                       misc_states=misc)
     return state, packed
 
+  def BaseZeroState(self, theta, encoder_outputs, bs, misc_zero_states,
+                    per_step_source_padding=None):
+    """→ (rnn_states, atten_context, atten_probs, atten_states, packed_src): the RNN and
+    attention part of the initial step state (ref :464)."""
+    del per_step_source_padding
+    packed = self.atten_rnn.InitForSourcePacked(theta.atten_rnn, encoder_outputs.encoded,
+                                                encoder_outputs.padding)
+    self.contextualizer.InitAttention(theta.contextualizer, packed, misc_zero_states)
+    st = self.atten_rnn.zero_state(theta.atten_rnn, encoder_outputs.encoded, packed, bs)
+    ctx = self.contextualizer.ZeroAttention(theta.contextualizer, bs, misc_zero_states,
+                                            st.atten, packed)
+    rnn_states = [st.rnn] + [r.zero_state(theta.rnn[i], bs) for i, r in enumerate(self.rnn)]
+    return rnn_states, ctx, st.atten_probs, st.atten_state, packed
+
+  def InitDecoder(self, theta, encoder_outputs, dec_bs):
+    """Initial state for inference-style stepping, as the flat tuple (rnn_states,
+    atten_context, atten_probs, atten_states, fusion_states, misc_states, packed_src)
+    (ref :696)."""
+    sos = torch.full((dec_bs, 1), self.params.target_sos_id, dtype=torch.long,
+                     device=encoder_outputs.encoded.device)
+    st, packed = self.DecoderStepZeroState(theta, encoder_outputs, sos, dec_bs)
+    return (st.rnn_states, st.atten_context, st.atten_probs, st.atten_states,
+            st.fusion_states, st.misc_states, packed)
+
+  def CreateTargetInfoMisc(self, targets):
+    """The `misc` field of the per-step `TargetInfo` (ref :770): FST bias probabilities when
+    the targets carry them."""
+    if 'fst_bias_probs' in targets:
+      return NestedMap(fst_bias_probs=targets.fst_bias_probs)
+    return NestedMap()
+
+  def AddAdditionalDecoderSummaries(self, encoder_outputs, targets, seq_out_tas,
+                                    softmax_input):
+    """Hook for model-specific summaries (ref :493)."""
+
+  def _AddDecoderActivationsSummary(self, encoder_outputs, targets, atten_probs, rnn_outs,
+                                    softmax_input, additional_atten_probs=None,
+                                    target_alignments=None):
+    """Attention-matrix image + activation-norm scalars of one unrolled batch (ref :511);
+    `atten_probs` is `[T, B, S]`."""
+    del rnn_outs, additional_atten_probs, target_alignments
+    if not summary_utils._ShouldAddSummary():   # pylint: disable=protected-access
+      return
+    name = self.params.name or 'decoder'
+    summary_utils.AddAttentionSummary(name, [atten_probs.detach()],
+                                      encoder_outputs.padding, targets.paddings.t())
+    summary_utils.scalar('%s/softmax_input_rms' % name,
+                         softmax_input.detach().float().square().mean().sqrt())
+
+  def ComputePredictionsFunctional(self, theta, encoder_outputs, targets):
+    """The unrolling expressed as ONE step function scanned by `recurrent.Recurrent`
+    (ref :1066) — rematerialised backward over long targets instead of T live step graphs.
+    Teacher forcing only (`min_ground_truth_prob == 1`, no fusion feedback)."""
+    from lingvo_b200.core import recurrent  # pylint: disable=g-import-not-at-top
+    p = self.params
+    assert p.min_ground_truth_prob == 1.0
+    ids = targets.ids.t().long()
+    b = ids.shape[1]
+    if 'weights' not in targets:
+      targets.weights = 1.0 - targets.paddings
+    embs = self.dropout.FProp(theta.dropout, self.emb.EmbLookup(theta.emb, ids))
+    state0, packed = self.DecoderStepZeroState(theta, encoder_outputs, targets.ids, b)
+    misc = self.CreateTargetInfoMisc(targets)
+    inputs = NestedMap(id=ids, label=targets.labels.t().long(),
+                       weight=targets.weights.t().float(), emb=embs,
+                       padding=targets.paddings.t().float().unsqueeze(-1))
+    # the per-step output rides along as a state field so that `Recurrent` stacks it
+    state0.step_outs = embs.new_zeros(b, p.rnn_cell_dim + state0.atten_context.shape[-1])
+
+    def Step(th, state, inp):
+      info = AsrDecoderBase.TargetInfo(id=inp.id, label=inp.label, weight=inp.weight,
+                                       emb=inp.emb, padding=inp.padding, misc=misc)
+      carried = NestedMap({k: v for k, v in state.items() if k != 'step_outs'})
+      step_out, new_state = self.SingleDecodeStep(th, packed, info, carried)
+      new_state.step_outs = step_out
+      return new_state, NestedMap()
+
+    acc, _ = recurrent.Recurrent(theta, state0, inputs, Step)
+    sm_in = acc.step_outs if p.softmax_uses_attention else acc.step_outs[..., :p.rnn_cell_dim]
+    return NestedMap(softmax_input=self.dropout.FProp(theta.dropout, sm_in),
+                     attention=NestedMap(probs=acc.atten_probs))
+
   def _Adapt(self, theta, i, x, misc):
     p = self.params
     if not p.adapter_task_id_field:

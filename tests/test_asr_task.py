@@ -335,3 +335,29 @@ def test_asr_decoder_shallow_fusion_and_adapters():
   pb = ad.ComputePredictions(ad.theta, enc3, tgt)
   assert not torch.allclose(pa.logits[0], pb.logits[0])      # utterance 0 changed task
   torch.testing.assert_close(pa.logits[1:], pb.logits[1:])   # the others did not
+
+
+def test_asr_decoder_functional_unrolling_and_init_helpers():
+  dec = _Decoder()
+  enc, tgt = _DecInputs()
+  seq = dec.ComputePredictions(dec.theta, enc, tgt)
+  fun = dec.ComputePredictionsFunctional(dec.theta, enc, tgt)
+  torch.testing.assert_close(fun.softmax_input, seq.softmax_input, atol=1e-5, rtol=1e-5)
+  torch.testing.assert_close(fun.attention.probs, seq.attention.probs, atol=1e-5, rtol=1e-5)
+  # gradients flow through the scanned step function
+  m, _ = dec.ComputeLoss(dec.theta, fun, tgt)
+  m['loss'][0].backward()
+  assert all(v.grad is not None for v in dec.vars.Flatten() if v.requires_grad)
+  # flat init tuple = fields of the step zero state
+  rnn, ctx, probs, atten, fusion, misc, packed = dec.InitDecoder(dec.theta, enc, 3)
+  state, _ = dec.DecoderStepZeroState(dec.theta, enc,
+                                      torch.full((3, 1), dec.params.target_sos_id), 3)
+  torch.testing.assert_close(ctx, state.atten_context)
+  assert len(rnn) == 2 and probs.shape == (3, 7) and packed is not None
+  assert isinstance(misc, NestedMap) and fusion is not None and atten is not None
+  base = dec.BaseZeroState(dec.theta, enc, 3, misc)
+  torch.testing.assert_close(base[1], ctx)
+  assert dec.CreateTargetInfoMisc(tgt) == NestedMap()
+  tgt.fst_bias_probs = torch.zeros(3, 5)
+  assert 'fst_bias_probs' in dec.CreateTargetInfoMisc(tgt)
+  dec.AddAdditionalDecoderSummaries(enc, tgt, None, seq.softmax_input)
