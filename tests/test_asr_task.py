@@ -361,3 +361,73 @@ def test_asr_decoder_functional_unrolling_and_init_helpers():
   tgt.fst_bias_probs = torch.zeros(3, 5)
   assert 'fst_bias_probs' in dec.CreateTargetInfoMisc(tgt)
   dec.AddAdditionalDecoderSummaries(enc, tgt, None, seq.softmax_input)
+
+
+def _Encoder(**kw):
+  from lingvo_b200.models.asr import encoder as asr_encoder
+  p = asr_encoder.AsrEncoder.Params().Set(
+      name='enc', input_shape=[None, None, 12, 1], conv_filter_shapes=[(3, 3, 1, 4), (3, 3, 4, 4)],
+      lstm_cell_size=8, num_lstm_layers=3, pad_steps=2, random_seed=11, **kw)
+  enc = p.Instantiate()
+  enc.InstantiateVariables()
+  return enc
+
+
+def _EncBatch(b=2, t=20):
+  g = torch.Generator().manual_seed(0)
+  pad = torch.zeros(b, t)
+  pad[1, 14:] = 1
+  return NestedMap(src_inputs=torch.randn(b, t, 12, 1, generator=g), paddings=pad)
+
+
+def test_asr_encoder_layout_options():
+  base = _Encoder()
+  out = base.FProp(base.theta, _EncBatch())
+  # 22 frames (20 + pad_steps) → stride 4 → 6; frequency 12 → 3, ·4 channels = 12 → padded 16
+  assert out.encoded.shape == (6, 2, 16) and out.padding.shape == (6, 2)
+  assert base._first_lstm_input_dim == 16 and base._first_lstm_input_dim_pad == 4
+  assert base.FirstLstmLayerInputDimAndPadding([None, None, 4, 8]) == (32, 0)
+  assert out.state == NestedMap() and not base.supports_streaming
+  assert float(out.encoded[out.padding > 0].abs().max()) == 0.0       # padded frames zeroed
+  assert len(base.proj) == 2 and base.output_dim == 16
+  # per-layer outputs
+  ex = _Encoder(extra_per_layer_outputs=True)
+  o = ex.FProp(ex.theta, _EncBatch())
+  assert o.conv_0.encoded.shape == (11, 2, 6, 4) and o.conv_1.encoded.shape == (6, 2, 3, 4)
+  assert [o['rnn_%d' % i].encoded.shape for i in range(3)] == [(6, 2, 16)] * 3
+  torch.testing.assert_close(o.rnn_2.encoded, o.encoded)
+  # projection after the last layer too
+  assert len(_Encoder(project_after_last_lstm=True).proj) == 3
+
+
+def test_asr_encoder_residuals_highway_and_stacking():
+  res = _Encoder(residual_start=2, residual_stride=1)
+  out = res.FProp(res.theta, _EncBatch())
+  assert out.encoded.shape == (6, 2, 16)
+  hw = _Encoder(residual_start=2, highway_skip=True)
+  assert len(hw.highway_skip) == 2
+  assert hw.FProp(hw.theta, _EncBatch()).encoded.shape == (6, 2, 16)
+  # the residual changes the function (same seed → same weights otherwise)
+  plain = _Encoder()
+  assert (plain.FProp(plain.theta, _EncBatch()).encoded - out.encoded).abs().max() > 1e-4
+  from lingvo_b200.core import layers
+  st = _Encoder(layer_index_before_stacking=1,
+                stacking_layer_tpl=layers.StackingOverTime.Params().Set(
+                    left_context=1, right_context=0, stride=2))
+  o = st.FProp(st.theta, _EncBatch())
+  assert o.encoded.shape == (3, 2, 16) and o.padding.shape == (3, 2)   # time halved after L1
+  assert st.rnn[2].params.fwd.num_input_nodes == 32                     # 2 stacked frames
+
+
+def test_asr_encoder_conv_lstm_blocks_and_final_proj():
+  from lingvo_b200.core import layers
+  enc = _Encoder(num_conv_lstm_layers=1, extra_per_layer_outputs=True,
+                 final_proj=layers.ProjectionLayer.Params().Set(
+                     name='final', output_dim=5, activation='NONE'))
+  assert len(enc.conv_lstm_rnn) == 1
+  assert tuple(enc.conv_lstm_cnn[0].params.filter_shape) == (3, 3, 8, 4)
+  out = enc.FProp(enc.theta, _EncBatch())
+  assert out.conv_lstm_0.encoded.shape == (6, 2, 3, 4)
+  assert out.encoded.shape == (6, 2, 5) and enc.output_dim == 5
+  out.encoded.sum().backward()
+  assert all(v.grad is not None for v in enc.vars.Flatten() if v.requires_grad)
