@@ -431,3 +431,51 @@ def test_asr_encoder_conv_lstm_blocks_and_final_proj():
   assert out.encoded.shape == (6, 2, 5) and enc.output_dim == 5
   out.encoded.sum().backward()
   assert all(v.grad is not None for v in enc.vars.Flatten() if v.requires_grad)
+
+
+def test_asr_model_inference_from_wav_and_hooks(asr_records):
+  import io
+  import wave
+  inp = input_generator.AsrInput.Params().Set(
+      name='inp', file_pattern=asr_records, frame_size=80, bucket_upper_bound=[40],
+      bucket_batch_limit=[4], file_buffer_size=8, file_parallelism=1, num_batcher_threads=1,
+      target_max_length=16)
+  inp.tokenizer = tokenizers.AsciiTokenizer.Params()
+  p = asr_model.AsrModel.Params().Set(name='asr', input=inp)
+  ep = p.encoder
+  ep.Set(input_shape=[None, None, 80, 1], conv_filter_shapes=[(3, 3, 1, 2)],
+         conv_filter_strides=[(2, 2)], num_cnn_layers=1, lstm_cell_size=8, num_lstm_layers=1,
+         pad_steps=0)
+  dp = p.decoder
+  dp.Set(source_dim=16, emb_dim=4, rnn_cell_dim=8, rnn_layers=2, target_seq_len=5)
+  dp.emb.vocab_size = 76
+  dp.emb.max_num_shards = 1
+  dp.attention.hidden_dim = 8
+  dp.softmax.num_classes = 76
+  dp.beam_search.num_hyps_per_beam = 2
+  task = p.Instantiate()
+  assert type(task.decoder_metrics).__name__ == 'DecoderMetrics'
+  assert task.decoder_metrics.params.include_auxiliary_metrics
+  # 0.3 s of a 440 Hz tone as a 16-bit mono WAV
+  t = np.arange(int(0.3 * 16000)) / 16000.0
+  pcm = (0.3 * 32767 * np.sin(2 * np.pi * 440 * t)).astype(np.int16)
+  buf = io.BytesIO()
+  with wave.open(buf, 'wb') as w:
+    w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+    w.writeframes(pcm.tobytes())
+  out = task.Inference()['default'](buf.getvalue())
+  assert len(out.hypotheses) == 1 and len(out.hypotheses[0]) == 2
+  assert all(isinstance(h, str) for h in out.hypotheses[0])
+  assert out.scores.reshape(-1).shape[0] == 2
+  assert out.src_frames.shape[2:] == (80, 1)
+  assert out.encoder_frames.shape[1:] == (1, 16)
+  # hooks
+  batch = NestedMap(tgt=NestedMap(ids=torch.zeros(1, 2)), src=None)
+  assert task._GetDecoderTargets(batch) is batch.tgt
+  dt = task._MakeDecoderTheta(task.theta, batch)
+  dt.extra = 1
+  assert 'extra' not in task.theta.decoder
+  ps = task.ProgramSchedule()
+  assert ps.train_executions_per_eval == 0 and ps.train_program.steps_per_loop == 1000
+  with pytest.raises(ValueError):
+    asr_model.AsrModel.Params().Set(name='').Instantiate()
