@@ -97,9 +97,17 @@ class _Slot:
   name: str
   value: Any
   doc: str
+  default: Any = None
 
   def Clone(self) -> '_Slot':
-    return _Slot(self.name, _CloneValue(self.value), self.doc)
+    return _Slot(self.name, _CloneValue(self.value), self.doc, self.default)
+
+  def GetDefault(self):
+    """The value the parameter was defined with (ref :193)."""
+    return self.default
+
+  def ToString(self, nested_depth: int) -> str:
+    return self.Render(nested_depth)
 
   def Render(self, depth: int) -> str:
     def _r(v):
@@ -232,7 +240,16 @@ class Params:
         'Invalid param name: %r' % name)
     if name in self._slots:
       raise AttributeError('Parameter %s is already defined' % name)
-    self._slots[name] = _Slot(name, default_value, description)
+    self._slots[name] = _Slot(name, default_value, description, default_value)
+
+  def ParamIsSet(self, key: str) -> bool:
+    """True if the (possibly nested, dotted) parameter has a non-None value; raises
+    AttributeError if it does not exist (ref :478)."""
+    return self.Get(key) is not None
+
+  def MergeCommonKeysFrom(self, other: 'Params') -> 'Params':
+    """Copies the value of every key both params define (ref :368)."""
+    return CopyFieldsTo(other, self, ignore_unknown_keys=True)
 
   def Freeze(self) -> None:
     object.__setattr__(self, '_immutable', True)
@@ -625,12 +642,13 @@ class InstantiableParams(Params):
 
 
 def CopyFieldsTo(from_p: Params, to_p: Params,
-                 skip: Optional[List[str]] = None) -> Params:
-  """Copies fields from `from_p` to `to_p` (reference :197)."""
-  skip = list(skip or [])
+                 skip: Optional[List[str]] = None, ignore_unknown_keys: bool = False) -> Params:
+  """Copies fields from `from_p` to `to_p` (reference :197). `ignore_unknown_keys`: only the
+  keys both define are copied; otherwise an unknown key is an error."""
+  skip = [skip] if isinstance(skip, str) else list(skip or [])
   skip.append('cls')
   for n, p in from_p.IterParams():
-    if n in skip:
+    if n in skip or (ignore_unknown_keys and n not in to_p):
       continue
     if isinstance(p, Params):
       to_p.Set(**{n: p.Copy()})

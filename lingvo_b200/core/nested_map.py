@@ -118,6 +118,41 @@ class NestedMap(dict):
         cur = cur[i]
     return cur
 
+  @staticmethod
+  def SquareBracketIndex(key: str):
+    """`k[3]` → ('k', 3); a plain key → (key, None) (ref :206)."""
+    m = re.fullmatch(r'([A-Za-z_][A-Za-z0-9_]*)\[(\d+)\]', key)
+    return (m.group(1), int(m.group(2))) if m else (key, None)
+
+  @staticmethod
+  def FromNestedDataclass(x):
+    """A (nested) dataclass instance → NestedMap (ref :173)."""
+    import dataclasses  # pylint: disable=g-import-not-at-top
+    if not dataclasses.is_dataclass(x):
+      raise ValueError('%s must be a dataclass. Got %s.' % (x, type(x)))
+    return NestedMap.FromNestedDict(dataclasses.asdict(x))
+
+  def GetSlice(self, keys):
+    """Copy holding only the (possibly nested, `a.b[2].c`-style) `keys` (ref :259)."""
+    sliced = NestedMap()
+    for k in keys:
+      sliced.Set(k, self.GetItem(k))
+    return sliced
+
+  def Keys(self) -> List[str]:
+    """All leaf keys in nested / array form, in `Flatten` order (ref :276)."""
+    return [k for k, _ in self.FlattenItems()]
+
+  def Update(self, other):
+    """dict.update for nested keys: adds / replaces every leaf of `other` (ref :360)."""
+    for k, v in other.FlattenItems():
+      self.Set(k, v)
+    return self
+
+  def Union(self, other):
+    """A new map with the leaves of self, overridden / extended by `other` (ref :366)."""
+    return NestedMap().Update(self).Update(other)
+
   def Get(self, key: str, default=None):
     try:
       return self.GetItem(key)

@@ -279,3 +279,47 @@ def test_standalone_adafactor_optimizer_matches_layer():
   # the 2-D variable is factored: row / column accumulators, no full second moment
   kinds = {k for slots in opt.slots().values() for k in slots}
   assert {'vr', 'vc', 'v'} <= kinds
+
+
+def test_nested_map_and_params_small_methods():
+  import dataclasses
+  m = NestedMap(a=1, b=NestedMap(c=[NestedMap(d=5), 7]))
+  assert m.Keys() == ['a', 'b.c[0].d', 'b.c[1]']
+  assert m.GetSlice(['a', 'b.c[0].d']) == NestedMap(a=1, b=NestedMap(c=[NestedMap(d=5)]))
+  u = NestedMap(a=1, x=NestedMap(y=2)).Union(NestedMap(a=9, x=NestedMap(z=3)))
+  assert u == NestedMap(a=9, x=NestedMap(y=2, z=3))
+  base = NestedMap(a=1)
+  assert base.Update(NestedMap(b=NestedMap(c=2))) is base and base.b.c == 2
+  assert NestedMap.SquareBracketIndex('k[12]') == ('k', 12)
+  assert NestedMap.SquareBracketIndex('k') == ('k', None)
+
+  @dataclasses.dataclass
+  class Inner:
+    v: int = 3
+
+  @dataclasses.dataclass
+  class Outer:
+    name: str = 'n'
+    inner: Inner = dataclasses.field(default_factory=Inner)
+
+  nm = NestedMap.FromNestedDataclass(Outer())
+  assert nm.name == 'n' and nm.inner.v == 3 and isinstance(nm.inner, NestedMap)
+  with pytest.raises(ValueError):
+    NestedMap.FromNestedDataclass({'a': 1})
+
+  p = hyperparams.Params()
+  p.Define('x', 5, 'x'); p.Define('y', None, 'y'); p.Define('sub', hyperparams.Params(), '')
+  p.sub.Define('z', 0, '')
+  p.x = 6
+  assert p.ParamIsSet('x') and not p.ParamIsSet('y') and p.ParamIsSet('sub.z')
+  with pytest.raises(AttributeError):
+    p.ParamIsSet('nope')
+  assert p._slots['x'].GetDefault() == 5 and p.Copy()._slots['x'].GetDefault() == 5
+  assert p._slots['x'].ToString(1) == '  x: 6'
+  q = hyperparams.Params()
+  q.Define('x', 0, ''); q.Define('other', 1, '')
+  q.MergeCommonKeysFrom(p)
+  assert q.x == 6 and q.other == 1
+  with pytest.raises(AttributeError):
+    hyperparams.CopyFieldsTo(p, q)                       # unknown keys are an error by default
+  assert hyperparams.CopyFieldsTo(p, q, skip='y', ignore_unknown_keys=True).x == 6
