@@ -117,6 +117,15 @@ class _BuilderLayer(base_layer.BaseLayer):
         tp_layers.MarkSharded(self._private_vars[n], self._tp, dim, logical)
 
 
+def _CommonFrom(parent_params, p, name):
+  """Child params inheriting the builder handle and dtypes of `parent_params`."""
+  p.name = name
+  p.b = parent_params.b
+  p.dtype = parent_params.dtype
+  p.fprop_dtype = parent_params.fprop_dtype
+  return p
+
+
 class RmsNormLayer(_BuilderLayer):
   """Bias-less RMS "layer norm" `x·rsqrt(mean(x²)+eps)·scale` (:1833-1854)."""
 
@@ -278,6 +287,9 @@ class SelfAttentionLayer(_BuilderLayer):
     p = super().Params()
     p.Define('decoder', True, 'Causal (decoder) masking.')
     p.Define('relative_bias', False, 'Use T5 relative attention bias.')
+    p.Define('multi_dconv_head', False,
+             'Primer multi-dconv-head attention (ref :1349): a 3-tap causal depthwise '
+             'convolution over time on each of q, k, v after the projections.')
     return p
 
   def __init__(self, params):
@@ -292,6 +304,15 @@ class SelfAttentionLayer(_BuilderLayer):
       assert h % self._tp.tp_size == 0 and hk % self._tp.tp_size == 0, (
           'tensor parallelism needs heads (%d, kv %d) divisible by tp_size %d' %
           (h, hk, self._tp.tp_size))
+
+    if self.params.multi_dconv_head:
+      assert self._tp is None, 'multi-dconv-head attention is not tensor-parallel yet'
+      hh, hk2, dd = b.attention_num_heads, (b.attention_num_memory_heads or
+                                            b.attention_num_heads), b.attention_key_value_dim
+      for nm, heads in (('q_dconv', hh), ('k_dconv', hk2), ('v_dconv', hk2)):
+        self.CreateChild(nm, _CommonFrom(
+            self.params, DepthwiseConvAutoregressiveLayer.Params().Set(
+                kernel_size=3, model_dims=[heads, dd]), nm))
 
   def _LocalHeads(self):
     b = self.bp
@@ -451,7 +472,12 @@ class SelfAttentionLayer(_BuilderLayer):
     q = q.reshape(bsz, l, h, d)
     k = k.reshape(bsz, l, hk, d)
     v = v.reshape(bsz, l, hk, d)
-    if b.use_rotary_position_emb:
+    if self.params.multi_dconv_head:
+      live = (segment_id != 0).to(q.dtype).reshape(bsz, l, 1, 1)
+      q = self.q_dconv.FProp(theta.q_dconv, q * live, segment_pos)
+      k = self.k_dconv.FProp(theta.k_dconv, k * live, segment_pos)
+      v = self.v_dconv.FProp(theta.v_dconv, v * live, segment_pos)
+    if b.use_rotary_position_emb or (self.params.multi_dconv_head and b.mdha_rope):
       q = _Rope(q, segment_pos, b.rope_emb_max_timescale)
       k = _Rope(k, segment_pos, b.rope_emb_max_timescale)
     if _ContextParallel(b):
@@ -496,8 +522,13 @@ def _SelfAttentionInitCache(layer, batch, max_len, device, dtype):
   b = layer.bp
   _, hk = layer._LocalHeads()   # pylint: disable=protected-access
   d = b.attention_key_value_dim
-  return NestedMap(k=torch.zeros(batch, max_len, hk, d, device=device, dtype=dtype),
-                   v=torch.zeros(batch, max_len, hk, d, device=device, dtype=dtype))
+  cache = NestedMap(k=torch.zeros(batch, max_len, hk, d, device=device, dtype=dtype),
+                    v=torch.zeros(batch, max_len, hk, d, device=device, dtype=dtype))
+  if layer.params.multi_dconv_head:
+    cache.q_conv = layer.q_dconv.InitState(batch, device, dtype)
+    cache.k_conv = layer.k_dconv.InitState(batch, device, dtype)
+    cache.v_conv = layer.v_dconv.InitState(batch, device, dtype)
+  return cache
 
 
 def _SelfAttentionExtendStep(layer, theta, x, cache, t):
@@ -512,10 +543,14 @@ def _SelfAttentionExtendStep(layer, theta, x, cache, t):
   q = torch.matmul(x, theta.wq.to(xd)).reshape(bsz, 1, h, d)
   k = torch.matmul(x, theta.wk.to(xd)).reshape(bsz, 1, hk, d)
   v = torch.matmul(x, theta.wv.to(xd)).reshape(bsz, 1, hk, d)
+  if layer.params.multi_dconv_head:
+    q, cache.q_conv = layer.q_dconv.ExtendStep(theta.q_dconv, q, cache.q_conv)
+    k, cache.k_conv = layer.k_dconv.ExtendStep(theta.k_dconv, k, cache.k_conv)
+    v, cache.v_conv = layer.v_dconv.ExtendStep(theta.v_dconv, v, cache.v_conv)
   tmax = cache.k.shape[1]
   dev = x.device
   tt = torch.as_tensor(t, device=dev).reshape(())
-  if b.use_rotary_position_emb:
+  if b.use_rotary_position_emb or (layer.params.multi_dconv_head and b.mdha_rope):
     pos = tt.reshape(1, 1).expand(bsz, 1)
     q, k = _Rope(q, pos, b.rope_emb_max_timescale), _Rope(k, pos, b.rope_emb_max_timescale)
   onehot = (torch.arange(tmax, device=dev) == tt).to(xd).reshape(1, tmax, 1, 1)
@@ -587,6 +622,180 @@ def _AttentionCore(q, k, v, bias, logit_cap=0.0, extra_logit=None,
   if dropout_prob:
     probs = F.dropout(probs, dropout_prob, training=True)
   return torch.einsum('BHLM,BMHD->BLHD', probs, v)
+
+
+class DepthwiseConvAutoregressiveLayer(_BuilderLayer):
+  """Causal depthwise convolution over time (ref :1749; Primer / MTF
+  `sublayer_depthwise_conv_autoregressive`): `Y[:, t] = Σ_k W[k] ⊙ X[:, t − k]` with one
+  weight vector per tap (`w_k/scale`, init 0.5 for k = 0 and 0.5/K otherwise). The input may
+  carry several model dims (`[B, L, H, D]` for per-head convolutions). Positions do not
+  look across packed-segment boundaries when `segment_pos` is given (a tap that would reach
+  before position 0 of the segment reads zero)."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('kernel_size', 3, 'Number of taps K.')
+    p.Define('model_dims', None, 'Trailing dims of the input (default [model_dim]).')
+    return p
+
+  def _Dims(self):
+    return list(self.params.model_dims or [self.bp.model_dim])
+
+  def _CreateLayerVariables(self):
+    p = self.params
+    for k in range(p.kernel_size):
+      self.CreateVariable('w_%d' % k, WeightParams(
+          self._Dims(), WeightInit.Constant(0.5 if k == 0 else 0.5 / p.kernel_size),
+          p.dtype))
+
+  def FProp(self, theta, x, segment_pos=None):
+    p = self.params
+    out = x * theta.w_0.to(x.dtype)
+    shifted = x
+    for k in range(1, p.kernel_size):
+      shifted = torch.cat([torch.zeros_like(shifted[:, :1]), shifted[:, :-1]], 1)
+      term = shifted * theta['w_%d' % k].to(x.dtype)
+      if segment_pos is not None:
+        ok = (segment_pos >= k).to(x.dtype)
+        term = term * ok.reshape(list(ok.shape) + [1] * (x.dim() - 2))
+      out = out + term
+    return out
+
+  def InitState(self, batch, device, dtype):
+    """The K−1 previous inputs, newest last (incremental decoding)."""
+    return torch.zeros([batch, self.params.kernel_size - 1] + self._Dims(), device=device,
+                       dtype=dtype)
+
+  def ExtendStep(self, theta, x, state):
+    """x `[B, 1, …]` → (y `[B, 1, …]`, new state)."""
+    p = self.params
+    out = x * theta.w_0.to(x.dtype)
+    for k in range(1, p.kernel_size):
+      out = out + state[:, -k:state.shape[1] - k + 1 or None][:, :1] * theta['w_%d' % k].to(
+          x.dtype)
+    new_state = torch.cat([state[:, 1:], x.to(state.dtype)], 1) if p.kernel_size > 1 else state
+    return out, new_state
+
+
+class AttentionCoreLayer(_BuilderLayer):
+  """`softmax(q·kᵀ + bias)·v` for already projected `BLHD` / `BMHD` tensors (ref :1081
+  `Attention`): fp32 logits, optional tanh cap, extra logit and attention dropout."""
+
+  def FProp(self, theta, q, k, v, bias):
+    b = self.bp
+    while bias.dim() < 4:
+      bias = bias.unsqueeze(1)                       # BLM → B1LM
+    return _AttentionCore(q, k, v, bias.float(), b.atten_logit_cap, b.attention_extra_logit,
+                          b.attention_dropout_prob if not self.do_eval else 0.0)
+
+
+class CrossAttentionLayer(_BuilderLayer):
+  """Decoder → encoder attention (ref :1206 `DecEncAttention`): queries from the decoder
+  stream, keys / values from `encoder_output`; a query sees the encoder positions of its own
+  packed segment only (`_EncNotVisible`, ref :1171)."""
+
+  needs_encoder = True
+
+  def _CreateLayerVariables(self):
+    b = self.bp
+    h, d, m = b.attention_num_heads, b.attention_key_value_dim, b.model_dim
+    hk = b.attention_num_memory_heads or h
+    dt = self.params.dtype
+    self.CreateVariable('wq', WeightParams([m, h * d], WeightInit.Gaussian((m * d)**-0.5), dt))
+    self.CreateVariable('wk', WeightParams([m, hk * d], WeightInit.Gaussian(m**-0.5), dt))
+    self.CreateVariable('wv', WeightParams([m, hk * d], WeightInit.Gaussian(m**-0.5), dt))
+    self.CreateVariable('wo', WeightParams([h * d, m], WeightInit.Gaussian((h * d)**-0.5), dt))
+
+  def ProjectEncoder(self, theta, encoder_output):
+    """K / V of the encoder output — computed once per sequence when decoding."""
+    b = self.bp
+    bsz, s, _ = encoder_output.shape
+    hk = b.attention_num_memory_heads or b.attention_num_heads
+    d = b.attention_key_value_dim
+    xd = encoder_output.dtype
+    k = torch.matmul(encoder_output, theta.wk.to(xd)).reshape(bsz, s, hk, d)
+    v = torch.matmul(encoder_output, theta.wv.to(xd)).reshape(bsz, s, hk, d)
+    return k, v
+
+  def FProp(self, theta, x, segment_id, segment_pos, encoder_output=None,
+            encoder_segment_id=None, kv=None):
+    del segment_pos
+    b = self.bp
+    bsz, l, _ = x.shape
+    h, d = b.attention_num_heads, b.attention_key_value_dim
+    q = torch.matmul(x, theta.wq.to(x.dtype)).reshape(bsz, l, h, d)
+    k, v = kv if kv is not None else self.ProjectEncoder(theta, encoder_output)
+    a, c = segment_id.unsqueeze(-1), encoder_segment_id.unsqueeze(-2)
+    not_visible = ((a == 0) & (c == 0)) | (a != c)
+    bias = (not_visible.float() * -1e9).unsqueeze(1)                     # [B, 1, L, S]
+    o = _AttentionCore(q, k, v, bias, b.atten_logit_cap, b.attention_extra_logit,
+                       b.attention_dropout_prob if not self.do_eval else 0.0)
+    out = torch.matmul(o.reshape(bsz, l, h * d), theta.wo.to(x.dtype))
+    return out, torch.zeros((), device=x.device, dtype=torch.float32)
+
+
+class ParallelAttentionFFNLayer(_BuilderLayer):
+  """Attention and feed-forward applied to the SAME normalised input and summed (ref :2619
+  `ParallelDecSelfAttentionRelativeBiasFFN`; the PaLM / GPT-J block): one norm, two
+  branches, one residual add — the two branches' GEMMs are independent."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('atten', None, 'Self-attention layer params.')
+    p.Define('ffn', None, 'Feed-forward layer params.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self.CreateChild('atten', self.params.atten)
+    self.CreateChild('ffn', self.params.ffn)
+
+  def FProp(self, theta, x, segment_id, segment_pos):
+    a, aux_a = self.atten.FProp(theta.atten, x, segment_id, segment_pos)
+    f, aux_f = self.ffn.FProp(theta.ffn, x, segment_id, segment_pos)
+    return a + f, aux_a + aux_f
+
+
+class SmoothedSoftmaxLayer(_BuilderLayer):
+  """Output softmax with its own `[M, V]` weight and label-smoothed cross entropy
+  (ref :2258 `SmoothedSoftmax`): FProp(vec `[B, L, M]`, label ids, weights) →
+  NestedMap(logits, per_token_loss, loss); z-loss is added by the task."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('vocab_dim', 0, 'Vocabulary size V.')
+    p.Define('label_smoothing', None, 'Overrides the builder value.')
+    return p
+
+  def _CreateLayerVariables(self):
+    p = self.params
+    m = self.bp.model_dim
+    self.CreateVariable('w', WeightParams([m, p.vocab_dim], WeightInit.Gaussian(m**-0.5),
+                                          p.dtype))
+
+  def Logits(self, theta, vec):
+    return torch.matmul(vec, theta.w.to(vec.dtype))
+
+  def FProp(self, theta, vec, label_ids, label_weights=None):
+    p = self.params
+    ls = self.bp.label_smoothing if p.label_smoothing is None else p.label_smoothing
+    logits = self.Logits(theta, vec).float()
+    logp = torch.log_softmax(logits, -1)
+    nll = -logp.gather(-1, label_ids.long().unsqueeze(-1)).squeeze(-1)
+    if ls:
+      # off value ls/(V−1), on value 1−ls (the reference's smoothing)
+      off = ls / (p.vocab_dim - 1)
+      per_token = (1.0 - ls - off) * nll + off * (-logp.sum(-1))
+    else:
+      per_token = nll
+    if label_weights is None:
+      label_weights = torch.ones_like(per_token)
+    w = label_weights.float()
+    return NestedMap(logits=logits, per_token_loss=per_token,
+                     loss=(per_token * w).sum() / w.sum().clamp_min(1e-8))
 
 
 class DenseReluDenseLayer(_BuilderLayer):
@@ -834,6 +1043,7 @@ class DecoderBlock(_BuilderLayer):
     p.Define('norm', None, 'Norm layer params.')
     p.Define('norm_policy', 'pre', 'pre|primer|primer_hybrid.')
     p.Define('post_norm', None, 'Post-norm params for primer_hybrid.')
+    p.Define('residual_weight', 1.0, 'x + residual_weight · f(norm(x)) (ref :488).')
     return p
 
   def __init__(self, params):
@@ -860,6 +1070,7 @@ class DecoderBlock(_BuilderLayer):
     else:
       x = x_in
     fuse_res = (getattr(self.layer, 'supports_fused_residual', False) and
+                p.residual_weight == 1.0 and
                 i.get('expert_id') is None and p.post_norm is None and not (b.dropout_rate and not self.do_eval))
     if fuse_res:
       # x_in + f(x) comes out of the sub-layer's last GEMM epilogue.
@@ -868,7 +1079,11 @@ class DecoderBlock(_BuilderLayer):
       o.vec = y
       o.aux_loss = i.aux_loss + aux
       return o
-    if i.get('expert_id') is not None and isinstance(self.layer, MoELayer):
+    if getattr(self.layer, 'needs_encoder', False):
+      y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos,
+                                encoder_output=i.encoder_output,
+                                encoder_segment_id=i.encoder_segment_id)
+    elif i.get('expert_id') is not None and isinstance(self.layer, MoELayer):
       y, aux = self.layer.FProp(theta.layer, x, i.segment_id, i.segment_pos,
                                 expert_id=i.expert_id)
     else:
@@ -878,7 +1093,7 @@ class DecoderBlock(_BuilderLayer):
     if b.dropout_rate and not self.do_eval:
       y = F.dropout(y, b.dropout_rate, training=True)
     o = i.copy()
-    o.vec = x_res + y
+    o.vec = x_res + (y if p.residual_weight == 1.0 else y * p.residual_weight)
     o.aux_loss = i.aux_loss + aux
     return o
 
@@ -892,7 +1107,19 @@ class LayerStack(_BuilderLayer):
     return [(_SelfAttentionInitCache(blk.layer, batch, max_len, device, dtype)
              if isinstance(blk.layer, SelfAttentionLayer) else None) for blk in self.layers]
 
-  def ExtendStep(self, theta, vec, state, t):
+  def InitEncoderState(self, theta, encoder_output, encoder_segment_id=None):
+    """Per cross-attention block the encoder keys / values (computed once per sequence);
+    pass the result as `ExtendStep(..., encoder_state=…)`."""
+    if encoder_segment_id is None:
+      encoder_segment_id = torch.ones(encoder_output.shape[:2], dtype=torch.long,
+                                      device=encoder_output.device)
+    kvs = {}
+    for idx, blk in enumerate(self.layers):
+      if getattr(blk.layer, 'needs_encoder', False):
+        kvs[idx] = blk.layer.ProjectEncoder(theta.layers[idx].layer, encoder_output)
+    return NestedMap(kv=kvs, segment_id=encoder_segment_id)
+
+  def ExtendStep(self, theta, vec, state, t, encoder_state=None):
     """vec `[B,1,M]` at position t → `[B,1,M]`; `state` from `InitDecodeState`."""
     bsz = vec.shape[0]
     seg = torch.ones(bsz, 1, dtype=torch.long, device=vec.device)
@@ -903,8 +1130,14 @@ class LayerStack(_BuilderLayer):
       y = blk.ln.FProp(th.ln, x)
       if state[idx] is not None:
         y = _SelfAttentionExtendStep(blk.layer, th.layer, y, state[idx], t)
+      elif getattr(blk.layer, 'needs_encoder', False):
+        assert encoder_state is not None, 'cross-attention needs InitEncoderState()'
+        y, _ = blk.layer.FProp(th.layer, y, seg, pos, kv=encoder_state.kv[idx],
+                               encoder_segment_id=encoder_state.segment_id)
       else:
         y, _ = blk.layer.FProp(th.layer, y, seg, pos)
+      if blk.params.residual_weight != 1.0:
+        y = y * blk.params.residual_weight
       if blk.params.post_norm is not None:
         y = blk.post_ln.FProp(th.post_ln, y)
       x = x + y
@@ -1126,6 +1359,58 @@ class MoEBuilder(builder.Base):
 
   SharedEmbSoftmax = Embedding
 
+  def SoftmaxWeight(self, name, vocab_dim):
+    """A stand-alone `[M, V]` softmax weight (ref :468) as a logits layer."""
+    return self._Common(SmoothedSoftmaxLayer.Params().Set(vocab_dim=vocab_dim,
+                                                          label_smoothing=0.0), name)
+
+  def SmoothedSoftmax(self, name, vocab_dim, label_smoothing=None):
+    """Untied output softmax + label-smoothed cross entropy (ref :2258)."""
+    return self._Common(SmoothedSoftmaxLayer.Params().Set(
+        vocab_dim=vocab_dim, label_smoothing=label_smoothing), name)
+
+  def Mask(self):
+    """(vec, segment_id) → vec with padded positions (segment_id == 0) zeroed (ref :478)."""
+    return self._Fn('mask', lambda x, segment_id: x * (segment_id != 0).unsqueeze(-1).to(
+        x.dtype))
+
+  def Split(self, name):
+    """Batch-dim sharding annotation of the data-parallel axis (ref :1956): one process per
+    GPU already holds its own batch shard, so this is the identity layer."""
+    return self._Identity(name)
+
+  def LN(self, name):
+    return self._LN(name)
+
+  def PN(self, name):
+    return self._PN(name)
+
+  def Repeat(self, name, body, repeat=1, per_layer_vars=True, start_layer_id=0):
+    """`body` applied `repeat` times (ref :710): stacked variables + loop, or — with
+    `per_layer_vars` — `repeat` independently named copies (checkpoint compatible with an
+    unrolled stack)."""
+    del start_layer_id
+    from lingvo_b200.core import builder_layers   # pylint: disable=g-import-not-at-top
+    return builder_layers.RepeatLayer.Params().Set(name=name, body=body, repeat=repeat,
+                                                   per_layer_vars=per_layer_vars)
+
+  def ShardablePipeline(self, name, body, stages, num_micro_batches=1):
+    """`stages` copies of `body` run as a layer-wise shardable (shifting-buffer) pipeline
+    over micro-batches (ref :720)."""
+    from lingvo_b200.core import gshard_layers   # pylint: disable=g-import-not-at-top
+    return gshard_layers.LayerwiseShardablePipelinedLayer.Params().Set(
+        name=name, num_stages=stages, single_stage_body=body,
+        num_microbatches=num_micro_batches)
+
+  @classmethod
+  def SetFPropDtype(cls, p, fprop_dtype):
+    """Sets the activation dtype on builder params (ref :274); bf16 keeps fp32 attention
+    logits and gating."""
+    p.fprop_dtype = fprop_dtype
+    if fprop_dtype == torch.bfloat16 and not p.attention_logits_dtype:
+      p.attention_logits_dtype = torch.float32
+    return p
+
   # ---- attention ----------------------------------------------------------
   def _Atten(self, name, decoder, relative_bias):
     return self._Common(SelfAttentionLayer.Params().Set(
@@ -1146,6 +1431,44 @@ class MoEBuilder(builder.Base):
 
   EncSelfAttention = SelfAttention
 
+  def Attention(self, name):
+    """(q, k, v, bias) → context for already projected `BLHD` tensors (ref :1081)."""
+    return self._Common(AttentionCoreLayer.Params(), name)
+
+  def DecEncAttention(self, name, *unused):
+    """Decoder → encoder cross attention (ref :1206); the enclosing `DecoderLayer` feeds it
+    `encoder_output` / `encoder_segment_id` from the layer-stack input map."""
+    return self._Common(CrossAttentionLayer.Params(), name)
+
+  def DecMultiDconvHeadAttention(self, name, *unused):
+    """Primer's multi-dconv-head decoder self-attention (ref :1349)."""
+    return self._Common(SelfAttentionLayer.Params().Set(
+        decoder=True, relative_bias=False, multi_dconv_head=True), name)
+
+  def DecMultiDconvHeadAttentionRelativeBias(self, name, *unused):
+    assert self.params.relative_attention_type in ('bias', 'bias_shared')
+    return self._Common(SelfAttentionLayer.Params().Set(
+        decoder=True, relative_bias=True, multi_dconv_head=True), name)
+
+  def DepthwiseConvAutoregressive(self, name, kernel_size, model_dims=None):
+    """Causal depthwise conv over time with one weight vector per tap (ref :1749)."""
+    return self._Common(DepthwiseConvAutoregressiveLayer.Params().Set(
+        kernel_size=kernel_size, model_dims=list(model_dims) if model_dims else None), name)
+
+  CausalDepthwiseConv = DepthwiseConvAutoregressive        # same math, one fused layer here
+
+  def ParallelDecSelfAttentionRelativeBiasFFN(self, name, activation_fn='relu',
+                                              gated=False, relative_bias=True, **unused):
+    """Attention ‖ FFN on one normalised input (ref :2619)."""
+    if isinstance(activation_fn, str):
+      act = activation_fn
+    else:
+      act = getattr(activation_fn, '_lingvo_name', 'relu')
+    atten = self._Atten('atten', True, relative_bias)
+    ffn = (self.DenseReluDenseGated('ffn', act) if gated else
+           self.DenseReluDense('ffn', activation=act))
+    return self._Common(ParallelAttentionFFNLayer.Params().Set(atten=atten, ffn=ffn), name)
+
   # ---- FFN / MoE ----------------------------------------------------------
   def DenseReluDense(self, name, decoder=False, activation='relu'):
     return self._Common(DenseReluDenseLayer.Params().Set(
@@ -1156,6 +1479,12 @@ class MoEBuilder(builder.Base):
         activation_fn, '_lingvo_name', 'gelu')
     return self._Common(DenseReluDenseLayer.Params().Set(
         activation=act, gated=True), name)
+
+  def DenseReluDenseGatedGELU(self, name, decoder=False):
+    return self.DenseReluDenseGated(name, 'gelu', decoder=decoder)
+
+  def DenseReluDenseGatedSILU(self, name, decoder=False):
+    return self.DenseReluDenseGated(name, 'silu', decoder=decoder)
 
   def MoE(self, name, decoder=False):
     return self._Common(MoELayer.Params().Set(
@@ -1175,7 +1504,12 @@ class MoEBuilder(builder.Base):
         layer=layer.Copy(), norm=self._NormByType(norm_type, norm_type),
         norm_policy=norm_policy, post_norm=post), name)
 
-  EncoderLayer = DecoderLayer
+  def EncoderLayer(self, name, layer, residual_weight=1.0, norm_type='ln',
+                   norm_policy='pre'):
+    """Encoder block: x + residual_weight · layer(norm(x)) (ref :488)."""
+    blk = self.DecoderLayer(name, layer, None, norm_type, norm_policy)
+    blk.residual_weight = residual_weight
+    return blk
 
   def _LayerStack(self, name, sub_layers, num, conv_kernel_size=None,
                   norm_type='ln', norm_policy='pre', start_layer_id=0,
@@ -1326,7 +1660,7 @@ class UniTransformer(base_model.BaseTask):
     p.Define('activation', 'relu', 'Non-gated FFN activation.')
     p.Define('norm_type', 'ln', 'ln|pn|true_ln|jax_replica_ln|no_ln.')
     p.Define('norm_policy', 'pre', 'pre|primer|primer_hybrid.')
-    p.Define('multi_dconv_head_att', False, 'Kept for parity.')
+    p.Define('multi_dconv_head_att', False, "Primer's multi-dconv-head attention.")
     p.Define('decoder_max_steps', 64, 'Max decode steps.')
     p.Define('decoder_beam_size', 4, 'Beam size.')
     p.Define('decoder_eos_id', 1, '</s> id.')
@@ -1358,7 +1692,10 @@ class UniTransformer(base_model.BaseTask):
         else:
           self.CreateChild('dec_pos_emb', b.Embedding('dec_pos_emb',
                                                       p.max_length))
-    if p.positional_embedding:
+    if p.multi_dconv_head_att:
+      atten = (b.DecMultiDconvHeadAttention('multi_dconv_head_att') if p.positional_embedding
+               else b.DecMultiDconvHeadAttentionRelativeBias('multi_dconv_head_att'))
+    elif p.positional_embedding:
       atten = b.DecSelfAttention('dec_self_attention')
     else:
       atten = b.DecSelfAttentionRelativeBias('dec_self_attention')
