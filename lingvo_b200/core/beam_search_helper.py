@@ -104,6 +104,8 @@ class BeamSearchHelper(BeamSearchSharedParams):
         'atten_probs') is not None else 1
     state = bs_ops.init_state(b, k, max_steps, src_len, dev)
     step_ids = torch.full((n, 1), p.target_sos_id, dtype=torch.int64, device=dev)
+    if init_results.get('step_ids') is not None:     # decoder-provided first input ids
+      step_ids = init_results.step_ids.reshape(n, 1).to(torch.int64)
     steps_run = 0
     path_ids = torch.zeros(n, dtype=torch.int64, device=dev) if p.merge_paths else None
     for t in range(max_steps):

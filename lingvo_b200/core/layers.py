@@ -1652,20 +1652,24 @@ class SharedSoftmaxLayer(base_layer.BaseLayer):
     p.Define('vocab_size', 0, 'Vocab size.')
     p.Define('embedding_dim', 0, 'Embedding dim.')
     p.Define('scale_sqrt_depth', False, 'Scale by sqrt(dim).')
+    p.Define('input_dim', 0, 'Softmax-side name of embedding_dim (either may be set).')
+    p.Define('num_classes', 0, 'Softmax-side name of vocab_size (either may be set).')
+    p.Define('num_shards', 1, 'Kept for the softmax interface; the weight is one shard.')
     return p
 
   def __init__(self, params):
     super().__init__(params)
     p = self.params
-    sp = p.softmax.Copy().Set(name='softmax', input_dim=p.embedding_dim,
-                              num_classes=p.vocab_size, num_shards=1,
-                              use_num_classes_major_weight=True)
+    self._dim = p.embedding_dim or p.input_dim
+    self._vocab = p.vocab_size or p.num_classes
+    sp = p.softmax.Copy().Set(name='softmax', input_dim=self._dim, num_classes=self._vocab,
+                              num_shards=1, use_num_classes_major_weight=True)
     self.CreateChild('softmax', sp)
 
   def EmbLookup(self, theta, ids):
     p = self.params
     out = F.embedding(ids.long(), theta.softmax.weight_0)
-    return out * (p.embedding_dim**0.5) if p.scale_sqrt_depth else out
+    return out * (self._dim**0.5) if p.scale_sqrt_depth else out
 
   def Logits(self, theta, inputs):
     return self.softmax.Logits(theta.softmax, inputs)

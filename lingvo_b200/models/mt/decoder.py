@@ -18,10 +18,13 @@ from lingvo_b200.core import layers
 from lingvo_b200.core import py_utils
 from lingvo_b200.core import rnn_cell
 from lingvo_b200.core import rnn_layers
+from lingvo_b200.core import summary_utils
 from lingvo_b200.core.nested_map import NestedMap
 
 
 class MTBaseDecoder(base_decoder.BaseBeamSearchDecoder):
+  """Softmax, label smoothing and loss / metric assembly shared by the MT decoders
+  (ref :34)."""
 
   @classmethod
   def Params(cls):
@@ -29,9 +32,12 @@ class MTBaseDecoder(base_decoder.BaseBeamSearchDecoder):
     p.Define('label_smoothing', None, 'Label smoother params.')
     p.Define('softmax', layers.SimpleFullSoftmax.Params(), 'Softmax.')
     p.Define('per_word_avg_loss', False, 'Average the loss per word (else per sentence).')
-    p.Define('per_example_tensors', False, 'Emit per-example tensors.')
-    p.Define('token_normalized_per_seq_loss', False, 'Kept for parity.')
-    p.Define('use_prev_atten_ctx', False, 'Kept for parity.')
+    p.Define('unidi_rnn_type', 'func', 'func: FRNN (the only flavour here).')
+    p.Define('feed_attention_context_vec_to_softmax', False,
+             'Concatenate the attention context to the RNN output before the softmax.')
+    p.Define('per_example_tensors', False, 'Return per-example tensors.')
+    p.Define('token_normalized_per_seq_loss', False, 'Deprecated; unused.')
+    p.softmax.num_classes = 32000
     return p
 
   def __init__(self, params):
@@ -39,51 +45,126 @@ class MTBaseDecoder(base_decoder.BaseBeamSearchDecoder):
     p = self.params
     if p.label_smoothing is not None:
       self.CreateChild('smoother', p.label_smoothing.Copy().Set(
-          num_classes=p.softmax.num_classes))
+          name='smoother', num_classes=p.softmax.num_classes))
 
   @classmethod
   def UpdateTargetVocabSize(cls, p, vocab_size, wpm_model=None):
     p.softmax.num_classes = vocab_size
     return p
 
-  def _FPropSoftmax(self, theta, softmax_input, target_labels, target_weights,
-                    target_paddings, target_segment_ids=None):
-    """softmax_input [T,B,D]; labels/weights/paddings [T,B] → (metrics, per_seq)."""
+  # -- loss ------------------------------------------------------------------------------------
+  def _ComputeXentLoss(self, theta, softmax_input, target_labels, target_weights,
+                       target_paddings, target_segment_ids=None, time_axis=0):
+    """softmax_input `[T, B, D]` (time_axis 0) or `[B, T, D]` (1) → the softmax layer's
+    output NestedMap for the flattened tokens (ref :81)."""
+    del target_segment_ids
     p = self.params
-    t, b, d = softmax_input.shape
-    w = target_weights.float()
+    flat = softmax_input.reshape(-1, softmax_input.shape[-1])
     kwargs = dict(class_ids=target_labels.reshape(-1, 1).long())
     if p.label_smoothing is not None:
-      probs = self.smoother.FProp(theta.smoother, target_paddings, target_labels.long(),
-                                  target_ids=None)
-      kwargs = dict(class_probabilities=probs.reshape(t * b, -1))
-    out = self.softmax.FProp(theta.softmax, softmax_input.reshape(t * b, d),
-                             w.reshape(-1, 1), **kwargs)
-    per_tok = out.per_example_xent.reshape(t, b)
-    seq_xent = (per_tok * w).sum(0)
+      if time_axis == 0:
+        probs = self.smoother.FProp(theta.smoother, target_paddings.t(),
+                                    target_labels.t().long(), target_ids=None).transpose(0, 1)
+      else:
+        probs = self.smoother.FProp(theta.smoother, target_paddings, target_labels.long(),
+                                    target_ids=None)
+      kwargs = dict(class_probabilities=probs.reshape(-1, p.softmax.num_classes))
+    return self.softmax.FProp(theta.softmax, flat, target_weights.float().reshape(-1, 1),
+                              **kwargs)
+
+  def _ComputeSoftmaxMetrics(self, xent_loss, target_labels, target_weights,
+                             target_segment_ids=None, time_axis=0):
+    """→ (metrics, per-example tensors) (ref :134). Per-sequence averaging divides by the
+    number of *sentences* — for packed inputs Σ_rows max(segment_id), not the row count."""
+    p = self.params
+    w = target_weights.float()
+    per_tok = xent_loss.per_example_xent.reshape(w.shape)
     num_words = w.sum().clamp_min(1e-8)
+    per_seq = (per_tok * w).sum(time_axis)
     if p.per_word_avg_loss:
-      loss, loss_w = out.total_xent / num_words, num_words
+      loss, loss_w = xent_loss.total_xent / num_words, num_words
     else:
-      loss = out.total_xent / float(b)
-      loss_w = torch.tensor(float(b), device=w.device)
-    correct = ((out.per_example_argmax.reshape(t, b) == target_labels).float() * w).sum() \
-        if out.get('per_example_argmax') is not None else torch.zeros((), device=w.device)
-    metrics = NestedMap(
-        loss=(loss, loss_w), log_pplx=(out.total_xent / num_words, num_words),
-        fraction_of_correct_next_step_preds=(correct / num_words, num_words),
-        num_predictions=(num_words, 1.0))
-    return metrics, NestedMap(per_sequence_xent=seq_xent)
+      if p.packed_input:
+        if target_segment_ids is None:
+          raise AssertionError('Need target segment ids for normalizing loss when training '
+                               'with packed inputs.')
+        num_samples = target_segment_ids.max(time_axis).values.sum().to(per_seq.dtype)
+        loss = per_seq.sum() / num_samples
+      else:
+        loss = per_seq.mean()
+      loss_w = torch.tensor(float(per_seq.shape[0]), device=w.device)
+    metrics = NestedMap(loss=(loss, loss_w),
+                        log_pplx=(xent_loss.total_xent / num_words, num_words),
+                        num_predictions=(num_words, 1.0))
+    per_example = NestedMap(per_sequence_xent=per_seq)
+    if p.per_example_tensors:
+      per_example.per_example_loss = per_tok
+      per_example.per_sequence_loss = per_seq
+      per_example.loss = per_seq
+      if xent_loss.get('logits') is not None:
+        per_example.logits = xent_loss.logits.reshape(tuple(w.shape) + (-1,))
+        per_example.log_probs = torch.log_softmax(per_example.logits.float(), -1)
+    argmax = xent_loss.get('per_example_argmax')
+    if argmax is not None:
+      correct = ((argmax.reshape(w.shape) == target_labels).float() * w).sum()
+      metrics.fraction_of_correct_next_step_preds = (correct / num_words, num_words)
+    return metrics, per_example
+
+  def _FPropSoftmax(self, theta, softmax_input, target_labels, target_weights,
+                    target_paddings, target_segment_ids=None, time_axis=0):
+    xent = self._ComputeXentLoss(theta, softmax_input, target_labels, target_weights,
+                                 target_paddings, target_segment_ids, time_axis)
+    return self._ComputeSoftmaxMetrics(xent, target_labels, target_weights,
+                                       target_segment_ids, time_axis)
 
   def ComputeLoss(self, theta, predictions, targets):
-    lab = targets.labels.t()
-    w = targets.weights.t()
-    pad = targets.paddings.t()
-    return self._FPropSoftmax(theta, predictions.softmax_input, lab, w, pad)
+    seg = targets.segment_ids.t() if self.params.packed_input else None
+    if isinstance(predictions, NestedMap):
+      predictions = predictions.softmax_input
+    return self._FPropSoftmax(theta, predictions, targets.labels.t(), targets.weights.t(),
+                              targets.paddings.t(), seg)
+
+  # -- helpers ---------------------------------------------------------------------------------
+  def _TruncateTargetSequence(self, targets):
+    """Cuts `[batch, time]` targets to the longest real sequence of the batch (ref :283)."""
+    targets = targets.Pack(targets.Flatten())
+    max_len = int(torch.round((1.0 - targets.paddings.float()).sum(1).max()))
+    summary_utils.scalar('max_seq_length', max_len)
+    assert bool((targets.paddings[:, max_len:] > 0.5).all())
+    py_utils.AssertIdShape([None, None], list(targets.ids.shape), list(targets.labels.shape),
+                           list(targets.paddings.shape), list(targets.weights.shape))
+    for k in ('ids', 'labels', 'weights', 'paddings'):
+      targets[k] = targets[k][:, :max_len]
+    return targets
+
+  def _AddAttenProbsSummary(self, source_paddings, targets, atten_probs):
+    """atten_probs: list of `[tgt_len, tgt_batch, src_len]` (ref :315)."""
+    if not summary_utils._ShouldAddSummary():   # pylint: disable=protected-access
+      return
+    self._AddAttenProbsImageSummary(source_paddings, targets, atten_probs)
+    self._AddAttenProbsHistogramSummary(atten_probs)
+
+  def _AddAttenProbsHistogramSummary(self, atten_probs):
+    for i, probs in enumerate(atten_probs):
+      summary_utils.histogram('atten{}'.format(i + 1), probs.detach())
+
+  def _AddAttenProbsImageSummary(self, source_paddings, targets, atten_probs):
+    summary_utils.AddAttentionSummary(
+        'decoder_example', [a.detach() for a in atten_probs], source_paddings.float(),
+        targets.paddings.t().float(), max_outputs=1)
+
+  def _ExpandToNumHyps(self, source_enc_len, num_hyps_per_beam):
+    """[3, 2, 1] with 2 hyps → [3, 2, 1, 3, 2, 1] (target batch is hyp-major) (ref :381)."""
+    return source_enc_len.repeat(num_hyps_per_beam)
 
 
 class MTDecoderV1(MTBaseDecoder):
-  """RNMT decoder."""
+  """RNMT decoder (ref :398): attention LSTM + stacked LSTMs with the attention context fed
+  to every layer, residuals from `residual_start`, optional clipping-cap schedule,
+  embedding / output projections, shared embedding-softmax, sentence-aligned and
+  single-token fast beam search."""
+
+  _FLOAT_DTYPE_MAX_SCALER = 0.7
 
   @classmethod
   def Params(cls):
@@ -92,98 +173,306 @@ class MTDecoderV1(MTBaseDecoder):
     p.Define('source_dim', 1024, 'Encoder output dim.')
     p.Define('attention', attention.AdditiveAttention.Params(), 'Attention.')
     p.Define('atten_rnn_cell_tpl', rnn_cell.LSTMCellSimple.Params(), 'Attention RNN cell.')
+    p.Define('emb_projection_tpl', None,
+             'ProjectionLayer params: when the embedding dim differs from rnn_cell_dim the '
+             'embeddings are projected up (and, with a shared softmax, the output down).')
     p.Define('rnn_cell_tpl', rnn_cell.LSTMCellSimple.Params(), 'Upper RNN cells.')
     p.Define('rnn_cell_dim', 1024, 'RNN cell dim.')
     p.Define('rnn_layers', 8, 'Total decoder RNN layers.')
     p.Define('residual_start', 2, 'First residual layer.')
     p.Define('atten_rnn_cls', rnn_layers.FRNNWithAttention, 'Attention RNN class.')
-    p.Define('feed_attention_context_vec_to_softmax', False, 'Concat context to softmax in.')
+    p.Define('use_prev_atten_ctx', False,
+             'Upper layers get the PREVIOUS step\'s attention context (else the current).')
     p.Define('dropout_prob', 0.0, 'Dropout.')
-    p.Define('cc_schedule', None, 'Kept for parity.')
-    p.Define('init_step_ids', False, 'Kept for parity.')
+    p.Define('use_zero_atten_state', False,
+             'Zero initial attention context instead of attending with a zero query.')
+    p.Define('cc_schedule', None, 'Clipping-cap schedule params (quantization-aware training).')
+    p.Define('init_step_ids', False,
+             'Beam search starts from the first target id (e.g. a target-language token) '
+             'instead of <s>.')
+    p.Define('force_alignment', False,
+             'Multi-sentence inputs: hypotheses must contain as many sentences as the source '
+             '(needs sentence_boundary_token_id and encoder_outputs.num_sentences).')
+    p.Define('sentence_boundary_token_id', None, 'Token id separating sentences.')
+    p.Define('single_token_fast_decode', False,
+             'Sources of length ≤ 1 finish decoding in one step (used for padding inputs).')
+    p.Define('zero_token_embs_first_time_step', False,
+             'The first step sees a zero embedding instead of emb(<s>).')
+    p.Define('use_sigmoid_activation', False, 'log-sigmoid instead of log-softmax scores.')
+    p.emb.vocab_size = 32000
+    p.attention.hidden_dim = 1024
+    p.target_seq_len = 300
+    p.beam_search.length_normalization = 0.2
+    p.beam_search.coverage_penalty = 0.2
     return p
 
   def __init__(self, params):
     super().__init__(params)
     p = self.params
-    self.CreateChild('emb', p.emb)
+    if p.force_alignment and p.sentence_boundary_token_id is None:
+      raise ValueError('When p.force_alignment is set, must specify '
+                       'p.sentence_boundary_token_id.')
+    self._share_sm_emb = p.softmax.cls is layers.SharedSoftmaxLayer
+    if p.cc_schedule is not None:
+      self.CreateChild('cc_schedule', p.cc_schedule)
+    else:
+      self.cc_schedule = None
+    if not self._share_sm_emb:
+      assert p.emb.vocab_size == p.softmax.num_classes, (p.emb.vocab_size,
+                                                         p.softmax.num_classes)
+      self.CreateChild('emb', p.emb)
+    emb_dim = ((p.softmax.embedding_dim or p.softmax.input_dim) if self._share_sm_emb
+               else p.emb.embedding_dim)
+    self._project_emb = bool(p.emb_projection_tpl) and emb_dim != p.rnn_cell_dim
+    self._project_out = self._project_emb and self._share_sm_emb
     self.CreateChild('dropout', layers.DropoutLayer.Params().Set(keep_prob=1.0 - p.dropout_prob))
     atten = p.attention.Copy().Set(source_dim=p.source_dim, query_dim=p.rnn_cell_dim)
-    if 'context_dim' in atten:
+    if 'packed_input' in atten:
+      atten.packed_input = p.packed_input
+    ctx_dim = p.source_dim
+    if atten.Get('enable_ctx_post_proj') if 'enable_ctx_post_proj' in atten else False:
+      ctx_dim = atten.ctx_post_proj_dim
+    elif 'context_dim' in atten:
       atten.context_dim = p.source_dim
+    self._ctx_dim = ctx_dim
+    in_dim = (p.rnn_cell_dim if self._project_emb else emb_dim) + ctx_dim
     cell = p.atten_rnn_cell_tpl.Copy().Set(
-        num_input_nodes=p.emb.embedding_dim + p.source_dim, num_output_nodes=p.rnn_cell_dim)
+        name='atten_rnn', num_input_nodes=in_dim, num_output_nodes=p.rnn_cell_dim,
+        reset_cell_state=p.packed_input)
     self.CreateChild('frnn_with_atten', p.atten_rnn_cls.Params().Set(
-        cell=cell, attention=atten, output_prev_atten_ctx=False, use_zero_atten_state=True,
-        atten_context_dim=p.source_dim, packed_input=p.packed_input))
+        cell=cell, attention=atten, output_prev_atten_ctx=p.use_prev_atten_ctx,
+        use_zero_atten_state=p.use_zero_atten_state, atten_context_dim=ctx_dim,
+        packed_input=p.packed_input))
     rnns = []
     for i in range(1, p.rnn_layers):
       rnns.append(rnn_layers.FRNN.Params().Set(
           name='frnn_%d' % i, packed_input=p.packed_input,
-          cell=p.rnn_cell_tpl.Copy().Set(num_input_nodes=p.rnn_cell_dim + p.source_dim,
-                                         num_output_nodes=p.rnn_cell_dim)))
+          cell=p.rnn_cell_tpl.Copy().Set(num_input_nodes=p.rnn_cell_dim + ctx_dim,
+                                         num_output_nodes=p.rnn_cell_dim,
+                                         reset_cell_state=p.packed_input)))
     self.CreateChildren('frnn', rnns)
-    sm_in = p.rnn_cell_dim + (p.source_dim if p.feed_attention_context_vec_to_softmax else 0)
-    self.CreateChild('softmax', p.softmax.Copy().Set(input_dim=sm_in))
+    if p.feed_attention_context_vec_to_softmax:
+      assert not (self._share_sm_emb or self._project_emb or self._project_out)
+      sm_in = p.rnn_cell_dim + ctx_dim
+    else:
+      sm_in = p.rnn_cell_dim
+    if self._project_emb:
+      self._CreateProjection(p.emb_projection_tpl, 'emb_proj', emb_dim, p.rnn_cell_dim)
+    if self._project_out:
+      sm_in = emb_dim
+      self._CreateProjection(p.emb_projection_tpl, 'out_proj', p.rnn_cell_dim, emb_dim)
+    sm = p.softmax.Copy()
+    if not (self._share_sm_emb and sm.embedding_dim):
+      sm.input_dim = sm_in
+    self.CreateChild('softmax', sm)
 
-  def _Upper(self, theta, xs, ctx, pad, states=None, step=False):
+  def _CreateProjection(self, proj_tpl, name, input_dim, output_dim):
+    assert proj_tpl.cls is layers.ProjectionLayer
+    self.CreateChild(name, proj_tpl.Copy().Set(name=name, input_dim=input_dim,
+                                               output_dim=output_dim))
+
+  # -- small pieces ------------------------------------------------------------------------------
+  def ApplyDropout(self, x_in):
+    p = self.params
+    assert 0 <= p.dropout_prob < 1.0
+    if self.do_eval or p.dropout_prob == 0.0:
+      return x_in
+    return torch.nn.functional.dropout(x_in, p.dropout_prob, training=True)
+
+  def ApplyClipping(self, theta, x):
+    if self.cc_schedule is not None:
+      return self.cc_schedule.ApplyClipping(theta.cc_schedule, x)
+    return x
+
+  def _ZeroOutFirstTimeStep(self, token_embs, batch=None, time=None):
+    """`[time, batch, dim]` embeddings with step 0 zeroed (ref :657)."""
+    del batch, time
+    mask = torch.ones(token_embs.shape[0], 1, 1, device=token_embs.device,
+                      dtype=token_embs.dtype)
+    mask[0] = 0.0
+    return token_embs * mask
+
+  def _EmbLookup(self, theta, ids):
+    if self._share_sm_emb:
+      return self.softmax.EmbLookup(theta.softmax, ids)
+    return self.emb.EmbLookup(theta.emb, ids)
+
+  def AddExtraDecodingInfo(self, encoder_outputs, targets):
+    if self.params.init_step_ids:
+      encoder_outputs['init_step_ids'] = targets.ids[:, 0]
+    return encoder_outputs
+
+  # -- training ----------------------------------------------------------------------------------
+  def _Upper(self, theta, xs, ctx, pad, states=None, step=False, segment_id=None):
     p = self.params
     new_states = []
     for i, r in enumerate(self.frnn):
       inp = torch.cat([xs, ctx], -1)
       if step:
-        st, _ = r.cell.FProp(theta.frnn[i].cell, states[i],
-                             NestedMap(act=[inp], padding=pad))
+        st, _ = r.cell.FProp(theta.frnn[i].cell, states[i], NestedMap(
+            act=[inp], padding=pad, reset_mask=torch.ones_like(pad)))
         ys = r.cell.GetOutput(st)
         new_states.append(st)
       else:
-        ys, _ = r.FProp(theta.frnn[i], self.dropout.FProp(theta.dropout, inp), pad)
-      xs = xs + ys if i + 1 >= p.residual_start else ys
+        kw = {'segment_id': segment_id} if (segment_id is not None and p.packed_input) else {}
+        ys, _ = r.FProp(theta.frnn[i], inp, pad, **kw)
+        ys = self.ApplyDropout(ys)
+      if i + 1 >= p.residual_start:
+        xs = self.ApplyClipping(theta, xs + ys)
+      else:
+        xs = ys
+      if not step:
+        summary_utils.histogram('layer_out_%s' % i, xs.detach())
     return xs, new_states
 
   def ComputePredictions(self, theta, encoder_outputs, targets):
+    """→ NestedMap(softmax_input `[T, B, D]`, attention.probs `[B, T, S]`, source_enc_len)."""
     p = self.params
     ids = targets.ids.t().long()
     pad = targets.paddings.t().float().unsqueeze(-1)
-    emb = self.dropout.FProp(theta.dropout, self.emb.EmbLookup(theta.emb, ids))
+    seg = targets.segment_ids.t().float().unsqueeze(-1) if p.packed_input else None
+    emb = self._EmbLookup(theta, ids)
+    if p.zero_token_embs_first_time_step:
+      emb = self._ZeroOutFirstTimeStep(emb)
+    emb = self.ApplyClipping(theta, emb)
+    summary_utils.histogram('input_emb', emb.detach())
+    emb = self.ApplyDropout(emb)
+    if self._project_emb:
+      emb = self.ApplyClipping(theta, self.emb_proj.FProp(theta.emb_proj, emb))
+    kw = {}
+    if p.packed_input:
+      kw = dict(src_segment_id=encoder_outputs.get('segment_id'), segment_id=seg)
     ctx, xs, probs, _ = self.frnn_with_atten.FProp(
-        theta.frnn_with_atten, encoder_outputs.encoded, encoder_outputs.padding, emb, pad)
-    xs, _ = self._Upper(theta, xs, ctx, pad)
-    sm_in = torch.cat([xs, ctx], -1) if p.feed_attention_context_vec_to_softmax else xs
-    sm_in = self.dropout.FProp(theta.dropout, sm_in)
-    return NestedMap(softmax_input=sm_in, attention=NestedMap(probs=probs))
+        theta.frnn_with_atten, encoder_outputs.encoded, encoder_outputs.padding, emb, pad, **kw)
+    self._AddAttenProbsSummary(encoder_outputs.padding, targets, [probs])
+    ctx = self.ApplyClipping(theta, ctx)
+    summary_utils.histogram('atten_ctxs', ctx.detach())
+    xs, _ = self._Upper(theta, xs, ctx, pad, segment_id=seg)
+    if p.feed_attention_context_vec_to_softmax:
+      xs = torch.cat([xs, ctx], -1)
+    if self._project_out:
+      xs = self.ApplyClipping(theta, self.out_proj.FProp(theta.out_proj, xs))
+    return NestedMap(softmax_input=xs, attention=NestedMap(probs=probs.transpose(0, 1)),
+                     source_enc_len=(1.0 - encoder_outputs.padding.float()).sum(0))
 
-  # -- beam search callbacks ------------------------------------------------------
-  def _InitBeamSearchStateCallback(self, theta, encoder_outputs, num_hyps_per_beam):
-    p = self.params
-    src_b = encoder_outputs.encoded.shape[1]
-    n = src_b * num_hyps_per_beam
+  # -- beam search -----------------------------------------------------------------------------------
+  def _InitDecoder(self, theta, encoder_outputs, num_hyps):
+    """→ (rnn_states, atten_context, atten_probs, atten_states); stores `packed_src`."""
     fa = self.frnn_with_atten
     packed = fa.InitForSourcePacked(theta.frnn_with_atten, encoder_outputs.encoded,
                                     encoder_outputs.padding)
     encoder_outputs.packed_src = packed
-    st = fa.zero_state(theta.frnn_with_atten, encoder_outputs.encoded, packed, n)
-    upper = [r.zero_state(theta.frnn[i], n) for i, r in enumerate(self.frnn)]
-    s_len = encoder_outputs.encoded.shape[0]
+    st = fa.zero_state(theta.frnn_with_atten, encoder_outputs.encoded, packed, num_hyps)
+    rnn_states = [st.rnn] + [r.zero_state(theta.frnn[i], num_hyps)
+                             for i, r in enumerate(self.frnn)]
+    return rnn_states, st.atten, st.atten_probs, st.atten_state
+
+  def _DecodeStep(self, theta, encoder_outputs, embs, step_paddings, prev_atten_context,
+                  rnn_states, prev_atten_states):
+    """One step → (cur_atten_context, atten_probs, new_rnn_states, step_out, atten_states)."""
+    p = self.params
+    if self._project_emb:
+      embs = self.ApplyClipping(theta, self.emb_proj.FProp(theta.emb_proj, embs))
+    fa = self.frnn_with_atten
+    s0, _ = fa.cell.FProp(theta.frnn_with_atten.cell, rnn_states[0], NestedMap(
+        act=[torch.cat([embs, prev_atten_context.to(embs.dtype)], 1)], padding=step_paddings,
+        reset_mask=torch.ones_like(step_paddings)))
+    rnn_out = fa.cell.GetOutput(s0)
+    cur_ctx, probs, atten_states = fa.atten.ComputeContextVectorWithSource(
+        theta.frnn_with_atten.atten, encoder_outputs.packed_src, rnn_out,
+        attention_state=prev_atten_states)
+    ctx = prev_atten_context if p.use_prev_atten_ctx else cur_ctx
+    xs, upper = self._Upper(theta, rnn_out, ctx.to(rnn_out.dtype), step_paddings,
+                            rnn_states[1:], step=True)
+    step_out = torch.cat([xs, ctx.to(xs.dtype)], 1) if p.feed_attention_context_vec_to_softmax \
+        else xs
+    if self._project_out:
+      step_out = self.ApplyClipping(theta, self.out_proj.FProp(theta.out_proj, step_out))
+    return cur_ctx, probs, [s0] + upper, step_out, atten_states
+
+  def _InitBeamSearchStateCallback(self, theta, encoder_outputs, num_hyps_per_beam):
+    p = self.params
+    num_beams = encoder_outputs.padding.shape[1]
+    n = num_beams * num_hyps_per_beam
+    rnn_states, ctx, probs, atten_states = self._InitDecoder(theta, encoder_outputs, n)
     dev = encoder_outputs.encoded.device
     init = NestedMap(log_probs=torch.zeros(n, p.softmax.num_classes, device=dev),
-                     atten_probs=torch.zeros(n, s_len, device=dev))
-    return init, NestedMap(atten=st, upper=upper)
+                     atten_probs=probs)
+    if p.init_step_ids and 'init_step_ids' in encoder_outputs:
+      init.step_ids = self._ExpandToNumHyps(encoder_outputs.init_step_ids,
+                                            num_hyps_per_beam).unsqueeze(1)
+    states = NestedMap(time_step=torch.zeros((), dtype=torch.int64, device=dev),
+                       rnn_states=rnn_states, atten_context=ctx, atten_probs=probs,
+                       atten_states=atten_states)
+    if p.force_alignment:
+      states.num_sentences = torch.ones(n, dtype=torch.int32, device=dev)
+    return init, states
 
   def _PreBeamSearchStepCallback(self, theta, encoder_outputs, step_ids, states,
                                  num_hyps_per_beam, cur_step):
     p = self.params
     n = step_ids.shape[0]
-    emb = self.emb.EmbLookup(theta.emb, step_ids.squeeze(1).long())
-    pad = torch.zeros(n, 1, device=emb.device)
-    st = self.frnn_with_atten.Step(theta.frnn_with_atten, encoder_outputs.packed_src,
-                                   states.atten, emb, pad)
-    xs = self.frnn_with_atten.cell.GetOutput(st.rnn)
-    xs, upper = self._Upper(theta, xs, st.atten, pad, states.upper, step=True)
-    sm_in = torch.cat([xs, st.atten], -1) if p.feed_attention_context_vec_to_softmax else xs
-    logits = self.softmax.Logits(theta.softmax, sm_in)
-    return (NestedMap(log_probs=torch.log_softmax(logits.float(), -1),
-                      atten_probs=st.atten_probs), NestedMap(atten=st, upper=upper))
+    embs = self._EmbLookup(theta, step_ids.reshape(-1).long())
+    if p.zero_token_embs_first_time_step and int(cur_step) == 0:
+      embs = torch.zeros_like(embs)
+    embs = self.ApplyClipping(theta, embs)
+    pad = torch.zeros(n, 1, device=embs.device, dtype=embs.dtype)
+    ctx, probs, rnn_states, step_out, atten_states = self._DecodeStep(
+        theta, encoder_outputs, embs, pad, states.atten_context, states.rnn_states,
+        states.atten_states)
+    probs = probs.reshape(states.atten_probs.shape)
+    logits = self.softmax.Logits(theta.softmax, step_out).float()
+    log_probs = torch.nn.functional.logsigmoid(logits) if p.use_sigmoid_activation \
+        else torch.log_softmax(logits, -1)
+    if p.force_alignment:
+      if 'num_sentences' not in encoder_outputs:
+        raise ValueError('Model does not support p.force_alignment as key "num_sentences" '
+                         'is missing from encoder_outputs.')
+      log_probs = self._ForceAlignment(
+          log_probs, encoder_outputs['num_sentences'].repeat(num_hyps_per_beam),
+          states.num_sentences)
+    if p.single_token_fast_decode:
+      single = (1.0 - encoder_outputs.padding.float()).sum(0) <= 1.0
+      if bool(single.any()):
+        log_probs = self._UpdateLogitsForSingleTokenFastDecode(log_probs, single,
+                                                               num_hyps_per_beam)
+    results = NestedMap(log_probs=log_probs,
+                        atten_probs=states.atten_probs if p.use_prev_atten_ctx else probs)
+    new_states = NestedMap(time_step=states.time_step + 1, rnn_states=rnn_states,
+                           atten_context=ctx, atten_probs=probs, atten_states=atten_states)
+    if p.force_alignment:
+      new_states.num_sentences = states.num_sentences
+    return results, new_states
+
+  def _PostBeamSearchStepCallback(self, theta, encoder_outputs, new_step_ids, states):
+    p = self.params
+    if p.force_alignment:
+      add = (new_step_ids.reshape(-1) == p.sentence_boundary_token_id)
+      states.num_sentences = states.num_sentences + add.to(states.num_sentences.dtype)
+    return states
+
+  def _ForceAlignment(self, log_probs, source_num_sentences, hyp_num_sentences):
+    """EOS is forbidden while the hypothesis has fewer sentences than the source; the
+    sentence-boundary token once it has as many (ref :1144)."""
+    p = self.params
+    neg = -self._FLOAT_DTYPE_MAX_SCALER * torch.finfo(log_probs.dtype).max
+    out = log_probs.clone()
+    eos, boundary = p.target_eos_id, p.sentence_boundary_token_id
+    out[:, eos] = torch.where(source_num_sentences > hyp_num_sentences,
+                              torch.full_like(out[:, eos], neg), log_probs[:, eos])
+    out[:, boundary] = torch.where(source_num_sentences <= hyp_num_sentences,
+                                   torch.full_like(out[:, boundary], neg),
+                                   log_probs[:, boundary])
+    return out
+
+  def _UpdateLogitsForSingleTokenFastDecode(self, log_probs, is_single_token,
+                                            num_hyps_per_beam):
+    """Rows of single-token sources: all mass on EOS (ref :1189)."""
+    neg = -self._FLOAT_DTYPE_MAX_SCALER * torch.finfo(log_probs.dtype).max
+    forced = torch.full_like(log_probs, neg)
+    forced[:, self.params.target_eos_id] = 0.0
+    rows = is_single_token.repeat(num_hyps_per_beam).unsqueeze(1)
+    return torch.where(rows, forced, log_probs)
 
 
 class TransformerDecoder(MTBaseDecoder):
