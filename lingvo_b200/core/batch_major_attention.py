@@ -1365,10 +1365,12 @@ class StackedTransformerLayers(base_layer.BaseLayer):
 
   def FProp(self, theta, query_vec, paddings, aux_vec=None, aux_paddings=None,
             segment_mask=None, aux_segment_mask=None):
+    """`aux_vec` may be a list with one source encoding per layer (transparent encoders)."""
     p = self.params
     x = query_vec
     for i, layer in enumerate(self.x_layers):
-      x, _ = layer.FProp(theta.x_layers[i], x, paddings, aux_vec, aux_paddings,
+      aux_i = aux_vec[i] if isinstance(aux_vec, (list, tuple)) else aux_vec
+      x, _ = layer.FProp(theta.x_layers[i], x, paddings, aux_i, aux_paddings,
                          segment_mask=segment_mask,
                          aux_segment_mask=aux_segment_mask)
     if p.final_layer_norm:
@@ -1386,7 +1388,8 @@ class StackedTransformerLayers(base_layer.BaseLayer):
     x = query_vec
     new_states = NestedMap(x_layers=[])
     for i, layer in enumerate(self.x_layers):
-      x, _, st = layer.ExtendStep(theta.x_layers[i], x, aux_vec, aux_paddings,
+      aux_i = aux_vec[i] if isinstance(aux_vec, (list, tuple)) else aux_vec
+      x, _, st = layer.ExtendStep(theta.x_layers[i], x, aux_i, aux_paddings,
                                   cached_states.x_layers[i], time_step,
                                   use_short_seq_opt, **kwargs)
       new_states.x_layers.append(st)

@@ -476,21 +476,38 @@ class MTDecoderV1(MTBaseDecoder):
 
 
 class TransformerDecoder(MTBaseDecoder):
-  """Transformer decoder."""
+  """Transformer decoder (ref :1219): token + position (+ task) embeddings, masked
+  self-attention / cross-attention stack (fused attention kernels, pre-allocated KV cache for
+  `ExtendStep`), optional transparent per-layer source encodings."""
 
   @classmethod
   def Params(cls):
     p = super().Params()
     p.Define('token_emb', layers.SimpleEmbeddingLayer.Params(), 'Token embedding.')
-    p.Define('shared_emb', None, 'Kept for parity.')
+    p.Define('shared_emb', None, 'Shared embedding-softmax params (replaces token_emb and '
+             'softmax).')
     p.Define('position_emb', layers.PositionalEmbeddingLayer.Params(), 'Positions.')
     p.Define('source_dim', 512, 'Encoder dim.')
     p.Define('model_dim', 512, 'Model dim.')
     p.Define('num_trans_layers', 6, 'Layers.')
     p.Define('trans_tpl', bma.TransformerDecoderLayer.Params(), 'Layer template.')
     p.Define('input_dropout_prob', 0.0, 'Input dropout.')
-    p.Define('is_transparent', False, 'Kept for parity.')
+    p.Define('is_transparent', False,
+             'Source encodings are `[time, batch, source_dim, num_trans_layers]`: layer i '
+             'attends to slice i (transparent encoder).')
+    p.Define('add_multiheaded_attention_scalar_summary', False,
+             'Scalar summaries of the attention entropy per layer.')
+    p.Define('ln_tpl', layers.LayerNorm.Params(), 'Layer norm template.')
+    p.Define('ln_output', False, 'Layer-normalise the decoder output (alias of '
+             'final_layer_norm).')
     p.Define('final_layer_norm', True, 'LN before the softmax.')
+    p.Define('task_emb', None, 'Task embedding params: added to every target position.')
+    p.Define('init_step_ids', False, 'Beam search starts from targets.ids[:, 0].')
+    p.Define('use_lang_dependent_atten', False, 'Unsupported: one cross-attention for all '
+             'languages.')
+    p.Define('zero_token_embs_first_time_step', False,
+             'The first step sees a zero token embedding.')
+    p.Define('ln_input', None, 'LayerNorm params applied to the embedded inputs.')
     p.Define('hidden_dim', 2048, 'FFN hidden dim.')
     p.Define('num_atten_heads', 8, 'Heads.')
     p.Define('residual_dropout_prob', 0.0, 'Residual dropout.')
@@ -500,8 +517,19 @@ class TransformerDecoder(MTBaseDecoder):
   def __init__(self, params):
     super().__init__(params)
     p = self.params
-    self.CreateChild('token_emb', p.token_emb.Copy().Set(embedding_dim=p.model_dim))
+    assert not p.use_lang_dependent_atten, 'language-dependent attention is not supported'
+    self._share_sm_emb = p.shared_emb is not None
+    if self._share_sm_emb:
+      self.CreateChild('softmax', p.shared_emb.Copy().Set(name='softmax'))
+    else:
+      self.CreateChild('token_emb', p.token_emb.Copy().Set(embedding_dim=p.model_dim))
+      self.CreateChild('softmax', p.softmax.Copy().Set(input_dim=p.model_dim))
     self.CreateChild('position_emb', p.position_emb.Copy().Set(embedding_dim=p.model_dim))
+    if p.task_emb is not None:
+      self.CreateChild('task_emb', p.task_emb.Copy().Set(embedding_dim=p.model_dim))
+    if p.ln_input is not None:
+      self.CreateChild('layer_norm_input', p.ln_input.Copy().Set(
+          name='decoder_ln_input', input_dim=p.model_dim))
     self.CreateChild('input_dropout', layers.DropoutLayer.Params().Set(
         keep_prob=1.0 - p.input_dropout_prob))
     tpl = p.trans_tpl.Copy()
@@ -512,25 +540,92 @@ class TransformerDecoder(MTBaseDecoder):
         num_layers=p.num_trans_layers, mdl_dim=p.model_dim, hidden_dim=p.hidden_dim,
         num_atten_heads=p.num_atten_heads, dropout_prob=p.residual_dropout_prob,
         mask_self_atten=True, has_aux_atten=True, packed_input=p.packed_input,
-        final_layer_norm=p.final_layer_norm, transformer_layer_params_tpl=tpl))
-    self.CreateChild('softmax', p.softmax.Copy().Set(input_dim=p.model_dim))
+        final_layer_norm=p.final_layer_norm or p.ln_output, transformer_layer_params_tpl=tpl))
 
-  def _Embed(self, theta, ids, t0=None):
+  def _TokenEmb(self, theta, ids):
+    if self._share_sm_emb:
+      return self.softmax.EmbLookup(theta.softmax, ids.long())
+    return self.token_emb.EmbLookup(theta.token_emb, ids.long())
+
+  def _ZeroOutFirstTimeStep(self, token_embs, batch=None, target_time=None):
+    """`[batch, time, dim]` embeddings with step 0 zeroed (ref :1433)."""
+    del batch, target_time
+    mask = torch.ones(1, token_embs.shape[1], 1, device=token_embs.device,
+                      dtype=token_embs.dtype)
+    mask[:, 0] = 0.0
+    return token_embs * mask
+
+  def _Embed(self, theta, ids, t0=None, task_ids=None, segment_pos=None):
+    """ids `[B, T]` → `[B, T, D]`; `t0`: position of the first column (incremental decode)."""
     p = self.params
-    x = self.token_emb.EmbLookup(theta.token_emb, ids.long()) * (p.model_dim ** 0.5)
+    x = self._TokenEmb(theta, ids) * (p.model_dim ** 0.5)
+    if p.zero_token_embs_first_time_step:
+      if t0 is None:
+        x = self._ZeroOutFirstTimeStep(x)
+      elif int(t0) == 0:
+        x = torch.zeros_like(x)
     t = ids.shape[1]
-    if t0 is None:
+    if p.packed_input and segment_pos is not None:
+      pos = self.position_emb.FPropWithPosition(theta.position_emb, segment_pos)
+    elif t0 is None:
       pos = self.position_emb.FProp(theta.position_emb, t).unsqueeze(0)
     else:
       pos = self.position_emb.FProp(theta.position_emb, t0 + t)[t0:t0 + t].unsqueeze(0)
-    return x + pos.to(x.dtype)
+    x = x + pos.to(x.dtype)
+    if p.task_emb is not None and task_ids is not None:
+      x = x + self.task_emb.EmbLookup(theta.task_emb, task_ids.long())
+    if p.ln_input is not None:
+      x = self.layer_norm_input.FProp(theta.layer_norm_input, x)
+    return x
+
+  def _Sources(self, encoder_outputs):
+    """→ (aux `[B, S, D]` or a per-layer list for transparent encoders, paddings `[B, S]`)."""
+    enc = encoder_outputs.encoded
+    if self.params.is_transparent:
+      assert enc.dim() == 4 and enc.shape[-1] == self.params.num_trans_layers, enc.shape
+      aux = [enc[..., i].transpose(0, 1) for i in range(enc.shape[-1])]
+    else:
+      aux = enc.transpose(0, 1)
+    return aux, encoder_outputs.padding.t()
+
+  def AddExtraDecodingInfo(self, encoder_outputs, targets):
+    p = self.params
+    if p.task_emb is not None:
+      encoder_outputs['target_task_ids'] = targets.task_ids[:, 0]
+    if p.init_step_ids:
+      encoder_outputs['init_step_ids'] = targets.ids[:, 0]
+    return encoder_outputs
+
+  def _FProp(self, theta, encoder_outputs, targets):
+    p = self.params
+    x = self._Embed(theta, targets.ids, task_ids=targets.get('task_ids'),
+                    segment_pos=targets.get('segment_pos'))
+    x = self.input_dropout.FProp(theta.input_dropout, x)
+    aux, aux_pad = self._Sources(encoder_outputs)
+    seg_mask = aux_seg_mask = None
+    if p.packed_input:
+      seg_mask = bma.SegmentMask(targets.segment_ids, targets.segment_ids, dtype=x.dtype)
+      aux_seg_mask = bma.SegmentMask(targets.segment_ids, encoder_outputs.segment_id.t(),
+                                     dtype=x.dtype)
+    out, _ = self.stack.FProp(theta.stack, x, targets.paddings.float(), aux, aux_pad,
+                              segment_mask=seg_mask, aux_segment_mask=aux_seg_mask)
+    return NestedMap(softmax_input=out.transpose(0, 1),
+                     source_enc_len=(1.0 - encoder_outputs.padding.float()).sum(0))
 
   def ComputePredictions(self, theta, encoder_outputs, targets):
-    x = self.input_dropout.FProp(theta.input_dropout, self._Embed(theta, targets.ids))
-    aux = encoder_outputs.encoded.transpose(0, 1)
-    aux_pad = encoder_outputs.padding.t()
-    out, _ = self.stack.FProp(theta.stack, x, targets.paddings.float(), aux, aux_pad)
-    return NestedMap(softmax_input=out.transpose(0, 1))
+    return self._FProp(theta, encoder_outputs, targets)
+
+  def ExtendStep(self, theta, encoder_outputs, new_ids, t, prefix_states):
+    """One incremental step for ids `[B]` at position `t` (ref :1629) → (softmax input
+    `[B, D]`, new prefix states). `prefix_states` comes from `InitPrefixStates`."""
+    x = self._Embed(theta, new_ids.reshape(-1, 1), t0=int(t),
+                    task_ids=encoder_outputs.get('target_task_ids'))
+    aux, aux_pad = self._Sources(encoder_outputs)
+    out, new_states = self.stack.ExtendStep(theta.stack, x, aux, aux_pad, prefix_states, int(t))
+    return out.squeeze(1), new_states
+
+  def InitPrefixStates(self, theta, batch, max_len=None):
+    return self.stack.InitStates(theta.stack, batch, max_len or self.params.target_seq_len)
 
   def _InitBeamSearchStateCallback(self, theta, encoder_outputs, num_hyps_per_beam):
     p = self.params
@@ -538,20 +633,29 @@ class TransformerDecoder(MTBaseDecoder):
     n = src_b * num_hyps_per_beam
     dev = encoder_outputs.encoded.device
     t_max = p.target_seq_len
-    aux = encoder_outputs.encoded.transpose(0, 1)              # [B,S,D]
+    aux, aux_pad = self._Sources(encoder_outputs)
     # hyp index = hyp_id * src_b + beam → tile sources along dim 0
-    encoder_outputs.aux_tiled = aux.repeat(num_hyps_per_beam, 1, 1)
-    encoder_outputs.aux_pad_tiled = encoder_outputs.padding.t().repeat(num_hyps_per_beam, 1)
+    tile = lambda a: a.repeat(num_hyps_per_beam, 1, 1)
+    encoder_outputs.aux_tiled = [tile(a) for a in aux] if isinstance(aux, list) else tile(aux)
+    encoder_outputs.aux_pad_tiled = aux_pad.repeat(num_hyps_per_beam, 1)
     cache = self.stack.InitStates(theta.stack, n, t_max)
     # caches are [T, n, N, H]: make dim 0 the hyp dim for the helper's re-ordering
     cache = cache.Transform(lambda x: x.transpose(0, 1).contiguous())
+    s_len = aux_pad.shape[1]
     init = NestedMap(log_probs=torch.zeros(n, p.softmax.num_classes, device=dev),
-                     atten_probs=torch.zeros(n, aux.shape[1], device=dev))
+                     atten_probs=torch.zeros(n, s_len, device=dev))
+    if p.init_step_ids and 'init_step_ids' in encoder_outputs:
+      init.step_ids = self._ExpandToNumHyps(encoder_outputs.init_step_ids,
+                                            num_hyps_per_beam).unsqueeze(1)
+    if p.task_emb is not None and 'target_task_ids' in encoder_outputs:
+      encoder_outputs.task_ids_tiled = self._ExpandToNumHyps(
+          encoder_outputs.target_task_ids, num_hyps_per_beam).unsqueeze(1)
     return init, NestedMap(cache=cache, time_step=torch.zeros(n, dtype=torch.int64, device=dev))
 
   def _PreBeamSearchStepCallback(self, theta, encoder_outputs, step_ids, states,
                                  num_hyps_per_beam, cur_step):
-    x = self._Embed(theta, step_ids, t0=cur_step)
+    x = self._Embed(theta, step_ids, t0=cur_step,
+                    task_ids=encoder_outputs.get('task_ids_tiled'))
     cache = states.cache.Transform(lambda c: c.transpose(0, 1))
     out, new_cache = self.stack.ExtendStep(
         theta.stack, x, encoder_outputs.aux_tiled, encoder_outputs.aux_pad_tiled, cache,
@@ -559,8 +663,8 @@ class TransformerDecoder(MTBaseDecoder):
     logits = self.softmax.Logits(theta.softmax, out.squeeze(1))
     n = step_ids.shape[0]
     new_cache = new_cache.Transform(lambda c: c.transpose(0, 1).contiguous())
-    atten = torch.full((n, encoder_outputs.aux_tiled.shape[1]),
-                       1.0 / encoder_outputs.aux_tiled.shape[1], device=logits.device)
+    s_len = encoder_outputs.aux_pad_tiled.shape[1]
+    atten = torch.full((n, s_len), 1.0 / s_len, device=logits.device)
     return (NestedMap(log_probs=torch.log_softmax(logits.float(), -1), atten_probs=atten),
             NestedMap(cache=new_cache, time_step=states.time_step + 1))
 

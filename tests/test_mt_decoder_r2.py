@@ -186,3 +186,68 @@ def test_packed_inputs_normalise_by_sentence_count():
   tgt.pop('segment_ids')
   with pytest.raises((AssertionError, AttributeError, KeyError)):
     dec.ComputeLoss(dec.theta, pred, tgt)
+
+
+def _TransformerDecoder(**kw):
+  p = mt_decoder.TransformerDecoder.Params().Set(
+      name='tdec', source_dim=8, model_dim=8, num_trans_layers=2, hidden_dim=16,
+      num_atten_heads=2, target_seq_len=6, random_seed=5, **kw)
+  p.token_emb.vocab_size = V
+  if 'max_num_shards' in p.token_emb:
+    p.token_emb.max_num_shards = 1
+  p.softmax.num_classes = V
+  p.softmax.num_shards = 1
+  p.beam_search.num_hyps_per_beam = 2
+  dec = p.Instantiate()
+  dec.InstantiateVariables()
+  return dec
+
+
+def _TInputs(b=2, t=5, s=4, layers_dim=None):
+  g = torch.Generator().manual_seed(4)
+  shape = (s, b, 8) if layers_dim is None else (s, b, 8, layers_dim)
+  enc = NestedMap(encoded=torch.randn(*shape, generator=g), padding=torch.zeros(s, b))
+  ids = torch.randint(3, V, (b, t), generator=g)
+  tgt = NestedMap(ids=ids, labels=torch.roll(ids, -1, 1), paddings=torch.zeros(b, t),
+                  weights=torch.ones(b, t))
+  return enc, tgt
+
+
+def test_transformer_decoder_extend_step_matches_full_pass():
+  dec = _TransformerDecoder()
+  enc, tgt = _TInputs()
+  full = dec.ComputePredictions(dec.theta, enc, tgt).softmax_input           # [T, B, D]
+  states = dec.InitPrefixStates(dec.theta, 2, 5)
+  for t in range(5):
+    step, states = dec.ExtendStep(dec.theta, enc, tgt.ids[:, t], t, states)
+    torch.testing.assert_close(step, full[t], atol=2e-4, rtol=2e-4)
+  assert dec.BeamSearchDecode(enc).topk_hyps.ids.shape[:2] == (2, 2)
+
+
+def test_transformer_decoder_transparent_task_emb_and_zero_first_step():
+  tr = _TransformerDecoder(is_transparent=True)
+  enc, tgt = _TInputs(layers_dim=2)
+  out = tr.ComputePredictions(tr.theta, enc, tgt).softmax_input
+  # layer 1 reads slice 1 only: perturbing slice 0 must still change the output (layer 0),
+  # and both slices matter
+  e0 = NestedMap(enc); e0.encoded = enc.encoded.clone(); e0.encoded[..., 0] += 1.0
+  e1 = NestedMap(enc); e1.encoded = enc.encoded.clone(); e1.encoded[..., 1] += 1.0
+  assert (tr.ComputePredictions(tr.theta, e0, tgt).softmax_input - out).abs().max() > 1e-4
+  assert (tr.ComputePredictions(tr.theta, e1, tgt).softmax_input - out).abs().max() > 1e-4
+  assert tr.BeamSearchDecode(enc).topk_hyps.ids.shape[0] == 2
+  task = _TransformerDecoder(
+      task_emb=layers.SimpleEmbeddingLayer.Params().Set(vocab_size=3, embedding_dim=8),
+      init_step_ids=True, zero_token_embs_first_time_step=True,
+      ln_input=layers.LayerNorm.Params())
+  enc, tgt = _TInputs()
+  tgt.task_ids = torch.tensor([[1] * 5, [2] * 5])
+  a = task.ComputePredictions(task.theta, enc, tgt).softmax_input
+  tgt2 = NestedMap(tgt); tgt2.task_ids = torch.zeros(2, 5, dtype=torch.long)
+  assert (task.ComputePredictions(task.theta, enc, tgt2).softmax_input - a).abs().max() > 1e-4
+  tgt3 = NestedMap(tgt); tgt3.ids = tgt.ids.clone(); tgt3.ids[:, 0] = 9
+  torch.testing.assert_close(task.ComputePredictions(task.theta, enc, tgt3).softmax_input, a)
+  enc = task.AddExtraDecodingInfo(enc, tgt)
+  assert enc.target_task_ids.tolist() == [1, 2] and torch.equal(enc.init_step_ids, tgt.ids[:, 0])
+  init, _ = task._InitBeamSearchStateCallback(task.theta, enc, 2)
+  assert init.step_ids.reshape(-1).tolist() == tgt.ids[:, 0].tolist() * 2
+  assert task.BeamSearchDecode(enc).topk_hyps.ids.shape[0] == 2
