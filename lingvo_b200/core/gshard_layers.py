@@ -1204,23 +1204,31 @@ _BaseComputeGating = ComputeGating
 
 
 def ComputeGating(w, inputs, paddings, num_devices, experts_dim, expert_capacity_dim,   # pylint: disable=function-redefined
-                  local_dispatch, fprop_dtype, gating_func='top_2', **kwargs):
+                  local_dispatch, fprop_dtype, gating_func='top_2', use_xla_sharding=True,
+                  second_expert_policy='all', second_expert_threshold=0.0,
+                  legacy_mtf_behavior=True, capacity_factor=None,
+                  model_dim_reshape_segments=None, mask_dtype=None,
+                  gating_logits_dtype=None, expert_id=None, expert_padding_idx=None,
+                  seeds=None):
   """`ComputeGating` including the `token_shuffle_v2` and `optimal_transport` policies."""
   if gating_func not in ('token_shuffle_v2', 'optimal_transport'):
-    return _BaseComputeGating(w, inputs, paddings, num_devices, experts_dim,
-                              expert_capacity_dim, local_dispatch, fprop_dtype,
-                              gating_func=gating_func, **kwargs)
+    return _BaseComputeGating(
+        w, inputs, paddings, num_devices, experts_dim, expert_capacity_dim, local_dispatch,
+        fprop_dtype, gating_func, use_xla_sharding, second_expert_policy,
+        second_expert_threshold, legacy_mtf_behavior, capacity_factor,
+        model_dim_reshape_segments, mask_dtype, gating_logits_dtype, expert_id,
+        expert_padding_idx, seeds)
   orig = inputs
   if not local_dispatch:
     inputs = inputs.reshape(1, inputs.shape[0] * inputs.shape[1], -1)
     paddings = None if paddings is None else paddings.reshape(1, -1)
-  ldt = kwargs.get('gating_logits_dtype') or fprop_dtype
+  ldt = gating_logits_dtype or fprop_dtype
   logits = EinsumWithModelDim('GSM,ME->GSE', inputs.to(ldt), w.to(ldt),
-                              kwargs.get('model_dim_reshape_segments'))
+                              model_dim_reshape_segments)
   if gating_func == 'token_shuffle_v2':
     aux, comb, disp = TokenShufflingOnlogitsV2(
         logits, paddings, num_devices, experts_dim, expert_capacity_dim, fprop_dtype,
-        capacity_factor=kwargs.get('capacity_factor'))
+        capacity_factor=capacity_factor)
   else:
     aux, comb, disp = OptimalTransportOnlogits(logits, experts_dim, fprop_dtype=fprop_dtype)
   if not local_dispatch:

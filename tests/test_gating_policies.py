@@ -138,3 +138,16 @@ def test_conv1d_state_layer_matches_full_causal_window():
   assert torch.equal(re[0, 0], stx[0, 1]) and torch.equal(re[1, 1], stx[1, 0])
   assert gl.ShardedWeightParams([4, 8], tensor_split_dims_mapping=[-1, 0]
                                 ).tensor_split_dims_mapping == [-1, 0]
+
+
+def test_compute_gating_accepts_the_reference_positional_signature():
+  torch.manual_seed(0)
+  g, s, m, e = 2, 8, 4, 4
+  w, x = torch.randn(m, e), torch.randn(g, s, m)
+  pad = torch.zeros(g, s)
+  pos = gl.ComputeGating(w, x, pad, 1, e, 0, True, torch.float32, 'top_2', False, 'all', 0.0,
+                         True, 2.0, None, torch.float32, torch.float32)
+  kw = gl.ComputeGating(w, x, pad, 1, e, 0, True, torch.float32, gating_func='top_2',
+                        use_xla_sharding=False, capacity_factor=2.0, mask_dtype=torch.float32,
+                        gating_logits_dtype=torch.float32)
+  torch.testing.assert_close(pos.combine_tensor, kw.combine_tensor)
