@@ -1496,9 +1496,40 @@ class Builder(builder.Base):
     p.Define('funnel_pool_tpl', FunnelPoolingLayer.Params(), 'Funnel pooling tpl.')
     p.Define('survival_prob', 1.0, 'Stochastic depth survival.')
     p.Define('atten_tpl', MultiHeadedAttention.Params(), 'Attention template.')
+    p.Define('ff_use_paddings', True, 'Zero the padded positions after the FFN.')
+    p.Define('ff_apply_residual', True, 'x + f(x) (else f(x) only).')
+    p.Define('num_experts', 0, 'MoE: number of experts.')
+    p.Define('num_groups', 1, 'MoE: token groups.')
+    p.Define('expert_capacity_dim', 0, 'MoE: fixed expert capacity (0: from the factor).')
+    p.Define('expert_capacity_factor', 1.5, 'MoE: capacity = factor · S / E.')
+    p.Define('moe_activation', 'RELU', 'MoE expert activation.')
     return p
 
   # -- leaves -------------------------------------------------------------------
+  def _ExpandDims(self, name):
+    return self._Fn(name, lambda x: x.unsqueeze(2))
+
+  def _Squeeze(self, name):
+    return self._Fn(name, lambda x: x.squeeze(2))
+
+  def _Glu(self, name):
+    """[gate ‖ act] halves → act · σ(gate) (tanh(act) with `glu_with_tanh`) (ref :8760)."""
+    with_tanh = self.params.glu_with_tanh
+
+    def Fn(x):
+      gate, act = x.chunk(2, -1)
+      return (torch.tanh(act) if with_tanh else act) * torch.sigmoid(gate)
+    return self._Fn(name, Fn)
+
+  def Seq(self, name, *subs):
+    return self._Seq(name, *subs)
+
+  def _Stride(self, name, stride, first_n=None, axis=1):
+    return StrideLayer.Params().Set(name=name, stride=stride, first_n=first_n, axis=axis)
+
+  def _Pool(self, name, stride, first_n=None):
+    return self.params.funnel_pool_tpl.Copy().Set(name=name, stride=stride, first_n=first_n)
+
   def _DefaultLN(self, name):
     p = self.params
     return (p.norm_layer_tpl or p.layernorm_tpl).Copy().Set(
@@ -1558,6 +1589,134 @@ class Builder(builder.Base):
   def _Id(self, name):
     return layers.IdentityLayer.Params().Set(name=name)
 
+  def GatedFeedforward(self, name, is_causal=False, ff_hidden_dim=None, activation_fn='RELU',
+                       use_paddings=None):
+    """LN → act(x·wi0) ⊙ (x·wi1) → wo, bias-free (T5 v1.1 / GLU-variants FFN) (ref :8880)."""
+    del is_causal
+    p = self.params
+    use_paddings = p.ff_use_paddings if use_paddings is None else use_paddings
+    h = ff_hidden_dim or p.ff_hidden_dim
+    act = activations.GetFn(activation_fn) if isinstance(activation_fn, str) else activation_fn
+    sub_list = [
+        ('i.vec->after_gelu', self._Graph(
+            'feedforward', ['x'], ['y'],
+            ('x->x1', self._DefaultLN('ln')),
+            ('x1->h0', self._Linear('wi0', p.model_dim, h)),
+            ('x1->h1', self._Linear('wi1', p.model_dim, h)),
+            ('h0,h1->h', self._Fn('gelu', lambda a, b: act(a) * b)),
+            ('h->h_dropout', self._Dropout('dropout', p.relu_dropout_prob)),
+            ('h_dropout->y', self._Linear('wo', h, p.model_dim)))),
+        ('after_gelu->y', self._Dropout('dropout', p.residual_dropout_prob)),
+        ('i.vec,y->added', ResidualAddLayer.Params().Set(
+            name='add', residual_weight=p.ff_residual_weight,
+            apply_residual=p.ff_apply_residual)),
+    ]
+    if use_paddings:
+      sub_list += [('added,i.paddings->o.vec', self._Pad('pad')),
+                   ('i.paddings->o.paddings', self._Id('id'))]
+    else:
+      sub_list += [('added->o.vec', self._Id('id_vec')),
+                   ('i.paddings->o.paddings', self._Id('id'))]
+    if p.packed_input:
+      sub_list.append(('i.segment_mask->o.segment_mask', self._Id('segment_mask')))
+    return self._Graph(name, ['i'], ['o'], *sub_list)
+
+  def GatedGeluFeedforward(self, name, is_causal=False, ff_hidden_dim=None):
+    return self.GatedFeedforward(name, is_causal, ff_hidden_dim,
+                                 activation_fn='GELU_APPROXIMATE')
+
+  def MoE(self, name, is_causal=False, ff_hidden_dim=None):
+    """Sharded mixture-of-experts FFN in place of the dense one (ref :8836)."""
+    del is_causal
+    from lingvo_b200.core import layers_with_attention   # pylint: disable=g-import-not-at-top
+    p = self.params
+    assert not p.packed_input and p.num_experts > 0 and p.expert_capacity_factor >= 1.0
+    moe_p = layers_with_attention.TransformerShardedMoeLayer.Params().Set(
+        name=name, input_dim=p.model_dim, output_dim=p.model_dim,
+        hidden_dim=ff_hidden_dim or p.ff_hidden_dim, activation=p.moe_activation,
+        residual_weight=p.ff_residual_weight, residual_dropout_prob=p.residual_dropout_prob,
+        relu_dropout_prob=p.relu_dropout_prob, num_groups=p.num_groups,
+        expert_capacity_dim=p.expert_capacity_dim, min_group_size=None,
+        num_experts=p.num_experts, expert_capacity_factor=p.expert_capacity_factor)
+    if p.deterministic_dropout:
+      moe_p.dropout_tpl = layers.DeterministicDropoutLayer.Params()
+    return self._Graph(name, ['i'], ['o'],
+                       ('i.vec,i.paddings->o.vec', moe_p),
+                       ('i.paddings->o.paddings', self._Id('id')))
+
+  # -- lightweight convolutions (https://arxiv.org/abs/1901.10430) -----------------------------
+  def _NormalizedDepthwiseConv2D(self, name, kernel_size, is_causal=False, qdomain=None):
+    del qdomain
+    from lingvo_b200.core import conv_layers_builder   # pylint: disable=g-import-not-at-top
+    p = self.params
+    return conv_layers_builder.Builder.Params().Instantiate().NormalizedDepthwiseConv2D(
+        name=name, kernel_size=kernel_size, num_heads=p.num_heads, in_dim=p.model_dim,
+        dropconnect_prob=p.atten_dropout_prob, deterministic_dropout=p.deterministic_dropout,
+        is_causal=is_causal)
+
+  def LConv(self, name, kernel_size, is_causal=False, convolution_fn=None,
+            linear_qdomain=None, conv_qdomain=None):
+    """LN → linear(2D) → GLU → softmax-normalised depthwise conv over time → linear →
+    dropout → residual: the self-attention replacement of "Pay Less Attention" (ref :8985)."""
+    del linear_qdomain, conv_qdomain
+    p = self.params
+    convolution_fn = convolution_fn or self._NormalizedDepthwiseConv2D
+    sub_list = [
+        ('i.vec->pre_conv', self._Seq(
+            'pre_conv', self._DefaultLN('ln'),
+            self._Linear('linear', p.model_dim, p.model_dim * 2),
+            self._Bias('bias', p.model_dim * 2), self._Glu('glu'),
+            self._ExpandDims('expand'))),
+        ('pre_conv,i.paddings->post_conv,o.paddings',
+         convolution_fn('conv', kernel_size, is_causal)),
+        ('post_conv->after_dropout', self._Seq(
+            'post_conv', self._Squeeze('squeeze'),
+            self._Linear('linear', p.model_dim, p.model_dim), self._Bias('bias', p.model_dim),
+            self._Dropout('dropout', p.residual_dropout_prob))),
+        ('i.vec,after_dropout->o.vec', self._Add('add')),
+    ]
+    if p.packed_input:
+      sub_list.append(('i.segment_mask->o.segment_mask', self._Id('segment_mask')))
+    return self._Graph(name, ['i'], ['o'], *sub_list)
+
+  def LconvBlock(self, name, kernel_size, is_causal, convolution_fn):
+    return self._Seq(name,
+                     self.LConv('lconv', kernel_size, is_causal, convolution_fn),
+                     self.Feedforward('ff', is_causal))
+
+  def LConvStack(self, name, kernel_sizes, is_causal=False):
+    blocks = [self.LconvBlock('block_{}'.format(i), k, is_causal, None)
+              for i, k in enumerate(kernel_sizes)]
+    return self._MaybeSplit(name, blocks) or self._Seq(name, *blocks)
+
+  def _MaybeSplit(self, name, blocks):
+    """With `num_splits` / `num_micro_batches` > 1 the blocks become GPipe cells."""
+    p = self.params
+    if p.num_splits == 1 and p.num_micro_batches == 1:
+      return None
+    from lingvo_b200.core import gpipe   # pylint: disable=g-import-not-at-top
+    assert len(blocks) >= p.num_splits
+    per = (len(blocks) - 1) // p.num_splits + 1
+    cells = [self._Seq('cell_{}'.format(i // per), *blocks[i:i + per])
+             for i in range(0, len(blocks), per)]
+    assert len(cells) == p.num_splits
+    return gpipe.PipeliningLayer.Params().Set(
+        name=name, cell_tpl=cells, nested_map_fprop=True,
+        num_micro_batches=p.num_micro_batches)
+
+  def FunnelEncoderLayer(self, name, stride=1, first_n=None, ff_hidden_dim=None,
+                         num_heads=None):
+    """Funnel-Transformer block (ref :9290): the query (and the shortcut) is pooled by
+    `stride`, keys / values stay at full resolution; then a feed-forward block."""
+    p = self.params
+    tr = FunnelTransformerAttentionAdapter.Params().Set(
+        name='self_atten', stride=stride, first_n=first_n,
+        pool=self._Pool('pool', stride, first_n), ln=self._DefaultLN('LN'),
+        atten=self._MultiHeadedAtten('atten', num_heads),
+        dropout=self._Dropout('dropout', p.residual_dropout_prob),
+        add_unnormalized_input=p.selfatten_add_unnormalized_input)
+    return self._Seq(name, tr, self.Feedforward('ff', False, ff_hidden_dim))
+
   def SelfAttention(self, name, is_causal=False, num_heads=None):
     p = self.params
     tr = TransformerAttentionLayer.Params().Set(
@@ -1583,6 +1742,41 @@ class Builder(builder.Base):
         for i in range(num_layers)])
 
   Stack = TransformerEncoderStack
+
+
+class FunnelTransformerAttentionAdapter(base_layer.BaseLayer):
+  """NestedMap(vec, paddings) → NestedMap at 1/stride of the time resolution: pooled
+  queries attend to the full-resolution normalised input; residual on the pooled input."""
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('stride', 1, 'Pooling stride of the query.')
+    p.Define('first_n', None, 'Only the first n positions are pooled / output.')
+    p.Define('pool', None, 'FunnelPoolingLayer params.')
+    p.Define('ln', None, 'LayerNorm params.')
+    p.Define('atten', None, 'MultiHeadedAttention params.')
+    p.Define('dropout', None, 'Dropout params.')
+    p.Define('add_unnormalized_input', True, 'Residual on the raw (pooled) input.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    p = self.params
+    for n in ('pool', 'ln', 'atten', 'dropout'):
+      self.CreateChild(n, p.Get(n))
+
+  def FProp(self, theta, i):
+    p = self.params
+    after_ln = self.ln.FProp(theta.ln, i.vec)
+    query, out_pad = self.pool.FProp(theta.pool, after_ln, i.paddings)
+    ctx, _ = self.atten.FProp(theta.atten, query, after_ln, after_ln, i.paddings)
+    ctx = self.dropout.FProp(theta.dropout, ctx)
+    if p.add_unnormalized_input:
+      shortcut, _ = self.pool.FProp(theta.pool, i.vec, i.paddings)
+    else:
+      shortcut = query
+    return NestedMap(vec=shortcut + ctx, paddings=out_pad)
 
 
 class _SelfAttenAdapter(base_layer.BaseLayer):

@@ -256,3 +256,63 @@ def test_favor_chunked_causal_custom_gradients_match_autograd():
   dq, dk, dv = fa.chunked_causal_numerator_grad(qs.detach(), ks.detach(), vs.detach(), sums, wn)
   torch.testing.assert_close(out, ref_num.detach())
   assert dq.shape == qs.shape and dk.shape == ks.shape and dv.shape == vs.shape
+
+
+def _BmaBuilder(**kw):
+  return bma.Builder.Params().Set(model_dim=8, num_heads=2, ff_hidden_dim=16, **kw).Instantiate()
+
+
+def _BInput(b=2, t=8, d=8):
+  torch.manual_seed(0)
+  pad = torch.zeros(b, t)
+  pad[1, 6:] = 1
+  return NestedMap(vec=torch.randn(b, t, d), paddings=pad)
+
+
+def test_builder_gated_feedforward_and_glu():
+  from lingvo_b200.core.nested_map import NestedMap as NM
+  b = _BmaBuilder()
+  ffn = b.GatedGeluFeedforward('gff').Instantiate()
+  i = _BInput()
+  o = ffn.FPropDefaultTheta(i)
+  assert o.vec.shape == i.vec.shape and float(o.vec[1, 6:].abs().max()) == 0
+  names = {v.var_name for v in ffn.vars.Flatten()}
+  assert any(n.endswith('feedforward/wi0/w/var') for n in names)
+  assert len(names) == 5                                        # LN scale+bias, wi0, wi1, wo: no linear biases
+  ff = ffn.GetDescendant('feedforward') if hasattr(ffn, 'GetDescendant') else None
+  x = i.vec
+  ln = ff.ln.FPropDefaultTheta(x)
+  h = torch.nn.functional.gelu(ln @ ff.wi0.vars.w, approximate='tanh') * (ln @ ff.wi1.vars.w)
+  want = (x + h @ ff.wo.vars.w) * (1 - i.paddings).unsqueeze(-1)
+  torch.testing.assert_close(o.vec, want, atol=1e-5, rtol=1e-5)
+  glu = b._Glu('glu').Instantiate()
+  v = torch.randn(2, 3, 8)
+  torch.testing.assert_close(glu.FProp(NM(), v), v[..., 4:] * torch.sigmoid(v[..., :4]))
+  tanh = _BmaBuilder(glu_with_tanh=True)._Glu('glu').Instantiate()
+  torch.testing.assert_close(tanh.FProp(NM(), v), torch.tanh(v[..., 4:]) * torch.sigmoid(v[..., :4]))
+  nores = _BmaBuilder(ff_apply_residual=False, ff_use_paddings=False).GatedFeedforward('g').Instantiate()
+  assert nores.FPropDefaultTheta(i).vec.shape == i.vec.shape
+
+
+def test_builder_lconv_stack_moe_and_funnel_layer():
+  b = _BmaBuilder()
+  stack = b.LConvStack('lconv', [3, 5], is_causal=True).Instantiate()
+  i = _BInput()
+  o = stack.FPropDefaultTheta(i)
+  assert o.vec.shape == i.vec.shape
+  i2 = NestedMap(vec=i.vec.clone(), paddings=i.paddings)
+  i2.vec[0, 5:] += 1.0                                        # causal: the past is unaffected
+  o2 = stack.FPropDefaultTheta(i2)
+  torch.testing.assert_close(o.vec[0, :5], o2.vec[0, :5], atol=1e-5, rtol=1e-5)
+  piped = _BmaBuilder(num_splits=2, num_micro_batches=2).LConvStack('lp', [3, 3]).Instantiate()
+  assert type(piped).__name__ == 'PipeliningLayer' and piped.num_stages == 2
+  moe = _BmaBuilder(num_experts=2, num_groups=1).MoE('moe').Instantiate()
+  om = moe.FPropDefaultTheta(i)
+  assert om.vec.shape == i.vec.shape and torch.isfinite(om.vec).all()
+  fun = b.FunnelEncoderLayer('funnel', stride=2).Instantiate()
+  of = fun.FPropDefaultTheta(i)
+  assert of.vec.shape == (2, 4, 8) and of.paddings.shape == (2, 4)
+  assert of.paddings[1].tolist() == [0, 0, 0, 1]
+  same = b.FunnelEncoderLayer('f1', stride=1).Instantiate().FPropDefaultTheta(i)
+  assert same.vec.shape == i.vec.shape
+  assert b.Seq('s', b._Id('a'), b._Id('b')).cls.__name__ == 'SequentialLayer'
