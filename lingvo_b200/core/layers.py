@@ -1583,8 +1583,50 @@ class SingleShardFullSoftmax(SoftmaxLayer):
     logits = self.bias.FProp(theta.bias, self.linear.FProp(theta.linear, inputs))
     return _CapLogits(logits, p.logits_abs_max, p.logits_soft_max)
 
+  def DenseWeights(self, theta):
+    """NestedMap(wm `[D, C]`, b `[C]`) — the dense view of the softmax weights (ref :4523)."""
+    return NestedMap(wm=theta.linear.w, b=theta.bias.b)
+
+  def XentLossByChunk(self, theta, activation, class_ids, class_probabilities=None):
+    """Per-example (xent, argmax) with the `[chunk, C]` logits of ONE row chunk alive at a
+    time: every chunk is rematerialised in the backward pass (ref :4583). The number of rows
+    must be a multiple of `chunk_size`."""
+    from torch.utils.checkpoint import checkpoint   # pylint: disable=g-import-not-at-top
+    p = self.params
+    n, chunk = activation.shape[0], p.chunk_size
+    assert chunk > 0 and n % chunk == 0, (n, chunk)
+
+    def One(act, ids, probs):
+      logits = self.Logits(theta, act).float()
+      if probs is not None:
+        xent = -(probs.float() * F.log_softmax(logits, -1)).sum(-1)
+      else:
+        xent = F.cross_entropy(logits, ids.reshape(-1).long(), reduction='none')
+      return xent, logits.argmax(-1)
+
+    xs, am = [], []
+    for s in range(0, n, chunk):
+      ids = None if class_ids is None else class_ids[s:s + chunk]
+      probs = None if class_probabilities is None else class_probabilities[s:s + chunk]
+      x, a = checkpoint(One, activation[s:s + chunk], ids, probs, use_reentrant=False)
+      xs.append(x)
+      am.append(a)
+    return torch.cat(xs), torch.cat(am)
+
   def _FProp2D(self, theta, inputs, class_weights, class_ids=None,
                class_probabilities=None):
+    p = self.params
+    if p.chunk_size:
+      if isinstance(inputs, (list, tuple)):
+        inputs = inputs[0]
+      xent, amax = self.XentLossByChunk(
+          theta, inputs, None if class_ids is None else class_ids.reshape(-1),
+          class_probabilities)
+      cw = class_weights.reshape(-1).float()
+      tx, tw = (xent * cw).sum(), cw.sum()
+      return NestedMap(logits=None, log_probs=None, per_example_argmax=amax,
+                       per_example_xent=xent, per_example_weight=cw, total_xent=tx,
+                       total_weight=tw, avg_xent=tx / torch.clamp(tw, min=1e-8))
     logits = self.Logits(theta, inputs)
     return SimpleFullSoftmax.XentLossFromLogits(
         self, theta, logits, class_weights.reshape(-1),

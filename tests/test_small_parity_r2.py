@@ -323,3 +323,28 @@ def test_nested_map_and_params_small_methods():
   with pytest.raises(AttributeError):
     hyperparams.CopyFieldsTo(p, q)                       # unknown keys are an error by default
   assert hyperparams.CopyFieldsTo(p, q, skip='y', ignore_unknown_keys=True).x == 6
+
+
+def test_single_shard_softmax_chunked_xent_matches_dense():
+  common = dict(name='sm', input_dim=6, num_classes=9, random_seed=4)
+  dense = layers.SingleShardFullSoftmax.Params().Set(**common).Instantiate()
+  chunked = layers.SingleShardFullSoftmax.Params().Set(chunk_size=4, **common).Instantiate()
+  x = torch.randn(12, 6, requires_grad=True)
+  ids = torch.randint(0, 9, (12, 1))
+  w = torch.rand(12, 1)
+  a = dense.FProp(dense.theta, x, w, class_ids=ids)
+  b = chunked.FProp(chunked.theta, x, w, class_ids=ids)
+  torch.testing.assert_close(a.per_example_xent, b.per_example_xent)
+  torch.testing.assert_close(a.avg_xent, b.avg_xent)
+  assert torch.equal(a.per_example_argmax, b.per_example_argmax) and b.logits is None
+  ga, = torch.autograd.grad(a.total_xent, x, retain_graph=True)
+  gb, = torch.autograd.grad(b.total_xent, x)
+  torch.testing.assert_close(ga, gb)
+  probs = torch.softmax(torch.randn(12, 9), -1)
+  xe, _ = chunked.XentLossByChunk(chunked.theta, x, None, probs)
+  want = -(probs * torch.log_softmax(dense.Logits(dense.theta, x), -1)).sum(-1)
+  torch.testing.assert_close(xe, want, atol=1e-5, rtol=1e-5)
+  dw = dense.DenseWeights(dense.theta)
+  assert dw.wm.shape == (6, 9) and dw.b.shape == (9,)
+  with pytest.raises(AssertionError):
+    chunked.XentLossByChunk(chunked.theta, x[:10], ids[:10].reshape(-1))
