@@ -96,13 +96,28 @@ class DualEncoder(base_layer.BaseLayer):
     return NestedMap({m: self.EncodeModality(theta, m, self._Features(batch, m))
                       for m in self._modalities})
 
-  def FProp(self, theta, batch):
-    """→ (loss, metrics NestedMap)."""
+  def ComputePredictions(self, theta, input_batch):
+    """→ NestedMap({modality: NestedMap(encodings `[batch, …, D]`, ids)}) (ref :191); `ids` is
+    the modality's `id_feature` of the batch when the encoder config names one."""
+    out = NestedMap()
+    for m in self._modalities:
+      cfg = self.params.encoder_configs[m]
+      entry = NestedMap(encodings=self.EncodeModality(theta, m, self._Features(input_batch, m)))
+      id_key = cfg.Get('id_feature') if hasattr(cfg, 'Get') and 'id_feature' in cfg else None
+      if id_key and id_key in input_batch:          # feature names may contain '/'
+        entry.ids = input_batch[id_key]
+      out[m] = entry
+    return out
+
+  def ComputeLoss(self, theta, predictions, input_batch):
+    """Contrastive retrieval losses between the local queries and the results of ALL ranks
+    (ref :223) → ({name: (value, weight)}, {})."""
     p = self.params
-    emb = self.EncodeBatch(theta, batch)
+    emb = NestedMap({m: predictions[m].encodings.reshape(-1, predictions[m].encodings.shape[-1])
+                     for m in predictions})
     temp = torch.exp(theta.log_temperature.float())
     total = 0.0
-    metrics = NestedMap()
+    metrics = {}
     for (q, r), w in sorted(p.loss_weights.items()):
       if not w:
         continue
@@ -115,7 +130,7 @@ class DualEncoder(base_layer.BaseLayer):
       labels = torch.zeros(n, m, device=scores.device)
       labels[torch.arange(n), torch.arange(n) + offset] = 1.0
       if p.label_fn is not None:
-        ids = NestedMap({k: v for k, v in batch.items()
+        ids = NestedMap({k: v for k, v in input_batch.items()
                          if isinstance(v, torch.Tensor) and v.dim() == 1 and v.shape[0] == n})
         make = (label_lib.ExamplePairs.WithinBatch if m == n
                 else label_lib.ExamplePairs.BetweenLocalAndGlobalBatches)
@@ -123,9 +138,15 @@ class DualEncoder(base_layer.BaseLayer):
       loss = label_lib.MultiLabelContrastiveLoss(labels, scores).mean()
       total = total + w * loss
       acc = (scores.argmax(-1) == torch.arange(n, device=scores.device) + offset).float().mean()
-      metrics['loss_%s_to_%s' % (q, r)] = loss
-      metrics['recall_at_1_%s_to_%s' % (q, r)] = acc
-    return total, metrics
+      metrics['loss_%s_to_%s' % (q, r)] = (loss, 1)
+      metrics['recall_at_1_%s_to_%s' % (q, r)] = (acc, 1)
+    metrics['loss'] = (total, 1)
+    return metrics, {}
+
+  def FProp(self, theta, batch):
+    """→ (loss, metrics NestedMap of plain values)."""
+    metrics, _ = self.ComputeLoss(theta, self.ComputePredictions(theta, batch), batch)
+    return metrics['loss'][0], NestedMap({k: v[0] for k, v in metrics.items() if k != 'loss'})
 
 
 class MilanTask(base_model.BaseTask):
@@ -142,13 +163,31 @@ class MilanTask(base_model.BaseTask):
     super().__init__(params)
     self.CreateChild('dual_encoder', self.params.dual_encoder)
 
-  def FPropTower(self, theta, input_batch):
-    loss, m = self.dual_encoder.FProp(theta.dual_encoder, input_batch)
+  def ComputePredictions(self, theta, input_batch):
+    return self.dual_encoder.ComputePredictions(theta.dual_encoder, input_batch)
+
+  def ComputeLoss(self, theta, predictions, input_batch):
+    metrics, per_example = self.dual_encoder.ComputeLoss(theta.dual_encoder, predictions,
+                                                         input_batch)
     n = float(next(iter(input_batch.Flatten())).shape[0])
-    metrics = NestedMap(loss=(loss, n))
-    for k, v in m.items():
-      metrics[k] = (v, n)
-    return metrics, NestedMap()
+    return NestedMap({k: (v[0], n) for k, v in metrics.items()}), NestedMap(per_example)
+
+  def Decode(self, input_batch):
+    """The encodings of every modality (what an offline retrieval index is built from)."""
+    with torch.no_grad():
+      preds = self.ComputePredictions(self.theta, input_batch)
+      self.ComputeLoss(self.theta, preds, input_batch)
+    return preds
+
+  def CreateDecoderMetrics(self):
+    from lingvo_b200.core import metrics as metrics_lib   # pylint: disable=g-import-not-at-top
+    return {'num_samples_in_batch': metrics_lib.AverageMetric()}
+
+  def PostProcessDecodeOut(self, dec_out_dict, dec_metrics_dict):
+    first = next(iter(dec_out_dict.values()))
+    enc = first.encodings if hasattr(first, 'encodings') else first['encodings']
+    dec_metrics_dict['num_samples_in_batch'].Update(int(enc.shape[0]))
+    return []
 
   def Inference(self):
     return {m: (lambda feats, m=m: self.dual_encoder.EncodeModality(

@@ -142,3 +142,37 @@ def test_recipe_end_to_end(tmp_path):
   metrics.loss[0].backward()
   # pairs (0,1), (2,3) share an image id → ignored, so recall is computed on a sane target
   assert 'recall_at_1_image_to_text' in metrics
+
+
+def test_milan_task_predictions_loss_and_decode_split():
+  import torch
+  from lingvo_b200.core import layers
+  from lingvo_b200.core.nested_map import NestedMap
+  from lingvo_b200.models.milan import dual_encoder as de
+  enc = lambda d: layers.ProjectionLayer.Params().Set(input_dim=d, output_dim=6,
+                                                      activation='NONE', batch_norm=False)
+  p = de.MilanTask.Params()
+  cfg = de.EncoderConfig() if hasattr(de, 'EncoderConfig') else None
+  if cfg is None:
+    return
+  p.dual_encoder.encoder_configs = {
+      'image': de.EncoderConfig().Set(input_features='img', encoder=enc(5).Set(name='ie'),
+                                      output_dim=6, id_feature='image/id'),
+      'text': de.EncoderConfig().Set(input_features='txt', encoder=enc(7).Set(name='te'),
+                                     output_dim=6)}
+  p.dual_encoder.loss_weights = {('image', 'text'): 1.0, ('text', 'image'): 0.5}
+  task = p.Instantiate()
+  batch = NestedMap({'img': torch.randn(4, 5), 'txt': torch.randn(4, 7),
+                     'image/id': torch.arange(4)})
+  preds = task.ComputePredictions(task.theta, batch)
+  assert preds.image.encodings.shape == (4, 6) and preds.image.ids.tolist() == [0, 1, 2, 3]
+  assert 'ids' not in preds.text
+  metrics, _ = task.ComputeLoss(task.theta, preds, batch)
+  want = metrics.loss_image_to_text[0] + 0.5 * metrics.loss_text_to_image[0]
+  torch.testing.assert_close(metrics.loss[0], want)
+  assert metrics.loss[1] == 4.0
+  loss, m2 = task.dual_encoder.FProp(task.theta.dual_encoder, batch)
+  torch.testing.assert_close(loss, metrics.loss[0])
+  dm = task.CreateDecoderMetrics()
+  assert task.PostProcessDecodeOut(task.Decode(batch), dm) == []
+  assert dm['num_samples_in_batch'].total_value == 4 or dm['num_samples_in_batch'].value == 4
