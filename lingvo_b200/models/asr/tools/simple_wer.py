@@ -54,6 +54,61 @@ def ComputeWER(hyp, ref, diagnosis=False):
   return info, ''.join(html)
 
 
+# -- the v1 entry points (ref `simple_wer.py:46-292`) ------------------------------------------
+def ComputeEditDistanceMatrix(hs, rs):
+  """Word-level Levenshtein DP table `[len(rs) + 1, len(hs) + 1]` (int32 numpy): entry
+  (r, h) is the distance between the first r reference and first h hypothesis words."""
+  import numpy as np  # pylint: disable=g-import-not-at-top
+  dr, dh = len(rs) + 1, len(hs) + 1
+  dists = np.zeros((dr, dh), np.int32)
+  dists[:, 0] = np.arange(dr)
+  dists[0, :] = np.arange(dh)
+  for i in range(1, dr):
+    for j in range(1, dh):
+      if rs[i - 1] == hs[j - 1]:
+        dists[i, j] = dists[i - 1, j - 1]
+      else:
+        dists[i, j] = 1 + min(dists[i - 1, j - 1], dists[i, j - 1], dists[i - 1, j])
+  return dists
+
+
+def PreprocessTxtBeforeWER(txt):
+  """Lower-cases, drops [noise]-style comments and " - ", squeezes blanks (v1 rules)."""
+  txt = re.sub(r'\[\w+\]', '', txt.lower())
+  txt = txt.replace(' - ', ' ')
+  return ' '.join(txt.replace('\n', ' ').split())
+
+
+def GenerateSummaryFromErrs(nref, errs):
+  """→ ('total error = …, total word = …, wer = …%', 'Error breakdown: del …, ins …, sub …')."""
+  total = sum(errs[k] for k in ('sub', 'ins', 'del'))
+  nref = max(nref, 1)
+  return ('total error = %d, total word = %d, wer = %.2f%%' % (total, nref,
+                                                                total * 100.0 / nref),
+          'Error breakdown: del = %.2f%%, ins=%.2f%%, sub=%.2f%%' % (
+              errs['del'] * 100.0 / nref, errs['ins'] * 100.0 / nref,
+              errs['sub'] * 100.0 / nref))
+
+
+def AverageWERs(hyps, refs, verbose=True, diagnosis=False):
+  """Corpus-level errors over paired lists → (errs dict, number of reference words, list of
+  aligned diagnosis html strings)."""
+  total = {'sub': 0, 'ins': 0, 'del': 0}
+  totalw = 0
+  htmls = []
+  for hyp, ref in zip(hyps, refs):
+    info, html = ComputeWER(PreprocessTxtBeforeWER(hyp), PreprocessTxtBeforeWER(ref), diagnosis)
+    if diagnosis:
+      htmls.append(html)
+    totalw += info['nw']
+    for k in total:
+      total[k] += info[k]
+  if verbose:
+    for line in GenerateSummaryFromErrs(totalw, total):
+      print(line)
+  return total, totalw, htmls
+
+
 def AnalyzeKeyPhrases(hyp, ref, keyphrases):
   """Counts key phrases present in ref (`ref_nkp`) and recovered in hyp (`hyp_nkp`)
   (ref :183)."""

@@ -162,3 +162,17 @@ def test_metrics_calculator_aggregates_error_rates():
   # token error rate: utt0 exact (4 tokens), utt1 one substitution over 3 tokens
   assert abs(d['ter'].value - 1 / 7) < 1e-9
   assert mc.GetRefIds([1, 2, 3], [0, 1, 0]) == [1, 3]
+
+
+def test_simple_wer_v1_entry_points(capsys):
+  from lingvo_b200.models.asr.tools import simple_wer
+  d = simple_wer.ComputeEditDistanceMatrix('a b c d'.split(), 'a x c'.split())
+  assert d.shape == (4, 5) and int(d[-1, -1]) == 2 and d[0].tolist() == [0, 1, 2, 3, 4]
+  assert simple_wer.PreprocessTxtBeforeWER('Hello [noise]  World - again\n') == 'hello world again'
+  errs, nref, html = simple_wer.AverageWERs(['the cat sat', 'a b'], ['the cat sat down', 'a c'],
+                                            diagnosis=True)
+  assert errs == {'sub': 1, 'ins': 0, 'del': 1} and nref == 6 and len(html) == 2
+  out = capsys.readouterr().out
+  assert 'total error = 2, total word = 6, wer = 33.33%' in out and 'Error breakdown' in out
+  s, det = simple_wer.GenerateSummaryFromErrs(10, {'sub': 1, 'ins': 2, 'del': 0})
+  assert s.endswith('wer = 30.00%') and 'ins=20.00%' in det
