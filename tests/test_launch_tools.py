@@ -90,3 +90,34 @@ def test_wheel_builder_makes_an_installable_archive(tmp_path):
     assert b'lingvo_b200.trainer:main_cli' in z.read(
         'lingvo_b200-0.2.0.dist-info/entry_points.txt')
     assert not any(n.endswith('.so') for n in names)              # --skip-native
+
+
+def test_compare_params_text_diff_and_stats_collector(capsys, tmp_path):
+  import numpy as np
+  from lingvo_b200.tools import compare_params
+  from lingvo_b200.tools import compute_stats
+  a = 'x.cls : type/old.module/Layer\nx.dim : 4\nonly_a : 1\n'
+  b = 'x.cls : type/new.module/Layer\nx.dim : 8\nonly_b : 2\n'
+  only_a, only_b, diff = compare_params.hyperparams_text_diff(a, b)
+  assert only_a == ['only_a'] and only_b == ['only_b'] and diff == {'x.dim': ('4', '8')}
+  compare_params.print_hyperparams_text_diff('A', 'B', only_a, only_b, diff)
+  out = capsys.readouterr().out
+  assert 'Keys in A but not B' in out and 'x.dim:' in out and 'vs. [8]' in out
+  f = tmp_path / 'params.txt'
+  f.write_text(a)
+  assert compare_params.get_model_params_as_text(str(f)) == a
+  sc = compute_stats.StatsCollector('frames', frame_size=2, num_buckets=4)
+  rng = np.random.RandomState(0)
+  allf = []
+  for n in range(1, 41):
+    x = rng.randn(n, 2) * [1.0, 3.0] + [5.0, -2.0]
+    allf.append(x)
+    sc.Accumulate({'frames': x.reshape(-1).astype(np.float32)})
+  mean, std = sc.MeanVar()
+  allf = np.concatenate(allf)
+  np.testing.assert_allclose(mean, allf.mean(0), rtol=1e-5)
+  np.testing.assert_allclose(std, allf.std(0), rtol=1e-4)
+  buckets, alt = sc.LengthBuckets()
+  assert buckets == [11, 21, 31, 40] and alt[0.02] == 40
+  sc.Print()
+  assert 'bucket upper limits' in capsys.readouterr().out
