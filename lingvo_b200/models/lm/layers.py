@@ -41,11 +41,39 @@ class BaseLanguageModel(base_layer.BaseLayer):
     p.Define('vocab_size', 0, 'Vocabulary size.')
     return p
 
+  @classmethod
+  def UpdateTargetVocabSize(cls, p, vocab_size, wpm_model=None):
+    """Sets the vocabulary size on LM params (and, in subclasses, on their softmax /
+    embedding) (ref :40)."""
+    del wpm_model
+    p.vocab_size = vocab_size
+    for name in ('softmax', 'emb'):
+      if name in p and p.Get(name) is not None:
+        sub = p.Get(name)
+        for key in ('num_classes', 'vocab_size'):
+          if key in sub:
+            sub.Set(**{key: vocab_size})
+    return p
+
   def zero_state(self, theta, batch_size):
     raise NotImplementedError
 
   def FProp(self, theta, inputs, paddings, state0, labels=None, direct_features=None):
     raise NotImplementedError
+
+  def GetFeedDict(self):
+    """Optional extra inputs of the LM keyed by name (ref :149)."""
+    return {}
+
+  def CombineStates(self, state0, state1, switch_cond):
+    """Per batch element: `state0` where `switch_cond [batch]` is true, else `state1`
+    (ref :153) — used by beam search / shallow fusion to roll back rejected steps. The
+    default works for any state whose tensors have the batch in dim 0."""
+    def Pick(a, b):
+      cond = switch_cond.reshape([-1] + [1] * (a.dim() - 1))
+      return torch.where(cond, a, b)
+    return py_utils.Transform(Pick, state0, state1) if not isinstance(state0, NestedMap) \
+        else state0.Pack([Pick(a, b) for a, b in zip(state0.Flatten(), state1.Flatten())])
 
   def Logits(self, theta, inputs, paddings, *args, **kwargs):
     xent, _ = self.FProp(theta, inputs, paddings, *args, **kwargs)
@@ -79,6 +107,28 @@ class BaseLanguageModel(base_layer.BaseLayer):
     if out.get('per_example_argmax') is not None:
       res.per_example_argmax = out.per_example_argmax.reshape(t, b)
     return res
+
+
+def ComputeXentOutput(softmax_layer, softmax_theta, activations, labels, num_samples=1):
+  """Softmax cross entropy of `[time, batch · num_samples, dim]` activations (ref :233):
+  without labels only the logits; `labels.class_ids` / `class_probabilities` (+
+  `class_weights`) are tiled `num_samples` times along the batch."""
+  t, b = activations.shape[:2]
+  if labels is None:
+    logits = softmax_layer.Logits(softmax_theta, activations.reshape(t * b, -1))
+    return NestedMap(logits=logits.reshape(t, b, -1))
+  tile = (lambda x: x.repeat(1, num_samples)) if num_samples > 1 else (lambda x: x)
+  flat = activations.reshape(t * b, -1)
+  weights = tile(labels.class_weights).reshape(t * b, 1)
+  if 'class_ids' in labels:
+    return softmax_layer.FProp(softmax_theta, flat, weights,
+                               class_ids=tile(labels.class_ids).reshape(t * b, 1))
+  assert 'class_probabilities' in labels
+  probs = labels.class_probabilities
+  if num_samples > 1:
+    probs = probs.repeat(1, num_samples, 1)
+  return softmax_layer.FProp(softmax_theta, flat, weights,
+                             class_probabilities=probs.reshape(t * b, -1))
 
 
 class NullLm(BaseLanguageModel):

@@ -208,3 +208,36 @@ def test_gshard_lm_decode_tool(tmp_path):
   assert len(lines) == 3 and lines[0].split('\t')[0] == '5 6 7'
   assert len(lines[0].split('\t')[1].split()) >= 1
   assert dec.DecodeFiles([str(f)], str(tmp_path / 'out')) == []      # restart-safe skip
+
+
+def test_lm_layer_state_combination_and_xent_output():
+  import torch
+  from lingvo_b200.core import layers as core_layers
+  from lingvo_b200.core.nested_map import NestedMap
+  from lingvo_b200.models.lm import layers as lm_layers
+  p = lm_layers.RnnLm.CommonParams(vocab_size=11, emb_dim=4, num_layers=2, rnn_dims=6)
+  p.name = 'lm'
+  lm_layers.RnnLm.UpdateTargetVocabSize(p, 13)
+  assert p.vocab_size == 13 and p.softmax.num_classes == 13 and p.emb.vocab_size == 13
+  lm = p.Instantiate()
+  s0 = lm.zero_state(lm.theta, 3)
+  s1 = s0.Transform(lambda x: x + 1.0)
+  mixed = lm.CombineStates(s0, s1, torch.tensor([True, False, True]))
+  for a in mixed.Flatten():
+    assert a[0].abs().sum() == 0 and a[2].abs().sum() == 0 and bool((a[1] == 1).all())
+  assert lm.GetFeedDict() == {}
+  sm = core_layers.SimpleFullSoftmax.Params().Set(name='sm', input_dim=5, num_classes=7).Instantiate()
+  acts = torch.randn(4, 6, 5)                         # batch 3 × 2 samples
+  only_logits = lm_layers.ComputeXentOutput(sm, sm.theta, acts, None)
+  assert only_logits.logits.shape == (4, 6, 7)
+  labels = NestedMap(class_ids=torch.randint(0, 7, (4, 3)), class_weights=torch.ones(4, 3))
+  out = lm_layers.ComputeXentOutput(sm, sm.theta, acts, labels, num_samples=2)
+  want = torch.nn.functional.cross_entropy(
+      sm.Logits(sm.theta, acts.reshape(24, 5)).float(),
+      labels.class_ids.repeat(1, 2).reshape(-1), reduction='mean')
+  torch.testing.assert_close(out.avg_xent, want, atol=1e-5, rtol=1e-5)
+  probs = torch.softmax(torch.randn(4, 3, 7), -1)
+  out2 = lm_layers.ComputeXentOutput(
+      sm, sm.theta, acts[:, :3], NestedMap(class_probabilities=probs,
+                                           class_weights=torch.ones(4, 3)))
+  assert out2.per_example_xent.shape[0] == 12
