@@ -46,6 +46,10 @@ class IdentitySeqLayer(base_layer.BaseLayer):
   def zero_state(self, theta, batch_size):
     return NestedMap()
 
+  def FPropFullSequence(self, theta, inputs, paddings):
+    del theta, paddings
+    return inputs
+
   def FProp(self, theta, inputs, *args, **kwargs):
     return inputs
 
@@ -287,6 +291,15 @@ class StackedFRNNLayerByLayer(StackedRNNBase, quant_utils.QuantizableLayer):
     return xs, NestedMap(rnn=finals)
 
 
+def _StackedFPropFullSequence(self, theta, inputs, paddings):
+  """Outputs of the whole sequence only (no final state) (ref :287, :361)."""
+  out = self.FProp(theta, inputs, paddings)
+  return out[0] if isinstance(out, tuple) else out
+
+
+StackedFRNNLayerByLayer.FPropFullSequence = _StackedFPropFullSequence
+
+
 class StackedBiFRNNLayerByLayer(StackedRNNBase, quant_utils.QuantizableLayer):
   """N bidirectional FRNNs (ref :291); each direction has `num_output_nodes/2`."""
 
@@ -412,6 +425,83 @@ class FRNNWithAttention(base_layer.BaseLayer):
       outs.append(self.cell.GetOutput(state.rnn))
       probs.append(state.atten_probs)
     return torch.stack(ctxs, 0), torch.stack(outs, 0), torch.stack(probs, 0), state
+
+
+StackedBiFRNNLayerByLayer.FPropFullSequence = _StackedFPropFullSequence
+
+
+def _FrnnAttenInitAttention(self, theta, src_encs, src_paddings, src_contexts=None,
+                            src_segment_id=None):
+  """Alias of `InitForSourcePacked` under the reference's name (ref :806)."""
+  return self.InitForSourcePacked(theta, src_encs, src_paddings, src_contexts, src_segment_id)
+
+
+def _FrnnAttenResetAttenState(self, theta, state, inputs):
+  """Packed inputs: zero the attention context / probs / state where a new segment starts
+  (`inputs.reset_mask` is 0 there) (ref :898)."""
+  del theta
+  m = inputs.reset_mask
+  state.atten = m.to(state.atten.dtype) * state.atten
+  if isinstance(state.atten_state, NestedMap):
+    if 'inner' not in state.atten_state:
+      raise ValueError('Unknown .atten_state, expecting field "inner": %s' % state.atten_state)
+    state.atten_state.inner = m.to(state.atten_state.inner.dtype) * state.atten_state.inner
+  elif isinstance(state.atten_state, torch.Tensor) and state.atten_state.numel():
+    state.atten_state = m.to(state.atten_state.dtype) * state.atten_state
+  state.atten_probs = m.to(state.atten_probs.dtype) * state.atten_probs
+  return state
+
+
+def _FrnnAttenAccumulateStates(self, theta, src_encs, src_paddings, inputs, paddings,
+                               src_contexts=None, state0=None, src_segment_id=None,
+                               segment_id=None):
+  """The recurrence only (ref :911) → (accumulated states stacked over time, final state,
+  side info for `PostProcessStates`). Splitting FProp this way lets a caller reuse the raw
+  per-step states (attention states of monotonic / location-aware attention, …)."""
+  p = self.params
+  packed = self.InitForSourcePacked(theta, src_encs, src_paddings, src_contexts,
+                                    src_segment_id)
+  t, b = inputs.shape[:2]
+  paddings = _Pad3(paddings)
+  if state0 is None:
+    state0 = self.zero_state(theta, src_encs, packed, b)
+  else:
+    assert not p.packed_input, 'packed input is only supported with default initial states.'
+  reset = torch.zeros_like(paddings)
+  if p.packed_input and segment_id is not None:
+    reset = GeneratePackedInputResetMask(_Pad3(segment_id))
+  state = state0
+  steps = []
+  for i in range(t):
+    qseg = None
+    if p.packed_input and segment_id is not None:
+      qseg = _Pad3(segment_id)[i].squeeze(-1)
+    state = self.Step(theta, packed, state, inputs[i], paddings[i],
+                      reset[i] if p.packed_input else None, qseg)
+    steps.append(state)
+  flat = [s.Flatten() for s in steps]
+  acc = steps[0].Pack([torch.stack([f[k] for f in flat], 0) if isinstance(
+      flat[0][k], torch.Tensor) else flat[0][k] for k in range(len(flat[0]))])
+  return acc, state, NestedMap(state0=state0, reset_mask=reset)
+
+
+def _FrnnAttenPostProcessStates(self, acc_state, side_info):
+  """→ (attention context `[T, B, C]`, rnn output `[T, B, D]`, attention probs `[T, B, S]`)
+  (ref :1013); with `output_prev_atten_ctx` the contexts are shifted right by one step
+  (step 0 gets the initial context; packed inputs restart at segment boundaries)."""
+  p = self.params
+  ctx = acc_state.atten
+  if p.output_prev_atten_ctx:
+    ctx = torch.cat([side_info.state0.atten.unsqueeze(0).to(ctx.dtype), ctx[:-1]], 0)
+    if p.packed_input:
+      ctx = ctx * side_info.reset_mask.to(ctx.dtype)
+  return ctx, self.cell.GetOutput(acc_state.rnn), acc_state.atten_probs
+
+
+FRNNWithAttention.InitAttention = _FrnnAttenInitAttention
+FRNNWithAttention.reset_atten_state = _FrnnAttenResetAttenState
+FRNNWithAttention.AccumulateStates = _FrnnAttenAccumulateStates
+FRNNWithAttention.PostProcessStates = _FrnnAttenPostProcessStates
 
 
 class MultiSourceFRNNWithAttention(base_layer.BaseLayer):

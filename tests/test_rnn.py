@@ -408,3 +408,41 @@ def test_stacked_recurrent_matches_layer_by_layer():
       [None, None], [_GruLikeCell, _GruLikeCell], [None, None], [out_fn, out_fn], [None, None],
       [theta, theta2], [s0, s0], inp, unused_acc_state=True)
   assert none_acc is None
+
+
+def test_frnn_with_attention_accumulate_and_postprocess_equal_fprop():
+  from lingvo_b200.core import attention as attention_lib
+  for prev in (False, True):
+    p = rnn_layers.FRNNWithAttention.Params().Set(
+        name='fa', output_prev_atten_ctx=prev, use_zero_atten_state=True,
+        atten_context_dim=5, random_seed=8,
+        cell=rnn_cell.LSTMCellSimple.Params().Set(name='c', num_input_nodes=3 + 5,
+                                                  num_output_nodes=6),
+        attention=attention_lib.AdditiveAttention.Params().Set(
+            source_dim=5, query_dim=6, hidden_dim=4))
+    layer = p.Instantiate()
+    src, spad = torch.randn(4, 2, 5), torch.zeros(4, 2)
+    x, pad = torch.randn(3, 2, 3), torch.zeros(3, 2, 1)
+    ctx, out, probs, final = layer.FProp(layer.theta, src, spad, x, pad)
+    acc, final2, side = layer.AccumulateStates(layer.theta, src, spad, x, pad)
+    ctx2, out2, probs2 = layer.PostProcessStates(acc, side)
+    torch.testing.assert_close(ctx2, ctx)
+    torch.testing.assert_close(out2, out)
+    torch.testing.assert_close(probs2, probs)
+    torch.testing.assert_close(final2.atten, final.atten)
+    assert acc.atten_probs.shape == (3, 2, 4)
+  packed = layer.InitAttention(layer.theta, src, spad)
+  assert packed is not None
+  st = NestedMap(atten=torch.ones(2, 5), atten_probs=torch.ones(2, 4), atten_state=torch.ones(2, 1))
+  st = layer.reset_atten_state(layer.theta, st, NestedMap(reset_mask=torch.tensor([[0.0], [1.0]])))
+  assert st.atten[0].sum() == 0 and st.atten[1].sum() == 5 and st.atten_probs[0].sum() == 0
+  with pytest.raises(ValueError):
+    layer.reset_atten_state(layer.theta, NestedMap(
+        atten=torch.ones(2, 5), atten_probs=torch.ones(2, 4),
+        atten_state=NestedMap(other=torch.ones(2))), NestedMap(reset_mask=torch.ones(2, 1)))
+  stack = rnn_layers.StackedFRNNLayerByLayer.Params().Set(
+      name='st', num_layers=2, num_input_nodes=3, num_output_nodes=3,
+      cell_tpl=rnn_cell.LSTMCellSimple.Params().Set(
+          num_input_nodes=3, num_output_nodes=3)).Instantiate()
+  full = stack.FPropFullSequence(stack.theta, x, pad)
+  assert full.shape == (3, 2, 3)
