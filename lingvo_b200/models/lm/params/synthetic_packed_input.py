@@ -251,6 +251,38 @@ class DenseLm175B32x32DP(DenseLm175B32x32):
 
 
 @model_registry.RegisterSingleTaskModel
+class DenseLm175B1K(DenseLm175B32x32):
+  """175B LM on a 1024-device [64, 16] mesh (ref :280)."""
+  DEVICE_MESH_SHAPE = [64, 16]
+  DEVICE_MESH = np.arange(1024).reshape(DEVICE_MESH_SHAPE)
+
+
+@model_registry.RegisterSingleTaskModel
+class DenseLm175B8x8Decode2D(DenseLm175B32x32):
+  """175B LM decoding on 128 devices with a 2-D logical mesh (ref :297): heads do not divide
+  the device count, so both the model dim and the heads are sharded. Loads
+  `DenseLm175B32x32` checkpoints."""
+  BATCH_DIM_PER_DEVICE = 0.125
+  NUM_DEVICES_PER_SPLIT = 128
+  DEVICE_MESH_SHAPE = [8, 16]
+  DEVICE_MESH = np.arange(128).reshape(DEVICE_MESH_SHAPE)
+
+  def Task(self):
+    p = super().Task()
+    b = p.builder
+    # packed relative positions are per example when decoding
+    b.relative_attention_use_universal_1d_position = False
+    b.model_dim_reshape_segments = self.DEVICE_MESH_SHAPE[0]
+    b.emb_w_split = [1, 0]
+    b.emb_out_split = [-1, -1, 0]
+    b.blm_split = [-1, -1, 0]
+    b.blh_split = [-1, -1, 1]
+    b.qkv_split = [0, -1, 1, -1]
+    b.logits_split = [-1, -1, 1]
+    return p
+
+
+@model_registry.RegisterSingleTaskModel
 class DenseLM13B32x32(DenseLm128B16x16):
   """13B LM."""
   HIDDEN_DIM = 5120 * 4
@@ -279,7 +311,39 @@ class DenseLm128B32x32(DenseLm128B16x16):
 
 
 class ShardedAdamOptimizer(optimizer.Adam):
-  """Adam whose slot vars inherit the variable sharding (reference :358-398)."""
+  """Adam whose slot variables inherit the variable sharding, with optional accumulation of
+  `num_micro_batches` gradients before every update (reference :358-405)."""
+
+  SLOT_SUFFIX = dict(getattr(optimizer.Adam, 'SLOT_SUFFIX', {}), grad_accum='grad_accum')
+  COUNTER_ATTRS = tuple(getattr(optimizer.Adam, 'COUNTER_ATTRS', ())) + ('_micro_count',)
+
+  @classmethod
+  def Params(cls):
+    p = super().Params()
+    p.Define('num_micro_batches', 1, 'Number of accumulated micro-batches per update.')
+    return p
+
+  def __init__(self, params):
+    super().__init__(params)
+    self._micro_count = 0
+
+  def Apply(self, lr, var_grad, grad_scale=None):
+    n = self.params.num_micro_batches
+    if n <= 1:
+      return super().Apply(lr, var_grad, grad_scale=grad_scale)
+    pairs = optimizer._Pairs(var_grad)   # pylint: disable=protected-access
+    with torch.no_grad():
+      accs = [self._Slot(v, 'grad_accum') for v, _ in pairs]
+      torch._foreach_add_(accs, optimizer._ScaledF32(pairs, grad_scale))   # pylint: disable=protected-access
+    self._micro_count += 1
+    if self._micro_count % n:
+      return None
+    with torch.no_grad():
+      avg = torch._foreach_div(accs, float(n))
+    super().Apply(lr, [py_utils.VarGrad(v, g) for (v, _), g in zip(pairs, avg)])
+    with torch.no_grad():
+      torch._foreach_zero_(accs)
+    return None
 
 
 @model_registry.RegisterSingleTaskModel
@@ -290,11 +354,12 @@ class DenseLm12kWide41BAdam16x16(DenseLm128B16x16):
   NUM_HEADS = 96
   NUM_TRANSFORMER_LAYERS = 36
   GATED_GELU = False
+  NUM_MICRO_BATCHES = 1
 
   def Task(self):
     p = super().Task()
     p.train.optimizer = ShardedAdamOptimizer.Params().Set(
-        beta1=0.9, beta2=0.999, epsilon=1e-6)
+        beta1=0.9, beta2=0.999, epsilon=1e-6, num_micro_batches=self.NUM_MICRO_BATCHES)
     p.train.learning_rate = 0.005
     return p
 
@@ -311,6 +376,26 @@ class DenseLm12kWide41BAdam8x8(DenseLm12kWide41BAdam16x16):
 class DenseLm12kWide162BAdam16x16(DenseLm12kWide41BAdam16x16):
   """162B LM, Adam, v3-512 (~12.5k tokens/s)."""
   NUM_TRANSFORMER_LAYERS = 144
+
+
+@model_registry.RegisterSingleTaskModel
+class DenseLm12kWide162BAdamBS25616x16(DenseLm12kWide162BAdam16x16):
+  """Same model, global batch 256 as 4 micro-batches of 64 (ref :469)."""
+  BATCH_DIM_PER_DEVICE = 0.125
+  NUM_MICRO_BATCHES = 4
+
+
+@model_registry.RegisterSingleTaskModel
+class DenseLm12kWide162BAdam32x32(DenseLm12kWide162BAdam16x16):
+  """162B LM, Adam, 2048 devices on a [64, 32] mesh (heads sharded 32 ways) (ref :481)."""
+  TRAIN_STEPS_PER_LOOP = 20
+  NUM_DEVICES_PER_SPLIT = 2048
+  BATCH_DIM_PER_DEVICE = 0.125
+  DEVICE_MESH_SHAPE = [64, 32]
+  DEVICE_MESH = np.reshape(np.arange(2048), [32, 64]).transpose()
+
+
+ShardedAdam = ShardedAdamOptimizer
 
 
 class MoELmTemplate(DenseLmTemplate):

@@ -241,3 +241,41 @@ def test_lm_layer_state_combination_and_xent_output():
       sm, sm.theta, acts[:, :3], NestedMap(class_probabilities=probs,
                                            class_weights=torch.ones(4, 3)))
   assert out2.per_example_xent.shape[0] == 12
+
+
+def test_new_dense_lm_configs_and_sharded_adam_micro_batches():
+  import numpy as np
+  import torch
+  from lingvo_b200 import model_registry
+  from lingvo_b200.core import py_utils
+  from lingvo_b200.models.lm.params import synthetic_packed_input as sp
+  for name, mesh in [('DenseLm175B1K', [64, 16]), ('DenseLm175B8x8Decode2D', [8, 16]),
+                     ('DenseLm12kWide162BAdamBS25616x16', None),
+                     ('DenseLm12kWide162BAdam32x32', [64, 32])]:
+    cls = getattr(sp, name)
+    mp = model_registry.GetParams('lm.synthetic_packed_input.' + name, 'Train')
+    if mesh is not None:
+      assert list(cls.DEVICE_MESH.shape) == mesh
+    assert mp.task.builder.model_dim == cls.MODEL_DIM
+  dec = model_registry.GetParams('lm.synthetic_packed_input.DenseLm175B8x8Decode2D', 'Train')
+  assert dec.task.builder.relative_attention_use_universal_1d_position is False
+  assert dec.task.builder.model_dim_reshape_segments == 8 and dec.task.builder.emb_w_split == [1, 0]
+  bs = model_registry.GetParams('lm.synthetic_packed_input.DenseLm12kWide162BAdamBS25616x16',
+                                'Train')
+  assert bs.task.train.optimizer.num_micro_batches == 4
+  big = sp.DenseLm12kWide162BAdam32x32
+  assert big.DEVICE_MESH[1, 0] == 1 and big.DEVICE_MESH[0, 1] == 64     # transposed device order
+  assert sp.ShardedAdam is sp.ShardedAdamOptimizer
+  # 2 micro-batches: the update happens on the second Apply, with the averaged gradient
+  opt = sp.ShardedAdam.Params().Set(name='a', num_micro_batches=2, beta1=0.0, beta2=0.0,
+                                    epsilon=1e-8).Instantiate()
+  ref = sp.ShardedAdam.Params().Set(name='b', beta1=0.0, beta2=0.0, epsilon=1e-8).Instantiate()
+  w = torch.nn.Parameter(torch.ones(3)); w2 = torch.nn.Parameter(torch.ones(3))
+  g1, g2 = torch.tensor([1.0, 2.0, 3.0]), torch.tensor([3.0, 2.0, -1.0])
+  opt.Apply(0.1, [py_utils.VarGrad(w, g1)])
+  assert torch.equal(w.detach(), torch.ones(3))
+  opt.Apply(0.1, [py_utils.VarGrad(w, g2)])
+  ref.Apply(0.1, [py_utils.VarGrad(w2, (g1 + g2) / 2)])
+  torch.testing.assert_close(w.detach(), w2.detach())
+  assert float(opt._Slot(w, 'grad_accum').abs().sum()) == 0.0
+  del np
