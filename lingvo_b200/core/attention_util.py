@@ -83,21 +83,79 @@ def AttenContext(probs, value, qlayer=None):
 class PositionalAttenLogits(quant_utils.QuantizableLayer):
   """Transformer-XL terms (b) and (d): q·R and v·R with relative shift (ref :384)."""
 
-  def AttenLogitsXL(self, content_logits, query, abs_pos_emb, content_bias, positional_bias,
+  def AttenLogitsXL(self, query, key, abs_pos_emb, content_bias, positional_bias,
                     skip_term_b=False):
-    """content_logits [B,N,T,S]; query [B,T,N,H]; abs_pos_emb [2T−1,N,H] (distance
-    T−1 … −(T−1)); biases [N,H]."""
-    t = query.shape[1]
-    term_d_src = positional_bias if skip_term_b else None
-    q = query + (positional_bias if not skip_term_b else 0)
-    term_bd = torch.einsum('BTNH,RNH->BNTR', q, abs_pos_emb) if not skip_term_b else \
-        torch.einsum('NH,RNH->NR', term_d_src, abs_pos_emb).view(1, -1, 1, 2 * t - 1).expand(
-            query.shape[0], -1, t, -1)
-    idx = (torch.arange(t, device=query.device).unsqueeze(0) -
-           torch.arange(t, device=query.device).unsqueeze(1) + (t - 1))
-    term_bd = term_bd.gather(-1, idx.expand(*term_bd.shape[:2], t, t))
-    del content_bias
-    return content_logits + term_bd
+    """Transformer-XL logits (ref :497): query/key [B,T,N,H]; abs_pos_emb [2T−1,N,H] with row
+    r the embedding of distance r−(T−1); biases [N,H] → [B,N,T,T]."""
+    return self._AttenLogits(query, key, abs_pos_emb, content_bias, positional_bias,
+                             skip_term_b)
+
+  @staticmethod
+  def RelPositionBias(content, abs_pos_emb, skip_term_b=False):
+    """Relative-position logits (ref :392). `content` is [B,T,N,H] (or the bare [N,H] bias when
+    `skip_term_b`), `abs_pos_emb` [2T−1,N,H] with row r the embedding of distance r−(T−1).
+    out[b,n,i,j] = content[b,i,n] · abs_pos_emb[i−j+T−1, n]; shape [B,N,T,T] ([N,T,T] when
+    `skip_term_b`). One gather over the distance axis replaces the pad-and-reshape skew."""
+    r = abs_pos_emb.shape[0]
+    t = (r + 1) // 2
+    ar = torch.arange(t, device=abs_pos_emb.device)
+    idx = ar.unsqueeze(1) - ar.unsqueeze(0) + (t - 1)                      # [T(i), T(j)]
+    if skip_term_b:
+      full = torch.einsum('NH,RNH->NR', content, abs_pos_emb)              # [N, 2T-1]
+      return full[:, idx]
+    full = torch.einsum('BTNH,RNH->BNTR', content, abs_pos_emb)
+    return full.gather(-1, idx.expand(*full.shape[:2], t, t))
+
+  @staticmethod
+  def _ValidateBiases(content_bias, positional_bias, n, h):
+    for b in (content_bias, positional_bias):
+      if b is not None and tuple(b.shape) != (n, h):
+        raise ValueError(f'bias shape {tuple(b.shape)} != {(n, h)}')
+
+  def _AttenLogits(self, query, key, abs_pos_emb, content_bias=None, positional_bias=None,
+                   skip_term_b=False):
+    """term (a)+(c) = (q+u)·k, term (b)+(d) = RelPositionBias(q+v) (ref :448). query/key
+    [B,T,N,H] → [B,N,T,T]."""
+    b, t, n, h = query.shape
+    self._ValidateBiases(content_bias, positional_bias, n, h)
+    content = query if content_bias is None else query + content_bias
+    term_ac = torch.einsum('BTNH,BSNH->BNTS', content, key)
+    if skip_term_b:
+      if positional_bias is None:
+        return term_ac
+      return term_ac + self.RelPositionBias(positional_bias, abs_pos_emb, True).unsqueeze(0)
+    pos = query if positional_bias is None else query + positional_bias
+    return term_ac + self.RelPositionBias(pos, abs_pos_emb, False)
+
+  def AttenLogitsRPE(self, query, key, abs_pos_emb):
+    """Shaw-style relative position logits: no biases (ref :531)."""
+    return self._AttenLogits(query, key, abs_pos_emb)
+
+  def AttenLogitsXLOneStep(self, query, key, abs_pos_emb, content_bias, positional_bias,
+                           skip_term_b=False):
+    """One decode step (ref :562): query [B,N,H], key [S,B,N,H], abs_pos_emb [S,N,H] (all
+    sequences at the same time step) or [B,S,N,H] (per-sequence steps) → [S,B,N]."""
+    s, b = key.shape[:2]
+    _, n, h = query.shape
+    key = key.reshape(s, b, n, h)
+    self._ValidateBiases(content_bias, positional_bias, n, h)
+    term_ac = torch.einsum('BNH,SBNH->SBN', query + content_bias, key)
+    synced = abs_pos_emb.dim() == 3
+    if not skip_term_b:
+      pos = query + positional_bias
+      term_bd = torch.einsum('BNH,SNH->SBN' if synced else 'BNH,BSNH->SBN', pos, abs_pos_emb)
+    elif synced:
+      term_bd = torch.einsum('NH,SNH->SN', positional_bias, abs_pos_emb).unsqueeze(1)
+    else:
+      term_bd = torch.einsum('NH,BSNH->SBN', positional_bias, abs_pos_emb)
+    return term_ac + term_bd
+
+  def AttenLogitsRPEOneStep(self, query, key, abs_pos_emb):
+    """One decode step of RPE (ref :628): query [B,N,H], key [S,B,N,H], abs_pos_emb
+    [S,1,N,H] → [S,B,N]."""
+    s, b = key.shape[:2]
+    _, n, h = query.shape
+    return torch.einsum('BNH,SBNH->SBN', query, key.reshape(s, b, n, h) + abs_pos_emb)
 
 
 class KMeansClusteringForAtten(base_layer.BaseLayer):

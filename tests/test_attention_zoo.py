@@ -316,3 +316,48 @@ def test_builder_lconv_stack_moe_and_funnel_layer():
   same = b.FunnelEncoderLayer('f1', stride=1).Instantiate().FPropDefaultTheta(i)
   assert same.vec.shape == i.vec.shape
   assert b.Seq('s', b._Id('a'), b._Id('b')).cls.__name__ == 'SequentialLayer'
+
+
+def test_positional_atten_logits_rel_position_bias_and_one_step():
+  from lingvo_b200.core import attention_util
+  torch.manual_seed(0)
+  b, t, n, h = 2, 5, 3, 4
+  lyr = attention_util.PositionalAttenLogits.Params().Set(name='pal').Instantiate()
+  q, k = torch.randn(b, t, n, h), torch.randn(b, t, n, h)
+  emb = torch.randn(2 * t - 1, n, h)
+  u, v = torch.randn(n, h), torch.randn(n, h)
+  want = torch.zeros(b, n, t, t)
+  for i in range(t):
+    for j in range(t):
+      want[:, :, i, j] = ((q[:, i] + u) * k[:, j]).sum(-1) + \
+          ((q[:, i] + v) * emb[i - j + t - 1]).sum(-1)
+  got = lyr._AttenLogits(q, k, emb, u, v)
+  torch.testing.assert_close(got, want, atol=1e-5, rtol=1e-5)
+  content = torch.einsum('BTNH,BSNH->BNTS', q + u, k)
+  torch.testing.assert_close(lyr.AttenLogitsXL(q, k, emb, u, v), want, atol=1e-5,
+                             rtol=1e-5)
+  # skip_term_b drops the q·R term.
+  skip = lyr._AttenLogits(q, k, emb, u, v, skip_term_b=True)
+  want_skip = content + lyr.RelPositionBias(v, emb, True).unsqueeze(0)
+  torch.testing.assert_close(skip, want_skip)
+  assert lyr.RelPositionBias(v, emb, True).shape == (n, t, t)
+  rpe = lyr.AttenLogitsRPE(q, k, emb)
+  torch.testing.assert_close(rpe, lyr._AttenLogits(q, k, emb, torch.zeros(n, h),
+                                                   torch.zeros(n, h)))
+  # One step at time i equals row i of the full logits when fed the right embedding rows.
+  i = 3
+  key_sb = k.transpose(0, 1)                                         # [S,B,N,H]
+  step_emb = torch.stack([emb[i - j + t - 1] for j in range(t)])     # [S,N,H]
+  one = lyr.AttenLogitsXLOneStep(q[:, i], key_sb, step_emb, u, v)
+  torch.testing.assert_close(one, want[:, :, i, :].permute(2, 0, 1), atol=1e-5, rtol=1e-5)
+  per_seq = lyr.AttenLogitsXLOneStep(q[:, i], key_sb, step_emb.unsqueeze(0).expand(b, -1, -1, -1),
+                                     u, v)
+  torch.testing.assert_close(per_seq, one)
+  one_skip = lyr.AttenLogitsXLOneStep(q[:, i], key_sb, step_emb, u, v, skip_term_b=True)
+  torch.testing.assert_close(one_skip, skip[:, :, i, :].permute(2, 0, 1), atol=1e-5, rtol=1e-5)
+  rpe1 = lyr.AttenLogitsRPEOneStep(q[:, i], key_sb, step_emb.unsqueeze(1))
+  want_rpe1 = torch.einsum('BNH,SBNH->SBN', q[:, i], key_sb + step_emb.unsqueeze(1))
+  torch.testing.assert_close(rpe1, want_rpe1)
+  import pytest
+  with pytest.raises(ValueError):
+    lyr._AttenLogits(q, k, emb, torch.zeros(n, h + 1), v)
