@@ -65,8 +65,21 @@ class AverageMetric(BaseMetric):
     self._total_value += float(value) * float(weight)
     self._total_weight += float(weight)
 
-  total_value = property(lambda self: self._total_value)
-  total_weight = property(lambda self: self._total_weight)
+  def GetTotalValue(self):
+    return self._total_value
+
+  def SetTotalValue(self, val):
+    self._total_value = val
+
+  total_value = property(GetTotalValue, SetTotalValue)
+
+  def GetTotalWeight(self):
+    return self._total_weight
+
+  def SetTotalWeight(self, val):
+    self._total_weight = val
+
+  total_weight = property(GetTotalWeight, SetTotalWeight)
 
   @property
   def value(self):
@@ -89,6 +102,10 @@ class UniqueAverageMetric(AverageMetric):
       return
     self._map[key] = (value, weight)
     super().Update(value, weight)
+
+  @property
+  def num_keys(self):
+    return len(self._map)
 
 
 class F1Metric(BaseMetric):
@@ -192,6 +209,27 @@ class CorpusBleuMetric(BaseMetric):
     return geo * bp
 
 
+def _CurvePng(xs, ys, size=256):
+  """Polyline through (xs, ys) ∈ [0,1]² on a white `size`×`size` canvas with a light 0.25
+  grid; y grows upwards. Dependency-free stand-in for the matplotlib curve plot."""
+  from lingvo_b200.utils import tfevents  # pylint: disable=g-import-not-at-top
+  img = np.full((size, size), 255, np.uint8)
+  for g in (0.25, 0.5, 0.75):
+    k = int(round(g * (size - 1)))
+    img[k, :] = 224
+    img[:, k] = 224
+  img[[0, -1], :] = 128
+  img[:, [0, -1]] = 128
+  xs = np.clip(np.asarray(xs, np.float64), 0.0, 1.0) * (size - 1)
+  ys = (1.0 - np.clip(np.asarray(ys, np.float64), 0.0, 1.0)) * (size - 1)
+  for i in range(len(xs) - 1):
+    n = int(max(abs(xs[i + 1] - xs[i]), abs(ys[i + 1] - ys[i]))) + 2
+    cx = np.round(np.linspace(xs[i], xs[i + 1], n)).astype(int)
+    cy = np.round(np.linspace(ys[i], ys[i + 1], n)).astype(int)
+    img[cy, cx] = 0
+  return tfevents.EncodePng(img)
+
+
 class AUCMetric(BaseMetric):
   """ROC-AUC or PR-AUC over accumulated (label, prob[, weight])."""
 
@@ -235,6 +273,42 @@ class AUCMetric(BaseMetric):
     stop = int(np.searchsorted(tp, tp[-1]))      # first threshold reaching full recall
     sl = slice(stop, None, -1)
     return np.r_[precision[sl], 1.0], np.r_[recall[sl], 0.0], th[sl]
+
+  def Curve(self):
+    """(xs, ys, axis labels) of the curve the AUC integrates: (FPR, TPR) for 'roc',
+    (recall, precision) for 'pr'."""
+    if self._mode == 'pr':
+      precision, recall, _ = self._PrCurve()
+      return recall, precision, ('Recall', 'Precision')
+    st = self._Sorted()
+    if st is None:
+      return np.array([0.0, 1.0]), np.array([0.0, 1.0]), ('False Positive Rate',
+                                                           'True Positive Rate')
+    tp, fp, _ = st
+    return (np.r_[0.0, fp / fp[-1]], np.r_[0.0, tp / tp[-1]],
+            ('False Positive Rate', 'True Positive Rate'))
+
+  def Summary(self, name):
+    """The scalar AUC plus an image of the curve under the same tag (ref :533). With
+    matplotlib the plot has a grid / axis labels; without, the curve is rasterised on a unit
+    square by `_CurvePng`."""
+    from lingvo_b200.core import plot  # pylint: disable=g-import-not-at-top
+    from lingvo_b200.utils import tfevents  # pylint: disable=g-import-not-at-top
+    xs, ys, labels = self.Curve()
+
+    def _Setter(fig, axes):
+      ticks = np.arange(0, 1.05, 0.05)
+      axes.grid(visible=True)
+      axes.set_xlabel(labels[0])
+      axes.set_xticks(ticks)
+      axes.set_ylabel(labels[1])
+      axes.set_yticks(ticks)
+      fig.tight_layout()
+
+    png = plot.Curve(name=name, figsize=(12, 12), xs=xs, ys=ys, setter=_Setter)
+    if png is None:
+      png = _CurvePng(xs, ys)
+    return tfevents.ImageValue(name, png) + CreateScalarSummary(name, self.value)
 
   @property
   def value(self):
@@ -500,9 +574,70 @@ class DeviceEvalMetrics:
   all-reduced across ranks) once per program run.
   """
 
-  def __init__(self):
+  def __init__(self, max_metrics: int = 256):
     self._names: List[str] = []
     self._acc: Optional[torch.Tensor] = None  # [n, 2] (sum v·w, sum w)
+    self._max_metrics = int(max_metrics)
+    self._metrics = None
+    self._initial_values = [torch.zeros((), dtype=torch.float32)
+                            for _ in range(2 * self._max_metrics)]
+
+  # -- loop-carried form (ref :288-384): a flat [v0·w0, w0, v1·w1, w1, …] list of scalars that
+  # a device loop threads through its iterations.
+  @property
+  def initial_values(self):
+    return self._initial_values
+
+  @property
+  def metrics(self):
+    return self._metrics
+
+  def PackStepMetricsForAccumulation(self, metric_dict, step_args):
+    """This step's (value·weight, weight) pairs in sorted-name order, followed by the
+    untouched tail of `step_args`."""
+    n = len(metric_dict)
+    assert n <= self._max_metrics, 'Increase max_metrics to >= %d' % n
+    self._metrics = metric_dict
+    ret = []
+    for _, (value, weight) in sorted(metric_dict.items()):
+      weight = torch.as_tensor(weight, dtype=torch.float32).detach()
+      value = torch.as_tensor(value, dtype=torch.float32).detach() * weight
+      assert value.numel() == 1 and weight.numel() == 1, (value.shape, weight.shape)
+      ret += [value.reshape(()), weight.reshape(())]
+    return ret + list(step_args)[len(ret):]
+
+  def FinalizeMetrics(self, loop_carried_metrics, group=None):
+    """Sums the carried scalars over the ranks (one fused all-reduce) and returns the flat
+    [avg0, total_weight0, avg1, …] list."""
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    n = 2 * len(self._metrics)
+    dev = next((x.device for x in loop_carried_metrics[:n] if x.is_cuda), None)
+    flat = torch.stack([torch.as_tensor(x, dtype=torch.float32).to(dev or 'cpu')
+                        for x in loop_carried_metrics[:n]])
+    if dist.is_available() and dist.is_initialized():
+      dist.all_reduce(flat, group=group)
+    pairs = flat.reshape(-1, 2)
+    avg = torch.where(pairs[:, 1] > 0, pairs[:, 0] / pairs[:, 1].clamp(min=1e-30),
+                      torch.zeros_like(pairs[:, 0]))
+    out = torch.stack([avg, pairs[:, 1]], 1).reshape(-1)
+    return list(out.unbind(0))
+
+  def PackMetricsValues(self, values):
+    """Stores fetched host values back as {name: (value, weight)}."""
+    vals = [float(v) for v in values]
+    for i, k in enumerate(sorted(self._metrics.keys())):
+      self._metrics[k] = (vals[2 * i], vals[2 * i + 1])
+
+  @classmethod
+  def ToAverageMetric(cls, value, weight=1.0) -> AverageMetric:
+    m = AverageMetric()
+    m.total_weight = weight
+    m.total_value = weight * value
+    return m
+
+  def ToAverageMetrics(self) -> Dict[str, AverageMetric]:
+    return {name: self.ToAverageMetric(value, weight)
+            for name, (value, weight) in self._metrics.items()}
 
   def Update(self, metrics: Dict[str, Tuple[torch.Tensor, torch.Tensor]]):
     if not self._names:

@@ -121,3 +121,51 @@ def test_device_variable_metrics_fixed_slots():
   assert float(sum(m.variables)) == 0.0
   with pytest.raises(AssertionError):
     m.AccumulateStepMetrics({str(i): (1.0, 1.0) for i in range(5)})
+
+
+def test_tpu_eval_metrics_loop_carried_form_and_average_metric_setters():
+  import torch
+  from lingvo_b200.core import metrics
+  m = metrics.TpuEvalMetrics(max_metrics=4)
+  assert len(m.initial_values) == 8
+  carried = m.initial_values
+  for step in range(3):
+    step_out = m.PackStepMetricsForAccumulation(
+        {'loss': (torch.tensor(float(step)), torch.tensor(2.0)),
+         'acc': (torch.tensor(0.5), torch.tensor(1.0))}, carried)
+    assert len(step_out) == 8
+    carried = [a + b for a, b in zip(carried, step_out[:4])] + list(carried[4:])
+  final = m.FinalizeMetrics(carried)
+  assert len(final) == 4
+  m.PackMetricsValues(final)
+  assert m.metrics['acc'] == (0.5, 3.0)
+  assert m.metrics['loss'] == (1.0, 6.0)
+  avg = m.ToAverageMetrics()
+  assert avg['loss'].value == 1.0 and avg['loss'].total_weight == 6.0
+  a = metrics.AverageMetric()
+  a.SetTotalValue(6.0)
+  a.SetTotalWeight(4.0)
+  assert a.GetTotalValue() == 6.0 and a.GetTotalWeight() == 4.0 and a.value == 1.5
+  import pytest
+  with pytest.raises(AssertionError):
+    metrics.TpuEvalMetrics(max_metrics=1).PackStepMetricsForAccumulation(
+        {'a': (torch.tensor(1.), torch.tensor(1.)), 'b': (torch.tensor(1.), torch.tensor(1.))},
+        [])
+
+
+def test_auc_metric_summary_has_scalar_and_curve_image(tmp_path):
+  from lingvo_b200.core import metrics
+  from lingvo_b200.utils import tfevents
+  for mode in ('roc', 'pr'):
+    m = metrics.AUCMetric(mode=mode)
+    m.Update([1, 0, 1, 0, 1], [0.9, 0.8, 0.7, 0.3, 0.2])
+    xs, ys, labels = m.Curve()
+    assert len(xs) == len(ys) and len(labels) == 2
+    summ = m.Summary('auc_' + mode)
+    w = tfevents.EventFileWriter(str(tmp_path / mode))
+    w.add_summary_bytes(summ, 1)
+    w.close()
+    assert isinstance(summ, bytes) and b'\x89PNG' in summ
+    imgs = list(tfevents.ReadImages(w.path))
+    assert len(imgs) == 1 and imgs[0][1] == 'auc_' + mode and imgs[0][2].shape[0] >= 64
+    assert (imgs[0][2] == 0).any()                     # the curve was drawn
