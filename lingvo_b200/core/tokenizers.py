@@ -52,33 +52,115 @@ class BaseTokenizer(base_layer.BaseLayer):
   def _Decode(self, ids) -> str:
     raise NotImplementedError
 
-  def _Assemble(self, token_lists, max_length):
+  def _Assemble(self, token_lists, max_length, append_eos=None, extras=()):
+    """Pads token lists into (ids, labels, paddings) [+ one int tensor per `extras` entry,
+    each a per-sample list aligned with the labels; the eos label repeats the last entry]."""
     p = self.params
+    append_eos = p.append_eos if append_eos is None else append_eos
     b = len(token_lists)
     if not p.pad_to_max_length:
       max_length = min(max_length, max([len(t) + 1 for t in token_lists] + [1]))
     ids = np.full((b, max_length), p.target_eos_id, np.int32)
     labels = np.full((b, max_length), p.target_eos_id, np.int32)
     paddings = np.ones((b, max_length), np.float32)
+    aligned = [np.zeros((b, max_length), np.int32) for _ in extras]
     for i, toks in enumerate(token_lists):
       toks = list(toks)
       inp = ([p.target_sos_id] + toks)[:max_length]
-      lab = (toks + ([p.target_eos_id] if p.append_eos else []))[:max_length]
+      lab = (toks + ([p.target_eos_id] if append_eos else []))[:max_length]
       ids[i, :len(inp)] = inp
       labels[i, :len(lab)] = lab
-      paddings[i, :max(len(lab), 1) if p.append_eos else len(lab)] = 0.0
-    return (torch.from_numpy(ids), torch.from_numpy(labels), torch.from_numpy(paddings))
+      paddings[i, :max(len(lab), 1) if append_eos else len(lab)] = 0.0
+      for out, per_sample in zip(aligned, extras):
+        vals = list(per_sample[i])
+        vals = (vals + [vals[-1] if vals else 0] * (len(lab) - len(vals)))[:len(lab)]
+        out[i, :len(vals)] = vals
+    return (torch.from_numpy(ids), torch.from_numpy(labels), torch.from_numpy(paddings)) + \
+        tuple(torch.from_numpy(a) for a in aligned)
+
+  @staticmethod
+  def _ToText(strs):
+    return [s.decode('utf-8') if isinstance(s, bytes) else s for s in strs]
+
+  def _AppendEos(self, external_append_eos):
+    return self.params.append_eos if external_append_eos is None else external_append_eos
 
   def StringsToIds(self, strs, max_length, external_append_eos=None, languages=None):
+    return self._StringsToIdsImpl(strs, max_length, self._AppendEos(external_append_eos),
+                                  languages)
+
+  def _StringsToIdsImpl(self, strs, max_length, append_eos, languages):
     del languages
-    if external_append_eos is not None:
-      saved = self.params.append_eos
-      try:
-        object.__setattr__(self, '_append_eos_override', external_append_eos)
-      finally:
-        del saved
-    strs = [s.decode('utf-8') if isinstance(s, bytes) else s for s in strs]
-    return self._Assemble([self._Encode(s) for s in strs], max_length)
+    return self._Assemble([self._Encode(s) for s in self._ToText(strs)], max_length, append_eos)
+
+  # -- byte offsets (ref :134) -------------------------------------------------------------------
+  def _EncodeWithOffsets(self, text):
+    """(ids, start byte offsets, end byte offsets). Generic alignment: every id is decoded on
+    its own and its surface form located in the UTF-8 bytes at or after the end of the
+    previous token (tokenizer case-folding is honoured); tokens with no surface form in the
+    text (unk, control pieces) get an empty span at the cursor."""
+    ids = list(self._Encode(text))
+    raw = text.encode('utf-8')
+    low = raw.lower()
+    starts, ends, cur = [], [], 0
+    for i in ids:
+      surface = self._Decode([int(i)]).replace('\u2581', ' ')
+      piece = (surface.strip() or surface).encode('utf-8')   # whitespace tokens stay as is
+      pos = -1
+      if piece:
+        pos = raw.find(piece, cur)
+        if pos < 0:
+          pos = low.find(piece.lower(), cur)
+      if pos < 0:
+        starts.append(cur)
+        ends.append(cur)
+      else:
+        starts.append(pos)
+        cur = pos + len(piece)
+        ends.append(cur)
+    return ids, starts, ends
+
+  def StringsToIdsWithOffsets(self, strs, max_length, external_append_eos=None,
+                              languages=None):
+    """(ids, labels, paddings, start_offsets, end_offsets), all [batch, maxlen]; the offsets
+    are byte positions of label j in the original string."""
+    return self._StringsToIdsWithOffsetsImpl(strs, max_length,
+                                             self._AppendEos(external_append_eos), languages)
+
+  def _StringsToIdsWithOffsetsImpl(self, strs, max_length, append_eos, languages):
+    del languages
+    enc = [self._EncodeWithOffsets(s) for s in self._ToText(strs)]
+    # The eos label sits at the end of the string: an empty span at the last token's end.
+    ends = [e[2] for e in enc]
+    starts = [e[1] + e[2][-1:] for e in enc]
+    return self._Assemble([e[0] for e in enc], max_length, append_eos, extras=(starts, ends))
+
+  # -- segments (ref :95) ------------------------------------------------------------------------
+  SEGMENT_DELIMITER = '<segment>'
+
+  def StringsToIdsWithSegments(self, strs, max_length, external_append_eos=None,
+                               languages=None):
+    """Strings made of `<segment>`-separated parts → (ids, labels, paddings, segment_ids);
+    segment_ids[i, j] is the 0-based part label j came from (eos: the last part)."""
+    return self._StringsToIdsWithSegmentsImpl(strs, max_length,
+                                              self._AppendEos(external_append_eos), languages)
+
+  def _StringsToIdsWithSegmentsImpl(self, strs, max_length, append_eos, languages):
+    del languages
+    toks, segs = [], []
+    for s in self._ToText(strs):
+      t, g = [], []
+      for k, part in enumerate(s.split(self.SEGMENT_DELIMITER)):
+        piece = list(self._Encode(part.strip()))
+        t += piece
+        g += [k] * len(piece)
+      toks.append(t)
+      segs.append(g)
+    return self._Assemble(toks, max_length, append_eos, extras=(segs,))
+
+  def Initialize(self, sess=None):
+    """Tokenizers hold no deferred state here (vocab files load in the constructor)."""
+    del sess
 
   def IdsToStrings(self, ids, lens, languages=None):
     del languages
