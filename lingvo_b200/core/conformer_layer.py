@@ -145,8 +145,32 @@ class LConvLayer(base_layer.BaseLayer):
     x = self.dropout.FProp(theta.dropout, x)
     return x + residual, paddings
 
+  @classmethod
+  def SetCanonicalShardingParams(cls, params):
+    """Canonical 2-D mesh sharding: projections split [data, model], activations on the
+    feature axis (ref :133)."""
+    assert params.device_mesh is not None and params.device_mesh.ndim >= 2
+    params.weight_split_dims_mapping = NestedMap(df=[0, 1], hwim=[-1, -1, 1, -1], fd=[1, 0])
+    params.activation_split_dims_mapping = NestedMap(blf=[0, -1, 1], bld=[1, -1, -1])
+
+  def _ApplyActivation(self, inputs, act_name):
+    return inputs if act_name == 'NONE' else activations.GetFn(act_name)(inputs)
+
+  def _NormalizeStep(self, theta, x, paddings, state0, state1):
+    """Streaming normalisation (ref :361): a cumulative GroupNorm carries its running
+    statistics in `norm_state`; BatchNorm (eval statistics) and LayerNorm are stateless."""
+    n = self.norm
+    if isinstance(n, bn_layers.GroupNormLayer) and n.params.cumulative:
+      y, paddings, state1.norm_state = n.StreamStep(theta.norm, x.unsqueeze(2), paddings,
+                                                    state0.norm_state)
+      return y.squeeze(2), paddings
+    return self._Normalize(theta, x, paddings), paddings
+
   def zero_state(self, batch_size):
-    return NestedMap(conv_state=self.depthwise_conv1d.zero_state(batch_size))
+    st = NestedMap(conv_state=self.depthwise_conv1d.zero_state(batch_size))
+    if isinstance(self.norm, bn_layers.GroupNormLayer) and self.norm.params.cumulative:
+      st.norm_state = self.norm.zero_state(batch_size)
+    return st
 
   def StreamStep(self, theta, inputs, paddings, state0):
     """Causal streaming step over a chunk `[B, Q, D]`."""
@@ -159,10 +183,11 @@ class LConvLayer(base_layer.BaseLayer):
     x, paddings, conv_state1 = self.depthwise_conv1d.StreamStep(
         theta.depthwise_conv1d, x.unsqueeze(2), paddings, state0.conv_state)
     x = x.squeeze(2)
-    x = self._Normalize(theta, x, paddings)
-    x = activations.GetFn(p.conv_activation)(x)
+    state1 = NestedMap(conv_state=conv_state1)
+    x, paddings = self._NormalizeStep(theta, x, paddings, state0, state1)
+    x = self._ApplyActivation(x, p.conv_activation)
     x = self.linear_end.FProp(theta.linear_end, x)
-    return x + residual, paddings, NestedMap(conv_state=conv_state1)
+    return x + residual, paddings, state1
 
 
 def _AttenCtxIsSet(atten_context):
@@ -176,6 +201,10 @@ def GShardMoELayerParams(num_devices, num_experts, num_groups=None,
   return gshard_builder.MoEBuilder.Params().Set(
       num_devices=num_devices, e_dim=num_experts,
       num_groups=num_groups or num_devices, c_dim=per_expert_capacity_dim or 0)
+
+
+def _PGet(params, name, default=None):
+  return params.Get(name) if name in params else default
 
 
 class ConformerLayer(base_layer.BaseLayer):
@@ -309,10 +338,72 @@ class ConformerLayer(base_layer.BaseLayer):
   def NumOutputNodes(cls, p):
     return p.input_dim
 
+  @classmethod
+  def Stride(cls, params):
+    """Time reduction of the block: the funnel attention's stride, else 1 (ref :730)."""
+    if 'funnel_tpl' in params.trans_atten_tpl:
+      return params.trans_atten_tpl.funnel_tpl.stride
+    return 1
+
+  @classmethod
+  def RightContext(cls, params):
+    if 'atten_tpl' in params:
+      return params.atten_tpl.right_context
+    raise ValueError(
+        f'Failed to resolve right context for {params.cls}: "atten_tpl" should have been '
+        'declared in the ConformerLayer params')
+
+  @classmethod
+  def ConfigMoEParams(cls, *, tpl, input_dim, hidden_dim, activation, residual_weight,
+                      dropout_prob):
+    """A gshard MoE builder configured as this block's FFN (ref :823)."""
+    from lingvo_b200.core import gshard_builder  # pylint: disable=g-import-not-at-top
+    moe_p = tpl.Copy().Set(model_dim=input_dim, dropout_rate=dropout_prob,
+                           moe_hidden_dim=hidden_dim, moe_activation=activation)
+    if moe_p.cls is gshard_builder.MoEBuilder and moe_p.num_devices is None:
+      raise ValueError('num_devices must be specified for MoEBuilder.')
+    if residual_weight != 0.5:
+      raise ValueError('residual_weight must be 0.5')
+    return moe_p
+
+  @staticmethod
+  def _IsMoE(tpl):
+    from lingvo_b200.core import gshard_builder  # pylint: disable=g-import-not-at-top
+    return tpl is not None and isinstance(tpl.cls, type) and issubclass(
+        tpl.cls, gshard_builder.MoEBuilder)
+
+  @staticmethod
+  def _IsHashMoE(tpl):
+    from lingvo_b200.core import gshard_builder  # pylint: disable=g-import-not-at-top
+    return tpl is not None and isinstance(tpl.cls, type) and issubclass(
+        tpl.cls, gshard_builder.MoEHashBuilder)
+
+  def _ConfigFFLayerOrMoEParams(self, fflayer_tpl, name_prefix):
+    """A dense FFN template bound to `input_dim`, or — for a MoE builder template — the
+    builder's `EncoderLayer(MoE)` block named `<prefix>_moe` (ref :932)."""
+    p = self.params
+    fflayer_tpl = fflayer_tpl.Copy()
+    if not self._IsMoE(fflayer_tpl):
+      if 'input_dim' in fflayer_tpl:
+        fflayer_tpl.Set(input_dim=p.input_dim)
+      if _PGet(fflayer_tpl, 'num_tasks', 0):
+        assert p.fflayer_task_ids, 'fflayer_task_ids must be provided for multitask FFNs.'
+      if p.dropout_prob is not None:
+        for n in ('residual_dropout_prob', 'relu_dropout_prob'):
+          if n in fflayer_tpl:
+            fflayer_tpl.Set(**{n: p.dropout_prob})
+      return fflayer_tpl
+    fflayer_tpl.model_dim = p.input_dim
+    moe_builder = fflayer_tpl.Instantiate()
+    name = name_prefix + '_moe'
+    return moe_builder.EncoderLayer(name, moe_builder.MoE(name), residual_weight=0.5)
+
   def __init__(self, params):
     super().__init__(params)
     p = self.params
     assert p.layer_order in ('mhsa', 'conv', 'mhsa_before_conv', 'conv_before_mhsa')
+    if p.layer_order == 'mhsa':
+      assert not self.has_lconv, 'mhsa must not have a lconv block.'
     d = p.input_dim
 
     def _Drop(tpl, *names):
@@ -322,78 +413,237 @@ class ConformerLayer(base_layer.BaseLayer):
             tpl.Set(**{n: p.dropout_prob})
       return tpl
 
-    self.CreateChild('fflayer_start', _Drop(
-        p.fflayer_start_tpl.Copy().Set(input_dim=d),
-        'residual_dropout_prob', 'relu_dropout_prob'))
+    start_p = None
+    if self.has_fflayer_start:
+      start_p = self._ConfigFFLayerOrMoEParams(p.fflayer_start_tpl, 'fflayer_start')
+      if start_p.name:
+        assert start_p.name == 'fflayer_start_moe'
+      else:
+        start_p.name = 'fflayer_start'
+      self.CreateChild(start_p.name, start_p)
+    end_p = self._ConfigFFLayerOrMoEParams(p.fflayer_end_tpl, 'fflayer_end')
+    if end_p.name:
+      assert end_p.name == 'fflayer_end_moe'
+    else:
+      end_p.name = 'fflayer_end'
     if not p.fflayer_weight_sharing:
-      self.CreateChild('fflayer_end', _Drop(
-          p.fflayer_end_tpl.Copy().Set(input_dim=d),
-          'residual_dropout_prob', 'relu_dropout_prob'))
-    if 'mhsa' in p.layer_order:
+      self.CreateChild(end_p.name, end_p)
+    else:
+      assert start_p is not None, 'fflayer_weight_sharing needs a start FFN.'
+      # Same module under both names; only the start FFN owns the variables.
+      self.__dict__['_shared_ff_end'] = (end_p.name, start_p.name)
+    if self.has_mhsa:
       self.CreateChild('trans_atten', _Drop(
           p.trans_atten_tpl.Copy().Set(input_dim=d),
           'residual_dropout_prob', 'atten_dropout_prob'))
-    if 'conv' in p.layer_order:
-      assert p.lconv_tpl is not None
+    if self.has_lconv:
       self.CreateChild('lconv', _Drop(
           p.lconv_tpl.Copy().Set(input_dim=d, is_causal=p.is_causal), 'dropout_prob'))
     self.CreateChild('final_ln', p.final_ln_tpl.Copy().Set(input_dim=d))
     if p.adapter_tpl is not None:
-      self.CreateChild('adapter', p.adapter_tpl)
+      tpl = p.adapter_tpl
+      if hasattr(tpl.cls, 'SetNumInputNodes'):
+        tpl.cls.SetNumInputNodes(tpl, d)
+      elif 'input_dim' in tpl and not tpl.input_dim:
+        tpl = tpl.Copy().Set(input_dim=d)
+      if p.adapter_pos in ('block_sequential', 'block_parallel'):
+        self.CreateChild('adapter', tpl.Copy())
+      elif p.adapter_pos in ('ff_sequential', 'ff_parallel'):
+        if start_p is not None:
+          self.CreateChild('fflayer_start_adapter', tpl.Copy().Set(name='fflayer_start_adapter'))
+        self.CreateChild('fflayer_end_adapter', tpl.Copy().Set(name='fflayer_end_adapter'))
+      else:
+        raise ValueError(
+            f'Wrong adapter_pos: {p.adapter_pos}. Valid options are '
+            '[block_sequential, block_parallel, ff_sequential, ff_parallel].')
 
   @property
   def has_lconv(self):
-    return 'conv' in self.params.layer_order
+    return bool(self.params.lconv_tpl) and 'conv' in self.params.layer_order
 
   @property
   def has_mhsa(self):
     return 'mhsa' in self.params.layer_order
 
+  @property
+  def has_fflayer_start(self):
+    return bool(self.params.fflayer_start_tpl)
+
+  def _FF(self, theta, name):
+    """(layer, theta) of the FFN child `name` or its `_moe` twin; None when absent."""
+    shared = self.__dict__.get('_shared_ff_end')
+    if shared is not None and name in ('fflayer_end', shared[0]):
+      name = shared[1] if name == shared[0] else 'fflayer_start'
+    for n in (name, name + '_moe'):
+      if n in self.children:
+        return n, self.children[n], theta.GetItem(n)
+    raise AssertionError('{} child layer not present.'.format(name + '_moe'))
+
+  def _RunAdapter(self, adapter, adapter_theta, nmap):
+    """Adapters come in two call conventions: NestedMap → NestedMap[, extra] wrappers and
+    per-task residual adapters `FProp(theta, inputs, tasks)`; returns the adapter features."""
+    p = self.params
+    tasks = nmap.Get(p.fflayer_task_ids) if p.fflayer_task_ids else nmap.Get('task_ids')
+    if hasattr(adapter.params, 'num_tasks') and tasks is not None:
+      t = tasks.reshape(tasks.shape[0], -1)[:, :1].expand(-1, nmap.features.shape[1])
+      return adapter.FProp(adapter_theta, nmap.features, t)
+    out = adapter.FProp(adapter_theta, nmap)
+    out = out[0] if isinstance(out, tuple) else out
+    return out.features if isinstance(out, NestedMap) else out
+
+  def _MaybeFFLayerAdapter(self, theta, fflayer_name, in_nmap, features):
+    """Adds the `<ffn>_adapter` output inside the FFN's residual branch (ref :979)."""
+    p = self.params
+    if p.adapter_tpl is None or p.adapter_pos not in ('ff_sequential', 'ff_parallel'):
+      return features
+    _, fflayer, _ = self._FF(theta, fflayer_name)
+    fp = fflayer.params
+    assert _PGet(fp, 'residual_droppath_prob', 0.0) == 0.0, (
+        'residual droppath prob is not supported by adapter.')
+    adapter = self.children[fflayer_name + '_adapter']
+    adapter_theta = theta.GetItem(fflayer_name + '_adapter')
+    skip = _PGet(fp, 'add_skip_connection', True)
+    rw = _PGet(fp, 'residual_weight', 1.0)
+    if skip:
+      features = (features - in_nmap.features) / rw
+    if p.adapter_pos == 'ff_sequential':
+      in_nmap = in_nmap.copy()
+      residual_in = in_nmap.features
+      in_nmap.features = features
+    else:
+      residual_in = in_nmap.features
+    features = features + self._RunAdapter(adapter, adapter_theta, in_nmap)
+    if skip:
+      features = residual_in + features * rw
+    return features
+
+  def _MoeOrFFLayer(self, theta, fflayer_name, features, paddings, aux_loss, expert_ids=None,
+                    task_ids=None):
+    """Dense FFN or MoE block (ref :1006) → (features, paddings, aux_loss). The MoE auxiliary
+    (load-balancing) loss is added to `aux_loss` (broadcast over a per-example vector)."""
+    name, fflayer, ff_theta = self._FF(theta, fflayer_name)
+    if not name.endswith('_moe'):
+      if _PGet(fflayer.params, 'num_tasks', 0):
+        assert task_ids is not None, 'task_ids should not be None for multitask FFN layers.'
+        out = fflayer.FProp(ff_theta, features, paddings, task_ids.reshape(features.shape[0]))
+      else:
+        out = fflayer.FProp(ff_theta, features, paddings)
+      return out, paddings, aux_loss
+    assert task_ids is None, 'MoE layer does not support multitask yet.'
+    seg = (1.0 - paddings.float()).to(torch.int32)
+    moe_in = NestedMap(vec=features, segment_id=seg, segment_pos=torch.zeros_like(seg),
+                       aux_loss=torch.zeros((), dtype=torch.float32, device=features.device))
+    if expert_ids is not None:
+      moe_in.expert_id = expert_ids
+    moe_out = fflayer.FProp(ff_theta, moe_in)
+    moe_aux = moe_out.aux_loss
+    if aux_loss is not None:
+      assert moe_aux.dim() == 0, 'MoE aux-loss should be a scalar.'
+      aux_loss = aux_loss + (moe_aux.expand(aux_loss.shape[0]) if aux_loss.dim() == 1
+                             else moe_aux)
+    else:
+      aux_loss = moe_aux
+    return moe_out.vec, paddings, aux_loss
+
   def _SelfAtten(self, theta, x, paddings):
-    out, _ = self.trans_atten.FProp(theta.trans_atten, x, None, paddings)
-    return out
+    """→ (features, paddings, atten_probs); a funnel attention also pools the paddings."""
+    out = self.trans_atten.FProp(theta.trans_atten, x, None, paddings)
+    if len(out) == 3:
+      return out
+    return out[0], paddings, out[1]
 
   def _LConv(self, theta, x, paddings):
-    out, _ = self.lconv.FProp(theta.lconv, x, paddings)
-    return out
+    return self.lconv.FProp(theta.lconv, x, paddings)
 
-  def _Body(self, theta, x, paddings):
+  def _AddAttentionSummaries(self, name, atten_probs):
     p = self.params
-    x = self.fflayer_start.FProp(theta.fflayer_start, x, paddings)
+    if not p.allow_attention_summaries or atten_probs is None:
+      return
+    from lingvo_b200.core import summary_utils  # pylint: disable=g-import-not-at-top
+    probs = atten_probs.detach().float()
+    summary_utils.histogram(f'{name}/atten_probs', probs)
+    if probs.dim() == 4:                     # [B, N, T, S]: one image per head of example 0
+      for h in range(min(probs.shape[1], 4)):
+        summary_utils.image(f'{name}/atten_probs_head{h}', probs[0, h].unsqueeze(0))
+
+  def _Body(self, theta, in_nmap, x, paddings):
+    p = self.params
+    hash_moe = (self.has_fflayer_start and self._IsHashMoE(p.fflayer_start_tpl)) or \
+        self._IsHashMoE(p.fflayer_end_tpl)
+    expert_ids = None
+    if hash_moe:
+      expert_ids = in_nmap.Get(p.moe_expert_id_field_name)
+      expert_ids = expert_ids.reshape(x.shape[0], -1)[:, :1].expand(-1, x.shape[1])
+    aux_loss = in_nmap.Get('aux_loss')
+    task_ids = in_nmap.Get(p.fflayer_task_ids) if p.fflayer_task_ids else None
+    if self.has_fflayer_start:
+      ad_in = in_nmap.copy()
+      ad_in.features = x
+      x, paddings, aux_loss = self._MoeOrFFLayer(theta, 'fflayer_start', x, paddings, aux_loss,
+                                                 expert_ids, task_ids)
+      x = self._MaybeFFLayerAdapter(theta, 'fflayer_start', ad_in, x)
+    atten_probs = None
     if p.layer_order == 'mhsa':
-      x = self._SelfAtten(theta, x, paddings)
+      x, paddings, atten_probs = self._SelfAtten(theta, x, paddings)
     elif p.layer_order == 'conv':
-      x = self._LConv(theta, x, paddings)
+      x, paddings = self._LConv(theta, x, paddings)
     elif p.layer_order == 'mhsa_before_conv':
-      x = self._LConv(theta, self._SelfAtten(theta, x, paddings), paddings)
+      x, paddings, atten_probs = self._SelfAtten(theta, x, paddings)
+      x, paddings = self._LConv(theta, x, paddings)
     else:
-      x = self._SelfAtten(theta, self._LConv(theta, x, paddings), paddings)
-    if p.fflayer_weight_sharing:
-      x = self.fflayer_start.FProp(theta.fflayer_start, x, paddings)
-    else:
-      x = self.fflayer_end.FProp(theta.fflayer_end, x, paddings)
+      x, paddings = self._LConv(theta, x, paddings)
+      x, paddings, atten_probs = self._SelfAtten(theta, x, paddings)
+    ad_in = in_nmap.copy()
+    ad_in.features, ad_in.paddings = x, paddings
+    if expert_ids is not None and expert_ids.shape[1] != x.shape[1]:
+      expert_ids = expert_ids[:, :1].expand(-1, x.shape[1])
+    x, paddings, aux_loss = self._MoeOrFFLayer(theta, 'fflayer_end', x, paddings, aux_loss,
+                                               expert_ids, task_ids)
+    x = self._MaybeFFLayerAdapter(theta, 'fflayer_end', ad_in, x)
     x = self.final_ln.FProp(theta.final_ln, x)
-    return x
+    if p.adapter_tpl is not None and p.adapter_pos in ('block_sequential', 'block_parallel'):
+      ad_in = in_nmap.copy()
+      if p.adapter_pos == 'block_sequential':
+        ad_in.features, ad_in.paddings = x, paddings
+      x = x + self._RunAdapter(self.adapter, theta.adapter, ad_in)
+    return x, paddings, aux_loss, atten_probs
 
-  def FProp(self, theta, in_nmap):
-    """in_nmap: NestedMap(features [B,T,D], paddings [B,T]) → same keys."""
-    p = self.params
+  def _FProp(self, theta, in_nmap):
     x, paddings = in_nmap.features, in_nmap.paddings
     x = self._CastToFPropDtype(x)
-    if p.remat and torch.is_grad_enabled():
-      from torch.utils import checkpoint as ckpt  # pylint: disable=g-import-not-at-top
-      x = ckpt.checkpoint(lambda a: self._Body(theta, a, paddings), x, use_reentrant=False)
-    else:
-      x = self._Body(theta, x, paddings)
+    x, paddings, aux_loss, atten_probs = self._Body(theta, in_nmap, x, paddings)
     x = py_utils.ApplyPadding(paddings.unsqueeze(-1), x)
-    out = in_nmap.copy() if hasattr(in_nmap, 'copy') else NestedMap(in_nmap)
-    out = NestedMap(out)
-    out.features = x
+    out = NestedMap(in_nmap.copy() if hasattr(in_nmap, 'copy') else in_nmap)
+    out.features = self._CastToFPropDtype(x)
     out.paddings = paddings
-    if p.adapter_tpl is not None:
-      out = self.adapter.FProp(theta.adapter, out)
-      out = out[0] if isinstance(out, tuple) else out
+    if aux_loss is not None:
+      out.aux_loss = aux_loss
+    self._AddAttentionSummaries(self.params.name, atten_probs)
     return out
+
+  def FProp(self, theta, in_nmap):
+    """in_nmap: NestedMap(features [B,T,D], paddings [B,T][, aux_loss, task / expert ids]) →
+    same keys (time pooled by `Stride` under a funnel attention)."""
+    p = self.params
+    if not (p.remat and torch.is_grad_enabled()):
+      return self._FProp(theta, in_nmap)
+    from torch.utils import checkpoint as ckpt  # pylint: disable=g-import-not-at-top
+    keys = [k for k, v in in_nmap.FlattenItems() if isinstance(v, torch.Tensor)]
+    side = {}
+
+    def _Fn(*tensors):
+      nm = in_nmap.copy()
+      for k, t in zip(keys, tensors):
+        nm.Set(k, t)
+      out = self._FProp(theta, nm)
+      side['keys'] = [k for k, v in out.FlattenItems() if isinstance(v, torch.Tensor)]
+      return tuple(out.GetItem(k) for k in side['keys'])
+
+    outs = ckpt.checkpoint(_Fn, *[in_nmap.GetItem(k) for k in keys], use_reentrant=False)
+    res = in_nmap.copy()
+    for k, t in zip(side['keys'], outs):
+      res.Set(k, t)
+    return res
 
   def zero_state(self, batch_size):
     st = NestedMap()
@@ -409,7 +659,8 @@ class ConformerLayer(base_layer.BaseLayer):
     assert p.is_causal
     x, paddings = in_nmap.features, in_nmap.paddings
     st = NestedMap()
-    x = self.fflayer_start.FProp(theta.fflayer_start, x, paddings)
+    if self.has_fflayer_start:
+      x, _, _ = self._MoeOrFFLayer(theta, 'fflayer_start', x, paddings, None)
 
     def _Atten(x):
       ta, tt = self.trans_atten, theta.trans_atten
@@ -434,9 +685,7 @@ class ConformerLayer(base_layer.BaseLayer):
       x = _Conv(_Atten(x))
     else:
       x = _Atten(_Conv(x))
-    ff_end = self.fflayer_start if p.fflayer_weight_sharing else self.fflayer_end
-    ff_th = theta.fflayer_start if p.fflayer_weight_sharing else theta.fflayer_end
-    x = ff_end.FProp(ff_th, x, paddings)
+    x, _, _ = self._MoeOrFFLayer(theta, 'fflayer_end', x, paddings, None)
     x = self.final_ln.FProp(theta.final_ln, x)
     x = py_utils.ApplyPadding(paddings.unsqueeze(-1), x)
     return NestedMap(features=x, paddings=paddings), st
