@@ -16,6 +16,8 @@ integer (checkpointed as `global_step`).
 
 from __future__ import annotations
 
+import dataclasses
+
 import collections
 import re
 from typing import Any, Dict, List, Optional, Tuple
@@ -67,6 +69,36 @@ def DecodeOutAsTensors(dec_out):
   out = NestedMap()
   for k, v in dict(dec_out).items():
     out[k] = conv(v)
+  return out
+
+
+@dataclasses.dataclass(frozen=True)
+class DecodeEmailOptions:
+  """Options for `BaseTask.EmailDecodeSummary` (ref :57)."""
+  job_name: str
+  train_executions_per_eval: int
+  global_step: int
+
+
+@dataclasses.dataclass(frozen=True)
+class ExecutorEma:
+  """What an executor prepares for EMA (ref :69): the name → shadow-tensor map and the
+  decay (a float or a schedule layer)."""
+  ema: Optional[Dict[str, torch.Tensor]] = None
+  ema_decay: Any = None
+
+
+def _VariablesForEMA(params, model_var_list):
+  """The variables EMA applies to (ref :77): trainable floating-point ones, plus the
+  non-trainable moving statistics when `train.ema_decay_moving_vars`; de-duplicated, in
+  `model_var_list` order."""
+  out, seen = [], set()
+  for v in model_var_list:
+    name = getattr(v, 'var_name', '')
+    moving = bool(params.train.ema_decay_moving_vars) and 'moving' in name
+    if (v.requires_grad or moving) and v.is_floating_point() and id(v) not in seen:
+      seen.add(id(v))
+      out.append(v)
   return out
 
 
@@ -169,8 +201,12 @@ class BaseTask(base_layer.BaseLayer):
       if isinstance(tp.learner, (list, tuple)):
         names = [l.name for l in tp.learner]
         assert len(set(names)) == len(names), 'learner names must be unique'
+    params = params.Copy()
+    self._UpdateVnConfigOn(params)
     super().__init__(params)
     p = self.params
+    self._post_training_loop_op = None
+    self._per_input_gradient_mask = None
     self._encoder = None
     self._online_encoder = None
     self._decoder = None
@@ -210,6 +246,106 @@ class BaseTask(base_layer.BaseLayer):
         self._early_stop = early_stop.EarlyStop(tp.early_stop)
       else:
         self._early_stop = None
+
+  @classmethod
+  def UpdateTargetVocabSize(cls, p, vocab_size, wpm_model=None):
+    """Propagates the vocabulary size (and word-piece model) to the decoder (ref :338)."""
+    dp = p.decoder
+    p.decoder = dp.cls.UpdateTargetVocabSize(dp, vocab_size, wpm_model)
+    return p
+
+  @staticmethod
+  def _UpdateVnConfigOn(p):
+    """`train.vn_std` / `train.vn_start_step` drive the layers' variational noise (ref
+    :1084): noise is on only when training, `vn_std > 0` and `p.vn` asks for global or
+    per-step noise; the layer-level scale / start_step must be left unset."""
+    from lingvo_b200.core import cluster_factory  # pylint: disable=g-import-not-at-top
+    tp = p.train
+    if not tp:
+      return
+    enabled = (tp.vn_std > 0) and p.vn and (p.vn.global_vn or p.vn.per_step_vn)
+    if cluster_factory.Current().do_eval or not enabled:
+      p.vn = py_utils.VariationalNoiseParams(None, False, False)
+      return
+    if p.vn.scale is not None:
+      raise ValueError('A value should not be specified for p.vn.scale. It will be '
+                       'overwritten by p.train.vn_std.')
+    if p.vn.start_step:
+      raise ValueError('A value should not be specified for p.vn.start_step. It will be '
+                       'overwritten by p.train.vn_start_step.')
+    p.vn = p.vn.Copy().Set(scale=tp.vn_std, start_step=tp.vn_start_step)
+
+  def _UpdateVnConfig(self):
+    """Applied to the params copy before construction; see `_UpdateVnConfigOn`."""
+
+  def _SetLearnerFromLegacyParams(self, tp):
+    if tp.learner is None:
+      tp.learner = learner_lib.ExtractLearnerFromLegacyParams(tp)
+
+  def _ComputeGradientMask(self, bprop_variable_filters):
+    """mask[var][i] = 1 iff the variable's name matches filter i (ref :837): with
+    cross-batch input mixing, the batch's source one-hot dotted with this row decides
+    whether the variable is updated by that batch."""
+    import re  # pylint: disable=g-import-not-at-top
+    n = len(bprop_variable_filters)
+    self._per_input_gradient_mask = NestedMap()
+    for v in self.vars.Flatten():
+      row = torch.zeros(n, dtype=torch.float32)
+      for i, rx in enumerate(bprop_variable_filters):
+        if re.search(rx, v.var_name):
+          row[i] += 1.0
+      self._per_input_gradient_mask[v.var_name] = row
+    return self._per_input_gradient_mask
+
+  def _GetMaskUpdateOp(self):
+    """The pruning mask update to run after the optimizer step (ref :1105), or None."""
+    tp = self.params.train
+    if not tp.pruning_hparams_dict:
+      return None
+    assert isinstance(tp.pruning_hparams_dict, dict)
+    from lingvo_b200.core import pruning_utils  # pylint: disable=g-import-not-at-top
+    getter = getattr(pruning_utils.PruningOp, 'GetPruningUpdate', None)
+    return getter() if getter is not None else None
+
+  def CreateExponentialMovingAverage(self, ema=None):
+    """Allocates the EMA shadows (initialised to the current values) ahead of the first
+    `ApplyExponentialMovingAverage` (ref :859) — checkpoints restored before step 1 then
+    find their `<var>/ExponentialMovingAverage` targets."""
+    tp = self.params.train
+    if ema is None and not (tp.ema_decay and tp.ema_decay > 0):
+      return
+    if self._ema_map is None:
+      self._ema_map = {}
+    for layer, key, var in self._EmaVars():
+      if var.var_name not in self._ema_map:
+        shadow = var.detach().clone()
+        self._ema_map[var.var_name] = shadow
+        layer.SetEmaShadow(key, shadow)
+
+  def PostTrainingLoop(self, outfeed=None):
+    """Runs every learner's post-loop hook (ref :708) and keeps the results."""
+    del outfeed
+    with py_utils.GlobalStepContext(self._global_step):
+      self._post_training_loop_op = [
+          l.ApplyPostTrainingLoop() if hasattr(l, 'ApplyPostTrainingLoop') else None
+          for l in self.learners]
+
+  @property
+  def post_training_loop_op(self):
+    assert self._post_training_loop_op is not None, (
+        'No post_training_loop_op op is defined. Call PostTrainingLoop first.')
+    return self._post_training_loop_op
+
+  def InferenceEager(self):
+    """{signature: callable} for eager serving; the default reuses `Inference()`."""
+    return self.Inference()
+
+  def EmailDecodeSummary(self, summaries, emails, options):
+    raise NotImplementedError('Abstract method')
+
+  def Export(self, train_dir):
+    """Hook an eval job calls before evaluation to write extra files (ref :1126)."""
+    del train_dir
 
   # ------------------------------------------------------------- properties --
   @property
@@ -573,6 +709,30 @@ class BaseModel(base_layer.BaseLayer):
   def ConstructPostTrainingLoop(self, *args, **kwargs):
     return None
 
+  @property
+  def variables_for_ema(self):
+    return _VariablesForEMA(self.params, self.vars.Flatten())
+
+  @property
+  def ema_decay(self):
+    return self.params.train.ema_decay
+
+  def MakeEMAVariablesDictTF2(self):
+    """{checkpoint key: shadow tensor} over all tasks (ref :1253)."""
+    res = {}
+    for task in self.tasks:
+      res.update(task.EmaShadowTensors())
+    self._ema_variables_dict = res
+    return res
+
+  def ProcessFPropResults(self, sess, global_step, metrics, per_example):
+    for task in self.tasks:
+      task.ProcessFPropResults(sess, global_step, metrics, per_example)
+
+  def Export(self, train_dir):
+    for task in self.tasks:
+      task.Export(train_dir)
+
   def ConstructDecodeGraph(self, task_name=None, input_batch=None):
     task = self.GetTask(task_name)
     if input_batch is None:
@@ -617,18 +777,25 @@ class SingleTaskModel(SingleTaskBase):
     p.Define('task', None,
              '`InstantiableParams` object for a `BaseTask` subclass.')
     if task_params is not None:
-      # Copy over model parameters from the task parameters.
-      p.task = task_params
-      p.Set(name=task_params.name)
-      tp = p.train
-      tt = task_params.train
-      for k, _ in tp.IterParams():
-        if k in tt:
-          tp.Set(**{k: tt.Get(k)})
-      p.eval.samples_per_summary = task_params.eval.samples_per_summary
-      p.eval.decoder_samples_per_summary = (
-          task_params.eval.decoder_samples_per_summary)
-      p.input = task_params.input
+      cls.CopyTaskParams(task_params, p)
+    return p
+
+  @classmethod
+  def CopyTaskParams(cls, task_params, p):
+    """Mirrors the task's name / train / eval / input settings on the model params (ref
+    :1392) so runners can read them without reaching into the task."""
+    assert task_params is not None
+    p.task = task_params
+    p.Set(name=task_params.name)
+    tp = p.train
+    tt = task_params.train
+    for k, _ in tp.IterParams():
+      if k in tt:
+        tp.Set(**{k: tt.Get(k)})
+    p.eval.samples_per_summary = task_params.eval.samples_per_summary
+    p.eval.decoder_samples_per_summary = (
+        task_params.eval.decoder_samples_per_summary)
+    p.input = task_params.input
     return p
 
   def __init__(self, params):
@@ -667,6 +834,11 @@ class MultiTaskSubModel(SingleTaskBase):
     self._model = shared_model
     self._task = self._model.children[p.task_name]
 
+  def GetVariablesDict(self):
+    """The whole shared model's variables: a sub-model checkpoints everything (ref
+    :1468)."""
+    return {v.var_name: v for v in self._model.vars.Flatten()}
+
 
 class MultiTaskModel(BaseModel):
   """Model that consists of multiple tasks (reference :1480-1640)."""
@@ -704,6 +876,10 @@ class MultiTaskModel(BaseModel):
       if p.task_global_step:
         tp.task_global_step = True
       self.CreateChild(name, tp)
+
+  @staticmethod
+  def TaskNames(params):
+    return sorted(name for name, _ in params.task_params.IterParams())
 
   def _ChildScope(self, child_key, child):
     if not self.params.task_name_var_scope and child_key in self._task_names:

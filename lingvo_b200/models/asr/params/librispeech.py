@@ -81,6 +81,7 @@ class Librispeech960Base(base_model_params.SingleTaskModelParams):
     tp.learning_rate = 1e-3
     tp.lr_schedule = schedule.ContinuousSchedule.Params().Set(
         start_step=50000, half_life_steps=100000, min=0.01)
+    p.vn.global_vn = True
     tp.vn_start_step = 20000
     tp.vn_std = 0.075
     tp.l2_regularizer_weight = 1e-6
