@@ -123,3 +123,42 @@ def test_distillation_student_follows_teacher():
   assert float(metrics['accuracy'][0]) > 0.9                      # learned from soft targets alone
   torch.testing.assert_close(task.teacher.enc.vars.w.detach(), before)   # teacher untouched
   assert not task.teacher.enc.vars.w.requires_grad
+
+
+def test_distillation_train_teacher_blends_ground_truth_and_delegates_decoding():
+  torch.manual_seed(0)
+  p = distillation_task.DistillationTask.Params().Set(name='distill2', train_teacher=True)
+  p.input = _ClsInput.Params().Set(name='in', batch_size=16)
+  p.teacher = _TaskParams('teacher', hidden=8)
+  p.student = _TaskParams('student', hidden=4)
+  p.distillation_loss_weight = schedule.Constant.Params().Set(value=0.25)
+  p.train.optimizer = optimizer.Adam.Params()
+  p.train.learning_rate = 1e-2
+  p.train.lr_schedule = schedule.Constant.Params()
+  task = p.Instantiate()
+  metrics, _ = task.FPropDefaultTheta()
+  for k in ('student_groundtruth_loss', 'teacher_groundtruth_loss', 'groundtruth_loss',
+            'distillation_loss', 'loss'):
+    assert k in metrics, k
+  (tv, tw), (sv, sw) = metrics['teacher_groundtruth_loss'], metrics['student_groundtruth_loss']
+  gt = (float(tv) * float(tw) + float(sv) * float(sw)) / (float(tw) + float(sw))
+  assert abs(float(metrics['groundtruth_loss'][0]) - gt) < 1e-5
+  want = 0.75 * gt + 0.25 * float(metrics['distillation_loss'][0])
+  assert abs(float(metrics['loss'][0]) - want) < 1e-5
+  before = task.teacher.enc.vars.w.detach().clone()
+  task.BProp()
+  assert not torch.equal(task.teacher.enc.vars.w.detach(), before)      # teacher trains too
+  # custom distillation loss hook
+  class _L2(distillation_task.DistillationTask):
+    def ComputeDistillationLoss(self, theta, predictions, input_batch):
+      d = (predictions.teacher.logits.detach() - predictions.student.logits) ** 2
+      return {'loss': (d.mean(), torch.tensor(float(d.shape[0])))}, {'sq': d}
+  p2 = p.Copy().Set(name='distill3', train_teacher=False)
+  p2.cls = _L2
+  t2 = p2.Instantiate()
+  m2, per_ex = t2.FPropDefaultTheta()
+  assert 'sq' in per_ex and float(m2['distillation_loss'][0]) >= 0
+  import pytest
+  bad = p.Copy().Set(name='distill4', teacher_target_type='nope')
+  with pytest.raises(ValueError):
+    bad.Instantiate().FPropDefaultTheta()
