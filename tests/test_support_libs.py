@@ -109,3 +109,42 @@ def test_profiling_roofline_and_nvtx_wrappers():
   torch.testing.assert_close(layer.FPropDefaultTheta(x), want)
   with profiling.Range('noop'):
     pass
+
+
+def test_test_utils_numeric_gradient_tape_and_summary_reader(tmp_path):
+  import numpy as np
+  import torch
+  from lingvo_b200.core import test_utils
+  from lingvo_b200.utils import tfevents
+  x = torch.tensor([[1.0, 2.0], [3.0, 4.0]], dtype=torch.float64)
+  g = test_utils.ComputeNumericGradientEager(lambda v: (v ** 2).sum(), x, step=2)
+  np.testing.assert_allclose(g.numpy(), [[2.0, 0.0], [6.0, 0.0]], atol=1e-6)
+  assert test_utils.PickEveryN(np.arange(6).reshape(2, 3), 2).tolist() == [0, 2, 4]
+  with test_utils.TapeIfEager() as tape:
+    w = torch.tensor([1.0, 2.0])
+    tape.watch(w)
+    y = (w ** 3).sum()
+    dw = tape.gradient(y, w)
+  torch.testing.assert_close(dw, torch.tensor([3.0, 12.0]))
+  got = test_utils.DefineAndTrace(((2, 3), torch.float32), torch.ones(3))(
+      lambda a, b: (a + b).shape)
+  assert tuple(got) == (2, 3)
+  wr = tfevents.EventFileWriter(str(tmp_path))
+  wr.add_scalar('loss', 1.5, 1)
+  wr.add_scalar('loss', 0.5, 2)
+  wr.add_scalar('acc', 0.9, 2)
+  wr.close()
+  tc = test_utils.TestCase()
+  vals = tc.GetScalarSummaryValues(str(tmp_path), ['loss'])
+  assert vals == {'loss': {1: 1.5, 2: 0.5}}
+
+  class _T(test_utils.TestCase):
+    @test_utils.SkipIfEager
+    def testGraphOnly(self):
+      raise AssertionError('must be skipped')
+  import unittest
+  res = unittest.TestResult()
+  _T('testGraphOnly').run(res)
+  assert len(res.skipped) == 1 and not res.failures and not res.errors
+  line = '    test_utils.CompareToGoldenSingleFloat(self, 0.25, v)\n'
+  assert '0.500000' in test_utils.ReplaceGoldenSingleFloat(line, 0.5)
