@@ -86,6 +86,71 @@ class Predictor:
   def subgraphs(self) -> List[str]:
     return sorted(self._subgraphs)
 
+  # -- signature introspection (ref :157-222) ----------------------------------------------------
+  def _get_subgraph(self, subgraph_name=None):   # pylint: disable=invalid-name
+    name = subgraph_name or self._default_subgraph
+    if name not in self._subgraphs:
+      raise KeyError('Subgraph %s not defined. Valid subgraphs: %s' % (name, self.subgraphs))
+    return name, self._subgraphs[name], (self._graph.subgraphs or {}).get(name, {})
+
+  def _get_subgraph_feeds(self, subgraph_name=None):   # pylint: disable=invalid-name
+    """{feed key: shape or None}: keys from the bundle's signature, else from the callable's
+    arguments; shapes from the bundle's `feeds_meta` when recorded."""
+    import inspect  # pylint: disable=g-import-not-at-top
+    _, fn, spec = self._get_subgraph(subgraph_name)
+    keys = list(spec.get('feeds') or [])
+    if not keys:
+      try:
+        keys = [q.name for q in inspect.signature(fn).parameters.values()
+                if q.kind in (q.POSITIONAL_OR_KEYWORD, q.KEYWORD_ONLY)]
+      except (TypeError, ValueError):
+        keys = []
+    meta = spec.get('feeds_meta') or {}
+    return {k: (meta.get(k) or {}).get('shape') for k in keys}
+
+  def _get_subgraph_fetches(self, subgraph_name=None):   # pylint: disable=invalid-name
+    """{fetch key: shape or None}: from the bundle's signature, completed by what the
+    subgraph returned on earlier `Run`s."""
+    name, _, spec = self._get_subgraph(subgraph_name)
+    meta = spec.get('fetches_meta') or {}
+    out = {k: (meta.get(k) or {}).get('shape') for k in (spec.get('fetches') or [])}
+    for k, shape in self.__dict__.setdefault('_seen_fetches', {}).get(name, {}).items():
+      out.setdefault(k, shape)
+      if out[k] is None:
+        out[k] = shape
+    return out
+
+  @property
+  def fetch_keys(self):
+    return sorted(self._get_subgraph_fetches())
+
+  @property
+  def feed_keys(self):
+    return sorted(self._get_subgraph_feeds())
+
+  @property
+  def fetch_shapes(self):
+    return NestedMap(self._get_subgraph_fetches())
+
+  @property
+  def feed_shapes(self):
+    return NestedMap(self._get_subgraph_feeds())
+
+  def subgraph_fetch_keys(self, subgraph_name):   # pylint: disable=invalid-name
+    return sorted(self._get_subgraph_fetches(subgraph_name))
+
+  def subgraph_feed_keys(self, subgraph_name):   # pylint: disable=invalid-name
+    return sorted(self._get_subgraph_feeds(subgraph_name))
+
+  def subgraph_fetch_shapes(self, subgraph_name):   # pylint: disable=invalid-name
+    return NestedMap(self._get_subgraph_fetches(subgraph_name))
+
+  def subgraph_feed_shapes(self, subgraph_name):   # pylint: disable=invalid-name
+    return NestedMap(self._get_subgraph_feeds(subgraph_name))
+
+  def _LoadCheckpoint(self, checkpoint):
+    self.Load(checkpoint)
+
   def Load(self, checkpoint):
     from lingvo_b200.core import checkpointer  # pylint: disable=g-import-not-at-top
     checkpointer.Checkpointer(os.path.dirname(checkpoint), self._model).RestoreFromPath(
@@ -110,6 +175,9 @@ class Predictor:
       out = self._RunGraphed(name, fn, feeds) if self._use_cuda_graph else fn(**feeds)
     if not isinstance(out, NestedMap):
       out = NestedMap(out) if isinstance(out, dict) else NestedMap(output=out)
+    seen = self.__dict__.setdefault('_seen_fetches', {}).setdefault(name, {})
+    for k, v in out.items():
+      seen[k] = list(v.shape) if isinstance(v, torch.Tensor) else None
     if fetch_keys is None:
       return out
     if isinstance(fetch_keys, str):

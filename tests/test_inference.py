@@ -40,6 +40,14 @@ def test_export_and_predict(tmp_path):
   got = pred.Run(['log_pplx_per_token'], ids=ids, paddings=pads)[0]
   want = model.tasks[0]._InferenceDefault(ids, pads).log_pplx_per_token
   torch.testing.assert_close(got, want.detach(), atol=1e-5, rtol=1e-5)
+  # signature introspection (reference predictor.py:157-222)
+  assert pred.feed_keys == ['ids', 'paddings'] == pred.subgraph_feed_keys('default')
+  assert 'log_pplx_per_token' in pred.fetch_keys
+  assert pred.fetch_shapes.log_pplx_per_token in (None, [2, 7], list(got.shape))
+  assert set(pred.subgraph_feed_shapes('default').keys()) == {'ids', 'paddings'}
+  import pytest
+  with pytest.raises(KeyError):
+    pred.subgraph_fetch_keys('no_such_subgraph')
 
 
 def test_inference_graph_proto_round_trip(tmp_path):
