@@ -579,8 +579,74 @@ class BaseLayer(metaclass=BaseLayerMeta):
       if isinstance(c, BaseLayer):
         c.PostEmaUpdate()
 
-  def AddFunction(self, name: str, fn: Callable):
+  def AddFunction(self, name: str, fn: Callable, replace: bool = False):
+    if not replace and name in self._private_fns:
+      raise AttributeError('Function "%s" is already defined on layer "%s"' %
+                           (name, self.params.name))
     self._private_fns[name] = fn
+
+  @property
+  def fns(self):
+    """Read-only view (index or attribute access) of the layer's local functions (ref
+    :705)."""
+    return py_utils.ReadOnlyAttrDictView(self._private_fns)
+
+  @property
+  def ema(self):
+    """The EMA shadow map of the task / model this layer belongs to, if any (ref :587)."""
+    root = self
+    while root.parent is not None:
+      root = root.parent
+      if getattr(root, '_ema_map', None):
+        return root._ema_map   # pylint: disable=protected-access
+    return getattr(root, '_ema_map', None)
+
+  def _GetSelfVariablesDict(self):
+    return {v.var_name: v for v in self._private_vars.values()}
+
+  def GetVariablesDict(self, visited=None):
+    """{variable name: Parameter} of this layer and all its children; shared layers are
+    visited once (ref :322)."""
+    if visited is None:
+      visited = set()
+    elif id(self) in visited:
+      return {}
+    visited.add(id(self))
+    res = self._GetSelfVariablesDict()
+    for child in self._private_children.Flatten():
+      if isinstance(child, BaseLayer):
+        res = py_utils.MergeDictsWithValueCheck(res, child.GetVariablesDict(visited))
+    return res
+
+  def GetVariableSymbolicShape(self, var_name):
+    """Shapes are static here: the symbolic shape of a variable is its shape."""
+    return list(self._private_vars[var_name].shape)
+
+  def AddVN(self, value, per_step=False):
+    return py_utils.AddVN(self.params, value, per_step)
+
+  def AddGlobalVN(self, theta):
+    """Global (per-weight) variational noise on a theta that bypassed `self.theta` — e.g.
+    values restored from a checkpoint or produced by another layer (ref :937). `self.theta`
+    itself already carries the noise."""
+    if self.do_eval:
+      return theta
+    out = theta.copy() if hasattr(theta, 'copy') else theta
+    for name, child in self._private_children.items():
+      if name not in theta:
+        continue
+      if isinstance(child, BaseLayer):
+        out[name] = child.AddGlobalVN(theta[name])
+      elif isinstance(child, (list, tuple)):
+        out[name] = [c.AddGlobalVN(t) if isinstance(c, BaseLayer) else t
+                     for c, t in zip(child, theta[name])]
+    vn = self.params.vn
+    if vn is not None and vn.global_vn:
+      for name in self._private_vars:
+        if name in theta and isinstance(theta[name], torch.Tensor) and \
+            theta[name].is_floating_point():
+          out[name] = py_utils.AddVN(self.params, theta[name])
+    return out
 
   def _CastToFPropDtype(self, value):
     def cast(x):

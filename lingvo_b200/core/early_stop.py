@@ -70,6 +70,36 @@ class MetricHistory:
   def minimize(self):
     return self._minimize
 
+  @property
+  def metric(self):
+    return self.params.metric
+
+  @property
+  def tfevent_file(self):
+    return self.params.tfevent_file if 'tfevent_file' in self.params else False
+
+  @staticmethod
+  def SetLogdirInMetricHistories(params, logdir):
+    """Points every MetricHistory params found anywhere under `params` at `logdir` (ref
+    :100)."""
+    def _Visit(p):
+      for _, v in p.IterParams():
+        if isinstance(v, hyperparams.Params):
+          if isinstance(getattr(v, 'cls', None), type) and issubclass(v.cls, MetricHistory):
+            v.logdir = logdir
+          _Visit(v)
+        elif isinstance(v, (list, tuple)):
+          for x in v:
+            if isinstance(x, hyperparams.Params):
+              _Visit(x)
+    _Visit(params)
+
+  def Append(self, step, value):
+    """Unconditionally records (step, value)."""
+    os.makedirs(os.path.dirname(self.hist_file) or '.', exist_ok=True)
+    with open(self.hist_file, 'a') as f:
+      f.write('%d %f\n' % (step, value))
+
   def ConditionalAppend(self, jobname, metric, step, value) -> bool:
     p = self.params
     if jobname == p.jobname and metric == p.metric:

@@ -108,6 +108,24 @@ class Learner(base_layer.BaseLayer):
     p = self.params
     return float(p.learning_rate) * float(self.lr_schedule.Value())
 
+  def ApplyPostTrainingLoop(self):
+    """Forwards the end-of-loop hook to the optimizer (ref :216)."""
+    return self.optimizer.ApplyPostTrainingLoop()
+
+  def ComputeLosses(self, metrics):
+    """The loss tensor(s) named by `loss_name` (default: the learner's name), in order
+    (ref :283)."""
+    p = self.params
+    names = p.loss_name or p.name
+    names = [names] if not isinstance(names, (list, tuple)) else list(names)
+    out = []
+    for name in names:
+      item = metrics.get(name, None)
+      if item is None:
+        raise ValueError('Loss %s not found in metrics %s' % (name, list(metrics.keys())))
+      out.append(item[0] if isinstance(item, (tuple, list)) else item)
+    return out
+
   # ------------------------------------------------------------------ apply --
   def Apply(self, metrics, vmap: NestedMap, gradient_mask=None,
             gradient_adjuster=None, retain_graph=False):

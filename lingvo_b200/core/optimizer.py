@@ -159,6 +159,36 @@ class Base(base_layer.BaseLayer):
         slots[k] = slots[k].to(device)
     return self
 
+  def GetOptimizer(self, lr):
+    """The object that applies updates at learning rate `lr` (ref :116): the optimizer
+    layer itself, bound to `lr` through `apply_gradients(var_grad)`."""
+    outer = self
+
+    class _Bound:
+      learning_rate = lr
+
+      @staticmethod
+      def apply_gradients(var_grad, grad_scale=None):   # pylint: disable=invalid-name
+        return outer.Apply(lr, var_grad, grad_scale=grad_scale)
+
+    return _Bound()
+
+  def GetLrScheduleValue(self, lr_schedule=None, step=None):
+    """Value of a learning-rate schedule layer at the current (or given) step."""
+    if lr_schedule is None:
+      return 1.0
+    return float(lr_schedule.Value() if step is None else lr_schedule.Value(step))
+
+  def ApplyPostTrainingLoop(self):
+    """Work an optimizer defers to the end of a device training loop (e.g. Shampoo's
+    preconditioner refresh); nothing for first-order optimizers (ref :215)."""
+    return None
+
+  @staticmethod
+  def VarReuseForSlotVars():
+    import contextlib  # pylint: disable=g-import-not-at-top
+    return contextlib.nullcontext()
+
   # ------------------------------------------------------------------ apply --
   def ComputeGradients(self, loss, vmap, *args, **kwargs):
     return py_utils.ComputeGradients(loss, vmap, *args, **kwargs)

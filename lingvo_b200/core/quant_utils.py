@@ -113,6 +113,12 @@ class _Fns:
     except KeyError:
       raise AttributeError(name) from None
 
+  def __getitem__(self, name):
+    return self._table[name]
+
+  def __contains__(self, name):
+    return name in self._table
+
   def __dir__(self):
     return sorted(self._table)
 

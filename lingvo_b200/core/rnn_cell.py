@@ -83,6 +83,24 @@ class RNNCell(quant_utils.QuantizableLayer):
   def GetOutput(self, state):
     raise NotImplementedError
 
+  @property
+  def output_size(self):
+    """Width of `GetOutput(state)`."""
+    return self.params.num_output_nodes
+
+  @staticmethod
+  def LayerNorm(x, scale=None, bias=None, epsilon=1e-6):
+    """Mean/variance normalisation over the last axis, `(1 + scale)`-gained (the cells'
+    layer-norm convention)."""
+    mean = x.mean(-1, keepdim=True)
+    var = ((x - mean) ** 2).mean(-1, keepdim=True)
+    y = (x - mean) * torch.rsqrt(var + epsilon)
+    if scale is not None:
+      y = y * (1.0 + scale)
+    if bias is not None:
+      y = y + bias
+    return y
+
   def batch_size(self, inputs):
     return self._Act(inputs).shape[0]
 

@@ -636,3 +636,63 @@ def test_tpu_summary_context_and_predictor_runner(tmp_path):
   assert (step_dir / 'out.txt').read_text().splitlines() == ['[0, 0]', '[2, 2]', '[4, 4]']
   r.Run()                                                         # already DONE: nothing re-runs
   assert pred.calls == 3
+
+
+def test_layer_variable_dict_fns_global_vn_and_optimizer_hooks(tmp_path):
+  import pytest
+  import torch
+  from lingvo_b200.core import early_stop, layers, learner, optimizer, py_utils, rnn_cell
+  from lingvo_b200.core.nested_map import NestedMap
+  p = layers.FeedForwardNet.Params().Set(name='ffn', input_dim=4, hidden_layer_dims=[8, 2],
+                                         activation=['RELU', 'NONE'])
+  p.vn = py_utils.VariationalNoiseParams(0.5, global_vn=True)
+  net = p.Instantiate()
+  vd = net.GetVariablesDict()
+  assert len(vd) == len(net.vars.Flatten()) and all(k.endswith('/var') for k in vd)
+  some = next(iter(vd))
+  leaf = [l for l in net.children.Flatten()][0] if hasattr(net.children, 'Flatten') else None
+  net.AddFunction('double', lambda x: 2 * x)
+  assert net.fns.double(3) == 6 and net.fns['double'](1) == 2
+  with pytest.raises(AttributeError):
+    net.AddFunction('double', lambda x: x)
+  net.AddFunction('double', lambda x: 3 * x, replace=True)
+  assert net.fns.double(1) == 3
+  assert net.ema is None
+  clean = net.vars.Transform(lambda v: v.detach().clone())
+  noisy = net.AddGlobalVN(clean)
+  diffs = [float((a - b).abs().max()) for a, b in zip(noisy.Flatten(), clean.Flatten())]
+  assert max(diffs) > 0                                  # noise was added on a raw theta
+  from lingvo_b200.core import cluster_factory
+  with cluster_factory.SetEval(True):
+    same = net.AddGlobalVN(clean)
+  assert all(torch.equal(a, b) for a, b in zip(same.Flatten(), clean.Flatten()))
+  del some, leaf
+  # optimizer / learner hooks
+  lp = learner.Learner.Params().Set(name='loss', optimizer=optimizer.SGD.Params(),
+                                    learning_rate=0.5)
+  lrn = lp.Instantiate()
+  w = torch.nn.Parameter(torch.tensor([1.0, 2.0]))
+  w.var_name = 'w/var'
+  bound = lrn.optimizer.GetOptimizer(0.5)
+  bound.apply_gradients(NestedMap(w=py_utils.VarGrad(w, torch.tensor([1.0, 1.0]))))
+  torch.testing.assert_close(w.detach(), torch.tensor([0.5, 1.5]))
+  assert lrn.ApplyPostTrainingLoop() is None and lrn.optimizer.GetLrScheduleValue() == 1.0
+  assert [float(x) for x in lrn.ComputeLosses({'loss': (torch.tensor(2.0), 1.0)})] == [2.0]
+  with pytest.raises(ValueError):
+    lrn.ComputeLosses({'other': (torch.tensor(2.0), 1.0)})
+  # early stop helpers
+  mh = early_stop.MetricHistory.Params().Set(jobname='eval', metric='loss',
+                                             logdir=str(tmp_path)).Instantiate()
+  mh.Append(10, 1.0)
+  mh.Append(20, 0.5)
+  assert mh.metric == 'loss' and open(mh.hist_file).read().split() == \
+      ['10', '1.000000', '20', '0.500000']
+  es = early_stop.EarlyStop.Params()
+  early_stop.MetricHistory.SetLogdirInMetricHistories(es, '/some/dir')
+  assert es.metric_history.logdir == '/some/dir'
+  # rnn cell sizes
+  cell = rnn_cell.LSTMCellSimple.Params().Set(name='c', num_input_nodes=3,
+                                               num_output_nodes=5).Instantiate()
+  assert cell.output_size == 5
+  y = rnn_cell.RNNCell.LayerNorm(torch.randn(2, 6))
+  torch.testing.assert_close(y.mean(-1), torch.zeros(2), atol=1e-5, rtol=0)
