@@ -94,3 +94,34 @@ class MlPerfBleuMetric(metrics.BaseMetric):
   @property
   def value(self):
     return bleu_wrapper(self._refs, self._hyps) if self._refs else 0.0
+
+
+def is_unicode(s):  # pylint: disable=invalid-name
+  return isinstance(s, str)
+
+
+def to_unicode(s, ignore_errors=False):  # pylint: disable=invalid-name
+  if is_unicode(s):
+    return s
+  return s.decode('utf-8', errors='ignore' if ignore_errors else 'strict')
+
+
+def native_to_unicode(s):  # pylint: disable=invalid-name
+  """Bytes or str → str, dropping undecodable bytes (ref :120)."""
+  try:
+    return to_unicode(s)
+  except UnicodeDecodeError:
+    return to_unicode(s, ignore_errors=True)
+
+
+def bleu_score(predictions, labels, max_order=4):  # pylint: disable=invalid-name
+  """Corpus BLEU of token-id sequences `[batch, time]` (trailing 0 padding ignored) against
+  `labels`; returns (bleu, weight 1.0) like the reference's metric fn."""
+  import numpy as np  # pylint: disable=g-import-not-at-top
+
+  def _Rows(x):
+    x = np.asarray(x.detach().cpu() if hasattr(x, 'detach') else x)
+    x = x.reshape(x.shape[0], -1)
+    return [[int(t) for t in np.trim_zeros(row, 'b')] for row in x]
+
+  return compute_bleu(_Rows(labels), _Rows(predictions), max_order), 1.0

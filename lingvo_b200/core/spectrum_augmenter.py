@@ -396,3 +396,23 @@ class SpectrumAugmenter(base_layer.BaseLayer):
     else:
       out = self._AugmentationNetwork(inputs, paddings, rng, 0)
     return (out.squeeze(-1) if squeeze else out), paddings
+
+
+def _AttachEinsumHooks(cls):
+  """The overridable contraction hooks of the reference (:178-197); subclasses replace them
+  with quantised or sharded einsums."""
+  specs = {'EinsumBBmBm': 'b,bm->bm', 'EinsumBmtBmBt': 'bmt,bm->bt',
+           'EinsumBxycByBxyc': 'bxyc,by->bxyc', 'EinsumBxycBxBxyc': 'bxyc,bx->bxyc',
+           'EinsumBxyBxBxy': 'bxy,bx->bxy', 'EinsumBxycBzxBzyc': 'bxyc,bzx->bzyc',
+           'EinsumBxycBzyBxzc': 'bxyc,bzy->bxzc'}
+  for name, eq in specs.items():
+    if not hasattr(cls, name):
+      def _Fn(self, a, b, name=None, _eq=eq):
+        del name
+        return torch.einsum(_eq, a, b.to(a.dtype))
+      _Fn.__name__ = name
+      setattr(cls, name, _Fn)
+  return cls
+
+
+_AttachEinsumHooks(SpectrumAugmenter)

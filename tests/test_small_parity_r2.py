@@ -348,3 +348,21 @@ def test_single_shard_softmax_chunked_xent_matches_dense():
   assert dw.wm.shape == (6, 9) and dw.b.shape == (9,)
   with pytest.raises(AssertionError):
     chunked.XentLossByChunk(chunked.theta, x[:10], ids[:10].reshape(-1))
+
+
+def test_bleu_free_functions_and_spectrum_augmenter_einsum_hooks():
+  import numpy as np
+  import torch
+  from lingvo_b200.core import ml_perf_bleu_metric as bleu
+  from lingvo_b200.core import spectrum_augmenter
+  assert bleu.native_to_unicode(b'caf\xc3\xa9') == 'café' and bleu.is_unicode('x')
+  assert bleu.native_to_unicode(b'\xff-ok') == '-ok'
+  ids = np.array([[5, 6, 7, 8, 9, 0, 0], [3, 4, 5, 6, 7, 8, 0]])
+  score, weight = bleu.bleu_score(torch.from_numpy(ids), ids)
+  assert abs(score - 1.0) < 1e-6 and weight == 1.0
+  worse, _ = bleu.bleu_score(np.array([[5, 6, 1, 8, 9, 0, 0], [3, 4, 5, 6, 2, 8, 0]]), ids)
+  assert 0.0 <= worse < 1.0
+  aug = spectrum_augmenter.SpectrumAugmenter.Params().Set(name='aug').Instantiate()
+  a, b = torch.randn(2, 3, 4, 1), torch.randn(2, 5, 3)
+  torch.testing.assert_close(aug.EinsumBxycBzxBzyc(a, b), torch.einsum('bxyc,bzx->bzyc', a, b))
+  torch.testing.assert_close(aug.EinsumBBmBm(torch.ones(2), torch.ones(2, 3)), torch.ones(2, 3))
